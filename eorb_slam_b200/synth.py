@@ -1,0 +1,139 @@
+"""Deterministic synthetic inputs of the shapes BASELINE.json names.
+
+There is no network for datasets, so every test and bench input is generated here from a seed:
+  * frames    — EuRoC-shaped 8-bit images: background 128 + ~400 random axis-aligned rectangles
+                (side 6..39 px, grey 0..255) + uniform noise -6..+6, clamped; gives 7-8x the per-level
+                quota of FAST candidates on every pyramid level and a few dozen minThFAST fallback cells.
+  * events    — DAVIS-shaped streams: positions on moving straight edges + 10 % uniform noise,
+                sub-pixel float coordinates, strictly increasing timestamps, Bernoulli(0.5) polarity.
+                Record layout = EventData {double ts; float x; float y; bool p} (24 B,
+                reference include/Event/EventData.h:36-58).
+  * descriptors — uniform random 256-bit rows plus planted near-duplicates for the Hamming search.
+"""
+from __future__ import annotations
+
+import numpy as np
+
+EVENT_DTYPE = np.dtype(
+    {"names": ["ts", "x", "y", "p"], "formats": ["<f8", "<f4", "<f4", "u1"], "offsets": [0, 8, 12, 16], "itemsize": 24}
+)
+KEYPOINT_DTYPE = np.dtype(
+    [("x", "<f4"), ("y", "<f4"), ("size", "<f4"), ("angle", "<f4"), ("response", "<f4"), ("octave", "<i4"), ("class_id", "<i4")]
+)
+MATCH_DTYPE = np.dtype([("best_dist", "<i4"), ("best_idx", "<i4"), ("second_dist", "<i4"), ("accepted", "<i4")])
+
+
+def make_frame(seed: int, w: int = 752, h: int = 480, nrect: int = 400, noise: int = 6, kind: str = "textured") -> np.ndarray:
+    """One synthetic u8 frame (h, w)."""
+    rng = np.random.default_rng(np.random.SeedSequence([0xE0B5, int(seed)]))
+    if kind == "zero":
+        return np.zeros((h, w), np.uint8)
+    if kind == "flat":  # low texture: exercises the minThFAST fallback and empty cells
+        img = np.full((h, w), 110, np.int16)
+        img += rng.integers(-2, 3, size=(h, w), dtype=np.int16)
+        # a handful of faint blobs so that some cells only fire at the fallback threshold
+        for _ in range(30):
+            x0 = int(rng.integers(0, w - 12)); y0 = int(rng.integers(0, h - 12))
+            img[y0:y0 + int(rng.integers(4, 12)), x0:x0 + int(rng.integers(4, 12))] += int(rng.integers(9, 16))
+        return np.clip(img, 0, 255).astype(np.uint8)
+    img = np.full((h, w), 128, np.int16)
+    nrect = max(1, int(nrect * (w * h) / (752 * 480)))
+    xs = rng.integers(0, w, nrect); ys = rng.integers(0, h, nrect)
+    ws = rng.integers(6, 40, nrect); hs = rng.integers(6, 40, nrect)
+    gs = rng.integers(0, 256, nrect)
+    for x0, y0, rw, rh, g in zip(xs, ys, ws, hs, gs):
+        img[y0:y0 + rh, x0:x0 + rw] = g
+    img += rng.integers(-noise, noise + 1, size=(h, w), dtype=np.int16)
+    return np.clip(img, 0, 255).astype(np.uint8)
+
+
+def make_frames(n: int, seed0: int = 0, w: int = 752, h: int = 480, unique: int | None = None) -> np.ndarray:
+    """(n, h, w) u8 batch; if `unique` < n the first `unique` frames are generated and cycled with a
+    per-frame circular shift so that every frame is still distinct."""
+    unique = n if unique is None else min(unique, n)
+    base = np.stack([make_frame(seed0 + i, w, h) for i in range(unique)])
+    if unique == n:
+        return base
+    out = np.empty((n, h, w), np.uint8)
+    for i in range(n):
+        out[i] = np.roll(base[i % unique], shift=(i // unique) * 7, axis=1)
+    return out
+
+
+def make_events(n: int, seed: int, w: int = 240, h: int = 180, n_edges: int = 30, noise_frac: float = 0.1,
+                mean_dt: float = 1e-6, t0: float = 0.0) -> np.ndarray:
+    """n events as a structured array with EVENT_DTYPE (24-byte records)."""
+    rng = np.random.default_rng(np.random.SeedSequence([0xE7E7, int(seed)]))
+    ev = np.zeros(n, EVENT_DTYPE)
+    ts = t0 + np.cumsum(rng.exponential(mean_dt, n) + 1e-9)
+    ev["ts"] = ts
+    # moving straight edges: point p0 + s*dir, drifting with velocity vel over time
+    p0 = rng.uniform([0, 0], [w, h], size=(n_edges, 2))
+    ang = rng.uniform(0, np.pi, n_edges)
+    length = rng.uniform(20, 0.6 * min(w, h), n_edges)
+    drift = rng.uniform(-6.0, 6.0, size=(n_edges, 2))   # total edge motion (px) over the stream
+    which = rng.integers(0, n_edges, n)
+    s = rng.uniform(-0.5, 0.5, n) * length[which]
+    frac = (ts - t0) / max(ts[-1] - t0, 1e-12)
+    x = p0[which, 0] + s * np.cos(ang[which]) + drift[which, 0] * frac + rng.normal(0, 0.35, n)
+    y = p0[which, 1] + s * np.sin(ang[which]) + drift[which, 1] * frac + rng.normal(0, 0.35, n)
+    noise = rng.random(n) < noise_frac
+    x[noise] = rng.uniform(0, w, int(noise.sum()))
+    y[noise] = rng.uniform(0, h, int(noise.sum()))
+    # keep a few events outside the image so the in-image test is exercised
+    ev["x"] = np.clip(x, -4.0, w + 3.0).astype(np.float32)
+    ev["y"] = np.clip(y, -4.0, h + 3.0).astype(np.float32)
+    ev["p"] = (rng.random(n) < 0.5).astype(np.uint8)
+    return ev
+
+
+def rotation_tcw(omega_xyz, translation=(0.0, 0.0, 0.0)) -> np.ndarray:
+    """4x4 float32 Tcw from a rotation vector (Rodrigues) and a translation."""
+    w = np.asarray(omega_xyz, np.float64)
+    th = float(np.linalg.norm(w))
+    K = np.zeros((3, 3))
+    if th > 0:
+        k = w / th
+        K = np.array([[0, -k[2], k[1]], [k[2], 0, -k[0]], [-k[1], k[0], 0]])
+    R = np.eye(3) + np.sin(th) * K + (1 - np.cos(th)) * (K @ K)
+    T = np.eye(4)
+    T[:3, :3] = R
+    T[:3, 3] = translation
+    return T.astype(np.float32)
+
+
+def make_descriptor_db(n: int, seed: int) -> np.ndarray:
+    """(n, 32) u8 uniform random descriptors."""
+    rng = np.random.default_rng(np.random.SeedSequence([0xDB, int(seed)]))
+    return rng.integers(0, 256, size=(n, 32), dtype=np.uint8)
+
+
+def make_queries(db: np.ndarray, nq: int, seed: int, max_flips: int = 40, plant_duplicates: bool = True):
+    """nq query rows: first half = DB rows with k~U{0..max_flips} bit flips (true matches), second half
+    uniform random (best ~ 90-100 -> rejected by TH_LOW).  Returns (queries, src_idx) with src_idx=-1 for
+    the random half.  With plant_duplicates the k=0 queries' source rows are also copied to a second DB
+    index (done by the caller through `plant_duplicate_rows`) so ties on distance are exercised."""
+    rng = np.random.default_rng(np.random.SeedSequence([0x9E, int(seed)]))
+    n = db.shape[0]
+    nm = nq // 2
+    src = rng.integers(0, n, nm)
+    q = np.empty((nq, 32), np.uint8)
+    bits = np.unpackbits(db[src], axis=1)
+    flips = rng.integers(0, max_flips + 1, nm)
+    for i in range(nm):
+        if flips[i]:
+            pos = rng.choice(256, int(flips[i]), replace=False)
+            bits[i, pos] ^= 1
+    q[:nm] = np.packbits(bits, axis=1)
+    q[nm:] = rng.integers(0, 256, size=(nq - nm, 32), dtype=np.uint8)
+    src_idx = np.full(nq, -1, np.int64)
+    src_idx[:nm] = src
+    return q, src_idx
+
+
+def plant_duplicate_rows(db: np.ndarray, src_rows: np.ndarray, seed: int) -> np.ndarray:
+    """Copy each of `src_rows` to another random index (in place); returns the destination indices."""
+    rng = np.random.default_rng(np.random.SeedSequence([0xD0, int(seed)]))
+    dst = rng.integers(0, db.shape[0], len(src_rows))
+    db[dst] = db[src_rows]
+    return dst

@@ -1,0 +1,203 @@
+// oracle/event_oracle.cc — CPU ORACLE (test infrastructure, never linked into the product).
+//
+// Restates reference src/Event/EventConversion.cc:
+//   resolvePolarity :26-30, resolveMinMaxVals :32-39, roundFloatCoord :46-49, breakFloatCoords :51-57,
+//   exp_XY2f :59-65, normalizeImage :67-72, ev2im :173-212, ev2im_gauss :215-269,
+//   ev2mci_gg_f(Tcw,medDepth) :279-360, ev2mci_gg_f(params2D) :362-448,
+// with Pinhole::project/unproject (src/CameraModels/Pinhole.cpp:30-62), MyCalibrator::isInImage
+// (src/Utils/MyCalibrator.cpp:36-39) and Eigen::AngleAxisd(R) / AngleAxisd::toRotationMatrix (Eigen 3.3
+// Geometry: matrix -> quaternion (Shepperd) -> angle/axis; Rodrigues) restated inline.
+// Sums are accumulated sequentially in event order in float32, exactly like the reference; the running
+// min/max over every intermediate sum (:257) is reproduced.  Pin for the degenerate DT==0 window (single
+// timestamp): warp rate r := 0 (the reference computes 0*inf = NaN).
+#include "oracle.h"
+
+#include <cmath>
+#include <cstring>
+#include <vector>
+
+namespace {
+
+inline float resolvePolarity(bool withPol, bool evPol) { return (withPol && !evPol) ? -1.0f : 1.0f; }
+
+inline void resolveMinMax(float v, float& mn, float& mx) {
+    if (v > mx) mx = v;
+    if (v < mn) mn = v;
+}
+
+inline bool inImage(float x, float y, int w, int h) { return (x >= 0 && x < float(w)) && (y >= 0 && y < float(h)); }
+
+inline void breakFloatCoords(float X, float Y, int& x, int& y, float& xr, float& yr) {
+    x = static_cast<int>(std::floor(X)); xr = X - float(x);
+    y = static_cast<int>(std::floor(Y)); yr = Y - float(y);
+}
+
+inline float expXY2f(float x, float y, float sig2) {
+    float dd = powf(x, 2) + powf(y, 2);
+    dd /= 2.0f * sig2;
+    return expf(-dd) / (2.0f * float(M_PI) * sig2);
+}
+
+struct Splat {
+    float* img; int w, h; float sig2; int half; bool pol;
+    float mn = 0.0f, mx = -1000000.0f;
+    void add(float X, float Y, bool p) {
+        int xi, yi; float xr, yr;
+        breakFloatCoords(X, Y, xi, yi, xr, yr);
+        for (int i = -half; i <= half; i++)
+            for (int j = -half; j <= half; j++) {
+                int xn = xi + i, yn = yi + j;
+                float val = expXY2f(i - xr, j - yr, sig2);
+                if (!inImage((float)xn, (float)yn, w, h)) continue;
+                float nv = img[(size_t)yn * w + xn] + resolvePolarity(pol, p) * val;
+                img[(size_t)yn * w + xn] = nv;
+                resolveMinMax(nv, mn, mx);
+            }
+    }
+};
+
+// Eigen::AngleAxisd(const Matrix3d&)
+void angleAxisFromR(const double R[3][3], double& angle, double axis[3]) {
+    double q[4];  // x y z w
+    double t = R[0][0] + R[1][1] + R[2][2];
+    if (t > 0) {
+        t = std::sqrt(t + 1.0);
+        q[3] = 0.5 * t;
+        t = 0.5 / t;
+        q[0] = (R[2][1] - R[1][2]) * t;
+        q[1] = (R[0][2] - R[2][0]) * t;
+        q[2] = (R[1][0] - R[0][1]) * t;
+    } else {
+        int i = 0;
+        if (R[1][1] > R[0][0]) i = 1;
+        if (R[2][2] > R[i][i]) i = 2;
+        int j = (i + 1) % 3, k = (j + 1) % 3;
+        t = std::sqrt(R[i][i] - R[j][j] - R[k][k] + 1.0);
+        q[i] = 0.5 * t;
+        t = 0.5 / t;
+        q[3] = (R[k][j] - R[j][k]) * t;
+        q[j] = (R[j][i] + R[i][j]) * t;
+        q[k] = (R[k][i] + R[i][k]) * t;
+    }
+    double n = std::sqrt(q[0] * q[0] + q[1] * q[1] + q[2] * q[2]);
+    if (n != 0.0) {
+        angle = 2.0 * std::atan2(n, std::fabs(q[3]));
+        if (q[3] < 0) n = -n;
+        axis[0] = q[0] / n; axis[1] = q[1] / n; axis[2] = q[2] / n;
+    } else {
+        angle = 0; axis[0] = 1; axis[1] = 0; axis[2] = 0;
+    }
+}
+
+// Eigen::AngleAxisd::toRotationMatrix()
+void rotFromAngleAxis(double angle, const double a[3], double R[3][3]) {
+    double s = std::sin(angle), c = std::cos(angle);
+    double sa[3] = {s * a[0], s * a[1], s * a[2]};
+    double ca[3] = {(1 - c) * a[0], (1 - c) * a[1], (1 - c) * a[2]};
+    double tmp;
+    tmp = ca[0] * a[1]; R[0][1] = tmp - sa[2]; R[1][0] = tmp + sa[2];
+    tmp = ca[0] * a[2]; R[0][2] = tmp + sa[1]; R[2][0] = tmp - sa[1];
+    tmp = ca[1] * a[2]; R[1][2] = tmp - sa[0]; R[2][1] = tmp + sa[0];
+    R[0][0] = ca[0] * a[0] + c; R[1][1] = ca[1] * a[1] + c; R[2][2] = ca[2] * a[2] + c;
+}
+
+}  // namespace
+
+extern "C" {
+
+int orc_ev_accumulate(const orc_event* evs, int64_t n, int w, int h, float sigma, int mode, const float* Tcw16,
+                      float depth, const float* K4, const float* se2, int se2_n, int pol, int normalize,
+                      float* img, float* minmax2) {
+    std::memset(img, 0, sizeof(float) * (size_t)w * h);
+    float mn = 0.0f, mx = -1000000.0f;
+    if (mode == 0) {
+        for (int64_t i = 0; i < n; i++) {
+            float ps = resolvePolarity(pol != 0, evs[i].p != 0);
+            int px = static_cast<int>(roundf(evs[i].x)), py = static_cast<int>(roundf(evs[i].y));
+            if (!inImage((float)px, (float)py, w, h)) continue;
+            float nv = img[(size_t)py * w + px] + (ps * 0.001f);
+            img[(size_t)py * w + px] = nv;
+            resolveMinMax(nv, mn, mx);
+        }
+        if (minmax2) { minmax2[0] = mn; minmax2[1] = mx; }
+        return (normalize && mx > mn) ? 1 : 0;   // 1: caller applies normalizeImage
+    }
+    Splat sp;
+    sp.img = img; sp.w = w; sp.h = h; sp.sig2 = powf(sigma, 2);
+    sp.half = static_cast<int>(std::ceil(sigma * 3.0)); sp.pol = pol != 0;
+    if (mode == 1) {
+        for (int64_t k = 0; k < n; k++) sp.add(evs[k].x, evs[k].y, evs[k].p != 0);
+    } else if (mode == 2) {
+        if (n <= 0) { if (minmax2) { minmax2[0] = mn; minmax2[1] = mx; } return 0; }
+        double R[3][3], tt[3];
+        for (int r = 0; r < 3; r++) { for (int c = 0; c < 3; c++) R[r][c] = (double)Tcw16[r * 4 + c]; tt[r] = (double)Tcw16[r * 4 + 3]; }
+        double ang, ax[3];
+        angleAxisFromR(R, ang, ax);
+        const float fx = K4[0], fy = K4[1], cx = K4[2], cy = K4[3];
+        double t1 = evs[n - 1].ts, DT = t1 - evs[0].ts, invDT = 1.0 / DT;
+        for (int64_t k = 0; k < n; k++) {
+            double rate = DT > 0 ? (t1 - evs[k].ts) * invDT : 0.0;
+            float X = (evs[k].x - cx) / fx, Y = (evs[k].y - cy) / fy, Z = 1.f;
+            double P[3] = {(double)X, (double)Y, (double)Z};
+            double nR[3][3];
+            rotFromAngleAxis(ang * rate, ax, nR);
+            double np[3];
+            for (int r = 0; r < 3; r++) {
+                double md[3] = {(double)depth * nR[r][0], (double)depth * nR[r][1], (double)depth * nR[r][2]};
+                np[r] = (md[0] * P[0] + md[1] * P[1] + md[2] * P[2]) + tt[r] * rate;
+            }
+            double u = fx * np[0] / np[2] + cx, v = fy * np[1] / np[2] + cy;
+            sp.add((float)u, (float)v, evs[k].p != 0);
+        }
+    } else if (mode == 3) {
+        if (n <= 0) { if (minmax2) { minmax2[0] = mn; minmax2[1] = mx; } return 0; }
+        const float fx = K4[0], fy = K4[1], cx = K4[2], cy = K4[3];
+        double t1 = evs[n - 1].ts;
+        float DT = static_cast<float>(t1 - evs[0].ts);
+        float invDT = 1.f / DT;
+        float omega0 = se2[0] * invDT, vx0 = se2[1] * invDT, vy0 = se2[2] * invDT;
+        float sc = 1.f;
+        if (se2_n > 3) sc = se2[3];
+        float scDiff = 1.f - sc;
+        for (int64_t k = 0; k < n; k++) {
+            float tk = static_cast<float>(t1 - evs[k].ts);
+            float X = (evs[k].x - cx) / fx, Y = (evs[k].y - cy) / fy, Z = 1.f;
+            float th = tk * omega0;
+            float cs = scDiff * (1 - tk * invDT) + sc;
+            float xp = cs * (X * cosf(th) - Y * sinf(th)) + vx0 * tk;
+            float yp = cs * (X * sinf(th) + Y * cosf(th)) + vy0 * tk;
+            float u = fx * xp / Z + cx, v = fy * yp / Z + cy;
+            sp.add(u, v, evs[k].p != 0);
+        }
+    } else {
+        return -3;
+    }
+    if (minmax2) { minmax2[0] = sp.mn; minmax2[1] = sp.mx; }
+    return normalize ? 1 : 0;
+}
+
+void orc_normalize_convert_u8(const float* img, int n, float maxVal, float minVal, uint8_t* out) {
+    float alpha = 255.f / (maxVal - minVal);
+    float beta = -minVal * alpha;
+    for (int i = 0; i < n; i++) {
+        float v = img[i] * alpha + beta;
+        int r = (int)lrintf(v);
+        out[i] = (uint8_t)(r < 0 ? 0 : (r > 255 ? 255 : r));
+    }
+}
+
+void orc_normalize_minmax_u8(const float* img, int n, uint8_t* out) {
+    if (n <= 0) return;
+    double smin = img[0], smax = img[0];
+    for (int i = 1; i < n; i++) { if (img[i] < smin) smin = img[i]; if (img[i] > smax) smax = img[i]; }
+    double scale = 255.0 * (smax - smin > 2.220446049250313e-16 ? 1. / (smax - smin) : 0);
+    double shift = 0.0 - smin * scale;
+    float a = (float)scale, b = (float)shift;
+    for (int i = 0; i < n; i++) {
+        float v = img[i] * a + b;
+        int r = (int)lrintf(v);
+        out[i] = (uint8_t)(r < 0 ? 0 : (r > 255 ? 255 : r));
+    }
+}
+
+}  // extern "C"

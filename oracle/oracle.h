@@ -1,0 +1,127 @@
+/*
+ * oracle/oracle.h — C API of the CPU ORACLE.  TEST INFRASTRUCTURE ONLY.
+ *
+ * This library is a from-scratch CPU restatement of the reference's front-end hot path
+ * (src/ORBextractor.cc, src/ORBmatcher.cc:2360-2378 + best-2 loops, src/Event/EventConversion.cc)
+ * including the OpenCV primitive semantics those files rely on (resize/INTER_LINEAR u8, REFLECT_101,
+ * FAST-9/16 + NMS, fastAtan2, GaussianBlur 5x5 u8, cvRound, convertTo/normalize).
+ *
+ * It is the checker for tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference
+ * leg.  NOTHING in the product (eorb_slam_b200/, include/) links, imports or calls it.
+ *
+ * Parity pin: the reference ships no tests/golden vectors and cannot be compiled here
+ * (needs OpenCV 3.4.1 C++ headers, Eigen, glog ...).  Every OpenCV primitive restated here is pinned
+ * bit-exactly against the Python cv2 4.13.0 wheel by tests/golden/make_golden.py (fixtures committed in
+ * tests/golden/ as .npz files); the full-pipeline goldens come from an independent cv2-assisted restatement in
+ * that same script.  Where the reference itself is not a function of its inputs (octree size ties by
+ * heap pointer, FMA contraction, OOB descriptor taps for margin<19, float summation order) the pin
+ * chosen is documented at the function.
+ */
+#ifndef EORB_ORACLE_H
+#define EORB_ORACLE_H
+#include <stdint.h>
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct {
+    int   nfeatures;
+    float scaleFactor;
+    int   nlevels;
+    int   iniThFAST;
+    int   minThFAST;
+    int   edgeTh;      /* <0: adaptive 19*W/752 forced odd (ORBextractor.cc:481-485) */
+    int   imW, imH;    /* only used for the adaptive edge threshold */
+} orc_orb_params;
+
+/* mirrors cv::KeyPoint (28 bytes) */
+typedef struct {
+    float x, y, size, angle, response;
+    int   octave, class_id;
+} orc_keypoint;
+
+/* mirrors EORB_SLAM::EventData (24 bytes, include/Event/EventData.h:36-58) */
+typedef struct {
+    double  ts;
+    float   x, y;
+    uint8_t p;
+    uint8_t _pad[7];
+} orc_event;
+
+typedef struct {
+    int32_t best_dist;   /* 256 if no candidate */
+    int32_t best_idx;    /* -1 if none */
+    int32_t second_dist; /* 256 if fewer than two candidates */
+    int32_t accepted;    /* best<=th && best < ratio*second */
+} orc_match;
+
+typedef struct orc_orb orc_orb;
+
+/* ---- primitives (each pinned against cv2 in tests) ---- */
+int   orc_cv_round_f(float v);
+int   orc_cv_round_d(double v);
+void  orc_resize_linear_u8(const uint8_t* src, int sw, int sh, size_t sstride,
+                           uint8_t* dst, int dw, int dh, size_t dstride);
+void  orc_copy_make_border_reflect101(const uint8_t* src, int w, int h, size_t sstride,
+                                      uint8_t* dst, int border, size_t dstride);
+void  orc_gauss5x5_s2_u8(const uint8_t* src, int w, int h, size_t sstride, uint8_t* dst, size_t dstride);
+/* FAST-9/16 on a ROI; returns count, writes up to cap (x,y,score) in row-major order */
+int   orc_fast9_16(const uint8_t* img, int w, int h, size_t stride, int threshold, int nms,
+                   int* xs, int* ys, int* scores, int cap);
+float orc_fast_atan2(float y, float x);
+/* DistributeOctTree on keys relative to (minX,minY); returns count; out_idx = index into input */
+int   orc_distribute_octtree(const float* kx, const float* ky, const float* kresp, int n,
+                             int minX, int maxX, int minY, int maxY, int N, int* out_idx, int cap);
+
+/* ---- ORB extractor ---- */
+orc_orb* orc_orb_create(const orc_orb_params* p);
+void  orc_orb_destroy(orc_orb* h);
+int   orc_orb_edge_threshold(const orc_orb* h);
+int   orc_orb_features_per_level(const orc_orb* h, int* out /*nlevels*/);
+int   orc_orb_scale_factors(const orc_orb* h, float* scale, float* inv_scale, float* sigma2, float* inv_sigma2);
+int   orc_orb_umax(const orc_orb* h, int* out16);
+/* returns monoIndex (or -1 on empty image); *n_out = number of keypoints; desc may be NULL */
+int   orc_orb_extract(orc_orb* h, const uint8_t* img, int w, int hgt, size_t stride,
+                      int lap0, int lap1, int want_desc,
+                      orc_keypoint* kps, uint8_t* desc, int cap, int* n_out);
+/* stage taps of the LAST extract call */
+int   orc_orb_level_size(const orc_orb* h, int level, int* w, int* hgt);
+int   orc_orb_get_level(const orc_orb* h, int level, uint8_t* dst, size_t dstride);   /* unbordered */
+int   orc_orb_get_blurred(const orc_orb* h, int level, uint8_t* dst, size_t dstride); /* valid if level had kps */
+int   orc_orb_num_candidates(const orc_orb* h, int level);
+int   orc_orb_get_candidates(const orc_orb* h, int level, int* xs, int* ys, int* scores, int cap);
+int   orc_orb_num_level_kps(const orc_orb* h, int level);
+int   orc_orb_get_level_kps(const orc_orb* h, int level, int* xs, int* ys, int* scores, float* angles, int cap);
+int   orc_orb_num_fallback_cells(const orc_orb* h);
+/* thread-pool batch (CPU baseline): frames are w*h contiguous; returns total keypoints */
+long  orc_orb_extract_batch_mt(const orc_orb_params* p, const uint8_t* imgs, int nframes, int w, int hgt,
+                               int nthreads, int want_desc, int* n_per_frame);
+/* descriptors for given keypoints (ComputeTrackedKPtsDesc / AssignKPtLevelByBestDesc) */
+int   orc_orb_tracked_desc(orc_orb* h, const uint8_t* img, int w, int hgt, size_t stride,
+                           const orc_keypoint* kps, int n, uint8_t* desc);
+int   orc_orb_assign_level_by_best_desc(orc_orb* h, const uint8_t* ref_desc, const uint8_t* img, int w, int hgt,
+                                        size_t stride, orc_keypoint* kps, int n);
+
+/* ---- matcher ---- */
+int   orc_descriptor_distance(const uint8_t* a, const uint8_t* b);
+void  orc_hamming_best2(const uint8_t* q, int nq, const uint8_t* db, int64_t ndb,
+                        int th, float ratio, int ratio_mode, orc_match* out, int nthreads);
+/* rotation-consistency filter (ORBmatcher.cc:784-823, 2314-2355). match12[i] = idx or -1; returns #kept */
+int   orc_rotation_filter(const float* angle1, const float* angle2, int32_t* match12, int n1);
+
+/* ---- event frames ---- */
+/* mode: 0 nearest (ev2im), 1 gauss (ev2im_gauss), 2 gauss+SE3 (Tcw16,depth,K4), 3 gauss+SE2 (se2[4],K4) */
+int   orc_ev_accumulate(const orc_event* evs, int64_t n, int w, int h, float sigma, int mode,
+                        const float* Tcw16, float depth, const float* K4, const float* se2, int se2_n,
+                        int pol, int normalize, float* img_f32, float* minmax2);
+/* normalizeImage(convertTo) : u8 = sat(rint(v*alpha+beta)), alpha=255/(max-min), beta=-min*alpha */
+void  orc_normalize_convert_u8(const float* img, int n, float maxVal, float minVal, uint8_t* out);
+/* cv::normalize(img,out,255,0,NORM_MINMAX,CV_8UC1) */
+void  orc_normalize_minmax_u8(const float* img, int n, uint8_t* out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,291 @@
+"""ctypes binding of the CPU oracle (oracle/_build/liboracle.so).  TEST INFRASTRUCTURE ONLY.
+
+Imported by tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference leg — never by
+the product package.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ORACLE_DIR = os.path.join(ROOT, "oracle")
+LIB_PATH = os.path.join(ORACLE_DIR, "_build", "liboracle.so")
+
+KEYPOINT_DTYPE = np.dtype(
+    [("x", "<f4"), ("y", "<f4"), ("size", "<f4"), ("angle", "<f4"), ("response", "<f4"), ("octave", "<i4"), ("class_id", "<i4")]
+)
+MATCH_DTYPE = np.dtype([("best_dist", "<i4"), ("best_idx", "<i4"), ("second_dist", "<i4"), ("accepted", "<i4")])
+
+
+class OrbParams(C.Structure):
+    _fields_ = [("nfeatures", C.c_int), ("scaleFactor", C.c_float), ("nlevels", C.c_int), ("iniThFAST", C.c_int),
+                ("minThFAST", C.c_int), ("edgeTh", C.c_int), ("imW", C.c_int), ("imH", C.c_int)]
+
+
+def build(force: bool = False) -> str:
+    srcs = [os.path.join(ORACLE_DIR, f) for f in ("orb_oracle.cc", "match_oracle.cc", "event_oracle.cc", "oracle.h",
+                                                  "brief_pattern_31.inc", "Makefile")]
+    stale = force or not os.path.exists(LIB_PATH) or any(os.path.getmtime(s) > os.path.getmtime(LIB_PATH) for s in srcs)
+    if stale:
+        subprocess.check_call(["make", "-C", ORACLE_DIR, "-s"] + (["-B"] if force else []))
+    return LIB_PATH
+
+
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is not None:
+        return _lib
+    build()
+    L = C.CDLL(LIB_PATH)
+    u8p, i32p, f32p = C.POINTER(C.c_uint8), C.POINTER(C.c_int), C.POINTER(C.c_float)
+    vp = C.c_void_p
+    L.orc_cv_round_f.argtypes = [C.c_float]; L.orc_cv_round_f.restype = C.c_int
+    L.orc_resize_linear_u8.argtypes = [vp, C.c_int, C.c_int, C.c_size_t, vp, C.c_int, C.c_int, C.c_size_t]
+    L.orc_resize_linear_u8.restype = None
+    L.orc_copy_make_border_reflect101.argtypes = [vp, C.c_int, C.c_int, C.c_size_t, vp, C.c_int, C.c_size_t]
+    L.orc_copy_make_border_reflect101.restype = None
+    L.orc_gauss5x5_s2_u8.argtypes = [vp, C.c_int, C.c_int, C.c_size_t, vp, C.c_size_t]; L.orc_gauss5x5_s2_u8.restype = None
+    L.orc_fast9_16.argtypes = [vp, C.c_int, C.c_int, C.c_size_t, C.c_int, C.c_int, vp, vp, vp, C.c_int]
+    L.orc_fast9_16.restype = C.c_int
+    L.orc_fast_atan2.argtypes = [C.c_float, C.c_float]; L.orc_fast_atan2.restype = C.c_float
+    L.orc_distribute_octtree.argtypes = [vp, vp, vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, vp, C.c_int]
+    L.orc_distribute_octtree.restype = C.c_int
+    L.orc_orb_create.argtypes = [C.POINTER(OrbParams)]; L.orc_orb_create.restype = vp
+    L.orc_orb_destroy.argtypes = [vp]; L.orc_orb_destroy.restype = None
+    L.orc_orb_edge_threshold.argtypes = [vp]; L.orc_orb_edge_threshold.restype = C.c_int
+    L.orc_orb_features_per_level.argtypes = [vp, vp]; L.orc_orb_features_per_level.restype = C.c_int
+    L.orc_orb_scale_factors.argtypes = [vp, vp, vp, vp, vp]; L.orc_orb_scale_factors.restype = C.c_int
+    L.orc_orb_umax.argtypes = [vp, vp]; L.orc_orb_umax.restype = C.c_int
+    L.orc_orb_extract.argtypes = [vp, vp, C.c_int, C.c_int, C.c_size_t, C.c_int, C.c_int, C.c_int, vp, vp, C.c_int, vp]
+    L.orc_orb_extract.restype = C.c_int
+    L.orc_orb_level_size.argtypes = [vp, C.c_int, vp, vp]; L.orc_orb_level_size.restype = C.c_int
+    L.orc_orb_get_level.argtypes = [vp, C.c_int, vp, C.c_size_t]; L.orc_orb_get_level.restype = C.c_int
+    L.orc_orb_get_blurred.argtypes = [vp, C.c_int, vp, C.c_size_t]; L.orc_orb_get_blurred.restype = C.c_int
+    L.orc_orb_num_candidates.argtypes = [vp, C.c_int]; L.orc_orb_num_candidates.restype = C.c_int
+    L.orc_orb_get_candidates.argtypes = [vp, C.c_int, vp, vp, vp, C.c_int]; L.orc_orb_get_candidates.restype = C.c_int
+    L.orc_orb_num_level_kps.argtypes = [vp, C.c_int]; L.orc_orb_num_level_kps.restype = C.c_int
+    L.orc_orb_get_level_kps.argtypes = [vp, C.c_int, vp, vp, vp, vp, C.c_int]; L.orc_orb_get_level_kps.restype = C.c_int
+    L.orc_orb_num_fallback_cells.argtypes = [vp]; L.orc_orb_num_fallback_cells.restype = C.c_int
+    L.orc_orb_extract_batch_mt.argtypes = [C.POINTER(OrbParams), vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, vp]
+    L.orc_orb_extract_batch_mt.restype = C.c_long
+    L.orc_orb_tracked_desc.argtypes = [vp, vp, C.c_int, C.c_int, C.c_size_t, vp, C.c_int, vp]; L.orc_orb_tracked_desc.restype = C.c_int
+    L.orc_orb_assign_level_by_best_desc.argtypes = [vp, vp, vp, C.c_int, C.c_int, C.c_size_t, vp, C.c_int]
+    L.orc_orb_assign_level_by_best_desc.restype = C.c_int
+    L.orc_descriptor_distance.argtypes = [vp, vp]; L.orc_descriptor_distance.restype = C.c_int
+    L.orc_hamming_best2.argtypes = [vp, C.c_int, vp, C.c_int64, C.c_int, C.c_float, C.c_int, vp, C.c_int]
+    L.orc_hamming_best2.restype = None
+    L.orc_rotation_filter.argtypes = [vp, vp, vp, C.c_int]; L.orc_rotation_filter.restype = C.c_int
+    L.orc_ev_accumulate.argtypes = [vp, C.c_int64, C.c_int, C.c_int, C.c_float, C.c_int, vp, C.c_float, vp, vp, C.c_int,
+                                    C.c_int, C.c_int, vp, vp]
+    L.orc_ev_accumulate.restype = C.c_int
+    L.orc_normalize_convert_u8.argtypes = [vp, C.c_int, C.c_float, C.c_float, vp]; L.orc_normalize_convert_u8.restype = None
+    L.orc_normalize_minmax_u8.argtypes = [vp, C.c_int, vp]; L.orc_normalize_minmax_u8.restype = None
+    _lib = L
+    return L
+
+
+def _p(a):
+    return a.ctypes.data_as(C.c_void_p) if a is not None else None
+
+
+# ----------------------------------------------------------------------------- primitives
+def resize_linear(src: np.ndarray, dw: int, dh: int) -> np.ndarray:
+    src = np.ascontiguousarray(src, np.uint8)
+    dst = np.empty((dh, dw), np.uint8)
+    lib().orc_resize_linear_u8(_p(src), src.shape[1], src.shape[0], src.strides[0], _p(dst), dw, dh, dst.strides[0])
+    return dst
+
+
+def border_reflect101(src: np.ndarray, b: int) -> np.ndarray:
+    src = np.ascontiguousarray(src, np.uint8)
+    dst = np.empty((src.shape[0] + 2 * b, src.shape[1] + 2 * b), np.uint8)
+    lib().orc_copy_make_border_reflect101(_p(src), src.shape[1], src.shape[0], src.strides[0], _p(dst), b, dst.strides[0])
+    return dst
+
+
+def gauss5(src: np.ndarray) -> np.ndarray:
+    src = np.ascontiguousarray(src, np.uint8)
+    dst = np.empty_like(src)
+    lib().orc_gauss5x5_s2_u8(_p(src), src.shape[1], src.shape[0], src.strides[0], _p(dst), dst.strides[0])
+    return dst
+
+
+def fast(img: np.ndarray, threshold: int, nms: bool = True):
+    img = np.ascontiguousarray(img, np.uint8)
+    cap = img.size
+    xs = np.empty(cap, np.int32); ys = np.empty(cap, np.int32); sc = np.empty(cap, np.int32)
+    n = lib().orc_fast9_16(_p(img), img.shape[1], img.shape[0], img.strides[0], threshold, int(nms), _p(xs), _p(ys), _p(sc), cap)
+    return xs[:n].copy(), ys[:n].copy(), sc[:n].copy()
+
+
+def fast_atan2(y: float, x: float) -> float:
+    return float(lib().orc_fast_atan2(C.c_float(y), C.c_float(x)))
+
+
+def distribute_octtree(kx, ky, kresp, minX, maxX, minY, maxY, N) -> np.ndarray:
+    kx = np.ascontiguousarray(kx, np.float32); ky = np.ascontiguousarray(ky, np.float32)
+    kr = np.ascontiguousarray(kresp, np.float32)
+    cap = len(kx) + 8
+    out = np.empty(cap, np.int32)
+    n = lib().orc_distribute_octtree(_p(kx), _p(ky), _p(kr), len(kx), minX, maxX, minY, maxY, N, _p(out), cap)
+    return out[:n].copy()
+
+
+# ----------------------------------------------------------------------------- extractor
+class OrbOracle:
+    def __init__(self, nfeatures=1000, scale_factor=1.2, nlevels=8, ini_th=20, min_th=7, edge_th=19, im_w=752, im_h=480):
+        self.params = OrbParams(nfeatures, scale_factor, nlevels, ini_th, min_th, edge_th, im_w, im_h)
+        self.h = lib().orc_orb_create(C.byref(self.params))
+        assert self.h
+        self.nlevels = nlevels
+        self.cap = nfeatures + 3 * nlevels + 64
+
+    def __del__(self):
+        try:
+            if self.h:
+                lib().orc_orb_destroy(self.h); self.h = None
+        except Exception:
+            pass
+
+    @property
+    def edge(self):
+        return lib().orc_orb_edge_threshold(self.h)
+
+    def features_per_level(self):
+        out = np.empty(self.nlevels, np.int32)
+        lib().orc_orb_features_per_level(self.h, _p(out))
+        return out
+
+    def scale_factors(self):
+        a = [np.empty(self.nlevels, np.float32) for _ in range(4)]
+        lib().orc_orb_scale_factors(self.h, *[_p(x) for x in a])
+        return a
+
+    def umax(self):
+        out = np.empty(16, np.int32)
+        lib().orc_orb_umax(self.h, _p(out))
+        return out
+
+    def extract(self, img: np.ndarray, lapping=(0, 1000), want_desc=True):
+        """-> (ret, keypoints[KEYPOINT_DTYPE], descriptors (n,32) u8 or None)"""
+        if img is None or img.size == 0:
+            return -1, np.empty(0, KEYPOINT_DTYPE), None
+        img = np.ascontiguousarray(img, np.uint8)
+        kps = np.zeros(self.cap, KEYPOINT_DTYPE)
+        desc = np.zeros((self.cap, 32), np.uint8)
+        n = C.c_int(0)
+        ret = lib().orc_orb_extract(self.h, _p(img), img.shape[1], img.shape[0], img.strides[0], int(lapping[0]),
+                                    int(lapping[1]), int(want_desc), _p(kps), _p(desc), self.cap, C.byref(n))
+        assert ret != -2, "oracle capacity exceeded"
+        return ret, kps[:n.value].copy(), (desc[:n.value].copy() if want_desc else None)
+
+    def level_size(self, l):
+        w = C.c_int(); h = C.c_int()
+        lib().orc_orb_level_size(self.h, l, C.byref(w), C.byref(h))
+        return w.value, h.value
+
+    def level(self, l):
+        w, h = self.level_size(l)
+        out = np.empty((h, w), np.uint8)
+        lib().orc_orb_get_level(self.h, l, _p(out), out.strides[0])
+        return out
+
+    def blurred(self, l):
+        w, h = self.level_size(l)
+        out = np.empty((h, w), np.uint8)
+        r = lib().orc_orb_get_blurred(self.h, l, _p(out), out.strides[0])
+        return out if r == 0 else None
+
+    def candidates(self, l):
+        n = lib().orc_orb_num_candidates(self.h, l)
+        xs = np.empty(n, np.int32); ys = np.empty(n, np.int32); sc = np.empty(n, np.int32)
+        lib().orc_orb_get_candidates(self.h, l, _p(xs), _p(ys), _p(sc), n)
+        return xs, ys, sc
+
+    def level_kps(self, l):
+        n = lib().orc_orb_num_level_kps(self.h, l)
+        xs = np.empty(n, np.int32); ys = np.empty(n, np.int32); sc = np.empty(n, np.int32); an = np.empty(n, np.float32)
+        lib().orc_orb_get_level_kps(self.h, l, _p(xs), _p(ys), _p(sc), _p(an), n)
+        return xs, ys, sc, an
+
+    def fallback_cells(self):
+        return lib().orc_orb_num_fallback_cells(self.h)
+
+    def tracked_desc(self, img, kps):
+        img = np.ascontiguousarray(img, np.uint8)
+        kps = np.ascontiguousarray(kps, KEYPOINT_DTYPE)
+        desc = np.zeros((len(kps), 32), np.uint8)
+        lib().orc_orb_tracked_desc(self.h, _p(img), img.shape[1], img.shape[0], img.strides[0], _p(kps), len(kps), _p(desc))
+        return desc
+
+    def assign_level_by_best_desc(self, ref_desc, img, kps):
+        img = np.ascontiguousarray(img, np.uint8)
+        kps = np.ascontiguousarray(kps, KEYPOINT_DTYPE).copy()
+        ref_desc = np.ascontiguousarray(ref_desc, np.uint8)
+        lib().orc_orb_assign_level_by_best_desc(self.h, _p(ref_desc), _p(img), img.shape[1], img.shape[0], img.strides[0],
+                                                _p(kps), len(kps))
+        return kps
+
+
+def orb_extract_batch_mt(frames: np.ndarray, nthreads: int, want_desc=True, **kw):
+    frames = np.ascontiguousarray(frames, np.uint8)
+    n, h, w = frames.shape
+    p = OrbParams(kw.get("nfeatures", 1000), kw.get("scale_factor", 1.2), kw.get("nlevels", 8), kw.get("ini_th", 20),
+                  kw.get("min_th", 7), kw.get("edge_th", 19), w, h)
+    counts = np.zeros(n, np.int32)
+    total = lib().orc_orb_extract_batch_mt(C.byref(p), _p(frames), n, w, h, nthreads, int(want_desc), _p(counts))
+    return total, counts
+
+
+# ----------------------------------------------------------------------------- matcher
+def descriptor_distance(a, b) -> int:
+    a = np.ascontiguousarray(a, np.uint8); b = np.ascontiguousarray(b, np.uint8)
+    return lib().orc_descriptor_distance(_p(a), _p(b))
+
+
+def hamming_best2(q, db, th=50, ratio=0.7, ratio_mode=0, nthreads=8):
+    q = np.ascontiguousarray(q, np.uint8); db = np.ascontiguousarray(db, np.uint8)
+    out = np.zeros(len(q), MATCH_DTYPE)
+    lib().orc_hamming_best2(_p(q), len(q), _p(db), len(db), th, ratio, ratio_mode, _p(out), nthreads)
+    return out
+
+
+def rotation_filter(angle1, angle2, match12):
+    a1 = np.ascontiguousarray(angle1, np.float32); a2 = np.ascontiguousarray(angle2, np.float32)
+    m = np.ascontiguousarray(match12, np.int32).copy()
+    n = lib().orc_rotation_filter(_p(a1), _p(a2), _p(m), len(m))
+    return n, m
+
+
+# ----------------------------------------------------------------------------- events
+def ev_accumulate(evs, w, h, sigma=1.0, mode=1, Tcw=None, depth=1.0, K=None, se2=None, pol=False, normalize=False):
+    """-> (img_f32 (h,w), (min,max), u8 or None)"""
+    evs = np.ascontiguousarray(evs)
+    assert evs.dtype.itemsize == 24
+    img = np.zeros((h, w), np.float32)
+    mm = np.zeros(2, np.float32)
+    T = np.ascontiguousarray(Tcw, np.float32).reshape(16) if Tcw is not None else None
+    Kc = np.ascontiguousarray(K, np.float32) if K is not None else None
+    s2 = np.ascontiguousarray(se2, np.float32) if se2 is not None else None
+    r = lib().orc_ev_accumulate(_p(evs), len(evs), w, h, sigma, mode, _p(T), depth, _p(Kc), _p(s2),
+                                0 if s2 is None else len(s2), int(pol), int(normalize), _p(img), _p(mm))
+    assert r >= 0
+    u8 = None
+    if r == 1:
+        u8 = np.empty((h, w), np.uint8)
+        lib().orc_normalize_convert_u8(_p(img), w * h, float(mm[1]), float(mm[0]), _p(u8))
+    return img, (float(mm[0]), float(mm[1])), u8
+
+
+def normalize_minmax_u8(img):
+    img = np.ascontiguousarray(img, np.float32)
+    out = np.empty(img.shape, np.uint8)
+    lib().orc_normalize_minmax_u8(_p(img), img.size, _p(out))
+    return out
