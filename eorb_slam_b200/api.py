@@ -1,0 +1,441 @@
+"""ctypes host mirror of the reference's class surface over the C ABI (include/eorb_b200.h).
+
+The reference is C++; the drop-in C++ shims live in eorb_slam_b200/shim/.  This module gives tests and bench.py
+the same names and argument meaning from Python:
+
+    ORBextractor(ORBxParams)(image, mask, vLappingArea)          include/ORBextractor.h:62-136
+    ORBmatcher(nnratio, checkOri).DescriptorDistance / best-2     include/ORBmatcher.h:35-114
+    EvImConverter.ev2im / ev2im_gauss / ev2mci_gg_f               include/Event/EventConversion.h:40-81
+
+There is no CPU fallback: importing this module raises if libeorb_b200.so is missing, and every compute call
+raises EorbError when no CUDA device is present.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from dataclasses import dataclass
+
+import numpy as np
+
+from .synth import EVENT_DTYPE, KEYPOINT_DTYPE, MATCH_DTYPE
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libeorb_b200.so")
+BEST2_DTYPE = np.dtype([("key1", "<u8"), ("key2", "<u8")])
+
+EORB_OK, EORB_EMPTY = 0, -1
+EV_NEAREST, EV_GAUSS, EV_SE3, EV_SE2 = 0, 1, 2, 3
+NORM_NONE, NORM_RUNNING, NORM_MINMAX = 0, 1, 2
+
+
+class EorbError(RuntimeError):
+    pass
+
+
+class _OrbParams(C.Structure):
+    _fields_ = [("nfeatures", C.c_int), ("scaleFactor", C.c_float), ("nlevels", C.c_int), ("iniThFAST", C.c_int),
+                ("minThFAST", C.c_int), ("edgeTh", C.c_int), ("imW", C.c_int), ("imH", C.c_int)]
+
+
+class _EvParams(C.Structure):
+    _fields_ = [("mode", C.c_int), ("width", C.c_int), ("height", C.c_int), ("sigma", C.c_float), ("pol", C.c_int),
+                ("normalize", C.c_int), ("Tcw", C.c_float * 16), ("med_depth", C.c_float), ("K", C.c_float * 4),
+                ("se2", C.c_float * 4), ("se2_n", C.c_int)]
+
+
+def _load():
+    if not os.path.exists(LIB_PATH):
+        raise ImportError("libeorb_b200.so not built (run `python -c 'import __graft_entry__ as g; g.build()'`): "
+                          "eorb_slam_b200 has no CPU fallback")
+    L = C.CDLL(LIB_PATH)
+    vp, i, f, sz, i64 = C.c_void_p, C.c_int, C.c_float, C.c_size_t, C.c_int64
+    sig = {
+        "eorb_version": ([], i), "eorb_last_error": ([], C.c_char_p), "eorb_device_count": ([], i),
+        "eorb_timer_create": ([C.POINTER(vp)], i), "eorb_timer_destroy": ([vp], i), "eorb_timer_start": ([vp, vp], i),
+        "eorb_timer_stop": ([vp, vp], i), "eorb_timer_elapsed_ms": ([vp, C.POINTER(f)], i),
+        "eorb_probe_popc_rate": ([i, C.POINTER(C.c_double)], i),
+        "eorb_orb_create": ([C.POINTER(_OrbParams), i, i, C.POINTER(vp)], i), "eorb_orb_destroy": ([vp], i),
+        "eorb_orb_set_stream": ([vp, vp], i), "eorb_orb_get_stream": ([vp], vp), "eorb_orb_synchronize": ([vp], i),
+        "eorb_orb_tables": ([vp, vp, vp, vp, vp, vp, vp, vp], i), "eorb_orb_max_keypoints": ([vp], i),
+        "eorb_orb_extract": ([vp, vp, i, i, sz, i, i, i, vp, vp, i, vp], i),
+        "eorb_orb_extract_batch": ([vp, vp, i, i, i, sz, sz, i, i, i, vp, vp, i, vp, vp], i),
+        "eorb_orb_extract_batch_device": ([vp, vp, i, i, i, sz, sz, i, i, i, vp, vp, i, vp, vp], i),
+        "eorb_orb_level_size": ([vp, i, vp, vp], i), "eorb_orb_pyramid_level": ([vp, i, i, vp, sz], i),
+        "eorb_orb_tracked_desc": ([vp, vp, i, i, sz, vp, i, vp], i),
+        "eorb_orb_assign_level_by_best_desc": ([vp, vp, vp, i, i, sz, vp, i], i),
+        "eorb_orb_debug_blurred": ([vp, i, i, vp, sz], i), "eorb_orb_debug_candidates": ([vp, i, i, vp, vp, vp, i], i),
+        "eorb_orb_debug_level_kps": ([vp, i, i, vp, vp, vp, vp, i], i), "eorb_orb_launch_count": ([vp], C.c_longlong),
+        "eorb_descriptor_distance": ([vp, vp], i),
+        "eorb_matcher_create": ([i, C.POINTER(vp)], i), "eorb_matcher_destroy": ([vp], i),
+        "eorb_matcher_set_stream": ([vp, vp], i), "eorb_matcher_synchronize": ([vp], i),
+        "eorb_matcher_launch_count": ([vp], C.c_longlong),
+        "eorb_matcher_set_db_host": ([vp, vp, i64, i64], i), "eorb_matcher_set_db_device": ([vp, vp, i64, i64], i),
+        "eorb_matcher_search": ([vp, vp, i, i, f, vp], i), "eorb_matcher_search_device": ([vp, vp, i, vp], i),
+        "eorb_matcher_merge_device": ([vp, vp, i, i, i, f, vp], i),
+        "eorb_hamming_best2": ([vp, i, vp, i64, i, f, vp], i), "eorb_rotation_filter": ([vp, vp, vp, i], i),
+        "eorb_ev_create": ([i, i, i64, i, i, C.POINTER(vp)], i), "eorb_ev_destroy": ([vp], i),
+        "eorb_ev_set_stream": ([vp, vp], i), "eorb_ev_synchronize": ([vp], i), "eorb_ev_launch_count": ([vp], C.c_longlong),
+        "eorb_ev_accumulate": ([vp, vp, i64, C.POINTER(_EvParams), vp, vp, vp], i),
+        "eorb_ev_accumulate_batch_device": ([vp, vp, vp, i, C.POINTER(_EvParams), vp, vp, vp], i),
+    }
+    for name, (args, res) in sig.items():
+        fn = getattr(L, name)   # AttributeError here == header/library mismatch
+        fn.argtypes = args
+        fn.restype = res
+    return L, list(sig)
+
+
+lib, EXPORTED = _load()
+
+
+def _p(a):
+    if a is None:
+        return None
+    if isinstance(a, np.ndarray):
+        return a.ctypes.data_as(C.c_void_p)
+    return C.c_void_p(int(a))
+
+
+def _check(rc: int, what: str) -> int:
+    if rc <= -2:
+        raise EorbError("%s: error %d: %s" % (what, rc, lib.eorb_last_error().decode(errors="replace")))
+    return rc
+
+
+def device_count() -> int:
+    return lib.eorb_device_count()
+
+
+def probe_popc_rate(device: int = 0) -> float:
+    r = C.c_double(0)
+    _check(lib.eorb_probe_popc_rate(device, C.byref(r)), "probe_popc_rate")
+    return r.value
+
+
+class CudaTimer:
+    """cudaEvent pair recorded on a given stream (the stream the kernels are launched on)."""
+
+    def __init__(self):
+        self.h = C.c_void_p()
+        _check(lib.eorb_timer_create(C.byref(self.h)), "timer_create")
+
+    def start(self, stream):
+        _check(lib.eorb_timer_start(self.h, _p(stream)), "timer_start")
+
+    def stop(self, stream):
+        _check(lib.eorb_timer_stop(self.h, _p(stream)), "timer_stop")
+
+    def elapsed_ms(self) -> float:
+        ms = C.c_float(0)
+        _check(lib.eorb_timer_elapsed_ms(self.h, C.byref(ms)), "timer_elapsed")
+        return ms.value
+
+    def __del__(self):
+        try:
+            lib.eorb_timer_destroy(self.h)
+        except Exception:
+            pass
+
+
+# ================================================================================================ ORB
+@dataclass
+class ORBxParams:
+    """ORB_SLAM3::ORBxParams (include/ORBextractor.h:33-47)"""
+    nfeatures: int = 1000
+    scaleFactor: float = 1.2
+    nlevels: int = 8
+    iniThFAST: int = 20
+    minThFAST: int = 7
+    edgeTh: int = 19
+    imSize: tuple = (752, 480)
+
+
+class ORBextractor:
+    def __init__(self, params: ORBxParams, device: int = 0, max_batch: int = 1):
+        self.params = params
+        cp = _OrbParams(params.nfeatures, params.scaleFactor, params.nlevels, params.iniThFAST, params.minThFAST,
+                        params.edgeTh, params.imSize[0], params.imSize[1])
+        self.h = C.c_void_p()
+        _check(lib.eorb_orb_create(C.byref(cp), device, max_batch, C.byref(self.h)), "ORBextractor")
+        self.max_batch = max_batch
+        self.nlevels = params.nlevels
+        self.cap = lib.eorb_orb_max_keypoints(self.h)
+        self._last = None
+
+    def __del__(self):
+        try:
+            if self.h:
+                lib.eorb_orb_destroy(self.h); self.h = None
+        except Exception:
+            pass
+
+    # --- reference getters (ORBextractor.h:83-107)
+    def _tables(self):
+        nl = self.nlevels
+        n = C.c_int(); e = C.c_int()
+        arrs = [np.empty(nl, np.float32) for _ in range(4)]
+        fpl = np.empty(nl, np.int32)
+        _check(lib.eorb_orb_tables(self.h, C.byref(n), C.byref(e), *[_p(a) for a in arrs], _p(fpl)), "tables")
+        return n.value, e.value, arrs, fpl
+
+    def GetLevels(self): return self._tables()[0]
+    def GetScaleFactor(self): return float(np.float32(self.params.scaleFactor))
+    def GetScaleFactors(self): return self._tables()[2][0]
+    def GetInverseScaleFactors(self): return self._tables()[2][1]
+    def GetScaleSigmaSquares(self): return self._tables()[2][2]
+    def GetInverseScaleSigmaSquares(self): return self._tables()[2][3]
+    def GetNumFeatures(self): return self.params.nfeatures
+    def edge_threshold(self): return self._tables()[1]
+    def features_per_level(self): return self._tables()[3]
+
+    def set_stream(self, stream): _check(lib.eorb_orb_set_stream(self.h, _p(stream)), "set_stream")
+    def stream(self): return lib.eorb_orb_get_stream(self.h)
+    def synchronize(self): _check(lib.eorb_orb_synchronize(self.h), "synchronize")
+    def launch_count(self): return lib.eorb_orb_launch_count(self.h)
+
+    # --- operator() (ORBextractor.cc:1092-1238)
+    def __call__(self, image, mask=None, vLappingArea=(0, 1000), want_desc=True):
+        """-> (ret, keypoints[KEYPOINT_DTYPE], descriptors (n,32) u8 | None).  ret = monoIndex, -1 for an empty image."""
+        if image is None or np.size(image) == 0:
+            return EORB_EMPTY, np.empty(0, KEYPOINT_DTYPE), None
+        img = np.ascontiguousarray(image, np.uint8)
+        assert img.ndim == 2, "CV_8UC1 expected (ORBextractor.cc:1100)"
+        kps = np.zeros(self.cap, KEYPOINT_DTYPE)
+        desc = np.zeros((self.cap, 32), np.uint8) if want_desc else None
+        n = C.c_int(0)
+        ret = _check(lib.eorb_orb_extract(self.h, _p(img), img.shape[1], img.shape[0], img.strides[0], int(vLappingArea[0]),
+                                          int(vLappingArea[1]), int(want_desc), _p(kps), _p(desc), self.cap, C.byref(n)), "extract")
+        return ret, kps[:n.value].copy(), (desc[:n.value].copy() if want_desc else None)
+
+    def extract_batch(self, frames, vLappingArea=(0, 1000), want_desc=True, out=None):
+        """frames: (n,h,w) u8 host array.  -> (kps (n,cap), desc (n,cap,32), n_out (n,), mono (n,))"""
+        frames = np.ascontiguousarray(frames, np.uint8) if isinstance(frames, np.ndarray) else frames
+        n, h, w = frames.shape
+        if out is None:
+            kps = np.zeros((n, self.cap), KEYPOINT_DTYPE)
+            desc = np.zeros((n, self.cap, 32), np.uint8) if want_desc else None
+            nout = np.zeros(n, np.int32); mono = np.zeros(n, np.int32)
+        else:
+            kps, desc, nout, mono = out
+        _check(lib.eorb_orb_extract_batch(self.h, _p(frames), n, w, h, w, w * h, int(vLappingArea[0]), int(vLappingArea[1]),
+                                          int(want_desc), _p(kps), _p(desc), self.cap, _p(nout), _p(mono)), "extract_batch")
+        return kps, desc, nout, mono
+
+    def extract_batch_raw(self, imgs_ptr, n, w, h, row_stride, frame_stride, lap, want_desc, kps_ptr, desc_ptr, cap, n_ptr, mono_ptr,
+                          device=False):
+        """raw-pointer form (host or device pointers); used by bench.py with pinned / resident buffers"""
+        fn = lib.eorb_orb_extract_batch_device if device else lib.eorb_orb_extract_batch
+        return _check(fn(self.h, _p(imgs_ptr), n, w, h, row_stride, frame_stride, int(lap[0]), int(lap[1]), int(want_desc),
+                         _p(kps_ptr), _p(desc_ptr), cap, _p(n_ptr), _p(mono_ptr)), "extract_batch_raw")
+
+    # --- mvImagePyramid (ORBextractor.h:105)
+    def level_size(self, level):
+        w = C.c_int(); h = C.c_int()
+        _check(lib.eorb_orb_level_size(self.h, level, C.byref(w), C.byref(h)), "level_size")
+        return w.value, h.value
+
+    def pyramid_level(self, level, frame=0):
+        w, h = self.level_size(level)
+        out = np.empty((h, w), np.uint8)
+        _check(lib.eorb_orb_pyramid_level(self.h, frame, level, _p(out), out.strides[0]), "pyramid_level")
+        return out
+
+    @property
+    def mvImagePyramid(self):
+        return [self.pyramid_level(l) for l in range(self.nlevels)]
+
+    # --- stage taps (tests)
+    def debug_blurred(self, level, frame=0):
+        w, h = self.level_size(level)
+        out = np.empty((h, w), np.uint8)
+        _check(lib.eorb_orb_debug_blurred(self.h, frame, level, _p(out), out.strides[0]), "debug_blurred")
+        return out
+
+    def debug_candidates(self, level, frame=0, cap=1 << 20):
+        xs = np.empty(cap, np.int32); ys = np.empty(cap, np.int32); sc = np.empty(cap, np.int32)
+        n = _check(lib.eorb_orb_debug_candidates(self.h, frame, level, _p(xs), _p(ys), _p(sc), cap), "debug_candidates")
+        return xs[:n].copy(), ys[:n].copy(), sc[:n].copy()
+
+    def debug_level_kps(self, level, frame=0):
+        cap = self.cap + 64
+        xs = np.empty(cap, np.int32); ys = np.empty(cap, np.int32); sc = np.empty(cap, np.int32); an = np.empty(cap, np.float32)
+        n = _check(lib.eorb_orb_debug_level_kps(self.h, frame, level, _p(xs), _p(ys), _p(sc), _p(an), cap), "debug_level_kps")
+        return xs[:n].copy(), ys[:n].copy(), sc[:n].copy(), an[:n].copy()
+
+    # --- secondary API (ORBextractor.cc:1267-1363)
+    def ComputeTrackedKPtsDesc(self, trackedImage, trackedKPts):
+        img = np.ascontiguousarray(trackedImage, np.uint8)
+        kps = np.ascontiguousarray(trackedKPts, KEYPOINT_DTYPE)
+        desc = np.zeros((len(kps), 32), np.uint8)
+        _check(lib.eorb_orb_tracked_desc(self.h, _p(img), img.shape[1], img.shape[0], img.strides[0], _p(kps), len(kps), _p(desc)),
+               "ComputeTrackedKPtsDesc")
+        return desc
+
+    def AssignKPtLevelByBestDesc(self, refDescs, trackedImage, trackedKPts):
+        img = np.ascontiguousarray(trackedImage, np.uint8)
+        kps = np.ascontiguousarray(trackedKPts, KEYPOINT_DTYPE).copy()
+        ref = np.ascontiguousarray(refDescs, np.uint8)
+        _check(lib.eorb_orb_assign_level_by_best_desc(self.h, _p(ref), _p(img), img.shape[1], img.shape[0], img.strides[0],
+                                                      _p(kps), len(kps)), "AssignKPtLevelByBestDesc")
+        return kps
+
+
+# ================================================================================================ matcher
+class ORBmatcher:
+    TH_LOW = 50      # ORBmatcher.cc:36-38
+    TH_HIGH = 100
+    HISTO_LENGTH = 30
+
+    def __init__(self, nnratio: float = 0.6, checkOri: bool = True, device: int = 0):
+        self.mfNNratio = float(nnratio)
+        self.mbCheckOrientation = bool(checkOri)
+        self.h = C.c_void_p()
+        _check(lib.eorb_matcher_create(device, C.byref(self.h)), "ORBmatcher")
+        self._db_keep = None
+
+    def __del__(self):
+        try:
+            if self.h:
+                lib.eorb_matcher_destroy(self.h); self.h = None
+        except Exception:
+            pass
+
+    @staticmethod
+    def DescriptorDistance(a, b) -> int:
+        a = np.ascontiguousarray(a, np.uint8); b = np.ascontiguousarray(b, np.uint8)
+        return _check(lib.eorb_descriptor_distance(_p(a), _p(b)), "DescriptorDistance")
+
+    def set_stream(self, stream): _check(lib.eorb_matcher_set_stream(self.h, _p(stream)), "set_stream")
+    def synchronize(self): _check(lib.eorb_matcher_synchronize(self.h), "synchronize")
+    def launch_count(self): return lib.eorb_matcher_launch_count(self.h)
+
+    def set_db(self, db, index_offset=0):
+        db = np.ascontiguousarray(db, np.uint8)
+        assert db.ndim == 2 and db.shape[1] == 32
+        _check(lib.eorb_matcher_set_db_host(self.h, _p(db), len(db), index_offset), "set_db")
+
+    def set_db_device(self, d_ptr, ndb, index_offset=0):
+        _check(lib.eorb_matcher_set_db_device(self.h, _p(d_ptr), ndb, index_offset), "set_db_device")
+
+    def search(self, q, th=None):
+        """best-2 + TH + ratio over the resident database -> MATCH_DTYPE[nq]"""
+        q = np.ascontiguousarray(q, np.uint8)
+        out = np.zeros(len(q), MATCH_DTYPE)
+        _check(lib.eorb_matcher_search(self.h, _p(q), len(q), self.TH_LOW if th is None else th, self.mfNNratio, _p(out)), "search")
+        return out
+
+    def search_raw(self, q_ptr, nq, out_ptr, th=None):
+        return _check(lib.eorb_matcher_search(self.h, _p(q_ptr), nq, self.TH_LOW if th is None else th, self.mfNNratio, _p(out_ptr)), "search")
+
+    def search_device(self, d_q, nq, d_partial):
+        _check(lib.eorb_matcher_search_device(self.h, _p(d_q), nq, _p(d_partial)), "search_device")
+
+    def merge_device(self, d_gathered, nshards, nq, d_out, th=None):
+        _check(lib.eorb_matcher_merge_device(self.h, _p(d_gathered), nshards, nq, self.TH_LOW if th is None else th, self.mfNNratio,
+                                             _p(d_out)), "merge_device")
+
+    def SearchBruteForce(self, desc1, desc2, angles1=None, angles2=None, th=None):
+        """Frame-to-frame brute force in the shape of Frame.cc:1228-1235 with the ORBmatcher acceptance rule and,
+        if checkOri and angles are given, the rotation-histogram filter (ORBmatcher.cc:784-823).
+        -> (nmatches, vnMatches12 int32[n1])"""
+        self.set_db(desc2)
+        m = self.search(desc1, th)
+        match12 = np.where(m["accepted"] == 1, m["best_idx"], -1).astype(np.int32)
+        n = int((match12 >= 0).sum())
+        if self.mbCheckOrientation and angles1 is not None and angles2 is not None:
+            a1 = np.ascontiguousarray(angles1, np.float32); a2 = np.ascontiguousarray(angles2, np.float32)
+            n = _check(lib.eorb_rotation_filter(_p(a1), _p(a2), _p(match12), len(match12)), "rotation_filter")
+        return n, match12
+
+
+def rotation_filter(angle1, angle2, match12):
+    a1 = np.ascontiguousarray(angle1, np.float32); a2 = np.ascontiguousarray(angle2, np.float32)
+    m = np.ascontiguousarray(match12, np.int32).copy()
+    n = _check(lib.eorb_rotation_filter(_p(a1), _p(a2), _p(m), len(m)), "rotation_filter")
+    return n, m
+
+
+def hamming_best2(q, db, th=50, ratio=0.7):
+    q = np.ascontiguousarray(q, np.uint8); db = np.ascontiguousarray(db, np.uint8)
+    out = np.zeros(len(q), MATCH_DTYPE)
+    _check(lib.eorb_hamming_best2(_p(q), len(q), _p(db), len(db), th, ratio, _p(out)), "hamming_best2")
+    return out
+
+
+# ================================================================================================ events
+class EvImConverter:
+    """EORB_SLAM::EvImConverter (static methods in the reference; here bound to a converter handle that owns the
+    device workspace).  `camera` = (fx, fy, cx, cy) of the Pinhole model."""
+
+    def __init__(self, device=0, max_windows=1, max_events=1 << 20, max_width=346, max_height=260):
+        self.h = C.c_void_p()
+        _check(lib.eorb_ev_create(device, max_windows, max_events, max_width, max_height, C.byref(self.h)), "EvImConverter")
+
+    def __del__(self):
+        try:
+            if self.h:
+                lib.eorb_ev_destroy(self.h); self.h = None
+        except Exception:
+            pass
+
+    def set_stream(self, stream): _check(lib.eorb_ev_set_stream(self.h, _p(stream)), "set_stream")
+    def synchronize(self): _check(lib.eorb_ev_synchronize(self.h), "synchronize")
+    def launch_count(self): return lib.eorb_ev_launch_count(self.h)
+
+    @staticmethod
+    def make_params(mode, w, h, sigma=1.0, pol=False, normalize=NORM_NONE, Tcw=None, medDepth=1.0, camera=None, params2D=None):
+        p = _EvParams()
+        p.mode = mode; p.width = w; p.height = h; p.sigma = sigma; p.pol = int(pol); p.normalize = normalize
+        T = np.eye(4, dtype=np.float32) if Tcw is None else np.asarray(Tcw, np.float32).reshape(4, 4)
+        for k, v in enumerate(T.reshape(16)):
+            p.Tcw[k] = float(v)
+        p.med_depth = medDepth
+        cam = (1.0, 1.0, 0.0, 0.0) if camera is None else camera
+        for k in range(4):
+            p.K[k] = float(cam[k])
+        p.se2_n = 0
+        if params2D is not None:
+            s = np.asarray(params2D, np.float32).reshape(-1)
+            p.se2_n = len(s)
+            for k in range(len(s)):
+                p.se2[k] = float(s[k])
+        return p
+
+    def _run(self, evs, p):
+        evs = np.ascontiguousarray(evs)
+        assert evs.dtype.itemsize == 24, "EventData is a 24-byte record (include/Event/EventData.h:36-58)"
+        img = np.zeros((p.height, p.width), np.float32)
+        u8 = np.zeros((p.height, p.width), np.uint8) if p.normalize != NORM_NONE else None
+        mm = np.zeros(2, np.float32)
+        rc = _check(lib.eorb_ev_accumulate(self.h, _p(evs) if len(evs) else None, len(evs), C.byref(p), _p(img), _p(u8), _p(mm)), "ev_accumulate")
+        return rc, img, u8, mm
+
+    def ev2im(self, vEvData, imWidth, imHeight, pol=False, normalized=True):
+        p = self.make_params(EV_NEAREST, imWidth, imHeight, 1.0, pol, NORM_RUNNING if normalized else NORM_NONE)
+        _, img, u8, _ = self._run(vEvData, p)
+        return u8 if normalized else img
+
+    def ev2im_gauss(self, vEvData, imWidth, imHeight, sigma, pol=False, normalized=True, both=False):
+        p = self.make_params(EV_GAUSS, imWidth, imHeight, sigma, pol, NORM_RUNNING if normalized else NORM_NONE)
+        _, img, u8, _ = self._run(vEvData, p)
+        return (img, u8) if both else (u8 if normalized else img)
+
+    def ev2mci_gg_f(self, vEvData, camera, Tcw, medDepth, imWidth, imHeight, imSigma, pol=False, normalized=True, both=False,
+                    norm_mode=None):
+        nm = (NORM_RUNNING if normalized else NORM_NONE) if norm_mode is None else norm_mode
+        p = self.make_params(EV_SE3, imWidth, imHeight, imSigma, pol, nm, Tcw=Tcw, medDepth=medDepth, camera=camera)
+        _, img, u8, _ = self._run(vEvData, p)
+        return (img, u8) if both else (u8 if nm != NORM_NONE else img)
+
+    def ev2mci_gg_f_2d(self, vEvData, camera, params2D, imWidth, imHeight, sigma, pol=False, normalized=True, both=False):
+        p = self.make_params(EV_SE2, imWidth, imHeight, sigma, pol, NORM_RUNNING if normalized else NORM_NONE, camera=camera,
+                             params2D=params2D)
+        _, img, u8, _ = self._run(vEvData, p)
+        return (img, u8) if both else (u8 if normalized else img)
+
+    def accumulate_batch_device(self, d_evs, win_offsets, p, d_img_f32, d_img_u8=None, poses=None):
+        offs = np.ascontiguousarray(win_offsets, np.int64)
+        ps = np.ascontiguousarray(poses, np.float32) if poses is not None else None
+        _check(lib.eorb_ev_accumulate_batch_device(self.h, _p(d_evs), _p(offs), len(offs) - 1, C.byref(p), _p(ps), _p(d_img_f32),
+                                                   _p(d_img_u8)), "ev_accumulate_batch_device")

@@ -1,0 +1,964 @@
+// capi.cu — the C ABI of libeorb_b200.so (include/eorb_b200.h): handles, geometry plans, HBM slabs, streams,
+// launch sequences.  Host code only; every compute step is a kernel in orb_kernels.cu / match_kernels.cu /
+// event_kernels.cu.  No CPU fallback: without a CUDA device the entry points return EORB_ERR_CUDA.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "../../include/eorb_b200.h"
+#include "event_kernels.h"
+#include "match_kernels.h"
+#include "octree_core.cuh"
+#include "orb_kernels.h"
+#include "orb_plan.h"
+
+using namespace eorb;
+
+// ------------------------------------------------------------------------------------------------ errors
+static thread_local char g_err[512] = "";
+
+static int fail(int code, const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+    return code;
+}
+
+#define CU(call)                                                                                         \
+    do {                                                                                                 \
+        cudaError_t e__ = (call);                                                                        \
+        if (e__ != cudaSuccess)                                                                          \
+            return fail(EORB_ERR_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e__), __FILE__, __LINE__); \
+    } while (0)
+
+template <class T>
+static cudaError_t devAlloc(T** p, size_t count) {
+    *p = nullptr;
+    if (count == 0) count = 1;
+    return cudaMalloc((void**)p, count * sizeof(T));
+}
+
+static inline int roundUp(int v, int a) { return (v + a - 1) / a * a; }
+static inline int rne(float v) { return (int)lrintf(v); }
+static inline short satShort(float v) { int i = rne(v); return (short)(i < -32768 ? -32768 : (i > 32767 ? 32767 : i)); }
+
+extern "C" int eorb_version(void) { return 100; }
+extern "C" const char* eorb_last_error(void) { return g_err; }
+extern "C" int eorb_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+    return n;
+}
+
+// ------------------------------------------------------------------------------------------------ timers
+struct EorbTimer { cudaEvent_t a, b; };
+extern "C" int eorb_timer_create(void** t) {
+    if (!t) return fail(EORB_ERR_ARG, "null timer");
+    EorbTimer* x = new EorbTimer();
+    CU(cudaEventCreate(&x->a));
+    CU(cudaEventCreate(&x->b));
+    *t = x;
+    return EORB_OK;
+}
+extern "C" int eorb_timer_destroy(void* t) {
+    if (!t) return EORB_OK;
+    EorbTimer* x = (EorbTimer*)t;
+    cudaEventDestroy(x->a); cudaEventDestroy(x->b);
+    delete x;
+    return EORB_OK;
+}
+extern "C" int eorb_timer_start(void* t, void* s) { CU(cudaEventRecord(((EorbTimer*)t)->a, (cudaStream_t)s)); return EORB_OK; }
+extern "C" int eorb_timer_stop(void* t, void* s) { CU(cudaEventRecord(((EorbTimer*)t)->b, (cudaStream_t)s)); return EORB_OK; }
+extern "C" int eorb_timer_elapsed_ms(void* t, float* ms) {
+    EorbTimer* x = (EorbTimer*)t;
+    CU(cudaEventSynchronize(x->b));
+    CU(cudaEventElapsedTime(ms, x->a, x->b));
+    return EORB_OK;
+}
+
+extern "C" int eorb_probe_popc_rate(int device, double* rate) {
+    if (!rate) return fail(EORB_ERR_ARG, "null rate");
+    CU(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    CU(cudaGetDeviceProperties(&prop, device));
+    unsigned* d = nullptr;
+    CU(devAlloc(&d, 4));
+    const int blocks = prop.multiProcessorCount * 8, iters = 4096;
+    cudaEvent_t a, b;
+    CU(cudaEventCreate(&a)); CU(cudaEventCreate(&b));
+    CU(launch_popc_probe(d, blocks, 64, 0));   // warm-up
+    float best = 1e30f;
+    for (int rep = 0; rep < 5; rep++) {
+        CU(cudaEventRecord(a, 0));
+        CU(launch_popc_probe(d, blocks, iters, 0));
+        CU(cudaEventRecord(b, 0));
+        CU(cudaEventSynchronize(b));
+        float ms = 0;
+        CU(cudaEventElapsedTime(&ms, a, b));
+        best = std::min(best, ms);
+    }
+    cudaEventDestroy(a); cudaEventDestroy(b); cudaFree(d);
+    *rate = (double)blocks * 256.0 * 8.0 * iters / (best * 1e-3);
+    return EORB_OK;
+}
+
+// ================================================================================================ ORB
+struct eorb_orb {
+    eorb_orb_params par{};
+    int device = 0, maxBatch = 1, sms = 148;
+    cudaStream_t ownStream = nullptr, stream = nullptr;
+    int nlevels = 0, edge = 19;
+    std::vector<float> scale, invScale, sigma2, invSigma2;
+    std::vector<int> quota;
+    int umax[16];
+    // plan
+    int planW = 0, planH = 0;
+    OrbPlan hp{};
+    std::vector<CellPlan> cells;
+    OrbPlan* d_plan = nullptr; CellPlan* d_cells = nullptr; short4* d_xtab = nullptr; short4* d_ytab = nullptr;
+    float* d_invScale = nullptr;
+    // slabs (maxBatch frames)
+    int pitch0 = 0;
+    uint8_t* d_img0 = nullptr; uint8_t* d_pyr = nullptr; uint8_t* d_blur = nullptr;
+    uint16_t* d_cellCount = nullptr; uint32_t* d_cand = nullptr; uint32_t* d_okeys = nullptr; uint16_t* d_knode = nullptr;
+    uint32_t* d_sel = nullptr; int* d_selCount = nullptr; int* d_candCount = nullptr; int* d_dstIdx = nullptr;
+    float* d_levelAngle = nullptr;
+    // internal outputs for the host entry points
+    int cap = 0;
+    eorb_keypoint* d_outKps = nullptr; uint8_t* d_outDesc = nullptr; int* d_outN = nullptr; int* d_outMono = nullptr;
+    eorb_keypoint* h_kps = nullptr; uint8_t* h_desc = nullptr; int* h_n = nullptr; int* h_mono = nullptr;   // pinned
+    // last call (for the stage taps)
+    const uint8_t* lastLvl0 = nullptr; long long lastPitch0 = 0, lastFrameStride0 = 0; int lastFrames = 0;
+    long long launches = 0;
+};
+
+static void orbFreePlan(eorb_orb* h) {
+    cudaFree(h->d_plan); cudaFree(h->d_cells); cudaFree(h->d_xtab); cudaFree(h->d_ytab); cudaFree(h->d_invScale);
+    cudaFree(h->d_img0); cudaFree(h->d_pyr); cudaFree(h->d_blur); cudaFree(h->d_cellCount); cudaFree(h->d_cand);
+    cudaFree(h->d_okeys); cudaFree(h->d_knode); cudaFree(h->d_sel); cudaFree(h->d_selCount); cudaFree(h->d_candCount);
+    cudaFree(h->d_dstIdx); cudaFree(h->d_levelAngle); cudaFree(h->d_outKps); cudaFree(h->d_outDesc);
+    cudaFree(h->d_outN); cudaFree(h->d_outMono);
+    cudaFreeHost(h->h_kps); cudaFreeHost(h->h_desc); cudaFreeHost(h->h_n); cudaFreeHost(h->h_mono);
+    h->d_plan = nullptr; h->d_cells = nullptr; h->d_xtab = nullptr; h->d_ytab = nullptr; h->d_invScale = nullptr;
+    h->d_img0 = h->d_pyr = h->d_blur = nullptr; h->d_cellCount = nullptr; h->d_cand = h->d_okeys = nullptr;
+    h->d_knode = nullptr; h->d_sel = nullptr; h->d_selCount = h->d_candCount = h->d_dstIdx = nullptr;
+    h->d_levelAngle = nullptr; h->d_outKps = nullptr; h->d_outDesc = nullptr; h->d_outN = h->d_outMono = nullptr;
+    h->h_kps = nullptr; h->h_desc = nullptr; h->h_n = h->h_mono = nullptr;
+    h->planW = h->planH = 0;
+}
+
+// ORBextractor::ORBextractor (ORBextractor.cc:420-489): scale tables, per-level quotas, umax, edge threshold
+static void orbTables(eorb_orb* h) {
+    const eorb_orb_params& p = h->par;
+    const int nl = p.nlevels;
+    h->nlevels = nl;
+    const double sf = (double)p.scaleFactor;   // member is a double holding the float value (ORBextractor.h:123)
+    h->scale.assign(nl, 1.f); h->sigma2.assign(nl, 1.f);
+    for (int i = 1; i < nl; i++) {
+        h->scale[i] = (float)((double)h->scale[i - 1] * sf);
+        h->sigma2[i] = h->scale[i] * h->scale[i];
+    }
+    h->invScale.resize(nl); h->invSigma2.resize(nl);
+    for (int i = 0; i < nl; i++) { h->invScale[i] = 1.0f / h->scale[i]; h->invSigma2[i] = 1.0f / h->sigma2[i]; }
+    h->quota.assign(nl, 0);
+    const float factor = (float)(1.0 / sf);
+    float desired = (float)p.nfeatures * (1.f - factor) / (1.f - (float)std::pow((double)factor, (double)nl));
+    int sum = 0;
+    for (int l = 0; l < nl - 1; l++) {
+        h->quota[l] = rne(desired);
+        sum += h->quota[l];
+        desired *= factor;
+    }
+    h->quota[nl - 1] = std::max(p.nfeatures - sum, 0);
+    // circular patch row extents (:463-478)
+    for (int v = 0; v < 16; v++) h->umax[v] = 0;
+    const int vmax = (int)std::floor(15 * std::sqrt(2.f) / 2 + 1), vmin = (int)std::ceil(15 * std::sqrt(2.f) / 2);
+    for (int v = 0; v <= vmax; ++v) h->umax[v] = (int)lrint(std::sqrt(225.0 - (double)v * v));
+    for (int v = 15, v0 = 0; v >= vmin; --v) {
+        while (h->umax[v0] == h->umax[v0 + 1]) ++v0;
+        h->umax[v] = v0;
+        ++v0;
+    }
+    if (p.edgeTh < 0) {
+        int e = (int)(19.f * ((float)p.imW / 752.f));
+        e += (e % 2 - 1);
+        h->edge = e;
+    } else {
+        h->edge = p.edgeTh;
+    }
+}
+
+static int orbBuildPlan(eorb_orb* h, int W, int H) {
+    if (h->planW == W && h->planH == H) return EORB_OK;
+    if (W < 1 || H < 1 || W > EORB_MAX_DIM || H > EORB_MAX_DIM) return fail(EORB_ERR_ARG, "image size %dx%d unsupported (1..%d)", W, H, EORB_MAX_DIM);
+    CU(cudaStreamSynchronize(h->stream));
+    orbFreePlan(h);
+    OrbPlan& P = h->hp;
+    memset(&P, 0, sizeof(P));
+    const int nl = h->nlevels, E = h->edge;
+    P.nlevels = nl; P.edge = E; P.iniTh = h->par.iniThFAST; P.minTh = h->par.minThFAST; P.W = W; P.H = H;
+    for (int i = 0; i < 16; i++) P.umax[i] = h->umax[i];
+    h->cells.clear();
+    std::vector<short4> xtab, ytab;
+    long long pyrOff = 0, blurOff = 0;
+    int slot = 0, sel = 0, rowBlocks = 0, maxCW = 7, maxCH = 7, octSmem = 0;
+    for (int l = 0; l < nl; l++) {
+        LevelPlan& lp = P.lv[l];
+        lp.w = rne((float)W * h->invScale[l]);
+        lp.h = rne((float)H * h->invScale[l]);
+        if (lp.w < 1 || lp.h < 1) return fail(EORB_ERR_ARG, "pyramid level %d is empty (%dx%d)", l, lp.w, lp.h);
+        lp.pitch = roundUp(lp.w, 16);
+        lp.bpitch = roundUp(lp.w, 16);
+        lp.off = 0;
+        if (l > 0) { lp.off = pyrOff; pyrOff += (long long)lp.pitch * lp.h; }
+        lp.blurOff = blurOff; blurOff += (long long)lp.bpitch * lp.h;
+        lp.scale = h->scale[l];
+        lp.sizeF = (float)(int)(31 * h->scale[l]);
+        lp.quota = h->quota[l];
+        lp.rowBlockBase = rowBlocks; rowBlocks += (lp.h + 7) / 8;
+        // FAST grid (:792-828)
+        lp.minBX = E - 3; lp.minBY = E - 3; lp.maxBX = lp.w - E + 3; lp.maxBY = lp.h - E + 3;
+        const float width = (float)(lp.maxBX - lp.minBX), height = (float)(lp.maxBY - lp.minBY);
+        lp.nCols = (int)(width / 30.f); lp.nRows = (int)(height / 30.f);
+        lp.cellBase = (int)h->cells.size(); lp.slotBase = slot;
+        if (lp.nCols > 0 && lp.nRows > 0) {
+            lp.wCell = (int)std::ceil(width / lp.nCols); lp.hCell = (int)std::ceil(height / lp.nRows);
+            for (int i = 0; i < lp.nRows; i++) {
+                const int iniY = lp.minBY + i * lp.hCell;
+                int maxY = iniY + lp.hCell + 6;
+                if (iniY >= lp.maxBY - 3) continue;
+                if (maxY > lp.maxBY) maxY = lp.maxBY;
+                for (int j = 0; j < lp.nCols; j++) {
+                    const int iniX = lp.minBX + j * lp.wCell;
+                    int maxX = iniX + lp.wCell + 6;
+                    if (iniX >= lp.maxBX - 3) continue;
+                    if (maxX > lp.maxBX) maxX = lp.maxBX;
+                    CellPlan c{};
+                    c.x0 = (short)iniX; c.y0 = (short)iniY; c.w = (short)(maxX - iniX); c.h = (short)(maxY - iniY);
+                    c.level = (short)l; c.ox = (short)(j * lp.wCell); c.oy = (short)(i * lp.hCell);
+                    const int cw = c.w - 6, ch = c.h - 6;
+                    c.slotCap = (cw > 0 && ch > 0) ? ((cw + 1) / 2) * ((ch + 1) / 2) : 0;   // strict 3x3 maxima cannot touch
+                    c.slotOff = slot; slot += c.slotCap;
+                    maxCW = std::max(maxCW, (int)c.w); maxCH = std::max(maxCH, (int)c.h);
+                    h->cells.push_back(c);
+                }
+            }
+        }
+        lp.nCells = (int)h->cells.size() - lp.cellBase;
+        lp.slotCount = slot - lp.slotBase;
+        if (lp.slotCount > (1 << 20)) return fail(EORB_ERR_ARG, "level %d too large for the 20-bit candidate index", l);
+        // octree roots (:562-563)
+        lp.nIni = 0; lp.hX = 1.f;
+        if (lp.maxBX > lp.minBX && lp.maxBY > lp.minBY) {
+            lp.nIni = (int)std::round((float)(lp.maxBX - lp.minBX) / (float)(lp.maxBY - lp.minBY));
+            if (lp.nIni > 0) lp.hX = (float)(lp.maxBX - lp.minBX) / (float)lp.nIni;
+        }
+        lp.nodeCap = std::max(lp.quota + 3, 4 * lp.nIni) + 1;
+        if (lp.nodeCap > 65535) return fail(EORB_ERR_ARG, "nfeatures too large (node capacity %d)", lp.nodeCap);
+        lp.selBase = sel; sel += lp.nodeCap;
+        octSmem = std::max(octSmem, (int)oct_smem_bytes(lp.nodeCap));
+        // resize taps (cv::resize INTER_LINEAR 8-bit, reference call :1253)
+        lp.xtabOff = (int)xtab.size(); lp.ytabOff = (int)ytab.size();
+        if (l > 0) {
+            const int sw = P.lv[l - 1].w, sh = P.lv[l - 1].h;
+            const double scale_x = 1.0 / ((double)lp.w / sw), scale_y = 1.0 / ((double)lp.h / sh);
+            for (int dx = 0; dx < lp.w; dx++) {
+                float fx = (float)((dx + 0.5) * scale_x - 0.5);
+                int sx = (int)std::floor(fx);
+                fx -= sx;
+                if (sx < 0) { fx = 0; sx = 0; }
+                if (sx >= sw - 1) { fx = 0; sx = sw - 1; }
+                short4 t;
+                t.x = (short)sx; t.y = (short)std::min(sx + 1, sw - 1);
+                t.z = satShort((1.f - fx) * 2048.f); t.w = satShort(fx * 2048.f);
+                xtab.push_back(t);
+            }
+            for (int dy = 0; dy < lp.h; dy++) {
+                float fy = (float)((dy + 0.5) * scale_y - 0.5);
+                int sy = (int)std::floor(fy);
+                fy -= sy;
+                short4 t;
+                t.x = (short)std::min(std::max(sy, 0), sh - 1); t.y = (short)std::min(std::max(sy + 1, 0), sh - 1);
+                t.z = satShort((1.f - fy) * 2048.f); t.w = satShort(fy * 2048.f);
+                ytab.push_back(t);
+            }
+        }
+    }
+    P.nCells = (int)h->cells.size();
+    P.slotsPerFrame = std::max(slot, 1);
+    P.selPerFrame = sel;
+    P.pyrBytesPerFrame = std::max(pyrOff, 16ll);
+    P.blurBytesPerFrame = blurOff;
+    P.rowBlocksTotal = rowBlocks;
+    P.cellTileStride = ((maxCW + 6) >> 2) << 2;
+    P.cellMapStride = roundUp(maxCW - 6 + 2, 4);
+    P.cellMapOff = roundUp(maxCH * P.cellTileStride, 16);
+    P.cellListOff = P.cellMapOff + roundUp((maxCH - 6 + 2) * P.cellMapStride, 16);
+    P.cellSmemPerWarp = roundUp(P.cellListOff + (maxCW - 6) * (maxCH - 6) * 2, 16);
+    P.octSmemBytes = octSmem;
+    if (P.cellSmemPerWarp * EORB_FAST_WARPS > 200 * 1024 || octSmem > 200 * 1024)
+        return fail(EORB_ERR_ARG, "shared-memory budget exceeded (fast %d B, octree %d B)", P.cellSmemPerWarp * EORB_FAST_WARPS, octSmem);
+
+    const size_t B = (size_t)h->maxBatch;
+    h->pitch0 = roundUp(W, 16);
+    h->cap = eorb_orb_max_keypoints(h);
+    CU(devAlloc(&h->d_plan, 1));
+    CU(devAlloc(&h->d_cells, h->cells.size()));
+    CU(devAlloc(&h->d_xtab, xtab.size()));
+    CU(devAlloc(&h->d_ytab, ytab.size()));
+    CU(devAlloc(&h->d_invScale, (size_t)nl));
+    CU(devAlloc(&h->d_img0, B * (size_t)h->pitch0 * H));
+    CU(devAlloc(&h->d_pyr, B * (size_t)P.pyrBytesPerFrame));
+    CU(devAlloc(&h->d_blur, B * (size_t)P.blurBytesPerFrame));
+    CU(devAlloc(&h->d_cellCount, B * (size_t)std::max(P.nCells, 1)));
+    CU(devAlloc(&h->d_cand, B * (size_t)P.slotsPerFrame));
+    CU(devAlloc(&h->d_okeys, B * (size_t)P.slotsPerFrame));
+    CU(devAlloc(&h->d_knode, B * (size_t)P.slotsPerFrame));
+    CU(devAlloc(&h->d_sel, B * (size_t)P.selPerFrame));
+    CU(devAlloc(&h->d_selCount, B * (size_t)nl));
+    CU(devAlloc(&h->d_candCount, B * (size_t)nl));
+    CU(devAlloc(&h->d_dstIdx, B * (size_t)P.selPerFrame));
+    CU(devAlloc(&h->d_levelAngle, B * (size_t)P.selPerFrame));
+    CU(devAlloc(&h->d_outKps, B * (size_t)h->cap));
+    CU(devAlloc(&h->d_outDesc, B * (size_t)h->cap * 32));
+    CU(devAlloc(&h->d_outN, B));
+    CU(devAlloc(&h->d_outMono, B));
+    CU(cudaMallocHost((void**)&h->h_kps, B * (size_t)h->cap * sizeof(eorb_keypoint)));
+    CU(cudaMallocHost((void**)&h->h_desc, B * (size_t)h->cap * 32));
+    CU(cudaMallocHost((void**)&h->h_n, B * sizeof(int)));
+    CU(cudaMallocHost((void**)&h->h_mono, B * sizeof(int)));
+    CU(cudaMemcpy(h->d_plan, &P, sizeof(P), cudaMemcpyHostToDevice));
+    if (!h->cells.empty()) CU(cudaMemcpy(h->d_cells, h->cells.data(), h->cells.size() * sizeof(CellPlan), cudaMemcpyHostToDevice));
+    if (!xtab.empty()) CU(cudaMemcpy(h->d_xtab, xtab.data(), xtab.size() * sizeof(short4), cudaMemcpyHostToDevice));
+    if (!ytab.empty()) CU(cudaMemcpy(h->d_ytab, ytab.data(), ytab.size() * sizeof(short4), cudaMemcpyHostToDevice));
+    CU(cudaMemcpy(h->d_invScale, h->invScale.data(), nl * sizeof(float), cudaMemcpyHostToDevice));
+    CU(orb_kernels_configure(P));
+    h->planW = W; h->planH = H;
+    return EORB_OK;
+}
+
+static OrbArgs orbArgs(eorb_orb* h, const uint8_t* lvl0, long long pitch0, long long frameStride0, int lap0, int lap1,
+                       int wantDesc, eorb_keypoint* kps, uint8_t* desc, int cap, int* nOut, int* monoOut) {
+    OrbArgs a{};
+    a.plan = h->d_plan; a.cells = h->d_cells; a.xtab = h->d_xtab; a.ytab = h->d_ytab;
+    a.lvl0 = lvl0; a.lvl0Pitch = pitch0; a.lvl0FrameStride = frameStride0;
+    a.pyr = h->d_pyr; a.blur = h->d_blur; a.cellCount = h->d_cellCount; a.cand = h->d_cand; a.okeys = h->d_okeys;
+    a.knode = h->d_knode; a.sel = h->d_sel; a.selCount = h->d_selCount; a.candCount = h->d_candCount;
+    a.dstIdx = h->d_dstIdx; a.levelAngle = h->d_levelAngle;
+    a.outKps = kps; a.outDesc = desc; a.outN = nOut; a.outMono = monoOut; a.cap = cap;
+    a.lap0 = lap0; a.lap1 = lap1; a.wantDesc = wantDesc;
+    return a;
+}
+
+extern "C" int eorb_orb_create(const eorb_orb_params* params, int device, int max_batch, eorb_orb** out) {
+    if (!params || !out) return fail(EORB_ERR_ARG, "null argument");
+    if (params->nlevels < 1 || params->nlevels > EORB_MAX_LEVELS) return fail(EORB_ERR_ARG, "nlevels must be 1..%d", EORB_MAX_LEVELS);
+    if (params->nfeatures < 0 || !(params->scaleFactor >= 1.0f)) return fail(EORB_ERR_ARG, "bad nfeatures/scaleFactor");
+    if (max_batch < 1) return fail(EORB_ERR_ARG, "max_batch must be >= 1");
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) { cudaGetLastError(); return fail(EORB_ERR_CUDA, "no CUDA device: eorb_b200 has no CPU fallback"); }
+    if (device < 0 || device >= ndev) return fail(EORB_ERR_ARG, "device %d out of range", device);
+    CU(cudaSetDevice(device));
+    eorb_orb* h = new eorb_orb();
+    h->par = *params; h->device = device; h->maxBatch = max_batch;
+    cudaDeviceProp prop;
+    CU(cudaGetDeviceProperties(&prop, device));
+    h->sms = prop.multiProcessorCount;
+    CU(cudaStreamCreateWithFlags(&h->ownStream, cudaStreamNonBlocking));
+    h->stream = h->ownStream;
+    orbTables(h);
+    *out = h;
+    return EORB_OK;
+}
+
+extern "C" int eorb_orb_destroy(eorb_orb* h) {
+    if (!h) return EORB_OK;
+    cudaSetDevice(h->device);
+    cudaStreamSynchronize(h->stream);
+    orbFreePlan(h);
+    cudaStreamDestroy(h->ownStream);
+    delete h;
+    return EORB_OK;
+}
+
+extern "C" int eorb_orb_set_stream(eorb_orb* h, void* s) {
+    if (!h) return fail(EORB_ERR_ARG, "null handle");
+    CU(cudaStreamSynchronize(h->stream));
+    h->stream = s ? (cudaStream_t)s : h->ownStream;
+    return EORB_OK;
+}
+extern "C" void* eorb_orb_get_stream(eorb_orb* h) { return h ? (void*)h->stream : nullptr; }
+extern "C" int eorb_orb_synchronize(eorb_orb* h) {
+    if (!h) return fail(EORB_ERR_ARG, "null handle");
+    CU(cudaSetDevice(h->device));
+    CU(cudaStreamSynchronize(h->stream));
+    return EORB_OK;
+}
+extern "C" long long eorb_orb_launch_count(const eorb_orb* h) { return h ? h->launches : 0; }
+
+extern "C" int eorb_orb_tables(const eorb_orb* h, int* nlevels, int* edge, float* scale, float* inv_scale, float* sigma2,
+                               float* inv_sigma2, int* fpl) {
+    if (!h) return fail(EORB_ERR_ARG, "null handle");
+    if (nlevels) *nlevels = h->nlevels;
+    if (edge) *edge = h->edge;
+    for (int i = 0; i < h->nlevels; i++) {
+        if (scale) scale[i] = h->scale[i];
+        if (inv_scale) inv_scale[i] = h->invScale[i];
+        if (sigma2) sigma2[i] = h->sigma2[i];
+        if (inv_sigma2) inv_sigma2[i] = h->invSigma2[i];
+        if (fpl) fpl[i] = h->quota[i];
+    }
+    return EORB_OK;
+}
+
+extern "C" int eorb_orb_max_keypoints(const eorb_orb* h) {
+    if (!h) return 0;
+    // every level may overshoot its quota by up to 3 (octree) or reach 4*nIni nodes when the quota is tiny
+    int cap = 0;
+    for (int l = 0; l < h->nlevels; l++) cap += std::max(h->quota[l] + 3, 16);
+    return cap;
+}
+
+static bool lvl0ZeroCopyOk(const uint8_t* p, int w, size_t rowStride, size_t frameStride) {
+    return ((uintptr_t)p % 16 == 0) && (rowStride % 4 == 0) && (frameStride % 4 == 0) && rowStride >= (size_t)roundUp(w, 4);
+}
+
+extern "C" int eorb_orb_extract_batch_device(eorb_orb* h, const uint8_t* d_imgs, int nframes, int w, int hgt, size_t row_stride,
+                                             size_t frame_stride, int lap0, int lap1, int want_desc, eorb_keypoint* d_kps,
+                                             uint8_t* d_desc, int cap, int* d_n_out, int* d_mono_out) {
+    if (!h) return fail(EORB_ERR_ARG, "null handle");
+    if (!d_imgs || w <= 0 || hgt <= 0 || nframes <= 0) return EORB_EMPTY;
+    if (nframes > h->maxBatch) return fail(EORB_ERR_CAPACITY, "nframes %d > max_batch %d", nframes, h->maxBatch);
+    if (!d_kps || !d_n_out || !d_mono_out || (want_desc && !d_desc) || cap < 1) return fail(EORB_ERR_ARG, "null output / cap");
+    CU(cudaSetDevice(h->device));
+    int rc = orbBuildPlan(h, w, hgt);
+    if (rc != EORB_OK) return rc;
+    const uint8_t* lvl0 = d_imgs; long long p0 = (long long)row_stride, fs0 = (long long)frame_stride;
+    if (!lvl0ZeroCopyOk(d_imgs, w, row_stride, frame_stride)) {
+        for (int f = 0; f < nframes; f++)
+            CU(cudaMemcpy2DAsync(h->d_img0 + (size_t)f * h->pitch0 * hgt, h->pitch0, d_imgs + (size_t)f * frame_stride, row_stride,
+                                 w, hgt, cudaMemcpyDeviceToDevice, h->stream));
+        lvl0 = h->d_img0; p0 = h->pitch0; fs0 = (long long)h->pitch0 * hgt;
+    }
+    OrbArgs a = orbArgs(h, lvl0, p0, fs0, lap0, lap1, want_desc, d_kps, d_desc, cap, d_n_out, d_mono_out);
+    CU(launch_orb_pipeline(a, h->hp, nframes, h->stream, &h->launches));
+    h->lastLvl0 = lvl0; h->lastPitch0 = p0; h->lastFrameStride0 = fs0; h->lastFrames = nframes;
+    return EORB_OK;
+}
+
+extern "C" int eorb_orb_extract_batch(eorb_orb* h, const uint8_t* imgs, int nframes, int w, int hgt, size_t row_stride,
+                                      size_t frame_stride, int lap0, int lap1, int want_desc, eorb_keypoint* kps, uint8_t* desc,
+                                      int cap, int* n_out, int* mono_out) {
+    if (!h) return fail(EORB_ERR_ARG, "null handle");
+    if (!imgs || w <= 0 || hgt <= 0 || nframes <= 0) return EORB_EMPTY;
+    if (!kps || !n_out || (want_desc && !desc) || cap < 1) return fail(EORB_ERR_ARG, "null output / cap");
+    CU(cudaSetDevice(h->device));
+    int rc = orbBuildPlan(h, w, hgt);
+    if (rc != EORB_OK) return rc;
+    const int B = h->maxBatch, icap = h->cap;
+    int status = EORB_OK;
+    for (int f0 = 0; f0 < nframes; f0 += B) {
+        const int nb = std::min(B, nframes - f0);
+        if (row_stride == (size_t)w && frame_stride == (size_t)w * hgt && h->pitch0 == w) {
+            CU(cudaMemcpyAsync(h->d_img0, imgs + (size_t)f0 * frame_stride, (size_t)nb * frame_stride, cudaMemcpyHostToDevice, h->stream));
+        } else {
+            for (int f = 0; f < nb; f++)
+                CU(cudaMemcpy2DAsync(h->d_img0 + (size_t)f * h->pitch0 * hgt, h->pitch0, imgs + (size_t)(f0 + f) * frame_stride,
+                                     row_stride, w, hgt, cudaMemcpyHostToDevice, h->stream));
+        }
+        OrbArgs a = orbArgs(h, h->d_img0, h->pitch0, (long long)h->pitch0 * hgt, lap0, lap1, want_desc, h->d_outKps, h->d_outDesc,
+                            icap, h->d_outN, h->d_outMono);
+        CU(launch_orb_pipeline(a, h->hp, nb, h->stream, &h->launches));
+        CU(cudaMemcpyAsync(h->h_n, h->d_outN, nb * sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+        CU(cudaMemcpyAsync(h->h_mono, h->d_outMono, nb * sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+        CU(cudaMemcpyAsync(h->h_kps, h->d_outKps, (size_t)nb * icap * sizeof(eorb_keypoint), cudaMemcpyDeviceToHost, h->stream));
+        if (want_desc) CU(cudaMemcpyAsync(h->h_desc, h->d_outDesc, (size_t)nb * icap * 32, cudaMemcpyDeviceToHost, h->stream));
+        CU(cudaStreamSynchronize(h->stream));
+        for (int f = 0; f < nb; f++) {
+            const int n = h->h_n[f];
+            n_out[f0 + f] = n;
+            if (mono_out) mono_out[f0 + f] = h->h_mono[f];
+            if (n > cap || n > icap) { status = fail(EORB_ERR_CAPACITY, "frame %d produced %d keypoints > cap %d", f0 + f, n, std::min(cap, icap)); continue; }
+            memcpy(kps + (size_t)(f0 + f) * cap, h->h_kps + (size_t)f * icap, (size_t)n * sizeof(eorb_keypoint));
+            if (want_desc) memcpy(desc + (size_t)(f0 + f) * cap * 32, h->h_desc + (size_t)f * icap * 32, (size_t)n * 32);
+        }
+        h->lastLvl0 = h->d_img0; h->lastPitch0 = h->pitch0; h->lastFrameStride0 = (long long)h->pitch0 * hgt; h->lastFrames = nb;
+    }
+    return status;
+}
+
+extern "C" int eorb_orb_extract(eorb_orb* h, const uint8_t* img, int w, int hgt, size_t stride, int lap0, int lap1, int want_desc,
+                                eorb_keypoint* kps, uint8_t* desc, int cap, int* n_out) {
+    if (n_out) *n_out = 0;
+    if (!h) return fail(EORB_ERR_ARG, "null handle");
+    if (!img || w <= 0 || hgt <= 0) return EORB_EMPTY;   // _image.empty() -> -1 (ORBextractor.cc:1096)
+    int n = 0, mono = 0;
+    int rc = eorb_orb_extract_batch(h, img, 1, w, hgt, stride, stride * (size_t)hgt, lap0, lap1, want_desc, kps, desc, cap, &n, &mono);
+    if (n_out) *n_out = n;
+    if (rc != EORB_OK) return rc;
+    return mono;
+}
+
+extern "C" int eorb_orb_level_size(const eorb_orb* h, int level, int* w, int* hgt) {
+    if (!h || h->planW == 0) return fail(EORB_ERR_STATE, "no image processed yet");
+    if (level < 0 || level >= h->nlevels) return fail(EORB_ERR_ARG, "level out of range");
+    if (w) *w = h->hp.lv[level].w;
+    if (hgt) *hgt = h->hp.lv[level].h;
+    return EORB_OK;
+}
+
+extern "C" int eorb_orb_pyramid_level(eorb_orb* h, int frame, int level, uint8_t* dst, size_t dst_stride) {
+    if (!h || h->planW == 0 || !h->lastLvl0) return fail(EORB_ERR_STATE, "no image processed yet");
+    if (level < 0 || level >= h->nlevels || frame < 0 || frame >= h->lastFrames || !dst) return fail(EORB_ERR_ARG, "bad frame/level");
+    CU(cudaSetDevice(h->device));
+    const LevelPlan& lp = h->hp.lv[level];
+    const uint8_t* src; size_t sp;
+    if (level == 0) { src = h->lastLvl0 + (size_t)frame * h->lastFrameStride0; sp = (size_t)h->lastPitch0; }
+    else { src = h->d_pyr + (size_t)frame * h->hp.pyrBytesPerFrame + lp.off; sp = lp.pitch; }
+    CU(cudaMemcpy2DAsync(dst, dst_stride, src, sp, lp.w, lp.h, cudaMemcpyDeviceToHost, h->stream));
+    CU(cudaStreamSynchronize(h->stream));
+    return EORB_OK;
+}
+
+extern "C" int eorb_orb_debug_blurred(eorb_orb* h, int frame, int level, uint8_t* dst, size_t dst_stride) {
+    if (!h || h->planW == 0) return fail(EORB_ERR_STATE, "no image processed yet");
+    if (level < 0 || level >= h->nlevels || frame < 0 || frame >= h->lastFrames || !dst) return fail(EORB_ERR_ARG, "bad frame/level");
+    CU(cudaSetDevice(h->device));
+    const LevelPlan& lp = h->hp.lv[level];
+    CU(cudaMemcpy2DAsync(dst, dst_stride, h->d_blur + (size_t)frame * h->hp.blurBytesPerFrame + lp.blurOff, lp.bpitch, lp.w, lp.h,
+                         cudaMemcpyDeviceToHost, h->stream));
+    CU(cudaStreamSynchronize(h->stream));
+    return EORB_OK;
+}
+
+extern "C" int eorb_orb_debug_candidates(eorb_orb* h, int frame, int level, int* xs, int* ys, int* scores, int cap) {
+    if (!h || h->planW == 0) return fail(EORB_ERR_STATE, "no image processed yet");
+    if (level < 0 || level >= h->nlevels || frame < 0 || frame >= h->lastFrames) return fail(EORB_ERR_ARG, "bad frame/level");
+    CU(cudaSetDevice(h->device));
+    CU(cudaStreamSynchronize(h->stream));
+    int n = 0;
+    CU(cudaMemcpy(&n, h->d_candCount + (size_t)frame * h->nlevels + level, sizeof(int), cudaMemcpyDeviceToHost));
+    std::vector<uint32_t> k((size_t)std::max(n, 1));
+    if (n > 0) CU(cudaMemcpy(k.data(), h->d_okeys + (size_t)frame * h->hp.slotsPerFrame + h->hp.lv[level].slotBase, (size_t)n * 4, cudaMemcpyDeviceToHost));
+    for (int i = 0; i < n && i < cap; i++) { xs[i] = k[i] & 0xFFF; ys[i] = (k[i] >> 12) & 0xFFF; scores[i] = k[i] >> 24; }
+    return n;
+}
+
+extern "C" int eorb_orb_debug_level_kps(eorb_orb* h, int frame, int level, int* xs, int* ys, int* scores, float* angles, int cap) {
+    if (!h || h->planW == 0) return fail(EORB_ERR_STATE, "no image processed yet");
+    if (level < 0 || level >= h->nlevels || frame < 0 || frame >= h->lastFrames) return fail(EORB_ERR_ARG, "bad frame/level");
+    CU(cudaSetDevice(h->device));
+    CU(cudaStreamSynchronize(h->stream));
+    int n = 0;
+    CU(cudaMemcpy(&n, h->d_selCount + (size_t)frame * h->nlevels + level, sizeof(int), cudaMemcpyDeviceToHost));
+    const LevelPlan& lp = h->hp.lv[level];
+    std::vector<uint32_t> k((size_t)std::max(n, 1));
+    std::vector<float> an((size_t)std::max(n, 1));
+    if (n > 0) {
+        CU(cudaMemcpy(k.data(), h->d_sel + (size_t)frame * h->hp.selPerFrame + lp.selBase, (size_t)n * 4, cudaMemcpyDeviceToHost));
+        CU(cudaMemcpy(an.data(), h->d_levelAngle + (size_t)frame * h->hp.selPerFrame + lp.selBase, (size_t)n * 4, cudaMemcpyDeviceToHost));
+    }
+    for (int i = 0; i < n && i < cap; i++) {
+        xs[i] = (int)(k[i] & 0xFFF) + lp.minBX; ys[i] = (int)((k[i] >> 12) & 0xFFF) + lp.minBY; scores[i] = k[i] >> 24;
+        if (angles) angles[i] = an[i];
+    }
+    return n;
+}
+
+// ComputeTrackedKPtsDesc (:1316-1363) / AssignKPtLevelByBestDesc (:1267-1314): pyramid + blur of every level,
+// then one warp per (keypoint, level)
+static int orbTracked(eorb_orb* h, const uint8_t* img, int w, int hgt, size_t stride, eorb_keypoint* kps, int n, int mode,
+                      const uint8_t* ref_desc, uint8_t* desc) {
+    if (!h) return fail(EORB_ERR_ARG, "null handle");
+    if (!img || w <= 0 || hgt <= 0) return EORB_EMPTY;   // trackedImage.empty() -> return
+    if (n <= 0) return EORB_OK;
+    if (!kps || (mode == 0 && !desc) || (mode == 1 && !ref_desc)) return fail(EORB_ERR_ARG, "null argument");
+    CU(cudaSetDevice(h->device));
+    int rc = orbBuildPlan(h, w, hgt);
+    if (rc != EORB_OK) return rc;
+    CU(cudaMemcpy2DAsync(h->d_img0, h->pitch0, img, stride, w, hgt, cudaMemcpyHostToDevice, h->stream));
+    OrbArgs a = orbArgs(h, h->d_img0, h->pitch0, (long long)h->pitch0 * hgt, 0, 0, 1, h->d_outKps, h->d_outDesc, h->cap, h->d_outN, h->d_outMono);
+    CU(launch_pyramid_and_blur(a, h->hp, h->stream, &h->launches));
+    eorb_keypoint* d_k = nullptr; uint8_t* d_ref = nullptr; uint8_t* d_desc = nullptr; int* d_dist = nullptr;
+    CU(devAlloc(&d_k, (size_t)n));
+    CU(cudaMemcpyAsync(d_k, kps, (size_t)n * sizeof(eorb_keypoint), cudaMemcpyHostToDevice, h->stream));
+    if (mode == 0) { CU(devAlloc(&d_desc, (size_t)n * 32)); CU(cudaMemsetAsync(d_desc, 0, (size_t)n * 32, h->stream)); }
+    else {
+        CU(devAlloc(&d_ref, (size_t)n * 32)); CU(devAlloc(&d_dist, (size_t)n * h->nlevels));
+        CU(cudaMemcpyAsync(d_ref, ref_desc, (size_t)n * 32, cudaMemcpyHostToDevice, h->stream));
+    }
+    CU(launch_tracked_desc(a, h->hp, d_k, n, mode, h->d_invScale, d_ref, d_desc, d_dist, h->stream, &h->launches));
+    if (mode == 0) {
+        CU(cudaMemcpyAsync(desc, d_desc, (size_t)n * 32, cudaMemcpyDeviceToHost, h->stream));
+        CU(cudaStreamSynchronize(h->stream));
+    } else {
+        std::vector<int> dist((size_t)n * h->nlevels);
+        CU(cudaMemcpyAsync(dist.data(), d_dist, dist.size() * sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+        CU(cudaStreamSynchronize(h->stream));
+        for (int i = 0; i < n; i++) {
+            int best = INT32_MAX;
+            for (int l = 0; l < h->nlevels; l++) {
+                const int d = dist[(size_t)l * n + i];
+                if (d < best) { best = d; kps[i].octave = l; }   // strict '<': lowest level wins ties (:1308-1311)
+            }
+        }
+    }
+    cudaFree(d_k); cudaFree(d_ref); cudaFree(d_desc); cudaFree(d_dist);
+    h->lastLvl0 = h->d_img0; h->lastPitch0 = h->pitch0; h->lastFrameStride0 = (long long)h->pitch0 * hgt; h->lastFrames = 1;
+    return EORB_OK;
+}
+
+extern "C" int eorb_orb_tracked_desc(eorb_orb* h, const uint8_t* img, int w, int hgt, size_t stride, const eorb_keypoint* kps,
+                                     int n, uint8_t* desc) {
+    return orbTracked(h, img, w, hgt, stride, const_cast<eorb_keypoint*>(kps), n, 0, nullptr, desc);
+}
+extern "C" int eorb_orb_assign_level_by_best_desc(eorb_orb* h, const uint8_t* ref_desc, const uint8_t* img, int w, int hgt,
+                                                  size_t stride, eorb_keypoint* kps, int n) {
+    return orbTracked(h, img, w, hgt, stride, kps, n, 1, ref_desc, nullptr);
+}
+
+// ================================================================================================ matcher
+struct eorb_matcher {
+    int device = 0, sms = 148;
+    cudaStream_t ownStream = nullptr, stream = nullptr;
+    const uint8_t* d_db = nullptr; uint8_t* ownedDb = nullptr;
+    long long ndb = 0, indexOffset = 0, chunkRows = 0;
+    int nchunks = 0;
+    eorb_best2* d_partial = nullptr; size_t partialCap = 0;
+    uint8_t* d_q = nullptr; size_t qCap = 0;
+    eorb_match* d_out = nullptr; size_t outCap = 0;
+    long long launches = 0;
+};
+
+extern "C" int eorb_descriptor_distance(const uint8_t* a, const uint8_t* b) {
+    if (!a || !b) return fail(EORB_ERR_ARG, "null descriptor");
+    uint32_t x[8], y[8];
+    memcpy(x, a, 32); memcpy(y, b, 32);
+    int d = 0;
+    for (int i = 0; i < 8; i++) d += __builtin_popcount(x[i] ^ y[i]);
+    return d;
+}
+
+extern "C" int eorb_matcher_create(int device, eorb_matcher** out) {
+    if (!out) return fail(EORB_ERR_ARG, "null argument");
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) { cudaGetLastError(); return fail(EORB_ERR_CUDA, "no CUDA device: eorb_b200 has no CPU fallback"); }
+    if (device < 0 || device >= ndev) return fail(EORB_ERR_ARG, "device %d out of range", device);
+    CU(cudaSetDevice(device));
+    eorb_matcher* m = new eorb_matcher();
+    m->device = device;
+    cudaDeviceProp prop;
+    CU(cudaGetDeviceProperties(&prop, device));
+    m->sms = prop.multiProcessorCount;
+    CU(cudaStreamCreateWithFlags(&m->ownStream, cudaStreamNonBlocking));
+    m->stream = m->ownStream;
+    *out = m;
+    return EORB_OK;
+}
+extern "C" int eorb_matcher_destroy(eorb_matcher* m) {
+    if (!m) return EORB_OK;
+    cudaSetDevice(m->device);
+    cudaStreamSynchronize(m->stream);
+    cudaFree(m->ownedDb); cudaFree(m->d_partial); cudaFree(m->d_q); cudaFree(m->d_out);
+    cudaStreamDestroy(m->ownStream);
+    delete m;
+    return EORB_OK;
+}
+extern "C" int eorb_matcher_set_stream(eorb_matcher* m, void* s) {
+    if (!m) return fail(EORB_ERR_ARG, "null handle");
+    CU(cudaStreamSynchronize(m->stream));
+    m->stream = s ? (cudaStream_t)s : m->ownStream;
+    return EORB_OK;
+}
+extern "C" int eorb_matcher_synchronize(eorb_matcher* m) {
+    if (!m) return fail(EORB_ERR_ARG, "null handle");
+    CU(cudaSetDevice(m->device));
+    CU(cudaStreamSynchronize(m->stream));
+    return EORB_OK;
+}
+extern "C" long long eorb_matcher_launch_count(const eorb_matcher* m) { return m ? m->launches : 0; }
+
+static int matcherAdopt(eorb_matcher* m, const uint8_t* d_db, long long ndb, long long indexOffset) {
+    if (ndb < 0 || indexOffset < 0 || indexOffset + ndb > 0x7fffffffLL) return fail(EORB_ERR_ARG, "database rows must fit int32 indices");
+    if ((uintptr_t)d_db % 16 != 0) return fail(EORB_ERR_ARG, "database pointer must be 16-byte aligned");
+    m->d_db = d_db; m->ndb = ndb; m->indexOffset = indexOffset;
+    m->nchunks = ndb > 0 ? hamming_chunks(ndb, m->sms, &m->chunkRows) : 0;
+    return EORB_OK;
+}
+extern "C" int eorb_matcher_set_db_device(eorb_matcher* m, const uint8_t* d_db, int64_t ndb, int64_t index_offset) {
+    if (!m || (!d_db && ndb > 0)) return fail(EORB_ERR_ARG, "null argument");
+    CU(cudaSetDevice(m->device));
+    CU(cudaStreamSynchronize(m->stream));
+    cudaFree(m->ownedDb); m->ownedDb = nullptr;
+    return matcherAdopt(m, d_db, ndb, index_offset);
+}
+extern "C" int eorb_matcher_set_db_host(eorb_matcher* m, const uint8_t* db, int64_t ndb, int64_t index_offset) {
+    if (!m || (!db && ndb > 0)) return fail(EORB_ERR_ARG, "null argument");
+    CU(cudaSetDevice(m->device));
+    CU(cudaStreamSynchronize(m->stream));
+    cudaFree(m->ownedDb); m->ownedDb = nullptr;
+    CU(devAlloc(&m->ownedDb, (size_t)std::max<int64_t>(ndb, 1) * 32));
+    if (ndb > 0) CU(cudaMemcpy(m->ownedDb, db, (size_t)ndb * 32, cudaMemcpyHostToDevice));
+    return matcherAdopt(m, m->ownedDb, ndb, index_offset);
+}
+
+static int matcherReserve(eorb_matcher* m, int nq) {
+    const size_t needP = (size_t)std::max(m->nchunks, 1) * nq;
+    if (needP > m->partialCap) { cudaFree(m->d_partial); CU(devAlloc(&m->d_partial, needP)); m->partialCap = needP; }
+    return EORB_OK;
+}
+
+extern "C" int eorb_matcher_search_device(eorb_matcher* m, const uint8_t* d_q, int nq, eorb_best2* d_partial) {
+    if (!m || !d_partial) return fail(EORB_ERR_ARG, "null argument");
+    if (nq <= 0) return EORB_OK;
+    if ((uintptr_t)d_q % 16 != 0) return fail(EORB_ERR_ARG, "query pointer must be 16-byte aligned");
+    CU(cudaSetDevice(m->device));
+    int rc = matcherReserve(m, nq);
+    if (rc != EORB_OK) return rc;
+    if (m->nchunks > 0) {
+        CU(launch_hamming_best2(d_q, nq, m->d_db, m->ndb, m->indexOffset, m->chunkRows, m->nchunks, m->d_partial, m->stream));
+        m->launches++;
+    }
+    CU(launch_merge_best2(m->d_partial, m->nchunks, nq, d_partial, nullptr, 0, 0.f, m->stream));
+    m->launches++;
+    return EORB_OK;
+}
+
+extern "C" int eorb_matcher_merge_device(eorb_matcher* m, const eorb_best2* d_gathered, int nshards, int nq, int th, float ratio,
+                                         eorb_match* d_out) {
+    if (!m || !d_gathered || !d_out || nshards < 1) return fail(EORB_ERR_ARG, "null argument");
+    if (nq <= 0) return EORB_OK;
+    CU(cudaSetDevice(m->device));
+    CU(launch_merge_best2(d_gathered, nshards, nq, nullptr, d_out, th, ratio, m->stream));
+    m->launches++;
+    return EORB_OK;
+}
+
+extern "C" int eorb_matcher_search(eorb_matcher* m, const uint8_t* q, int nq, int th, float ratio, eorb_match* out) {
+    if (!m || !out || (!q && nq > 0)) return fail(EORB_ERR_ARG, "null argument");
+    if (nq <= 0) return EORB_OK;
+    CU(cudaSetDevice(m->device));
+    if ((size_t)nq * 32 > m->qCap) { cudaFree(m->d_q); CU(devAlloc(&m->d_q, (size_t)nq * 32)); m->qCap = (size_t)nq * 32; }
+    if ((size_t)nq > m->outCap) { cudaFree(m->d_out); CU(devAlloc(&m->d_out, (size_t)nq)); m->outCap = nq; }
+    int rc = matcherReserve(m, nq);
+    if (rc != EORB_OK) return rc;
+    CU(cudaMemcpyAsync(m->d_q, q, (size_t)nq * 32, cudaMemcpyHostToDevice, m->stream));
+    if (m->nchunks > 0) {
+        CU(launch_hamming_best2(m->d_q, nq, m->d_db, m->ndb, m->indexOffset, m->chunkRows, m->nchunks, m->d_partial, m->stream));
+        m->launches++;
+    }
+    CU(launch_merge_best2(m->d_partial, m->nchunks, nq, nullptr, m->d_out, th, ratio, m->stream));
+    m->launches++;
+    CU(cudaMemcpyAsync(out, m->d_out, (size_t)nq * sizeof(eorb_match), cudaMemcpyDeviceToHost, m->stream));
+    CU(cudaStreamSynchronize(m->stream));
+    return EORB_OK;
+}
+
+extern "C" int eorb_hamming_best2(const uint8_t* q, int nq, const uint8_t* db, int64_t ndb, int th, float ratio, eorb_match* out) {
+    eorb_matcher* m = nullptr;
+    int rc = eorb_matcher_create(0, &m);
+    if (rc != EORB_OK) return rc;
+    rc = eorb_matcher_set_db_host(m, db, ndb, 0);
+    if (rc == EORB_OK) rc = eorb_matcher_search(m, q, nq, th, ratio, out);
+    eorb_matcher_destroy(m);
+    return rc;
+}
+
+// ORBmatcher.cc:784-794 (histogram fill), :800-823 (filter), ComputeThreeMaxima :2314-2355.  Host code like the
+// reference: O(matches), sequential list semantics.  factor = 1/HISTO_LENGTH is the reference's (quirky) bin width.
+extern "C" int eorb_rotation_filter(const float* angle1, const float* angle2, int32_t* match12, int n1) {
+    if ((!angle1 || !angle2 || !match12) && n1 > 0) return fail(EORB_ERR_ARG, "null argument");
+    const int L = 30;
+    const float factor = 1.0f / L;
+    std::vector<std::vector<int>> hist(L);
+    int nmatches = 0;
+    for (int i = 0; i < n1; i++) {
+        const int j = match12[i];
+        if (j < 0) continue;
+        nmatches++;
+        float rot = angle1[i] - angle2[j];
+        if (rot < 0.0) rot += 360.0f;
+        int bin = (int)std::round(rot * factor);
+        if (bin == L) bin = 0;
+        if (bin >= 0 && bin < L) hist[bin].push_back(i);
+    }
+    int top[3] = {-1, -1, -1}, cnt[3] = {0, 0, 0};
+    for (int b = 0; b < L; b++) {
+        const int s = (int)hist[b].size();
+        if (s > cnt[0]) { cnt[2] = cnt[1]; top[2] = top[1]; cnt[1] = cnt[0]; top[1] = top[0]; cnt[0] = s; top[0] = b; }
+        else if (s > cnt[1]) { cnt[2] = cnt[1]; top[2] = top[1]; cnt[1] = s; top[1] = b; }
+        else if (s > cnt[2]) { cnt[2] = s; top[2] = b; }
+    }
+    if ((float)cnt[1] < 0.1f * (float)cnt[0]) { top[1] = -1; top[2] = -1; }
+    else if ((float)cnt[2] < 0.1f * (float)cnt[0]) { top[2] = -1; }
+    for (int b = 0; b < L; b++) {
+        if (b == top[0] || b == top[1] || b == top[2]) continue;
+        for (int i : hist[b])
+            if (match12[i] >= 0) { match12[i] = -1; nmatches--; }
+    }
+    return nmatches;
+}
+
+// ================================================================================================ events
+struct eorb_evconv {
+    int device = 0;
+    cudaStream_t ownStream = nullptr, stream = nullptr;
+    int maxWindows = 0, maxW = 0, maxH = 0;
+    long long maxEvents = 0;
+    eorb_event* d_evs = nullptr; float* d_img = nullptr; uint8_t* d_u8 = nullptr; float* d_minmax = nullptr;
+    EvWindow* d_wins = nullptr;
+    std::vector<EvWindow> h_wins;
+    long long launches = 0;
+};
+
+extern "C" int eorb_ev_create(int device, int max_windows, int64_t max_events, int max_width, int max_height, eorb_evconv** out) {
+    if (!out || max_windows < 1 || max_events < 1 || max_width < 1 || max_height < 1) return fail(EORB_ERR_ARG, "bad argument");
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) { cudaGetLastError(); return fail(EORB_ERR_CUDA, "no CUDA device: eorb_b200 has no CPU fallback"); }
+    if (device < 0 || device >= ndev) return fail(EORB_ERR_ARG, "device %d out of range", device);
+    CU(cudaSetDevice(device));
+    eorb_evconv* c = new eorb_evconv();
+    c->device = device; c->maxWindows = max_windows; c->maxEvents = max_events; c->maxW = max_width; c->maxH = max_height;
+    CU(cudaStreamCreateWithFlags(&c->ownStream, cudaStreamNonBlocking));
+    c->stream = c->ownStream;
+    CU(devAlloc(&c->d_evs, (size_t)max_events));
+    CU(devAlloc(&c->d_img, (size_t)max_width * max_height));      // single-window host path
+    CU(devAlloc(&c->d_u8, (size_t)max_width * max_height));
+    CU(devAlloc(&c->d_minmax, (size_t)max_windows * 2));
+    CU(devAlloc(&c->d_wins, (size_t)max_windows));
+    *out = c;
+    return EORB_OK;
+}
+extern "C" int eorb_ev_destroy(eorb_evconv* c) {
+    if (!c) return EORB_OK;
+    cudaSetDevice(c->device);
+    cudaStreamSynchronize(c->stream);
+    cudaFree(c->d_evs); cudaFree(c->d_img); cudaFree(c->d_u8); cudaFree(c->d_minmax); cudaFree(c->d_wins);
+    cudaStreamDestroy(c->ownStream);
+    delete c;
+    return EORB_OK;
+}
+extern "C" int eorb_ev_set_stream(eorb_evconv* c, void* s) {
+    if (!c) return fail(EORB_ERR_ARG, "null handle");
+    CU(cudaStreamSynchronize(c->stream));
+    c->stream = s ? (cudaStream_t)s : c->ownStream;
+    return EORB_OK;
+}
+extern "C" int eorb_ev_synchronize(eorb_evconv* c) {
+    if (!c) return fail(EORB_ERR_ARG, "null handle");
+    CU(cudaSetDevice(c->device));
+    CU(cudaStreamSynchronize(c->stream));
+    return EORB_OK;
+}
+extern "C" long long eorb_ev_launch_count(const eorb_evconv* c) { return c ? c->launches : 0; }
+
+// Eigen::AngleAxisd(const Matrix3d&) (matrix -> quaternion -> angle/axis), used at EventConversion.cc:303
+static void angleAxisFromPose(const float* T, EvWindow& w) {
+    double R[3][3];
+    for (int r = 0; r < 3; r++) { for (int c = 0; c < 3; c++) R[r][c] = (double)T[4 * r + c]; w.t[r] = (double)T[4 * r + 3]; }
+    double q[4];
+    double tr = R[0][0] + R[1][1] + R[2][2];
+    if (tr > 0) {
+        double s = std::sqrt(tr + 1.0);
+        q[3] = 0.5 * s; s = 0.5 / s;
+        q[0] = (R[2][1] - R[1][2]) * s; q[1] = (R[0][2] - R[2][0]) * s; q[2] = (R[1][0] - R[0][1]) * s;
+    } else {
+        int i = 0;
+        if (R[1][1] > R[0][0]) i = 1;
+        if (R[2][2] > R[i][i]) i = 2;
+        const int j = (i + 1) % 3, k = (j + 1) % 3;
+        double s = std::sqrt(R[i][i] - R[j][j] - R[k][k] + 1.0);
+        q[i] = 0.5 * s; s = 0.5 / s;
+        q[3] = (R[k][j] - R[j][k]) * s; q[j] = (R[j][i] + R[i][j]) * s; q[k] = (R[k][i] + R[i][k]) * s;
+    }
+    double n = std::sqrt(q[0] * q[0] + q[1] * q[1] + q[2] * q[2]);
+    if (n != 0.0) {
+        w.angle = 2.0 * std::atan2(n, std::fabs(q[3]));
+        if (q[3] < 0) n = -n;
+        w.axis[0] = q[0] / n; w.axis[1] = q[1] / n; w.axis[2] = q[2] / n;
+    } else {
+        w.angle = 0; w.axis[0] = 1; w.axis[1] = 0; w.axis[2] = 0;
+    }
+}
+
+static int evConst(const eorb_ev_params* p, EvConst& c) {
+    if (!p) return fail(EORB_ERR_ARG, "null params");
+    if (p->mode < EORB_EV_NEAREST || p->mode > EORB_EV_SE2) return fail(EORB_ERR_ARG, "bad mode %d", p->mode);
+    if (p->width < 1 || p->height < 1) return fail(EORB_ERR_ARG, "bad image size");
+    if (p->mode != EORB_EV_NEAREST && !(p->sigma > 0.f)) return fail(EORB_ERR_ARG, "sigma must be > 0");
+    c.mode = p->mode; c.width = p->width; c.height = p->height; c.pol = p->pol;
+    c.sigma = p->sigma; c.sig2 = p->sigma * p->sigma;
+    c.norm = 2.0f * (float)M_PI * c.sig2;
+    c.half = (int)std::ceil(p->sigma * 3.0);
+    c.depth = p->med_depth;
+    c.fx = p->K[0]; c.fy = p->K[1]; c.cx = p->K[2]; c.cy = p->K[3];
+    for (int i = 0; i < 4; i++) c.se2[i] = p->se2[i];
+    c.se2_n = p->se2_n;
+    return EORB_OK;
+}
+
+extern "C" int eorb_ev_accumulate_batch_device(eorb_evconv* c, const eorb_event* d_evs, const int64_t* win_offsets, int nwin,
+                                               const eorb_ev_params* p, const float* poses, float* d_img_f32, uint8_t* d_img_u8) {
+    if (!c || !d_evs || !win_offsets || !d_img_f32) return fail(EORB_ERR_ARG, "null argument");
+    if (nwin < 1) return EORB_OK;
+    if (nwin > c->maxWindows) return fail(EORB_ERR_CAPACITY, "nwin %d > max_windows %d", nwin, c->maxWindows);
+    EvConst k;
+    int rc = evConst(p, k);
+    if (rc != EORB_OK) return rc;
+    if (p->normalize != EORB_NORM_NONE && !d_img_u8) return fail(EORB_ERR_ARG, "normalize requested without a u8 output");
+    CU(cudaSetDevice(c->device));
+    c->h_wins.resize(nwin);
+    long long maxEv = 0;
+    for (int i = 0; i < nwin; i++) {
+        EvWindow& w = c->h_wins[i];
+        w.begin = win_offsets[i]; w.end = win_offsets[i + 1];
+        if (w.end < w.begin) return fail(EORB_ERR_ARG, "window offsets must be non-decreasing");
+        maxEv = std::max(maxEv, w.end - w.begin);
+        w.angle = 0; w.axis[0] = 1; w.axis[1] = w.axis[2] = 0; w.t[0] = w.t[1] = w.t[2] = 0;
+        if (p->mode == EORB_EV_SE3) angleAxisFromPose(poses ? poses + 16 * (size_t)i : p->Tcw, w);
+    }
+    const int npix = p->width * p->height;
+    CU(cudaMemcpyAsync(c->d_wins, c->h_wins.data(), (size_t)nwin * sizeof(EvWindow), cudaMemcpyHostToDevice, c->stream));
+    CU(cudaMemsetAsync(d_img_f32, 0, (size_t)nwin * npix * sizeof(float), c->stream));
+    c->launches++;   // memset node
+    CU(launch_ev_splat(d_evs, c->d_wins, nwin, maxEv, k, d_img_f32, c->stream, &c->launches));
+    CU(launch_ev_normalize(d_img_f32, nwin, npix, p->normalize, c->d_minmax, d_img_u8, c->stream, &c->launches));
+    return EORB_OK;
+}
+
+extern "C" int eorb_ev_accumulate(eorb_evconv* c, const eorb_event* evs, int64_t n, const eorb_ev_params* p, float* img_f32,
+                                  uint8_t* img_u8, float* minmax) {
+    if (!c || !p) return fail(EORB_ERR_ARG, "null argument");
+    if (p->width > c->maxW || p->height > c->maxH || (long long)p->width * p->height > (long long)c->maxW * c->maxH)
+        return fail(EORB_ERR_CAPACITY, "image %dx%d exceeds the converter's %dx%d", p->width, p->height, c->maxW, c->maxH);
+    if (n > c->maxEvents) return fail(EORB_ERR_CAPACITY, "%lld events > max_events %lld", (long long)n, c->maxEvents);
+    const int npix = p->width * p->height;
+    if (n <= 0 || !evs) {
+        // reference: zero image; the SE3/SE2 overloads log "no events" and return it un-normalised (:292-295)
+        if (img_f32) memset(img_f32, 0, (size_t)npix * sizeof(float));
+        if (img_u8) memset(img_u8, 0, (size_t)npix);
+        if (minmax) { minmax[0] = 0.f; minmax[1] = 0.f; }
+        return EORB_EMPTY;
+    }
+    CU(cudaSetDevice(c->device));
+    CU(cudaMemcpyAsync(c->d_evs, evs, (size_t)n * sizeof(eorb_event), cudaMemcpyHostToDevice, c->stream));
+    const int64_t offs[2] = {0, n};
+    eorb_ev_params q = *p;
+    if (!img_u8) q.normalize = EORB_NORM_NONE;
+    int rc = eorb_ev_accumulate_batch_device(c, c->d_evs, offs, 1, &q, nullptr, c->d_img, c->d_u8);
+    if (rc != EORB_OK) return rc;
+    if (img_f32) CU(cudaMemcpyAsync(img_f32, c->d_img, (size_t)npix * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
+    if (img_u8 && q.normalize != EORB_NORM_NONE) CU(cudaMemcpyAsync(img_u8, c->d_u8, (size_t)npix, cudaMemcpyDeviceToHost, c->stream));
+    else if (img_u8) memset(img_u8, 0, (size_t)npix);
+    if (minmax) CU(cudaMemcpyAsync(minmax, c->d_minmax, 2 * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    return EORB_OK;
+}

@@ -1,0 +1,125 @@
+// eorb_math.cuh — scalar arithmetic shared by the CUDA kernels and (compiled as plain C++) by the host-model
+// unit tests.  Every function here is the exact integer / no-FMA float arithmetic the reference gets from
+// OpenCV on the CPU; see DESIGN.md §"Arithmetic pins".
+#pragma once
+#include <stdint.h>
+#include <math.h>
+
+#ifdef __CUDACC__
+#define EORB_HD __host__ __device__ __forceinline__
+#else
+#define EORB_HD inline
+#endif
+
+namespace eorb {
+
+// float ops that must never be contracted into FMA (reference arithmetic is mul-then-add)
+#ifdef __CUDA_ARCH__
+__device__ __forceinline__ float fmul(float a, float b) { return __fmul_rn(a, b); }
+__device__ __forceinline__ float fadd(float a, float b) { return __fadd_rn(a, b); }
+__device__ __forceinline__ float fsub(float a, float b) { return __fsub_rn(a, b); }
+__device__ __forceinline__ float fdiv(float a, float b) { return __fdiv_rn(a, b); }
+__device__ __forceinline__ int   round_rne(float v) { return __float2int_rn(v); }
+#else
+// host build of this header must be compiled with -ffp-contract=off
+inline float fmul(float a, float b) { volatile float r = a * b; return r; }
+inline float fadd(float a, float b) { volatile float r = a + b; return r; }
+inline float fsub(float a, float b) { volatile float r = a - b; return r; }
+inline float fdiv(float a, float b) { volatile float r = a / b; return r; }
+inline int   round_rne(float v) { return (int)lrintf(v); }
+#endif
+
+EORB_HD int reflect101(int p, int len) {
+    if (len == 1) return 0;
+    while (p < 0 || p >= len) { p = p < 0 ? -p : 2 * len - 2 - p; }
+    return p;
+}
+
+// ---- cv::resize INTER_LINEAR 8-bit, one output pixel from the two horizontally-interpolated sums
+// (VResizeLinear<uchar,int,short,FixedPtCast<int,uchar,22>>; reference call ORBextractor.cc:1253)
+EORB_HD int resize_hsum(int p0, int p1, int a0, int a1) { return p0 * a0 + p1 * a1; }
+EORB_HD int resize_vsum(int r0, int r1, int b0, int b1) {
+    return (((b0 * (r0 >> 4)) >> 16) + ((b1 * (r1 >> 4)) >> 16) + 2) >> 2;
+}
+
+// ---- cv::GaussianBlur 5x5 sigma 2 on 8-bit: 8.8 fixed-point separable kernel [39 57 64 57 39]
+// (reference call ORBextractor.cc:1141-1142).  hsum of 5 pixels, then vsum of 5 hsums -> (s+32768)>>16.
+EORB_HD int gauss5_h(int p0, int p1, int p2, int p3, int p4) { return 39 * (p0 + p4) + 57 * (p1 + p3) + 64 * p2; }
+EORB_HD int gauss5_v(int h0, int h1, int h2, int h3, int h4) {
+    return (39 * (h0 + h4) + 57 * (h1 + h3) + 64 * h2 + 32768) >> 16;
+}
+
+// ---- FAST-9/16 (cv::FAST called at ORBextractor.cc:832,851).  d[k] = v - ring[k], k = 0..15 in the ring order
+// (0,3),(1,3),(2,2),(3,1),(3,0),(3,-1),(2,-2),(1,-3),(0,-3),(-1,-3),(-2,-2),(-3,-1),(-3,0),(-3,1),(-2,2),(-1,3).
+// Returns m = max over the 16 arcs of 9 contiguous ring pixels of min(|v-p|) with a common sign, clamped at 0.
+// corner at threshold t  <=>  m > t ;  OpenCV's NMS score (cornerScore<16>) = m - 1.
+EORB_HD int fast_max_arc_min(const int* d) {
+    // sliding-window min/max over windows of 9 on a circular array of 16 by doubling: 2,4,8 then +1
+    int mn2[16], mx2[16];
+#pragma unroll
+    for (int k = 0; k < 16; k++) { int a = d[k], b = d[(k + 1) & 15]; mn2[k] = a < b ? a : b; mx2[k] = a > b ? a : b; }
+    int mn4[16], mx4[16];
+#pragma unroll
+    for (int k = 0; k < 16; k++) {
+        int a = mn2[k], b = mn2[(k + 2) & 15]; mn4[k] = a < b ? a : b;
+        int c = mx2[k], e = mx2[(k + 2) & 15]; mx4[k] = c > e ? c : e;
+    }
+    int best = 0;
+#pragma unroll
+    for (int k = 0; k < 16; k++) {
+        int a = mn4[k], b = mn4[(k + 4) & 15]; int mn8 = a < b ? a : b;
+        int c = mx4[k], e = mx4[(k + 4) & 15]; int mx8 = c > e ? c : e;
+        int x = d[(k + 8) & 15];
+        int mn9 = mn8 < x ? mn8 : x;
+        int mx9 = mx8 > x ? mx8 : x;
+        best = best > mn9 ? best : mn9;       // ring darker than the centre
+        best = best > -mx9 ? best : -mx9;     // ring brighter than the centre
+    }
+    return best;
+}
+
+// ---- cv::fastAtan2 (degrees, [0,360]); called at ORBextractor.cc:103
+EORB_HD float fast_atan2_deg(float y, float x) {
+    const float p1 = 0.9997878412794807f * (float)(180 / 3.14159265358979323846);
+    const float p3 = -0.3258083974640975f * (float)(180 / 3.14159265358979323846);
+    const float p5 = 0.1555786518463281f * (float)(180 / 3.14159265358979323846);
+    const float p7 = -0.04432655554792128f * (float)(180 / 3.14159265358979323846);
+    const float eps = (float)2.2204460492503131e-16;
+    float ax = fabsf(x), ay = fabsf(y);
+    float a, c, c2;
+    if (ax >= ay) {
+        c = fdiv(ay, fadd(ax, eps));
+        c2 = fmul(c, c);
+        a = fmul(fadd(fmul(fadd(fmul(fadd(fmul(p7, c2), p5), c2), p3), c2), p1), c);
+    } else {
+        c = fdiv(ax, fadd(ay, eps));
+        c2 = fmul(c, c);
+        a = fsub(90.f, fmul(fadd(fmul(fadd(fmul(fadd(fmul(p7, c2), p5), c2), p3), c2), p1), c));
+    }
+    if (x < 0) a = fsub(180.f, a);
+    if (y < 0) a = fsub(360.f, a);
+    return a;
+}
+
+// ---- steered BRIEF sample offset (computeOrbDescriptor, ORBextractor.cc:118-123): a = cos, b = sin
+EORB_HD void brief_offset(int px, int py, float a, float b, int& row, int& col) {
+    float fx = (float)px, fy = (float)py;
+    row = round_rne(fadd(fmul(fx, b), fmul(fy, a)));
+    col = round_rne(fsub(fmul(fx, a), fmul(fy, b)));
+}
+
+// ---- DescriptorDistance (ORBmatcher.cc:2360-2378): 8 x popcount(xor)
+EORB_HD int hamming256(const uint32_t* a, const uint32_t* b) {
+    int d = 0;
+#pragma unroll
+    for (int i = 0; i < 8; i++) {
+#ifdef __CUDA_ARCH__
+        d += __popc(a[i] ^ b[i]);
+#else
+        d += __builtin_popcount(a[i] ^ b[i]);
+#endif
+    }
+    return d;
+}
+
+}  // namespace eorb

@@ -1,0 +1,206 @@
+// event_kernels.cu — event windows -> event frames (reference src/Event/EventConversion.cc):
+//   ev_splat_nearest_kernel   ev2im                      :173-212
+//   ev_splat_gauss_kernel     ev2im_gauss                :215-269
+//                             ev2mci_gg_f(Tcw,medDepth)  :279-360   (per-event rigid warp, double geometry)
+//                             ev2mci_gg_f(params2D)      :362-448   (per-event SE2(+scale) warp, float)
+//   ev_minmax_kernel + ev_normalize_kernel   normalizeImage :67-72 / cv::normalize(NORM_MINMAX, CV_8UC1)
+//
+// Accumulation model: the frames of all windows of a batch live in HBM/L2 and every splat tap is one
+// fire-and-forget fp32 reduction (RED.E.ADD.F32) — shared-memory fp32 atomics are CAS loops on this
+// architecture and a 346x260 frame does not fit next to them anyway.  A group of LPE lanes owns one event:
+// lane i handles column xi+i-half and walks the rows, so the lanes of a group hit consecutive addresses of
+// one image row (one or two 32-byte sectors per warp-wide reduction).  Event records are read in the
+// reference's 24-byte AoS layout.  Sums are order-dependent in fp32, hence toleranced parity (<= 1e-4*peak).
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/eorb_b200.h"
+#include "event_kernels.h"
+
+namespace eorb {
+
+__device__ __forceinline__ void splat_taps(float* __restrict__ im, int W, int H, float X, float Y, float polSign,
+                                           const EvConst& c, int sub, int lpe) {
+    const float fxi = floorf(X), fyi = floorf(Y);
+    const int xi = (int)fxi, yi = (int)fyi;
+    const float xr = __fsub_rn(X, (float)xi), yr = __fsub_rn(Y, (float)yi);
+    const int half = c.half;
+    const float den = __fmul_rn(2.0f, c.sig2);
+    for (int ii = sub; ii <= 2 * half; ii += lpe) {
+        const int i = ii - half;
+        const int xn = xi + i;
+        if (xn < 0 || xn >= W) continue;
+        const float dx = __fsub_rn((float)i, xr);
+        const float dx2 = __fmul_rn(dx, dx);
+        for (int j = -half; j <= half; j++) {
+            const int yn = yi + j;
+            if (yn < 0 || yn >= H) continue;
+            const float dy = __fsub_rn((float)j, yr);
+            const float dd = __fdiv_rn(__fadd_rn(dx2, __fmul_rn(dy, dy)), den);
+            const float val = __fdiv_rn(expf(-dd), c.norm);
+            atomicAdd(im + (size_t)yn * W + xn, __fmul_rn(polSign, val));
+        }
+    }
+}
+
+__global__ void __launch_bounds__(256) ev_splat_gauss_kernel(const eorb_event* __restrict__ evs,
+                                                             const EvWindow* __restrict__ wins, EvConst c,
+                                                             float* __restrict__ img, int lpe) {
+    const EvWindow w = wins[blockIdx.y];
+    const long long nev = w.end - w.begin;
+    const int perBlock = blockDim.x / lpe;
+    const long long e = (long long)blockIdx.x * perBlock + threadIdx.x / lpe;
+    const int sub = threadIdx.x % lpe;
+    if (e >= nev) return;
+    const eorb_event* evp = evs + w.begin + e;
+    const double ts = evp->ts;
+    const float ex = evp->x, ey = evp->y;
+    const bool p = evp->p != 0;
+    const float polSign = (c.pol && !p) ? -1.0f : 1.0f;
+    float X = ex, Y = ey;
+    if (c.mode == EORB_EV_SE3) {
+        const double t1 = evs[w.end - 1].ts, DT = t1 - evs[w.begin].ts;
+        const double rate = DT > 0 ? (t1 - ts) * (1.0 / DT) : 0.0;
+        const float Xs = __fdiv_rn(__fsub_rn(ex, c.cx), c.fx), Ys = __fdiv_rn(__fsub_rn(ey, c.cy), c.fy);
+        const double P0 = (double)Xs, P1 = (double)Ys, P2 = 1.0;
+        // Eigen::AngleAxisd(angle*rate, axis).toRotationMatrix()
+        const double ang = w.angle * rate;
+        double s, co;
+        sincos(ang, &s, &co);
+        const double a0 = w.axis[0], a1 = w.axis[1], a2 = w.axis[2];
+        const double s0 = s * a0, s1 = s * a1, s2 = s * a2;
+        const double c0 = (1 - co) * a0, c1 = (1 - co) * a1, c2 = (1 - co) * a2;
+        double t;
+        double R01, R10, R02, R20, R12, R21;
+        t = c0 * a1; R01 = t - s2; R10 = t + s2;
+        t = c0 * a2; R02 = t + s1; R20 = t - s1;
+        t = c1 * a2; R12 = t - s0; R21 = t + s0;
+        const double R00 = c0 * a0 + co, R11 = c1 * a1 + co, R22 = c2 * a2 + co;
+        const double dep = (double)c.depth;
+        const double n0 = (dep * R00) * P0 + (dep * R01) * P1 + (dep * R02) * P2 + w.t[0] * rate;
+        const double n1 = (dep * R10) * P0 + (dep * R11) * P1 + (dep * R12) * P2 + w.t[1] * rate;
+        const double n2 = (dep * R20) * P0 + (dep * R21) * P1 + (dep * R22) * P2 + w.t[2] * rate;
+        X = (float)((double)c.fx * n0 / n2 + (double)c.cx);
+        Y = (float)((double)c.fy * n1 / n2 + (double)c.cy);
+    } else if (c.mode == EORB_EV_SE2) {
+        const double t1 = evs[w.end - 1].ts;
+        const float DT = (float)(t1 - evs[w.begin].ts);
+        const float invDT = __fdiv_rn(1.f, DT);
+        const float omega0 = __fmul_rn(c.se2[0], invDT), vx0 = __fmul_rn(c.se2[1], invDT), vy0 = __fmul_rn(c.se2[2], invDT);
+        const float sc = c.se2_n > 3 ? c.se2[3] : 1.f;
+        const float scDiff = __fsub_rn(1.f, sc);
+        const float tk = (float)(t1 - ts);
+        const float Xs = __fdiv_rn(__fsub_rn(ex, c.cx), c.fx), Ys = __fdiv_rn(__fsub_rn(ey, c.cy), c.fy);
+        const float th = __fmul_rn(tk, omega0);
+        const float cs = __fadd_rn(__fmul_rn(scDiff, __fsub_rn(1.f, __fmul_rn(tk, invDT))), sc);
+        const float ct = cosf(th), st = sinf(th);
+        const float xp = __fadd_rn(__fmul_rn(cs, __fsub_rn(__fmul_rn(Xs, ct), __fmul_rn(Ys, st))), __fmul_rn(vx0, tk));
+        const float yp = __fadd_rn(__fmul_rn(cs, __fadd_rn(__fmul_rn(Xs, st), __fmul_rn(Ys, ct))), __fmul_rn(vy0, tk));
+        X = __fadd_rn(__fdiv_rn(__fmul_rn(c.fx, xp), 1.f), c.cx);
+        Y = __fadd_rn(__fdiv_rn(__fmul_rn(c.fy, yp), 1.f), c.cy);
+    }
+    float* im = img + (size_t)blockIdx.y * (size_t)c.width * c.height;
+    splat_taps(im, c.width, c.height, X, Y, polSign, c, sub, lpe);
+}
+
+__global__ void __launch_bounds__(256) ev_splat_nearest_kernel(const eorb_event* __restrict__ evs,
+                                                               const EvWindow* __restrict__ wins, EvConst c,
+                                                               float* __restrict__ img) {
+    const EvWindow w = wins[blockIdx.y];
+    const long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= w.end - w.begin) return;
+    const eorb_event* evp = evs + w.begin + e;
+    const float polSign = (c.pol && evp->p == 0) ? -1.0f : 1.0f;
+    const int px = (int)roundf(evp->x), py = (int)roundf(evp->y);
+    if (px < 0 || px >= c.width || py < 0 || py >= c.height) return;
+    float* im = img + (size_t)blockIdx.y * (size_t)c.width * c.height;
+    atomicAdd(im + (size_t)py * c.width + px, __fmul_rn(polSign, 0.001f));
+}
+
+// one block per window: (min, max) over the whole frame
+__global__ void __launch_bounds__(1024) ev_minmax_kernel(const float* __restrict__ img, int npix, float* __restrict__ minmax) {
+    __shared__ float s_mn[32], s_mx[32];
+    const float* im = img + (size_t)blockIdx.x * npix;
+    float mn = 3.4e38f, mx = -3.4e38f;
+    for (int i = threadIdx.x; i < npix; i += blockDim.x) { const float v = im[i]; mn = fminf(mn, v); mx = fmaxf(mx, v); }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        mn = fminf(mn, __shfl_xor_sync(0xffffffffu, mn, o));
+        mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    }
+    if ((threadIdx.x & 31) == 0) { s_mn[threadIdx.x >> 5] = mn; s_mx[threadIdx.x >> 5] = mx; }
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        const int nw = (blockDim.x + 31) >> 5;
+        mn = threadIdx.x < nw ? s_mn[threadIdx.x] : 3.4e38f;
+        mx = threadIdx.x < nw ? s_mx[threadIdx.x] : -3.4e38f;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            mn = fminf(mn, __shfl_xor_sync(0xffffffffu, mn, o));
+            mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+        }
+        if (threadIdx.x == 0) { minmax[2 * blockIdx.x] = mn; minmax[2 * blockIdx.x + 1] = mx; }
+    }
+}
+
+// u8 = saturate(rint(v*alpha + beta)) with the two parameterisations the reference uses
+__global__ void __launch_bounds__(256) ev_normalize_kernel(const float* __restrict__ img, int npix, int normMode,
+                                                           float* __restrict__ minmax, uint8_t* __restrict__ out) {
+    const int win = blockIdx.y;
+    const int i0 = (blockIdx.x * blockDim.x + threadIdx.x) * 4;
+    if (i0 >= npix) return;
+    float mn = minmax[2 * win], mx = minmax[2 * win + 1];
+    float alpha, beta;
+    if (normMode == EORB_NORM_RUNNING) {
+        // running min starts at 0, running max at -1e6 (EventConversion.cc:219-220)
+        mn = fminf(mn, 0.0f);
+        if (!(mx > mn)) { alpha = 0.f; beta = 0.f; }
+        else { alpha = __fdiv_rn(255.f, __fsub_rn(mx, mn)); beta = __fmul_rn(-mn, alpha); }
+    } else {
+        const double d = (double)mx - (double)mn;
+        const double scale = 255.0 * (d > 2.220446049250313e-16 ? 1.0 / d : 0.0);
+        alpha = (float)scale; beta = (float)(0.0 - (double)mn * scale);
+    }
+    const float* im = img + (size_t)win * npix;
+    uint8_t* o = out + (size_t)win * npix;
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+        const int i = i0 + k;
+        if (i < npix) {
+            const int r = __float2int_rn(__fadd_rn(__fmul_rn(im[i], alpha), beta));
+            o[i] = (uint8_t)min(max(r, 0), 255);
+        }
+    }
+}
+
+cudaError_t launch_ev_splat(const eorb_event* d_evs, const EvWindow* d_wins, int nwin, long long maxEventsPerWindow,
+                            const EvConst& c, float* d_img, cudaStream_t st, long long* launches) {
+    if (nwin <= 0 || maxEventsPerWindow <= 0) return cudaSuccess;
+    if (c.mode == EORB_EV_NEAREST) {
+        dim3 grd((unsigned)((maxEventsPerWindow + 255) / 256), nwin);
+        ev_splat_nearest_kernel<<<grd, 256, 0, st>>>(d_evs, d_wins, c, d_img);
+    } else {
+        const int win = 2 * c.half + 1;
+        const int lpe = win <= 8 ? 8 : (win <= 16 ? 16 : 32);
+        const int perBlock = 256 / lpe;
+        dim3 grd((unsigned)((maxEventsPerWindow + perBlock - 1) / perBlock), nwin);
+        ev_splat_gauss_kernel<<<grd, 256, 0, st>>>(d_evs, d_wins, c, d_img, lpe);
+    }
+    (*launches)++;
+    return cudaGetLastError();
+}
+
+cudaError_t launch_ev_normalize(const float* d_img, int nwin, int npix, int normMode, float* d_minmax, uint8_t* d_u8,
+                                cudaStream_t st, long long* launches) {
+    if (nwin <= 0) return cudaSuccess;
+    ev_minmax_kernel<<<nwin, 1024, 0, st>>>(d_img, npix, d_minmax);
+    (*launches)++;
+    if (normMode != EORB_NORM_NONE && d_u8) {
+        dim3 grd((npix / 4 + 255) / 256 + 1, nwin);
+        ev_normalize_kernel<<<grd, 256, 0, st>>>(d_img, npix, normMode, d_minmax, d_u8);
+        (*launches)++;
+    }
+    return cudaGetLastError();
+}
+
+}  // namespace eorb

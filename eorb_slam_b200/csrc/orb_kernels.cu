@@ -1,0 +1,551 @@
+// orb_kernels.cu — hand-written sm_100a kernels of the ORB extractor path
+// (reference src/ORBextractor.cc; one kernel per reference stage):
+//   K1 pyr_resize_kernel     ComputePyramid            :1240-1265  (cv::resize INTER_LINEAR, 11-bit fixed point)
+//   K2 fast_cells_kernel     ComputeKeyPointsOctTree   :784-878    (grid FAST 9/16 + cell-local NMS + threshold fallback)
+//   K3 octree_kernel         DistributeOctTree         :558-782    (level-synchronous node splitting)
+//   K7 orb_index_kernel      operator() ordering       :1152-1172  (level-major order, lapping split from both ends)
+//   K5 blur_kernel           GaussianBlur 5x5 s=2      :1141-1142
+//   K4+K6 orient_desc_kernel IC_Angle :77-104, computeOrbDescriptor :108-157
+// Integer stages are bit-exact with the CPU oracle; float stages use explicit no-FMA intrinsics.
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/eorb_b200.h"
+#include "eorb_math.cuh"
+#include "octree_core.cuh"
+#include "orb_kernels.h"
+
+namespace eorb {
+
+__device__ const signed char d_brief_pattern[1024] = {
+#include "brief_pattern_31.inc"
+};
+
+__device__ __forceinline__ const uint8_t* level_ptr(const OrbArgs& a, const LevelPlan& lp, int level, int f, int& pitch) {
+    if (level == 0) {
+        pitch = (int)a.lvl0Pitch;
+        return a.lvl0 + (size_t)f * (size_t)a.lvl0FrameStride;
+    }
+    pitch = lp.pitch;
+    return a.pyr + (size_t)f * (size_t)a.plan->pyrBytesPerFrame + (size_t)lp.off;
+}
+
+// ------------------------------------------------------------------------------------------------ K1
+// One thread = 4 horizontally adjacent destination pixels (one aligned 32-bit store).  Source taps and
+// 11-bit weights come from per-level tables computed on the host exactly like cv::resize does.
+__global__ void __launch_bounds__(256) pyr_resize_kernel(OrbArgs a, int level) {
+    const OrbPlan& P = *a.plan;
+    const LevelPlan& dl = P.lv[level];
+    const LevelPlan& sl = P.lv[level - 1];
+    const int f = blockIdx.z;
+    const int dx0 = (blockIdx.x * blockDim.x + threadIdx.x) * 4;
+    const int dy = blockIdx.y * blockDim.y + threadIdx.y;
+    if (dy >= dl.h || dx0 >= dl.w) return;
+    int sp;
+    const uint8_t* src = level_ptr(a, sl, level - 1, f, sp);
+    uint8_t* dst = a.pyr + (size_t)f * (size_t)P.pyrBytesPerFrame + (size_t)dl.off + (size_t)dy * dl.pitch;
+    const short4 yt = a.ytab[dl.ytabOff + dy];   // sy0, sy1, b0, b1
+    const uint8_t* S0 = src + (size_t)yt.x * sp;
+    const uint8_t* S1 = src + (size_t)yt.y * sp;
+    uint32_t outw = 0;
+#pragma unroll
+    for (int j = 0; j < 4; j++) {
+        const int dx = dx0 + j;
+        if (dx < dl.w) {
+            const short4 xt = __ldg(&a.xtab[dl.xtabOff + dx]);   // sx, sx1, a0, a1
+            const int r0 = resize_hsum(__ldg(S0 + xt.x), __ldg(S0 + xt.y), xt.z, xt.w);
+            const int r1 = resize_hsum(__ldg(S1 + xt.x), __ldg(S1 + xt.y), xt.z, xt.w);
+            int v = resize_vsum(r0, r1, yt.z, yt.w);
+            v = min(max(v, 0), 255);
+            outw |= (uint32_t)v << (8 * j);
+        }
+    }
+    *reinterpret_cast<uint32_t*>(dst + dx0) = outw;
+}
+
+// ------------------------------------------------------------------------------------------------ K2
+// One warp per FAST grid cell, no block-level barrier.  Cell ROI (<= ~66x66 incl. the 3-px apron) is staged
+// in shared memory with 32-bit loads; phase 1 rejects pixels with the 4-compass-point necessary condition
+// and compacts survivors with ballot/popc; phase 2 computes the exact arc score for survivors only;
+// phase 3 does the cell-local strict 3x3 NMS and emits corners in row-major order, first with iniThFAST and,
+// if the cell stayed empty, with minThFAST (the reference calls cv::FAST twice, :832-852).
+__global__ void __launch_bounds__(EORB_FAST_WARPS * 32) fast_cells_kernel(OrbArgs a) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const OrbPlan& P = *a.plan;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int cell = blockIdx.x * EORB_FAST_WARPS + warp;
+    const int f = blockIdx.y;
+    if (cell >= P.nCells) return;
+    const CellPlan c = a.cells[cell];
+    const LevelPlan& lp = P.lv[c.level];
+    unsigned char* ws = smem_raw + (size_t)warp * P.cellSmemPerWarp;
+    uint8_t* tile = ws;
+    uint8_t* smap = ws + P.cellMapOff;
+    uint16_t* list = reinterpret_cast<uint16_t*>(ws + P.cellListOff);
+    const int TS = P.cellTileStride, MS = P.cellMapStride;
+    const unsigned FULL = 0xffffffffu;
+    const unsigned lt = (1u << lane) - 1u;
+
+    uint32_t* slots = a.cand + (size_t)f * P.slotsPerFrame + c.slotOff;
+    uint16_t* countOut = a.cellCount + (size_t)f * P.nCells + cell;
+    const int cw = c.w - 6, ch = c.h - 6;
+    if (cw <= 0 || ch <= 0) { if (lane == 0) *countOut = 0; return; }
+
+    // ---- stage the ROI
+    int pitch;
+    const uint8_t* L = level_ptr(a, lp, c.level, f, pitch);
+    const int xw0 = c.x0 & ~3, aoff = c.x0 - xw0;
+    const int nwords = (aoff + c.w + 3) >> 2;
+    const int totalWords = nwords * c.h;
+    for (int i = lane; i < totalWords; i += 32) {
+        const int r = i / nwords, wi = i - r * nwords;
+        const uint32_t v = __ldg(reinterpret_cast<const uint32_t*>(L + (size_t)(c.y0 + r) * pitch + xw0 + wi * 4));
+        *reinterpret_cast<uint32_t*>(tile + r * TS + wi * 4) = v;
+    }
+    const int mapWords = ((ch + 2) * MS) >> 2;
+    for (int i = lane; i < mapWords; i += 32) reinterpret_cast<uint32_t*>(smap)[i] = 0u;
+    __syncwarp();
+
+    const int tA = min(max(P.iniTh, 0), 255), tB = min(max(P.minTh, 0), 255);
+    const int tlo = min(tA, tB);
+    const uint8_t* t0 = tile + aoff;
+    const int n = cw * ch;
+    const unsigned magic = (4194304u + (unsigned)cw - 1u) / (unsigned)cw;   // ceil(2^22 / cw)
+
+    // ---- phase 1: compass test + compaction
+    int nsurv = 0;
+    for (int base = 0; base < n; base += 32) {
+        const int i = base + lane;
+        bool flag = false;
+        if (i < n) {
+            const int yy = (int)(((unsigned)i * magic) >> 22), xx = i - yy * cw;
+            const uint8_t* p = t0 + (yy + 3) * TS + xx + 3;
+            const int v = p[0], hi = v + tlo, lo = v - tlo;
+            const int pN = p[3 * TS], pE = p[3], pS = p[-3 * TS], pW = p[-3];
+            const bool bN = pN > hi, bE = pE > hi, bS = pS > hi, bW = pW > hi;
+            const bool dN = pN < lo, dE = pE < lo, dS = pS < lo, dW = pW < lo;
+            flag = (bN & bE) | (bE & bS) | (bS & bW) | (bW & bN) | (dN & dE) | (dE & dS) | (dS & dW) | (dW & dN);
+        }
+        const unsigned m = __ballot_sync(FULL, flag);
+        if (flag) list[nsurv + __popc(m & lt)] = (uint16_t)i;
+        nsurv += __popc(m);
+    }
+    __syncwarp();
+
+    // ---- phase 2: exact arc score for survivors
+    for (int base = 0; base < nsurv; base += 32) {
+        const int s = base + lane;
+        if (s < nsurv) {
+            const int i = list[s];
+            const int yy = (int)(((unsigned)i * magic) >> 22), xx = i - yy * cw;
+            const uint8_t* p = t0 + (yy + 3) * TS + xx + 3;
+            const int v = p[0];
+            int d[16];
+            d[0] = v - p[3 * TS];      d[1] = v - p[3 * TS + 1];  d[2] = v - p[2 * TS + 2];   d[3] = v - p[TS + 3];
+            d[4] = v - p[3];           d[5] = v - p[-TS + 3];     d[6] = v - p[-2 * TS + 2];  d[7] = v - p[-3 * TS + 1];
+            d[8] = v - p[-3 * TS];     d[9] = v - p[-3 * TS - 1]; d[10] = v - p[-2 * TS - 2]; d[11] = v - p[-TS - 3];
+            d[12] = v - p[-3];         d[13] = v - p[TS - 3];     d[14] = v - p[2 * TS - 2];  d[15] = v - p[3 * TS - 1];
+            const int m = fast_max_arc_min(d);
+            if (m > tlo) smap[(yy + 1) * MS + xx + 1] = (uint8_t)m;
+        }
+    }
+    __syncwarp();
+
+    // ---- phase 3: NMS + ordered emission
+    auto emit = [&](int t) -> int {
+        int count = 0;
+        for (int base = 0; base < nsurv; base += 32) {
+            const int s = base + lane;
+            bool keep = false;
+            uint32_t packed = 0;
+            if (s < nsurv) {
+                const int i = list[s];
+                const int yy = (int)(((unsigned)i * magic) >> 22), xx = i - yy * cw;
+                const uint8_t* q = smap + (yy + 1) * MS + xx + 1;
+                const int m = q[0];
+                if (m > t) {
+                    keep = true;
+#pragma unroll
+                    for (int dy = -1; dy <= 1; dy++)
+#pragma unroll
+                        for (int dx = -1; dx <= 1; dx++) {
+                            if (dx == 0 && dy == 0) continue;
+                            const int mq = q[dy * MS + dx];
+                            const int e = mq > t ? mq : 1;   // non-corner neighbours score 0  (score = m-1)
+                            keep &= (m > e);
+                        }
+                    packed = (uint32_t)(xx + 3 + c.ox) | ((uint32_t)(yy + 3 + c.oy) << 12) | ((uint32_t)(m - 1) << 24);
+                }
+            }
+            const unsigned msk = __ballot_sync(FULL, keep);
+            if (keep) slots[count + __popc(msk & lt)] = packed;
+            count += __popc(msk);
+        }
+        return count;
+    };
+    int cnt = emit(tA);
+    if (cnt == 0 && tB != tA) cnt = emit(tB);
+    if (lane == 0) *countOut = (uint16_t)cnt;
+}
+
+// ------------------------------------------------------------------------------------------------ K3
+// One block per (level, frame).  Gathers the level's per-cell candidate lists into the reference's order
+// (cell-row-major, pixel-row-major inside a cell), then runs the shared level-synchronous distribution.
+__global__ void __launch_bounds__(OCT_MAX_THREADS) octree_kernel(OrbArgs a) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    __shared__ int s_arr[OCT_MAX_THREADS];
+    __shared__ int s_scr[OCT_MAX_THREADS];
+    const OrbPlan& P = *a.plan;
+    const int level = blockIdx.x, f = blockIdx.y;
+    const LevelPlan& lp = P.lv[level];
+    const int tid = threadIdx.x;
+    uint32_t* okeys = a.okeys + (size_t)f * P.slotsPerFrame + lp.slotBase;
+    uint16_t* knode = a.knode + (size_t)f * P.slotsPerFrame + lp.slotBase;
+    const uint16_t* counts = a.cellCount + (size_t)f * P.nCells + lp.cellBase;
+    const uint32_t* cand = a.cand + (size_t)f * P.slotsPerFrame;
+    int n = 0;
+    for (int c0 = 0; c0 < lp.nCells; c0 += OCT_MAX_THREADS) {
+        const int ci = c0 + tid;
+        const int cnt = (ci < lp.nCells) ? (int)counts[ci] : 0;
+        s_arr[tid] = cnt;
+        __syncthreads();
+        const int tot = oct_exclusive_scan(s_arr, OCT_MAX_THREADS, s_scr);
+        if (cnt > 0) {
+            const uint32_t* src = cand + a.cells[lp.cellBase + ci].slotOff;
+            uint32_t* dst = okeys + n + s_arr[tid];
+            for (int j = 0; j < cnt; j++) dst[j] = src[j];
+        }
+        n += tot;
+        __syncthreads();
+    }
+    __syncthreads();
+    uint32_t* out = a.sel + (size_t)f * P.selPerFrame + lp.selBase;
+    int L = 0;
+    if (lp.maxBX > lp.minBX && lp.maxBY > lp.minBY)
+        L = oct_distribute(okeys, knode, n, lp.maxBX - lp.minBX, lp.maxBY - lp.minBY, lp.nIni, lp.hX, lp.quota,
+                           lp.nodeCap, smem_raw, out);
+    if (tid == 0) {
+        a.selCount[(size_t)f * P.nlevels + level] = L < 0 ? 0 : L;
+        a.candCount[(size_t)f * P.nlevels + level] = n;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ K7
+// One block per frame: final position of every selected keypoint.  The reference walks levels in order and
+// keypoints in octree-list order, writing keypoints inside the lapping area from the END of the output and
+// the others from the front (:1152-1172); positions are prefix counts of the "inside" flag.
+__global__ void __launch_bounds__(OCT_MAX_THREADS) orb_index_kernel(OrbArgs a) {
+    __shared__ int s_arr[OCT_MAX_THREADS];
+    __shared__ int s_scr[OCT_MAX_THREADS];
+    __shared__ int s_start[EORB_MAX_LEVELS + 1];
+    const OrbPlan& P = *a.plan;
+    const int f = blockIdx.x, tid = threadIdx.x;
+    if (tid == 0) {
+        int acc = 0;
+        for (int l = 0; l < P.nlevels; l++) { s_start[l] = acc; acc += a.selCount[(size_t)f * P.nlevels + l]; }
+        s_start[P.nlevels] = acc;
+    }
+    __syncthreads();
+    const int nk = s_start[P.nlevels];
+    const uint32_t* sel = a.sel + (size_t)f * P.selPerFrame;
+    int* dstIdx = a.dstIdx + (size_t)f * P.selPerFrame;
+    const float lap0 = (float)a.lap0, lap1 = (float)a.lap1;
+    int stereoRun = 0;
+    for (int g0 = 0; g0 < nk; g0 += OCT_MAX_THREADS) {
+        const int g = g0 + tid;
+        int flag = 0, slot = 0;
+        if (g < nk) {
+            int l = 0;
+            while (g >= s_start[l + 1]) l++;
+            const LevelPlan& lp = P.lv[l];
+            slot = lp.selBase + (g - s_start[l]);
+            float x = (float)(oct_key_x(sel[slot]) + lp.minBX);
+            if (l != 0) x = fmul(x, lp.scale);
+            flag = (x >= lap0 && x <= lap1) ? 1 : 0;
+        }
+        s_arr[tid] = flag;
+        __syncthreads();
+        const int tot = oct_exclusive_scan(s_arr, OCT_MAX_THREADS, s_scr);
+        if (g < nk) {
+            const int stereoBefore = stereoRun + s_arr[tid];
+            dstIdx[slot] = flag ? (nk - 1 - stereoBefore) : (g - stereoBefore);
+        }
+        stereoRun += tot;
+        __syncthreads();
+    }
+    if (tid == 0) { a.outN[f] = nk; a.outMono[f] = nk - stereoRun; }
+}
+
+// ------------------------------------------------------------------------------------------------ K5
+// 5x5 sigma-2 Gaussian on every level (8.8 fixed-point separable weights, REFLECT_101).  One thread =
+// 4 adjacent outputs; interior threads read three aligned 32-bit words per source row.
+__global__ void __launch_bounds__(256) blur_kernel(OrbArgs a) {
+    const OrbPlan& P = *a.plan;
+    const int f = blockIdx.z;
+    int level = 0;
+    while (level + 1 < P.nlevels && (int)blockIdx.y >= P.lv[level + 1].rowBlockBase) level++;
+    const LevelPlan& lp = P.lv[level];
+    const int y = ((int)blockIdx.y - lp.rowBlockBase) * (int)blockDim.y + (int)threadIdx.y;
+    const int x0 = ((int)blockIdx.x * (int)blockDim.x + (int)threadIdx.x) * 4;
+    if (y >= lp.h || x0 >= lp.w) return;
+    int sp;
+    const uint8_t* src = level_ptr(a, lp, level, f, sp);
+    int acc[4] = {0, 0, 0, 0};
+    const int wv[5] = {39, 57, 64, 57, 39};
+    const bool interior = (x0 >= 4) && (x0 + 8 <= lp.w);
+#pragma unroll
+    for (int r = 0; r < 5; r++) {
+        const int yy = reflect101(y + r - 2, lp.h);
+        const uint8_t* row = src + (size_t)yy * sp;
+        int p[8];
+        if (interior) {
+            const uint32_t w0 = __ldg(reinterpret_cast<const uint32_t*>(row + x0 - 4));
+            const uint32_t w1 = __ldg(reinterpret_cast<const uint32_t*>(row + x0));
+            const uint32_t w2 = __ldg(reinterpret_cast<const uint32_t*>(row + x0 + 4));
+            p[0] = (w0 >> 16) & 255; p[1] = w0 >> 24;
+            p[2] = w1 & 255; p[3] = (w1 >> 8) & 255; p[4] = (w1 >> 16) & 255; p[5] = w1 >> 24;
+            p[6] = w2 & 255; p[7] = (w2 >> 8) & 255;
+        } else {
+#pragma unroll
+            for (int j = 0; j < 8; j++) p[j] = __ldg(row + reflect101(x0 - 2 + j, lp.w));
+        }
+#pragma unroll
+        for (int j = 0; j < 4; j++) acc[j] += wv[r] * gauss5_h(p[j], p[j + 1], p[j + 2], p[j + 3], p[j + 4]);
+    }
+    uint32_t outw = 0;
+#pragma unroll
+    for (int j = 0; j < 4; j++) {
+        int v = (acc[j] + 32768) >> 16;
+        v = min(v, 255);
+        outw |= (uint32_t)v << (8 * j);
+    }
+    uint8_t* dst = a.blur + (size_t)f * (size_t)P.blurBytesPerFrame + (size_t)lp.blurOff + (size_t)y * lp.bpitch;
+    *reinterpret_cast<uint32_t*>(dst + x0) = outw;
+}
+
+// ------------------------------------------------------------------------------------------------ K4 + K6
+// One warp per selected keypoint.  Orientation: lanes own the 31 columns of the circular patch, integer
+// moments reduced with shuffles, cv::fastAtan2 restated without FMA.  Descriptor: lane L evaluates pattern
+// pair 32*j+L in round j; __ballot_sync yields descriptor word j directly (bit k of byte i = pair 8i+k).
+__global__ void __launch_bounds__(256) orient_desc_kernel(OrbArgs a) {
+    const OrbPlan& P = *a.plan;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int slot = blockIdx.x * 8 + warp;
+    const int f = blockIdx.y;
+    if (slot >= P.selPerFrame) return;
+    int level = 0;
+    while (level + 1 < P.nlevels && slot >= P.lv[level + 1].selBase) level++;
+    const LevelPlan& lp = P.lv[level];
+    const int idx = slot - lp.selBase;
+    if (idx >= a.selCount[(size_t)f * P.nlevels + level]) return;
+    const uint32_t key = a.sel[(size_t)f * P.selPerFrame + slot];
+    const int x = oct_key_x(key) + lp.minBX, y = oct_key_y(key) + lp.minBY;
+    const unsigned FULL = 0xffffffffu;
+    int sp;
+    const uint8_t* img = level_ptr(a, lp, level, f, sp);
+
+    // ---- IC_Angle on the (virtually REFLECT_101-bordered) level
+    int m10 = 0, m01 = 0;
+    {
+        const int u = lane - 15;
+        const bool inside = (x >= 15) && (y >= 15) && (x + 15 < lp.w) && (y + 15 < lp.h);
+        if (lane < 31) {
+            const int au = u < 0 ? -u : u;
+            int colsum = 0;
+            if (inside) {
+                const uint8_t* c = img + (size_t)y * sp + x + u;
+#pragma unroll
+                for (int v = -15; v <= 15; v++) {
+                    const int av = v < 0 ? -v : v;
+                    if (au <= P.umax[av]) {
+                        const int val = __ldg(c + v * sp);
+                        colsum += val; m01 += v * val;
+                    }
+                }
+            } else {
+                const int xx = reflect101(x + u, lp.w);
+                for (int v = -15; v <= 15; v++) {
+                    const int av = v < 0 ? -v : v;
+                    if (au <= P.umax[av]) {
+                        const int val = __ldg(img + (size_t)reflect101(y + v, lp.h) * sp + xx);
+                        colsum += val; m01 += v * val;
+                    }
+                }
+            }
+            m10 = u * colsum;
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            m10 += __shfl_xor_sync(FULL, m10, o);
+            m01 += __shfl_xor_sync(FULL, m01, o);
+        }
+    }
+    const float angle = fast_atan2_deg((float)m01, (float)m10);
+    const int dst = a.dstIdx[(size_t)f * P.selPerFrame + slot];
+    if (dst < 0 || dst >= a.cap) return;
+
+    if (lane == 0) {
+        eorb_keypoint kp;
+        const float xf = (float)x, yf = (float)y;
+        kp.x = level ? fmul(xf, lp.scale) : xf;
+        kp.y = level ? fmul(yf, lp.scale) : yf;
+        kp.size = lp.sizeF;
+        kp.angle = angle;
+        kp.response = (float)oct_key_score(key);
+        kp.octave = level;
+        kp.class_id = -1;
+        a.outKps[(size_t)f * a.cap + dst] = kp;
+    }
+    if (a.levelAngle) a.levelAngle[(size_t)f * P.selPerFrame + slot] = angle;
+    if (!a.wantDesc) return;
+
+    // ---- steered BRIEF on the blurred level
+    const float factorPI = (float)(3.14159265358979323846 / 180.f);
+    const float ang = fmul(angle, factorPI);
+    const float ca = (float)cos((double)ang), sa = (float)sin((double)ang);
+    const uint8_t* B = a.blur + (size_t)f * (size_t)P.blurBytesPerFrame + (size_t)lp.blurOff;
+    const int bp = lp.bpitch;
+    const bool safe = (x >= 19) && (y >= 19) && (x + 19 < lp.w) && (y + 19 < lp.h);
+    uint32_t myword = 0;
+#pragma unroll
+    for (int j = 0; j < 8; j++) {
+        const char4 pt = __ldg(reinterpret_cast<const char4*>(d_brief_pattern) + 32 * j + lane);
+        int r0, c0, r1, c1;
+        brief_offset(pt.x, pt.y, ca, sa, r0, c0);
+        brief_offset(pt.z, pt.w, ca, sa, r1, c1);
+        int y0 = y + r0, x0 = x + c0, y1 = y + r1, x1 = x + c1;
+        if (!safe) {   // margin < 19: the reference reads out of bounds; pinned to REFLECT_101 (see oracle)
+            y0 = reflect101(y0, lp.h); x0 = reflect101(x0, lp.w);
+            y1 = reflect101(y1, lp.h); x1 = reflect101(x1, lp.w);
+        }
+        const int t0 = __ldg(B + (size_t)y0 * bp + x0);
+        const int t1 = __ldg(B + (size_t)y1 * bp + x1);
+        const uint32_t word = __ballot_sync(FULL, t0 < t1);
+        if (lane == j) myword = word;
+    }
+    if (lane < 8) reinterpret_cast<uint32_t*>(a.outDesc + ((size_t)f * a.cap + dst) * 32)[lane] = myword;
+}
+
+// ------------------------------------------------------------------------------------------------ O10
+// Descriptors for caller-supplied keypoints (ComputeTrackedKPtsDesc :1316-1363 and the inner loop of
+// AssignKPtLevelByBestDesc :1267-1314): one warp per (keypoint, level); position scaled by
+// mvInvScaleFactor[level], the keypoint's own angle is used.  mode 0: only kp.octave == level, writes desc;
+// mode 1: every level, writes the Hamming distance to refDesc into dist[level*n + i].
+__global__ void __launch_bounds__(256) tracked_desc_kernel(OrbArgs a, const eorb_keypoint* kps, int n, int mode,
+                                                          const float* invScale, const uint8_t* refDesc,
+                                                          uint8_t* descOut, int* distOut) {
+    const OrbPlan& P = *a.plan;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int i = blockIdx.x * 8 + warp;
+    const int level = blockIdx.y;
+    if (i >= n) return;
+    const eorb_keypoint kp = kps[i];
+    if (mode == 0 && kp.octave != level) return;
+    const LevelPlan& lp = P.lv[level];
+    const float sc = invScale[level];
+    const int x = round_rne(fmul(kp.x, sc)), y = round_rne(fmul(kp.y, sc));
+    const float factorPI = (float)(3.14159265358979323846 / 180.f);
+    const float ang = fmul(kp.angle, factorPI);
+    const float ca = (float)cos((double)ang), sa = (float)sin((double)ang);
+    const uint8_t* B = a.blur + (size_t)lp.blurOff;
+    const int bp = lp.bpitch;
+    const unsigned FULL = 0xffffffffu;
+    uint32_t myword = 0;
+#pragma unroll
+    for (int j = 0; j < 8; j++) {
+        const char4 pt = __ldg(reinterpret_cast<const char4*>(d_brief_pattern) + 32 * j + lane);
+        int r0, c0, r1, c1;
+        brief_offset(pt.x, pt.y, ca, sa, r0, c0);
+        brief_offset(pt.z, pt.w, ca, sa, r1, c1);
+        const int y0 = reflect101(y + r0, lp.h), x0 = reflect101(x + c0, lp.w);
+        const int y1 = reflect101(y + r1, lp.h), x1 = reflect101(x + c1, lp.w);
+        const int t0 = __ldg(B + (size_t)y0 * bp + x0);
+        const int t1 = __ldg(B + (size_t)y1 * bp + x1);
+        const uint32_t word = __ballot_sync(FULL, t0 < t1);
+        if (lane == j) myword = word;
+    }
+    if (mode == 0) {
+        if (lane < 8) reinterpret_cast<uint32_t*>(descOut + (size_t)i * 32)[lane] = myword;
+    } else {
+        int d = 0;
+        if (lane < 8) d = __popc(myword ^ reinterpret_cast<const uint32_t*>(refDesc + (size_t)i * 32)[lane]);
+#pragma unroll
+        for (int o = 4; o > 0; o >>= 1) d += __shfl_xor_sync(FULL, d, o);
+        if (lane == 0) distOut[(size_t)level * n + i] = d;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ launches
+static inline unsigned cdiv(unsigned a, unsigned b) { return (a + b - 1) / b; }
+
+cudaError_t launch_orb_pipeline(const OrbArgs& a, const OrbPlan& hp, int nframes, cudaStream_t st, long long* launches) {
+    // K1: pyramid, level by level (each level is resized from the previous one)
+    for (int l = 1; l < hp.nlevels; l++) {
+        if (hp.lv[l].w <= 0 || hp.lv[l].h <= 0) continue;
+        dim3 blk(32, 8), grd(cdiv(cdiv(hp.lv[l].w, 4), 32), cdiv(hp.lv[l].h, 8), nframes);
+        pyr_resize_kernel<<<grd, blk, 0, st>>>(a, l);
+        (*launches)++;
+    }
+    // K2: FAST over every cell of every level
+    if (hp.nCells > 0) {
+        dim3 grd(cdiv(hp.nCells, EORB_FAST_WARPS), nframes);
+        fast_cells_kernel<<<grd, EORB_FAST_WARPS * 32, (size_t)hp.cellSmemPerWarp * EORB_FAST_WARPS, st>>>(a);
+        (*launches)++;
+    }
+    // K3: octree distribution per (level, frame)
+    {
+        dim3 grd(hp.nlevels, nframes);
+        octree_kernel<<<grd, OCT_MAX_THREADS, hp.octSmemBytes, st>>>(a);
+        (*launches)++;
+    }
+    // K7: output order
+    orb_index_kernel<<<nframes, OCT_MAX_THREADS, 0, st>>>(a);
+    (*launches)++;
+    // K5: blur (only needed for descriptors)
+    if (a.wantDesc && hp.rowBlocksTotal > 0) {
+        dim3 blk(32, 8), grd(cdiv(cdiv(hp.lv[0].w, 4), 32), hp.rowBlocksTotal, nframes);
+        blur_kernel<<<grd, blk, 0, st>>>(a);
+        (*launches)++;
+    }
+    // K4 + K6
+    {
+        dim3 grd(cdiv(hp.selPerFrame, 8), nframes);
+        orient_desc_kernel<<<grd, 256, 0, st>>>(a);
+        (*launches)++;
+    }
+    return cudaGetLastError();
+}
+
+cudaError_t launch_pyramid_and_blur(const OrbArgs& a, const OrbPlan& hp, cudaStream_t st, long long* launches) {
+    for (int l = 1; l < hp.nlevels; l++) {
+        if (hp.lv[l].w <= 0 || hp.lv[l].h <= 0) continue;
+        dim3 blk(32, 8), grd(cdiv(cdiv(hp.lv[l].w, 4), 32), cdiv(hp.lv[l].h, 8), 1);
+        pyr_resize_kernel<<<grd, blk, 0, st>>>(a, l);
+        (*launches)++;
+    }
+    if (hp.rowBlocksTotal > 0) {
+        dim3 blk(32, 8), grd(cdiv(cdiv(hp.lv[0].w, 4), 32), hp.rowBlocksTotal, 1);
+        blur_kernel<<<grd, blk, 0, st>>>(a);
+        (*launches)++;
+    }
+    return cudaGetLastError();
+}
+
+cudaError_t launch_tracked_desc(const OrbArgs& a, const OrbPlan& hp, const eorb_keypoint* d_kps, int n, int mode,
+                                const float* d_invScale, const uint8_t* d_refDesc, uint8_t* d_desc, int* d_dist,
+                                cudaStream_t st, long long* launches) {
+    if (n <= 0) return cudaSuccess;
+    dim3 grd(cdiv(n, 8), hp.nlevels);
+    tracked_desc_kernel<<<grd, 256, 0, st>>>(a, d_kps, n, mode, d_invScale, d_refDesc, d_desc, d_dist);
+    (*launches)++;
+    return cudaGetLastError();
+}
+
+cudaError_t orb_kernels_configure(const OrbPlan& hp) {
+    cudaError_t e = cudaFuncSetAttribute(fast_cells_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         hp.cellSmemPerWarp * EORB_FAST_WARPS);
+    if (e != cudaSuccess) return e;
+    return cudaFuncSetAttribute(octree_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, hp.octSmemBytes);
+}
+
+}  // namespace eorb

@@ -1,0 +1,47 @@
+// orb_kernels.h — launch interface between the C-ABI host code (capi.cu) and orb_kernels.cu
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/eorb_b200.h"
+#include "orb_plan.h"
+
+namespace eorb {
+
+// Everything a kernel needs, passed by value.  Per-frame slabs are indexed by the frame's position in the
+// current batch; offsets inside a slab come from the plan.
+struct OrbArgs {
+    const OrbPlan* plan;         // device copy
+    const CellPlan* cells;       // device
+    const short4* xtab;          // device: resize taps per destination column  {sx, sx+1, a0, a1}
+    const short4* ytab;          // device: resize taps per destination row     {sy0, sy1, b0, b1}
+    const uint8_t* lvl0;         // level 0 = the input frames (zero-copy when aligned, else staged)
+    long long lvl0Pitch, lvl0FrameStride;
+    uint8_t* pyr;                // [B][pyrBytesPerFrame]   levels >= 1
+    uint8_t* blur;               // [B][blurBytesPerFrame]  all levels
+    uint16_t* cellCount;         // [B][nCells]
+    uint32_t* cand;              // [B][slotsPerFrame]      per-cell candidate lists (packed x|y<<12|score<<24)
+    uint32_t* okeys;             // [B][slotsPerFrame]      per-level ordered candidates
+    uint16_t* knode;             // [B][slotsPerFrame]      octree: list position of each candidate's node
+    uint32_t* sel;               // [B][selPerFrame]        selected candidates per level, list order
+    int* selCount;               // [B][nlevels]
+    int* candCount;              // [B][nlevels]
+    int* dstIdx;                 // [B][selPerFrame]        final output position
+    float* levelAngle;           // [B][selPerFrame]        (debug tap) or nullptr
+    eorb_keypoint* outKps;       // [B][cap]
+    uint8_t* outDesc;            // [B][cap][32]
+    int* outN;                   // [B]
+    int* outMono;                // [B]
+    int cap;
+    int lap0, lap1;
+    int wantDesc;
+};
+
+cudaError_t orb_kernels_configure(const OrbPlan& hp);
+cudaError_t launch_orb_pipeline(const OrbArgs& a, const OrbPlan& hp, int nframes, cudaStream_t st, long long* launches);
+cudaError_t launch_pyramid_and_blur(const OrbArgs& a, const OrbPlan& hp, cudaStream_t st, long long* launches);
+cudaError_t launch_tracked_desc(const OrbArgs& a, const OrbPlan& hp, const eorb_keypoint* d_kps, int n, int mode,
+                                const float* d_invScale, const uint8_t* d_refDesc, uint8_t* d_desc, int* d_dist,
+                                cudaStream_t st, long long* launches);
+
+}  // namespace eorb

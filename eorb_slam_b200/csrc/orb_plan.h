@@ -1,0 +1,61 @@
+// orb_plan.h — per-extractor geometry tables shared by host code and kernels (plain POD, lives in HBM).
+// Everything here is derived once per (params, image size) on the host exactly as the reference derives it:
+// ctor tables ORBextractor.cc:420-489, level sizes :1244-1245, FAST grid :792-828, octree roots :562-563.
+#pragma once
+#include <stdint.h>
+
+#define EORB_MAX_LEVELS 32
+#define EORB_MAX_DIM 4095          // candidate coordinates are packed in 12 bits
+#define EORB_FAST_WARPS 8          // warps (= grid cells) per FAST thread block
+
+namespace eorb {
+
+struct LevelPlan {
+    int w, h, pitch;               // level size, row pitch in bytes (multiple of 16); level 0 pitch is the input's
+    long long off;                 // byte offset inside one frame's pyramid slab (levels >= 1)
+    long long blurOff;             // byte offset inside one frame's blurred slab (all levels, own pitch = bpitch)
+    int bpitch;
+    int minBX, minBY, maxBX, maxBY;
+    int nCols, nRows, wCell, hCell;
+    int cellBase, nCells;          // cells of this level are [cellBase, cellBase + nCells), row-major
+    int slotBase, slotCount;       // candidate slots of this level inside one frame's candidate slab
+    int quota;                     // mnFeaturesPerLevel[level]
+    int nIni;                      // octree roots: round(width/height)
+    float hX;                      // width / nIni
+    int nodeCap;                   // octree node capacity = max(quota+3, 4*nIni)+1
+    int selBase;                   // offset of this level's selected-keypoint slots inside one frame's slab
+    float scale;                   // mvScaleFactor[level]
+    float sizeF;                   // (float)(int)(31*scale)
+    int xtabOff, ytabOff;          // offsets (in short4 units) into the resize tables (levels >= 1)
+    int rowBlockBase;              // first flattened row-block of this level (blur grid)
+};
+
+struct CellPlan {
+    short x0, y0;                  // ROI origin in level coordinates (iniX, iniY)
+    short w, h;                    // ROI size (maxX-iniX, maxY-iniY), includes the 3-px FAST apron
+    short level, _pad;
+    int slotOff;                   // first candidate slot of this cell (relative to the frame's slab)
+    short ox, oy;                  // j*wCell, i*hCell: added to ROI coordinates (ORBextractor.cc:871-872)
+    int slotCap;
+};
+
+struct OrbPlan {
+    int nlevels, edge, iniTh, minTh;
+    int W, H;
+    int nCells;                    // total cells over all levels
+    int slotsPerFrame;             // candidate slots per frame
+    int selPerFrame;               // selected-keypoint slots per frame (sum of nodeCap)
+    long long pyrBytesPerFrame;    // levels >= 1
+    long long blurBytesPerFrame;
+    int cellTileStride;            // FAST: smem bytes per tile row (multiple of 4)
+    int cellMapStride;             // FAST: score-map row stride (multiple of 4)
+    int cellMapOff;                // FAST: byte offset of the score map inside a warp's smem region
+    int cellListOff;               // FAST: byte offset of the survivor list
+    int cellSmemPerWarp;           // bytes (multiple of 16)
+    int octSmemBytes;              // max over levels
+    int rowBlocksTotal;            // blur grid
+    int umax[16];
+    LevelPlan lv[EORB_MAX_LEVELS];
+};
+
+}  // namespace eorb

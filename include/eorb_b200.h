@@ -1,0 +1,234 @@
+/*
+ * eorb_b200.h — C ABI of libeorb_b200.so: the B200 (sm_100a) front-end hot path of EORB-SLAM.
+ *
+ * The reference (m-dayani/EORB_SLAM) has no FFI layer: the hot path sits behind three C++ class
+ * surfaces linked into libORB_SLAM3.so.  This header is the thin C boundary those classes are
+ * re-implemented on (shims with the reference signatures live in eorb_slam_b200/shim/ and
+ * INTEGRATION.md shows the binding a maintainer adds).  Each entry point names the reference
+ * interface it replaces (paths relative to the reference tree).
+ *
+ * Conventions
+ *   - plain pointers and sizes only; no C++/torch types cross this boundary; no exceptions.
+ *   - return value: >= 0 success (0, or the value the reference function returns),
+ *       EORB_EMPTY (-1)  empty input, mirroring `return -1` at ORBextractor.cc:1096 /
+ *                         the zero image returned at EventConversion.cc:292-295,
+ *       <= -2            error (see codes); eorb_last_error() gives a thread-local message.
+ *   - "host" entry points take host buffers and do H2D/D2H on the handle's stream, then synchronise.
+ *     "_device" entry points take device pointers, enqueue on the handle's stream and do NOT synchronise.
+ *   - a handle is not re-entrant (like the reference extractor, ORBextractor.h:105); distinct handles may
+ *     be used concurrently from distinct threads (Frame.cc:122-125, EvImBuilder.cpp:1165-1193).
+ *   - there is no CPU fallback: without a CUDA device every compute entry point returns EORB_ERR_CUDA.
+ */
+#ifndef EORB_B200_H
+#define EORB_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define EORB_OK            0
+#define EORB_EMPTY        (-1)
+#define EORB_ERR_ARG      (-2)
+#define EORB_ERR_CAPACITY (-3)
+#define EORB_ERR_STATE    (-4)
+#define EORB_ERR_CUDA     (-10)
+
+#define EORB_DESC_BYTES 32
+
+/* mirrors ORB_SLAM3::ORBxParams (include/ORBextractor.h:33-47); patchSize is fixed at 31 */
+typedef struct eorb_orb_params {
+    int   nfeatures;
+    float scaleFactor;
+    int   nlevels;
+    int   iniThFAST;
+    int   minThFAST;
+    int   edgeTh;       /* < 0 : adaptive 19*imW/752 forced odd (ORBextractor.cc:481-485) */
+    int   imW, imH;     /* ORBxParams::imSize; only used for the adaptive edge threshold */
+} eorb_orb_params;
+
+/* bit-compatible with cv::KeyPoint (28 bytes) */
+typedef struct eorb_keypoint {
+    float x, y, size, angle, response;
+    int32_t octave, class_id;
+} eorb_keypoint;
+
+/* bit-compatible with EORB_SLAM::EventData (include/Event/EventData.h:36-58): 24 bytes */
+typedef struct eorb_event {
+    double  ts;
+    float   x, y;
+    uint8_t p;
+    uint8_t _pad[7];
+} eorb_event;
+
+/* result of the best-2 scan of ORBmatcher (ORBmatcher.cc:741-772 / :318-382) for one query */
+typedef struct eorb_match {
+    int32_t best_dist;    /* 256 when the database is empty */
+    int32_t best_idx;     /* global row index, -1 when none; lowest index wins distance ties */
+    int32_t second_dist;  /* 256 when fewer than two rows */
+    int32_t accepted;     /* best_dist <= th && (float)best_dist < ratio*(float)second_dist */
+} eorb_match;
+
+/* per-shard partial result exchanged between GPUs (16 bytes): keys are (dist << 32) | global_idx */
+typedef struct eorb_best2 {
+    uint64_t key1;        /* smallest  (dist, idx); ~0 when none */
+    uint64_t key2;        /* second smallest */
+} eorb_best2;
+
+typedef struct eorb_orb     eorb_orb;
+typedef struct eorb_matcher eorb_matcher;
+typedef struct eorb_evconv  eorb_evconv;
+
+/* ---------------------------------------------------------------- library */
+int         eorb_version(void);
+const char* eorb_last_error(void);
+int         eorb_device_count(void);                 /* 0 when no CUDA device / driver */
+/* CUDA-event timing on a handle's stream, so callers never need the CUDA runtime themselves */
+int         eorb_timer_create(void** timer);         /* a pair of cudaEvents */
+int         eorb_timer_destroy(void* timer);
+int         eorb_timer_start(void* timer, void* cuda_stream);
+int         eorb_timer_stop(void* timer, void* cuda_stream);
+int         eorb_timer_elapsed_ms(void* timer, float* ms);   /* synchronises on the stop event */
+/* integer-pipe POPC throughput probe used as the Hamming roofline denominator */
+int         eorb_probe_popc_rate(int device, double* popc32_per_sec);
+
+/* ---------------------------------------------------------------- ORB extractor
+ * replaces ORB_SLAM3::ORBextractor (include/ORBextractor.h:62-136, src/ORBextractor.cc) */
+
+/* ORBextractor::ORBextractor(const ORBxParams&)  ORBextractor.cc:420-489.
+ * max_batch = frames processed per launch set by the batch entry points (>=1). */
+int eorb_orb_create(const eorb_orb_params* params, int device, int max_batch, eorb_orb** out);
+int eorb_orb_destroy(eorb_orb* h);
+/* use a caller-owned cudaStream_t (e.g. the framework's current stream); NULL restores the handle's own */
+int eorb_orb_set_stream(eorb_orb* h, void* cuda_stream);
+void* eorb_orb_get_stream(eorb_orb* h);
+int eorb_orb_synchronize(eorb_orb* h);
+
+/* GetLevels / GetScaleFactors / GetInverseScaleFactors / GetScaleSigmaSquares / GetInverseScaleSigmaSquares
+ * (ORBextractor.h:83-101), mnFeaturesPerLevel and the per-instance EDGE_THRESHOLD.  Any pointer may be NULL. */
+int eorb_orb_tables(const eorb_orb* h, int* nlevels, int* edge_threshold, float* scale, float* inv_scale,
+                    float* sigma2, float* inv_sigma2, int* features_per_level);
+/* capacity a caller must provide per frame: nfeatures + slack for the per-level overshoot (<= 3/level) */
+int eorb_orb_max_keypoints(const eorb_orb* h);
+
+/* int ORBextractor::operator()(image, mask, keypoints, descriptors, vLappingArea)   ORBextractor.cc:1092-1176
+ * and the keypoints-only overload :1178-1238 (want_desc = 0, desc may be NULL).
+ * Host buffers.  Returns monoIndex (>= 0), EORB_EMPTY for an empty image, or an error. */
+int eorb_orb_extract(eorb_orb* h, const uint8_t* img, int w, int hgt, size_t stride,
+                     int lap0, int lap1, int want_desc,
+                     eorb_keypoint* kps, uint8_t* desc, int cap, int* n_out);
+
+/* Config-3 shape: nframes images (host), frame f at imgs + f*frame_stride.  Outputs are [nframes][cap]
+ * (kps), [nframes][cap][32] (desc), [nframes] (n_out, mono_out).  Frames are processed max_batch at a time
+ * with H2D / compute / D2H overlapped on internal streams. */
+int eorb_orb_extract_batch(eorb_orb* h, const uint8_t* imgs, int nframes, int w, int hgt, size_t row_stride,
+                           size_t frame_stride, int lap0, int lap1, int want_desc,
+                           eorb_keypoint* kps, uint8_t* desc, int cap, int* n_out, int* mono_out);
+
+/* Same with everything resident in HBM (device pointers); nframes <= max_batch; asynchronous. */
+int eorb_orb_extract_batch_device(eorb_orb* h, const uint8_t* d_imgs, int nframes, int w, int hgt, size_t row_stride,
+                                  size_t frame_stride, int lap0, int lap1, int want_desc,
+                                  eorb_keypoint* d_kps, uint8_t* d_desc, int cap, int* d_n_out, int* d_mono_out);
+
+/* std::vector<cv::Mat> mvImagePyramid (ORBextractor.h:105, read by Frame.cc:876,966-985): lazy D2H of one
+ * level of frame `frame` of the last call.  dst is w_l x h_l (unbordered; the reference's border is the
+ * REFLECT_101 image of these pixels). */
+int eorb_orb_level_size(const eorb_orb* h, int level, int* w, int* hgt);
+int eorb_orb_pyramid_level(eorb_orb* h, int frame, int level, uint8_t* dst, size_t dst_stride);
+
+/* ORBextractor::ComputeTrackedKPtsDesc (ORBextractor.cc:1316-1363) */
+int eorb_orb_tracked_desc(eorb_orb* h, const uint8_t* img, int w, int hgt, size_t stride,
+                          const eorb_keypoint* kps, int n, uint8_t* desc);
+/* ORBextractor::AssignKPtLevelByBestDesc (ORBextractor.cc:1267-1314): updates kps[i].octave */
+int eorb_orb_assign_level_by_best_desc(eorb_orb* h, const uint8_t* ref_desc, const uint8_t* img, int w, int hgt,
+                                       size_t stride, eorb_keypoint* kps, int n);
+
+/* stage taps of the last call (parity tests; not part of the reference surface) */
+int eorb_orb_debug_blurred(eorb_orb* h, int frame, int level, uint8_t* dst, size_t dst_stride);
+int eorb_orb_debug_candidates(eorb_orb* h, int frame, int level, int* xs, int* ys, int* scores, int cap);
+int eorb_orb_debug_level_kps(eorb_orb* h, int frame, int level, int* xs, int* ys, int* scores, float* angles, int cap);
+/* counts kernel launches issued by this handle since creation (bench.py's gpu_launches) */
+long long eorb_orb_launch_count(const eorb_orb* h);
+
+/* ---------------------------------------------------------------- matcher
+ * replaces ORBmatcher::DescriptorDistance (ORBmatcher.cc:2360-2378) and the best/second-best scan +
+ * ratio test that every ORBmatcher::Search* bottoms out in (:318-382, :741-772), in the brute-force shape
+ * of Frame.cc:1228-1235 */
+
+int eorb_descriptor_distance(const uint8_t* a, const uint8_t* b);     /* host helper, 0..256 */
+
+int eorb_matcher_create(int device, eorb_matcher** out);
+int eorb_matcher_destroy(eorb_matcher* m);
+int eorb_matcher_set_stream(eorb_matcher* m, void* cuda_stream);
+int eorb_matcher_synchronize(eorb_matcher* m);
+long long eorb_matcher_launch_count(const eorb_matcher* m);
+/* database shard: rows [index_offset, index_offset+ndb) of the global database.
+ * _host copies into HBM; _device adopts a device pointer (not owned). */
+int eorb_matcher_set_db_host(eorb_matcher* m, const uint8_t* db, int64_t ndb, int64_t index_offset);
+int eorb_matcher_set_db_device(eorb_matcher* m, const uint8_t* d_db, int64_t ndb, int64_t index_offset);
+/* one-call brute force, host buffers: best-2 + threshold + ratio -> out[nq] */
+int eorb_matcher_search(eorb_matcher* m, const uint8_t* q, int nq, int th, float ratio, eorb_match* out);
+/* per-shard partials, device buffers, asynchronous: d_partial[nq] */
+int eorb_matcher_search_device(eorb_matcher* m, const uint8_t* d_q, int nq, eorb_best2* d_partial);
+/* merge nshards gathered partial arrays ([nshards][nq], e.g. the output of an NCCL all-gather) with the
+ * (dist, global index) ordering, then threshold + ratio -> d_out[nq]; asynchronous */
+int eorb_matcher_merge_device(eorb_matcher* m, const eorb_best2* d_gathered, int nshards, int nq,
+                              int th, float ratio, eorb_match* d_out);
+/* convenience: one-call stateless form on host buffers (creates/destroys a matcher) */
+int eorb_hamming_best2(const uint8_t* q, int nq, const uint8_t* db, int64_t ndb, int th, float ratio, eorb_match* out);
+/* rotation-consistency filter: ORBmatcher.cc:784-794, 800-823 and ComputeThreeMaxima :2314-2355.
+ * match12[i] = matched index or -1; entries outside the three dominant rotation bins are set to -1.
+ * Returns the number of remaining matches.  Host code (the reference's is too, and it is O(matches)). */
+int eorb_rotation_filter(const float* angle1, const float* angle2, int32_t* match12, int n1);
+
+/* ---------------------------------------------------------------- event frames
+ * replaces EORB_SLAM::EvImConverter::ev2im / ev2im_gauss / ev2mci_gg_f (include/Event/EventConversion.h:52-75,
+ * src/Event/EventConversion.cc:173-448) and the normalisation that follows them
+ * (normalizeImage :67-72; cv::normalize NORM_MINMAX at EvImBuilder.cpp:976,1055,1076,1140) */
+
+#define EORB_EV_NEAREST 0   /* ev2im                       EventConversion.cc:173-212 */
+#define EORB_EV_GAUSS   1   /* ev2im_gauss                 :215-269 */
+#define EORB_EV_SE3     2   /* ev2mci_gg_f(Tcw, medDepth)  :279-360 */
+#define EORB_EV_SE2     3   /* ev2mci_gg_f(params2D)       :362-448 */
+
+#define EORB_NORM_NONE    0
+#define EORB_NORM_RUNNING 1 /* normalizeImage(max,min) as inside ev2im* when normalized=true */
+#define EORB_NORM_MINMAX  2 /* cv::normalize(img,img,255,0,NORM_MINMAX,CV_8UC1) as in EvImBuilder */
+
+typedef struct eorb_ev_params {
+    int   mode;            /* EORB_EV_* */
+    int   width, height;
+    float sigma;           /* Gaussian splat sigma (ignored for NEAREST) */
+    int   pol;             /* 1: subtract events with p == false */
+    int   normalize;       /* EORB_NORM_* */
+    float Tcw[16];         /* SE3: row-major 4x4 float pose (cv::Mat CV_32F) */
+    float med_depth;       /* SE3 */
+    float K[4];            /* Pinhole fx, fy, cx, cy (Pinhole.cpp:30-62) for SE3/SE2 */
+    float se2[4];          /* SE2: omega, vx, vy, [scale] */
+    int   se2_n;           /* 3 or 4 */
+} eorb_ev_params;
+
+int eorb_ev_create(int device, int max_windows, int64_t max_events, int max_width, int max_height, eorb_evconv** out);
+int eorb_ev_destroy(eorb_evconv* c);
+int eorb_ev_set_stream(eorb_evconv* c, void* cuda_stream);
+int eorb_ev_synchronize(eorb_evconv* c);
+long long eorb_ev_launch_count(const eorb_evconv* c);
+/* one window, host buffers.  img_f32 (h*w floats) and img_u8 (h*w) may each be NULL.  minmax[2] optional.
+ * Returns EORB_EMPTY (outputs zeroed) when n == 0 for the SE3/SE2 modes, like the reference. */
+int eorb_ev_accumulate(eorb_evconv* c, const eorb_event* evs, int64_t n, const eorb_ev_params* p,
+                       float* img_f32, uint8_t* img_u8, float* minmax);
+/* nwin windows, device buffers, asynchronous.  Window i covers events [win_offsets[i], win_offsets[i+1]) of
+ * d_evs (win_offsets is a HOST array of nwin+1 entries: the fixed-count slicing of
+ * EvTrackManager::consumeEventsBegin, EvTrackManager.cpp:272-286).  All windows share p except the pose:
+ * poses (HOST, nwin x 16 floats) may be NULL to use p->Tcw for every window.
+ * d_img_f32 is [nwin][h][w]; d_img_u8 likewise (may be NULL when normalize == NONE). */
+int eorb_ev_accumulate_batch_device(eorb_evconv* c, const eorb_event* d_evs, const int64_t* win_offsets, int nwin,
+                                    const eorb_ev_params* p, const float* poses,
+                                    float* d_img_f32, uint8_t* d_img_u8);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* EORB_B200_H */

@@ -1,0 +1,104 @@
+"""GPU parity: Hamming best-2 + ratio test against the CPU oracle (bit-exact incl. ties: lowest index wins)."""
+import numpy as np
+import pytest
+
+import oracle_lib as O
+from eorb_slam_b200 import synth
+
+pytestmark = pytest.mark.gpu
+
+
+def _api():
+    from eorb_slam_b200 import api
+    return api
+
+
+def _same(a, b):
+    for k in ("best_dist", "best_idx", "second_dist", "accepted"):
+        assert np.array_equal(a[k], b[k]), k
+
+
+@pytest.mark.parametrize("ndb,nq", [(1, 3), (2, 5), (255, 17), (256, 1), (257, 1025), (5000, 2000), (70001, 1500)])
+def test_best2_matches_oracle(ndb, nq):
+    api = _api()
+    db = synth.make_descriptor_db(ndb, seed=ndb)
+    q, src = synth.make_queries(db, nq, seed=nq)
+    dup_src = src[: max(1, nq // 8)]
+    synth.plant_duplicate_rows(db, dup_src[dup_src >= 0], seed=3)     # exact duplicates -> distance ties
+    q2, _ = synth.make_queries(db, nq, seed=nq + 1, max_flips=0)      # k=0 queries hit the duplicates
+    q = np.concatenate([q, q2[: nq // 4]])
+    for ratio in (0.7, 0.9):
+        m = api.ORBmatcher(ratio, True)
+        m.set_db(db)
+        got = m.search(q)
+        exp = O.hamming_best2(q, db, th=50, ratio=ratio)
+        _same(got, exp)
+    got = api.hamming_best2(q, db, 50, 0.7)
+    _same(got, O.hamming_best2(q, db, 50, 0.7))
+
+
+def test_best2_empty_and_tiny():
+    api = _api()
+    m = api.ORBmatcher(0.7)
+    m.set_db(np.zeros((0, 32), np.uint8))
+    q = synth.make_descriptor_db(9, 1)
+    got = m.search(q)
+    assert (got["best_idx"] == -1).all() and (got["best_dist"] == 256).all() and (got["accepted"] == 0).all()
+    m.set_db(q[:1])
+    got = m.search(q)
+    exp = O.hamming_best2(q, q[:1], 50, 0.7)
+    _same(got, exp)
+    assert got["second_dist"][0] == 256 and got["best_dist"][0] == 0 and got["accepted"][0] == 1
+
+
+def test_sharded_merge_equals_global_search():
+    """config 4 shape on one GPU: 4 row shards searched separately (device API), partials concatenated as an
+    all-gather would, merged with the (dist, global index) ordering == one global scan."""
+    import torch
+    api = _api()
+    ndb, nq, shards = 40000, 700, 4
+    db = synth.make_descriptor_db(ndb, seed=5)
+    q, src = synth.make_queries(db, nq, seed=6)
+    # duplicates planted across shard boundaries: the lower global index must win
+    db[30000:30050] = db[100:150]; q[:50] = db[100:150]
+    exp = O.hamming_best2(q, db, 50, 0.7)
+    d_q = torch.from_numpy(q).cuda()
+    gathered = torch.zeros(shards * nq * 16, dtype=torch.uint8, device="cuda")
+    ms = []
+    per = ndb // shards
+    stream = torch.cuda.current_stream().cuda_stream
+    for s in range(shards):
+        m = api.ORBmatcher(0.7)
+        m.set_stream(stream)
+        m.set_db(db[s * per:(s + 1) * per], index_offset=s * per)
+        m.search_device(d_q.data_ptr(), nq, gathered.data_ptr() + s * nq * 16)
+        ms.append(m)
+    d_out = torch.zeros(nq * 16, dtype=torch.uint8, device="cuda")
+    ms[0].merge_device(gathered.data_ptr(), shards, nq, d_out.data_ptr())
+    torch.cuda.synchronize()
+    got = d_out.cpu().numpy().view(synth.MATCH_DTYPE)
+    _same(got, exp)
+    assert (got["best_idx"][:50] == np.arange(100, 150)).all()
+
+
+def test_frame_to_frame_matching_with_rotation_check():
+    api = _api()
+    p = api.ORBxParams()
+    ex = api.ORBextractor(p)
+    f1 = synth.make_frame(51)
+    f2 = np.roll(f1, (3, 5), axis=(0, 1))
+    _, k1, d1 = ex(f1)
+    _, k2, d2 = ex(f2)
+    m = api.ORBmatcher(0.9, True)
+    n, match12 = m.SearchBruteForce(d1, d2, k1["angle"], k2["angle"])
+    exp = O.hamming_best2(d1, d2, 50, 0.9)
+    m12 = np.where(exp["accepted"] == 1, exp["best_idx"], -1).astype(np.int32)
+    n_ref, m_ref = O.rotation_filter(k1["angle"], k2["angle"], m12)
+    assert n == n_ref and np.array_equal(match12, m_ref)
+    assert n > 200
+
+
+def test_popc_probe_reports_a_rate():
+    api = _api()
+    r = api.probe_popc_rate(0)
+    assert 1e11 < r < 1e14

@@ -1,0 +1,200 @@
+"""GPU parity: the CUDA ORB extractor (through the C ABI) against the CPU oracle and the golden fixtures.
+Integer stages bit-exact; keypoint angles bit-exact (required: <= 1e-3 rad)."""
+import ast
+import os
+
+import numpy as np
+import pytest
+
+import oracle_lib as O
+from eorb_slam_b200 import synth
+
+pytestmark = pytest.mark.gpu
+
+ANGLE_TOL_RAD = 1e-3   # BASELINE.json north_star tolerance; the kernels are expected to be bit-exact
+
+
+def _api():
+    from eorb_slam_b200 import api
+    return api
+
+
+def _mk(api, okw, w, h, max_batch=1):
+    p = api.ORBxParams(okw["nfeatures"], okw["scale_factor"], okw["nlevels"], okw["ini_th"], okw["min_th"], okw["edge"], (w, h))
+    return api.ORBextractor(p, 0, max_batch)
+
+
+def _orc(okw, w, h):
+    return O.OrbOracle(okw["nfeatures"], okw["scale_factor"], okw["nlevels"], okw["ini_th"], okw["min_th"], okw["edge"], w, h)
+
+
+CFG1 = dict(nfeatures=1000, scale_factor=1.2, nlevels=8, ini_th=20, min_th=7, edge=19)
+
+
+def _compare_stages(ex, orc, nlevels, want_desc=True):
+    for l in range(nlevels):
+        assert ex.level_size(l) == orc.level_size(l)
+        assert np.array_equal(ex.pyramid_level(l), orc.level(l)), "pyramid level %d" % l
+    for l in range(nlevels):
+        gx, gy, gs = ex.debug_candidates(l)
+        ox, oy, os_ = orc.candidates(l)
+        assert len(gx) == len(ox), "FAST candidate count level %d: %d vs %d" % (l, len(gx), len(ox))
+        # sets compared sorted by (y, x) ...
+        go = np.lexsort((gx, gy)); oo = np.lexsort((ox, oy))
+        assert np.array_equal(np.stack([gx, gy, gs], 1)[go], np.stack([ox, oy, os_], 1)[oo]), "FAST set level %d" % l
+        # ... and the emission order itself equals the reference order (cell-row-major, pixel-row-major)
+        assert np.array_equal(gx, ox) and np.array_equal(gy, oy), "FAST order level %d" % l
+    for l in range(nlevels):
+        gx, gy, gs, ga = ex.debug_level_kps(l)
+        ox, oy, os_, oa = orc.level_kps(l)
+        assert len(gx) == len(ox), "octree count level %d: %d vs %d" % (l, len(gx), len(ox))
+        assert np.array_equal(gx, ox) and np.array_equal(gy, oy) and np.array_equal(gs, os_), "octree selection level %d" % l
+        assert np.abs(np.deg2rad(ga - oa)).max(initial=0) <= ANGLE_TOL_RAD
+        assert np.array_equal(ga.view(np.uint32), oa.view(np.uint32)), "angle bits level %d" % l
+    if want_desc:
+        for l in range(nlevels):
+            ob = orc.blurred(l)
+            if ob is not None:
+                assert np.array_equal(ex.debug_blurred(l), ob), "blur level %d" % l
+
+
+@pytest.mark.parametrize("name", ["cfg1_seed0", "cfg1_seed1_stereo", "cfg1_flat", "mvsec_346x260", "ethz_240x180_e9", "ev_single_level"])
+def test_orb_matches_oracle_and_golden(golden_dir, name):
+    api = _api()
+    g = np.load(os.path.join(golden_dir, "orb_%s.npz" % name))
+    fkw = ast.literal_eval(str(g["frame_kw"])); okw = ast.literal_eval(str(g["orb_kw"]))
+    img = synth.make_frame(**fkw)
+    lap = tuple(int(v) for v in g["lapping"])
+    ex = _mk(api, okw, fkw["w"], fkw["h"])
+    ret, kps, desc = ex(img, None, lap, True)
+    orc = _orc(okw, fkw["w"], fkw["h"])
+    oret, okps, odesc = orc.extract(img, lap, True)
+    assert list(ex.features_per_level()) == list(orc.features_per_level())
+    assert ex.edge_threshold() == orc.edge
+    _compare_stages(ex, orc, okw["nlevels"])
+    assert ret == oret == int(g["ret"][0])
+    assert len(kps) == len(okps)
+    assert kps.tobytes() == okps.tobytes() == g["kps"].tobytes(), "keypoints"
+    bad = int((desc != odesc).any(axis=1).sum())
+    assert bad == 0, "%d descriptor rows differ" % bad
+    assert np.array_equal(desc, g["desc"])
+    # keypoints-only overload (extDesc = false for event frames, EventFrame.h:38)
+    ret2, kps2, d2 = ex(img, None, lap, False)
+    assert ret2 == ret and d2 is None and kps2.tobytes() == kps.tobytes()
+
+
+@pytest.mark.parametrize("seed", [11, 12, 13])
+def test_orb_cfg1_three_seeds(seed):
+    api = _api()
+    img = synth.make_frame(seed)
+    ex = _mk(api, CFG1, 752, 480)
+    orc = _orc(CFG1, 752, 480)
+    ret, kps, desc = ex(img)
+    oret, okps, odesc = orc.extract(img)
+    _compare_stages(ex, orc, 8)
+    assert ret == oret and kps.tobytes() == okps.tobytes() and np.array_equal(desc, odesc)
+
+
+def test_orb_edge_cases():
+    api = _api()
+    ex = _mk(api, CFG1, 752, 480)
+    ret, kps, desc = ex(np.zeros((0, 0), np.uint8))
+    assert ret == -1 and len(kps) == 0                       # return -1 on empty image (ORBextractor.cc:1096)
+    ret, kps, desc = ex(np.zeros((480, 752), np.uint8))
+    assert ret == 0 and len(kps) == 0 and desc.shape == (0, 32)   # released descriptors
+    ret, kps, desc = ex(np.full((480, 752), 255, np.uint8))
+    assert len(kps) == 0
+    # image size change on the same handle re-plans (the reference sizes its pyramid per call)
+    img = synth.make_frame(21, 346, 260)
+    ret, kps, desc = ex(img)
+    orc = _orc(CFG1, 752, 480)
+    oret, okps, odesc = orc.extract(img)
+    assert ret == oret and kps.tobytes() == okps.tobytes() and np.array_equal(desc, odesc)
+    # non-contiguous rows (stride > width)
+    big = np.zeros((480, 800), np.uint8); big[:, :752] = synth.make_frame(22)
+    view = big[:, :752]
+    img = np.ascontiguousarray(view)
+    r1, k1, d1 = ex(img)
+    orc2 = _orc(CFG1, 752, 480)
+    r2, k2, d2 = orc2.extract(img)
+    assert r1 == r2 and k1.tobytes() == k2.tobytes() and np.array_equal(d1, d2)
+    # tiny image: upper levels have no FAST grid
+    small = synth.make_frame(23, 97, 131)
+    exs = _mk(api, dict(CFG1, nfeatures=200), 97, 131)
+    orcs = _orc(dict(CFG1, nfeatures=200), 97, 131)
+    r1, k1, d1 = exs(small)
+    r2, k2, d2 = orcs.extract(small)
+    assert r1 == r2 and k1.tobytes() == k2.tobytes() and np.array_equal(d1, d2)
+
+
+def test_orb_ini_extractor_5x_features():
+    # Tracking.cc:369-373 uses 5*nFeatures until initialised: bigger quotas -> bigger octree tables
+    api = _api()
+    okw = dict(CFG1, nfeatures=5000)
+    img = synth.make_frame(31)
+    ex = _mk(api, okw, 752, 480)
+    orc = _orc(okw, 752, 480)
+    ret, kps, desc = ex(img)
+    oret, okps, odesc = orc.extract(img)
+    _compare_stages(ex, orc, 8, want_desc=False)
+    assert ret == oret and kps.tobytes() == okps.tobytes() and np.array_equal(desc, odesc)
+
+
+def test_orb_batch_matches_single_and_oracle():
+    api = _api()
+    n = 12
+    frames = synth.make_frames(n, seed0=100)
+    frames[3] = 0                                   # an empty-result frame inside the batch
+    frames[7] = synth.make_frame(7, kind="flat")
+    ex = _mk(api, CFG1, 752, 480, max_batch=5)      # 12 frames in chunks of 5,5,2
+    kps, desc, nout, mono = ex.extract_batch(frames)
+    orc = _orc(CFG1, 752, 480)
+    for f in range(n):
+        oret, okps, odesc = orc.extract(frames[f])
+        assert nout[f] == len(okps) and mono[f] == oret
+        assert kps[f, :nout[f]].tobytes() == okps.tobytes(), f
+        assert np.array_equal(desc[f, :nout[f]], odesc), f
+    tot, counts = O.orb_extract_batch_mt(frames, 4)
+    assert list(counts) == list(nout)
+
+
+def test_orb_batch_device_resident():
+    import torch
+    api = _api()
+    n = 6
+    frames = synth.make_frames(n, seed0=200)
+    ex = _mk(api, CFG1, 752, 480, max_batch=n)
+    cap = ex.cap
+    d_img = torch.from_numpy(frames).cuda()
+    d_kps = torch.zeros(n * cap * 28, dtype=torch.uint8, device="cuda")
+    d_desc = torch.zeros(n * cap * 32, dtype=torch.uint8, device="cuda")
+    d_n = torch.zeros(n, dtype=torch.int32, device="cuda"); d_mono = torch.zeros(n, dtype=torch.int32, device="cuda")
+    ex.set_stream(torch.cuda.current_stream().cuda_stream)
+    ex.extract_batch_raw(d_img.data_ptr(), n, 752, 480, 752, 752 * 480, (0, 1000), True, d_kps.data_ptr(), d_desc.data_ptr(), cap,
+                         d_n.data_ptr(), d_mono.data_ptr(), device=True)
+    torch.cuda.synchronize()
+    nout = d_n.cpu().numpy()
+    kps = d_kps.cpu().numpy().view(synth.KEYPOINT_DTYPE).reshape(n, cap)
+    desc = d_desc.cpu().numpy().reshape(n, cap, 32)
+    orc = _orc(CFG1, 752, 480)
+    for f in range(n):
+        oret, okps, odesc = orc.extract(frames[f])
+        assert nout[f] == len(okps)
+        assert kps[f, :nout[f]].tobytes() == okps.tobytes() and np.array_equal(desc[f, :nout[f]], odesc)
+    ex.set_stream(None)
+
+
+def test_tracked_descriptors_and_level_assignment():
+    api = _api()
+    img = synth.make_frame(41)
+    ex = _mk(api, CFG1, 752, 480)
+    orc = _orc(CFG1, 752, 480)
+    ret, kps, desc = ex(img)
+    sub = kps[::7].copy()
+    got = ex.ComputeTrackedKPtsDesc(img, sub)
+    exp = orc.tracked_desc(img, sub)
+    assert np.array_equal(got, exp)
+    ref_desc = desc[::7]
+    k_gpu = ex.AssignKPtLevelByBestDesc(ref_desc, img, sub)
+    k_cpu = orc.assign_level_by_best_desc(ref_desc, img, sub)
+    assert np.array_equal(k_gpu["octave"], k_cpu["octave"])
