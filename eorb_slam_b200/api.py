@@ -54,7 +54,7 @@ def _load():
         "eorb_version": ([], i), "eorb_last_error": ([], C.c_char_p), "eorb_device_count": ([], i),
         "eorb_timer_create": ([C.POINTER(vp)], i), "eorb_timer_destroy": ([vp], i), "eorb_timer_start": ([vp, vp], i),
         "eorb_timer_stop": ([vp, vp], i), "eorb_timer_elapsed_ms": ([vp, C.POINTER(f)], i),
-        "eorb_probe_popc_rate": ([i, C.POINTER(C.c_double)], i),
+        "eorb_probe_popc_rate": ([i, C.POINTER(C.c_double)], i), "eorb_selftest_math": ([i, C.POINTER(i)], i),
         "eorb_orb_create": ([C.POINTER(_OrbParams), i, i, C.POINTER(vp)], i), "eorb_orb_destroy": ([vp], i),
         "eorb_orb_set_stream": ([vp, vp], i), "eorb_orb_get_stream": ([vp], vp), "eorb_orb_synchronize": ([vp], i),
         "eorb_orb_tables": ([vp, vp, vp, vp, vp, vp, vp, vp], i), "eorb_orb_max_keypoints": ([vp], i),
@@ -111,6 +111,12 @@ def probe_popc_rate(device: int = 0) -> float:
     r = C.c_double(0)
     _check(lib.eorb_probe_popc_rate(device, C.byref(r)), "probe_popc_rate")
     return r.value
+
+
+def selftest_math(device: int = 0) -> int:
+    n = C.c_int(-1)
+    _check(lib.eorb_selftest_math(device, C.byref(n)), "selftest_math")
+    return n.value
 
 
 class CudaTimer:

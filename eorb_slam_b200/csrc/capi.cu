@@ -110,6 +110,63 @@ extern "C" int eorb_probe_popc_rate(int device, double* rate) {
     return EORB_OK;
 }
 
+// Runs the shared scalar arithmetic (eorb_math.cuh) on the device and compares it with the host compilation of
+// the same header on pseudo-random inputs.  *mismatches = number of differing results (0 expected).
+#include "eorb_math.cuh"
+extern "C" int eorb_selftest_math(int device, int* mismatches) {
+    if (!mismatches) return fail(EORB_ERR_ARG, "null argument");
+    CU(cudaSetDevice(device));
+    const int nF = 20000, nA = 20000;
+    std::vector<int> fin((size_t)nF * 17), fout(nF), bout((size_t)nA * 2);
+    std::vector<float> ain((size_t)nA * 2), aout(nA);
+    uint64_t s = 0x9E3779B97F4A7C15ull;
+    auto rnd = [&]() { s ^= s << 13; s ^= s >> 7; s ^= s << 17; return (uint32_t)(s >> 20); };
+    for (int i = 0; i < nF; i++) {
+        const int base = rnd() % 256, spread = (i % 4 == 0) ? 255 : (int)(rnd() % 40) + 1;
+        for (int k = 0; k < 17; k++) {
+            int v = base + (int)(rnd() % (2 * spread + 1)) - spread;
+            fin[(size_t)17 * i + k] = v < 0 ? 0 : (v > 255 ? 255 : v);
+        }
+        if (i % 3 == 0) {   // plant a contiguous dark/bright arc so that real corners are exercised
+            const int start = rnd() % 16, len = 8 + rnd() % 4, delta = (rnd() & 1) ? 60 : -60;
+            for (int k = 0; k < len; k++) {
+                int v = fin[(size_t)17 * i] + delta + (int)(rnd() % 9) - 4;
+                fin[(size_t)17 * i + 1 + (start + k) % 16] = v < 0 ? 0 : (v > 255 ? 255 : v);
+            }
+        }
+    }
+    for (int i = 0; i < nA; i++) {
+        ain[2 * i] = (float)((int)(rnd() % 6000001) - 3000000);
+        ain[2 * i + 1] = (float)((int)(rnd() % 6000001) - 3000000);
+        if (i < 16) { ain[2 * i] = (float)((i & 3) - 1); ain[2 * i + 1] = (float)(((i >> 2) & 3) - 1); }
+    }
+    int *d_fin = nullptr, *d_fout = nullptr, *d_bout = nullptr; float *d_ain = nullptr, *d_aout = nullptr;
+    CU(devAlloc(&d_fin, fin.size())); CU(devAlloc(&d_fout, fout.size())); CU(devAlloc(&d_bout, bout.size()));
+    CU(devAlloc(&d_ain, ain.size())); CU(devAlloc(&d_aout, aout.size()));
+    CU(cudaMemcpy(d_fin, fin.data(), fin.size() * 4, cudaMemcpyHostToDevice));
+    CU(cudaMemcpy(d_ain, ain.data(), ain.size() * 4, cudaMemcpyHostToDevice));
+    CU(launch_selftest_math(d_fin, nF, d_fout, d_ain, nA, d_aout, d_bout, 0));
+    CU(cudaMemcpy(fout.data(), d_fout, fout.size() * 4, cudaMemcpyDeviceToHost));
+    CU(cudaMemcpy(aout.data(), d_aout, aout.size() * 4, cudaMemcpyDeviceToHost));
+    CU(cudaMemcpy(bout.data(), d_bout, bout.size() * 4, cudaMemcpyDeviceToHost));
+    cudaFree(d_fin); cudaFree(d_fout); cudaFree(d_bout); cudaFree(d_ain); cudaFree(d_aout);
+    int bad = 0;
+    for (int i = 0; i < nF; i++) bad += (fout[i] != eorb::fast_max_arc_min(fin[(size_t)17 * i], &fin[(size_t)17 * i + 1]));
+    for (int i = 0; i < nA; i++) {
+        const float ang = eorb::fast_atan2_deg(ain[2 * i], ain[2 * i + 1]);
+        uint32_t a, b;
+        memcpy(&a, &ang, 4); memcpy(&b, &aout[i], 4);
+        bad += (a != b);
+        const float rad = eorb::fmul(ang, (float)(M_PI / 180.f));
+        const float ca = (float)std::cos((double)rad), sa = (float)std::sin((double)rad);
+        int r, c;
+        eorb::brief_offset((i % 27) - 13, ((i / 27) % 27) - 13, ca, sa, r, c);
+        bad += (r != bout[2 * i] || c != bout[2 * i + 1]);
+    }
+    *mismatches = bad;
+    return EORB_OK;
+}
+
 // ================================================================================================ ORB
 struct eorb_orb {
     eorb_orb_params par{};

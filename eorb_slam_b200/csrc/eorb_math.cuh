@@ -49,33 +49,41 @@ EORB_HD int gauss5_v(int h0, int h1, int h2, int h3, int h4) {
     return (39 * (h0 + h4) + 57 * (h1 + h3) + 64 * h2 + 32768) >> 16;
 }
 
-// ---- FAST-9/16 (cv::FAST called at ORBextractor.cc:832,851).  d[k] = v - ring[k], k = 0..15 in the ring order
+// ---- FAST-9/16 (cv::FAST called at ORBextractor.cc:832,851).  v = centre, ring[k], k = 0..15 in the ring order
 // (0,3),(1,3),(2,2),(3,1),(3,0),(3,-1),(2,-2),(1,-3),(0,-3),(-1,-3),(-2,-2),(-3,-1),(-3,0),(-3,1),(-2,2),(-1,3).
 // Returns m = max over the 16 arcs of 9 contiguous ring pixels of min(|v-p|) with a common sign, clamped at 0.
 // corner at threshold t  <=>  m > t ;  OpenCV's NMS score (cornerScore<16>) = m - 1.
-EORB_HD int fast_max_arc_min(const int* d) {
-    // sliding-window min/max over windows of 9 on a circular array of 16 by doubling: 2,4,8 then +1
-    int mn2[16], mx2[16];
+//
+// Written as two MIN-only sliding-window networks over d = v-p and e = p-v (window 9 on a circular array of
+// 16 by doubling: 2, 4, 8, +1).  Do NOT fold the second one into max(-max(d)): ptxas 12.9 for sm_100a fuses
+// `max(best, mn, -mx)` into VIMNMX3 and drops the negation (measured on B200: returns max(d) instead), see
+// DESIGN.md "Toolchain findings".
+EORB_HD int fast_arc_min16(const int* d) {
+    int m2[16], m4[16];
 #pragma unroll
-    for (int k = 0; k < 16; k++) { int a = d[k], b = d[(k + 1) & 15]; mn2[k] = a < b ? a : b; mx2[k] = a > b ? a : b; }
-    int mn4[16], mx4[16];
+    for (int k = 0; k < 16; k++) { const int a = d[k], b = d[(k + 1) & 15]; m2[k] = a < b ? a : b; }
+#pragma unroll
+    for (int k = 0; k < 16; k++) { const int a = m2[k], b = m2[(k + 2) & 15]; m4[k] = a < b ? a : b; }
+    int best = -100000;
 #pragma unroll
     for (int k = 0; k < 16; k++) {
-        int a = mn2[k], b = mn2[(k + 2) & 15]; mn4[k] = a < b ? a : b;
-        int c = mx2[k], e = mx2[(k + 2) & 15]; mx4[k] = c > e ? c : e;
-    }
-    int best = 0;
-#pragma unroll
-    for (int k = 0; k < 16; k++) {
-        int a = mn4[k], b = mn4[(k + 4) & 15]; int mn8 = a < b ? a : b;
-        int c = mx4[k], e = mx4[(k + 4) & 15]; int mx8 = c > e ? c : e;
-        int x = d[(k + 8) & 15];
-        int mn9 = mn8 < x ? mn8 : x;
-        int mx9 = mx8 > x ? mx8 : x;
-        best = best > mn9 ? best : mn9;       // ring darker than the centre
-        best = best > -mx9 ? best : -mx9;     // ring brighter than the centre
+        const int a = m4[k], b = m4[(k + 4) & 15];
+        int m = a < b ? a : b;
+        const int x = d[(k + 8) & 15];
+        m = m < x ? m : x;
+        best = best > m ? best : m;
     }
     return best;
+}
+
+EORB_HD int fast_max_arc_min(int v, const int* ring) {
+    int d[16], e[16];
+#pragma unroll
+    for (int k = 0; k < 16; k++) { d[k] = v - ring[k]; e[k] = ring[k] - v; }
+    const int a = fast_arc_min16(d);   // ring darker than the centre
+    const int b = fast_arc_min16(e);   // ring brighter than the centre
+    int m = a > b ? a : b;
+    return m > 0 ? m : 0;
 }
 
 // ---- cv::fastAtan2 (degrees, [0,360]); called at ORBextractor.cc:103

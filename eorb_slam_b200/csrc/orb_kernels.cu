@@ -140,12 +140,12 @@ __global__ void __launch_bounds__(EORB_FAST_WARPS * 32) fast_cells_kernel(OrbArg
             const int yy = (int)(((unsigned)i * magic) >> 22), xx = i - yy * cw;
             const uint8_t* p = t0 + (yy + 3) * TS + xx + 3;
             const int v = p[0];
-            int d[16];
-            d[0] = v - p[3 * TS];      d[1] = v - p[3 * TS + 1];  d[2] = v - p[2 * TS + 2];   d[3] = v - p[TS + 3];
-            d[4] = v - p[3];           d[5] = v - p[-TS + 3];     d[6] = v - p[-2 * TS + 2];  d[7] = v - p[-3 * TS + 1];
-            d[8] = v - p[-3 * TS];     d[9] = v - p[-3 * TS - 1]; d[10] = v - p[-2 * TS - 2]; d[11] = v - p[-TS - 3];
-            d[12] = v - p[-3];         d[13] = v - p[TS - 3];     d[14] = v - p[2 * TS - 2];  d[15] = v - p[3 * TS - 1];
-            const int m = fast_max_arc_min(d);
+            int ring[16];
+            ring[0] = p[3 * TS];       ring[1] = p[3 * TS + 1];   ring[2] = p[2 * TS + 2];    ring[3] = p[TS + 3];
+            ring[4] = p[3];            ring[5] = p[-TS + 3];      ring[6] = p[-2 * TS + 2];   ring[7] = p[-3 * TS + 1];
+            ring[8] = p[-3 * TS];      ring[9] = p[-3 * TS - 1];  ring[10] = p[-2 * TS - 2];  ring[11] = p[-TS - 3];
+            ring[12] = p[-3];          ring[13] = p[TS - 3];      ring[14] = p[2 * TS - 2];   ring[15] = p[3 * TS - 1];
+            const int m = fast_max_arc_min(v, ring);
             if (m > tlo) smap[(yy + 1) * MS + xx + 1] = (uint8_t)m;
         }
     }
@@ -473,6 +473,39 @@ __global__ void __launch_bounds__(256) tracked_desc_kernel(OrbArgs a, const eorb
         for (int o = 4; o > 0; o >>= 1) d += __shfl_xor_sync(FULL, d, o);
         if (lane == 0) distOut[(size_t)level * n + i] = d;
     }
+}
+
+// ------------------------------------------------------------------------------------------------ self-test
+// Device evaluation of the shared scalar arithmetic on caller-supplied inputs; capi.cu compares it with the
+// HOST compilation of the same header (guards against toolchain miscompiles such as the VIMNMX3 one).
+__global__ void selftest_math_kernel(const int* __restrict__ fastIn, int nFast, int* __restrict__ fastOut,
+                                     const float* __restrict__ atanIn, int nAtan, float* __restrict__ atanOut,
+                                     int* __restrict__ briefOut) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < nFast) {
+        int ring[16];
+#pragma unroll
+        for (int k = 0; k < 16; k++) ring[k] = fastIn[17 * i + 1 + k];
+        fastOut[i] = fast_max_arc_min(fastIn[17 * i], ring);
+    }
+    if (i < nAtan) {
+        const float y = atanIn[2 * i], x = atanIn[2 * i + 1];
+        const float ang = fast_atan2_deg(y, x);
+        atanOut[i] = ang;
+        const float rad = fmul(ang, (float)(3.14159265358979323846 / 180.f));
+        const float ca = (float)cos((double)rad), sa = (float)sin((double)rad);
+        int r, c;
+        brief_offset((i % 27) - 13, ((i / 27) % 27) - 13, ca, sa, r, c);
+        briefOut[2 * i] = r; briefOut[2 * i + 1] = c;
+    }
+}
+
+cudaError_t launch_selftest_math(const int* fastIn, int nFast, int* fastOut, const float* atanIn, int nAtan, float* atanOut,
+                                 int* briefOut, cudaStream_t st) {
+    const int n = nFast > nAtan ? nFast : nAtan;
+    if (n <= 0) return cudaSuccess;
+    selftest_math_kernel<<<(n + 255) / 256, 256, 0, st>>>(fastIn, nFast, fastOut, atanIn, nAtan, atanOut, briefOut);
+    return cudaGetLastError();
 }
 
 // ------------------------------------------------------------------------------------------------ launches

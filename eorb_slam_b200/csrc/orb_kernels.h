@@ -44,4 +44,7 @@ cudaError_t launch_tracked_desc(const OrbArgs& a, const OrbPlan& hp, const eorb_
                                 const float* d_invScale, const uint8_t* d_refDesc, uint8_t* d_desc, int* d_dist,
                                 cudaStream_t st, long long* launches);
 
+cudaError_t launch_selftest_math(const int* fastIn, int nFast, int* fastOut, const float* atanIn, int nAtan, float* atanOut,
+                                 int* briefOut, cudaStream_t st);
+
 }  // namespace eorb

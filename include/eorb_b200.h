@@ -93,6 +93,9 @@ int         eorb_timer_stop(void* timer, void* cuda_stream);
 int         eorb_timer_elapsed_ms(void* timer, float* ms);   /* synchronises on the stop event */
 /* integer-pipe POPC throughput probe used as the Hamming roofline denominator */
 int         eorb_probe_popc_rate(int device, double* popc32_per_sec);
+/* device-vs-host evaluation of the shared scalar arithmetic (FAST arc score, fastAtan2, steered-BRIEF offsets);
+ * *mismatches must come back 0.  Guards against toolchain miscompiles (see DESIGN.md "Toolchain findings"). */
+int         eorb_selftest_math(int device, int* mismatches);
 
 /* ---------------------------------------------------------------- ORB extractor
  * replaces ORB_SLAM3::ORBextractor (include/ORBextractor.h:62-136, src/ORBextractor.cc) */

@@ -53,7 +53,7 @@ def host_model():
                                "-o", so, srcs[0]])
     L = C.CDLL(so)
     L.hm_octree.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int]
-    L.hm_fast_max_arc_min.argtypes = [C.c_void_p]
+    L.hm_fast_max_arc_min.argtypes = [C.c_int, C.c_void_p]
     L.hm_fast_atan2.argtypes = [C.c_float, C.c_float]; L.hm_fast_atan2.restype = C.c_float
     L.hm_brief_offset.argtypes = [C.c_int, C.c_int, C.c_float, C.c_float, C.c_void_p, C.c_void_p]
     L.hm_resize_px.argtypes = [C.c_int] * 8

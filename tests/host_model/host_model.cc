@@ -23,7 +23,7 @@ int hm_octree(const uint32_t* keys, int n, int width, int height, int N, uint32_
     return r;
 }
 
-int hm_fast_max_arc_min(const int* d16) { return eorb::fast_max_arc_min(d16); }
+int hm_fast_max_arc_min(int v, const int* ring16) { return eorb::fast_max_arc_min(v, ring16); }
 float hm_fast_atan2(float y, float x) { return eorb::fast_atan2_deg(y, x); }
 void hm_brief_offset(int px, int py, float a, float b, int* row, int* col) { eorb::brief_offset(px, py, a, b, *row, *col); }
 int hm_resize_px(int p00, int p01, int p10, int p11, int a0, int a1, int b0, int b1) {

@@ -198,3 +198,8 @@ def test_tracked_descriptors_and_level_assignment():
     k_gpu = ex.AssignKPtLevelByBestDesc(ref_desc, img, sub)
     k_cpu = orc.assign_level_by_best_desc(ref_desc, img, sub)
     assert np.array_equal(k_gpu["octave"], k_cpu["octave"])
+
+
+def test_device_math_equals_host_math():
+    """shared scalar arithmetic compiled for sm_100a vs the host compile of the same header (toolchain guard)"""
+    assert _api().selftest_math(0) == 0

@@ -63,8 +63,8 @@ def test_fast_arc_score_matches_oracle(host_model):
         tile = rng.integers(0, 256, (7, 7), dtype=np.uint8)
         if trial % 3 == 0:
             tile[:] = 100; tile[0:4, :] = rng.integers(0, 256)   # structured: a real corner/edge
-        d = np.array([int(tile[3, 3]) - int(tile[3 + dy[k], 3 + dx[k]]) for k in range(16)], np.int32)
-        m = host_model.hm_fast_max_arc_min(d.ctypes.data)
+        ring = np.array([int(tile[3 + dy[k], 3 + dx[k]]) for k in range(16)], np.int32)
+        m = host_model.hm_fast_max_arc_min(int(tile[3, 3]), ring.ctypes.data)
         for t in (0, 7, 20):
             xs, ys, sc = O.fast(tile, t, False)
             assert (len(xs) == 1) == (m > t)
