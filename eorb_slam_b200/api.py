@@ -56,7 +56,7 @@ def _load():
         "eorb_timer_stop": ([vp, vp], i), "eorb_timer_elapsed_ms": ([vp, C.POINTER(f)], i),
         "eorb_probe_popc_rate": ([i, C.POINTER(C.c_double)], i), "eorb_selftest_math": ([i, C.POINTER(i)], i),
         "eorb_orb_create": ([C.POINTER(_OrbParams), i, i, C.POINTER(vp)], i), "eorb_orb_destroy": ([vp], i),
-        "eorb_orb_set_stream": ([vp, vp], i), "eorb_orb_get_stream": ([vp], vp), "eorb_orb_synchronize": ([vp], i),
+        "eorb_orb_set_stream": ([vp, vp], i), "eorb_orb_reset_stream": ([vp], i), "eorb_orb_get_stream": ([vp], vp), "eorb_orb_synchronize": ([vp], i),
         "eorb_orb_tables": ([vp, vp, vp, vp, vp, vp, vp, vp], i), "eorb_orb_max_keypoints": ([vp], i),
         "eorb_orb_extract": ([vp, vp, i, i, sz, i, i, i, vp, vp, i, vp], i),
         "eorb_orb_extract_batch": ([vp, vp, i, i, i, sz, sz, i, i, i, vp, vp, i, vp, vp], i),
@@ -66,16 +66,17 @@ def _load():
         "eorb_orb_assign_level_by_best_desc": ([vp, vp, vp, i, i, sz, vp, i], i),
         "eorb_orb_debug_blurred": ([vp, i, i, vp, sz], i), "eorb_orb_debug_candidates": ([vp, i, i, vp, vp, vp, i], i),
         "eorb_orb_debug_level_kps": ([vp, i, i, vp, vp, vp, vp, i], i), "eorb_orb_launch_count": ([vp], C.c_longlong),
+        "eorb_orb_stage_timing": ([vp, i], i), "eorb_orb_stage_times": ([vp, vp, vp], i),
         "eorb_descriptor_distance": ([vp, vp], i),
         "eorb_matcher_create": ([i, C.POINTER(vp)], i), "eorb_matcher_destroy": ([vp], i),
-        "eorb_matcher_set_stream": ([vp, vp], i), "eorb_matcher_synchronize": ([vp], i),
+        "eorb_matcher_set_stream": ([vp, vp], i), "eorb_matcher_reset_stream": ([vp], i), "eorb_matcher_synchronize": ([vp], i),
         "eorb_matcher_launch_count": ([vp], C.c_longlong),
         "eorb_matcher_set_db_host": ([vp, vp, i64, i64], i), "eorb_matcher_set_db_device": ([vp, vp, i64, i64], i),
         "eorb_matcher_search": ([vp, vp, i, i, f, vp], i), "eorb_matcher_search_device": ([vp, vp, i, vp], i),
         "eorb_matcher_merge_device": ([vp, vp, i, i, i, f, vp], i),
         "eorb_hamming_best2": ([vp, i, vp, i64, i, f, vp], i), "eorb_rotation_filter": ([vp, vp, vp, i], i),
         "eorb_ev_create": ([i, i, i64, i, i, C.POINTER(vp)], i), "eorb_ev_destroy": ([vp], i),
-        "eorb_ev_set_stream": ([vp, vp], i), "eorb_ev_synchronize": ([vp], i), "eorb_ev_launch_count": ([vp], C.c_longlong),
+        "eorb_ev_set_stream": ([vp, vp], i), "eorb_ev_reset_stream": ([vp], i), "eorb_ev_synchronize": ([vp], i), "eorb_ev_launch_count": ([vp], C.c_longlong),
         "eorb_ev_accumulate": ([vp, vp, i64, C.POINTER(_EvParams), vp, vp, vp], i),
         "eorb_ev_accumulate_batch_device": ([vp, vp, vp, i, C.POINTER(_EvParams), vp, vp, vp], i),
     }
@@ -127,10 +128,10 @@ class CudaTimer:
         _check(lib.eorb_timer_create(C.byref(self.h)), "timer_create")
 
     def start(self, stream):
-        _check(lib.eorb_timer_start(self.h, _p(stream)), "timer_start")
+        _check(lib.eorb_timer_start(self.h, C.c_void_p(int(stream or 0))), "timer_start")
 
     def stop(self, stream):
-        _check(lib.eorb_timer_stop(self.h, _p(stream)), "timer_stop")
+        _check(lib.eorb_timer_stop(self.h, C.c_void_p(int(stream or 0))), "timer_stop")
 
     def elapsed_ms(self) -> float:
         ms = C.c_float(0)
@@ -195,10 +196,24 @@ class ORBextractor:
     def edge_threshold(self): return self._tables()[1]
     def features_per_level(self): return self._tables()[3]
 
-    def set_stream(self, stream): _check(lib.eorb_orb_set_stream(self.h, _p(stream)), "set_stream")
+    def set_stream(self, stream):
+        """adopt a cudaStream_t given as an int (0 = CUDA default stream); None returns to the handle's own stream"""
+        if stream is None:
+            _check(lib.eorb_orb_reset_stream(self.h), "reset_stream")
+        else:
+            _check(lib.eorb_orb_set_stream(self.h, C.c_void_p(int(stream))), "set_stream")
     def stream(self): return lib.eorb_orb_get_stream(self.h)
     def synchronize(self): _check(lib.eorb_orb_synchronize(self.h), "synchronize")
     def launch_count(self): return lib.eorb_orb_launch_count(self.h)
+
+    STAGES = ("pyramid", "fast", "octree", "index", "blur", "orient_desc")
+
+    def stage_timing(self, enable=True): _check(lib.eorb_orb_stage_timing(self.h, int(enable)), "stage_timing")
+
+    def stage_times(self):
+        ms = np.zeros(6, np.float32); ln = np.zeros(6, np.int64)
+        _check(lib.eorb_orb_stage_times(self.h, _p(ms), _p(ln)), "stage_times")
+        return dict(zip(self.STAGES, ms.tolist())), dict(zip(self.STAGES, ln.tolist()))
 
     # --- operator() (ORBextractor.cc:1092-1238)
     def __call__(self, image, mask=None, vLappingArea=(0, 1000), want_desc=True):
@@ -312,7 +327,11 @@ class ORBmatcher:
         a = np.ascontiguousarray(a, np.uint8); b = np.ascontiguousarray(b, np.uint8)
         return _check(lib.eorb_descriptor_distance(_p(a), _p(b)), "DescriptorDistance")
 
-    def set_stream(self, stream): _check(lib.eorb_matcher_set_stream(self.h, _p(stream)), "set_stream")
+    def set_stream(self, stream):
+        if stream is None:
+            _check(lib.eorb_matcher_reset_stream(self.h), "reset_stream")
+        else:
+            _check(lib.eorb_matcher_set_stream(self.h, C.c_void_p(int(stream))), "set_stream")
     def synchronize(self): _check(lib.eorb_matcher_synchronize(self.h), "synchronize")
     def launch_count(self): return lib.eorb_matcher_launch_count(self.h)
 
@@ -385,7 +404,11 @@ class EvImConverter:
         except Exception:
             pass
 
-    def set_stream(self, stream): _check(lib.eorb_ev_set_stream(self.h, _p(stream)), "set_stream")
+    def set_stream(self, stream):
+        if stream is None:
+            _check(lib.eorb_ev_reset_stream(self.h), "reset_stream")
+        else:
+            _check(lib.eorb_ev_set_stream(self.h, C.c_void_p(int(stream))), "set_stream")
     def synchronize(self): _check(lib.eorb_ev_synchronize(self.h), "synchronize")
     def launch_count(self): return lib.eorb_ev_launch_count(self.h)
 

@@ -195,7 +195,28 @@ struct eorb_orb {
     // last call (for the stage taps)
     const uint8_t* lastLvl0 = nullptr; long long lastPitch0 = 0, lastFrameStride0 = 0; int lastFrames = 0;
     long long launches = 0;
+    // optional per-stage timing (bench.py): event sets recorded around every stage of every call
+    bool stageTiming = false;
+    std::vector<cudaEvent_t> evPool;   // (EORB_ORB_STAGES+1) events per recorded call
+    size_t evCalls = 0;
+    long long stageLaunches[EORB_ORB_STAGES] = {0, 0, 0, 0, 0, 0};
 };
+
+static cudaEvent_t* orbStageEvents(eorb_orb* h) {
+    if (!h->stageTiming) return nullptr;
+    const size_t per = EORB_ORB_STAGES + 1;
+    if ((h->evCalls + 1) * per > h->evPool.size()) {
+        const size_t old = h->evPool.size();
+        h->evPool.resize(old + 64 * per);
+        for (size_t i = old; i < h->evPool.size(); i++) cudaEventCreate(&h->evPool[i]);
+    }
+    cudaEvent_t* e = &h->evPool[h->evCalls * per];
+    h->evCalls++;
+    const int lv = h->hp.nlevels;
+    h->stageLaunches[0] += lv - 1; h->stageLaunches[1]++; h->stageLaunches[2]++; h->stageLaunches[3]++;
+    h->stageLaunches[4]++; h->stageLaunches[5]++;
+    return e;
+}
 
 static void orbFreePlan(eorb_orb* h) {
     cudaFree(h->d_plan); cudaFree(h->d_cells); cudaFree(h->d_xtab); cudaFree(h->d_ytab); cudaFree(h->d_invScale);
@@ -441,6 +462,7 @@ extern "C" int eorb_orb_destroy(eorb_orb* h) {
     cudaSetDevice(h->device);
     cudaStreamSynchronize(h->stream);
     orbFreePlan(h);
+    for (cudaEvent_t e : h->evPool) cudaEventDestroy(e);
     cudaStreamDestroy(h->ownStream);
     delete h;
     return EORB_OK;
@@ -449,7 +471,13 @@ extern "C" int eorb_orb_destroy(eorb_orb* h) {
 extern "C" int eorb_orb_set_stream(eorb_orb* h, void* s) {
     if (!h) return fail(EORB_ERR_ARG, "null handle");
     CU(cudaStreamSynchronize(h->stream));
-    h->stream = s ? (cudaStream_t)s : h->ownStream;
+    h->stream = (cudaStream_t)s;   // NULL is the CUDA legacy default stream, a legitimate choice
+    return EORB_OK;
+}
+extern "C" int eorb_orb_reset_stream(eorb_orb* h) {
+    if (!h) return fail(EORB_ERR_ARG, "null handle");
+    CU(cudaStreamSynchronize(h->stream));
+    h->stream = h->ownStream;
     return EORB_OK;
 }
 extern "C" void* eorb_orb_get_stream(eorb_orb* h) { return h ? (void*)h->stream : nullptr; }
@@ -460,6 +488,34 @@ extern "C" int eorb_orb_synchronize(eorb_orb* h) {
     return EORB_OK;
 }
 extern "C" long long eorb_orb_launch_count(const eorb_orb* h) { return h ? h->launches : 0; }
+
+extern "C" int eorb_orb_stage_timing(eorb_orb* h, int enable) {
+    if (!h) return fail(EORB_ERR_ARG, "null handle");
+    CU(cudaSetDevice(h->device));
+    CU(cudaStreamSynchronize(h->stream));
+    h->stageTiming = enable != 0;
+    h->evCalls = 0;
+    for (int i = 0; i < EORB_ORB_STAGES; i++) h->stageLaunches[i] = 0;
+    return EORB_OK;
+}
+
+extern "C" int eorb_orb_stage_times(eorb_orb* h, float* ms6, long long* launches6) {
+    if (!h || !ms6) return fail(EORB_ERR_ARG, "null argument");
+    CU(cudaSetDevice(h->device));
+    CU(cudaStreamSynchronize(h->stream));
+    const size_t per = EORB_ORB_STAGES + 1;
+    for (int i = 0; i < EORB_ORB_STAGES; i++) ms6[i] = 0.f;
+    for (size_t c = 0; c < h->evCalls; c++)
+        for (int i = 0; i < EORB_ORB_STAGES; i++) {
+            float ms = 0.f;
+            CU(cudaEventElapsedTime(&ms, h->evPool[c * per + i], h->evPool[c * per + i + 1]));
+            ms6[i] += ms;
+        }
+    if (launches6) for (int i = 0; i < EORB_ORB_STAGES; i++) launches6[i] = h->stageLaunches[i];
+    h->evCalls = 0;
+    for (int i = 0; i < EORB_ORB_STAGES; i++) h->stageLaunches[i] = 0;
+    return EORB_OK;
+}
 
 extern "C" int eorb_orb_tables(const eorb_orb* h, int* nlevels, int* edge, float* scale, float* inv_scale, float* sigma2,
                                float* inv_sigma2, int* fpl) {
@@ -506,7 +562,7 @@ extern "C" int eorb_orb_extract_batch_device(eorb_orb* h, const uint8_t* d_imgs,
         lvl0 = h->d_img0; p0 = h->pitch0; fs0 = (long long)h->pitch0 * hgt;
     }
     OrbArgs a = orbArgs(h, lvl0, p0, fs0, lap0, lap1, want_desc, d_kps, d_desc, cap, d_n_out, d_mono_out);
-    CU(launch_orb_pipeline(a, h->hp, nframes, h->stream, &h->launches));
+    CU(launch_orb_pipeline(a, h->hp, nframes, h->stream, &h->launches, orbStageEvents(h)));
     h->lastLvl0 = lvl0; h->lastPitch0 = p0; h->lastFrameStride0 = fs0; h->lastFrames = nframes;
     return EORB_OK;
 }
@@ -533,7 +589,7 @@ extern "C" int eorb_orb_extract_batch(eorb_orb* h, const uint8_t* imgs, int nfra
         }
         OrbArgs a = orbArgs(h, h->d_img0, h->pitch0, (long long)h->pitch0 * hgt, lap0, lap1, want_desc, h->d_outKps, h->d_outDesc,
                             icap, h->d_outN, h->d_outMono);
-        CU(launch_orb_pipeline(a, h->hp, nb, h->stream, &h->launches));
+        CU(launch_orb_pipeline(a, h->hp, nb, h->stream, &h->launches, orbStageEvents(h)));
         CU(cudaMemcpyAsync(h->h_n, h->d_outN, nb * sizeof(int), cudaMemcpyDeviceToHost, h->stream));
         CU(cudaMemcpyAsync(h->h_mono, h->d_outMono, nb * sizeof(int), cudaMemcpyDeviceToHost, h->stream));
         CU(cudaMemcpyAsync(h->h_kps, h->d_outKps, (size_t)nb * icap * sizeof(eorb_keypoint), cudaMemcpyDeviceToHost, h->stream));
@@ -732,7 +788,13 @@ extern "C" int eorb_matcher_destroy(eorb_matcher* m) {
 extern "C" int eorb_matcher_set_stream(eorb_matcher* m, void* s) {
     if (!m) return fail(EORB_ERR_ARG, "null handle");
     CU(cudaStreamSynchronize(m->stream));
-    m->stream = s ? (cudaStream_t)s : m->ownStream;
+    m->stream = (cudaStream_t)s;   // NULL is the CUDA legacy default stream, a legitimate choice
+    return EORB_OK;
+}
+extern "C" int eorb_matcher_reset_stream(eorb_matcher* m) {
+    if (!m) return fail(EORB_ERR_ARG, "null handle");
+    CU(cudaStreamSynchronize(m->stream));
+    m->stream = m->ownStream;
     return EORB_OK;
 }
 extern "C" int eorb_matcher_synchronize(eorb_matcher* m) {
@@ -906,7 +968,13 @@ extern "C" int eorb_ev_destroy(eorb_evconv* c) {
 extern "C" int eorb_ev_set_stream(eorb_evconv* c, void* s) {
     if (!c) return fail(EORB_ERR_ARG, "null handle");
     CU(cudaStreamSynchronize(c->stream));
-    c->stream = s ? (cudaStream_t)s : c->ownStream;
+    c->stream = (cudaStream_t)s;   // NULL is the CUDA legacy default stream, a legitimate choice
+    return EORB_OK;
+}
+extern "C" int eorb_ev_reset_stream(eorb_evconv* c) {
+    if (!c) return fail(EORB_ERR_ARG, "null handle");
+    CU(cudaStreamSynchronize(c->stream));
+    c->stream = c->ownStream;
     return EORB_OK;
 }
 extern "C" int eorb_ev_synchronize(eorb_evconv* c) {

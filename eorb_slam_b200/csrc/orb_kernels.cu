@@ -511,7 +511,10 @@ cudaError_t launch_selftest_math(const int* fastIn, int nFast, int* fastOut, con
 // ------------------------------------------------------------------------------------------------ launches
 static inline unsigned cdiv(unsigned a, unsigned b) { return (a + b - 1) / b; }
 
-cudaError_t launch_orb_pipeline(const OrbArgs& a, const OrbPlan& hp, int nframes, cudaStream_t st, long long* launches) {
+cudaError_t launch_orb_pipeline(const OrbArgs& a, const OrbPlan& hp, int nframes, cudaStream_t st, long long* launches,
+                                cudaEvent_t* ev) {
+    // ev (optional, EORB_ORB_STAGES+1 events): recorded around every stage for the per-kernel timings of bench.py
+    if (ev) cudaEventRecord(ev[0], st);
     // K1: pyramid, level by level (each level is resized from the previous one)
     for (int l = 1; l < hp.nlevels; l++) {
         if (hp.lv[l].w <= 0 || hp.lv[l].h <= 0) continue;
@@ -519,33 +522,39 @@ cudaError_t launch_orb_pipeline(const OrbArgs& a, const OrbPlan& hp, int nframes
         pyr_resize_kernel<<<grd, blk, 0, st>>>(a, l);
         (*launches)++;
     }
+    if (ev) cudaEventRecord(ev[1], st);
     // K2: FAST over every cell of every level
     if (hp.nCells > 0) {
         dim3 grd(cdiv(hp.nCells, EORB_FAST_WARPS), nframes);
         fast_cells_kernel<<<grd, EORB_FAST_WARPS * 32, (size_t)hp.cellSmemPerWarp * EORB_FAST_WARPS, st>>>(a);
         (*launches)++;
     }
+    if (ev) cudaEventRecord(ev[2], st);
     // K3: octree distribution per (level, frame)
     {
         dim3 grd(hp.nlevels, nframes);
         octree_kernel<<<grd, OCT_MAX_THREADS, hp.octSmemBytes, st>>>(a);
         (*launches)++;
     }
+    if (ev) cudaEventRecord(ev[3], st);
     // K7: output order
     orb_index_kernel<<<nframes, OCT_MAX_THREADS, 0, st>>>(a);
     (*launches)++;
+    if (ev) cudaEventRecord(ev[4], st);
     // K5: blur (only needed for descriptors)
     if (a.wantDesc && hp.rowBlocksTotal > 0) {
         dim3 blk(32, 8), grd(cdiv(cdiv(hp.lv[0].w, 4), 32), hp.rowBlocksTotal, nframes);
         blur_kernel<<<grd, blk, 0, st>>>(a);
         (*launches)++;
     }
+    if (ev) cudaEventRecord(ev[5], st);
     // K4 + K6
     {
         dim3 grd(cdiv(hp.selPerFrame, 8), nframes);
         orient_desc_kernel<<<grd, 256, 0, st>>>(a);
         (*launches)++;
     }
+    if (ev) cudaEventRecord(ev[6], st);
     return cudaGetLastError();
 }
 

@@ -38,7 +38,9 @@ struct OrbArgs {
 };
 
 cudaError_t orb_kernels_configure(const OrbPlan& hp);
-cudaError_t launch_orb_pipeline(const OrbArgs& a, const OrbPlan& hp, int nframes, cudaStream_t st, long long* launches);
+#define EORB_ORB_STAGES 6   // pyramid, fast, octree, index, blur, orient+desc
+cudaError_t launch_orb_pipeline(const OrbArgs& a, const OrbPlan& hp, int nframes, cudaStream_t st, long long* launches,
+                                cudaEvent_t* ev);
 cudaError_t launch_pyramid_and_blur(const OrbArgs& a, const OrbPlan& hp, cudaStream_t st, long long* launches);
 cudaError_t launch_tracked_desc(const OrbArgs& a, const OrbPlan& hp, const eorb_keypoint* d_kps, int n, int mode,
                                 const float* d_invScale, const uint8_t* d_refDesc, uint8_t* d_desc, int* d_dist,

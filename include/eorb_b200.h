@@ -104,8 +104,10 @@ int         eorb_selftest_math(int device, int* mismatches);
  * max_batch = frames processed per launch set by the batch entry points (>=1). */
 int eorb_orb_create(const eorb_orb_params* params, int device, int max_batch, eorb_orb** out);
 int eorb_orb_destroy(eorb_orb* h);
-/* use a caller-owned cudaStream_t (e.g. the framework's current stream); NULL restores the handle's own */
+/* use a caller-owned cudaStream_t (e.g. the framework's current stream; NULL = the CUDA default stream);
+ * _reset_stream returns to the handle's own non-blocking stream */
 int eorb_orb_set_stream(eorb_orb* h, void* cuda_stream);
+int eorb_orb_reset_stream(eorb_orb* h);
 void* eorb_orb_get_stream(eorb_orb* h);
 int eorb_orb_synchronize(eorb_orb* h);
 
@@ -154,6 +156,11 @@ int eorb_orb_debug_candidates(eorb_orb* h, int frame, int level, int* xs, int* y
 int eorb_orb_debug_level_kps(eorb_orb* h, int frame, int level, int* xs, int* ys, int* scores, float* angles, int cap);
 /* counts kernel launches issued by this handle since creation (bench.py's gpu_launches) */
 long long eorb_orb_launch_count(const eorb_orb* h);
+/* per-stage device timing for bench.py: when enabled, cudaEvents are recorded on the handle's stream around
+ * each of the 6 stages (pyramid, fast, octree, index, blur, orient+desc) of every call; _stage_times
+ * synchronises, returns the summed milliseconds and launch counts since the last call, and resets them. */
+int eorb_orb_stage_timing(eorb_orb* h, int enable);
+int eorb_orb_stage_times(eorb_orb* h, float* ms6, long long* launches6);
 
 /* ---------------------------------------------------------------- matcher
  * replaces ORBmatcher::DescriptorDistance (ORBmatcher.cc:2360-2378) and the best/second-best scan +
@@ -165,6 +172,7 @@ int eorb_descriptor_distance(const uint8_t* a, const uint8_t* b);     /* host he
 int eorb_matcher_create(int device, eorb_matcher** out);
 int eorb_matcher_destroy(eorb_matcher* m);
 int eorb_matcher_set_stream(eorb_matcher* m, void* cuda_stream);
+int eorb_matcher_reset_stream(eorb_matcher* m);
 int eorb_matcher_synchronize(eorb_matcher* m);
 long long eorb_matcher_launch_count(const eorb_matcher* m);
 /* database shard: rows [index_offset, index_offset+ndb) of the global database.
@@ -216,6 +224,7 @@ typedef struct eorb_ev_params {
 int eorb_ev_create(int device, int max_windows, int64_t max_events, int max_width, int max_height, eorb_evconv** out);
 int eorb_ev_destroy(eorb_evconv* c);
 int eorb_ev_set_stream(eorb_evconv* c, void* cuda_stream);
+int eorb_ev_reset_stream(eorb_evconv* c);
 int eorb_ev_synchronize(eorb_evconv* c);
 long long eorb_ev_launch_count(const eorb_evconv* c);
 /* one window, host buffers.  img_f32 (h*w floats) and img_u8 (h*w) may each be NULL.  minmax[2] optional.
