@@ -1,0 +1,41 @@
+// Drop-in replacement for the live entry points of the reference's include/Event/EventConversion.h:40-81
+// (EORB_SLAM::EvImConverter): same static method names, argument order and cv::Mat return convention
+// (CV_32FC1 when normalized == false, CV_8UC1 when true), forwarding to the C ABI.
+#ifndef EVENT_CONVERSION_B200_H
+#define EVENT_CONVERSION_B200_H
+
+#include <vector>
+#include <opencv2/core/core.hpp>
+#ifdef EORB_SHIM_MOCK
+#include "ref_mock.h"
+#else
+#include "EventData.h"
+#include "GeometricCamera.h"
+#endif
+
+namespace EORB_SLAM
+{
+    class EvImConverter
+    {
+    public:
+        static cv::Mat ev2im(const std::vector<EventData> &vEvData, unsigned imWidth, unsigned imHeight,
+                             bool pol = false, bool normalized = true);
+
+        static cv::Mat ev2im_gauss(const std::vector<EventData> &vEvData, unsigned imWidth, unsigned imHeight,
+                                   float sigma, bool pol = false, bool normalized = true);
+
+        static cv::Mat ev2mci_gg_f(const std::vector<EventData> &vEvData, ORB_SLAM3::GeometricCamera* pCamera,
+                                   const cv::Mat& Tcw, float medDepth, unsigned imWidth,
+                                   unsigned imHeight, float imSigma, bool pol = false, bool normalized = true);
+
+        static cv::Mat ev2mci_gg_f(const std::vector<EventData> &vEvData, ORB_SLAM3::GeometricCamera* pCamera,
+                                   const cv::Mat& params2D, unsigned imWidth, unsigned imHeight, float sigma,
+                                   bool pol = false, bool normalized = true);
+
+        // cv::normalize(img, img, 255, 0, NORM_MINMAX, CV_8UC1) as applied by the callers (EvImBuilder.cpp:976,...)
+        // fused on the device: returns the CV_8UC1 frame directly.
+        static cv::Mat ev2mci_gg_f_minmax_u8(const std::vector<EventData> &vEvData, ORB_SLAM3::GeometricCamera* pCamera,
+                                             const cv::Mat& Tcw, float medDepth, unsigned imWidth, unsigned imHeight, float imSigma);
+    };
+}// namespace EORB_SLAM
+#endif

@@ -1,0 +1,40 @@
+// Stand-ins for the few reference types the matcher / event shims mention, so that they compile without the
+// reference tree (which does not travel with this repository).  A real build includes the reference headers:
+//   include/ORBmatcher.h:35-114, include/Event/EventData.h:36-58, include/CameraModels/GeometricCamera.h:41-134
+#pragma once
+#include <vector>
+#include <opencv2/core/core.hpp>
+
+namespace ORB_SLAM3 {
+class GeometricCamera {
+public:
+    explicit GeometricCamera(std::vector<float> p) : mvParameters(std::move(p)) {}
+    float getParameter(const int i) { return mvParameters[i]; }   // GeometricCamera.h:133
+protected:
+    std::vector<float> mvParameters;   // fx, fy, cx, cy (Pinhole)
+};
+
+class ORBmatcher {   // the members this path touches (ORBmatcher.h:39-42, 96-113)
+public:
+    explicit ORBmatcher(float nnratio = 0.6, bool checkOri = true) : mfNNratio(nnratio), mbCheckOrientation(checkOri) {}
+    static int DescriptorDistance(const cv::Mat& a, const cv::Mat& b);
+    static const int TH_LOW;
+    static const int TH_HIGH;
+    static const int HISTO_LENGTH;
+protected:
+    void ComputeThreeMaxima(std::vector<int>* histo, int L, int& ind1, int& ind2, int& ind3);
+    float mfNNratio;
+    bool mbCheckOrientation;
+};
+}  // namespace ORB_SLAM3
+
+namespace EORB_SLAM {
+struct EventData {   // EventData.h:36-58
+    EventData() = default;
+    EventData(double ts, float x, float y, bool p) : ts(ts), x(x), y(y), p(p) {}
+    double ts = 0.0;
+    float x = 0.f;
+    float y = 0.f;
+    bool p = false;
+};
+}  // namespace EORB_SLAM

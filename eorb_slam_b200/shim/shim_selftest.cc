@@ -1,0 +1,54 @@
+// Compiles and links the three shims against the cv mock and libeorb_b200.so and drives them once through the
+// reference call shapes.  With a CUDA device it prints counts that tests/test_shim.py cross-checks; without one
+// it verifies the loud-failure path (no CPU fallback): -1 / empty results and an error message.
+#include <cstdio>
+#include <cstdlib>
+#include <vector>
+
+#include "ORBextractor.h"
+#include "ORBmatcher_b200.h"
+#include "EventConversion_b200.h"
+#include "eorb_b200.h"
+
+int main(int argc, char** argv)
+{
+    const int W = 752, H = 480;
+    cv::Mat im(H, W, CV_8UC1);
+    unsigned s = 12345;
+    for (int y = 0; y < H; y++) for (int x = 0; x < W; x++) { s = s * 1664525u + 1013904223u; im.at<unsigned char>(y, x) = (unsigned char)(((x / 24 + y / 24) & 1) * 90 + 60 + (s >> 28)); }
+    ORB_SLAM3::ORBxParams par(1000, 1.2f, 8, 20, 7, 19, cv::Size(W, H));
+    ORB_SLAM3::ORBextractor ex(par);
+    std::vector<cv::KeyPoint> kps, kps2;
+    cv::Mat desc, mask;
+    std::vector<int> lap = {0, 1000};
+    int ret = ex(im, mask, kps, desc, lap);
+    int ret2 = ex(im, mask, kps2, lap);
+    std::printf("devices=%d ret=%d n=%zu desc_rows=%d ret2=%d n2=%zu levels=%d pyr0=%dx%d\n", eorb_device_count(), ret, kps.size(), desc.rows,
+                ret2, kps2.size(), ex.GetLevels(), ex.mvImagePyramid[0].cols, ex.mvImagePyramid[0].rows);
+    cv::Mat empty;
+    std::printf("empty_ret=%d\n", ex(empty, mask, kps2, lap));
+    if (desc.rows >= 2) {
+        std::printf("dist01=%d\n", ORB_SLAM3::ORBmatcher::DescriptorDistance(desc.row(0), desc.row(1)));
+        ORB_SLAM3::BruteForceBest2 bf(0.9f, true);
+        bf.SetTrainDescriptors(desc);
+        std::vector<int> m12;
+        int nm = bf.Match(desc, kps, kps, m12);
+        int self = 0;
+        for (size_t i = 0; i < m12.size(); i++) self += (m12[i] == (int)i);
+        std::printf("selfmatch=%d of %d (nm=%d)\n", self, (int)m12.size(), nm);
+    }
+    std::vector<EORB_SLAM::EventData> evs;
+    for (int i = 0; i < 2000; i++) { s = s * 1664525u + 1013904223u; float x = (s >> 8) % 24000 / 100.f; s = s * 1664525u + 1013904223u; float y = (s >> 8) % 18000 / 100.f; evs.emplace_back(1e-6 * i, x, y, (s >> 5) & 1); }
+    cv::Mat f = EORB_SLAM::EvImConverter::ev2im_gauss(evs, 240, 180, 1.0f, false, false);
+    cv::Mat u = EORB_SLAM::EvImConverter::ev2im_gauss(evs, 240, 180, 1.0f);
+    double sum = 0; int mx = 0;
+    for (int y = 0; y < 180; y++) for (int x = 0; x < 240; x++) { sum += f.at<float>(y, x); if (u.at<unsigned char>(y, x) > mx) mx = u.at<unsigned char>(y, x); }
+    ORB_SLAM3::GeometricCamera cam({199.09f, 198.83f, 132.19f, 110.71f});
+    cv::Mat T = cv::Mat::zeros(4, 4, CV_32F);
+    for (int i = 0; i < 4; i++) T.at<float>(i, i) = 1.f;
+    cv::Mat g = EORB_SLAM::EvImConverter::ev2mci_gg_f(evs, &cam, T, 1.0f, 240, 180, 1.0f, false, false);
+    double sum2 = 0;
+    for (int y = 0; y < 180; y++) for (int x = 0; x < 240; x++) sum2 += g.at<float>(y, x);
+    std::printf("ev_sum=%.3f ev_u8_max=%d types=%d,%d mci_sum=%.3f\n", sum, mx, f.type(), u.type(), sum2);
+    return 0;
+}

@@ -1,0 +1,69 @@
+"""The C++ shims with the reference's class signatures (eorb_slam_b200/shim/) compile against a minimal cv mock,
+link against libeorb_b200.so and behave like the reference surface.  CPU: loud failure, no fallback.
+GPU: results equal the oracle's on the same image."""
+import os
+import re
+import subprocess
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+SHIM = os.path.join(ROOT, "eorb_slam_b200", "shim")
+EXE = os.path.join(SHIM, "_shim_selftest")
+
+
+def _build():
+    srcs = [os.path.join(SHIM, f) for f in ("shim_selftest.cc", "ORBextractor.cc", "ORBmatcher_b200.cc", "EventConversion_b200.cc")]
+    cmd = ["g++", "-std=c++17", "-O1", "-DEORB_SHIM_MOCK", "-I" + os.path.join(SHIM, "cv_mock"), "-I" + SHIM,
+           "-I" + os.path.join(ROOT, "include"), "-o", EXE] + srcs + ["-L" + os.path.join(ROOT, "eorb_slam_b200"), "-leorb_b200",
+                                                                      "-Wl,-rpath," + os.path.join(ROOT, "eorb_slam_b200")]
+    subprocess.check_call(cmd)
+
+
+def _run():
+    from eorb_slam_b200 import api  # noqa: F401  (makes sure the library exists)
+    _build()
+    r = subprocess.run([EXE], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stderr
+    return r.stdout, r.stderr
+
+
+def _lcg_image():
+    W, H = 752, 480
+    s = 12345
+    out = np.empty((H, W), np.uint8)
+    for y in range(H):
+        row = out[y]
+        for x in range(W):
+            s = (s * 1664525 + 1013904223) & 0xFFFFFFFF
+            row[x] = (((x // 24 + y // 24) & 1) * 90 + 60 + (s >> 28)) & 0xFF
+    return out
+
+
+def test_shims_compile_and_fail_loudly_without_device():
+    from eorb_slam_b200 import api
+    out, err = _run()
+    if api.device_count() > 0:
+        pytest.skip("a CUDA device is present")
+    assert "ret=-1 n=0" in out and "empty_ret=-1" in out
+    assert "no CUDA device" in err
+
+
+@pytest.mark.gpu
+def test_shims_match_oracle_on_gpu():
+    import oracle_lib as O
+    out, err = _run()
+    m = re.search(r"ret=(-?\d+) n=(\d+) desc_rows=(\d+) ret2=(-?\d+) n2=(\d+) levels=(\d+) pyr0=(\d+)x(\d+)", out)
+    assert m, out + err
+    ret, n, drows, ret2, n2, levels, pw, ph = map(int, m.groups())
+    oret, okps, odesc = O.OrbOracle().extract(_lcg_image())
+    assert (ret, n, drows, ret2, n2, levels, pw, ph) == (oret, len(okps), len(okps), oret, len(okps), 8, 752, 480)
+    assert "empty_ret=-1" in out
+    d01 = int(re.search(r"dist01=(\d+)", out).group(1))
+    assert d01 == O.descriptor_distance(odesc[0], odesc[1])
+    sm = re.search(r"selfmatch=(\d+) of (\d+)", out)
+    assert int(sm.group(2)) == len(okps) and int(sm.group(1)) > 0.5 * len(okps)
+    ev = re.search(r"ev_sum=([\d.]+) ev_u8_max=(\d+) types=(\d+),(\d+) mci_sum=([\d.]+)", out)
+    assert int(ev.group(2)) == 255 and (int(ev.group(3)), int(ev.group(4))) == (5, 0)     # CV_32FC1, CV_8UC1
+    assert abs(float(ev.group(1)) - float(ev.group(5))) < 1e-2 * float(ev.group(1))        # identity pose == plain splat
