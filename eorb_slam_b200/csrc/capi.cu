@@ -301,7 +301,7 @@ static int orbBuildPlan(eorb_orb* h, int W, int H) {
         lp.scale = h->scale[l];
         lp.sizeF = (float)(int)(31 * h->scale[l]);
         lp.quota = h->quota[l];
-        lp.rowBlockBase = rowBlocks; rowBlocks += (lp.h + 7) / 8;
+        lp.rowBlockBase = rowBlocks; rowBlocks += (lp.h + 31) / 32;   // blur bands of EORB_BLUR_BAND rows
         // FAST grid (:792-828)
         lp.minBX = E - 3; lp.minBY = E - 3; lp.maxBX = lp.w - E + 3; lp.maxBY = lp.h - E + 3;
         const float width = (float)(lp.maxBX - lp.minBX), height = (float)(lp.maxBY - lp.minBY);

@@ -31,36 +31,91 @@ __device__ __forceinline__ const uint8_t* level_ptr(const OrbArgs& a, const Leve
 }
 
 // ------------------------------------------------------------------------------------------------ K1
-// One thread = 4 horizontally adjacent destination pixels (one aligned 32-bit store).  Source taps and
-// 11-bit weights come from per-level tables computed on the host exactly like cv::resize does.
-__global__ void __launch_bounds__(256) pyr_resize_kernel(OrbArgs a, int level) {
+// cv::resize INTER_LINEAR (11-bit fixed point) of level l-1 into level l.  One warp owns 128 destination columns
+// x EORB_PYR_BAND destination rows and streams down the rows.  A lane owns 4 destination columns; its source taps
+// are per-lane constants: two pairs of aligned 32-bit words per source row (columns 0-1 and 2-3), a byte-permute
+// selector per column that extracts the two adjacent taps, and the two 11-bit weights packed as 16-bit halves so
+// that ONE dp2a gives S = a0*p[sx] + a1*p[sx+1].  The horizontally interpolated source row is cached in
+// registers and reused by the next destination row (each source row feeds ~1.7 destination rows at s = 1.2),
+// so a destination pixel costs ~1.2 aligned word loads instead of 4 byte loads.
+#define EORB_PYR_BAND 16
+
+__device__ __forceinline__ void pyr_hrow(const uint8_t* __restrict__ row, const int* off, const unsigned* sel, const unsigned* wt, unsigned* h) {
+    const unsigned A0 = __ldg(reinterpret_cast<const unsigned*>(row + off[0]));
+    const unsigned A1 = __ldg(reinterpret_cast<const unsigned*>(row + off[1]));
+    const unsigned B0 = __ldg(reinterpret_cast<const unsigned*>(row + off[2]));
+    const unsigned B1 = __ldg(reinterpret_cast<const unsigned*>(row + off[3]));
+    h[0] = __dp2a_lo(wt[0], __byte_perm(A0, A1, sel[0]), 0u);
+    h[1] = __dp2a_lo(wt[1], __byte_perm(A0, A1, sel[1]), 0u);
+    h[2] = __dp2a_lo(wt[2], __byte_perm(B0, B1, sel[2]), 0u);
+    h[3] = __dp2a_lo(wt[3], __byte_perm(B0, B1, sel[3]), 0u);
+}
+
+__global__ void __launch_bounds__(128) pyr_resize_kernel(OrbArgs a, int level) {
     const OrbPlan& P = *a.plan;
     const LevelPlan& dl = P.lv[level];
     const LevelPlan& sl = P.lv[level - 1];
     const int f = blockIdx.z;
-    const int dx0 = (blockIdx.x * blockDim.x + threadIdx.x) * 4;
-    const int dy = blockIdx.y * blockDim.y + threadIdx.y;
-    if (dy >= dl.h || dx0 >= dl.w) return;
+    const int lane = threadIdx.x;
+    const int dx0 = blockIdx.x * 128 + lane * 4;
+    const int y0 = (blockIdx.y * blockDim.y + threadIdx.y) * EORB_PYR_BAND;
+    if (y0 >= dl.h || blockIdx.x * 128 >= dl.w) return;     // warp-uniform
+    const int y1 = min(y0 + EORB_PYR_BAND, dl.h);
     int sp;
     const uint8_t* src = level_ptr(a, sl, level - 1, f, sp);
-    uint8_t* dst = a.pyr + (size_t)f * (size_t)P.pyrBytesPerFrame + (size_t)dl.off + (size_t)dy * dl.pitch;
-    const short4 yt = a.ytab[dl.ytabOff + dy];   // sy0, sy1, b0, b1
-    const uint8_t* S0 = src + (size_t)yt.x * sp;
-    const uint8_t* S1 = src + (size_t)yt.y * sp;
-    uint32_t outw = 0;
+    uint8_t* dst = a.pyr + (size_t)f * (size_t)P.pyrBytesPerFrame + (size_t)dl.off;
+    const bool active = dx0 < dl.w;
+    // per-lane constant taps
+    int off[4];
+    unsigned sel[4], wt[4];
+    {
+        const int lastWord = ((sl.w + 3) & ~3) - 4;          // last aligned word that belongs to a source row
+        int sx[4];
 #pragma unroll
-    for (int j = 0; j < 4; j++) {
-        const int dx = dx0 + j;
-        if (dx < dl.w) {
-            const short4 xt = __ldg(&a.xtab[dl.xtabOff + dx]);   // sx, sx1, a0, a1
-            const int r0 = resize_hsum(__ldg(S0 + xt.x), __ldg(S0 + xt.y), xt.z, xt.w);
-            const int r1 = resize_hsum(__ldg(S1 + xt.x), __ldg(S1 + xt.y), xt.z, xt.w);
-            int v = resize_vsum(r0, r1, yt.z, yt.w);
-            v = min(max(v, 0), 255);
-            outw |= (uint32_t)v << (8 * j);
+        for (int j = 0; j < 4; j++) {
+            const short4 xt = __ldg(&a.xtab[dl.xtabOff + min(dx0 + j, dl.w - 1)]);   // sx, sx+1 (clamped), a0, a1
+            sx[j] = xt.x;
+            wt[j] = (unsigned)(unsigned short)xt.z | ((unsigned)(unsigned short)xt.w << 16);
         }
+        const int baseA = sx[0] & ~3, baseB = sx[2] & ~3;
+        off[0] = baseA; off[1] = min(baseA + 4, lastWord); off[2] = baseB; off[3] = min(baseB + 4, lastWord);
+        // byte positions inside the 8-byte pair; when the second word was clamped (only possible at the right edge,
+        // where a1 == 0) the second tap is irrelevant, keep the selector inside 0..7
+        const int o0 = sx[0] - baseA, o1 = sx[1] - baseA, o2 = sx[2] - baseB, o3 = sx[3] - baseB;
+        sel[0] = (unsigned)(o0 | (min(o0 + 1, 7) << 4));
+        sel[1] = (unsigned)(min(o1, 7) | (min(o1 + 1, 7) << 4));
+        sel[2] = (unsigned)(o2 | (min(o2 + 1, 7) << 4));
+        sel[3] = (unsigned)(min(o3, 7) | (min(o3 + 1, 7) << 4));
+        if (!active) { off[0] = off[1] = off[2] = off[3] = 0; }
     }
-    *reinterpret_cast<uint32_t*>(dst + dx0) = outw;
+    unsigned hA[4], hB[4];
+    int idxA = -1, idxB = -1;
+    for (int dy = y0; dy < y1; dy++) {
+        const short4 yt = a.ytab[dl.ytabOff + dy];   // sy0, sy1 (clamped), b0, b1   (warp-uniform)
+        const int s0 = yt.x, s1 = yt.y;
+        if (s0 == idxB) {
+#pragma unroll
+            for (int j = 0; j < 4; j++) hA[j] = hB[j];
+            idxA = idxB;
+        } else if (s0 != idxA) {
+            pyr_hrow(src + (size_t)s0 * sp, off, sel, wt, hA);
+            idxA = s0;
+        }
+        if (s1 == idxA) {
+#pragma unroll
+            for (int j = 0; j < 4; j++) hB[j] = hA[j];
+            idxB = idxA;
+        } else if (s1 != idxB) {
+            pyr_hrow(src + (size_t)s1 * sp, off, sel, wt, hB);
+            idxB = s1;
+        }
+        int v[4];
+#pragma unroll
+        for (int j = 0; j < 4; j++) v[j] = resize_vsum((int)hA[j], (int)hB[j], yt.z, yt.w);
+        const unsigned lo = __byte_perm((unsigned)v[0], (unsigned)v[1], 0x0040);
+        const unsigned hi = __byte_perm((unsigned)v[2], (unsigned)v[3], 0x0040);
+        if (active) *reinterpret_cast<unsigned*>(dst + (size_t)dy * dl.pitch + dx0) = __byte_perm(lo, hi, 0x5410);
+    }
 }
 
 // ------------------------------------------------------------------------------------------------ K2
@@ -277,50 +332,105 @@ __global__ void __launch_bounds__(OCT_MAX_THREADS) orb_index_kernel(OrbArgs a) {
 }
 
 // ------------------------------------------------------------------------------------------------ K5
-// 5x5 sigma-2 Gaussian on every level (8.8 fixed-point separable weights, REFLECT_101).  One thread =
-// 4 adjacent outputs; interior threads read three aligned 32-bit words per source row.
-__global__ void __launch_bounds__(256) blur_kernel(OrbArgs a) {
+// 5x5 sigma-2 Gaussian on every level (8.8 fixed-point separable weights [39 57 64 57 39], REFLECT_101).
+// One warp owns a strip of 128 columns x EORB_BLUR_BAND rows and streams down the rows: each lane loads ONE
+// aligned 32-bit word per source row (4 pixels), gets its left/right neighbour words by shuffle, forms the four
+// horizontal sums with byte-permutes + unsigned dp4a (weights packed in a register, the 5th tap by a second dp4a
+// with a one-hot weight word), keeps a 5-row ring of horizontal sums in registers and emits one packed output
+// word per row.  Horizontal sums are < 2^16 and the vertical sum < 2^24, so byte 2 of the accumulator IS the
+// result ((s + 32768) >> 16) and no shift/saturation is needed.  Image borders: the left edge is a byte-permute
+// of the lane's own word, the right edge rebuilds the last lane's two words with REFLECT_101 byte loads.
+#define EORB_BLUR_BAND 32
+
+__device__ __forceinline__ void blur_hrow(const uint8_t* __restrict__ row, int x0, int w, int lane, bool leftEdge, int rightKind,
+                                          bool strip0, unsigned* h) {
+    // rightKind: 0 interior lane, 1 last lane with 4 valid pixels, 2 last lane with < 4 valid pixels, 3 idle lane (x0 >= w)
+    unsigned W = 0, R;
+    if (rightKind < 2) W = __ldg(reinterpret_cast<const unsigned*>(row + x0));
+    unsigned Rfix = 0;
+    if (rightKind == 2) {
+        unsigned b[8];
+#pragma unroll
+        for (int j = 0; j < 8; j++) b[j] = __ldg(row + reflect101(x0 + j, w));
+        W = b[0] | (b[1] << 8) | (b[2] << 16) | (b[3] << 24);
+        Rfix = b[4] | (b[5] << 8) | (b[6] << 16) | (b[7] << 24);
+    }
+    unsigned L = __shfl_up_sync(0xffffffffu, W, 1);
+    R = __shfl_down_sync(0xffffffffu, W, 1);
+    if (lane == 0) L = leftEdge ? __byte_perm(W, 0, 0x1200) : (strip0 ? 0u : __ldg(reinterpret_cast<const unsigned*>(row + x0 - 4)));
+    if (lane == 31 && rightKind == 0) R = (x0 + 4 < w) ? __ldg(reinterpret_cast<const unsigned*>(row + x0 + 4)) : 0u;
+    if (rightKind == 1) R = __byte_perm(W, 0, 0x0012);      // p[w] = p[w-2], p[w+1] = p[w-3]
+    if (rightKind == 2) R = Rfix;
+    if (lane == 31 && rightKind == 0 && x0 + 4 >= w) {
+        // the strip ends exactly at the image end inside the NEXT strip's first lane: cannot happen (lane 31 with
+        // x0+4 >= w is itself the last lane, handled by rightKind 1/2)
+    }
+    const unsigned WT = 0x39403927u;   // bytes (39, 57, 64, 57)
+    const unsigned q0 = __byte_perm(L, W, 0x5432);   // x0-2 .. x0+1
+    const unsigned q1 = __byte_perm(L, W, 0x6543);   // x0-1 .. x0+2
+    const unsigned q3 = __byte_perm(W, R, 0x4321);   // x0+1 .. x0+4
+    h[0] = __dp4a(W, 0x00270000u, __dp4a(q0, WT, 0u));   // + 39 * p[x0+2]
+    h[1] = __dp4a(W, 0x27000000u, __dp4a(q1, WT, 0u));   // + 39 * p[x0+3]
+    h[2] = __dp4a(R, 0x00000027u, __dp4a(W, WT, 0u));    // + 39 * p[x0+4]
+    h[3] = __dp4a(R, 0x00002700u, __dp4a(q3, WT, 0u));   // + 39 * p[x0+5]
+}
+
+__device__ __forceinline__ unsigned blur_vout(const unsigned* a, const unsigned* b, const unsigned* c, const unsigned* d, const unsigned* e) {
+    unsigned acc[4];
+#pragma unroll
+    for (int j = 0; j < 4; j++) acc[j] = 39u * (a[j] + e[j]) + 57u * (b[j] + d[j]) + 64u * c[j] + 32768u;
+    const unsigned lo = __byte_perm(acc[0], acc[1], 0x0062);   // (acc0.b2, acc1.b2, -, -)
+    const unsigned hi = __byte_perm(acc[2], acc[3], 0x0062);
+    return __byte_perm(lo, hi, 0x5410);
+}
+
+__global__ void __launch_bounds__(128) blur_kernel(OrbArgs a) {
     const OrbPlan& P = *a.plan;
     const int f = blockIdx.z;
+    const int lane = threadIdx.x;
+    const int band = blockIdx.y * blockDim.y + threadIdx.y;
+    if (band >= P.rowBlocksTotal) return;
     int level = 0;
-    while (level + 1 < P.nlevels && (int)blockIdx.y >= P.lv[level + 1].rowBlockBase) level++;
+    while (level + 1 < P.nlevels && band >= P.lv[level + 1].rowBlockBase) level++;
     const LevelPlan& lp = P.lv[level];
-    const int y = ((int)blockIdx.y - lp.rowBlockBase) * (int)blockDim.y + (int)threadIdx.y;
-    const int x0 = ((int)blockIdx.x * (int)blockDim.x + (int)threadIdx.x) * 4;
-    if (y >= lp.h || x0 >= lp.w) return;
+    const int w = lp.w, hgt = lp.h;
+    const int xs = blockIdx.x * 128;
+    if (xs >= w) return;
+    const int x0 = xs + lane * 4;
+    const int y0 = (band - lp.rowBlockBase) * EORB_BLUR_BAND;
+    const int y1 = min(y0 + EORB_BLUR_BAND, hgt);
     int sp;
     const uint8_t* src = level_ptr(a, lp, level, f, sp);
-    int acc[4] = {0, 0, 0, 0};
-    const int wv[5] = {39, 57, 64, 57, 39};
-    const bool interior = (x0 >= 4) && (x0 + 8 <= lp.w);
-#pragma unroll
-    for (int r = 0; r < 5; r++) {
-        const int yy = reflect101(y + r - 2, lp.h);
-        const uint8_t* row = src + (size_t)yy * sp;
-        int p[8];
-        if (interior) {
-            const uint32_t w0 = __ldg(reinterpret_cast<const uint32_t*>(row + x0 - 4));
-            const uint32_t w1 = __ldg(reinterpret_cast<const uint32_t*>(row + x0));
-            const uint32_t w2 = __ldg(reinterpret_cast<const uint32_t*>(row + x0 + 4));
-            p[0] = (w0 >> 16) & 255; p[1] = w0 >> 24;
-            p[2] = w1 & 255; p[3] = (w1 >> 8) & 255; p[4] = (w1 >> 16) & 255; p[5] = w1 >> 24;
-            p[6] = w2 & 255; p[7] = (w2 >> 8) & 255;
-        } else {
-#pragma unroll
-            for (int j = 0; j < 8; j++) p[j] = __ldg(row + reflect101(x0 - 2 + j, lp.w));
-        }
-#pragma unroll
-        for (int j = 0; j < 4; j++) acc[j] += wv[r] * gauss5_h(p[j], p[j + 1], p[j + 2], p[j + 3], p[j + 4]);
+    uint8_t* dst = a.blur + (size_t)f * (size_t)P.blurBytesPerFrame + (size_t)lp.blurOff;
+    const int bp = lp.bpitch;
+    const bool leftEdge = (x0 == 0), strip0 = (xs == 0);
+    int rightKind = 0;
+    if (x0 >= w) rightKind = 3;
+    else if (x0 + 4 >= w) rightKind = (w - x0 == 4) ? 1 : 2;
+    if (w < 6) rightKind = (x0 < w) ? 2 : 3;   // degenerate widths: every active lane takes the generic path
+    const bool store = x0 < w;
+
+    unsigned r0[4], r1[4], r2[4], r3[4], r4[4];
+#define HROW(yy, dstv) blur_hrow(src + (size_t)reflect101((yy), hgt) * sp, x0, w, lane, leftEdge, rightKind, strip0, dstv)
+#define OUT(yy, A, B, C, D, E)                                                                      \
+    do {                                                                                            \
+        const unsigned o = blur_vout(A, B, C, D, E);                                                \
+        if (store) *reinterpret_cast<unsigned*>(dst + (size_t)(yy) * bp + x0) = o;                  \
+    } while (0)
+    HROW(y0 - 2, r0); HROW(y0 - 1, r1); HROW(y0, r2); HROW(y0 + 1, r3);
+    for (int y = y0; y < y1; y += 5) {
+        HROW(y + 2, r4); OUT(y, r0, r1, r2, r3, r4);
+        if (y + 1 >= y1) break;
+        HROW(y + 3, r0); OUT(y + 1, r1, r2, r3, r4, r0);
+        if (y + 2 >= y1) break;
+        HROW(y + 4, r1); OUT(y + 2, r2, r3, r4, r0, r1);
+        if (y + 3 >= y1) break;
+        HROW(y + 5, r2); OUT(y + 3, r3, r4, r0, r1, r2);
+        if (y + 4 >= y1) break;
+        HROW(y + 6, r3); OUT(y + 4, r4, r0, r1, r2, r3);
     }
-    uint32_t outw = 0;
-#pragma unroll
-    for (int j = 0; j < 4; j++) {
-        int v = (acc[j] + 32768) >> 16;
-        v = min(v, 255);
-        outw |= (uint32_t)v << (8 * j);
-    }
-    uint8_t* dst = a.blur + (size_t)f * (size_t)P.blurBytesPerFrame + (size_t)lp.blurOff + (size_t)y * lp.bpitch;
-    *reinterpret_cast<uint32_t*>(dst + x0) = outw;
+#undef HROW
+#undef OUT
 }
 
 // ------------------------------------------------------------------------------------------------ K4 + K6
@@ -518,7 +628,7 @@ cudaError_t launch_orb_pipeline(const OrbArgs& a, const OrbPlan& hp, int nframes
     // K1: pyramid, level by level (each level is resized from the previous one)
     for (int l = 1; l < hp.nlevels; l++) {
         if (hp.lv[l].w <= 0 || hp.lv[l].h <= 0) continue;
-        dim3 blk(32, 8), grd(cdiv(cdiv(hp.lv[l].w, 4), 32), cdiv(hp.lv[l].h, 8), nframes);
+        dim3 blk(32, 4), grd(cdiv(hp.lv[l].w, 128), cdiv(hp.lv[l].h, 4 * EORB_PYR_BAND), nframes);
         pyr_resize_kernel<<<grd, blk, 0, st>>>(a, l);
         (*launches)++;
     }
@@ -543,7 +653,7 @@ cudaError_t launch_orb_pipeline(const OrbArgs& a, const OrbPlan& hp, int nframes
     if (ev) cudaEventRecord(ev[4], st);
     // K5: blur (only needed for descriptors)
     if (a.wantDesc && hp.rowBlocksTotal > 0) {
-        dim3 blk(32, 8), grd(cdiv(cdiv(hp.lv[0].w, 4), 32), hp.rowBlocksTotal, nframes);
+        dim3 blk(32, 4), grd(cdiv(hp.lv[0].w, 128), cdiv(hp.rowBlocksTotal, 4), nframes);
         blur_kernel<<<grd, blk, 0, st>>>(a);
         (*launches)++;
     }
@@ -561,12 +671,12 @@ cudaError_t launch_orb_pipeline(const OrbArgs& a, const OrbPlan& hp, int nframes
 cudaError_t launch_pyramid_and_blur(const OrbArgs& a, const OrbPlan& hp, cudaStream_t st, long long* launches) {
     for (int l = 1; l < hp.nlevels; l++) {
         if (hp.lv[l].w <= 0 || hp.lv[l].h <= 0) continue;
-        dim3 blk(32, 8), grd(cdiv(cdiv(hp.lv[l].w, 4), 32), cdiv(hp.lv[l].h, 8), 1);
+        dim3 blk(32, 4), grd(cdiv(hp.lv[l].w, 128), cdiv(hp.lv[l].h, 4 * EORB_PYR_BAND), 1);
         pyr_resize_kernel<<<grd, blk, 0, st>>>(a, l);
         (*launches)++;
     }
     if (hp.rowBlocksTotal > 0) {
-        dim3 blk(32, 8), grd(cdiv(cdiv(hp.lv[0].w, 4), 32), hp.rowBlocksTotal, 1);
+        dim3 blk(32, 4), grd(cdiv(hp.lv[0].w, 128), cdiv(hp.rowBlocksTotal, 4), 1);
         blur_kernel<<<grd, blk, 0, st>>>(a);
         (*launches)++;
     }

@@ -27,7 +27,7 @@ struct LevelPlan {
     float scale;                   // mvScaleFactor[level]
     float sizeF;                   // (float)(int)(31*scale)
     int xtabOff, ytabOff;          // offsets (in short4 units) into the resize tables (levels >= 1)
-    int rowBlockBase;              // first flattened row-block of this level (blur grid)
+    int rowBlockBase;              // first flattened 32-row band of this level (blur grid)
 };
 
 struct CellPlan {
@@ -53,7 +53,7 @@ struct OrbPlan {
     int cellListOff;               // FAST: byte offset of the survivor list
     int cellSmemPerWarp;           // bytes (multiple of 16)
     int octSmemBytes;              // max over levels
-    int rowBlocksTotal;            // blur grid
+    int rowBlocksTotal;            // blur grid: total 32-row bands over all levels
     int umax[16];
     LevelPlan lv[EORB_MAX_LEVELS];
 };
