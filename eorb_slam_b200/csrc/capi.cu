@@ -182,16 +182,24 @@ struct eorb_orb {
     std::vector<CellPlan> cells;
     OrbPlan* d_plan = nullptr; CellPlan* d_cells = nullptr; short4* d_xtab = nullptr; short4* d_ytab = nullptr;
     float* d_invScale = nullptr;
-    // slabs (maxBatch frames)
+    // slabs (maxBatch frames): `main` serves the device entry points and single calls; `pipe` holds the extra
+    // slots (own stream + slabs + pinned staging) that eorb_orb_extract_batch cycles through so that the H2D copy
+    // of chunk i+1, the kernels of chunk i and the D2H copy of chunk i-1 overlap
     int pitch0 = 0;
-    uint8_t* d_img0 = nullptr; uint8_t* d_pyr = nullptr; uint8_t* d_blur = nullptr;
-    uint16_t* d_cellCount = nullptr; uint32_t* d_cand = nullptr; uint32_t* d_okeys = nullptr; uint16_t* d_knode = nullptr;
-    uint32_t* d_sel = nullptr; int* d_selCount = nullptr; int* d_candCount = nullptr; int* d_dstIdx = nullptr;
-    float* d_levelAngle = nullptr;
-    // internal outputs for the host entry points
     int cap = 0;
-    eorb_keypoint* d_outKps = nullptr; uint8_t* d_outDesc = nullptr; int* d_outN = nullptr; int* d_outMono = nullptr;
-    eorb_keypoint* h_kps = nullptr; uint8_t* h_desc = nullptr; int* h_n = nullptr; int* h_mono = nullptr;   // pinned
+    struct Bufs {
+        uint8_t* d_img0 = nullptr; uint8_t* d_pyr = nullptr; uint8_t* d_blur = nullptr;
+        uint16_t* d_cellCount = nullptr; uint32_t* d_cand = nullptr; uint32_t* d_okeys = nullptr; uint16_t* d_knode = nullptr;
+        uint32_t* d_sel = nullptr; int* d_selCount = nullptr; int* d_candCount = nullptr; int* d_dstIdx = nullptr;
+        float* d_levelAngle = nullptr;
+        eorb_keypoint* d_outKps = nullptr; uint8_t* d_outDesc = nullptr; int* d_outN = nullptr; int* d_outMono = nullptr;
+        eorb_keypoint* h_kps = nullptr; uint8_t* h_desc = nullptr; int* h_n = nullptr; int* h_mono = nullptr;   // pinned
+        cudaStream_t stream = nullptr; cudaEvent_t done = nullptr;   // pipeline slots only
+        int f0 = 0, nb = 0; bool pending = false;
+    };
+    Bufs main;
+    std::vector<Bufs> pipe;
+    Bufs* last = nullptr;          // buffers of the most recent launch set (stage taps)
     // last call (for the stage taps)
     const uint8_t* lastLvl0 = nullptr; long long lastPitch0 = 0, lastFrameStride0 = 0; int lastFrames = 0;
     long long launches = 0;
@@ -218,18 +226,55 @@ static cudaEvent_t* orbStageEvents(eorb_orb* h) {
     return e;
 }
 
+static void orbFreeBufs(eorb_orb::Bufs& b) {
+    cudaFree(b.d_img0); cudaFree(b.d_pyr); cudaFree(b.d_blur); cudaFree(b.d_cellCount); cudaFree(b.d_cand);
+    cudaFree(b.d_okeys); cudaFree(b.d_knode); cudaFree(b.d_sel); cudaFree(b.d_selCount); cudaFree(b.d_candCount);
+    cudaFree(b.d_dstIdx); cudaFree(b.d_levelAngle); cudaFree(b.d_outKps); cudaFree(b.d_outDesc);
+    cudaFree(b.d_outN); cudaFree(b.d_outMono);
+    cudaFreeHost(b.h_kps); cudaFreeHost(b.h_desc); cudaFreeHost(b.h_n); cudaFreeHost(b.h_mono);
+    if (b.done) cudaEventDestroy(b.done);
+    if (b.stream) cudaStreamDestroy(b.stream);
+    b = eorb_orb::Bufs();
+}
+
+static int orbAllocBufs(eorb_orb* h, eorb_orb::Bufs& b, bool pipeline) {
+    const OrbPlan& P = h->hp;
+    const size_t B = (size_t)h->maxBatch;
+    const int nl = h->nlevels;
+    CU(devAlloc(&b.d_img0, B * (size_t)h->pitch0 * P.H));
+    CU(devAlloc(&b.d_pyr, B * (size_t)P.pyrBytesPerFrame));
+    CU(devAlloc(&b.d_blur, B * (size_t)P.blurBytesPerFrame));
+    CU(devAlloc(&b.d_cellCount, B * (size_t)std::max(P.nCells, 1)));
+    CU(devAlloc(&b.d_cand, B * (size_t)P.slotsPerFrame));
+    CU(devAlloc(&b.d_okeys, B * (size_t)P.slotsPerFrame));
+    CU(devAlloc(&b.d_knode, B * (size_t)P.slotsPerFrame));
+    CU(devAlloc(&b.d_sel, B * (size_t)P.selPerFrame));
+    CU(devAlloc(&b.d_selCount, B * (size_t)nl));
+    CU(devAlloc(&b.d_candCount, B * (size_t)nl));
+    CU(devAlloc(&b.d_dstIdx, B * (size_t)P.selPerFrame));
+    CU(devAlloc(&b.d_levelAngle, B * (size_t)P.selPerFrame));
+    CU(devAlloc(&b.d_outKps, B * (size_t)h->cap));
+    CU(devAlloc(&b.d_outDesc, B * (size_t)h->cap * 32));
+    CU(devAlloc(&b.d_outN, B));
+    CU(devAlloc(&b.d_outMono, B));
+    CU(cudaMallocHost((void**)&b.h_kps, B * (size_t)h->cap * sizeof(eorb_keypoint)));
+    CU(cudaMallocHost((void**)&b.h_desc, B * (size_t)h->cap * 32));
+    CU(cudaMallocHost((void**)&b.h_n, B * sizeof(int)));
+    CU(cudaMallocHost((void**)&b.h_mono, B * sizeof(int)));
+    if (pipeline) {
+        CU(cudaStreamCreateWithFlags(&b.stream, cudaStreamNonBlocking));
+        CU(cudaEventCreateWithFlags(&b.done, cudaEventDisableTiming));
+    }
+    return EORB_OK;
+}
+
 static void orbFreePlan(eorb_orb* h) {
     cudaFree(h->d_plan); cudaFree(h->d_cells); cudaFree(h->d_xtab); cudaFree(h->d_ytab); cudaFree(h->d_invScale);
-    cudaFree(h->d_img0); cudaFree(h->d_pyr); cudaFree(h->d_blur); cudaFree(h->d_cellCount); cudaFree(h->d_cand);
-    cudaFree(h->d_okeys); cudaFree(h->d_knode); cudaFree(h->d_sel); cudaFree(h->d_selCount); cudaFree(h->d_candCount);
-    cudaFree(h->d_dstIdx); cudaFree(h->d_levelAngle); cudaFree(h->d_outKps); cudaFree(h->d_outDesc);
-    cudaFree(h->d_outN); cudaFree(h->d_outMono);
-    cudaFreeHost(h->h_kps); cudaFreeHost(h->h_desc); cudaFreeHost(h->h_n); cudaFreeHost(h->h_mono);
     h->d_plan = nullptr; h->d_cells = nullptr; h->d_xtab = nullptr; h->d_ytab = nullptr; h->d_invScale = nullptr;
-    h->d_img0 = h->d_pyr = h->d_blur = nullptr; h->d_cellCount = nullptr; h->d_cand = h->d_okeys = nullptr;
-    h->d_knode = nullptr; h->d_sel = nullptr; h->d_selCount = h->d_candCount = h->d_dstIdx = nullptr;
-    h->d_levelAngle = nullptr; h->d_outKps = nullptr; h->d_outDesc = nullptr; h->d_outN = h->d_outMono = nullptr;
-    h->h_kps = nullptr; h->h_desc = nullptr; h->h_n = h->h_mono = nullptr;
+    orbFreeBufs(h->main);
+    for (auto& b : h->pipe) orbFreeBufs(b);
+    h->pipe.clear();
+    h->last = nullptr;
     h->planW = h->planH = 0;
 }
 
@@ -385,7 +430,6 @@ static int orbBuildPlan(eorb_orb* h, int W, int H) {
     if (P.cellSmemPerWarp * EORB_FAST_WARPS > 200 * 1024 || octSmem > 200 * 1024)
         return fail(EORB_ERR_ARG, "shared-memory budget exceeded (fast %d B, octree %d B)", P.cellSmemPerWarp * EORB_FAST_WARPS, octSmem);
 
-    const size_t B = (size_t)h->maxBatch;
     h->pitch0 = roundUp(W, 16);
     h->cap = eorb_orb_max_keypoints(h);
     CU(devAlloc(&h->d_plan, 1));
@@ -393,26 +437,10 @@ static int orbBuildPlan(eorb_orb* h, int W, int H) {
     CU(devAlloc(&h->d_xtab, xtab.size()));
     CU(devAlloc(&h->d_ytab, ytab.size()));
     CU(devAlloc(&h->d_invScale, (size_t)nl));
-    CU(devAlloc(&h->d_img0, B * (size_t)h->pitch0 * H));
-    CU(devAlloc(&h->d_pyr, B * (size_t)P.pyrBytesPerFrame));
-    CU(devAlloc(&h->d_blur, B * (size_t)P.blurBytesPerFrame));
-    CU(devAlloc(&h->d_cellCount, B * (size_t)std::max(P.nCells, 1)));
-    CU(devAlloc(&h->d_cand, B * (size_t)P.slotsPerFrame));
-    CU(devAlloc(&h->d_okeys, B * (size_t)P.slotsPerFrame));
-    CU(devAlloc(&h->d_knode, B * (size_t)P.slotsPerFrame));
-    CU(devAlloc(&h->d_sel, B * (size_t)P.selPerFrame));
-    CU(devAlloc(&h->d_selCount, B * (size_t)nl));
-    CU(devAlloc(&h->d_candCount, B * (size_t)nl));
-    CU(devAlloc(&h->d_dstIdx, B * (size_t)P.selPerFrame));
-    CU(devAlloc(&h->d_levelAngle, B * (size_t)P.selPerFrame));
-    CU(devAlloc(&h->d_outKps, B * (size_t)h->cap));
-    CU(devAlloc(&h->d_outDesc, B * (size_t)h->cap * 32));
-    CU(devAlloc(&h->d_outN, B));
-    CU(devAlloc(&h->d_outMono, B));
-    CU(cudaMallocHost((void**)&h->h_kps, B * (size_t)h->cap * sizeof(eorb_keypoint)));
-    CU(cudaMallocHost((void**)&h->h_desc, B * (size_t)h->cap * 32));
-    CU(cudaMallocHost((void**)&h->h_n, B * sizeof(int)));
-    CU(cudaMallocHost((void**)&h->h_mono, B * sizeof(int)));
+    {
+        int rcb = orbAllocBufs(h, h->main, false);
+        if (rcb != EORB_OK) return rcb;
+    }
     CU(cudaMemcpy(h->d_plan, &P, sizeof(P), cudaMemcpyHostToDevice));
     if (!h->cells.empty()) CU(cudaMemcpy(h->d_cells, h->cells.data(), h->cells.size() * sizeof(CellPlan), cudaMemcpyHostToDevice));
     if (!xtab.empty()) CU(cudaMemcpy(h->d_xtab, xtab.data(), xtab.size() * sizeof(short4), cudaMemcpyHostToDevice));
@@ -423,16 +451,17 @@ static int orbBuildPlan(eorb_orb* h, int W, int H) {
     return EORB_OK;
 }
 
-static OrbArgs orbArgs(eorb_orb* h, const uint8_t* lvl0, long long pitch0, long long frameStride0, int lap0, int lap1,
+static OrbArgs orbArgs(eorb_orb* h, eorb_orb::Bufs& b, const uint8_t* lvl0, long long pitch0, long long frameStride0, int lap0, int lap1,
                        int wantDesc, eorb_keypoint* kps, uint8_t* desc, int cap, int* nOut, int* monoOut) {
     OrbArgs a{};
     a.plan = h->d_plan; a.cells = h->d_cells; a.xtab = h->d_xtab; a.ytab = h->d_ytab;
     a.lvl0 = lvl0; a.lvl0Pitch = pitch0; a.lvl0FrameStride = frameStride0;
-    a.pyr = h->d_pyr; a.blur = h->d_blur; a.cellCount = h->d_cellCount; a.cand = h->d_cand; a.okeys = h->d_okeys;
-    a.knode = h->d_knode; a.sel = h->d_sel; a.selCount = h->d_selCount; a.candCount = h->d_candCount;
-    a.dstIdx = h->d_dstIdx; a.levelAngle = h->d_levelAngle;
+    a.pyr = b.d_pyr; a.blur = b.d_blur; a.cellCount = b.d_cellCount; a.cand = b.d_cand; a.okeys = b.d_okeys;
+    a.knode = b.d_knode; a.sel = b.d_sel; a.selCount = b.d_selCount; a.candCount = b.d_candCount;
+    a.dstIdx = b.d_dstIdx; a.levelAngle = b.d_levelAngle;
     a.outKps = kps; a.outDesc = desc; a.outN = nOut; a.outMono = monoOut; a.cap = cap;
     a.lap0 = lap0; a.lap1 = lap1; a.wantDesc = wantDesc;
+    h->last = &b;
     return a;
 }
 
@@ -557,14 +586,40 @@ extern "C" int eorb_orb_extract_batch_device(eorb_orb* h, const uint8_t* d_imgs,
     const uint8_t* lvl0 = d_imgs; long long p0 = (long long)row_stride, fs0 = (long long)frame_stride;
     if (!lvl0ZeroCopyOk(d_imgs, w, row_stride, frame_stride)) {
         for (int f = 0; f < nframes; f++)
-            CU(cudaMemcpy2DAsync(h->d_img0 + (size_t)f * h->pitch0 * hgt, h->pitch0, d_imgs + (size_t)f * frame_stride, row_stride,
+            CU(cudaMemcpy2DAsync(h->main.d_img0 + (size_t)f * h->pitch0 * hgt, h->pitch0, d_imgs + (size_t)f * frame_stride, row_stride,
                                  w, hgt, cudaMemcpyDeviceToDevice, h->stream));
-        lvl0 = h->d_img0; p0 = h->pitch0; fs0 = (long long)h->pitch0 * hgt;
+        lvl0 = h->main.d_img0; p0 = h->pitch0; fs0 = (long long)h->pitch0 * hgt;
     }
-    OrbArgs a = orbArgs(h, lvl0, p0, fs0, lap0, lap1, want_desc, d_kps, d_desc, cap, d_n_out, d_mono_out);
+    OrbArgs a = orbArgs(h, h->main, lvl0, p0, fs0, lap0, lap1, want_desc, d_kps, d_desc, cap, d_n_out, d_mono_out);
     CU(launch_orb_pipeline(a, h->hp, nframes, h->stream, &h->launches, orbStageEvents(h)));
     h->lastLvl0 = lvl0; h->lastPitch0 = p0; h->lastFrameStride0 = fs0; h->lastFrames = nframes;
     return EORB_OK;
+}
+
+// drains one pipeline slot: waits for its D2H copies, then hands the results to the caller's arrays
+static int orbCollect(eorb_orb* h, eorb_orb::Bufs& b, int want_desc, eorb_keypoint* kps, uint8_t* desc, int cap, int* n_out, int* mono_out,
+                      bool direct) {
+    if (!b.pending) return EORB_OK;
+    b.pending = false;
+    CU(b.done ? cudaEventSynchronize(b.done) : cudaStreamSynchronize(h->stream));
+    int status = EORB_OK;
+    const int icap = h->cap;
+    for (int f = 0; f < b.nb; f++) {
+        const int n = b.h_n[f];
+        n_out[b.f0 + f] = n;
+        if (mono_out) mono_out[b.f0 + f] = b.h_mono[f];
+        if (n > cap || n > icap) { status = fail(EORB_ERR_CAPACITY, "frame %d produced %d keypoints > cap %d", b.f0 + f, n, std::min(cap, icap)); continue; }
+        if (direct) continue;   // the device wrote straight into the caller's pinned arrays
+        memcpy(kps + (size_t)(b.f0 + f) * cap, b.h_kps + (size_t)f * icap, (size_t)n * sizeof(eorb_keypoint));
+        if (want_desc) memcpy(desc + (size_t)(b.f0 + f) * cap * 32, b.h_desc + (size_t)f * icap * 32, (size_t)n * 32);
+    }
+    return status;
+}
+
+static bool isPinnedHost(const void* p) {
+    cudaPointerAttributes at;
+    if (cudaPointerGetAttributes(&at, p) != cudaSuccess) { cudaGetLastError(); return false; }
+    return at.type == cudaMemoryTypeHost;
 }
 
 extern "C" int eorb_orb_extract_batch(eorb_orb* h, const uint8_t* imgs, int nframes, int w, int hgt, size_t row_stride,
@@ -577,33 +632,52 @@ extern "C" int eorb_orb_extract_batch(eorb_orb* h, const uint8_t* imgs, int nfra
     int rc = orbBuildPlan(h, w, hgt);
     if (rc != EORB_OK) return rc;
     const int B = h->maxBatch, icap = h->cap;
+    const int nchunks = (nframes + B - 1) / B;
+    // more than one chunk: cycle through up to 3 pipeline slots (own streams) so copies and kernels overlap
+    const int nslots = nchunks > 1 ? std::min(nchunks, 3) : 0;
+    while ((int)h->pipe.size() < nslots) {
+        h->pipe.emplace_back();
+        int rcb = orbAllocBufs(h, h->pipe.back(), true);
+        if (rcb != EORB_OK) { orbFreeBufs(h->pipe.back()); h->pipe.pop_back(); return rcb; }
+    }
+    // when the caller's arrays are pinned and laid out like ours, D2H goes straight into them (no staging copy)
+    const bool direct = nslots > 0 && cap == icap && isPinnedHost(kps) && (!want_desc || isPinnedHost(desc));
+    if (nslots > 0) CU(cudaStreamSynchronize(h->stream));   // order after earlier work on the handle's stream
     int status = EORB_OK;
-    for (int f0 = 0; f0 < nframes; f0 += B) {
-        const int nb = std::min(B, nframes - f0);
+    for (int c = 0; c < nchunks; c++) {
+        const int f0 = c * B, nb = std::min(B, nframes - f0);
+        eorb_orb::Bufs& b = nslots > 0 ? h->pipe[c % nslots] : h->main;
+        cudaStream_t st = nslots > 0 ? b.stream : h->stream;
+        int rcc = orbCollect(h, b, want_desc, kps, desc, cap, n_out, mono_out, direct);
+        if (rcc != EORB_OK) status = rcc;
         if (row_stride == (size_t)w && frame_stride == (size_t)w * hgt && h->pitch0 == w) {
-            CU(cudaMemcpyAsync(h->d_img0, imgs + (size_t)f0 * frame_stride, (size_t)nb * frame_stride, cudaMemcpyHostToDevice, h->stream));
+            CU(cudaMemcpyAsync(b.d_img0, imgs + (size_t)f0 * frame_stride, (size_t)nb * frame_stride, cudaMemcpyHostToDevice, st));
         } else {
             for (int f = 0; f < nb; f++)
-                CU(cudaMemcpy2DAsync(h->d_img0 + (size_t)f * h->pitch0 * hgt, h->pitch0, imgs + (size_t)(f0 + f) * frame_stride,
-                                     row_stride, w, hgt, cudaMemcpyHostToDevice, h->stream));
+                CU(cudaMemcpy2DAsync(b.d_img0 + (size_t)f * h->pitch0 * hgt, h->pitch0, imgs + (size_t)(f0 + f) * frame_stride,
+                                     row_stride, w, hgt, cudaMemcpyHostToDevice, st));
         }
-        OrbArgs a = orbArgs(h, h->d_img0, h->pitch0, (long long)h->pitch0 * hgt, lap0, lap1, want_desc, h->d_outKps, h->d_outDesc,
-                            icap, h->d_outN, h->d_outMono);
-        CU(launch_orb_pipeline(a, h->hp, nb, h->stream, &h->launches, orbStageEvents(h)));
-        CU(cudaMemcpyAsync(h->h_n, h->d_outN, nb * sizeof(int), cudaMemcpyDeviceToHost, h->stream));
-        CU(cudaMemcpyAsync(h->h_mono, h->d_outMono, nb * sizeof(int), cudaMemcpyDeviceToHost, h->stream));
-        CU(cudaMemcpyAsync(h->h_kps, h->d_outKps, (size_t)nb * icap * sizeof(eorb_keypoint), cudaMemcpyDeviceToHost, h->stream));
-        if (want_desc) CU(cudaMemcpyAsync(h->h_desc, h->d_outDesc, (size_t)nb * icap * 32, cudaMemcpyDeviceToHost, h->stream));
-        CU(cudaStreamSynchronize(h->stream));
-        for (int f = 0; f < nb; f++) {
-            const int n = h->h_n[f];
-            n_out[f0 + f] = n;
-            if (mono_out) mono_out[f0 + f] = h->h_mono[f];
-            if (n > cap || n > icap) { status = fail(EORB_ERR_CAPACITY, "frame %d produced %d keypoints > cap %d", f0 + f, n, std::min(cap, icap)); continue; }
-            memcpy(kps + (size_t)(f0 + f) * cap, h->h_kps + (size_t)f * icap, (size_t)n * sizeof(eorb_keypoint));
-            if (want_desc) memcpy(desc + (size_t)(f0 + f) * cap * 32, h->h_desc + (size_t)f * icap * 32, (size_t)n * 32);
+        OrbArgs a = orbArgs(h, b, b.d_img0, h->pitch0, (long long)h->pitch0 * hgt, lap0, lap1, want_desc, b.d_outKps, b.d_outDesc,
+                            icap, b.d_outN, b.d_outMono);
+        CU(launch_orb_pipeline(a, h->hp, nb, st, &h->launches, nslots > 0 ? nullptr : orbStageEvents(h)));
+        CU(cudaMemcpyAsync(b.h_n, b.d_outN, nb * sizeof(int), cudaMemcpyDeviceToHost, st));
+        CU(cudaMemcpyAsync(b.h_mono, b.d_outMono, nb * sizeof(int), cudaMemcpyDeviceToHost, st));
+        eorb_keypoint* kdst = direct ? kps + (size_t)f0 * cap : b.h_kps;
+        uint8_t* ddst = direct ? desc + (size_t)f0 * cap * 32 : b.h_desc;
+        CU(cudaMemcpyAsync(kdst, b.d_outKps, (size_t)nb * icap * sizeof(eorb_keypoint), cudaMemcpyDeviceToHost, st));
+        if (want_desc) CU(cudaMemcpyAsync(ddst, b.d_outDesc, (size_t)nb * icap * 32, cudaMemcpyDeviceToHost, st));
+        if (b.done) CU(cudaEventRecord(b.done, st));
+        b.f0 = f0; b.nb = nb; b.pending = true;
+        h->lastLvl0 = b.d_img0; h->lastPitch0 = h->pitch0; h->lastFrameStride0 = (long long)h->pitch0 * hgt; h->lastFrames = nb;
+    }
+    if (nslots > 0) {
+        for (int c = nchunks; c < nchunks + nslots; c++) {   // drain in issue order
+            int rcc = orbCollect(h, h->pipe[c % nslots], want_desc, kps, desc, cap, n_out, mono_out, direct);
+            if (rcc != EORB_OK) status = rcc;
         }
-        h->lastLvl0 = h->d_img0; h->lastPitch0 = h->pitch0; h->lastFrameStride0 = (long long)h->pitch0 * hgt; h->lastFrames = nb;
+    } else {
+        int rcc = orbCollect(h, h->main, want_desc, kps, desc, cap, n_out, mono_out, false);
+        if (rcc != EORB_OK) status = rcc;
     }
     return status;
 }
@@ -635,7 +709,7 @@ extern "C" int eorb_orb_pyramid_level(eorb_orb* h, int frame, int level, uint8_t
     const LevelPlan& lp = h->hp.lv[level];
     const uint8_t* src; size_t sp;
     if (level == 0) { src = h->lastLvl0 + (size_t)frame * h->lastFrameStride0; sp = (size_t)h->lastPitch0; }
-    else { src = h->d_pyr + (size_t)frame * h->hp.pyrBytesPerFrame + lp.off; sp = lp.pitch; }
+    else { src = h->last->d_pyr + (size_t)frame * h->hp.pyrBytesPerFrame + lp.off; sp = lp.pitch; }
     CU(cudaMemcpy2DAsync(dst, dst_stride, src, sp, lp.w, lp.h, cudaMemcpyDeviceToHost, h->stream));
     CU(cudaStreamSynchronize(h->stream));
     return EORB_OK;
@@ -646,7 +720,7 @@ extern "C" int eorb_orb_debug_blurred(eorb_orb* h, int frame, int level, uint8_t
     if (level < 0 || level >= h->nlevels || frame < 0 || frame >= h->lastFrames || !dst) return fail(EORB_ERR_ARG, "bad frame/level");
     CU(cudaSetDevice(h->device));
     const LevelPlan& lp = h->hp.lv[level];
-    CU(cudaMemcpy2DAsync(dst, dst_stride, h->d_blur + (size_t)frame * h->hp.blurBytesPerFrame + lp.blurOff, lp.bpitch, lp.w, lp.h,
+    CU(cudaMemcpy2DAsync(dst, dst_stride, h->last->d_blur + (size_t)frame * h->hp.blurBytesPerFrame + lp.blurOff, lp.bpitch, lp.w, lp.h,
                          cudaMemcpyDeviceToHost, h->stream));
     CU(cudaStreamSynchronize(h->stream));
     return EORB_OK;
@@ -658,9 +732,9 @@ extern "C" int eorb_orb_debug_candidates(eorb_orb* h, int frame, int level, int*
     CU(cudaSetDevice(h->device));
     CU(cudaStreamSynchronize(h->stream));
     int n = 0;
-    CU(cudaMemcpy(&n, h->d_candCount + (size_t)frame * h->nlevels + level, sizeof(int), cudaMemcpyDeviceToHost));
+    CU(cudaMemcpy(&n, h->last->d_candCount + (size_t)frame * h->nlevels + level, sizeof(int), cudaMemcpyDeviceToHost));
     std::vector<uint32_t> k((size_t)std::max(n, 1));
-    if (n > 0) CU(cudaMemcpy(k.data(), h->d_okeys + (size_t)frame * h->hp.slotsPerFrame + h->hp.lv[level].slotBase, (size_t)n * 4, cudaMemcpyDeviceToHost));
+    if (n > 0) CU(cudaMemcpy(k.data(), h->last->d_okeys + (size_t)frame * h->hp.slotsPerFrame + h->hp.lv[level].slotBase, (size_t)n * 4, cudaMemcpyDeviceToHost));
     for (int i = 0; i < n && i < cap; i++) { xs[i] = k[i] & 0xFFF; ys[i] = (k[i] >> 12) & 0xFFF; scores[i] = k[i] >> 24; }
     return n;
 }
@@ -671,13 +745,13 @@ extern "C" int eorb_orb_debug_level_kps(eorb_orb* h, int frame, int level, int* 
     CU(cudaSetDevice(h->device));
     CU(cudaStreamSynchronize(h->stream));
     int n = 0;
-    CU(cudaMemcpy(&n, h->d_selCount + (size_t)frame * h->nlevels + level, sizeof(int), cudaMemcpyDeviceToHost));
+    CU(cudaMemcpy(&n, h->last->d_selCount + (size_t)frame * h->nlevels + level, sizeof(int), cudaMemcpyDeviceToHost));
     const LevelPlan& lp = h->hp.lv[level];
     std::vector<uint32_t> k((size_t)std::max(n, 1));
     std::vector<float> an((size_t)std::max(n, 1));
     if (n > 0) {
-        CU(cudaMemcpy(k.data(), h->d_sel + (size_t)frame * h->hp.selPerFrame + lp.selBase, (size_t)n * 4, cudaMemcpyDeviceToHost));
-        CU(cudaMemcpy(an.data(), h->d_levelAngle + (size_t)frame * h->hp.selPerFrame + lp.selBase, (size_t)n * 4, cudaMemcpyDeviceToHost));
+        CU(cudaMemcpy(k.data(), h->last->d_sel + (size_t)frame * h->hp.selPerFrame + lp.selBase, (size_t)n * 4, cudaMemcpyDeviceToHost));
+        CU(cudaMemcpy(an.data(), h->last->d_levelAngle + (size_t)frame * h->hp.selPerFrame + lp.selBase, (size_t)n * 4, cudaMemcpyDeviceToHost));
     }
     for (int i = 0; i < n && i < cap; i++) {
         xs[i] = (int)(k[i] & 0xFFF) + lp.minBX; ys[i] = (int)((k[i] >> 12) & 0xFFF) + lp.minBY; scores[i] = k[i] >> 24;
@@ -697,8 +771,8 @@ static int orbTracked(eorb_orb* h, const uint8_t* img, int w, int hgt, size_t st
     CU(cudaSetDevice(h->device));
     int rc = orbBuildPlan(h, w, hgt);
     if (rc != EORB_OK) return rc;
-    CU(cudaMemcpy2DAsync(h->d_img0, h->pitch0, img, stride, w, hgt, cudaMemcpyHostToDevice, h->stream));
-    OrbArgs a = orbArgs(h, h->d_img0, h->pitch0, (long long)h->pitch0 * hgt, 0, 0, 1, h->d_outKps, h->d_outDesc, h->cap, h->d_outN, h->d_outMono);
+    CU(cudaMemcpy2DAsync(h->main.d_img0, h->pitch0, img, stride, w, hgt, cudaMemcpyHostToDevice, h->stream));
+    OrbArgs a = orbArgs(h, h->main, h->main.d_img0, h->pitch0, (long long)h->pitch0 * hgt, 0, 0, 1, h->main.d_outKps, h->main.d_outDesc, h->cap, h->main.d_outN, h->main.d_outMono);
     CU(launch_pyramid_and_blur(a, h->hp, h->stream, &h->launches));
     eorb_keypoint* d_k = nullptr; uint8_t* d_ref = nullptr; uint8_t* d_desc = nullptr; int* d_dist = nullptr;
     CU(devAlloc(&d_k, (size_t)n));
@@ -725,7 +799,7 @@ static int orbTracked(eorb_orb* h, const uint8_t* img, int w, int hgt, size_t st
         }
     }
     cudaFree(d_k); cudaFree(d_ref); cudaFree(d_desc); cudaFree(d_dist);
-    h->lastLvl0 = h->d_img0; h->lastPitch0 = h->pitch0; h->lastFrameStride0 = (long long)h->pitch0 * hgt; h->lastFrames = 1;
+    h->lastLvl0 = h->main.d_img0; h->lastPitch0 = h->pitch0; h->lastFrameStride0 = (long long)h->pitch0 * hgt; h->lastFrames = 1;
     return EORB_OK;
 }
 

@@ -51,29 +51,44 @@ __device__ __forceinline__ void pyr_hrow(const uint8_t* __restrict__ row, const 
     h[3] = __dp2a_lo(wt[3], __byte_perm(B0, B1, sel[3]), 0u);
 }
 
+__device__ __forceinline__ unsigned pyr_vrow(const unsigned* __restrict__ h0, const unsigned* __restrict__ h1, int b0, int b1) {
+    int v[4];
+#pragma unroll
+    for (int j = 0; j < 4; j++) v[j] = resize_vsum((int)h0[j], (int)h1[j], b0, b1);
+    const unsigned lo = __byte_perm((unsigned)v[0], (unsigned)v[1], 0x0040);
+    const unsigned hi = __byte_perm((unsigned)v[2], (unsigned)v[3], 0x0040);
+    return __byte_perm(lo, hi, 0x5410);
+}
+
 __global__ void __launch_bounds__(128) pyr_resize_kernel(OrbArgs a, int level) {
     const OrbPlan& P = *a.plan;
-    const LevelPlan& dl = P.lv[level];
-    const LevelPlan& sl = P.lv[level - 1];
+    // everything needed from the plan is copied to registers up front: the plan lives in global memory and would
+    // otherwise be re-read after every store of the row loop
+    const int dw = P.lv[level].w, dh = P.lv[level].h, dpitch = P.lv[level].pitch;
+    const int sw = P.lv[level - 1].w;
+    const int xtabOff = P.lv[level].xtabOff, ytabOff = P.lv[level].ytabOff;
+    const long long doff = P.lv[level].off;
+    const long long pyrBytes = P.pyrBytesPerFrame;
     const int f = blockIdx.z;
     const int lane = threadIdx.x;
     const int dx0 = blockIdx.x * 128 + lane * 4;
     const int y0 = (blockIdx.y * blockDim.y + threadIdx.y) * EORB_PYR_BAND;
-    if (y0 >= dl.h || blockIdx.x * 128 >= dl.w) return;     // warp-uniform
-    const int y1 = min(y0 + EORB_PYR_BAND, dl.h);
+    if (y0 >= dh || blockIdx.x * 128 >= dw) return;     // warp-uniform
+    const int y1 = min(y0 + EORB_PYR_BAND, dh);
     int sp;
-    const uint8_t* src = level_ptr(a, sl, level - 1, f, sp);
-    uint8_t* dst = a.pyr + (size_t)f * (size_t)P.pyrBytesPerFrame + (size_t)dl.off;
-    const bool active = dx0 < dl.w;
+    const uint8_t* __restrict__ src = level_ptr(a, P.lv[level - 1], level - 1, f, sp);
+    uint8_t* __restrict__ dst = a.pyr + (size_t)f * (size_t)pyrBytes + (size_t)doff + dx0;
+    const short4* __restrict__ ytab = a.ytab + ytabOff;
+    const bool active = dx0 < dw;
     // per-lane constant taps
     int off[4];
     unsigned sel[4], wt[4];
     {
-        const int lastWord = ((sl.w + 3) & ~3) - 4;          // last aligned word that belongs to a source row
+        const int lastWord = ((sw + 3) & ~3) - 4;          // last aligned word that belongs to a source row
         int sx[4];
 #pragma unroll
         for (int j = 0; j < 4; j++) {
-            const short4 xt = __ldg(&a.xtab[dl.xtabOff + min(dx0 + j, dl.w - 1)]);   // sx, sx+1 (clamped), a0, a1
+            const short4 xt = __ldg(&a.xtab[xtabOff + min(dx0 + j, dw - 1)]);   // sx, sx+1 (clamped), a0, a1
             sx[j] = xt.x;
             wt[j] = (unsigned)(unsigned short)xt.z | ((unsigned)(unsigned short)xt.w << 16);
         }
@@ -88,33 +103,25 @@ __global__ void __launch_bounds__(128) pyr_resize_kernel(OrbArgs a, int level) {
         sel[3] = (unsigned)(min(o3, 7) | (min(o3 + 1, 7) << 4));
         if (!active) { off[0] = off[1] = off[2] = off[3] = 0; }
     }
-    unsigned hA[4], hB[4];
-    int idxA = -1, idxB = -1;
+    // source row r lives in buffer r&1; have[] remembers which row each buffer holds (no register shuffling)
+    unsigned hE[4], hO[4];
+    int haveE = -1, haveO = -1;
+    short4 yt = __ldg(&ytab[y0]);
     for (int dy = y0; dy < y1; dy++) {
-        const short4 yt = a.ytab[dl.ytabOff + dy];   // sy0, sy1 (clamped), b0, b1   (warp-uniform)
-        const int s0 = yt.x, s1 = yt.y;
-        if (s0 == idxB) {
-#pragma unroll
-            for (int j = 0; j < 4; j++) hA[j] = hB[j];
-            idxA = idxB;
-        } else if (s0 != idxA) {
-            pyr_hrow(src + (size_t)s0 * sp, off, sel, wt, hA);
-            idxA = s0;
-        }
-        if (s1 == idxA) {
-#pragma unroll
-            for (int j = 0; j < 4; j++) hB[j] = hA[j];
-            idxB = idxA;
-        } else if (s1 != idxB) {
-            pyr_hrow(src + (size_t)s1 * sp, off, sel, wt, hB);
-            idxB = s1;
-        }
-        int v[4];
-#pragma unroll
-        for (int j = 0; j < 4; j++) v[j] = resize_vsum((int)hA[j], (int)hB[j], yt.z, yt.w);
-        const unsigned lo = __byte_perm((unsigned)v[0], (unsigned)v[1], 0x0040);
-        const unsigned hi = __byte_perm((unsigned)v[2], (unsigned)v[3], 0x0040);
-        if (active) *reinterpret_cast<unsigned*>(dst + (size_t)dy * dl.pitch + dx0) = __byte_perm(lo, hi, 0x5410);
+        const short4 ytn = __ldg(&ytab[min(dy + 1, dh - 1)]);   // prefetch next row's taps (warp-uniform)
+        const int s0 = yt.x, s1 = yt.y, b0 = yt.z, b1 = yt.w;
+        if ((s0 & 1) == 0) { if (haveE != s0) { pyr_hrow(src + (size_t)s0 * sp, off, sel, wt, hE); haveE = s0; } }
+        else               { if (haveO != s0) { pyr_hrow(src + (size_t)s0 * sp, off, sel, wt, hO); haveO = s0; } }
+        if ((s1 & 1) == 0) { if (haveE != s1) { pyr_hrow(src + (size_t)s1 * sp, off, sel, wt, hE); haveE = s1; } }
+        else               { if (haveO != s1) { pyr_hrow(src + (size_t)s1 * sp, off, sel, wt, hO); haveO = s1; } }
+        unsigned o;
+        const int par = (s0 & 1) | ((s1 & 1) << 1);
+        if (par == 2) o = pyr_vrow(hE, hO, b0, b1);
+        else if (par == 1) o = pyr_vrow(hO, hE, b0, b1);
+        else if (par == 0) o = pyr_vrow(hE, hE, b0, b1);
+        else o = pyr_vrow(hO, hO, b0, b1);
+        if (active) *reinterpret_cast<unsigned*>(dst + (size_t)dy * dpitch) = o;
+        yt = ytn;
     }
 }
 
@@ -342,29 +349,28 @@ __global__ void __launch_bounds__(OCT_MAX_THREADS) orb_index_kernel(OrbArgs a) {
 // of the lane's own word, the right edge rebuilds the last lane's two words with REFLECT_101 byte loads.
 #define EORB_BLUR_BAND 32
 
+// right image edge, last active lane with fewer than 4 valid pixels (or degenerate widths): rebuild the lane's
+// own word and its right neighbour word pixel by pixel with REFLECT_101 (rare, kept out of line)
+__device__ __noinline__ void blur_edge_words(const uint8_t* __restrict__ row, int x0, int w, unsigned& W, unsigned& R) {
+    unsigned b[8];
+#pragma unroll
+    for (int j = 0; j < 8; j++) b[j] = __ldg(row + reflect101(x0 + j, w));
+    W = b[0] | (b[1] << 8) | (b[2] << 16) | (b[3] << 24);
+    R = b[4] | (b[5] << 8) | (b[6] << 16) | (b[7] << 24);
+}
+
 __device__ __forceinline__ void blur_hrow(const uint8_t* __restrict__ row, int x0, int w, int lane, bool leftEdge, int rightKind,
                                           bool strip0, unsigned* h) {
     // rightKind: 0 interior lane, 1 last lane with 4 valid pixels, 2 last lane with < 4 valid pixels, 3 idle lane (x0 >= w)
-    unsigned W = 0, R;
+    unsigned W = 0, Rfix = 0;
     if (rightKind < 2) W = __ldg(reinterpret_cast<const unsigned*>(row + x0));
-    unsigned Rfix = 0;
-    if (rightKind == 2) {
-        unsigned b[8];
-#pragma unroll
-        for (int j = 0; j < 8; j++) b[j] = __ldg(row + reflect101(x0 + j, w));
-        W = b[0] | (b[1] << 8) | (b[2] << 16) | (b[3] << 24);
-        Rfix = b[4] | (b[5] << 8) | (b[6] << 16) | (b[7] << 24);
-    }
+    else if (rightKind == 2) blur_edge_words(row, x0, w, W, Rfix);
     unsigned L = __shfl_up_sync(0xffffffffu, W, 1);
-    R = __shfl_down_sync(0xffffffffu, W, 1);
+    unsigned R = __shfl_down_sync(0xffffffffu, W, 1);
     if (lane == 0) L = leftEdge ? __byte_perm(W, 0, 0x1200) : (strip0 ? 0u : __ldg(reinterpret_cast<const unsigned*>(row + x0 - 4)));
     if (lane == 31 && rightKind == 0) R = (x0 + 4 < w) ? __ldg(reinterpret_cast<const unsigned*>(row + x0 + 4)) : 0u;
     if (rightKind == 1) R = __byte_perm(W, 0, 0x0012);      // p[w] = p[w-2], p[w+1] = p[w-3]
     if (rightKind == 2) R = Rfix;
-    if (lane == 31 && rightKind == 0 && x0 + 4 >= w) {
-        // the strip ends exactly at the image end inside the NEXT strip's first lane: cannot happen (lane 31 with
-        // x0+4 >= w is itself the last lane, handled by rightKind 1/2)
-    }
     const unsigned WT = 0x39403927u;   // bytes (39, 57, 64, 57)
     const unsigned q0 = __byte_perm(L, W, 0x5432);   // x0-2 .. x0+1
     const unsigned q1 = __byte_perm(L, W, 0x6543);   // x0-1 .. x0+2
@@ -400,8 +406,8 @@ __global__ void __launch_bounds__(128) blur_kernel(OrbArgs a) {
     const int y0 = (band - lp.rowBlockBase) * EORB_BLUR_BAND;
     const int y1 = min(y0 + EORB_BLUR_BAND, hgt);
     int sp;
-    const uint8_t* src = level_ptr(a, lp, level, f, sp);
-    uint8_t* dst = a.blur + (size_t)f * (size_t)P.blurBytesPerFrame + (size_t)lp.blurOff;
+    const uint8_t* __restrict__ src = level_ptr(a, lp, level, f, sp);
+    uint8_t* __restrict__ dst = a.blur + (size_t)f * (size_t)P.blurBytesPerFrame + (size_t)lp.blurOff;
     const int bp = lp.bpitch;
     const bool leftEdge = (x0 == 0), strip0 = (xs == 0);
     int rightKind = 0;
