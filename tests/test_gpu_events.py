@@ -124,3 +124,40 @@ def test_windows_batch_device_then_orb_on_event_frames():
         r2, k2, _ = orc.extract(ref8, (0, 1000), False)
         assert r1 == r2 and k1.tobytes() == k2.tobytes()
     cv.set_stream(None)
+
+
+def test_config5_mvsec_mc_frames_orb_and_frame_to_frame_matching():
+    """configs[4]: MVSEC-shaped 346x260, 50k events/window, motion-compensated frames from a synthetic rotation
+    (t = 0, medDepth = 1) -> cv::normalize(MINMAX) -> ORB (EvMVSEC_ETHZ.yaml values, margin raised to 19 for the
+    descriptor-parity run) -> brute-force best-2 + ratio 0.9 + TH_LOW + rotation histogram between consecutive
+    windows.  Event frames are toleranced; everything downstream is bit-exact on the oracle's u8 frames."""
+    api = _api()
+    per, nwin = 50000, 3
+    ev = synth.make_events(per * nwin, seed=91, w=346, h=260, mean_dt=2e-7, n_edges=60)
+    cv = api.EvImConverter(0, 1, per, 346, 260)
+    ex = api.ORBextractor(api.ORBxParams(1000, 1.26, 6, 10, 1, 19, (346, 260)))
+    orc = O.OrbOracle(1000, 1.26, 6, 10, 1, 19, 346, 260)
+    Kc = np.array(K_MVSEC, np.float32)
+    frames = []
+    for i in range(nwin):
+        w_ev = ev[i * per:(i + 1) * per]
+        dt = float(w_ev["ts"][-1] - w_ev["ts"][0])
+        omega = np.array([0.8, -1.1, 2.0]) * dt * (1 + 0.2 * i)          # |omega| <= 3 rad/s over the window's DT
+        T = synth.rotation_tcw(omega)
+        img, u8 = cv.ev2mci_gg_f(w_ev, K_MVSEC, T, 1.0, 346, 260, 1.0, False, False, both=True, norm_mode=api.NORM_MINMAX)
+        ref, _, _ = O.ev_accumulate(w_ev, 346, 260, 1.0, mode=2, Tcw=T, depth=1.0, K=Kc)
+        _close(img, ref)
+        ref8 = O.normalize_minmax_u8(ref)
+        assert np.abs(u8.astype(int) - ref8.astype(int)).max() <= 1
+        r1, k1, d1 = ex(ref8)
+        r2, k2, d2 = orc.extract(ref8)
+        assert r1 == r2 and k1.tobytes() == k2.tobytes() and np.array_equal(d1, d2)
+        assert len(k1) > 100
+        frames.append((k1, d1))
+    m = api.ORBmatcher(0.9, True)
+    for (ka, da), (kb, db) in zip(frames[:-1], frames[1:]):
+        n, m12 = m.SearchBruteForce(da, db, ka["angle"], kb["angle"])
+        exp = O.hamming_best2(da, db, 50, 0.9)
+        e12 = np.where(exp["accepted"] == 1, exp["best_idx"], -1).astype(np.int32)
+        n_ref, m_ref = O.rotation_filter(ka["angle"], kb["angle"], e12)
+        assert n == n_ref and np.array_equal(m12, m_ref)
