@@ -1,6 +1,8 @@
 // capi.cu — the C ABI of libeorb_b200.so (include/eorb_b200.h): handles, geometry plans, HBM slabs, streams,
 // launch sequences.  Host code only; every compute step is a kernel in orb_kernels.cu / match_kernels.cu /
 // event_kernels.cu.  No CPU fallback: without a CUDA device the entry points return EORB_ERR_CUDA.
+#include <cuda.h>
+#include <cudaTypedefs.h>
 #include <cuda_runtime.h>
 
 #include <algorithm>
@@ -47,6 +49,36 @@ static cudaError_t devAlloc(T** p, size_t count) {
 }
 
 static inline int roundUp(int v, int a) { return (v + a - 1) / a * a; }
+
+// ---- TMA tensor maps (driver entry point resolved through the runtime: no link-time dependency on libcuda)
+static PFN_cuTensorMapEncodeTiled_v12000 g_tmaEncode = nullptr;
+static std::once_flag g_tmaOnce;
+static int tmaEncoder() {
+    std::call_once(g_tmaOnce, [] {
+        void* fn = nullptr;
+        cudaDriverEntryPointQueryResult q = cudaDriverEntryPointSymbolNotFound;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
+            g_tmaEncode = (PFN_cuTensorMapEncodeTiled_v12000)fn;
+        else
+            cudaGetLastError();
+    });
+    return g_tmaEncode ? EORB_OK : fail(EORB_ERR_CUDA, "cuTensorMapEncodeTiled is not available from this driver");
+}
+
+// u8 tensor {x = w, y = h, z = frames} with byte strides {pitch, frameStride}; box {boxW, boxH, 1}; zero fill outside
+static int tmaEncodeFrames(CUtensorMap* out, const void* base, int w, int hgt, int frames, size_t pitch, size_t frameStride, int boxW, int boxH) {
+    int rc = tmaEncoder();
+    if (rc != EORB_OK) return rc;
+    if (((uintptr_t)base & 15) || (pitch & 15) || (frameStride & 15)) return fail(EORB_ERR_ARG, "TMA source must be 16-byte aligned with 16-byte strides");
+    cuuint64_t dims[3] = {(cuuint64_t)w, (cuuint64_t)hgt, (cuuint64_t)std::max(frames, 1)};
+    cuuint64_t strides[2] = {(cuuint64_t)pitch, (cuuint64_t)std::max(frameStride, (size_t)16)};
+    cuuint32_t box[3] = {(cuuint32_t)boxW, (cuuint32_t)boxH, 1u};
+    cuuint32_t estr[3] = {1u, 1u, 1u};
+    CUresult r = g_tmaEncode(out, CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                             CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return fail(EORB_ERR_CUDA, "cuTensorMapEncodeTiled failed (%d) for %dx%dx%d pitch %zu", (int)r, w, hgt, frames, pitch);
+    return EORB_OK;
+}
 static inline int rne(float v) { return (int)lrintf(v); }
 static inline short satShort(float v) { int i = rne(v); return (short)(i < -32768 ? -32768 : (i > 32767 ? 32767 : i)); }
 
@@ -192,6 +224,7 @@ struct eorb_orb {
         uint16_t* d_cellCount = nullptr; uint32_t* d_cand = nullptr; uint32_t* d_okeys = nullptr; uint16_t* d_knode = nullptr;
         uint32_t* d_sel = nullptr; int* d_selCount = nullptr; int* d_candCount = nullptr; int* d_dstIdx = nullptr;
         float* d_levelAngle = nullptr;
+        CUtensorMap* d_tmaps = nullptr;   // [nlevels] maps of this slab's pyramid levels >= 1
         eorb_keypoint* d_outKps = nullptr; uint8_t* d_outDesc = nullptr; int* d_outN = nullptr; int* d_outMono = nullptr;
         eorb_keypoint* h_kps = nullptr; uint8_t* h_desc = nullptr; int* h_n = nullptr; int* h_mono = nullptr;   // pinned
         cudaStream_t stream = nullptr; cudaEvent_t done = nullptr;   // pipeline slots only
@@ -229,7 +262,7 @@ static cudaEvent_t* orbStageEvents(eorb_orb* h) {
 static void orbFreeBufs(eorb_orb::Bufs& b) {
     cudaFree(b.d_img0); cudaFree(b.d_pyr); cudaFree(b.d_blur); cudaFree(b.d_cellCount); cudaFree(b.d_cand);
     cudaFree(b.d_okeys); cudaFree(b.d_knode); cudaFree(b.d_sel); cudaFree(b.d_selCount); cudaFree(b.d_candCount);
-    cudaFree(b.d_dstIdx); cudaFree(b.d_levelAngle); cudaFree(b.d_outKps); cudaFree(b.d_outDesc);
+    cudaFree(b.d_dstIdx); cudaFree(b.d_levelAngle); cudaFree(b.d_tmaps); cudaFree(b.d_outKps); cudaFree(b.d_outDesc);
     cudaFree(b.d_outN); cudaFree(b.d_outMono);
     cudaFreeHost(b.h_kps); cudaFreeHost(b.h_desc); cudaFreeHost(b.h_n); cudaFreeHost(b.h_mono);
     if (b.done) cudaEventDestroy(b.done);
@@ -253,6 +286,17 @@ static int orbAllocBufs(eorb_orb* h, eorb_orb::Bufs& b, bool pipeline) {
     CU(devAlloc(&b.d_candCount, B * (size_t)nl));
     CU(devAlloc(&b.d_dstIdx, B * (size_t)P.selPerFrame));
     CU(devAlloc(&b.d_levelAngle, B * (size_t)P.selPerFrame));
+    {   // TMA maps of the pyramid levels held by this slab (FAST stages its cell tiles with them)
+        std::vector<CUtensorMap> maps((size_t)nl);
+        memset(maps.data(), 0, maps.size() * sizeof(CUtensorMap));
+        for (int l = 1; l < nl; l++) {
+            int rct = tmaEncodeFrames(&maps[l], b.d_pyr + P.lv[l].off, P.lv[l].w, P.lv[l].h, (int)B, (size_t)P.lv[l].pitch,
+                                      (size_t)P.pyrBytesPerFrame, P.cellTileStride, P.cellTileRows);
+            if (rct != EORB_OK) return rct;
+        }
+        CU(devAlloc(&b.d_tmaps, (size_t)nl));
+        CU(cudaMemcpy(b.d_tmaps, maps.data(), maps.size() * sizeof(CUtensorMap), cudaMemcpyHostToDevice));
+    }
     CU(devAlloc(&b.d_outKps, B * (size_t)h->cap));
     CU(devAlloc(&b.d_outDesc, B * (size_t)h->cap * 32));
     CU(devAlloc(&b.d_outN, B));
@@ -421,11 +465,15 @@ static int orbBuildPlan(eorb_orb* h, int W, int H) {
     P.pyrBytesPerFrame = std::max(pyrOff, 16ll);
     P.blurBytesPerFrame = blurOff;
     P.rowBlocksTotal = rowBlocks;
-    P.cellTileStride = ((maxCW + 6) >> 2) << 2;
+    // FAST smem region of one warp: [TMA tile BW x BH][score map (ch+2) x MS][survivor list u16][mbarrier]
+    P.cellTileStride = roundUp(maxCW + 15, 16);   // the TMA box starts at x0 & ~15 (16-byte inner-coordinate rule)
+    P.cellTileRows = maxCH;
     P.cellMapStride = roundUp(maxCW - 6 + 2, 4);
-    P.cellMapOff = roundUp(maxCH * P.cellTileStride, 16);
+    P.cellMapOff = roundUp(P.cellTileRows * P.cellTileStride, 16);
     P.cellListOff = P.cellMapOff + roundUp((maxCH - 6 + 2) * P.cellMapStride, 16);
-    P.cellSmemPerWarp = roundUp(P.cellListOff + (maxCW - 6) * (maxCH - 6) * 2, 16);
+    P.cellBarOff = roundUp(P.cellListOff + (maxCW - 6) * (maxCH - 6) * 2, 16);
+    P.cellSmemPerWarp = roundUp(P.cellBarOff + 16, 128);
+    if (P.cellTileStride > 256 || P.cellTileRows > 256) return fail(EORB_ERR_ARG, "FAST cell %dx%d exceeds the TMA box limit", maxCW, maxCH);
     P.octSmemBytes = octSmem;
     if (P.cellSmemPerWarp * EORB_FAST_WARPS > 200 * 1024 || octSmem > 200 * 1024)
         return fail(EORB_ERR_ARG, "shared-memory budget exceeded (fast %d B, octree %d B)", P.cellSmemPerWarp * EORB_FAST_WARPS, octSmem);
@@ -456,6 +504,7 @@ static OrbArgs orbArgs(eorb_orb* h, eorb_orb::Bufs& b, const uint8_t* lvl0, long
     OrbArgs a{};
     a.plan = h->d_plan; a.cells = h->d_cells; a.xtab = h->d_xtab; a.ytab = h->d_ytab;
     a.lvl0 = lvl0; a.lvl0Pitch = pitch0; a.lvl0FrameStride = frameStride0;
+    a.tmaps = b.d_tmaps;
     a.pyr = b.d_pyr; a.blur = b.d_blur; a.cellCount = b.d_cellCount; a.cand = b.d_cand; a.okeys = b.d_okeys;
     a.knode = b.d_knode; a.sel = b.d_sel; a.selCount = b.d_selCount; a.candCount = b.d_candCount;
     a.dstIdx = b.d_dstIdx; a.levelAngle = b.d_levelAngle;
@@ -570,7 +619,8 @@ extern "C" int eorb_orb_max_keypoints(const eorb_orb* h) {
 }
 
 static bool lvl0ZeroCopyOk(const uint8_t* p, int w, size_t rowStride, size_t frameStride) {
-    return ((uintptr_t)p % 16 == 0) && (rowStride % 4 == 0) && (frameStride % 4 == 0) && rowStride >= (size_t)roundUp(w, 4);
+    // TMA (FAST cell tiles) needs a 16-byte aligned base and 16-byte strides; the vectorised kernels read whole words
+    return ((uintptr_t)p % 16 == 0) && (rowStride % 16 == 0) && (frameStride % 16 == 0) && rowStride >= (size_t)roundUp(w, 4);
 }
 
 extern "C" int eorb_orb_extract_batch_device(eorb_orb* h, const uint8_t* d_imgs, int nframes, int w, int hgt, size_t row_stride,
@@ -591,7 +641,10 @@ extern "C" int eorb_orb_extract_batch_device(eorb_orb* h, const uint8_t* d_imgs,
         lvl0 = h->main.d_img0; p0 = h->pitch0; fs0 = (long long)h->pitch0 * hgt;
     }
     OrbArgs a = orbArgs(h, h->main, lvl0, p0, fs0, lap0, lap1, want_desc, d_kps, d_desc, cap, d_n_out, d_mono_out);
-    CU(launch_orb_pipeline(a, h->hp, nframes, h->stream, &h->launches, orbStageEvents(h)));
+    CUtensorMap tm0;
+    rc = tmaEncodeFrames(&tm0, lvl0, w, hgt, nframes, (size_t)p0, (size_t)fs0, h->hp.cellTileStride, h->hp.cellTileRows);
+    if (rc != EORB_OK) return rc;
+    CU(launch_orb_pipeline(a, h->hp, nframes, tm0, h->stream, &h->launches, orbStageEvents(h)));
     h->lastLvl0 = lvl0; h->lastPitch0 = p0; h->lastFrameStride0 = fs0; h->lastFrames = nframes;
     return EORB_OK;
 }
@@ -659,7 +712,10 @@ extern "C" int eorb_orb_extract_batch(eorb_orb* h, const uint8_t* imgs, int nfra
         }
         OrbArgs a = orbArgs(h, b, b.d_img0, h->pitch0, (long long)h->pitch0 * hgt, lap0, lap1, want_desc, b.d_outKps, b.d_outDesc,
                             icap, b.d_outN, b.d_outMono);
-        CU(launch_orb_pipeline(a, h->hp, nb, st, &h->launches, nslots > 0 ? nullptr : orbStageEvents(h)));
+        CUtensorMap tm0;
+        rc = tmaEncodeFrames(&tm0, b.d_img0, w, hgt, nb, (size_t)h->pitch0, (size_t)h->pitch0 * hgt, h->hp.cellTileStride, h->hp.cellTileRows);
+        if (rc != EORB_OK) return rc;
+        CU(launch_orb_pipeline(a, h->hp, nb, tm0, st, &h->launches, nslots > 0 ? nullptr : orbStageEvents(h)));
         CU(cudaMemcpyAsync(b.h_n, b.d_outN, nb * sizeof(int), cudaMemcpyDeviceToHost, st));
         CU(cudaMemcpyAsync(b.h_mono, b.d_outMono, nb * sizeof(int), cudaMemcpyDeviceToHost, st));
         eorb_keypoint* kdst = direct ? kps + (size_t)f0 * cap : b.h_kps;

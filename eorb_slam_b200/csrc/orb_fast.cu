@@ -1,0 +1,229 @@
+// orb_fast.cu — K2: grid FAST-9/16 with cell-local NMS and the iniThFAST -> minThFAST fallback
+// (reference: ComputeKeyPointsOctTree grid loop src/ORBextractor.cc:784-878 calling cv::FAST at :832,851).
+//
+// One warp per FAST grid cell, no block-level barrier.
+//   stage    the cell ROI (<= 66x66 incl. the 3-px apron) arrives in shared memory as ONE TMA tile
+//            (cp.async.bulk.tensor.3d on a per-level {x, y, frame} tensor map, zero fill outside the level),
+//            completion on the warp's own mbarrier; the score map is cleared while the copy is in flight.
+//            Measured on B200: the innermost TMA coordinate must be a multiple of 16 bytes (x = 4 raises "illegal
+//            instruction", x = 0 / 16 / -16 work), so the box starts at x0 & ~15 and the ROI sits at column
+//            aoff = x0 & 15 of the tile.
+//   phase 1  necessary condition, 8 pixels per lane per step on packed bytes: a 9-arc of the 16-ring always
+//            contains one of {N, S} and one of {E, W}, so a corner at threshold t needs
+//            (|N-v| > t or |S-v| > t) and (|E-v| > t or |W-v| > t).  |.| is one VABSDIFF4 per 4 pixels; "> t" is
+//            bit 7 of ((a + (127 - t)) | a) per byte (a carry out of a byte can only turn the next byte's test
+//            into ">= t", i.e. the filter stays a superset).  Survivors are compacted in row-major order.
+//   phase 2  exact score m = max over the 16 arcs of min(|v - p|) with a common sign for survivors only; both
+//            polarities ride in one register as s16x2 (lo = p - v, hi = v - p) through a MIN3/MAX3 network
+//            (VIMNMX3.S16x2): 32 + 8 instructions instead of two scalar networks.
+//   phase 3  cell-local strict 3x3 NMS on the score map and ordered emission (corner at t <=> m > t,
+//            OpenCV score = m - 1).  If the cell produced nothing at iniThFAST the three phases re-run at
+//            minThFAST (:849-852); only a few per cent of the cells take that path.
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/eorb_b200.h"
+#include "eorb_math.cuh"
+#include "fast_score.cuh"
+#include "orb_kernels.h"
+
+namespace eorb {
+
+// ---- mbarrier / TMA ------------------------------------------------------------------------------------------
+__device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(unsigned bar, unsigned count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned bar, unsigned bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned bar, unsigned parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_%=:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra DONE_%=;\n"
+        "bra WAIT_%=;\n"
+        "DONE_%=:\n"
+        "}\n" ::"r"(bar), "r"(parity)
+        : "memory");
+}
+__device__ __forceinline__ void tma_load_3d(unsigned dst, const CUtensorMap* tm, int x, int y, int z, unsigned bar) {
+    asm volatile(
+        "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];" ::"r"(dst),
+        "l"(tm), "r"(x), "r"(y), "r"(z), "r"(bar)
+        : "memory");
+}
+
+// ---- phase-1 helper: bit 7 of byte j set  <=>  pixel j may be a corner at the threshold encoded in K ---------------
+__device__ __forceinline__ unsigned fast_compass4(unsigned C, unsigned N, unsigned S, unsigned E, unsigned W, unsigned K) {
+    const unsigned aN = __vabsdiffu4(N, C), aS = __vabsdiffu4(S, C), aE = __vabsdiffu4(E, C), aW = __vabsdiffu4(W, C);
+    const unsigned ns = (aN + K) | aN | (aS + K) | aS;
+    const unsigned ew = (aE + K) | aE | (aW + K) | aW;
+    return ns & ew & 0x80808080u;
+}
+
+__global__ void __launch_bounds__(EORB_FAST_WARPS * 32) fast_cells_kernel(OrbArgs a, const __grid_constant__ CUtensorMap tm0) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    const OrbPlan& P = *a.plan;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int cell = blockIdx.x * EORB_FAST_WARPS + warp;
+    const int f = blockIdx.y;
+    if (cell >= P.nCells) return;
+    const CellPlan c = a.cells[cell];
+    unsigned char* ws = smem_raw + (size_t)warp * P.cellSmemPerWarp;
+    const uint8_t* tile = ws;
+    uint8_t* smap = ws + P.cellMapOff;
+    uint16_t* list = reinterpret_cast<uint16_t*>(ws + P.cellListOff);
+    const unsigned bar = smem_u32(ws + P.cellBarOff);
+    const int TS = P.cellTileStride, MS = P.cellMapStride;
+    const unsigned FULL = 0xffffffffu;
+    const unsigned lt = (1u << lane) - 1u;
+
+    uint32_t* slots = a.cand + (size_t)f * P.slotsPerFrame + c.slotOff;
+    uint16_t* countOut = a.cellCount + (size_t)f * P.nCells + cell;
+    const int w = c.w, h = c.h;
+    const int cw = w - 6, ch = h - 6;
+    if (cw <= 0 || ch <= 0) { if (lane == 0) *countOut = 0; return; }
+
+    // ---- stage: one TMA tile per cell
+    if (lane == 0) {
+        mbar_init(bar, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        mbar_expect_tx(bar, (unsigned)(TS * P.cellTileRows));
+        const CUtensorMap* tm = c.level == 0 ? &tm0 : a.tmaps + c.level;
+        tma_load_3d(smem_u32(tile), tm, c.x0 & ~15, c.y0, f, bar);
+    }
+    {
+        const int mapWords = ((ch + 2) * MS) >> 2;
+        for (int i = lane; i < mapWords; i += 32) reinterpret_cast<uint32_t*>(smap)[i] = 0u;
+    }
+    __syncwarp();
+    mbar_wait(bar, 0);
+
+    const int tA = min(max(P.iniTh, 0), 255), tB = min(max(P.minTh, 0), 255);
+    // interior = tile columns [aoff + 3, aoff + w - 3); phase 1 walks it in aligned groups of 8 columns
+    const int aoff = c.x0 & 15;
+    const int p0 = (aoff + 3) >> 3;
+    const int np = ((aoff + w - 4) >> 3) - p0 + 1;
+    const int ntask = np * ch;
+    const unsigned magic = (4194304u + (unsigned)np - 1u) / (unsigned)np;   // ceil(2^22 / np); exact for i < 2^22/np
+    const unsigned firstMask = (0xffu << ((aoff + 3) & 7)) & 0xffu;
+    const int lastBits = aoff + w - 3 - 8 * (p0 + np - 1);
+    const unsigned lastMask = lastBits >= 8 ? 0xffu : ((1u << lastBits) - 1u);
+
+    int cnt = 0;
+    for (int pass = 0; pass < 2; pass++) {
+        const int t = pass ? tB : tA;
+        const unsigned K = (unsigned)(127 - min(t, 127)) * 0x01010101u;
+
+        // ---- phase 1: packed compass test + ordered compaction
+        int nsurv = 0;
+        for (int base = 0; base < ntask; base += 32) {
+            const int i = base + lane;
+            unsigned m8 = 0, code = 0;
+            if (i < ntask) {
+                const int rr = (int)(((unsigned)i * magic) >> 22), pp = i - rr * np;
+                const uint8_t* q = tile + (rr + 3) * TS + (p0 + pp) * 8;
+                const uint2 C = *reinterpret_cast<const uint2*>(q);
+                const uint2 N = *reinterpret_cast<const uint2*>(q + 3 * TS);
+                const uint2 S = *reinterpret_cast<const uint2*>(q - 3 * TS);
+                const unsigned L = *reinterpret_cast<const unsigned*>(q - 4);
+                const unsigned R = *reinterpret_cast<const unsigned*>(q + 8);
+                const unsigned f0 = fast_compass4(C.x, N.x, S.x, __byte_perm(C.x, C.y, 0x6543), __byte_perm(L, C.x, 0x4321), K);
+                const unsigned f1 = fast_compass4(C.y, N.y, S.y, __byte_perm(C.y, R, 0x6543), __byte_perm(C.x, C.y, 0x4321), K);
+                // gather the four bit-7 flags of each word into a nibble (multiplier places bits 7,15,23,31 at 28..31)
+                m8 = ((f0 * 0x00204081u) >> 28) | (((f1 * 0x00204081u) >> 28) << 4);
+                // interior columns only
+                unsigned vm = pp == 0 ? firstMask : 0xffu;
+                if (pp == np - 1) vm &= lastMask;
+                m8 &= vm;
+                code = ((unsigned)rr << 7) | (unsigned)((p0 + pp) * 8);
+            }
+            if (__ballot_sync(FULL, m8 != 0) == 0) continue;
+            const int k = __popc(m8);
+            int incl = k;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const int up = __shfl_up_sync(FULL, incl, o);
+                if (lane >= o) incl += up;
+            }
+            int pos = nsurv + incl - k;
+            nsurv += __shfl_sync(FULL, incl, 31);
+            while (m8) {
+                const int j = __ffs((int)m8) - 1;
+                m8 &= m8 - 1;
+                list[pos++] = (uint16_t)(code + j);
+            }
+        }
+        __syncwarp();
+
+        // ---- phase 2: exact arc score for survivors
+        for (int base = 0; base < nsurv; base += 32) {
+            const int s = base + lane;
+            if (s < nsurv) {
+                const int code = list[s];
+                const int rr = code >> 7, col = code & 127;
+                const uint8_t* p = tile + (rr + 3) * TS + col;
+                const int v = p[0];
+                int ring[16];
+                ring[0] = p[3 * TS];       ring[1] = p[3 * TS + 1];   ring[2] = p[2 * TS + 2];    ring[3] = p[TS + 3];
+                ring[4] = p[3];            ring[5] = p[-TS + 3];      ring[6] = p[-2 * TS + 2];   ring[7] = p[-3 * TS + 1];
+                ring[8] = p[-3 * TS];      ring[9] = p[-3 * TS - 1];  ring[10] = p[-2 * TS - 2];  ring[11] = p[-TS - 3];
+                ring[12] = p[-3];          ring[13] = p[TS - 3];      ring[14] = p[2 * TS - 2];   ring[15] = p[3 * TS - 1];
+                const int m = fast_max_arc_min_packed(v, ring);
+                if (m > t) smap[(rr + 1) * MS + col - aoff - 2] = (uint8_t)m;   // map column = interior x + 1
+            }
+        }
+        __syncwarp();
+
+        // ---- phase 3: strict 3x3 NMS + ordered emission
+        cnt = 0;
+        for (int base = 0; base < nsurv; base += 32) {
+            const int s = base + lane;
+            bool keep = false;
+            uint32_t packed = 0;
+            if (s < nsurv) {
+                const int code = list[s];
+                const int rr = code >> 7, col = code & 127;
+                const uint8_t* q = smap + (rr + 1) * MS + col - aoff - 2;
+                const int m = q[0];
+                if (m > t) {
+                    keep = true;
+#pragma unroll
+                    for (int dy = -1; dy <= 1; dy++)
+#pragma unroll
+                        for (int dx = -1; dx <= 1; dx++) {
+                            if (dx == 0 && dy == 0) continue;
+                            const int mq = q[dy * MS + dx];
+                            const int e = mq > t ? mq : 1;   // non-corner neighbours score 0  (score = m-1)
+                            keep &= (m > e);
+                        }
+                    packed = (uint32_t)(col - aoff + c.ox) | ((uint32_t)(rr + 3 + c.oy) << 12) | ((uint32_t)(m - 1) << 24);
+                }
+            }
+            const unsigned msk = __ballot_sync(FULL, keep);
+            if (keep) slots[cnt + __popc(msk & lt)] = packed;
+            cnt += __popc(msk);
+        }
+        if (cnt > 0 || tB >= tA) break;
+        __syncwarp();
+    }
+    if (lane == 0) *countOut = (uint16_t)cnt;
+}
+
+cudaError_t launch_fast_cells(const OrbArgs& a, const OrbPlan& hp, int nframes, const CUtensorMap& tm0, cudaStream_t st) {
+    dim3 grd((hp.nCells + EORB_FAST_WARPS - 1) / EORB_FAST_WARPS, nframes);
+    fast_cells_kernel<<<grd, EORB_FAST_WARPS * 32, (size_t)hp.cellSmemPerWarp * EORB_FAST_WARPS, st>>>(a, tm0);
+    return cudaGetLastError();
+}
+
+cudaError_t fast_cells_configure(const OrbPlan& hp) {
+    return cudaFuncSetAttribute(fast_cells_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, hp.cellSmemPerWarp * EORB_FAST_WARPS);
+}
+
+}  // namespace eorb

@@ -1,7 +1,7 @@
 // orb_kernels.cu — hand-written sm_100a kernels of the ORB extractor path
 // (reference src/ORBextractor.cc; one kernel per reference stage):
 //   K1 pyr_resize_kernel     ComputePyramid            :1240-1265  (cv::resize INTER_LINEAR, 11-bit fixed point)
-//   K2 fast_cells_kernel     ComputeKeyPointsOctTree   :784-878    (grid FAST 9/16 + cell-local NMS + threshold fallback)
+//   K2 fast_cells_kernel     ComputeKeyPointsOctTree   :784-878    (grid FAST 9/16 + cell-local NMS + threshold fallback; orb_fast.cu)
 //   K3 octree_kernel         DistributeOctTree         :558-782    (level-synchronous node splitting)
 //   K7 orb_index_kernel      operator() ordering       :1152-1172  (level-major order, lapping split from both ends)
 //   K5 blur_kernel           GaussianBlur 5x5 s=2      :1141-1142
@@ -12,6 +12,7 @@
 
 #include "../../include/eorb_b200.h"
 #include "eorb_math.cuh"
+#include "fast_score.cuh"
 #include "octree_core.cuh"
 #include "orb_kernels.h"
 
@@ -123,131 +124,6 @@ __global__ void __launch_bounds__(128) pyr_resize_kernel(OrbArgs a, int level) {
         if (active) *reinterpret_cast<unsigned*>(dst + (size_t)dy * dpitch) = o;
         yt = ytn;
     }
-}
-
-// ------------------------------------------------------------------------------------------------ K2
-// One warp per FAST grid cell, no block-level barrier.  Cell ROI (<= ~66x66 incl. the 3-px apron) is staged
-// in shared memory with 32-bit loads; phase 1 rejects pixels with the 4-compass-point necessary condition
-// and compacts survivors with ballot/popc; phase 2 computes the exact arc score for survivors only;
-// phase 3 does the cell-local strict 3x3 NMS and emits corners in row-major order, first with iniThFAST and,
-// if the cell stayed empty, with minThFAST (the reference calls cv::FAST twice, :832-852).
-__global__ void __launch_bounds__(EORB_FAST_WARPS * 32) fast_cells_kernel(OrbArgs a) {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    const OrbPlan& P = *a.plan;
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int cell = blockIdx.x * EORB_FAST_WARPS + warp;
-    const int f = blockIdx.y;
-    if (cell >= P.nCells) return;
-    const CellPlan c = a.cells[cell];
-    const LevelPlan& lp = P.lv[c.level];
-    unsigned char* ws = smem_raw + (size_t)warp * P.cellSmemPerWarp;
-    uint8_t* tile = ws;
-    uint8_t* smap = ws + P.cellMapOff;
-    uint16_t* list = reinterpret_cast<uint16_t*>(ws + P.cellListOff);
-    const int TS = P.cellTileStride, MS = P.cellMapStride;
-    const unsigned FULL = 0xffffffffu;
-    const unsigned lt = (1u << lane) - 1u;
-
-    uint32_t* slots = a.cand + (size_t)f * P.slotsPerFrame + c.slotOff;
-    uint16_t* countOut = a.cellCount + (size_t)f * P.nCells + cell;
-    const int cw = c.w - 6, ch = c.h - 6;
-    if (cw <= 0 || ch <= 0) { if (lane == 0) *countOut = 0; return; }
-
-    // ---- stage the ROI
-    int pitch;
-    const uint8_t* L = level_ptr(a, lp, c.level, f, pitch);
-    const int xw0 = c.x0 & ~3, aoff = c.x0 - xw0;
-    const int nwords = (aoff + c.w + 3) >> 2;
-    const int totalWords = nwords * c.h;
-    for (int i = lane; i < totalWords; i += 32) {
-        const int r = i / nwords, wi = i - r * nwords;
-        const uint32_t v = __ldg(reinterpret_cast<const uint32_t*>(L + (size_t)(c.y0 + r) * pitch + xw0 + wi * 4));
-        *reinterpret_cast<uint32_t*>(tile + r * TS + wi * 4) = v;
-    }
-    const int mapWords = ((ch + 2) * MS) >> 2;
-    for (int i = lane; i < mapWords; i += 32) reinterpret_cast<uint32_t*>(smap)[i] = 0u;
-    __syncwarp();
-
-    const int tA = min(max(P.iniTh, 0), 255), tB = min(max(P.minTh, 0), 255);
-    const int tlo = min(tA, tB);
-    const uint8_t* t0 = tile + aoff;
-    const int n = cw * ch;
-    const unsigned magic = (4194304u + (unsigned)cw - 1u) / (unsigned)cw;   // ceil(2^22 / cw)
-
-    // ---- phase 1: compass test + compaction
-    int nsurv = 0;
-    for (int base = 0; base < n; base += 32) {
-        const int i = base + lane;
-        bool flag = false;
-        if (i < n) {
-            const int yy = (int)(((unsigned)i * magic) >> 22), xx = i - yy * cw;
-            const uint8_t* p = t0 + (yy + 3) * TS + xx + 3;
-            const int v = p[0], hi = v + tlo, lo = v - tlo;
-            const int pN = p[3 * TS], pE = p[3], pS = p[-3 * TS], pW = p[-3];
-            const bool bN = pN > hi, bE = pE > hi, bS = pS > hi, bW = pW > hi;
-            const bool dN = pN < lo, dE = pE < lo, dS = pS < lo, dW = pW < lo;
-            flag = (bN & bE) | (bE & bS) | (bS & bW) | (bW & bN) | (dN & dE) | (dE & dS) | (dS & dW) | (dW & dN);
-        }
-        const unsigned m = __ballot_sync(FULL, flag);
-        if (flag) list[nsurv + __popc(m & lt)] = (uint16_t)i;
-        nsurv += __popc(m);
-    }
-    __syncwarp();
-
-    // ---- phase 2: exact arc score for survivors
-    for (int base = 0; base < nsurv; base += 32) {
-        const int s = base + lane;
-        if (s < nsurv) {
-            const int i = list[s];
-            const int yy = (int)(((unsigned)i * magic) >> 22), xx = i - yy * cw;
-            const uint8_t* p = t0 + (yy + 3) * TS + xx + 3;
-            const int v = p[0];
-            int ring[16];
-            ring[0] = p[3 * TS];       ring[1] = p[3 * TS + 1];   ring[2] = p[2 * TS + 2];    ring[3] = p[TS + 3];
-            ring[4] = p[3];            ring[5] = p[-TS + 3];      ring[6] = p[-2 * TS + 2];   ring[7] = p[-3 * TS + 1];
-            ring[8] = p[-3 * TS];      ring[9] = p[-3 * TS - 1];  ring[10] = p[-2 * TS - 2];  ring[11] = p[-TS - 3];
-            ring[12] = p[-3];          ring[13] = p[TS - 3];      ring[14] = p[2 * TS - 2];   ring[15] = p[3 * TS - 1];
-            const int m = fast_max_arc_min(v, ring);
-            if (m > tlo) smap[(yy + 1) * MS + xx + 1] = (uint8_t)m;
-        }
-    }
-    __syncwarp();
-
-    // ---- phase 3: NMS + ordered emission
-    auto emit = [&](int t) -> int {
-        int count = 0;
-        for (int base = 0; base < nsurv; base += 32) {
-            const int s = base + lane;
-            bool keep = false;
-            uint32_t packed = 0;
-            if (s < nsurv) {
-                const int i = list[s];
-                const int yy = (int)(((unsigned)i * magic) >> 22), xx = i - yy * cw;
-                const uint8_t* q = smap + (yy + 1) * MS + xx + 1;
-                const int m = q[0];
-                if (m > t) {
-                    keep = true;
-#pragma unroll
-                    for (int dy = -1; dy <= 1; dy++)
-#pragma unroll
-                        for (int dx = -1; dx <= 1; dx++) {
-                            if (dx == 0 && dy == 0) continue;
-                            const int mq = q[dy * MS + dx];
-                            const int e = mq > t ? mq : 1;   // non-corner neighbours score 0  (score = m-1)
-                            keep &= (m > e);
-                        }
-                    packed = (uint32_t)(xx + 3 + c.ox) | ((uint32_t)(yy + 3 + c.oy) << 12) | ((uint32_t)(m - 1) << 24);
-                }
-            }
-            const unsigned msk = __ballot_sync(FULL, keep);
-            if (keep) slots[count + __popc(msk & lt)] = packed;
-            count += __popc(msk);
-        }
-        return count;
-    };
-    int cnt = emit(tA);
-    if (cnt == 0 && tB != tA) cnt = emit(tB);
-    if (lane == 0) *countOut = (uint16_t)cnt;
 }
 
 // ------------------------------------------------------------------------------------------------ K3
@@ -602,7 +478,7 @@ __global__ void selftest_math_kernel(const int* __restrict__ fastIn, int nFast, 
         int ring[16];
 #pragma unroll
         for (int k = 0; k < 16; k++) ring[k] = fastIn[17 * i + 1 + k];
-        fastOut[i] = fast_max_arc_min(fastIn[17 * i], ring);
+        fastOut[i] = fast_max_arc_min_packed(fastIn[17 * i], ring);   // the device form used by K2
     }
     if (i < nAtan) {
         const float y = atanIn[2 * i], x = atanIn[2 * i + 1];
@@ -627,8 +503,8 @@ cudaError_t launch_selftest_math(const int* fastIn, int nFast, int* fastOut, con
 // ------------------------------------------------------------------------------------------------ launches
 static inline unsigned cdiv(unsigned a, unsigned b) { return (a + b - 1) / b; }
 
-cudaError_t launch_orb_pipeline(const OrbArgs& a, const OrbPlan& hp, int nframes, cudaStream_t st, long long* launches,
-                                cudaEvent_t* ev) {
+cudaError_t launch_orb_pipeline(const OrbArgs& a, const OrbPlan& hp, int nframes, const CUtensorMap& tm0, cudaStream_t st,
+                                long long* launches, cudaEvent_t* ev) {
     // ev (optional, EORB_ORB_STAGES+1 events): recorded around every stage for the per-kernel timings of bench.py
     if (ev) cudaEventRecord(ev[0], st);
     // K1: pyramid, level by level (each level is resized from the previous one)
@@ -641,8 +517,8 @@ cudaError_t launch_orb_pipeline(const OrbArgs& a, const OrbPlan& hp, int nframes
     if (ev) cudaEventRecord(ev[1], st);
     // K2: FAST over every cell of every level
     if (hp.nCells > 0) {
-        dim3 grd(cdiv(hp.nCells, EORB_FAST_WARPS), nframes);
-        fast_cells_kernel<<<grd, EORB_FAST_WARPS * 32, (size_t)hp.cellSmemPerWarp * EORB_FAST_WARPS, st>>>(a);
+        cudaError_t e = launch_fast_cells(a, hp, nframes, tm0, st);
+        if (e != cudaSuccess) return e;
         (*launches)++;
     }
     if (ev) cudaEventRecord(ev[2], st);
@@ -700,8 +576,7 @@ cudaError_t launch_tracked_desc(const OrbArgs& a, const OrbPlan& hp, const eorb_
 }
 
 cudaError_t orb_kernels_configure(const OrbPlan& hp) {
-    cudaError_t e = cudaFuncSetAttribute(fast_cells_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         hp.cellSmemPerWarp * EORB_FAST_WARPS);
+    cudaError_t e = fast_cells_configure(hp);
     if (e != cudaSuccess) return e;
     return cudaFuncSetAttribute(octree_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, hp.octSmemBytes);
 }

@@ -1,5 +1,6 @@
 // orb_kernels.h — launch interface between the C-ABI host code (capi.cu) and orb_kernels.cu
 #pragma once
+#include <cuda.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 
@@ -17,6 +18,8 @@ struct OrbArgs {
     const short4* ytab;          // device: resize taps per destination row     {sy0, sy1, b0, b1}
     const uint8_t* lvl0;         // level 0 = the input frames (zero-copy when aligned, else staged)
     long long lvl0Pitch, lvl0FrameStride;
+    const CUtensorMap* tmaps;    // device: [nlevels] TMA maps {x, y, frame} of the pyramid levels >= 1 (entry 0 unused:
+                                 //         level 0 is the caller's buffer, its map travels as a kernel parameter)
     uint8_t* pyr;                // [B][pyrBytesPerFrame]   levels >= 1
     uint8_t* blur;               // [B][blurBytesPerFrame]  all levels
     uint16_t* cellCount;         // [B][nCells]
@@ -39,8 +42,10 @@ struct OrbArgs {
 
 cudaError_t orb_kernels_configure(const OrbPlan& hp);
 #define EORB_ORB_STAGES 6   // pyramid, fast, octree, index, blur, orient+desc
-cudaError_t launch_orb_pipeline(const OrbArgs& a, const OrbPlan& hp, int nframes, cudaStream_t st, long long* launches,
-                                cudaEvent_t* ev);
+cudaError_t launch_orb_pipeline(const OrbArgs& a, const OrbPlan& hp, int nframes, const CUtensorMap& tm0, cudaStream_t st,
+                                long long* launches, cudaEvent_t* ev);
+cudaError_t launch_fast_cells(const OrbArgs& a, const OrbPlan& hp, int nframes, const CUtensorMap& tm0, cudaStream_t st);
+cudaError_t fast_cells_configure(const OrbPlan& hp);
 cudaError_t launch_pyramid_and_blur(const OrbArgs& a, const OrbPlan& hp, cudaStream_t st, long long* launches);
 cudaError_t launch_tracked_desc(const OrbArgs& a, const OrbPlan& hp, const eorb_keypoint* d_kps, int n, int mode,
                                 const float* d_invScale, const uint8_t* d_refDesc, uint8_t* d_desc, int* d_dist,

@@ -47,11 +47,13 @@ struct OrbPlan {
     int selPerFrame;               // selected-keypoint slots per frame (sum of nodeCap)
     long long pyrBytesPerFrame;    // levels >= 1
     long long blurBytesPerFrame;
-    int cellTileStride;            // FAST: smem bytes per tile row (multiple of 4)
+    int cellTileStride;            // FAST: TMA box width = smem bytes per tile row (multiple of 16)
+    int cellTileRows;              // FAST: TMA box height (largest cell ROI height)
     int cellMapStride;             // FAST: score-map row stride (multiple of 4)
     int cellMapOff;                // FAST: byte offset of the score map inside a warp's smem region
     int cellListOff;               // FAST: byte offset of the survivor list
-    int cellSmemPerWarp;           // bytes (multiple of 16)
+    int cellBarOff;                // FAST: byte offset of the warp's mbarrier
+    int cellSmemPerWarp;           // bytes (multiple of 128: TMA destinations are 128-byte aligned)
     int octSmemBytes;              // max over levels
     int rowBlocksTotal;            // blur grid: total 32-row bands over all levels
     int umax[16];
