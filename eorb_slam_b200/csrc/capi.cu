@@ -390,7 +390,7 @@ static int orbBuildPlan(eorb_orb* h, int W, int H) {
         lp.scale = h->scale[l];
         lp.sizeF = (float)(int)(31 * h->scale[l]);
         lp.quota = h->quota[l];
-        lp.rowBlockBase = rowBlocks; rowBlocks += (lp.h + 31) / 32;   // blur bands of EORB_BLUR_BAND rows
+        lp.blurTaskBase = rowBlocks; rowBlocks += ((lp.h + 29) / 30) * ((lp.w + 127) / 128);   // (EORB_BLUR_BAND = 30 rows) x (128 columns)
         // FAST grid (:792-828)
         lp.minBX = E - 3; lp.minBY = E - 3; lp.maxBX = lp.w - E + 3; lp.maxBY = lp.h - E + 3;
         const float width = (float)(lp.maxBX - lp.minBX), height = (float)(lp.maxBY - lp.minBY);
@@ -464,7 +464,7 @@ static int orbBuildPlan(eorb_orb* h, int W, int H) {
     P.selPerFrame = sel;
     P.pyrBytesPerFrame = std::max(pyrOff, 16ll);
     P.blurBytesPerFrame = blurOff;
-    P.rowBlocksTotal = rowBlocks;
+    P.blurTasksTotal = rowBlocks;
     // FAST smem region of one warp: [TMA tile BW x BH][score map (ch+2) x MS][survivor list u16][mbarrier]
     P.cellTileStride = roundUp(maxCW + 15, 16);   // the TMA box starts at x0 & ~15 (16-byte inner-coordinate rule)
     P.cellTileRows = maxCH;

@@ -216,45 +216,74 @@ __global__ void __launch_bounds__(OCT_MAX_THREADS) orb_index_kernel(OrbArgs a) {
 
 // ------------------------------------------------------------------------------------------------ K5
 // 5x5 sigma-2 Gaussian on every level (8.8 fixed-point separable weights [39 57 64 57 39], REFLECT_101).
-// One warp owns a strip of 128 columns x EORB_BLUR_BAND rows and streams down the rows: each lane loads ONE
-// aligned 32-bit word per source row (4 pixels), gets its left/right neighbour words by shuffle, forms the four
-// horizontal sums with byte-permutes + unsigned dp4a (weights packed in a register, the 5th tap by a second dp4a
-// with a one-hot weight word), keeps a 5-row ring of horizontal sums in registers and emits one packed output
-// word per row.  Horizontal sums are < 2^16 and the vertical sum < 2^24, so byte 2 of the accumulator IS the
-// result ((s + 32768) >> 16) and no shift/saturation is needed.  Image borders: the left edge is a byte-permute
-// of the lane's own word, the right edge rebuilds the last lane's two words with REFLECT_101 byte loads.
-#define EORB_BLUR_BAND 32
+// One warp owns a strip of 128 columns x EORB_BLUR_BAND rows and streams down the rows.  Per source row a lane
+// loads ONE aligned 32-bit word (4 pixels) and gets its neighbours' words by shuffle; the five byte windows the
+// horizontal pass needs are cut out with byte-permutes whose selectors are per-lane constants computed once:
+// they already contain the REFLECT_101 mapping of the image's left/right border (and of a partial last word), so
+// the row loop is straight-line code with no edge branches.  Horizontal sums: unsigned dp4a on packed weights
+// (the 5th tap by a second dp4a with a one-hot weight word).  A 5-row ring of horizontal sums lives in registers
+// (loop unrolled by 5, no moves).  Horizontal sums are < 2^16 and the vertical sum < 2^24, so byte 2 of the
+// accumulator IS the result ((s + 32768) >> 16).
+#define EORB_BLUR_BAND 30   // multiple of 5: full bands run the unrolled ring loop without a tail
 
-// right image edge, last active lane with fewer than 4 valid pixels (or degenerate widths): rebuild the lane's
-// own word and its right neighbour word pixel by pixel with REFLECT_101 (rare, kept out of line)
-__device__ __noinline__ void blur_edge_words(const uint8_t* __restrict__ row, int x0, int w, unsigned& W, unsigned& R) {
-    unsigned b[8];
-#pragma unroll
-    for (int j = 0; j < 8; j++) b[j] = __ldg(row + reflect101(x0 + j, w));
-    W = b[0] | (b[1] << 8) | (b[2] << 16) | (b[3] << 24);
-    R = b[4] | (b[5] << 8) | (b[6] << 16) | (b[7] << 24);
+// REFLECT_101 of a row index that overshoots [0, len) by at most 2 (single bounce when len >= 3)
+__device__ __forceinline__ int reflect101_near(int p, int len) {
+    if (len < 3) return reflect101(p, len);
+    p = p < 0 ? -p : p;
+    return p >= len ? 2 * len - 2 - p : p;
 }
 
-__device__ __forceinline__ void blur_hrow(const uint8_t* __restrict__ row, int x0, int w, int lane, bool leftEdge, int rightKind,
-                                          bool strip0, unsigned* h) {
-    // rightKind: 0 interior lane, 1 last lane with 4 valid pixels, 2 last lane with < 4 valid pixels, 3 idle lane (x0 >= w)
-    unsigned W = 0, Rfix = 0;
-    if (rightKind < 2) W = __ldg(reinterpret_cast<const unsigned*>(row + x0));
-    else if (rightKind == 2) blur_edge_words(row, x0, w, W, Rfix);
+struct BlurLane {
+    unsigned selQ0, selQ1, selW, selQ3, selR;   // byte-permute selectors (see blur_hrow)
+    bool loadL, loadR;                          // lane 0 / lane 31 fetch their outer neighbour word themselves
+};
+
+// window byte index of image column x (after REFLECT_101) relative to column `base`; clamped into the 8-byte window
+template <bool TINY>
+__device__ __forceinline__ unsigned blur_sel(int x, int w, int base) {
+    int r;
+    if (TINY) {
+        r = reflect101(x, w);
+    } else {   // w >= 8 and -2 <= x <= w + 132: a single bounce
+        r = x < 0 ? -x : x;
+        r = r >= w ? 2 * w - 2 - r : r;
+    }
+    return (unsigned)min(max(r - base, 0), 7);
+}
+
+template <bool TINY>
+__device__ __forceinline__ void blur_selectors(BlurLane& bl, int x0, int w) {
+    const int b = x0 - 4;
+    unsigned s[6];   // columns x0-2 .. x0+3 in the (L,W) window
+#pragma unroll
+    for (int j = 0; j < 6; j++) s[j] = blur_sel<TINY>(x0 - 2 + j, w, b);
+    unsigned t[5];   // columns x0+1 .. x0+5 in the (W,R) window
+#pragma unroll
+    for (int j = 0; j < 5; j++) t[j] = blur_sel<TINY>(x0 + 1 + j, w, x0);
+    bl.selQ0 = s[0] | (s[1] << 4) | (s[2] << 8) | (s[3] << 12);
+    bl.selQ1 = s[1] | (s[2] << 4) | (s[3] << 8) | (s[4] << 12);
+    bl.selW = s[2] | (s[3] << 4) | (s[4] << 8) | (s[5] << 12);
+    bl.selQ3 = t[0] | (t[1] << 4) | (t[2] << 8) | (t[3] << 12);
+    bl.selR = t[3] | (t[4] << 4);
+}
+
+// rowp points at the lane's own word of the source row
+__device__ __forceinline__ void blur_hrow(const uint8_t* __restrict__ rowp, const BlurLane& bl, unsigned* h) {
+    const unsigned W = __ldg(reinterpret_cast<const unsigned*>(rowp));
     unsigned L = __shfl_up_sync(0xffffffffu, W, 1);
     unsigned R = __shfl_down_sync(0xffffffffu, W, 1);
-    if (lane == 0) L = leftEdge ? __byte_perm(W, 0, 0x1200) : (strip0 ? 0u : __ldg(reinterpret_cast<const unsigned*>(row + x0 - 4)));
-    if (lane == 31 && rightKind == 0) R = (x0 + 4 < w) ? __ldg(reinterpret_cast<const unsigned*>(row + x0 + 4)) : 0u;
-    if (rightKind == 1) R = __byte_perm(W, 0, 0x0012);      // p[w] = p[w-2], p[w+1] = p[w-3]
-    if (rightKind == 2) R = Rfix;
-    const unsigned WT = 0x39403927u;   // bytes (39, 57, 64, 57)
-    const unsigned q0 = __byte_perm(L, W, 0x5432);   // x0-2 .. x0+1
-    const unsigned q1 = __byte_perm(L, W, 0x6543);   // x0-1 .. x0+2
-    const unsigned q3 = __byte_perm(W, R, 0x4321);   // x0+1 .. x0+4
-    h[0] = __dp4a(W, 0x00270000u, __dp4a(q0, WT, 0u));   // + 39 * p[x0+2]
-    h[1] = __dp4a(W, 0x27000000u, __dp4a(q1, WT, 0u));   // + 39 * p[x0+3]
-    h[2] = __dp4a(R, 0x00000027u, __dp4a(W, WT, 0u));    // + 39 * p[x0+4]
-    h[3] = __dp4a(R, 0x00002700u, __dp4a(q3, WT, 0u));   // + 39 * p[x0+5]
+    if (bl.loadL) L = __ldg(reinterpret_cast<const unsigned*>(rowp - 4));
+    if (bl.loadR) R = __ldg(reinterpret_cast<const unsigned*>(rowp + 4));
+    const unsigned WT = 0x39403927u;                   // bytes (39, 57, 64, 57)
+    const unsigned q0 = __byte_perm(L, W, bl.selQ0);   // x0-2 .. x0+1
+    const unsigned q1 = __byte_perm(L, W, bl.selQ1);   // x0-1 .. x0+2
+    const unsigned Wc = __byte_perm(L, W, bl.selW);    // x0   .. x0+3
+    const unsigned q3 = __byte_perm(W, R, bl.selQ3);   // x0+1 .. x0+4
+    const unsigned Rc = __byte_perm(W, R, bl.selR);    // x0+4, x0+5 in bytes 0, 1
+    h[0] = __dp4a(Wc, 0x00270000u, __dp4a(q0, WT, 0u));   // + 39 * p[x0+2]
+    h[1] = __dp4a(Wc, 0x27000000u, __dp4a(q1, WT, 0u));   // + 39 * p[x0+3]
+    h[2] = __dp4a(Rc, 0x00000027u, __dp4a(Wc, WT, 0u));   // + 39 * p[x0+4]
+    h[3] = __dp4a(Rc, 0x00002700u, __dp4a(q3, WT, 0u));   // + 39 * p[x0+5]
 }
 
 __device__ __forceinline__ unsigned blur_vout(const unsigned* a, const unsigned* b, const unsigned* c, const unsigned* d, const unsigned* e) {
@@ -268,49 +297,86 @@ __device__ __forceinline__ unsigned blur_vout(const unsigned* a, const unsigned*
 
 __global__ void __launch_bounds__(128) blur_kernel(OrbArgs a) {
     const OrbPlan& P = *a.plan;
-    const int f = blockIdx.z;
+    const int f = blockIdx.y;
     const int lane = threadIdx.x;
-    const int band = blockIdx.y * blockDim.y + threadIdx.y;
-    if (band >= P.rowBlocksTotal) return;
+    const int task = blockIdx.x * blockDim.y + threadIdx.y;
+    if (task >= P.blurTasksTotal) return;
     int level = 0;
-    while (level + 1 < P.nlevels && band >= P.lv[level + 1].rowBlockBase) level++;
+    while (level + 1 < P.nlevels && task >= P.lv[level + 1].blurTaskBase) level++;
     const LevelPlan& lp = P.lv[level];
-    const int w = lp.w, hgt = lp.h;
-    const int xs = blockIdx.x * 128;
-    if (xs >= w) return;
-    const int x0 = xs + lane * 4;
-    const int y0 = (band - lp.rowBlockBase) * EORB_BLUR_BAND;
+    const int w = lp.w, hgt = lp.h, bp = lp.bpitch;
+    const int strips = (w + 127) >> 7;
+    const int t = task - lp.blurTaskBase;
+    const int band = t / strips, strip = t - band * strips;
+    const int x0 = strip * 128 + lane * 4;
+    const int y0 = band * EORB_BLUR_BAND;
     const int y1 = min(y0 + EORB_BLUR_BAND, hgt);
     int sp;
     const uint8_t* __restrict__ src = level_ptr(a, lp, level, f, sp);
     uint8_t* __restrict__ dst = a.blur + (size_t)f * (size_t)P.blurBytesPerFrame + (size_t)lp.blurOff;
-    const int bp = lp.bpitch;
-    const bool leftEdge = (x0 == 0), strip0 = (xs == 0);
-    int rightKind = 0;
-    if (x0 >= w) rightKind = 3;
-    else if (x0 + 4 >= w) rightKind = (w - x0 == 4) ? 1 : 2;
-    if (w < 6) rightKind = (x0 < w) ? 2 : 3;   // degenerate widths: every active lane takes the generic path
-    const bool store = x0 < w;
 
-    unsigned r0[4], r1[4], r2[4], r3[4], r4[4];
-#define HROW(yy, dstv) blur_hrow(src + (size_t)reflect101((yy), hgt) * sp, x0, w, lane, leftEdge, rightKind, strip0, dstv)
-#define OUT(yy, A, B, C, D, E)                                                                      \
+    if (hgt < 3) {   // degenerate level: rows bounce more than once; plain per-pixel evaluation
+        for (int y = y0; y < y1; y++)
+            for (int x = x0; x < min(x0 + 4, w); x++) {
+                int hs[5];
+#pragma unroll
+                for (int r = 0; r < 5; r++) {
+                    const uint8_t* row = src + (size_t)reflect101(y + r - 2, hgt) * sp;
+                    hs[r] = gauss5_h(row[reflect101(x - 2, w)], row[reflect101(x - 1, w)], row[x], row[reflect101(x + 1, w)], row[reflect101(x + 2, w)]);
+                }
+                dst[(size_t)y * bp + x] = (uint8_t)gauss5_v(hs[0], hs[1], hs[2], hs[3], hs[4]);
+            }
+        return;
+    }
+
+    // per-lane constants: own word offset and the REFLECT_101-aware selectors (windows: (L,W) starts at column
+    // x0-4, (W,R) at column x0); idle lanes (x0 >= w) read the row's last word and produce values nobody stores
+    const int lastWord = ((w + 3) & ~3) - 4;
+    const int off = min(x0, lastWord);
+    const bool store = x0 < w;
+    BlurLane bl;
+    {
+        bl.loadL = (lane == 0) && off >= 4;
+        bl.loadR = (lane == 31) && off + 4 <= lastWord;
+        if (w < 8) blur_selectors<true>(bl, x0, w);
+        else blur_selectors<false>(bl, x0, w);
+    }
+
+    // the source pointer walks the REFLECT_101 row sequence: from row index yy-1 to yy it moves one row DOWN when
+    // 1 <= yy <= hgt-1 and one row UP otherwise (single bounce: hgt >= 3 and the overshoot is at most 2 rows)
+    const uint8_t* rp = src + (size_t)reflect101(y0 - 2, hgt) * sp + off;
+    uint8_t* dp = dst + (size_t)y0 * bp + off;
+    int yy = y0 - 2;                       // row index rp currently stands for
+    const long long spl = sp;
+#define NEXTROW() do { yy++; rp += ((unsigned)(yy - 1) < (unsigned)(hgt - 1)) ? spl : -spl; } while (0)
+#define HROW(dstv) do { blur_hrow(rp, bl, dstv); NEXTROW(); } while (0)
+#define OUT(A, B, C, D, E)                                                                          \
     do {                                                                                            \
         const unsigned o = blur_vout(A, B, C, D, E);                                                \
-        if (store) *reinterpret_cast<unsigned*>(dst + (size_t)(yy) * bp + x0) = o;                  \
+        if (store) *reinterpret_cast<unsigned*>(dp) = o;                                            \
+        dp += bp;                                                                                   \
     } while (0)
-    HROW(y0 - 2, r0); HROW(y0 - 1, r1); HROW(y0, r2); HROW(y0 + 1, r3);
-    for (int y = y0; y < y1; y += 5) {
-        HROW(y + 2, r4); OUT(y, r0, r1, r2, r3, r4);
-        if (y + 1 >= y1) break;
-        HROW(y + 3, r0); OUT(y + 1, r1, r2, r3, r4, r0);
-        if (y + 2 >= y1) break;
-        HROW(y + 4, r1); OUT(y + 2, r2, r3, r4, r0, r1);
-        if (y + 3 >= y1) break;
-        HROW(y + 5, r2); OUT(y + 3, r3, r4, r0, r1, r2);
-        if (y + 4 >= y1) break;
-        HROW(y + 6, r3); OUT(y + 4, r4, r0, r1, r2, r3);
+    unsigned r0[4], r1[4], r2[4], r3[4], r4[4];
+    HROW(r0); HROW(r1); HROW(r2); HROW(r3);
+    int y = y0;
+    for (; y + 5 <= y1; y += 5) {          // full groups of 5 rows: the ring returns to its starting assignment
+        HROW(r4); OUT(r0, r1, r2, r3, r4);
+        HROW(r0); OUT(r1, r2, r3, r4, r0);
+        HROW(r1); OUT(r2, r3, r4, r0, r1);
+        HROW(r2); OUT(r3, r4, r0, r1, r2);
+        HROW(r3); OUT(r4, r0, r1, r2, r3);
     }
+    if (y < y1) {                          // last band of a level: up to 4 rows left
+        HROW(r4); OUT(r0, r1, r2, r3, r4);
+        if (y + 1 < y1) {
+            HROW(r0); OUT(r1, r2, r3, r4, r0);
+            if (y + 2 < y1) {
+                HROW(r1); OUT(r2, r3, r4, r0, r1);
+                if (y + 3 < y1) { HROW(r2); OUT(r3, r4, r0, r1, r2); }
+            }
+        }
+    }
+#undef NEXTROW
 #undef HROW
 #undef OUT
 }
@@ -534,8 +600,8 @@ cudaError_t launch_orb_pipeline(const OrbArgs& a, const OrbPlan& hp, int nframes
     (*launches)++;
     if (ev) cudaEventRecord(ev[4], st);
     // K5: blur (only needed for descriptors)
-    if (a.wantDesc && hp.rowBlocksTotal > 0) {
-        dim3 blk(32, 4), grd(cdiv(hp.lv[0].w, 128), cdiv(hp.rowBlocksTotal, 4), nframes);
+    if (a.wantDesc && hp.blurTasksTotal > 0) {
+        dim3 blk(32, 4), grd(cdiv(hp.blurTasksTotal, 4), nframes);
         blur_kernel<<<grd, blk, 0, st>>>(a);
         (*launches)++;
     }
@@ -557,8 +623,8 @@ cudaError_t launch_pyramid_and_blur(const OrbArgs& a, const OrbPlan& hp, cudaStr
         pyr_resize_kernel<<<grd, blk, 0, st>>>(a, l);
         (*launches)++;
     }
-    if (hp.rowBlocksTotal > 0) {
-        dim3 blk(32, 4), grd(cdiv(hp.lv[0].w, 128), cdiv(hp.rowBlocksTotal, 4), 1);
+    if (hp.blurTasksTotal > 0) {
+        dim3 blk(32, 4), grd(cdiv(hp.blurTasksTotal, 4), 1);
         blur_kernel<<<grd, blk, 0, st>>>(a);
         (*launches)++;
     }

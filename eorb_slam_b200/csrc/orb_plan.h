@@ -27,7 +27,7 @@ struct LevelPlan {
     float scale;                   // mvScaleFactor[level]
     float sizeF;                   // (float)(int)(31*scale)
     int xtabOff, ytabOff;          // offsets (in short4 units) into the resize tables (levels >= 1)
-    int rowBlockBase;              // first flattened 32-row band of this level (blur grid)
+    int blurTaskBase;              // first flattened (32-row band, 128-column strip) task of this level (blur grid)
 };
 
 struct CellPlan {
@@ -55,7 +55,7 @@ struct OrbPlan {
     int cellBarOff;                // FAST: byte offset of the warp's mbarrier
     int cellSmemPerWarp;           // bytes (multiple of 128: TMA destinations are 128-byte aligned)
     int octSmemBytes;              // max over levels
-    int rowBlocksTotal;            // blur grid: total 32-row bands over all levels
+    int blurTasksTotal;            // blur grid: total (band, strip) tasks over all levels
     int umax[16];
     LevelPlan lv[EORB_MAX_LEVELS];
 };

@@ -203,3 +203,26 @@ def test_tracked_descriptors_and_level_assignment():
 def test_device_math_equals_host_math():
     """shared scalar arithmetic compiled for sm_100a vs the host compile of the same header (toolchain guard)"""
     assert _api().selftest_math(0) == 0
+
+
+@pytest.mark.parametrize("wh", [(752, 480), (131, 97), (130, 40), (129, 33), (257, 35), (37, 29), (9, 31), (8, 64), (7, 5), (6, 3), (5, 2), (33, 1),
+                                (1, 9), (3, 3), (640, 31), (516, 30), (260, 61)])
+def test_pyramid_and_blur_odd_sizes(wh):
+    """K1/K5 on sizes that exercise partial last words, strips with idle lanes, single-strip levels, bands with a
+    tail, rows/columns that bounce more than once (REFLECT_101) — compared with the oracle's cv::resize /
+    cv::GaussianBlur restatements level by level (bit-exact)."""
+    api = _api()
+    w, h = wh
+    rng = np.random.default_rng(w * 1000 + h)
+    img = rng.integers(0, 256, (h, w), dtype=np.uint8)
+    okw = dict(CFG1, nlevels=4, nfeatures=100, edge=19)
+    ex = _mk(api, okw, w, h)
+    ex(img)
+    prev = img
+    for l in range(4):
+        lw, lh = ex.level_size(l)
+        if l > 0:
+            prev = O.resize_linear(prev, lw, lh)
+        got = ex.pyramid_level(l)
+        assert got.shape == prev.shape and np.array_equal(got, prev), "pyramid level %d" % l
+        assert np.array_equal(ex.debug_blurred(l), O.gauss5(prev)), "blurred level %d" % l
