@@ -212,7 +212,7 @@ struct eorb_orb {
     int planW = 0, planH = 0;
     OrbPlan hp{};
     std::vector<CellPlan> cells;
-    OrbPlan* d_plan = nullptr; CellPlan* d_cells = nullptr; short4* d_xtab = nullptr; short4* d_ytab = nullptr;
+    OrbPlan* d_plan = nullptr; CellPlan* d_cells = nullptr; short4* d_xtab = nullptr; int4* d_ytab = nullptr;
     float* d_invScale = nullptr;
     // slabs (maxBatch frames): `main` serves the device entry points and single calls; `pipe` holds the extra
     // slots (own stream + slabs + pinned staging) that eorb_orb_extract_batch cycles through so that the H2D copy
@@ -374,7 +374,8 @@ static int orbBuildPlan(eorb_orb* h, int W, int H) {
     P.nlevels = nl; P.edge = E; P.iniTh = h->par.iniThFAST; P.minTh = h->par.minThFAST; P.W = W; P.H = H;
     for (int i = 0; i < 16; i++) P.umax[i] = h->umax[i];
     h->cells.clear();
-    std::vector<short4> xtab, ytab;
+    std::vector<short4> xtab;
+    std::vector<int4> ytab;   // {sy0, sy1, b0 << 16, b1 << 16}
     long long pyrOff = 0, blurOff = 0;
     int slot = 0, sel = 0, rowBlocks = 0, maxCW = 7, maxCH = 7, octSmem = 0;
     for (int l = 0; l < nl; l++) {
@@ -452,9 +453,9 @@ static int orbBuildPlan(eorb_orb* h, int W, int H) {
                 float fy = (float)((dy + 0.5) * scale_y - 0.5);
                 int sy = (int)std::floor(fy);
                 fy -= sy;
-                short4 t;
-                t.x = (short)std::min(std::max(sy, 0), sh - 1); t.y = (short)std::min(std::max(sy + 1, 0), sh - 1);
-                t.z = satShort((1.f - fy) * 2048.f); t.w = satShort(fy * 2048.f);
+                int4 t;
+                t.x = std::min(std::max(sy, 0), sh - 1); t.y = std::min(std::max(sy + 1, 0), sh - 1);
+                t.z = (int)satShort((1.f - fy) * 2048.f) << 16; t.w = (int)satShort(fy * 2048.f) << 16;
                 ytab.push_back(t);
             }
         }
@@ -492,7 +493,7 @@ static int orbBuildPlan(eorb_orb* h, int W, int H) {
     CU(cudaMemcpy(h->d_plan, &P, sizeof(P), cudaMemcpyHostToDevice));
     if (!h->cells.empty()) CU(cudaMemcpy(h->d_cells, h->cells.data(), h->cells.size() * sizeof(CellPlan), cudaMemcpyHostToDevice));
     if (!xtab.empty()) CU(cudaMemcpy(h->d_xtab, xtab.data(), xtab.size() * sizeof(short4), cudaMemcpyHostToDevice));
-    if (!ytab.empty()) CU(cudaMemcpy(h->d_ytab, ytab.data(), ytab.size() * sizeof(short4), cudaMemcpyHostToDevice));
+    if (!ytab.empty()) CU(cudaMemcpy(h->d_ytab, ytab.data(), ytab.size() * sizeof(int4), cudaMemcpyHostToDevice));
     CU(cudaMemcpy(h->d_invScale, h->invScale.data(), nl * sizeof(float), cudaMemcpyHostToDevice));
     CU(orb_kernels_configure(P));
     h->planW = W; h->planH = H;

@@ -33,38 +33,41 @@ __device__ __forceinline__ const uint8_t* level_ptr(const OrbArgs& a, const Leve
 
 // ------------------------------------------------------------------------------------------------ K1
 // cv::resize INTER_LINEAR (11-bit fixed point) of level l-1 into level l.  One warp owns 128 destination columns
-// x EORB_PYR_BAND destination rows and streams down the rows.  A lane owns 4 destination columns; its source taps
-// are per-lane constants: two pairs of aligned 32-bit words per source row (columns 0-1 and 2-3), a byte-permute
-// selector per column that extracts the two adjacent taps, and the two 11-bit weights packed as 16-bit halves so
-// that ONE dp2a gives S = a0*p[sx] + a1*p[sx+1].  The horizontally interpolated source row is cached in
-// registers and reused by the next destination row (each source row feeds ~1.7 destination rows at s = 1.2),
-// so a destination pixel costs ~1.2 aligned word loads instead of 4 byte loads.
-#define EORB_PYR_BAND 16
+// x EORB_PYR_BAND destination rows.  A lane owns 4 destination columns; its source taps are per-lane constants:
+// two pairs of aligned 32-bit words per source row (columns 0-1 and 2-3), a byte-permute selector per column
+// that extracts the two adjacent taps, and the two 11-bit weights packed as 16-bit halves so that ONE dp2a gives
+// S = a0*p[sx] + a1*p[sx+1].  Both source rows of every destination row are interpolated in straight-line code
+// (no row cache: at s = 1.2 it would save 0.8 of 2 row interpolations but cost a branch tree per row), the
+// vertical step (b*(S>>4))>>16 is one IMAD.HI per tap, and the loop is unrolled so the loads of the next
+// destination row are in flight while the current one is combined.
+#define EORB_PYR_BAND 8
 
-__device__ __forceinline__ void pyr_hrow(const uint8_t* __restrict__ row, const int* off, const unsigned* sel, const unsigned* wt, unsigned* h) {
-    const unsigned A0 = __ldg(reinterpret_cast<const unsigned*>(row + off[0]));
-    const unsigned A1 = __ldg(reinterpret_cast<const unsigned*>(row + off[1]));
-    const unsigned B0 = __ldg(reinterpret_cast<const unsigned*>(row + off[2]));
-    const unsigned B1 = __ldg(reinterpret_cast<const unsigned*>(row + off[3]));
-    h[0] = __dp2a_lo(wt[0], __byte_perm(A0, A1, sel[0]), 0u);
-    h[1] = __dp2a_lo(wt[1], __byte_perm(A0, A1, sel[1]), 0u);
-    h[2] = __dp2a_lo(wt[2], __byte_perm(B0, B1, sel[2]), 0u);
-    h[3] = __dp2a_lo(wt[3], __byte_perm(B0, B1, sel[3]), 0u);
+// rowA / rowB point at the first word of the lane's two 8-byte source windows (columns 0-1 and 2-3)
+__device__ __forceinline__ void pyr_hrow(const uint8_t* __restrict__ rowA, const uint8_t* __restrict__ rowB, const unsigned* sel,
+                                         const unsigned* wt, unsigned* h) {
+    const unsigned A0 = __ldg(reinterpret_cast<const unsigned*>(rowA));
+    const unsigned A1 = __ldg(reinterpret_cast<const unsigned*>(rowA + 4));
+    const unsigned B0 = __ldg(reinterpret_cast<const unsigned*>(rowB));
+    const unsigned B1 = __ldg(reinterpret_cast<const unsigned*>(rowB + 4));
+    h[0] = __dp2a_lo(wt[0], __byte_perm(A0, A1, sel[0]), 0u) >> 4;
+    h[1] = __dp2a_lo(wt[1], __byte_perm(A0, A1, sel[1]), 0u) >> 4;
+    h[2] = __dp2a_lo(wt[2], __byte_perm(B0, B1, sel[2]), 0u) >> 4;
+    h[3] = __dp2a_lo(wt[3], __byte_perm(B0, B1, sel[3]), 0u) >> 4;
 }
 
-__device__ __forceinline__ unsigned pyr_vrow(const unsigned* __restrict__ h0, const unsigned* __restrict__ h1, int b0, int b1) {
-    int v[4];
+// (((b0 * (S0 >> 4)) >> 16) + ((b1 * (S1 >> 4)) >> 16) + 2) >> 2 for four columns, packed into one word.
+// bs0 = b0 << 16, bs1 = b1 << 16: (b * x) >> 16 == umulhi(b << 16, x) for the non-negative operands here.
+__device__ __forceinline__ unsigned pyr_vrow(const unsigned* __restrict__ h0, const unsigned* __restrict__ h1, unsigned bs0, unsigned bs1) {
+    unsigned v[4];
 #pragma unroll
-    for (int j = 0; j < 4; j++) v[j] = resize_vsum((int)h0[j], (int)h1[j], b0, b1);
-    const unsigned lo = __byte_perm((unsigned)v[0], (unsigned)v[1], 0x0040);
-    const unsigned hi = __byte_perm((unsigned)v[2], (unsigned)v[3], 0x0040);
+    for (int j = 0; j < 4; j++) v[j] = (__umulhi(bs0, h0[j]) + __umulhi(bs1, h1[j]) + 2u) >> 2;
+    const unsigned lo = __byte_perm(v[0], v[1], 0x0040);
+    const unsigned hi = __byte_perm(v[2], v[3], 0x0040);
     return __byte_perm(lo, hi, 0x5410);
 }
 
 __global__ void __launch_bounds__(128) pyr_resize_kernel(OrbArgs a, int level) {
     const OrbPlan& P = *a.plan;
-    // everything needed from the plan is copied to registers up front: the plan lives in global memory and would
-    // otherwise be re-read after every store of the row loop
     const int dw = P.lv[level].w, dh = P.lv[level].h, dpitch = P.lv[level].pitch;
     const int sw = P.lv[level - 1].w;
     const int xtabOff = P.lv[level].xtabOff, ytabOff = P.lv[level].ytabOff;
@@ -79,13 +82,28 @@ __global__ void __launch_bounds__(128) pyr_resize_kernel(OrbArgs a, int level) {
     int sp;
     const uint8_t* __restrict__ src = level_ptr(a, P.lv[level - 1], level - 1, f, sp);
     uint8_t* __restrict__ dst = a.pyr + (size_t)f * (size_t)pyrBytes + (size_t)doff + dx0;
-    const short4* __restrict__ ytab = a.ytab + ytabOff;
+    const int4* __restrict__ ytab = a.ytab + ytabOff;
     const bool active = dx0 < dw;
-    // per-lane constant taps
-    int off[4];
+    if (sw < 8) {   // degenerate source width: plain per-pixel evaluation (the windows below need two whole words)
+        if (active)
+            for (int dy = y0; dy < y1; dy++) {
+                const int4 yt = __ldg(&ytab[dy]);
+                const uint8_t* r0 = src + (size_t)yt.x * sp;
+                const uint8_t* r1 = src + (size_t)yt.y * sp;
+                for (int j = 0; j < 4 && dx0 + j < dw; j++) {
+                    const short4 xt = __ldg(&a.xtab[xtabOff + dx0 + j]);
+                    const int S0 = resize_hsum(r0[xt.x], r0[xt.y], xt.z, xt.w), S1 = resize_hsum(r1[xt.x], r1[xt.y], xt.z, xt.w);
+                    dst[(size_t)dy * dpitch + j] = (uint8_t)resize_vsum(S0, S1, yt.z >> 16, yt.w >> 16);
+                }
+            }
+        return;
+    }
+    // per-lane constant taps: window bases (aligned words; a window is the word and its right neighbour, moved one
+    // word left at the right edge of the row so that both words exist), byte selectors, packed weights
+    int baseA, baseB;
     unsigned sel[4], wt[4];
     {
-        const int lastWord = ((sw + 3) & ~3) - 4;          // last aligned word that belongs to a source row
+        const int lastBase = ((sw + 3) & ~3) - 8;          // last window start with both words inside the row
         int sx[4];
 #pragma unroll
         for (int j = 0; j < 4; j++) {
@@ -93,36 +111,28 @@ __global__ void __launch_bounds__(128) pyr_resize_kernel(OrbArgs a, int level) {
             sx[j] = xt.x;
             wt[j] = (unsigned)(unsigned short)xt.z | ((unsigned)(unsigned short)xt.w << 16);
         }
-        const int baseA = sx[0] & ~3, baseB = sx[2] & ~3;
-        off[0] = baseA; off[1] = min(baseA + 4, lastWord); off[2] = baseB; off[3] = min(baseB + 4, lastWord);
-        // byte positions inside the 8-byte pair; when the second word was clamped (only possible at the right edge,
-        // where a1 == 0) the second tap is irrelevant, keep the selector inside 0..7
+        baseA = min(sx[0] & ~3, lastBase); baseB = min(sx[2] & ~3, lastBase);
+        // byte positions inside the 8-byte window; a second tap that would fall outside (only at the right edge of
+        // the row, where its weight is 0) is kept inside 0..7
         const int o0 = sx[0] - baseA, o1 = sx[1] - baseA, o2 = sx[2] - baseB, o3 = sx[3] - baseB;
-        sel[0] = (unsigned)(o0 | (min(o0 + 1, 7) << 4));
+        sel[0] = (unsigned)(min(o0, 7) | (min(o0 + 1, 7) << 4));
         sel[1] = (unsigned)(min(o1, 7) | (min(o1 + 1, 7) << 4));
-        sel[2] = (unsigned)(o2 | (min(o2 + 1, 7) << 4));
+        sel[2] = (unsigned)(min(o2, 7) | (min(o2 + 1, 7) << 4));
         sel[3] = (unsigned)(min(o3, 7) | (min(o3 + 1, 7) << 4));
-        if (!active) { off[0] = off[1] = off[2] = off[3] = 0; }
     }
-    // source row r lives in buffer r&1; have[] remembers which row each buffer holds (no register shuffling)
-    unsigned hE[4], hO[4];
-    int haveE = -1, haveO = -1;
-    short4 yt = __ldg(&ytab[y0]);
+    const uint8_t* __restrict__ laneA = src + baseA;
+    const uint8_t* __restrict__ laneB = src + baseB;
+    uint8_t* dp = dst + (size_t)y0 * dpitch;
+#pragma unroll 2
     for (int dy = y0; dy < y1; dy++) {
-        const short4 ytn = __ldg(&ytab[min(dy + 1, dh - 1)]);   // prefetch next row's taps (warp-uniform)
-        const int s0 = yt.x, s1 = yt.y, b0 = yt.z, b1 = yt.w;
-        if ((s0 & 1) == 0) { if (haveE != s0) { pyr_hrow(src + (size_t)s0 * sp, off, sel, wt, hE); haveE = s0; } }
-        else               { if (haveO != s0) { pyr_hrow(src + (size_t)s0 * sp, off, sel, wt, hO); haveO = s0; } }
-        if ((s1 & 1) == 0) { if (haveE != s1) { pyr_hrow(src + (size_t)s1 * sp, off, sel, wt, hE); haveE = s1; } }
-        else               { if (haveO != s1) { pyr_hrow(src + (size_t)s1 * sp, off, sel, wt, hO); haveO = s1; } }
-        unsigned o;
-        const int par = (s0 & 1) | ((s1 & 1) << 1);
-        if (par == 2) o = pyr_vrow(hE, hO, b0, b1);
-        else if (par == 1) o = pyr_vrow(hO, hE, b0, b1);
-        else if (par == 0) o = pyr_vrow(hE, hE, b0, b1);
-        else o = pyr_vrow(hO, hO, b0, b1);
-        if (active) *reinterpret_cast<unsigned*>(dst + (size_t)dy * dpitch) = o;
-        yt = ytn;
+        const int4 yt = __ldg(&ytab[dy]);                  // sy0, sy1 (clamped), b0 << 16, b1 << 16 — warp-uniform
+        const size_t r0 = (size_t)(unsigned)yt.x * (unsigned)sp, r1 = (size_t)(unsigned)yt.y * (unsigned)sp;
+        unsigned h0[4], h1[4];
+        pyr_hrow(laneA + r0, laneB + r0, sel, wt, h0);
+        pyr_hrow(laneA + r1, laneB + r1, sel, wt, h1);
+        const unsigned o = pyr_vrow(h0, h1, (unsigned)yt.z, (unsigned)yt.w);
+        if (active) *reinterpret_cast<unsigned*>(dp) = o;
+        dp += dpitch;
     }
 }
 

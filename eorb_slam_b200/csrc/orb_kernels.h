@@ -15,7 +15,7 @@ struct OrbArgs {
     const OrbPlan* plan;         // device copy
     const CellPlan* cells;       // device
     const short4* xtab;          // device: resize taps per destination column  {sx, sx+1, a0, a1}
-    const short4* ytab;          // device: resize taps per destination row     {sy0, sy1, b0, b1}
+    const int4* ytab;            // device: resize taps per destination row     {sy0, sy1, b0 << 16, b1 << 16}
     const uint8_t* lvl0;         // level 0 = the input frames (zero-copy when aligned, else staged)
     long long lvl0Pitch, lvl0FrameStride;
     const CUtensorMap* tmaps;    // device: [nlevels] TMA maps {x, y, frame} of the pyramid levels >= 1 (entry 0 unused:

@@ -26,7 +26,7 @@ struct LevelPlan {
     int selBase;                   // offset of this level's selected-keypoint slots inside one frame's slab
     float scale;                   // mvScaleFactor[level]
     float sizeF;                   // (float)(int)(31*scale)
-    int xtabOff, ytabOff;          // offsets (in short4 units) into the resize tables (levels >= 1)
+    int xtabOff, ytabOff;          // offsets (in entries) into the resize tables (levels >= 1)
     int blurTaskBase;              // first flattened (32-row band, 128-column strip) task of this level (blur grid)
 };
 
