@@ -7,14 +7,17 @@
 namespace eorb {
 
 // ---- exact arc score on packed s16x2 lanes -------------------------------------------------------------------
+// D_k = (ring_k - v, v - ring_k) per 16-bit half; arcs of 9 = min3 of min3 (VIMNMX3.S16x2), then a max3 tree.
 // ring[k] in the order of eorb_math.cuh::fast_max_arc_min; result identical to that function (device-vs-host
 // equality is checked by eorb_selftest_math on 20 000 rings).
 __device__ __forceinline__ int fast_max_arc_min_packed(int v, const int* ring) {
-    // Vp: lo half = -v, hi half = +v;  ring byte r * 0xFFFF0001 = (r, -r);  D = (r - v, v - r) per half
-    const unsigned Vp = __byte_perm((unsigned)(-v), (unsigned)v, 0x5410);
+    // one IMAD per ring pixel builds both polarities: r * 0xFFFF0001 = (lo: r, hi: -r), plus C = (lo: 0x4000 - v,
+    // hi: +v) gives D = (lo: r - v + 0x4000, hi: v - r).  The low half is biased by 0x4000 so that it never
+    // carries into the high half (0 <= r - v + 0x4000 < 2^16); min/max commute with the common bias.
+    const unsigned C = ((unsigned)v << 16) | (unsigned)(0x4000 - v);
     unsigned D[16], A[16];
 #pragma unroll
-    for (int k = 0; k < 16; k++) D[k] = __vadd2((unsigned)ring[k] * 0xFFFF0001u, Vp);
+    for (int k = 0; k < 16; k++) D[k] = (unsigned)ring[k] * 0xFFFF0001u + C;
 #pragma unroll
     for (int k = 0; k < 16; k++) A[k] = __vimin3_s16x2(D[k], D[(k + 1) & 15], D[(k + 2) & 15]);          // arcs of 3
 #pragma unroll
@@ -27,7 +30,7 @@ __device__ __forceinline__ int fast_max_arc_min_packed(int v, const int* ring) {
     b0 = __vimax3_s16x2(b0, b1, b2);
     b3 = __vimax3_s16x2(b3, b4, D[15]);
     b0 = __vmaxs2(b0, b3);
-    const int bright = (int)(short)(b0 & 0xffffu), dark = (int)b0 >> 16;
+    const int bright = (int)(b0 & 0xffffu) - 0x4000, dark = (int)b0 >> 16;
     return max(max(bright, dark), 0);
 }
 

@@ -99,22 +99,28 @@ __global__ void __launch_bounds__(EORB_FAST_WARPS * 32) fast_cells_kernel(OrbArg
         tma_load_3d(smem_u32(tile), tm, c.x0 & ~15, c.y0, f, bar);
     }
     {
-        const int mapWords = ((ch + 2) * MS) >> 2;
-        for (int i = lane; i < mapWords; i += 32) reinterpret_cast<uint32_t*>(smap)[i] = 0u;
+        const int mapVecs = ((ch + 2) * MS + 15) >> 4;   // the map region is padded to 16 bytes in the plan
+        for (int i = lane; i < mapVecs; i += 32) reinterpret_cast<uint4*>(smap)[i] = make_uint4(0u, 0u, 0u, 0u);
     }
     __syncwarp();
     mbar_wait(bar, 0);
 
     const int tA = min(max(P.iniTh, 0), 255), tB = min(max(P.minTh, 0), 255);
-    // interior = tile columns [aoff + 3, aoff + w - 3); phase 1 walks it in aligned groups of 8 columns
+    // interior = tile columns [aoff + 3, aoff + w - 3); phase 1 walks it in aligned groups of 8 columns.
+    // Fixed lane -> (row-in-step, group) assignment: a step covers rps rows x np groups in row-major lane order.
     const int aoff = c.x0 & 15;
     const int p0 = (aoff + 3) >> 3;
-    const int np = ((aoff + w - 4) >> 3) - p0 + 1;
-    const int ntask = np * ch;
-    const unsigned magic = (4194304u + (unsigned)np - 1u) / (unsigned)np;   // ceil(2^22 / np); exact for i < 2^22/np
+    const int np = ((aoff + w - 4) >> 3) - p0 + 1;                 // 1..10 groups per interior row
+    const int rps = 32 / np;                                      // rows per step
+    const int lr = lane / np, lp = lane - lr * np;
+    const bool laneUsed = lr < rps;
     const unsigned firstMask = (0xffu << ((aoff + 3) & 7)) & 0xffu;
     const int lastBits = aoff + w - 3 - 8 * (p0 + np - 1);
     const unsigned lastMask = lastBits >= 8 ? 0xffu : ((1u << lastBits) - 1u);
+    unsigned vm = lp == 0 ? firstMask : 0xffu;                    // interior columns of this lane's group
+    if (lp == np - 1) vm &= lastMask;
+    const int colBase = (p0 + lp) * 8;
+    const uint8_t* qLane = tile + (lr + 3) * TS + colBase;
 
     int cnt = 0;
     for (int pass = 0; pass < 2; pass++) {
@@ -123,12 +129,11 @@ __global__ void __launch_bounds__(EORB_FAST_WARPS * 32) fast_cells_kernel(OrbArg
 
         // ---- phase 1: packed compass test + ordered compaction
         int nsurv = 0;
-        for (int base = 0; base < ntask; base += 32) {
-            const int i = base + lane;
-            unsigned m8 = 0, code = 0;
-            if (i < ntask) {
-                const int rr = (int)(((unsigned)i * magic) >> 22), pp = i - rr * np;
-                const uint8_t* q = tile + (rr + 3) * TS + (p0 + pp) * 8;
+        const uint8_t* q = qLane;
+        for (int rbase = 0; rbase < ch; rbase += rps, q += rps * TS) {
+            const int rr = rbase + lr;
+            unsigned m8 = 0;
+            if (laneUsed && rr < ch) {
                 const uint2 C = *reinterpret_cast<const uint2*>(q);
                 const uint2 N = *reinterpret_cast<const uint2*>(q + 3 * TS);
                 const uint2 S = *reinterpret_cast<const uint2*>(q - 3 * TS);
@@ -137,12 +142,7 @@ __global__ void __launch_bounds__(EORB_FAST_WARPS * 32) fast_cells_kernel(OrbArg
                 const unsigned f0 = fast_compass4(C.x, N.x, S.x, __byte_perm(C.x, C.y, 0x6543), __byte_perm(L, C.x, 0x4321), K);
                 const unsigned f1 = fast_compass4(C.y, N.y, S.y, __byte_perm(C.y, R, 0x6543), __byte_perm(C.x, C.y, 0x4321), K);
                 // gather the four bit-7 flags of each word into a nibble (multiplier places bits 7,15,23,31 at 28..31)
-                m8 = ((f0 * 0x00204081u) >> 28) | (((f1 * 0x00204081u) >> 28) << 4);
-                // interior columns only
-                unsigned vm = pp == 0 ? firstMask : 0xffu;
-                if (pp == np - 1) vm &= lastMask;
-                m8 &= vm;
-                code = ((unsigned)rr << 7) | (unsigned)((p0 + pp) * 8);
+                m8 = (((f0 * 0x00204081u) >> 28) | (((f1 * 0x00204081u) >> 28) << 4)) & vm;
             }
             if (__ballot_sync(FULL, m8 != 0) == 0) continue;
             const int k = __popc(m8);
@@ -152,13 +152,12 @@ __global__ void __launch_bounds__(EORB_FAST_WARPS * 32) fast_cells_kernel(OrbArg
                 const int up = __shfl_up_sync(FULL, incl, o);
                 if (lane >= o) incl += up;
             }
-            int pos = nsurv + incl - k;
+            uint16_t* lp16 = list + nsurv + incl - k;
             nsurv += __shfl_sync(FULL, incl, 31);
-            while (m8) {
-                const int j = __ffs((int)m8) - 1;
-                m8 &= m8 - 1;
-                list[pos++] = (uint16_t)(code + j);
-            }
+            const unsigned code = ((unsigned)rr << 7) | (unsigned)colBase;
+#pragma unroll
+            for (int j = 0; j < 8; j++)
+                if (m8 & (1u << j)) *lp16++ = (uint16_t)(code + j);
         }
         __syncwarp();
 
@@ -193,16 +192,12 @@ __global__ void __launch_bounds__(EORB_FAST_WARPS * 32) fast_cells_kernel(OrbArg
                 const uint8_t* q = smap + (rr + 1) * MS + col - aoff - 2;
                 const int m = q[0];
                 if (m > t) {
-                    keep = true;
-#pragma unroll
-                    for (int dy = -1; dy <= 1; dy++)
-#pragma unroll
-                        for (int dx = -1; dx <= 1; dx++) {
-                            if (dx == 0 && dy == 0) continue;
-                            const int mq = q[dy * MS + dx];
-                            const int e = mq > t ? mq : 1;   // non-corner neighbours score 0  (score = m-1)
-                            keep &= (m > e);
-                        }
+                    // every stored score is > t, everything else is 0: strict maximum over the 8 neighbours, and the
+                    // OpenCV score m - 1 must beat a non-corner's 0
+                    const int n0 = max(max((int)q[-MS - 1], (int)q[-MS]), (int)q[-MS + 1]);
+                    const int n1 = max(max((int)q[-1], (int)q[1]), 1);
+                    const int n2 = max(max((int)q[MS - 1], (int)q[MS]), (int)q[MS + 1]);
+                    keep = m > max(max(n0, n1), n2);
                     packed = (uint32_t)(col - aoff + c.ox) | ((uint32_t)(rr + 3 + c.oy) << 12) | ((uint32_t)(m - 1) << 24);
                 }
             }

@@ -6,7 +6,7 @@
 
 #define EORB_MAX_LEVELS 32
 #define EORB_MAX_DIM 4095          // candidate coordinates are packed in 12 bits
-#define EORB_FAST_WARPS 8          // warps (= grid cells) per FAST thread block
+#define EORB_FAST_WARPS 4          // warps (= grid cells) per FAST thread block
 
 namespace eorb {
 
