@@ -212,7 +212,7 @@ struct eorb_orb {
     int planW = 0, planH = 0;
     OrbPlan hp{};
     std::vector<CellPlan> cells;
-    OrbPlan* d_plan = nullptr; CellPlan* d_cells = nullptr; short4* d_xtab = nullptr; int4* d_ytab = nullptr;
+    OrbPlan* d_plan = nullptr; CellPlan* d_cells = nullptr; short4* d_xtab = nullptr; int4* d_ytab = nullptr; int2* d_icTab = nullptr;
     float* d_invScale = nullptr;
     // slabs (maxBatch frames): `main` serves the device entry points and single calls; `pipe` holds the extra
     // slots (own stream + slabs + pinned staging) that eorb_orb_extract_batch cycles through so that the H2D copy
@@ -223,6 +223,7 @@ struct eorb_orb {
         uint8_t* d_img0 = nullptr; uint8_t* d_pyr = nullptr; uint8_t* d_blur = nullptr;
         uint16_t* d_cellCount = nullptr; uint32_t* d_cand = nullptr; uint32_t* d_okeys = nullptr; uint16_t* d_knode = nullptr;
         uint32_t* d_sel = nullptr; int* d_selCount = nullptr; int* d_candCount = nullptr; int* d_dstIdx = nullptr;
+        uint32_t* d_kpList = nullptr;
         float* d_levelAngle = nullptr;
         CUtensorMap* d_tmaps = nullptr;   // [nlevels] maps of this slab's pyramid levels >= 1
         eorb_keypoint* d_outKps = nullptr; uint8_t* d_outDesc = nullptr; int* d_outN = nullptr; int* d_outMono = nullptr;
@@ -262,7 +263,7 @@ static cudaEvent_t* orbStageEvents(eorb_orb* h) {
 static void orbFreeBufs(eorb_orb::Bufs& b) {
     cudaFree(b.d_img0); cudaFree(b.d_pyr); cudaFree(b.d_blur); cudaFree(b.d_cellCount); cudaFree(b.d_cand);
     cudaFree(b.d_okeys); cudaFree(b.d_knode); cudaFree(b.d_sel); cudaFree(b.d_selCount); cudaFree(b.d_candCount);
-    cudaFree(b.d_dstIdx); cudaFree(b.d_levelAngle); cudaFree(b.d_tmaps); cudaFree(b.d_outKps); cudaFree(b.d_outDesc);
+    cudaFree(b.d_dstIdx); cudaFree(b.d_kpList); cudaFree(b.d_levelAngle); cudaFree(b.d_tmaps); cudaFree(b.d_outKps); cudaFree(b.d_outDesc);
     cudaFree(b.d_outN); cudaFree(b.d_outMono);
     cudaFreeHost(b.h_kps); cudaFreeHost(b.h_desc); cudaFreeHost(b.h_n); cudaFreeHost(b.h_mono);
     if (b.done) cudaEventDestroy(b.done);
@@ -285,6 +286,7 @@ static int orbAllocBufs(eorb_orb* h, eorb_orb::Bufs& b, bool pipeline) {
     CU(devAlloc(&b.d_selCount, B * (size_t)nl));
     CU(devAlloc(&b.d_candCount, B * (size_t)nl));
     CU(devAlloc(&b.d_dstIdx, B * (size_t)P.selPerFrame));
+    CU(devAlloc(&b.d_kpList, B * (size_t)P.selPerFrame));
     CU(devAlloc(&b.d_levelAngle, B * (size_t)P.selPerFrame));
     {   // TMA maps of the pyramid levels held by this slab (FAST stages its cell tiles with them)
         std::vector<CUtensorMap> maps((size_t)nl);
@@ -313,8 +315,8 @@ static int orbAllocBufs(eorb_orb* h, eorb_orb::Bufs& b, bool pipeline) {
 }
 
 static void orbFreePlan(eorb_orb* h) {
-    cudaFree(h->d_plan); cudaFree(h->d_cells); cudaFree(h->d_xtab); cudaFree(h->d_ytab); cudaFree(h->d_invScale);
-    h->d_plan = nullptr; h->d_cells = nullptr; h->d_xtab = nullptr; h->d_ytab = nullptr; h->d_invScale = nullptr;
+    cudaFree(h->d_plan); cudaFree(h->d_cells); cudaFree(h->d_xtab); cudaFree(h->d_ytab); cudaFree(h->d_invScale); cudaFree(h->d_icTab);
+    h->d_plan = nullptr; h->d_cells = nullptr; h->d_xtab = nullptr; h->d_ytab = nullptr; h->d_invScale = nullptr; h->d_icTab = nullptr;
     orbFreeBufs(h->main);
     for (auto& b : h->pipe) orbFreeBufs(b);
     h->pipe.clear();
@@ -486,6 +488,24 @@ static int orbBuildPlan(eorb_orb* h, int W, int H) {
     CU(devAlloc(&h->d_xtab, xtab.size()));
     CU(devAlloc(&h->d_ytab, ytab.size()));
     CU(devAlloc(&h->d_invScale, (size_t)nl));
+    {   // IC_Angle weight table (:77-104): for alignment a = (x-15)&3, row r = v+15, aligned word k the four columns are
+        // u = 4k + j - a - 15; weight u (m10) / v (m01) inside the circle |u| <= umax[|v|], 0 outside; row 31 is padding
+        std::vector<int2> tab(4 * 288);
+        for (int al = 0; al < 4; al++)
+            for (int i = 0; i < 288; i++) {
+                const int r = i / 9, k = i % 9, v = r - 15;
+                uint32_t w10 = 0, w01 = 0;
+                for (int j = 0; j < 4 && r < 31; j++) {
+                    const int u = 4 * k + j - al - 15;
+                    if (u < -15 || u > 15 || std::abs(u) > h->umax[std::abs(v)]) continue;
+                    w10 |= (uint32_t)(uint8_t)(int8_t)u << (8 * j);
+                    w01 |= (uint32_t)(uint8_t)(int8_t)v << (8 * j);
+                }
+                tab[(size_t)al * 288 + i] = make_int2((int)w10, (int)w01);
+            }
+        CU(devAlloc(&h->d_icTab, tab.size()));
+        CU(cudaMemcpy(h->d_icTab, tab.data(), tab.size() * sizeof(int2), cudaMemcpyHostToDevice));
+    }
     {
         int rcb = orbAllocBufs(h, h->main, false);
         if (rcb != EORB_OK) return rcb;
@@ -508,7 +528,7 @@ static OrbArgs orbArgs(eorb_orb* h, eorb_orb::Bufs& b, const uint8_t* lvl0, long
     a.tmaps = b.d_tmaps;
     a.pyr = b.d_pyr; a.blur = b.d_blur; a.cellCount = b.d_cellCount; a.cand = b.d_cand; a.okeys = b.d_okeys;
     a.knode = b.d_knode; a.sel = b.d_sel; a.selCount = b.d_selCount; a.candCount = b.d_candCount;
-    a.dstIdx = b.d_dstIdx; a.levelAngle = b.d_levelAngle;
+    a.dstIdx = b.d_dstIdx; a.kpList = b.d_kpList; a.icTab = h->d_icTab; a.levelAngle = b.d_levelAngle;
     a.outKps = kps; a.outDesc = desc; a.outN = nOut; a.outMono = monoOut; a.cap = cap;
     a.lap0 = lap0; a.lap1 = lap1; a.wantDesc = wantDesc;
     h->last = &b;

@@ -210,6 +210,7 @@ __global__ void __launch_bounds__(OCT_MAX_THREADS) orb_index_kernel(OrbArgs a) {
             float x = (float)(oct_key_x(sel[slot]) + lp.minBX);
             if (l != 0) x = fmul(x, lp.scale);
             flag = (x >= lap0 && x <= lap1) ? 1 : 0;
+            a.kpList[(size_t)f * P.selPerFrame + g] = (uint32_t)slot | ((uint32_t)l << 24);   // work list of K4+K6
         }
         s_arr[tid] = flag;
         __syncthreads();
@@ -392,52 +393,76 @@ __global__ void __launch_bounds__(128) blur_kernel(OrbArgs a) {
 }
 
 // ------------------------------------------------------------------------------------------------ K4 + K6
-// One warp per selected keypoint.  Orientation: lanes own the 31 columns of the circular patch, integer
-// moments reduced with shuffles, cv::fastAtan2 restated without FMA.  Descriptor: lane L evaluates pattern
-// pair 32*j+L in round j; __ballot_sync yields descriptor word j directly (bit k of byte i = pair 8i+k).
-__global__ void __launch_bounds__(256) orient_desc_kernel(OrbArgs a) {
+// One warp per selected keypoint (taken from the compact list K7 writes), EORB_KP_GROUP keypoints per block.
+// Orientation (IC_Angle): the 31x31 patch is read as aligned 32-bit words, 9 words per row; lane <-> (row, word)
+// tasks, 9 steps per keypoint.  The circular mask and the u / v moment weights of every (alignment, row, word)
+// are a table of packed s8x4 pairs, so a task is one word load, one table load and two mixed-sign dp4a
+// (m10 += sum u*I, m01 += sum v*I); integer moments reduced with shuffles, cv::fastAtan2 restated without FMA.
+// sin/cos: the block's angles meet in shared memory and threads 0..G-1 evaluate them together, one pass of the
+// double-precision sincos per G keypoints instead of one per keypoint.  Descriptor: lane L evaluates pattern pair 32*j+L in round j;
+// __ballot_sync yields descriptor word j directly (bit k of byte i = pair 8i+k).
+#define EORB_KP_GROUP 8
+#define EORB_IC_WORDS 9                    // aligned words covering 31 columns at any alignment
+#define EORB_IC_TASKS 288                  // 32 rows x 9 words (row 31 is padding with zero weights)
+
+__device__ __forceinline__ int dp4a_u8_s8(unsigned data, int weights, int acc) {
+    int d;
+    asm("dp4a.u32.s32 %0, %1, %2, %3;" : "=r"(d) : "r"(data), "r"(weights), "r"(acc));
+    return d;
+}
+
+__global__ void __launch_bounds__(32 * EORB_KP_GROUP) orient_desc_kernel(OrbArgs a) {
+    __shared__ float s_angle[EORB_KP_GROUP], s_cos[EORB_KP_GROUP], s_sin[EORB_KP_GROUP];
     const OrbPlan& P = *a.plan;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int slot = blockIdx.x * 8 + warp;
     const int f = blockIdx.y;
-    if (slot >= P.selPerFrame) return;
-    int level = 0;
-    while (level + 1 < P.nlevels && slot >= P.lv[level + 1].selBase) level++;
-    const LevelPlan& lp = P.lv[level];
-    const int idx = slot - lp.selBase;
-    if (idx >= a.selCount[(size_t)f * P.nlevels + level]) return;
-    const uint32_t key = a.sel[(size_t)f * P.selPerFrame + slot];
-    const int x = oct_key_x(key) + lp.minBX, y = oct_key_y(key) + lp.minBY;
+    const int nk = min(a.outN[f], P.selPerFrame);
+    const int kidx = blockIdx.x * EORB_KP_GROUP + warp;
+    if (blockIdx.x * EORB_KP_GROUP >= nk) return;      // block-uniform
+    const bool valid = kidx < nk;
     const unsigned FULL = 0xffffffffu;
-    int sp;
-    const uint8_t* img = level_ptr(a, lp, level, f, sp);
 
-    // ---- IC_Angle on the (virtually REFLECT_101-bordered) level
-    int m10 = 0, m01 = 0;
-    {
-        const int u = lane - 15;
+    int slot = 0, level = 0, x = 0, y = 0;
+    uint32_t key = 0;
+    if (valid) {
+        const uint32_t e = a.kpList[(size_t)f * P.selPerFrame + kidx];
+        slot = e & 0xffffff; level = e >> 24;
+        key = a.sel[(size_t)f * P.selPerFrame + slot];
+        x = oct_key_x(key) + P.lv[level].minBX; y = oct_key_y(key) + P.lv[level].minBY;
+    }
+    const LevelPlan& lp = P.lv[level];
+
+    // ---- orientation (one warp per keypoint)
+    if (valid) {
+        int sp;
+        const uint8_t* img = level_ptr(a, lp, level, f, sp);
+        int m10 = 0, m01 = 0;
         const bool inside = (x >= 15) && (y >= 15) && (x + 15 < lp.w) && (y + 15 < lp.h);
-        if (lane < 31) {
-            const int au = u < 0 ? -u : u;
-            int colsum = 0;
-            if (inside) {
-                const uint8_t* c = img + (size_t)y * sp + x + u;
+        if (inside) {
+            const int xs = x - 15, xa = xs & ~3;
+            const int wAligned = (lp.w + 3) & ~3;
+            const int2* __restrict__ tab = a.icTab + (xs & 3) * EORB_IC_TASKS + lane;
+            const uint8_t* base = img + (size_t)(y - 15) * sp + xa;
 #pragma unroll
-                for (int v = -15; v <= 15; v++) {
-                    const int av = v < 0 ? -v : v;
-                    if (au <= P.umax[av]) {
-                        const int val = __ldg(c + v * sp);
-                        colsum += val; m01 += v * val;
-                    }
-                }
-            } else {
-                const int xx = reflect101(x + u, lp.w);
-                for (int v = -15; v <= 15; v++) {
-                    const int av = v < 0 ? -v : v;
-                    if (au <= P.umax[av]) {
-                        const int val = __ldg(img + (size_t)reflect101(y + v, lp.h) * sp + xx);
-                        colsum += val; m01 += v * val;
-                    }
+            for (int it = 0; it < EORB_IC_TASKS / 32; it++) {
+                const int i = it * 32 + lane;
+                const int r = (i * 57) >> 9, k = i - r * EORB_IC_WORDS;     // i / 9 for i < 288
+                const int2 wgt = __ldg(tab + it * 32);
+                unsigned data = 0;
+                if (r < 31 && xa + 4 * k < wAligned) data = __ldg(reinterpret_cast<const unsigned*>(base + (size_t)r * sp + 4 * k));
+                m10 = dp4a_u8_s8(data, wgt.x, m10);
+                m01 = dp4a_u8_s8(data, wgt.y, m01);
+            }
+        } else if (lane < 31) {   // patch crosses the level border (margin < 15): REFLECT_101, byte by byte
+            const int u = lane - 15;
+            const int au = u < 0 ? -u : u;
+            const int xx = reflect101(x + u, lp.w);
+            int colsum = 0;
+            for (int v = -15; v <= 15; v++) {
+                const int av = v < 0 ? -v : v;
+                if (au <= P.umax[av]) {
+                    const int val = __ldg(img + (size_t)reflect101(y + v, lp.h) * sp + xx);
+                    colsum += val; m01 += v * val;
                 }
             }
             m10 = u * colsum;
@@ -447,11 +472,28 @@ __global__ void __launch_bounds__(256) orient_desc_kernel(OrbArgs a) {
             m10 += __shfl_xor_sync(FULL, m10, o);
             m01 += __shfl_xor_sync(FULL, m01, o);
         }
+        if (lane == 0) s_angle[warp] = fast_atan2_deg((float)m01, (float)m10);
+    } else if (lane == 0) {
+        s_angle[warp] = 0.f;
     }
-    const float angle = fast_atan2_deg((float)m01, (float)m10);
-    const int dst = a.dstIdx[(size_t)f * P.selPerFrame + slot];
-    if (dst < 0 || dst >= a.cap) return;
+    __syncthreads();
 
+    // ---- sin / cos of the block's angles in one pass: thread g <-> keypoint g (one double-precision sincos per
+    //      EORB_KP_GROUP keypoints instead of one per keypoint)
+    if (threadIdx.x < EORB_KP_GROUP) {
+        const float factorPI = (float)(3.14159265358979323846 / 180.f);
+        double sd, cd;
+        sincos((double)fmul(s_angle[threadIdx.x], factorPI), &sd, &cd);
+        s_cos[threadIdx.x] = (float)cd; s_sin[threadIdx.x] = (float)sd;
+    }
+    __syncthreads();
+    if (!valid) return;
+
+    // ---- keypoint record + steered BRIEF on the blurred level
+    const float angle = s_angle[warp], ca = s_cos[warp], sa = s_sin[warp];
+    const int dst = a.dstIdx[(size_t)f * P.selPerFrame + slot];
+    if (a.levelAngle && lane == 0) a.levelAngle[(size_t)f * P.selPerFrame + slot] = angle;
+    if (dst < 0 || dst >= a.cap) return;
     if (lane == 0) {
         eorb_keypoint kp;
         const float xf = (float)x, yf = (float)y;
@@ -464,16 +506,11 @@ __global__ void __launch_bounds__(256) orient_desc_kernel(OrbArgs a) {
         kp.class_id = -1;
         a.outKps[(size_t)f * a.cap + dst] = kp;
     }
-    if (a.levelAngle) a.levelAngle[(size_t)f * P.selPerFrame + slot] = angle;
     if (!a.wantDesc) return;
-
-    // ---- steered BRIEF on the blurred level
-    const float factorPI = (float)(3.14159265358979323846 / 180.f);
-    const float ang = fmul(angle, factorPI);
-    const float ca = (float)cos((double)ang), sa = (float)sin((double)ang);
     const uint8_t* B = a.blur + (size_t)f * (size_t)P.blurBytesPerFrame + (size_t)lp.blurOff;
     const int bp = lp.bpitch;
     const bool safe = (x >= 19) && (y >= 19) && (x + 19 < lp.w) && (y + 19 < lp.h);
+    const uint8_t* Bc = B + (size_t)y * bp + x;
     uint32_t myword = 0;
 #pragma unroll
     for (int j = 0; j < 8; j++) {
@@ -481,13 +518,14 @@ __global__ void __launch_bounds__(256) orient_desc_kernel(OrbArgs a) {
         int r0, c0, r1, c1;
         brief_offset(pt.x, pt.y, ca, sa, r0, c0);
         brief_offset(pt.z, pt.w, ca, sa, r1, c1);
-        int y0 = y + r0, x0 = x + c0, y1 = y + r1, x1 = x + c1;
-        if (!safe) {   // margin < 19: the reference reads out of bounds; pinned to REFLECT_101 (see oracle)
-            y0 = reflect101(y0, lp.h); x0 = reflect101(x0, lp.w);
-            y1 = reflect101(y1, lp.h); x1 = reflect101(x1, lp.w);
+        int t0, t1;
+        if (safe) {
+            t0 = __ldg(Bc + r0 * bp + c0);
+            t1 = __ldg(Bc + r1 * bp + c1);
+        } else {   // margin < 19: the reference reads out of bounds; pinned to REFLECT_101 (see oracle)
+            t0 = __ldg(B + (size_t)reflect101(y + r0, lp.h) * bp + reflect101(x + c0, lp.w));
+            t1 = __ldg(B + (size_t)reflect101(y + r1, lp.h) * bp + reflect101(x + c1, lp.w));
         }
-        const int t0 = __ldg(B + (size_t)y0 * bp + x0);
-        const int t1 = __ldg(B + (size_t)y1 * bp + x1);
         const uint32_t word = __ballot_sync(FULL, t0 < t1);
         if (lane == j) myword = word;
     }
@@ -618,8 +656,8 @@ cudaError_t launch_orb_pipeline(const OrbArgs& a, const OrbPlan& hp, int nframes
     if (ev) cudaEventRecord(ev[5], st);
     // K4 + K6
     {
-        dim3 grd(cdiv(hp.selPerFrame, 8), nframes);
-        orient_desc_kernel<<<grd, 256, 0, st>>>(a);
+        dim3 grd(cdiv(hp.selPerFrame, EORB_KP_GROUP), nframes);
+        orient_desc_kernel<<<grd, 32 * EORB_KP_GROUP, 0, st>>>(a);
         (*launches)++;
     }
     if (ev) cudaEventRecord(ev[6], st);

@@ -30,6 +30,8 @@ struct OrbArgs {
     int* selCount;               // [B][nlevels]
     int* candCount;              // [B][nlevels]
     int* dstIdx;                 // [B][selPerFrame]        final output position
+    uint32_t* kpList;            // [B][selPerFrame]        compact list of selected keypoints: slot | level << 24
+    const int2* icTab;           // device: [4][288] IC_Angle weights (u, v) as packed s8x4 per (alignment, row, word)
     float* levelAngle;           // [B][selPerFrame]        (debug tap) or nullptr
     eorb_keypoint* outKps;       // [B][cap]
     uint8_t* outDesc;            // [B][cap][32]
