@@ -31,7 +31,7 @@ sys.path.insert(0, os.path.join(ROOT, "tests"))
 W, H = 752, 480
 ORB_KW = dict(nfeatures=1000, scale_factor=1.2, nlevels=8, ini_th=20, min_th=7, edge_th=19)
 FRAMES_PER_GPU = 4096
-CHUNK = 128                      # frames per launch set
+CHUNK = 1024                     # frames per launch set of the device-resident path (the host path pipelines 128-frame slots)
 UNIQUE_FRAMES = 256              # generated frames; the rest are circular shifts of these (all distinct)
 # algorithmic bytes per frame (SURVEY.md §8d / BASELINE.md §2 / DESIGN.md)
 LEVELS = [(752, 480), (627, 400), (522, 333), (435, 278), (363, 231), (302, 193), (252, 161), (210, 134)]
@@ -241,7 +241,7 @@ def run_ours(args):
     torch.cuda.set_device(local)
     dev = local
     nfr = args.frames
-    chunk = min(CHUNK, nfr)
+    chunk = min(args.chunk, nfr)
 
     frames = make_batch(nfr, seed0=rank * 100000)
     p = api.ORBxParams(ORB_KW["nfeatures"], ORB_KW["scale_factor"], ORB_KW["nlevels"], ORB_KW["ini_th"], ORB_KW["min_th"],
@@ -418,6 +418,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--frames", type=int, default=FRAMES_PER_GPU, help="frames per GPU per step")
+    ap.add_argument("--chunk", type=int, default=CHUNK, help="frames per launch set")
     ap.add_argument("--no-extras", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     args = ap.parse_args()

@@ -202,7 +202,7 @@ extern "C" int eorb_selftest_math(int device, int* mismatches) {
 // ================================================================================================ ORB
 struct eorb_orb {
     eorb_orb_params par{};
-    int device = 0, maxBatch = 1, sms = 148;
+    int device = 0, maxBatch = 1, pipeBatch = 1, sms = 148;   // pipeBatch: frames per slot of the host pipeline
     cudaStream_t ownStream = nullptr, stream = nullptr;
     int nlevels = 0, edge = 19;
     std::vector<float> scale, invScale, sigma2, invSigma2;
@@ -273,7 +273,7 @@ static void orbFreeBufs(eorb_orb::Bufs& b) {
 
 static int orbAllocBufs(eorb_orb* h, eorb_orb::Bufs& b, bool pipeline) {
     const OrbPlan& P = h->hp;
-    const size_t B = (size_t)h->maxBatch;
+    const size_t B = (size_t)(pipeline ? h->pipeBatch : h->maxBatch);
     const int nl = h->nlevels;
     CU(devAlloc(&b.d_img0, B * (size_t)h->pitch0 * P.H));
     CU(devAlloc(&b.d_pyr, B * (size_t)P.pyrBytesPerFrame));
@@ -546,6 +546,7 @@ extern "C" int eorb_orb_create(const eorb_orb_params* params, int device, int ma
     CU(cudaSetDevice(device));
     eorb_orb* h = new eorb_orb();
     h->par = *params; h->device = device; h->maxBatch = max_batch;
+    h->pipeBatch = std::min(max_batch, 128);   // measured on B200: H2D/compute/D2H overlap is best with 128-frame slots
     cudaDeviceProp prop;
     CU(cudaGetDeviceProperties(&prop, device));
     h->sms = prop.multiProcessorCount;
@@ -705,7 +706,8 @@ extern "C" int eorb_orb_extract_batch(eorb_orb* h, const uint8_t* imgs, int nfra
     CU(cudaSetDevice(h->device));
     int rc = orbBuildPlan(h, w, hgt);
     if (rc != EORB_OK) return rc;
-    const int B = h->maxBatch, icap = h->cap;
+    // up to maxBatch frames: one launch set on the main slab; more: pipeline slots of pipeBatch frames
+    const int B = nframes <= h->maxBatch && nframes <= 2 * h->pipeBatch ? h->maxBatch : h->pipeBatch, icap = h->cap;
     const int nchunks = (nframes + B - 1) / B;
     // more than one chunk: cycle through up to 3 pipeline slots (own streams) so copies and kernels overlap
     const int nslots = nchunks > 1 ? std::min(nchunks, 3) : 0;
