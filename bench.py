@@ -96,6 +96,15 @@ class ClockSampler:
         return {"sm_mhz": med, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons), "samples": len(self.samples)}
 
 
+def _traffic():
+    """DRAM bytes per frame of each stage from the committed `ncu --set full` capture (profiles/r01_traffic.json)"""
+    p = os.path.join(ROOT, "profiles", "r01_traffic.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return {k: v["dram_bytes_per_frame"] for k, v in d["stages"].items()}, d.get("source")
+    return {}, None
+
+
 def make_batch(n, seed0):
     from eorb_slam_b200 import synth
     return synth.make_frames(n, seed0=seed0, w=W, h=H, unique=min(UNIQUE_FRAMES, n))
@@ -293,6 +302,15 @@ def run_ours(args):
     value = world * nfr / (ms_step * 1e-3)
     nkp = int(d_n.sum().item())
 
+    # ---- PCIe H2D rate of the same pinned batch (the ceiling of the end-to-end number: 360 960 B per frame must cross it)
+    ev0 = torch.cuda.Event(enable_timing=True); ev1 = torch.cuda.Event(enable_timing=True)
+    d_frames.copy_(h_frames, non_blocking=True); torch.cuda.synchronize()
+    ev0.record()
+    for _ in range(2):
+        d_frames.copy_(h_frames, non_blocking=True)
+    ev1.record(); torch.cuda.synchronize()
+    h2d_gbs = 2 * nfr * W * H / (ev0.elapsed_time(ev1) * 1e-3) / 1e9
+
     # ---- end to end: pinned host frames -> C-ABI host call -> pinned host keypoints/descriptors
     h_kps = torch.empty(nfr * cap * 28, dtype=torch.uint8).pin_memory()
     h_desc = torch.empty(nfr * cap * 32, dtype=torch.uint8).pin_memory()
@@ -324,26 +342,32 @@ def run_ours(args):
     dom = max(stage_ms, key=stage_ms.get)
     frames_timed = nfr * args.steps
     per_stage = {}
+    traffic, traffic_src = _traffic()
     for k, v in stage_ms.items():
         e = {"ms_per_frame": v / frames_timed, "share": v / max(sum(stage_ms.values()), 1e-9), "launches": stage_launches[k]}
         if k in ALGO_BYTES:
             e["algo_bytes_per_frame"] = ALGO_BYTES[k]
             e["achieved_gbs"] = ALGO_BYTES[k] * frames_timed / (v * 1e-3) / 1e9 if v > 0 else None
             e["frac_of_hbm_peak"] = e["achieved_gbs"] / peak if v > 0 else None
+        if k in traffic:
+            e["ncu_dram_bytes_per_frame"] = traffic[k]
         per_stage[k] = e
     if dom in ALGO_BYTES:
         dom_bytes_launch = ALGO_BYTES[dom] * chunk / (stage_launches[dom] / (frames_timed / chunk))
         dom_ms_launch = stage_ms[dom] / stage_launches[dom]
         achieved = dom_bytes_launch / (dom_ms_launch * 1e-3) / 1e9
         roof = {"kernel": dom, "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": None, "peak_source": peak_src, "avg_launch_ms": dom_ms_launch,
-                "algo_bytes_per_launch": dom_bytes_launch}
+                "traffic": (traffic[dom] * chunk / (stage_launches[dom] / (frames_timed / chunk))) if dom in traffic else None,
+                "traffic_source": ("profiles/r01_traffic.json (%s), bytes per frame x frames per launch" % traffic_src) if dom in traffic else None,
+                "peak_source": peak_src, "avg_launch_ms": dom_ms_launch, "algo_bytes_per_launch": dom_bytes_launch,
+                "note": "byte-granular integer kernel: issue-bound on the ALU pipe, not on HBM (see profiles/ and DESIGN.md)"}
     else:
         # latency-bound stage (octree / index / orient+desc): no HBM roofline applies; report the best HBM-bound stage too
         hb = max((k for k in ALGO_BYTES), key=lambda k: stage_ms[k])
         achieved = ALGO_BYTES[hb] * frames_timed / (stage_ms[hb] * 1e-3) / 1e9
         roof = {"kernel": hb, "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": None, "peak_source": peak_src, "avg_launch_ms": stage_ms[hb] / max(stage_launches[hb], 1),
+                "traffic": (traffic[hb] * chunk / (stage_launches[hb] / (frames_timed / chunk))) if hb in traffic else None,
+                "peak_source": peak_src, "avg_launch_ms": stage_ms[hb] / max(stage_launches[hb], 1),
                 "note": "largest share of the step is '%s' (latency-bound, no HBM roofline); this entry is the largest HBM-bound kernel" % dom}
 
     extra = {}
@@ -380,7 +404,8 @@ def run_ours(args):
                        "partition": "by frame, no collective"},
             "clocks": clk,
             "e2e": {"value": e2e_value, "unit": "frames/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                    "ms_per_step": e2e_ms, "call": "eorb_orb_extract_batch (pinned host buffers)"},
+                    "ms_per_step": e2e_ms, "call": "eorb_orb_extract_batch (pinned host buffers)",
+                    "pcie_h2d_gbs_measured": h2d_gbs, "pcie_bound_frames_per_s": world * h2d_gbs * 1e9 / (W * H)},
             "gpu_launches": int(launches),
             "roofline": roof,
             "stages": per_stage,

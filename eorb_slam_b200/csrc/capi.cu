@@ -379,7 +379,7 @@ static int orbBuildPlan(eorb_orb* h, int W, int H) {
     std::vector<short4> xtab;
     std::vector<int4> ytab;   // {sy0, sy1, b0 << 16, b1 << 16}
     long long pyrOff = 0, blurOff = 0;
-    int slot = 0, sel = 0, rowBlocks = 0, maxCW = 7, maxCH = 7, octSmem = 0;
+    int slot = 0, sel = 0, rowBlocks = 0, maxCW = 7, maxCH = 7, octSmem = 0, maxTasks = 1;
     for (int l = 0; l < nl; l++) {
         LevelPlan& lp = P.lv[l];
         lp.w = rne((float)W * h->invScale[l]);
@@ -417,6 +417,16 @@ static int orbBuildPlan(eorb_orb* h, int W, int H) {
                     const int cw = c.w - 6, ch = c.h - 6;
                     c.slotCap = (cw > 0 && ch > 0) ? ((cw + 1) / 2) * ((ch + 1) / 2) : 0;   // strict 3x3 maxima cannot touch
                     c.slotOff = slot; slot += c.slotCap;
+                    {
+                        const int aoff = iniX & 15, p0 = (aoff + 3) >> 3;
+                        const int np = std::max(((aoff + c.w - 4) >> 3) - p0 + 1, 1);
+                        const int lastBits = aoff + c.w - 3 - 8 * (p0 + np - 1);
+                        c.aoff = (unsigned char)aoff; c.p0 = (unsigned char)p0; c.np = (unsigned char)np; c.rps = (unsigned char)(32 / np);
+                        c.firstMask = (unsigned char)((0xffu << ((aoff + 3) & 7)) & 0xffu);
+                        c.lastMask = (unsigned char)(lastBits >= 8 ? 0xffu : (lastBits <= 0 ? 0u : ((1u << lastBits) - 1u)));
+                        c.rcpNpM1 = (unsigned short)((65536 + np - 1) / np - 1);
+                        maxTasks = std::max(maxTasks, np * std::max(ch, 0));
+                    }
                     maxCW = std::max(maxCW, (int)c.w); maxCH = std::max(maxCH, (int)c.h);
                     h->cells.push_back(c);
                 }
@@ -468,13 +478,14 @@ static int orbBuildPlan(eorb_orb* h, int W, int H) {
     P.pyrBytesPerFrame = std::max(pyrOff, 16ll);
     P.blurBytesPerFrame = blurOff;
     P.blurTasksTotal = rowBlocks;
-    // FAST smem region of one warp: [TMA tile BW x BH][score map (ch+2) x MS][survivor list u16][mbarrier]
+    // FAST smem region of one warp: [TMA tile BW x BH][score map (ch+2) x MS][survivor list u16][flagged groups u32][mbarrier]
     P.cellTileStride = roundUp(maxCW + 15, 16);   // the TMA box starts at x0 & ~15 (16-byte inner-coordinate rule)
     P.cellTileRows = maxCH;
     P.cellMapStride = roundUp(maxCW - 6 + 2, 4);
     P.cellMapOff = roundUp(P.cellTileRows * P.cellTileStride, 16);
     P.cellListOff = P.cellMapOff + roundUp((maxCH - 6 + 2) * P.cellMapStride, 16);
-    P.cellBarOff = roundUp(P.cellListOff + (maxCW - 6) * (maxCH - 6) * 2, 16);
+    P.cellTaskOff = roundUp(P.cellListOff + (maxCW - 6) * (maxCH - 6) * 2, 16);
+    P.cellBarOff = roundUp(P.cellTaskOff + maxTasks * 4, 16);
     P.cellSmemPerWarp = roundUp(P.cellBarOff + 16, 128);
     if (P.cellTileStride > 256 || P.cellTileRows > 256) return fail(EORB_ERR_ARG, "FAST cell %dx%d exceeds the TMA box limit", maxCW, maxCH);
     P.octSmemBytes = octSmem;

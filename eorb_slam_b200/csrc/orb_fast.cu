@@ -66,25 +66,33 @@ __device__ __forceinline__ unsigned fast_compass4(unsigned C, unsigned N, unsign
     return ns & ew & 0x80808080u;
 }
 
-__global__ void __launch_bounds__(EORB_FAST_WARPS * 32) fast_cells_kernel(OrbArgs a, const __grid_constant__ CUtensorMap tm0) {
+// plan constants of the kernel, passed by value (constant bank) instead of being re-read from the plan in HBM
+struct FastConst {
+    int nCells, slotsPerFrame;
+    int smemPerWarp, mapOff, listOff, taskOff, barOff;
+    int TS, tileRows, MS;
+    int tA, tB;
+};
+
+__global__ void __launch_bounds__(EORB_FAST_WARPS * 32) fast_cells_kernel(OrbArgs a, const __grid_constant__ CUtensorMap tm0, FastConst K0) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
-    const OrbPlan& P = *a.plan;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int cell = blockIdx.x * EORB_FAST_WARPS + warp;
     const int f = blockIdx.y;
-    if (cell >= P.nCells) return;
+    if (cell >= K0.nCells) return;
     const CellPlan c = a.cells[cell];
-    unsigned char* ws = smem_raw + (size_t)warp * P.cellSmemPerWarp;
+    unsigned char* ws = smem_raw + (size_t)warp * K0.smemPerWarp;
     const uint8_t* tile = ws;
-    uint8_t* smap = ws + P.cellMapOff;
-    uint16_t* list = reinterpret_cast<uint16_t*>(ws + P.cellListOff);
-    const unsigned bar = smem_u32(ws + P.cellBarOff);
-    const int TS = P.cellTileStride, MS = P.cellMapStride;
+    uint8_t* smap = ws + K0.mapOff;
+    uint16_t* list = reinterpret_cast<uint16_t*>(ws + K0.listOff);
+    uint32_t* tlist = reinterpret_cast<uint32_t*>(ws + K0.taskOff);
+    const unsigned bar = smem_u32(ws + K0.barOff);
+    const int TS = K0.TS, MS = K0.MS;
     const unsigned FULL = 0xffffffffu;
     const unsigned lt = (1u << lane) - 1u;
 
-    uint32_t* slots = a.cand + (size_t)f * P.slotsPerFrame + c.slotOff;
-    uint16_t* countOut = a.cellCount + (size_t)f * P.nCells + cell;
+    uint32_t* slots = a.cand + (size_t)f * K0.slotsPerFrame + c.slotOff;
+    uint16_t* countOut = a.cellCount + (size_t)f * K0.nCells + cell;
     const int w = c.w, h = c.h;
     const int cw = w - 6, ch = h - 6;
     if (cw <= 0 || ch <= 0) { if (lane == 0) *countOut = 0; return; }
@@ -94,7 +102,7 @@ __global__ void __launch_bounds__(EORB_FAST_WARPS * 32) fast_cells_kernel(OrbArg
         mbar_init(bar, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-        mbar_expect_tx(bar, (unsigned)(TS * P.cellTileRows));
+        mbar_expect_tx(bar, (unsigned)(TS * K0.tileRows));
         const CUtensorMap* tm = c.level == 0 ? &tm0 : a.tmaps + c.level;
         tma_load_3d(smem_u32(tile), tm, c.x0 & ~15, c.y0, f, bar);
     }
@@ -105,21 +113,16 @@ __global__ void __launch_bounds__(EORB_FAST_WARPS * 32) fast_cells_kernel(OrbArg
     __syncwarp();
     mbar_wait(bar, 0);
 
-    const int tA = min(max(P.iniTh, 0), 255), tB = min(max(P.minTh, 0), 255);
+    const int tA = K0.tA, tB = K0.tB;
     // interior = tile columns [aoff + 3, aoff + w - 3); phase 1 walks it in aligned groups of 8 columns.
-    // Fixed lane -> (row-in-step, group) assignment: a step covers rps rows x np groups in row-major lane order.
-    const int aoff = c.x0 & 15;
-    const int p0 = (aoff + 3) >> 3;
-    const int np = ((aoff + w - 4) >> 3) - p0 + 1;                 // 1..10 groups per interior row
-    const int rps = 32 / np;                                      // rows per step
-    const int lr = lane / np, lp = lane - lr * np;
+    // Fixed lane -> (row-in-step, group) assignment: a step covers rps rows x np groups in row-major lane order
+    // (the walk constants come precomputed with the cell).
+    const int aoff = c.aoff, np = c.np, rps = c.rps;
+    const int lr = (lane * ((int)c.rcpNpM1 + 1)) >> 16, lp = lane - lr * np;
     const bool laneUsed = lr < rps;
-    const unsigned firstMask = (0xffu << ((aoff + 3) & 7)) & 0xffu;
-    const int lastBits = aoff + w - 3 - 8 * (p0 + np - 1);
-    const unsigned lastMask = lastBits >= 8 ? 0xffu : ((1u << lastBits) - 1u);
-    unsigned vm = lp == 0 ? firstMask : 0xffu;                    // interior columns of this lane's group
-    if (lp == np - 1) vm &= lastMask;
-    const int colBase = (p0 + lp) * 8;
+    unsigned vm = lp == 0 ? (unsigned)c.firstMask : 0xffu;        // interior columns of this lane's group
+    if (lp == np - 1) vm &= (unsigned)c.lastMask;
+    const int colBase = ((int)c.p0 + lp) * 8;
     const uint8_t* qLane = tile + (lr + 3) * TS + colBase;
 
     int cnt = 0;
@@ -127,24 +130,35 @@ __global__ void __launch_bounds__(EORB_FAST_WARPS * 32) fast_cells_kernel(OrbArg
         const int t = pass ? tB : tA;
         const unsigned K = (unsigned)(127 - min(t, 127)) * 0x01010101u;
 
-        // ---- phase 1: packed compass test + ordered compaction
-        int nsurv = 0;
-        const uint8_t* q = qLane;
-        for (int rbase = 0; rbase < ch; rbase += rps, q += rps * TS) {
-            const int rr = rbase + lr;
-            unsigned m8 = 0;
-            if (laneUsed && rr < ch) {
-                const uint2 C = *reinterpret_cast<const uint2*>(q);
-                const uint2 N = *reinterpret_cast<const uint2*>(q + 3 * TS);
-                const uint2 S = *reinterpret_cast<const uint2*>(q - 3 * TS);
-                const unsigned L = *reinterpret_cast<const unsigned*>(q - 4);
-                const unsigned R = *reinterpret_cast<const unsigned*>(q + 8);
-                const unsigned f0 = fast_compass4(C.x, N.x, S.x, __byte_perm(C.x, C.y, 0x6543), __byte_perm(L, C.x, 0x4321), K);
-                const unsigned f1 = fast_compass4(C.y, N.y, S.y, __byte_perm(C.y, R, 0x6543), __byte_perm(C.x, C.y, 0x4321), K);
-                // gather the four bit-7 flags of each word into a nibble (multiplier places bits 7,15,23,31 at 28..31)
-                m8 = (((f0 * 0x00204081u) >> 28) | (((f1 * 0x00204081u) >> 28) << 4)) & vm;
+        // ---- phase 1a: packed compass test; groups with at least one flagged pixel go to the group list
+        int ntask = 0;
+        {
+            const uint8_t* q = qLane;
+            for (int rbase = 0; rbase < ch; rbase += rps, q += rps * TS) {
+                const int rr = rbase + lr;
+                unsigned m8 = 0;
+                if (laneUsed && rr < ch) {
+                    const uint2 C = *reinterpret_cast<const uint2*>(q);
+                    const uint2 N = *reinterpret_cast<const uint2*>(q + 3 * TS);
+                    const uint2 S = *reinterpret_cast<const uint2*>(q - 3 * TS);
+                    const unsigned L = *reinterpret_cast<const unsigned*>(q - 4);
+                    const unsigned R = *reinterpret_cast<const unsigned*>(q + 8);
+                    const unsigned f0 = fast_compass4(C.x, N.x, S.x, __byte_perm(C.x, C.y, 0x6543), __byte_perm(L, C.x, 0x4321), K);
+                    const unsigned f1 = fast_compass4(C.y, N.y, S.y, __byte_perm(C.y, R, 0x6543), __byte_perm(C.x, C.y, 0x4321), K);
+                    // gather the four bit-7 flags of each word into a nibble (multiplier places bits 7,15,23,31 at 28..31)
+                    m8 = (((f0 * 0x00204081u) >> 28) | (((f1 * 0x00204081u) >> 28) << 4)) & vm;
+                }
+                const unsigned bal = __ballot_sync(FULL, m8 != 0);
+                if (m8 != 0) tlist[ntask + __popc(bal & lt)] = (m8 << 16) | ((unsigned)rr << 7) | (unsigned)colBase;
+                ntask += __popc(bal);
             }
-            if (__ballot_sync(FULL, m8 != 0) == 0) continue;
+        }
+        __syncwarp();
+        // ---- phase 1b: expand the flagged groups into the pixel list (row-major order is preserved)
+        int nsurv = 0;
+        for (int base = 0; base < ntask; base += 32) {
+            const unsigned e = base + lane < ntask ? tlist[base + lane] : 0u;
+            const unsigned m8 = e >> 16, code = e & 0xffffu;
             const int k = __popc(m8);
             int incl = k;
 #pragma unroll
@@ -154,7 +168,6 @@ __global__ void __launch_bounds__(EORB_FAST_WARPS * 32) fast_cells_kernel(OrbArg
             }
             uint16_t* lp16 = list + nsurv + incl - k;
             nsurv += __shfl_sync(FULL, incl, 31);
-            const unsigned code = ((unsigned)rr << 7) | (unsigned)colBase;
 #pragma unroll
             for (int j = 0; j < 8; j++)
                 if (m8 & (1u << j)) *lp16++ = (uint16_t)(code + j);
@@ -213,7 +226,13 @@ __global__ void __launch_bounds__(EORB_FAST_WARPS * 32) fast_cells_kernel(OrbArg
 
 cudaError_t launch_fast_cells(const OrbArgs& a, const OrbPlan& hp, int nframes, const CUtensorMap& tm0, cudaStream_t st) {
     dim3 grd((hp.nCells + EORB_FAST_WARPS - 1) / EORB_FAST_WARPS, nframes);
-    fast_cells_kernel<<<grd, EORB_FAST_WARPS * 32, (size_t)hp.cellSmemPerWarp * EORB_FAST_WARPS, st>>>(a, tm0);
+    FastConst k;
+    k.nCells = hp.nCells; k.slotsPerFrame = hp.slotsPerFrame;
+    k.smemPerWarp = hp.cellSmemPerWarp; k.mapOff = hp.cellMapOff; k.listOff = hp.cellListOff; k.taskOff = hp.cellTaskOff; k.barOff = hp.cellBarOff;
+    k.TS = hp.cellTileStride; k.tileRows = hp.cellTileRows; k.MS = hp.cellMapStride;
+    k.tA = hp.iniTh < 0 ? 0 : (hp.iniTh > 255 ? 255 : hp.iniTh);
+    k.tB = hp.minTh < 0 ? 0 : (hp.minTh > 255 ? 255 : hp.minTh);
+    fast_cells_kernel<<<grd, EORB_FAST_WARPS * 32, (size_t)hp.cellSmemPerWarp * EORB_FAST_WARPS, st>>>(a, tm0, k);
     return cudaGetLastError();
 }
 

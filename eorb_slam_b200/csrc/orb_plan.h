@@ -37,6 +37,11 @@ struct CellPlan {
     int slotOff;                   // first candidate slot of this cell (relative to the frame's slab)
     short ox, oy;                  // j*wCell, i*hCell: added to ROI coordinates (ORBextractor.cc:871-872)
     int slotCap;
+    // FAST phase-1 walk, precomputed on the host: the TMA tile starts at column x0 & ~15, the interior is tile
+    // columns [aoff+3, aoff+w-3), walked in np aligned groups of 8 columns starting at group p0, rps rows per step
+    unsigned char aoff, p0, np, rps;
+    unsigned char firstMask, lastMask;   // interior columns inside the first / last group
+    unsigned short rcpNpM1;        // ceil(65536 / np) - 1: lane / np == (lane * (rcpNpM1 + 1)) >> 16 for lane < 32
 };
 
 struct OrbPlan {
@@ -51,7 +56,8 @@ struct OrbPlan {
     int cellTileRows;              // FAST: TMA box height (largest cell ROI height)
     int cellMapStride;             // FAST: score-map row stride (multiple of 4)
     int cellMapOff;                // FAST: byte offset of the score map inside a warp's smem region
-    int cellListOff;               // FAST: byte offset of the survivor list
+    int cellListOff;               // FAST: byte offset of the survivor (pixel) list
+    int cellTaskOff;               // FAST: byte offset of the flagged-group list of phase 1
     int cellBarOff;                // FAST: byte offset of the warp's mbarrier
     int cellSmemPerWarp;           // bytes (multiple of 128: TMA destinations are 128-byte aligned)
     int octSmemBytes;              // max over levels

@@ -1,0 +1,23 @@
+#!/usr/bin/env python3
+"""DRAM traffic per frame of each ORB stage from one `ncu --set full` capture (dram__bytes_read.sum + dram__bytes_write.sum).
+usage: ncu_traffic.py rep frames_per_launch out.json"""
+import csv, json, subprocess, sys
+rep, frames, outp = sys.argv[1], int(sys.argv[2]), sys.argv[3]
+out = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+rows = list(csv.reader(out.splitlines()))
+hdr, units = rows[0], rows[1]
+kn = hdr.index("Kernel Name"); ir = hdr.index("dram__bytes_read.sum"); iw = hdr.index("dram__bytes_write.sum"); it = hdr.index("gpu__time_duration.sum")
+scale = {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+stage_of = {"pyr_resize_kernel": "pyramid", "fast_cells_kernel": "fast", "octree_kernel": "octree", "orb_index_kernel": "index", "blur_kernel": "blur",
+            "orient_desc_kernel": "orient_desc"}
+acc = {}
+for r in rows[2:]:
+    name = r[kn].split("(")[0].split("::")[-1]
+    st = stage_of.get(name)
+    if not st: continue
+    b = float(r[ir]) * scale[units[ir]] + float(r[iw]) * scale[units[iw]]
+    e = acc.setdefault(st, {"dram_bytes_per_frame": 0.0, "ncu_us_per_frame": 0.0, "launches": 0})
+    e["dram_bytes_per_frame"] += b / frames; e["ncu_us_per_frame"] += float(r[it]) / frames; e["launches"] += 1
+json.dump({"source": rep.split("/")[-1], "frames_per_launch": frames, "note": "ncu --set full --clock-control none, cold-cache serialised replays; one launch set",
+           "stages": acc}, open(outp, "w"), indent=1)
+print(json.dumps(acc, indent=1))
