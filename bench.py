@@ -175,7 +175,8 @@ def bench_events(api, torch, dev, steps, warmup):
            "atomic_adds_per_s": nev * 49 / (ms * 1e-3), "gpu_launches": launches,
            "roofline": {"bound": "hbm", "achieved": algo_bytes / (ms * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
                         "frac": algo_bytes / (ms * 1e-3) / 1e9 / peak, "traffic": None,
-                        "note": "splat is bounded by L2 fp32 reduction throughput, not HBM; see atomic_adds_per_s"}}
+                        "note": "7x7 splat accumulates in shared memory (int32 fixed point, native ATOMS.ADD), frame written once; "
+                                "bounded by instruction issue + smem atomics, not HBM; see atomic_adds_per_s"}}
     cv.set_stream(None)
     return out
 

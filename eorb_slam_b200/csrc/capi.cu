@@ -1214,12 +1214,8 @@ extern "C" int eorb_ev_accumulate_batch_device(eorb_evconv* c, const eorb_event*
         w.angle = 0; w.axis[0] = 1; w.axis[1] = w.axis[2] = 0; w.t[0] = w.t[1] = w.t[2] = 0;
         if (p->mode == EORB_EV_SE3) angleAxisFromPose(poses ? poses + 16 * (size_t)i : p->Tcw, w);
     }
-    const int npix = p->width * p->height;
     CU(cudaMemcpyAsync(c->d_wins, c->h_wins.data(), (size_t)nwin * sizeof(EvWindow), cudaMemcpyHostToDevice, c->stream));
-    CU(cudaMemsetAsync(d_img_f32, 0, (size_t)nwin * npix * sizeof(float), c->stream));
-    c->launches++;   // memset node
-    CU(launch_ev_splat(d_evs, c->d_wins, nwin, maxEv, k, d_img_f32, c->stream, &c->launches));
-    CU(launch_ev_normalize(d_img_f32, nwin, npix, p->normalize, c->d_minmax, d_img_u8, c->stream, &c->launches));
+    CU(launch_ev_frames(d_evs, c->d_wins, nwin, maxEv, k, p->normalize, d_img_f32, c->d_minmax, d_img_u8, c->stream, &c->launches));
     return EORB_OK;
 }
 

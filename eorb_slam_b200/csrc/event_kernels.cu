@@ -43,21 +43,9 @@ __device__ __forceinline__ void splat_taps(float* __restrict__ im, int W, int H,
     }
 }
 
-__global__ void __launch_bounds__(256) ev_splat_gauss_kernel(const eorb_event* __restrict__ evs,
-                                                             const EvWindow* __restrict__ wins, EvConst c,
-                                                             float* __restrict__ img, int lpe) {
-    const EvWindow w = wins[blockIdx.y];
-    const long long nev = w.end - w.begin;
-    const int perBlock = blockDim.x / lpe;
-    const long long e = (long long)blockIdx.x * perBlock + threadIdx.x / lpe;
-    const int sub = threadIdx.x % lpe;
-    if (e >= nev) return;
-    const eorb_event* evp = evs + w.begin + e;
-    const double ts = evp->ts;
-    const float ex = evp->x, ey = evp->y;
-    const bool p = evp->p != 0;
-    const float polSign = (c.pol && !p) ? -1.0f : 1.0f;
-    float X = ex, Y = ey;
+// per-event warp of the SE3 (:279-360) and SE2 (:362-448) overloads; X, Y come in as the event position
+__device__ __forceinline__ void ev_warp_point(const eorb_event* __restrict__ evs, const EvWindow& w, const EvConst& c, double ts, float ex,
+                                              float ey, float& X, float& Y) {
     if (c.mode == EORB_EV_SE3) {
         const double t1 = evs[w.end - 1].ts, DT = t1 - evs[w.begin].ts;
         const double rate = DT > 0 ? (t1 - ts) * (1.0 / DT) : 0.0;
@@ -99,8 +87,139 @@ __global__ void __launch_bounds__(256) ev_splat_gauss_kernel(const eorb_event* _
         X = __fadd_rn(__fdiv_rn(__fmul_rn(c.fx, xp), 1.f), c.cx);
         Y = __fadd_rn(__fdiv_rn(__fmul_rn(c.fy, yp), 1.f), c.cy);
     }
+}
+
+__global__ void __launch_bounds__(256) ev_splat_gauss_kernel(const eorb_event* __restrict__ evs,
+                                                             const EvWindow* __restrict__ wins, EvConst c,
+                                                             float* __restrict__ img, int lpe) {
+    const EvWindow w = wins[blockIdx.y];
+    const long long nev = w.end - w.begin;
+    const int perBlock = blockDim.x / lpe;
+    const long long e = (long long)blockIdx.x * perBlock + threadIdx.x / lpe;
+    const int sub = threadIdx.x % lpe;
+    if (e >= nev) return;
+    const eorb_event* evp = evs + w.begin + e;
+    const double ts = evp->ts;
+    const float ex = evp->x, ey = evp->y;
+    const bool p = evp->p != 0;
+    const float polSign = (c.pol && !p) ? -1.0f : 1.0f;
+    float X = ex, Y = ey;
+    ev_warp_point(evs, w, c, ts, ex, ey, X, Y);
     float* im = img + (size_t)blockIdx.y * (size_t)c.width * c.height;
     splat_taps(im, c.width, c.height, X, Y, polSign, c, sub, lpe);
+}
+
+// ---- shared-memory event frames (sigma with ceil(3*sigma) == 3, i.e. the 7x7 splat every live caller uses) ----------
+// One block per (window, row band); the band of the frame lives in shared memory as int32 fixed point, so a tap is
+// a NATIVE shared-memory atomic (ATOMS.ADD; fp32 shared atomics are CAS loops) and the sum is order independent.
+// Scale 2^k with k = min(24, floor(log2(2^31 / (events * peakTap)))): no pixel can overflow whatever the event
+// distribution is.  One thread per event: warp geometry once, the Gaussian is evaluated separably
+// (7 + 7 expf instead of 49; exp(-(dx^2+dy^2)/2s^2) = exp(-dx^2/2s^2) * exp(-dy^2/2s^2), a few ulp from the
+// reference's single expf, far inside the 1e-4*peak parity tolerance).  The band is written out once as fp32
+// (coalesced) and, when the frame is a single band, min/max + the u8 normalisation are fused into the same block.
+#define EV_SMEM_HALF 3
+#define EV_SMEM_THREADS 1024
+
+__device__ __forceinline__ void ev_norm_coeffs(int normMode, float mn, float mx, float& alpha, float& beta) {
+    if (normMode == EORB_NORM_RUNNING) {
+        // running min starts at 0, running max at -1e6 (EventConversion.cc:219-220)
+        mn = fminf(mn, 0.0f);
+        if (!(mx > mn)) { alpha = 0.f; beta = 0.f; }
+        else { alpha = __fdiv_rn(255.f, __fsub_rn(mx, mn)); beta = __fmul_rn(-mn, alpha); }
+    } else {
+        const double d = (double)mx - (double)mn;
+        const double scale = 255.0 * (d > 2.220446049250313e-16 ? 1.0 / d : 0.0);
+        alpha = (float)scale; beta = (float)(0.0 - (double)mn * scale);
+    }
+}
+
+__global__ void __launch_bounds__(EV_SMEM_THREADS) ev_frame_smem_kernel(const eorb_event* __restrict__ evs, const EvWindow* __restrict__ wins,
+                                                                        EvConst c, int bandRows, int fuseNorm, int normMode,
+                                                                        float* __restrict__ img, float* __restrict__ minmax,
+                                                                        uint8_t* __restrict__ u8) {
+    extern __shared__ __align__(16) int s_acc[];
+    __shared__ float s_mn[32], s_mx[32];
+    const EvWindow w = wins[blockIdx.y];
+    const int W = c.width, H = c.height;
+    const int r0 = blockIdx.x * bandRows, r1 = min(r0 + bandRows, H);
+    const int nrow = r1 - r0, npx = nrow * W;
+    const int tid = threadIdx.x;
+    for (int i = tid; i < npx; i += EV_SMEM_THREADS) s_acc[i] = 0;
+    const long long nev = w.end - w.begin;
+    // fixed-point scale: |pixel sum| <= nev * peakTap, peakTap = 1 / (2*pi*sigma^2)
+    const float peakTap = __fdiv_rn(1.0f, c.norm);
+    int k = (int)floorf(log2f(2147483648.0f / ((float)nev * peakTap + 1.0f)));
+    k = min(max(k, 0), 24);
+    const float scale = exp2f((float)k), invScale = exp2f(-(float)k);
+    const float invDen = __fdiv_rn(1.0f, __fmul_rn(2.0f, c.sig2));
+    __syncthreads();
+
+    for (long long e = tid; e < nev; e += EV_SMEM_THREADS) {
+        const eorb_event* evp = evs + w.begin + e;
+        const double ts = evp->ts;
+        const float ex = evp->x, ey = evp->y;
+        const float polSign = (c.pol && evp->p == 0) ? -1.0f : 1.0f;
+        float X = ex, Y = ey;
+        ev_warp_point(evs, w, c, ts, ex, ey, X, Y);
+        const float fxi = floorf(X), fyi = floorf(Y);
+        if (!(fxi >= -8.f && fxi <= (float)(W + 8) && fyi >= -8.f && fyi <= (float)(H + 8))) continue;   // also NaN / inf
+        const int xi = (int)fxi, yi = (int)fyi;
+        if (yi + EV_SMEM_HALF < r0 || yi - EV_SMEM_HALF >= r1) continue;
+        const float xr = __fsub_rn(X, fxi), yr = __fsub_rn(Y, fyi);
+        float gx[2 * EV_SMEM_HALF + 1], gy[2 * EV_SMEM_HALF + 1];
+        const float amp = polSign * peakTap * scale;
+#pragma unroll
+        for (int i = -EV_SMEM_HALF; i <= EV_SMEM_HALF; i++) {
+            const float dx = __fsub_rn((float)i, xr), dy = __fsub_rn((float)i, yr);
+            gx[i + EV_SMEM_HALF] = expf(-(dx * dx) * invDen) * amp;
+            gy[i + EV_SMEM_HALF] = expf(-(dy * dy) * invDen);
+        }
+#pragma unroll
+        for (int j = -EV_SMEM_HALF; j <= EV_SMEM_HALF; j++) {
+            const int yn = yi + j;
+            if (yn < r0 || yn >= r1) continue;
+            int* row = s_acc + (yn - r0) * W;
+#pragma unroll
+            for (int i = -EV_SMEM_HALF; i <= EV_SMEM_HALF; i++) {
+                const int xn = xi + i;
+                if (xn >= 0 && xn < W) atomicAdd(row + xn, __float2int_rn(gx[i + EV_SMEM_HALF] * gy[j + EV_SMEM_HALF]));
+            }
+        }
+    }
+    __syncthreads();
+
+    // ---- write the band out as fp32, track min / max
+    float* im = img + (size_t)blockIdx.y * (size_t)W * H + (size_t)r0 * W;
+    float mn = 3.4e38f, mx = -3.4e38f;
+    for (int i = tid; i < npx; i += EV_SMEM_THREADS) {
+        const float v = (float)s_acc[i] * invScale;
+        im[i] = v;
+        mn = fminf(mn, v); mx = fmaxf(mx, v);
+    }
+    if (!fuseNorm) return;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        mn = fminf(mn, __shfl_xor_sync(0xffffffffu, mn, o));
+        mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    }
+    if ((tid & 31) == 0) { s_mn[tid >> 5] = mn; s_mx[tid >> 5] = mx; }
+    __syncthreads();
+    mn = s_mn[tid & 31]; mx = s_mx[tid & 31];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        mn = fminf(mn, __shfl_xor_sync(0xffffffffu, mn, o));
+        mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    }
+    if (tid == 0) { minmax[2 * blockIdx.y] = mn; minmax[2 * blockIdx.y + 1] = mx; }
+    if (normMode == EORB_NORM_NONE || !u8) return;
+    float alpha, beta;
+    ev_norm_coeffs(normMode, mn, mx, alpha, beta);
+    uint8_t* o8 = u8 + (size_t)blockIdx.y * (size_t)W * H;
+    for (int i = tid; i < npx; i += EV_SMEM_THREADS) {
+        const float v = (float)s_acc[i] * invScale;
+        const int r = __float2int_rn(__fadd_rn(__fmul_rn(v, alpha), beta));
+        o8[i] = (uint8_t)min(max(r, 0), 255);
+    }
 }
 
 __global__ void __launch_bounds__(256) ev_splat_nearest_kernel(const eorb_event* __restrict__ evs,
@@ -149,18 +268,8 @@ __global__ void __launch_bounds__(256) ev_normalize_kernel(const float* __restri
     const int win = blockIdx.y;
     const int i0 = (blockIdx.x * blockDim.x + threadIdx.x) * 4;
     if (i0 >= npix) return;
-    float mn = minmax[2 * win], mx = minmax[2 * win + 1];
     float alpha, beta;
-    if (normMode == EORB_NORM_RUNNING) {
-        // running min starts at 0, running max at -1e6 (EventConversion.cc:219-220)
-        mn = fminf(mn, 0.0f);
-        if (!(mx > mn)) { alpha = 0.f; beta = 0.f; }
-        else { alpha = __fdiv_rn(255.f, __fsub_rn(mx, mn)); beta = __fmul_rn(-mn, alpha); }
-    } else {
-        const double d = (double)mx - (double)mn;
-        const double scale = 255.0 * (d > 2.220446049250313e-16 ? 1.0 / d : 0.0);
-        alpha = (float)scale; beta = (float)(0.0 - (double)mn * scale);
-    }
+    ev_norm_coeffs(normMode, minmax[2 * win], minmax[2 * win + 1], alpha, beta);
     const float* im = img + (size_t)win * npix;
     uint8_t* o = out + (size_t)win * npix;
 #pragma unroll
@@ -188,6 +297,36 @@ cudaError_t launch_ev_splat(const eorb_event* d_evs, const EvWindow* d_wins, int
     }
     (*launches)++;
     return cudaGetLastError();
+}
+
+// whole path: zero + splat + min/max + normalise.  7x7 Gaussian windows take the shared-memory kernel (which also
+// zeroes and, for single-band frames, normalises); everything else the L2-reduction kernels.
+cudaError_t launch_ev_frames(const eorb_event* d_evs, const EvWindow* d_wins, int nwin, long long maxEventsPerWindow, const EvConst& c,
+                             int normMode, float* d_img, float* d_minmax, uint8_t* d_u8, cudaStream_t st, long long* launches) {
+    if (nwin <= 0) return cudaSuccess;
+    const int npix = c.width * c.height;
+    const size_t smemBudget = 200 * 1024;
+    if (c.mode != EORB_EV_NEAREST && c.half == EV_SMEM_HALF && maxEventsPerWindow > 0 && (size_t)c.width * 4 * 8 <= smemBudget) {
+        const int bands = (int)(((size_t)npix * 4 + smemBudget - 1) / smemBudget);
+        const int bandRows = (c.height + bands - 1) / bands;
+        const size_t smem = (size_t)bandRows * c.width * 4;
+        cudaError_t ea = cudaFuncSetAttribute(ev_frame_smem_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemBudget + 4096);
+        if (ea != cudaSuccess) return ea;
+        const int nb = (c.height + bandRows - 1) / bandRows;
+        const int fuse = nb == 1 ? 1 : 0;
+        dim3 grd(nb, nwin);
+        ev_frame_smem_kernel<<<grd, EV_SMEM_THREADS, smem, st>>>(d_evs, d_wins, c, bandRows, fuse, normMode, d_img, d_minmax, d_u8);
+        (*launches)++;
+        cudaError_t e = cudaGetLastError();
+        if (e != cudaSuccess || fuse) return e;
+        return launch_ev_normalize(d_img, nwin, npix, normMode, d_minmax, d_u8, st, launches);
+    }
+    cudaError_t e = cudaMemsetAsync(d_img, 0, (size_t)nwin * npix * sizeof(float), st);
+    if (e != cudaSuccess) return e;
+    (*launches)++;   // memset node
+    e = launch_ev_splat(d_evs, d_wins, nwin, maxEventsPerWindow, c, d_img, st, launches);
+    if (e != cudaSuccess) return e;
+    return launch_ev_normalize(d_img, nwin, npix, normMode, d_minmax, d_u8, st, launches);
 }
 
 cudaError_t launch_ev_normalize(const float* d_img, int nwin, int npix, int normMode, float* d_minmax, uint8_t* d_u8,
