@@ -105,6 +105,19 @@ def _traffic():
     return {}, None
 
 
+def _bind_to_gpu_cpus(index):
+    """one process per GPU: run on the CPUs NVML reports as local to this GPU so that the pinned batch and the
+    library's pinned staging land on the GPU's NUMA node (H2D/D2H do not cross the socket interconnect)"""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(index)
+        pynvml.nvmlDeviceSetCpuAffinity(h)
+        return sorted(os.sched_getaffinity(0))[:4]
+    except Exception as e:   # best effort: affinity is an optimisation, not a requirement
+        return "unbound (%s)" % type(e).__name__
+
+
 def make_batch(n, seed0):
     from eorb_slam_b200 import synth
     return synth.make_frames(n, seed0=seed0, w=W, h=H, unique=min(UNIQUE_FRAMES, n))
@@ -250,6 +263,7 @@ def run_ours(args):
         raise SystemExit("bench.py: no CUDA device; eorb_slam_b200 has no CPU fallback")
     torch.cuda.set_device(local)
     dev = local
+    numa = _bind_to_gpu_cpus(local)      # pinned host buffers are first-touched on the GPU's NUMA node
     nfr = args.frames
     chunk = min(args.chunk, nfr)
 
@@ -402,7 +416,7 @@ def run_ours(args):
             "config": {"workload": "configs[2]: ORB 752x480 nFeatures=1000 8 levels 1.2 FAST 20/7, %d frames per GPU per step" % nfr,
                        "frames_per_gpu": nfr, "chunk_frames_per_launch_set": chunk, "keypoints_per_frame": nkp / nfr,
                        "l2_policy": "inputs larger than L2 (%.0f MB of frames per step per GPU)" % (nfr * W * H / 1e6),
-                       "partition": "by frame, no collective"},
+                       "partition": "by frame, no collective", "host_cpu_affinity_first4": numa},
             "clocks": clk,
             "e2e": {"value": e2e_value, "unit": "frames/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "ms_per_step": e2e_ms, "call": "eorb_orb_extract_batch (pinned host buffers)",
