@@ -116,6 +116,18 @@ EORB_HD void brief_offset(int px, int py, float a, float b, int& row, int& col) 
     col = round_rne(fsub(fmul(fx, a), fmul(fy, b)));
 }
 
+// same with float pattern coordinates and, on the device, round-half-even through the 1.5*2^23 trick (an FADD and
+// an integer subtract instead of two conversion-pipe F2I; exact for |v| < 2^22, pattern offsets are < 32)
+#ifdef __CUDA_ARCH__
+__device__ __forceinline__ int round_rne_small(float v) { return __float_as_int(__fadd_rn(v, 12582912.0f)) - 0x4B400000; }
+#else
+inline int round_rne_small(float v) { return round_rne(v); }
+#endif
+EORB_HD void brief_offset_f(float fx, float fy, float a, float b, int& row, int& col) {
+    row = round_rne_small(fadd(fmul(fx, b), fmul(fy, a)));
+    col = round_rne_small(fsub(fmul(fx, a), fmul(fy, b)));
+}
+
 // ---- DescriptorDistance (ORBmatcher.cc:2360-2378): 8 x popcount(xor)
 EORB_HD int hamming256(const uint32_t* a, const uint32_t* b) {
     int d = 0;

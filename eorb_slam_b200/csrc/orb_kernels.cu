@@ -21,6 +21,10 @@ namespace eorb {
 __device__ const signed char d_brief_pattern[1024] = {
 #include "brief_pattern_31.inc"
 };
+// the same pattern as floats: K6 multiplies the coordinates by cos / sin, this saves the int -> float conversions
+__device__ const float d_brief_pattern_f[1024] = {
+#include "brief_pattern_31.inc"
+};
 
 __device__ __forceinline__ const uint8_t* level_ptr(const OrbArgs& a, const LevelPlan& lp, int level, int f, int& pitch) {
     if (level == 0) {
@@ -443,15 +447,19 @@ __global__ void __launch_bounds__(32 * EORB_KP_GROUP) orient_desc_kernel(OrbArgs
             const int wAligned = (lp.w + 3) & ~3;
             const int2* __restrict__ tab = a.icTab + (xs & 3) * EORB_IC_TASKS + lane;
             const uint8_t* base = img + (size_t)(y - 15) * sp + xa;
+            // task i = it*32 + lane <-> (row r = i / 9, word k = i % 9); stepping i by 32 moves (r, k) by (3, 5) with a
+            // carry.  Words past the row's last aligned word and the padding row 31 only meet zero weights, so their
+            // addresses are clamped instead of predicated.
+            int r = (lane * 57) >> 9, k = lane - r * EORB_IC_WORDS;
+            const int kMax = (wAligned - 4 - xa) >> 2;
 #pragma unroll
             for (int it = 0; it < EORB_IC_TASKS / 32; it++) {
-                const int i = it * 32 + lane;
-                const int r = (i * 57) >> 9, k = i - r * EORB_IC_WORDS;     // i / 9 for i < 288
                 const int2 wgt = __ldg(tab + it * 32);
-                unsigned data = 0;
-                if (r < 31 && xa + 4 * k < wAligned) data = __ldg(reinterpret_cast<const unsigned*>(base + (size_t)r * sp + 4 * k));
+                const unsigned data = __ldg(reinterpret_cast<const unsigned*>(base + min(r, 30) * sp + 4 * min(k, kMax)));
                 m10 = dp4a_u8_s8(data, wgt.x, m10);
                 m01 = dp4a_u8_s8(data, wgt.y, m01);
+                r += 3; k += 5;
+                if (k >= EORB_IC_WORDS) { k -= EORB_IC_WORDS; r++; }
             }
         } else if (lane < 31) {   // patch crosses the level border (margin < 15): REFLECT_101, byte by byte
             const int u = lane - 15;
@@ -514,10 +522,10 @@ __global__ void __launch_bounds__(32 * EORB_KP_GROUP) orient_desc_kernel(OrbArgs
     uint32_t myword = 0;
 #pragma unroll
     for (int j = 0; j < 8; j++) {
-        const char4 pt = __ldg(reinterpret_cast<const char4*>(d_brief_pattern) + 32 * j + lane);
+        const float4 pt = __ldg(reinterpret_cast<const float4*>(d_brief_pattern_f) + 32 * j + lane);
         int r0, c0, r1, c1;
-        brief_offset(pt.x, pt.y, ca, sa, r0, c0);
-        brief_offset(pt.z, pt.w, ca, sa, r1, c1);
+        brief_offset_f(pt.x, pt.y, ca, sa, r0, c0);
+        brief_offset_f(pt.z, pt.w, ca, sa, r1, c1);
         int t0, t1;
         if (safe) {
             t0 = __ldg(Bc + r0 * bp + c0);
@@ -601,7 +609,7 @@ __global__ void selftest_math_kernel(const int* __restrict__ fastIn, int nFast, 
         const float rad = fmul(ang, (float)(3.14159265358979323846 / 180.f));
         const float ca = (float)cos((double)rad), sa = (float)sin((double)rad);
         int r, c;
-        brief_offset((i % 27) - 13, ((i / 27) % 27) - 13, ca, sa, r, c);
+        brief_offset_f((float)((i % 27) - 13), (float)(((i / 27) % 27) - 13), ca, sa, r, c);   // the device form used by K6
         briefOut[2 * i] = r; briefOut[2 * i + 1] = c;
     }
 }
