@@ -74,6 +74,8 @@ def _load():
         "eorb_matcher_set_db_host": ([vp, vp, i64, i64], i), "eorb_matcher_set_db_device": ([vp, vp, i64, i64], i),
         "eorb_matcher_search": ([vp, vp, i, i, f, vp], i), "eorb_matcher_search_device": ([vp, vp, i, vp], i),
         "eorb_matcher_merge_device": ([vp, vp, i, i, i, f, vp], i),
+        "eorb_matcher_search_sharded": ([vp, vp, i, i, f, vp, i, vp], i),
+        "eorb_nccl_unique_id": ([vp], i), "eorb_nccl_comm_init_rank": ([C.POINTER(vp), i, vp, i, i], i), "eorb_nccl_comm_destroy": ([vp], i),
         "eorb_hamming_best2": ([vp, i, vp, i64, i, f, vp], i), "eorb_rotation_filter": ([vp, vp, vp, i], i),
         "eorb_ev_create": ([i, i, i64, i, i, C.POINTER(vp)], i), "eorb_ev_destroy": ([vp], i),
         "eorb_ev_set_stream": ([vp, vp], i), "eorb_ev_reset_stream": ([vp], i), "eorb_ev_synchronize": ([vp], i), "eorb_ev_launch_count": ([vp], C.c_longlong),
@@ -88,6 +90,24 @@ def _load():
 
 
 lib, EXPORTED = _load()
+
+
+def nccl_unique_id() -> np.ndarray:
+    """128-byte ncclUniqueId (rank 0 creates it, every rank passes the same bytes to nccl_comm_init_rank)"""
+    out = np.zeros(128, np.uint8)
+    _check(lib.eorb_nccl_unique_id(out.ctypes.data_as(C.c_void_p)), "nccl_unique_id")
+    return out
+
+
+def nccl_comm_init_rank(nranks: int, unique_id: np.ndarray, rank: int, device: int) -> int:
+    comm = C.c_void_p()
+    uid = np.ascontiguousarray(unique_id, np.uint8)
+    _check(lib.eorb_nccl_comm_init_rank(C.byref(comm), nranks, uid.ctypes.data_as(C.c_void_p), rank, device), "nccl_comm_init_rank")
+    return comm.value
+
+
+def nccl_comm_destroy(comm: int):
+    _check(lib.eorb_nccl_comm_destroy(C.c_void_p(int(comm))), "nccl_comm_destroy")
 
 
 def _p(a):
@@ -359,6 +379,11 @@ class ORBmatcher:
     def merge_device(self, d_gathered, nshards, nq, d_out, th=None):
         _check(lib.eorb_matcher_merge_device(self.h, _p(d_gathered), nshards, nq, self.TH_LOW if th is None else th, self.mfNNratio,
                                              _p(d_out)), "merge_device")
+
+    def search_sharded(self, d_q, nq, comm, nshards, d_out, th=None):
+        """this rank's shard scan + ncclAllGather + merge, all on the matcher's stream (asynchronous)"""
+        _check(lib.eorb_matcher_search_sharded(self.h, _p(d_q), nq, self.TH_LOW if th is None else th, self.mfNNratio,
+                                               C.c_void_p(int(comm)), nshards, _p(d_out)), "search_sharded")
 
     def SearchBruteForce(self, desc1, desc2, angles1=None, angles2=None, th=None):
         """Frame-to-frame brute force in the shape of Frame.cc:1228-1235 with the ORBmatcher acceptance rule and,

@@ -15,7 +15,7 @@ SOURCES = ["capi.cu", "orb_kernels.cu", "orb_fast.cu", "match_kernels.cu", "even
 HEADERS = ["eorb_math.cuh", "fast_score.cuh", "octree_core.cuh", "orb_plan.h", "orb_kernels.h", "match_kernels.h", "event_kernels.h",
            "brief_pattern_31.inc", os.path.join("..", "..", "include", "eorb_b200.h")]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "--fmad=true",
-              "-Xcompiler", "-fPIC,-O2,-ffp-contract=off,-fvisibility=default", "-shared", "-cudart", "static"]
+              "-Xcompiler", "-fPIC,-O2,-ffp-contract=off,-fvisibility=default", "-shared", "-cudart", "static", "-ldl"]
 
 
 def is_stale() -> bool:

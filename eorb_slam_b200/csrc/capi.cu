@@ -5,6 +5,8 @@
 #include <cudaTypedefs.h>
 #include <cuda_runtime.h>
 
+#include <dlfcn.h>
+
 #include <algorithm>
 #include <cmath>
 #include <cstdarg>
@@ -912,6 +914,7 @@ struct eorb_matcher {
     eorb_best2* d_partial = nullptr; size_t partialCap = 0;
     uint8_t* d_q = nullptr; size_t qCap = 0;
     eorb_match* d_out = nullptr; size_t outCap = 0;
+    eorb_best2* d_mine = nullptr; eorb_best2* d_gathered = nullptr; size_t gatherCap = 0;   // sharded search: own + all shards' partials
     long long launches = 0;
 };
 
@@ -944,7 +947,7 @@ extern "C" int eorb_matcher_destroy(eorb_matcher* m) {
     if (!m) return EORB_OK;
     cudaSetDevice(m->device);
     cudaStreamSynchronize(m->stream);
-    cudaFree(m->ownedDb); cudaFree(m->d_partial); cudaFree(m->d_q); cudaFree(m->d_out);
+    cudaFree(m->ownedDb); cudaFree(m->d_partial); cudaFree(m->d_q); cudaFree(m->d_out); cudaFree(m->d_mine); cudaFree(m->d_gathered);
     cudaStreamDestroy(m->ownStream);
     delete m;
     return EORB_OK;
@@ -1023,6 +1026,93 @@ extern "C" int eorb_matcher_merge_device(eorb_matcher* m, const eorb_best2* d_ga
     CU(launch_merge_best2(d_gathered, nshards, nq, nullptr, d_out, th, ratio, m->stream));
     m->launches++;
     return EORB_OK;
+}
+
+// ---- NCCL, resolved at run time (the process may already hold torch's bundled libnccl.so.2; a C++ host loads the
+//      system one).  Only the four entry points the sharded search needs.
+struct EorbNcclId { char internal[128]; };
+struct EorbNccl {
+    void* lib = nullptr;
+    int (*getUniqueId)(EorbNcclId*) = nullptr;
+    int (*commInitRank)(void**, int, EorbNcclId, int) = nullptr;
+    int (*commDestroy)(void*) = nullptr;
+    int (*allGather)(const void*, void*, size_t, int, void*, cudaStream_t) = nullptr;
+    const char* (*getErrorString)(int) = nullptr;
+};
+static EorbNccl g_nccl;
+static std::once_flag g_ncclOnce;
+static int ncclApi() {
+    std::call_once(g_ncclOnce, [] {
+        const char* names[] = {"libnccl.so.2", "libnccl.so"};
+        for (const char* n : names) {
+            g_nccl.lib = dlopen(n, RTLD_NOW | RTLD_GLOBAL);
+            if (g_nccl.lib) break;
+        }
+        if (!g_nccl.lib) return;
+        g_nccl.getUniqueId = (int (*)(EorbNcclId*))dlsym(g_nccl.lib, "ncclGetUniqueId");
+        g_nccl.commInitRank = (int (*)(void**, int, EorbNcclId, int))dlsym(g_nccl.lib, "ncclCommInitRank");
+        g_nccl.commDestroy = (int (*)(void*))dlsym(g_nccl.lib, "ncclCommDestroy");
+        g_nccl.allGather = (int (*)(const void*, void*, size_t, int, void*, cudaStream_t))dlsym(g_nccl.lib, "ncclAllGather");
+        g_nccl.getErrorString = (const char* (*)(int))dlsym(g_nccl.lib, "ncclGetErrorString");
+    });
+    if (!g_nccl.lib || !g_nccl.getUniqueId || !g_nccl.commInitRank || !g_nccl.commDestroy || !g_nccl.allGather)
+        return fail(EORB_ERR_STATE, "libnccl.so.2 could not be loaded (%s)", dlerror() ? dlerror() : "missing symbols");
+    return EORB_OK;
+}
+#define NCCL_CALL(call)                                                                                              \
+    do {                                                                                                             \
+        int r__ = (call);                                                                                            \
+        if (r__ != 0) return fail(EORB_ERR_CUDA, "%s failed: %s", #call, g_nccl.getErrorString ? g_nccl.getErrorString(r__) : "nccl error"); \
+    } while (0)
+
+extern "C" int eorb_nccl_unique_id(uint8_t* id128) {
+    if (!id128) return fail(EORB_ERR_ARG, "null argument");
+    int rc = ncclApi();
+    if (rc != EORB_OK) return rc;
+    EorbNcclId id;
+    NCCL_CALL(g_nccl.getUniqueId(&id));
+    memcpy(id128, id.internal, 128);
+    return EORB_OK;
+}
+
+extern "C" int eorb_nccl_comm_init_rank(void** comm, int nranks, const uint8_t* id128, int rank, int device) {
+    if (!comm || !id128 || nranks < 1 || rank < 0 || rank >= nranks) return fail(EORB_ERR_ARG, "bad communicator arguments");
+    int rc = ncclApi();
+    if (rc != EORB_OK) return rc;
+    CU(cudaSetDevice(device));
+    EorbNcclId id;
+    memcpy(id.internal, id128, 128);
+    NCCL_CALL(g_nccl.commInitRank(comm, nranks, id, rank));
+    return EORB_OK;
+}
+
+extern "C" int eorb_nccl_comm_destroy(void* comm) {
+    if (!comm) return EORB_OK;
+    int rc = ncclApi();
+    if (rc != EORB_OK) return rc;
+    NCCL_CALL(g_nccl.commDestroy(comm));
+    return EORB_OK;
+}
+
+// database sharded by rows over the ranks; each rank scans its shard, ONE ncclAllGather moves nq x 16 B per
+// rank over NVLink, every rank merges with the (dist, global index) ordering and applies threshold + ratio.
+extern "C" int eorb_matcher_search_sharded(eorb_matcher* m, const uint8_t* d_q, int nq, int th, float ratio, void* nccl_comm,
+                                           int nshards, eorb_match* d_out) {
+    if (!m || !d_out || !nccl_comm || nshards < 1) return fail(EORB_ERR_ARG, "null argument");
+    if (nq <= 0) return EORB_OK;
+    int rc = ncclApi();
+    if (rc != EORB_OK) return rc;
+    CU(cudaSetDevice(m->device));
+    const size_t need = (size_t)nshards * nq;
+    if (need > m->gatherCap) {
+        cudaFree(m->d_gathered); cudaFree(m->d_mine);
+        CU(devAlloc(&m->d_gathered, need)); CU(devAlloc(&m->d_mine, (size_t)nq));
+        m->gatherCap = need;
+    }
+    rc = eorb_matcher_search_device(m, d_q, nq, m->d_mine);
+    if (rc != EORB_OK) return rc;
+    NCCL_CALL(g_nccl.allGather(m->d_mine, m->d_gathered, (size_t)nq * sizeof(eorb_best2), /*ncclChar*/ 0, nccl_comm, m->stream));
+    return eorb_matcher_merge_device(m, m->d_gathered, nshards, nq, th, ratio, d_out);
 }
 
 extern "C" int eorb_matcher_search(eorb_matcher* m, const uint8_t* q, int nq, int th, float ratio, eorb_match* out) {

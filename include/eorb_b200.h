@@ -187,6 +187,16 @@ int eorb_matcher_search_device(eorb_matcher* m, const uint8_t* d_q, int nq, eorb
  * (dist, global index) ordering, then threshold + ratio -> d_out[nq]; asynchronous */
 int eorb_matcher_merge_device(eorb_matcher* m, const eorb_best2* d_gathered, int nshards, int nq,
                               int th, float ratio, eorb_match* d_out);
+/* sharded search in one call (the brute-force shape of Frame.cc:1228-1235 over a database split by rows
+ * across the GPUs of a box): scan of this rank's shard, ONE ncclAllGather of nq x 16 B per rank on the matcher's stream,
+ * merge with the (dist, global index) ordering, threshold + ratio -> d_out[nq] on every rank; asynchronous.
+ * nccl_comm is an ncclComm_t of nshards ranks.  libnccl.so.2 is resolved at run time (dlopen): no link-time dependency. */
+int eorb_matcher_search_sharded(eorb_matcher* m, const uint8_t* d_q, int nq, int th, float ratio, void* nccl_comm,
+                                int nshards, eorb_match* d_out);
+/* thin NCCL helpers for host languages without NCCL bindings: ncclGetUniqueId / ncclCommInitRank / ncclCommDestroy */
+int eorb_nccl_unique_id(uint8_t* id128);
+int eorb_nccl_comm_init_rank(void** comm, int nranks, const uint8_t* id128, int rank, int device);
+int eorb_nccl_comm_destroy(void* comm);
 /* convenience: one-call stateless form on host buffers (creates/destroys a matcher) */
 int eorb_hamming_best2(const uint8_t* q, int nq, const uint8_t* db, int64_t ndb, int th, float ratio, eorb_match* out);
 /* rotation-consistency filter: ORBmatcher.cc:784-794, 800-823 and ComputeThreeMaxima :2314-2355.

@@ -102,3 +102,27 @@ def test_popc_probe_reports_a_rate():
     api = _api()
     r = api.probe_popc_rate(0)
     assert 1e11 < r < 1e14
+
+
+def test_sharded_search_entry_point_single_rank_communicator():
+    """eorb_matcher_search_sharded with a one-rank ncclComm_t: scan + ncclAllGather + merge through the C ABI give
+    exactly the one-call result (multi-rank behaviour of the merge is covered on the CPU by tests/test_dist_gloo.py
+    and on two B200s by bench.py --gpus 2)."""
+    import torch
+    api = _api()
+    db = synth.make_descriptor_db(30000, 5)
+    q, _ = synth.make_queries(db, 500, 6)
+    m = api.ORBmatcher(0.7, True)
+    m.set_db(db, index_offset=1000)
+    exp = O.hamming_best2(q, db, 50, 0.7)
+    comm = api.nccl_comm_init_rank(1, api.nccl_unique_id(), 0, 0)
+    d_q = torch.from_numpy(q).cuda()
+    d_out = torch.zeros(len(q) * 16, dtype=torch.uint8, device="cuda")
+    torch.cuda.synchronize()
+    m.search_sharded(d_q.data_ptr(), len(q), comm, 1, d_out.data_ptr())
+    m.synchronize()
+    got = np.frombuffer(d_out.cpu().numpy().tobytes(), dtype=api.MATCH_DTYPE)
+    assert np.array_equal(got["best_dist"], exp["best_dist"]) and np.array_equal(got["second_dist"], exp["second_dist"])
+    assert np.array_equal(got["accepted"], exp["accepted"])
+    assert np.array_equal(got["best_idx"], np.where(exp["best_idx"] >= 0, exp["best_idx"] + 1000, -1))
+    api.nccl_comm_destroy(comm)
