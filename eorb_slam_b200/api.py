@@ -81,6 +81,11 @@ def _load():
         "eorb_ev_set_stream": ([vp, vp], i), "eorb_ev_reset_stream": ([vp], i), "eorb_ev_synchronize": ([vp], i), "eorb_ev_launch_count": ([vp], C.c_longlong),
         "eorb_ev_accumulate": ([vp, vp, i64, C.POINTER(_EvParams), vp, vp, vp], i),
         "eorb_ev_accumulate_batch_device": ([vp, vp, vp, i, C.POINTER(_EvParams), vp, vp, vp], i),
+        "eorb_lk_create": ([i, i, i, i, C.POINTER(vp)], i), "eorb_lk_destroy": ([vp], i),
+        "eorb_lk_set_stream": ([vp, vp], i), "eorb_lk_reset_stream": ([vp], i), "eorb_lk_launch_count": ([vp], C.c_longlong),
+        "eorb_lk_set_ref": ([vp, vp, i, i, sz, vp, i, i, i], i), "eorb_lk_set_ref_device": ([vp, vp, i, i, sz, vp, i, i, i], i),
+        "eorb_lk_track": ([vp, vp, sz, vp, i, C.c_double, f, vp, vp, vp], i),
+        "eorb_lk_track_device": ([vp, vp, sz, vp, i, C.c_double, f, vp, vp, vp], i),
     }
     for name, (args, res) in sig.items():
         fn = getattr(L, name)   # AttributeError here == header/library mismatch
@@ -493,3 +498,50 @@ class EvImConverter:
         ps = np.ascontiguousarray(poses, np.float32) if poses is not None else None
         _check(lib.eorb_ev_accumulate_batch_device(self.h, _p(d_evs), _p(offs), len(offs) - 1, C.byref(p), _p(ps), _p(d_img_f32),
                                                    _p(d_img_u8)), "ev_accumulate_batch_device")
+
+
+class ELK_Tracker:
+    """Mirror of EORB_SLAM::ELK_Tracker (include/Event/KLT_Tracker.h; src/Event/KLT_Tracker.cpp:14-91): setRefImage keeps the
+    reference frame and its points, trackCurrImage runs the pyramidal LK of cv::calcOpticalFlowPyrLK against a new frame.
+    Defaults are the EvETHZ.yaml values (kltWinSize 23, maxLevel 1, kltMaxItr 10, kltEps 0.03)."""
+
+    def __init__(self, kltWinSize=23, maxLevel=1, kltMaxItr=10, kltEps=0.03, device=0, max_size=(752, 480), max_points=4096):
+        self.mPatchSz, self.mMaxLevel, self.maxItr, self.eps = kltWinSize, maxLevel, kltMaxItr, kltEps
+        h = C.c_void_p()
+        _check(lib.eorb_lk_create(device, max_size[0], max_size[1], max_points, C.byref(h)), "lk_create")
+        self.h = h
+        self.n = 0
+
+    def __del__(self):
+        if getattr(self, "h", None):
+            lib.eorb_lk_destroy(self.h)
+            self.h = None
+
+    def launch_count(self): return lib.eorb_lk_launch_count(self.h)
+
+    def setRefImage(self, image, refPts):
+        """refPts: (n, 2) float32 (x, y) — or a KEYPOINT_DTYPE array, whose pt is used (KLT_Tracker.cpp:34-43)"""
+        image = np.ascontiguousarray(image, np.uint8)
+        if isinstance(refPts, np.ndarray) and refPts.dtype.names:
+            refPts = np.stack([refPts["x"], refPts["y"]], 1)
+        pts = np.ascontiguousarray(refPts, np.float32).reshape(-1, 2)
+        rc = _check(lib.eorb_lk_set_ref(self.h, _p(image), image.shape[1], image.shape[0], image.strides[0], _p(pts), len(pts),
+                                        self.mPatchSz, self.mMaxLevel), "lk_set_ref")
+        self.n = len(pts) if rc == 0 else 0
+        self.shape = image.shape
+        return rc
+
+    def trackCurrImage(self, currImage, initPts=None):
+        """-> (kpts float32[n,2], status uint8[n], err float32[n]); initPts given = OPTFLOW_USE_INITIAL_FLOW"""
+        currImage = np.ascontiguousarray(currImage, np.uint8)
+        assert currImage.shape == self.shape
+        out = np.zeros((self.n, 2), np.float32); status = np.zeros(self.n, np.uint8); err = np.zeros(self.n, np.float32)
+        init = None
+        if initPts is not None:
+            if isinstance(initPts, np.ndarray) and initPts.dtype.names:
+                initPts = np.stack([initPts["x"], initPts["y"]], 1)
+            init = np.ascontiguousarray(initPts, np.float32).reshape(-1, 2)
+            assert len(init) == self.n
+        self.levels_used = _check(lib.eorb_lk_track(self.h, _p(currImage), currImage.strides[0], _p(init), self.maxItr, float(self.eps), 1e-4,
+                                                    _p(out), _p(status), _p(err)), "lk_track")
+        return out, status, err

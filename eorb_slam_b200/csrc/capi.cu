@@ -35,6 +35,8 @@ static int fail(int code, const char* fmt, ...) {
     va_end(ap);
     return code;
 }
+// the same for the other translation units of the library (capi_lk.cu); not part of the public header
+extern "C" int eorb_internal_fail(int code, const char* msg) { return fail(code, "%s", msg); }
 
 #define CU(call)                                                                                         \
     do {                                                                                                 \

@@ -1,0 +1,218 @@
+// lk_kernels.cu — pyramidal Lucas-Kanade tracking of event-frame keypoints.
+// Reference call: ELK_Tracker::trackCurrImage (src/Event/KLT_Tracker.cpp:49-91) -> cv::calcOpticalFlowPyrLK with
+// win 23, maxLevel 1, 10 iterations, eps 0.03 (Examples/Event/EvETHZ.yaml:205-208).  Restates OpenCV's algorithm
+// (see oracle/lk_oracle.cc for the step-by-step description and the pin against cv2):
+//   lk_pyrdown_kernel  cv::pyrDown u8: [1 4 6 4 1] x [1 4 6 4 1], (sum + 128) >> 8, REFLECT_101
+//   lk_scharr_kernel   calcSharrDeriv: (Ix, Iy) int16, REFLECT_101 inside the level
+//   lk_track_kernel    LKTrackerInvoker: ONE WARP PER POINT walks all pyramid levels in one launch; the bilinear
+//                      patch (14-bit fixed point) lives in shared memory as int16 triples (I, Ix, Iy); the five sums
+//                      A11 A12 A22 b1 b2 are accumulated as EXACT integers (int64, warp-shuffle reduction) and
+//                      converted to float once — order independent, hence bit-equal to the oracle, and within one
+//                      float rounding of whichever lane order OpenCV's SIMD build uses; the scalar float algebra
+//                      uses explicit no-FMA intrinsics in the oracle's operation order.
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "eorb_math.cuh"
+#include "lk_kernels.h"
+
+namespace eorb {
+
+__global__ void __launch_bounds__(256) lk_pyrdown_kernel(const uint8_t* __restrict__ src, int w, int h, int pitch, uint8_t* __restrict__ dst,
+                                                         int dw, int dh, int dpitch) {
+    const int x = blockIdx.x * 32 + threadIdx.x, y = blockIdx.y * 8 + threadIdx.y;
+    if (x >= dw || y >= dh) return;
+    const int wt[5] = {1, 4, 6, 4, 1};
+    int xs[5];
+#pragma unroll
+    for (int j = 0; j < 5; j++) xs[j] = reflect101(2 * x + j - 2, w);
+    int acc = 0;
+#pragma unroll
+    for (int k = 0; k < 5; k++) {
+        const uint8_t* r = src + (size_t)reflect101(2 * y + k - 2, h) * pitch;
+        int rs = 0;
+#pragma unroll
+        for (int j = 0; j < 5; j++) rs += wt[j] * (int)__ldg(r + xs[j]);
+        acc += wt[k] * rs;
+    }
+    dst[(size_t)y * dpitch + x] = (uint8_t)((acc + 128) >> 8);
+}
+
+__global__ void __launch_bounds__(256) lk_scharr_kernel(const uint8_t* __restrict__ src, int w, int h, int pitch, short2* __restrict__ dst) {
+    const int x = blockIdx.x * 32 + threadIdx.x, y = blockIdx.y * 8 + threadIdx.y;
+    if (x >= w || y >= h) return;
+    const uint8_t* r0 = src + (size_t)reflect101(y - 1, h) * pitch;
+    const uint8_t* r1 = src + (size_t)y * pitch;
+    const uint8_t* r2 = src + (size_t)reflect101(y + 1, h) * pitch;
+    const int xl = reflect101(x - 1, w), xr = reflect101(x + 1, w);
+    // vertical pass at the three columns: t0 = smoothing, t1 = difference
+    const int t0l = ((int)__ldg(r0 + xl) + (int)__ldg(r2 + xl)) * 3 + (int)__ldg(r1 + xl) * 10;
+    const int t0r = ((int)__ldg(r0 + xr) + (int)__ldg(r2 + xr)) * 3 + (int)__ldg(r1 + xr) * 10;
+    const int t1l = (int)__ldg(r2 + xl) - (int)__ldg(r0 + xl);
+    const int t1c = (int)__ldg(r2 + x) - (int)__ldg(r0 + x);
+    const int t1r = (int)__ldg(r2 + xr) - (int)__ldg(r0 + xr);
+    dst[(size_t)y * w + x] = make_short2((short)(t0r - t0l), (short)((t1r + t1l) * 3 + t1c * 10));
+}
+
+__device__ __forceinline__ int lk_descale(int x, int n) { return (x + (1 << (n - 1))) >> n; }
+
+__device__ __forceinline__ void lk_weights(float a, float b, int& w00, int& w01, int& w10, int& w11) {
+    const float oa = fsub(1.f, a), ob = fsub(1.f, b);
+    w00 = round_rne(fmul(fmul(oa, ob), 16384.f));
+    w01 = round_rne(fmul(fmul(a, ob), 16384.f));
+    w10 = round_rne(fmul(fmul(oa, b), 16384.f));
+    w11 = 16384 - w00 - w01 - w10;
+}
+
+__device__ __forceinline__ long long warp_sum_ll(long long v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+// bilinear sample of a u8 level with the REFLECT_101 border OpenCV pads its pyramid with, scaled by 32
+__device__ __forceinline__ int lk_sample32(const LkLevelDev& L, const uint8_t* __restrict__ img, int X, int Y, int w00, int w01, int w10, int w11) {
+    const int x0 = reflect101(X, L.w), x1 = reflect101(X + 1, L.w);
+    const uint8_t* r0 = img + (size_t)reflect101(Y, L.h) * L.pitch;
+    const uint8_t* r1 = img + (size_t)reflect101(Y + 1, L.h) * L.pitch;
+    return lk_descale((int)__ldg(r0 + x0) * w00 + (int)__ldg(r0 + x1) * w01 + (int)__ldg(r1 + x0) * w10 + (int)__ldg(r1 + x1) * w11, 14 - 5);
+}
+
+__device__ __forceinline__ short2 lk_deriv_at(const LkLevelDev& L, int X, int Y) {   // zero border
+    if (X < 0 || X >= L.w || Y < 0 || Y >= L.h) return make_short2(0, 0);
+    return __ldg(L.dI + (size_t)Y * L.w + X);
+}
+
+#define LK_WARPS 4
+__global__ void __launch_bounds__(LK_WARPS * 32) lk_track_kernel(LkLevels LV, LkParams prm, const float2* __restrict__ prevPts,
+                                                                 float2* __restrict__ nextPts, int n, uint8_t* __restrict__ status,
+                                                                 float* __restrict__ err) {
+    extern __shared__ short s_patch[];   // per warp: win*win x (I, Ix, Iy)
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int p = blockIdx.x * LK_WARPS + warp;
+    if (p >= n) return;
+    const int win = prm.win, area = win * win;
+    short* pI = s_patch + (size_t)warp * area * 3;
+    short* pIx = pI + area;
+    short* pIy = pIx + area;
+    const float halfWin = fmul((float)(win - 1), 0.5f);
+    const float FLT_SCALE = 1.f / (1 << 20);
+    const float2 pp = prevPts[p];
+    float2 np = nextPts[p];          // only meaningful with useInitialFlow
+    bool ok = true;                  // status[p]
+    float errv = 0.f;
+
+    for (int level = LV.maxLevel; level >= 0; level--) {
+        const LkLevelDev& L = LV.lv[level];
+        const float sc = (float)(1. / (double)(1 << level));
+        float px = fmul(pp.x, sc), py = fmul(pp.y, sc);
+        float nx, ny;
+        if (level == LV.maxLevel) {
+            if (prm.useInitialFlow) { nx = fmul(np.x, sc); ny = fmul(np.y, sc); }
+            else { nx = px; ny = py; }
+        } else {
+            nx = fmul(np.x, 2.f); ny = fmul(np.y, 2.f);
+        }
+        np = make_float2(nx, ny);
+        px = fsub(px, halfWin); py = fsub(py, halfWin);
+        const int ipx = (int)floorf(px), ipy = (int)floorf(py);
+        if (ipx < -win || ipx >= L.w || ipy < -win || ipy >= L.h) {
+            if (level == 0) { ok = false; errv = 0.f; }
+            continue;
+        }
+        int w00, w01, w10, w11;
+        lk_weights(fsub(px, (float)ipx), fsub(py, (float)ipy), w00, w01, w10, w11);
+        long long sA11 = 0, sA12 = 0, sA22 = 0;
+        __syncwarp();
+        for (int i = lane; i < area; i += 32) {
+            const int y = i / win, x = i - y * win;
+            const int X = ipx + x, Y = ipy + y;
+            const int ival = lk_sample32(L, L.I, X, Y, w00, w01, w10, w11);
+            const short2 d00 = lk_deriv_at(L, X, Y), d01 = lk_deriv_at(L, X + 1, Y), d10 = lk_deriv_at(L, X, Y + 1), d11 = lk_deriv_at(L, X + 1, Y + 1);
+            const int ixval = lk_descale((int)d00.x * w00 + (int)d01.x * w01 + (int)d10.x * w10 + (int)d11.x * w11, 14);
+            const int iyval = lk_descale((int)d00.y * w00 + (int)d01.y * w01 + (int)d10.y * w10 + (int)d11.y * w11, 14);
+            pI[i] = (short)ival; pIx[i] = (short)ixval; pIy[i] = (short)iyval;
+            sA11 += (long long)ixval * ixval; sA12 += (long long)ixval * iyval; sA22 += (long long)iyval * iyval;
+        }
+        __syncwarp();
+        const float A11 = fmul(__ll2float_rn(warp_sum_ll(sA11)), FLT_SCALE);
+        const float A12 = fmul(__ll2float_rn(warp_sum_ll(sA12)), FLT_SCALE);
+        const float A22 = fmul(__ll2float_rn(warp_sum_ll(sA22)), FLT_SCALE);
+        float D = fsub(fmul(A11, A22), fmul(A12, A12));
+        const float dif = fsub(A11, A22);
+        const float minEig = fdiv(fsub(fadd(A22, A11), __fsqrt_rn(fadd(fmul(dif, dif), fmul(fmul(4.f, A12), A12)))), (float)(2 * win * win));
+        if (minEig < prm.minEigThreshold || D < 1.1920929e-07f) {
+            if (level == 0) ok = false;
+            continue;
+        }
+        D = fdiv(1.f, D);
+        nx = fsub(nx, halfWin); ny = fsub(ny, halfWin);
+        float pdx = 0.f, pdy = 0.f;
+        for (int j = 0; j < prm.maxIter; j++) {
+            const int inx = (int)floorf(nx), iny = (int)floorf(ny);
+            if (inx < -win || inx >= L.w || iny < -win || iny >= L.h) {
+                if (level == 0) ok = false;
+                break;
+            }
+            lk_weights(fsub(nx, (float)inx), fsub(ny, (float)iny), w00, w01, w10, w11);
+            long long sb1 = 0, sb2 = 0;
+            for (int i = lane; i < area; i += 32) {
+                const int y = i / win, x = i - y * win;
+                const int diff = lk_sample32(L, L.J, inx + x, iny + y, w00, w01, w10, w11) - (int)pI[i];
+                sb1 += (long long)diff * (int)pIx[i]; sb2 += (long long)diff * (int)pIy[i];
+            }
+            const float b1 = fmul(__ll2float_rn(warp_sum_ll(sb1)), FLT_SCALE), b2 = fmul(__ll2float_rn(warp_sum_ll(sb2)), FLT_SCALE);
+            const float dx = fmul(fsub(fmul(A12, b2), fmul(A22, b1)), D), dy = fmul(fsub(fmul(A12, b1), fmul(A11, b2)), D);
+            nx = fadd(nx, dx); ny = fadd(ny, dy);
+            np = make_float2(fadd(nx, halfWin), fadd(ny, halfWin));
+            if (__dadd_rn(__dmul_rn((double)dx, (double)dx), __dmul_rn((double)dy, (double)dy)) <= prm.epsilon2) break;
+            if (j > 0 && (double)fabsf(fadd(dx, pdx)) < 0.01 && (double)fabsf(fadd(dy, pdy)) < 0.01) {
+                np.x = fsub(np.x, fmul(dx, 0.5f)); np.y = fsub(np.y, fmul(dy, 0.5f));
+                break;
+            }
+            pdx = dx; pdy = dy;
+        }
+        if (ok && level == 0) {   // L1 patch error at the final position
+            const float ex = fsub(np.x, halfWin), ey = fsub(np.y, halfWin);
+            const int iex = (int)floorf(ex), iey = (int)floorf(ey);
+            if (iex < -win || iex >= L.w || iey < -win || iey >= L.h) { ok = false; continue; }
+            lk_weights(fsub(ex, (float)iex), fsub(ey, (float)iey), w00, w01, w10, w11);
+            long long se = 0;
+            for (int i = lane; i < area; i += 32) {
+                const int y = i / win, x = i - y * win;
+                const int diff = lk_sample32(L, L.J, iex + x, iey + y, w00, w01, w10, w11) - (int)pI[i];
+                se += diff < 0 ? -diff : diff;
+            }
+            errv = fdiv(fmul(__ll2float_rn(warp_sum_ll(se)), 1.f), (float)(32 * win * win));
+        }
+    }
+    if (lane == 0) {
+        nextPts[p] = np;
+        status[p] = ok ? 1 : 0;
+        if (err) err[p] = errv;
+    }
+}
+
+cudaError_t launch_lk_pyrdown(const uint8_t* src, int w, int h, int pitch, uint8_t* dst, int dw, int dh, int dpitch, cudaStream_t st) {
+    dim3 blk(32, 8), grd((dw + 31) / 32, (dh + 7) / 8);
+    lk_pyrdown_kernel<<<grd, blk, 0, st>>>(src, w, h, pitch, dst, dw, dh, dpitch);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_lk_scharr(const uint8_t* src, int w, int h, int pitch, short2* dst, cudaStream_t st) {
+    dim3 blk(32, 8), grd((w + 31) / 32, (h + 7) / 8);
+    lk_scharr_kernel<<<grd, blk, 0, st>>>(src, w, h, pitch, dst);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_lk_track(const LkLevels& L, const LkParams& p, const float2* prevPts, float2* nextPts, int n, uint8_t* status, float* err,
+                            cudaStream_t st) {
+    if (n <= 0) return cudaSuccess;
+    const size_t smem = (size_t)LK_WARPS * p.win * p.win * 3 * sizeof(short);
+    cudaError_t e = cudaFuncSetAttribute(lk_track_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    lk_track_kernel<<<(n + LK_WARPS - 1) / LK_WARPS, LK_WARPS * 32, smem, st>>>(L, p, prevPts, nextPts, n, status, err);
+    return cudaGetLastError();
+}
+
+}  // namespace eorb

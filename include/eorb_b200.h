@@ -250,6 +250,29 @@ int eorb_ev_accumulate_batch_device(eorb_evconv* c, const eorb_event* d_evs, con
                                     const eorb_ev_params* p, const float* poses,
                                     float* d_img_f32, uint8_t* d_img_u8);
 
+/* ---------------------------------------------------------------- LK tracker (first "next" row)
+ * replaces EORB_SLAM::ELK_Tracker::setRefImage / trackCurrImage (include/Event/KLT_Tracker.h,
+ * src/Event/KLT_Tracker.cpp:22-91), i.e. cv::calcOpticalFlowPyrLK(ref, cur, refPts, pts, status, err,
+ * Size(win, win), maxLevel, TermCriteria(COUNT+EPS, maxItr, eps) [, OPTFLOW_USE_INITIAL_FLOW]) on 8-bit frames.
+ * Points are (x, y) float pairs.  The reference frame's pyramid and Scharr derivatives are built once in set_ref. */
+typedef struct eorb_lk eorb_lk;
+int eorb_lk_create(int device, int max_width, int max_height, int max_points, eorb_lk** out);
+int eorb_lk_destroy(eorb_lk* h);
+int eorb_lk_set_stream(eorb_lk* h, void* cuda_stream);
+int eorb_lk_reset_stream(eorb_lk* h);
+long long eorb_lk_launch_count(const eorb_lk* h);
+/* EORB_EMPTY when the image or the point list is empty (the reference asserts, KLT_Tracker.cpp:24) */
+int eorb_lk_set_ref(eorb_lk* h, const uint8_t* img, int w, int hgt, size_t stride, const float* pts_xy, int n, int win, int max_level);
+int eorb_lk_set_ref_device(eorb_lk* h, const uint8_t* d_img, int w, int hgt, size_t stride, const float* pts_xy, int n, int win,
+                           int max_level);
+/* init_xy == NULL: start from the reference points; else OPTFLOW_USE_INITIAL_FLOW (KLT_Tracker.cpp:63-65, 86-88).
+ * min_eig: minEigThreshold (OpenCV default 1e-4).  err may be NULL.  Returns the number of pyramid levels - 1 used
+ * (OpenCV lowers maxLevel when a level would be no larger than the window). */
+int eorb_lk_track(eorb_lk* h, const uint8_t* img, size_t stride, const float* init_xy, int max_iter, double eps, float min_eig,
+                  float* out_xy, uint8_t* status, float* err);
+int eorb_lk_track_device(eorb_lk* h, const uint8_t* d_img, size_t stride, const float* init_xy, int max_iter, double eps, float min_eig,
+                         float* out_xy, uint8_t* status, float* err);
+
 #ifdef __cplusplus
 }
 #endif

@@ -27,7 +27,7 @@ class OrbParams(C.Structure):
 
 
 def build(force: bool = False) -> str:
-    srcs = [os.path.join(ORACLE_DIR, f) for f in ("orb_oracle.cc", "match_oracle.cc", "event_oracle.cc", "oracle.h",
+    srcs = [os.path.join(ORACLE_DIR, f) for f in ("orb_oracle.cc", "match_oracle.cc", "event_oracle.cc", "lk_oracle.cc", "oracle.h",
                                                   "brief_pattern_31.inc", "Makefile")]
     stale = force or not os.path.exists(LIB_PATH) or any(os.path.getmtime(s) > os.path.getmtime(LIB_PATH) for s in srcs)
     if stale:
@@ -87,6 +87,11 @@ def lib():
     L.orc_ev_accumulate.restype = C.c_int
     L.orc_normalize_convert_u8.argtypes = [vp, C.c_int, C.c_float, C.c_float, vp]; L.orc_normalize_convert_u8.restype = None
     L.orc_normalize_minmax_u8.argtypes = [vp, C.c_int, vp]; L.orc_normalize_minmax_u8.restype = None
+    L.orc_pyrdown_u8.argtypes = [vp, C.c_int, C.c_int, C.c_size_t, vp, C.c_int, C.c_int, C.c_size_t]; L.orc_pyrdown_u8.restype = None
+    L.orc_scharr_deriv.argtypes = [vp, C.c_int, C.c_int, C.c_size_t, vp]; L.orc_scharr_deriv.restype = None
+    L.orc_lk_track.argtypes = [vp, vp, C.c_int, C.c_int, C.c_size_t, vp, vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_double, C.c_int,
+                               C.c_float, vp, vp]
+    L.orc_lk_track.restype = C.c_int
     _lib = L
     return L
 
@@ -289,3 +294,36 @@ def normalize_minmax_u8(img):
     out = np.empty(img.shape, np.uint8)
     lib().orc_normalize_minmax_u8(_p(img), img.size, _p(out))
     return out
+
+
+# ----------------------------------------------------------------------------- pyramidal LK
+def pyrdown(src: np.ndarray) -> np.ndarray:
+    src = np.ascontiguousarray(src, np.uint8)
+    h, w = src.shape
+    dst = np.zeros(((h + 1) // 2, (w + 1) // 2), np.uint8)
+    lib().orc_pyrdown_u8(_p(src), w, h, src.strides[0], _p(dst), dst.shape[1], dst.shape[0], dst.strides[0])
+    return dst
+
+
+def scharr_deriv(src: np.ndarray) -> np.ndarray:
+    """(h, w, 2) int16: [..., 0] = Ix, [..., 1] = Iy (calcSharrDeriv)"""
+    src = np.ascontiguousarray(src, np.uint8)
+    h, w = src.shape
+    dst = np.zeros((h, w, 2), np.int16)
+    lib().orc_scharr_deriv(_p(src), w, h, src.strides[0], _p(dst))
+    return dst
+
+
+def lk_track(prev_img, next_img, prev_pts, next_pts=None, win=23, max_level=1, max_iter=10, eps=0.03, min_eig=1e-4):
+    """cv::calcOpticalFlowPyrLK restatement -> (next_pts float32[n,2], status uint8[n], err float32[n], levels_used)"""
+    prev_img = np.ascontiguousarray(prev_img, np.uint8); next_img = np.ascontiguousarray(next_img, np.uint8)
+    assert prev_img.shape == next_img.shape
+    h, w = prev_img.shape
+    pp = np.ascontiguousarray(prev_pts, np.float32).reshape(-1, 2)
+    n = len(pp)
+    use_init = next_pts is not None
+    npts = np.ascontiguousarray(next_pts, np.float32).reshape(-1, 2).copy() if use_init else np.zeros((n, 2), np.float32)
+    status = np.zeros(n, np.uint8); err = np.zeros(n, np.float32)
+    lv = lib().orc_lk_track(_p(prev_img), _p(next_img), w, h, prev_img.strides[0], _p(pp), _p(npts), n, win, max_level, max_iter, float(eps),
+                            1 if use_init else 0, float(min_eig), _p(status), _p(err))
+    return npts, status, err, lv
