@@ -249,6 +249,52 @@ def bench_hamming(api, torch, dev, steps, warmup, world, rank, dist):
                          "note": "algorithmic 8 POPC32 per pair; peak measured live by eorb_probe_popc_rate"}}
 
 
+def bench_lk(api, torch, dev, steps, warmup):
+    """ELK_Tracker on DAVIS240-shaped event frames, EvETHZ.yaml values (400 points, win 23, maxLevel 1,
+    10 iterations, eps 0.03).  A step = one trackCurrImage call through the host C ABI (frame H2D, pyramid, tracker,
+    points/status/err D2H).  CPU beside it: the oracle port and real OpenCV (cv2.calcOpticalFlowPyrLK) on the same input."""
+    import oracle_lib as O
+    from eorb_slam_b200 import synth
+    per, w, h = 2000, 240, 180
+    ev = synth.make_events(per * 2, seed=7, w=w, h=h)
+    i0 = O.normalize_minmax_u8(O.ev_accumulate(ev[:per], w, h, 1.0, mode=1)[0])
+    i1 = O.normalize_minmax_u8(O.ev_accumulate(ev[per // 2:per + per // 2], w, h, 1.0, mode=1)[0])
+    _, kps, _ = O.OrbOracle(400, 1.0, 1, 0, 0, 9, w, h).extract(i0, (0, 1000), False)
+    pts = np.stack([kps["x"], kps["y"]], 1).astype(np.float32)
+    tr = api.ELK_Tracker(23, 1, 10, 0.03, dev, (w, h), len(pts))
+    tr.setRefImage(i0, pts)
+    for _ in range(max(warmup, 3)):
+        tr.trackCurrImage(i1)
+    n = max(steps, 3) * 20
+    l0 = tr.launch_count()
+    t0 = time.perf_counter()
+    for _ in range(n):
+        p, s, e = tr.trackCurrImage(i1)
+    ms = (time.perf_counter() - t0) * 1e3 / n
+    launches = (tr.launch_count() - l0) // n
+    ep, es, ee, _ = O.lk_track(i0, i1, pts)
+    t0 = time.perf_counter()
+    for _ in range(5):
+        O.lk_track(i0, i1, pts)
+    ms_port = (time.perf_counter() - t0) * 1e3 / 5
+    out = {"metric": "lk_tracked_points_per_s", "value": len(pts) / (ms * 1e-3), "unit": "points/s", "ms_per_call": ms,
+           "workload": "ELK_Tracker: %d keypoints of a 240x180 event frame tracked into the next one, win 23, maxLevel 1, 10 it, eps 0.03" % len(pts),
+           "gpu_launches_per_call": int(launches), "bit_exact_vs_oracle": bool(p.tobytes() == ep.tobytes() and np.array_equal(s, es)),
+           "cpu_baseline": {"kind": "port", "cores": 1, "ms_per_call": ms_port, "value": len(pts) / (ms_port * 1e-3), "unit": "points/s"}}
+    try:
+        import cv2
+        crit = (cv2.TERM_CRITERIA_COUNT + cv2.TERM_CRITERIA_EPS, 10, 0.03)
+        t0 = time.perf_counter()
+        for _ in range(20):
+            cv2.calcOpticalFlowPyrLK(i0, i1, pts.reshape(-1, 1, 2), None, winSize=(23, 23), maxLevel=1, criteria=crit)
+        ms_cv = (time.perf_counter() - t0) * 1e3 / 20
+        out["opencv_cpu"] = {"ms_per_call": ms_cv, "value": len(pts) / (ms_cv * 1e-3), "unit": "points/s", "threads": cv2.getNumThreads(),
+                             "note": "cv2 %s calcOpticalFlowPyrLK, the library the reference calls" % cv2.__version__}
+    except Exception as ex:   # cv2 is optional
+        out["opencv_cpu"] = {"error": repr(ex)}
+    return out
+
+
 # ------------------------------------------------------------------------------------------------ main arm
 def run_ours(args):
     import torch
@@ -391,6 +437,11 @@ def run_ours(args):
             extra["events"] = bench_events(api, torch, dev, max(args.steps, 3), max(args.warmup, 3))
         except Exception as e:   # extras never invalidate the headline line
             extra["events"] = {"error": repr(e)}
+        try:
+            if rank == 0:
+                extra["lk"] = bench_lk(api, torch, dev, args.steps, args.warmup)
+        except Exception as e:
+            extra["lk"] = {"error": repr(e)}
         try:
             extra["hamming"] = bench_hamming(api, torch, dev, max(min(args.steps, 3), 1), 3, world, rank, dist)
         except Exception as e:

@@ -34,7 +34,9 @@ struct eorb_lk {
     size_t off[EORB_LK_MAX_LEVELS] = {0}, doff[EORB_LK_MAX_LEVELS] = {0}, slabBytes = 0, derivCount = 0;
     int lw[EORB_LK_MAX_LEVELS] = {0}, lh[EORB_LK_MAX_LEVELS] = {0}, lpitch[EORB_LK_MAX_LEVELS] = {0};
     int w = 0, h = 0, win = 0, maxLevel = -1, nref = 0;
+    // outputs share one device buffer [next float2[maxPts] | err float[maxPts] | status u8[maxPts]] and one pinned mirror: one D2H
     float2* d_prev = nullptr; float2* d_next = nullptr; uint8_t* d_status = nullptr; float* d_err = nullptr;
+    uint8_t* d_out = nullptr; uint8_t* h_out = nullptr; uint8_t* h_img = nullptr; float* h_init = nullptr;
     long long launches = 0;
 };
 
@@ -59,8 +61,14 @@ extern "C" int eorb_lk_create(int device, int max_width, int max_height, int max
     h->slabBytes = bytes; h->derivCount = dcount;
     CU(cudaMalloc((void**)&h->d_ref, bytes)); CU(cudaMalloc((void**)&h->d_cur, bytes));
     CU(cudaMalloc((void**)&h->d_deriv, dcount * sizeof(short2)));
-    CU(cudaMalloc((void**)&h->d_prev, (size_t)max_points * sizeof(float2))); CU(cudaMalloc((void**)&h->d_next, (size_t)max_points * sizeof(float2)));
-    CU(cudaMalloc((void**)&h->d_status, (size_t)max_points)); CU(cudaMalloc((void**)&h->d_err, (size_t)max_points * sizeof(float)));
+    CU(cudaMalloc((void**)&h->d_prev, (size_t)max_points * sizeof(float2)));
+    const size_t outBytes = (size_t)max_points * (sizeof(float2) + sizeof(float) + 1);
+    CU(cudaMalloc((void**)&h->d_out, outBytes));
+    h->d_next = (float2*)h->d_out; h->d_err = (float*)(h->d_out + (size_t)max_points * sizeof(float2));
+    h->d_status = h->d_out + (size_t)max_points * (sizeof(float2) + sizeof(float));
+    CU(cudaMallocHost((void**)&h->h_out, outBytes));
+    CU(cudaMallocHost((void**)&h->h_img, (size_t)max_width * max_height));
+    CU(cudaMallocHost((void**)&h->h_init, (size_t)max_points * sizeof(float2)));
     *out = h;
     return EORB_OK;
 }
@@ -69,7 +77,8 @@ extern "C" int eorb_lk_destroy(eorb_lk* h) {
     if (!h) return EORB_OK;
     cudaSetDevice(h->device);
     cudaStreamSynchronize(h->stream);
-    cudaFree(h->d_ref); cudaFree(h->d_cur); cudaFree(h->d_deriv); cudaFree(h->d_prev); cudaFree(h->d_next); cudaFree(h->d_status); cudaFree(h->d_err);
+    cudaFree(h->d_ref); cudaFree(h->d_cur); cudaFree(h->d_deriv); cudaFree(h->d_prev); cudaFree(h->d_out);
+    cudaFreeHost(h->h_out); cudaFreeHost(h->h_img); cudaFreeHost(h->h_init);
     cudaStreamDestroy(h->ownStream);
     delete h;
     return EORB_OK;
@@ -104,7 +113,12 @@ static void lkGeometry(eorb_lk* h, int w, int hgt, int win, int maxLevel) {
 }
 
 static int lkBuildPyramid(eorb_lk* h, uint8_t* slab, const uint8_t* img, size_t stride, bool deviceSrc) {
-    CU(cudaMemcpy2DAsync(slab, h->lpitch[0], img, stride, h->w, h->h, deviceSrc ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, h->stream));
+    if (deviceSrc) {
+        CU(cudaMemcpy2DAsync(slab, h->lpitch[0], img, stride, h->w, h->h, cudaMemcpyDeviceToDevice, h->stream));
+    } else {   // through the pinned staging image: a truly asynchronous H2D instead of the driver's pageable path
+        for (int y = 0; y < h->h; y++) memcpy(h->h_img + (size_t)y * h->w, img + (size_t)y * stride, (size_t)h->w);
+        CU(cudaMemcpy2DAsync(slab, h->lpitch[0], h->h_img, h->w, h->w, h->h, cudaMemcpyHostToDevice, h->stream));
+    }
     for (int l = 1; l <= h->maxLevel; l++) {
         CU(launch_lk_pyrdown(slab + h->off[l - 1], h->lw[l - 1], h->lh[l - 1], h->lpitch[l - 1], slab + h->off[l], h->lw[l], h->lh[l], h->lpitch[l], h->stream));
         h->launches++;
@@ -150,7 +164,10 @@ static int lkTrack(eorb_lk* h, const uint8_t* img, size_t stride, bool deviceImg
     const int n = h->nref;
     int rc = lkBuildPyramid(h, h->d_cur, img, stride, deviceImg);
     if (rc != EORB_OK) return rc;
-    if (init_xy) CU(cudaMemcpyAsync(h->d_next, init_xy, (size_t)n * sizeof(float2), cudaMemcpyHostToDevice, h->stream));
+    if (init_xy) {
+        memcpy(h->h_init, init_xy, (size_t)n * sizeof(float2));
+        CU(cudaMemcpyAsync(h->d_next, h->h_init, (size_t)n * sizeof(float2), cudaMemcpyHostToDevice, h->stream));
+    }
     LkLevels L{};
     L.maxLevel = h->maxLevel;
     for (int l = 0; l <= h->maxLevel; l++) {
@@ -163,10 +180,12 @@ static int lkTrack(eorb_lk* h, const uint8_t* img, size_t stride, bool deviceImg
     p.epsilon2 = e * e; p.minEigThreshold = min_eig;
     CU(launch_lk_track(L, p, h->d_prev, h->d_next, n, h->d_status, err ? h->d_err : nullptr, h->stream));
     h->launches++;
-    CU(cudaMemcpyAsync(out_xy, h->d_next, (size_t)n * sizeof(float2), cudaMemcpyDeviceToHost, h->stream));
-    CU(cudaMemcpyAsync(status, h->d_status, (size_t)n, cudaMemcpyDeviceToHost, h->stream));
-    if (err) CU(cudaMemcpyAsync(err, h->d_err, (size_t)n * sizeof(float), cudaMemcpyDeviceToHost, h->stream));
+    const size_t outBytes = (size_t)h->maxPts * (sizeof(float2) + sizeof(float) + 1);
+    CU(cudaMemcpyAsync(h->h_out, h->d_out, outBytes, cudaMemcpyDeviceToHost, h->stream));
     CU(cudaStreamSynchronize(h->stream));
+    memcpy(out_xy, h->h_out, (size_t)n * sizeof(float2));
+    if (err) memcpy(err, h->h_out + (size_t)h->maxPts * sizeof(float2), (size_t)n * sizeof(float));
+    memcpy(status, h->h_out + (size_t)h->maxPts * (sizeof(float2) + sizeof(float)), (size_t)n);
     return h->maxLevel;
 }
 

@@ -4,9 +4,10 @@
 // (see oracle/lk_oracle.cc for the step-by-step description and the pin against cv2):
 //   lk_pyrdown_kernel  cv::pyrDown u8: [1 4 6 4 1] x [1 4 6 4 1], (sum + 128) >> 8, REFLECT_101
 //   lk_scharr_kernel   calcSharrDeriv: (Ix, Iy) int16, REFLECT_101 inside the level
-//   lk_track_kernel    LKTrackerInvoker: ONE WARP PER POINT walks all pyramid levels in one launch; the bilinear
-//                      patch (14-bit fixed point) lives in shared memory as int16 triples (I, Ix, Iy); the five sums
-//                      A11 A12 A22 b1 b2 are accumulated as EXACT integers (int64, warp-shuffle reduction) and
+//   lk_track_kernel    LKTrackerInvoker: ONE BLOCK (128 threads) PER POINT walks all pyramid levels in one launch; the
+//                      bilinear patch (14-bit fixed point) lives in shared memory as int16 triples (I, Ix, Iy), the
+//                      current frame's window is staged in shared memory once per level; the five sums
+//                      A11 A12 A22 b1 b2 are accumulated as EXACT integers (int64, shuffle + smem reduction) and
 //                      converted to float once — order independent, hence bit-equal to the oracle, and within one
 //                      float rounding of whichever lane order OpenCV's SIMD build uses; the scalar float algebra
 //                      uses explicit no-FMA intrinsics in the oracle's operation order.
@@ -83,25 +84,61 @@ __device__ __forceinline__ short2 lk_deriv_at(const LkLevelDev& L, int X, int Y)
     return __ldg(L.dI + (size_t)Y * L.w + X);
 }
 
-#define LK_WARPS 4
-__global__ void __launch_bounds__(LK_WARPS * 32) lk_track_kernel(LkLevels LV, LkParams prm, const float2* __restrict__ prevPts,
-                                                                 float2* __restrict__ nextPts, int n, uint8_t* __restrict__ status,
-                                                                 float* __restrict__ err) {
-    extern __shared__ short s_patch[];   // per warp: win*win x (I, Ix, Iy)
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int p = blockIdx.x * LK_WARPS + warp;
-    if (p >= n) return;
+#define LK_THREADS 128       // one block per point: the 23x23 patch is ~4 pixels per thread, so a Newton step is short
+#define LK_MARGIN 4          // the current-frame window is staged with this many spare pixels on every side
+
+// Stage the (win + 1 + 2*LK_MARGIN)^2 neighbourhood of the current frame around window origin (ox, oy) into shared
+// memory with the REFLECT_101 border applied, all loads independent (one memory latency instead of one per Newton
+// step and pixel).  Region origin = (ox - LK_MARGIN, oy - LK_MARGIN).
+__device__ __forceinline__ void lk_stage_region(const LkLevelDev& L, const uint8_t* __restrict__ img, int ox, int oy, int S, uint8_t* reg) {
+    const int x0 = ox - LK_MARGIN, y0 = oy - LK_MARGIN;
+    for (int i = threadIdx.x; i < S * S; i += LK_THREADS) {
+        const int y = i / S, x = i - y * S;
+        reg[i] = __ldg(img + (size_t)reflect101(y0 + y, L.h) * L.pitch + reflect101(x0 + x, L.w));
+    }
+}
+
+__device__ __forceinline__ int lk_sample32_smem(const uint8_t* reg, int S, int rx, int ry, int w00, int w01, int w10, int w11) {
+    const uint8_t* r0 = reg + ry * S + rx;
+    return lk_descale((int)r0[0] * w00 + (int)r0[1] * w01 + (int)r0[S] * w10 + (int)r0[S + 1] * w11, 14 - 5);
+}
+
+// exact block-wide sums of up to three int64 values; every thread gets the totals.  `slot` alternates between
+// consecutive calls so that one __syncthreads per call is enough.
+__device__ __forceinline__ void lk_block_sum(long long& a, long long& b, long long& c, long long (*scratch)[LK_THREADS / 32][3], int slot) {
+    a = warp_sum_ll(a); b = warp_sum_ll(b); c = warp_sum_ll(c);
+    const int warp = threadIdx.x >> 5;
+    if ((threadIdx.x & 31) == 0) { scratch[slot][warp][0] = a; scratch[slot][warp][1] = b; scratch[slot][warp][2] = c; }
+    __syncthreads();
+    a = b = c = 0;
+#pragma unroll
+    for (int w = 0; w < LK_THREADS / 32; w++) { a += scratch[slot][w][0]; b += scratch[slot][w][1]; c += scratch[slot][w][2]; }
+}
+
+__global__ void __launch_bounds__(LK_THREADS) lk_track_kernel(LkLevels LV, LkParams prm, const float2* __restrict__ prevPts,
+                                                              float2* __restrict__ nextPts, int n, uint8_t* __restrict__ status,
+                                                              float* __restrict__ err) {
+    extern __shared__ short s_patch[];   // win*win x (I, Ix, Iy), then the staged window of the current frame
+    __shared__ long long s_scratch[2][LK_THREADS / 32][3];
+    const int tid = threadIdx.x;
+    const int p = blockIdx.x;
     const int win = prm.win, area = win * win;
-    short* pI = s_patch + (size_t)warp * area * 3;
+    short* pI = s_patch;
     short* pIx = pI + area;
     short* pIy = pIx + area;
+    const int S = win + 1 + 2 * LK_MARGIN;
+    uint8_t* reg = reinterpret_cast<uint8_t*>(s_patch + (size_t)area * 3);
     const float halfWin = fmul((float)(win - 1), 0.5f);
     const float FLT_SCALE = 1.f / (1 << 20);
     const float2 pp = prevPts[p];
     float2 np = nextPts[p];          // only meaningful with useInitialFlow
     bool ok = true;                  // status[p]
     float errv = 0.f;
+    int slot = 0;
+    long long z = 0;
 
+    // every decision below depends only on block-uniform values (the sums are exact integers), so all threads take
+    // the same path through the level / iteration structure
     for (int level = LV.maxLevel; level >= 0; level--) {
         const LkLevelDev& L = LV.lv[level];
         const float sc = (float)(1. / (double)(1 << level));
@@ -123,8 +160,9 @@ __global__ void __launch_bounds__(LK_WARPS * 32) lk_track_kernel(LkLevels LV, Lk
         int w00, w01, w10, w11;
         lk_weights(fsub(px, (float)ipx), fsub(py, (float)ipy), w00, w01, w10, w11);
         long long sA11 = 0, sA12 = 0, sA22 = 0;
-        __syncwarp();
-        for (int i = lane; i < area; i += 32) {
+        __syncthreads();                 // the previous level is done with the patch and the staged window
+#pragma unroll 2
+        for (int i = tid; i < area; i += LK_THREADS) {
             const int y = i / win, x = i - y * win;
             const int X = ipx + x, Y = ipy + y;
             const int ival = lk_sample32(L, L.I, X, Y, w00, w01, w10, w11);
@@ -134,10 +172,10 @@ __global__ void __launch_bounds__(LK_WARPS * 32) lk_track_kernel(LkLevels LV, Lk
             pI[i] = (short)ival; pIx[i] = (short)ixval; pIy[i] = (short)iyval;
             sA11 += (long long)ixval * ixval; sA12 += (long long)ixval * iyval; sA22 += (long long)iyval * iyval;
         }
-        __syncwarp();
-        const float A11 = fmul(__ll2float_rn(warp_sum_ll(sA11)), FLT_SCALE);
-        const float A12 = fmul(__ll2float_rn(warp_sum_ll(sA12)), FLT_SCALE);
-        const float A22 = fmul(__ll2float_rn(warp_sum_ll(sA22)), FLT_SCALE);
+        lk_block_sum(sA11, sA12, sA22, s_scratch, slot); slot ^= 1;     // also publishes the patch (one barrier inside)
+        const float A11 = fmul(__ll2float_rn(sA11), FLT_SCALE);
+        const float A12 = fmul(__ll2float_rn(sA12), FLT_SCALE);
+        const float A22 = fmul(__ll2float_rn(sA22), FLT_SCALE);
         float D = fsub(fmul(A11, A22), fmul(A12, A12));
         const float dif = fsub(A11, A22);
         const float minEig = fdiv(fsub(fadd(A22, A11), __fsqrt_rn(fadd(fmul(dif, dif), fmul(fmul(4.f, A12), A12)))), (float)(2 * win * win));
@@ -148,20 +186,32 @@ __global__ void __launch_bounds__(LK_WARPS * 32) lk_track_kernel(LkLevels LV, Lk
         D = fdiv(1.f, D);
         nx = fsub(nx, halfWin); ny = fsub(ny, halfWin);
         float pdx = 0.f, pdy = 0.f;
+        int rox = 0, roy = 0;            // window origin the staged region was centred on
+        bool staged = false;
         for (int j = 0; j < prm.maxIter; j++) {
             const int inx = (int)floorf(nx), iny = (int)floorf(ny);
             if (inx < -win || inx >= L.w || iny < -win || iny >= L.h) {
                 if (level == 0) ok = false;
                 break;
             }
+            if (!staged || inx < rox - LK_MARGIN || inx > rox + LK_MARGIN || iny < roy - LK_MARGIN || iny > roy + LK_MARGIN) {
+                __syncthreads();
+                lk_stage_region(L, L.J, inx, iny, S, reg);
+                rox = inx; roy = iny; staged = true;
+                __syncthreads();
+            }
             lk_weights(fsub(nx, (float)inx), fsub(ny, (float)iny), w00, w01, w10, w11);
             long long sb1 = 0, sb2 = 0;
-            for (int i = lane; i < area; i += 32) {
+            const int bx = inx - rox + LK_MARGIN, by = iny - roy + LK_MARGIN;
+#pragma unroll 2
+            for (int i = tid; i < area; i += LK_THREADS) {
                 const int y = i / win, x = i - y * win;
-                const int diff = lk_sample32(L, L.J, inx + x, iny + y, w00, w01, w10, w11) - (int)pI[i];
+                const int diff = lk_sample32_smem(reg, S, bx + x, by + y, w00, w01, w10, w11) - (int)pI[i];
                 sb1 += (long long)diff * (int)pIx[i]; sb2 += (long long)diff * (int)pIy[i];
             }
-            const float b1 = fmul(__ll2float_rn(warp_sum_ll(sb1)), FLT_SCALE), b2 = fmul(__ll2float_rn(warp_sum_ll(sb2)), FLT_SCALE);
+            z = 0;
+            lk_block_sum(sb1, sb2, z, s_scratch, slot); slot ^= 1;
+            const float b1 = fmul(__ll2float_rn(sb1), FLT_SCALE), b2 = fmul(__ll2float_rn(sb2), FLT_SCALE);
             const float dx = fmul(fsub(fmul(A12, b2), fmul(A22, b1)), D), dy = fmul(fsub(fmul(A12, b1), fmul(A11, b2)), D);
             nx = fadd(nx, dx); ny = fadd(ny, dy);
             np = make_float2(fadd(nx, halfWin), fadd(ny, halfWin));
@@ -177,16 +227,21 @@ __global__ void __launch_bounds__(LK_WARPS * 32) lk_track_kernel(LkLevels LV, Lk
             const int iex = (int)floorf(ex), iey = (int)floorf(ey);
             if (iex < -win || iex >= L.w || iey < -win || iey >= L.h) { ok = false; continue; }
             lk_weights(fsub(ex, (float)iex), fsub(ey, (float)iey), w00, w01, w10, w11);
-            long long se = 0;
-            for (int i = lane; i < area; i += 32) {
+            long long se = 0, z1 = 0, z2 = 0;
+            const bool inReg = staged && iex >= rox - LK_MARGIN && iex <= rox + LK_MARGIN && iey >= roy - LK_MARGIN && iey <= roy + LK_MARGIN;
+            const int bx = iex - rox + LK_MARGIN, by = iey - roy + LK_MARGIN;
+            for (int i = tid; i < area; i += LK_THREADS) {
                 const int y = i / win, x = i - y * win;
-                const int diff = lk_sample32(L, L.J, iex + x, iey + y, w00, w01, w10, w11) - (int)pI[i];
+                const int v = inReg ? lk_sample32_smem(reg, S, bx + x, by + y, w00, w01, w10, w11)
+                                    : lk_sample32(L, L.J, iex + x, iey + y, w00, w01, w10, w11);
+                const int diff = v - (int)pI[i];
                 se += diff < 0 ? -diff : diff;
             }
-            errv = fdiv(fmul(__ll2float_rn(warp_sum_ll(se)), 1.f), (float)(32 * win * win));
+            lk_block_sum(se, z1, z2, s_scratch, slot); slot ^= 1;
+            errv = fdiv(fmul(__ll2float_rn(se), 1.f), (float)(32 * win * win));
         }
     }
-    if (lane == 0) {
+    if (tid == 0) {
         nextPts[p] = np;
         status[p] = ok ? 1 : 0;
         if (err) err[p] = errv;
@@ -208,10 +263,9 @@ cudaError_t launch_lk_scharr(const uint8_t* src, int w, int h, int pitch, short2
 cudaError_t launch_lk_track(const LkLevels& L, const LkParams& p, const float2* prevPts, float2* nextPts, int n, uint8_t* status, float* err,
                             cudaStream_t st) {
     if (n <= 0) return cudaSuccess;
-    const size_t smem = (size_t)LK_WARPS * p.win * p.win * 3 * sizeof(short);
-    cudaError_t e = cudaFuncSetAttribute(lk_track_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return e;
-    lk_track_kernel<<<(n + LK_WARPS - 1) / LK_WARPS, LK_WARPS * 32, smem, st>>>(L, p, prevPts, nextPts, n, status, err);
+    const int S = p.win + 1 + 2 * LK_MARGIN;
+    const size_t smem = (size_t)p.win * p.win * 3 * sizeof(short) + (size_t)S * S;
+    lk_track_kernel<<<n, LK_THREADS, smem, st>>>(L, p, prevPts, nextPts, n, status, err);
     return cudaGetLastError();
 }
 
