@@ -8,6 +8,7 @@
 #include "ORBextractor.h"
 #include "ORBmatcher_b200.h"
 #include "EventConversion_b200.h"
+#include "KLT_b200.h"
 #include "eorb_b200.h"
 
 int main(int argc, char** argv)
@@ -50,5 +51,17 @@ int main(int argc, char** argv)
     double sum2 = 0;
     for (int y = 0; y < 180; y++) for (int x = 0; x < 240; x++) sum2 += g.at<float>(y, x);
     std::printf("ev_sum=%.3f ev_u8_max=%d types=%d,%d mci_sum=%.3f\n", sum, mx, f.type(), u.type(), sum2);
+    // ELK_Tracker's call: track the extractor's keypoints from the image into a copy shifted by (2, 1) pixels
+    {
+        cv::Mat im2(H, W, CV_8UC1);
+        for (int y = 0; y < H; y++) for (int x = 0; x < W; x++) im2.at<unsigned char>(y, x) = im.at<unsigned char>(y >= 1 ? y - 1 : 0, x >= 2 ? x - 2 : 0);
+        std::vector<cv::Point2f> p0, p1;
+        for (size_t i = 0; i < kps.size(); i++) p0.push_back(kps[i].pt);
+        std::vector<unsigned char> st; std::vector<float> er;
+        const bool okk = EORB_SLAM::b200::calcOpticalFlowPyrLK(im, im2, p0, p1, st, er, 23, 1, 10, 0.03, false);
+        int good = 0, tracked = 0;
+        for (size_t i = 0; i < st.size(); i++) if (st[i]) { tracked++; const float dx = p1[i].x - p0[i].x - 2.f, dy = p1[i].y - p0[i].y - 1.f; good += (dx * dx + dy * dy < 0.25f); }
+        std::printf("lk_ok=%d lk_n=%zu lk_tracked=%d lk_good=%d\n", (int)okk, p1.size(), tracked, good);
+    }
     return 0;
 }

@@ -14,7 +14,7 @@ EXE = os.path.join(SHIM, "_shim_selftest")
 
 
 def _build():
-    srcs = [os.path.join(SHIM, f) for f in ("shim_selftest.cc", "ORBextractor.cc", "ORBmatcher_b200.cc", "EventConversion_b200.cc")]
+    srcs = [os.path.join(SHIM, f) for f in ("shim_selftest.cc", "ORBextractor.cc", "ORBmatcher_b200.cc", "EventConversion_b200.cc", "KLT_b200.cc")]
     cmd = ["g++", "-std=c++17", "-O1", "-DEORB_SHIM_MOCK", "-I" + os.path.join(SHIM, "cv_mock"), "-I" + SHIM,
            "-I" + os.path.join(ROOT, "include"), "-o", EXE] + srcs + ["-L" + os.path.join(ROOT, "eorb_slam_b200"), "-leorb_b200",
                                                                       "-Wl,-rpath," + os.path.join(ROOT, "eorb_slam_b200")]
@@ -48,6 +48,7 @@ def test_shims_compile_and_fail_loudly_without_device():
         pytest.skip("a CUDA device is present")
     assert "ret=-1 n=0" in out and "empty_ret=-1" in out
     assert "no CUDA device" in err
+    assert "lk_ok=0 lk_n=0" in out
 
 
 @pytest.mark.gpu
@@ -67,3 +68,6 @@ def test_shims_match_oracle_on_gpu():
     ev = re.search(r"ev_sum=([\d.]+) ev_u8_max=(\d+) types=(\d+),(\d+) mci_sum=([\d.]+)", out)
     assert int(ev.group(2)) == 255 and (int(ev.group(3)), int(ev.group(4))) == (5, 0)     # CV_32FC1, CV_8UC1
     assert abs(float(ev.group(1)) - float(ev.group(5))) < 1e-2 * float(ev.group(1))        # identity pose == plain splat
+    lk = re.search(r"lk_ok=(\d+) lk_n=(\d+) lk_tracked=(\d+) lk_good=(\d+)", out)
+    assert lk and int(lk.group(1)) == 1 and int(lk.group(2)) == len(okps)
+    assert int(lk.group(3)) > 0.8 * len(okps) and int(lk.group(4)) > 0.9 * int(lk.group(3))      # the (2, 1) shift is recovered
