@@ -81,6 +81,7 @@ def _load():
         "eorb_ev_set_stream": ([vp, vp], i), "eorb_ev_reset_stream": ([vp], i), "eorb_ev_synchronize": ([vp], i), "eorb_ev_launch_count": ([vp], C.c_longlong),
         "eorb_ev_accumulate": ([vp, vp, i64, C.POINTER(_EvParams), vp, vp, vp], i),
         "eorb_ev_accumulate_batch_device": ([vp, vp, vp, i, C.POINTER(_EvParams), vp, vp, vp], i),
+        "eorb_ev_image_focus_device": ([vp, vp, i, i, i, i, i, vp], i), "eorb_ev_image_focus": ([vp, vp, i, i, sz, i, i, vp], i),
         "eorb_lk_create": ([i, i, i, i, C.POINTER(vp)], i), "eorb_lk_destroy": ([vp], i),
         "eorb_lk_set_stream": ([vp, vp], i), "eorb_lk_reset_stream": ([vp], i), "eorb_lk_launch_count": ([vp], C.c_longlong),
         "eorb_lk_set_ref": ([vp, vp, i, i, sz, vp, i, i, i], i), "eorb_lk_set_ref_device": ([vp, vp, i, i, sz, vp, i, i, i], i),
@@ -474,6 +475,34 @@ class EvImConverter:
         p = self.make_params(EV_NEAREST, imWidth, imHeight, 1.0, pol, NORM_RUNNING if normalized else NORM_NONE)
         _, img, u8, _ = self._run(vEvData, p)
         return u8 if normalized else img
+
+    # ---- contrast metric (EventConversion.cc:74-162)
+    FOCUS_LOCAL_STD, FOCUS_GLOBAL_STD, FOCUS_LOCAL_MEAN = 0, 1, 2
+
+    def measureImageFocusLocal(self, image, avg=True):
+        return self._focus(image, self.FOCUS_LOCAL_STD, avg)
+
+    def measureImageFocus(self, image):
+        return self._focus(image, self.FOCUS_LOCAL_STD, True)
+
+    def measureImageFocusGlobal(self, image):
+        return self._focus(image, self.FOCUS_GLOBAL_STD, True)
+
+    def imageMeanLocal(self, image, avg=True):
+        return self._focus(image, self.FOCUS_LOCAL_MEAN, avg)
+
+    def _focus(self, image, what, avg):
+        image = np.ascontiguousarray(image, np.float32)
+        out = np.zeros(1, np.float32)
+        _check(lib.eorb_ev_image_focus(self.h, _p(image), image.shape[1], image.shape[0], image.strides[0], what, 1 if avg else 0, _p(out)),
+               "image_focus")
+        return float(out[0])
+
+    def image_focus_device(self, d_img_f32, nwin, w, h, what=0, avg=True):
+        """metric of nwin device-resident frames -> float32[nwin]; argmax = the reference's best-of-N candidate choice"""
+        out = np.zeros(nwin, np.float32)
+        _check(lib.eorb_ev_image_focus_device(self.h, _p(d_img_f32), nwin, w, h, what, 1 if avg else 0, _p(out)), "image_focus_device")
+        return out
 
     def ev2im_gauss(self, vEvData, imWidth, imHeight, sigma, pol=False, normalized=True, both=False):
         p = self.make_params(EV_GAUSS, imWidth, imHeight, sigma, pol, NORM_RUNNING if normalized else NORM_NONE)

@@ -1311,6 +1311,32 @@ extern "C" int eorb_ev_accumulate_batch_device(eorb_evconv* c, const eorb_event*
     return EORB_OK;
 }
 
+// measureImageFocusLocal / measureImageFocusGlobal / imageMeanLocal (EventConversion.cc:79-162) of nwin device frames
+extern "C" int eorb_ev_image_focus_device(eorb_evconv* c, const float* d_img_f32, int nwin, int w, int hgt, int what, int avg, float* focus_out) {
+    if (!c || !d_img_f32 || !focus_out) return fail(EORB_ERR_ARG, "null argument");
+    if (nwin < 1) return EORB_OK;
+    if (w < 1 || hgt < 1 || what < 0 || what > 2) return fail(EORB_ERR_ARG, "bad image size / metric");
+    if (nwin > c->maxWindows) return fail(EORB_ERR_CAPACITY, "nwin %d > max_windows %d", nwin, c->maxWindows);
+    const int patch = 30;   // DEF_PATCH_SIZE_STD (include/Event/EventConversion.h:28)
+    if (((w + patch - 1) / patch) * ((hgt + patch - 1) / patch) > EORB_EV_FOCUS_MAX_CELLS) return fail(EORB_ERR_CAPACITY, "image too large for the focus metric");
+    CU(cudaSetDevice(c->device));
+    // the per-window min/max slots double as the output scratch (2 floats per window)
+    CU(launch_ev_focus(d_img_f32, nwin, w, hgt, patch, what, avg ? 1 : 0, c->d_minmax, c->stream, &c->launches));
+    CU(cudaMemcpyAsync(focus_out, c->d_minmax, (size_t)nwin * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    return EORB_OK;
+}
+
+// the same for one host image (the shape of the reference's static call): H2D, metric, result
+extern "C" int eorb_ev_image_focus(eorb_evconv* c, const float* img_f32, int w, int hgt, size_t stride_bytes, int what, int avg, float* focus_out) {
+    if (!c || !focus_out) return fail(EORB_ERR_ARG, "null argument");
+    if (!img_f32 || w < 1 || hgt < 1) return EORB_EMPTY;
+    if ((long long)w * hgt > (long long)c->maxW * c->maxH) return fail(EORB_ERR_CAPACITY, "image %dx%d exceeds the converter's %dx%d", w, hgt, c->maxW, c->maxH);
+    CU(cudaSetDevice(c->device));
+    CU(cudaMemcpy2DAsync(c->d_img, (size_t)w * 4, img_f32, stride_bytes, (size_t)w * 4, hgt, cudaMemcpyHostToDevice, c->stream));
+    return eorb_ev_image_focus_device(c, c->d_img, 1, w, hgt, what, avg, focus_out);
+}
+
 extern "C" int eorb_ev_accumulate(eorb_evconv* c, const eorb_event* evs, int64_t n, const eorb_ev_params* p, float* img_f32,
                                   uint8_t* img_u8, float* minmax) {
     if (!c || !p) return fail(EORB_ERR_ARG, "null argument");

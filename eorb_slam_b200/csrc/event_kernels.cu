@@ -299,6 +299,77 @@ cudaError_t launch_ev_splat(const eorb_event* d_evs, const EvWindow* d_wins, int
     return cudaGetLastError();
 }
 
+// ---- contrast metric of event frames -------------------------------------------------------
+// EvImConverter::measureImageFocusLocal / measureImageFocusGlobal / imageMeanLocal (EventConversion.cc:79-162): the
+// image is cut into patch x patch cells (30, DEF_PATCH_SIZE_STD), cv::meanStdDev of every cell (sum and sum of
+// squares in double), the per-cell value cast to float and accumulated in float IN CELL ORDER, or sorted for the
+// median.  One block per frame, one warp per cell (double shuffle reduction), thread 0 does the ordered float part.
+// what: 0 local std-dev, 1 global std-dev, 2 local mean;  avg: 1 average, 0 median.
+#define EV_FOCUS_MAX_CELLS 1024
+__device__ __forceinline__ double warp_sum_d(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+__global__ void __launch_bounds__(256) ev_focus_kernel(const float* __restrict__ img, int W, int H, int patch, int what, int avg,
+                                                       float* __restrict__ out) {
+    __shared__ float s_val[EV_FOCUS_MAX_CELLS];
+    __shared__ double s_part[8][2];
+    const float* im = img + (size_t)blockIdx.x * (size_t)W * H;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (what == 1) {   // one cell = the whole frame, all warps
+        double s = 0, sq = 0;
+        for (int i = threadIdx.x; i < W * H; i += 256) { const double v = im[i]; s += v; sq += v * v; }
+        s = warp_sum_d(s); sq = warp_sum_d(sq);
+        if (lane == 0) { s_part[warp][0] = s; s_part[warp][1] = sq; }
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            s = 0; sq = 0;
+            for (int k = 0; k < 8; k++) { s += s_part[k][0]; sq += s_part[k][1]; }
+            const double n = (double)W * H, mean = s / n, var = sq / n - mean * mean;
+            out[blockIdx.x] = (float)sqrt(var > 0 ? var : 0);
+        }
+        return;
+    }
+    const int npc = (W + patch - 1) / patch, npr = (H + patch - 1) / patch, cells = npc * npr;
+    for (int c = warp; c < cells; c += 8) {
+        const int cr = c / npc, cc = c - cr * npc;
+        const int r0 = cr * patch, r1 = min(r0 + patch, H), c0 = cc * patch, c1 = min(c0 + patch, W);
+        const int pw = c1 - c0, area = pw * (r1 - r0);
+        double s = 0, sq = 0;
+        for (int i = lane; i < area; i += 32) {
+            const int y = i / pw, x = i - y * pw;
+            const double v = im[(size_t)(r0 + y) * W + c0 + x];
+            s += v; sq += v * v;
+        }
+        s = warp_sum_d(s); sq = warp_sum_d(sq);
+        if (lane == 0) {
+            const double n = (double)area, mean = s / n, var = sq / n - mean * mean;
+            s_val[c] = (float)(what == 2 ? mean : sqrt(var > 0 ? var : 0));
+        }
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        if (avg) {
+            float acc = 0.f;
+            for (int c = 0; c < cells; c++) acc = __fadd_rn(acc, s_val[c]);
+            out[blockIdx.x] = __fdiv_rn(acc, (float)cells);
+        } else {
+            for (int a = 1; a < cells; a++) { const float v = s_val[a]; int b = a - 1; while (b >= 0 && s_val[b] > v) { s_val[b + 1] = s_val[b]; b--; } s_val[b + 1] = v; }
+            out[blockIdx.x] = s_val[cells / 2];
+        }
+    }
+}
+
+cudaError_t launch_ev_focus(const float* d_img, int nwin, int W, int H, int patch, int what, int avg, float* d_out, cudaStream_t st,
+                            long long* launches) {
+    if (nwin <= 0) return cudaSuccess;
+    ev_focus_kernel<<<nwin, 256, 0, st>>>(d_img, W, H, patch, what, avg, d_out);
+    (*launches)++;
+    return cudaGetLastError();
+}
+
 // whole path: zero + splat + min/max + normalise.  7x7 Gaussian windows take the shared-memory kernel (which also
 // zeroes and, for single-band frames, normalises); everything else the L2-reduction kernels.
 cudaError_t launch_ev_frames(const eorb_event* d_evs, const EvWindow* d_wins, int nwin, long long maxEventsPerWindow, const EvConst& c,

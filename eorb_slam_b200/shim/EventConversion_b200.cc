@@ -109,4 +109,26 @@ cv::Mat EvImConverter::ev2mci_gg_f_minmax_u8(const std::vector<EventData> &vEvDa
     for (int r = 0; r < 4; r++) for (int c = 0; c < 4; c++) p.Tcw[4 * r + c] = Tcw.at<float>(r, c);
     return run(vEvData, p, true);
 }
+
+namespace {
+float focus(const cv::Mat& image, int what, bool avg)
+{
+    if (image.empty() || image.type() != CV_32FC1) {
+        std::fprintf(stderr, "EvImConverter(b200): the contrast metric expects a non-empty CV_32FC1 frame\n");
+        return 0.f;
+    }
+    eorb_evconv* c = t_conv.get(1, image.cols, image.rows);
+    if (!c) return 0.f;
+    float v = 0.f;
+    int rc = eorb_ev_image_focus(c, image.ptr<float>(), image.cols, image.rows, image.step, what, avg ? 1 : 0, &v);
+    if (rc < EORB_EMPTY) std::fprintf(stderr, "EvImConverter(b200): %s\n", eorb_last_error());
+    return v;
+}
+} // namespace
+
+float EvImConverter::measureImageFocus(const cv::Mat& image) { return focus(image, EORB_FOCUS_LOCAL_STD, true); }
+float EvImConverter::measureImageFocusLocal(const cv::Mat& image, const bool avg) { return focus(image, EORB_FOCUS_LOCAL_STD, avg); }
+float EvImConverter::measureImageFocusGlobal(const cv::Mat& image) { return focus(image, EORB_FOCUS_GLOBAL_STD, true); }
+float EvImConverter::imageMeanLocal(const cv::Mat& image, const bool avg) { return focus(image, EORB_FOCUS_LOCAL_MEAN, avg); }
+
 }// namespace EORB_SLAM

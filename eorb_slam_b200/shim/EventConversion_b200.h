@@ -32,6 +32,13 @@ namespace EORB_SLAM
                                    const cv::Mat& params2D, unsigned imWidth, unsigned imHeight, float sigma,
                                    bool pol = false, bool normalized = true);
 
+        // contrast metric (EventConversion.h:45-50, EventConversion.cc:74-162); image: CV_32FC1 (the un-normalised
+        // frame the callers pass, EvImBuilder.cpp:969-973).  Returns 0 and logs on error.
+        static float measureImageFocus(const cv::Mat& image);
+        static float measureImageFocusLocal(const cv::Mat& image, bool avg = true);
+        static float measureImageFocusGlobal(const cv::Mat& image);
+        static float imageMeanLocal(const cv::Mat& image, bool avg = true);
+
         // cv::normalize(img, img, 255, 0, NORM_MINMAX, CV_8UC1) as applied by the callers (EvImBuilder.cpp:976,...)
         // fused on the device: returns the CV_8UC1 frame directly.
         static cv::Mat ev2mci_gg_f_minmax_u8(const std::vector<EventData> &vEvData, ORB_SLAM3::GeometricCamera* pCamera,

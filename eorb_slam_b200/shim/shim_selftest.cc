@@ -51,6 +51,9 @@ int main(int argc, char** argv)
     double sum2 = 0;
     for (int y = 0; y < 180; y++) for (int x = 0; x < 240; x++) sum2 += g.at<float>(y, x);
     std::printf("ev_sum=%.3f ev_u8_max=%d types=%d,%d mci_sum=%.3f\n", sum, mx, f.type(), u.type(), sum2);
+    std::printf("focus=%.6f focus_med=%.6f focus_glob=%.6f mean_loc=%.6f\n", EORB_SLAM::EvImConverter::measureImageFocus(f),
+                EORB_SLAM::EvImConverter::measureImageFocusLocal(f, false), EORB_SLAM::EvImConverter::measureImageFocusGlobal(f),
+                EORB_SLAM::EvImConverter::imageMeanLocal(f));
     // ELK_Tracker's call: track the extractor's keypoints from the image into a copy shifted by (2, 1) pixels
     {
         cv::Mat im2(H, W, CV_8UC1);

@@ -250,6 +250,17 @@ int eorb_ev_accumulate_batch_device(eorb_evconv* c, const eorb_event* d_evs, con
                                     const eorb_ev_params* p, const float* poses,
                                     float* d_img_f32, uint8_t* d_img_u8);
 
+/* contrast metric of event frames (second "next" row): EvImConverter::measureImageFocusLocal (what = 0),
+ * measureImageFocusGlobal (1), imageMeanLocal (2) — src/Event/EventConversion.cc:79-162, 30x30 cells, cv::meanStdDev
+ * per cell; avg != 0: average of the cell values (measureImageFocus), avg == 0: their median.  The reference picks the
+ * motion-compensated candidate with the largest value (EvImBuilder.cpp:1206-1215); with the _device form the
+ * candidates never leave the GPU.  focus_out is a host array. */
+#define EORB_FOCUS_LOCAL_STD  0
+#define EORB_FOCUS_GLOBAL_STD 1
+#define EORB_FOCUS_LOCAL_MEAN 2
+int eorb_ev_image_focus_device(eorb_evconv* c, const float* d_img_f32, int nwin, int w, int hgt, int what, int avg, float* focus_out);
+int eorb_ev_image_focus(eorb_evconv* c, const float* img_f32, int w, int hgt, size_t stride_bytes, int what, int avg, float* focus_out);
+
 /* ---------------------------------------------------------------- LK tracker (first "next" row)
  * replaces EORB_SLAM::ELK_Tracker::setRefImage / trackCurrImage (include/Event/KLT_Tracker.h,
  * src/Event/KLT_Tracker.cpp:22-91), i.e. cv::calcOpticalFlowPyrLK(ref, cur, refPts, pts, status, err,

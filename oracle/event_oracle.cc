@@ -200,4 +200,41 @@ void orc_normalize_minmax_u8(const float* img, int n, uint8_t* out) {
     }
 }
 
+// ---- contrast metric of a (motion-compensated) event frame: SURVEY.md §8f rank 2
+// EvImConverter::measureImageFocusLocal / measureImageFocusGlobal / imageMeanLocal, src/Event/EventConversion.cc:79-162,
+// DEF_PATCH_SIZE_STD = 30 (include/Event/EventConversion.h:28).  cv::meanStdDev on CV_32F accumulates sum and
+// sum of squares in double; mean = s/N, std = sqrt(max(sq/N - mean^2, 0)).  The per-patch values are cast to float
+// and accumulated in float in patch order (:98-101), the median variant sorts them (:108-109).
+// what: 0 = local std-dev (measureImageFocusLocal), 1 = global std-dev (measureImageFocusGlobal), 2 = local mean (imageMeanLocal)
+// avg:  1 = average of the patch values, 0 = median (vLocalStd[cnt/2] after sorting)
+static void patch_mean_std(const float* img, int w, int r0, int r1, int c0, int c1, double& mean, double& sd) {
+    double s = 0, sq = 0;
+    for (int y = r0; y < r1; y++)
+        for (int x = c0; x < c1; x++) { const double v = img[(size_t)y * w + x]; s += v; sq += v * v; }
+    const double n = (double)(r1 - r0) * (c1 - c0);
+    mean = s / n;
+    const double var = sq / n - mean * mean;
+    sd = sqrt(var > 0 ? var : 0);
+}
+
+float orc_image_focus(const float* img, int w, int h, int patch, int what, int avg) {
+    if (what == 1) { double m, sd; patch_mean_std(img, w, 0, h, 0, w, m, sd); return (float)sd; }
+    float acc = 0.f;
+    int cnt = 0;
+    float vals[4096];
+    for (int i = 0; i < h; i += patch)
+        for (int j = 0; j < w; j += patch) {
+            double m, sd;
+            patch_mean_std(img, w, i, i + patch < h ? i + patch : h, j, j + patch < w ? j + patch : w, m, sd);
+            const float v = (float)(what == 2 ? m : sd);
+            acc += v;
+            if (cnt < 4096) vals[cnt] = v;
+            cnt++;
+        }
+    if (avg) return acc / (float)cnt;
+    const int n = cnt < 4096 ? cnt : 4096;
+    for (int a = 1; a < n; a++) { const float v = vals[a]; int b = a - 1; while (b >= 0 && vals[b] > v) { vals[b + 1] = vals[b]; b--; } vals[b + 1] = v; }
+    return vals[cnt / 2];
+}
+
 }  // extern "C"

@@ -120,6 +120,8 @@ int   orc_ev_accumulate(const orc_event* evs, int64_t n, int w, int h, float sig
 void  orc_normalize_convert_u8(const float* img, int n, float maxVal, float minVal, uint8_t* out);
 /* cv::normalize(img,out,255,0,NORM_MINMAX,CV_8UC1) */
 void  orc_normalize_minmax_u8(const float* img, int n, uint8_t* out);
+/* measureImageFocusLocal / Global, imageMeanLocal (EventConversion.cc:79-162); see event_oracle.cc */
+float orc_image_focus(const float* img, int w, int h, int patch, int what, int avg);
 
 #ifdef __cplusplus
 }

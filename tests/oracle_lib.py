@@ -87,6 +87,7 @@ def lib():
     L.orc_ev_accumulate.restype = C.c_int
     L.orc_normalize_convert_u8.argtypes = [vp, C.c_int, C.c_float, C.c_float, vp]; L.orc_normalize_convert_u8.restype = None
     L.orc_normalize_minmax_u8.argtypes = [vp, C.c_int, vp]; L.orc_normalize_minmax_u8.restype = None
+    L.orc_image_focus.argtypes = [vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int]; L.orc_image_focus.restype = C.c_float
     L.orc_pyrdown_u8.argtypes = [vp, C.c_int, C.c_int, C.c_size_t, vp, C.c_int, C.c_int, C.c_size_t]; L.orc_pyrdown_u8.restype = None
     L.orc_scharr_deriv.argtypes = [vp, C.c_int, C.c_int, C.c_size_t, vp]; L.orc_scharr_deriv.restype = None
     L.orc_lk_track.argtypes = [vp, vp, C.c_int, C.c_int, C.c_size_t, vp, vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_double, C.c_int,
@@ -327,3 +328,12 @@ def lk_track(prev_img, next_img, prev_pts, next_pts=None, win=23, max_level=1, m
     lv = lib().orc_lk_track(_p(prev_img), _p(next_img), w, h, prev_img.strides[0], _p(pp), _p(npts), n, win, max_level, max_iter, float(eps),
                             1 if use_init else 0, float(min_eig), _p(status), _p(err))
     return npts, status, err, lv
+
+
+# ----------------------------------------------------------------------------- contrast metric
+FOCUS_LOCAL_STD, FOCUS_GLOBAL_STD, FOCUS_LOCAL_MEAN = 0, 1, 2
+
+
+def image_focus(img: np.ndarray, what=FOCUS_LOCAL_STD, avg=True, patch=30) -> float:
+    img = np.ascontiguousarray(img, np.float32)
+    return float(lib().orc_image_focus(_p(img), img.shape[1], img.shape[0], patch, what, 1 if avg else 0))

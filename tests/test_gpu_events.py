@@ -161,3 +161,37 @@ def test_config5_mvsec_mc_frames_orb_and_frame_to_frame_matching():
         e12 = np.where(exp["accepted"] == 1, exp["best_idx"], -1).astype(np.int32)
         n_ref, m_ref = O.rotation_filter(ka["angle"], kb["angle"], e12)
         assert n == n_ref and np.array_equal(m12, m_ref)
+
+
+def test_contrast_metric_and_best_candidate_selection_on_device():
+    """measureImageFocus* / imageMeanLocal of event frames (EventConversion.cc:79-162) and the
+    best-of-N motion-compensated candidate choice (EvImBuilder.cpp:1206-1215) without the frames leaving the GPU.
+    Tolerance 2e-6 relative (double sums in a different order, cast to float once per cell)."""
+    import torch
+    api = _api()
+    w, h, per = 346, 260, 20000
+    ev = synth.make_events(per, seed=17, w=w, h=h, mean_dt=2e-7, n_edges=40)
+    cv = api.EvImConverter(0, 4, per * 4, w, h)
+    ref, _, _ = O.ev_accumulate(ev, w, h, 1.0, mode=1)
+    for what in (0, 1, 2):
+        for avg in (True, False):
+            got = cv._focus(ref, what, avg)
+            exp = O.image_focus(ref, what, avg)
+            assert abs(got - exp) <= 2e-6 * max(abs(exp), 1e-3), (what, avg, got, exp)
+    assert cv.measureImageFocus(ref) == cv.measureImageFocusLocal(ref, True)
+    small = (np.random.default_rng(3).random((47, 61)) * 3).astype(np.float32)          # partial cells on both edges
+    assert abs(cv.measureImageFocus(small) - O.image_focus(small)) <= 2e-6 * O.image_focus(small)
+    # four motion-compensation candidates (different rotation hypotheses) of the same window, frames stay on the device
+    dt = float(ev["ts"][-1] - ev["ts"][0])
+    hyps = [np.array([0.0, 0.0, 0.0]), np.array([0.5, -0.7, 1.5]) * dt, np.array([-1.0, 0.4, -2.0]) * dt, np.array([0.2, 0.1, 3.0]) * dt]
+    poses = np.stack([synth.rotation_tcw(o) for o in hyps]).astype(np.float32).reshape(4, 16)
+    d_ev = torch.from_numpy(np.tile(ev.view(np.uint8).reshape(-1), 4)).cuda()
+    d_img = torch.empty(4 * h * w, dtype=torch.float32, device="cuda")
+    p = cv.make_params(api.EV_SE3, w, h, 1.0, False, api.NORM_NONE, medDepth=1.0, camera=K_MVSEC)
+    offs = np.arange(5, dtype=np.int64) * per
+    cv.accumulate_batch_device(d_ev.data_ptr(), offs, p, d_img.data_ptr(), None, poses=poses)
+    focus = cv.image_focus_device(d_img.data_ptr(), 4, w, h)
+    frames = d_img.cpu().numpy().reshape(4, h, w)
+    exp = np.array([O.image_focus(f) for f in frames], np.float32)
+    assert np.all(np.abs(focus - exp) <= 2e-6 * exp)
+    assert int(np.argmax(focus)) == int(np.argmax(exp))

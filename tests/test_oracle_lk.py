@@ -69,3 +69,34 @@ def test_lk_matches_cv2_within_summation_order_freedom(cfg):
     ok2 = same2 & (ref_s2 == 1)
     d2 = np.abs(got_p2[ok2] - ref_p2[ok2]).max(axis=1)
     assert (d2 <= 0.02).mean() >= 0.99
+
+
+# ---- contrast metric of event frames: oracle vs a cv2.meanStdDev restatement of the reference loop
+def _focus_cv2(img, what, avg, patch=30):
+    h, w = img.shape
+    if what == O.FOCUS_GLOBAL_STD:
+        return np.float32(cv2.meanStdDev(img)[1][0, 0])
+    vals = []
+    acc = np.float32(0)
+    for i in range(0, h, patch):
+        for j in range(0, w, patch):
+            m, s = cv2.meanStdDev(img[i:min(i + patch, h), j:min(j + patch, w)])
+            v = np.float32(m[0, 0] if what == O.FOCUS_LOCAL_MEAN else s[0, 0])
+            acc = np.float32(acc + v); vals.append(v)
+    if avg:
+        return np.float32(acc / np.float32(len(vals)))
+    return sorted(vals)[len(vals) // 2]
+
+
+@pytest.mark.parametrize("wh", [(240, 180), (346, 260), (61, 47), (30, 30), (29, 95)])
+def test_image_focus_equals_cv2_mean_std_dev(wh):
+    w, h = wh
+    if w >= 200:
+        ev = synth.make_events(20000, seed=w, w=w, h=h)
+        img, _, _ = O.ev_accumulate(ev, w, h, 1.0, mode=1)
+    else:
+        img = (np.random.default_rng(w * h).random((h, w)) ** 3 * 4).astype(np.float32)
+    for what in (O.FOCUS_LOCAL_STD, O.FOCUS_GLOBAL_STD, O.FOCUS_LOCAL_MEAN):
+        for avg in (True, False):
+            got, exp = O.image_focus(img, what, avg), float(_focus_cv2(img, what, avg))
+            assert abs(got - exp) <= 2e-6 * max(abs(exp), 1e-3), (what, avg, got, exp)

@@ -71,3 +71,6 @@ def test_shims_match_oracle_on_gpu():
     lk = re.search(r"lk_ok=(\d+) lk_n=(\d+) lk_tracked=(\d+) lk_good=(\d+)", out)
     assert lk and int(lk.group(1)) == 1 and int(lk.group(2)) == len(okps)
     assert int(lk.group(3)) > 0.8 * len(okps) and int(lk.group(4)) > 0.9 * int(lk.group(3))      # the (2, 1) shift is recovered
+    fo = re.search(r"focus=([\d.]+) focus_med=([\d.]+) focus_glob=([\d.]+) mean_loc=([\d.]+)", out)
+    fv = [float(fo.group(k)) for k in range(1, 5)]
+    assert fv[0] > 0 and fv[1] > 0 and fv[2] > fv[0] * 0.5 and abs(fv[3] * 240 * 180 - float(ev.group(1))) < 0.02 * float(ev.group(1))   # mean x pixels = sum
