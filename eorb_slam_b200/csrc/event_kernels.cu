@@ -144,7 +144,7 @@ __global__ void __launch_bounds__(EV_SMEM_THREADS) ev_frame_smem_kernel(const eo
     const int r0 = blockIdx.x * bandRows, r1 = min(r0 + bandRows, H);
     const int nrow = r1 - r0, npx = nrow * W;
     const int tid = threadIdx.x;
-    for (int i = tid; i < npx; i += EV_SMEM_THREADS) s_acc[i] = 0;
+    for (int i = tid; i < (npx + 3) >> 2; i += EV_SMEM_THREADS) reinterpret_cast<int4*>(s_acc)[i] = make_int4(0, 0, 0, 0);   // band is padded to 16 B
     const long long nev = w.end - w.begin;
     // fixed-point scale: |pixel sum| <= nev * peakTap, peakTap = 1 / (2*pi*sigma^2)
     const float peakTap = __fdiv_rn(1.0f, c.norm);
@@ -188,13 +188,23 @@ __global__ void __launch_bounds__(EV_SMEM_THREADS) ev_frame_smem_kernel(const eo
     }
     __syncthreads();
 
-    // ---- write the band out as fp32, track min / max
+    // ---- write the band out as fp32, track min / max (four pixels per thread and step when the band is 16-byte aligned)
     float* im = img + (size_t)blockIdx.y * (size_t)W * H + (size_t)r0 * W;
     float mn = 3.4e38f, mx = -3.4e38f;
-    for (int i = tid; i < npx; i += EV_SMEM_THREADS) {
-        const float v = (float)s_acc[i] * invScale;
-        im[i] = v;
-        mn = fminf(mn, v); mx = fmaxf(mx, v);
+    const bool vec = ((npx & 3) == 0) && ((reinterpret_cast<uintptr_t>(im) & 15) == 0);
+    if (vec) {
+        for (int i = tid; i < npx >> 2; i += EV_SMEM_THREADS) {
+            const int4 a = reinterpret_cast<const int4*>(s_acc)[i];
+            const float4 v = make_float4((float)a.x * invScale, (float)a.y * invScale, (float)a.z * invScale, (float)a.w * invScale);
+            reinterpret_cast<float4*>(im)[i] = v;
+            mn = fminf(fminf(mn, fminf(v.x, v.y)), fminf(v.z, v.w)); mx = fmaxf(fmaxf(mx, fmaxf(v.x, v.y)), fmaxf(v.z, v.w));
+        }
+    } else {
+        for (int i = tid; i < npx; i += EV_SMEM_THREADS) {
+            const float v = (float)s_acc[i] * invScale;
+            im[i] = v;
+            mn = fminf(mn, v); mx = fmaxf(mx, v);
+        }
     }
     if (!fuseNorm) return;
 #pragma unroll
@@ -215,10 +225,21 @@ __global__ void __launch_bounds__(EV_SMEM_THREADS) ev_frame_smem_kernel(const eo
     float alpha, beta;
     ev_norm_coeffs(normMode, mn, mx, alpha, beta);
     uint8_t* o8 = u8 + (size_t)blockIdx.y * (size_t)W * H;
-    for (int i = tid; i < npx; i += EV_SMEM_THREADS) {
-        const float v = (float)s_acc[i] * invScale;
-        const int r = __float2int_rn(__fadd_rn(__fmul_rn(v, alpha), beta));
-        o8[i] = (uint8_t)min(max(r, 0), 255);
+    if (((npx & 3) == 0) && ((reinterpret_cast<uintptr_t>(o8) & 3) == 0)) {
+        for (int i = tid; i < npx >> 2; i += EV_SMEM_THREADS) {
+            const int4 a = reinterpret_cast<const int4*>(s_acc)[i];
+            const int q0 = min(max(__float2int_rn(__fadd_rn(__fmul_rn((float)a.x * invScale, alpha), beta)), 0), 255);
+            const int q1 = min(max(__float2int_rn(__fadd_rn(__fmul_rn((float)a.y * invScale, alpha), beta)), 0), 255);
+            const int q2 = min(max(__float2int_rn(__fadd_rn(__fmul_rn((float)a.z * invScale, alpha), beta)), 0), 255);
+            const int q3 = min(max(__float2int_rn(__fadd_rn(__fmul_rn((float)a.w * invScale, alpha), beta)), 0), 255);
+            reinterpret_cast<uint32_t*>(o8)[i] = (uint32_t)q0 | ((uint32_t)q1 << 8) | ((uint32_t)q2 << 16) | ((uint32_t)q3 << 24);
+        }
+    } else {
+        for (int i = tid; i < npx; i += EV_SMEM_THREADS) {
+            const float v = (float)s_acc[i] * invScale;
+            const int r = __float2int_rn(__fadd_rn(__fmul_rn(v, alpha), beta));
+            o8[i] = (uint8_t)min(max(r, 0), 255);
+        }
     }
 }
 
@@ -380,7 +401,7 @@ cudaError_t launch_ev_frames(const eorb_event* d_evs, const EvWindow* d_wins, in
     if (c.mode != EORB_EV_NEAREST && c.half == EV_SMEM_HALF && maxEventsPerWindow > 0 && (size_t)c.width * 4 * 8 <= smemBudget) {
         const int bands = (int)(((size_t)npix * 4 + smemBudget - 1) / smemBudget);
         const int bandRows = (c.height + bands - 1) / bands;
-        const size_t smem = (size_t)bandRows * c.width * 4;
+        const size_t smem = (((size_t)bandRows * c.width * 4) + 15) & ~(size_t)15;
         cudaError_t ea = cudaFuncSetAttribute(ev_frame_smem_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemBudget + 4096);
         if (ea != cudaSuccess) return ea;
         const int nb = (c.height + bandRows - 1) / bandRows;
