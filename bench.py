@@ -131,7 +131,7 @@ def run_reference(args):
         return 0
     import oracle_lib as O
     cores = os.cpu_count() or 1
-    n = max(cores, min(4 * cores, 128))
+    n = max(cores, min(64 * cores, 1024))
     frames = make_batch(n, 0)
     for _ in range(max(args.warmup, 1)):
         O.orb_extract_batch_mt(frames[:cores], cores)
@@ -451,7 +451,7 @@ def run_ours(args):
     if rank == 0 and world == 1 and not args.no_cpu:
         import oracle_lib as O
         cores = os.cpu_count() or 1
-        nsamp = max(cores, min(8 * cores, 256))
+        nsamp = min(nfr, max(cores, 256 * cores))   # ~5-10 s of CPU work on the box's cores
         O.orb_extract_batch_mt(frames[:cores], cores)
         t0 = time.perf_counter()
         O.orb_extract_batch_mt(frames[:nsamp], cores)
