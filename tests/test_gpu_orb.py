@@ -184,6 +184,44 @@ def test_orb_batch_device_resident():
     ex.set_stream(None)
 
 
+@pytest.mark.parametrize("layout", ["unaligned_base", "odd_row_stride", "padded_frames"])
+def test_orb_device_input_layouts(layout):
+    """device frames that the TMA / word loads cannot read in place (base not 16-byte aligned, row stride not a
+    multiple of 16) are staged; padded but aligned layouts are read zero-copy.  Same results either way."""
+    import torch
+    api = _api()
+    n, w, h = 3, 750, 478
+    frames = np.stack([synth.make_frame(300 + i, w, h) for i in range(n)])
+    if layout == "unaligned_base":
+        stride, fstride, off = w, w * h, 3
+    elif layout == "odd_row_stride":
+        stride, fstride, off = w + 7, (w + 7) * h + 5, 0
+    else:
+        stride, fstride, off = 768, 768 * 480, 0
+    buf = np.zeros(off + n * fstride + 64, np.uint8)
+    for i in range(n):
+        for y in range(h):
+            o = off + i * fstride + y * stride
+            buf[o:o + w] = frames[i, y]
+    okw = dict(CFG1)
+    ex = _mk(api, okw, w, h, max_batch=n)
+    cap = ex.cap
+    d_buf = torch.from_numpy(buf).cuda()
+    d_kps = torch.zeros(n * cap * 28, dtype=torch.uint8, device="cuda"); d_desc = torch.zeros(n * cap * 32, dtype=torch.uint8, device="cuda")
+    d_n = torch.zeros(n, dtype=torch.int32, device="cuda"); d_mono = torch.zeros(n, dtype=torch.int32, device="cuda")
+    ex.set_stream(torch.cuda.current_stream().cuda_stream)
+    ex.extract_batch_raw(d_buf.data_ptr() + off, n, w, h, stride, fstride, (0, 1000), True, d_kps.data_ptr(), d_desc.data_ptr(), cap,
+                         d_n.data_ptr(), d_mono.data_ptr(), device=True)
+    torch.cuda.synchronize()
+    nout = d_n.cpu().numpy()
+    kps = d_kps.cpu().numpy().view(synth.KEYPOINT_DTYPE).reshape(n, cap); desc = d_desc.cpu().numpy().reshape(n, cap, 32)
+    orc = _orc(okw, w, h)
+    for f in range(n):
+        _, okps, odesc = orc.extract(frames[f])
+        assert nout[f] == len(okps) and kps[f, :nout[f]].tobytes() == okps.tobytes() and np.array_equal(desc[f, :nout[f]], odesc)
+    ex.set_stream(None)
+
+
 def test_tracked_descriptors_and_level_assignment():
     api = _api()
     img = synth.make_frame(41)
@@ -226,3 +264,42 @@ def test_pyramid_and_blur_odd_sizes(wh):
         got = ex.pyramid_level(l)
         assert got.shape == prev.shape and np.array_equal(got, prev), "pyramid level %d" % l
         assert np.array_equal(ex.debug_blurred(l), O.gauss5(prev)), "blurred level %d" % l
+
+
+SWEEP = [
+    # (w, h, nfeatures, scale, levels, ini, min, edge)  — Appendix A parameter sets and other common sensor shapes
+    (346, 260, 1000, 1.1, 16, 10, 1, 30),        # EvMVSEC.yaml
+    (240, 180, 1000, 1.07177, 20, 10, 0, 30),    # EvETHZ_EuRoC.yaml
+    (346, 260, 1000, 1.26, 6, 10, 1, 15),        # EvMVSEC_ETHZ.yaml (margin 15: descriptor taps reflect)
+    (240, 180, 1000, 1.2, 4, 7, 0, 9),           # EvETHZ_SLIDER.yaml
+    (640, 480, 1500, 1.2, 8, 20, 7, 19),
+    (1241, 376, 2000, 1.2, 8, 20, 7, 19),        # KITTI-shaped: 3 octree roots
+    (1280, 720, 1000, 1.2, 8, 20, 7, 19),
+    (320, 240, 500, 1.5, 5, 12, 5, 19),
+    (853, 481, 1200, 1.33, 7, 25, 25, 21),       # ini == min, odd sizes
+    (500, 377, 800, 1.2, 8, 5, 30, 19),          # min > ini (no fallback possible)
+    (401, 303, 300, 2.0, 4, 15, 3, 16),
+    (752, 480, 100, 1.2, 8, 20, 7, 19),          # tiny quotas
+]
+
+
+@pytest.mark.parametrize("cfg", SWEEP)
+def test_orb_parameter_sweep_bit_exact(cfg):
+    """geometry sweep: image shapes, pyramid depths / factors, FAST thresholds and margins change every per-level table
+    (cell grids, tile alignments, group counts, quotas, octree roots); keypoints and descriptors stay bit-exact."""
+    api = _api()
+    w, h, nf, sf, nl, ini, mn, edge = cfg
+    okw = dict(nfeatures=nf, scale_factor=sf, nlevels=nl, ini_th=ini, min_th=mn, edge=edge)
+    img = synth.make_frame(w * 7 + nl, w, h)
+    ex = _mk(api, okw, w, h)
+    orc = _orc(okw, w, h)
+    ret, kps, desc = ex(img)
+    oret, okps, odesc = orc.extract(img)
+    assert ret == oret and len(kps) == len(okps)
+    assert kps.tobytes() == okps.tobytes() and np.array_equal(desc, odesc)
+    # a low-texture frame of the same shape exercises the minThFAST fallback cells
+    flat = (128 + np.random.default_rng(w + h).integers(-9, 10, (h, w))).astype(np.uint8)
+    flat[h // 3:h // 3 + 40, w // 4:w // 4 + 60] += 40
+    ret, kps, desc = ex(flat)
+    oret, okps, odesc = orc.extract(flat)
+    assert ret == oret and kps.tobytes() == okps.tobytes() and np.array_equal(desc, odesc)
