@@ -249,6 +249,34 @@ def bench_hamming(api, torch, dev, steps, warmup, world, rank, dist):
                          "note": "algorithmic 8 POPC32 per pair; peak measured live by eorb_probe_popc_rate"}}
 
 
+def bench_mci_jac(api, dev, steps, warmup):
+    """one ev2mci_gg_f_jac call (the optimiser calls it once per iteration) on a 6000-event MC window."""
+    import oracle_lib as O
+    from eorb_slam_b200 import synth
+    n, w, h = 6000, 240, 180
+    ev = synth.make_events(n, seed=5, w=w, h=h)
+    K = (199.09, 198.83, 132.19, 110.71)
+    dt = float(ev["ts"][-1] - ev["ts"][0])
+    T = synth.rotation_tcw(np.array([0.5, -0.7, 1.5]) * dt).astype(np.float64)
+    R, t = T[:3, :3], np.array([0.02, -0.01, 0.03])
+    cv = api.EvImConverter(dev, 1, n, w, h)
+    for _ in range(max(warmup, 3)):
+        got = cv.ev2mci_gg_f_jac(ev, K, R, t, 1.0, w, h, 1.0)
+    reps = max(steps, 3) * 20
+    t0 = time.perf_counter()
+    for _ in range(reps):
+        got = cv.ev2mci_gg_f_jac(ev, K, R, t, 1.0, w, h, 1.0)
+    ms = (time.perf_counter() - t0) * 1e3 / reps
+    t0 = time.perf_counter()
+    for _ in range(5):
+        exp = O.ev_mci_jac(ev, w, h, 1.0, R, t, 1.0, K)
+    ms_port = (time.perf_counter() - t0) * 1e3 / 5
+    return {"metric": "mci_jacobian_mev_per_s", "value": n / ms / 1e3, "unit": "Mev/s", "ms_per_call": ms,
+            "workload": "ev2mci_gg_f_jac: %d events, 240x180, sigma 1: 7 splat frames (343 reductions per event) + 6 product means, host call" % n,
+            "max_rel_err_vs_oracle": float(np.abs(got - exp).max() / np.abs(exp).max()),
+            "cpu_baseline": {"kind": "port", "cores": 1, "ms_per_call": ms_port, "value": n / ms_port / 1e3, "unit": "Mev/s"}}
+
+
 def bench_lk(api, torch, dev, steps, warmup):
     """ELK_Tracker on DAVIS240-shaped event frames, EvETHZ.yaml values (400 points, win 23, maxLevel 1,
     10 iterations, eps 0.03).  A step = one trackCurrImage call through the host C ABI (frame H2D, pyramid, tracker,
@@ -442,6 +470,11 @@ def run_ours(args):
                 extra["lk"] = bench_lk(api, torch, dev, args.steps, args.warmup)
         except Exception as e:
             extra["lk"] = {"error": repr(e)}
+        try:
+            if rank == 0:
+                extra["mci_jac"] = bench_mci_jac(api, dev, args.steps, args.warmup)
+        except Exception as e:
+            extra["mci_jac"] = {"error": repr(e)}
         try:
             extra["hamming"] = bench_hamming(api, torch, dev, max(min(args.steps, 3), 1), 3, world, rank, dist)
         except Exception as e:

@@ -81,6 +81,7 @@ def _load():
         "eorb_ev_set_stream": ([vp, vp], i), "eorb_ev_reset_stream": ([vp], i), "eorb_ev_synchronize": ([vp], i), "eorb_ev_launch_count": ([vp], C.c_longlong),
         "eorb_ev_accumulate": ([vp, vp, i64, C.POINTER(_EvParams), vp, vp, vp], i),
         "eorb_ev_accumulate_batch_device": ([vp, vp, vp, i, C.POINTER(_EvParams), vp, vp, vp], i),
+        "eorb_ev_mci_jac": ([vp, vp, i64, i, i, f, vp, f, vp, i, i, vp], i),
         "eorb_ev_image_focus_device": ([vp, vp, i, i, i, i, i, vp], i), "eorb_ev_image_focus": ([vp, vp, i, i, sz, i, i, vp], i),
         "eorb_lk_create": ([i, i, i, i, C.POINTER(vp)], i), "eorb_lk_destroy": ([vp], i),
         "eorb_lk_set_stream": ([vp, vp], i), "eorb_lk_reset_stream": ([vp], i), "eorb_lk_launch_count": ([vp], C.c_longlong),
@@ -475,6 +476,16 @@ class EvImConverter:
         p = self.make_params(EV_NEAREST, imWidth, imHeight, 1.0, pol, NORM_RUNNING if normalized else NORM_NONE)
         _, img, u8, _ = self._run(vEvData, p)
         return u8 if normalized else img
+
+    def ev2mci_gg_f_jac(self, vEvData, camera, R, t, medDepth, imWidth, imHeight, sigma, pol=False, global_mean=False):
+        """EvImConverter::ev2mci_gg_f_jac (EventConversion.cc:533-662): R (3x3), t (3) = the SE3 vertex estimate -> float64[6]"""
+        ev = np.ascontiguousarray(vEvData)
+        Rt = np.concatenate([np.asarray(R, np.float64).reshape(9), np.asarray(t, np.float64).reshape(3)])
+        K = np.ascontiguousarray(camera, np.float32)
+        out = np.zeros(6, np.float64)
+        _check(lib.eorb_ev_mci_jac(self.h, _p(ev), len(ev), imWidth, imHeight, float(sigma), _p(Rt), float(medDepth), _p(K), int(pol),
+                                   int(global_mean), _p(out)), "ev2mci_gg_f_jac")
+        return out
 
     # ---- contrast metric (EventConversion.cc:74-162)
     FOCUS_LOCAL_STD, FOCUS_GLOBAL_STD, FOCUS_LOCAL_MEAN = 0, 1, 2

@@ -1189,6 +1189,7 @@ struct eorb_evconv {
     int maxWindows = 0, maxW = 0, maxH = 0;
     long long maxEvents = 0;
     eorb_event* d_evs = nullptr; float* d_img = nullptr; uint8_t* d_u8 = nullptr; float* d_minmax = nullptr;
+    float* d_jac = nullptr;   // 7 frames (I, dI/d[wx wy wz vx vy vz]) of ev2mci_gg_f_jac, allocated on first use
     EvWindow* d_wins = nullptr;
     std::vector<EvWindow> h_wins;
     long long launches = 0;
@@ -1207,7 +1208,7 @@ extern "C" int eorb_ev_create(int device, int max_windows, int64_t max_events, i
     CU(devAlloc(&c->d_evs, (size_t)max_events));
     CU(devAlloc(&c->d_img, (size_t)max_width * max_height));      // single-window host path
     CU(devAlloc(&c->d_u8, (size_t)max_width * max_height));
-    CU(devAlloc(&c->d_minmax, (size_t)max_windows * 2));
+    CU(devAlloc(&c->d_minmax, (size_t)std::max(max_windows * 2, 8)));   // also the 6-value scratch of the Jacobian / focus calls
     CU(devAlloc(&c->d_wins, (size_t)max_windows));
     *out = c;
     return EORB_OK;
@@ -1216,7 +1217,7 @@ extern "C" int eorb_ev_destroy(eorb_evconv* c) {
     if (!c) return EORB_OK;
     cudaSetDevice(c->device);
     cudaStreamSynchronize(c->stream);
-    cudaFree(c->d_evs); cudaFree(c->d_img); cudaFree(c->d_u8); cudaFree(c->d_minmax); cudaFree(c->d_wins);
+    cudaFree(c->d_evs); cudaFree(c->d_img); cudaFree(c->d_u8); cudaFree(c->d_minmax); cudaFree(c->d_jac); cudaFree(c->d_wins);
     cudaStreamDestroy(c->ownStream);
     delete c;
     return EORB_OK;
@@ -1242,9 +1243,14 @@ extern "C" int eorb_ev_synchronize(eorb_evconv* c) {
 extern "C" long long eorb_ev_launch_count(const eorb_evconv* c) { return c ? c->launches : 0; }
 
 // Eigen::AngleAxisd(const Matrix3d&) (matrix -> quaternion -> angle/axis), used at EventConversion.cc:303
+static void angleAxisFromR(const double R[3][3], EvWindow& w);
 static void angleAxisFromPose(const float* T, EvWindow& w) {
     double R[3][3];
     for (int r = 0; r < 3; r++) { for (int c = 0; c < 3; c++) R[r][c] = (double)T[4 * r + c]; w.t[r] = (double)T[4 * r + 3]; }
+    angleAxisFromR(R, w);
+}
+// Eigen::AngleAxisd(const Matrix3d&): through the quaternion, as Eigen does
+static void angleAxisFromR(const double R[3][3], EvWindow& w) {
     double q[4];
     double tr = R[0][0] + R[1][1] + R[2][2];
     if (tr > 0) {
@@ -1308,6 +1314,42 @@ extern "C" int eorb_ev_accumulate_batch_device(eorb_evconv* c, const eorb_event*
     }
     CU(cudaMemcpyAsync(c->d_wins, c->h_wins.data(), (size_t)nwin * sizeof(EvWindow), cudaMemcpyHostToDevice, c->stream));
     CU(launch_ev_frames(d_evs, c->d_wins, nwin, maxEv, k, p->normalize, d_img_f32, c->d_minmax, d_img_u8, c->stream, &c->launches));
+    return EORB_OK;
+}
+
+// EvImConverter::ev2mci_gg_f_jac (EventConversion.cc:533-662; one call per optimiser iteration, MyOptimTypes.cpp:16)
+extern "C" int eorb_ev_mci_jac(eorb_evconv* c, const eorb_event* evs, int64_t n, int w, int hgt, float sigma, const double* Rt12, float med_depth,
+                               const float* K4, int pol, int global_mean, double* jac6) {
+    if (!c || !jac6 || !Rt12 || !K4) return fail(EORB_ERR_ARG, "null argument");
+    for (int k = 0; k < 6; k++) jac6[k] = 0.0;
+    if (n <= 0 || !evs) return EORB_EMPTY;   // "no events": the reference returns a zero Jacobian (:543-546)
+    if (w < 1 || hgt < 1 || (long long)w * hgt > (long long)c->maxW * c->maxH) return fail(EORB_ERR_CAPACITY, "image %dx%d exceeds the converter's %dx%d", w, hgt, c->maxW, c->maxH);
+    if (n > c->maxEvents) return fail(EORB_ERR_CAPACITY, "%lld events > max_events %lld", (long long)n, c->maxEvents);
+    if (!(sigma > 0.f)) return fail(EORB_ERR_ARG, "sigma must be > 0");
+    const int patch = 30;
+    if (((w + patch - 1) / patch) * ((hgt + patch - 1) / patch) > EORB_EV_FOCUS_MAX_CELLS) return fail(EORB_ERR_CAPACITY, "image too large for the local mean");
+    CU(cudaSetDevice(c->device));
+    if (!c->d_jac) CU(devAlloc(&c->d_jac, (size_t)7 * c->maxW * c->maxH));
+    EvConst k{};
+    k.mode = EORB_EV_SE3; k.width = w; k.height = hgt; k.pol = pol; k.sigma = sigma; k.sig2 = sigma * sigma;
+    k.norm = 2.0f * (float)M_PI * k.sig2; k.half = (int)std::ceil(sigma * 3.0); k.depth = med_depth;
+    k.fx = K4[0]; k.fy = K4[1]; k.cx = K4[2]; k.cy = K4[3];
+    EvWindow win{};
+    win.begin = 0; win.end = n;
+    double R[3][3];
+    for (int r = 0; r < 3; r++) { for (int cc = 0; cc < 3; cc++) R[r][cc] = Rt12[3 * r + cc]; win.t[r] = Rt12[9 + r]; }
+    angleAxisFromR(R, win);
+    const size_t npx = (size_t)w * hgt;
+    CU(cudaMemcpyAsync(c->d_evs, evs, (size_t)n * sizeof(eorb_event), cudaMemcpyHostToDevice, c->stream));
+    CU(cudaMemcpyAsync(c->d_wins, &win, sizeof(EvWindow), cudaMemcpyHostToDevice, c->stream));
+    CU(cudaStreamSynchronize(c->stream));   // `win` is a stack object
+    CU(cudaMemsetAsync(c->d_jac, 0, 7 * npx * sizeof(float), c->stream));
+    c->launches++;
+    CU(launch_ev_jac(c->d_evs, c->d_wins, n, k, global_mean, c->d_jac, c->d_minmax, c->stream, &c->launches));
+    float m[6];
+    CU(cudaMemcpyAsync(m, c->d_minmax, sizeof(m), cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    for (int i = 0; i < 6; i++) jac6[i] = (double)(-m[i] * 2);
     return EORB_OK;
 }
 

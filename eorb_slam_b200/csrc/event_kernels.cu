@@ -333,15 +333,18 @@ __device__ __forceinline__ double warp_sum_d(double v) {
     return v;
 }
 
-__global__ void __launch_bounds__(256) ev_focus_kernel(const float* __restrict__ img, int W, int H, int patch, int what, int avg,
-                                                       float* __restrict__ out) {
+// With img2 != nullptr the metric is taken of the pixel-wise float product img (fixed) x img2 (frame blockIdx.x): that is
+// I.mul(I_k) followed by imageMean of ev2mci_gg_f_jac (EventConversion.cc:646-659); what == 3 is cv::mean (global mean).
+__global__ void __launch_bounds__(256) ev_focus_kernel(const float* __restrict__ img, const float* __restrict__ img2, int W, int H, int patch,
+                                                       int what, int avg, float* __restrict__ out) {
     __shared__ float s_val[EV_FOCUS_MAX_CELLS];
     __shared__ double s_part[8][2];
-    const float* im = img + (size_t)blockIdx.x * (size_t)W * H;
+    const float* im = img2 ? img : img + (size_t)blockIdx.x * (size_t)W * H;
+    const float* im2 = img2 ? img2 + (size_t)blockIdx.x * (size_t)W * H : nullptr;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    if (what == 1) {   // one cell = the whole frame, all warps
+    if (what == 1 || what == 3) {   // one cell = the whole frame, all warps
         double s = 0, sq = 0;
-        for (int i = threadIdx.x; i < W * H; i += 256) { const double v = im[i]; s += v; sq += v * v; }
+        for (int i = threadIdx.x; i < W * H; i += 256) { const double v = im2 ? (double)__fmul_rn(im[i], im2[i]) : (double)im[i]; s += v; sq += v * v; }
         s = warp_sum_d(s); sq = warp_sum_d(sq);
         if (lane == 0) { s_part[warp][0] = s; s_part[warp][1] = sq; }
         __syncthreads();
@@ -349,7 +352,7 @@ __global__ void __launch_bounds__(256) ev_focus_kernel(const float* __restrict__
             s = 0; sq = 0;
             for (int k = 0; k < 8; k++) { s += s_part[k][0]; sq += s_part[k][1]; }
             const double n = (double)W * H, mean = s / n, var = sq / n - mean * mean;
-            out[blockIdx.x] = (float)sqrt(var > 0 ? var : 0);
+            out[blockIdx.x] = what == 3 ? (float)mean : (float)sqrt(var > 0 ? var : 0);
         }
         return;
     }
@@ -361,7 +364,8 @@ __global__ void __launch_bounds__(256) ev_focus_kernel(const float* __restrict__
         double s = 0, sq = 0;
         for (int i = lane; i < area; i += 32) {
             const int y = i / pw, x = i - y * pw;
-            const double v = im[(size_t)(r0 + y) * W + c0 + x];
+            const size_t o = (size_t)(r0 + y) * W + c0 + x;
+            const double v = im2 ? (double)__fmul_rn(im[o], im2[o]) : (double)im[o];
             s += v; sq += v * v;
         }
         s = warp_sum_d(s); sq = warp_sum_d(sq);
@@ -386,7 +390,95 @@ __global__ void __launch_bounds__(256) ev_focus_kernel(const float* __restrict__
 cudaError_t launch_ev_focus(const float* d_img, int nwin, int W, int H, int patch, int what, int avg, float* d_out, cudaStream_t st,
                             long long* launches) {
     if (nwin <= 0) return cudaSuccess;
-    ev_focus_kernel<<<nwin, 256, 0, st>>>(d_img, W, H, patch, what, avg, d_out);
+    ev_focus_kernel<<<nwin, 256, 0, st>>>(d_img, nullptr, W, H, patch, what, avg, d_out);
+    (*launches)++;
+    return cudaGetLastError();
+}
+
+// ---- Jacobian of the contrast objective (second half): ev2mci_gg_f_jac, EventConversion.cc:533-662
+// Seven frames (I and its derivatives w.r.t. the six components of the window motion) are splatted with fp32 L2
+// reductions; a group of LPE lanes owns one event (lane = tap column), the per-event geometry and the 2x6 image
+// Jacobian are evaluated in double exactly as the reference does through Eigen.
+__global__ void __launch_bounds__(256) ev_jac_splat_kernel(const eorb_event* __restrict__ evs, const EvWindow* __restrict__ wins, EvConst c,
+                                                           float* __restrict__ frames, int lpe) {
+    const EvWindow w = wins[0];
+    const long long nev = w.end - w.begin;
+    const int perBlock = blockDim.x / lpe;
+    const long long e = (long long)blockIdx.x * perBlock + threadIdx.x / lpe;
+    const int sub = threadIdx.x % lpe;
+    if (e >= nev) return;
+    const eorb_event* evp = evs + w.begin + e;
+    const double t1 = evs[w.end - 1].ts, DT = t1 - evs[w.begin].ts, invDT = 1.0 / DT;
+    const double rate = (t1 - evp->ts) * invDT;
+    const float ux = __fdiv_rn(__fsub_rn(evp->x, c.cx), c.fx), uy = __fdiv_rn(__fsub_rn(evp->y, c.cy), c.fy);
+    const double dep = (double)c.depth;
+    const double X0 = dep * (double)ux, X1 = dep * (double)uy, X2 = dep * 1.0;
+    double s, co;
+    sincos(w.angle * rate, &s, &co);
+    const double a0 = w.axis[0], a1 = w.axis[1], a2 = w.axis[2];
+    const double s0 = s * a0, s1 = s * a1, s2 = s * a2;
+    const double c0 = (1 - co) * a0, c1 = (1 - co) * a1, c2 = (1 - co) * a2;
+    double t;
+    double R01, R10, R02, R20, R12, R21;
+    t = c0 * a1; R01 = t - s2; R10 = t + s2;
+    t = c0 * a2; R02 = t + s1; R20 = t - s1;
+    t = c1 * a2; R12 = t - s0; R21 = t + s0;
+    const double R00 = c0 * a0 + co, R11 = c1 * a1 + co, R22 = c2 * a2 + co;
+    const double X = __dadd_rn(__dadd_rn(__dadd_rn(__dmul_rn(R00, X0), __dmul_rn(R01, X1)), __dmul_rn(R02, X2)), __dmul_rn(w.t[0], rate));
+    const double Y = __dadd_rn(__dadd_rn(__dadd_rn(__dmul_rn(R10, X0), __dmul_rn(R11, X1)), __dmul_rn(R12, X2)), __dmul_rn(w.t[1], rate));
+    const double Z = __dadd_rn(__dadd_rn(__dadd_rn(__dmul_rn(R20, X0), __dmul_rn(R21, X1)), __dmul_rn(R22, X2)), __dmul_rn(w.t[2], rate));
+    // JP2D = -projectJac(xyz) * (SE3deriv * rate)      (Pinhole::projectJac, Pinhole.cpp:81-91)
+    const double J00 = (double)c.fx / Z, J02 = -(double)c.fx * X / (Z * Z), J11 = (double)c.fy / Z, J12 = -(double)c.fy * Y / (Z * Z);
+    const double S0[6] = {0.0, Z * rate, -Y * rate, rate, 0.0, 0.0};
+    const double S1[6] = {-Z * rate, 0.0, X * rate, 0.0, rate, 0.0};
+    const double S2[6] = {Y * rate, -X * rate, 0.0, 0.0, 0.0, rate};
+    double JP0[6], JP1[6];
+#pragma unroll
+    for (int k = 0; k < 6; k++) {
+        JP0[k] = -__dadd_rn(__dmul_rn(J00, S0[k]), __dmul_rn(J02, S2[k]));
+        JP1[k] = -__dadd_rn(__dmul_rn(J11, S1[k]), __dmul_rn(J12, S2[k]));
+    }
+    const float U = (float)((double)c.fx * X / Z + (double)c.cx), V = (float)((double)c.fy * Y / Z + (double)c.cy);
+    const float fxi = floorf(U), fyi = floorf(V);
+    if (!(fxi >= -64.f && fxi <= (float)(c.width + 64) && fyi >= -64.f && fyi <= (float)(c.height + 64))) return;   // also NaN / inf
+    const int xi = (int)fxi, yi = (int)fyi;
+    const float xr = __fsub_rn(U, fxi), yr = __fsub_rn(V, fyi);
+    const float ps = (c.pol && evp->p == 0) ? -1.0f : 1.0f;
+    const float invSig2 = __fdiv_rn(1.f, c.sig2), den = __fmul_rn(2.0f, c.sig2);
+    const size_t npx = (size_t)c.width * c.height;
+    for (int ii = sub; ii <= 2 * c.half; ii += lpe) {
+        const int i = ii - c.half, xn = xi + i;
+        if (xn < 0 || xn >= c.width) continue;
+        const float dx = __fsub_rn((float)i, xr), dx2 = __fmul_rn(dx, dx);
+        for (int j = -c.half; j <= c.half; j++) {
+            const int yn = yi + j;
+            if (yn < 0 || yn >= c.height) continue;
+            const float dy = __fsub_rn((float)j, yr);
+            const float val = __fdiv_rn(expf(-__fdiv_rn(__fadd_rn(dx2, __fmul_rn(dy, dy)), den)), c.norm);
+            const float gx = __fmul_rn(__fmul_rn(invSig2, dx), val), gy = __fmul_rn(__fmul_rn(invSig2, dy), val);
+            float* p = frames + (size_t)yn * c.width + xn;
+            atomicAdd(p, __fmul_rn(ps, val));
+#pragma unroll
+            for (int k = 0; k < 6; k++) {
+                const double JI = __dadd_rn(__dmul_rn((double)gx, JP0[k]), __dmul_rn((double)gy, JP1[k]));
+                atomicAdd(p + (size_t)(k + 1) * npx, (float)__dmul_rn((double)ps, JI));
+            }
+        }
+    }
+}
+
+cudaError_t launch_ev_jac(const eorb_event* d_evs, const EvWindow* d_win, long long nev, const EvConst& c, int globalMean, float* d_frames7,
+                          float* d_out6, cudaStream_t st, long long* launches) {
+    const int win = 2 * c.half + 1;
+    const int lpe = win <= 8 ? 8 : (win <= 16 ? 16 : 32);
+    const int perBlock = 256 / lpe;
+    ev_jac_splat_kernel<<<(unsigned)((nev + perBlock - 1) / perBlock), 256, 0, st>>>(d_evs, d_win, c, d_frames7, lpe);
+    (*launches)++;
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return e;
+    const size_t npx = (size_t)c.width * c.height;
+    // six products I x I_k, mean over all pixels (cv::mean) or mean of the 30x30-cell means (imageMeanLocal)
+    ev_focus_kernel<<<6, 256, 0, st>>>(d_frames7, d_frames7 + npx, c.width, c.height, 30, globalMean ? 3 : 2, 1, d_out6);
     (*launches)++;
     return cudaGetLastError();
 }

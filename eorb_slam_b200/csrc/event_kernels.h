@@ -32,6 +32,8 @@ cudaError_t launch_ev_frames(const eorb_event* d_evs, const EvWindow* d_wins, in
 #define EORB_EV_FOCUS_MAX_CELLS 1024
 cudaError_t launch_ev_focus(const float* d_img, int nwin, int W, int H, int patch, int what, int avg, float* d_out, cudaStream_t st,
                             long long* launches);
+cudaError_t launch_ev_jac(const eorb_event* d_evs, const EvWindow* d_win, long long nev, const EvConst& c, int globalMean, float* d_frames7,
+                          float* d_out6, cudaStream_t st, long long* launches);
 cudaError_t launch_ev_normalize(const float* d_img, int nwin, int npix, int normMode, float* d_minmax, uint8_t* d_u8,
                                 cudaStream_t st, long long* launches);
 

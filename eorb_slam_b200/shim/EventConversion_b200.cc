@@ -131,4 +131,25 @@ float EvImConverter::measureImageFocusLocal(const cv::Mat& image, const bool avg
 float EvImConverter::measureImageFocusGlobal(const cv::Mat& image) { return focus(image, EORB_FOCUS_GLOBAL_STD, true); }
 float EvImConverter::imageMeanLocal(const cv::Mat& image, const bool avg) { return focus(image, EORB_FOCUS_LOCAL_MEAN, avg); }
 
+
+bool EvImConverter::ev2mci_gg_f_jac(const std::vector<EventData> &vEvData, ORB_SLAM3::GeometricCamera* pCamera, const double Rt12[12],
+                                    const float medDepth, const unsigned imWidth, const unsigned imHeight, const float sigma,
+                                    const bool pol, const bool global, double jac6[6])
+{
+    for (int k = 0; k < 6; k++) jac6[k] = 0.0;
+    if (vEvData.empty()) {
+        std::fprintf(stderr, "EvImConverter::ev2mci_gg_f_jac: no events.\n");
+        return false;
+    }
+    eorb_evconv* c = t_conv.get((long long)vEvData.size(), (int)imWidth, (int)imHeight);
+    if (!c) return false;
+    eorb_ev_params p;
+    baseParams(p, EORB_EV_SE3, imWidth, imHeight, sigma, pol, EORB_NORM_NONE);
+    camParams(p, pCamera);
+    int rc = eorb_ev_mci_jac(c, reinterpret_cast<const eorb_event*>(vEvData.data()), (int64_t)vEvData.size(), (int)imWidth, (int)imHeight, sigma,
+                             Rt12, medDepth, p.K, pol ? 1 : 0, global ? 1 : 0, jac6);
+    if (rc < EORB_EMPTY) { std::fprintf(stderr, "EvImConverter(b200): %s\n", eorb_last_error()); return false; }
+    return rc == EORB_OK;
+}
+
 }// namespace EORB_SLAM

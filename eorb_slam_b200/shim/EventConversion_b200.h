@@ -39,6 +39,18 @@ namespace EORB_SLAM
         static float measureImageFocusGlobal(const cv::Mat& image);
         static float imageMeanLocal(const cv::Mat& image, bool avg = true);
 
+        // Jacobian of the contrast objective (EventConversion.h:65-68, EventConversion.cc:533-662).  The reference takes the
+        // g2o vertex; here its estimate is passed as plain doubles so that the shim needs neither g2o nor Eigen:
+        //   const auto& est = vSE3->estimate();  Eigen::Matrix3d R = est.rotation().toRotationMatrix();
+        //   double Rt[12];  Eigen::Map<Eigen::Matrix<double,3,3,Eigen::RowMajor>>(Rt) = R;
+        //   Eigen::Map<Eigen::Vector3d>(Rt + 9) = est.translation();
+        //   double j[6];  EvImConverter::ev2mci_gg_f_jac(evs, cam, Rt, medDepth, W, H, sigma, pol, global, j);
+        //   Eigen::Map<Eigen::Matrix<double,1,6>> jac(j);                       (MyOptimTypes.cpp:16)
+        // Returns false and a zero Jacobian when there are no events or the library reports an error.
+        static bool ev2mci_gg_f_jac(const std::vector<EventData> &vEvData, ORB_SLAM3::GeometricCamera* pCamera,
+                                    const double Rt12[12], float medDepth, unsigned imWidth, unsigned imHeight,
+                                    float sigma, bool pol, bool global, double jac6[6]);
+
         // cv::normalize(img, img, 255, 0, NORM_MINMAX, CV_8UC1) as applied by the callers (EvImBuilder.cpp:976,...)
         // fused on the device: returns the CV_8UC1 frame directly.
         static cv::Mat ev2mci_gg_f_minmax_u8(const std::vector<EventData> &vEvData, ORB_SLAM3::GeometricCamera* pCamera,

@@ -54,6 +54,12 @@ int main(int argc, char** argv)
     std::printf("focus=%.6f focus_med=%.6f focus_glob=%.6f mean_loc=%.6f\n", EORB_SLAM::EvImConverter::measureImageFocus(f),
                 EORB_SLAM::EvImConverter::measureImageFocusLocal(f, false), EORB_SLAM::EvImConverter::measureImageFocusGlobal(f),
                 EORB_SLAM::EvImConverter::imageMeanLocal(f));
+    {
+        const double Rt[12] = {1, 0, 0, 0, 1, 0, 0, 0, 1, 0.02, -0.01, 0.03};
+        double j[6];
+        const bool okj = EORB_SLAM::EvImConverter::ev2mci_gg_f_jac(evs, &cam, Rt, 1.0f, 240, 180, 1.0f, false, true, j);
+        std::printf("jac_ok=%d jac=%.6g,%.6g,%.6g,%.6g,%.6g,%.6g\n", (int)okj, j[0], j[1], j[2], j[3], j[4], j[5]);
+    }
     // ELK_Tracker's call: track the extractor's keypoints from the image into a copy shifted by (2, 1) pixels
     {
         cv::Mat im2(H, W, CV_8UC1);

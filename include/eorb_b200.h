@@ -255,6 +255,13 @@ int eorb_ev_accumulate_batch_device(eorb_evconv* c, const eorb_event* d_evs, con
  * per cell; avg != 0: average of the cell values (measureImageFocus), avg == 0: their median.  The reference picks the
  * motion-compensated candidate with the largest value (EvImBuilder.cpp:1206-1215); with the _device form the
  * candidates never leave the GPU.  focus_out is a host array. */
+/* Jacobian of the contrast objective w.r.t. the window's SE3 motion: EvImConverter::ev2mci_gg_f_jac
+ * (src/Event/EventConversion.cc:533-662, called once per optimiser iteration by src/Utils/MyOptimTypes.cpp:16).
+ * Rt12 = rotation (row-major 3x3) then translation of the vertex estimate, double; K4 = fx, fy, cx, cy (Pinhole);
+ * global_mean != 0: cv::mean of the product images, else the mean of their 30x30-cell means (`global` argument of the
+ * reference).  jac6 (host) = d/d[wx wy wz vx vy vz].  EORB_EMPTY and a zero Jacobian when there are no events. */
+int eorb_ev_mci_jac(eorb_evconv* c, const eorb_event* evs, int64_t n, int w, int hgt, float sigma, const double* Rt12, float med_depth,
+                    const float* K4, int pol, int global_mean, double* jac6);
 #define EORB_FOCUS_LOCAL_STD  0
 #define EORB_FOCUS_GLOBAL_STD 1
 #define EORB_FOCUS_LOCAL_MEAN 2

@@ -105,6 +105,8 @@ void rotFromAngleAxis(double angle, const double a[3], double R[3][3]) {
 
 extern "C" {
 
+float orc_image_focus(const float* img, int w, int h, int patch, int what, int avg);
+
 int orc_ev_accumulate(const orc_event* evs, int64_t n, int w, int h, float sigma, int mode, const float* Tcw16,
                       float depth, const float* K4, const float* se2, int se2_n, int pol, int normalize,
                       float* img, float* minmax2) {
@@ -197,6 +199,71 @@ void orc_normalize_minmax_u8(const float* img, int n, uint8_t* out) {
         float v = img[i] * a + b;
         int r = (int)lrintf(v);
         out[i] = (uint8_t)(r < 0 ? 0 : (r > 255 ? 255 : r));
+    }
+}
+
+// ---- Jacobian of the contrast objective w.r.t. the window's SE3 motion: SURVEY.md §8f rank 2 (second half)
+// EvImConverter::ev2mci_gg_f_jac, src/Event/EventConversion.cc:533-662 (called once per optimiser iteration by
+// EvMciEdge::linearizeOplus, src/Utils/MyOptimTypes.cpp:16).  Rt12 = rotation (row-major 3x3) then translation of the
+// vertex estimate, in double as the reference reads them from g2o.  Seven float images (I and dI/d[wx wy wz vx vy vz])
+// are splatted, jac[k] = -2 * imageMean(I .* I_k, global): cv::mean (global) or the mean of 30x30-cell means.
+void orc_ev_mci_jac(const orc_event* evs, int64_t n, int w, int h, float sigma, const double* Rt12, float medDepth, const float* K4, int pol,
+                    int global, double* jac6) {
+    for (int k = 0; k < 6; k++) jac6[k] = 0.0;
+    if (n <= 0) return;
+    const float sig2 = powf(sigma, 2), invSig2 = 1.f / sig2;
+    const int half = static_cast<int>(ceil(sigma * 3.0));
+    const size_t npx = (size_t)w * h;
+    std::vector<float> im(7 * npx, 0.f);
+    double R[3][3], ang, ax[3];
+    for (int r = 0; r < 3; r++) for (int c = 0; c < 3; c++) R[r][c] = Rt12[3 * r + c];
+    const double t[3] = {Rt12[9], Rt12[10], Rt12[11]};
+    angleAxisFromR(R, ang, ax);
+    const double t1 = evs[n - 1].ts, DT = t1 - evs[0].ts, invDT = 1.0 / DT;
+    const float fx = K4[0], fy = K4[1], cx = K4[2], cy = K4[3];
+    for (int64_t e = 0; e < n; e++) {
+        const float ex = evs[e].x, ey = evs[e].y;
+        const double rate = (t1 - evs[e].ts) * invDT;
+        const float ux = (ex - cx) / fx, uy = (ey - cy) / fy;              // Pinhole::unproject (float)
+        const double X3[3] = {(double)medDepth * (double)ux, (double)medDepth * (double)uy, (double)medDepth * 1.0};
+        double Rk[3][3];
+        rotFromAngleAxis(ang * rate, ax, Rk);
+        double P[3];
+        for (int r = 0; r < 3; r++) P[r] = (Rk[r][0] * X3[0] + Rk[r][1] * X3[1] + Rk[r][2] * X3[2]) + t[r] * rate;
+        const double X = P[0], Y = P[1], Z = P[2];
+        double S[3][6] = {{0, Z, -Y, 1, 0, 0}, {-Z, 0, X, 0, 1, 0}, {Y, -X, 0, 0, 0, 1}};
+        for (int r = 0; r < 3; r++) for (int c = 0; c < 6; c++) S[r][c] *= rate;
+        const double J00 = (double)fx / Z, J02 = -(double)fx * X / (Z * Z), J11 = (double)fy / Z, J12 = -(double)fy * Y / (Z * Z);
+        double JP[2][6];
+        for (int c = 0; c < 6; c++) {
+            JP[0][c] = -(J00 * S[0][c] + 0.0 * S[1][c] + J02 * S[2][c]);
+            JP[1][c] = -(0.0 * S[0][c] + J11 * S[1][c] + J12 * S[2][c]);
+        }
+        const double u = (double)fx * X / Z + (double)cx, v = (double)fy * Y / Z + (double)cy;   // Pinhole::project
+        int xi, yi; float xr, yr;
+        breakFloatCoords((float)u, (float)v, xi, yi, xr, yr);
+        const float ps = resolvePolarity(pol != 0, evs[e].p != 0);
+        for (int i = -half; i <= half; i++)
+            for (int j = -half; j <= half; j++) {
+                const int xn = xi + i, yn = yi + j;
+                if (!inImage((float)xn, (float)yn, w, h)) continue;
+                const float val = expXY2f(i - xr, j - yr, sig2);
+                const float gx = invSig2 * (i - xr) * val, gy = invSig2 * (j - yr) * val;
+                const size_t o = (size_t)yn * w + xn;
+                im[o] = im[o] + ps * val;
+                for (int k = 0; k < 6; k++) {
+                    const double JI = (double)gx * JP[0][k] + (double)gy * JP[1][k];
+                    im[(size_t)(k + 1) * npx + o] = (float)((double)im[(size_t)(k + 1) * npx + o] + (double)ps * JI);
+                }
+            }
+    }
+    std::vector<float> prod(npx);
+    for (int k = 0; k < 6; k++) {
+        for (size_t o = 0; o < npx; o++) prod[o] = im[o] * im[(size_t)(k + 1) * npx + o];
+        float m;
+        if (global) { double s = 0; for (size_t o = 0; o < npx; o++) s += prod[o]; m = (float)(s / (double)npx); }
+        else m = orc_image_focus(prod.data(), w, h, 30, 2, 1);
+        jac6[k] = (double)(-m * 2);
     }
 }
 

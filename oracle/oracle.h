@@ -122,6 +122,9 @@ void  orc_normalize_convert_u8(const float* img, int n, float maxVal, float minV
 void  orc_normalize_minmax_u8(const float* img, int n, uint8_t* out);
 /* measureImageFocusLocal / Global, imageMeanLocal (EventConversion.cc:79-162); see event_oracle.cc */
 float orc_image_focus(const float* img, int w, int h, int patch, int what, int avg);
+/* ev2mci_gg_f_jac (EventConversion.cc:533-662); Rt12 = row-major R (9) then t (3), double */
+void  orc_ev_mci_jac(const orc_event* evs, int64_t n, int w, int h, float sigma, const double* Rt12, float medDepth, const float* K4,
+                     int pol, int global, double* jac6);
 
 #ifdef __cplusplus
 }

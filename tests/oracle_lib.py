@@ -87,6 +87,7 @@ def lib():
     L.orc_ev_accumulate.restype = C.c_int
     L.orc_normalize_convert_u8.argtypes = [vp, C.c_int, C.c_float, C.c_float, vp]; L.orc_normalize_convert_u8.restype = None
     L.orc_normalize_minmax_u8.argtypes = [vp, C.c_int, vp]; L.orc_normalize_minmax_u8.restype = None
+    L.orc_ev_mci_jac.argtypes = [vp, C.c_int64, C.c_int, C.c_int, C.c_float, vp, C.c_float, vp, C.c_int, C.c_int, vp]; L.orc_ev_mci_jac.restype = None
     L.orc_image_focus.argtypes = [vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int]; L.orc_image_focus.restype = C.c_float
     L.orc_pyrdown_u8.argtypes = [vp, C.c_int, C.c_int, C.c_size_t, vp, C.c_int, C.c_int, C.c_size_t]; L.orc_pyrdown_u8.restype = None
     L.orc_scharr_deriv.argtypes = [vp, C.c_int, C.c_int, C.c_size_t, vp]; L.orc_scharr_deriv.restype = None
@@ -337,3 +338,13 @@ FOCUS_LOCAL_STD, FOCUS_GLOBAL_STD, FOCUS_LOCAL_MEAN = 0, 1, 2
 def image_focus(img: np.ndarray, what=FOCUS_LOCAL_STD, avg=True, patch=30) -> float:
     img = np.ascontiguousarray(img, np.float32)
     return float(lib().orc_image_focus(_p(img), img.shape[1], img.shape[0], patch, what, 1 if avg else 0))
+
+
+def ev_mci_jac(evs, w, h, sigma, R, t, med_depth, K, pol=False, global_mean=False) -> np.ndarray:
+    """ev2mci_gg_f_jac -> float64[6] (d contrast / d [wx wy wz vx vy vz])"""
+    evs = np.ascontiguousarray(evs)
+    Rt = np.concatenate([np.asarray(R, np.float64).reshape(9), np.asarray(t, np.float64).reshape(3)])
+    Kc = np.ascontiguousarray(K, np.float32)
+    out = np.zeros(6, np.float64)
+    lib().orc_ev_mci_jac(_p(evs), len(evs), w, h, float(sigma), _p(Rt), float(med_depth), _p(Kc), int(pol), int(global_mean), _p(out))
+    return out

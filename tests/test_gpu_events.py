@@ -195,3 +195,23 @@ def test_contrast_metric_and_best_candidate_selection_on_device():
     exp = np.array([O.image_focus(f) for f in frames], np.float32)
     assert np.all(np.abs(focus - exp) <= 2e-6 * exp)
     assert int(np.argmax(focus)) == int(np.argmax(exp))
+
+
+@pytest.mark.parametrize("cfg", [dict(w=240, h=180, n=6000, K=(199.09, 198.83, 132.19, 110.71)), dict(w=346, h=260, n=30000, K=K_MVSEC)])
+def test_mci_jacobian_matches_oracle(cfg):
+    """SURVEY §8f rank 2 (second half): ev2mci_gg_f_jac (EventConversion.cc:533-662).  Seven splat images + six product
+    means; float sums in another order, hence toleranced: 2e-4 of the largest component (measured ~1e-6)."""
+    api = _api()
+    w, h, n, K = cfg["w"], cfg["h"], cfg["n"], cfg["K"]
+    ev = synth.make_events(n, seed=n, w=w, h=h, mean_dt=2e-7, n_edges=40)
+    dt = float(ev["ts"][-1] - ev["ts"][0])
+    T = synth.rotation_tcw(np.array([0.5, -0.7, 1.5]) * dt).astype(np.float64)
+    R, t = T[:3, :3], np.array([0.02, -0.01, 0.03])
+    cv = api.EvImConverter(0, 1, n, w, h)
+    for glob in (False, True):
+        for pol in (False, True):
+            got = cv.ev2mci_gg_f_jac(ev, K, R, t, 1.3, w, h, 1.0, pol, glob)
+            exp = O.ev_mci_jac(ev, w, h, 1.0, R, t, 1.3, K, pol, glob)
+            assert np.abs(got - exp).max() <= 2e-4 * np.abs(exp).max(), (glob, pol, got, exp)
+    # no events: zero Jacobian and EORB_EMPTY, like the reference's early return (:543-546)
+    assert np.all(cv.ev2mci_gg_f_jac(ev[:0], K, R, t, 1.0, w, h, 1.0) == 0)

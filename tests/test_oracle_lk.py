@@ -100,3 +100,27 @@ def test_image_focus_equals_cv2_mean_std_dev(wh):
         for avg in (True, False):
             got, exp = O.image_focus(img, what, avg), float(_focus_cv2(img, what, avg))
             assert abs(got - exp) <= 2e-6 * max(abs(exp), 1e-3), (what, avg, got, exp)
+
+
+def test_mci_jacobian_oracle_agrees_with_finite_differences_of_the_contrast():
+    """ev2mci_gg_f_jac (EventConversion.cc:533-662) is the gradient of mean(I^2) of the motion-compensated frame w.r.t.
+    the window motion; for the translation part the reference's per-event model (t_k = t * rate) is exactly linear, so a
+    central difference of the oracle's own E4 frames must reproduce jac[3:6] up to the frame's float discretisation."""
+    w, h = 240, 180
+    ev = synth.make_events(6000, seed=3, w=w, h=h)
+    K = np.array((199.09, 198.83, 132.19, 110.71), np.float32)
+    dt = float(ev["ts"][-1] - ev["ts"][0])
+    T = synth.rotation_tcw(np.array([0.5, -0.7, 1.5]) * dt).astype(np.float64)
+    t0 = np.array([0.02, -0.01, 0.03])
+
+    def contrast(t):
+        Tm = T.copy(); Tm[:3, 3] = t
+        img, _, _ = O.ev_accumulate(ev, w, h, 1.0, mode=2, Tcw=Tm.astype(np.float32), depth=1.0, K=K)
+        return float((img.astype(np.float64) ** 2).mean())
+
+    jac = O.ev_mci_jac(ev, w, h, 1.0, T[:3, :3], t0, 1.0, K, False, True)
+    step = 1e-3
+    fd = np.array([(contrast(t0 + step * np.eye(3)[k]) - contrast(t0 - step * np.eye(3)[k])) / (2 * step) for k in range(3)])
+    big = np.abs(fd) > 0.1
+    assert big.any() and np.all(np.sign(jac[3:][big]) == np.sign(fd[big]))
+    assert np.all(np.abs(jac[3:][big] - fd[big]) <= 0.5 * np.abs(fd[big]))

@@ -74,3 +74,6 @@ def test_shims_match_oracle_on_gpu():
     fo = re.search(r"focus=([\d.]+) focus_med=([\d.]+) focus_glob=([\d.]+) mean_loc=([\d.]+)", out)
     fv = [float(fo.group(k)) for k in range(1, 5)]
     assert fv[0] > 0 and fv[1] > 0 and fv[2] > fv[0] * 0.5 and abs(fv[3] * 240 * 180 - float(ev.group(1))) < 0.02 * float(ev.group(1))   # mean x pixels = sum
+    jm = re.search(r"jac_ok=(\d) jac=([-\d.e+,]+)", out)
+    jv = [float(x) for x in jm.group(2).split(",")]
+    assert int(jm.group(1)) == 1 and any(abs(v) > 0 for v in jv[3:])
