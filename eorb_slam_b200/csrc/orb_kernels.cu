@@ -405,7 +405,7 @@ __global__ void __launch_bounds__(128) blur_kernel(OrbArgs a) {
 // sin/cos: the block's angles meet in shared memory and threads 0..G-1 evaluate them together, one pass of the
 // double-precision sincos per G keypoints instead of one per keypoint.  Descriptor: lane L evaluates pattern pair 32*j+L in round j;
 // __ballot_sync yields descriptor word j directly (bit k of byte i = pair 8i+k).
-#define EORB_KP_GROUP 8
+#define EORB_KP_GROUP 4
 #define EORB_IC_WORDS 9                    // aligned words covering 31 columns at any alignment
 #define EORB_IC_TASKS 288                  // 32 rows x 9 words (row 31 is padding with zero weights)
 
@@ -415,7 +415,7 @@ __device__ __forceinline__ int dp4a_u8_s8(unsigned data, int weights, int acc) {
     return d;
 }
 
-__global__ void __launch_bounds__(32 * EORB_KP_GROUP) orient_desc_kernel(OrbArgs a) {
+__global__ void __launch_bounds__(32 * EORB_KP_GROUP, 16) orient_desc_kernel(OrbArgs a) {
     __shared__ float s_angle[EORB_KP_GROUP], s_cos[EORB_KP_GROUP], s_sin[EORB_KP_GROUP];
     const OrbPlan& P = *a.plan;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
