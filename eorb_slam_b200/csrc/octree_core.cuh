@@ -42,7 +42,7 @@ __device__ __forceinline__ int oct_atomic_min(int* p, int v) { return atomicMin(
 
 namespace eorb {
 
-#define OCT_MAX_THREADS 256
+#define OCT_MAX_THREADS 128
 
 struct OctBox { short x0, y0, x1, y1; };
 
