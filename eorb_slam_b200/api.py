@@ -21,7 +21,8 @@ import numpy as np
 from .synth import EVENT_DTYPE, KEYPOINT_DTYPE, MATCH_DTYPE
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libeorb_b200.so")
+# EORB_B200_LIB selects another build of the same library (kernel-tuning A/B runs); there is still no CPU fallback
+LIB_PATH = os.environ.get("EORB_B200_LIB") or os.path.join(_HERE, "libeorb_b200.so")
 BEST2_DTYPE = np.dtype([("key1", "<u8"), ("key2", "<u8")])
 
 EORB_OK, EORB_EMPTY = 0, -1

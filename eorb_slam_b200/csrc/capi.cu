@@ -397,7 +397,7 @@ static int orbBuildPlan(eorb_orb* h, int W, int H) {
         lp.scale = h->scale[l];
         lp.sizeF = (float)(int)(31 * h->scale[l]);
         lp.quota = h->quota[l];
-        lp.blurTaskBase = rowBlocks; rowBlocks += ((lp.h + 29) / 30) * ((lp.w + 127) / 128);   // (EORB_BLUR_BAND = 30 rows) x (128 columns)
+        lp.blurTaskBase = rowBlocks; rowBlocks += ((lp.h + EORB_BLUR_BAND - 1) / EORB_BLUR_BAND) * ((lp.w + 127) / 128);   // (EORB_BLUR_BAND rows) x (128 columns)
         // FAST grid (:792-828)
         lp.minBX = E - 3; lp.minBY = E - 3; lp.maxBX = lp.w - E + 3; lp.maxBY = lp.h - E + 3;
         const float width = (float)(lp.maxBX - lp.minBX), height = (float)(lp.maxBY - lp.minBY);

@@ -42,7 +42,9 @@ __device__ __forceinline__ int oct_atomic_min(int* p, int v) { return atomicMin(
 
 namespace eorb {
 
+#ifndef OCT_MAX_THREADS
 #define OCT_MAX_THREADS 128
+#endif
 
 struct OctBox { short x0, y0, x1, y1; };
 

@@ -80,7 +80,25 @@ __global__ void __launch_bounds__(EORB_FAST_WARPS * 32) fast_cells_kernel(OrbArg
     const int cell = blockIdx.x * EORB_FAST_WARPS + warp;
     const int f = blockIdx.y;
     if (cell >= K0.nCells) return;
-    const CellPlan c = a.cells[cell];
+    // The 32-byte CellPlan is fetched as two 128-bit words and unpacked by hand: besides saving six loads this avoids a
+    // ptxas 12.9 miscompile seen with one-warp blocks, where the struct copy's `y0` (high half of word 0) was replaced
+    // by the high word of an unrelated 64-bit product before it reached the TMA coordinate (every cell row then saw
+    // tile row 0; caught by the parity tests).
+    CellPlan c;
+    {
+        const uint4* cp = reinterpret_cast<const uint4*>(a.cells + cell);
+        const uint4 c0 = __ldg(cp), c1 = __ldg(cp + 1);
+        c.x0 = (short)(c0.x & 0xffffu); c.y0 = (short)(c0.x >> 16);
+        c.w = (short)(c0.y & 0xffffu);  c.h = (short)(c0.y >> 16);
+        c.level = (short)(c0.z & 0xffffu); c._pad = 0;
+        c.slotOff = (int)c0.w;
+        c.ox = (short)(c1.x & 0xffffu); c.oy = (short)(c1.x >> 16);
+        c.slotCap = (int)c1.y;
+        c.aoff = (unsigned char)(c1.z & 0xffu); c.p0 = (unsigned char)((c1.z >> 8) & 0xffu);
+        c.np = (unsigned char)((c1.z >> 16) & 0xffu); c.rps = (unsigned char)(c1.z >> 24);
+        c.firstMask = (unsigned char)(c1.w & 0xffu); c.lastMask = (unsigned char)((c1.w >> 8) & 0xffu);
+        c.rcpNpM1 = (unsigned short)(c1.w >> 16);
+    }
     unsigned char* ws = smem_raw + (size_t)warp * K0.smemPerWarp;
     const uint8_t* tile = ws;
     uint8_t* smap = ws + K0.mapOff;

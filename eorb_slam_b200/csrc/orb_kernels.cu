@@ -239,7 +239,7 @@ __global__ void __launch_bounds__(OCT_MAX_THREADS) orb_index_kernel(OrbArgs a) {
 // (the 5th tap by a second dp4a with a one-hot weight word).  A 5-row ring of horizontal sums lives in registers
 // (loop unrolled by 5, no moves).  Horizontal sums are < 2^16 and the vertical sum < 2^24, so byte 2 of the
 // accumulator IS the result ((s + 32768) >> 16).
-#define EORB_BLUR_BAND 30   // multiple of 5: full bands run the unrolled ring loop without a tail
+// EORB_BLUR_BAND (orb_plan.h) is a multiple of 5: full bands run the unrolled ring loop without a tail
 
 // REFLECT_101 of a row index that overshoots [0, len) by at most 2 (single bounce when len >= 3)
 __device__ __forceinline__ int reflect101_near(int p, int len) {

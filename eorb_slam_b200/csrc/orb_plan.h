@@ -6,7 +6,12 @@
 
 #define EORB_MAX_LEVELS 32
 #define EORB_MAX_DIM 4095          // candidate coordinates are packed in 12 bits
-#define EORB_FAST_WARPS 4          // warps (= grid cells) per FAST thread block
+#ifndef EORB_BLUR_BAND
+#define EORB_BLUR_BAND 60          // rows per blur task; multiple of 5 (the row ring is unrolled by 5)
+#endif
+#ifndef EORB_FAST_WARPS
+#define EORB_FAST_WARPS 1          // warps (= grid cells) per FAST thread block
+#endif
 
 namespace eorb {
 
