@@ -323,6 +323,57 @@ def bench_lk(api, torch, dev, steps, warmup):
     return out
 
 
+def bench_guided(api, torch, dev, steps, warmup):
+    """SURVEY §8f rank 3: ORBmatcher::SearchForInitialization between two frames of the initialisation extractor
+    (5 x nFeatures keypoints, 100-px window, ratio 0.9, rotation check).  Two numbers: the host call (keypoints +
+    descriptors H2D, three kernels, matches D2H) and the device-resident call; CPU beside it: the oracle port."""
+    import oracle_lib as O
+    from eorb_slam_b200 import synth
+    k1, d1, k2, d2, b = synth.make_keypoint_frame_pair(5000, 5000, 31)
+    prev = np.stack([k1["x"], k1["y"]], 1)
+    gm = api.GuidedMatcher(dev, 0.9, True)
+    for _ in range(max(warmup, 3)):
+        n, m12, p = gm.SearchForInitialization(k1, d1, k2, d2, b, prev, 100)
+    reps = max(steps, 3) * 20
+    l0 = gm.launch_count()
+    t0 = time.perf_counter()
+    for _ in range(reps):
+        n, m12, p = gm.SearchForInitialization(k1, d1, k2, d2, b, prev, 100)
+    ms = (time.perf_counter() - t0) * 1e3 / reps
+    launches = (gm.launch_count() - l0) // reps
+    # device-resident: inputs already in HBM, CUDA-event time of the three kernels
+    tk1 = torch.from_numpy(k1.view(np.uint8).reshape(-1).copy()).cuda(); tk2 = torch.from_numpy(k2.view(np.uint8).reshape(-1).copy()).cuda()
+    td1 = torch.from_numpy(d1).cuda(); td2 = torch.from_numpy(d2).cuda()
+    tprev0 = torch.from_numpy(prev.astype(np.float32)).cuda(); tprev = tprev0.clone(); tm12 = torch.zeros(len(k1), dtype=torch.int32, device="cuda")
+    st = torch.cuda.current_stream().cuda_stream
+    gm.set_stream(st)
+    e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
+    dev_ms = []
+    for it in range(reps + 3):
+        tprev.copy_(tprev0)
+        e0.record()
+        nd = gm.SearchForInitialization_device(tk1.data_ptr(), td1.data_ptr(), len(k1), tk2.data_ptr(), td2.data_ptr(), len(k2), b,
+                                               tprev.data_ptr(), tm12.data_ptr(), 100)
+        e1.record(); torch.cuda.synchronize()
+        if it >= 3:
+            dev_ms.append(e0.elapsed_time(e1))
+    gm.set_stream(None)
+    en, em12, ep = O.search_for_initialization(k1, d1, k2, d2, b, prev, 100, 0.9, True)
+    t0 = time.perf_counter()
+    for _ in range(5):
+        O.search_for_initialization(k1, d1, k2, d2, b, prev, 100, 0.9, True)
+    ms_port = (time.perf_counter() - t0) * 1e3 / 5
+    lvl0 = int((k1["octave"] == 0).sum())
+    return {"metric": "search_for_initialization_calls_per_s", "value": 1e3 / ms, "unit": "calls/s", "ms_per_call": ms,
+            "ms_per_call_device_resident": float(np.median(dev_ms)),
+            "workload": "ORBmatcher::SearchForInitialization: 5000 x 5000 keypoints (%d level-0 queries), window 100, ratio 0.9, "
+                        "rotation check; %d matches" % (lvl0, en),
+            "gpu_launches_per_call": int(launches),
+            "bit_exact_vs_oracle": bool(n == en and nd == en and np.array_equal(m12, em12) and p.tobytes() == ep.tobytes()
+                                        and np.array_equal(tm12.cpu().numpy(), em12)),
+            "cpu_baseline": {"kind": "port", "cores": 1, "ms_per_call": ms_port, "value": 1e3 / ms_port, "unit": "calls/s"}}
+
+
 # ------------------------------------------------------------------------------------------------ main arm
 def run_ours(args):
     import torch
@@ -482,6 +533,11 @@ def run_ours(args):
                 extra["mci_jac"] = bench_mci_jac(api, dev, args.steps, args.warmup)
         except Exception as e:
             extra["mci_jac"] = {"error": repr(e)}
+        try:
+            if rank == 0:
+                extra["guided"] = bench_guided(api, torch, dev, args.steps, args.warmup)
+        except Exception as e:
+            extra["guided"] = {"error": repr(e)}
         try:
             extra["hamming"] = bench_hamming(api, torch, dev, max(min(args.steps, 3), 1), 3, world, rank, dist)
         except Exception as e:

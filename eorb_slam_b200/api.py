@@ -89,6 +89,12 @@ def _load():
         "eorb_lk_set_ref": ([vp, vp, i, i, sz, vp, i, i, i], i), "eorb_lk_set_ref_device": ([vp, vp, i, i, sz, vp, i, i, i], i),
         "eorb_lk_track": ([vp, vp, sz, vp, i, C.c_double, f, vp, vp, vp], i),
         "eorb_lk_track_device": ([vp, vp, sz, vp, i, C.c_double, f, vp, vp, vp], i),
+        "eorb_guided_create": ([i, C.POINTER(vp)], i), "eorb_guided_destroy": ([vp], i),
+        "eorb_guided_set_stream": ([vp, vp], i), "eorb_guided_reset_stream": ([vp], i), "eorb_guided_launch_count": ([vp], C.c_longlong),
+        "eorb_guided_frame_grid": ([vp, vp, i, vp, vp, vp, vp], i),
+        "eorb_guided_features_in_area": ([vp, vp, i, vp, vp, i, vp, vp, i], i),
+        "eorb_guided_search_for_initialization": ([vp, vp, vp, i, vp, vp, i, vp, vp, i, f, i, vp, vp], i),
+        "eorb_guided_search_for_initialization_device": ([vp, vp, vp, i, vp, vp, i, vp, vp, i, f, i, vp, vp], i),
     }
     for name, (args, res) in sig.items():
         fn = getattr(L, name)   # AttributeError here == header/library mismatch
@@ -586,3 +592,81 @@ class ELK_Tracker:
         self.levels_used = _check(lib.eorb_lk_track(self.h, _p(currImage), currImage.strides[0], _p(init), self.maxItr, float(self.eps), 1e-4,
                                                     _p(out), _p(status), _p(err)), "lk_track")
         return out, status, err
+
+
+# ================================================================================================ guided matching
+AREA_QUERY_DTYPE = np.dtype([("x", "<f4"), ("y", "<f4"), ("r", "<f4"), ("min_level", "<i4"), ("max_level", "<i4")])
+FRAME_GRID_COLS, FRAME_GRID_ROWS = 64, 48
+
+
+class FrameGrid:
+    """Mirror of the keypoint grid of ORB_SLAM3::Frame (src/Frame.cc): AssignFeaturesToGrid (:431-460), PosInGrid (:783-793)
+    and GetFeaturesInArea (:709-777) for one frame's (undistorted) keypoints.  bounds = (mnMinX, mnMinY, mnMaxX, mnMaxY)."""
+
+    def __init__(self, keypoints, bounds, device=0, guided=None):
+        self.kps = np.ascontiguousarray(keypoints, KEYPOINT_DTYPE)
+        self.bounds = np.ascontiguousarray(bounds, np.float32)
+        self.g = guided or GuidedMatcher(device)
+
+    def AssignFeaturesToGrid(self):
+        """-> (cell_start[64*48+1], cell_idx): CSR form of mGrid[col][row], cell id = col*48 + row"""
+        cs = np.zeros(FRAME_GRID_COLS * FRAME_GRID_ROWS + 1, np.int32); ci = np.zeros(max(len(self.kps), 1), np.int32)
+        na = C.c_int(0)
+        _check(lib.eorb_guided_frame_grid(self.g.h, _p(self.kps), len(self.kps), _p(self.bounds), _p(cs), _p(ci), C.byref(na)), "frame_grid")
+        return cs, ci[:na.value].copy()
+
+    def GetFeaturesInArea(self, x, y, r, minLevel=-1, maxLevel=-1):
+        return self.GetFeaturesInAreaBatch(np.array([(x, y, r, minLevel, maxLevel)], AREA_QUERY_DTYPE))[0]
+
+    def GetFeaturesInAreaBatch(self, queries):
+        """queries: AREA_QUERY_DTYPE array -> list of index arrays in the reference's order"""
+        q = np.ascontiguousarray(queries, AREA_QUERY_DTYPE)
+        cap = max(len(self.kps), 1)
+        cnt = np.zeros(max(len(q), 1), np.int32); out = np.zeros((max(len(q), 1), cap), np.int32)
+        _check(lib.eorb_guided_features_in_area(self.g.h, _p(self.kps), len(self.kps), _p(self.bounds), _p(q), len(q), _p(cnt), _p(out), cap),
+               "features_in_area")
+        return [out[k, :cnt[k]].copy() for k in range(len(q))]
+
+
+class GuidedMatcher:
+    """Mirror of the guided-matching entry points of ORB_SLAM3::ORBmatcher (src/ORBmatcher.cc) that walk the Frame grid:
+    SearchForInitialization (:714-831)."""
+
+    def __init__(self, device=0, nnratio=0.9, checkOri=True):
+        h = C.c_void_p()
+        _check(lib.eorb_guided_create(device, C.byref(h)), "guided_create")
+        self.h = h
+        self.mfNNratio = float(nnratio); self.mbCheckOrientation = bool(checkOri)
+
+    def __del__(self):
+        if getattr(self, "h", None):
+            lib.eorb_guided_destroy(self.h)
+            self.h = None
+
+    def set_stream(self, s):
+        _check(lib.eorb_guided_set_stream(self.h, C.c_void_p(s)) if s is not None else lib.eorb_guided_reset_stream(self.h), "guided_set_stream")
+
+    def launch_count(self): return lib.eorb_guided_launch_count(self.h)
+
+    def SearchForInitialization(self, kps1, desc1, kps2, desc2, bounds, vbPrevMatched, windowSize=100):
+        """-> (nmatches, vnMatches12[n1], vbPrevMatched updated copy (n1, 2))"""
+        k1 = np.ascontiguousarray(kps1, KEYPOINT_DTYPE); k2 = np.ascontiguousarray(kps2, KEYPOINT_DTYPE)
+        d1 = np.ascontiguousarray(desc1, np.uint8); d2 = np.ascontiguousarray(desc2, np.uint8)
+        b = np.ascontiguousarray(bounds, np.float32)
+        prev = np.array(vbPrevMatched, np.float32, copy=True).reshape(-1, 2)
+        m12 = np.full(max(len(k1), 1), -1, np.int32)
+        nm = C.c_int(0)
+        _check(lib.eorb_guided_search_for_initialization(self.h, _p(k1), _p(d1), len(k1), _p(k2), _p(d2), len(k2), _p(b), _p(prev),
+                                                         int(windowSize), self.mfNNratio, int(self.mbCheckOrientation), _p(m12),
+                                                         C.byref(nm)), "SearchForInitialization")
+        return nm.value, m12[:len(k1)].copy(), prev
+
+    def SearchForInitialization_device(self, d_kps1, d_desc1, n1, d_kps2, d_desc2, n2, bounds, d_prev, d_matches12, windowSize=100):
+        """all pointers are device addresses (ints); returns nmatches"""
+        b = np.ascontiguousarray(bounds, np.float32)
+        nm = C.c_int(0)
+        _check(lib.eorb_guided_search_for_initialization_device(self.h, C.c_void_p(d_kps1), C.c_void_p(d_desc1), n1, C.c_void_p(d_kps2),
+                                                                C.c_void_p(d_desc2), n2, _p(b), C.c_void_p(d_prev), int(windowSize),
+                                                                self.mfNNratio, int(self.mbCheckOrientation), C.c_void_p(d_matches12),
+                                                                C.byref(nm)), "SearchForInitialization_device")
+        return nm.value

@@ -1,0 +1,265 @@
+// capi_guided.cu — C ABI of the guided-matching row (include/eorb_b200.h, section "guided matching"):
+// Frame::AssignFeaturesToGrid / GetFeaturesInArea (src/Frame.cc:431-460, 709-793) and
+// ORBmatcher::SearchForInitialization (src/ORBmatcher.cc:714-831).  Host code only; the compute steps are the kernels of
+// guided_kernels.cu.  No CPU fallback.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cstdio>
+#include <cstring>
+#include <mutex>
+
+#include "../../include/eorb_b200.h"
+#include "guided_kernels.h"
+
+using namespace eorb;
+
+extern "C" int eorb_internal_fail(int code, const char* msg);
+static int gFail(int code, const char* what, const char* detail) {
+    char buf[400];
+    snprintf(buf, sizeof(buf), "%s%s%s", what, detail ? ": " : "", detail ? detail : "");
+    return eorb_internal_fail(code, buf);
+}
+#define CU(call)                                                                                  \
+    do {                                                                                          \
+        cudaError_t e__ = (call);                                                                 \
+        if (e__ != cudaSuccess) return gFail(EORB_ERR_CUDA, #call, cudaGetErrorString(e__));      \
+    } while (0)
+
+struct eorb_guided {
+    int device = 0;
+    cudaStream_t ownStream = nullptr, stream = nullptr;
+    // staging for the host entry points (frames 1 and 2) + work buffers, grown on demand
+    eorb_keypoint* d_kps[2] = {nullptr, nullptr}; uint8_t* d_desc[2] = {nullptr, nullptr}; int kpCap[2] = {0, 0};
+    float* d_prev = nullptr; int32_t* d_m12 = nullptr; int q1Cap = 0;
+    GuidedWork w{};
+    int workN1 = 0, workN2 = 0;
+    int* d_nm = nullptr; int* h_nm = nullptr;          // [nmatches, total candidates] device + pinned mirror
+    eorb_area_query* d_q = nullptr; int* d_cnt = nullptr; int* d_out = nullptr; size_t qCap = 0, outCap = 0;
+    long long launches = 0;
+};
+
+static std::once_flag g_cfgOnce;
+static cudaError_t g_cfgErr = cudaSuccess;
+
+static GuidedGrid gridGeom(const float* b) {
+    GuidedGrid g;
+    g.minX = b[0]; g.minY = b[1];
+    g.wInv = (float)EORB_GRID_COLS / (b[2] - b[0]);   // Frame.cc:165-166, float arithmetic
+    g.hInv = (float)EORB_GRID_ROWS / (b[3] - b[1]);
+    return g;
+}
+
+extern "C" int eorb_guided_create(int device, eorb_guided** out) {
+    if (!out) return gFail(EORB_ERR_ARG, "eorb_guided_create", "null argument");
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) { cudaGetLastError(); return gFail(EORB_ERR_CUDA, "no CUDA device: eorb_b200 has no CPU fallback", nullptr); }
+    if (device < 0 || device >= ndev) return gFail(EORB_ERR_ARG, "eorb_guided_create", "device out of range");
+    CU(cudaSetDevice(device));
+    std::call_once(g_cfgOnce, [] { g_cfgErr = guided_configure(); });
+    if (g_cfgErr != cudaSuccess) return gFail(EORB_ERR_CUDA, "guided_configure", cudaGetErrorString(g_cfgErr));
+    eorb_guided* g = new eorb_guided();
+    g->device = device;
+    CU(cudaStreamCreateWithFlags(&g->ownStream, cudaStreamNonBlocking));
+    g->stream = g->ownStream;
+    CU(cudaMalloc((void**)&g->w.cellStart, (EORB_GRID_CELLS + 1) * sizeof(int)));
+    CU(cudaMalloc((void**)&g->w.assigned, sizeof(int)));
+    CU(cudaMalloc((void**)&g->d_nm, 2 * sizeof(int)));
+    g->w.total = g->d_nm + 1;
+    CU(cudaMallocHost((void**)&g->h_nm, 2 * sizeof(int)));
+    *out = g;
+    return EORB_OK;
+}
+
+extern "C" int eorb_guided_destroy(eorb_guided* g) {
+    if (!g) return EORB_OK;
+    cudaSetDevice(g->device);
+    cudaStreamSynchronize(g->stream);
+    for (int k = 0; k < 2; k++) { cudaFree(g->d_kps[k]); cudaFree(g->d_desc[k]); }
+    cudaFree(g->d_prev); cudaFree(g->d_m12);
+    cudaFree(g->w.cellStart); cudaFree(g->w.cellIdx); cudaFree(g->w.assigned); cudaFree(g->w.candOff); cudaFree(g->w.candCnt);
+    cudaFree(g->w.top); cudaFree(g->w.bin); cudaFree(g->w.cand);
+    cudaFree(g->d_nm); cudaFreeHost(g->h_nm); cudaFree(g->d_q); cudaFree(g->d_cnt); cudaFree(g->d_out);
+    cudaStreamDestroy(g->ownStream);
+    delete g;
+    return EORB_OK;
+}
+
+extern "C" int eorb_guided_set_stream(eorb_guided* g, void* s) {
+    if (!g) return gFail(EORB_ERR_ARG, "eorb_guided_set_stream", "null handle");
+    CU(cudaStreamSynchronize(g->stream));
+    g->stream = (cudaStream_t)s;
+    return EORB_OK;
+}
+extern "C" int eorb_guided_reset_stream(eorb_guided* g) {
+    if (!g) return gFail(EORB_ERR_ARG, "eorb_guided_reset_stream", "null handle");
+    CU(cudaStreamSynchronize(g->stream));
+    g->stream = g->ownStream;
+    return EORB_OK;
+}
+extern "C" long long eorb_guided_launch_count(const eorb_guided* g) { return g ? g->launches : 0; }
+
+static int stageFrame(eorb_guided* g, int k, const eorb_keypoint* kps, const uint8_t* desc, int n) {
+    if (n > g->kpCap[k]) {
+        CU(cudaStreamSynchronize(g->stream));
+        cudaFree(g->d_kps[k]); cudaFree(g->d_desc[k]);
+        g->d_kps[k] = nullptr; g->d_desc[k] = nullptr; g->kpCap[k] = 0;
+        const int cap = std::max(1024, n);
+        CU(cudaMalloc((void**)&g->d_kps[k], (size_t)cap * sizeof(eorb_keypoint)));
+        CU(cudaMalloc((void**)&g->d_desc[k], (size_t)cap * 32));
+        g->kpCap[k] = cap;
+    }
+    if (n > 0) {
+        CU(cudaMemcpyAsync(g->d_kps[k], kps, (size_t)n * sizeof(eorb_keypoint), cudaMemcpyHostToDevice, g->stream));
+        if (desc) CU(cudaMemcpyAsync(g->d_desc[k], desc, (size_t)n * 32, cudaMemcpyHostToDevice, g->stream));
+    }
+    return EORB_OK;
+}
+
+static int reserveWork(eorb_guided* g, int n1, int n2) {
+    if (n2 > g->workN2) {
+        CU(cudaStreamSynchronize(g->stream));
+        cudaFree(g->w.cellIdx); g->w.cellIdx = nullptr; g->workN2 = 0;
+        const int cap = std::max(1024, n2);
+        CU(cudaMalloc((void**)&g->w.cellIdx, (size_t)cap * sizeof(int)));
+        g->workN2 = cap;
+    }
+    if (n1 > g->workN1) {
+        CU(cudaStreamSynchronize(g->stream));
+        cudaFree(g->w.candOff); cudaFree(g->w.candCnt); cudaFree(g->w.top); cudaFree(g->w.bin);
+        g->w.candOff = g->w.candCnt = nullptr; g->w.top = nullptr; g->w.bin = nullptr; g->workN1 = 0;
+        const int cap = std::max(1024, n1);
+        CU(cudaMalloc((void**)&g->w.candOff, (size_t)cap * sizeof(int)));
+        CU(cudaMalloc((void**)&g->w.candCnt, (size_t)cap * sizeof(int)));
+        CU(cudaMalloc((void**)&g->w.top, (size_t)cap * EORB_GUIDED_TOP * sizeof(unsigned long long)));
+        CU(cudaMalloc((void**)&g->w.bin, (size_t)cap));
+        g->workN1 = cap;
+    }
+    if (!g->w.cand) {
+        g->w.candCap = 1 << 20;   // 4 MB; grown to the exact need when a search overflows it
+        CU(cudaMalloc((void**)&g->w.cand, (size_t)g->w.candCap * sizeof(uint32_t)));
+    }
+    return EORB_OK;
+}
+
+static int checkFrames(const void* k1, int n1, const void* k2, int n2, const float* b) {
+    if (n1 < 0 || n2 < 0 || (n1 > 0 && !k1) || (n2 > 0 && !k2) || !b) return gFail(EORB_ERR_ARG, "guided matching", "null argument");
+    if (n1 > EORB_GUIDED_MAX_KEYPOINTS || n2 > EORB_GUIDED_MAX_KEYPOINTS) return gFail(EORB_ERR_CAPACITY, "guided matching", "more than EORB_GUIDED_MAX_KEYPOINTS keypoints");
+    if (!(b[2] > b[0]) || !(b[3] > b[1])) return gFail(EORB_ERR_ARG, "guided matching", "empty image bounds");
+    return EORB_OK;
+}
+
+extern "C" int eorb_guided_frame_grid(eorb_guided* g, const eorb_keypoint* kps, int n, const float* bounds4, int* cell_start, int* cell_idx,
+                                      int* assigned) {
+    if (!g || !cell_start || (n > 0 && !cell_idx)) return gFail(EORB_ERR_ARG, "eorb_guided_frame_grid", "null argument");
+    int rc = checkFrames(nullptr, 0, kps, n, bounds4);
+    if (rc != EORB_OK) return rc;
+    CU(cudaSetDevice(g->device));
+    if ((rc = stageFrame(g, 1, kps, nullptr, n)) != EORB_OK) return rc;
+    if ((rc = reserveWork(g, 0, n)) != EORB_OK) return rc;
+    CU(launch_frame_grid(g->d_kps[1], n, gridGeom(bounds4), g->w.cellStart, g->w.cellIdx, g->w.assigned, g->stream));
+    g->launches++;
+    CU(cudaMemcpyAsync(cell_start, g->w.cellStart, (EORB_GRID_CELLS + 1) * sizeof(int), cudaMemcpyDeviceToHost, g->stream));
+    CU(cudaMemcpyAsync(g->h_nm, g->w.assigned, sizeof(int), cudaMemcpyDeviceToHost, g->stream));
+    CU(cudaStreamSynchronize(g->stream));
+    const int na = g->h_nm[0];
+    if (na > 0) CU(cudaMemcpy(cell_idx, g->w.cellIdx, (size_t)na * sizeof(int), cudaMemcpyDeviceToHost));
+    if (assigned) *assigned = na;
+    return EORB_OK;
+}
+
+extern "C" int eorb_guided_features_in_area(eorb_guided* g, const eorb_keypoint* kps, int n, const float* bounds4, const eorb_area_query* queries,
+                                            int nq, int* counts, int* idx_out, int cap_per_query) {
+    if (!g || nq < 0 || (nq > 0 && (!queries || !counts)) || cap_per_query < 0 || (cap_per_query > 0 && nq > 0 && !idx_out))
+        return gFail(EORB_ERR_ARG, "eorb_guided_features_in_area", "bad argument");
+    int rc = checkFrames(nullptr, 0, kps, n, bounds4);
+    if (rc != EORB_OK) return rc;
+    if (nq == 0) return EORB_OK;
+    CU(cudaSetDevice(g->device));
+    if ((rc = stageFrame(g, 1, kps, nullptr, n)) != EORB_OK) return rc;
+    if ((rc = reserveWork(g, 0, n)) != EORB_OK) return rc;
+    const size_t outNeed = std::max<size_t>((size_t)nq * cap_per_query, 1);
+    if ((size_t)nq > g->qCap || outNeed > g->outCap) {
+        CU(cudaStreamSynchronize(g->stream));
+        cudaFree(g->d_q); cudaFree(g->d_cnt); cudaFree(g->d_out);
+        g->d_q = nullptr; g->d_cnt = nullptr; g->d_out = nullptr;
+        g->qCap = std::max<size_t>(g->qCap, (size_t)nq); g->outCap = std::max(g->outCap, outNeed);
+        CU(cudaMalloc((void**)&g->d_q, g->qCap * sizeof(eorb_area_query)));
+        CU(cudaMalloc((void**)&g->d_cnt, g->qCap * sizeof(int)));
+        CU(cudaMalloc((void**)&g->d_out, g->outCap * sizeof(int)));
+    }
+    const GuidedGrid gg = gridGeom(bounds4);
+    CU(cudaMemcpyAsync(g->d_q, queries, (size_t)nq * sizeof(eorb_area_query), cudaMemcpyHostToDevice, g->stream));
+    CU(launch_frame_grid(g->d_kps[1], n, gg, g->w.cellStart, g->w.cellIdx, g->w.assigned, g->stream));
+    CU(launch_features_in_area(g->d_kps[1], gg, g->w.cellStart, g->w.cellIdx, g->d_q, nq, g->d_cnt, g->d_out, cap_per_query, g->stream));
+    g->launches += 2;
+    CU(cudaMemcpyAsync(counts, g->d_cnt, (size_t)nq * sizeof(int), cudaMemcpyDeviceToHost, g->stream));
+    if (cap_per_query > 0) CU(cudaMemcpyAsync(idx_out, g->d_out, (size_t)nq * cap_per_query * sizeof(int), cudaMemcpyDeviceToHost, g->stream));
+    CU(cudaStreamSynchronize(g->stream));
+    return EORB_OK;
+}
+
+// runs the three kernels; when the candidate buffer was too small it is grown to the exact need and the search repeated
+static int searchInitRun(eorb_guided* g, const eorb_keypoint* d_k1, const uint8_t* d_d1, int n1, const eorb_keypoint* d_k2, const uint8_t* d_d2,
+                         int n2, const float* bounds4, float* d_prev, int window, float nnratio, int checkOri, int32_t* d_m12, int* nmatches) {
+    int rc = reserveWork(g, n1, n2);
+    if (rc != EORB_OK) return rc;
+    GuidedFrame f1{d_k1, d_d1, n1}, f2{d_k2, d_d2, n2};
+    const GuidedGrid gg = gridGeom(bounds4);
+    for (int attempt = 0; attempt < 2; attempt++) {
+        CU(launch_search_init(f1, f2, gg, d_prev, window, nnratio, checkOri, g->w, d_m12, g->d_nm, g->stream, &g->launches));
+        CU(cudaMemcpyAsync(g->h_nm, g->d_nm, 2 * sizeof(int), cudaMemcpyDeviceToHost, g->stream));
+        CU(cudaStreamSynchronize(g->stream));
+        if (g->h_nm[1] <= g->w.candCap) { if (nmatches) *nmatches = g->h_nm[0]; return EORB_OK; }
+        cudaFree(g->w.cand); g->w.cand = nullptr;
+        g->w.candCap = g->h_nm[1] + g->h_nm[1] / 4;
+        CU(cudaMalloc((void**)&g->w.cand, (size_t)g->w.candCap * sizeof(uint32_t)));
+    }
+    return gFail(EORB_ERR_STATE, "eorb_guided_search_for_initialization", "candidate buffer overflow after growth");
+}
+
+extern "C" int eorb_guided_search_for_initialization_device(eorb_guided* g, const eorb_keypoint* d_kps1, const uint8_t* d_desc1, int n1,
+                                                            const eorb_keypoint* d_kps2, const uint8_t* d_desc2, int n2, const float* bounds4,
+                                                            float* d_prev_xy, int window_size, float nnratio, int check_ori,
+                                                            int32_t* d_matches12, int* nmatches) {
+    if (!g) return gFail(EORB_ERR_ARG, "eorb_guided_search_for_initialization_device", "null handle");
+    int rc = checkFrames(d_kps1, n1, d_kps2, n2, bounds4);
+    if (rc != EORB_OK) return rc;
+    if (nmatches) *nmatches = 0;
+    if (n1 == 0) return EORB_OK;
+    if (!d_prev_xy || !d_matches12 || !d_desc1 || (n2 > 0 && !d_desc2)) return gFail(EORB_ERR_ARG, "eorb_guided_search_for_initialization_device", "null argument");
+    if (((uintptr_t)d_desc1 | (uintptr_t)d_desc2) & 15) return gFail(EORB_ERR_ARG, "eorb_guided_search_for_initialization_device", "descriptors must be 16-byte aligned");
+    CU(cudaSetDevice(g->device));
+    return searchInitRun(g, d_kps1, d_desc1, n1, d_kps2, d_desc2, n2, bounds4, d_prev_xy, window_size, nnratio, check_ori, d_matches12, nmatches);
+}
+
+extern "C" int eorb_guided_search_for_initialization(eorb_guided* g, const eorb_keypoint* kps1, const uint8_t* desc1, int n1,
+                                                     const eorb_keypoint* kps2, const uint8_t* desc2, int n2, const float* bounds4, float* prev_xy,
+                                                     int window_size, float nnratio, int check_ori, int32_t* matches12, int* nmatches) {
+    if (!g) return gFail(EORB_ERR_ARG, "eorb_guided_search_for_initialization", "null handle");
+    int rc = checkFrames(kps1, n1, kps2, n2, bounds4);
+    if (rc != EORB_OK) return rc;
+    if (nmatches) *nmatches = 0;
+    if (n1 == 0) return EORB_OK;   // vnMatches12 is empty, nothing to do (ORBmatcher.cc:718)
+    if (!prev_xy || !matches12 || !desc1 || (n2 > 0 && !desc2)) return gFail(EORB_ERR_ARG, "eorb_guided_search_for_initialization", "null argument");
+    CU(cudaSetDevice(g->device));
+    if ((rc = stageFrame(g, 0, kps1, desc1, n1)) != EORB_OK) return rc;
+    if ((rc = stageFrame(g, 1, kps2, desc2, n2)) != EORB_OK) return rc;
+    if (n1 > g->q1Cap) {
+        CU(cudaStreamSynchronize(g->stream));
+        cudaFree(g->d_prev); cudaFree(g->d_m12);
+        g->d_prev = nullptr; g->d_m12 = nullptr; g->q1Cap = 0;
+        const int cap = std::max(1024, n1);
+        CU(cudaMalloc((void**)&g->d_prev, (size_t)cap * 2 * sizeof(float)));
+        CU(cudaMalloc((void**)&g->d_m12, (size_t)cap * sizeof(int32_t)));
+        g->q1Cap = cap;
+    }
+    CU(cudaMemcpyAsync(g->d_prev, prev_xy, (size_t)n1 * 2 * sizeof(float), cudaMemcpyHostToDevice, g->stream));
+    rc = searchInitRun(g, g->d_kps[0], g->d_desc[0], n1, g->d_kps[1], g->d_desc[1], n2, bounds4, g->d_prev, window_size, nnratio, check_ori,
+                       g->d_m12, nmatches);
+    if (rc != EORB_OK) return rc;
+    CU(cudaMemcpyAsync(matches12, g->d_m12, (size_t)n1 * sizeof(int32_t), cudaMemcpyDeviceToHost, g->stream));
+    CU(cudaMemcpyAsync(prev_xy, g->d_prev, (size_t)n1 * 2 * sizeof(float), cudaMemcpyDeviceToHost, g->stream));
+    CU(cudaStreamSynchronize(g->stream));
+    return EORB_OK;
+}

@@ -1,0 +1,422 @@
+// guided_kernels.cu — guided matching around the Hamming kernel.
+//
+//   G1 frame_grid_kernel        Frame::AssignFeaturesToGrid + PosInGrid (src/Frame.cc:431-460, 783-793): 64 x 48 cells,
+//                               lists in keypoint-index order.  One block sorts the unique keys (cell << 16 | index)
+//                               with a shared-memory bitonic network; the CSR row pointers fall out of the sorted keys.
+//                               Cell id = col * 48 + row, so the cells GetFeaturesInArea visits for one column are ONE
+//                               contiguous CSR range in exactly the reference's order (columns outer, rows inner).
+//   G2 guided_candidates_kernel one warp per frame-1 keypoint (level 0 only, ORBmatcher.cc:732-734): walks the window's
+//                               columns 32 entries at a time (ballot compaction keeps the reference's visiting order),
+//                               computes the Hamming distance of every candidate and keeps the 32 smallest
+//                               (distance, position) keys sorted across the lanes (shuffle bitonic sort + merge).
+//   G3 guided_resolve_kernel    the stateful part of ORBmatcher::SearchForInitialization (:747-796): candidates already
+//                               matched with a smaller-or-equal distance are skipped, a better query takes a frame-2
+//                               keypoint over.  That is a sequential dependency over the queries, so ONE warp replays the
+//                               queries (compacted to those with candidates) in order — but each step is only "first two unfiltered entries of a sorted
+//                               32-entry head" (a ballot) with the whole state (matched distance, owner, angles) in shared
+//                               memory; the other seven warps stage the next 64 heads behind it (double buffer).  The full-list scan is kept as the
+//                               slow path for heads that run dry.  Rotation histogram (:784-794, with the entries of
+//                               matches that are taken over later, as in the reference), ComputeThreeMaxima
+//                               (:2314-2355), the filter (:800-823) and the vbPrevMatched update (:826-828) follow in
+//                               the same launch.
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "guided_kernels.h"
+
+namespace eorb {
+
+typedef unsigned long long u64;
+#define GUIDED_STAGE 64     // queries staged per round of the resolve kernel
+#define GUIDED_NONE 0xffffu
+#define FULLMASK 0xffffffffu
+
+// ---- GetFeaturesInArea cell window (Frame.cc:722-744), all float like the reference
+__device__ __forceinline__ bool area_cells(const GuidedGrid& g, float x, float y, float r, int& c0, int& c1, int& r0, int& r1) {
+    c0 = max(0, (int)floorf(__fmul_rn(__fsub_rn(__fsub_rn(x, g.minX), r), g.wInv)));
+    if (c0 >= EORB_GRID_COLS) return false;
+    c1 = min(EORB_GRID_COLS - 1, (int)ceilf(__fmul_rn(__fadd_rn(__fsub_rn(x, g.minX), r), g.wInv)));
+    if (c1 < 0) return false;
+    r0 = max(0, (int)floorf(__fmul_rn(__fsub_rn(__fsub_rn(y, g.minY), r), g.hInv)));
+    if (r0 >= EORB_GRID_ROWS) return false;
+    r1 = min(EORB_GRID_ROWS - 1, (int)ceilf(__fmul_rn(__fadd_rn(__fsub_rn(y, g.minY), r), g.hInv)));
+    if (r1 < 0) return false;
+    return true;
+}
+
+// candidate test of one list entry (Frame.cc:756-773)
+__device__ __forceinline__ bool area_accept(const eorb_keypoint* __restrict__ kps, int i2, float x, float y, float r, bool check, int minLevel,
+                                            int maxLevel) {
+    const eorb_keypoint& kp = kps[i2];
+    if (check) {
+        const int level = kp.octave;
+        if (level < minLevel) return false;
+        if (maxLevel >= 0 && level > maxLevel) return false;
+    }
+    return fabsf(__fsub_rn(kp.x, x)) < r && fabsf(__fsub_rn(kp.y, y)) < r;
+}
+
+// ------------------------------------------------------------------------------------------------ G1
+__global__ void __launch_bounds__(1024) frame_grid_kernel(const eorb_keypoint* __restrict__ kps, int n, GuidedGrid g, int* __restrict__ cellStart,
+                                                          int* __restrict__ cellIdx, int* __restrict__ assigned) {
+    extern __shared__ uint32_t keys[];
+    int np2 = 2;
+    while (np2 < n) np2 <<= 1;
+    const int tid = threadIdx.x;
+    for (int i = tid; i < np2; i += 1024) {
+        uint32_t key = 0xffffffffu;
+        if (i < n) {
+            // PosInGrid: round() of a float is std::round(float) = roundf, half away from zero
+            const int px = (int)roundf(__fmul_rn(__fsub_rn(kps[i].x, g.minX), g.wInv));
+            const int py = (int)roundf(__fmul_rn(__fsub_rn(kps[i].y, g.minY), g.hInv));
+            if (px >= 0 && px < EORB_GRID_COLS && py >= 0 && py < EORB_GRID_ROWS) key = ((uint32_t)(px * EORB_GRID_ROWS + py) << 16) | (uint32_t)i;
+        }
+        keys[i] = key;
+    }
+    __syncthreads();
+    for (int k = 2; k <= np2; k <<= 1)
+        for (int j = k >> 1; j > 0; j >>= 1) {
+            for (int i = tid; i < np2; i += 1024) {
+                const int o = i ^ j;
+                if (o > i) {
+                    const uint32_t a = keys[i], b = keys[o];
+                    const bool up = (i & k) == 0;
+                    if ((a > b) == up) { keys[i] = b; keys[o] = a; }
+                }
+            }
+            __syncthreads();
+        }
+    for (int i = tid; i < np2; i += 1024) {
+        const uint32_t key = keys[i];
+        const int cell = key == 0xffffffffu ? EORB_GRID_CELLS : (int)(key >> 16);
+        int prevCell = -1;
+        if (i > 0) prevCell = keys[i - 1] == 0xffffffffu ? EORB_GRID_CELLS : (int)(keys[i - 1] >> 16);
+        if (key != 0xffffffffu) cellIdx[i] = (int)(key & 0xffffu);
+        for (int c = prevCell + 1; c <= cell; c++) cellStart[c] = i;   // first sorted position whose cell is >= c
+        if (cell == EORB_GRID_CELLS && prevCell != EORB_GRID_CELLS) *assigned = i;
+    }
+    if (tid == 0 && keys[np2 - 1] != 0xffffffffu) {   // every slot valid (n == np2): close the tail
+        for (int c = (int)(keys[np2 - 1] >> 16) + 1; c <= EORB_GRID_CELLS; c++) cellStart[c] = np2;
+        *assigned = np2;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ GetFeaturesInArea batch
+__global__ void __launch_bounds__(256) features_in_area_kernel(const eorb_keypoint* __restrict__ kps, GuidedGrid g, const int* __restrict__ cellStart,
+                                                               const int* __restrict__ cellIdx, const eorb_area_query* __restrict__ qs, int nq,
+                                                               int* __restrict__ count, int* __restrict__ out, int cap) {
+    const int q = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+    if (q >= nq) return;
+    const eorb_area_query Q = qs[q];
+    const unsigned lt = (1u << lane) - 1u;
+    int c0, c1, r0, r1, cnt = 0;
+    if (area_cells(g, Q.x, Q.y, Q.r, c0, c1, r0, r1)) {
+        const bool check = Q.min_level > 0 || Q.max_level >= 0;
+        for (int ix = c0; ix <= c1; ix++) {
+            const int b = cellStart[ix * EORB_GRID_ROWS + r0], e = cellStart[ix * EORB_GRID_ROWS + r1 + 1];
+            for (int base = b; base < e; base += 32) {
+                const int j = base + lane;
+                int i2 = -1;
+                bool ok = false;
+                if (j < e) { i2 = cellIdx[j]; ok = area_accept(kps, i2, Q.x, Q.y, Q.r, check, Q.min_level, Q.max_level); }
+                const unsigned m = __ballot_sync(FULLMASK, ok);
+                const int pos = cnt + __popc(m & lt);
+                if (ok && pos < cap) out[(size_t)q * cap + pos] = i2;
+                cnt += __popc(m);
+            }
+        }
+    }
+    if (lane == 0) count[q] = cnt;
+}
+
+// ------------------------------------------------------------------------------------------------ G2
+__device__ __forceinline__ u64 shfl_xor_u64(u64 v, int m) { return __shfl_xor_sync(FULLMASK, v, m); }
+
+__device__ __forceinline__ u64 warp_sort32(u64 v, int lane) {
+#pragma unroll
+    for (int k = 2; k <= 32; k <<= 1)
+#pragma unroll
+        for (int j = k >> 1; j > 0; j >>= 1) {
+            const u64 o = shfl_xor_u64(v, j);
+            const bool up = (lane & k) == 0, lower = (lane & j) == 0;
+            v = (lower == up) ? (v < o ? v : o) : (v < o ? o : v);
+        }
+    return v;
+}
+
+__global__ void __launch_bounds__(256) guided_candidates_kernel(GuidedFrame f1, GuidedFrame f2, GuidedGrid g, const float* __restrict__ prevXY,
+                                                                float r, GuidedWork w) {
+    const int i1 = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+    if (i1 >= f1.n) return;
+    const unsigned lt = (1u << lane) - 1u;
+    if (lane == 0) w.bin[i1] = -1;
+    const int level1 = f1.kps[i1].octave;
+    int c0 = 0, c1 = -1, r0 = 0, r1 = 0;
+    const float x = prevXY[2 * i1], y = prevXY[2 * i1 + 1];
+    bool live = level1 <= 0 && area_cells(g, x, y, r, c0, c1, r0, r1);
+    // pass 1: count (minLevel = maxLevel = level1 = 0 -> bCheckLevels is true, Frame.cc:746)
+    int cnt = 0;
+    if (live)
+        for (int ix = c0; ix <= c1; ix++) {
+            const int b = w.cellStart[ix * EORB_GRID_ROWS + r0], e = w.cellStart[ix * EORB_GRID_ROWS + r1 + 1];
+            for (int base = b; base < e; base += 32) {
+                const int j = base + lane;
+                const bool ok = j < e && area_accept(f2.kps, w.cellIdx[j], x, y, r, true, level1, level1);
+                cnt += __popc(__ballot_sync(FULLMASK, ok));
+            }
+        }
+    int off = 0;
+    if (lane == 0 && cnt > 0) off = atomicAdd(w.total, cnt);
+    off = __shfl_sync(FULLMASK, off, 0);
+    if (lane == 0) { w.candCnt[i1] = cnt; w.candOff[i1] = off; }
+    if (cnt == 0 || off + cnt > w.candCap) return;   // overflow: the host sees total > candCap, grows the buffer and retries
+
+    // pass 2: distances, full list in visiting order, sorted head of the 32 smallest (distance, position) keys
+    uint32_t qd[8];
+    {
+        const uint4* qp = reinterpret_cast<const uint4*>(f1.desc + (size_t)i1 * 32);
+        const uint4 a = __ldg(qp), b = __ldg(qp + 1);
+        qd[0] = a.x; qd[1] = a.y; qd[2] = a.z; qd[3] = a.w; qd[4] = b.x; qd[5] = b.y; qd[6] = b.z; qd[7] = b.w;
+    }
+    u64 top = ~0ull;
+    int pos0 = 0;
+    for (int ix = c0; ix <= c1; ix++) {
+        const int b = w.cellStart[ix * EORB_GRID_ROWS + r0], e = w.cellStart[ix * EORB_GRID_ROWS + r1 + 1];
+        for (int base = b; base < e; base += 32) {
+            const int j = base + lane;
+            int i2 = 0;
+            bool ok = false;
+            if (j < e) { i2 = w.cellIdx[j]; ok = area_accept(f2.kps, i2, x, y, r, true, level1, level1); }
+            const unsigned m = __ballot_sync(FULLMASK, ok);
+            if (m == 0) continue;
+            u64 key = ~0ull;
+            if (ok) {
+                const uint4* dp = reinterpret_cast<const uint4*>(f2.desc + (size_t)i2 * 32);
+                const uint4 a = __ldg(dp), c = __ldg(dp + 1);
+                const int dist = __popc(a.x ^ qd[0]) + __popc(a.y ^ qd[1]) + __popc(a.z ^ qd[2]) + __popc(a.w ^ qd[3]) + __popc(c.x ^ qd[4]) +
+                                 __popc(c.y ^ qd[5]) + __popc(c.z ^ qd[6]) + __popc(c.w ^ qd[7]);
+                const int pos = pos0 + __popc(m & lt);
+                w.cand[off + pos] = ((uint32_t)dist << 16) | (uint32_t)i2;
+                key = ((u64)dist << 32) | ((u64)pos << 16) | (u64)i2;
+            }
+            pos0 += __popc(m);
+            if (!__any_sync(FULLMASK, key < __shfl_sync(FULLMASK, top, 31))) continue;   // nothing here beats the current 32nd smallest
+            key = warp_sort32(key, lane);
+            const u64 rev = __shfl_sync(FULLMASK, key, 31 - lane);
+            top = top < rev ? top : rev;          // the 32 smallest of both, as a bitonic sequence
+#pragma unroll
+            for (int jj = 16; jj > 0; jj >>= 1) {
+                const u64 o = shfl_xor_u64(top, jj);
+                top = (lane & jj) == 0 ? (top < o ? top : o) : (top < o ? o : top);
+            }
+        }
+    }
+    w.top[(size_t)i1 * EORB_GUIDED_TOP + lane] = top;
+}
+
+// ------------------------------------------------------------------------------------------------ G3
+// Only what truly depends on the order of the queries stays in the one-warp loop: the filter against the matched
+// distances and the two state writes.  vnMatches12 / nmatches fall out of the final owner table (a frame-2 keypoint's
+// last claimer owns it; a query claims at most once), and the rotation bin of a claim only depends on (query, claimed
+// keypoint), so both are computed by the whole block after the loop.  Inside the loop matches12[i1] records the claim.
+__global__ void __launch_bounds__(256) guided_resolve_kernel(GuidedFrame f1, GuidedFrame f2, float* __restrict__ prevXY, float nnratio, int checkOri,
+                                                             GuidedWork w, int32_t* __restrict__ matches12, int* __restrict__ nmatchesOut) {
+    extern __shared__ __align__(16) unsigned char sm[];
+    const int n1 = f1.n, n2 = f2.n, n2r = (n2 + 3) & ~3;
+    u64* stop = reinterpret_cast<u64*>(sm);                               // [2][GUIDED_STAGE][32] double-buffered heads
+    int* scnt = reinterpret_cast<int*>(stop + 2 * GUIDED_STAGE * 32);     // [2][GUIDED_STAGE]
+    int* soff = scnt + 2 * GUIDED_STAGE;                                  // [2][GUIDED_STAGE]
+    int* hist = soff + 2 * GUIDED_STAGE;                                  // [32]
+    unsigned short* md = reinterpret_cast<unsigned short*>(hist + 32);    // [n2r] matched distance (0xffff = INT_MAX)
+    unsigned short* m21 = md + n2r;                                       // [n2r] owner in frame 1 (0xffff = none)
+    unsigned short* qlist = m21 + n2r;                                    // [n1] queries that have candidates, ascending
+    __shared__ int sNm, sInd[3], sWarp[8];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+
+    if (*w.total > w.candCap) {   // candidate buffer overflow: nothing below may run on partial lists
+        if (tid == 0) *nmatchesOut = -1;
+        return;
+    }
+    for (int i = tid; i < n2; i += 256) { md[i] = GUIDED_NONE; m21[i] = GUIDED_NONE; }
+    for (int i = tid; i < n1; i += 256) matches12[i] = -1;
+    if (tid < 32) hist[tid] = 0;
+    if (tid == 0) sNm = 0;
+    // compact the queries that have candidates (level-0 keypoints with a non-empty window), keeping their order
+    int nact = 0;
+    for (int base = 0; base < n1; base += 256) {
+        const int i1 = base + tid;
+        const bool act = i1 < n1 && w.candCnt[i1] > 0;
+        const unsigned bm = __ballot_sync(FULLMASK, act);
+        if (lane == 0) sWarp[warp] = __popc(bm);
+        __syncthreads();
+        int before = 0, total = 0;
+#pragma unroll
+        for (int k = 0; k < 8; k++) { const int v = sWarp[k]; total += v; if (k < warp) before += v; }
+        if (act) qlist[nact + before + __popc(bm & ((1u << lane) - 1u))] = (unsigned short)i1;
+        nact += total;
+        __syncthreads();
+    }
+    const int nrounds = (nact + GUIDED_STAGE - 1) / GUIDED_STAGE;
+
+    // stage `r` = heads + list ranges of queries qlist[r*64 ..]; loaded by `nth` threads starting at thread `t0`
+    auto loadStage = [&](int r, int t0, int nth) {
+        u64* sp = stop + (r & 1) * GUIDED_STAGE * 32;
+        int* sc = scnt + (r & 1) * GUIDED_STAGE;
+        int* so = soff + (r & 1) * GUIDED_STAGE;
+        for (int t = tid - t0; t < GUIDED_STAGE * 32; t += nth) {
+            const int q = r * GUIDED_STAGE + (t >> 5);
+            sp[t] = q < nact ? w.top[(size_t)qlist[q] * EORB_GUIDED_TOP + (t & 31)] : ~0ull;
+        }
+        for (int k = tid - t0; k < GUIDED_STAGE; k += nth) {
+            const int q = r * GUIDED_STAGE + k;
+            sc[k] = q < nact ? w.candCnt[qlist[q]] : 0;
+            so[k] = q < nact ? w.candOff[qlist[q]] : 0;
+        }
+    };
+    if (nrounds > 0) loadStage(0, 0, 256);
+    __syncthreads();
+
+    for (int r = 0; r < nrounds; r++) {
+        if (warp != 0) {
+            if (r + 1 < nrounds) loadStage(r + 1, 32, 224);   // warps 1..7 fetch the next stage behind the sequential warp
+        } else {
+            const u64* sp = stop + (r & 1) * GUIDED_STAGE * 32;
+            const int* sc = scnt + (r & 1) * GUIDED_STAGE;
+            const int kend = min(GUIDED_STAGE, nact - r * GUIDED_STAGE);
+            u64 eN = sp[lane];
+            for (int k = 0; k < kend; k++) {
+                const u64 e = eN;
+                if (k + 1 < kend) eN = sp[(k + 1) * 32 + lane];           // independent of the state: prefetched
+                const uint32_t dist = (uint32_t)(e >> 32), i2 = e != ~0ull ? (uint32_t)e & 0xffffu : 0u;   // padding never indexes the state
+                const uint32_t di = (dist << 16) | i2;
+                const bool ok = e != ~0ull && (uint32_t)md[i2] > dist;   // vMatchedDistance[i2] <= dist -> skipped (:755)
+                const unsigned mask = __ballot_sync(FULLMASK, ok);
+                const unsigned m2 = mask & (mask - 1);
+                int bestDist = 0x7fffffff, bestDist2 = 0x7fffffff, bestIdx = -1;
+                if (m2 != 0 || sc[k] <= EORB_GUIDED_TOP) {
+                    const uint32_t b1 = __shfl_sync(FULLMASK, di, __ffs(mask) - 1);
+                    const uint32_t b2 = __shfl_sync(FULLMASK, di, __ffs(m2) - 1);
+                    if (mask) { bestDist = (int)(b1 >> 16); bestIdx = (int)(b1 & 0xffffu); }
+                    if (m2) bestDist2 = (int)(b2 >> 16);
+                } else {   // the head ran dry: scan the whole list (order-independent thanks to the position in the key)
+                    uint32_t k1 = 0xffffffffu, k2 = 0xffffffffu;
+                    const int c = sc[k], off = soff[(r & 1) * GUIDED_STAGE + k];
+                    for (int p = lane; p < c; p += 32) {
+                        const uint32_t ce = w.cand[off + p];
+                        const uint32_t d = ce >> 16;
+                        if ((uint32_t)md[ce & 0xffffu] > d) {
+                            const uint32_t key = (d << 16) | (uint32_t)p;
+                            if (key < k1) { k2 = k1; k1 = key; } else if (key < k2) k2 = key;
+                        }
+                    }
+#pragma unroll
+                    for (int o = 16; o > 0; o >>= 1) {
+                        const uint32_t a1 = __shfl_xor_sync(FULLMASK, k1, o), a2 = __shfl_xor_sync(FULLMASK, k2, o);
+                        const uint32_t lo = min(k1, a1), hi = max(k1, a1);
+                        k2 = min(hi, min(k2, a2)); k1 = lo;
+                    }
+                    if (k1 != 0xffffffffu) { bestDist = (int)(k1 >> 16); bestIdx = (int)(w.cand[off + (k1 & 0xffffu)] & 0xffffu); }
+                    if (k2 != 0xffffffffu) bestDist2 = (int)(k2 >> 16);
+                }
+                if (bestDist <= 50 && (float)bestDist < __fmul_rn((float)bestDist2, nnratio)) {   // TH_LOW, mfNNratio (:770-772)
+                    if (lane == 0) {
+                        const int i1 = qlist[r * GUIDED_STAGE + k];
+                        m21[bestIdx] = (unsigned short)i1;              // takes the keypoint over from an earlier query (:774-780)
+                        md[bestIdx] = (unsigned short)bestDist;
+                        matches12[i1] = bestIdx;                        // the claim; ownership is settled after the loop
+                    }
+                    __syncwarp();
+                }
+            }
+        }
+        __syncthreads();
+    }
+    // claims -> rotation histogram (every claim counts, also the ones taken over later: rotHist keeps them, :793) and owners
+    for (int i1 = tid; i1 < n1; i1 += 256) {
+        const int f = matches12[i1];
+        int bin = -1;
+        if (f >= 0) {
+            if (checkOri) {
+                float rot = __fsub_rn(f1.kps[i1].angle, f2.kps[f].angle);
+                if (rot < 0.0f) rot = __fadd_rn(rot, 360.0f);
+                bin = (int)roundf(__fmul_rn(rot, 1.0f / 30));          // factor = 1.0f / HISTO_LENGTH (:723)
+                if (bin == 30) bin = 0;
+                if (bin >= 0 && bin < 30) atomicAdd(&hist[bin], 1); else bin = -1;
+            }
+            if ((int)m21[f] == i1) atomicAdd(&sNm, 1); else matches12[i1] = -1;
+        }
+        w.bin[i1] = (signed char)bin;
+    }
+    __syncthreads();
+    if (tid == 0) {
+        int ind1 = -1, ind2 = -1, ind3 = -1;
+        if (checkOri) {   // ComputeThreeMaxima (:2314-2355)
+            int max1 = 0, max2 = 0, max3 = 0;
+            for (int i = 0; i < 30; i++) {
+                const int s = hist[i];
+                if (s > max1) { max3 = max2; max2 = max1; max1 = s; ind3 = ind2; ind2 = ind1; ind1 = i; }
+                else if (s > max2) { max3 = max2; max2 = s; ind3 = ind2; ind2 = i; }
+                else if (s > max3) { max3 = s; ind3 = i; }
+            }
+            if ((float)max2 < __fmul_rn(0.1f, (float)max1)) { ind2 = -1; ind3 = -1; }
+            else if ((float)max3 < __fmul_rn(0.1f, (float)max1)) ind3 = -1;
+        }
+        sInd[0] = ind1; sInd[1] = ind2; sInd[2] = ind3;
+    }
+    __syncthreads();
+    if (checkOri)
+        for (int i1 = tid; i1 < n1; i1 += 256) {
+            const int b = w.bin[i1];
+            if (b >= 0 && b != sInd[0] && b != sInd[1] && b != sInd[2] && matches12[i1] >= 0) { matches12[i1] = -1; atomicSub(&sNm, 1); }
+        }
+    __syncthreads();
+    for (int i1 = tid; i1 < n1; i1 += 256) {
+        const int m = matches12[i1];
+        if (m >= 0) { prevXY[2 * i1] = f2.kps[m].x; prevXY[2 * i1 + 1] = f2.kps[m].y; }
+    }
+    if (tid == 0) *nmatchesOut = sNm;
+}
+
+// ------------------------------------------------------------------------------------------------ launches
+static size_t resolveSmem(int n1, int n2) {
+    const size_t n2r = (size_t)((n2 + 3) & ~3);
+    return (size_t)2 * GUIDED_STAGE * 32 * 8 + 2 * GUIDED_STAGE * 4 * 2 + 32 * 4 + n2r * 2 * 2 + (size_t)n1 * 2 + 16;
+}
+
+cudaError_t guided_configure() {
+    cudaError_t e = cudaFuncSetAttribute(guided_resolve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)resolveSmem(EORB_GUIDED_MAX_KPS, EORB_GUIDED_MAX_KPS));
+    if (e != cudaSuccess) return e;
+    return cudaFuncSetAttribute(frame_grid_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, EORB_GUIDED_MAX_KPS * 4);
+}
+
+cudaError_t launch_frame_grid(const eorb_keypoint* d_kps, int n, GuidedGrid g, int* d_cellStart, int* d_cellIdx, int* d_assigned, cudaStream_t st) {
+    int np2 = 2;
+    while (np2 < n) np2 <<= 1;
+    frame_grid_kernel<<<1, 1024, (size_t)np2 * 4, st>>>(d_kps, n, g, d_cellStart, d_cellIdx, d_assigned);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_features_in_area(const eorb_keypoint* d_kps, GuidedGrid g, const int* d_cellStart, const int* d_cellIdx,
+                                    const eorb_area_query* d_q, int nq, int* d_count, int* d_out, int capPerQuery, cudaStream_t st) {
+    if (nq <= 0) return cudaSuccess;
+    features_in_area_kernel<<<(nq + 7) / 8, 256, 0, st>>>(d_kps, g, d_cellStart, d_cellIdx, d_q, nq, d_count, d_out, capPerQuery);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_search_init(const GuidedFrame& f1, const GuidedFrame& f2, GuidedGrid g, float* d_prevXY, int window, float nnratio, int checkOri,
+                               const GuidedWork& w, int32_t* d_matches12, int* d_nmatches, cudaStream_t st, long long* launches) {
+    cudaError_t e = cudaMemsetAsync(w.total, 0, sizeof(int), st);
+    if (e != cudaSuccess) return e;
+    e = launch_frame_grid(f2.kps, f2.n, g, w.cellStart, w.cellIdx, w.assigned, st);
+    if (e != cudaSuccess) return e;
+    (*launches)++;
+    if (f1.n > 0) {
+        guided_candidates_kernel<<<(f1.n + 7) / 8, 256, 0, st>>>(f1, f2, g, d_prevXY, (float)window, w);
+        (*launches)++;
+    }
+    guided_resolve_kernel<<<1, 256, resolveSmem(f1.n, f2.n), st>>>(f1, f2, d_prevXY, nnratio, checkOri, w, d_matches12, d_nmatches);
+    (*launches)++;
+    return cudaGetLastError();
+}
+
+}  // namespace eorb

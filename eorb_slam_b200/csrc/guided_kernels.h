@@ -1,0 +1,44 @@
+// guided_kernels.h — launch interface of the guided-matching kernels: the Frame grid
+// (Frame::AssignFeaturesToGrid / GetFeaturesInArea, src/Frame.cc:431-460, 709-793) and
+// ORBmatcher::SearchForInitialization (src/ORBmatcher.cc:714-831).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/eorb_b200.h"
+
+namespace eorb {
+
+#define EORB_GRID_COLS 64          // FRAME_GRID_COLS (include/Frame.h:46)
+#define EORB_GRID_ROWS 48          // FRAME_GRID_ROWS (include/Frame.h:45)
+#define EORB_GRID_CELLS (EORB_GRID_COLS * EORB_GRID_ROWS)
+#define EORB_GUIDED_MAX_KPS 16384  // keypoints per frame (the reference extracts <= 5 * nFeatures = 5000)
+#define EORB_GUIDED_TOP 32         // sorted head of every query's candidate list kept for the sequential pass
+
+// grid geometry, computed on the host in float exactly as Frame.cc:165-166
+struct GuidedGrid { float minX, minY, wInv, hInv; };
+
+struct GuidedFrame {
+    const eorb_keypoint* kps; const uint8_t* desc; int n;
+};
+
+struct GuidedWork {
+    // frame-2 grid (CSR): cellStart[EORB_GRID_CELLS + 1], cellIdx[n2]
+    int* cellStart; int* cellIdx; int* assigned;
+    // per query (frame-1 keypoint): candidate range, sorted head (dist<<32 | pos<<16 | i2), histogram bin
+    int* candOff; int* candCnt; unsigned long long* top; signed char* bin;
+    uint32_t* cand; int candCap;   // all candidates in the reference's visiting order: dist<<16 | i2
+    int* total;                    // candidates produced (may exceed candCap: the host grows the buffer and retries)
+};
+
+cudaError_t launch_frame_grid(const eorb_keypoint* d_kps, int n, GuidedGrid g, int* d_cellStart, int* d_cellIdx, int* d_assigned,
+                              cudaStream_t st);
+// batch of GetFeaturesInArea queries: q = (x, y, r, minLevel, maxLevel as floats/ints packed in eorb_area_query)
+cudaError_t launch_features_in_area(const eorb_keypoint* d_kps, GuidedGrid g, const int* d_cellStart, const int* d_cellIdx,
+                                    const eorb_area_query* d_q, int nq, int* d_count, int* d_out, int capPerQuery, cudaStream_t st);
+cudaError_t launch_search_init(const GuidedFrame& f1, const GuidedFrame& f2, GuidedGrid g, float* d_prevXY, int window, float nnratio,
+                               int checkOri, const GuidedWork& w, int32_t* d_matches12, int* d_nmatches, cudaStream_t st,
+                               long long* launches);
+cudaError_t guided_configure();
+
+}  // namespace eorb

@@ -1,4 +1,4 @@
-// Stand-ins for the few reference types the matcher / event shims mention, so that they compile without the
+// Stand-ins for the few reference types the matcher / event / guided-matching shims mention, so that they compile without the
 // reference tree (which does not travel with this repository).  A real build includes the reference headers:
 //   include/ORBmatcher.h:35-114, include/Event/EventData.h:36-58, include/CameraModels/GeometricCamera.h:41-134
 #pragma once
@@ -14,8 +14,21 @@ protected:
     std::vector<float> mvParameters;   // fx, fy, cx, cy (Pinhole)
 };
 
-class ORBmatcher {   // the members this path touches (ORBmatcher.h:39-42, 96-113)
+class Frame {   // the accessors SearchForInitialization uses (include/Frame.h:173, 193, 197, 247, 370-373)
 public:
+    int numAllKPts() const { return (int)mvKeysUn.size(); }
+    cv::KeyPoint getUndistKPtMono(int idx) const { return mvKeysUn[idx]; }
+    std::vector<cv::KeyPoint>& getAllUndistKPtsMono() { return mvKeysUn; }
+    int getKPtLevelMono(int idx) const { return mvKeysUn[idx].octave; }
+    cv::Mat& getAllORBDescMono() { return mDescriptors; }
+    static float mnMinX, mnMaxX, mnMinY, mnMaxY;
+    std::vector<cv::KeyPoint> mvKeysUn;
+    cv::Mat mDescriptors;
+};
+
+class ORBmatcher {   // the members this path touches (ORBmatcher.h:39-42, 67-68, 96-113)
+public:
+    int SearchForInitialization(Frame& F1, Frame& F2, std::vector<cv::Point2f>& vbPrevMatched, std::vector<int>& vnMatches12, int windowSize = 10);
     explicit ORBmatcher(float nnratio = 0.6, bool checkOri = true) : mfNNratio(nnratio), mbCheckOrientation(checkOri) {}
     static int DescriptorDistance(const cv::Mat& a, const cv::Mat& b);
     static const int TH_LOW;

@@ -72,5 +72,25 @@ int main(int argc, char** argv)
         for (size_t i = 0; i < st.size(); i++) if (st[i]) { tracked++; const float dx = p1[i].x - p0[i].x - 2.f, dy = p1[i].y - p0[i].y - 1.f; good += (dx * dx + dy * dy < 0.25f); }
         std::printf("lk_ok=%d lk_n=%zu lk_tracked=%d lk_good=%d\n", (int)okk, p1.size(), tracked, good);
     }
+    // ORBmatcher::SearchForInitialization, the reference signature: a frame against a copy whose keypoints moved by (3, -2)
+    {
+        ORB_SLAM3::Frame F1, F2;
+        ORB_SLAM3::Frame::mnMinX = 0.f; ORB_SLAM3::Frame::mnMinY = 0.f; ORB_SLAM3::Frame::mnMaxX = (float)W; ORB_SLAM3::Frame::mnMaxY = (float)H;
+        F1.mvKeysUn = kps; F1.mDescriptors = desc;
+        F2.mvKeysUn = kps; F2.mDescriptors = desc;
+        for (auto& k : F2.mvKeysUn) { k.pt.x += 3.f; k.pt.y -= 2.f; }
+        std::vector<cv::Point2f> prev;
+        for (auto& k : F1.mvKeysUn) prev.push_back(k.pt);
+        std::vector<int> m12;
+        ORB_SLAM3::ORBmatcher matcher(0.9f, true);
+        const int nm = matcher.SearchForInitialization(F1, F2, prev, m12, 100);
+        int self = 0, lvl0 = 0, moved = 0;
+        for (size_t i = 0; i < m12.size(); i++) {
+            lvl0 += (kps[i].octave == 0);
+            self += (m12[i] == (int)i);
+            if (m12[i] >= 0) moved += (prev[i].x == F2.mvKeysUn[m12[i]].pt.x && prev[i].y == F2.mvKeysUn[m12[i]].pt.y);
+        }
+        std::printf("sfi_nm=%d sfi_self=%d sfi_lvl0=%d sfi_prev=%d\n", nm, self, lvl0, moved);
+    }
     return 0;
 }

@@ -137,3 +137,47 @@ def plant_duplicate_rows(db: np.ndarray, src_rows: np.ndarray, seed: int) -> np.
     dst = rng.integers(0, db.shape[0], len(src_rows))
     db[dst] = db[src_rows]
     return dst
+
+
+def make_keypoint_frame_pair(n1: int, n2: int, seed: int, w: int = 752, h: int = 480, nlevels: int = 8, shift=(7.0, -4.0),
+                             max_flips: int = 48, twin_frac: float = 0.15):
+    """Two synthetic frames' keypoints + descriptors for the guided-matching tests (SearchForInitialization):
+    frame 2 = frame 1 moved by `shift` + jitter with up to max_flips flipped descriptor bits, plus unrelated keypoints;
+    a fraction of frame-1 keypoints get a near-twin (close position, nearly the same descriptor) so that two queries
+    compete for the same frame-2 keypoint (the vnMatches21 take-over path), some coordinates fall outside the image
+    bounds (PosInGrid rejects them) and ~half the keypoints sit on levels > 0 (skipped / filtered).
+    Returns (kps1, desc1, kps2, desc2, bounds4)."""
+    rng = np.random.default_rng(seed)
+    def kp_array(n):
+        k = np.zeros(n, KEYPOINT_DTYPE)
+        k["x"] = rng.uniform(-3.0, w + 3.0, n).astype(np.float32); k["y"] = rng.uniform(-3.0, h + 3.0, n).astype(np.float32)
+        k["octave"] = np.where(rng.random(n) < 0.55, 0, rng.integers(1, nlevels, n)).astype(np.int32)
+        k["size"] = 31.0; k["angle"] = rng.uniform(0, 360, n).astype(np.float32); k["response"] = rng.integers(8, 120, n)
+        k["class_id"] = -1
+        return k
+    kps1 = kp_array(n1)
+    desc1 = rng.integers(0, 256, (n1, 32), dtype=np.uint8)
+    ntw = int(n1 * twin_frac)
+    if ntw > 0:   # twins: the second half of the twin pairs copies the first half with tiny changes
+        src = rng.choice(n1 // 2, ntw, replace=False); dst = n1 // 2 + rng.choice(n1 - n1 // 2, ntw, replace=False)
+        kps1["x"][dst] = kps1["x"][src] + rng.uniform(-2, 2, ntw).astype(np.float32)
+        kps1["y"][dst] = kps1["y"][src] + rng.uniform(-2, 2, ntw).astype(np.float32)
+        kps1["octave"][dst] = kps1["octave"][src]
+        desc1[dst] = desc1[src]
+        for d in dst[: ntw // 2]:   # half of the twins differ in a few bits, the others are exact duplicates (distance ties)
+            b = rng.integers(0, 256, 3); desc1[d, b // 8] ^= (1 << (b % 8)).astype(np.uint8)
+    kps2 = kp_array(n2)
+    desc2 = rng.integers(0, 256, (n2, 32), dtype=np.uint8)
+    nm = min(n1, n2) * 3 // 4
+    a = rng.choice(n1, nm, replace=False); b = rng.choice(n2, nm, replace=False)
+    kps2["x"][b] = kps1["x"][a] + np.float32(shift[0]) + rng.normal(0, 2.0, nm).astype(np.float32)
+    kps2["y"][b] = kps1["y"][a] + np.float32(shift[1]) + rng.normal(0, 2.0, nm).astype(np.float32)
+    kps2["octave"][b] = kps1["octave"][a]
+    kps2["angle"][b] = np.mod(kps1["angle"][a] + rng.normal(3.0, 4.0, nm).astype(np.float32), np.float32(360.0)).astype(np.float32)
+    desc2[b] = desc1[a]
+    for i, row in enumerate(b):
+        k = int(rng.integers(0, max_flips + 1))
+        bits = rng.choice(256, k, replace=False)
+        np.bitwise_xor.at(desc2[row], bits // 8, (1 << (bits % 8)).astype(np.uint8))
+    bounds = np.array([0.0, 0.0, float(w), float(h)], np.float32)
+    return kps1, desc1, kps2, desc2, bounds

@@ -291,6 +291,46 @@ int eorb_lk_track(eorb_lk* h, const uint8_t* img, size_t stride, const float* in
 int eorb_lk_track_device(eorb_lk* h, const uint8_t* d_img, size_t stride, const float* init_xy, int max_iter, double eps, float min_eig,
                          float* out_xy, uint8_t* status, float* err);
 
+/* ---------------------------------------------------------------- guided matching (third "next" row)
+ * The per-frame callers of DescriptorDistance in tracking:
+ *   eorb_guided_frame_grid            replaces Frame::AssignFeaturesToGrid + Frame::PosInGrid (src/Frame.cc:431-460, 783-793)
+ *   eorb_guided_features_in_area      replaces Frame::GetFeaturesInArea (src/Frame.cc:709-777), a batch of queries per call
+ *   eorb_guided_search_for_initialization  replaces ORBmatcher::SearchForInitialization (src/ORBmatcher.cc:714-831)
+ * Keypoints are eorb_keypoint records (the undistorted keypoints the reference's grid holds), descriptors n x 32 bytes,
+ * bounds4 = {mnMinX, mnMinY, mnMaxX, mnMaxY} (Frame.cc:846-866).  The grid is FRAME_GRID_COLS x FRAME_GRID_ROWS = 64 x 48
+ * (include/Frame.h:45-46); cell id = col * 48 + row; lists hold keypoint indices in ascending order, like push_back does.
+ * At most EORB_GUIDED_MAX_KEYPOINTS keypoints per frame (the reference extracts <= 5 * nFeatures). */
+#define EORB_GUIDED_MAX_KEYPOINTS 16384
+#define EORB_GRID_NCELLS (64 * 48)
+typedef struct eorb_area_query {
+    float x, y, r;          /* window centre and half size (factorX = factorY = r) */
+    int min_level, max_level;   /* as in the reference: levels are checked iff min_level > 0 || max_level >= 0 */
+} eorb_area_query;
+typedef struct eorb_guided eorb_guided;
+int eorb_guided_create(int device, eorb_guided** out);
+int eorb_guided_destroy(eorb_guided* g);
+int eorb_guided_set_stream(eorb_guided* g, void* cuda_stream);
+int eorb_guided_reset_stream(eorb_guided* g);
+long long eorb_guided_launch_count(const eorb_guided* g);
+/* cell_start[EORB_GRID_NCELLS + 1], cell_idx[n] (host); *assigned = keypoints inside the grid */
+int eorb_guided_frame_grid(eorb_guided* g, const eorb_keypoint* kps, int n, const float* bounds4, int* cell_start, int* cell_idx,
+                           int* assigned);
+/* counts[nq] = size of every answer; idx_out[nq * cap_per_query]: the first cap_per_query indices of every answer in the
+ * reference's order (cells column by column, rows inside, list order inside a cell) */
+int eorb_guided_features_in_area(eorb_guided* g, const eorb_keypoint* kps, int n, const float* bounds4, const eorb_area_query* queries,
+                                 int nq, int* counts, int* idx_out, int cap_per_query);
+/* prev_xy = vbPrevMatched (n1 x 2 floats, in/out), matches12[n1] = vnMatches12; returns nmatches in *nmatches.
+ * window_size = the reference's int windowSize (100 at Tracking.cc's call), nnratio = mfNNratio, check_ori = mbCheckOrientation. */
+int eorb_guided_search_for_initialization(eorb_guided* g, const eorb_keypoint* kps1, const uint8_t* desc1, int n1,
+                                          const eorb_keypoint* kps2, const uint8_t* desc2, int n2, const float* bounds4, float* prev_xy,
+                                          int window_size, float nnratio, int check_ori, int32_t* matches12, int* nmatches);
+/* the same with every array resident in HBM (16-byte aligned descriptors), e.g. straight from eorb_orb_extract_batch_device;
+ * d_prev_xy and d_matches12 are written on the device, *nmatches (host) after a stream synchronisation */
+int eorb_guided_search_for_initialization_device(eorb_guided* g, const eorb_keypoint* d_kps1, const uint8_t* d_desc1, int n1,
+                                                 const eorb_keypoint* d_kps2, const uint8_t* d_desc2, int n2, const float* bounds4,
+                                                 float* d_prev_xy, int window_size, float nnratio, int check_ori, int32_t* d_matches12,
+                                                 int* nmatches);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,0 +1,160 @@
+// oracle/guided_oracle.cc — CPU ORACLE (test infrastructure, never linked into the product).
+//
+// Restates the guided-matching callers of the Hamming kernel:
+//   Frame::PosInGrid               src/Frame.cc:783-793   (64 x 48 grid, FRAME_GRID_COLS/ROWS include/Frame.h:45-46)
+//   Frame::AssignFeaturesToGrid    src/Frame.cc:431-460   (cell lists in keypoint-index order)
+//   Frame::GetFeaturesInArea       src/Frame.cc:709-777   (cells column by column, rows inside, list order inside)
+//   ORBmatcher::SearchForInitialization  src/ORBmatcher.cc:714-831 (stateful sequential scan: vMatchedDistance /
+//        vnMatches21 take-over, TH_LOW, nnratio, rotation histogram WITH the entries of matches that were taken over
+//        later, ComputeThreeMaxima :2314-2355, vbPrevMatched update)
+// The reference has no tests for these; tests/test_oracle_guided.py pins this file against an independent pure-Python
+// restatement written from the same reference lines.
+#include "oracle.h"
+
+#include <climits>
+#include <cmath>
+#include <vector>
+
+namespace {
+const int GC = 64, GR = 48;   // FRAME_GRID_COLS, FRAME_GRID_ROWS
+
+struct GridGeom {
+    float minX, minY, wInv, hInv;
+    explicit GridGeom(const float* b) {
+        minX = b[0]; minY = b[1];
+        // Frame.cc:165-166 / :268-269: static_cast<float>(FRAME_GRID_COLS)/(mnMaxX-mnMinX), all float
+        wInv = (float)GC / (b[2] - b[0]);
+        hInv = (float)GR / (b[3] - b[1]);
+    }
+};
+
+bool posInGrid(const GridGeom& g, float x, float y, int& px, int& py) {
+    px = (int)std::round((x - g.minX) * g.wInv);   // std::round(float): half away from zero
+    py = (int)std::round((y - g.minY) * g.hInv);
+    return !(px < 0 || px >= GC || py < 0 || py >= GR);
+}
+
+void featuresInArea(const orc_keypoint* kps, const GridGeom& g, const int* cellStart, const int* cellIdx, float x, float y, float r,
+                    int minLevel, int maxLevel, std::vector<int>& out) {
+    out.clear();
+    const float fx = r, fy = r;
+    const int nMinCellX = std::max(0, (int)std::floor((x - g.minX - fx) * g.wInv));
+    if (nMinCellX >= GC) return;
+    const int nMaxCellX = std::min(GC - 1, (int)std::ceil((x - g.minX + fx) * g.wInv));
+    if (nMaxCellX < 0) return;
+    const int nMinCellY = std::max(0, (int)std::floor((y - g.minY - fy) * g.hInv));
+    if (nMinCellY >= GR) return;
+    const int nMaxCellY = std::min(GR - 1, (int)std::ceil((y - g.minY + fy) * g.hInv));
+    if (nMaxCellY < 0) return;
+    const bool bCheckLevels = (minLevel > 0) || (maxLevel >= 0);
+    for (int ix = nMinCellX; ix <= nMaxCellX; ix++)
+        for (int iy = nMinCellY; iy <= nMaxCellY; iy++) {
+            const int c = ix * GR + iy;
+            for (int j = cellStart[c]; j < cellStart[c + 1]; j++) {
+                const orc_keypoint& kp = kps[cellIdx[j]];
+                if (bCheckLevels) {
+                    if (kp.octave < minLevel) continue;
+                    if (maxLevel >= 0 && kp.octave > maxLevel) continue;
+                }
+                const float dx = kp.x - x, dy = kp.y - y;
+                if (std::fabs(dx) < fx && std::fabs(dy) < fy) out.push_back(cellIdx[j]);
+            }
+        }
+}
+}  // namespace
+
+extern "C" {
+
+int orc_frame_grid(const orc_keypoint* kps, int n, const float* bounds4, int* cell_start, int* cell_idx) {
+    const GridGeom g(bounds4);
+    std::vector<std::vector<int>> cells(GC * GR);
+    int assigned = 0;
+    for (int i = 0; i < n; i++) {
+        int px, py;
+        if (posInGrid(g, kps[i].x, kps[i].y, px, py)) { cells[px * GR + py].push_back(i); assigned++; }
+    }
+    int k = 0;
+    for (int c = 0; c < GC * GR; c++) {
+        cell_start[c] = k;
+        for (int i : cells[c]) cell_idx[k++] = i;
+    }
+    cell_start[GC * GR] = k;
+    return assigned;
+}
+
+int orc_features_in_area(const orc_keypoint* kps, int n, const float* bounds4, const int* cell_start, const int* cell_idx, float x,
+                         float y, float r, int min_level, int max_level, int* out, int cap) {
+    (void)n;
+    std::vector<int> v;
+    featuresInArea(kps, GridGeom(bounds4), cell_start, cell_idx, x, y, r, min_level, max_level, v);
+    for (size_t i = 0; i < v.size() && (int)i < cap; i++) out[i] = v[i];
+    return (int)v.size();
+}
+
+int orc_search_for_initialization(const orc_keypoint* kps1, const uint8_t* desc1, int n1, const orc_keypoint* kps2, const uint8_t* desc2,
+                                  int n2, const float* bounds4, float* prev_xy, int window_size, float nnratio, int check_ori,
+                                  int32_t* matches12) {
+    const int TH_LOW = 50, HISTO_LENGTH = 30;
+    const GridGeom g(bounds4);
+    std::vector<int> cellStart(GC * GR + 1), cellIdx(std::max(n2, 1));
+    orc_frame_grid(kps2, n2, bounds4, cellStart.data(), cellIdx.data());
+
+    int nmatches = 0;
+    for (int i = 0; i < n1; i++) matches12[i] = -1;
+    std::vector<int> rotHist[HISTO_LENGTH];
+    const float factor = 1.0f / HISTO_LENGTH;
+    std::vector<int> vMatchedDistance(std::max(n2, 1), INT_MAX), vnMatches21(std::max(n2, 1), -1);
+    std::vector<int> vIndices2;
+    for (int i1 = 0; i1 < n1; i1++) {
+        const int level1 = kps1[i1].octave;
+        if (level1 > 0) continue;
+        featuresInArea(kps2, g, cellStart.data(), cellIdx.data(), prev_xy[2 * i1], prev_xy[2 * i1 + 1], (float)window_size, level1, level1,
+                       vIndices2);
+        if (vIndices2.empty()) continue;
+        const uint8_t* d1 = desc1 + (size_t)i1 * 32;
+        int bestDist = INT_MAX, bestDist2 = INT_MAX, bestIdx2 = -1;
+        for (int i2 : vIndices2) {
+            const int dist = orc_descriptor_distance(d1, desc2 + (size_t)i2 * 32);
+            if (vMatchedDistance[i2] <= dist) continue;
+            if (dist < bestDist) { bestDist2 = bestDist; bestDist = dist; bestIdx2 = i2; }
+            else if (dist < bestDist2) bestDist2 = dist;
+        }
+        if (bestDist <= TH_LOW) {
+            if (bestDist < (float)bestDist2 * nnratio) {
+                if (vnMatches21[bestIdx2] >= 0) { matches12[vnMatches21[bestIdx2]] = -1; nmatches--; }
+                matches12[i1] = bestIdx2;
+                vnMatches21[bestIdx2] = i1;
+                vMatchedDistance[bestIdx2] = bestDist;
+                nmatches++;
+                if (check_ori) {
+                    float rot = kps1[i1].angle - kps2[bestIdx2].angle;
+                    if (rot < 0.0) rot += 360.0f;
+                    int bin = (int)std::round(rot * factor);
+                    if (bin == HISTO_LENGTH) bin = 0;
+                    rotHist[bin].push_back(i1);
+                }
+            }
+        }
+    }
+    if (check_ori) {
+        int max1 = 0, max2 = 0, max3 = 0, ind1 = -1, ind2 = -1, ind3 = -1;
+        for (int i = 0; i < HISTO_LENGTH; i++) {
+            const int s = (int)rotHist[i].size();
+            if (s > max1) { max3 = max2; max2 = max1; max1 = s; ind3 = ind2; ind2 = ind1; ind1 = i; }
+            else if (s > max2) { max3 = max2; max2 = s; ind3 = ind2; ind2 = i; }
+            else if (s > max3) { max3 = s; ind3 = i; }
+        }
+        if (max2 < 0.1f * (float)max1) { ind2 = -1; ind3 = -1; }
+        else if (max3 < 0.1f * (float)max1) { ind3 = -1; }
+        for (int i = 0; i < HISTO_LENGTH; i++) {
+            if (i == ind1 || i == ind2 || i == ind3) continue;
+            for (int idx1 : rotHist[i])
+                if (matches12[idx1] >= 0) { matches12[idx1] = -1; nmatches--; }
+        }
+    }
+    for (int i1 = 0; i1 < n1; i1++)
+        if (matches12[i1] >= 0) { prev_xy[2 * i1] = kps2[matches12[i1]].x; prev_xy[2 * i1 + 1] = kps2[matches12[i1]].y; }
+    return nmatches;
+}
+
+}  // extern "C"

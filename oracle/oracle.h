@@ -111,6 +111,19 @@ void  orc_hamming_best2(const uint8_t* q, int nq, const uint8_t* db, int64_t ndb
 /* rotation-consistency filter (ORBmatcher.cc:784-823, 2314-2355). match12[i] = idx or -1; returns #kept */
 int   orc_rotation_filter(const float* angle1, const float* angle2, int32_t* match12, int n1);
 
+/* ---- guided matching (guided_oracle.cc) ---- */
+/* Frame::AssignFeaturesToGrid + PosInGrid (Frame.cc:431-460, 783-793): 64 x 48 cells, cell id = col*48 + row; CSR lists
+   (cell_start[3073], cell_idx[n]) with keypoint indices ascending inside a cell.  bounds4 = mnMinX, mnMinY, mnMaxX, mnMaxY.
+   Returns the number of keypoints that fell inside the grid. */
+int   orc_frame_grid(const orc_keypoint* kps, int n, const float* bounds4, int* cell_start, int* cell_idx);
+/* Frame::GetFeaturesInArea (Frame.cc:709-777); returns the count, writes up to cap indices in the reference's order */
+int   orc_features_in_area(const orc_keypoint* kps, int n, const float* bounds4, const int* cell_start, const int* cell_idx, float x,
+                           float y, float r, int min_level, int max_level, int* out, int cap);
+/* ORBmatcher::SearchForInitialization (ORBmatcher.cc:714-831); prev_xy = vbPrevMatched (n1 x 2, in/out); returns nmatches */
+int   orc_search_for_initialization(const orc_keypoint* kps1, const uint8_t* desc1, int n1, const orc_keypoint* kps2,
+                                    const uint8_t* desc2, int n2, const float* bounds4, float* prev_xy, int window_size, float nnratio,
+                                    int check_ori, int32_t* matches12);
+
 /* ---- event frames ---- */
 /* mode: 0 nearest (ev2im), 1 gauss (ev2im_gauss), 2 gauss+SE3 (Tcw16,depth,K4), 3 gauss+SE2 (se2[4],K4) */
 int   orc_ev_accumulate(const orc_event* evs, int64_t n, int w, int h, float sigma, int mode,

@@ -27,7 +27,7 @@ class OrbParams(C.Structure):
 
 
 def build(force: bool = False) -> str:
-    srcs = [os.path.join(ORACLE_DIR, f) for f in ("orb_oracle.cc", "match_oracle.cc", "event_oracle.cc", "lk_oracle.cc", "oracle.h",
+    srcs = [os.path.join(ORACLE_DIR, f) for f in ("orb_oracle.cc", "match_oracle.cc", "guided_oracle.cc", "event_oracle.cc", "lk_oracle.cc", "oracle.h",
                                                   "brief_pattern_31.inc", "Makefile")]
     stale = force or not os.path.exists(LIB_PATH) or any(os.path.getmtime(s) > os.path.getmtime(LIB_PATH) for s in srcs)
     if stale:
@@ -348,3 +348,42 @@ def ev_mci_jac(evs, w, h, sigma, R, t, med_depth, K, pol=False, global_mean=Fals
     out = np.zeros(6, np.float64)
     lib().orc_ev_mci_jac(_p(evs), len(evs), w, h, float(sigma), _p(Rt), float(med_depth), _p(Kc), int(pol), int(global_mean), _p(out))
     return out
+
+
+# ---- guided matching
+GRID_COLS, GRID_ROWS = 64, 48
+
+
+def frame_grid(kps, bounds):
+    """Frame::AssignFeaturesToGrid -> (cell_start[3073], cell_idx[assigned])"""
+    L = lib()
+    kps = np.ascontiguousarray(kps, KEYPOINT_DTYPE); b = np.ascontiguousarray(bounds, np.float32)
+    cs = np.zeros(GRID_COLS * GRID_ROWS + 1, np.int32); ci = np.zeros(max(len(kps), 1), np.int32)
+    L.orc_frame_grid.restype = C.c_int
+    n = L.orc_frame_grid(_p(kps), C.c_int(len(kps)), _p(b), _p(cs), _p(ci))
+    return cs, ci[:n].copy()
+
+
+def features_in_area(kps, bounds, cs, ci, x, y, r, min_level=0, max_level=-1):
+    L = lib()
+    kps = np.ascontiguousarray(kps, KEYPOINT_DTYPE); b = np.ascontiguousarray(bounds, np.float32)
+    ci = np.ascontiguousarray(ci, np.int32) if len(ci) else np.zeros(1, np.int32)
+    out = np.zeros(max(len(kps), 1), np.int32)
+    L.orc_features_in_area.restype = C.c_int
+    n = L.orc_features_in_area(_p(kps), C.c_int(len(kps)), _p(b), _p(cs), _p(ci), C.c_float(x), C.c_float(y), C.c_float(r),
+                               C.c_int(min_level), C.c_int(max_level), _p(out), C.c_int(len(out)))
+    return out[:n].copy()
+
+
+def search_for_initialization(kps1, desc1, kps2, desc2, bounds, prev_xy, window_size=100, nnratio=0.9, check_ori=True):
+    """ORBmatcher::SearchForInitialization -> (nmatches, matches12[n1], prev_xy updated copy)"""
+    L = lib()
+    kps1 = np.ascontiguousarray(kps1, KEYPOINT_DTYPE); kps2 = np.ascontiguousarray(kps2, KEYPOINT_DTYPE)
+    d1 = np.ascontiguousarray(desc1, np.uint8); d2 = np.ascontiguousarray(desc2, np.uint8)
+    b = np.ascontiguousarray(bounds, np.float32)
+    prev = np.array(prev_xy, np.float32, copy=True).reshape(-1, 2)
+    m12 = np.full(max(len(kps1), 1), -1, np.int32)
+    L.orc_search_for_initialization.restype = C.c_int
+    n = L.orc_search_for_initialization(_p(kps1), _p(d1), C.c_int(len(kps1)), _p(kps2), _p(d2), C.c_int(len(kps2)), _p(b), _p(prev),
+                                        C.c_int(window_size), C.c_float(nnratio), C.c_int(int(check_ori)), _p(m12))
+    return n, m12[:len(kps1)].copy(), prev

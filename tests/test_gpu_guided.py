@@ -1,0 +1,121 @@
+"""GPU parity of the guided-matching row: Frame grid, GetFeaturesInArea and
+ORBmatcher::SearchForInitialization through the C ABI against the CPU oracle — every index, count and float bit-exact."""
+import numpy as np
+import pytest
+
+import oracle_lib as O
+from eorb_slam_b200 import synth
+
+pytestmark = pytest.mark.gpu
+
+
+def _api():
+    from eorb_slam_b200 import api
+    return api
+
+
+@pytest.mark.parametrize("n,seed,bounds", [(0, 1, None), (1, 2, None), (700, 3, None), (4096, 4, None), (5003, 5, (-12.5, -9.25, 771.0, 493.5))])
+def test_frame_grid_and_features_in_area(n, seed, bounds):
+    api = _api()
+    _, _, k2, _, b = synth.make_keypoint_frame_pair(max(n, 2), max(n, 2), seed)
+    k2 = k2[:n]
+    if bounds is not None:
+        b = np.array(bounds, np.float32)
+    fg = api.FrameGrid(k2, b)
+    cs, ci = fg.AssignFeaturesToGrid()
+    ecs, eci = O.frame_grid(k2, b)
+    assert np.array_equal(cs, ecs) and np.array_equal(ci, eci)
+    rng = np.random.default_rng(seed)
+    nq = 300
+    q = np.zeros(nq, api.AREA_QUERY_DTYPE)
+    q["x"] = rng.uniform(-60, 820, nq); q["y"] = rng.uniform(-60, 540, nq)
+    q["r"] = rng.choice([5.0, 15.0, 100.0, 900.0], nq)
+    lv = [(0, -1), (0, 0), (2, 4), (1, -1), (3, 2), (-1, -1)]
+    for i in range(nq):
+        q["min_level"][i], q["max_level"][i] = lv[i % len(lv)]
+    got = fg.GetFeaturesInAreaBatch(q)
+    for i in range(nq):
+        exp = O.features_in_area(k2, b, ecs, eci, float(q["x"][i]), float(q["y"][i]), float(q["r"][i]), int(q["min_level"][i]), int(q["max_level"][i]))
+        assert np.array_equal(got[i], exp), i
+
+
+@pytest.mark.parametrize("n1,n2,seed,window,ratio,ori", [
+    (500, 520, 3, 100, 0.9, True), (500, 520, 4, 30, 0.7, True), (500, 520, 5, 100, 0.9, False), (300, 1, 6, 100, 0.9, True),
+    (5000, 5000, 7, 100, 0.9, True),        # the initialisation extractor's 5 x nFeatures keypoints (Tracking.cc:127-128)
+    (3000, 3000, 8, 2000, 0.9, True),       # window covers the whole image: > 32 candidates everywhere, buffer growth + slow path
+    (64, 3000, 9, 15, 0.95, True), (1, 1, 10, 100, 0.9, True)])
+def test_search_for_initialization(n1, n2, seed, window, ratio, ori):
+    api = _api()
+    k1, d1, k2, d2, b = synth.make_keypoint_frame_pair(max(n1, 2), max(n2, 2), seed)
+    k1, d1, k2, d2 = k1[:n1], d1[:n1], k2[:n2], d2[:n2]
+    prev = np.stack([k1["x"], k1["y"]], 1)
+    gm = api.GuidedMatcher(0, ratio, ori)
+    n, m12, p = gm.SearchForInitialization(k1, d1, k2, d2, b, prev, window)
+    en, em12, ep = O.search_for_initialization(k1, d1, k2, d2, b, prev, window, ratio, ori)
+    assert n == en and np.array_equal(m12, em12) and p.tobytes() == ep.tobytes()
+    # second round with the updated vbPrevMatched, same handle (state must not leak between calls)
+    n_b, m12_b, p_b = gm.SearchForInitialization(k1, d1, k2, d2, b, p, window)
+    en_b, em12_b, ep_b = O.search_for_initialization(k1, d1, k2, d2, b, ep, window, ratio, ori)
+    assert n_b == en_b and np.array_equal(m12_b, em12_b) and p_b.tobytes() == ep_b.tobytes()
+
+
+def test_search_for_initialization_duplicate_descriptors_take_over():
+    """several frame-1 keypoints with IDENTICAL descriptors and positions compete for one frame-2 keypoint: the first claims it,
+    the later ones are filtered by vMatchedDistance <= dist (ORBmatcher.cc:755) and fall back to their second candidate"""
+    api = _api()
+    rng = np.random.default_rng(11)
+    n = 200
+    k1 = np.zeros(n, synth.KEYPOINT_DTYPE); k2 = np.zeros(n, synth.KEYPOINT_DTYPE)
+    k1["x"] = 100 + (np.arange(n) % 10) * 3; k1["y"] = 100 + (np.arange(n) // 10) * 3
+    k2["x"] = k1["x"] + 1; k2["y"] = k1["y"] - 1
+    k1["angle"] = 10; k2["angle"] = 15
+    base = rng.integers(0, 256, (4, 32), dtype=np.uint8)
+    d1 = base[np.arange(n) % 4].copy(); d2 = base[(np.arange(n) // 3) % 4].copy()
+    d2[:, 1] ^= 3                             # distance 2 to the twin (0 < 0 * ratio would never pass the ratio test)
+    d2[::7, 0] ^= 1                           # a few one-bit variations -> distance ties and near ties everywhere
+    b = np.array([0, 0, 752, 480], np.float32)
+    prev = np.stack([k1["x"], k1["y"]], 1).astype(np.float32)
+    for ratio in (0.9, 1.5):                  # 1.5: the ratio test passes even for equal best / second distances
+        gm = api.GuidedMatcher(0, ratio, True)
+        n_, m12, p = gm.SearchForInitialization(k1, d1, k2, d2, b, prev, 100)
+        en, em12, ep = O.search_for_initialization(k1, d1, k2, d2, b, prev, 100, ratio, True)
+        assert n_ == en and np.array_equal(m12, em12) and p.tobytes() == ep.tobytes()
+    assert en > 0
+
+
+def test_extract_two_frames_then_guided_search_without_leaving_hbm():
+    """frame pair -> ORB extraction on the device -> SearchForInitialization on the device outputs (level-0 keypoints,
+    100-px window), checked against oracle extraction + oracle search"""
+    import torch
+    api = _api()
+    img1 = synth.make_frame(21)
+    img2 = np.roll(img1, (3, -5), axis=(0, 1))
+    p = api.ORBxParams(5000, 1.2, 8, 20, 7, 19, (752, 480))      # the initialisation extractor: 5 x nFeatures
+    ex = api.ORBextractor(p, 0, 2)
+    cap = ex.cap
+    st = torch.cuda.current_stream().cuda_stream
+    ex.set_stream(st)
+    d_frames = torch.from_numpy(np.stack([img1, img2])).cuda()
+    d_kps = torch.zeros(2 * cap * 28, dtype=torch.uint8, device="cuda"); d_desc = torch.zeros(2 * cap * 32, dtype=torch.uint8, device="cuda")
+    d_n = torch.zeros(2, dtype=torch.int32, device="cuda"); d_mono = torch.zeros(2, dtype=torch.int32, device="cuda")
+    ex.extract_batch_raw(d_frames.data_ptr(), 2, 752, 480, 752, 752 * 480, (0, 0), True, d_kps.data_ptr(), d_desc.data_ptr(), cap,
+                         d_n.data_ptr(), d_mono.data_ptr(), device=True)
+    torch.cuda.synchronize()
+    n1, n2 = (int(v) for v in d_n.cpu().numpy())
+    kps = d_kps.cpu().numpy().view(synth.KEYPOINT_DTYPE).reshape(2, cap)
+    desc = d_desc.cpu().numpy().reshape(2, cap, 32)
+    d_prev = torch.from_numpy(np.stack([kps[0]["x"][:n1], kps[0]["y"][:n1]], 1).astype(np.float32).copy()).cuda()
+    d_m12 = torch.zeros(n1, dtype=torch.int32, device="cuda")
+    gm = api.GuidedMatcher(0, 0.9, True)
+    gm.set_stream(st)
+    b = np.array([0, 0, 752, 480], np.float32)
+    nm = gm.SearchForInitialization_device(d_kps.data_ptr(), d_desc.data_ptr(), n1, d_kps.data_ptr() + cap * 28, d_desc.data_ptr() + cap * 32,
+                                           n2, b, d_prev.data_ptr(), d_m12.data_ptr(), 100)
+    torch.cuda.synchronize()
+    orc = O.OrbOracle(5000, 1.2, 8, 20, 7, 19, 752, 480)
+    _, ok1, od1 = orc.extract(img1, (0, 0), True); _, ok2, od2 = orc.extract(img2, (0, 0), True)
+    assert ok1.tobytes() == kps[0][:n1].tobytes() and ok2.tobytes() == kps[1][:n2].tobytes()
+    en, em12, ep = O.search_for_initialization(ok1, od1, ok2, od2, b, np.stack([ok1["x"], ok1["y"]], 1), 100, 0.9, True)
+    assert nm == en and np.array_equal(d_m12.cpu().numpy(), em12) and d_prev.cpu().numpy().tobytes() == ep.tobytes()
+    assert en > 100          # a shifted copy of a textured frame matches well
+    gm.set_stream(None); ex.set_stream(None)

@@ -14,7 +14,7 @@ EXE = os.path.join(SHIM, "_shim_selftest")
 
 
 def _build():
-    srcs = [os.path.join(SHIM, f) for f in ("shim_selftest.cc", "ORBextractor.cc", "ORBmatcher_b200.cc", "EventConversion_b200.cc", "KLT_b200.cc")]
+    srcs = [os.path.join(SHIM, f) for f in ("shim_selftest.cc", "ORBextractor.cc", "ORBmatcher_b200.cc", "EventConversion_b200.cc", "KLT_b200.cc", "ORBmatcher_guided_b200.cc")]
     cmd = ["g++", "-std=c++17", "-O1", "-DEORB_SHIM_MOCK", "-I" + os.path.join(SHIM, "cv_mock"), "-I" + SHIM,
            "-I" + os.path.join(ROOT, "include"), "-o", EXE] + srcs + ["-L" + os.path.join(ROOT, "eorb_slam_b200"), "-leorb_b200",
                                                                       "-Wl,-rpath," + os.path.join(ROOT, "eorb_slam_b200")]
@@ -49,6 +49,7 @@ def test_shims_compile_and_fail_loudly_without_device():
     assert "ret=-1 n=0" in out and "empty_ret=-1" in out
     assert "no CUDA device" in err
     assert "lk_ok=0 lk_n=0" in out
+    assert "sfi_nm=0 sfi_self=0" in out
 
 
 @pytest.mark.gpu
@@ -77,3 +78,7 @@ def test_shims_match_oracle_on_gpu():
     jm = re.search(r"jac_ok=(\d) jac=([-\d.e+,]+)", out)
     jv = [float(x) for x in jm.group(2).split(",")]
     assert int(jm.group(1)) == 1 and any(abs(v) > 0 for v in jv[3:])
+    sf = re.search(r"sfi_nm=(\d+) sfi_self=(\d+) sfi_lvl0=(\d+) sfi_prev=(\d+)", out)
+    nm, self_, lvl0, prev = map(int, sf.groups())
+    # only level-0 keypoints are queried; a frame matched against its own shifted keypoints finds (nearly) all of them
+    assert 0 < nm <= lvl0 and self_ > 0.8 * nm and prev == nm
