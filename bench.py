@@ -374,6 +374,48 @@ def bench_guided(api, torch, dev, steps, warmup):
             "cpu_baseline": {"kind": "port", "cores": 1, "ms_per_call": ms_port, "value": 1e3 / ms_port, "unit": "calls/s"}}
 
 
+def bench_bow(api, torch, dev, steps, warmup):
+    """SURVEY §8f rank 4: Frame::ComputeBoW = ORBVocabulary::transform(descriptors, BowVector, FeatureVector, 4) for one frame's
+    descriptors against a synthetic vocabulary of ORBvoc.txt's size (k = 10, L = 6), host call; plus Frame::UndistortKeyPoints."""
+    import oracle_lib as O
+    from eorb_slam_b200 import synth
+    voc = synth.make_vocabulary_regular(10, 6, 3)
+    leaves = np.flatnonzero(voc["is_leaf"])
+    rng = np.random.default_rng(4)
+    feats = voc["desc"][rng.choice(leaves, 1009)].copy()
+    feats[:, :4] ^= rng.integers(0, 256, (1009, 4), dtype=np.uint8)          # perturbed words
+    v = api.ORBVocabulary(voc, dev)
+    for _ in range(max(warmup, 3)):
+        got = v.transform(feats, 4)
+    reps = max(steps, 3) * 20
+    l0 = v.launch_count()
+    t0 = time.perf_counter()
+    for _ in range(reps):
+        got = v.transform(feats, 4)
+    ms = (time.perf_counter() - t0) * 1e3 / reps
+    launches = (v.launch_count() - l0) // reps
+    orc = O.VocabOracle(voc)
+    exp = orc.transform(feats, 4)
+    t0 = time.perf_counter()
+    for _ in range(5):
+        orc.transform(feats, 4)
+    ms_port = (time.perf_counter() - t0) * 1e3 / 5
+    same = all(np.array_equal(got[k], exp[k]) for k in ("bow_ids", "fv_nodes", "fv_start", "fv_feats")) and got["bow_vals"].tobytes() == exp["bow_vals"].tobytes()
+    k1, _, _, _, _ = synth.make_keypoint_frame_pair(1009, 10, 13)
+    K, D = (458.654, 457.296, 367.215, 248.375), (-0.28340811, 0.07395907, 0.00019359, 1.76187114e-05, 0.0)
+    api.UndistortKeyPoints(k1, K, D)
+    t0 = time.perf_counter()
+    for _ in range(reps):
+        un = api.UndistortKeyPoints(k1, K, D)
+    ms_un = (time.perf_counter() - t0) * 1e3 / reps
+    return {"metric": "bow_transform_features_per_s", "value": len(feats) / (ms * 1e-3), "unit": "features/s", "ms_per_call": ms,
+            "workload": "ORBVocabulary::transform: %d descriptors, vocabulary k=10 L=6 (%d nodes, %d words), levelsup 4, host call" %
+                        (len(feats), len(voc["parent"]), len(leaves)),
+            "gpu_launches_per_call": int(launches), "bit_exact_vs_oracle": bool(same), "bow_words": int(len(exp["bow_ids"])),
+            "cpu_baseline": {"kind": "port", "cores": 1, "ms_per_call": ms_port, "value": len(feats) / (ms_port * 1e-3), "unit": "features/s"},
+            "undistort_keypoints": {"ms_per_call": ms_un, "n": len(k1), "note": "Frame::UndistortKeyPoints, host call (malloc + H2D + kernel + D2H)"}}
+
+
 # ------------------------------------------------------------------------------------------------ main arm
 def run_ours(args):
     import torch
@@ -538,6 +580,11 @@ def run_ours(args):
                 extra["guided"] = bench_guided(api, torch, dev, args.steps, args.warmup)
         except Exception as e:
             extra["guided"] = {"error": repr(e)}
+        try:
+            if rank == 0:
+                extra["bow"] = bench_bow(api, torch, dev, args.steps, args.warmup)
+        except Exception as e:
+            extra["bow"] = {"error": repr(e)}
         try:
             extra["hamming"] = bench_hamming(api, torch, dev, max(min(args.steps, 3), 1), 3, world, rank, dist)
         except Exception as e:

@@ -95,6 +95,11 @@ def _load():
         "eorb_guided_features_in_area": ([vp, vp, i, vp, vp, i, vp, vp, i], i),
         "eorb_guided_search_for_initialization": ([vp, vp, vp, i, vp, vp, i, vp, vp, i, f, i, vp, vp], i),
         "eorb_guided_search_for_initialization_device": ([vp, vp, vp, i, vp, vp, i, vp, vp, i, f, i, vp, vp], i),
+        "eorb_vocab_create": ([i, i, i, i, i, i, vp, vp, vp, vp, C.POINTER(vp)], i), "eorb_vocab_destroy": ([vp], i),
+        "eorb_vocab_set_stream": ([vp, vp], i), "eorb_vocab_reset_stream": ([vp], i), "eorb_vocab_launch_count": ([vp], C.c_longlong),
+        "eorb_vocab_transform": ([vp, vp, i, i, vp, vp, vp, vp, vp, vp, vp, vp, vp], i),
+        "eorb_vocab_transform_device": ([vp, vp, i, i, vp, vp, vp, vp, vp, vp, vp, vp, vp], i),
+        "eorb_undistort_keypoints": ([vp, i, vp, vp, vp], i), "eorb_undistort_keypoints_device": ([vp, vp, i, vp, vp, vp], i),
     }
     for name, (args, res) in sig.items():
         fn = getattr(L, name)   # AttributeError here == header/library mismatch
@@ -670,3 +675,56 @@ class GuidedMatcher:
                                                                 self.mfNNratio, int(self.mbCheckOrientation), C.c_void_p(d_matches12),
                                                                 C.byref(nm)), "SearchForInitialization_device")
         return nm.value
+
+
+# ================================================================================================ bag of words + undistortion
+class ORBVocabulary:
+    """Mirror of ORB_SLAM3::ORBVocabulary = DBoW2::TemplatedVocabulary<FORB::TDescriptor, FORB> for the call the front end
+    makes: transform(features, BowVector, FeatureVector, levelsup) (Thirdparty/DBoW2/DBoW2/TemplatedVocabulary.h:1127-1258;
+    Frame::ComputeBoW src/Frame.cc:796-803).  `voc` is the flat tree (see eorb_vocab_create / synth.make_vocabulary)."""
+
+    def __init__(self, voc, device=0):
+        h = C.c_void_p()
+        par = np.ascontiguousarray(voc["parent"], np.int32); lf = np.ascontiguousarray(voc["is_leaf"], np.uint8)
+        d = np.ascontiguousarray(voc["desc"], np.uint8); w = np.ascontiguousarray(voc["weight"], np.float64)
+        _check(lib.eorb_vocab_create(device, int(voc["k"]), int(voc["L"]), int(voc["scoring"]), int(voc["weighting"]), len(par), _p(par), _p(lf),
+                                     _p(d), _p(w), C.byref(h)), "vocab_create")
+        self.h = h
+
+    def __del__(self):
+        if getattr(self, "h", None):
+            lib.eorb_vocab_destroy(self.h)
+            self.h = None
+
+    def set_stream(self, s):
+        _check(lib.eorb_vocab_set_stream(self.h, C.c_void_p(s)) if s is not None else lib.eorb_vocab_reset_stream(self.h), "vocab_set_stream")
+
+    def launch_count(self): return lib.eorb_vocab_launch_count(self.h)
+
+    def _run(self, fn, feats_ptr, n, levelsup):
+        m = max(n, 1)
+        bi = np.zeros(m, np.uint32); bv = np.zeros(m, np.float64); fn_ = np.zeros(m, np.uint32); fs = np.zeros(m + 1, np.int32)
+        ff = np.zeros(m, np.uint32); wid = np.zeros(m, np.uint32); nid = np.zeros(m, np.uint32)
+        nb = C.c_int(0); nf = C.c_int(0)
+        _check(fn(self.h, feats_ptr, n, int(levelsup), _p(bi), _p(bv), C.byref(nb), _p(fn_), _p(fs), _p(ff), C.byref(nf), _p(wid), _p(nid)),
+               "vocab_transform")
+        nbow, nfv = nb.value, nf.value
+        return dict(word_id=wid[:n], node_id=nid[:n], bow_ids=bi[:nbow].copy(), bow_vals=bv[:nbow].copy(), fv_nodes=fn_[:nfv].copy(),
+                    fv_start=fs[:nfv + 1].copy(), fv_feats=ff[:fs[nfv]].copy())
+
+    def transform(self, features, levelsup=4):
+        """features: (n, 32) u8 -> dict(bow_ids, bow_vals (BowVector), fv_nodes, fv_start, fv_feats (FeatureVector), word_id, node_id)"""
+        f = np.ascontiguousarray(features, np.uint8).reshape(-1, 32)
+        return self._run(lib.eorb_vocab_transform, _p(f), len(f), levelsup)
+
+    def transform_device(self, d_feats_ptr, n, levelsup=4):
+        return self._run(lib.eorb_vocab_transform_device, C.c_void_p(d_feats_ptr), n, levelsup)
+
+
+def UndistortKeyPoints(keypoints, K4, distCoef5):
+    """Mirror of Frame::UndistortKeyPoints (src/Frame.cc:805-840): -> mvKeysUn (KEYPOINT_DTYPE array)"""
+    k = np.ascontiguousarray(keypoints, KEYPOINT_DTYPE)
+    out = np.zeros_like(k)
+    K = np.ascontiguousarray(K4, np.float32); D = np.ascontiguousarray(distCoef5, np.float32)
+    _check(lib.eorb_undistort_keypoints(_p(k), len(k), _p(K), _p(D), _p(out)), "UndistortKeyPoints")
+    return out

@@ -2,6 +2,7 @@
 // reference call shapes.  With a CUDA device it prints counts that tests/test_shim.py cross-checks; without one
 // it verifies the loud-failure path (no CPU fallback): -1 / empty results and an error message.
 #include <cstdio>
+#include <cmath>
 #include <cstdlib>
 #include <vector>
 
@@ -9,6 +10,7 @@
 #include "ORBmatcher_b200.h"
 #include "EventConversion_b200.h"
 #include "KLT_b200.h"
+#include "ORBVocabulary_b200.h"
 #include "eorb_b200.h"
 
 int main(int argc, char** argv)
@@ -91,6 +93,41 @@ int main(int argc, char** argv)
             if (m12[i] >= 0) moved += (prev[i].x == F2.mvKeysUn[m12[i]].pt.x && prev[i].y == F2.mvKeysUn[m12[i]].pt.y);
         }
         std::printf("sfi_nm=%d sfi_self=%d sfi_lvl0=%d sfi_prev=%d\n", nm, self, lvl0, moved);
+    }
+    // ORBVocabulary::transform through a text file in ORB-SLAM's vocabulary format (k = 3, L = 2: 3 inner nodes, 9 words whose
+    // descriptors are rows of `desc`), then Frame::UndistortKeyPoints with the EuRoC cam0 calibration
+    {
+        const char* path = argc > 1 ? argv[1] : "/tmp/_eorb_shim_voc.txt";
+        int nw = 0;
+        if (desc.rows >= 12) {
+            FILE* fp = std::fopen(path, "w");
+            std::fprintf(fp, "3 2 0 0\n");
+            for (int c = 0; c < 3; c++) {
+                std::fprintf(fp, "0 0"); for (int b = 0; b < 32; b++) std::fprintf(fp, " %d", desc.at<unsigned char>(c * 4, b)); std::fprintf(fp, " 0\n");
+            }
+            for (int c = 0; c < 3; c++) for (int w = 0; w < 3; w++) {
+                std::fprintf(fp, "%d 1", c + 1); for (int b = 0; b < 32; b++) std::fprintf(fp, " %d", desc.at<unsigned char>(c * 4 + w + 1, b)); std::fprintf(fp, " %.6f\n", 1.0 + 0.25 * nw++);
+            }
+            std::fclose(fp);
+        }
+        ORB_SLAM3::ORBVocabularyB200 voc;
+        const bool okv = desc.rows >= 12 && voc.loadFromTextFile(path);
+        std::vector<cv::Mat> feats;
+        for (int i = 0; i < desc.rows; i++) feats.push_back(desc.row(i));
+        DBoW2::BowVector bv; DBoW2::FeatureVector fv;
+        voc.transform(feats, bv, fv, 1);
+        double sum = 0; size_t nf = 0;
+        for (auto& e : bv) sum += e.second;
+        for (auto& e : fv) nf += e.second.size();
+        std::printf("voc_ok=%d voc_words=%u bow=%zu bow_sum=%.9f fv_nodes=%zu fv_feats=%zu\n", (int)okv, voc.size(), bv.size(), sum, fv.size(), nf);
+        cv::Mat Kc = cv::Mat::zeros(3, 3, CV_32F), Dc = cv::Mat::zeros(4, 1, CV_32F);
+        Kc.at<float>(0, 0) = 458.654f; Kc.at<float>(1, 1) = 457.296f; Kc.at<float>(0, 2) = 367.215f; Kc.at<float>(1, 2) = 248.375f; Kc.at<float>(2, 2) = 1.f;
+        Dc.at<float>(0, 0) = -0.28340811f; Dc.at<float>(1, 0) = 0.07395907f; Dc.at<float>(2, 0) = 0.00019359f; Dc.at<float>(3, 0) = 1.76187114e-05f;
+        std::vector<cv::KeyPoint> un;
+        const bool oku = ORB_SLAM3::b200::UndistortKeyPoints(kps, Kc, Dc, un);
+        double shift = 0;
+        for (size_t i = 0; i < un.size() && i < kps.size(); i++) shift += std::fabs(un[i].pt.x - kps[i].pt.x) + std::fabs(un[i].pt.y - kps[i].pt.y);
+        std::printf("undist_ok=%d undist_n=%zu undist_shift=%.3f\n", (int)(oku && !kps.empty()), un.size(), shift);
     }
     return 0;
 }

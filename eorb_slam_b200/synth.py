@@ -181,3 +181,83 @@ def make_keypoint_frame_pair(n1: int, n2: int, seed: int, w: int = 752, h: int =
         np.bitwise_xor.at(desc2[row], bits // 8, (1 << (bits % 8)).astype(np.uint8))
     bounds = np.array([0.0, 0.0, float(w), float(h)], np.float32)
     return kps1, desc1, kps2, desc2, bounds
+
+
+def make_vocabulary(k: int = 10, L: int = 4, seed: int = 0, scoring: int = 0, weighting: int = 0, prune: float = 0.08, zero_weight: float = 0.02):
+    """Synthetic DBoW2 vocabulary tree in the flat form TemplatedVocabulary::loadFromTextFile builds
+    (Thirdparty/DBoW2/DBoW2/TemplatedVocabulary.h:1330-1417; the real ORBvoc.txt — k = 10, L = 6 — is a missing blob):
+    node 0 is the root, a node's children are created together (contiguous ids, parent id < child id), a child descriptor is
+    its parent's with random bits flipped (so the descent is meaningful), a fraction `prune` of the inner nodes stays a leaf
+    early or gets fewer than k children, some siblings share a descriptor (distance ties: the first child wins) and a
+    fraction `zero_weight` of the words has weight 0 (stopped words are skipped by transform)."""
+    rng = np.random.default_rng(seed)
+    parent = [0]; desc = [np.zeros(32, np.uint8)]; leaf = [0]; level = [0]
+    frontier = [0]
+    for lv in range(1, L + 1):
+        nxt = []
+        for p in frontier:
+            nch = k if rng.random() > prune else int(rng.integers(1, k + 1))
+            base = desc[p] if lv > 1 else None
+            for c in range(nch):
+                if base is None:
+                    d = rng.integers(0, 256, 32, dtype=np.uint8)
+                else:
+                    d = base.copy()
+                    bits = rng.choice(256, int(rng.integers(8, 64 // lv + 9)), replace=False)
+                    np.bitwise_xor.at(d, bits // 8, (1 << (bits % 8)).astype(np.uint8))
+                if c > 0 and rng.random() < 0.03:
+                    d = desc[-1].copy()                       # twin sibling
+                nid = len(parent)
+                parent.append(p); desc.append(d); level.append(lv)
+                is_leaf = lv == L or (lv > 1 and rng.random() < prune)
+                leaf.append(1 if is_leaf else 0)
+                if not is_leaf:
+                    nxt.append(nid)
+        frontier = nxt
+    n = len(parent)
+    weight = np.zeros(n, np.float64)
+    lf = np.array(leaf, bool)
+    weight[lf] = np.log(rng.uniform(2.0, 4000.0, int(lf.sum())))          # idf-like
+    weight[lf & (rng.random(n) < zero_weight)] = 0.0
+    return dict(k=k, L=L, scoring=scoring, weighting=weighting, parent=np.array(parent, np.int32), is_leaf=np.array(leaf, np.uint8),
+                desc=np.stack(desc).astype(np.uint8), weight=weight, level=np.array(level, np.int32))
+
+
+def make_vocabulary_features(voc, n: int, seed: int, max_flips: int = 30) -> np.ndarray:
+    """n descriptors: leaves of the vocabulary with up to max_flips flipped bits (several per word) + 10 % random rows"""
+    rng = np.random.default_rng(seed)
+    leaves = np.flatnonzero(voc["is_leaf"])
+    src = rng.choice(leaves, n)
+    src[: n // 5] = src[n // 5: 2 * (n // 5)]                 # repeated words -> accumulated weights
+    f = voc["desc"][src].copy()
+    for i in range(n):
+        bits = rng.choice(256, int(rng.integers(0, max_flips + 1)), replace=False)
+        np.bitwise_xor.at(f[i], bits // 8, (1 << (bits % 8)).astype(np.uint8))
+    rnd = rng.random(n) < 0.1
+    f[rnd] = rng.integers(0, 256, (int(rnd.sum()), 32), dtype=np.uint8)
+    return f
+
+
+def make_vocabulary_regular(k: int = 10, L: int = 6, seed: int = 0):
+    """A complete k-ary tree of depth L in level order (vectorised; k = 10, L = 6 is the size of ORBvoc.txt: 1 111 111 nodes,
+    10^6 words, 35 MB of descriptors).  Child descriptor = parent's with ~1/8 of ... bits flipped less at deeper levels."""
+    rng = np.random.default_rng(seed)
+    parents = [np.zeros(1, np.int32)]; descs = [np.zeros((1, 32), np.uint8)]
+    first = 0; count = 1
+    for lv in range(1, L + 1):
+        n = count * k
+        par = first + np.repeat(np.arange(count, dtype=np.int32), k)
+        if lv == 1:
+            d = rng.integers(0, 256, (n, 32), dtype=np.uint8)
+        else:
+            flip = rng.integers(0, 256, (n, 32), dtype=np.uint8) & rng.integers(0, 256, (n, 32), dtype=np.uint8)
+            for _ in range(lv - 1):
+                flip &= rng.integers(0, 256, (n, 32), dtype=np.uint8)
+            d = np.repeat(descs[-1], k, axis=0) ^ flip
+        parents.append(par); descs.append(d)
+        first += count; count = n
+    parent = np.concatenate(parents); desc = np.concatenate(descs)
+    nn = len(parent)
+    leaf = np.zeros(nn, np.uint8); leaf[nn - count:] = 1
+    weight = np.zeros(nn, np.float64); weight[nn - count:] = np.log(rng.uniform(2.0, 4000.0, count))
+    return dict(k=k, L=L, scoring=0, weighting=0, parent=parent, is_leaf=leaf, desc=desc, weight=weight)

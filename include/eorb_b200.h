@@ -331,6 +331,39 @@ int eorb_guided_search_for_initialization_device(eorb_guided* g, const eorb_keyp
                                                  float* d_prev_xy, int window_size, float nnratio, int check_ori, int32_t* d_matches12,
                                                  int* nmatches);
 
+/* ---------------------------------------------------------------- bag of words + undistortion (fourth "next" row)
+ * The two steps that follow extraction in the reference's Frame:
+ *   eorb_vocab_transform        replaces DBoW2 TemplatedVocabulary<FORB::TDescriptor, FORB>::transform(features, BowVector,
+ *                               FeatureVector, levelsup) (Thirdparty/DBoW2/DBoW2/TemplatedVocabulary.h:1127-1258) as called by
+ *                               Frame::ComputeBoW / KeyFrame::ComputeBoW (src/Frame.cc:796-803, src/KeyFrame.cc:205-213, levelsup 4)
+ *   eorb_undistort_keypoints    replaces Frame::UndistortKeyPoints (src/Frame.cc:805-840): cv::undistortPoints(K, dist, P = K)
+ * A vocabulary is passed in the flat form TemplatedVocabulary::loadFromTextFile builds (:1330-1417; reading ORBvoc.txt stays
+ * with the caller): node 0 = root, parent[nid] < nid (file order), is_leaf / 32-byte descriptor / weight per node; k, L,
+ * scoring (L1_NORM 0, L2_NORM 1, CHI_SQUARE 2, KL 3, BHATTACHARYYA 4, DOT_PRODUCT 5) and weighting (TF_IDF 0, TF 1, IDF 2,
+ * BINARY 3) are the file header's.  It stays resident in HBM.  At most EORB_BOW_MAX_FEATURES features per call. */
+#define EORB_BOW_MAX_FEATURES 8192
+typedef struct eorb_vocab eorb_vocab;
+int eorb_vocab_create(int device, int k, int L, int scoring, int weighting, int nnodes, const int32_t* parent, const uint8_t* is_leaf,
+                      const uint8_t* desc, const double* weight, eorb_vocab** out);
+int eorb_vocab_destroy(eorb_vocab* v);
+int eorb_vocab_set_stream(eorb_vocab* v, void* cuda_stream);
+int eorb_vocab_reset_stream(eorb_vocab* v);
+long long eorb_vocab_launch_count(const eorb_vocab* v);
+/* feats: n x 32 bytes.  BowVector = (bow_ids, bow_vals)[*nbow] in ascending word id (std::map order); FeatureVector in CSR form:
+ * fv_nodes[*nfv] ascending, features of node q = fv_feats[fv_start[q] .. fv_start[q+1]) in ascending feature index (push_back
+ * order).  Output arrays hold n entries (fv_start n + 1).  word_id / node_id (optional, n entries): the per-feature leaf word
+ * and the node at level L - levelsup.  Doubles are bit-identical to DBoW2's (same summation order). */
+int eorb_vocab_transform(eorb_vocab* v, const uint8_t* feats, int n, int levelsup, uint32_t* bow_ids, double* bow_vals, int* nbow,
+                         uint32_t* fv_nodes, int32_t* fv_start, uint32_t* fv_feats, int* nfv, uint32_t* word_id, uint32_t* node_id);
+/* the same with the descriptors resident in HBM (16-byte aligned), e.g. straight from eorb_orb_extract_batch_device */
+int eorb_vocab_transform_device(eorb_vocab* v, const uint8_t* d_feats, int n, int levelsup, uint32_t* bow_ids, double* bow_vals, int* nbow,
+                                uint32_t* fv_nodes, int32_t* fv_start, uint32_t* fv_feats, int* nfv, uint32_t* word_id, uint32_t* node_id);
+/* K4 = fx, fy, cx, cy; dist5 = k1, k2, p1, p2, k3 (mDistCoef).  Positions are replaced, the other fields copied
+ * (Frame.cc:833-838); k1 == 0 copies the keypoints unchanged (:807-811).  out may alias kps. */
+int eorb_undistort_keypoints(const eorb_keypoint* kps, int n, const float* K4, const float* dist5, eorb_keypoint* out);
+int eorb_undistort_keypoints_device(const eorb_keypoint* d_kps, eorb_keypoint* d_out, int n, const float* K4, const float* dist5,
+                                    void* cuda_stream);
+
 #ifdef __cplusplus
 }
 #endif

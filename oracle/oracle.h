@@ -124,6 +124,21 @@ int   orc_search_for_initialization(const orc_keypoint* kps1, const uint8_t* des
                                     const uint8_t* desc2, int n2, const float* bounds4, float* prev_xy, int window_size, float nnratio,
                                     int check_ori, int32_t* matches12);
 
+/* ---- bag of words + undistortion (bow_oracle.cc) ---- */
+typedef struct orc_vocab orc_vocab;
+/* flat form of what TemplatedVocabulary::loadFromTextFile builds: node 0 = root, parent[nid] < nid, children in id order,
+   words numbered in order of appearance; scoring / weighting = DBoW2's enums (L1_NORM 0 ... DOT_PRODUCT 5; TF_IDF 0 ... BINARY 3) */
+orc_vocab* orc_vocab_create(int k, int L, int scoring, int weighting, int nnodes, const int32_t* parent, const uint8_t* is_leaf,
+                            const uint8_t* desc, const double* weight);
+void  orc_vocab_destroy(orc_vocab* v);
+/* transform(features, BowVector, FeatureVector, levelsup): per-feature (word, weight, node at level L-levelsup), the
+   BowVector as sorted (id, value) arrays and the FeatureVector as CSR (fv_nodes[nfv], fv_start[nfv+1], fv_feats) */
+int   orc_vocab_transform(const orc_vocab* v, const uint8_t* feats, int n, int levelsup, uint32_t* word_id, double* word_w,
+                          uint32_t* node_id, uint32_t* bow_ids, double* bow_vals, int* nbow, uint32_t* fv_nodes, int32_t* fv_start,
+                          uint32_t* fv_feats, int* nfv);
+/* cv::undistortPoints(src, dst, K, dist, noArray(), K) (Frame::UndistortKeyPoints, Frame.cc:805-840) */
+void  orc_undistort_points(const float* xy, int n, const float* K4, const float* dist5, float* out_xy);
+
 /* ---- event frames ---- */
 /* mode: 0 nearest (ev2im), 1 gauss (ev2im_gauss), 2 gauss+SE3 (Tcw16,depth,K4), 3 gauss+SE2 (se2[4],K4) */
 int   orc_ev_accumulate(const orc_event* evs, int64_t n, int w, int h, float sigma, int mode,

@@ -27,7 +27,7 @@ class OrbParams(C.Structure):
 
 
 def build(force: bool = False) -> str:
-    srcs = [os.path.join(ORACLE_DIR, f) for f in ("orb_oracle.cc", "match_oracle.cc", "guided_oracle.cc", "event_oracle.cc", "lk_oracle.cc", "oracle.h",
+    srcs = [os.path.join(ORACLE_DIR, f) for f in ("orb_oracle.cc", "match_oracle.cc", "guided_oracle.cc", "bow_oracle.cc", "event_oracle.cc", "lk_oracle.cc", "oracle.h",
                                                   "brief_pattern_31.inc", "Makefile")]
     stale = force or not os.path.exists(LIB_PATH) or any(os.path.getmtime(s) > os.path.getmtime(LIB_PATH) for s in srcs)
     if stale:
@@ -387,3 +387,41 @@ def search_for_initialization(kps1, desc1, kps2, desc2, bounds, prev_xy, window_
     n = L.orc_search_for_initialization(_p(kps1), _p(d1), C.c_int(len(kps1)), _p(kps2), _p(d2), C.c_int(len(kps2)), _p(b), _p(prev),
                                         C.c_int(window_size), C.c_float(nnratio), C.c_int(int(check_ori)), _p(m12))
     return n, m12[:len(kps1)].copy(), prev
+
+
+# ---- bag of words + undistortion
+class VocabOracle:
+    def __init__(self, voc):
+        """voc: dict from synth.make_vocabulary (k, L, scoring, weighting, parent, is_leaf, desc, weight)"""
+        L = lib()
+        L.orc_vocab_create.restype = C.c_void_p
+        self.voc = voc
+        self.h = C.c_void_p(L.orc_vocab_create(C.c_int(voc["k"]), C.c_int(voc["L"]), C.c_int(voc["scoring"]), C.c_int(voc["weighting"]),
+                                               C.c_int(len(voc["parent"])), _p(voc["parent"]), _p(voc["is_leaf"]), _p(voc["desc"]),
+                                               _p(voc["weight"])))
+
+    def __del__(self):
+        if getattr(self, "h", None):
+            lib().orc_vocab_destroy(self.h)
+            self.h = None
+
+    def transform(self, feats, levelsup=4):
+        """-> dict(word_id, word_w, node_id, bow_ids, bow_vals, fv_nodes, fv_start, fv_feats)"""
+        f = np.ascontiguousarray(feats, np.uint8).reshape(-1, 32)
+        n = len(f); m = max(n, 1)
+        wid = np.zeros(m, np.uint32); ww = np.zeros(m, np.float64); nid = np.zeros(m, np.uint32)
+        bi = np.zeros(m, np.uint32); bv = np.zeros(m, np.float64); fn = np.zeros(m, np.uint32); fs = np.zeros(m + 1, np.int32)
+        ff = np.zeros(m, np.uint32); nb = C.c_int(0); nf = C.c_int(0)
+        lib().orc_vocab_transform(self.h, _p(f), C.c_int(n), C.c_int(levelsup), _p(wid), _p(ww), _p(nid), _p(bi), _p(bv), C.byref(nb),
+                                  _p(fn), _p(fs), _p(ff), C.byref(nf))
+        nbow, nfv = nb.value, nf.value
+        return dict(word_id=wid[:n], word_w=ww[:n], node_id=nid[:n], bow_ids=bi[:nbow].copy(), bow_vals=bv[:nbow].copy(),
+                    fv_nodes=fn[:nfv].copy(), fv_start=fs[:nfv + 1].copy(), fv_feats=ff[:fs[nfv]].copy())
+
+
+def undistort_points(xy, K4, dist5):
+    xy = np.ascontiguousarray(xy, np.float32).reshape(-1, 2)
+    out = np.zeros_like(xy)
+    K = np.ascontiguousarray(K4, np.float32); D = np.ascontiguousarray(dist5, np.float32)
+    lib().orc_undistort_points(_p(xy), C.c_int(len(xy)), _p(K), _p(D), _p(out))
+    return out

@@ -14,7 +14,7 @@ EXE = os.path.join(SHIM, "_shim_selftest")
 
 
 def _build():
-    srcs = [os.path.join(SHIM, f) for f in ("shim_selftest.cc", "ORBextractor.cc", "ORBmatcher_b200.cc", "EventConversion_b200.cc", "KLT_b200.cc", "ORBmatcher_guided_b200.cc")]
+    srcs = [os.path.join(SHIM, f) for f in ("shim_selftest.cc", "ORBextractor.cc", "ORBmatcher_b200.cc", "EventConversion_b200.cc", "KLT_b200.cc", "ORBmatcher_guided_b200.cc", "ORBVocabulary_b200.cc")]
     cmd = ["g++", "-std=c++17", "-O1", "-DEORB_SHIM_MOCK", "-I" + os.path.join(SHIM, "cv_mock"), "-I" + SHIM,
            "-I" + os.path.join(ROOT, "include"), "-o", EXE] + srcs + ["-L" + os.path.join(ROOT, "eorb_slam_b200"), "-leorb_b200",
                                                                       "-Wl,-rpath," + os.path.join(ROOT, "eorb_slam_b200")]
@@ -50,6 +50,7 @@ def test_shims_compile_and_fail_loudly_without_device():
     assert "no CUDA device" in err
     assert "lk_ok=0 lk_n=0" in out
     assert "sfi_nm=0 sfi_self=0" in out
+    assert "voc_ok=0" in out and "undist_ok=0" in out
 
 
 @pytest.mark.gpu
@@ -82,3 +83,9 @@ def test_shims_match_oracle_on_gpu():
     nm, self_, lvl0, prev = map(int, sf.groups())
     # only level-0 keypoints are queried; a frame matched against its own shifted keypoints finds (nearly) all of them
     assert 0 < nm <= lvl0 and self_ > 0.8 * nm and prev == nm
+    vo = re.search(r"voc_ok=(\d) voc_words=(\d+) bow=(\d+) bow_sum=([\d.]+) fv_nodes=(\d+) fv_feats=(\d+)", out)
+    okv, words, nbow, bsum, fvn, fvf = vo.groups()
+    assert int(okv) == 1 and int(words) == 9 and 0 < int(nbow) <= 9 and abs(float(bsum) - 1.0) < 1e-6      # L1-normalised BowVector
+    assert 0 < int(fvn) <= 3 and int(fvf) == len(okps)                                                    # every feature under one of 3 nodes
+    un = re.search(r"undist_ok=(\d) undist_n=(\d+) undist_shift=([\d.]+)", out)
+    assert int(un.group(1)) == 1 and int(un.group(2)) == len(okps) and float(un.group(3)) > len(okps)      # EuRoC distortion moves points by pixels
