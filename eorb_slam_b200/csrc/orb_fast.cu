@@ -192,11 +192,15 @@ __global__ void __launch_bounds__(EORB_FAST_WARPS * 32) fast_cells_kernel(OrbArg
         }
         __syncwarp();
 
-        // ---- phase 2: exact arc score for survivors
+        // ---- phase 2: exact arc score for survivors; corners (m > t) are compacted IN PLACE at the head of the list
+        // (still row-major: a chunk only overwrites entries at or before its own, which it has already read)
+        int ncorn = 0;
         for (int base = 0; base < nsurv; base += 32) {
             const int s = base + lane;
+            bool corner = false;
+            int code = 0;
             if (s < nsurv) {
-                const int code = list[s];
+                code = list[s];
                 const int rr = code >> 7, col = code & 127;
                 const uint8_t* p = tile + (rr + 3) * TS + col;
                 const int v = p[0];
@@ -206,31 +210,33 @@ __global__ void __launch_bounds__(EORB_FAST_WARPS * 32) fast_cells_kernel(OrbArg
                 ring[8] = p[-3 * TS];      ring[9] = p[-3 * TS - 1];  ring[10] = p[-2 * TS - 2];  ring[11] = p[-TS - 3];
                 ring[12] = p[-3];          ring[13] = p[TS - 3];      ring[14] = p[2 * TS - 2];   ring[15] = p[3 * TS - 1];
                 const int m = fast_max_arc_min_packed(v, ring);
-                if (m > t) smap[(rr + 1) * MS + col - aoff - 2] = (uint8_t)m;   // map column = interior x + 1
+                corner = m > t;
+                if (corner) smap[(rr + 1) * MS + col - aoff - 2] = (uint8_t)m;   // map column = interior x + 1
             }
+            const unsigned cm = __ballot_sync(FULL, corner);
+            if (corner) list[ncorn + __popc(cm & lt)] = (uint16_t)code;
+            ncorn += __popc(cm);
         }
         __syncwarp();
 
-        // ---- phase 3: strict 3x3 NMS + ordered emission
+        // ---- phase 3: strict 3x3 NMS over the corners + ordered emission
         cnt = 0;
-        for (int base = 0; base < nsurv; base += 32) {
+        for (int base = 0; base < ncorn; base += 32) {
             const int s = base + lane;
             bool keep = false;
             uint32_t packed = 0;
-            if (s < nsurv) {
+            if (s < ncorn) {
                 const int code = list[s];
                 const int rr = code >> 7, col = code & 127;
                 const uint8_t* q = smap + (rr + 1) * MS + col - aoff - 2;
                 const int m = q[0];
-                if (m > t) {
-                    // every stored score is > t, everything else is 0: strict maximum over the 8 neighbours, and the
-                    // OpenCV score m - 1 must beat a non-corner's 0
-                    const int n0 = max(max((int)q[-MS - 1], (int)q[-MS]), (int)q[-MS + 1]);
-                    const int n1 = max(max((int)q[-1], (int)q[1]), 1);
-                    const int n2 = max(max((int)q[MS - 1], (int)q[MS]), (int)q[MS + 1]);
-                    keep = m > max(max(n0, n1), n2);
-                    packed = (uint32_t)(col - aoff + c.ox) | ((uint32_t)(rr + 3 + c.oy) << 12) | ((uint32_t)(m - 1) << 24);
-                }
+                // every stored score is > t, everything else is 0: strict maximum over the 8 neighbours, and the
+                // OpenCV score m - 1 must beat a non-corner's 0
+                const int n0 = max(max((int)q[-MS - 1], (int)q[-MS]), (int)q[-MS + 1]);
+                const int n1 = max(max((int)q[-1], (int)q[1]), 1);
+                const int n2 = max(max((int)q[MS - 1], (int)q[MS]), (int)q[MS + 1]);
+                keep = m > max(max(n0, n1), n2);
+                packed = (uint32_t)(col - aoff + c.ox) | ((uint32_t)(rr + 3 + c.oy) << 12) | ((uint32_t)(m - 1) << 24);
             }
             const unsigned msk = __ballot_sync(FULL, keep);
             if (keep) slots[cnt + __popc(msk & lt)] = packed;
