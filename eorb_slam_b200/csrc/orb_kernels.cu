@@ -238,8 +238,8 @@ __global__ void __launch_bounds__(OCT_MAX_THREADS) orb_index_kernel(OrbArgs a) {
 // the row loop is straight-line code with no edge branches.  Horizontal sums: unsigned dp4a on packed weights
 // (the 5th tap by a second dp4a with a one-hot weight word).  A 5-row ring of horizontal sums lives in registers
 // (loop unrolled by 5, no moves).  Horizontal sums are < 2^16 and the vertical sum < 2^24, so byte 2 of the
-// accumulator IS the result ((s + 32768) >> 16).
-// EORB_BLUR_BAND (orb_plan.h) is a multiple of 5: full bands run the unrolled ring loop without a tail
+// accumulator IS the result ((s + 32768) >> 16).  (The vertical pass works on packed row pairs, see the kernel.)
+// EORB_BLUR_BAND (orb_plan.h) is a multiple of 4: full bands run the unrolled ring loop without a tail
 
 // REFLECT_101 of a row index that overshoots [0, len) by at most 2 (single bounce when len >= 3)
 __device__ __forceinline__ int reflect101_near(int p, int len) {
@@ -301,16 +301,10 @@ __device__ __forceinline__ void blur_hrow(const uint8_t* __restrict__ rowp, cons
     h[3] = __dp4a(Rc, 0x00002700u, __dp4a(q3, WT, 0u));   // + 39 * p[x0+5]
 }
 
-__device__ __forceinline__ unsigned blur_vout(const unsigned* a, const unsigned* b, const unsigned* c, const unsigned* d, const unsigned* e) {
-    unsigned acc[4];
-#pragma unroll
-    for (int j = 0; j < 4; j++) acc[j] = 39u * (a[j] + e[j]) + 57u * (b[j] + d[j]) + 64u * c[j] + 32768u;
-    const unsigned lo = __byte_perm(acc[0], acc[1], 0x0062);   // (acc0.b2, acc1.b2, -, -)
-    const unsigned hi = __byte_perm(acc[2], acc[3], 0x0062);
-    return __byte_perm(lo, hi, 0x5410);
-}
-
-__global__ void __launch_bounds__(128) blur_kernel(OrbArgs a) {
+#ifndef EORB_BLUR_MINB
+#define EORB_BLUR_MINB 8
+#endif
+__global__ void __launch_bounds__(128, EORB_BLUR_MINB) blur_kernel(OrbArgs a) {
     const OrbPlan& P = *a.plan;
     const int f = blockIdx.y;
     const int lane = threadIdx.x;
@@ -365,35 +359,50 @@ __global__ void __launch_bounds__(128) blur_kernel(OrbArgs a) {
     const long long spl = sp;
 #define NEXTROW() do { yy++; rp += ((unsigned)(yy - 1) < (unsigned)(hgt - 1)) ? spl : -spl; } while (0)
 #define HROW(dstv) do { blur_hrow(rp, bl, dstv); NEXTROW(); } while (0)
-#define OUT(A, B, C, D, E)                                                                          \
+    // Vertical pass on PAIRS of rows: horizontal sums are < 2^16, so two vertically adjacent sums share one register
+    // (lo = upper row) and a 5-tap column costs  dp2a(P(y-2,y-1), {39,57}) + dp2a(P(y,y+1), {64,57}) + 39 * h(y+2):
+    // one pack + two IDP.2A + one IMAD per pixel.  Every pair P(k,k+1) is packed once and used twice; the ring holds four
+    // pairs and the newest raw row, and returns to its starting assignment every 4 rows (no register moves).
+#define PACK(P, E, L)                                                                               \
     do {                                                                                            \
-        const unsigned o = blur_vout(A, B, C, D, E);                                                \
-        if (store) *reinterpret_cast<unsigned*>(dp) = o;                                            \
+        _Pragma("unroll") for (int j_ = 0; j_ < 4; j_++) P[j_] = __byte_perm(E[j_], L[j_], 0x5410);   \
+    } while (0)
+#define OUT(P1, P2, HN)                                                                             \
+    do {                                                                                            \
+        unsigned acc_[4];                                                                           \
+        _Pragma("unroll") for (int j_ = 0; j_ < 4; j_++)                                              \
+            acc_[j_] = 39u * HN[j_] + __dp2a_lo(P2[j_], 0x00003940u, __dp2a_lo(P1[j_], 0x00003927u, 32768u)); \
+        const unsigned lo_ = __byte_perm(acc_[0], acc_[1], 0x0062);                                 \
+        const unsigned hi_ = __byte_perm(acc_[2], acc_[3], 0x0062);                                 \
+        const unsigned o_ = __byte_perm(lo_, hi_, 0x5410);                                          \
+        if (store) *reinterpret_cast<unsigned*>(dp) = o_;                                           \
         dp += bp;                                                                                   \
     } while (0)
-    unsigned r0[4], r1[4], r2[4], r3[4], r4[4];
-    HROW(r0); HROW(r1); HROW(r2); HROW(r3);
-    int y = y0;
-    for (; y + 5 <= y1; y += 5) {          // full groups of 5 rows: the ring returns to its starting assignment
-        HROW(r4); OUT(r0, r1, r2, r3, r4);
-        HROW(r0); OUT(r1, r2, r3, r4, r0);
-        HROW(r1); OUT(r2, r3, r4, r0, r1);
-        HROW(r2); OUT(r3, r4, r0, r1, r2);
-        HROW(r3); OUT(r4, r0, r1, r2, r3);
+    unsigned pa[4], pb[4], pc[4], pd[4], hx[4], hy[4];
+    {
+        unsigned h0[4], h1[4];
+        HROW(h0); HROW(h1); PACK(pa, h0, h1);     // P(y0-2, y0-1)
+        HROW(h0); PACK(pb, h1, h0);               // P(y0-1, y0)
+        HROW(hy); PACK(pc, h0, hy);               // P(y0,   y0+1); hy = newest raw row
     }
-    if (y < y1) {                          // last band of a level: up to 4 rows left
-        HROW(r4); OUT(r0, r1, r2, r3, r4);
+    int y = y0;
+    for (; y + 4 <= y1; y += 4) {
+        HROW(hx); PACK(pd, hy, hx); OUT(pa, pc, hx);
+        HROW(hy); PACK(pa, hx, hy); OUT(pb, pd, hy);
+        HROW(hx); PACK(pb, hy, hx); OUT(pc, pa, hx);
+        HROW(hy); PACK(pc, hx, hy); OUT(pd, pb, hy);
+    }
+    if (y < y1) {                          // last band of a level: up to 3 rows left
+        HROW(hx); PACK(pd, hy, hx); OUT(pa, pc, hx);
         if (y + 1 < y1) {
-            HROW(r0); OUT(r1, r2, r3, r4, r0);
-            if (y + 2 < y1) {
-                HROW(r1); OUT(r2, r3, r4, r0, r1);
-                if (y + 3 < y1) { HROW(r2); OUT(r3, r4, r0, r1, r2); }
-            }
+            HROW(hy); PACK(pa, hx, hy); OUT(pb, pd, hy);
+            if (y + 2 < y1) { HROW(hx); OUT(pc, pa, hx); }
         }
     }
 #undef NEXTROW
 #undef HROW
 #undef OUT
+#undef PACK
 }
 
 // ------------------------------------------------------------------------------------------------ K4 + K6
