@@ -41,10 +41,13 @@ __device__ __forceinline__ const uint8_t* level_ptr(const OrbArgs& a, const Leve
 // two pairs of aligned 32-bit words per source row (columns 0-1 and 2-3), a byte-permute selector per column
 // that extracts the two adjacent taps, and the two 11-bit weights packed as 16-bit halves so that ONE dp2a gives
 // S = a0*p[sx] + a1*p[sx+1].  Both source rows of every destination row are interpolated in straight-line code
-// (no row cache: at s = 1.2 it would save 0.8 of 2 row interpolations but cost a branch tree per row), the
+// (no row cache: at s = 1.2 it would save 0.8 of 2 row interpolations, but the warp-uniform branch per row stops the
+// loads of consecutive rows from overlapping — measured 0.92 -> 1.19 us/frame), the
 // vertical step (b*(S>>4))>>16 is one IMAD.HI per tap, and the loop is unrolled so the loads of the next
 // destination row are in flight while the current one is combined.
-#define EORB_PYR_BAND 8
+#ifndef EORB_PYR_BAND
+#define EORB_PYR_BAND 16   // measured: 8 -> 0.924, 16 -> 0.904 us/frame
+#endif
 
 // rowA / rowB point at the first word of the lane's two 8-byte source windows (columns 0-1 and 2-3)
 __device__ __forceinline__ void pyr_hrow(const uint8_t* __restrict__ rowA, const uint8_t* __restrict__ rowB, const unsigned* sel,
