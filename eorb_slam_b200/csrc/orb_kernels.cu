@@ -45,6 +45,9 @@ __device__ __forceinline__ const uint8_t* level_ptr(const OrbArgs& a, const Leve
 // loads of consecutive rows from overlapping — measured 0.92 -> 1.19 us/frame), the
 // vertical step (b*(S>>4))>>16 is one IMAD.HI per tap, and the loop is unrolled so the loads of the next
 // destination row are in flight while the current one is combined.
+#ifndef EORB_PYR_HOIST
+#define EORB_PYR_HOIST 1
+#endif
 #ifndef EORB_PYR_BAND
 #define EORB_PYR_BAND 16   // measured: 8 -> 0.924, 16 -> 0.904 us/frame
 #endif
@@ -62,6 +65,20 @@ __device__ __forceinline__ void pyr_hrow(const uint8_t* __restrict__ rowA, const
     h[3] = __dp2a_lo(wt[3], __byte_perm(B0, B1, sel[3]), 0u) >> 4;
 }
 
+#define PYR_LOAD4(W, PA, PB)                                                   \
+    do {                                                                       \
+        W[0] = __ldg(reinterpret_cast<const unsigned*>(PA));                   \
+        W[1] = __ldg(reinterpret_cast<const unsigned*>(PA + 4));               \
+        W[2] = __ldg(reinterpret_cast<const unsigned*>(PB));                   \
+        W[3] = __ldg(reinterpret_cast<const unsigned*>(PB + 4));               \
+    } while (0)
+__device__ __forceinline__ void pyr_hcalc(const unsigned* w, const unsigned* sel, const unsigned* wt, unsigned* h) {
+    h[0] = __dp2a_lo(wt[0], __byte_perm(w[0], w[1], sel[0]), 0u) >> 4;
+    h[1] = __dp2a_lo(wt[1], __byte_perm(w[0], w[1], sel[1]), 0u) >> 4;
+    h[2] = __dp2a_lo(wt[2], __byte_perm(w[2], w[3], sel[2]), 0u) >> 4;
+    h[3] = __dp2a_lo(wt[3], __byte_perm(w[2], w[3], sel[3]), 0u) >> 4;
+}
+
 // (((b0 * (S0 >> 4)) >> 16) + ((b1 * (S1 >> 4)) >> 16) + 2) >> 2 for four columns, packed into one word.
 // bs0 = b0 << 16, bs1 = b1 << 16: (b * x) >> 16 == umulhi(b << 16, x) for the non-negative operands here.
 __device__ __forceinline__ unsigned pyr_vrow(const unsigned* __restrict__ h0, const unsigned* __restrict__ h1, unsigned bs0, unsigned bs1) {
@@ -73,7 +90,10 @@ __device__ __forceinline__ unsigned pyr_vrow(const unsigned* __restrict__ h0, co
     return __byte_perm(lo, hi, 0x5410);
 }
 
-__global__ void __launch_bounds__(128) pyr_resize_kernel(OrbArgs a, int level) {
+#ifndef EORB_PYR_MINB
+#define EORB_PYR_MINB 8
+#endif
+__global__ void __launch_bounds__(128, EORB_PYR_MINB) pyr_resize_kernel(OrbArgs a, int level) {
     const OrbPlan& P = *a.plan;
     const int dw = P.lv[level].w, dh = P.lv[level].h, dpitch = P.lv[level].pitch;
     const int sw = P.lv[level - 1].w;
@@ -130,6 +150,29 @@ __global__ void __launch_bounds__(128) pyr_resize_kernel(OrbArgs a, int level) {
     const uint8_t* __restrict__ laneA = src + baseA;
     const uint8_t* __restrict__ laneB = src + baseB;
     uint8_t* dp = dst + (size_t)y0 * dpitch;
+#if EORB_PYR_HOIST
+    // two destination rows per step, all sixteen source words requested before the first interpolation
+    for (int dy = y0; dy < y1; dy += 2) {
+        const bool two = dy + 1 < y1;
+        const int4 ya = __ldg(&ytab[dy]);                  // sy0, sy1 (clamped), b0 << 16, b1 << 16 — warp-uniform
+        const int4 yb = __ldg(&ytab[two ? dy + 1 : dy]);
+        const uint8_t* pa0 = laneA + (size_t)(unsigned)ya.x * (unsigned)sp; const uint8_t* pb0 = laneB + (size_t)(unsigned)ya.x * (unsigned)sp;
+        const uint8_t* pa1 = laneA + (size_t)(unsigned)ya.y * (unsigned)sp; const uint8_t* pb1 = laneB + (size_t)(unsigned)ya.y * (unsigned)sp;
+        const uint8_t* pa2 = laneA + (size_t)(unsigned)yb.x * (unsigned)sp; const uint8_t* pb2 = laneB + (size_t)(unsigned)yb.x * (unsigned)sp;
+        const uint8_t* pa3 = laneA + (size_t)(unsigned)yb.y * (unsigned)sp; const uint8_t* pb3 = laneB + (size_t)(unsigned)yb.y * (unsigned)sp;
+        unsigned w[4][4];
+        PYR_LOAD4(w[0], pa0, pb0); PYR_LOAD4(w[1], pa1, pb1); PYR_LOAD4(w[2], pa2, pb2); PYR_LOAD4(w[3], pa3, pb3);
+        unsigned h0[4], h1[4];
+        pyr_hcalc(w[0], sel, wt, h0); pyr_hcalc(w[1], sel, wt, h1);
+        const unsigned o0 = pyr_vrow(h0, h1, (unsigned)ya.z, (unsigned)ya.w);
+        if (active) *reinterpret_cast<unsigned*>(dp) = o0;
+        dp += dpitch;
+        pyr_hcalc(w[2], sel, wt, h0); pyr_hcalc(w[3], sel, wt, h1);
+        const unsigned o1 = pyr_vrow(h0, h1, (unsigned)yb.z, (unsigned)yb.w);
+        if (active && two) *reinterpret_cast<unsigned*>(dp) = o1;
+        dp += dpitch;
+    }
+#else
 #pragma unroll 2
     for (int dy = y0; dy < y1; dy++) {
         const int4 yt = __ldg(&ytab[dy]);                  // sy0, sy1 (clamped), b0 << 16, b1 << 16 — warp-uniform
@@ -141,6 +184,7 @@ __global__ void __launch_bounds__(128) pyr_resize_kernel(OrbArgs a, int level) {
         if (active) *reinterpret_cast<unsigned*>(dp) = o;
         dp += dpitch;
     }
+#endif
 }
 
 // ------------------------------------------------------------------------------------------------ K3
