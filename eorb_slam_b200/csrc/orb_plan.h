@@ -7,7 +7,7 @@
 #define EORB_MAX_LEVELS 32
 #define EORB_MAX_DIM 4095          // candidate coordinates are packed in 12 bits
 #ifndef EORB_BLUR_BAND
-#define EORB_BLUR_BAND 60          // rows per blur task; multiple of 4 (the row-pair ring is unrolled by 4)
+#define EORB_BLUR_BAND 64          // rows per blur task; multiple of 8 (eight rows are loaded per group, the row-pair ring has period 4)
 #endif
 #ifndef EORB_FAST_WARPS
 #define EORB_FAST_WARPS 1          // warps (= grid cells) per FAST thread block
