@@ -190,11 +190,20 @@ OCT_DEV int oct_distribute(const uint32_t* keys, uint16_t* knode, int n, int wid
         s.box[cur][i] = b; s.cnt[cur][i] = 0; s.seq[cur][i] = i;
     }
     OCT_SYNC();
-    for (int k = tid; k < n; k += nt) {
-        int slot = (int)((float)oct_key_x(keys[k]) / hX);
-        if (slot >= nIni) slot = nIni - 1;
-        knode[k] = (uint16_t)slot;
-        oct_atomic_add(&s.cnt[cur][slot], 1);
+    for (int k0 = tid; k0 < n; k0 += 4 * nt) {
+        uint32_t ky[4];
+#pragma unroll
+        for (int j = 0; j < 4; j++) { const int k = k0 + j * nt; ky[j] = k < n ? keys[k] : 0u; }
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            const int k = k0 + j * nt;
+            if (k < n) {
+                int slot = (int)((float)oct_key_x(ky[j]) / hX);
+                if (slot >= nIni) slot = nIni - 1;
+                knode[k] = (uint16_t)slot;
+                oct_atomic_add(&s.cnt[cur][slot], 1);
+            }
+        }
     }
     OCT_SYNC();
     // drop empty roots (:590-603)
@@ -220,9 +229,17 @@ OCT_DEV int oct_distribute(const uint32_t* keys, uint16_t* knode, int n, int wid
         // ---- pass 1: child populations of every candidate node
         for (int i = tid; i < 4 * L; i += nt) s.cc[i] = 0;
         OCT_SYNC();
-        for (int k = tid; k < n; k += nt) {
-            int p = knode[k];
-            if (cand[p]) oct_atomic_add(&s.cc[4 * p + oct_child_of(keys[k], box[p])], 1);
+        // key passes are unrolled by 4 with the loads first: the passes wait on global memory (keys, node positions), and
+        // the shared-memory atomics in the body keep the compiler from overlapping the loads of consecutive keys itself
+        for (int k0 = tid; k0 < n; k0 += 4 * nt) {
+            int pp[4]; uint32_t ky[4];
+#pragma unroll
+            for (int j = 0; j < 4; j++) { const int k = k0 + j * nt; pp[j] = k < n ? (int)knode[k] : 0; ky[j] = k < n ? keys[k] : 0u; }
+#pragma unroll
+            for (int j = 0; j < 4; j++) {
+                const int k = k0 + j * nt, p = pp[j];
+                if (k < n && cand[p]) oct_atomic_add(&s.cc[4 * p + oct_child_of(ky[j], box[p])], 1);
+            }
         }
         OCT_SYNC();
         for (int p = tid; p < L; p += nt) {
@@ -307,9 +324,15 @@ OCT_DEV int oct_distribute(const uint32_t* keys, uint16_t* knode, int n, int wid
             }
         }
         OCT_SYNC();
-        for (int k = tid; k < n; k += nt) {
-            int p = knode[k];
-            knode[k] = (uint16_t)(s.split[p] ? s.cc[4 * p + oct_child_of(keys[k], box[p])] : s.newpos[p]);
+        for (int k0 = tid; k0 < n; k0 += 4 * nt) {
+            int pp[4]; uint32_t ky[4];
+#pragma unroll
+            for (int j = 0; j < 4; j++) { const int k = k0 + j * nt; pp[j] = k < n ? (int)knode[k] : 0; ky[j] = k < n ? keys[k] : 0u; }
+#pragma unroll
+            for (int j = 0; j < 4; j++) {
+                const int k = k0 + j * nt, p = pp[j];
+                if (k < n) knode[k] = (uint16_t)(s.split[p] ? s.cc[4 * p + oct_child_of(ky[j], box[p])] : s.newpos[p]);
+            }
         }
         // nToExpand = children with more than one key
         for (int p = tid; p < Lnew; p += nt) s.scanA[p] = 0;
@@ -326,8 +349,16 @@ OCT_DEV int oct_distribute(const uint32_t* keys, uint16_t* knode, int n, int wid
     unsigned* best = (unsigned*)s.scanA;
     for (int p = tid; p < L; p += nt) best[p] = 0;
     OCT_SYNC();
-    for (int k = tid; k < n; k += nt)
-        oct_atomic_max(&best[knode[k]], ((unsigned)oct_key_score(keys[k]) << 20) | (unsigned)(0xFFFFF - k));
+    for (int k0 = tid; k0 < n; k0 += 4 * nt) {
+        int pp[4]; uint32_t ky[4];
+#pragma unroll
+        for (int j = 0; j < 4; j++) { const int k = k0 + j * nt; pp[j] = k < n ? (int)knode[k] : 0; ky[j] = k < n ? keys[k] : 0u; }
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            const int k = k0 + j * nt;
+            if (k < n) oct_atomic_max(&best[pp[j]], ((unsigned)oct_key_score(ky[j]) << 20) | (unsigned)(0xFFFFF - k));
+        }
+    }
     OCT_SYNC();
     for (int p = tid; p < L; p += nt) out[p] = keys[0xFFFFF - (int)(best[p] & 0xFFFFFu)];
     OCT_SYNC();
