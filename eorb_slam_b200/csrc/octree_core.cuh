@@ -46,6 +46,10 @@ namespace eorb {
 #define OCT_MAX_THREADS 128
 #endif
 
+#ifndef OCT_KU
+#define OCT_KU 2   // keys per thread and step of the key passes, loads first (measured: 1 -> 0.48, 2 -> 0.38, 4 -> 0.39, 8 -> 0.49 us/frame)
+#endif
+
 struct OctBox { short x0, y0, x1, y1; };
 
 // packed candidate: x | y << 12 | score << 24   (x, y relative to (minBorderX, minBorderY), < 4096)
@@ -190,12 +194,12 @@ OCT_DEV int oct_distribute(const uint32_t* keys, uint16_t* knode, int n, int wid
         s.box[cur][i] = b; s.cnt[cur][i] = 0; s.seq[cur][i] = i;
     }
     OCT_SYNC();
-    for (int k0 = tid; k0 < n; k0 += 4 * nt) {
-        uint32_t ky[4];
+    for (int k0 = tid; k0 < n; k0 += OCT_KU * nt) {
+        uint32_t ky[OCT_KU];
 #pragma unroll
-        for (int j = 0; j < 4; j++) { const int k = k0 + j * nt; ky[j] = k < n ? keys[k] : 0u; }
+        for (int j = 0; j < OCT_KU; j++) { const int k = k0 + j * nt; ky[j] = k < n ? keys[k] : 0u; }
 #pragma unroll
-        for (int j = 0; j < 4; j++) {
+        for (int j = 0; j < OCT_KU; j++) {
             const int k = k0 + j * nt;
             if (k < n) {
                 int slot = (int)((float)oct_key_x(ky[j]) / hX);
@@ -231,12 +235,12 @@ OCT_DEV int oct_distribute(const uint32_t* keys, uint16_t* knode, int n, int wid
         OCT_SYNC();
         // key passes are unrolled by 4 with the loads first: the passes wait on global memory (keys, node positions), and
         // the shared-memory atomics in the body keep the compiler from overlapping the loads of consecutive keys itself
-        for (int k0 = tid; k0 < n; k0 += 4 * nt) {
-            int pp[4]; uint32_t ky[4];
+        for (int k0 = tid; k0 < n; k0 += OCT_KU * nt) {
+            int pp[OCT_KU]; uint32_t ky[OCT_KU];
 #pragma unroll
-            for (int j = 0; j < 4; j++) { const int k = k0 + j * nt; pp[j] = k < n ? (int)knode[k] : 0; ky[j] = k < n ? keys[k] : 0u; }
+            for (int j = 0; j < OCT_KU; j++) { const int k = k0 + j * nt; pp[j] = k < n ? (int)knode[k] : 0; ky[j] = k < n ? keys[k] : 0u; }
 #pragma unroll
-            for (int j = 0; j < 4; j++) {
+            for (int j = 0; j < OCT_KU; j++) {
                 const int k = k0 + j * nt, p = pp[j];
                 if (k < n && cand[p]) oct_atomic_add(&s.cc[4 * p + oct_child_of(ky[j], box[p])], 1);
             }
@@ -324,12 +328,12 @@ OCT_DEV int oct_distribute(const uint32_t* keys, uint16_t* knode, int n, int wid
             }
         }
         OCT_SYNC();
-        for (int k0 = tid; k0 < n; k0 += 4 * nt) {
-            int pp[4]; uint32_t ky[4];
+        for (int k0 = tid; k0 < n; k0 += OCT_KU * nt) {
+            int pp[OCT_KU]; uint32_t ky[OCT_KU];
 #pragma unroll
-            for (int j = 0; j < 4; j++) { const int k = k0 + j * nt; pp[j] = k < n ? (int)knode[k] : 0; ky[j] = k < n ? keys[k] : 0u; }
+            for (int j = 0; j < OCT_KU; j++) { const int k = k0 + j * nt; pp[j] = k < n ? (int)knode[k] : 0; ky[j] = k < n ? keys[k] : 0u; }
 #pragma unroll
-            for (int j = 0; j < 4; j++) {
+            for (int j = 0; j < OCT_KU; j++) {
                 const int k = k0 + j * nt, p = pp[j];
                 if (k < n) knode[k] = (uint16_t)(s.split[p] ? s.cc[4 * p + oct_child_of(ky[j], box[p])] : s.newpos[p]);
             }
@@ -349,12 +353,12 @@ OCT_DEV int oct_distribute(const uint32_t* keys, uint16_t* knode, int n, int wid
     unsigned* best = (unsigned*)s.scanA;
     for (int p = tid; p < L; p += nt) best[p] = 0;
     OCT_SYNC();
-    for (int k0 = tid; k0 < n; k0 += 4 * nt) {
-        int pp[4]; uint32_t ky[4];
+    for (int k0 = tid; k0 < n; k0 += OCT_KU * nt) {
+        int pp[OCT_KU]; uint32_t ky[OCT_KU];
 #pragma unroll
-        for (int j = 0; j < 4; j++) { const int k = k0 + j * nt; pp[j] = k < n ? (int)knode[k] : 0; ky[j] = k < n ? keys[k] : 0u; }
+        for (int j = 0; j < OCT_KU; j++) { const int k = k0 + j * nt; pp[j] = k < n ? (int)knode[k] : 0; ky[j] = k < n ? keys[k] : 0u; }
 #pragma unroll
-        for (int j = 0; j < 4; j++) {
+        for (int j = 0; j < OCT_KU; j++) {
             const int k = k0 + j * nt;
             if (k < n) oct_atomic_max(&best[pp[j]], ((unsigned)oct_key_score(ky[j]) << 20) | (unsigned)(0xFFFFF - k));
         }

@@ -212,7 +212,13 @@ __global__ void __launch_bounds__(OCT_MAX_THREADS) octree_kernel(OrbArgs a) {
         if (cnt > 0) {
             const uint32_t* src = cand + a.cells[lp.cellBase + ci].slotOff;
             uint32_t* dst = okeys + n + s_arr[tid];
-            for (int j = 0; j < cnt; j++) dst[j] = src[j];
+            for (int j = 0; j < cnt; j += 4) {       // loads first (a cell holds ~5 candidates; the copies wait on L2)
+                uint32_t v[4];
+#pragma unroll
+                for (int u = 0; u < 4; u++) v[u] = j + u < cnt ? src[j + u] : 0u;
+#pragma unroll
+                for (int u = 0; u < 4; u++) if (j + u < cnt) dst[j + u] = v[u];
+            }
         }
         n += tot;
         __syncthreads();
