@@ -119,6 +119,7 @@ __global__ void __launch_bounds__(256) ev_splat_gauss_kernel(const eorb_event* _
 // (coalesced) and, when the frame is a single band, min/max + the u8 normalisation are fused into the same block.
 #define EV_SMEM_HALF 3
 #define EV_SMEM_THREADS 1024
+#define EV_SMEM_PAD 8
 
 __device__ __forceinline__ void ev_norm_coeffs(int normMode, float mn, float mx, float& alpha, float& beta) {
     if (normMode == EORB_NORM_RUNNING) {
@@ -137,7 +138,10 @@ __global__ void __launch_bounds__(EV_SMEM_THREADS) ev_frame_smem_kernel(const eo
                                                                         EvConst c, int bandRows, int fuseNorm, int normMode,
                                                                         float* __restrict__ img, float* __restrict__ minmax,
                                                                         uint8_t* __restrict__ u8) {
-    extern __shared__ __align__(16) int s_acc[];
+    // the band is preceded and followed by EV_SMEM_PAD ints: taps that fall outside the frame add 0 to a clamped row at an
+    // unclamped column, which may run up to 6 ints past either end of the band (see the tap loop)
+    extern __shared__ __align__(16) int s_raw[];
+    int* const s_acc = s_raw + EV_SMEM_PAD;
     __shared__ float s_mn[32], s_mx[32];
     const EvWindow w = wins[blockIdx.y];
     const int W = c.width, H = c.height;
@@ -165,25 +169,26 @@ __global__ void __launch_bounds__(EV_SMEM_THREADS) ev_frame_smem_kernel(const eo
         if (!(fxi >= -8.f && fxi <= (float)(W + 8) && fyi >= -8.f && fyi <= (float)(H + 8))) continue;   // also NaN / inf
         const int xi = (int)fxi, yi = (int)fyi;
         if (yi + EV_SMEM_HALF < r0 || yi - EV_SMEM_HALF >= r1) continue;
+        if (xi + EV_SMEM_HALF < 0 || xi - EV_SMEM_HALF >= W) continue;          // no tap inside the frame
         const float xr = __fsub_rn(X, fxi), yr = __fsub_rn(Y, fyi);
         float gx[2 * EV_SMEM_HALF + 1], gy[2 * EV_SMEM_HALF + 1];
         const float amp = polSign * peakTap * scale;
+        // Branch-free taps: a column / row outside the frame gets a ZERO factor instead of a test around its atomics, and
+        // its row pointer is clamped into the band, so every tap is FMUL + F2I + ATOMS at a compile-time offset (adding 0
+        // changes nothing; the uniform form keeps the 32 events of a warp converged).
 #pragma unroll
         for (int i = -EV_SMEM_HALF; i <= EV_SMEM_HALF; i++) {
             const float dx = __fsub_rn((float)i, xr), dy = __fsub_rn((float)i, yr);
-            gx[i + EV_SMEM_HALF] = expf(-(dx * dx) * invDen) * amp;
-            gy[i + EV_SMEM_HALF] = expf(-(dy * dy) * invDen);
+            const float ex_ = expf(-(dx * dx) * invDen) * amp, ey_ = expf(-(dy * dy) * invDen);
+            gx[i + EV_SMEM_HALF] = (unsigned)(xi + i) < (unsigned)W ? ex_ : 0.0f;
+            gy[i + EV_SMEM_HALF] = (yi + i >= r0 && yi + i < r1) ? ey_ : 0.0f;
         }
 #pragma unroll
         for (int j = -EV_SMEM_HALF; j <= EV_SMEM_HALF; j++) {
-            const int yn = yi + j;
-            if (yn < r0 || yn >= r1) continue;
-            int* row = s_acc + (yn - r0) * W;
+            int* row = s_acc + (min(max(yi + j, r0), r1 - 1) - r0) * W + xi;
 #pragma unroll
-            for (int i = -EV_SMEM_HALF; i <= EV_SMEM_HALF; i++) {
-                const int xn = xi + i;
-                if (xn >= 0 && xn < W) atomicAdd(row + xn, __float2int_rn(gx[i + EV_SMEM_HALF] * gy[j + EV_SMEM_HALF]));
-            }
+            for (int i = -EV_SMEM_HALF; i <= EV_SMEM_HALF; i++)
+                atomicAdd(row + i, __float2int_rn(gx[i + EV_SMEM_HALF] * gy[j + EV_SMEM_HALF]));
         }
     }
     __syncthreads();
@@ -493,7 +498,7 @@ cudaError_t launch_ev_frames(const eorb_event* d_evs, const EvWindow* d_wins, in
     if (c.mode != EORB_EV_NEAREST && c.half == EV_SMEM_HALF && maxEventsPerWindow > 0 && (size_t)c.width * 4 * 8 <= smemBudget) {
         const int bands = (int)(((size_t)npix * 4 + smemBudget - 1) / smemBudget);
         const int bandRows = (c.height + bands - 1) / bands;
-        const size_t smem = (((size_t)bandRows * c.width * 4) + 15) & ~(size_t)15;
+        const size_t smem = ((((size_t)bandRows * c.width + 2 * EV_SMEM_PAD) * 4) + 15) & ~(size_t)15;
         cudaError_t ea = cudaFuncSetAttribute(ev_frame_smem_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemBudget + 4096);
         if (ea != cudaSuccess) return ea;
         const int nb = (c.height + bandRows - 1) / bandRows;
