@@ -1189,6 +1189,7 @@ struct eorb_evconv {
     int maxWindows = 0, maxW = 0, maxH = 0;
     long long maxEvents = 0;
     eorb_event* d_evs = nullptr; float* d_img = nullptr; uint8_t* d_u8 = nullptr; float* d_minmax = nullptr;
+    float2* d_xy = nullptr; long long xyCap = 0;   // warped event positions (multi-band motion-compensated frames), grown on demand
     float* d_jac = nullptr;   // 7 frames (I, dI/d[wx wy wz vx vy vz]) of ev2mci_gg_f_jac, allocated on first use
     EvWindow* d_wins = nullptr;
     std::vector<EvWindow> h_wins;
@@ -1217,7 +1218,7 @@ extern "C" int eorb_ev_destroy(eorb_evconv* c) {
     if (!c) return EORB_OK;
     cudaSetDevice(c->device);
     cudaStreamSynchronize(c->stream);
-    cudaFree(c->d_evs); cudaFree(c->d_img); cudaFree(c->d_u8); cudaFree(c->d_minmax); cudaFree(c->d_jac); cudaFree(c->d_wins);
+    cudaFree(c->d_evs); cudaFree(c->d_img); cudaFree(c->d_u8); cudaFree(c->d_minmax); cudaFree(c->d_jac); cudaFree(c->d_wins); cudaFree(c->d_xy);
     cudaStreamDestroy(c->ownStream);
     delete c;
     return EORB_OK;
@@ -1313,7 +1314,18 @@ extern "C" int eorb_ev_accumulate_batch_device(eorb_evconv* c, const eorb_event*
         if (p->mode == EORB_EV_SE3) angleAxisFromPose(poses ? poses + 16 * (size_t)i : p->Tcw, w);
     }
     CU(cudaMemcpyAsync(c->d_wins, c->h_wins.data(), (size_t)nwin * sizeof(EvWindow), cudaMemcpyHostToDevice, c->stream));
-    CU(launch_ev_frames(d_evs, c->d_wins, nwin, maxEv, k, p->normalize, d_img_f32, c->d_minmax, d_img_u8, c->stream, &c->launches));
+    float2* xy = nullptr;
+    if ((p->mode == EORB_EV_SE3 || p->mode == EORB_EV_SE2) && (size_t)k.width * k.height * 4 > 200 * 1024) {
+        const long long need = win_offsets[nwin];
+        if (need > c->xyCap) {
+            CU(cudaStreamSynchronize(c->stream));
+            cudaFree(c->d_xy); c->d_xy = nullptr; c->xyCap = 0;
+            CU(devAlloc(&c->d_xy, (size_t)need));
+            c->xyCap = need;
+        }
+        xy = c->d_xy;
+    }
+    CU(launch_ev_frames(d_evs, c->d_wins, nwin, maxEv, k, p->normalize, d_img_f32, c->d_minmax, d_img_u8, c->stream, &c->launches, xy));
     return EORB_OK;
 }
 

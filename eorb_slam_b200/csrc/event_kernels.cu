@@ -136,10 +136,24 @@ __device__ __forceinline__ void ev_norm_coeffs(int normMode, float mn, float mx,
     }
 }
 
+// warped position of every event of every window, once (used when a frame is split into row bands: every band block would
+// otherwise repeat the warp, and the SE3 warp is ~300 double-precision instructions per event)
+__global__ void __launch_bounds__(256) ev_warp_kernel(const eorb_event* __restrict__ evs, const EvWindow* __restrict__ wins, EvConst c,
+                                                      float2* __restrict__ xy) {
+    const EvWindow w = wins[blockIdx.y];
+    const long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= w.end - w.begin) return;
+    const eorb_event* evp = evs + w.begin + e;
+    const float ex = evp->x, ey = evp->y;
+    float X = ex, Y = ey;
+    ev_warp_point(evs, w, c, evp->ts, ex, ey, X, Y);
+    xy[w.begin + e] = make_float2(X, Y);
+}
+
 __global__ void __launch_bounds__(EV_SMEM_THREADS) ev_frame_smem_kernel(const eorb_event* __restrict__ evs, const EvWindow* __restrict__ wins,
                                                                         EvConst c, int bandRows, int fuseNorm, int normMode,
                                                                         float* __restrict__ img, float* __restrict__ minmax,
-                                                                        uint8_t* __restrict__ u8) {
+                                                                        uint8_t* __restrict__ u8, const float2* __restrict__ xy) {
     // the band is preceded and followed by EV_SMEM_PAD ints: taps that fall outside the frame add 0 to a clamped row at an
     // unclamped column, which may run up to 6 ints past either end of the band (see the tap loop)
     extern __shared__ __align__(16) int s_raw[];
@@ -162,11 +176,17 @@ __global__ void __launch_bounds__(EV_SMEM_THREADS) ev_frame_smem_kernel(const eo
 
     for (long long e = tid; e < nev; e += EV_SMEM_THREADS) {
         const eorb_event* evp = evs + w.begin + e;
-        const double ts = evp->ts;
-        const float ex = evp->x, ey = evp->y;
         const float polSign = (c.pol && evp->p == 0) ? -1.0f : 1.0f;
-        float X = ex, Y = ey;
-        ev_warp_point(evs, w, c, ts, ex, ey, X, Y);
+        float X, Y;
+        if (xy) {   // multi-band warped frames: the per-event warp (double precision for SE3) was done once by ev_warp_kernel
+            const float2 v = __ldg(xy + w.begin + e);
+            X = v.x; Y = v.y;
+        } else {
+            const double ts = evp->ts;
+            const float ex = evp->x, ey = evp->y;
+            X = ex; Y = ey;
+            ev_warp_point(evs, w, c, ts, ex, ey, X, Y);
+        }
         const float fxi = floorf(X), fyi = floorf(Y);
         if (!(fxi >= -8.f && fxi <= (float)(W + 8) && fyi >= -8.f && fyi <= (float)(H + 8))) continue;   // also NaN / inf
         const int xi = (int)fxi, yi = (int)fyi;
@@ -221,7 +241,10 @@ __global__ void __launch_bounds__(EV_SMEM_THREADS) ev_frame_smem_kernel(const eo
     }
     if ((tid & 31) == 0) { s_mn[tid >> 5] = mn; s_mx[tid >> 5] = mx; }
     __syncthreads();
-    mn = s_mn[tid & 31]; mx = s_mx[tid & 31];
+    {   // second stage over the block's warps (fewer than 32 when the block has fewer than 1024 threads)
+        const bool has = (tid & 31) < EV_SMEM_THREADS / 32;
+        mn = has ? s_mn[tid & 31] : 3.4e38f; mx = has ? s_mx[tid & 31] : -3.4e38f;
+    }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
         mn = fminf(mn, __shfl_xor_sync(0xffffffffu, mn, o));
@@ -493,7 +516,8 @@ cudaError_t launch_ev_jac(const eorb_event* d_evs, const EvWindow* d_win, long l
 // whole path: zero + splat + min/max + normalise.  7x7 Gaussian windows take the shared-memory kernel (which also
 // zeroes and, for single-band frames, normalises); everything else the L2-reduction kernels.
 cudaError_t launch_ev_frames(const eorb_event* d_evs, const EvWindow* d_wins, int nwin, long long maxEventsPerWindow, const EvConst& c,
-                             int normMode, float* d_img, float* d_minmax, uint8_t* d_u8, cudaStream_t st, long long* launches) {
+                             int normMode, float* d_img, float* d_minmax, uint8_t* d_u8, cudaStream_t st, long long* launches,
+                             float2* d_xyScratch) {
     if (nwin <= 0) return cudaSuccess;
     const int npix = c.width * c.height;
     const size_t smemBudget = 200 * 1024;
@@ -506,7 +530,14 @@ cudaError_t launch_ev_frames(const eorb_event* d_evs, const EvWindow* d_wins, in
         const int nb = (c.height + bandRows - 1) / bandRows;
         const int fuse = nb == 1 ? 1 : 0;
         dim3 grd(nb, nwin);
-        ev_frame_smem_kernel<<<grd, EV_SMEM_THREADS, smem, st>>>(d_evs, d_wins, c, bandRows, fuse, normMode, d_img, d_minmax, d_u8);
+        const float2* xy = nullptr;
+        if (nb > 1 && d_xyScratch && (c.mode == EORB_EV_SE3 || c.mode == EORB_EV_SE2)) {
+            dim3 gw((unsigned)((maxEventsPerWindow + 255) / 256), nwin);
+            ev_warp_kernel<<<gw, 256, 0, st>>>(d_evs, d_wins, c, d_xyScratch);
+            (*launches)++;
+            xy = d_xyScratch;
+        }
+        ev_frame_smem_kernel<<<grd, EV_SMEM_THREADS, smem, st>>>(d_evs, d_wins, c, bandRows, fuse, normMode, d_img, d_minmax, d_u8, xy);
         (*launches)++;
         cudaError_t e = cudaGetLastError();
         if (e != cudaSuccess || fuse) return e;

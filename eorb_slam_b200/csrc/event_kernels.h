@@ -28,7 +28,8 @@ struct EvConst {
 cudaError_t launch_ev_splat(const eorb_event* d_evs, const EvWindow* d_wins, int nwin, long long maxEventsPerWindow,
                             const EvConst& c, float* d_img, cudaStream_t st, long long* launches);
 cudaError_t launch_ev_frames(const eorb_event* d_evs, const EvWindow* d_wins, int nwin, long long maxEventsPerWindow, const EvConst& c,
-                             int normMode, float* d_img, float* d_minmax, uint8_t* d_u8, cudaStream_t st, long long* launches);
+                             int normMode, float* d_img, float* d_minmax, uint8_t* d_u8, cudaStream_t st, long long* launches,
+                             float2* d_xyScratch = nullptr);   // [>= last window end] floats pairs: enables the one-pass warp for multi-band frames
 #define EORB_EV_FOCUS_MAX_CELLS 1024
 cudaError_t launch_ev_focus(const float* d_img, int nwin, int W, int H, int patch, int what, int avg, float* d_out, cudaStream_t st,
                             long long* launches);
