@@ -392,7 +392,29 @@ def bench_guided(api, torch, dev, steps, warmup):
         O.search_for_initialization(k1, d1, k2, d2, b, prev, 100, 0.9, True)
     ms_port = (time.perf_counter() - t0) * 1e3 / 5
     lvl0 = int((k1["octave"] == 0).sum())
-    return {"metric": "search_for_initialization_calls_per_s", "value": 1e3 / ms, "unit": "calls/s", "ms_per_call": ms,
+    # the tracking-rate caller: SearchByProjection(CurrentFrame, LastFrame, th = 15, bMono) between two 1000-feature frames
+    proj = {}
+    try:
+        c = synth.make_projection_case(1009, 1009, 41)
+        gp = api.GuidedMatcher(dev, 0.9, True)
+        a = (c["x3Dc"], c["valid1"], c["obs1"], c["kps1"], c["descMP"], c["kps2"], c["desc2"], c["bounds"], c["K"], c["scale_factors"])
+        for _ in range(3):
+            pn, pmc = gp.SearchByProjection(*a, 15.0)
+        t0 = time.perf_counter()
+        for _ in range(reps):
+            pn, pmc = gp.SearchByProjection(*a, 15.0)
+        pms = (time.perf_counter() - t0) * 1e3 / reps
+        pen, pemc = O.search_by_projection(*a, 15.0, True)
+        t0 = time.perf_counter()
+        for _ in range(20):
+            O.search_by_projection(*a, 15.0, True)
+        pms_port = (time.perf_counter() - t0) * 1e3 / 20
+        proj = {"ms_per_call": pms, "workload": "ORBmatcher::SearchByProjection(CurrentFrame, LastFrame, 15, mono): 1009 x 1009 keypoints, %d valid map points, "
+                "%d matches; host call" % (int(c["valid1"].sum()), pen), "bit_exact_vs_oracle": bool(pn == pen and np.array_equal(pmc, pemc)),
+                "cpu_port_ms_per_call": pms_port}
+    except Exception as e:
+        proj = {"error": repr(e)}
+    return {"search_by_projection": proj, "metric": "search_for_initialization_calls_per_s", "value": 1e3 / ms, "unit": "calls/s", "ms_per_call": ms,
             "ms_per_call_device_resident": float(np.median(dev_ms)),
             "workload": "ORBmatcher::SearchForInitialization: 5000 x 5000 keypoints (%d level-0 queries), window 100, ratio 0.9, "
                         "rotation check; %d matches" % (lvl0, en),

@@ -95,6 +95,8 @@ def _load():
         "eorb_guided_features_in_area": ([vp, vp, i, vp, vp, i, vp, vp, i], i),
         "eorb_guided_search_for_initialization": ([vp, vp, vp, i, vp, vp, i, vp, vp, i, f, i, vp, vp], i),
         "eorb_guided_search_for_initialization_device": ([vp, vp, vp, i, vp, vp, i, vp, vp, i, f, i, vp, vp], i),
+        "eorb_guided_search_by_projection": ([vp, vp, vp, vp, vp, vp, i, vp, vp, i, vp, vp, vp, i, f, i, vp, vp], i),
+        "eorb_guided_search_by_projection_device": ([vp, vp, vp, vp, vp, vp, i, vp, vp, i, vp, vp, vp, i, f, i, vp, vp], i),
         "eorb_vocab_create": ([i, i, i, i, i, i, vp, vp, vp, vp, C.POINTER(vp)], i), "eorb_vocab_destroy": ([vp], i),
         "eorb_vocab_set_stream": ([vp, vp], i), "eorb_vocab_reset_stream": ([vp], i), "eorb_vocab_launch_count": ([vp], C.c_longlong),
         "eorb_vocab_transform": ([vp, vp, i, i, vp, vp, vp, vp, vp, vp, vp, vp, vp], i),
@@ -665,6 +667,20 @@ class GuidedMatcher:
                                                          int(windowSize), self.mfNNratio, int(self.mbCheckOrientation), _p(m12),
                                                          C.byref(nm)), "SearchForInitialization")
         return nm.value, m12[:len(k1)].copy(), prev
+
+    def SearchByProjection(self, x3Dc, valid1, obs1, kps1, descMP, kps2, desc2, bounds, K4, scale_factors, th=15.0):
+        """ORBmatcher::SearchByProjection(CurrentFrame, LastFrame, th, bMono=True) (:1969-2150) -> (nmatches, match_cur[n2]):
+        match_cur[i2] = last-frame index whose map point is assigned to current-frame keypoint i2, or -1"""
+        x = np.ascontiguousarray(x3Dc, np.float32).reshape(-1, 3); v = np.ascontiguousarray(valid1, np.uint8); o = np.ascontiguousarray(obs1, np.int32)
+        k1 = np.ascontiguousarray(kps1, KEYPOINT_DTYPE); k2 = np.ascontiguousarray(kps2, KEYPOINT_DTYPE)
+        dm = np.ascontiguousarray(descMP, np.uint8); d2 = np.ascontiguousarray(desc2, np.uint8)
+        b = np.ascontiguousarray(bounds, np.float32); K = np.ascontiguousarray(K4, np.float32); sf = np.ascontiguousarray(scale_factors, np.float32)
+        mc = np.full(max(len(k2), 1), -1, np.int32)
+        nm = C.c_int(0)
+        _check(lib.eorb_guided_search_by_projection(self.h, _p(x), _p(v), _p(o), _p(k1), _p(dm), len(k1), _p(k2), _p(d2), len(k2), _p(b), _p(K),
+                                                    _p(sf), len(sf), float(th), int(self.mbCheckOrientation), _p(mc), C.byref(nm)),
+               "SearchByProjection")
+        return nm.value, mc[:len(k2)].copy()
 
     def SearchForInitialization_device(self, d_kps1, d_desc1, n1, d_kps2, d_desc2, n2, bounds, d_prev, d_matches12, windowSize=100):
         """all pointers are device addresses (ints); returns nmatches"""

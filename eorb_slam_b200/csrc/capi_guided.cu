@@ -32,6 +32,9 @@ struct eorb_guided {
     // staging for the host entry points (frames 1 and 2) + work buffers, grown on demand
     eorb_keypoint* d_kps[2] = {nullptr, nullptr}; uint8_t* d_desc[2] = {nullptr, nullptr}; int kpCap[2] = {0, 0};
     float* d_prev = nullptr; int32_t* d_m12 = nullptr; int q1Cap = 0;
+    // SearchByProjection staging: camera-frame points, validity, observations (frame 1), match table (frame 2)
+    float* d_x3 = nullptr; uint8_t* d_valid = nullptr; int32_t* d_obs = nullptr; int pCap1 = 0;
+    int32_t* d_mc = nullptr; int pCap2 = 0;
     GuidedWork w{};
     int workN1 = 0, workN2 = 0;
     int* d_nm = nullptr; int* h_nm = nullptr;          // [nmatches, total candidates] device + pinned mirror
@@ -76,7 +79,7 @@ extern "C" int eorb_guided_destroy(eorb_guided* g) {
     cudaSetDevice(g->device);
     cudaStreamSynchronize(g->stream);
     for (int k = 0; k < 2; k++) { cudaFree(g->d_kps[k]); cudaFree(g->d_desc[k]); }
-    cudaFree(g->d_prev); cudaFree(g->d_m12);
+    cudaFree(g->d_prev); cudaFree(g->d_m12); cudaFree(g->d_x3); cudaFree(g->d_valid); cudaFree(g->d_obs); cudaFree(g->d_mc); cudaFree(g->w.q);
     cudaFree(g->w.cellStart); cudaFree(g->w.cellIdx); cudaFree(g->w.assigned); cudaFree(g->w.candOff); cudaFree(g->w.candCnt);
     cudaFree(g->w.top); cudaFree(g->w.bin); cudaFree(g->w.cand);
     cudaFree(g->d_nm); cudaFreeHost(g->h_nm); cudaFree(g->d_q); cudaFree(g->d_cnt); cudaFree(g->d_out);
@@ -126,13 +129,14 @@ static int reserveWork(eorb_guided* g, int n1, int n2) {
     }
     if (n1 > g->workN1) {
         CU(cudaStreamSynchronize(g->stream));
-        cudaFree(g->w.candOff); cudaFree(g->w.candCnt); cudaFree(g->w.top); cudaFree(g->w.bin);
-        g->w.candOff = g->w.candCnt = nullptr; g->w.top = nullptr; g->w.bin = nullptr; g->workN1 = 0;
+        cudaFree(g->w.candOff); cudaFree(g->w.candCnt); cudaFree(g->w.top); cudaFree(g->w.bin); cudaFree(g->w.q);
+        g->w.candOff = g->w.candCnt = nullptr; g->w.top = nullptr; g->w.bin = nullptr; g->w.q = nullptr; g->workN1 = 0;
         const int cap = std::max(1024, n1);
         CU(cudaMalloc((void**)&g->w.candOff, (size_t)cap * sizeof(int)));
         CU(cudaMalloc((void**)&g->w.candCnt, (size_t)cap * sizeof(int)));
         CU(cudaMalloc((void**)&g->w.top, (size_t)cap * EORB_GUIDED_TOP * sizeof(unsigned long long)));
         CU(cudaMalloc((void**)&g->w.bin, (size_t)cap));
+        CU(cudaMalloc((void**)&g->w.q, (size_t)cap * sizeof(eorb_area_query)));
         g->workN1 = cap;
     }
     if (!g->w.cand) {
@@ -260,6 +264,108 @@ extern "C" int eorb_guided_search_for_initialization(eorb_guided* g, const eorb_
     if (rc != EORB_OK) return rc;
     CU(cudaMemcpyAsync(matches12, g->d_m12, (size_t)n1 * sizeof(int32_t), cudaMemcpyDeviceToHost, g->stream));
     CU(cudaMemcpyAsync(prev_xy, g->d_prev, (size_t)n1 * 2 * sizeof(float), cudaMemcpyDeviceToHost, g->stream));
+    CU(cudaStreamSynchronize(g->stream));
+    return EORB_OK;
+}
+
+// ------------------------------------------------------------------------------------------------ SearchByProjection
+static int projConst(const float* bounds4, const float* K4, const float* scale_factors, int nlevels, float th, GuidedProj& pr) {
+    if (!K4 || !scale_factors || nlevels < 1 || nlevels > 32) return gFail(EORB_ERR_ARG, "eorb_guided_search_by_projection", "bad intrinsics / scale table (1..32 levels)");
+    pr.fx = K4[0]; pr.fy = K4[1]; pr.cx = K4[2]; pr.cy = K4[3];
+    pr.minX = bounds4[0]; pr.minY = bounds4[1]; pr.maxX = bounds4[2]; pr.maxY = bounds4[3];
+    pr.th = th; pr.nlevels = nlevels;
+    for (int i = 0; i < 32; i++) pr.scale[i] = i < nlevels ? scale_factors[i] : 1.0f;
+    return EORB_OK;
+}
+
+static int searchProjRun(eorb_guided* g, const float* d_x3, const uint8_t* d_valid, const int32_t* d_obs, const eorb_keypoint* d_k1,
+                         const uint8_t* d_dmp, int n1, const eorb_keypoint* d_k2, const uint8_t* d_d2, int n2, const float* bounds4,
+                         const GuidedProj& pr, int checkOri, int32_t* d_mc, int* nmatches) {
+    int rc = reserveWork(g, n1, n2);
+    if (rc != EORB_OK) return rc;
+    if (n1 > g->q1Cap) {   // claim[n1] lives in the matches12 staging buffer
+        CU(cudaStreamSynchronize(g->stream));
+        cudaFree(g->d_prev); cudaFree(g->d_m12);
+        g->d_prev = nullptr; g->d_m12 = nullptr; g->q1Cap = 0;
+        const int cap = std::max(1024, n1);
+        CU(cudaMalloc((void**)&g->d_prev, (size_t)cap * 2 * sizeof(float)));
+        CU(cudaMalloc((void**)&g->d_m12, (size_t)cap * sizeof(int32_t)));
+        g->q1Cap = cap;
+    }
+    GuidedFrame f2{d_k2, d_d2, n2};
+    const GuidedGrid gg = gridGeom(bounds4);
+    for (int attempt = 0; attempt < 2; attempt++) {
+        CU(launch_search_proj(d_x3, d_valid, d_obs, d_k1, d_dmp, n1, f2, gg, pr, checkOri, g->w, g->d_m12, d_mc, g->d_nm, g->stream, &g->launches));
+        CU(cudaMemcpyAsync(g->h_nm, g->d_nm, 2 * sizeof(int), cudaMemcpyDeviceToHost, g->stream));
+        CU(cudaStreamSynchronize(g->stream));
+        if (g->h_nm[1] <= g->w.candCap) { if (nmatches) *nmatches = g->h_nm[0]; return EORB_OK; }
+        cudaFree(g->w.cand); g->w.cand = nullptr;
+        g->w.candCap = g->h_nm[1] + g->h_nm[1] / 4;
+        CU(cudaMalloc((void**)&g->w.cand, (size_t)g->w.candCap * sizeof(uint32_t)));
+    }
+    return gFail(EORB_ERR_STATE, "eorb_guided_search_by_projection", "candidate buffer overflow after growth");
+}
+
+extern "C" int eorb_guided_search_by_projection_device(eorb_guided* g, const float* d_x3Dc, const uint8_t* d_valid1, const int32_t* d_obs1,
+                                                       const eorb_keypoint* d_kps1, const uint8_t* d_descMP, int n1, const eorb_keypoint* d_kps2,
+                                                       const uint8_t* d_desc2, int n2, const float* bounds4, const float* K4,
+                                                       const float* scale_factors, int nlevels, float th, int check_ori,
+                                                       int32_t* d_match_cur, int* nmatches) {
+    if (!g) return gFail(EORB_ERR_ARG, "eorb_guided_search_by_projection_device", "null handle");
+    int rc = checkFrames(d_kps1, n1, d_kps2, n2, bounds4);
+    if (rc != EORB_OK) return rc;
+    if (nmatches) *nmatches = 0;
+    if (n2 == 0) return EORB_OK;
+    if (!d_match_cur || !d_desc2 || (n1 > 0 && (!d_x3Dc || !d_valid1 || !d_obs1 || !d_descMP)))
+        return gFail(EORB_ERR_ARG, "eorb_guided_search_by_projection_device", "null argument");
+    if (((uintptr_t)d_descMP | (uintptr_t)d_desc2) & 15) return gFail(EORB_ERR_ARG, "eorb_guided_search_by_projection_device", "descriptors must be 16-byte aligned");
+    GuidedProj pr;
+    if ((rc = projConst(bounds4, K4, scale_factors, nlevels, th, pr)) != EORB_OK) return rc;
+    CU(cudaSetDevice(g->device));
+    return searchProjRun(g, d_x3Dc, d_valid1, d_obs1, d_kps1, d_descMP, n1, d_kps2, d_desc2, n2, bounds4, pr, check_ori, d_match_cur, nmatches);
+}
+
+extern "C" int eorb_guided_search_by_projection(eorb_guided* g, const float* x3Dc, const uint8_t* valid1, const int32_t* obs1,
+                                                const eorb_keypoint* kps1, const uint8_t* descMP, int n1, const eorb_keypoint* kps2,
+                                                const uint8_t* desc2, int n2, const float* bounds4, const float* K4, const float* scale_factors,
+                                                int nlevels, float th, int check_ori, int32_t* match_cur, int* nmatches) {
+    if (!g) return gFail(EORB_ERR_ARG, "eorb_guided_search_by_projection", "null handle");
+    int rc = checkFrames(kps1, n1, kps2, n2, bounds4);
+    if (rc != EORB_OK) return rc;
+    if (nmatches) *nmatches = 0;
+    if (n2 == 0) return EORB_OK;
+    if (!match_cur || !desc2 || (n1 > 0 && (!x3Dc || !valid1 || !obs1 || !descMP))) return gFail(EORB_ERR_ARG, "eorb_guided_search_by_projection", "null argument");
+    GuidedProj pr;
+    if ((rc = projConst(bounds4, K4, scale_factors, nlevels, th, pr)) != EORB_OK) return rc;
+    CU(cudaSetDevice(g->device));
+    if ((rc = stageFrame(g, 0, kps1, descMP, n1)) != EORB_OK) return rc;
+    if ((rc = stageFrame(g, 1, kps2, desc2, n2)) != EORB_OK) return rc;
+    if (n1 > g->pCap1) {
+        CU(cudaStreamSynchronize(g->stream));
+        cudaFree(g->d_x3); cudaFree(g->d_valid); cudaFree(g->d_obs);
+        g->d_x3 = nullptr; g->d_valid = nullptr; g->d_obs = nullptr; g->pCap1 = 0;
+        const int cap = std::max(1024, n1);
+        CU(cudaMalloc((void**)&g->d_x3, (size_t)cap * 3 * sizeof(float)));
+        CU(cudaMalloc((void**)&g->d_valid, (size_t)cap));
+        CU(cudaMalloc((void**)&g->d_obs, (size_t)cap * sizeof(int32_t)));
+        g->pCap1 = cap;
+    }
+    if (n2 > g->pCap2) {
+        CU(cudaStreamSynchronize(g->stream));
+        cudaFree(g->d_mc); g->d_mc = nullptr; g->pCap2 = 0;
+        const int cap = std::max(1024, n2);
+        CU(cudaMalloc((void**)&g->d_mc, (size_t)cap * sizeof(int32_t)));
+        g->pCap2 = cap;
+    }
+    if (n1 > 0) {
+        CU(cudaMemcpyAsync(g->d_x3, x3Dc, (size_t)n1 * 3 * sizeof(float), cudaMemcpyHostToDevice, g->stream));
+        CU(cudaMemcpyAsync(g->d_valid, valid1, (size_t)n1, cudaMemcpyHostToDevice, g->stream));
+        CU(cudaMemcpyAsync(g->d_obs, obs1, (size_t)n1 * sizeof(int32_t), cudaMemcpyHostToDevice, g->stream));
+    }
+    rc = searchProjRun(g, g->d_x3, g->d_valid, g->d_obs, g->d_kps[0], g->d_desc[0], n1, g->d_kps[1], g->d_desc[1], n2, bounds4, pr, check_ori,
+                       g->d_mc, nmatches);
+    if (rc != EORB_OK) return rc;
+    CU(cudaMemcpyAsync(match_cur, g->d_mc, (size_t)n2 * sizeof(int32_t), cudaMemcpyDeviceToHost, g->stream));
     CU(cudaStreamSynchronize(g->stream));
     return EORB_OK;
 }

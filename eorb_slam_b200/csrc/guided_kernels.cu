@@ -144,24 +144,38 @@ __device__ __forceinline__ u64 warp_sort32(u64 v, int lane) {
     return v;
 }
 
+// Queries: SearchForInitialization (qs == nullptr): frame-1 keypoint i1 at level 0, window `r0win` around prevXY[i1], levels
+// [0, 0] (ORBmatcher.cc:732-736).  SearchByProjection (qs != nullptr): the window and level range guided_project_kernel
+// prepared for last-frame keypoint i1 (r <= 0: no query); f1.desc then holds the map points' descriptors.
 __global__ void __launch_bounds__(256) guided_candidates_kernel(GuidedFrame f1, GuidedFrame f2, GuidedGrid g, const float* __restrict__ prevXY,
-                                                                float r, GuidedWork w) {
+                                                                float r0win, const eorb_area_query* __restrict__ qs, GuidedWork w) {
     const int i1 = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
     if (i1 >= f1.n) return;
     const unsigned lt = (1u << lane) - 1u;
     if (lane == 0) w.bin[i1] = -1;
-    const int level1 = f1.kps[i1].octave;
+    float x, y, r;
+    int minL, maxL;
+    bool live;
+    if (qs) {
+        const eorb_area_query q = qs[i1];
+        x = q.x; y = q.y; r = q.r; minL = q.min_level; maxL = q.max_level;
+        live = r > 0.0f;
+    } else {
+        const int level1 = f1.kps[i1].octave;
+        x = prevXY[2 * i1]; y = prevXY[2 * i1 + 1]; r = r0win; minL = level1; maxL = level1;
+        live = level1 <= 0;
+    }
+    const bool check = minL > 0 || maxL >= 0;              // bCheckLevels (Frame.cc:746)
     int c0 = 0, c1 = -1, r0 = 0, r1 = 0;
-    const float x = prevXY[2 * i1], y = prevXY[2 * i1 + 1];
-    bool live = level1 <= 0 && area_cells(g, x, y, r, c0, c1, r0, r1);
-    // pass 1: count (minLevel = maxLevel = level1 = 0 -> bCheckLevels is true, Frame.cc:746)
+    live = live && area_cells(g, x, y, r, c0, c1, r0, r1);
+    // pass 1: count
     int cnt = 0;
     if (live)
         for (int ix = c0; ix <= c1; ix++) {
             const int b = w.cellStart[ix * EORB_GRID_ROWS + r0], e = w.cellStart[ix * EORB_GRID_ROWS + r1 + 1];
             for (int base = b; base < e; base += 32) {
                 const int j = base + lane;
-                const bool ok = j < e && area_accept(f2.kps, w.cellIdx[j], x, y, r, true, level1, level1);
+                const bool ok = j < e && area_accept(f2.kps, w.cellIdx[j], x, y, r, check, minL, maxL);
                 cnt += __popc(__ballot_sync(FULLMASK, ok));
             }
         }
@@ -186,7 +200,7 @@ __global__ void __launch_bounds__(256) guided_candidates_kernel(GuidedFrame f1, 
             const int j = base + lane;
             int i2 = 0;
             bool ok = false;
-            if (j < e) { i2 = w.cellIdx[j]; ok = area_accept(f2.kps, i2, x, y, r, true, level1, level1); }
+            if (j < e) { i2 = w.cellIdx[j]; ok = area_accept(f2.kps, i2, x, y, r, check, minL, maxL); }
             const unsigned m = __ballot_sync(FULLMASK, ok);
             if (m == 0) continue;
             u64 key = ~0ull;
@@ -377,14 +391,193 @@ __global__ void __launch_bounds__(256) guided_resolve_kernel(GuidedFrame f1, Gui
     if (tid == 0) *nmatchesOut = sNm;
 }
 
+// ------------------------------------------------------------------------------------------------ SearchByProjection
+// P1 guided_project_kernel: per last-frame keypoint the window of ORBmatcher::SearchByProjection(CurrentFrame, LastFrame, th,
+// bMono = true) (ORBmatcher.cc:1995-2032): camera-frame point (formed by the caller) -> invzc < 0 test, Pinhole::project in
+// float (Pinhole.cpp:30-33), image-bounds test, radius = th * mvScaleFactors[clamp(octave)], levels [octave-1, octave+1].
+__global__ void __launch_bounds__(256) guided_project_kernel(const float* __restrict__ x3Dc, const uint8_t* __restrict__ valid1,
+                                                             const eorb_keypoint* __restrict__ kps1, int n1, GuidedProj pr,
+                                                             eorb_area_query* __restrict__ qs) {
+    const int i = blockIdx.x * 256 + threadIdx.x;
+    if (i >= n1) return;
+    eorb_area_query q;
+    q.x = 0.f; q.y = 0.f; q.r = -1.f; q.min_level = 0; q.max_level = -1;
+    if (valid1[i]) {
+        const float xc = x3Dc[3 * i], yc = x3Dc[3 * i + 1], zc = x3Dc[3 * i + 2];
+        if (zc > 0.0f || zc != zc) {   // invzc = 1.0 / zc < 0 (and the undefined z == 0) are skipped; NaN passes like in the reference
+            const float u = __fadd_rn(__fdiv_rn(__fmul_rn(pr.fx, xc), zc), pr.cx), v = __fadd_rn(__fdiv_rn(__fmul_rn(pr.fy, yc), zc), pr.cy);
+            if (!(u < pr.minX || u > pr.maxX) && !(v < pr.minY || v > pr.maxY)) {
+                const int oct = kps1[i].octave;
+                const int lv = oct < 0 ? 0 : (oct >= pr.nlevels ? pr.nlevels - 1 : oct);
+                q.x = u; q.y = v; q.r = __fmul_rn(pr.th, pr.scale[lv]); q.min_level = oct - 1; q.max_level = oct + 1;
+            }
+        }
+    }
+    qs[i] = q;
+}
+
+// P3 guided_resolve_proj_kernel: the order-dependent part (:2042-2070): a current-frame keypoint whose slot holds a map point
+// WITH observations is skipped by every later query, so the best candidate of a query is the first unblocked entry of its
+// sorted head.  Same structure as guided_resolve_kernel (one ordered warp, seven staging warps, full-list slow path); a
+// query's claim is recorded in claim[i]; the owner of a slot is its LAST claimer; every claim enters the rotation histogram
+// (:2073-2089) and a claim in a non-maximal bin un-sets its slot whoever owns it by then (:2141-2150).
+__global__ void __launch_bounds__(256) guided_resolve_proj_kernel(const eorb_keypoint* __restrict__ kps1, const int32_t* __restrict__ obs1, int n1,
+                                                                  GuidedFrame f2, int checkOri, GuidedWork w, int32_t* __restrict__ claim,
+                                                                  int32_t* __restrict__ matchCur, int* __restrict__ nmatchesOut) {
+    extern __shared__ __align__(16) unsigned char sm[];
+    const int n2 = f2.n, n2r = (n2 + 3) & ~3;
+    u64* stop = reinterpret_cast<u64*>(sm);                               // [2][GUIDED_STAGE][32]
+    int* scnt = reinterpret_cast<int*>(stop + 2 * GUIDED_STAGE * 32);     // [2][GUIDED_STAGE]
+    int* soff = scnt + 2 * GUIDED_STAGE;                                  // [2][GUIDED_STAGE]
+    int* sobs = soff + 2 * GUIDED_STAGE;                                  // [2][GUIDED_STAGE] observations of the query's map point
+    int* hist = sobs + 2 * GUIDED_STAGE;                                  // [32]
+    unsigned short* owner = reinterpret_cast<unsigned short*>(hist + 32); // [n2r] last claimer (0xffff = none)
+    unsigned short* qlist = owner + n2r;                                  // [n1]
+    unsigned char* blk = reinterpret_cast<unsigned char*>(qlist + ((n1 + 1) & ~1));   // [n2r] slot blocked / (later) un-set flag
+    __shared__ int sNm, sInd[3], sWarp[8];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+
+    if (*w.total > w.candCap) {
+        if (tid == 0) *nmatchesOut = -1;
+        return;
+    }
+    for (int i = tid; i < n2; i += 256) { owner[i] = GUIDED_NONE; blk[i] = 0; }
+    for (int i = tid; i < n1; i += 256) claim[i] = -1;
+    if (tid < 32) hist[tid] = 0;
+    if (tid == 0) sNm = 0;
+    int nact = 0;
+    for (int base = 0; base < n1; base += 256) {
+        const int i1 = base + tid;
+        const bool act = i1 < n1 && w.candCnt[i1] > 0;
+        const unsigned bm = __ballot_sync(FULLMASK, act);
+        if (lane == 0) sWarp[warp] = __popc(bm);
+        __syncthreads();
+        int before = 0, total = 0;
+#pragma unroll
+        for (int k = 0; k < 8; k++) { const int v = sWarp[k]; total += v; if (k < warp) before += v; }
+        if (act) qlist[nact + before + __popc(bm & ((1u << lane) - 1u))] = (unsigned short)i1;
+        nact += total;
+        __syncthreads();
+    }
+    const int nrounds = (nact + GUIDED_STAGE - 1) / GUIDED_STAGE;
+    auto loadStage = [&](int r, int t0, int nth) {
+        u64* sp = stop + (r & 1) * GUIDED_STAGE * 32;
+        for (int t = tid - t0; t < GUIDED_STAGE * 32; t += nth) {
+            const int q = r * GUIDED_STAGE + (t >> 5);
+            sp[t] = q < nact ? w.top[(size_t)qlist[q] * EORB_GUIDED_TOP + (t & 31)] : ~0ull;
+        }
+        for (int k = tid - t0; k < GUIDED_STAGE; k += nth) {
+            const int q = r * GUIDED_STAGE + k, o = (r & 1) * GUIDED_STAGE + k;
+            scnt[o] = q < nact ? w.candCnt[qlist[q]] : 0;
+            soff[o] = q < nact ? w.candOff[qlist[q]] : 0;
+            sobs[o] = q < nact ? obs1[qlist[q]] : 0;
+        }
+    };
+    if (nrounds > 0) loadStage(0, 0, 256);
+    __syncthreads();
+
+    for (int r = 0; r < nrounds; r++) {
+        if (warp != 0) {
+            if (r + 1 < nrounds) loadStage(r + 1, 32, 224);
+        } else {
+            const u64* sp = stop + (r & 1) * GUIDED_STAGE * 32;
+            const int so = (r & 1) * GUIDED_STAGE;
+            const int kend = min(GUIDED_STAGE, nact - r * GUIDED_STAGE);
+            u64 eN = sp[lane];
+            for (int k = 0; k < kend; k++) {
+                const u64 e = eN;
+                if (k + 1 < kend) eN = sp[(k + 1) * 32 + lane];
+                const uint32_t dist = (uint32_t)(e >> 32), i2 = e != ~0ull ? (uint32_t)e & 0xffffu : 0u;
+                const bool ok = e != ~0ull && blk[i2] == 0;               // slot held by a point with observations -> skipped (:2046)
+                const unsigned mask = __ballot_sync(FULLMASK, ok);
+                int bestDist = 256, bestIdx = -1;
+                if (mask != 0 || scnt[so + k] <= EORB_GUIDED_TOP) {
+                    const uint32_t b1 = __shfl_sync(FULLMASK, (dist << 16) | i2, __ffs(mask) - 1);
+                    if (mask) { bestDist = (int)(b1 >> 16); bestIdx = (int)(b1 & 0xffffu); }
+                } else {   // every head entry is blocked: scan the whole list
+                    uint32_t k1 = 0xffffffffu;
+                    const int c = scnt[so + k], off = soff[so + k];
+                    for (int p = lane; p < c; p += 32) {
+                        const uint32_t ce = w.cand[off + p];
+                        if (blk[ce & 0xffffu] == 0) k1 = min(k1, ((ce >> 16) << 16) | (uint32_t)p);
+                    }
+                    k1 = __reduce_min_sync(FULLMASK, k1);
+                    if (k1 != 0xffffffffu) { bestDist = (int)(k1 >> 16); bestIdx = (int)(w.cand[off + (k1 & 0xffffu)] & 0xffffu); }
+                }
+                if (bestDist <= 100) {                                    // TH_HIGH (:2068)
+                    if (lane == 0) {
+                        const int i1 = qlist[r * GUIDED_STAGE + k];
+                        owner[bestIdx] = (unsigned short)i1;
+                        blk[bestIdx] = sobs[so + k] > 0 ? 1 : 0;
+                        claim[i1] = bestIdx;
+                    }
+                    __syncwarp();
+                }
+            }
+        }
+        __syncthreads();
+    }
+    // claims -> nmatches and the rotation histogram; blk[] is reused as the "un-set by the rotation filter" flag
+    for (int i = tid; i < n2; i += 256) blk[i] = 0;
+    __syncthreads();
+    for (int i1 = tid; i1 < n1; i1 += 256) {
+        const int f = claim[i1];
+        int bin = -1;
+        if (f >= 0) {
+            atomicAdd(&sNm, 1);
+            if (checkOri) {
+                float rot = __fsub_rn(kps1[i1].angle, f2.kps[f].angle);
+                if (rot < 0.0f) rot = __fadd_rn(rot, 360.0f);
+                bin = (int)roundf(__fmul_rn(rot, 1.0f / 30));
+                if (bin == 30) bin = 0;
+                if (bin >= 0 && bin < 30) atomicAdd(&hist[bin], 1); else bin = -1;
+            }
+        }
+        w.bin[i1] = (signed char)bin;
+    }
+    __syncthreads();
+    if (tid == 0) {
+        int ind1 = -1, ind2 = -1, ind3 = -1;
+        if (checkOri) {
+            int max1 = 0, max2 = 0, max3 = 0;
+            for (int i = 0; i < 30; i++) {
+                const int s = hist[i];
+                if (s > max1) { max3 = max2; max2 = max1; max1 = s; ind3 = ind2; ind2 = ind1; ind1 = i; }
+                else if (s > max2) { max3 = max2; max2 = s; ind3 = ind2; ind2 = i; }
+                else if (s > max3) { max3 = s; ind3 = i; }
+            }
+            if ((float)max2 < __fmul_rn(0.1f, (float)max1)) { ind2 = -1; ind3 = -1; }
+            else if ((float)max3 < __fmul_rn(0.1f, (float)max1)) ind3 = -1;
+        }
+        sInd[0] = ind1; sInd[1] = ind2; sInd[2] = ind3;
+    }
+    __syncthreads();
+    if (checkOri)
+        for (int i1 = tid; i1 < n1; i1 += 256) {
+            const int b = w.bin[i1];
+            if (b >= 0 && b != sInd[0] && b != sInd[1] && b != sInd[2]) { blk[claim[i1]] = 1; atomicSub(&sNm, 1); }   // one nmatches-- per entry
+        }
+    __syncthreads();
+    for (int i = tid; i < n2; i += 256) matchCur[i] = (owner[i] != GUIDED_NONE && blk[i] == 0) ? (int)owner[i] : -1;
+    if (tid == 0) *nmatchesOut = sNm;
+}
+
 // ------------------------------------------------------------------------------------------------ launches
 static size_t resolveSmem(int n1, int n2) {
     const size_t n2r = (size_t)((n2 + 3) & ~3);
     return (size_t)2 * GUIDED_STAGE * 32 * 8 + 2 * GUIDED_STAGE * 4 * 2 + 32 * 4 + n2r * 2 * 2 + (size_t)n1 * 2 + 16;
 }
 
+static size_t resolveProjSmem(int n1, int n2) {
+    const size_t n2r = (size_t)((n2 + 3) & ~3);
+    return (size_t)2 * GUIDED_STAGE * 32 * 8 + 2 * GUIDED_STAGE * 4 * 3 + 32 * 4 + n2r * 2 + (size_t)((n1 + 1) & ~1) * 2 + n2r + 16;
+}
+
 cudaError_t guided_configure() {
-    cudaError_t e = cudaFuncSetAttribute(guided_resolve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)resolveSmem(EORB_GUIDED_MAX_KPS, EORB_GUIDED_MAX_KPS));
+    cudaError_t e = cudaFuncSetAttribute(guided_resolve_proj_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         (int)resolveProjSmem(EORB_GUIDED_MAX_KPS, EORB_GUIDED_MAX_KPS));
+    if (e != cudaSuccess) return e;
+    e = cudaFuncSetAttribute(guided_resolve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)resolveSmem(EORB_GUIDED_MAX_KPS, EORB_GUIDED_MAX_KPS));
     if (e != cudaSuccess) return e;
     return cudaFuncSetAttribute(frame_grid_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, EORB_GUIDED_MAX_KPS * 4);
 }
@@ -411,10 +604,29 @@ cudaError_t launch_search_init(const GuidedFrame& f1, const GuidedFrame& f2, Gui
     if (e != cudaSuccess) return e;
     (*launches)++;
     if (f1.n > 0) {
-        guided_candidates_kernel<<<(f1.n + 7) / 8, 256, 0, st>>>(f1, f2, g, d_prevXY, (float)window, w);
+        guided_candidates_kernel<<<(f1.n + 7) / 8, 256, 0, st>>>(f1, f2, g, d_prevXY, (float)window, nullptr, w);
         (*launches)++;
     }
     guided_resolve_kernel<<<1, 256, resolveSmem(f1.n, f2.n), st>>>(f1, f2, d_prevXY, nnratio, checkOri, w, d_matches12, d_nmatches);
+    (*launches)++;
+    return cudaGetLastError();
+}
+
+cudaError_t launch_search_proj(const float* d_x3Dc, const uint8_t* d_valid1, const int32_t* d_obs1, const eorb_keypoint* d_kps1,
+                               const uint8_t* d_descMP, int n1, const GuidedFrame& f2, GuidedGrid g, const GuidedProj& pr, int checkOri,
+                               const GuidedWork& w, int32_t* d_claim, int32_t* d_matchCur, int* d_nmatches, cudaStream_t st, long long* launches) {
+    cudaError_t e = cudaMemsetAsync(w.total, 0, sizeof(int), st);
+    if (e != cudaSuccess) return e;
+    e = launch_frame_grid(f2.kps, f2.n, g, w.cellStart, w.cellIdx, w.assigned, st);
+    if (e != cudaSuccess) return e;
+    (*launches)++;
+    if (n1 > 0) {
+        guided_project_kernel<<<(n1 + 255) / 256, 256, 0, st>>>(d_x3Dc, d_valid1, d_kps1, n1, pr, w.q);
+        GuidedFrame f1{d_kps1, d_descMP, n1};
+        guided_candidates_kernel<<<(n1 + 7) / 8, 256, 0, st>>>(f1, f2, g, nullptr, 0.f, w.q, w);
+        (*launches) += 2;
+    }
+    guided_resolve_proj_kernel<<<1, 256, resolveProjSmem(n1, f2.n), st>>>(d_kps1, d_obs1, n1, f2, checkOri, w, d_claim, d_matchCur, d_nmatches);
     (*launches)++;
     return cudaGetLastError();
 }

@@ -27,6 +27,7 @@ struct GuidedWork {
     int* cellStart; int* cellIdx; int* assigned;
     // per query (frame-1 keypoint): candidate range, sorted head (dist<<32 | pos<<16 | i2), histogram bin
     int* candOff; int* candCnt; unsigned long long* top; signed char* bin;
+    eorb_area_query* q;            // per query window of SearchByProjection (guided_project_kernel)
     uint32_t* cand; int candCap;   // all candidates in the reference's visiting order: dist<<16 | i2
     int* total;                    // candidates produced (may exceed candCap: the host grows the buffer and retries)
 };
@@ -38,6 +39,12 @@ cudaError_t launch_features_in_area(const eorb_keypoint* d_kps, GuidedGrid g, co
                                     const eorb_area_query* d_q, int nq, int* d_count, int* d_out, int capPerQuery, cudaStream_t st);
 cudaError_t launch_search_init(const GuidedFrame& f1, const GuidedFrame& f2, GuidedGrid g, float* d_prevXY, int window, float nnratio,
                                int checkOri, const GuidedWork& w, int32_t* d_matches12, int* d_nmatches, cudaStream_t st,
+                               long long* launches);
+// SearchByProjection(CurrentFrame, LastFrame, th, bMono = true): projection constants (Pinhole intrinsics, image bounds, scale table)
+struct GuidedProj { float fx, fy, cx, cy, minX, minY, maxX, maxY, th; int nlevels; float scale[32]; };
+cudaError_t launch_search_proj(const float* d_x3Dc, const uint8_t* d_valid1, const int32_t* d_obs1, const eorb_keypoint* d_kps1,
+                               const uint8_t* d_descMP, int n1, const GuidedFrame& f2, GuidedGrid g, const GuidedProj& pr, int checkOri,
+                               const GuidedWork& w, int32_t* d_claim, int32_t* d_matchCur, int* d_nmatches, cudaStream_t st,
                                long long* launches);
 cudaError_t guided_configure();
 

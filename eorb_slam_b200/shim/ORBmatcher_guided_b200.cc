@@ -1,4 +1,5 @@
-// B200 replacement for ORBmatcher::SearchForInitialization (src/ORBmatcher.cc:714-831), same signature: drop the
+// B200 replacements for ORBmatcher::SearchForInitialization (src/ORBmatcher.cc:714-831) and the monocular path of
+// ORBmatcher::SearchByProjection(CurrentFrame, LastFrame, th, bMono) (:1969-2150, Tracking::TrackWithMotionModel), same signatures: drop the
 // reference's definition of this one member and link this file (Tracking.cc's MonocularInitialization keeps calling
 // matcher.SearchForInitialization(mInitialFrame, mCurrentFrame, mvbPrevMatched, mvIniMatches, 100) unchanged).
 // The Frame grid (AssignFeaturesToGrid / GetFeaturesInArea, src/Frame.cc:431-460, 709-793) is rebuilt on the device from
@@ -14,6 +15,7 @@
 #else
 #include "ORBmatcher.h"
 #include "Frame.h"
+#include "MapPoint.h"
 #endif
 
 namespace ORB_SLAM3
@@ -69,6 +71,55 @@ int ORBmatcher::SearchForInitialization(Frame &F1, Frame &F2, std::vector<cv::Po
         vnMatches12.assign(n1, -1);
         return 0;
     }
+    return nmatches;
+}
+int ORBmatcher::SearchByProjection(Frame &CurrentFrame, const Frame &LastFrame, const float th, const bool bMono)
+{
+    // stereo / fisheye frames use the forward / backward level ranges and the right-image test (:1990-1991, 2050-2056): keep the
+    // reference's implementation for those (rename it and call it here); the monocular path below is the tracking-rate case
+    (void)bMono;
+    const int n1 = LastFrame.numAllKPts(), n2 = CurrentFrame.numAllKPts();
+    eorb_guided* g = threadHandle();
+    if (!g || n1 == 0 || n2 == 0) return 0;
+    std::vector<eorb_keypoint> k1(n1), k2;
+    std::vector<unsigned char> dmp((size_t)n1 * 32, 0), d2, valid(n1, 0);
+    std::vector<float> x3(3 * (size_t)n1, 0.f);
+    std::vector<int> obs(n1, 0);
+    const cv::Mat& T = CurrentFrame.mTcw;
+    for (int i = 0; i < n1; i++) {
+        const cv::KeyPoint kp = LastFrame.getUndistKPtMono(i);
+        k1[i].x = kp.pt.x; k1[i].y = kp.pt.y; k1[i].size = kp.size; k1[i].angle = kp.angle; k1[i].response = kp.response;
+        k1[i].octave = LastFrame.getKPtLevelMono(i); k1[i].class_id = kp.class_id;
+        MapPoint* pMP = LastFrame.getMapPoint(i);
+        if (!pMP || LastFrame.getMPOutlier(i)) continue;
+        valid[i] = 1;
+        obs[i] = pMP->Observations();
+        const cv::Mat x3Dw = pMP->GetWorldPos();
+#ifdef EORB_SHIM_MOCK
+        for (int r = 0; r < 3; r++)   // the cv mock has no matrix product; a real build uses the expression of the reference below
+            x3[3 * i + r] = T.at<float>(r, 0) * x3Dw.at<float>(0, 0) + T.at<float>(r, 1) * x3Dw.at<float>(1, 0) + T.at<float>(r, 2) * x3Dw.at<float>(2, 0) + T.at<float>(r, 3);
+#else
+        const cv::Mat x3Dc = T.rowRange(0, 3).colRange(0, 3) * x3Dw + T.rowRange(0, 3).col(3);   // :2000-2001, OpenCV's own arithmetic
+        for (int r = 0; r < 3; r++) x3[3 * i + r] = x3Dc.at<float>(r);
+#endif
+        const cv::Mat dMP = pMP->GetDescriptor();
+        std::memcpy(&dmp[(size_t)i * 32], dMP.ptr<unsigned char>(), 32);
+    }
+    packFrame(CurrentFrame, k2, d2);
+    const float bounds[4] = {Frame::mnMinX, Frame::mnMinY, Frame::mnMaxX, Frame::mnMaxY};
+    const float K4[4] = {CurrentFrame.mpCamera->getParameter(0), CurrentFrame.mpCamera->getParameter(1), CurrentFrame.mpCamera->getParameter(2),
+                         CurrentFrame.mpCamera->getParameter(3)};
+    const std::vector<float> sf = CurrentFrame.getAllORBScaleFactors();
+    std::vector<int> mc(n2, -1);
+    int nmatches = 0;
+    const int rc = eorb_guided_search_by_projection(g, x3.data(), valid.data(), obs.data(), k1.data(), dmp.data(), n1, k2.data(), d2.data(), n2, bounds,
+                                                    K4, sf.data(), (int)sf.size(), th, mbCheckOrientation ? 1 : 0, mc.data(), &nmatches);
+    if (rc != EORB_OK) {
+        std::fprintf(stderr, "ORBmatcher(b200)::SearchByProjection: %s\n", eorb_last_error());
+        return 0;
+    }
+    for (int i2 = 0; i2 < n2; i2++)
+        if (mc[i2] >= 0) CurrentFrame.setMapPoint(i2, LastFrame.getMapPoint(mc[i2]));
     return nmatches;
 }
 } // namespace ORB_SLAM3

@@ -14,8 +14,28 @@ protected:
     std::vector<float> mvParameters;   // fx, fy, cx, cy (Pinhole)
 };
 
-class Frame {   // the accessors SearchForInitialization uses (include/Frame.h:173, 193, 197, 247, 370-373)
+class MapPoint {   // what SearchByProjection reads (include/MapPoint.h: GetWorldPos, GetDescriptor, Observations)
 public:
+    MapPoint(const cv::Mat& pos, const cv::Mat& desc, int nObs) : mWorldPos(pos), mDescriptor(desc), mnObs(nObs) {}
+    cv::Mat GetWorldPos() { return mWorldPos; }
+    cv::Mat GetDescriptor() { return mDescriptor; }
+    int Observations() { return mnObs; }
+protected:
+    cv::Mat mWorldPos, mDescriptor;   // 3x1 CV_32F, 1x32 CV_8U
+    int mnObs;
+};
+
+class Frame {   // the accessors SearchForInitialization / SearchByProjection use (include/Frame.h:173, 193, 197, 230, 247, 370-373)
+public:
+    MapPoint* getMapPoint(int idx) const { return mvpMapPoints[idx]; }
+    void setMapPoint(int idx, MapPoint* p) { mvpMapPoints[idx] = p; }
+    bool getMPOutlier(int idx) const { return mvbOutlier[idx]; }
+    std::vector<float> getAllORBScaleFactors() const { return mvScaleFactors; }
+    cv::Mat mTcw;                                // 4x4 CV_32F
+    GeometricCamera* mpCamera = nullptr;
+    std::vector<MapPoint*> mvpMapPoints;
+    std::vector<bool> mvbOutlier;
+    std::vector<float> mvScaleFactors;
     int numAllKPts() const { return (int)mvKeysUn.size(); }
     cv::KeyPoint getUndistKPtMono(int idx) const { return mvKeysUn[idx]; }
     std::vector<cv::KeyPoint>& getAllUndistKPtsMono() { return mvKeysUn; }
@@ -29,6 +49,7 @@ public:
 class ORBmatcher {   // the members this path touches (ORBmatcher.h:39-42, 67-68, 96-113)
 public:
     int SearchForInitialization(Frame& F1, Frame& F2, std::vector<cv::Point2f>& vbPrevMatched, std::vector<int>& vnMatches12, int windowSize = 10);
+    int SearchByProjection(Frame& CurrentFrame, const Frame& LastFrame, const float th, const bool bMono);
     explicit ORBmatcher(float nnratio = 0.6, bool checkOri = true) : mfNNratio(nnratio), mbCheckOrientation(checkOri) {}
     static int DescriptorDistance(const cv::Mat& a, const cv::Mat& b);
     static const int TH_LOW;

@@ -93,6 +93,30 @@ int main(int argc, char** argv)
             if (m12[i] >= 0) moved += (prev[i].x == F2.mvKeysUn[m12[i]].pt.x && prev[i].y == F2.mvKeysUn[m12[i]].pt.y);
         }
         std::printf("sfi_nm=%d sfi_self=%d sfi_lvl0=%d sfi_prev=%d\n", nm, self, lvl0, moved);
+        // ORBmatcher::SearchByProjection(CurrentFrame, LastFrame, th, bMono): every last-frame keypoint carries a map point 4 m in
+        // front of the camera that projects onto the keypoint's position in the current (shifted) frame; identity pose
+        ORB_SLAM3::GeometricCamera cam2({458.654f, 457.296f, 367.215f, 248.375f});
+        std::vector<ORB_SLAM3::MapPoint*> mps;
+        F1.mvpMapPoints.assign(kps.size(), nullptr); F1.mvbOutlier.assign(kps.size(), false);
+        for (size_t i = 0; i < kps.size(); i++) {
+            cv::Mat pos(3, 1, CV_32F);
+            pos.at<float>(2, 0) = 4.f;
+            pos.at<float>(0, 0) = (F2.mvKeysUn[i].pt.x - 367.215f) / 458.654f * 4.f;
+            pos.at<float>(1, 0) = (F2.mvKeysUn[i].pt.y - 248.375f) / 457.296f * 4.f;
+            mps.push_back(new ORB_SLAM3::MapPoint(pos, desc.row((int)i), 2));
+            F1.mvpMapPoints[i] = mps.back();
+        }
+        F2.mvpMapPoints.assign(kps.size(), nullptr); F2.mvbOutlier.assign(kps.size(), false);
+        F2.mTcw = cv::Mat::zeros(4, 4, CV_32F);
+        for (int i = 0; i < 4; i++) F2.mTcw.at<float>(i, i) = 1.f;
+        F2.mpCamera = &cam2;
+        F2.mvScaleFactors.assign(8, 1.f);
+        for (int i = 1; i < 8; i++) F2.mvScaleFactors[i] = F2.mvScaleFactors[i - 1] * 1.2f;
+        const int np = matcher.SearchByProjection(F2, F1, 15.f, true);
+        int same = 0, set = 0;
+        for (size_t i = 0; i < kps.size(); i++) { set += (F2.mvpMapPoints[i] != nullptr); same += (F2.mvpMapPoints[i] == F1.mvpMapPoints[i]); }
+        std::printf("sbp_nm=%d sbp_set=%d sbp_same=%d\n", np, set, same);
+        for (auto* p : mps) delete p;
     }
     // ORBVocabulary::transform through a text file in ORB-SLAM's vocabulary format (k = 3, L = 2: 3 inner nodes, 9 words whose
     // descriptors are rows of `desc`), then Frame::UndistortKeyPoints with the EuRoC cam0 calibration

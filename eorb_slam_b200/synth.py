@@ -261,3 +261,31 @@ def make_vocabulary_regular(k: int = 10, L: int = 6, seed: int = 0):
     leaf = np.zeros(nn, np.uint8); leaf[nn - count:] = 1
     weight = np.zeros(nn, np.float64); weight[nn - count:] = np.log(rng.uniform(2.0, 4000.0, count))
     return dict(k=k, L=L, scoring=0, weighting=0, parent=parent, is_leaf=leaf, desc=desc, weight=weight)
+
+
+def make_projection_case(n1: int, n2: int, seed: int, w: int = 752, h: int = 480, nlevels: int = 8, K=(458.654, 457.296, 367.215, 248.375),
+                         shift=(7.0, -4.0), valid_frac: float = 0.7, zero_obs_frac: float = 0.05):
+    """Inputs of ORBmatcher::SearchByProjection(CurrentFrame, LastFrame, th, bMono=True) for the guided-matching tests: a
+    keypoint frame pair (make_keypoint_frame_pair) plus, per last-frame keypoint, a camera-frame point x3Dc that projects onto the
+    keypoint moved by `shift` (so the search window contains its counterpart), a validity flag (map point present, not an
+    outlier), an observation count (a few are 0: such claims can be overwritten) and the map point's descriptor.  A few points
+    lie behind the camera or project outside the image.  Returns a dict."""
+    rng = np.random.default_rng(seed + 1000)
+    k1, d1, k2, d2, bounds = make_keypoint_frame_pair(n1, n2, seed, w, h, nlevels, shift)
+    fx, fy, cx, cy = (np.float32(v) for v in K)
+    z = rng.uniform(1.0, 10.0, n1).astype(np.float32)
+    z[rng.random(n1) < 0.03] *= np.float32(-1.0)                       # behind the camera
+    u = k1["x"] + np.float32(shift[0]) + rng.normal(0, 1.5, n1).astype(np.float32)
+    v = k1["y"] + np.float32(shift[1]) + rng.normal(0, 1.5, n1).astype(np.float32)
+    far = rng.random(n1) < 0.03
+    u[far] += np.float32(2000.0)                                       # projects outside the image
+    x3 = np.stack([(u - cx) / fx * z, (v - cy) / fy * z, z], 1).astype(np.float32)
+    valid = (rng.random(n1) < valid_frac).astype(np.uint8)
+    obs = rng.integers(1, 9, n1).astype(np.int32)
+    obs[rng.random(n1) < zero_obs_frac] = 0
+    sf = np.float32(1.2) ** np.arange(nlevels, dtype=np.float32)
+    scale = np.ones(nlevels, np.float32)
+    for i in range(1, nlevels):
+        scale[i] = np.float32(np.float64(scale[i - 1]) * np.float64(np.float32(1.2)))
+    return dict(x3Dc=x3, valid1=valid, obs1=obs, kps1=k1, descMP=d1, kps2=k2, desc2=d2, bounds=bounds, K=np.array(K, np.float32),
+                scale_factors=scale)

@@ -331,6 +331,26 @@ int eorb_guided_search_for_initialization_device(eorb_guided* g, const eorb_keyp
                                                  float* d_prev_xy, int window_size, float nnratio, int check_ori, int32_t* d_matches12,
                                                  int* nmatches);
 
+/* ORBmatcher::SearchByProjection(Frame& CurrentFrame, const Frame& LastFrame, float th, bool bMono = true)
+ * (src/ORBmatcher.cc:1969-2150, monocular path): the tracking-rate caller of the matcher (Tracking::TrackWithMotionModel).
+ * Per last-frame keypoint i: x3Dc = Rcw * x3Dw + tcw (3 floats, formed by the caller with its own cv::Mat arithmetic), valid1[i] =
+ * LastFrame holds a map point at i that is not an outlier, obs1[i] = that point's Observations(), descMP = its descriptor,
+ * kps1[i].octave / .angle = the last frame's keypoint.  kps2 / desc2 = the current frame (undistorted keypoints); K4 = fx, fy, cx,
+ * cy of its Pinhole camera; scale_factors[nlevels] = mvScaleFactors; bounds4 = mnMinX, mnMinY, mnMaxX, mnMaxY.
+ * match_cur[n2] = index of the last-frame keypoint whose map point ends up in CurrentFrame.mvpMapPoints[i2] (-1: none); the
+ * return value of the reference goes to *nmatches.  (Stereo / fisheye second view and forward/backward level ranges: not on the
+ * monocular path.) */
+int eorb_guided_search_by_projection(eorb_guided* g, const float* x3Dc, const uint8_t* valid1, const int32_t* obs1,
+                                     const eorb_keypoint* kps1, const uint8_t* descMP, int n1, const eorb_keypoint* kps2,
+                                     const uint8_t* desc2, int n2, const float* bounds4, const float* K4, const float* scale_factors,
+                                     int nlevels, float th, int check_ori, int32_t* match_cur, int* nmatches);
+/* the same with every array resident in HBM; d_match_cur is written on the device, *nmatches after a stream synchronisation */
+int eorb_guided_search_by_projection_device(eorb_guided* g, const float* d_x3Dc, const uint8_t* d_valid1, const int32_t* d_obs1,
+                                            const eorb_keypoint* d_kps1, const uint8_t* d_descMP, int n1, const eorb_keypoint* d_kps2,
+                                            const uint8_t* d_desc2, int n2, const float* bounds4, const float* K4,
+                                            const float* scale_factors, int nlevels, float th, int check_ori, int32_t* d_match_cur,
+                                            int* nmatches);
+
 /* ---------------------------------------------------------------- bag of words + undistortion (fourth "next" row)
  * The two steps that follow extraction in the reference's Frame:
  *   eorb_vocab_transform        replaces DBoW2 TemplatedVocabulary<FORB::TDescriptor, FORB>::transform(features, BowVector,

@@ -157,4 +157,78 @@ int orc_search_for_initialization(const orc_keypoint* kps1, const uint8_t* desc1
     return nmatches;
 }
 
+// ORBmatcher::SearchByProjection(Frame& CurrentFrame, const Frame& LastFrame, float th, bool bMono = true)
+// (src/ORBmatcher.cc:1969-2150, monocular path: bForward = bBackward = false, mvuRight < 0, Nleft == -1).
+// x3Dc = Rcw * x3Dw + tcw is formed by the CALLER (cv::Mat arithmetic stays with OpenCV); everything after it is restated:
+// invzc < 0 test (:2007-2010), Pinhole::project in float (src/CameraModels/Pinhole.cpp:30-33), image-bounds test (:2014-2017),
+// radius = th * mvScaleFactors[clamp(octave)] (:2023; Frame::checkORBLevel src/Frame.cc:1408-1415), GetFeaturesInArea with
+// levels [octave-1, octave+1] (:2032), best distance among candidates whose slot is not held by a map point with observations
+// (:2046-2048; a slot taken by a point WITHOUT observations can be overwritten and counted again, as the reference does),
+// TH_HIGH (:2068), rotation histogram of the CLAIMED current-frame indices (:2073-2089) and the final un-setting of the
+// claims in the non-maximal bins (:2141-2150, one nmatches-- per histogram entry).
+// valid1[i] = LastFrame has a map point at i that is not an outlier; obs1[i] = that point's Observations().
+// match_cur[i2] = last-frame index whose map point ends up in CurrentFrame.mvpMapPoints[i2], or -1.  z == 0 (inf / NaN
+// projection; the reference's behaviour is undefined there) is treated like z < 0.
+int orc_search_by_projection(const float* x3Dc, const uint8_t* valid1, const int32_t* obs1, const orc_keypoint* kps1,
+                             const uint8_t* descMP, int n1, const orc_keypoint* kps2, const uint8_t* desc2, int n2, const float* bounds4,
+                             const float* K4, const float* scale_factors, int nlevels, float th, int check_ori, int32_t* match_cur) {
+    const int TH_HIGH = 100, HISTO_LENGTH = 30;
+    const GridGeom g(bounds4);
+    std::vector<int> cellStart(GC * GR + 1), cellIdx(std::max(n2, 1));
+    orc_frame_grid(kps2, n2, bounds4, cellStart.data(), cellIdx.data());
+    for (int i = 0; i < n2; i++) match_cur[i] = -1;
+    int nmatches = 0;
+    std::vector<int> rotHist[HISTO_LENGTH];
+    const float factor = 1.0f / HISTO_LENGTH;
+    std::vector<int> vIndices2;
+    for (int i = 0; i < n1; i++) {
+        if (!valid1[i]) continue;
+        const float xc = x3Dc[3 * i], yc = x3Dc[3 * i + 1], zc = x3Dc[3 * i + 2];
+        const float invzc = (float)(1.0 / zc);
+        if (invzc < 0 || zc == 0) continue;
+        const float u = K4[0] * xc / zc + K4[2], v = K4[1] * yc / zc + K4[3];
+        if (u < bounds4[0] || u > bounds4[2]) continue;
+        if (v < bounds4[1] || v > bounds4[3]) continue;
+        const int oct = kps1[i].octave;
+        const int lv = oct < 0 ? 0 : (oct >= nlevels ? nlevels - 1 : oct);
+        const float radius = th * scale_factors[lv];
+        featuresInArea(kps2, g, cellStart.data(), cellIdx.data(), u, v, radius, oct - 1, oct + 1, vIndices2);
+        if (vIndices2.empty()) continue;
+        const uint8_t* dMP = descMP + (size_t)i * 32;
+        int bestDist = 256, bestIdx2 = -1;
+        for (int i2 : vIndices2) {
+            if (match_cur[i2] >= 0 && obs1[match_cur[i2]] > 0) continue;
+            const int dist = orc_descriptor_distance(dMP, desc2 + (size_t)i2 * 32);
+            if (dist < bestDist) { bestDist = dist; bestIdx2 = i2; }
+        }
+        if (bestDist <= TH_HIGH) {
+            match_cur[bestIdx2] = i;
+            nmatches++;
+            if (check_ori) {
+                float rot = kps1[i].angle - kps2[bestIdx2].angle;
+                if (rot < 0.0) rot += 360.0f;
+                int bin = (int)std::round(rot * factor);
+                if (bin == HISTO_LENGTH) bin = 0;
+                rotHist[bin].push_back(bestIdx2);
+            }
+        }
+    }
+    if (check_ori) {
+        int max1 = 0, max2 = 0, max3 = 0, ind1 = -1, ind2 = -1, ind3 = -1;
+        for (int i = 0; i < HISTO_LENGTH; i++) {
+            const int s = (int)rotHist[i].size();
+            if (s > max1) { max3 = max2; max2 = max1; max1 = s; ind3 = ind2; ind2 = ind1; ind1 = i; }
+            else if (s > max2) { max3 = max2; max2 = s; ind3 = ind2; ind2 = i; }
+            else if (s > max3) { max3 = s; ind3 = i; }
+        }
+        if (max2 < 0.1f * (float)max1) { ind2 = -1; ind3 = -1; }
+        else if (max3 < 0.1f * (float)max1) { ind3 = -1; }
+        for (int i = 0; i < HISTO_LENGTH; i++) {
+            if (i != ind1 && i != ind2 && i != ind3)
+                for (int idx : rotHist[i]) { match_cur[idx] = -1; nmatches--; }
+        }
+    }
+    return nmatches;
+}
+
 }  // extern "C"

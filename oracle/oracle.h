@@ -124,6 +124,14 @@ int   orc_search_for_initialization(const orc_keypoint* kps1, const uint8_t* des
                                     const uint8_t* desc2, int n2, const float* bounds4, float* prev_xy, int window_size, float nnratio,
                                     int check_ori, int32_t* matches12);
 
+/* ORBmatcher::SearchByProjection(CurrentFrame, LastFrame, th, bMono = true) (ORBmatcher.cc:1969-2150); x3Dc = Rcw*x3Dw+tcw per
+   last-frame keypoint (n1 x 3, formed by the caller), valid1 = has a non-outlier map point, obs1 = its Observations(),
+   descMP = its descriptor; match_cur[n2] = last-frame index assigned to every current-frame keypoint or -1; returns nmatches */
+int   orc_search_by_projection(const float* x3Dc, const uint8_t* valid1, const int32_t* obs1, const orc_keypoint* kps1,
+                               const uint8_t* descMP, int n1, const orc_keypoint* kps2, const uint8_t* desc2, int n2,
+                               const float* bounds4, const float* K4, const float* scale_factors, int nlevels, float th, int check_ori,
+                               int32_t* match_cur);
+
 /* ---- bag of words + undistortion (bow_oracle.cc) ---- */
 typedef struct orc_vocab orc_vocab;
 /* flat form of what TemplatedVocabulary::loadFromTextFile builds: node 0 = root, parent[nid] < nid, children in id order,

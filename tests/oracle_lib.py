@@ -389,6 +389,20 @@ def search_for_initialization(kps1, desc1, kps2, desc2, bounds, prev_xy, window_
     return n, m12[:len(kps1)].copy(), prev
 
 
+def search_by_projection(x3Dc, valid1, obs1, kps1, descMP, kps2, desc2, bounds, K4, scale_factors, th=15.0, check_ori=True):
+    """ORBmatcher::SearchByProjection(CurrentFrame, LastFrame, th, bMono=True) -> (nmatches, match_cur[n2])"""
+    L = lib()
+    x = np.ascontiguousarray(x3Dc, np.float32).reshape(-1, 3); v = np.ascontiguousarray(valid1, np.uint8); o = np.ascontiguousarray(obs1, np.int32)
+    k1 = np.ascontiguousarray(kps1, KEYPOINT_DTYPE); k2 = np.ascontiguousarray(kps2, KEYPOINT_DTYPE)
+    dm = np.ascontiguousarray(descMP, np.uint8); d2 = np.ascontiguousarray(desc2, np.uint8)
+    b = np.ascontiguousarray(bounds, np.float32); K = np.ascontiguousarray(K4, np.float32); sf = np.ascontiguousarray(scale_factors, np.float32)
+    mc = np.full(max(len(k2), 1), -1, np.int32)
+    L.orc_search_by_projection.restype = C.c_int
+    n = L.orc_search_by_projection(_p(x), _p(v), _p(o), _p(k1), _p(dm), C.c_int(len(k1)), _p(k2), _p(d2), C.c_int(len(k2)), _p(b), _p(K),
+                                   _p(sf), C.c_int(len(sf)), C.c_float(th), C.c_int(int(check_ori)), _p(mc))
+    return n, mc[:len(k2)].copy()
+
+
 # ---- bag of words + undistortion (SURVEY 8f rank 4)
 class VocabOracle:
     def __init__(self, voc):

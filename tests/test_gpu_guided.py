@@ -119,3 +119,51 @@ def test_extract_two_frames_then_guided_search_without_leaving_hbm():
     assert nm == en and np.array_equal(d_m12.cpu().numpy(), em12) and d_prev.cpu().numpy().tobytes() == ep.tobytes()
     assert en > 100          # a shifted copy of a textured frame matches well
     gm.set_stream(None); ex.set_stream(None)
+
+
+@pytest.mark.parametrize("n1,n2,seed,th,ori,zero_obs", [
+    (500, 520, 21, 15.0, True, 0.05), (500, 520, 22, 7.0, True, 0.0), (500, 520, 23, 15.0, False, 0.3), (500, 520, 24, 40.0, True, 0.5),
+    (1009, 1009, 25, 15.0, True, 0.02),      # tracking-rate call: two frames of the 1000-feature extractor (th = 15, Tracking.cc)
+    (3000, 3000, 26, 400.0, True, 0.1),      # whole-image windows: long candidate lists, blocked heads -> the slow path
+    (64, 2000, 27, 15.0, True, 0.0), (0, 10, 28, 15.0, True, 0.0), (300, 1, 29, 15.0, True, 0.0)])
+def test_search_by_projection(n1, n2, seed, th, ori, zero_obs):
+    """ORBmatcher::SearchByProjection(CurrentFrame, LastFrame, th, bMono=True): match table and nmatches bit-exact"""
+    api = _api()
+    c = synth.make_projection_case(max(n1, 2), max(n2, 2), seed, zero_obs_frac=zero_obs)
+    for k in ("x3Dc", "valid1", "obs1", "kps1", "descMP"):
+        c[k] = c[k][:n1]
+    c["kps2"], c["desc2"] = c["kps2"][:n2], c["desc2"][:n2]
+    gm = api.GuidedMatcher(0, 0.9, ori)
+    for rep in range(2):       # twice on one handle: no state may leak between calls
+        n, mc = gm.SearchByProjection(c["x3Dc"], c["valid1"], c["obs1"], c["kps1"], c["descMP"], c["kps2"], c["desc2"], c["bounds"], c["K"],
+                                      c["scale_factors"], th)
+        en, emc = O.search_by_projection(c["x3Dc"], c["valid1"], c["obs1"], c["kps1"], c["descMP"], c["kps2"], c["desc2"], c["bounds"], c["K"],
+                                         c["scale_factors"], th, ori)
+        assert n == en and np.array_equal(mc, emc)
+    if n1 >= 500:
+        assert (emc >= 0).sum() > 50
+
+
+def test_search_by_projection_contested_slots():
+    """many last-frame points project onto the same few current-frame keypoints: first come first served for points with
+    observations, overwrite (and double counting, as in the reference) for points without"""
+    api = _api()
+    rng = np.random.default_rng(31)
+    n1, n2 = 400, 40
+    c = synth.make_projection_case(n1, n2, 31)
+    K = c["K"]
+    tgt = rng.integers(0, n2, n1)
+    z = rng.uniform(1, 5, n1).astype(np.float32)
+    u = c["kps2"]["x"][tgt] + rng.normal(0, 1, n1).astype(np.float32); v = c["kps2"]["y"][tgt] + rng.normal(0, 1, n1).astype(np.float32)
+    c["x3Dc"] = np.stack([(u - K[2]) / K[0] * z, (v - K[3]) / K[1] * z, z], 1).astype(np.float32)
+    c["valid1"][:] = 1
+    c["kps1"]["octave"] = c["kps2"]["octave"][tgt]
+    c["descMP"] = c["desc2"][tgt].copy()
+    c["descMP"][:, 0] ^= rng.integers(0, 4, n1).astype(np.uint8)
+    for zero in (0.0, 0.5, 1.0):
+        c["obs1"] = np.where(rng.random(n1) < zero, 0, 3).astype(np.int32)
+        n, mc = api.GuidedMatcher(0, 0.9, True).SearchByProjection(c["x3Dc"], c["valid1"], c["obs1"], c["kps1"], c["descMP"], c["kps2"], c["desc2"],
+                                                                 c["bounds"], K, c["scale_factors"], 15.0)
+        en, emc = O.search_by_projection(c["x3Dc"], c["valid1"], c["obs1"], c["kps1"], c["descMP"], c["kps2"], c["desc2"], c["bounds"], K,
+                                         c["scale_factors"], 15.0, True)
+        assert n == en and np.array_equal(mc, emc)

@@ -161,3 +161,73 @@ def test_search_for_initialization_second_round_uses_updated_prev_matched():
     n2, m12b, p2 = O.search_for_initialization(k1, d1, k2, d2, b, p, 100, 0.9, True)
     en2, em12b, ep2 = py_search_init(k1, d1, k2, d2, b, p, 100, 0.9, True)
     assert n2 == en2 and np.array_equal(m12b, em12b) and p2.tobytes() == ep2.tobytes()
+
+
+def py_search_by_projection(c, th, check_ori):
+    k1, k2 = c["kps1"], c["kps2"]
+    grid, geom = py_grid(k2, c["bounds"])
+    fx, fy, cx, cy = (F(v) for v in c["K"])
+    b = [F(v) for v in c["bounds"]]
+    n2 = len(k2)
+    mc = [-1] * n2
+    hist = [[] for _ in range(30)]
+    nm = 0
+    nl = len(c["scale_factors"])
+    for i in range(len(k1)):
+        if not c["valid1"][i]:
+            continue
+        xc, yc, zc = (F(v) for v in c["x3Dc"][i])
+        if zc == 0 or F(1.0 / float(zc)) < 0:
+            continue
+        u = fx * xc / zc + cx; v = fy * yc / zc + cy
+        if u < b[0] or u > b[2] or v < b[1] or v > b[3]:
+            continue
+        octv = int(k1["octave"][i])
+        radius = F(th) * F(c["scale_factors"][min(max(octv, 0), nl - 1)])
+        cand = py_area(k2, grid, geom, u, v, radius, octv - 1, octv + 1)
+        best, bidx = 256, -1
+        for i2 in cand:
+            if mc[i2] >= 0 and c["obs1"][mc[i2]] > 0:
+                continue
+            d = _ham(c["descMP"][i], c["desc2"][i2])
+            if d < best:
+                best, bidx = d, i2
+        if best <= 100:
+            mc[bidx] = i; nm += 1
+            if check_ori:
+                rot = F(k1["angle"][i]) - F(k2["angle"][bidx])
+                if rot < 0:
+                    rot = rot + F(360.0)
+                bb = _round_away(F(rot) * (F(1.0) / F(30)))
+                hist[0 if bb == 30 else bb].append(bidx)
+    if check_ori:
+        mx = [0, 0, 0]; ind = [-1, -1, -1]
+        for i in range(30):
+            s = len(hist[i])
+            if s > mx[0]:
+                mx = [s, mx[0], mx[1]]; ind = [i, ind[0], ind[1]]
+            elif s > mx[1]:
+                mx = [mx[0], s, mx[1]]; ind = [ind[0], i, ind[1]]
+            elif s > mx[2]:
+                mx[2] = s; ind[2] = i
+        if mx[1] < F(0.1) * F(mx[0]):
+            ind[1] = ind[2] = -1
+        elif mx[2] < F(0.1) * F(mx[0]):
+            ind[2] = -1
+        for i in range(30):
+            if i not in ind:
+                for idx in hist[i]:
+                    mc[idx] = -1; nm -= 1
+    return nm, np.array(mc, np.int32)
+
+
+@pytest.mark.parametrize("seed,th,ori,zero_obs", [(21, 15.0, True, 0.05), (22, 7.0, True, 0.0), (23, 15.0, False, 0.3), (24, 40.0, True, 0.5)])
+def test_search_by_projection_matches_python(seed, th, ori, zero_obs):
+    c = synth.make_projection_case(500, 520, seed, zero_obs_frac=zero_obs)
+    n, mc = O.search_by_projection(c["x3Dc"], c["valid1"], c["obs1"], c["kps1"], c["descMP"], c["kps2"], c["desc2"], c["bounds"], c["K"],
+                                   c["scale_factors"], th, ori)
+    en, emc = py_search_by_projection(c, th, ori)
+    assert n == en and np.array_equal(mc, emc)
+    assert (mc >= 0).sum() > 50
+    if zero_obs == 0.0 and not ori:
+        assert n == int((mc >= 0).sum())

@@ -49,7 +49,7 @@ def test_shims_compile_and_fail_loudly_without_device():
     assert "ret=-1 n=0" in out and "empty_ret=-1" in out
     assert "no CUDA device" in err
     assert "lk_ok=0 lk_n=0" in out
-    assert "sfi_nm=0 sfi_self=0" in out
+    assert "sfi_nm=0 sfi_self=0" in out and "sbp_nm=0 sbp_set=0" in out
     assert "voc_ok=0" in out and "undist_ok=0" in out
 
 
@@ -89,3 +89,7 @@ def test_shims_match_oracle_on_gpu():
     assert 0 < int(fvn) <= 3 and int(fvf) == len(okps)                                                    # every feature under one of 3 nodes
     un = re.search(r"undist_ok=(\d) undist_n=(\d+) undist_shift=([\d.]+)", out)
     assert int(un.group(1)) == 1 and int(un.group(2)) == len(okps) and float(un.group(3)) > len(okps)      # EuRoC distortion moves points by pixels
+    sb = re.search(r"sbp_nm=(\d+) sbp_set=(\d+) sbp_same=(\d+)", out)
+    nmp, nset, nsame = map(int, sb.groups())
+    # every map point projects exactly onto its keypoint in the current frame: (nearly) all are found, and at their own index
+    assert nmp == nset and nmp > 0.9 * len(okps) and nsame > 0.95 * nset
