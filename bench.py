@@ -101,7 +101,9 @@ def _traffic():
     p = os.path.join(ROOT, "profiles", "r01_traffic.json")
     if os.path.exists(p):
         d = json.load(open(p))
+        _traffic.inst = {k: v.get("warp_inst_per_frame") for k, v in d["stages"].items()}
         return {k: v["dram_bytes_per_frame"] for k, v in d["stages"].items()}, d.get("source")
+    _traffic.inst = {}
     return {}, None
 
 
@@ -590,6 +592,12 @@ def run_ours(args):
             e["frac_of_hbm_peak"] = e["achieved_gbs"] / peak if v > 0 else None
         if k in traffic:
             e["ncu_dram_bytes_per_frame"] = traffic[k]
+        wi = getattr(_traffic, "inst", {}).get(k)
+        if wi and v > 0:
+            # instruction-issue roofline: executed warp instructions per frame (ncu, profiles/r01_traffic.json) over the live
+            # CUDA-event time, against SMs x 4 schedulers x 1 warp instruction per clock at the sampled SM clock
+            e["warp_inst_per_frame"] = wi
+            e["issue_slots_frac"] = (wi * frames_timed / (v * 1e-3)) / (148 * 4 * (clk.get("sm_mhz") or 1965.0) * 1e6)
         per_stage[k] = e
     if dom in ALGO_BYTES:
         dom_bytes_launch = ALGO_BYTES[dom] * chunk / (stage_launches[dom] / (frames_timed / chunk))
@@ -599,7 +607,10 @@ def run_ours(args):
                 "traffic": (traffic[dom] * chunk / (stage_launches[dom] / (frames_timed / chunk))) if dom in traffic else None,
                 "traffic_source": ("profiles/r01_traffic.json (%s), bytes per frame x frames per launch" % traffic_src) if dom in traffic else None,
                 "peak_source": peak_src, "avg_launch_ms": dom_ms_launch, "algo_bytes_per_launch": dom_bytes_launch,
-                "note": "byte-granular integer kernel: issue-bound on the ALU pipe, not on HBM (see profiles/ and DESIGN.md)"}
+                "note": "byte-granular integer kernel: issue-bound on the ALU pipe, not on HBM (see profiles/ and DESIGN.md)",
+                "issue_roofline": {"bound": "instruction issue (integer pipes)", "frac": per_stage[dom].get("issue_slots_frac"),
+                                   "warp_inst_per_frame": per_stage[dom].get("warp_inst_per_frame"),
+                                   "peak": "148 SMs x 4 schedulers x 1 warp instruction / clk"}}
     else:
         # latency-bound stage (octree / index / orient+desc): no HBM roofline applies; report the best HBM-bound stage too
         hb = max((k for k in ALGO_BYTES), key=lambda k: stage_ms[k])

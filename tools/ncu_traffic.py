@@ -7,6 +7,7 @@ out = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_outpu
 rows = list(csv.reader(out.splitlines()))
 hdr, units = rows[0], rows[1]
 kn = hdr.index("Kernel Name"); ir = hdr.index("dram__bytes_read.sum"); iw = hdr.index("dram__bytes_write.sum"); it = hdr.index("gpu__time_duration.sum")
+ii = hdr.index("smsp__inst_executed.sum")
 scale = {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
 stage_of = {"pyr_resize_kernel": "pyramid", "fast_cells_kernel": "fast", "octree_kernel": "octree", "orb_index_kernel": "index", "blur_kernel": "blur",
             "orient_desc_kernel": "orient_desc"}
@@ -16,8 +17,9 @@ for r in rows[2:]:
     st = stage_of.get(name)
     if not st: continue
     b = float(r[ir]) * scale[units[ir]] + float(r[iw]) * scale[units[iw]]
-    e = acc.setdefault(st, {"dram_bytes_per_frame": 0.0, "ncu_us_per_frame": 0.0, "launches": 0})
+    e = acc.setdefault(st, {"dram_bytes_per_frame": 0.0, "ncu_us_per_frame": 0.0, "warp_inst_per_frame": 0.0, "launches": 0})
     e["dram_bytes_per_frame"] += b / frames; e["ncu_us_per_frame"] += float(r[it]) / frames; e["launches"] += 1
+    e["warp_inst_per_frame"] += float(r[ii]) / frames
 json.dump({"source": rep.split("/")[-1], "frames_per_launch": frames, "note": "ncu --set full --clock-control none, cold-cache serialised replays; one launch set",
            "stages": acc}, open(outp, "w"), indent=1)
 print(json.dumps(acc, indent=1))
