@@ -28,7 +28,11 @@ namespace eorb {
 
 typedef unsigned long long u64;
 #define GUIDED_STAGE 64     // queries staged per round of the resolve kernel
+#define GUIDED_ROW 33       // u64 entries per staged head row: 32 + 1 pad, so that lanes walking DIFFERENT rows hit different banks
 #define GUIDED_NONE 0xffffu
+#ifndef EORB_GUIDED_SPEC
+#define EORB_GUIDED_SPEC 1
+#endif
 #define FULLMASK 0xffffffffu
 
 // ---- GetFeaturesInArea cell window (Frame.cc:722-744), all float like the reference
@@ -238,12 +242,13 @@ __global__ void __launch_bounds__(256) guided_resolve_kernel(GuidedFrame f1, Gui
     extern __shared__ __align__(16) unsigned char sm[];
     const int n1 = f1.n, n2 = f2.n, n2r = (n2 + 3) & ~3;
     u64* stop = reinterpret_cast<u64*>(sm);                               // [2][GUIDED_STAGE][32] double-buffered heads
-    int* scnt = reinterpret_cast<int*>(stop + 2 * GUIDED_STAGE * 32);     // [2][GUIDED_STAGE]
+    int* scnt = reinterpret_cast<int*>(stop + 2 * GUIDED_STAGE * GUIDED_ROW);     // [2][GUIDED_STAGE]
     int* soff = scnt + 2 * GUIDED_STAGE;                                  // [2][GUIDED_STAGE]
     int* hist = soff + 2 * GUIDED_STAGE;                                  // [32]
     unsigned short* md = reinterpret_cast<unsigned short*>(hist + 32);    // [n2r] matched distance (0xffff = INT_MAX)
     unsigned short* m21 = md + n2r;                                       // [n2r] owner in frame 1 (0xffff = none)
     unsigned short* qlist = m21 + n2r;                                    // [n1] queries that have candidates, ascending
+    unsigned* ctab = reinterpret_cast<unsigned*>(qlist + ((n1 + 1) & ~1));  // [n2r] lowest lane of the current chunk claiming a slot
     __shared__ int sNm, sInd[3], sWarp[8];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
 
@@ -251,7 +256,7 @@ __global__ void __launch_bounds__(256) guided_resolve_kernel(GuidedFrame f1, Gui
         if (tid == 0) *nmatchesOut = -1;
         return;
     }
-    for (int i = tid; i < n2; i += 256) { md[i] = GUIDED_NONE; m21[i] = GUIDED_NONE; }
+    for (int i = tid; i < n2; i += 256) { md[i] = GUIDED_NONE; m21[i] = GUIDED_NONE; ctab[i] = 0xffffffffu; }
     for (int i = tid; i < n1; i += 256) matches12[i] = -1;
     if (tid < 32) hist[tid] = 0;
     if (tid == 0) sNm = 0;
@@ -274,12 +279,12 @@ __global__ void __launch_bounds__(256) guided_resolve_kernel(GuidedFrame f1, Gui
 
     // stage `r` = heads + list ranges of queries qlist[r*64 ..]; loaded by `nth` threads starting at thread `t0`
     auto loadStage = [&](int r, int t0, int nth) {
-        u64* sp = stop + (r & 1) * GUIDED_STAGE * 32;
+        u64* sp = stop + (r & 1) * GUIDED_STAGE * GUIDED_ROW;
         int* sc = scnt + (r & 1) * GUIDED_STAGE;
         int* so = soff + (r & 1) * GUIDED_STAGE;
         for (int t = tid - t0; t < GUIDED_STAGE * 32; t += nth) {
             const int q = r * GUIDED_STAGE + (t >> 5);
-            sp[t] = q < nact ? w.top[(size_t)qlist[q] * EORB_GUIDED_TOP + (t & 31)] : ~0ull;
+            sp[(t >> 5) * GUIDED_ROW + (t & 31)] = q < nact ? w.top[(size_t)qlist[q] * EORB_GUIDED_TOP + (t & 31)] : ~0ull;
         }
         for (int k = tid - t0; k < GUIDED_STAGE; k += nth) {
             const int q = r * GUIDED_STAGE + k;
@@ -294,13 +299,12 @@ __global__ void __launch_bounds__(256) guided_resolve_kernel(GuidedFrame f1, Gui
         if (warp != 0) {
             if (r + 1 < nrounds) loadStage(r + 1, 32, 224);   // warps 1..7 fetch the next stage behind the sequential warp
         } else {
-            const u64* sp = stop + (r & 1) * GUIDED_STAGE * 32;
+            const u64* sp = stop + (r & 1) * GUIDED_STAGE * GUIDED_ROW;
             const int* sc = scnt + (r & 1) * GUIDED_STAGE;
             const int kend = min(GUIDED_STAGE, nact - r * GUIDED_STAGE);
-            u64 eN = sp[lane];
-            for (int k = 0; k < kend; k++) {
-                const u64 e = eN;
-                if (k + 1 < kend) eN = sp[(k + 1) * 32 + lane];           // independent of the state: prefetched
+            // one query, all 32 lanes on its head (and on its full list when the head runs dry)
+            auto seqStep = [&](int k) {
+                const u64 e = sp[k * GUIDED_ROW + lane];
                 const uint32_t dist = (uint32_t)(e >> 32), i2 = e != ~0ull ? (uint32_t)e & 0xffffu : 0u;   // padding never indexes the state
                 const uint32_t di = (dist << 16) | i2;
                 const bool ok = e != ~0ull && (uint32_t)md[i2] > dist;   // vMatchedDistance[i2] <= dist -> skipped (:755)
@@ -341,7 +345,69 @@ __global__ void __launch_bounds__(256) guided_resolve_kernel(GuidedFrame f1, Gui
                     }
                     __syncwarp();
                 }
+            };
+#if EORB_GUIDED_SPEC
+            // Speculative chunks: lane L evaluates query k + L on its own against the current state (first two unfiltered
+            // entries of its sorted head, four entries fetched per step).  Accepting lanes post their lane number on the
+            // slot they claim (ctab, atomicMin); a lane is DIRTY when an EARLIER lane of the chunk claims one of its two
+            // entries' slots — only then can the order matter (conservative: the claim's distance is not looked at, a dirty
+            // lane is simply evaluated again).  The clean prefix is committed at once — it cannot contain two claimers of
+            // one slot — and the chunk restarts at the first dirty lane; a query whose head cannot decide (fewer than two
+            // unfiltered entries of a longer list) is run by seqStep.  Lane 0 is never dirty: every round makes progress.
+            int k = 0;
+            while (k < kend) {
+                const int q = k + lane;
+                const bool have = q < kend;
+                uint32_t b1 = 0xffffffffu, b2 = 0xffffffffu;
+                bool slow = false;
+                if (have) {
+                    const u64* hp = sp + q * GUIDED_ROW;
+                    int found = 0;
+                    for (int en = 0; en < EORB_GUIDED_TOP && found < 2; en += 4) {
+                        u64 he[4]; uint32_t mv[4];
+#pragma unroll
+                        for (int u = 0; u < 4; u++) he[u] = hp[en + u];
+#pragma unroll
+                        for (int u = 0; u < 4; u++) mv[u] = he[u] != ~0ull ? (uint32_t)md[(uint32_t)he[u] & 0xffffu] : 0u;   // padding: never "unfiltered"
+#pragma unroll
+                        for (int u = 0; u < 4; u++) {
+                            const uint32_t d = (uint32_t)(he[u] >> 32);
+                            if (found < 2 && he[u] != ~0ull && mv[u] > d) {
+                                const uint32_t key = (d << 16) | ((uint32_t)he[u] & 0xffffu);
+                                if (found == 0) b1 = key; else b2 = key;
+                                found++;
+                            }
+                        }
+                        if (he[3] == ~0ull) break;       // sorted: padding only at the end
+                    }
+                    slow = found < 2 && sc[q] > EORB_GUIDED_TOP;
+                }
+                const int bd1 = b1 != 0xffffffffu ? (int)(b1 >> 16) : 0x7fffffff, bd2 = b2 != 0xffffffffu ? (int)(b2 >> 16) : 0x7fffffff;
+                const bool acc = have && !slow && bd1 <= 50 && (float)bd1 < __fmul_rn((float)bd2, nnratio);
+                if (acc) atomicMin(&ctab[b1 & 0xffffu], (unsigned)lane);
+                __syncwarp();
+                bool dirty = false;
+                if (have && b1 != 0xffffffffu && ctab[b1 & 0xffffu] < (unsigned)lane) dirty = true;
+                if (have && b2 != 0xffffffffu && ctab[b2 & 0xffffu] < (unsigned)lane) dirty = true;
+                const unsigned stopMask = __ballot_sync(FULLMASK, have && (dirty || slow));
+                const int ncommit = stopMask ? __ffs(stopMask) - 1 : min(32, kend - k);
+                __syncwarp();
+                if (acc) {
+                    ctab[b1 & 0xffffu] = 0xffffffffu;                     // leave the table clean for the next round
+                    if (lane < ncommit) {
+                        const int i1 = qlist[r * GUIDED_STAGE + q];
+                        matches12[i1] = (int)(b1 & 0xffffu);
+                        m21[b1 & 0xffffu] = (unsigned short)i1;
+                        md[b1 & 0xffffu] = (unsigned short)(b1 >> 16);
+                    }
+                }
+                __syncwarp();
+                k += ncommit;
+                if (stopMask && __shfl_sync(FULLMASK, (int)slow, ncommit & 31)) { seqStep(k); k++; }
             }
+#else
+            for (int k = 0; k < kend; k++) seqStep(k);
+#endif
         }
         __syncthreads();
     }
@@ -427,13 +493,14 @@ __global__ void __launch_bounds__(256) guided_resolve_proj_kernel(const eorb_key
     extern __shared__ __align__(16) unsigned char sm[];
     const int n2 = f2.n, n2r = (n2 + 3) & ~3;
     u64* stop = reinterpret_cast<u64*>(sm);                               // [2][GUIDED_STAGE][32]
-    int* scnt = reinterpret_cast<int*>(stop + 2 * GUIDED_STAGE * 32);     // [2][GUIDED_STAGE]
+    int* scnt = reinterpret_cast<int*>(stop + 2 * GUIDED_STAGE * GUIDED_ROW);     // [2][GUIDED_STAGE]
     int* soff = scnt + 2 * GUIDED_STAGE;                                  // [2][GUIDED_STAGE]
     int* sobs = soff + 2 * GUIDED_STAGE;                                  // [2][GUIDED_STAGE] observations of the query's map point
     int* hist = sobs + 2 * GUIDED_STAGE;                                  // [32]
     unsigned short* owner = reinterpret_cast<unsigned short*>(hist + 32); // [n2r] last claimer (0xffff = none)
     unsigned short* qlist = owner + n2r;                                  // [n1]
-    unsigned char* blk = reinterpret_cast<unsigned char*>(qlist + ((n1 + 1) & ~1));   // [n2r] slot blocked / (later) un-set flag
+    unsigned* ctab = reinterpret_cast<unsigned*>(qlist + ((n1 + 1) & ~1));             // [n2r] lowest lane of the current chunk claiming a slot
+    unsigned char* blk = reinterpret_cast<unsigned char*>(ctab + n2r);                 // [n2r] slot blocked / (later) un-set flag
     __shared__ int sNm, sInd[3], sWarp[8];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
 
@@ -441,7 +508,7 @@ __global__ void __launch_bounds__(256) guided_resolve_proj_kernel(const eorb_key
         if (tid == 0) *nmatchesOut = -1;
         return;
     }
-    for (int i = tid; i < n2; i += 256) { owner[i] = GUIDED_NONE; blk[i] = 0; }
+    for (int i = tid; i < n2; i += 256) { owner[i] = GUIDED_NONE; blk[i] = 0; ctab[i] = 0xffffffffu; }
     for (int i = tid; i < n1; i += 256) claim[i] = -1;
     if (tid < 32) hist[tid] = 0;
     if (tid == 0) sNm = 0;
@@ -461,10 +528,10 @@ __global__ void __launch_bounds__(256) guided_resolve_proj_kernel(const eorb_key
     }
     const int nrounds = (nact + GUIDED_STAGE - 1) / GUIDED_STAGE;
     auto loadStage = [&](int r, int t0, int nth) {
-        u64* sp = stop + (r & 1) * GUIDED_STAGE * 32;
+        u64* sp = stop + (r & 1) * GUIDED_STAGE * GUIDED_ROW;
         for (int t = tid - t0; t < GUIDED_STAGE * 32; t += nth) {
             const int q = r * GUIDED_STAGE + (t >> 5);
-            sp[t] = q < nact ? w.top[(size_t)qlist[q] * EORB_GUIDED_TOP + (t & 31)] : ~0ull;
+            sp[(t >> 5) * GUIDED_ROW + (t & 31)] = q < nact ? w.top[(size_t)qlist[q] * EORB_GUIDED_TOP + (t & 31)] : ~0ull;
         }
         for (int k = tid - t0; k < GUIDED_STAGE; k += nth) {
             const int q = r * GUIDED_STAGE + k, o = (r & 1) * GUIDED_STAGE + k;
@@ -480,13 +547,11 @@ __global__ void __launch_bounds__(256) guided_resolve_proj_kernel(const eorb_key
         if (warp != 0) {
             if (r + 1 < nrounds) loadStage(r + 1, 32, 224);
         } else {
-            const u64* sp = stop + (r & 1) * GUIDED_STAGE * 32;
+            const u64* sp = stop + (r & 1) * GUIDED_STAGE * GUIDED_ROW;
             const int so = (r & 1) * GUIDED_STAGE;
             const int kend = min(GUIDED_STAGE, nact - r * GUIDED_STAGE);
-            u64 eN = sp[lane];
-            for (int k = 0; k < kend; k++) {
-                const u64 e = eN;
-                if (k + 1 < kend) eN = sp[(k + 1) * 32 + lane];
+            auto seqStep = [&](int k) {
+                const u64 e = sp[k * GUIDED_ROW + lane];
                 const uint32_t dist = (uint32_t)(e >> 32), i2 = e != ~0ull ? (uint32_t)e & 0xffffu : 0u;
                 const bool ok = e != ~0ull && blk[i2] == 0;               // slot held by a point with observations -> skipped (:2046)
                 const unsigned mask = __ballot_sync(FULLMASK, ok);
@@ -513,7 +578,54 @@ __global__ void __launch_bounds__(256) guided_resolve_proj_kernel(const eorb_key
                     }
                     __syncwarp();
                 }
+            };
+#if EORB_GUIDED_SPEC
+            // speculative chunks as in guided_resolve_kernel: lane L takes query k + L (first unblocked entry of its head); it is
+            // dirty when an earlier lane of the chunk claims the slot it chose
+            int k = 0;
+            while (k < kend) {
+                const int q = k + lane;
+                const bool have = q < kend;
+                uint32_t b1 = 0xffffffffu;
+                bool slow = false;
+                if (have) {
+                    const u64* hp = sp + q * GUIDED_ROW;
+                    for (int en = 0; en < EORB_GUIDED_TOP && b1 == 0xffffffffu; en += 4) {
+                        u64 he[4]; uint32_t bv[4];
+#pragma unroll
+                        for (int u = 0; u < 4; u++) he[u] = hp[en + u];
+#pragma unroll
+                        for (int u = 0; u < 4; u++) bv[u] = he[u] != ~0ull ? (uint32_t)blk[(uint32_t)he[u] & 0xffffu] : 1u;
+#pragma unroll
+                        for (int u = 0; u < 4; u++)
+                            if (b1 == 0xffffffffu && bv[u] == 0) b1 = ((uint32_t)(he[u] >> 32) << 16) | ((uint32_t)he[u] & 0xffffu);
+                        if (he[3] == ~0ull) break;
+                    }
+                    slow = b1 == 0xffffffffu && scnt[so + q] > EORB_GUIDED_TOP;
+                }
+                const bool acc = have && !slow && b1 != 0xffffffffu && (b1 >> 16) <= 100u;
+                if (acc) atomicMin(&ctab[b1 & 0xffffu], (unsigned)lane);
+                __syncwarp();
+                const bool dirty = have && b1 != 0xffffffffu && ctab[b1 & 0xffffu] < (unsigned)lane;
+                const unsigned stopMask = __ballot_sync(FULLMASK, have && (dirty || slow));
+                const int ncommit = stopMask ? __ffs(stopMask) - 1 : min(32, kend - k);
+                __syncwarp();
+                if (acc) {
+                    ctab[b1 & 0xffffu] = 0xffffffffu;
+                    if (lane < ncommit) {
+                        const int i1 = qlist[r * GUIDED_STAGE + q];
+                        claim[i1] = (int)(b1 & 0xffffu);
+                        owner[b1 & 0xffffu] = (unsigned short)i1;
+                        blk[b1 & 0xffffu] = sobs[so + q] > 0 ? 1 : 0;
+                    }
+                }
+                __syncwarp();
+                k += ncommit;
+                if (stopMask && __shfl_sync(FULLMASK, (int)slow, ncommit & 31)) { seqStep(k); k++; }
             }
+#else
+            for (int k = 0; k < kend; k++) seqStep(k);
+#endif
         }
         __syncthreads();
     }
@@ -565,12 +677,12 @@ __global__ void __launch_bounds__(256) guided_resolve_proj_kernel(const eorb_key
 // ------------------------------------------------------------------------------------------------ launches
 static size_t resolveSmem(int n1, int n2) {
     const size_t n2r = (size_t)((n2 + 3) & ~3);
-    return (size_t)2 * GUIDED_STAGE * 32 * 8 + 2 * GUIDED_STAGE * 4 * 2 + 32 * 4 + n2r * 2 * 2 + (size_t)n1 * 2 + 16;
+    return (size_t)2 * GUIDED_STAGE * GUIDED_ROW * 8 + 2 * GUIDED_STAGE * 4 * 2 + 32 * 4 + n2r * 2 * 2 + (size_t)((n1 + 1) & ~1) * 2 + n2r * 4 + 16;
 }
 
 static size_t resolveProjSmem(int n1, int n2) {
     const size_t n2r = (size_t)((n2 + 3) & ~3);
-    return (size_t)2 * GUIDED_STAGE * 32 * 8 + 2 * GUIDED_STAGE * 4 * 3 + 32 * 4 + n2r * 2 + (size_t)((n1 + 1) & ~1) * 2 + n2r + 16;
+    return (size_t)2 * GUIDED_STAGE * GUIDED_ROW * 8 + 2 * GUIDED_STAGE * 4 * 3 + 32 * 4 + n2r * 2 + (size_t)((n1 + 1) & ~1) * 2 + n2r * 4 + n2r + 16;
 }
 
 cudaError_t guided_configure() {
