@@ -627,6 +627,21 @@ def run_ours(args):
         except Exception as e:   # extras never invalidate the headline line
             extra["events"] = {"error": repr(e)}
         try:
+            if rank == 0:   # configs[0]: ONE frame through ORBextractor::operator() (host image in, keypoints + descriptors out)
+                from eorb_slam_b200 import synth as _s
+                one = api.ORBextractor(p, dev, 1)
+                fr = [_s.make_frame(900 + i) for i in range(4)]
+                for i in range(10):
+                    one(fr[i % 4])
+                lat = []
+                for i in range(100):
+                    t0 = time.perf_counter(); one(fr[i % 4]); lat.append((time.perf_counter() - t0) * 1e3)
+                extra["single_frame"] = {"metric": "orb_single_frame_latency_ms", "value": float(np.median(lat)), "unit": "ms",
+                                         "p90": float(np.percentile(lat, 90)),
+                                         "workload": "configs[0]: one 752x480 frame per call, pageable host image, 12 kernels, results on the host"}
+        except Exception as e:
+            extra["single_frame"] = {"error": repr(e)}
+        try:
             if rank == 0:
                 extra["lk"] = bench_lk(api, torch, dev, args.steps, args.warmup)
         except Exception as e:
