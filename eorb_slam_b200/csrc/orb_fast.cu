@@ -23,6 +23,8 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include <mutex>
+
 #include "../../include/eorb_b200.h"
 #include "eorb_math.cuh"
 #include "fast_score.cuh"
@@ -261,7 +263,20 @@ cudaError_t launch_fast_cells(const OrbArgs& a, const OrbPlan& hp, int nframes, 
 }
 
 cudaError_t fast_cells_configure(const OrbPlan& hp) {
-    return cudaFuncSetAttribute(fast_cells_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, hp.cellSmemPerWarp * EORB_FAST_WARPS);
+    // The attribute belongs to the KERNEL, not to an extractor: several extractors with different plans live in one process
+    // (image ORB, event L1 / L2: Tracking.cc:115-137, EvBaseTracker.cpp:163), so it is set once to the largest size a plan can
+    // ask for (orbBuildPlan rejects plans above 200 KB) instead of to this plan's size, which a later, smaller plan would undo.
+    (void)hp;
+    static std::mutex mu;
+    static bool done[64] = {false};
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return e;
+    std::lock_guard<std::mutex> lk(mu);
+    if (dev >= 0 && dev < 64 && done[dev]) return cudaSuccess;
+    e = cudaFuncSetAttribute(fast_cells_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    if (e == cudaSuccess && dev >= 0 && dev < 64) done[dev] = true;
+    return e;
 }
 
 }  // namespace eorb

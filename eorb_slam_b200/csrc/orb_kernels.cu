@@ -8,6 +8,7 @@
 //   K4+K6 orient_desc_kernel IC_Angle :77-104, computeOrbDescriptor :108-157
 // Integer stages are bit-exact with the CPU oracle; float stages use explicit no-FMA intrinsics.
 #include <cuda_runtime.h>
+#include <mutex>
 #include <stdint.h>
 
 #include "../../include/eorb_b200.h"
@@ -814,7 +815,17 @@ cudaError_t launch_tracked_desc(const OrbArgs& a, const OrbPlan& hp, const eorb_
 cudaError_t orb_kernels_configure(const OrbPlan& hp) {
     cudaError_t e = fast_cells_configure(hp);
     if (e != cudaSuccess) return e;
-    return cudaFuncSetAttribute(octree_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, hp.octSmemBytes);
+    // per-kernel attribute shared by every extractor of the process: set once to the plan limit (see fast_cells_configure)
+    static std::mutex mu;
+    static bool done[64] = {false};
+    int dev = 0;
+    e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return e;
+    std::lock_guard<std::mutex> lk(mu);
+    if (dev >= 0 && dev < 64 && done[dev]) return cudaSuccess;
+    e = cudaFuncSetAttribute(octree_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    if (e == cudaSuccess && dev >= 0 && dev < 64) done[dev] = true;
+    return e;
 }
 
 }  // namespace eorb

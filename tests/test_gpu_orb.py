@@ -303,3 +303,27 @@ def test_orb_parameter_sweep_bit_exact(cfg):
     ret, kps, desc = ex(flat)
     oret, okps, odesc = orc.extract(flat)
     assert ret == oret and kps.tobytes() == okps.tobytes() and np.array_equal(desc, odesc)
+
+
+def test_extractors_with_different_plans_alternate():
+    """EORB-SLAM runs three extractors with different parameters in one process (image ORB, event L1 / L2; Tracking.cc:115-137,
+    EvBaseTracker.cpp:163): a later, smaller plan must not undo the kernel attributes an earlier, larger one needs"""
+    api = _api()
+    img = synth.make_frame(3)
+    big = api.ORBextractor(api.ORBxParams(5000, 1.2, 8, 20, 7, 19, (752, 480)))
+    r1, k1, d1 = big(img)
+    small = api.ORBextractor(api.ORBxParams(400, 1.0, 1, 0, 0, 9, (240, 180)))
+    ev = np.ascontiguousarray(img[:180, :240])
+    s1 = small(ev, None, (0, 1000), False)
+    mid = api.ORBextractor(api.ORBxParams())
+    m1 = mid(img)
+    for _ in range(2):
+        r2, k2, d2 = big(img)
+        assert r2 == r1 and k2.tobytes() == k1.tobytes() and np.array_equal(d2, d1)
+        s2 = small(ev, None, (0, 1000), False)
+        assert s2[0] == s1[0] and s2[1].tobytes() == s1[1].tobytes()
+        m2 = mid(img)
+        assert m2[1].tobytes() == m1[1].tobytes() and np.array_equal(m2[2], m1[2])
+    orc = O.OrbOracle(5000, 1.2, 8, 20, 7, 19, 752, 480)
+    _, ok, od = orc.extract(img)
+    assert ok.tobytes() == k1.tobytes() and np.array_equal(od, d1)

@@ -19,3 +19,7 @@ for i in range(300):
     t0 = time.perf_counter(); ex2(ev[i % 8], None, (0, 1000), False); ts.append(time.perf_counter() - t0)
 ts = np.array(ts) * 1e3
 print("event L1 extractor (240x180, 1 level, keypoints only): median %.3f ms" % np.median(ts))
+ex.stage_timing(True)
+for i in range(50): ex(imgs[i % 8])
+ms, launches = ex.stage_times()
+print("per-stage us per frame (single-frame calls):", {k: round(v / 50 * 1000, 1) for k, v in ms.items()})
