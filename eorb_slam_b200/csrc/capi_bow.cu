@@ -38,8 +38,16 @@ struct eorb_vocab {
     long long launches = 0;
 };
 
-static std::once_flag g_bowOnce;
-static cudaError_t g_bowErr = cudaSuccess;
+// kernel attributes (dynamic shared-memory limits) are per device: configured once for every device a handle is created on
+static std::mutex g_cfgMu;
+static bool g_cfgDone[64] = {false};
+static cudaError_t configureDevice(int device) {
+    std::lock_guard<std::mutex> lk(g_cfgMu);
+    if (device >= 0 && device < 64 && g_cfgDone[device]) return cudaSuccess;
+    const cudaError_t e = bow_configure();
+    if (e == cudaSuccess && device >= 0 && device < 64) g_cfgDone[device] = true;
+    return e;
+}
 
 extern "C" int eorb_vocab_create(int device, int k, int L, int scoring, int weighting, int nnodes, const int32_t* parent, const uint8_t* is_leaf,
                                  const uint8_t* desc, const double* weight, eorb_vocab** out) {
@@ -52,8 +60,7 @@ extern "C" int eorb_vocab_create(int device, int k, int L, int scoring, int weig
     if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) { cudaGetLastError(); return bFail(EORB_ERR_CUDA, "no CUDA device: eorb_b200 has no CPU fallback", nullptr); }
     if (device < 0 || device >= ndev) return bFail(EORB_ERR_ARG, "eorb_vocab_create", "device out of range");
     CU(cudaSetDevice(device));
-    std::call_once(g_bowOnce, [] { g_bowErr = bow_configure(); });
-    if (g_bowErr != cudaSuccess) return bFail(EORB_ERR_CUDA, "bow_configure", cudaGetErrorString(g_bowErr));
+    { const cudaError_t ec = configureDevice(device); if (ec != cudaSuccess) return bFail(EORB_ERR_CUDA, "bow_configure", cudaGetErrorString(ec)); }
     // children lists in id order, word ids in order of appearance — exactly what loadFromTextFile builds (:1375-1412)
     std::vector<int> cnt(nnodes, 0), childStart(nnodes + 1, 0), children(std::max(nnodes - 1, 1));
     std::vector<uint32_t> wordId(nnodes, 0);

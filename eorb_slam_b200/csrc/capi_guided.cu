@@ -42,8 +42,16 @@ struct eorb_guided {
     long long launches = 0;
 };
 
-static std::once_flag g_cfgOnce;
-static cudaError_t g_cfgErr = cudaSuccess;
+// kernel attributes (dynamic shared-memory limits) are per device: configured once for every device a handle is created on
+static std::mutex g_cfgMu;
+static bool g_cfgDone[64] = {false};
+static cudaError_t configureDevice(int device) {
+    std::lock_guard<std::mutex> lk(g_cfgMu);
+    if (device >= 0 && device < 64 && g_cfgDone[device]) return cudaSuccess;
+    const cudaError_t e = guided_configure();
+    if (e == cudaSuccess && device >= 0 && device < 64) g_cfgDone[device] = true;
+    return e;
+}
 
 static GuidedGrid gridGeom(const float* b) {
     GuidedGrid g;
@@ -59,8 +67,7 @@ extern "C" int eorb_guided_create(int device, eorb_guided** out) {
     if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) { cudaGetLastError(); return gFail(EORB_ERR_CUDA, "no CUDA device: eorb_b200 has no CPU fallback", nullptr); }
     if (device < 0 || device >= ndev) return gFail(EORB_ERR_ARG, "eorb_guided_create", "device out of range");
     CU(cudaSetDevice(device));
-    std::call_once(g_cfgOnce, [] { g_cfgErr = guided_configure(); });
-    if (g_cfgErr != cudaSuccess) return gFail(EORB_ERR_CUDA, "guided_configure", cudaGetErrorString(g_cfgErr));
+    { const cudaError_t ec = configureDevice(device); if (ec != cudaSuccess) return gFail(EORB_ERR_CUDA, "guided_configure", cudaGetErrorString(ec)); }
     eorb_guided* g = new eorb_guided();
     g->device = device;
     CU(cudaStreamCreateWithFlags(&g->ownStream, cudaStreamNonBlocking));
