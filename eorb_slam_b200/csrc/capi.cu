@@ -246,6 +246,12 @@ struct eorb_orb {
     std::vector<cudaEvent_t> evPool;   // (EORB_ORB_STAGES+1) events per recorded call
     size_t evCalls = 0;
     long long stageLaunches[EORB_ORB_STAGES] = {0, 0, 0, 0, 0, 0};
+    // CUDA graph of one launch set on the main slab + its result copies (the single-frame call is launch bound: 12 kernels and
+    // 4 copies per frame); replayed while (frames, lapping area, descriptors wanted) stay the same, rebuilt otherwise
+    cudaGraphExec_t graphExec = nullptr;
+    int graphKey[4] = {-1, 0, 0, 0};
+    long long graphLaunches = 0;   // kernel launches inside the captured graph
+    bool useGraph = true;          // EORB_ORB_GRAPH=0 disables
 };
 
 static cudaEvent_t* orbStageEvents(eorb_orb* h) {
@@ -318,7 +324,13 @@ static int orbAllocBufs(eorb_orb* h, eorb_orb::Bufs& b, bool pipeline) {
     return EORB_OK;
 }
 
+static void orbDropGraph(eorb_orb* h) {
+    if (h->graphExec) cudaGraphExecDestroy(h->graphExec);
+    h->graphExec = nullptr; h->graphKey[0] = -1;
+}
+
 static void orbFreePlan(eorb_orb* h) {
+    orbDropGraph(h);
     cudaFree(h->d_plan); cudaFree(h->d_cells); cudaFree(h->d_xtab); cudaFree(h->d_ytab); cudaFree(h->d_invScale); cudaFree(h->d_icTab);
     h->d_plan = nullptr; h->d_cells = nullptr; h->d_xtab = nullptr; h->d_ytab = nullptr; h->d_invScale = nullptr; h->d_icTab = nullptr;
     orbFreeBufs(h->main);
@@ -561,6 +573,7 @@ extern "C" int eorb_orb_create(const eorb_orb_params* params, int device, int ma
     CU(cudaSetDevice(device));
     eorb_orb* h = new eorb_orb();
     h->par = *params; h->device = device; h->maxBatch = max_batch;
+    if (const char* e = getenv("EORB_ORB_GRAPH")) h->useGraph = atoi(e) != 0;
     h->pipeBatch = std::min(max_batch, 128);   // measured on B200: H2D/compute/D2H overlap is best with 128-frame slots
     cudaDeviceProp prop;
     CU(cudaGetDeviceProperties(&prop, device));
@@ -578,6 +591,7 @@ extern "C" int eorb_orb_destroy(eorb_orb* h) {
     cudaStreamSynchronize(h->stream);
     orbFreePlan(h);
     for (cudaEvent_t e : h->evPool) cudaEventDestroy(e);
+    orbDropGraph(h);
     cudaStreamDestroy(h->ownStream);
     delete h;
     return EORB_OK;
@@ -586,6 +600,7 @@ extern "C" int eorb_orb_destroy(eorb_orb* h) {
 extern "C" int eorb_orb_set_stream(eorb_orb* h, void* s) {
     if (!h) return fail(EORB_ERR_ARG, "null handle");
     CU(cudaStreamSynchronize(h->stream));
+    orbDropGraph(h);
     h->stream = (cudaStream_t)s;   // NULL is the CUDA legacy default stream, a legitimate choice
     return EORB_OK;
 }
@@ -750,16 +765,45 @@ extern "C" int eorb_orb_extract_batch(eorb_orb* h, const uint8_t* imgs, int nfra
         }
         OrbArgs a = orbArgs(h, b, b.d_img0, h->pitch0, (long long)h->pitch0 * hgt, lap0, lap1, want_desc, b.d_outKps, b.d_outDesc,
                             icap, b.d_outN, b.d_outMono);
-        CUtensorMap tm0;
-        rc = tmaEncodeFrames(&tm0, b.d_img0, w, hgt, nb, (size_t)h->pitch0, (size_t)h->pitch0 * hgt, h->hp.cellTileStride, h->hp.cellTileRows);
-        if (rc != EORB_OK) return rc;
-        CU(launch_orb_pipeline(a, h->hp, nb, tm0, st, &h->launches, nslots > 0 ? nullptr : orbStageEvents(h)));
-        CU(cudaMemcpyAsync(b.h_n, b.d_outN, nb * sizeof(int), cudaMemcpyDeviceToHost, st));
-        CU(cudaMemcpyAsync(b.h_mono, b.d_outMono, nb * sizeof(int), cudaMemcpyDeviceToHost, st));
         eorb_keypoint* kdst = direct ? kps + (size_t)f0 * cap : b.h_kps;
         uint8_t* ddst = direct ? desc + (size_t)f0 * cap * 32 : b.h_desc;
-        CU(cudaMemcpyAsync(kdst, b.d_outKps, (size_t)nb * icap * sizeof(eorb_keypoint), cudaMemcpyDeviceToHost, st));
-        if (want_desc) CU(cudaMemcpyAsync(ddst, b.d_outDesc, (size_t)nb * icap * 32, cudaMemcpyDeviceToHost, st));
+        // the launch set and its result copies; with `capturing` they are recorded into a graph instead of being executed
+        auto issue = [&](long long* launchCounter, cudaEvent_t* stageEv) -> int {
+            CUtensorMap tm0;
+            int rct = tmaEncodeFrames(&tm0, b.d_img0, w, hgt, nb, (size_t)h->pitch0, (size_t)h->pitch0 * hgt, h->hp.cellTileStride, h->hp.cellTileRows);
+            if (rct != EORB_OK) return rct;
+            CU(launch_orb_pipeline(a, h->hp, nb, tm0, st, launchCounter, stageEv));
+            CU(cudaMemcpyAsync(b.h_n, b.d_outN, nb * sizeof(int), cudaMemcpyDeviceToHost, st));
+            CU(cudaMemcpyAsync(b.h_mono, b.d_outMono, nb * sizeof(int), cudaMemcpyDeviceToHost, st));
+            CU(cudaMemcpyAsync(kdst, b.d_outKps, (size_t)nb * icap * sizeof(eorb_keypoint), cudaMemcpyDeviceToHost, st));
+            if (want_desc) CU(cudaMemcpyAsync(ddst, b.d_outDesc, (size_t)nb * icap * 32, cudaMemcpyDeviceToHost, st));
+            return EORB_OK;
+        };
+        // single launch set on the handle's own stream, small batch: replay a CUDA graph (the call is launch bound)
+        const bool graphable = h->useGraph && nslots == 0 && !h->stageTiming && st == h->ownStream && nb <= 8;
+        if (graphable) {
+            const int key[4] = {nb, lap0, lap1, want_desc};
+            if (!h->graphExec || memcmp(key, h->graphKey, sizeof(key)) != 0) {
+                orbDropGraph(h);
+                cudaGraph_t g = nullptr;
+                long long cnt = 0;
+                CU(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
+                const int rci = issue(&cnt, nullptr);
+                const cudaError_t ce = cudaStreamEndCapture(st, &g);
+                if (rci != EORB_OK) { if (g) cudaGraphDestroy(g); return rci; }
+                if (ce != cudaSuccess) return fail(EORB_ERR_CUDA, "cudaStreamEndCapture failed: %s", cudaGetErrorString(ce));
+                const cudaError_t ie = cudaGraphInstantiate(&h->graphExec, g, 0);
+                cudaGraphDestroy(g);
+                if (ie != cudaSuccess) { h->graphExec = nullptr; return fail(EORB_ERR_CUDA, "cudaGraphInstantiate failed: %s", cudaGetErrorString(ie)); }
+                memcpy(h->graphKey, key, sizeof(key));
+                h->graphLaunches = cnt;
+            }
+            CU(cudaGraphLaunch(h->graphExec, st));
+            h->launches += h->graphLaunches;
+        } else {
+            rc = issue(&h->launches, nslots > 0 ? nullptr : orbStageEvents(h));
+            if (rc != EORB_OK) return rc;
+        }
         if (b.done) CU(cudaEventRecord(b.done, st));
         b.f0 = f0; b.nb = nb; b.pending = true;
         h->lastLvl0 = b.d_img0; h->lastPitch0 = h->pitch0; h->lastFrameStride0 = (long long)h->pitch0 * hgt; h->lastFrames = nb;
