@@ -193,6 +193,35 @@ def bench_events(api, torch, dev, steps, warmup):
                         "note": "7x7 splat accumulates in shared memory (int32 fixed point, native ATOMS.ADD), frame written once; "
                                 "bounded by instruction issue + smem atomics, not HBM; see atomic_adds_per_s"}}
     cv.set_stream(None)
+    # configs[1] as ONE device pipeline: the windows above -> u8 event frames -> single-level event extractor (N = 400, FAST 0/0,
+    # keypoints only, EvETHZ.yaml:185-199) on the frames where they lie in HBM
+    try:
+        exe = api.ORBextractor(api.ORBxParams(400, 1.0, 1, 0, 0, 9, (w, h)), dev, nwin)
+        exe.set_stream(st)
+        ecap = exe.cap
+        d_k = torch.empty(nwin * ecap * 28, dtype=torch.uint8, device="cuda"); d_d = torch.empty(nwin * ecap * 32, dtype=torch.uint8, device="cuda")
+        d_nn = torch.zeros(nwin, dtype=torch.int32, device="cuda"); d_mm = torch.zeros(nwin, dtype=torch.int32, device="cuda")
+        cv.set_stream(st)
+
+        def chain():
+            cv.accumulate_batch_device(d_ev.data_ptr(), offs, p, d_img.data_ptr(), d_u8.data_ptr())
+            exe.extract_batch_raw(d_u8.data_ptr(), nwin, w, h, w, w * h, (0, 1000), False, d_k.data_ptr(), d_d.data_ptr(), ecap, d_nn.data_ptr(),
+                                  d_mm.data_ptr(), device=True)
+        for _ in range(3):
+            chain()
+        torch.cuda.synchronize()
+        t.start(st)
+        for _ in range(10):
+            chain()
+        t.stop(st)
+        msc = t.elapsed_ms() / 10
+        out["chain_events_to_keypoints"] = {"value": nwin / (msc * 1e-3), "unit": "windows/s", "ms_per_step": msc, "mev_per_s": nev / msc / 1e3,
+                                            "keypoints_per_window": float(d_nn.float().mean().item()),
+                                            "workload": "configs[1]: %d windows x %d events -> 240x180 u8 event frames -> single-level ORB "
+                                                        "(N=400, FAST 0/0, keypoints only), all in HBM" % (nwin, per)}
+        cv.set_stream(None); exe.set_stream(None)
+    except Exception as e:
+        out["chain_events_to_keypoints"] = {"error": repr(e)}
     # configs[4]: MVSEC-shaped 346x260 frames, 50k events per window, motion compensated with a per-window rotation
     # (ev2mci_gg_f, SE3 warp in double per event), cv::normalize(MINMAX) to u8.  The 360 KB frame does not fit one SM's
     # shared memory, so it is split into row bands (every band scans the window's events).

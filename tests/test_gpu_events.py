@@ -215,3 +215,36 @@ def test_mci_jacobian_matches_oracle(cfg):
             assert np.abs(got - exp).max() <= 2e-4 * np.abs(exp).max(), (glob, pol, got, exp)
     # no events: zero Jacobian and EORB_EMPTY, like the reference's early return (:543-546)
     assert np.all(cv.ev2mci_gg_f_jac(ev[:0], K, R, t, 1.0, w, h, 1.0) == 0)
+
+
+def test_config2_chain_stays_on_the_device():
+    """configs[1] end to end without a host round trip: event windows -> Gaussian event frames (u8, in HBM) -> single-level event
+    extractor on those frames (eorb_orb_extract_batch_device).  The extractor's output must equal the oracle's extraction of the
+    very frames the device produced (downloaded only for the check)."""
+    import torch
+    api = _api()
+    nwin, per, w, h = 16, 2000, 240, 180
+    ev = synth.make_events(nwin * per, seed=8, w=w, h=h)
+    cv = api.EvImConverter(0, nwin, nwin * per, w, h)
+    st = torch.cuda.current_stream().cuda_stream
+    cv.set_stream(st)
+    d_ev = torch.from_numpy(ev.view(np.uint8).reshape(-1)).cuda()
+    d_img = torch.zeros(nwin * h * w, dtype=torch.float32, device="cuda"); d_u8 = torch.zeros(nwin * h * w, dtype=torch.uint8, device="cuda")
+    p = cv.make_params(api.EV_GAUSS, w, h, 1.0, False, api.NORM_RUNNING)
+    cv.accumulate_batch_device(d_ev.data_ptr(), np.arange(nwin + 1, dtype=np.int64) * per, p, d_img.data_ptr(), d_u8.data_ptr())
+    ex = api.ORBextractor(api.ORBxParams(400, 1.0, 1, 0, 0, 9, (w, h)), 0, nwin)
+    ex.set_stream(st)
+    cap = ex.cap
+    d_kps = torch.zeros(nwin * cap * 28, dtype=torch.uint8, device="cuda"); d_desc = torch.zeros(nwin * cap * 32, dtype=torch.uint8, device="cuda")
+    d_n = torch.zeros(nwin, dtype=torch.int32, device="cuda"); d_mono = torch.zeros(nwin, dtype=torch.int32, device="cuda")
+    ex.extract_batch_raw(d_u8.data_ptr(), nwin, w, h, w, w * h, (0, 1000), False, d_kps.data_ptr(), d_desc.data_ptr(), cap, d_n.data_ptr(),
+                         d_mono.data_ptr(), device=True)
+    torch.cuda.synchronize()
+    frames = d_u8.cpu().numpy().reshape(nwin, h, w)
+    ns = d_n.cpu().numpy(); kps = d_kps.cpu().numpy().view(synth.KEYPOINT_DTYPE).reshape(nwin, cap)
+    orc = O.OrbOracle(400, 1.0, 1, 0, 0, 9, w, h)
+    for i in range(nwin):
+        _, ok, _ = orc.extract(frames[i], (0, 1000), False)
+        assert ns[i] == len(ok) and kps[i][:ns[i]].tobytes() == ok.tobytes(), i
+    assert ns.min() > 50
+    cv.set_stream(None); ex.set_stream(None)
