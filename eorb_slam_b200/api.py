@@ -58,7 +58,7 @@ def _load():
         "eorb_probe_popc_rate": ([i, C.POINTER(C.c_double)], i), "eorb_selftest_math": ([i, C.POINTER(i)], i),
         "eorb_orb_create": ([C.POINTER(_OrbParams), i, i, C.POINTER(vp)], i), "eorb_orb_destroy": ([vp], i),
         "eorb_orb_set_stream": ([vp, vp], i), "eorb_orb_reset_stream": ([vp], i), "eorb_orb_get_stream": ([vp], vp), "eorb_orb_synchronize": ([vp], i),
-        "eorb_orb_tables": ([vp, vp, vp, vp, vp, vp, vp, vp], i), "eorb_orb_max_keypoints": ([vp], i),
+        "eorb_orb_tables": ([vp, vp, vp, vp, vp, vp, vp, vp], i), "eorb_orb_max_keypoints": ([vp], i), "eorb_orb_max_keypoints_for_size": ([vp, i, i], i),
         "eorb_orb_extract": ([vp, vp, i, i, sz, i, i, i, vp, vp, i, vp], i),
         "eorb_orb_extract_batch": ([vp, vp, i, i, i, sz, sz, i, i, i, vp, vp, i, vp, vp], i),
         "eorb_orb_extract_batch_device": ([vp, vp, i, i, i, sz, sz, i, i, i, vp, vp, i, vp, vp], i),
@@ -263,11 +263,12 @@ class ORBextractor:
             return EORB_EMPTY, np.empty(0, KEYPOINT_DTYPE), None
         img = np.ascontiguousarray(image, np.uint8)
         assert img.ndim == 2, "CV_8UC1 expected (ORBextractor.cc:1100)"
-        kps = np.zeros(self.cap, KEYPOINT_DTYPE)
-        desc = np.zeros((self.cap, 32), np.uint8) if want_desc else None
+        cap = lib.eorb_orb_max_keypoints_for_size(self.h, img.shape[1], img.shape[0])   # elongated frames have more octree roots
+        kps = np.zeros(cap, KEYPOINT_DTYPE)
+        desc = np.zeros((cap, 32), np.uint8) if want_desc else None
         n = C.c_int(0)
         ret = _check(lib.eorb_orb_extract(self.h, _p(img), img.shape[1], img.shape[0], img.strides[0], int(vLappingArea[0]),
-                                          int(vLappingArea[1]), int(want_desc), _p(kps), _p(desc), self.cap, C.byref(n)), "extract")
+                                          int(vLappingArea[1]), int(want_desc), _p(kps), _p(desc), cap, C.byref(n)), "extract")
         return ret, kps[:n.value].copy(), (desc[:n.value].copy() if want_desc else None)
 
     def extract_batch(self, frames, vLappingArea=(0, 1000), want_desc=True, out=None):

@@ -389,6 +389,8 @@ static int orbBuildPlan(eorb_orb* h, int W, int H) {
     OrbPlan& P = h->hp;
     memset(&P, 0, sizeof(P));
     const int nl = h->nlevels, E = h->edge;
+    // the FAST region starts at column / row E - 3 of the level (:792-795): below 3 the reference reads outside its bordered image
+    if (E < 3) return fail(EORB_ERR_ARG, "edge threshold %d < 3 is unsupported (the FAST region would start outside the image)", E);
     P.nlevels = nl; P.edge = E; P.iniTh = h->par.iniThFAST; P.minTh = h->par.minThFAST; P.W = W; P.H = H;
     for (int i = 0; i < 16; i++) P.umax[i] = h->umax[i];
     h->cells.clear();
@@ -509,7 +511,7 @@ static int orbBuildPlan(eorb_orb* h, int W, int H) {
         return fail(EORB_ERR_ARG, "shared-memory budget exceeded (fast %d B, octree %d B)", P.cellSmemPerWarp * EORB_FAST_WARPS, octSmem);
 
     h->pitch0 = roundUp(W, 16);
-    h->cap = eorb_orb_max_keypoints(h);
+    h->cap = eorb_orb_max_keypoints_for_size(h, W, H);
     CU(devAlloc(&h->d_plan, 1));
     CU(devAlloc(&h->d_cells, h->cells.size()));
     CU(devAlloc(&h->d_xtab, xtab.size()));
@@ -662,12 +664,28 @@ extern "C" int eorb_orb_tables(const eorb_orb* h, int* nlevels, int* edge, float
     return EORB_OK;
 }
 
+// Upper bound of the keypoints one frame of size w x hgt can produce: per level the octree ends with at most quota + 2 nodes
+// (its last splits add up to 3 to a list below the quota) or, when the quota is tiny, with the 4 * nIni children of its first
+// pass (:562-563, 620-683; nIni = round(width / height) of the level's FAST region, so elongated images have many roots).
+extern "C" int eorb_orb_max_keypoints_for_size(const eorb_orb* h, int w, int hgt) {
+    if (!h) return 0;
+    int cap = 0;
+    for (int l = 0; l < h->nlevels; l++) {
+        int nIni = 4;
+        if (w > 0 && hgt > 0) {
+            const int lw = rne((float)w * h->invScale[l]), lh = rne((float)hgt * h->invScale[l]);
+            const int bw = lw - 2 * h->edge + 6, bh = lh - 2 * h->edge + 6;   // maxBorder - minBorder
+            nIni = (bw > 0 && bh > 0) ? (int)std::round((float)bw / (float)bh) : 0;
+        }
+        cap += std::max(h->quota[l] + 3, std::max(4 * nIni, 16));
+    }
+    return cap;
+}
+
 extern "C" int eorb_orb_max_keypoints(const eorb_orb* h) {
     if (!h) return 0;
-    // every level may overshoot its quota by up to 3 (octree) or reach 4*nIni nodes when the quota is tiny
-    int cap = 0;
-    for (int l = 0; l < h->nlevels; l++) cap += std::max(h->quota[l] + 3, 16);
-    return cap;
+    if (h->planW > 0) return eorb_orb_max_keypoints_for_size(h, h->planW, h->planH);   // the size of the last frames
+    return eorb_orb_max_keypoints_for_size(h, h->par.imW, h->par.imH);                 // the size announced at construction
 }
 
 static bool lvl0ZeroCopyOk(const uint8_t* p, int w, size_t rowStride, size_t frameStride) {

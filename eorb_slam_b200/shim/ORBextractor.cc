@@ -62,7 +62,7 @@ int ORBextractor::extract(cv::InputArray _image, std::vector<cv::KeyPoint>& _key
         return -1;
     cv::Mat image = _image.getMat();
     assert(image.type() == CV_8UC1);                           // ORBextractor.cc:1100
-    const int cap = eorb_orb_max_keypoints(mpHandle);
+    const int cap = eorb_orb_max_keypoints_for_size(mpHandle, image.cols, image.rows);
     _keypoints = std::vector<cv::KeyPoint>(cap);
     if (desc) mScratchDesc.resize((size_t)cap * DEF_DESC_LEN);
     int n = 0;

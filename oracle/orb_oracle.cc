@@ -15,6 +15,8 @@
 //   * px*b+py*a is evaluated WITHOUT FMA contraction (build with -ffp-contract=off), cos/sin = libm cosf/sinf.
 //   * descriptor taps that fall outside the (borderless) blurred level (possible only when edgeTh < 19) are
 //     read with REFLECT_101 indexing (the reference reads out of bounds there).
+//   * orientation patches that run past the bordered level (possible only when the margin is below 8) are read with
+//     REFLECT_101 indexing of the level (the reference reads past its buffer there).
 //   * EDGE_THRESHOLD is per extractor instance (the reference has one mutable global, :73).
 //   * levels whose FAST grid has 0 rows or columns yield no keypoints (the reference divides by zero).
 #include "oracle.h"
@@ -495,8 +497,27 @@ static void computeKeyPointsOctTree(orc_orb* o) {
     }
     for (int level = 0; level < nl; ++level)
         for (auto& kp : o->lkps[level]) {
-            const uint8_t* c = o->levelPtr(level) + (size_t)cvRoundF(kp.y) * o->levelStride(level) + cvRoundF(kp.x);
-            kp.angle = icAngle(c, (int)o->levelStride(level), o->umax);
+            if (E >= 8) {   // keypoints lie >= E px inside the level: the 15-px patch stays inside the E-px reflected border
+                const uint8_t* c = o->levelPtr(level) + (size_t)cvRoundF(kp.y) * o->levelStride(level) + cvRoundF(kp.x);
+                kp.angle = icAngle(c, (int)o->levelStride(level), o->umax);
+            } else {
+                // Pin for margins below 8 (e.g. the adaptive margin of images narrower than 316 px): the reference's patch runs
+                // past its bordered buffer there (undefined reads).  Rule: REFLECT_101 indexing of the level, i.e. what a wide
+                // enough border would hold; identical to the branch above whenever that one is defined.
+                const int W = o->lw[level], H = o->lh[level], cx = cvRoundF(kp.x), cy = cvRoundF(kp.y);
+                const uint8_t* L = o->levelPtr(level);
+                const size_t st = o->levelStride(level);
+                int m01 = 0, m10 = 0;
+                for (int v = -kHalfPatch; v <= kHalfPatch; ++v) {
+                    const int d = o->umax[v < 0 ? -v : v];
+                    const uint8_t* row = L + (ptrdiff_t)reflect101(cy + v, H) * (ptrdiff_t)st;
+                    for (int u = -d; u <= d; ++u) {
+                        const int val = row[reflect101(cx + u, W)];
+                        m10 += u * val; m01 += v * val;
+                    }
+                }
+                kp.angle = fastAtan2f((float)m01, (float)m10);
+            }
         }
 }
 

@@ -152,7 +152,7 @@ class OrbOracle:
         self.h = lib().orc_orb_create(C.byref(self.params))
         assert self.h
         self.nlevels = nlevels
-        self.cap = nfeatures + 3 * nlevels + 64
+        self.cap = nfeatures + 3 * nlevels + 64 + 64 * nlevels   # elongated frames: up to 4 * round(aspect) nodes per level when the quota is tiny
 
     def __del__(self):
         try:

@@ -327,3 +327,13 @@ def test_extractors_with_different_plans_alternate():
     orc = O.OrbOracle(5000, 1.2, 8, 20, 7, 19, 752, 480)
     _, ok, od = orc.extract(img)
     assert ok.tobytes() == k1.tobytes() and np.array_equal(od, d1)
+
+
+def test_orb_random_parameter_fuzz():
+    """150 random configurations (sizes 64..900 x 48..620, 1..9 levels, scale 1.1..2.0, thresholds, margins incl. the adaptive one,
+    1..2500 features, lapping areas, textured / flat frames) against the oracle, bit for bit; documented limits must fail loudly
+    (tools/gpu_fuzz_orb.py)"""
+    import subprocess, sys, os
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, os.path.join(root, "tools", "gpu_fuzz_orb.py"), "150", "7"], capture_output=True, text=True, timeout=900)
+    assert r.returncode == 0 and "0 mismatches" in r.stdout, r.stdout[-3000:] + r.stderr[-2000:]
