@@ -22,9 +22,12 @@ namespace eorb {
 __device__ __forceinline__ void splat_taps(float* __restrict__ im, int W, int H, float X, float Y, float polSign,
                                            const EvConst& c, int sub, int lpe) {
     const float fxi = floorf(X), fyi = floorf(Y);
+    const int half = c.half;
+    // positions whose window cannot touch the frame — and NaN / inf (e.g. the SE2 warp of a single-timestamp window divides by
+    // DT = 0; the reference's float -> int conversion sends those far outside the image) — contribute nothing
+    if (!(fxi >= (float)(-half - 1) && fxi <= (float)(W + half) && fyi >= (float)(-half - 1) && fyi <= (float)(H + half))) return;
     const int xi = (int)fxi, yi = (int)fyi;
     const float xr = __fsub_rn(X, (float)xi), yr = __fsub_rn(Y, (float)yi);
-    const int half = c.half;
     const float den = __fmul_rn(2.0f, c.sig2);
     for (int ii = sub; ii <= 2 * half; ii += lpe) {
         const int i = ii - half;

@@ -248,3 +248,12 @@ def test_config2_chain_stays_on_the_device():
         assert ns[i] == len(ok) and kps[i][:ns[i]].tobytes() == ok.tobytes(), i
     assert ns.min() > 50
     cv.set_stream(None); ex.set_stream(None)
+
+
+def test_random_parameter_fuzz_of_the_other_rows():
+    """random sizes / parameters for the event-frame overloads (incl. sigma != 1, single-event windows), the LK tracker, both
+    guided matchers and the vocabulary transform against the oracle (tools/gpu_fuzz_rest.py)"""
+    import subprocess, sys, os
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, os.path.join(root, "tools", "gpu_fuzz_rest.py"), "40", "11"], capture_output=True, text=True, timeout=900)
+    assert r.returncode == 0 and "0 mismatches" in r.stdout, r.stdout[-3000:] + r.stderr[-2000:]
