@@ -18,7 +18,7 @@ from dataclasses import dataclass
 
 import numpy as np
 
-from .synth import EVENT_DTYPE, KEYPOINT_DTYPE, MATCH_DTYPE
+from .synth import EVENT_DTYPE, KEYPOINT_DTYPE, MATCH_DTYPE, TRACK_POINT_DTYPE
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 # EORB_B200_LIB selects another build of the same library (kernel-tuning A/B runs); there is still no CPU fallback
@@ -97,6 +97,8 @@ def _load():
         "eorb_guided_search_for_initialization_device": ([vp, vp, vp, i, vp, vp, i, vp, vp, i, f, i, vp, vp], i),
         "eorb_guided_search_by_projection": ([vp, vp, vp, vp, vp, vp, i, vp, vp, i, vp, vp, vp, i, f, i, vp, vp], i),
         "eorb_guided_search_by_projection_device": ([vp, vp, vp, vp, vp, vp, i, vp, vp, i, vp, vp, vp, i, f, i, vp, vp], i),
+        "eorb_guided_search_by_projection_map_points": ([vp, vp, vp, i, vp, vp, vp, i, vp, vp, i, f, i, f, f, vp, vp], i),
+        "eorb_guided_search_by_projection_map_points_device": ([vp, vp, vp, i, vp, vp, vp, i, vp, vp, i, f, i, f, f, vp, vp], i),
         "eorb_vocab_create": ([i, i, i, i, i, i, vp, vp, vp, vp, C.POINTER(vp)], i), "eorb_vocab_destroy": ([vp], i),
         "eorb_vocab_set_stream": ([vp, vp], i), "eorb_vocab_reset_stream": ([vp], i), "eorb_vocab_launch_count": ([vp], C.c_longlong),
         "eorb_vocab_transform": ([vp, vp, i, i, vp, vp, vp, vp, vp, vp, vp, vp, vp], i),
@@ -681,6 +683,21 @@ class GuidedMatcher:
         _check(lib.eorb_guided_search_by_projection(self.h, _p(x), _p(v), _p(o), _p(k1), _p(dm), len(k1), _p(k2), _p(d2), len(k2), _p(b), _p(K),
                                                     _p(sf), len(sf), float(th), int(self.mbCheckOrientation), _p(mc), C.byref(nm)),
                "SearchByProjection")
+        return nm.value, mc[:len(k2)].copy()
+
+    def SearchByProjectionMapPoints(self, pts, descMP, kps2, desc2, held2, bounds, scale_factors, th=1.0, bFarPoints=False, thFarPoints=0.0):
+        """ORBmatcher::SearchByProjection(F, vpMapPoints, th, bFarPoints, thFarPoints) (:44-218, monocular frame;
+        Tracking::SearchLocalPoints) -> (nmatches, match_cur[n2]).  pts: TRACK_POINT_DTYPE (what Frame::isInFrustum fills)."""
+        p = np.ascontiguousarray(pts, TRACK_POINT_DTYPE); k2 = np.ascontiguousarray(kps2, KEYPOINT_DTYPE)
+        dm = np.ascontiguousarray(descMP, np.uint8); d2 = np.ascontiguousarray(desc2, np.uint8)
+        hd = None if held2 is None else np.ascontiguousarray(held2, np.uint8)
+        b = np.ascontiguousarray(bounds, np.float32); sf = np.ascontiguousarray(scale_factors, np.float32)
+        mc = np.full(max(len(k2), 1), -1, np.int32)
+        nm = C.c_int(0)
+        _check(lib.eorb_guided_search_by_projection_map_points(self.h, _p(p), _p(dm), len(p), _p(k2), _p(d2), _p(hd) if hd is not None else None,
+                                                               len(k2), _p(b), _p(sf), len(sf), C.c_float(th), int(bool(bFarPoints)),
+                                                               C.c_float(thFarPoints), C.c_float(self.mfNNratio), _p(mc), C.byref(nm)),
+               "SearchByProjection(map points)")
         return nm.value, mc[:len(k2)].copy()
 
     def SearchForInitialization_device(self, d_kps1, d_desc1, n1, d_kps2, d_desc2, n2, bounds, d_prev, d_matches12, windowSize=100):

@@ -35,6 +35,7 @@ struct eorb_guided {
     // SearchByProjection staging: camera-frame points, validity, observations (frame 1), match table (frame 2)
     float* d_x3 = nullptr; uint8_t* d_valid = nullptr; int32_t* d_obs = nullptr; int pCap1 = 0;
     int32_t* d_mc = nullptr; int pCap2 = 0;
+    uint8_t* d_held = nullptr; int heldCap = 0;         // SearchByProjection (map points): slots of F held on entry
     GuidedWork w{};
     int workN1 = 0, workN2 = 0;
     int* d_nm = nullptr; int* h_nm = nullptr;          // [nmatches, total candidates] device + pinned mirror
@@ -86,7 +87,7 @@ extern "C" int eorb_guided_destroy(eorb_guided* g) {
     cudaSetDevice(g->device);
     cudaStreamSynchronize(g->stream);
     for (int k = 0; k < 2; k++) { cudaFree(g->d_kps[k]); cudaFree(g->d_desc[k]); }
-    cudaFree(g->d_prev); cudaFree(g->d_m12); cudaFree(g->d_x3); cudaFree(g->d_valid); cudaFree(g->d_obs); cudaFree(g->d_mc); cudaFree(g->w.q);
+    cudaFree(g->d_prev); cudaFree(g->d_m12); cudaFree(g->d_x3); cudaFree(g->d_valid); cudaFree(g->d_obs); cudaFree(g->d_mc); cudaFree(g->d_held); cudaFree(g->w.q);
     cudaFree(g->w.cellStart); cudaFree(g->w.cellIdx); cudaFree(g->w.assigned); cudaFree(g->w.candOff); cudaFree(g->w.candCnt);
     cudaFree(g->w.top); cudaFree(g->w.bin); cudaFree(g->w.cand);
     cudaFree(g->d_nm); cudaFreeHost(g->h_nm); cudaFree(g->d_q); cudaFree(g->d_cnt); cudaFree(g->d_out);
@@ -371,6 +372,94 @@ extern "C" int eorb_guided_search_by_projection(eorb_guided* g, const float* x3D
     }
     rc = searchProjRun(g, g->d_x3, g->d_valid, g->d_obs, g->d_kps[0], g->d_desc[0], n1, g->d_kps[1], g->d_desc[1], n2, bounds4, pr, check_ori,
                        g->d_mc, nmatches);
+    if (rc != EORB_OK) return rc;
+    CU(cudaMemcpyAsync(match_cur, g->d_mc, (size_t)n2 * sizeof(int32_t), cudaMemcpyDeviceToHost, g->stream));
+    CU(cudaStreamSynchronize(g->stream));
+    return EORB_OK;
+}
+
+// ------------------------------------------------------------------------------------------------ SearchByProjection (map points)
+static_assert(sizeof(eorb_track_point) == sizeof(eorb_keypoint), "the host entry point stages the track points in the frame-1 keypoint buffer");
+
+static int searchMapRun(eorb_guided* g, const eorb_track_point* d_pts, const uint8_t* d_dmp, int n1, const eorb_keypoint* d_k2, const uint8_t* d_d2,
+                        const uint8_t* d_held, int n2, const float* bounds4, const GuidedProj& pr, int farPoints, float thFar, float nnratio,
+                        int32_t* d_mc, int* nmatches) {
+    int rc = reserveWork(g, n1, n2);
+    if (rc != EORB_OK) return rc;
+    GuidedFrame f2{d_k2, d_d2, n2};
+    const GuidedGrid gg = gridGeom(bounds4);
+    for (int attempt = 0; attempt < 2; attempt++) {
+        CU(launch_search_map_points(d_pts, d_dmp, n1, f2, d_held, gg, pr, farPoints, thFar, nnratio, g->w, d_mc, g->d_nm, g->stream, &g->launches));
+        CU(cudaMemcpyAsync(g->h_nm, g->d_nm, 2 * sizeof(int), cudaMemcpyDeviceToHost, g->stream));
+        CU(cudaStreamSynchronize(g->stream));
+        if (g->h_nm[1] <= g->w.candCap) { if (nmatches) *nmatches = g->h_nm[0]; return EORB_OK; }
+        cudaFree(g->w.cand); g->w.cand = nullptr;
+        g->w.candCap = g->h_nm[1] + g->h_nm[1] / 4;
+        CU(cudaMalloc((void**)&g->w.cand, (size_t)g->w.candCap * sizeof(uint32_t)));
+    }
+    return gFail(EORB_ERR_STATE, "eorb_guided_search_by_projection_map_points", "candidate buffer overflow after growth");
+}
+
+static int mapConst(const float* scale_factors, int nlevels, float th, GuidedProj& pr) {
+    if (!scale_factors || nlevels < 1 || nlevels > 32) return gFail(EORB_ERR_ARG, "eorb_guided_search_by_projection_map_points", "bad scale table (1..32 levels)");
+    if (!(th > 0.0f)) return gFail(EORB_ERR_ARG, "eorb_guided_search_by_projection_map_points", "th must be positive");
+    pr = GuidedProj{};
+    pr.th = th; pr.nlevels = nlevels;
+    for (int i = 0; i < 32; i++) pr.scale[i] = i < nlevels ? scale_factors[i] : 1.0f;
+    return EORB_OK;
+}
+
+extern "C" int eorb_guided_search_by_projection_map_points_device(eorb_guided* g, const eorb_track_point* d_pts, const uint8_t* d_descMP, int n1,
+                                                                  const eorb_keypoint* d_kps2, const uint8_t* d_desc2, const uint8_t* d_held2,
+                                                                  int n2, const float* bounds4, const float* scale_factors, int nlevels, float th,
+                                                                  int far_points, float th_far, float nnratio, int32_t* d_match_cur,
+                                                                  int* nmatches) {
+    if (!g) return gFail(EORB_ERR_ARG, "eorb_guided_search_by_projection_map_points_device", "null handle");
+    int rc = checkFrames(d_pts, n1, d_kps2, n2, bounds4);
+    if (rc != EORB_OK) return rc;
+    if (nmatches) *nmatches = 0;
+    if (n2 == 0) return EORB_OK;
+    if (!d_match_cur || !d_desc2 || (n1 > 0 && !d_descMP)) return gFail(EORB_ERR_ARG, "eorb_guided_search_by_projection_map_points_device", "null argument");
+    if (((uintptr_t)d_descMP | (uintptr_t)d_desc2) & 15)
+        return gFail(EORB_ERR_ARG, "eorb_guided_search_by_projection_map_points_device", "descriptors must be 16-byte aligned");
+    GuidedProj pr;
+    if ((rc = mapConst(scale_factors, nlevels, th, pr)) != EORB_OK) return rc;
+    CU(cudaSetDevice(g->device));
+    return searchMapRun(g, d_pts, d_descMP, n1, d_kps2, d_desc2, d_held2, n2, bounds4, pr, far_points, th_far, nnratio, d_match_cur, nmatches);
+}
+
+extern "C" int eorb_guided_search_by_projection_map_points(eorb_guided* g, const eorb_track_point* pts, const uint8_t* descMP, int n1,
+                                                           const eorb_keypoint* kps2, const uint8_t* desc2, const uint8_t* held2, int n2,
+                                                           const float* bounds4, const float* scale_factors, int nlevels, float th, int far_points,
+                                                           float th_far, float nnratio, int32_t* match_cur, int* nmatches) {
+    if (!g) return gFail(EORB_ERR_ARG, "eorb_guided_search_by_projection_map_points", "null handle");
+    int rc = checkFrames(pts, n1, kps2, n2, bounds4);
+    if (rc != EORB_OK) return rc;
+    if (nmatches) *nmatches = 0;
+    if (n2 == 0) return EORB_OK;
+    if (!match_cur || !desc2 || (n1 > 0 && !descMP)) return gFail(EORB_ERR_ARG, "eorb_guided_search_by_projection_map_points", "null argument");
+    GuidedProj pr;
+    if ((rc = mapConst(scale_factors, nlevels, th, pr)) != EORB_OK) return rc;
+    CU(cudaSetDevice(g->device));
+    if ((rc = stageFrame(g, 0, reinterpret_cast<const eorb_keypoint*>(pts), descMP, n1)) != EORB_OK) return rc;
+    if ((rc = stageFrame(g, 1, kps2, desc2, n2)) != EORB_OK) return rc;
+    if (n2 > g->pCap2) {
+        CU(cudaStreamSynchronize(g->stream));
+        cudaFree(g->d_mc); g->d_mc = nullptr; g->pCap2 = 0;
+        const int cap = std::max(1024, n2);
+        CU(cudaMalloc((void**)&g->d_mc, (size_t)cap * sizeof(int32_t)));
+        g->pCap2 = cap;
+    }
+    if (held2 && n2 > g->heldCap) {
+        CU(cudaStreamSynchronize(g->stream));
+        cudaFree(g->d_held); g->d_held = nullptr; g->heldCap = 0;
+        const int cap = std::max(1024, n2);
+        CU(cudaMalloc((void**)&g->d_held, (size_t)cap));
+        g->heldCap = cap;
+    }
+    if (held2) CU(cudaMemcpyAsync(g->d_held, held2, (size_t)n2, cudaMemcpyHostToDevice, g->stream));
+    rc = searchMapRun(g, reinterpret_cast<const eorb_track_point*>(g->d_kps[0]), g->d_desc[0], n1, g->d_kps[1], g->d_desc[1],
+                      held2 ? g->d_held : nullptr, n2, bounds4, pr, far_points, th_far, nnratio, g->d_mc, nmatches);
     if (rc != EORB_OK) return rc;
     CU(cudaMemcpyAsync(match_cur, g->d_mc, (size_t)n2 * sizeof(int32_t), cudaMemcpyDeviceToHost, g->stream));
     CU(cudaStreamSynchronize(g->stream));

@@ -693,6 +693,202 @@ __global__ void __launch_bounds__(256) guided_resolve_proj_kernel(const eorb_key
     if (tid == 0) *nmatchesOut = sNm;
 }
 
+// ------------------------------------------------------------------------------------------------ SearchByProjection (map points)
+// L1 guided_mappoint_query_kernel: the window of ORBmatcher::SearchByProjection(F, vpMapPoints, th, bFarPoints, thFarPoints)
+// (ORBmatcher.cc:54-75) per local map point: in-view / far / bad gates, RadiusByViewingCos (:219-225: the float cosine is compared
+// with the DOUBLE constant 0.998), r *= th when th != 1.0, half size r * mvScaleFactors[clamp(level)], levels [level-1, level].
+__global__ void __launch_bounds__(256) guided_mappoint_query_kernel(const eorb_track_point* __restrict__ pts, int n1, GuidedProj pr, int farPoints,
+                                                                    float thFar, eorb_area_query* __restrict__ qs) {
+    const int i = blockIdx.x * 256 + threadIdx.x;
+    if (i >= n1) return;
+    eorb_area_query q;
+    q.x = 0.f; q.y = 0.f; q.r = -1.f; q.min_level = 0; q.max_level = -1;
+    const eorb_track_point p = pts[i];
+    if (p.in_view && !(farPoints && p.depth > thFar) && !p.bad) {
+        float r = ((double)p.view_cos > 0.998) ? 2.5f : 4.0f;
+        if (pr.th != 1.0f) r = __fmul_rn(r, pr.th);
+        const int lv = p.scale_level < 0 ? 0 : (p.scale_level >= pr.nlevels ? pr.nlevels - 1 : p.scale_level);
+        q.x = p.proj_x; q.y = p.proj_y; q.r = __fmul_rn(r, pr.scale[lv]); q.min_level = p.scale_level - 1; q.max_level = p.scale_level;
+    }
+    qs[i] = q;
+}
+
+// L3 guided_resolve_map_kernel: the order-dependent part (:87-137).  A slot of F that holds a map point WITH observations (on
+// entry: held2; later: a claim by such a point) is skipped by every later map point, so a point's best and second-best
+// candidates are the first TWO unblocked entries of its (distance, visiting position)-sorted head: the strict "<" updates of
+// :104-124 leave exactly that pair whatever the visiting order (a demoted best overwrites the second, a tie never replaces).
+// Accepted when best <= TH_HIGH and not (same level and best > ratio * second) (:128-131); the owner of a slot is its LAST
+// claimer (setMapPoint overwrites a point without observations), every claim counts in nmatches.  Same structure as
+// guided_resolve_proj_kernel: one ordered warp with speculative chunks of 32 points, seven warps staging the next heads.
+__global__ void __launch_bounds__(256) guided_resolve_map_kernel(const eorb_track_point* __restrict__ pts, int n1, GuidedFrame f2,
+                                                                 const uint8_t* __restrict__ held2, float nnratio, GuidedWork w,
+                                                                 int32_t* __restrict__ matchCur, int* __restrict__ nmatchesOut) {
+    extern __shared__ __align__(16) unsigned char sm[];
+    const int n2 = f2.n, n2r = (n2 + 3) & ~3;
+    u64* stop = reinterpret_cast<u64*>(sm);                               // [2][GUIDED_STAGE][32]
+    int* scnt = reinterpret_cast<int*>(stop + 2 * GUIDED_STAGE * GUIDED_ROW);     // [2][GUIDED_STAGE]
+    int* soff = scnt + 2 * GUIDED_STAGE;                                  // [2][GUIDED_STAGE]
+    int* sobs = soff + 2 * GUIDED_STAGE;                                  // [2][GUIDED_STAGE] observations of the query's map point
+    unsigned short* owner = reinterpret_cast<unsigned short*>(sobs + 2 * GUIDED_STAGE);   // [n2r] last claimer (0xffff = none)
+    unsigned short* qlist = owner + n2r;                                  // [n1]
+    unsigned* ctab = reinterpret_cast<unsigned*>(qlist + ((n1 + 1) & ~1));             // [n2r] lowest lane of the current chunk claiming a slot
+    unsigned char* blk = reinterpret_cast<unsigned char*>(ctab + n2r);                 // [n2r] slot holds a point with observations
+    signed char* lvl = reinterpret_cast<signed char*>(blk + n2r);                      // [n2r] octave of the frame's keypoints
+    __shared__ int sNm, sWarp[8];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+
+    if (*w.total > w.candCap) {
+        if (tid == 0) *nmatchesOut = -1;
+        return;
+    }
+    for (int i = tid; i < n2; i += 256) {
+        owner[i] = GUIDED_NONE; ctab[i] = 0xffffffffu;
+        blk[i] = held2 ? (held2[i] != 0) : 0;
+        const int o = f2.kps[i].octave;
+        lvl[i] = (signed char)(o < -100 ? -100 : (o > 100 ? 100 : o));
+    }
+    if (tid == 0) sNm = 0;
+    int nact = 0;
+    for (int base = 0; base < n1; base += 256) {
+        const int i1 = base + tid;
+        const bool act = i1 < n1 && w.candCnt[i1] > 0;
+        const unsigned bm = __ballot_sync(FULLMASK, act);
+        if (lane == 0) sWarp[warp] = __popc(bm);
+        __syncthreads();
+        int before = 0, total = 0;
+#pragma unroll
+        for (int k = 0; k < 8; k++) { const int v = sWarp[k]; total += v; if (k < warp) before += v; }
+        if (act) qlist[nact + before + __popc(bm & ((1u << lane) - 1u))] = (unsigned short)i1;
+        nact += total;
+        __syncthreads();
+    }
+    const int nrounds = (nact + GUIDED_STAGE - 1) / GUIDED_STAGE;
+    auto loadStage = [&](int r, int t0, int nth) {
+        u64* sp = stop + (r & 1) * GUIDED_STAGE * GUIDED_ROW;
+        for (int t = tid - t0; t < GUIDED_STAGE * 32; t += nth) {
+            const int q = r * GUIDED_STAGE + (t >> 5);
+            sp[(t >> 5) * GUIDED_ROW + (t & 31)] = q < nact ? w.top[(size_t)qlist[q] * EORB_GUIDED_TOP + (t & 31)] : ~0ull;
+        }
+        for (int k = tid - t0; k < GUIDED_STAGE; k += nth) {
+            const int q = r * GUIDED_STAGE + k, o = (r & 1) * GUIDED_STAGE + k;
+            scnt[o] = q < nact ? w.candCnt[qlist[q]] : 0;
+            soff[o] = q < nact ? w.candOff[qlist[q]] : 0;
+            sobs[o] = q < nact ? pts[qlist[q]].observations : 0;
+        }
+    };
+    if (nrounds > 0) loadStage(0, 0, 256);
+    __syncthreads();
+
+    // (:128-131) with b = dist << 16 | slot, 0xffffffff = none
+    auto accepted = [&](uint32_t b1, uint32_t b2) -> bool {
+        if (b1 == 0xffffffffu) return false;
+        const int d1 = (int)(b1 >> 16);
+        if (d1 > 100) return false;                                       // TH_HIGH
+        const int l1 = lvl[b1 & 0xffffu];
+        const int d2 = b2 != 0xffffffffu ? (int)(b2 >> 16) : 256, l2 = b2 != 0xffffffffu ? (int)lvl[b2 & 0xffffu] : -1;
+        return !(l1 == l2 && (float)d1 > __fmul_rn(nnratio, (float)d2));
+    };
+
+    for (int r = 0; r < nrounds; r++) {
+        if (warp != 0) {
+            if (r + 1 < nrounds) loadStage(r + 1, 32, 224);
+        } else {
+            const u64* sp = stop + (r & 1) * GUIDED_STAGE * GUIDED_ROW;
+            const int so = (r & 1) * GUIDED_STAGE;
+            const int kend = min(GUIDED_STAGE, nact - r * GUIDED_STAGE);
+            // whole warp on one query: head by ballot, or the full list when the head holds fewer than two unblocked entries
+            auto seqStep = [&](int k) {
+                const u64 e = sp[k * GUIDED_ROW + lane];
+                const uint32_t dist = (uint32_t)(e >> 32), i2 = e != ~0ull ? (uint32_t)e & 0xffffu : 0u;
+                const bool ok = e != ~0ull && blk[i2] == 0;
+                unsigned mask = __ballot_sync(FULLMASK, ok);
+                uint32_t b1 = 0xffffffffu, b2 = 0xffffffffu;
+                if (__popc(mask) >= 2 || scnt[so + k] <= EORB_GUIDED_TOP) {
+                    const uint32_t v = (dist << 16) | i2;
+                    if (mask) { b1 = __shfl_sync(FULLMASK, v, __ffs(mask) - 1); mask &= mask - 1; }
+                    if (mask) b2 = __shfl_sync(FULLMASK, v, __ffs(mask) - 1);
+                } else {
+                    uint32_t k1 = 0xffffffffu, k2 = 0xffffffffu;          // two smallest (dist << 16 | position) keys of this lane
+                    const int c = scnt[so + k], off = soff[so + k];
+                    for (int p = lane; p < c; p += 32) {
+                        const uint32_t ce = w.cand[off + p];
+                        if (blk[ce & 0xffffu] == 0) {
+                            const uint32_t key = ((ce >> 16) << 16) | (uint32_t)p;
+                            if (key < k1) { k2 = k1; k1 = key; } else if (key < k2) k2 = key;
+                        }
+                    }
+                    const uint32_t m1 = __reduce_min_sync(FULLMASK, k1);
+                    const uint32_t m2 = __reduce_min_sync(FULLMASK, k1 == m1 ? k2 : k1);
+                    if (m1 != 0xffffffffu) b1 = (m1 & 0xffff0000u) | (w.cand[off + (m1 & 0xffffu)] & 0xffffu);
+                    if (m2 != 0xffffffffu) b2 = (m2 & 0xffff0000u) | (w.cand[off + (m2 & 0xffffu)] & 0xffffu);
+                }
+                if (accepted(b1, b2)) {
+                    if (lane == 0) {
+                        const int i1 = qlist[r * GUIDED_STAGE + k];
+                        owner[b1 & 0xffffu] = (unsigned short)i1;
+                        blk[b1 & 0xffffu] = sobs[so + k] > 0 ? 1 : 0;
+                        sNm++;
+                    }
+                }
+                __syncwarp();
+            };
+#if EORB_GUIDED_SPEC
+            // lane L takes query k + L: the first two unblocked entries of its head.  It is dirty when an earlier lane of the
+            // chunk claims either of them (conservative for claims by points without observations); the clean prefix commits.
+            int k = 0;
+            while (k < kend) {
+                const int q = k + lane;
+                const bool have = q < kend;
+                uint32_t b1 = 0xffffffffu, b2 = 0xffffffffu;
+                bool slow = false;
+                if (have) {
+                    const u64* hp = sp + q * GUIDED_ROW;
+                    for (int en = 0; en < EORB_GUIDED_TOP && b2 == 0xffffffffu; en += 4) {
+                        u64 he[4]; uint32_t bv[4];
+#pragma unroll
+                        for (int u = 0; u < 4; u++) he[u] = hp[en + u];
+#pragma unroll
+                        for (int u = 0; u < 4; u++) bv[u] = he[u] != ~0ull ? (uint32_t)blk[(uint32_t)he[u] & 0xffffu] : 1u;
+#pragma unroll
+                        for (int u = 0; u < 4; u++)
+                            if (bv[u] == 0 && b2 == 0xffffffffu) {
+                                const uint32_t v = ((uint32_t)(he[u] >> 32) << 16) | ((uint32_t)he[u] & 0xffffu);
+                                if (b1 == 0xffffffffu) b1 = v; else b2 = v;
+                            }
+                        if (he[3] == ~0ull) break;
+                    }
+                    slow = b2 == 0xffffffffu && scnt[so + q] > EORB_GUIDED_TOP && (b1 == 0xffffffffu || (b1 >> 16) <= 100u);
+                }
+                const bool acc = have && !slow && accepted(b1, b2);
+                if (acc) atomicMin(&ctab[b1 & 0xffffu], (unsigned)lane);
+                __syncwarp();
+                const bool dirty = have && ((b1 != 0xffffffffu && ctab[b1 & 0xffffu] < (unsigned)lane) ||
+                                            (b2 != 0xffffffffu && ctab[b2 & 0xffffu] < (unsigned)lane));
+                const unsigned stopMask = __ballot_sync(FULLMASK, have && (dirty || slow));
+                const int ncommit = stopMask ? __ffs(stopMask) - 1 : min(32, kend - k);
+                __syncwarp();
+                const bool commit = acc && lane < ncommit;
+                if (acc) ctab[b1 & 0xffffu] = 0xffffffffu;
+                if (commit) {
+                    owner[b1 & 0xffffu] = qlist[r * GUIDED_STAGE + q];
+                    blk[b1 & 0xffffu] = sobs[so + q] > 0 ? 1 : 0;
+                }
+                const int nc = __popc(__ballot_sync(FULLMASK, commit));
+                if (lane == 0) sNm += nc;
+                __syncwarp();
+                k += ncommit;
+                if (stopMask && __shfl_sync(FULLMASK, (int)slow, ncommit & 31)) { seqStep(k); k++; }
+            }
+#else
+            for (int k = 0; k < kend; k++) seqStep(k);
+#endif
+        }
+        __syncthreads();
+    }
+    for (int i = tid; i < n2; i += 256) matchCur[i] = owner[i] != GUIDED_NONE ? (int)owner[i] : -1;
+    if (tid == 0) *nmatchesOut = sNm;
+}
+
 // ------------------------------------------------------------------------------------------------ launches
 static size_t resolveSmem(int n1, int n2) {
     const size_t n2r = (size_t)((n2 + 3) & ~3);
@@ -706,7 +902,17 @@ static size_t resolveProjSmem(int n1, int n2) {
     return (size_t)2 * GUIDED_STAGE * GUIDED_ROW * 8 + 2 * GUIDED_STAGE * 4 * 3 + 32 * 4 + n2r * 2 + (size_t)((n1 + 1) & ~1) * 2 + n2r * 4 + n2r + 16;
 }
 
+static size_t resolveMapSmem(int n1, int n2) {
+    const size_t n2r = (size_t)((n2 + 3) & ~3);
+    return (size_t)2 * GUIDED_STAGE * GUIDED_ROW * 8 + 2 * GUIDED_STAGE * 4 * 3 + n2r * 2 + (size_t)((n1 + 1) & ~1) * 2 + n2r * 4 + n2r * 2 + 16;
+}
+
 cudaError_t guided_configure() {
+    {
+        const cudaError_t e0 = cudaFuncSetAttribute(guided_resolve_map_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                                    (int)resolveMapSmem(EORB_GUIDED_MAX_KPS, EORB_GUIDED_MAX_KPS));
+        if (e0 != cudaSuccess) return e0;
+    }
     cudaError_t e = cudaFuncSetAttribute(guided_resolve_proj_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          (int)resolveProjSmem(EORB_GUIDED_MAX_KPS, EORB_GUIDED_MAX_KPS));
     if (e != cudaSuccess) return e;
@@ -758,6 +964,25 @@ cudaError_t launch_search_proj(const float* d_x3Dc, const uint8_t* d_valid1, con
         (*launches) += 2;
     }
     guided_resolve_proj_kernel<<<1, 256, resolveProjSmem(n1, f2.n), st>>>(d_kps1, d_obs1, n1, f2, checkOri, w, d_claim, d_matchCur, d_nmatches);
+    (*launches)++;
+    return cudaGetLastError();
+}
+
+cudaError_t launch_search_map_points(const eorb_track_point* d_pts, const uint8_t* d_descMP, int n1, const GuidedFrame& f2,
+                                     const uint8_t* d_held2, GuidedGrid g, const GuidedProj& pr, int farPoints, float thFar, float nnratio,
+                                     const GuidedWork& w, int32_t* d_matchCur, int* d_nmatches, cudaStream_t st, long long* launches) {
+    cudaError_t e = cudaMemsetAsync(w.total, 0, sizeof(int), st);
+    if (e != cudaSuccess) return e;
+    e = launch_frame_grid(f2.kps, f2.n, g, w.cellStart, w.cellIdx, w.assigned, st);
+    if (e != cudaSuccess) return e;
+    (*launches)++;
+    if (n1 > 0) {
+        guided_mappoint_query_kernel<<<(n1 + 255) / 256, 256, 0, st>>>(d_pts, n1, pr, farPoints, thFar, w.q);
+        GuidedFrame f1{nullptr, d_descMP, n1};
+        guided_candidates_kernel<<<(n1 + 7) / 8, 256, 0, st>>>(f1, f2, g, nullptr, 0.f, w.q, w);
+        (*launches) += 2;
+    }
+    guided_resolve_map_kernel<<<1, 256, resolveMapSmem(n1, f2.n), st>>>(d_pts, n1, f2, d_held2, nnratio, w, d_matchCur, d_nmatches);
     (*launches)++;
     return cudaGetLastError();
 }

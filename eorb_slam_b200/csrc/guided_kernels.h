@@ -46,6 +46,10 @@ cudaError_t launch_search_proj(const float* d_x3Dc, const uint8_t* d_valid1, con
                                const uint8_t* d_descMP, int n1, const GuidedFrame& f2, GuidedGrid g, const GuidedProj& pr, int checkOri,
                                const GuidedWork& w, int32_t* d_claim, int32_t* d_matchCur, int* d_nmatches, cudaStream_t st,
                                long long* launches);
+// SearchByProjection(F, vpMapPoints, th, bFarPoints, thFarPoints), monocular (ORBmatcher.cc:44-148); pr carries th, nlevels, scale
+cudaError_t launch_search_map_points(const eorb_track_point* d_pts, const uint8_t* d_descMP, int n1, const GuidedFrame& f2,
+                                     const uint8_t* d_held2, GuidedGrid g, const GuidedProj& pr, int farPoints, float thFar, float nnratio,
+                                     const GuidedWork& w, int32_t* d_matchCur, int* d_nmatches, cudaStream_t st, long long* launches);
 cudaError_t guided_configure();
 
 }  // namespace eorb

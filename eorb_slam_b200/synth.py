@@ -289,3 +289,36 @@ def make_projection_case(n1: int, n2: int, seed: int, w: int = 752, h: int = 480
         scale[i] = np.float32(np.float64(scale[i - 1]) * np.float64(np.float32(1.2)))
     return dict(x3Dc=x3, valid1=valid, obs1=obs, kps1=k1, descMP=d1, kps2=k2, desc2=d2, bounds=bounds, K=np.array(K, np.float32),
                 scale_factors=scale)
+
+
+TRACK_POINT_DTYPE = np.dtype([("proj_x", "<f4"), ("proj_y", "<f4"), ("view_cos", "<f4"), ("depth", "<f4"), ("scale_level", "<i4"),
+                              ("observations", "<i4"), ("in_view", "u1"), ("bad", "u1"), ("pad", "u1", (2,))])
+
+
+def make_local_map_case(n1: int, n2: int, seed: int, w: int = 752, h: int = 480, nlevels: int = 8, shift=(3.0, -2.0),
+                        in_view_frac: float = 0.8, zero_obs_frac: float = 0.05, held_frac: float = 0.2):
+    """Inputs of ORBmatcher::SearchByProjection(F, vpMapPoints, th, bFarPoints, thFarPoints) (Tracking::SearchLocalPoints): n1 local
+    map points whose tracking fields (what Frame::isInFrustum fills) put them near the keypoints of a frame of n2 keypoints
+    (make_keypoint_frame_pair: frame 1 plays the map points, its descriptors are theirs), a predicted level near the keypoint's
+    octave, viewing cosines on both sides of 0.998 (incl. exactly float(0.998)), some points out of view / bad / far / without
+    observations, and a fraction of the frame's slots already holding a point with observations."""
+    rng = np.random.default_rng(seed + 2000)
+    k1, d1, k2, d2, bounds = make_keypoint_frame_pair(n1, n2, seed, w, h, nlevels, shift)
+    pts = np.zeros(n1, TRACK_POINT_DTYPE)
+    pts["proj_x"] = k1["x"] + np.float32(shift[0]) + rng.normal(0, 1.0, n1).astype(np.float32)
+    pts["proj_y"] = k1["y"] + np.float32(shift[1]) + rng.normal(0, 1.0, n1).astype(np.float32)
+    vc = rng.uniform(0.99, 1.0, n1).astype(np.float32)
+    vc[rng.random(n1) < 0.05] = np.float32(0.998)
+    pts["view_cos"] = vc
+    pts["depth"] = rng.uniform(0.5, 30.0, n1).astype(np.float32)
+    pts["scale_level"] = np.clip(k1["octave"] + rng.integers(-1, 2, n1), -1, nlevels).astype(np.int32)
+    obs = rng.integers(1, 9, n1).astype(np.int32)
+    obs[rng.random(n1) < zero_obs_frac] = 0
+    pts["observations"] = obs
+    pts["in_view"] = (rng.random(n1) < in_view_frac).astype(np.uint8)
+    pts["bad"] = (rng.random(n1) < 0.03).astype(np.uint8)
+    held = (rng.random(n2) < held_frac).astype(np.uint8)
+    scale = np.ones(nlevels, np.float32)
+    for i in range(1, nlevels):
+        scale[i] = np.float32(np.float64(scale[i - 1]) * np.float64(np.float32(1.2)))
+    return dict(pts=pts, descMP=d1, kps2=k2, desc2=d2, held2=held, bounds=bounds, scale_factors=scale)

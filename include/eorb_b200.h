@@ -355,6 +355,29 @@ int eorb_guided_search_by_projection_device(eorb_guided* g, const float* d_x3Dc,
                                             const float* scale_factors, int nlevels, float th, int check_ori, int32_t* d_match_cur,
                                             int* nmatches);
 
+/* eorb_guided_search_by_projection_map_points replaces ORBmatcher::SearchByProjection(Frame& F, const vector<MapPoint*>&
+ * vpMapPoints, const float th, const bool bFarPoints, const float thFarPoints) (src/ORBmatcher.cc:44-218) as called by
+ * Tracking::SearchLocalPoints (src/Tracking-1.cc:2379) for a monocular frame (Nleft == -1, mvuRight < 0: the right-camera
+ * blocks never run).  pts[i] = the MapPoint fields Frame::isInFrustum fills (mTrackProjX/Y, mTrackViewCos, mTrackDepth,
+ * mnTrackScaleLevel, mbTrackInView) + Observations() + isBad(); descMP = GetDescriptor() (n1 x 32 bytes).  kps2 / desc2 = the
+ * frame's undistorted keypoints and descriptors; held2[i2] != 0 (may be NULL) = F.getMapPoint(i2) holds a point with
+ * observations on entry.  scale_factors = mvScaleFactors.  match_cur[i2] = index of the map point F.setMapPoint(i2, .)
+ * received in this call (the last one when points without observations are overwritten), or -1. */
+typedef struct eorb_track_point {
+    float proj_x, proj_y, view_cos, depth;
+    int32_t scale_level, observations;
+    uint8_t in_view, bad, pad[2];
+} eorb_track_point;
+int eorb_guided_search_by_projection_map_points(eorb_guided* g, const eorb_track_point* pts, const uint8_t* descMP, int n1,
+                                                const eorb_keypoint* kps2, const uint8_t* desc2, const uint8_t* held2, int n2,
+                                                const float* bounds4, const float* scale_factors, int nlevels, float th, int far_points,
+                                                float th_far, float nnratio, int32_t* match_cur, int* nmatches);
+int eorb_guided_search_by_projection_map_points_device(eorb_guided* g, const eorb_track_point* d_pts, const uint8_t* d_descMP, int n1,
+                                                       const eorb_keypoint* d_kps2, const uint8_t* d_desc2, const uint8_t* d_held2,
+                                                       int n2, const float* bounds4, const float* scale_factors, int nlevels, float th,
+                                                       int far_points, float th_far, float nnratio, int32_t* d_match_cur,
+                                                       int* nmatches);
+
 /* ---------------------------------------------------------------- bag of words + undistortion (fourth "next" row)
  * The two steps that follow extraction in the reference's Frame:
  *   eorb_vocab_transform        replaces DBoW2 TemplatedVocabulary<FORB::TDescriptor, FORB>::transform(features, BowVector,

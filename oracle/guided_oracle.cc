@@ -231,4 +231,57 @@ int orc_search_by_projection(const float* x3Dc, const uint8_t* valid1, const int
     return nmatches;
 }
 
+// ORBmatcher::SearchByProjection(Frame& F, const vector<MapPoint*>& vpMapPoints, float th, bool bFarPoints, float thFarPoints)
+// (src/ORBmatcher.cc:44-218; Tracking::SearchLocalPoints, src/Tracking-1.cc:2379), monocular frame: Nleft == -1 and
+// mvuRight < 0, so the right-camera blocks (:91-96, :139-141, :150-211) never run.  Per map point in list order: the
+// mbTrackInView / far / isBad gates (:54-61), r = RadiusByViewingCos(mTrackViewCos) (:219-225, a float compared with the DOUBLE
+// 0.998), r *= th when th != 1.0 (:70-71), GetFeaturesInArea(projX, projY, r * mvScaleFactors[clamp(level)], level-1, level)
+// (:73-75), best / second-best over the candidates whose slot does not hold a map point with observations (:87-89) with the
+// levels of both (:104-124), TH_HIGH and the ratio test only when both lie on the same level (:128-131), setMapPoint (:134).
+// pts[i]: the MapPoint tracking fields Frame::isInFrustum fills; held2[i2] != 0: F already holds a point with observations
+// at i2 on entry (may be null).  match_cur[i2] = index of the map point this call put at i2, or -1; returns nmatches.
+int orc_search_by_projection_map_points(const orc_track_point* pts, const uint8_t* descMP, int n1, const orc_keypoint* kps2,
+                                        const uint8_t* desc2, const uint8_t* held2, int n2, const float* bounds4,
+                                        const float* scale_factors, int nlevels, float th, int far_points, float th_far, float nnratio,
+                                        int32_t* match_cur) {
+    const int TH_HIGH = 100;
+    const GridGeom g(bounds4);
+    std::vector<int> cellStart(GC * GR + 1), cellIdx(std::max(n2, 1));
+    orc_frame_grid(kps2, n2, bounds4, cellStart.data(), cellIdx.data());
+    for (int i = 0; i < n2; i++) match_cur[i] = -1;
+    int nmatches = 0;
+    const bool bFactor = th != 1.0;
+    std::vector<int> vIndices;
+    for (int iMP = 0; iMP < n1; iMP++) {
+        const orc_track_point& p = pts[iMP];
+        if (!p.in_view) continue;
+        if (far_points && p.depth > th_far) continue;
+        if (p.bad) continue;
+        const int nPredictedLevel = p.scale_level;
+        float r = (p.view_cos > 0.998) ? 2.5f : 4.0f;
+        if (bFactor) r *= th;
+        const int lv = nPredictedLevel < 0 ? 0 : (nPredictedLevel >= nlevels ? nlevels - 1 : nPredictedLevel);
+        featuresInArea(kps2, g, cellStart.data(), cellIdx.data(), p.proj_x, p.proj_y, r * scale_factors[lv], nPredictedLevel - 1,
+                       nPredictedLevel, vIndices);
+        if (vIndices.empty()) continue;
+        const uint8_t* dMP = descMP + (size_t)iMP * 32;
+        int bestDist = 256, bestLevel = -1, bestDist2 = 256, bestLevel2 = -1, bestIdx = -1;
+        for (int idx : vIndices) {
+            if (match_cur[idx] >= 0 ? pts[match_cur[idx]].observations > 0 : (held2 && held2[idx])) continue;
+            const int dist = orc_descriptor_distance(dMP, desc2 + (size_t)idx * 32);
+            if (dist < bestDist) {
+                bestDist2 = bestDist; bestDist = dist; bestLevel2 = bestLevel; bestLevel = kps2[idx].octave; bestIdx = idx;
+            } else if (dist < bestDist2) {
+                bestLevel2 = kps2[idx].octave; bestDist2 = dist;
+            }
+        }
+        if (bestDist <= TH_HIGH) {
+            if (bestLevel == bestLevel2 && bestDist > nnratio * bestDist2) continue;
+            match_cur[bestIdx] = iMP;
+            nmatches++;
+        }
+    }
+    return nmatches;
+}
+
 }  // extern "C"

@@ -132,6 +132,20 @@ int   orc_search_by_projection(const float* x3Dc, const uint8_t* valid1, const i
                                const float* bounds4, const float* K4, const float* scale_factors, int nlevels, float th, int check_ori,
                                int32_t* match_cur);
 
+/* ORBmatcher::SearchByProjection(F, vpMapPoints, th, bFarPoints, thFarPoints) (ORBmatcher.cc:44-218), monocular frame.
+   orc_track_point = the MapPoint fields Frame::isInFrustum fills (mTrackProjX/Y, mTrackViewCos, mTrackDepth, mnTrackScaleLevel,
+   mbTrackInView) + Observations() + isBad(); held2 (may be null) = slots of F that hold a point with observations on entry;
+   match_cur[n2] = index of the map point put at every keypoint of F by this call, or -1; returns nmatches */
+typedef struct orc_track_point {
+    float proj_x, proj_y, view_cos, depth;
+    int32_t scale_level, observations;
+    uint8_t in_view, bad, pad[2];
+} orc_track_point;
+int   orc_search_by_projection_map_points(const orc_track_point* pts, const uint8_t* descMP, int n1, const orc_keypoint* kps2,
+                                          const uint8_t* desc2, const uint8_t* held2, int n2, const float* bounds4,
+                                          const float* scale_factors, int nlevels, float th, int far_points, float th_far,
+                                          float nnratio, int32_t* match_cur);
+
 /* ---- bag of words + undistortion (bow_oracle.cc) ---- */
 typedef struct orc_vocab orc_vocab;
 /* flat form of what TemplatedVocabulary::loadFromTextFile builds: node 0 = root, parent[nid] < nid, children in id order,

@@ -403,6 +403,23 @@ def search_by_projection(x3Dc, valid1, obs1, kps1, descMP, kps2, desc2, bounds, 
     return n, mc[:len(k2)].copy()
 
 
+def search_by_projection_map_points(pts, descMP, kps2, desc2, held2, bounds, scale_factors, th=1.0, far_points=False, th_far=0.0,
+                                    nnratio=0.8):
+    """ORBmatcher::SearchByProjection(F, vpMapPoints, th, bFarPoints, thFarPoints), monocular -> (nmatches, match_cur[n2])"""
+    from eorb_slam_b200.synth import TRACK_POINT_DTYPE
+    L = lib()
+    p = np.ascontiguousarray(pts, TRACK_POINT_DTYPE); k2 = np.ascontiguousarray(kps2, KEYPOINT_DTYPE)
+    dm = np.ascontiguousarray(descMP, np.uint8); d2 = np.ascontiguousarray(desc2, np.uint8)
+    hd = None if held2 is None else np.ascontiguousarray(held2, np.uint8)
+    b = np.ascontiguousarray(bounds, np.float32); sf = np.ascontiguousarray(scale_factors, np.float32)
+    mc = np.full(max(len(k2), 1), -1, np.int32)
+    L.orc_search_by_projection_map_points.restype = C.c_int
+    n = L.orc_search_by_projection_map_points(_p(p), _p(dm), C.c_int(len(p)), _p(k2), _p(d2), _p(hd) if hd is not None else None,
+                                              C.c_int(len(k2)), _p(b), _p(sf), C.c_int(len(sf)), C.c_float(th), C.c_int(int(far_points)),
+                                              C.c_float(th_far), C.c_float(nnratio), _p(mc))
+    return n, mc[:len(k2)].copy()
+
+
 # ---- bag of words + undistortion (SURVEY 8f rank 4)
 class VocabOracle:
     def __init__(self, voc):

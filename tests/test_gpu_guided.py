@@ -167,3 +167,53 @@ def test_search_by_projection_contested_slots():
         en, emc = O.search_by_projection(c["x3Dc"], c["valid1"], c["obs1"], c["kps1"], c["descMP"], c["kps2"], c["desc2"], c["bounds"], K,
                                          c["scale_factors"], 15.0, True)
         assert n == en and np.array_equal(mc, emc)
+
+
+@pytest.mark.parametrize("n1,n2,seed,th,far,ratio,zero_obs,held", [
+    (600, 520, 31, 1.0, False, 0.8, 0.05, True), (600, 520, 32, 3.0, True, 0.8, 0.0, True), (600, 520, 33, 5.0, False, 0.6, 0.4, False),
+    (2000, 1009, 34, 3.0, False, 0.8, 0.02, True),      # Tracking::SearchLocalPoints shape: a local map against one 1000-feature frame
+    (3000, 3000, 35, 60.0, False, 0.9, 0.1, True),      # very wide windows: long candidate lists, blocked heads -> the slow path
+    (5000, 5000, 36, 15.0, True, 0.8, 0.05, True), (0, 10, 37, 1.0, False, 0.8, 0.0, True), (300, 1, 38, 1.0, False, 0.8, 0.0, False)])
+def test_search_by_projection_map_points(n1, n2, seed, th, far, ratio, zero_obs, held):
+    """ORBmatcher::SearchByProjection(F, vpMapPoints, th, bFarPoints, thFarPoints), monocular: match table and nmatches bit-exact"""
+    api = _api()
+    c = synth.make_local_map_case(max(n1, 2), max(n2, 2), seed, zero_obs_frac=zero_obs)
+    c["pts"], c["descMP"] = c["pts"][:n1], c["descMP"][:n1]
+    c["kps2"], c["desc2"], c["held2"] = c["kps2"][:n2], c["desc2"][:n2], (c["held2"][:n2] if held else None)
+    gm = api.GuidedMatcher(0, ratio, True)
+    for rep in range(2):
+        n, mc = gm.SearchByProjectionMapPoints(c["pts"], c["descMP"], c["kps2"], c["desc2"], c["held2"], c["bounds"], c["scale_factors"], th, far, 20.0)
+        en, emc = O.search_by_projection_map_points(c["pts"], c["descMP"], c["kps2"], c["desc2"], c["held2"], c["bounds"], c["scale_factors"], th, far,
+                                                    20.0, ratio)
+        assert n == en and np.array_equal(mc, emc)
+    if n1 >= 600:
+        assert (emc >= 0).sum() > 40
+
+
+def test_search_by_projection_map_points_crowded():
+    """thousands of near-identical map points over a few hundred keypoints: every head runs dry (the full-list path), slots
+    fill up first come first served, points without observations are overwritten and counted again"""
+    api = _api()
+    rng = np.random.default_rng(41)
+    n1, n2 = 3000, 400
+    c = synth.make_local_map_case(n1, n2, 41)
+    base = rng.integers(0, 256, 32).astype(np.uint8)
+    def noisy(n, bits):
+        d = np.tile(base, (n, 1))
+        for _ in range(bits):
+            d[np.arange(n), rng.integers(0, 32, n)] ^= (1 << rng.integers(0, 8, n)).astype(np.uint8)
+        return d
+    c["descMP"], c["desc2"] = noisy(n1, 12), noisy(n2, 12)
+    c["kps2"]["x"] = rng.uniform(300, 380, n2).astype(np.float32); c["kps2"]["y"] = rng.uniform(200, 280, n2).astype(np.float32)
+    c["kps2"]["octave"] = rng.integers(0, 3, n2)
+    c["pts"]["proj_x"] = rng.uniform(300, 380, n1).astype(np.float32); c["pts"]["proj_y"] = rng.uniform(200, 280, n1).astype(np.float32)
+    c["pts"]["scale_level"] = rng.integers(0, 4, n1)
+    c["pts"]["in_view"] = 1; c["pts"]["bad"] = 0
+    for zero, ratio in ((0.0, 0.8), (0.3, 0.95), (1.0, 0.8)):
+        c["pts"]["observations"] = np.where(rng.random(n1) < zero, 0, 2).astype(np.int32)
+        n, mc = api.GuidedMatcher(0, ratio, True).SearchByProjectionMapPoints(c["pts"], c["descMP"], c["kps2"], c["desc2"], c["held2"], c["bounds"],
+                                                                              c["scale_factors"], 10.0)
+        en, emc = O.search_by_projection_map_points(c["pts"], c["descMP"], c["kps2"], c["desc2"], c["held2"], c["bounds"], c["scale_factors"], 10.0,
+                                                    False, 0.0, ratio)
+        assert n == en and np.array_equal(mc, emc)
+        assert en > 100

@@ -231,3 +231,52 @@ def test_search_by_projection_matches_python(seed, th, ori, zero_obs):
     assert (mc >= 0).sum() > 50
     if zero_obs == 0.0 and not ori:
         assert n == int((mc >= 0).sum())
+
+
+def py_search_local_points(c, th, far_points, th_far, nnratio):
+    """independent restatement of ORBmatcher.cc:44-148 (monocular) with Python lists"""
+    pts, k2 = c["pts"], c["kps2"]
+    grid, geom = py_grid(k2, c["bounds"])
+    n2 = len(k2)
+    holder = [(-2 if c["held2"][i] else -1) for i in range(n2)]   # -2: holds a point with observations on entry
+    nl = len(c["scale_factors"])
+    nm = 0
+    for i in range(len(pts)):
+        p = pts[i]
+        if not p["in_view"] or (far_points and F(p["depth"]) > F(th_far)) or p["bad"]:
+            continue
+        lvl = int(p["scale_level"])
+        r = F(2.5) if float(p["view_cos"]) > 0.998 else F(4.0)
+        if float(F(th)) != 1.0:
+            r = r * F(th)
+        cand = py_area(k2, grid, geom, F(p["proj_x"]), F(p["proj_y"]), F(r * F(c["scale_factors"][min(max(lvl, 0), nl - 1)])), lvl - 1, lvl)
+        seen = []
+        for i2 in cand:
+            h = holder[i2]
+            if h == -2 or (h >= 0 and pts["observations"][h] > 0):
+                continue
+            seen.append((_ham(c["descMP"][i], c["desc2"][i2]), len(seen), i2))
+        if not seen:
+            continue
+        seen.sort()                                             # first two of the (distance, visiting position) order
+        bd, _, bi = seen[0]
+        bl = int(k2["octave"][bi])
+        bd2, bl2 = (seen[1][0], int(k2["octave"][seen[1][2]])) if len(seen) > 1 else (256, -1)
+        if bd <= 100 and not (bl == bl2 and F(bd) > F(nnratio) * F(bd2)):
+            holder[bi] = i; nm += 1
+    return nm, np.array([h if h >= 0 else -1 for h in holder], np.int32)
+
+
+@pytest.mark.parametrize("seed,th,far,ratio,zero_obs", [(31, 1.0, False, 0.8, 0.05), (32, 3.0, True, 0.8, 0.0), (33, 5.0, False, 0.6, 0.4),
+                                                       (34, 15.0, True, 0.9, 0.2)])
+def test_search_by_projection_map_points_matches_python(seed, th, far, ratio, zero_obs):
+    c = synth.make_local_map_case(600, 520, seed, zero_obs_frac=zero_obs)
+    n, mc = O.search_by_projection_map_points(c["pts"], c["descMP"], c["kps2"], c["desc2"], c["held2"], c["bounds"], c["scale_factors"], th, far,
+                                              20.0, ratio)
+    en, emc = py_search_local_points(c, th, far, 20.0, ratio)
+    assert n == en and np.array_equal(mc, emc)
+    assert (mc >= 0).sum() > 40
+    assert not np.any((mc >= 0) & (c["held2"] != 0))           # a held slot is never taken
+    n0, mc0 = O.search_by_projection_map_points(c["pts"], c["descMP"], c["kps2"], c["desc2"], None, c["bounds"], c["scale_factors"], th, far,
+                                                20.0, ratio)
+    assert n0 >= n
