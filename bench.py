@@ -445,7 +445,29 @@ def bench_guided(api, torch, dev, steps, warmup):
                 "cpu_port_ms_per_call": pms_port}
     except Exception as e:
         proj = {"error": repr(e)}
-    return {"search_by_projection": proj, "metric": "search_for_initialization_calls_per_s", "value": 1e3 / ms, "unit": "calls/s", "ms_per_call": ms,
+    # Tracking::SearchLocalPoints: SearchByProjection(F, vpMapPoints, th = 3, ...) of a 3000-point local map against one 1000-feature frame
+    loc = {}
+    try:
+        c = synth.make_local_map_case(3000, 1009, 43)
+        gl = api.GuidedMatcher(dev, 0.8, True)
+        a = (c["pts"], c["descMP"], c["kps2"], c["desc2"], c["held2"], c["bounds"], c["scale_factors"])
+        for _ in range(3):
+            ln, lmc = gl.SearchByProjectionMapPoints(*a, 3.0, False, 0.0)
+        t0 = time.perf_counter()
+        for _ in range(reps):
+            ln, lmc = gl.SearchByProjectionMapPoints(*a, 3.0, False, 0.0)
+        lms = (time.perf_counter() - t0) * 1e3 / reps
+        len_, lemc = O.search_by_projection_map_points(*a, 3.0, False, 0.0, 0.8)
+        t0 = time.perf_counter()
+        for _ in range(20):
+            O.search_by_projection_map_points(*a, 3.0, False, 0.0, 0.8)
+        lms_port = (time.perf_counter() - t0) * 1e3 / 20
+        loc = {"ms_per_call": lms, "workload": "ORBmatcher::SearchByProjection(F, vpMapPoints, 3): 3000 local map points (%d in view) x 1009 keypoints, "
+               "%d matches; host call" % (int(c["pts"]["in_view"].sum()), len_), "bit_exact_vs_oracle": bool(ln == len_ and np.array_equal(lmc, lemc)),
+               "cpu_port_ms_per_call": lms_port}
+    except Exception as e:
+        loc = {"error": repr(e)}
+    return {"search_by_projection": proj, "search_local_points": loc, "metric": "search_for_initialization_calls_per_s", "value": 1e3 / ms, "unit": "calls/s", "ms_per_call": ms,
             "ms_per_call_device_resident": float(np.median(dev_ms)),
             "workload": "ORBmatcher::SearchForInitialization: 5000 x 5000 keypoints (%d level-0 queries), window 100, ratio 0.9, "
                         "rotation check; %d matches" % (lvl0, en),

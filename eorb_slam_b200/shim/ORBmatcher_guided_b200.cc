@@ -122,4 +122,45 @@ int ORBmatcher::SearchByProjection(Frame &CurrentFrame, const Frame &LastFrame, 
         if (mc[i2] >= 0) CurrentFrame.setMapPoint(i2, LastFrame.getMapPoint(mc[i2]));
     return nmatches;
 }
+
+// ORBmatcher::SearchByProjection(F, vpMapPoints, th, bFarPoints, thFarPoints) (:44-218; Tracking::SearchLocalPoints), monocular frame.
+// Stereo / fisheye frames (Nleft != -1 or mvuRight > 0) keep the reference's implementation.
+int ORBmatcher::SearchByProjection(Frame &F, const std::vector<MapPoint*> &vpMapPoints, const float th, const bool bFarPoints, const float thFarPoints)
+{
+    const int n1 = (int)vpMapPoints.size(), n2 = F.numAllKPts();
+    eorb_guided* g = threadHandle();
+    if (!g || n1 == 0 || n2 == 0) return 0;
+    std::vector<eorb_track_point> pts(n1);
+    std::vector<unsigned char> dmp((size_t)n1 * 32, 0), d2, held(n2, 0);
+    std::vector<eorb_keypoint> k2;
+    for (int i = 0; i < n1; i++) {
+        MapPoint* pMP = vpMapPoints[i];
+        eorb_track_point& p = pts[i];
+        std::memset(&p, 0, sizeof(p));
+        if (!pMP || !pMP->mbTrackInView) continue;
+        p.proj_x = pMP->mTrackProjX; p.proj_y = pMP->mTrackProjY; p.view_cos = pMP->mTrackViewCos; p.depth = pMP->mTrackDepth;
+        p.scale_level = pMP->mnTrackScaleLevel; p.observations = pMP->Observations();
+        p.in_view = 1; p.bad = pMP->isBad() ? 1 : 0;
+        const cv::Mat dMP = pMP->GetDescriptor();
+        std::memcpy(&dmp[(size_t)i * 32], dMP.ptr<unsigned char>(), 32);
+    }
+    packFrame(F, k2, d2);
+    for (int i2 = 0; i2 < n2; i2++) {
+        MapPoint* q = F.getMapPoint(i2);
+        held[i2] = (q && q->Observations() > 0) ? 1 : 0;
+    }
+    const float bounds[4] = {Frame::mnMinX, Frame::mnMinY, Frame::mnMaxX, Frame::mnMaxY};
+    const std::vector<float> sf = F.getAllORBScaleFactors();
+    std::vector<int> mc(n2, -1);
+    int nmatches = 0;
+    const int rc = eorb_guided_search_by_projection_map_points(g, pts.data(), dmp.data(), n1, k2.data(), d2.data(), held.data(), n2, bounds, sf.data(),
+                                                               (int)sf.size(), th, bFarPoints ? 1 : 0, thFarPoints, mfNNratio, mc.data(), &nmatches);
+    if (rc != EORB_OK) {
+        std::fprintf(stderr, "ORBmatcher(b200)::SearchByProjection(map points): %s\n", eorb_last_error());
+        return 0;
+    }
+    for (int i2 = 0; i2 < n2; i2++)
+        if (mc[i2] >= 0) F.setMapPoint(i2, vpMapPoints[mc[i2]]);
+    return nmatches;
+}
 } // namespace ORB_SLAM3

@@ -20,6 +20,12 @@ public:
     cv::Mat GetWorldPos() { return mWorldPos; }
     cv::Mat GetDescriptor() { return mDescriptor; }
     int Observations() { return mnObs; }
+    bool isBad() { return mbBad; }
+    // tracking fields Frame::isInFrustum fills (include/MapPoint.h:133-144)
+    float mTrackProjX = 0.f, mTrackProjY = 0.f, mTrackDepth = 0.f, mTrackViewCos = 1.f;
+    int mnTrackScaleLevel = 0;
+    bool mbTrackInView = false, mbTrackInViewR = false;
+    bool mbBad = false;
 protected:
     cv::Mat mWorldPos, mDescriptor;   // 3x1 CV_32F, 1x32 CV_8U
     int mnObs;
@@ -50,6 +56,8 @@ class ORBmatcher {   // the members this path touches (ORBmatcher.h:39-42, 67-68
 public:
     int SearchForInitialization(Frame& F1, Frame& F2, std::vector<cv::Point2f>& vbPrevMatched, std::vector<int>& vnMatches12, int windowSize = 10);
     int SearchByProjection(Frame& CurrentFrame, const Frame& LastFrame, const float th, const bool bMono);
+    int SearchByProjection(Frame& F, const std::vector<MapPoint*>& vpMapPoints, const float th = 3, const bool bFarPoints = false,
+                           const float thFarPoints = 50.0f);
     explicit ORBmatcher(float nnratio = 0.6, bool checkOri = true) : mfNNratio(nnratio), mbCheckOrientation(checkOri) {}
     static int DescriptorDistance(const cv::Mat& a, const cv::Mat& b);
     static const int TH_LOW;

@@ -116,6 +116,18 @@ int main(int argc, char** argv)
         int same = 0, set = 0;
         for (size_t i = 0; i < kps.size(); i++) { set += (F2.mvpMapPoints[i] != nullptr); same += (F2.mvpMapPoints[i] == F1.mvpMapPoints[i]); }
         std::printf("sbp_nm=%d sbp_set=%d sbp_same=%d\n", np, set, same);
+        // ORBmatcher::SearchByProjection(F, vpMapPoints, th, ...): the same map points as a local map, tracking fields set as
+        // Frame::isInFrustum would (projection = the keypoint, predicted level = its octave), into an empty frame
+        F2.mvpMapPoints.assign(kps.size(), nullptr);
+        for (size_t i = 0; i < kps.size(); i++) {
+            mps[i]->mbTrackInView = true; mps[i]->mTrackProjX = F2.mvKeysUn[i].pt.x; mps[i]->mTrackProjY = F2.mvKeysUn[i].pt.y;
+            mps[i]->mnTrackScaleLevel = F2.mvKeysUn[i].octave; mps[i]->mTrackViewCos = 0.9995f; mps[i]->mTrackDepth = 4.f;
+        }
+        ORB_SLAM3::ORBmatcher matcher08(0.8f);
+        const int nl = matcher08.SearchByProjection(F2, mps, 3.f, false, 50.f);
+        int lset = 0, lsame = 0;
+        for (size_t i = 0; i < kps.size(); i++) { lset += (F2.mvpMapPoints[i] != nullptr); lsame += (F2.mvpMapPoints[i] == mps[i]); }
+        std::printf("slp_nm=%d slp_set=%d slp_same=%d\n", nl, lset, lsame);
         for (auto* p : mps) delete p;
     }
     // ORBVocabulary::transform through a text file in ORB-SLAM's vocabulary format (k = 3, L = 2: 3 inner nodes, 9 words whose

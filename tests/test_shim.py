@@ -49,7 +49,7 @@ def test_shims_compile_and_fail_loudly_without_device():
     assert "ret=-1 n=0" in out and "empty_ret=-1" in out
     assert "no CUDA device" in err
     assert "lk_ok=0 lk_n=0" in out
-    assert "sfi_nm=0 sfi_self=0" in out and "sbp_nm=0 sbp_set=0" in out
+    assert "sfi_nm=0 sfi_self=0" in out and "sbp_nm=0 sbp_set=0" in out and "slp_nm=0 slp_set=0" in out
     assert "voc_ok=0" in out and "undist_ok=0" in out
 
 
@@ -93,3 +93,7 @@ def test_shims_match_oracle_on_gpu():
     nmp, nset, nsame = map(int, sb.groups())
     # every map point projects exactly onto its keypoint in the current frame: (nearly) all are found, and at their own index
     assert nmp == nset and nmp > 0.9 * len(okps) and nsame > 0.95 * nset
+    sl = re.search(r"slp_nm=(\d+) slp_set=(\d+) slp_same=(\d+)", out)
+    nlp, lset, lsame = map(int, sl.groups())
+    # SearchByProjection(F, vpMapPoints, ...): all points have observations, so nmatches = slots set; most at their own keypoint
+    assert nlp == lset and nlp > 0.8 * len(okps) and lsame > 0.9 * lset

@@ -83,6 +83,16 @@ for case in range(n_cases // 2):
         b = O.search_by_projection(c["x3Dc"], c["valid1"], c["obs1"], c["kps1"], c["descMP"], c["kps2"], c["desc2"], c["bounds"], c["K"], c["scale_factors"], th, ori)
         if not (a[0] == b[0] and np.array_equal(a[1], b[1])):
             report("search_proj", cfg)
+        lc = synth.make_local_map_case(max(n1, 2), max(n2, 2), int(rng.integers(0, 10**6)), w=w, h=h, zero_obs_frac=float(rng.choice([0.0, 0.1, 0.6])),
+                                       held_frac=float(rng.choice([0.0, 0.2, 0.9])))
+        lc["pts"], lc["descMP"] = lc["pts"][:n1], lc["descMP"][:n1]
+        lc["kps2"], lc["desc2"], lc["held2"] = lc["kps2"][:n2], lc["desc2"][:n2], lc["held2"][:n2]
+        far = bool(rng.integers(0, 2)); thl = float(rng.choice([1.0, 3.0, 15.0, 80.0]))
+        a = gm.SearchByProjectionMapPoints(lc["pts"], lc["descMP"], lc["kps2"], lc["desc2"], lc["held2"], lc["bounds"], lc["scale_factors"], thl, far, 15.0)
+        b = O.search_by_projection_map_points(lc["pts"], lc["descMP"], lc["kps2"], lc["desc2"], lc["held2"], lc["bounds"], lc["scale_factors"], thl, far,
+                                              15.0, ratio)
+        if not (a[0] == b[0] and np.array_equal(a[1], b[1])):
+            report("search_map_points", dict(cfg, thl=thl, far=far))
     except Exception as e:
         report("guided", cfg, repr(e)[:200])
 
