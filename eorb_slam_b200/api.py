@@ -97,6 +97,8 @@ def _load():
         "eorb_guided_search_for_initialization_device": ([vp, vp, vp, i, vp, vp, i, vp, vp, i, f, i, vp, vp], i),
         "eorb_guided_search_by_projection": ([vp, vp, vp, vp, vp, vp, i, vp, vp, i, vp, vp, vp, i, f, i, vp, vp], i),
         "eorb_guided_search_by_projection_device": ([vp, vp, vp, vp, vp, vp, i, vp, vp, i, vp, vp, vp, i, f, i, vp, vp], i),
+        "eorb_guided_search_by_bow": ([vp, vp, vp, vp, i, vp, vp, vp, i, vp, vp, i, vp, vp, vp, i, f, i, vp, vp], i),
+        "eorb_guided_search_by_bow_device": ([vp, vp, vp, vp, i, vp, vp, vp, i, vp, vp, i, vp, vp, vp, i, f, i, vp, vp], i),
         "eorb_guided_search_by_projection_map_points": ([vp, vp, vp, i, vp, vp, vp, i, vp, vp, i, f, i, f, f, vp, vp], i),
         "eorb_guided_search_by_projection_map_points_device": ([vp, vp, vp, i, vp, vp, vp, i, vp, vp, i, f, i, f, f, vp, vp], i),
         "eorb_vocab_create": ([i, i, i, i, i, i, vp, vp, vp, vp, C.POINTER(vp)], i), "eorb_vocab_destroy": ([vp], i),
@@ -699,6 +701,20 @@ class GuidedMatcher:
                                                                C.c_float(thFarPoints), C.c_float(self.mfNNratio), _p(mc), C.byref(nm)),
                "SearchByProjection(map points)")
         return nm.value, mc[:len(k2)].copy()
+
+    def SearchByBoW(self, kpsKF, descKF, validKF, fvKF, kpsF, descF, fvF):
+        """ORBmatcher::SearchByBoW(pKF, F, vpMapPointMatches) (:276-478, monocular) -> (nmatches, match_f[n2]); fv* = (nodes, start,
+        feats): the FeatureVector in the CSR form ORBVocabulary.transform returns (fv_nodes, fv_start, fv_feats)"""
+        k1 = np.ascontiguousarray(kpsKF, KEYPOINT_DTYPE); k2 = np.ascontiguousarray(kpsF, KEYPOINT_DTYPE)
+        d1 = np.ascontiguousarray(descKF, np.uint8); d2 = np.ascontiguousarray(descF, np.uint8); v = np.ascontiguousarray(validKF, np.uint8)
+        a = [np.ascontiguousarray(fvKF[0], np.uint32), np.ascontiguousarray(fvKF[1], np.int32), np.ascontiguousarray(fvKF[2], np.uint32)]
+        b = [np.ascontiguousarray(fvF[0], np.uint32), np.ascontiguousarray(fvF[1], np.int32), np.ascontiguousarray(fvF[2], np.uint32)]
+        mf = np.full(max(len(k2), 1), -1, np.int32)
+        nm = C.c_int(0)
+        _check(lib.eorb_guided_search_by_bow(self.h, _p(k1), _p(d1), _p(v), len(k1), _p(a[0]), _p(a[1]), _p(a[2]), len(a[0]), _p(k2), _p(d2), len(k2),
+                                             _p(b[0]), _p(b[1]), _p(b[2]), len(b[0]), C.c_float(self.mfNNratio), int(self.mbCheckOrientation), _p(mf),
+                                             C.byref(nm)), "SearchByBoW")
+        return nm.value, mf[:len(k2)].copy()
 
     def SearchForInitialization_device(self, d_kps1, d_desc1, n1, d_kps2, d_desc2, n2, bounds, d_prev, d_matches12, windowSize=100):
         """all pointers are device addresses (ints); returns nmatches"""

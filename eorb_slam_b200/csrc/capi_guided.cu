@@ -35,7 +35,9 @@ struct eorb_guided {
     // SearchByProjection staging: camera-frame points, validity, observations (frame 1), match table (frame 2)
     float* d_x3 = nullptr; uint8_t* d_valid = nullptr; int32_t* d_obs = nullptr; int pCap1 = 0;
     int32_t* d_mc = nullptr; int pCap2 = 0;
-    uint8_t* d_held = nullptr; int heldCap = 0;         // SearchByProjection (map points): slots of F held on entry
+    uint8_t* d_held = nullptr; int heldCap = 0;
+    unsigned char* d_blob = nullptr; size_t blobCap = 0;   // SearchByBoW staging: validity flags + both FeatureVectors
+         // SearchByProjection (map points): slots of F held on entry
     GuidedWork w{};
     int workN1 = 0, workN2 = 0;
     int* d_nm = nullptr; int* h_nm = nullptr;          // [nmatches, total candidates] device + pinned mirror
@@ -87,7 +89,7 @@ extern "C" int eorb_guided_destroy(eorb_guided* g) {
     cudaSetDevice(g->device);
     cudaStreamSynchronize(g->stream);
     for (int k = 0; k < 2; k++) { cudaFree(g->d_kps[k]); cudaFree(g->d_desc[k]); }
-    cudaFree(g->d_prev); cudaFree(g->d_m12); cudaFree(g->d_x3); cudaFree(g->d_valid); cudaFree(g->d_obs); cudaFree(g->d_mc); cudaFree(g->d_held); cudaFree(g->w.q);
+    cudaFree(g->d_prev); cudaFree(g->d_m12); cudaFree(g->d_x3); cudaFree(g->d_valid); cudaFree(g->d_obs); cudaFree(g->d_mc); cudaFree(g->d_held); cudaFree(g->d_blob); cudaFree(g->w.q);
     cudaFree(g->w.cellStart); cudaFree(g->w.cellIdx); cudaFree(g->w.assigned); cudaFree(g->w.candOff); cudaFree(g->w.candCnt);
     cudaFree(g->w.top); cudaFree(g->w.bin); cudaFree(g->w.cand);
     cudaFree(g->d_nm); cudaFreeHost(g->h_nm); cudaFree(g->d_q); cudaFree(g->d_cnt); cudaFree(g->d_out);
@@ -463,5 +465,95 @@ extern "C" int eorb_guided_search_by_projection_map_points(eorb_guided* g, const
     if (rc != EORB_OK) return rc;
     CU(cudaMemcpyAsync(match_cur, g->d_mc, (size_t)n2 * sizeof(int32_t), cudaMemcpyDeviceToHost, g->stream));
     CU(cudaStreamSynchronize(g->stream));
+    return EORB_OK;
+}
+
+// ------------------------------------------------------------------------------------------------ SearchByBoW
+static int checkFeatureVector(const char* who, const uint32_t* nodes, const int32_t* start, const uint32_t* feats, int nn, int n) {
+    if (nn < 0 || (nn > 0 && (!nodes || !start || !feats))) return gFail(EORB_ERR_ARG, who, "null FeatureVector");
+    if (nn == 0) return EORB_OK;
+    if (start[0] != 0 || start[nn] < 0 || start[nn] > n) return gFail(EORB_ERR_ARG, who, "FeatureVector offsets out of range");
+    for (int q = 0; q < nn; q++) {
+        if (start[q + 1] < start[q]) return gFail(EORB_ERR_ARG, who, "FeatureVector offsets not ascending");
+        if (q > 0 && nodes[q] <= nodes[q - 1]) return gFail(EORB_ERR_ARG, who, "FeatureVector node ids not ascending");
+    }
+    for (int p = 0; p < start[nn]; p++)
+        if (feats[p] >= (uint32_t)n) return gFail(EORB_ERR_ARG, who, "FeatureVector feature index out of range");
+    return EORB_OK;
+}
+
+extern "C" int eorb_guided_search_by_bow_device(eorb_guided* g, const eorb_keypoint* d_kps_kf, const uint8_t* d_desc_kf, const uint8_t* d_valid_kf,
+                                                int n1, const uint32_t* d_kf_nodes, const int32_t* d_kf_start, const uint32_t* d_kf_feats, int nkf,
+                                                const eorb_keypoint* d_kps_f, const uint8_t* d_desc_f, int n2, const uint32_t* d_f_nodes,
+                                                const int32_t* d_f_start, const uint32_t* d_f_feats, int nf, float nnratio, int check_ori,
+                                                int32_t* d_match_f, int* nmatches) {
+    const char* who = "eorb_guided_search_by_bow_device";
+    if (!g) return gFail(EORB_ERR_ARG, who, "null handle");
+    if (n1 < 0 || n2 < 0 || nkf < 0 || nf < 0) return gFail(EORB_ERR_ARG, who, "negative size");
+    if (n1 > EORB_GUIDED_MAX_KEYPOINTS || n2 > EORB_GUIDED_MAX_KEYPOINTS) return gFail(EORB_ERR_CAPACITY, who, "more than EORB_GUIDED_MAX_KEYPOINTS keypoints");
+    if (nmatches) *nmatches = 0;
+    if (n2 == 0) return EORB_OK;
+    if (!d_match_f || !d_kps_f || !d_desc_f || (n1 > 0 && (!d_kps_kf || !d_desc_kf || !d_valid_kf)) ||
+        (nkf > 0 && (!d_kf_nodes || !d_kf_start || !d_kf_feats)) || (nf > 0 && (!d_f_nodes || !d_f_start || !d_f_feats)))
+        return gFail(EORB_ERR_ARG, who, "null argument");
+    if (((uintptr_t)d_desc_kf | (uintptr_t)d_desc_f) & 15) return gFail(EORB_ERR_ARG, who, "descriptors must be 16-byte aligned");
+    CU(cudaSetDevice(g->device));
+    GuidedBowSide a{d_kps_kf, d_desc_kf, d_kf_nodes, d_kf_start, d_kf_feats, nkf, n1}, b{d_kps_f, d_desc_f, d_f_nodes, d_f_start, d_f_feats, nf, n2};
+    CU(launch_search_by_bow(a, d_valid_kf, b, nnratio, check_ori, d_match_f, g->d_nm, g->stream, &g->launches));
+    CU(cudaMemcpyAsync(g->h_nm, g->d_nm, sizeof(int), cudaMemcpyDeviceToHost, g->stream));
+    CU(cudaStreamSynchronize(g->stream));
+    if (nmatches) *nmatches = g->h_nm[0];
+    return EORB_OK;
+}
+
+extern "C" int eorb_guided_search_by_bow(eorb_guided* g, const eorb_keypoint* kps_kf, const uint8_t* desc_kf, const uint8_t* valid_kf, int n1,
+                                         const uint32_t* kf_nodes, const int32_t* kf_start, const uint32_t* kf_feats, int nkf,
+                                         const eorb_keypoint* kps_f, const uint8_t* desc_f, int n2, const uint32_t* f_nodes, const int32_t* f_start,
+                                         const uint32_t* f_feats, int nf, float nnratio, int check_ori, int32_t* match_f, int* nmatches) {
+    const char* who = "eorb_guided_search_by_bow";
+    if (!g) return gFail(EORB_ERR_ARG, who, "null handle");
+    if (n1 < 0 || n2 < 0) return gFail(EORB_ERR_ARG, who, "negative size");
+    if (n1 > EORB_GUIDED_MAX_KEYPOINTS || n2 > EORB_GUIDED_MAX_KEYPOINTS) return gFail(EORB_ERR_CAPACITY, who, "more than EORB_GUIDED_MAX_KEYPOINTS keypoints");
+    if (nmatches) *nmatches = 0;
+    if (n2 == 0) return EORB_OK;
+    if (!match_f || !kps_f || !desc_f || (n1 > 0 && (!kps_kf || !desc_kf || !valid_kf))) return gFail(EORB_ERR_ARG, who, "null argument");
+    int rc;
+    if ((rc = checkFeatureVector(who, kf_nodes, kf_start, kf_feats, nkf, n1)) != EORB_OK) return rc;
+    if ((rc = checkFeatureVector(who, f_nodes, f_start, f_feats, nf, n2)) != EORB_OK) return rc;
+    CU(cudaSetDevice(g->device));
+    if ((rc = stageFrame(g, 0, kps_kf, desc_kf, n1)) != EORB_OK) return rc;
+    if ((rc = stageFrame(g, 1, kps_f, desc_f, n2)) != EORB_OK) return rc;
+    if (n2 > g->pCap2) {
+        CU(cudaStreamSynchronize(g->stream));
+        cudaFree(g->d_mc); g->d_mc = nullptr; g->pCap2 = 0;
+        const int cap = std::max(1024, n2);
+        CU(cudaMalloc((void**)&g->d_mc, (size_t)cap * sizeof(int32_t)));
+        g->pCap2 = cap;
+    }
+    // one blob: [kf nodes | kf start | kf feats | f nodes | f start | f feats | valid], every part 16-byte aligned
+    const int nfk = nkf > 0 ? kf_start[nkf] : 0, nff = nf > 0 ? f_start[nf] : 0;
+    auto al = [](size_t v) { return (v + 15) & ~(size_t)15; };
+    size_t off[8]; off[0] = 0;
+    const size_t sz[7] = {(size_t)nkf * 4, (size_t)(nkf + 1) * 4, (size_t)nfk * 4, (size_t)nf * 4, (size_t)(nf + 1) * 4, (size_t)nff * 4, (size_t)n1};
+    for (int i = 0; i < 7; i++) off[i + 1] = off[i] + al(sz[i]);
+    if (off[7] > g->blobCap) {
+        CU(cudaStreamSynchronize(g->stream));
+        cudaFree(g->d_blob); g->d_blob = nullptr; g->blobCap = 0;
+        const size_t cap = std::max<size_t>(off[7] + off[7] / 4, 1 << 16);
+        CU(cudaMalloc((void**)&g->d_blob, cap));
+        g->blobCap = cap;
+    }
+    const int32_t zero2[2] = {0, 0};
+    const void* src[7] = {kf_nodes, nkf > 0 ? (const void*)kf_start : (const void*)zero2, kf_feats, f_nodes, nf > 0 ? (const void*)f_start : (const void*)zero2,
+                          f_feats, valid_kf};
+    for (int i = 0; i < 7; i++)
+        if (sz[i] > 0) CU(cudaMemcpyAsync(g->d_blob + off[i], src[i], sz[i], cudaMemcpyHostToDevice, g->stream));
+    GuidedBowSide a{g->d_kps[0], g->d_desc[0], (const uint32_t*)(g->d_blob + off[0]), (const int32_t*)(g->d_blob + off[1]), (const uint32_t*)(g->d_blob + off[2]), nkf, n1};
+    GuidedBowSide b{g->d_kps[1], g->d_desc[1], (const uint32_t*)(g->d_blob + off[3]), (const int32_t*)(g->d_blob + off[4]), (const uint32_t*)(g->d_blob + off[5]), nf, n2};
+    CU(launch_search_by_bow(a, g->d_blob + off[6], b, nnratio, check_ori, g->d_mc, g->d_nm, g->stream, &g->launches));
+    CU(cudaMemcpyAsync(g->h_nm, g->d_nm, sizeof(int), cudaMemcpyDeviceToHost, g->stream));
+    CU(cudaMemcpyAsync(match_f, g->d_mc, (size_t)n2 * sizeof(int32_t), cudaMemcpyDeviceToHost, g->stream));
+    CU(cudaStreamSynchronize(g->stream));
+    if (nmatches) *nmatches = g->h_nm[0];
     return EORB_OK;
 }

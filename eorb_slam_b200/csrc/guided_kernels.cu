@@ -889,6 +889,99 @@ __global__ void __launch_bounds__(256) guided_resolve_map_kernel(const eorb_trac
     if (tid == 0) *nmatchesOut = sNm;
 }
 
+// ------------------------------------------------------------------------------------------------ SearchByBoW
+// ORBmatcher::SearchByBoW(pKF, F, vpMapPointMatches) (ORBmatcher.cc:276-478), monocular.  A frame feature belongs to exactly one
+// vocabulary node, so the "already matched" state (:330-331) never crosses nodes: the nodes are independent, only the keyframe
+// features INSIDE a node are order-dependent.  One warp per common node (binary search of the keyframe's node in the frame's
+// ascending node list = the lower_bound walk of :296-447), its keyframe features in list order, the lanes striding over the
+// node's frame features: two smallest (distance << 16 | position) keys per lane, two warp min-reductions -> best (first of the
+// smallest, like the strict "<") and second-best distance.  TH_LOW + float ratio test (:370-372), then rotation histogram
+// (:382-406), ComputeThreeMaxima and the filter (:449-470) by the whole block.  One block: a frame has ~100 nodes of ~10 features.
+__global__ void __launch_bounds__(1024) search_by_bow_kernel(GuidedBowSide kf, const uint8_t* __restrict__ validKF, GuidedBowSide f, float nnratio,
+                                                             int checkOri, int32_t* matchF, int* __restrict__ nmatchesOut) {
+    __shared__ int hist[32], sNm, sInd[3];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    for (int i = tid; i < f.n; i += 1024) matchF[i] = -1;
+    if (tid < 32) hist[tid] = 0;
+    if (tid == 0) sNm = 0;
+    __syncthreads();
+    volatile int32_t* taken = matchF;
+    auto rotBin = [&](int ik, int jf) -> int {
+        float rot = __fsub_rn(kf.kps[ik].angle, f.kps[jf].angle);
+        if (rot < 0.0f) rot = __fadd_rn(rot, 360.0f);
+        int bin = (int)roundf(__fmul_rn(rot, 1.0f / 30));
+        if (bin == 30) bin = 0;
+        return (bin >= 0 && bin < 30) ? bin : -1;
+    };
+    for (int w = warp; w < kf.nnodes; w += 32) {
+        const uint32_t node = kf.nodes[w];
+        int lo = 0, hi = f.nnodes;
+        while (lo < hi) { const int mid = (lo + hi) >> 1; if (f.nodes[mid] < node) lo = mid + 1; else hi = mid; }
+        if (lo >= f.nnodes || f.nodes[lo] != node) continue;
+        const int fb = f.start[lo], fe = f.start[lo + 1];
+        for (int a = kf.start[w], ke = kf.start[w + 1]; a < ke; a++) {
+            const int ik = (int)kf.feats[a];
+            if (!validKF[ik]) continue;
+            uint32_t qd[8];
+            {
+                const uint4* qp = reinterpret_cast<const uint4*>(kf.desc + (size_t)ik * 32);
+                const uint4 x = __ldg(qp), y = __ldg(qp + 1);
+                qd[0] = x.x; qd[1] = x.y; qd[2] = x.z; qd[3] = x.w; qd[4] = y.x; qd[5] = y.y; qd[6] = y.z; qd[7] = y.w;
+            }
+            uint32_t k1 = 0xffffffffu, k2 = 0xffffffffu;
+            for (int p = fb + lane; p < fe; p += 32) {
+                const int jf = (int)f.feats[p];
+                if (taken[jf] >= 0) continue;
+                const uint4* dp = reinterpret_cast<const uint4*>(f.desc + (size_t)jf * 32);
+                const uint4 x = __ldg(dp), y = __ldg(dp + 1);
+                const int dist = __popc(x.x ^ qd[0]) + __popc(x.y ^ qd[1]) + __popc(x.z ^ qd[2]) + __popc(x.w ^ qd[3]) + __popc(y.x ^ qd[4]) +
+                                 __popc(y.y ^ qd[5]) + __popc(y.z ^ qd[6]) + __popc(y.w ^ qd[7]);
+                const uint32_t key = ((uint32_t)dist << 16) | (uint32_t)(p - fb);
+                if (key < k1) { k2 = k1; k1 = key; } else if (key < k2) k2 = key;
+            }
+            const uint32_t m1 = __reduce_min_sync(FULLMASK, k1);
+            const uint32_t m2 = __reduce_min_sync(FULLMASK, k1 == m1 ? k2 : k1);
+            if (m1 == 0xffffffffu) continue;
+            const int d1 = (int)(m1 >> 16), d2 = m2 != 0xffffffffu ? (int)(m2 >> 16) : 256;
+            if (d1 <= 50 && (float)d1 < __fmul_rn(nnratio, (float)d2)) {       // TH_LOW, mfNNratio
+                if (lane == 0) {
+                    const int jf = (int)f.feats[fb + (int)(m1 & 0xffffu)];
+                    taken[jf] = ik;
+                    atomicAdd(&sNm, 1);
+                    if (checkOri) { const int bin = rotBin(ik, jf); if (bin >= 0) atomicAdd(&hist[bin], 1); }
+                }
+                __syncwarp();
+            }
+        }
+    }
+    __syncthreads();
+    if (tid == 0) {
+        int ind1 = -1, ind2 = -1, ind3 = -1;
+        if (checkOri) {
+            int max1 = 0, max2 = 0, max3 = 0;
+            for (int i = 0; i < 30; i++) {
+                const int s = hist[i];
+                if (s > max1) { max3 = max2; max2 = max1; max1 = s; ind3 = ind2; ind2 = ind1; ind1 = i; }
+                else if (s > max2) { max3 = max2; max2 = s; ind3 = ind2; ind2 = i; }
+                else if (s > max3) { max3 = s; ind3 = i; }
+            }
+            if ((float)max2 < __fmul_rn(0.1f, (float)max1)) { ind2 = -1; ind3 = -1; }
+            else if ((float)max3 < __fmul_rn(0.1f, (float)max1)) ind3 = -1;
+        }
+        sInd[0] = ind1; sInd[1] = ind2; sInd[2] = ind3;
+    }
+    __syncthreads();
+    if (checkOri)
+        for (int i = tid; i < f.n; i += 1024) {
+            const int ik = matchF[i];
+            if (ik < 0) continue;
+            const int b = rotBin(ik, i);
+            if (b >= 0 && b != sInd[0] && b != sInd[1] && b != sInd[2]) { matchF[i] = -1; atomicSub(&sNm, 1); }
+        }
+    __syncthreads();
+    if (tid == 0) *nmatchesOut = sNm;
+}
+
 // ------------------------------------------------------------------------------------------------ launches
 static size_t resolveSmem(int n1, int n2) {
     const size_t n2r = (size_t)((n2 + 3) & ~3);
@@ -983,6 +1076,13 @@ cudaError_t launch_search_map_points(const eorb_track_point* d_pts, const uint8_
         (*launches) += 2;
     }
     guided_resolve_map_kernel<<<1, 256, resolveMapSmem(n1, f2.n), st>>>(d_pts, n1, f2, d_held2, nnratio, w, d_matchCur, d_nmatches);
+    (*launches)++;
+    return cudaGetLastError();
+}
+
+cudaError_t launch_search_by_bow(const GuidedBowSide& kf, const uint8_t* d_validKF, const GuidedBowSide& f, float nnratio, int checkOri,
+                                 int32_t* d_matchF, int* d_nmatches, cudaStream_t st, long long* launches) {
+    search_by_bow_kernel<<<1, 1024, 0, st>>>(kf, d_validKF, f, nnratio, checkOri, d_matchF, d_nmatches);
     (*launches)++;
     return cudaGetLastError();
 }

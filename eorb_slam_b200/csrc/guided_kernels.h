@@ -50,6 +50,11 @@ cudaError_t launch_search_proj(const float* d_x3Dc, const uint8_t* d_valid1, con
 cudaError_t launch_search_map_points(const eorb_track_point* d_pts, const uint8_t* d_descMP, int n1, const GuidedFrame& f2,
                                      const uint8_t* d_held2, GuidedGrid g, const GuidedProj& pr, int farPoints, float thFar, float nnratio,
                                      const GuidedWork& w, int32_t* d_matchCur, int* d_nmatches, cudaStream_t st, long long* launches);
+// SearchByBoW(pKF, F, vpMapPointMatches), monocular (ORBmatcher.cc:276-478): one side = keypoints, descriptors and the
+// FeatureVector in CSR form (nodes ascending, features of node q = feats[start[q] .. start[q+1]))
+struct GuidedBowSide { const eorb_keypoint* kps; const uint8_t* desc; const uint32_t* nodes; const int32_t* start; const uint32_t* feats; int nnodes, n; };
+cudaError_t launch_search_by_bow(const GuidedBowSide& kf, const uint8_t* d_validKF, const GuidedBowSide& f, float nnratio, int checkOri,
+                                 int32_t* d_matchF, int* d_nmatches, cudaStream_t st, long long* launches);
 cudaError_t guided_configure();
 
 }  // namespace eorb

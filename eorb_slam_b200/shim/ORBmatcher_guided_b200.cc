@@ -16,6 +16,7 @@
 #include "ORBmatcher.h"
 #include "Frame.h"
 #include "MapPoint.h"
+#include "KeyFrame.h"
 #endif
 
 namespace ORB_SLAM3
@@ -161,6 +162,56 @@ int ORBmatcher::SearchByProjection(Frame &F, const std::vector<MapPoint*> &vpMap
     }
     for (int i2 = 0; i2 < n2; i2++)
         if (mc[i2] >= 0) F.setMapPoint(i2, vpMapPoints[mc[i2]]);
+    return nmatches;
+}
+
+// ORBmatcher::SearchByBoW(pKF, F, vpMapPointMatches) (:276-478; Tracking::TrackReferenceKeyFrame, Relocalization), monocular frame.
+// The FeatureVectors (std::map<NodeId, vector<unsigned>>) are flattened in map order = ascending node id.
+namespace {
+void flattenFeatureVector(const DBoW2::FeatureVector& fv, std::vector<unsigned>& nodes, std::vector<int>& start, std::vector<unsigned>& feats)
+{
+    nodes.clear(); feats.clear(); start.assign(1, 0);
+    for (DBoW2::FeatureVector::const_iterator it = fv.begin(); it != fv.end(); ++it) {
+        nodes.push_back(it->first);
+        feats.insert(feats.end(), it->second.begin(), it->second.end());
+        start.push_back((int)feats.size());
+    }
+}
+} // namespace
+
+int ORBmatcher::SearchByBoW(KeyFrame* pKF, Frame &F, std::vector<MapPoint*> &vpMapPointMatches)
+{
+    const std::vector<MapPoint*> vpMapPointsKF = pKF->GetMapPointMatches();
+    const int n1 = pKF->numAllKPts(), n2 = F.numAllKPts();
+    vpMapPointMatches = std::vector<MapPoint*>(n2, static_cast<MapPoint*>(NULL));
+    eorb_guided* g = threadHandle();
+    if (!g || n1 == 0 || n2 == 0) return 0;
+    std::vector<eorb_keypoint> k1(n1), k2;
+    std::vector<unsigned char> d1((size_t)n1 * 32), d2, valid(n1, 0);
+    for (int i = 0; i < n1; i++) {
+        const cv::KeyPoint kp = pKF->getUndistKPtMono(i);
+        k1[i].x = kp.pt.x; k1[i].y = kp.pt.y; k1[i].size = kp.size; k1[i].angle = kp.angle; k1[i].response = kp.response;
+        k1[i].octave = kp.octave; k1[i].class_id = kp.class_id;
+        const cv::Mat d = pKF->getORBDescriptor(i);
+        std::memcpy(&d1[(size_t)i * 32], d.ptr<unsigned char>(), 32);
+        MapPoint* pMP = i < (int)vpMapPointsKF.size() ? vpMapPointsKF[i] : NULL;
+        valid[i] = (pMP && !pMP->isBad()) ? 1 : 0;
+    }
+    packFrame(F, k2, d2);
+    std::vector<unsigned> an, af, bn, bf;
+    std::vector<int> as, bs;
+    flattenFeatureVector(pKF->mFeatVec, an, as, af);
+    flattenFeatureVector(F.mFeatVec, bn, bs, bf);
+    std::vector<int> mf(n2, -1);
+    int nmatches = 0;
+    const int rc = eorb_guided_search_by_bow(g, k1.data(), d1.data(), valid.data(), n1, an.data(), as.data(), af.data(), (int)an.size(), k2.data(), d2.data(),
+                                             n2, bn.data(), bs.data(), bf.data(), (int)bn.size(), mfNNratio, mbCheckOrientation ? 1 : 0, mf.data(), &nmatches);
+    if (rc != EORB_OK) {
+        std::fprintf(stderr, "ORBmatcher(b200)::SearchByBoW: %s\n", eorb_last_error());
+        return 0;
+    }
+    for (int i2 = 0; i2 < n2; i2++)
+        if (mf[i2] >= 0) vpMapPointMatches[i2] = vpMapPointsKF[mf[i2]];
     return nmatches;
 }
 } // namespace ORB_SLAM3

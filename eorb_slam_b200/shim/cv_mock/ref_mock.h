@@ -4,6 +4,7 @@
 #pragma once
 #include <vector>
 #include <opencv2/core/core.hpp>
+#include "../ORBVocabulary_b200.h"   // the DBoW2::FeatureVector stand-in (a real build has Thirdparty/DBoW2)
 
 namespace ORB_SLAM3 {
 class GeometricCamera {
@@ -50,12 +51,26 @@ public:
     static float mnMinX, mnMaxX, mnMinY, mnMaxY;
     std::vector<cv::KeyPoint> mvKeysUn;
     cv::Mat mDescriptors;
+    DBoW2::FeatureVector mFeatVec;                // include/Frame.h:332
+};
+
+class KeyFrame {   // what SearchByBoW reads (include/KeyFrame.h:343, 395, 400, 407, 523)
+public:
+    std::vector<MapPoint*> GetMapPointMatches() { return mvpMapPoints; }
+    int numAllKPts() const { return (int)mvKeysUn.size(); }
+    cv::KeyPoint getUndistKPtMono(const int idx) const { return mvKeysUn[idx]; }
+    cv::Mat getORBDescriptor(const int idx) const { return mDescriptors.row(idx); }
+    DBoW2::FeatureVector mFeatVec;
+    std::vector<MapPoint*> mvpMapPoints;
+    std::vector<cv::KeyPoint> mvKeysUn;
+    cv::Mat mDescriptors;
 };
 
 class ORBmatcher {   // the members this path touches (ORBmatcher.h:39-42, 67-68, 96-113)
 public:
     int SearchForInitialization(Frame& F1, Frame& F2, std::vector<cv::Point2f>& vbPrevMatched, std::vector<int>& vnMatches12, int windowSize = 10);
     int SearchByProjection(Frame& CurrentFrame, const Frame& LastFrame, const float th, const bool bMono);
+    int SearchByBoW(KeyFrame* pKF, Frame& F, std::vector<MapPoint*>& vpMapPointMatches);
     int SearchByProjection(Frame& F, const std::vector<MapPoint*>& vpMapPoints, const float th = 3, const bool bFarPoints = false,
                            const float thFarPoints = 50.0f);
     explicit ORBmatcher(float nnratio = 0.6, bool checkOri = true) : mfNNratio(nnratio), mbCheckOrientation(checkOri) {}

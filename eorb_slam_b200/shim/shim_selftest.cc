@@ -156,6 +156,24 @@ int main(int argc, char** argv)
         for (auto& e : bv) sum += e.second;
         for (auto& e : fv) nf += e.second.size();
         std::printf("voc_ok=%d voc_words=%u bow=%zu bow_sum=%.9f fv_nodes=%zu fv_feats=%zu\n", (int)okv, voc.size(), bv.size(), sum, fv.size(), nf);
+        // ORBmatcher::SearchByBoW(pKF, F, matches): the frame matched against a keyframe made of the same features (every one with
+        // a map point) through the FeatureVector computed above: every feature that passes the ratio test finds itself
+        {
+            ORB_SLAM3::KeyFrame KF; ORB_SLAM3::Frame Fb;
+            KF.mvKeysUn = kps; KF.mDescriptors = desc; KF.mFeatVec = fv;
+            Fb.mvKeysUn = kps; Fb.mDescriptors = desc; Fb.mFeatVec = fv;
+            std::vector<ORB_SLAM3::MapPoint*> own;
+            cv::Mat pos = cv::Mat::zeros(3, 1, CV_32F);
+            for (int i = 0; i < desc.rows; i++) { own.push_back(new ORB_SLAM3::MapPoint(pos, desc.row(i), 1)); }
+            KF.mvpMapPoints = own;
+            std::vector<ORB_SLAM3::MapPoint*> mm;
+            ORB_SLAM3::ORBmatcher m07(0.7f, true);
+            const int nb = okv ? m07.SearchByBoW(&KF, Fb, mm) : 0;
+            int bset = 0, bself = 0;
+            for (size_t i = 0; i < mm.size(); i++) { bset += (mm[i] != nullptr); bself += (mm[i] != nullptr && mm[i] == own[i]); }
+            std::printf("sbb_nm=%d sbb_set=%d sbb_self=%d\n", nb, bset, bself);
+            for (auto* p : own) delete p;
+        }
         cv::Mat Kc = cv::Mat::zeros(3, 3, CV_32F), Dc = cv::Mat::zeros(4, 1, CV_32F);
         Kc.at<float>(0, 0) = 458.654f; Kc.at<float>(1, 1) = 457.296f; Kc.at<float>(0, 2) = 367.215f; Kc.at<float>(1, 2) = 248.375f; Kc.at<float>(2, 2) = 1.f;
         Dc.at<float>(0, 0) = -0.28340811f; Dc.at<float>(1, 0) = 0.07395907f; Dc.at<float>(2, 0) = 0.00019359f; Dc.at<float>(3, 0) = 1.76187114e-05f;

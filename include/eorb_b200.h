@@ -378,6 +378,23 @@ int eorb_guided_search_by_projection_map_points_device(eorb_guided* g, const eor
                                                        int far_points, float th_far, float nnratio, int32_t* d_match_cur,
                                                        int* nmatches);
 
+/* eorb_guided_search_by_bow replaces ORBmatcher::SearchByBoW(KeyFrame* pKF, Frame& F, vector<MapPoint*>& vpMapPointMatches)
+ * (src/ORBmatcher.cc:276-478) as called by Tracking::TrackReferenceKeyFrame and Relocalization (src/Tracking-1.cc:1680, 2625)
+ * for a monocular frame.  kps_kf / desc_kf = the keyframe's undistorted keypoints and descriptors, valid_kf[i] != 0 =
+ * GetMapPointMatches()[i] is set and not bad; the FeatureVectors pKF->mFeatVec and F.mFeatVec arrive in the CSR form
+ * eorb_vocab_transform writes (nodes ascending; features of node q = feats[start[q] .. start[q+1]) in push_back order).
+ * match_f[i2] = keyframe feature index whose map point ends up in vpMapPointMatches[i2], or -1. */
+int eorb_guided_search_by_bow(eorb_guided* g, const eorb_keypoint* kps_kf, const uint8_t* desc_kf, const uint8_t* valid_kf, int n1,
+                              const uint32_t* kf_nodes, const int32_t* kf_start, const uint32_t* kf_feats, int nkf,
+                              const eorb_keypoint* kps_f, const uint8_t* desc_f, int n2, const uint32_t* f_nodes, const int32_t* f_start,
+                              const uint32_t* f_feats, int nf, float nnratio, int check_ori, int32_t* match_f, int* nmatches);
+/* the same with every array resident in HBM (e.g. the FeatureVectors eorb_vocab_transform_device left there) */
+int eorb_guided_search_by_bow_device(eorb_guided* g, const eorb_keypoint* d_kps_kf, const uint8_t* d_desc_kf, const uint8_t* d_valid_kf,
+                                     int n1, const uint32_t* d_kf_nodes, const int32_t* d_kf_start, const uint32_t* d_kf_feats, int nkf,
+                                     const eorb_keypoint* d_kps_f, const uint8_t* d_desc_f, int n2, const uint32_t* d_f_nodes,
+                                     const int32_t* d_f_start, const uint32_t* d_f_feats, int nf, float nnratio, int check_ori,
+                                     int32_t* d_match_f, int* nmatches);
+
 /* ---------------------------------------------------------------- bag of words + undistortion (fourth "next" row)
  * The two steps that follow extraction in the reference's Frame:
  *   eorb_vocab_transform        replaces DBoW2 TemplatedVocabulary<FORB::TDescriptor, FORB>::transform(features, BowVector,

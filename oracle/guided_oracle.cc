@@ -284,4 +284,70 @@ int orc_search_by_projection_map_points(const orc_track_point* pts, const uint8_
     return nmatches;
 }
 
+// ORBmatcher::SearchByBoW(KeyFrame* pKF, Frame& F, vector<MapPoint*>& vpMapPointMatches) (src/ORBmatcher.cc:276-478;
+// Tracking::TrackReferenceKeyFrame src/Tracking-1.cc:1680, Relocalization :2625), monocular frame (Nleft == -1: the right-camera
+// bookkeeping :345-363, :410-438 never fires).  The two FeatureVectors arrive in the CSR form of orc_vocab_transform (node ids
+// ascending = std::map order, features of a node in ascending index = push_back order).  Walk of the common nodes (:296-447; the
+// lower_bound jumps are a plain merge of two ascending lists), per keyframe feature with a good map point (:307-313) the best /
+// second-best distance over the node's frame features that are still unmatched (:326-341), TH_LOW and the ratio test in float
+// (:370-372), rotation histogram of the matched frame indices (:382-406) and the final filter (:449-470).
+// valid_kf[i] = the keyframe has a map point at i that is not bad; match_f[i2] = keyframe feature index whose map point ends up in
+// vpMapPointMatches[i2], or -1; returns nmatches.
+int orc_search_by_bow(const orc_keypoint* kps_kf, const uint8_t* desc_kf, const uint8_t* valid_kf, const uint32_t* kf_nodes,
+                      const int32_t* kf_start, const uint32_t* kf_feats, int nkf, const orc_keypoint* kps_f, const uint8_t* desc_f, int n2,
+                      const uint32_t* f_nodes, const int32_t* f_start, const uint32_t* f_feats, int nf, float nnratio, int check_ori,
+                      int32_t* match_f) {
+    const int TH_LOW = 50, HISTO_LENGTH = 30;
+    for (int i = 0; i < n2; i++) match_f[i] = -1;
+    int nmatches = 0;
+    std::vector<int> rotHist[HISTO_LENGTH];
+    const float factor = 1.0f / HISTO_LENGTH;
+    int a = 0, b = 0;
+    while (a < nkf && b < nf) {
+        if (kf_nodes[a] == f_nodes[b]) {
+            for (int iKF = kf_start[a]; iKF < kf_start[a + 1]; iKF++) {
+                const unsigned realIdxKF = kf_feats[iKF];
+                if (!valid_kf[realIdxKF]) continue;
+                const uint8_t* dKF = desc_kf + (size_t)realIdxKF * 32;
+                int bestDist1 = 256, bestIdxF = -1, bestDist2 = 256;
+                for (int iF = f_start[b]; iF < f_start[b + 1]; iF++) {
+                    const unsigned realIdxF = f_feats[iF];
+                    if (match_f[realIdxF] >= 0) continue;
+                    const int dist = orc_descriptor_distance(dKF, desc_f + (size_t)realIdxF * 32);
+                    if (dist < bestDist1) { bestDist2 = bestDist1; bestDist1 = dist; bestIdxF = (int)realIdxF; }
+                    else if (dist < bestDist2) bestDist2 = dist;
+                }
+                if (bestDist1 <= TH_LOW && (float)bestDist1 < nnratio * (float)bestDist2) {
+                    match_f[bestIdxF] = (int)realIdxKF;
+                    if (check_ori) {
+                        float rot = kps_kf[realIdxKF].angle - kps_f[bestIdxF].angle;
+                        if (rot < 0.0) rot += 360.0f;
+                        int bin = (int)std::round(rot * factor);
+                        if (bin == HISTO_LENGTH) bin = 0;
+                        if (bin >= 0 && bin < HISTO_LENGTH) rotHist[bin].push_back(bestIdxF);
+                    }
+                    nmatches++;
+                }
+            }
+            a++; b++;
+        } else if (kf_nodes[a] < f_nodes[b]) a++;
+        else b++;
+    }
+    if (check_ori) {
+        int max1 = 0, max2 = 0, max3 = 0, ind1 = -1, ind2 = -1, ind3 = -1;
+        for (int i = 0; i < HISTO_LENGTH; i++) {
+            const int s = (int)rotHist[i].size();
+            if (s > max1) { max3 = max2; max2 = max1; max1 = s; ind3 = ind2; ind2 = ind1; ind1 = i; }
+            else if (s > max2) { max3 = max2; max2 = s; ind3 = ind2; ind2 = i; }
+            else if (s > max3) { max3 = s; ind3 = i; }
+        }
+        if (max2 < 0.1f * (float)max1) { ind2 = -1; ind3 = -1; }
+        else if (max3 < 0.1f * (float)max1) { ind3 = -1; }
+        for (int i = 0; i < HISTO_LENGTH; i++)
+            if (i != ind1 && i != ind2 && i != ind3)
+                for (int idx : rotHist[i]) { match_f[idx] = -1; nmatches--; }
+    }
+    return nmatches;
+}
+
 }  // extern "C"

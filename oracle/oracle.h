@@ -146,6 +146,13 @@ int   orc_search_by_projection_map_points(const orc_track_point* pts, const uint
                                           const float* scale_factors, int nlevels, float th, int far_points, float th_far,
                                           float nnratio, int32_t* match_cur);
 
+/* ORBmatcher::SearchByBoW(pKF, F, vpMapPointMatches) (ORBmatcher.cc:276-478), monocular; FeatureVectors in the CSR form of
+   orc_vocab_transform; valid_kf = keyframe map point present and not bad; match_f[n2] = keyframe feature index or -1 */
+int   orc_search_by_bow(const orc_keypoint* kps_kf, const uint8_t* desc_kf, const uint8_t* valid_kf, const uint32_t* kf_nodes,
+                        const int32_t* kf_start, const uint32_t* kf_feats, int nkf, const orc_keypoint* kps_f, const uint8_t* desc_f,
+                        int n2, const uint32_t* f_nodes, const int32_t* f_start, const uint32_t* f_feats, int nf, float nnratio,
+                        int check_ori, int32_t* match_f);
+
 /* ---- bag of words + undistortion (bow_oracle.cc) ---- */
 typedef struct orc_vocab orc_vocab;
 /* flat form of what TemplatedVocabulary::loadFromTextFile builds: node 0 = root, parent[nid] < nid, children in id order,

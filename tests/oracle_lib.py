@@ -420,6 +420,20 @@ def search_by_projection_map_points(pts, descMP, kps2, desc2, held2, bounds, sca
     return n, mc[:len(k2)].copy()
 
 
+def search_by_bow(kps_kf, desc_kf, valid_kf, fv_kf, kps_f, desc_f, fv_f, nnratio=0.7, check_ori=True):
+    """ORBmatcher::SearchByBoW(pKF, F, vpMapPointMatches), monocular; fv_* = (nodes, start, feats) CSR -> (nmatches, match_f[n2])"""
+    L = lib()
+    k1 = np.ascontiguousarray(kps_kf, KEYPOINT_DTYPE); k2 = np.ascontiguousarray(kps_f, KEYPOINT_DTYPE)
+    d1 = np.ascontiguousarray(desc_kf, np.uint8); d2 = np.ascontiguousarray(desc_f, np.uint8); v = np.ascontiguousarray(valid_kf, np.uint8)
+    a = [np.ascontiguousarray(fv_kf[0], np.uint32), np.ascontiguousarray(fv_kf[1], np.int32), np.ascontiguousarray(fv_kf[2], np.uint32)]
+    b = [np.ascontiguousarray(fv_f[0], np.uint32), np.ascontiguousarray(fv_f[1], np.int32), np.ascontiguousarray(fv_f[2], np.uint32)]
+    mf = np.full(max(len(k2), 1), -1, np.int32)
+    L.orc_search_by_bow.restype = C.c_int
+    n = L.orc_search_by_bow(_p(k1), _p(d1), _p(v), _p(a[0]), _p(a[1]), _p(a[2]), C.c_int(len(a[0])), _p(k2), _p(d2), C.c_int(len(k2)),
+                            _p(b[0]), _p(b[1]), _p(b[2]), C.c_int(len(b[0])), C.c_float(nnratio), C.c_int(int(check_ori)), _p(mf))
+    return n, mf[:len(k2)].copy()
+
+
 # ---- bag of words + undistortion (SURVEY 8f rank 4)
 class VocabOracle:
     def __init__(self, voc):

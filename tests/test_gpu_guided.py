@@ -217,3 +217,48 @@ def test_search_by_projection_map_points_crowded():
                                                     False, 0.0, ratio)
         assert n == en and np.array_equal(mc, emc)
         assert en > 100
+
+
+def _bow_case(api, n1, n2, seed, k, L, levelsup, valid_frac=0.8, max_flips=24):
+    """keyframe / frame features, their FeatureVectors through the device vocabulary transform (the reference's flow:
+    ComputeBoW on both, then SearchByBoW), and the keyframe's map-point flags"""
+    k1, d1, k2, d2, _ = synth.make_keypoint_frame_pair(max(n1, 2), max(n2, 2), seed, max_flips=max_flips)
+    k1, d1, k2, d2 = k1[:n1], d1[:n1], k2[:n2], d2[:n2]
+    v = api.ORBVocabulary(synth.make_vocabulary(k, L, seed))
+    def fv(d):
+        if len(d) == 0:
+            return (np.zeros(0, np.uint32), np.zeros(1, np.int32), np.zeros(0, np.uint32))
+        t = v.transform(d, levelsup)
+        return (t["fv_nodes"], t["fv_start"], t["fv_feats"])
+    valid = (np.random.default_rng(seed).random(n1) < valid_frac).astype(np.uint8)
+    return k1, d1, valid, fv(d1), k2, d2, fv(d2)
+
+
+@pytest.mark.parametrize("n1,n2,seed,k,L,levelsup,ratio,ori", [
+    (500, 520, 41, 6, 3, 2, 0.7, True), (500, 520, 42, 6, 3, 1, 0.9, True), (500, 520, 43, 6, 3, 0, 0.7, False),
+    (1009, 1009, 44, 10, 4, 2, 0.7, True),       # Tracking::TrackReferenceKeyFrame shape: ORBmatcher(0.7, true), ~100 nodes
+    (5000, 5000, 45, 10, 3, 2, 0.75, True),      # 10 nodes of ~500 features: long per-node lists
+    (800, 800, 46, 5, 2, 4, 0.8, True),          # levelsup >= L: everything under the root, one ordered list
+    (0, 10, 47, 6, 3, 2, 0.7, True), (300, 1, 48, 6, 3, 2, 0.7, True), (1, 300, 49, 6, 3, 2, 0.7, True)])
+def test_search_by_bow(n1, n2, seed, k, L, levelsup, ratio, ori):
+    """ORBmatcher::SearchByBoW(pKF, F, vpMapPointMatches), monocular: match table and nmatches bit-exact"""
+    api = _api()
+    c = _bow_case(api, n1, n2, seed, k, L, levelsup)
+    gm = api.GuidedMatcher(0, ratio, ori)
+    for rep in range(2):
+        n, mf = gm.SearchByBoW(*c)
+        en, emf = O.search_by_bow(*c, ratio, ori)
+        assert n == en and np.array_equal(mf, emf)
+    if n1 >= 500 and levelsup >= 2:
+        assert en > 50
+
+
+def test_search_by_bow_rejects_malformed_feature_vectors():
+    api = _api()
+    c = list(_bow_case(api, 200, 200, 51, 6, 3, 2))
+    nodes, start, feats = c[3]
+    bad = feats.copy(); bad[0] = 10**6
+    with pytest.raises(RuntimeError):
+        api.GuidedMatcher(0, 0.7, True).SearchByBoW(c[0], c[1], c[2], (nodes, start, bad), c[4], c[5], c[6])
+    with pytest.raises(RuntimeError):
+        api.GuidedMatcher(0, 0.7, True).SearchByBoW(c[0], c[1], c[2], (nodes[::-1].copy(), start, feats), c[4], c[5], c[6])

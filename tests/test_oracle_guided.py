@@ -280,3 +280,69 @@ def test_search_by_projection_map_points_matches_python(seed, th, far, ratio, ze
     n0, mc0 = O.search_by_projection_map_points(c["pts"], c["descMP"], c["kps2"], c["desc2"], None, c["bounds"], c["scale_factors"], th, far,
                                                 20.0, ratio)
     assert n0 >= n
+
+
+def py_search_by_bow(k1, d1, valid, fv1, k2, d2, fv2, ratio, ori):
+    """independent restatement of ORBmatcher.cc:276-478 (monocular) with dicts keyed by node id, like DBoW2's FeatureVector"""
+    m1 = {int(n): [int(x) for x in fv1[2][fv1[1][i]:fv1[1][i + 1]]] for i, n in enumerate(fv1[0])}
+    m2 = {int(n): [int(x) for x in fv2[2][fv2[1][i]:fv2[1][i + 1]]] for i, n in enumerate(fv2[0])}
+    mf = [-1] * len(k2)
+    hist = [[] for _ in range(30)]
+    nm = 0
+    for node in sorted(set(m1) & set(m2)):
+        for ik in m1[node]:
+            if not valid[ik]:
+                continue
+            ds = [(_ham(d1[ik], d2[j]), j) for j in m2[node] if mf[j] < 0]
+            if not ds:
+                continue
+            best = min(ds, key=lambda t: t[0])                 # first of the smallest
+            rest = sorted(t[0] for t in ds)
+            b2 = rest[1] if len(rest) > 1 else 256
+            if best[0] <= 50 and F(best[0]) < F(ratio) * F(b2):
+                mf[best[1]] = ik; nm += 1
+                if ori:
+                    rot = F(k1["angle"][ik]) - F(k2["angle"][best[1]])
+                    if rot < 0:
+                        rot = rot + F(360.0)
+                    bb = _round_away(F(rot) * (F(1.0) / F(30)))
+                    hist[0 if bb == 30 else bb].append(best[1])
+    if ori:
+        mx = [0, 0, 0]; ind = [-1, -1, -1]
+        for i in range(30):
+            s = len(hist[i])
+            if s > mx[0]:
+                mx = [s, mx[0], mx[1]]; ind = [i, ind[0], ind[1]]
+            elif s > mx[1]:
+                mx = [mx[0], s, mx[1]]; ind = [ind[0], i, ind[1]]
+            elif s > mx[2]:
+                mx[2] = s; ind[2] = i
+        if mx[1] < F(0.1) * F(mx[0]):
+            ind[1] = ind[2] = -1
+        elif mx[2] < F(0.1) * F(mx[0]):
+            ind[2] = -1
+        for i in range(30):
+            if i not in ind:
+                for idx in hist[i]:
+                    mf[idx] = -1; nm -= 1
+    return nm, np.array(mf, np.int32)
+
+
+def bow_case(n1, n2, seed, k=6, L=3, levelsup=2, valid_frac=0.8, max_flips=24):
+    """keyframe / frame keypoints + descriptors, their FeatureVectors through the vocabulary oracle, and the map-point flags"""
+    k1, d1, k2, d2, _ = synth.make_keypoint_frame_pair(n1, n2, seed, max_flips=max_flips)
+    vo = O.VocabOracle(synth.make_vocabulary(k, L, seed))
+    t1, t2 = vo.transform(d1, levelsup), vo.transform(d2, levelsup)
+    valid = (np.random.default_rng(seed).random(n1) < valid_frac).astype(np.uint8)
+    return k1, d1, valid, (t1["fv_nodes"], t1["fv_start"], t1["fv_feats"]), k2, d2, (t2["fv_nodes"], t2["fv_start"], t2["fv_feats"])
+
+
+@pytest.mark.parametrize("seed,ratio,ori,levelsup", [(41, 0.7, True, 2), (42, 0.9, True, 1), (43, 0.7, False, 3), (44, 0.6, True, 0)])
+def test_search_by_bow_matches_python(seed, ratio, ori, levelsup):
+    c = bow_case(500, 520, seed, levelsup=levelsup)
+    n, mf = O.search_by_bow(*c, ratio, ori)
+    en, emf = py_search_by_bow(*c, ratio, ori)
+    assert n == en and np.array_equal(mf, emf)
+    assert n == int((mf >= 0).sum())                           # one keyframe feature per matched frame keypoint
+    if levelsup >= 2:
+        assert n > 50

@@ -49,7 +49,7 @@ def test_shims_compile_and_fail_loudly_without_device():
     assert "ret=-1 n=0" in out and "empty_ret=-1" in out
     assert "no CUDA device" in err
     assert "lk_ok=0 lk_n=0" in out
-    assert "sfi_nm=0 sfi_self=0" in out and "sbp_nm=0 sbp_set=0" in out and "slp_nm=0 slp_set=0" in out
+    assert "sfi_nm=0 sfi_self=0" in out and "sbp_nm=0 sbp_set=0" in out and "slp_nm=0 slp_set=0" in out and "sbb_nm=0 sbb_set=0" in out
     assert "voc_ok=0" in out and "undist_ok=0" in out
 
 
@@ -97,3 +97,7 @@ def test_shims_match_oracle_on_gpu():
     nlp, lset, lsame = map(int, sl.groups())
     # SearchByProjection(F, vpMapPoints, ...): all points have observations, so nmatches = slots set; most at their own keypoint
     assert nlp == lset and nlp > 0.8 * len(okps) and lsame > 0.9 * lset
+    bb = re.search(r"sbb_nm=(\d+) sbb_set=(\d+) sbb_self=(\d+)", out)
+    nbb, bset, bself = map(int, bb.groups())
+    # SearchByBoW of a frame against a keyframe with the same features: distance 0 to itself, so every match is the feature itself
+    assert nbb == bset == bself and nbb > 0.5 * len(okps)
