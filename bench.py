@@ -511,7 +511,35 @@ def bench_bow(api, torch, dev, steps, warmup):
     for _ in range(reps):
         un = api.UndistortKeyPoints(k1, K, D)
     ms_un = (time.perf_counter() - t0) * 1e3 / reps
-    return {"metric": "bow_transform_features_per_s", "value": len(feats) / (ms * 1e-3), "unit": "features/s", "ms_per_call": ms,
+    # Tracking::TrackReferenceKeyFrame: ComputeBoW on the frame, then SearchByBoW(pKF, F, matches) with ORBmatcher(0.7, true)
+    sbb = {}
+    try:
+        kk1, _, kk2, _, _ = synth.make_keypoint_frame_pair(1009, 1009, 17)
+        dkf = feats
+        df = feats.copy()
+        flips = rng.integers(0, 256, (len(df), 2))
+        df[np.arange(len(df)), flips[:, 0] % 28 + 4] ^= (1 << (flips[:, 1] % 8)).astype(np.uint8)     # the frame sees the keyframe's features, a few bits off
+        order = rng.permutation(len(df)); df = df[order].copy(); kk2 = kk2[:len(df)]
+        t1 = v.transform(dkf, 4); t2 = v.transform(df, 4)
+        fv1 = (t1["fv_nodes"], t1["fv_start"], t1["fv_feats"]); fv2 = (t2["fv_nodes"], t2["fv_start"], t2["fv_feats"])
+        valid = np.ones(len(dkf), np.uint8)
+        gm = api.GuidedMatcher(dev, 0.7, False)
+        for _ in range(3):
+            bn, bmf = gm.SearchByBoW(kk1, dkf, valid, fv1, kk2, df, fv2)
+        t0 = time.perf_counter()
+        for _ in range(reps):
+            bn, bmf = gm.SearchByBoW(kk1, dkf, valid, fv1, kk2, df, fv2)
+        bms = (time.perf_counter() - t0) * 1e3 / reps
+        ben, bemf = O.search_by_bow(kk1, dkf, valid, fv1, kk2, df, fv2, 0.7, False)
+        t0 = time.perf_counter()
+        for _ in range(20):
+            O.search_by_bow(kk1, dkf, valid, fv1, kk2, df, fv2, 0.7, False)
+        bms_port = (time.perf_counter() - t0) * 1e3 / 20
+        sbb = {"ms_per_call": bms, "workload": "ORBmatcher::SearchByBoW(pKF, F): 1009 x 1009 features over %d / %d vocabulary nodes, %d matches; host call" %
+               (len(fv1[0]), len(fv2[0]), ben), "bit_exact_vs_oracle": bool(bn == ben and np.array_equal(bmf, bemf)), "cpu_port_ms_per_call": bms_port}
+    except Exception as e:
+        sbb = {"error": repr(e)}
+    return {"search_by_bow": sbb, "metric": "bow_transform_features_per_s", "value": len(feats) / (ms * 1e-3), "unit": "features/s", "ms_per_call": ms,
             "workload": "ORBVocabulary::transform: %d descriptors, vocabulary k=10 L=6 (%d nodes, %d words), levelsup 4, host call" %
                         (len(feats), len(voc["parent"]), len(leaves)),
             "gpu_launches_per_call": int(launches), "bit_exact_vs_oracle": bool(same), "bow_words": int(len(exp["bow_ids"])),

@@ -388,7 +388,7 @@ int eorb_guided_search_by_bow(eorb_guided* g, const eorb_keypoint* kps_kf, const
                               const uint32_t* kf_nodes, const int32_t* kf_start, const uint32_t* kf_feats, int nkf,
                               const eorb_keypoint* kps_f, const uint8_t* desc_f, int n2, const uint32_t* f_nodes, const int32_t* f_start,
                               const uint32_t* f_feats, int nf, float nnratio, int check_ori, int32_t* match_f, int* nmatches);
-/* the same with every array resident in HBM (e.g. the FeatureVectors eorb_vocab_transform_device left there) */
+/* the same with every array resident in HBM; d_match_f is written on the device, *nmatches after a stream synchronisation */
 int eorb_guided_search_by_bow_device(eorb_guided* g, const eorb_keypoint* d_kps_kf, const uint8_t* d_desc_kf, const uint8_t* d_valid_kf,
                                      int n1, const uint32_t* d_kf_nodes, const int32_t* d_kf_start, const uint32_t* d_kf_feats, int nkf,
                                      const eorb_keypoint* d_kps_f, const uint8_t* d_desc_f, int n2, const uint32_t* d_f_nodes,

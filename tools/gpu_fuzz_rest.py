@@ -96,6 +96,26 @@ for case in range(n_cases // 2):
     except Exception as e:
         report("guided", cfg, repr(e)[:200])
 
+# ---- SearchByBoW on FeatureVectors from the device transform
+for case in range(n_cases // 4):
+    k = int(rng.integers(2, 12)); L = int(rng.integers(1, 4)); lup = int(rng.integers(0, 5))
+    n1 = int(rng.choice([1, 30, 500, 1500])); n2 = int(rng.choice([1, 30, 500, 1500]))
+    ratio = float(rng.choice([0.6, 0.75, 0.9, 1.1])); ori = bool(rng.integers(0, 2)); flips = int(rng.choice([4, 24, 64]))
+    cfg = dict(k=k, L=L, lup=lup, n1=n1, n2=n2, ratio=ratio, ori=ori, flips=flips)
+    try:
+        k1, d1, k2, d2, _ = synth.make_keypoint_frame_pair(max(n1, 2), max(n2, 2), int(rng.integers(0, 10**6)), max_flips=flips)
+        k1, d1, k2, d2 = k1[:n1], d1[:n1], k2[:n2], d2[:n2]
+        v = api.ORBVocabulary(synth.make_vocabulary(k, L, int(rng.integers(0, 10**6))))
+        t1, t2 = v.transform(d1, lup), v.transform(d2, lup)
+        fv1 = (t1["fv_nodes"], t1["fv_start"], t1["fv_feats"]); fv2 = (t2["fv_nodes"], t2["fv_start"], t2["fv_feats"])
+        valid = (rng.random(n1) < float(rng.choice([0.3, 0.8, 1.0]))).astype(np.uint8)
+        a = api.GuidedMatcher(0, ratio, ori).SearchByBoW(k1, d1, valid, fv1, k2, d2, fv2)
+        b = O.search_by_bow(k1, d1, valid, fv1, k2, d2, fv2, ratio, ori)
+        if not (a[0] == b[0] and np.array_equal(a[1], b[1])):
+            report("search_by_bow", cfg)
+    except Exception as e:
+        report("search_by_bow", cfg, repr(e)[:200])
+
 # ---- bag of words
 for case in range(n_cases // 2):
     k = int(rng.integers(2, 21)); L = int(rng.integers(1, 5)); n = int(rng.choice([1, 10, 500, 3000])); lup = int(rng.integers(0, 7))
