@@ -36,7 +36,10 @@ struct eorb_guided {
     float* d_x3 = nullptr; uint8_t* d_valid = nullptr; int32_t* d_obs = nullptr; int pCap1 = 0;
     int32_t* d_mc = nullptr; int pCap2 = 0;
     uint8_t* d_held = nullptr; int heldCap = 0;
-    unsigned char* d_blob = nullptr; size_t blobCap = 0;   // SearchByBoW staging: validity flags + both FeatureVectors
+    // SearchByBoW host call: every input packed into ONE pinned blob -> one H2D copy; [nmatches | match table] -> one D2H copy
+    unsigned char* d_blob = nullptr; unsigned char* h_blob = nullptr; size_t blobCap = 0;
+    unsigned char* d_outb = nullptr; unsigned char* h_outb = nullptr; size_t outbCap = 0;
+    int* d_bowWork = nullptr;                           // rotation histogram, match count, block ticket
          // SearchByProjection (map points): slots of F held on entry
     GuidedWork w{};
     int workN1 = 0, workN2 = 0;
@@ -89,7 +92,7 @@ extern "C" int eorb_guided_destroy(eorb_guided* g) {
     cudaSetDevice(g->device);
     cudaStreamSynchronize(g->stream);
     for (int k = 0; k < 2; k++) { cudaFree(g->d_kps[k]); cudaFree(g->d_desc[k]); }
-    cudaFree(g->d_prev); cudaFree(g->d_m12); cudaFree(g->d_x3); cudaFree(g->d_valid); cudaFree(g->d_obs); cudaFree(g->d_mc); cudaFree(g->d_held); cudaFree(g->d_blob); cudaFree(g->w.q);
+    cudaFree(g->d_prev); cudaFree(g->d_m12); cudaFree(g->d_x3); cudaFree(g->d_valid); cudaFree(g->d_obs); cudaFree(g->d_mc); cudaFree(g->d_held); cudaFree(g->d_blob); cudaFreeHost(g->h_blob); cudaFree(g->d_outb); cudaFreeHost(g->h_outb); cudaFree(g->d_bowWork); cudaFree(g->w.q);
     cudaFree(g->w.cellStart); cudaFree(g->w.cellIdx); cudaFree(g->w.assigned); cudaFree(g->w.candOff); cudaFree(g->w.candCnt);
     cudaFree(g->w.top); cudaFree(g->w.bin); cudaFree(g->w.cand);
     cudaFree(g->d_nm); cudaFreeHost(g->h_nm); cudaFree(g->d_q); cudaFree(g->d_cnt); cudaFree(g->d_out);
@@ -499,7 +502,8 @@ extern "C" int eorb_guided_search_by_bow_device(eorb_guided* g, const eorb_keypo
     if (((uintptr_t)d_desc_kf | (uintptr_t)d_desc_f) & 15) return gFail(EORB_ERR_ARG, who, "descriptors must be 16-byte aligned");
     CU(cudaSetDevice(g->device));
     GuidedBowSide a{d_kps_kf, d_desc_kf, d_kf_nodes, d_kf_start, d_kf_feats, nkf, n1}, b{d_kps_f, d_desc_f, d_f_nodes, d_f_start, d_f_feats, nf, n2};
-    CU(launch_search_by_bow(a, d_valid_kf, b, nnratio, check_ori, d_match_f, g->d_nm, g->stream, &g->launches));
+    if (!g->d_bowWork) CU(cudaMalloc((void**)&g->d_bowWork, 64 * sizeof(int)));
+    CU(launch_search_by_bow(a, d_valid_kf, b, nnratio, check_ori, d_match_f, g->d_bowWork, g->d_nm, g->stream, &g->launches));
     CU(cudaMemcpyAsync(g->h_nm, g->d_nm, sizeof(int), cudaMemcpyDeviceToHost, g->stream));
     CU(cudaStreamSynchronize(g->stream));
     if (nmatches) *nmatches = g->h_nm[0];
@@ -521,39 +525,45 @@ extern "C" int eorb_guided_search_by_bow(eorb_guided* g, const eorb_keypoint* kp
     if ((rc = checkFeatureVector(who, kf_nodes, kf_start, kf_feats, nkf, n1)) != EORB_OK) return rc;
     if ((rc = checkFeatureVector(who, f_nodes, f_start, f_feats, nf, n2)) != EORB_OK) return rc;
     CU(cudaSetDevice(g->device));
-    if ((rc = stageFrame(g, 0, kps_kf, desc_kf, n1)) != EORB_OK) return rc;
-    if ((rc = stageFrame(g, 1, kps_f, desc_f, n2)) != EORB_OK) return rc;
-    if (n2 > g->pCap2) {
-        CU(cudaStreamSynchronize(g->stream));
-        cudaFree(g->d_mc); g->d_mc = nullptr; g->pCap2 = 0;
-        const int cap = std::max(1024, n2);
-        CU(cudaMalloc((void**)&g->d_mc, (size_t)cap * sizeof(int32_t)));
-        g->pCap2 = cap;
-    }
-    // one blob: [kf nodes | kf start | kf feats | f nodes | f start | f feats | valid], every part 16-byte aligned
+    // one blob, every part 16-byte aligned: [kf kps | kf desc | f kps | f desc | kf nodes | kf start | kf feats | f nodes | f start | f feats | valid]
     const int nfk = nkf > 0 ? kf_start[nkf] : 0, nff = nf > 0 ? f_start[nf] : 0;
     auto al = [](size_t v) { return (v + 15) & ~(size_t)15; };
-    size_t off[8]; off[0] = 0;
-    const size_t sz[7] = {(size_t)nkf * 4, (size_t)(nkf + 1) * 4, (size_t)nfk * 4, (size_t)nf * 4, (size_t)(nf + 1) * 4, (size_t)nff * 4, (size_t)n1};
-    for (int i = 0; i < 7; i++) off[i + 1] = off[i] + al(sz[i]);
-    if (off[7] > g->blobCap) {
+    const int NP = 11;
+    const int32_t zero2[2] = {0, 0};
+    const size_t sz[NP] = {(size_t)n1 * sizeof(eorb_keypoint), (size_t)n1 * 32, (size_t)n2 * sizeof(eorb_keypoint), (size_t)n2 * 32, (size_t)nkf * 4,
+                           (size_t)(nkf + 1) * 4, (size_t)nfk * 4, (size_t)nf * 4, (size_t)(nf + 1) * 4, (size_t)nff * 4, (size_t)n1};
+    const void* src[NP] = {kps_kf, desc_kf, kps_f, desc_f, kf_nodes, nkf > 0 ? (const void*)kf_start : (const void*)zero2, kf_feats,
+                           f_nodes, nf > 0 ? (const void*)f_start : (const void*)zero2, f_feats, valid_kf};
+    size_t off[NP + 1]; off[0] = 0;
+    for (int i = 0; i < NP; i++) off[i + 1] = off[i] + al(sz[i]);
+    if (off[NP] > g->blobCap) {
         CU(cudaStreamSynchronize(g->stream));
-        cudaFree(g->d_blob); g->d_blob = nullptr; g->blobCap = 0;
-        const size_t cap = std::max<size_t>(off[7] + off[7] / 4, 1 << 16);
+        cudaFree(g->d_blob); cudaFreeHost(g->h_blob); g->d_blob = nullptr; g->h_blob = nullptr; g->blobCap = 0;
+        const size_t cap = std::max<size_t>(off[NP] + off[NP] / 4, 1 << 18);
         CU(cudaMalloc((void**)&g->d_blob, cap));
+        CU(cudaMallocHost((void**)&g->h_blob, cap));
         g->blobCap = cap;
     }
-    const int32_t zero2[2] = {0, 0};
-    const void* src[7] = {kf_nodes, nkf > 0 ? (const void*)kf_start : (const void*)zero2, kf_feats, f_nodes, nf > 0 ? (const void*)f_start : (const void*)zero2,
-                          f_feats, valid_kf};
-    for (int i = 0; i < 7; i++)
-        if (sz[i] > 0) CU(cudaMemcpyAsync(g->d_blob + off[i], src[i], sz[i], cudaMemcpyHostToDevice, g->stream));
-    GuidedBowSide a{g->d_kps[0], g->d_desc[0], (const uint32_t*)(g->d_blob + off[0]), (const int32_t*)(g->d_blob + off[1]), (const uint32_t*)(g->d_blob + off[2]), nkf, n1};
-    GuidedBowSide b{g->d_kps[1], g->d_desc[1], (const uint32_t*)(g->d_blob + off[3]), (const int32_t*)(g->d_blob + off[4]), (const uint32_t*)(g->d_blob + off[5]), nf, n2};
-    CU(launch_search_by_bow(a, g->d_blob + off[6], b, nnratio, check_ori, g->d_mc, g->d_nm, g->stream, &g->launches));
-    CU(cudaMemcpyAsync(g->h_nm, g->d_nm, sizeof(int), cudaMemcpyDeviceToHost, g->stream));
-    CU(cudaMemcpyAsync(match_f, g->d_mc, (size_t)n2 * sizeof(int32_t), cudaMemcpyDeviceToHost, g->stream));
+    const size_t outBytes = 16 + (size_t)n2 * sizeof(int32_t);
+    if (outBytes > g->outbCap) {
+        CU(cudaStreamSynchronize(g->stream));
+        cudaFree(g->d_outb); cudaFreeHost(g->h_outb); g->d_outb = nullptr; g->h_outb = nullptr; g->outbCap = 0;
+        const size_t cap = std::max<size_t>(outBytes + outBytes / 4, 1 << 14);
+        CU(cudaMalloc((void**)&g->d_outb, cap));
+        CU(cudaMallocHost((void**)&g->h_outb, cap));
+        g->outbCap = cap;
+    }
+    for (int i = 0; i < NP; i++)
+        if (sz[i] > 0) std::memcpy(g->h_blob + off[i], src[i], sz[i]);
+    CU(cudaMemcpyAsync(g->d_blob, g->h_blob, off[NP], cudaMemcpyHostToDevice, g->stream));
+    unsigned char* B = g->d_blob;
+    GuidedBowSide a{(const eorb_keypoint*)(B + off[0]), B + off[1], (const uint32_t*)(B + off[4]), (const int32_t*)(B + off[5]), (const uint32_t*)(B + off[6]), nkf, n1};
+    GuidedBowSide b{(const eorb_keypoint*)(B + off[2]), B + off[3], (const uint32_t*)(B + off[7]), (const int32_t*)(B + off[8]), (const uint32_t*)(B + off[9]), nf, n2};
+    if (!g->d_bowWork) CU(cudaMalloc((void**)&g->d_bowWork, 64 * sizeof(int)));
+    CU(launch_search_by_bow(a, B + off[10], b, nnratio, check_ori, (int32_t*)(g->d_outb + 16), g->d_bowWork, (int*)g->d_outb, g->stream, &g->launches));
+    CU(cudaMemcpyAsync(g->h_outb, g->d_outb, outBytes, cudaMemcpyDeviceToHost, g->stream));
     CU(cudaStreamSynchronize(g->stream));
-    if (nmatches) *nmatches = g->h_nm[0];
+    std::memcpy(match_f, g->h_outb + 16, (size_t)n2 * sizeof(int32_t));
+    if (nmatches) *nmatches = *(const int*)g->h_outb;
     return EORB_OK;
 }

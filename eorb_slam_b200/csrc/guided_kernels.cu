@@ -896,15 +896,15 @@ __global__ void __launch_bounds__(256) guided_resolve_map_kernel(const eorb_trac
 // ascending node list = the lower_bound walk of :296-447), its keyframe features in list order, the lanes striding over the
 // node's frame features: two smallest (distance << 16 | position) keys per lane, two warp min-reductions -> best (first of the
 // smallest, like the strict "<") and second-best distance.  TH_LOW + float ratio test (:370-372), then rotation histogram
-// (:382-406), ComputeThreeMaxima and the filter (:449-470) by the whole block.  One block: a frame has ~100 nodes of ~10 features.
-__global__ void __launch_bounds__(1024) search_by_bow_kernel(GuidedBowSide kf, const uint8_t* __restrict__ validKF, GuidedBowSide f, float nnratio,
-                                                             int checkOri, int32_t* matchF, int* __restrict__ nmatchesOut) {
-    __shared__ int hist[32], sNm, sInd[3];
+// (:382-406) in global memory; the block that finishes last (ticket counter) runs ComputeThreeMaxima and the filter (:449-470).
+// Four nodes per block: a frame has ~100 nodes of ~10 features, so the ordered lists are short and the nodes spread over the SMs.
+#define BOW_WARPS 4     // warps (= vocabulary nodes) per block
+// work[0..29] rotation histogram, work[32] nmatches, work[33] blocks finished (zeroed before the launch); matchF preset to -1
+__global__ void __launch_bounds__(BOW_WARPS * 32) search_by_bow_kernel(GuidedBowSide kf, const uint8_t* __restrict__ validKF, GuidedBowSide f,
+                                                                        float nnratio, int checkOri, int32_t* matchF, int* work,
+                                                                        int* __restrict__ nmatchesOut) {
+    __shared__ int sInd[3], sLast;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    for (int i = tid; i < f.n; i += 1024) matchF[i] = -1;
-    if (tid < 32) hist[tid] = 0;
-    if (tid == 0) sNm = 0;
-    __syncthreads();
     volatile int32_t* taken = matchF;
     auto rotBin = [&](int ik, int jf) -> int {
         float rot = __fsub_rn(kf.kps[ik].angle, f.kps[jf].angle);
@@ -913,54 +913,64 @@ __global__ void __launch_bounds__(1024) search_by_bow_kernel(GuidedBowSide kf, c
         if (bin == 30) bin = 0;
         return (bin >= 0 && bin < 30) ? bin : -1;
     };
-    for (int w = warp; w < kf.nnodes; w += 32) {
+    const int w = blockIdx.x * BOW_WARPS + warp;
+    if (w < kf.nnodes) {
         const uint32_t node = kf.nodes[w];
         int lo = 0, hi = f.nnodes;
         while (lo < hi) { const int mid = (lo + hi) >> 1; if (f.nodes[mid] < node) lo = mid + 1; else hi = mid; }
-        if (lo >= f.nnodes || f.nodes[lo] != node) continue;
-        const int fb = f.start[lo], fe = f.start[lo + 1];
-        for (int a = kf.start[w], ke = kf.start[w + 1]; a < ke; a++) {
-            const int ik = (int)kf.feats[a];
-            if (!validKF[ik]) continue;
-            uint32_t qd[8];
-            {
-                const uint4* qp = reinterpret_cast<const uint4*>(kf.desc + (size_t)ik * 32);
-                const uint4 x = __ldg(qp), y = __ldg(qp + 1);
-                qd[0] = x.x; qd[1] = x.y; qd[2] = x.z; qd[3] = x.w; qd[4] = y.x; qd[5] = y.y; qd[6] = y.z; qd[7] = y.w;
-            }
-            uint32_t k1 = 0xffffffffu, k2 = 0xffffffffu;
-            for (int p = fb + lane; p < fe; p += 32) {
-                const int jf = (int)f.feats[p];
-                if (taken[jf] >= 0) continue;
-                const uint4* dp = reinterpret_cast<const uint4*>(f.desc + (size_t)jf * 32);
-                const uint4 x = __ldg(dp), y = __ldg(dp + 1);
-                const int dist = __popc(x.x ^ qd[0]) + __popc(x.y ^ qd[1]) + __popc(x.z ^ qd[2]) + __popc(x.w ^ qd[3]) + __popc(y.x ^ qd[4]) +
-                                 __popc(y.y ^ qd[5]) + __popc(y.z ^ qd[6]) + __popc(y.w ^ qd[7]);
-                const uint32_t key = ((uint32_t)dist << 16) | (uint32_t)(p - fb);
-                if (key < k1) { k2 = k1; k1 = key; } else if (key < k2) k2 = key;
-            }
-            const uint32_t m1 = __reduce_min_sync(FULLMASK, k1);
-            const uint32_t m2 = __reduce_min_sync(FULLMASK, k1 == m1 ? k2 : k1);
-            if (m1 == 0xffffffffu) continue;
-            const int d1 = (int)(m1 >> 16), d2 = m2 != 0xffffffffu ? (int)(m2 >> 16) : 256;
-            if (d1 <= 50 && (float)d1 < __fmul_rn(nnratio, (float)d2)) {       // TH_LOW, mfNNratio
-                if (lane == 0) {
-                    const int jf = (int)f.feats[fb + (int)(m1 & 0xffffu)];
-                    taken[jf] = ik;
-                    atomicAdd(&sNm, 1);
-                    if (checkOri) { const int bin = rotBin(ik, jf); if (bin >= 0) atomicAdd(&hist[bin], 1); }
+        if (lo < f.nnodes && f.nodes[lo] == node) {
+            const int fb = f.start[lo], fe = f.start[lo + 1];
+            int nm = 0;
+            for (int a = kf.start[w], ke = kf.start[w + 1]; a < ke; a++) {
+                const int ik = (int)kf.feats[a];
+                if (!validKF[ik]) continue;
+                uint32_t qd[8];
+                {
+                    const uint4* qp = reinterpret_cast<const uint4*>(kf.desc + (size_t)ik * 32);
+                    const uint4 x = __ldg(qp), y = __ldg(qp + 1);
+                    qd[0] = x.x; qd[1] = x.y; qd[2] = x.z; qd[3] = x.w; qd[4] = y.x; qd[5] = y.y; qd[6] = y.z; qd[7] = y.w;
                 }
-                __syncwarp();
+                uint32_t k1 = 0xffffffffu, k2 = 0xffffffffu;
+                for (int p = fb + lane; p < fe; p += 32) {
+                    const int jf = (int)f.feats[p];
+                    if (taken[jf] >= 0) continue;
+                    const uint4* dp = reinterpret_cast<const uint4*>(f.desc + (size_t)jf * 32);
+                    const uint4 x = __ldg(dp), y = __ldg(dp + 1);
+                    const int dist = __popc(x.x ^ qd[0]) + __popc(x.y ^ qd[1]) + __popc(x.z ^ qd[2]) + __popc(x.w ^ qd[3]) + __popc(y.x ^ qd[4]) +
+                                     __popc(y.y ^ qd[5]) + __popc(y.z ^ qd[6]) + __popc(y.w ^ qd[7]);
+                    const uint32_t key = ((uint32_t)dist << 16) | (uint32_t)(p - fb);
+                    if (key < k1) { k2 = k1; k1 = key; } else if (key < k2) k2 = key;
+                }
+                const uint32_t m1 = __reduce_min_sync(FULLMASK, k1);
+                const uint32_t m2 = __reduce_min_sync(FULLMASK, k1 == m1 ? k2 : k1);
+                if (m1 == 0xffffffffu) continue;
+                const int d1 = (int)(m1 >> 16), d2 = m2 != 0xffffffffu ? (int)(m2 >> 16) : 256;
+                if (d1 <= 50 && (float)d1 < __fmul_rn(nnratio, (float)d2)) {       // TH_LOW, mfNNratio
+                    if (lane == 0) {
+                        const int jf = (int)f.feats[fb + (int)(m1 & 0xffffu)];
+                        taken[jf] = ik;
+                        nm++;
+                        if (checkOri) { const int bin = rotBin(ik, jf); if (bin >= 0) atomicAdd(&work[bin], 1); }
+                    }
+                    __syncwarp();
+                }
             }
+            if (lane == 0 && nm > 0) atomicAdd(&work[32], nm);
         }
     }
+    // the block that finishes last filters the matches (:449-470)
+    __threadfence();
     __syncthreads();
+    if (tid == 0) sLast = (atomicAdd(&work[33], 1) == (int)gridDim.x - 1);
+    __syncthreads();
+    if (!sLast) return;
+    __threadfence();
     if (tid == 0) {
         int ind1 = -1, ind2 = -1, ind3 = -1;
         if (checkOri) {
             int max1 = 0, max2 = 0, max3 = 0;
             for (int i = 0; i < 30; i++) {
-                const int s = hist[i];
+                const int s = __ldcg(&work[i]);
                 if (s > max1) { max3 = max2; max2 = max1; max1 = s; ind3 = ind2; ind2 = ind1; ind1 = i; }
                 else if (s > max2) { max3 = max2; max2 = s; ind3 = ind2; ind2 = i; }
                 else if (s > max3) { max3 = s; ind3 = i; }
@@ -972,14 +982,14 @@ __global__ void __launch_bounds__(1024) search_by_bow_kernel(GuidedBowSide kf, c
     }
     __syncthreads();
     if (checkOri)
-        for (int i = tid; i < f.n; i += 1024) {
-            const int ik = matchF[i];
+        for (int i = tid; i < f.n; i += BOW_WARPS * 32) {
+            const int ik = __ldcg(&matchF[i]);
             if (ik < 0) continue;
             const int b = rotBin(ik, i);
-            if (b >= 0 && b != sInd[0] && b != sInd[1] && b != sInd[2]) { matchF[i] = -1; atomicSub(&sNm, 1); }
+            if (b >= 0 && b != sInd[0] && b != sInd[1] && b != sInd[2]) { matchF[i] = -1; atomicSub(&work[32], 1); }
         }
     __syncthreads();
-    if (tid == 0) *nmatchesOut = sNm;
+    if (tid == 0) *nmatchesOut = atomicAdd(&work[32], 0);
 }
 
 // ------------------------------------------------------------------------------------------------ launches
@@ -1081,8 +1091,13 @@ cudaError_t launch_search_map_points(const eorb_track_point* d_pts, const uint8_
 }
 
 cudaError_t launch_search_by_bow(const GuidedBowSide& kf, const uint8_t* d_validKF, const GuidedBowSide& f, float nnratio, int checkOri,
-                                 int32_t* d_matchF, int* d_nmatches, cudaStream_t st, long long* launches) {
-    search_by_bow_kernel<<<1, 1024, 0, st>>>(kf, d_validKF, f, nnratio, checkOri, d_matchF, d_nmatches);
+                                 int32_t* d_matchF, int* d_work, int* d_nmatches, cudaStream_t st, long long* launches) {
+    cudaError_t e = cudaMemsetAsync(d_matchF, 0xff, (size_t)f.n * sizeof(int32_t), st);
+    if (e != cudaSuccess) return e;
+    e = cudaMemsetAsync(d_work, 0, 64 * sizeof(int), st);
+    if (e != cudaSuccess) return e;
+    const int blocks = kf.nnodes > 0 ? (kf.nnodes + BOW_WARPS - 1) / BOW_WARPS : 1;
+    search_by_bow_kernel<<<blocks, BOW_WARPS * 32, 0, st>>>(kf, d_validKF, f, nnratio, checkOri, d_matchF, d_work, d_nmatches);
     (*launches)++;
     return cudaGetLastError();
 }
