@@ -716,6 +716,28 @@ class GuidedMatcher:
                                              C.byref(nm)), "SearchByBoW")
         return nm.value, mf[:len(k2)].copy()
 
+    def SearchByBoW_device(self, d_kpsKF, d_descKF, d_validKF, n1, d_fvKF, nkf, d_kpsF, d_descF, n2, d_fvF, nf, d_match_f):
+        """device pointers (ints); d_fv* = (nodes, start, feats) device pointers; returns nmatches"""
+        nm = C.c_int(0)
+        _check(lib.eorb_guided_search_by_bow_device(self.h, C.c_void_p(d_kpsKF), C.c_void_p(d_descKF), C.c_void_p(d_validKF), n1,
+                                                    C.c_void_p(d_fvKF[0]), C.c_void_p(d_fvKF[1]), C.c_void_p(d_fvKF[2]), nkf, C.c_void_p(d_kpsF),
+                                                    C.c_void_p(d_descF), n2, C.c_void_p(d_fvF[0]), C.c_void_p(d_fvF[1]), C.c_void_p(d_fvF[2]), nf,
+                                                    C.c_float(self.mfNNratio), int(self.mbCheckOrientation), C.c_void_p(d_match_f), C.byref(nm)),
+               "SearchByBoW_device")
+        return nm.value
+
+    def SearchByProjectionMapPoints_device(self, d_pts, d_descMP, n1, d_kps2, d_desc2, d_held2, n2, bounds, scale_factors, d_match_cur, th=1.0,
+                                           bFarPoints=False, thFarPoints=0.0):
+        """device pointers (ints; d_held2 may be 0); returns nmatches"""
+        b = np.ascontiguousarray(bounds, np.float32); sf = np.ascontiguousarray(scale_factors, np.float32)
+        nm = C.c_int(0)
+        _check(lib.eorb_guided_search_by_projection_map_points_device(self.h, C.c_void_p(d_pts), C.c_void_p(d_descMP), n1, C.c_void_p(d_kps2),
+                                                                      C.c_void_p(d_desc2), C.c_void_p(d_held2) if d_held2 else None, n2, _p(b), _p(sf),
+                                                                      len(sf), C.c_float(th), int(bool(bFarPoints)), C.c_float(thFarPoints),
+                                                                      C.c_float(self.mfNNratio), C.c_void_p(d_match_cur), C.byref(nm)),
+               "SearchByProjectionMapPoints_device")
+        return nm.value
+
     def SearchForInitialization_device(self, d_kps1, d_desc1, n1, d_kps2, d_desc2, n2, bounds, d_prev, d_matches12, windowSize=100):
         """all pointers are device addresses (ints); returns nmatches"""
         b = np.ascontiguousarray(bounds, np.float32)

@@ -262,3 +262,71 @@ def test_search_by_bow_rejects_malformed_feature_vectors():
         api.GuidedMatcher(0, 0.7, True).SearchByBoW(c[0], c[1], c[2], (nodes, start, bad), c[4], c[5], c[6])
     with pytest.raises(RuntimeError):
         api.GuidedMatcher(0, 0.7, True).SearchByBoW(c[0], c[1], c[2], (nodes[::-1].copy(), start, feats), c[4], c[5], c[6])
+
+
+def test_tracking_chain_on_the_device_extract_bow_search_by_bow_and_local_points():
+    """Tracking::TrackReferenceKeyFrame / SearchLocalPoints with the frame data resident in HBM: keyframe and frame are extracted
+    on the device, their descriptors go through the vocabulary transform where they lie, SearchByBoW and the local-map
+    SearchByProjection run on the device arrays; every result equals oracle extraction + oracle transform + oracle search"""
+    import torch
+    api = _api()
+    img1 = synth.make_frame(31)
+    img2 = np.roll(img1, (2, -3), axis=(0, 1))
+    p = api.ORBxParams(1000, 1.2, 8, 20, 7, 19, (752, 480))
+    ex = api.ORBextractor(p, 0, 2)
+    cap = ex.cap
+    st = torch.cuda.current_stream().cuda_stream
+    ex.set_stream(st)
+    d_frames = torch.from_numpy(np.stack([img1, img2])).cuda()
+    d_kps = torch.zeros(2 * cap * 28, dtype=torch.uint8, device="cuda"); d_desc = torch.zeros(2 * cap * 32, dtype=torch.uint8, device="cuda")
+    d_n = torch.zeros(2, dtype=torch.int32, device="cuda"); d_mono = torch.zeros(2, dtype=torch.int32, device="cuda")
+    ex.extract_batch_raw(d_frames.data_ptr(), 2, 752, 480, 752, 752 * 480, (0, 0), True, d_kps.data_ptr(), d_desc.data_ptr(), cap,
+                         d_n.data_ptr(), d_mono.data_ptr(), device=True)
+    torch.cuda.synchronize()
+    n1, n2 = (int(v) for v in d_n.cpu().numpy())
+    voc = synth.make_vocabulary(10, 4, 7)
+    v = api.ORBVocabulary(voc, 0); v.set_stream(st)
+    t1 = v.transform_device(d_desc.data_ptr(), n1, 2); t2 = v.transform_device(d_desc.data_ptr() + cap * 32, n2, 2)
+    def up(t):
+        a = [torch.from_numpy(np.ascontiguousarray(t[k]).view(np.int32).copy()).cuda() for k in ("fv_nodes", "fv_start", "fv_feats")]
+        return a, tuple(x.data_ptr() for x in a)
+    keep1, fv1 = up(t1); keep2, fv2 = up(t2)
+    rng = np.random.default_rng(5)
+    valid = (rng.random(n1) < 0.85).astype(np.uint8)
+    d_valid = torch.from_numpy(valid).cuda()
+    d_mf = torch.zeros(n2, dtype=torch.int32, device="cuda")
+    gm = api.GuidedMatcher(0, 0.7, True); gm.set_stream(st)
+    nb = gm.SearchByBoW_device(d_kps.data_ptr(), d_desc.data_ptr(), d_valid.data_ptr(), n1, fv1, len(t1["fv_nodes"]), d_kps.data_ptr() + cap * 28,
+                               d_desc.data_ptr() + cap * 32, n2, fv2, len(t2["fv_nodes"]), d_mf.data_ptr())
+    torch.cuda.synchronize()
+    orc = O.OrbOracle(1000, 1.2, 8, 20, 7, 19, 752, 480)
+    _, ok1, od1 = orc.extract(img1, (0, 0), True); _, ok2, od2 = orc.extract(img2, (0, 0), True)
+    vo = O.VocabOracle(voc)
+    e1, e2 = vo.transform(od1, 2), vo.transform(od2, 2)
+    for k in ("fv_nodes", "fv_start", "fv_feats"):
+        assert np.array_equal(t1[k], e1[k]) and np.array_equal(t2[k], e2[k])
+    en, emf = O.search_by_bow(ok1, od1, valid, (e1["fv_nodes"], e1["fv_start"], e1["fv_feats"]), ok2, od2,
+                              (e2["fv_nodes"], e2["fv_start"], e2["fv_feats"]), 0.7, True)
+    assert nb == en and np.array_equal(d_mf.cpu().numpy(), emf)
+    assert en > 100
+    # local map = the keyframe's features as map points predicted at their frame-2 positions
+    pts = np.zeros(n1, synth.TRACK_POINT_DTYPE)
+    pts["proj_x"] = ok1["x"] - 3.0 + rng.normal(0, 0.7, n1).astype(np.float32); pts["proj_y"] = ok1["y"] + 2.0 + rng.normal(0, 0.7, n1).astype(np.float32)
+    pts["view_cos"] = rng.uniform(0.99, 1.0, n1).astype(np.float32); pts["depth"] = 5.0
+    pts["scale_level"] = ok1["octave"]; pts["observations"] = rng.integers(0, 4, n1); pts["in_view"] = valid
+    held = (emf >= 0).astype(np.uint8)                      # slots TrackReferenceKeyFrame filled are not searched again
+    sf = np.ones(8, np.float32)
+    for i in range(1, 8):
+        sf[i] = np.float32(np.float64(sf[i - 1]) * np.float64(np.float32(1.2)))
+    b = np.array([0, 0, 752, 480], np.float32)
+    d_pts = torch.from_numpy(pts.view(np.uint8).copy()).cuda(); d_held = torch.from_numpy(held).cuda()
+    d_mc = torch.zeros(n2, dtype=torch.int32, device="cuda")
+    gl = api.GuidedMatcher(0, 0.8, True); gl.set_stream(st)
+    nl = gl.SearchByProjectionMapPoints_device(d_pts.data_ptr(), d_desc.data_ptr(), n1, d_kps.data_ptr() + cap * 28, d_desc.data_ptr() + cap * 32,
+                                               d_held.data_ptr(), n2, b, sf, d_mc.data_ptr(), 3.0)
+    torch.cuda.synchronize()
+    eln, elmc = O.search_by_projection_map_points(pts, od1, ok2, od2, held, b, sf, 3.0, False, 0.0, 0.8)
+    assert nl == eln and np.array_equal(d_mc.cpu().numpy(), elmc)
+    assert not np.any((elmc >= 0) & (held != 0)) and eln > 20
+    for h in (gm, gl, ex, v):
+        h.set_stream(None)
