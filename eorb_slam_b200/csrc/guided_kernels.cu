@@ -921,6 +921,58 @@ __global__ void __launch_bounds__(BOW_WARPS * 32) search_by_bow_kernel(GuidedBow
         if (lo < f.nnodes && f.nodes[lo] == node) {
             const int fb = f.start[lo], fe = f.start[lo + 1];
             int nm = 0;
+            if (fe - fb <= 32) {
+                // register path (the usual case: ~10 features per node): lane L keeps frame feature L of the node (index,
+                // descriptor, free flag); the keyframe side is loaded 32 features at a time, one per lane, and broadcast by
+                // shuffles, so the ordered loop touches no memory.  A lane is matched at most once: its rotation bin is added
+                // after the loop.
+                const bool hasF = fb + lane < fe;
+                const int jf = hasF ? (int)f.feats[fb + lane] : 0;
+                uint32_t fd[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+                if (hasF) {
+                    const uint4* dp = reinterpret_cast<const uint4*>(f.desc + (size_t)jf * 32);
+                    const uint4 x = __ldg(dp), y = __ldg(dp + 1);
+                    fd[0] = x.x; fd[1] = x.y; fd[2] = x.z; fd[3] = x.w; fd[4] = y.x; fd[5] = y.y; fd[6] = y.z; fd[7] = y.w;
+                }
+                bool freeF = hasF;
+                int mine = -1;
+                for (int a0 = kf.start[w], ke = kf.start[w + 1]; a0 < ke; a0 += 32) {
+                    const int cnt = min(32, ke - a0);
+                    int ikL = -1;
+                    uint32_t kd[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+                    if (lane < cnt) {
+                        const int t = (int)kf.feats[a0 + lane];
+                        if (validKF[t]) {
+                            ikL = t;
+                            const uint4* qp = reinterpret_cast<const uint4*>(kf.desc + (size_t)t * 32);
+                            const uint4 x = __ldg(qp), y = __ldg(qp + 1);
+                            kd[0] = x.x; kd[1] = x.y; kd[2] = x.z; kd[3] = x.w; kd[4] = y.x; kd[5] = y.y; kd[6] = y.z; kd[7] = y.w;
+                        }
+                    }
+                    unsigned todo = __ballot_sync(FULLMASK, ikL >= 0);
+                    while (todo) {
+                        const int sl = __ffs(todo) - 1;
+                        todo &= todo - 1;
+                        int dist = 0;
+#pragma unroll
+                        for (int j = 0; j < 8; j++) dist += __popc(__shfl_sync(FULLMASK, kd[j], sl) ^ fd[j]);
+                        const uint32_t key = freeF ? (((uint32_t)dist << 16) | (uint32_t)lane) : 0xffffffffu;
+                        const uint32_t m1 = __reduce_min_sync(FULLMASK, key);
+                        if (m1 == 0xffffffffu) break;                      // every frame feature of the node is matched
+                        const uint32_t m2 = __reduce_min_sync(FULLMASK, key == m1 ? 0xffffffffu : key);
+                        const int d1 = (int)(m1 >> 16), d2 = m2 != 0xffffffffu ? (int)(m2 >> 16) : 256;
+                        if (d1 <= 50 && (float)d1 < __fmul_rn(nnratio, (float)d2)) {
+                            const int ik = __shfl_sync(FULLMASK, ikL, sl);
+                            if (lane == (int)(m1 & 0xffffu)) { freeF = false; mine = ik; }
+                            nm++;
+                        }
+                    }
+                }
+                if (mine >= 0) {
+                    matchF[jf] = mine;
+                    if (checkOri) { const int bin = rotBin(mine, jf); if (bin >= 0) atomicAdd(&work[bin], 1); }
+                }
+            } else
             for (int a = kf.start[w], ke = kf.start[w + 1]; a < ke; a++) {
                 const int ik = (int)kf.feats[a];
                 if (!validKF[ik]) continue;
