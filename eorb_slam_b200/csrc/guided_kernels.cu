@@ -33,7 +33,29 @@ typedef unsigned long long u64;
 #ifndef EORB_GUIDED_SPEC
 #define EORB_GUIDED_SPEC 1
 #endif
+#ifndef EORB_GUIDED_FIXPOINT
+#define EORB_GUIDED_FIXPOINT 1   // local-map resolve: fixed-point passes over a chunk instead of restarts at contested lanes
+#endif
 #define FULLMASK 0xffffffffu
+
+// staging of one round of sorted heads (GUIDED_STAGE queries x 32 entries) by NTH threads: every thread requests all of its
+// entries before it stores the first one (the loop form waited for each L2 round trip in turn, and the staging warps, not the
+// ordered warp, set the pace of the resolve kernels)
+template <int NTH>
+__device__ __forceinline__ void guided_load_heads(u64* __restrict__ sp, const u64* __restrict__ top, const unsigned short* qlist, int r, int nact, int t) {
+    constexpr int PER = (GUIDED_STAGE * 32 + NTH - 1) / NTH;
+    u64 v[PER];
+#pragma unroll
+    for (int i = 0; i < PER; i++) {
+        const int e = t + i * NTH, q = r * GUIDED_STAGE + (e >> 5);
+        v[i] = (e < GUIDED_STAGE * 32 && q < nact) ? top[(size_t)qlist[q] * EORB_GUIDED_TOP + (e & 31)] : ~0ull;
+    }
+#pragma unroll
+    for (int i = 0; i < PER; i++) {
+        const int e = t + i * NTH;
+        if (e < GUIDED_STAGE * 32) sp[(e >> 5) * GUIDED_ROW + (e & 31)] = v[i];
+    }
+}
 
 // ---- GetFeaturesInArea cell window (Frame.cc:722-744), all float like the reference
 __device__ __forceinline__ bool area_cells(const GuidedGrid& g, float x, float y, float r, int& c0, int& c1, int& r0, int& r1) {
@@ -301,10 +323,7 @@ __global__ void __launch_bounds__(256) guided_resolve_kernel(GuidedFrame f1, Gui
         u64* sp = stop + (r & 1) * GUIDED_STAGE * GUIDED_ROW;
         int* sc = scnt + (r & 1) * GUIDED_STAGE;
         int* so = soff + (r & 1) * GUIDED_STAGE;
-        for (int t = tid - t0; t < GUIDED_STAGE * 32; t += nth) {
-            const int q = r * GUIDED_STAGE + (t >> 5);
-            sp[(t >> 5) * GUIDED_ROW + (t & 31)] = q < nact ? w.top[(size_t)qlist[q] * EORB_GUIDED_TOP + (t & 31)] : ~0ull;
-        }
+        if (nth == 256) guided_load_heads<256>(sp, w.top, qlist, r, nact, tid - t0); else guided_load_heads<224>(sp, w.top, qlist, r, nact, tid - t0);
         for (int k = tid - t0; k < GUIDED_STAGE; k += nth) {
             const int q = r * GUIDED_STAGE + k;
             sc[k] = q < nact ? w.candCnt[qlist[q]] : 0;
@@ -548,10 +567,7 @@ __global__ void __launch_bounds__(256) guided_resolve_proj_kernel(const eorb_key
     const int nrounds = (nact + GUIDED_STAGE - 1) / GUIDED_STAGE;
     auto loadStage = [&](int r, int t0, int nth) {
         u64* sp = stop + (r & 1) * GUIDED_STAGE * GUIDED_ROW;
-        for (int t = tid - t0; t < GUIDED_STAGE * 32; t += nth) {
-            const int q = r * GUIDED_STAGE + (t >> 5);
-            sp[(t >> 5) * GUIDED_ROW + (t & 31)] = q < nact ? w.top[(size_t)qlist[q] * EORB_GUIDED_TOP + (t & 31)] : ~0ull;
-        }
+        if (nth == 256) guided_load_heads<256>(sp, w.top, qlist, r, nact, tid - t0); else guided_load_heads<224>(sp, w.top, qlist, r, nact, tid - t0);
         for (int k = tid - t0; k < GUIDED_STAGE; k += nth) {
             const int q = r * GUIDED_STAGE + k, o = (r & 1) * GUIDED_STAGE + k;
             scnt[o] = q < nact ? w.candCnt[qlist[q]] : 0;
@@ -765,10 +781,7 @@ __global__ void __launch_bounds__(256) guided_resolve_map_kernel(const eorb_trac
     const int nrounds = (nact + GUIDED_STAGE - 1) / GUIDED_STAGE;
     auto loadStage = [&](int r, int t0, int nth) {
         u64* sp = stop + (r & 1) * GUIDED_STAGE * GUIDED_ROW;
-        for (int t = tid - t0; t < GUIDED_STAGE * 32; t += nth) {
-            const int q = r * GUIDED_STAGE + (t >> 5);
-            sp[(t >> 5) * GUIDED_ROW + (t & 31)] = q < nact ? w.top[(size_t)qlist[q] * EORB_GUIDED_TOP + (t & 31)] : ~0ull;
-        }
+        if (nth == 256) guided_load_heads<256>(sp, w.top, qlist, r, nact, tid - t0); else guided_load_heads<224>(sp, w.top, qlist, r, nact, tid - t0);
         for (int k = tid - t0; k < GUIDED_STAGE; k += nth) {
             const int q = r * GUIDED_STAGE + k, o = (r & 1) * GUIDED_STAGE + k;
             scnt[o] = q < nact ? w.candCnt[qlist[q]] : 0;
@@ -833,6 +846,75 @@ __global__ void __launch_bounds__(256) guided_resolve_map_kernel(const eorb_trac
                 __syncwarp();
             };
 #if EORB_GUIDED_SPEC
+#if EORB_GUIDED_FIXPOINT
+            // lane L takes query k + L.  Its answer depends on the lower lanes only through "is this slot claimed by a lower lane
+            // whose point has observations", so the chunk is solved as a fixed point: every lane picks the first two head entries
+            // that are neither blocked nor claimed (table ctab = lowest blocking claimer of a slot, rebuilt from the previous
+            // pass), until a pass changes nothing.  Lane j is final after pass j + 1 by induction, the fixed point is the
+            // sequential answer, and the number of passes is the longest chain of contested slots in the chunk (2-4) instead of
+            // one restart per contested lane.  A lane whose head runs dry stops the chunk: the lanes below it commit, it takes
+            // the full-list step.
+            int k = 0;
+            while (k < kend) {
+                const int q = k + lane;
+                const bool have = q < kend;
+                const bool blocking = have && sobs[so + q] > 0;
+                uint32_t b1 = 0xffffffffu, b2 = 0xffffffffu, p1 = 0xfffffffeu, p2 = 0xfffffffeu;
+                bool slow = false, acc = false, pacc = false, pslow = false;
+                int pass = 0;
+                for (;; pass++) {
+                    b1 = 0xffffffffu; b2 = 0xffffffffu; slow = false;
+                    if (have) {
+                        const u64* hp = sp + q * GUIDED_ROW;
+                        for (int en = 0; en < EORB_GUIDED_TOP && b2 == 0xffffffffu; en += 4) {
+                            u64 he[4]; uint32_t bv[4];
+#pragma unroll
+                            for (int u = 0; u < 4; u++) he[u] = hp[en + u];
+#pragma unroll
+                            for (int u = 0; u < 4; u++) {
+                                const uint32_t sl = (uint32_t)he[u] & 0xffffu;
+                                bv[u] = he[u] != ~0ull ? ((uint32_t)blk[sl] | (uint32_t)(ctab[sl] < (unsigned)lane)) : 1u;
+                            }
+#pragma unroll
+                            for (int u = 0; u < 4; u++)
+                                if (bv[u] == 0 && b2 == 0xffffffffu) {
+                                    const uint32_t v = ((uint32_t)(he[u] >> 32) << 16) | ((uint32_t)he[u] & 0xffffu);
+                                    if (b1 == 0xffffffffu) b1 = v; else b2 = v;
+                                }
+                            if (he[3] == ~0ull) break;
+                        }
+                        slow = b2 == 0xffffffffu && scnt[so + q] > EORB_GUIDED_TOP && (b1 == 0xffffffffu || (b1 >> 16) <= 100u);
+                    }
+                    acc = have && !slow && accepted(b1, b2);
+                    const bool changed = have && (b1 != p1 || b2 != p2 || acc != pacc || slow != pslow);
+                    if (!__any_sync(FULLMASK, changed) || pass >= 40) break;
+                    if (pacc && blocking) ctab[p1 & 0xffffu] = 0xffffffffu;          // rebuild the claim table from this pass
+                    __syncwarp();
+                    if (acc && blocking) atomicMin(&ctab[b1 & 0xffffu], (unsigned)lane);
+                    __syncwarp();
+                    p1 = b1; p2 = b2; pacc = acc; pslow = slow;
+                }
+                // here (b1, b2, acc, slow) == the previous pass and ctab holds exactly its blocking claims
+                const unsigned stopMask = pass >= 40 ? 0xfffffffeu : __ballot_sync(FULLMASK, have && slow);
+                const int ncommit = stopMask ? __ffs(stopMask) - 1 : min(32, kend - k);
+                if (pacc && blocking) ctab[p1 & 0xffffu] = 0xffffffffu;
+                __syncwarp();
+                const bool commit = acc && lane < ncommit;
+                // several points without observations may claim one slot in a chunk (the last one owns it); at most one blocking
+                // claim per slot, and it is the last
+                if (commit) atomicMin(&ctab[b1 & 0xffffu], (unsigned)(31 - lane));
+                __syncwarp();
+                if (commit && ctab[b1 & 0xffffu] == (unsigned)(31 - lane)) owner[b1 & 0xffffu] = qlist[r * GUIDED_STAGE + q];
+                if (commit && blocking) blk[b1 & 0xffffu] = 1;
+                __syncwarp();
+                if (commit) ctab[b1 & 0xffffu] = 0xffffffffu;
+                const int nc = __popc(__ballot_sync(FULLMASK, commit));
+                if (lane == 0) sNm += nc;
+                __syncwarp();
+                k += ncommit;
+                if (stopMask && pass < 40 && __shfl_sync(FULLMASK, (int)slow, ncommit & 31)) { seqStep(k); k++; }
+            }
+#else
             // lane L takes query k + L: the first two unblocked entries of its head.  It is dirty when an earlier lane of the
             // chunk claims either of them (conservative for claims by points without observations); the clean prefix commits.
             int k = 0;
@@ -879,6 +961,7 @@ __global__ void __launch_bounds__(256) guided_resolve_map_kernel(const eorb_trac
                 k += ncommit;
                 if (stopMask && __shfl_sync(FULLMASK, (int)slow, ncommit & 31)) { seqStep(k); k++; }
             }
+#endif
 #else
             for (int k = 0; k < kend; k++) seqStep(k);
 #endif

@@ -27,3 +27,33 @@ for _ in range(200):
 print("SearchByBoW host call: %.1f us, %d matches" % ((time.perf_counter() - t0) / 200 * 1e6, r[0]))
 e = O.search_by_bow(kk1, feats, valid, fv1, kk2, df, fv2, 0.7, False)
 print("bit exact:", r[0] == e[0] and np.array_equal(r[1], e[1]))
+lc = synth.make_local_map_case(3000, 1009, 43)
+a = (lc["pts"], lc["descMP"], lc["kps2"], lc["desc2"], lc["held2"], lc["bounds"], lc["scale_factors"])
+gl = api.GuidedMatcher(0, 0.8, True)
+for _ in range(5):
+    r = gl.SearchByProjectionMapPoints(*a, 3.0, False, 0.0)
+t0 = time.perf_counter()
+for _ in range(200):
+    r = gl.SearchByProjectionMapPoints(*a, 3.0, False, 0.0)
+print("SearchByProjection(map points) host call: %.1f us, %d matches" % ((time.perf_counter() - t0) / 200 * 1e6, r[0]))
+e = O.search_by_projection_map_points(*a, 3.0, False, 0.0, 0.8)
+print("bit exact:", r[0] == e[0] and np.array_equal(r[1], e[1]))
+import torch
+st = torch.cuda.current_stream().cuda_stream
+gl.set_stream(st)
+d = {k: torch.from_numpy(np.ascontiguousarray(v).view(np.uint8).reshape(-1).copy()).cuda() for k, v in
+     dict(pts=lc["pts"], dmp=lc["descMP"], k2=lc["kps2"], d2=lc["desc2"], held=lc["held2"]).items()}
+d_mc = torch.zeros(len(lc["kps2"]), dtype=torch.int32, device="cuda")
+n1, n2 = len(lc["pts"]), len(lc["kps2"])
+for _ in range(5):
+    nm = gl.SearchByProjectionMapPoints_device(d["pts"].data_ptr(), d["dmp"].data_ptr(), n1, d["k2"].data_ptr(), d["d2"].data_ptr(), d["held"].data_ptr(), n2,
+                                               lc["bounds"], lc["scale_factors"], d_mc.data_ptr(), 3.0)
+torch.cuda.synchronize()
+t0 = time.perf_counter()
+for _ in range(200):
+    nm = gl.SearchByProjectionMapPoints_device(d["pts"].data_ptr(), d["dmp"].data_ptr(), n1, d["k2"].data_ptr(), d["d2"].data_ptr(), d["held"].data_ptr(), n2,
+                                               lc["bounds"], lc["scale_factors"], d_mc.data_ptr(), 3.0)
+torch.cuda.synchronize()
+print("SearchByProjection(map points) device-resident call: %.1f us, %d matches, equal %s" %
+      ((time.perf_counter() - t0) / 200 * 1e6, nm, np.array_equal(d_mc.cpu().numpy(), e[1])))
+gl.set_stream(None)
