@@ -572,9 +572,12 @@ class ELK_Tracker:
         self.n = 0
 
     def __del__(self):
-        if getattr(self, "h", None):
-            lib.eorb_lk_destroy(self.h)
-            self.h = None
+        try:                                   # at interpreter exit the module globals may already be gone
+            if getattr(self, "h", None):
+                lib.eorb_lk_destroy(self.h)
+                self.h = None
+        except Exception:
+            pass
 
     def launch_count(self): return lib.eorb_lk_launch_count(self.h)
 
@@ -651,9 +654,12 @@ class GuidedMatcher:
         self.mfNNratio = float(nnratio); self.mbCheckOrientation = bool(checkOri)
 
     def __del__(self):
-        if getattr(self, "h", None):
-            lib.eorb_guided_destroy(self.h)
-            self.h = None
+        try:                                   # at interpreter exit the module globals may already be gone
+            if getattr(self, "h", None):
+                lib.eorb_guided_destroy(self.h)
+                self.h = None
+        except Exception:
+            pass
 
     def set_stream(self, s):
         _check(lib.eorb_guided_set_stream(self.h, C.c_void_p(s)) if s is not None else lib.eorb_guided_reset_stream(self.h), "guided_set_stream")
@@ -764,9 +770,12 @@ class ORBVocabulary:
         self.h = h
 
     def __del__(self):
-        if getattr(self, "h", None):
-            lib.eorb_vocab_destroy(self.h)
-            self.h = None
+        try:                                   # at interpreter exit the module globals may already be gone
+            if getattr(self, "h", None):
+                lib.eorb_vocab_destroy(self.h)
+                self.h = None
+        except Exception:
+            pass
 
     def set_stream(self, s):
         _check(lib.eorb_vocab_set_stream(self.h, C.c_void_p(s)) if s is not None else lib.eorb_vocab_reset_stream(self.h), "vocab_set_stream")
