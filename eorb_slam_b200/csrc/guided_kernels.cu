@@ -57,6 +57,32 @@ __device__ __forceinline__ void guided_load_heads(u64* __restrict__ sp, const u6
     }
 }
 
+// order-preserving compaction of the queries that have candidates into qlist (256 threads): four batches of 256 flags are
+// requested before the first ballot / scan round, so the block waits for L2 once per 1024 queries instead of once per 256
+__device__ __forceinline__ int guided_compact(const int* __restrict__ candCnt, int n1, unsigned short* qlist, int* sWarp, int tid) {
+    const int lane = tid & 31, warp = tid >> 5;
+    int nact = 0;
+    for (int base = 0; base < n1; base += 1024) {
+        bool act[4];
+#pragma unroll
+        for (int u = 0; u < 4; u++) { const int i1 = base + u * 256 + tid; act[u] = i1 < n1 && candCnt[i1] > 0; }
+#pragma unroll
+        for (int u = 0; u < 4; u++) {
+            const int i1 = base + u * 256 + tid;
+            const unsigned bm = __ballot_sync(FULLMASK, act[u]);
+            if (lane == 0) sWarp[warp] = __popc(bm);
+            __syncthreads();
+            int before = 0, total = 0;
+#pragma unroll
+            for (int k = 0; k < 8; k++) { const int v = sWarp[k]; total += v; if (k < warp) before += v; }
+            if (act[u]) qlist[nact + before + __popc(bm & ((1u << lane) - 1u))] = (unsigned short)i1;
+            nact += total;
+            __syncthreads();
+        }
+    }
+    return nact;
+}
+
 // ---- GetFeaturesInArea cell window (Frame.cc:722-744), all float like the reference
 __device__ __forceinline__ bool area_cells(const GuidedGrid& g, float x, float y, float r, int& c0, int& c1, int& r0, int& r1) {
     c0 = max(0, (int)floorf(__fmul_rn(__fsub_rn(__fsub_rn(x, g.minX), r), g.wInv)));
@@ -302,20 +328,7 @@ __global__ void __launch_bounds__(256) guided_resolve_kernel(GuidedFrame f1, Gui
     if (tid < 32) hist[tid] = 0;
     if (tid == 0) sNm = 0;
     // compact the queries that have candidates (level-0 keypoints with a non-empty window), keeping their order
-    int nact = 0;
-    for (int base = 0; base < n1; base += 256) {
-        const int i1 = base + tid;
-        const bool act = i1 < n1 && w.candCnt[i1] > 0;
-        const unsigned bm = __ballot_sync(FULLMASK, act);
-        if (lane == 0) sWarp[warp] = __popc(bm);
-        __syncthreads();
-        int before = 0, total = 0;
-#pragma unroll
-        for (int k = 0; k < 8; k++) { const int v = sWarp[k]; total += v; if (k < warp) before += v; }
-        if (act) qlist[nact + before + __popc(bm & ((1u << lane) - 1u))] = (unsigned short)i1;
-        nact += total;
-        __syncthreads();
-    }
+    const int nact = guided_compact(w.candCnt, n1, qlist, sWarp, tid);
     const int nrounds = (nact + GUIDED_STAGE - 1) / GUIDED_STAGE;
 
     // stage `r` = heads + list ranges of queries qlist[r*64 ..]; loaded by `nth` threads starting at thread `t0`
@@ -550,20 +563,7 @@ __global__ void __launch_bounds__(256) guided_resolve_proj_kernel(const eorb_key
     for (int i = tid; i < n1; i += 256) claim[i] = -1;
     if (tid < 32) hist[tid] = 0;
     if (tid == 0) sNm = 0;
-    int nact = 0;
-    for (int base = 0; base < n1; base += 256) {
-        const int i1 = base + tid;
-        const bool act = i1 < n1 && w.candCnt[i1] > 0;
-        const unsigned bm = __ballot_sync(FULLMASK, act);
-        if (lane == 0) sWarp[warp] = __popc(bm);
-        __syncthreads();
-        int before = 0, total = 0;
-#pragma unroll
-        for (int k = 0; k < 8; k++) { const int v = sWarp[k]; total += v; if (k < warp) before += v; }
-        if (act) qlist[nact + before + __popc(bm & ((1u << lane) - 1u))] = (unsigned short)i1;
-        nact += total;
-        __syncthreads();
-    }
+    const int nact = guided_compact(w.candCnt, n1, qlist, sWarp, tid);
     const int nrounds = (nact + GUIDED_STAGE - 1) / GUIDED_STAGE;
     auto loadStage = [&](int r, int t0, int nth) {
         u64* sp = stop + (r & 1) * GUIDED_STAGE * GUIDED_ROW;
@@ -764,20 +764,7 @@ __global__ void __launch_bounds__(256) guided_resolve_map_kernel(const eorb_trac
         lvl[i] = (signed char)(o < -100 ? -100 : (o > 100 ? 100 : o));
     }
     if (tid == 0) sNm = 0;
-    int nact = 0;
-    for (int base = 0; base < n1; base += 256) {
-        const int i1 = base + tid;
-        const bool act = i1 < n1 && w.candCnt[i1] > 0;
-        const unsigned bm = __ballot_sync(FULLMASK, act);
-        if (lane == 0) sWarp[warp] = __popc(bm);
-        __syncthreads();
-        int before = 0, total = 0;
-#pragma unroll
-        for (int k = 0; k < 8; k++) { const int v = sWarp[k]; total += v; if (k < warp) before += v; }
-        if (act) qlist[nact + before + __popc(bm & ((1u << lane) - 1u))] = (unsigned short)i1;
-        nact += total;
-        __syncthreads();
-    }
+    const int nact = guided_compact(w.candCnt, n1, qlist, sWarp, tid);
     const int nrounds = (nact + GUIDED_STAGE - 1) / GUIDED_STAGE;
     auto loadStage = [&](int r, int t0, int nth) {
         u64* sp = stop + (r & 1) * GUIDED_STAGE * GUIDED_ROW;
