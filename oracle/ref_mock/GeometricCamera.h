@@ -1,0 +1,23 @@
+// oracle/ref_mock/GeometricCamera.h — TEST INFRASTRUCTURE ONLY.  Stand-in for include/CameraModels/GeometricCamera.h (boost
+// serialization, TwoViewReconstruction ...): the four virtuals EventConversion.cc calls (GeometricCamera.h:94, 96, 101, 105).
+#pragma once
+#include <utility>
+#include <vector>
+#include <opencv2/core/core.hpp>
+#include <Eigen/Geometry>
+
+namespace ORB_SLAM3 {
+class GeometricCamera {
+public:
+    GeometricCamera() {}
+    explicit GeometricCamera(std::vector<float> p) : mvParameters(std::move(p)) {}
+    virtual ~GeometricCamera() = default;
+    virtual cv::Point2f project(const cv::Point3f& p3D) = 0;
+    virtual Eigen::Vector2d project(const Eigen::Vector3d& v3D) = 0;
+    virtual cv::Point3f unproject(const cv::Point2f& p2D) = 0;
+    virtual Eigen::Matrix<double, 2, 3> projectJac(const Eigen::Vector3d& v3D) = 0;
+    float getParameter(const int i) { return mvParameters[i]; }
+protected:
+    std::vector<float> mvParameters;
+};
+}  // namespace ORB_SLAM3

@@ -1,0 +1,201 @@
+"""ctypes binding of oracle/_ref/libref.so: the REFERENCE'S OWN sources (ORBextractor.cc, EventConversion.cc,
+ORBmatcher::DescriptorDistance) compiled unmodified against the stand-in headers of oracle/ref_mock/.
+
+TEST INFRASTRUCTURE ONLY.  libref.so can only be (re)built where /root/reference exists (this container); on the GPU
+box the prebuilt file travels with the snapshot, and everything that needs it skips when it is absent.  The committed
+fixtures tests/golden/ref_*.npz (tests/golden/make_ref_golden.py) carry its outputs everywhere else.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+import oracle_lib as O
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ORACLE_DIR = os.path.join(ROOT, "oracle")
+REF_SRC = os.environ.get("EORB_REFERENCE", "/root/reference")
+LIB_PATH = os.path.join(ORACLE_DIR, "_ref", "libref.so")
+FMA_LIB_PATH = os.path.join(ORACLE_DIR, "_ref", "libref_fma.so")
+
+ALLOC_MALLOC, ALLOC_BUMP = 0, 1
+
+
+def can_build() -> bool:
+    return os.path.exists(os.path.join(REF_SRC, "src", "ORBextractor.cc"))
+
+
+def build(target: str = "ref") -> None:
+    """(re)build through the committed recipe; no-op when up to date; needs the reference tree"""
+    O.build()
+    subprocess.check_call(["make", "-C", ORACLE_DIR, "-s", target, "REF=" + REF_SRC])
+
+
+def available() -> bool:
+    if can_build():
+        try:
+            build()
+        except Exception:
+            return os.path.exists(LIB_PATH)
+    return os.path.exists(LIB_PATH)
+
+
+_libs = {}
+
+
+def lib(path: str = LIB_PATH):
+    if path in _libs:
+        return _libs[path]
+    if path == LIB_PATH and can_build():
+        build()
+    O.lib()   # liboracle.so first: libref's primitives forward to it
+    L = C.CDLL(path)
+    vp = C.c_void_p
+    L.ref_version.restype = C.c_int
+    L.ref_orb_tables.argtypes = [C.POINTER(O.OrbParams), C.c_int, C.c_int] + [vp] * 9
+    L.ref_orb_tables.restype = C.c_int
+    L.ref_orb_extract.argtypes = [C.POINTER(O.OrbParams), vp, C.c_int, C.c_int, C.c_size_t, C.c_int, C.c_int, C.c_int, C.c_int, vp, vp,
+                                  C.c_int, vp, vp, vp, vp, vp]
+    L.ref_orb_extract.restype = C.c_int
+    L.ref_distribute_octtree.argtypes = [vp, vp, vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, vp, C.c_int]
+    L.ref_distribute_octtree.restype = C.c_int
+    L.ref_orb_tracked_desc.argtypes = [C.POINTER(O.OrbParams), vp, C.c_int, C.c_int, C.c_size_t, vp, C.c_int, vp]
+    L.ref_orb_tracked_desc.restype = C.c_int
+    L.ref_orb_assign_level_by_best_desc.argtypes = [C.POINTER(O.OrbParams), vp, vp, C.c_int, C.c_int, C.c_size_t, vp, C.c_int]
+    L.ref_orb_assign_level_by_best_desc.restype = C.c_int
+    L.ref_descriptor_distance.argtypes = [vp, vp]; L.ref_descriptor_distance.restype = C.c_int
+    L.ref_descriptor_distance_matrix.argtypes = [vp, C.c_int, vp, C.c_int, vp]; L.ref_descriptor_distance_matrix.restype = None
+    L.ref_orb_extract_batch_mt.argtypes = [C.POINTER(O.OrbParams), vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, vp]
+    L.ref_orb_extract_batch_mt.restype = C.c_long
+    if hasattr(L, "ref_ev_accumulate"):
+        L.ref_ev_accumulate.argtypes = [vp, C.c_int64, C.c_int, C.c_int, C.c_float, C.c_int, vp, C.c_float, vp, vp, C.c_int, C.c_int, C.c_int,
+                                        vp, vp]
+        L.ref_ev_accumulate.restype = C.c_int
+        L.ref_image_focus.argtypes = [vp, C.c_int, C.c_int, C.c_int, C.c_int]; L.ref_image_focus.restype = C.c_float
+        L.ref_ev_mci_jac.argtypes = [vp, C.c_int64, C.c_int, C.c_int, C.c_float, vp, C.c_float, vp, C.c_int, C.c_int, vp]
+        L.ref_ev_mci_jac.restype = None
+        L.ref_ev_accumulate_batch_mt.argtypes = [vp, C.c_int64, C.c_int64, C.c_int, C.c_int, C.c_float, C.c_int, vp, C.c_float, vp, C.c_int]
+        L.ref_ev_accumulate_batch_mt.restype = C.c_double
+    _libs[path] = L
+    return L
+
+
+_p = O._p
+
+
+class RefOrb:
+    """The reference's ORBextractor (ORBextractor.cc, unmodified) behind the same Python surface as oracle_lib.OrbOracle"""
+
+    def __init__(self, nfeatures=1000, scale_factor=1.2, nlevels=8, ini_th=20, min_th=7, edge_th=19, im_w=752, im_h=480,
+                 alloc_mode=ALLOC_BUMP, lib_path=LIB_PATH):
+        self.params = O.OrbParams(nfeatures, scale_factor, nlevels, ini_th, min_th, edge_th, im_w, im_h)
+        self.nlevels = nlevels
+        self.alloc_mode = alloc_mode
+        self.L = lib(lib_path)
+        self.cap = nfeatures + 3 * nlevels + 64 + 64 * nlevels
+        self.last = {}
+
+    def tables(self, w, h):
+        nl = self.nlevels
+        f = np.zeros(nl, np.int32); s = [np.zeros(nl, np.float32) for _ in range(4)]
+        um = np.zeros(16, np.int32); edge = C.c_int(0); lw = np.zeros(nl, np.int32); lh = np.zeros(nl, np.int32)
+        self.L.ref_orb_tables(C.byref(self.params), w, h, _p(f), _p(s[0]), _p(s[1]), _p(s[2]), _p(s[3]), _p(um), C.byref(edge), _p(lw), _p(lh))
+        return dict(features_per_level=f, scale=s[0], inv_scale=s[1], sigma2=s[2], inv_sigma2=s[3], umax=um, edge=edge.value,
+                    level_w=lw, level_h=lh)
+
+    def extract(self, img, lapping=(0, 1000), want_desc=True, taps=False):
+        """-> (ret, keypoints, descriptors or None); with taps=True self.last holds levels / blurred / FAST counters"""
+        if img is None or img.size == 0:
+            return -1, np.empty(0, O.KEYPOINT_DTYPE), None
+        img = np.ascontiguousarray(img, np.uint8)
+        h, w = img.shape
+        kps = np.zeros(self.cap, O.KEYPOINT_DTYPE)
+        desc = np.zeros((self.cap, 32), np.uint8)
+        n = C.c_int(0)
+        t = np.zeros(8, np.int64)
+        pyr = blur = present = None
+        if taps:
+            tb = self.tables(w, h)
+            tot = int((tb["level_w"].astype(np.int64) * tb["level_h"]).sum())
+            pyr = np.zeros(tot, np.uint8); blur = np.zeros(tot, np.uint8); present = np.zeros(self.nlevels, np.int32)
+        ret = self.L.ref_orb_extract(C.byref(self.params), _p(img), w, h, img.strides[0], int(lapping[0]), int(lapping[1]), int(want_desc),
+                                     self.alloc_mode, _p(kps), _p(desc), self.cap, C.byref(n), _p(pyr), _p(blur) if want_desc else None,
+                                     _p(present), _p(t))
+        assert n.value <= self.cap, "capacity exceeded"
+        self.last = dict(fast_calls=int(t[0]), fast_calls_nonempty=int(t[1]), candidates=int(t[2]), bump_overflow=int(t[3]), arena_bytes=int(t[4]))
+        assert self.last["bump_overflow"] == 0, "bump arena exhausted: pointer order no longer equals creation order"
+        if taps:
+            levels, blurred, o, ob = [], [], 0, 0
+            for l in range(self.nlevels):
+                lw, lh = int(tb["level_w"][l]), int(tb["level_h"][l])
+                levels.append(pyr[o:o + lw * lh].reshape(lh, lw).copy()); o += lw * lh
+                if want_desc and present[l]:
+                    blurred.append(blur[ob:ob + lw * lh].reshape(lh, lw).copy()); ob += lw * lh
+                else:
+                    blurred.append(None)
+            self.last.update(levels=levels, blurred=blurred)
+        return ret, kps[:n.value].copy(), (desc[:n.value].copy() if want_desc else None)
+
+    def tracked_desc(self, img, kps):
+        img = np.ascontiguousarray(img, np.uint8)
+        kps = np.ascontiguousarray(kps, O.KEYPOINT_DTYPE)
+        desc = np.zeros((len(kps), 32), np.uint8)
+        self.L.ref_orb_tracked_desc(C.byref(self.params), _p(img), img.shape[1], img.shape[0], img.strides[0], _p(kps), len(kps), _p(desc))
+        return desc
+
+    def assign_level_by_best_desc(self, ref_desc, img, kps):
+        img = np.ascontiguousarray(img, np.uint8)
+        kps = np.ascontiguousarray(kps, O.KEYPOINT_DTYPE).copy()
+        ref_desc = np.ascontiguousarray(ref_desc, np.uint8)
+        self.L.ref_orb_assign_level_by_best_desc(C.byref(self.params), _p(ref_desc), _p(img), img.shape[1], img.shape[0], img.strides[0],
+                                                 _p(kps), len(kps))
+        return kps
+
+
+def distribute_octtree(kx, ky, kresp, minX, maxX, minY, maxY, N, alloc_mode=ALLOC_BUMP) -> np.ndarray:
+    kx = np.ascontiguousarray(kx, np.float32); ky = np.ascontiguousarray(ky, np.float32); kr = np.ascontiguousarray(kresp, np.float32)
+    cap = len(kx) + 8
+    out = np.empty(cap, np.int32)
+    n = lib().ref_distribute_octtree(_p(kx), _p(ky), _p(kr), len(kx), minX, maxX, minY, maxY, N, alloc_mode, _p(out), cap)
+    return out[:n].copy()
+
+
+def descriptor_distance(a, b) -> int:
+    a = np.ascontiguousarray(a, np.uint8); b = np.ascontiguousarray(b, np.uint8)
+    return lib().ref_descriptor_distance(_p(a), _p(b))
+
+
+def descriptor_distance_matrix(q, db) -> np.ndarray:
+    q = np.ascontiguousarray(q, np.uint8); db = np.ascontiguousarray(db, np.uint8)
+    out = np.zeros((len(q), len(db)), np.int32)
+    lib().ref_descriptor_distance_matrix(_p(q), len(q), _p(db), len(db), _p(out))
+    return out
+
+
+def orb_extract_batch_mt(frames, nthreads, want_desc=True, **kw):
+    frames = np.ascontiguousarray(frames, np.uint8)
+    n, h, w = frames.shape
+    p = O.OrbParams(kw.get("nfeatures", 1000), kw.get("scale_factor", 1.2), kw.get("nlevels", 8), kw.get("ini_th", 20),
+                    kw.get("min_th", 7), kw.get("edge_th", 19), w, h)
+    counts = np.zeros(n, np.int32)
+    total = lib().ref_orb_extract_batch_mt(C.byref(p), _p(frames), n, w, h, nthreads, int(want_desc), _p(counts))
+    return total, counts
+
+
+# ----------------------------------------------------------------------------- events (EventConversion.cc, unmodified)
+def ev_accumulate(evs, w, h, sigma=1.0, mode=1, Tcw=None, depth=1.0, K=None, se2=None, pol=False, normalize=False):
+    """same contract as oracle_lib.ev_accumulate: -> (img_f32, (min, max) as the reference tracked them, u8 or None)"""
+    evs = np.ascontiguousarray(evs)
+    assert evs.dtype.itemsize == 24
+    img = np.zeros((h, w), np.float32)
+    u8 = np.zeros((h, w), np.uint8)
+    T = np.ascontiguousarray(Tcw, np.float32).reshape(16) if Tcw is not None else None
+    Kc = np.ascontiguousarray(K, np.float32) if K is not None else None
+    s2 = np.ascontiguousarray(se2, np.float32) if se2 is not None else None
+    r = lib().ref_ev_accumulate(_p(evs), len(evs), w, h, sigma, mode, _p(T), depth, _p(Kc), _p(s2), 0 if s2 is None else len(s2), int(pol),
+                                int(normalize), _p(img), _p(u8))
+    assert r >= 0
+    return img, (u8 if r == 1 else None)
