@@ -23,6 +23,7 @@
 #include <cstdint>
 #include <cstdlib>
 #include <cstring>
+#include <memory>
 #include <mutex>
 #include <new>
 #include <thread>
@@ -90,8 +91,13 @@ extern int EDGE_THRESHOLD;   // ORBextractor.cc:73 (a mutable global the constru
 
 namespace {
 // protected members are reached through a derived class; nothing is re-implemented
-struct RefExtractor : ORB_SLAM3::ORBextractor {
-    explicit RefExtractor(const ORB_SLAM3::ORBxParams& p) : ORB_SLAM3::ORBextractor(p) {}
+// EDGE_THRESHOLD is ONE mutable global that every constructor overwrites, and the adaptive rule (edgeTh < 0) scales its
+// CURRENT value (ORBextractor.cc:481-485): in the reference the margin of an adaptive extractor depends on which extractors
+// were built before it in the process.  The pin (oracle: "per extractor instance") is the first-extractor-in-a-fresh-process
+// value, so the global is put back to its initialiser (:73) before every construction here.
+struct FreshEdge { FreshEdge() { ORB_SLAM3::EDGE_THRESHOLD = 19; } };
+struct RefExtractor : FreshEdge, ORB_SLAM3::ORBextractor {
+    explicit RefExtractor(const ORB_SLAM3::ORBxParams& p) : FreshEdge(), ORB_SLAM3::ORBextractor(p) {}
     const std::vector<int>& featuresPerLevel() const { return mnFeaturesPerLevel; }
     const std::vector<int>& umaxTable() const { return umax; }
     static std::vector<cv::KeyPoint> distribute(const std::vector<cv::KeyPoint>& keys, int minX, int maxX, int minY, int maxY, int N) {
@@ -253,11 +259,13 @@ void ref_descriptor_distance_matrix(const uint8_t* q, int nq, const uint8_t* db,
 long ref_orb_extract_batch_mt(const orc_orb_params* p, const uint8_t* imgs, int nframes, int w, int h, int nthreads, int want_desc,
                               int* n_per_frame) {
     if (nthreads < 1) nthreads = 1;
-    { RefExtractor warm(toParams(p)); }   // EDGE_THRESHOLD is one global: set it once before the threads read it
+    // extractors are built one after the other on this thread (the constructor writes the EDGE_THRESHOLD global)
+    std::vector<std::unique_ptr<RefExtractor>> exs;
+    for (int t = 0; t < nthreads; t++) exs.emplace_back(new RefExtractor(toParams(p)));
     std::atomic<int> next{0};
     std::atomic<long> total{0};
-    auto work = [&]() {
-        RefExtractor ex(toParams(p));
+    auto work = [&](int tid) {
+        RefExtractor& ex = *exs[(size_t)tid];
         std::vector<int> lap = {0, 0};
         for (;;) {
             int f = next.fetch_add(1);
@@ -272,8 +280,8 @@ long ref_orb_extract_batch_mt(const orc_orb_params* p, const uint8_t* imgs, int 
         }
     };
     std::vector<std::thread> th;
-    for (int t = 1; t < nthreads; t++) th.emplace_back(work);
-    work();
+    for (int t = 1; t < nthreads; t++) th.emplace_back(work, t);
+    work(0);
     for (auto& t : th) t.join();
     return total.load();
 }

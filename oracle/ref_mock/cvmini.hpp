@@ -169,9 +169,14 @@ public:
         flags = t; rows = r; cols = c; step = (size_t)c * esz(t);
         size_t n = (size_t)r * step;
         if (n == 0) return;
-        uchar* p = (uchar*)std::malloc(n + 64);   // malloc, not operator new: keeps Mat pixels out of the bump arena (ref_api.cc)
+        // malloc, not operator new: keeps Mat pixels out of the bump arena (ref_api.cc).  A zeroed guard band of 32 rows + 4 KiB
+        // on either side makes the reference's out-of-bounds descriptor taps (edgeTh < 19, ORBextractor.cc:119-124 on the
+        // borderless clone of :1141) deterministic instead of a fault; rows that took such a tap are excluded from the goldens.
+        const size_t guard = 32 * step + 4096;
+        uchar* p = (uchar*)std::calloc(n + 2 * guard, 1);
+        if (!p) CVMINI_FAIL("out of memory");
         buf_.reset(p, std::free);
-        data = datastart = p; bufRows_ = r;
+        data = datastart = p + guard; bufRows_ = r;
     }
     void create(Size s, int t) { create(s.height, s.width, t); }
     void release() { buf_.reset(); data = datastart = nullptr; rows = cols = 0; step = 0; bufRows_ = 0; }

@@ -1,0 +1,146 @@
+"""The parity pin: the CPU oracle against the REFERENCE'S OWN CODE.
+
+tests/golden/ref_*.npz hold the outputs of oracle/_ref/libref.so — /root/reference/src/ORBextractor.cc,
+src/Event/EventConversion.cc and ORBmatcher::DescriptorDistance compiled unmodified behind the header-only stand-ins of
+oracle/ref_mock/ (recipe `make -C oracle ref`; generator tests/golden/make_ref_golden.py).  The oracle must reproduce them
+byte for byte.  Where libref itself is present (the authoring container; or its prebuilt .so on the GPU box) it is also run
+live, on the committed cases (fixtures not stale) and on fresh random ones."""
+import ctypes as C
+import json
+import os
+
+import numpy as np
+import pytest
+
+import oracle_lib as O
+import ref_cases as RC
+from eorb_slam_b200 import synth
+
+
+# ------------------------------------------------------------------------------------------------ oracle vs committed fixtures
+@pytest.mark.parametrize("name", RC.ORB_NAMES)
+def test_oracle_equals_reference_golden(name):
+    g, fkw, okw, img, lap = RC.orb_golden(name)
+    orc = O.OrbOracle(*RC.orb_args(okw, fkw))
+    ret, kps, desc = orc.extract(img, lap, True)
+    assert ret == int(g["ret"][0])
+    assert kps.tobytes() == g["kps"].tobytes(), "keypoints (coordinates, size, angle bits, response, octave) and their order"
+    rows = g["desc_rows_defined"]          # all rows when the margin is >= 19 (the reference reads out of bounds below that)
+    assert np.array_equal(desc[rows], g["desc"][rows])
+    assert orc.edge == int(g["edge"][0]) and list(orc.features_per_level()) == list(g["features_per_level"])
+    for a, b in zip(orc.scale_factors(), (g["scale"], g["inv_scale"], g["sigma2"], g["inv_sigma2"])):
+        assert a.tobytes() == b.tobytes()
+    assert np.array_equal(orc.umax(), g["umax"])
+    for l in range(okw["nlevels"]):
+        assert orc.level_size(l) == (int(g["level_w"][l]), int(g["level_h"][l]))
+        assert RC.sha(orc.level(l)) == str(g["level_sha"][l]), "pyramid level %d" % l
+        if str(g["blur_sha"][l]):
+            assert RC.sha(orc.blurred(l)) == str(g["blur_sha"][l]), "blurred level %d" % l
+    assert sum(len(orc.candidates(l)[0]) for l in range(okw["nlevels"])) == int(g["candidates"][0])
+    rk, kk, _ = orc.extract(img, lap, False)
+    assert rk == ret and kk.tobytes() == kps.tobytes()
+
+
+def test_oracle_equals_reference_fuzz():
+    """200 random configurations (sizes, 1..9 levels, scale factors, thresholds, margins incl. the adaptive one, 1..2500 features,
+    lapping areas, textured / flat frames), 78 646 keypoints: same return value, keypoint bytes and descriptor bytes"""
+    bad = []
+    for i, c, ret, n, ksha, dsha in RC.fuzz_cases():
+        r, k, d = O.OrbOracle(*RC.fuzz_args(c)).extract(RC.fuzz_frame(c), (c["lap0"], c["lap1"]), bool(c["want"]))
+        if not (r == ret and len(k) == n and RC.sha(k) == ksha and (not c["want"] or RC.sha(d) == dsha)):
+            bad.append((i, c))
+    assert not bad, bad[:3]
+
+
+def test_oracle_octree_equals_reference():
+    """DistributeOctTree alone on 300 candidate sets built to tie (lattices, blobs, few distinct responses)"""
+    for i, w, h, N, x, y, resp, osha, on in RC.octree_cases():
+        out = O.distribute_octtree(x, y, resp, 16, 16 + w, 16, 16 + h, N)
+        assert len(out) == on and RC.sha(out) == osha, ("octree case", i, w, h, N, len(x))
+
+
+def test_oracle_secondary_api_and_distance_equal_reference(golden_dir):
+    g = np.load(os.path.join(golden_dir, "ref_secondary.npz"))
+    img = synth.make_frame(int(g["frame_seed"][0]))
+    orc = O.OrbOracle()
+    assert np.array_equal(orc.tracked_desc(img, g["sel"]), g["tracked_desc"])
+    moved = np.roll(img, (2, 3), axis=(0, 1))
+    assert orc.assign_level_by_best_desc(g["tracked_desc"], moved, g["sel"]).tobytes() == g["assigned"].tobytes()
+    q, db, D = g["q"], g["db"], g["dist"].astype(np.int32)
+    assert np.array_equal(np.unpackbits(q[:, None, :] ^ db[None, :, :], axis=2).sum(2), D)     # the bit-hack == a popcount
+    out = O.hamming_best2(q, db, 256, 2.0)
+    assert np.array_equal(out["best_dist"], D.min(1)) and np.array_equal(out["best_idx"], D.argmin(1))
+
+
+def test_oracle_event_frames_equal_reference():
+    for i, s, ev, kw, g in RC.event_cases():
+        f, mm, u8 = O.ev_accumulate(ev, s["w"], s["h"], normalize=True, **kw)
+        assert RC.sha(f) == str(g["f_sha"][i]), ("float frame, bit for bit", i, s)
+        if "f%d" % i in g.files:
+            assert f.tobytes() == g["f%d" % i].tobytes()
+        if str(g["u_sha"][i]):
+            assert u8 is not None and np.array_equal(u8, g["u%d" % i]), ("normalised u8 frame", i)
+        else:
+            assert u8 is None
+    # motion-compensation Jacobian
+    evj = synth.make_events(6000, 21)
+    for glob in (0, 1):
+        jo = np.zeros(6)
+        O.lib().orc_ev_mci_jac(O._p(evj), len(evj), 240, 180, 1.0, O._p(np.ascontiguousarray(g["jac_Rt"])), 1.5,
+                               O._p(np.ascontiguousarray(g["jac_K"])), 0, glob, O._p(jo))
+        jr = g["jac%d" % glob]
+        assert np.abs(jo - jr).max() <= 1e-9 * max(1.0, float(np.abs(jr).max()))
+
+
+def test_reference_report_is_committed(golden_dir):
+    rep = json.load(open(os.path.join(golden_dir, "ref_report.json")))
+    assert rep["fuzz"]["oracle_equals_libref"] and rep["octree"]["oracle_equals_libref"]
+    assert set(rep["cases"]) == set(RC.ORB_NAMES)
+
+
+# ------------------------------------------------------------------------------------------------ libref live (when present)
+def _ref():
+    import ref_lib as R
+    if not R.available():
+        pytest.skip("oracle/_ref/libref.so absent and no reference tree to build it from")
+    return R
+
+
+def test_libref_reproduces_committed_goldens():
+    R = _ref()
+    for name in RC.ORB_NAMES:
+        g, fkw, okw, img, lap = RC.orb_golden(name)
+        ret, kps, desc = R.RefOrb(*RC.orb_args(okw, fkw)).extract(img, lap, True)
+        rows = g["desc_rows_defined"]
+        assert ret == int(g["ret"][0]) and kps.tobytes() == g["kps"].tobytes() and np.array_equal(desc[rows], g["desc"][rows]), name
+    for i, c, ret, n, ksha, dsha in list(RC.fuzz_cases())[::10]:
+        r, k, d = R.RefOrb(*RC.fuzz_args(c)).extract(RC.fuzz_frame(c), (c["lap0"], c["lap1"]), bool(c["want"]))
+        assert r == ret and RC.sha(k) == ksha and (not c["want"] or RC.sha(d) == dsha), (i, c)
+
+
+def test_libref_vs_oracle_fresh_cases():
+    """cases that are NOT in the fixtures: new seeds every frame shape of BASELINE.json's configs"""
+    R = _ref()
+    for seed, (w, h, args) in enumerate([(752, 480, (1000, 1.2, 8, 20, 7, 19)), (346, 260, (1000, 1.2, 8, 20, 7, 19)),
+                                         (240, 180, (500, 1.2, 4, 10, 0, 19)), (640, 480, (1500, 1.2, 8, 20, 7, 19)),
+                                         (1241, 376, (2000, 1.2, 8, 20, 7, 19)), (752, 480, (1000, 1.2, 8, 20, 7, -1))]):
+        for k in range(3):
+            img = synth.make_frame(1000 + 17 * seed + k, w, h)
+            a = args + (w, h)
+            rr, rk, rd = R.RefOrb(*a).extract(img, (0, 1000) if k else (200, 400), True)
+            orr, ok, od = O.OrbOracle(*a).extract(img, (0, 1000) if k else (200, 400), True)
+            assert rr == orr and rk.tobytes() == ok.tobytes() and np.array_equal(rd, od), (w, h, k)
+
+
+def test_libref_events_vs_oracle_fresh_cases():
+    R = _ref()
+    K = np.array([226.38, 226.15, 173.65, 133.73], np.float32)
+    T = np.eye(4, dtype=np.float32)
+    c, s = np.cos(0.07), np.sin(0.07)
+    T[:3, :3] = np.array([[c, -s, 0], [s, c, 0], [0, 0, 1]], np.float32); T[:3, 3] = [0.01, 0.0, -0.01]
+    for seed in (101, 102):
+        ev = synth.make_events(20000, seed, 346, 260)
+        for kw in (dict(mode=1), dict(mode=1, pol=True), dict(mode=2, Tcw=T, depth=1.2, K=K), dict(mode=3, se2=[0.02, -1.0, 0.5], K=K)):
+            rf, ru = R.ev_accumulate(ev, 346, 260, 1.0, normalize=True, **kw)
+            of, _, ou = O.ev_accumulate(ev, 346, 260, 1.0, normalize=True, **kw)
+            assert rf.tobytes() == of.tobytes() and np.array_equal(ru, ou), kw
