@@ -8,10 +8,14 @@ Contract (one JSON line on stdout from rank 0):
   e2e         same metric through the host-buffer C-ABI call (pinned host frames in, keypoints+descriptors out;
               H2D and D2H inside the timed region)
   roofline    dominant kernel of the step vs the measured HBM peak (MEASURED_PEAKS.json)
-  cpu_baseline  the CPU oracle (port of the reference path) on the box's host cores, bounded sample
-  extra       event-frame Mev/s (configs[1]) and Hamming Gmatch/s (configs[3]) with their own rooflines
-`--impl reference` times the CPU restatement of the reference path (the reference itself needs OpenCV C++ and
-cannot be built here) with all host threads on a bounded sample of the same workload.
+  cpu_baseline  the reference's own ORBextractor.cc compiled unmodified (oracle/_ref/libref.so, kind "reference"; the
+              oracle port when that library is absent) on the box's host cores, bounded sample; the event and Hamming
+              legs carry their own cpu_baseline (reference EventConversion.cc / threaded popcount)
+  parity_checked  outside the timed regions: every frame's keypoint count and the first frames' full keypoint +
+              descriptor bytes against the oracle; all 2000 match records of configs[3] against a threaded CPU best-2
+  extra       event-frame Mev/s (configs[1], aggregate over ranks) and Hamming Gmatch/s (configs[3]) with their rooflines,
+              strong scaling of configs[2] (4096 frames split over the ranks), PCIe link + solo/concurrent H2D per GPU
+`--impl reference` times the reference's CPU implementation (libref.so, all host threads) on the same config.
 """
 from __future__ import annotations
 
@@ -126,30 +130,54 @@ def make_batch(n, seed0):
 
 
 # ------------------------------------------------------------------------------------------------ reference arm
+WORKLOAD = "configs[2]: ORB 752x480 nFeatures=1000 8 levels 1.2 FAST 20/7, %d frames per GPU per step"
+
+
+def _config(nfr):
+    """the workload description, identical in both arms"""
+    return {"workload": WORKLOAD % nfr, "frames_per_gpu": nfr,
+            "l2_policy": "inputs larger than L2 (%.0f MB of frames per step per GPU)" % (nfr * W * H / 1e6),
+            "partition": "by frame, no collective"}
+
+
+def _cpu_reference_extractor():
+    """-> (batch function, kind, description): the reference's own code when oracle/_ref/libref.so is present"""
+    try:
+        import ref_lib as R
+        if R.available():
+            R.lib()
+            return R.orb_extract_batch_mt, "reference", ("oracle/_ref/libref.so = /root/reference/src/ORBextractor.cc compiled unmodified "
+                                                        "(OpenCV primitives: the cv2-pinned oracle primitives), glibc malloc")
+    except Exception:
+        pass
+    import oracle_lib as O
+    return O.orb_extract_batch_mt, "port", "CPU oracle port of src/ORBextractor.cc (libref.so absent)"
+
+
 def run_reference(args):
-    """CPU restatement of the reference path (oracle port), all host threads, bounded sample per step."""
+    """The reference's CPU implementation of the path, all host threads, the SAME config as our arm (4096 frames per step)."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return 0
-    import oracle_lib as O
+    fn, kind, what = _cpu_reference_extractor()
     cores = os.cpu_count() or 1
-    n = max(cores, min(64 * cores, 1024))
+    n = args.frames
     frames = make_batch(n, 0)
-    for _ in range(max(args.warmup, 1)):
-        O.orb_extract_batch_mt(frames[:cores], cores)
+    for _ in range(args.warmup):
+        fn(frames, cores)
     t0 = time.perf_counter()
     for _ in range(args.steps):
-        O.orb_extract_batch_mt(frames, cores)
+        fn(frames, cores)
     dt = time.perf_counter() - t0
     fps = n * args.steps / dt
     line = {
         "impl": "reference", "metric": "orb_frames_per_sec", "value": fps, "unit": "frames/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
-        "config": {"workload": "configs[2]: ORB 752x480 nFeatures=1000 8 levels 1.2 FAST 20/7, batch of frames",
-                   "frames_per_step": n, "note": "CPU oracle port of src/ORBextractor.cc (reference needs OpenCV 3.4.1 C++; not buildable here)"},
-        "cpu_baseline": {"value": fps, "unit": "frames/s", "cores": cores, "kind": "port",
-                         "sample": "%d frames per step, %d steps, std::thread pool, one extractor per thread" % (n, args.steps)},
+        "config": _config(n),
+        "cpu_baseline": {"value": fps, "unit": "frames/s", "cores": cores, "kind": kind,
+                         "sample": "%d frames per step (the whole batch), %d steps, std::thread pool over frames, one extractor per thread; %s"
+                                   % (n, args.steps, what)},
         "e2e": {"value": fps, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -157,12 +185,98 @@ def run_reference(args):
     return 0
 
 
+def cv2_assisted_baseline(frames, cores):
+    """BASELINE.md section 3, line 2: how fast could the reference's CPU path be with OpenCV's own SIMD kernels under it?
+    Dense stages (resize, copyMakeBorder, FAST, GaussianBlur) through the cv2 wheel on whole levels, one worker PROCESS per core
+    (no GIL), plus the non-dense remainder (grid bookkeeping, octree, orientation, BRIEF, assembly) taken from the oracle port:
+    its whole-frame time minus its own dense primitives on the same levels.  A composed estimate, reported as such."""
+    import multiprocessing as mp
+    import oracle_lib as O
+    n = min(len(frames), 16 * cores)
+    with mp.get_context("fork").Pool(cores) as pool:
+        pool.map(_cv2_dense_frame, [frames[i] for i in range(min(cores, n))])          # warm
+        t0 = time.perf_counter()
+        pool.map(_cv2_dense_frame, [frames[i] for i in range(n)], chunksize=max(1, n // (4 * cores)))
+        dense_wall = time.perf_counter() - t0
+    cv_dense_ms = dense_wall * cores / n * 1e3                   # per frame per core
+    # the oracle's split on one core
+    orc = O.OrbOracle(**{k: ORB_KW[k] for k in ("nfeatures", "scale_factor", "nlevels", "ini_th", "min_th", "edge_th")}, im_w=W, im_h=H)
+    k = 4
+    t0 = time.perf_counter()
+    for i in range(k):
+        orc.extract(frames[i])
+    whole_ms = (time.perf_counter() - t0) / k * 1e3
+    t0 = time.perf_counter()
+    for i in range(k):
+        prev = frames[i]
+        for l in range(ORB_KW["nlevels"]):
+            if l:
+                prev = O.resize_linear(prev, LEVELS[l][0], LEVELS[l][1])
+            O.border_reflect101(prev, 19); O.fast(prev, ORB_KW["ini_th"], True); O.gauss5(prev)
+    port_dense_ms = (time.perf_counter() - t0) / k * 1e3
+    rest_ms = max(whole_ms - port_dense_ms, 0.0)
+    per_frame_ms = cv_dense_ms + rest_ms
+    return {"value": cores * 1e3 / per_frame_ms, "unit": "frames/s", "cores": cores, "kind": "cv2-assisted (composed estimate)",
+            "ms_per_frame_per_core": {"cv2_dense": cv_dense_ms, "oracle_rest": rest_ms, "oracle_whole": whole_ms, "oracle_dense": port_dense_ms},
+            "sample": "%d frames through cv2 resize/copyMakeBorder/FAST/GaussianBlur on whole levels in %d worker processes; remainder = oracle "
+                      "whole-frame time minus its dense primitives, one core" % (n, cores)}
+
+
+def _cv2_dense_frame(img):
+    import cv2
+    cv2.setNumThreads(1)
+    fast = cv2.FastFeatureDetector_create(threshold=ORB_KW["ini_th"], nonmaxSuppression=True)
+    prev = img
+    nk = 0
+    for l in range(ORB_KW["nlevels"]):
+        if l:
+            prev = cv2.resize(prev, LEVELS[l], interpolation=cv2.INTER_LINEAR)
+        cv2.copyMakeBorder(prev, 19, 19, 19, 19, cv2.BORDER_REFLECT_101)
+        nk += len(fast.detect(prev, None))
+        cv2.GaussianBlur(prev, (5, 5), 2, 2, borderType=cv2.BORDER_REFLECT_101)
+    return nk
+
+
 # ------------------------------------------------------------------------------------------------ extras
-def bench_events(api, torch, dev, steps, warmup):
-    """configs[1]: DAVIS240 stream, fixed 2000-event windows -> Gaussian event frames (+ running normalisation)."""
+def _events_cpu_baseline(ev, per, w, h, sigma, mode, Tcw, depth, K, nwin_sample):
+    """the reference's EventConversion.cc (libref.so, unmodified) over consecutive windows, a std::thread pool over windows;
+    falls back to the oracle port window by window on one core when libref is absent"""
+    cores = os.cpu_count() or 1
+    n = nwin_sample * per
+    try:
+        import ref_lib as R
+        if R.available() and hasattr(R.lib(), "ref_ev_accumulate_batch_mt"):
+            T = np.ascontiguousarray(Tcw, np.float32).reshape(16) if Tcw is not None else None
+            Kc = np.ascontiguousarray(K, np.float32) if K is not None else np.zeros(4, np.float32)
+            evs = np.ascontiguousarray(ev[:n])
+            R.lib().ref_ev_accumulate_batch_mt(R._p(evs), min(n, cores * per), per, w, h, sigma, mode, R._p(T), depth, R._p(Kc), cores)
+            t0 = time.perf_counter()
+            reps = 0
+            while time.perf_counter() - t0 < 6.0:     # bounded sample: about 6 s of CPU work on all cores
+                R.lib().ref_ev_accumulate_batch_mt(R._p(evs), n, per, w, h, sigma, mode, R._p(T), depth, R._p(Kc), cores)
+                reps += 1
+            dt = time.perf_counter() - t0
+            return {"value": reps * n / dt / 1e6, "unit": "Mev/s", "cores": cores, "kind": "reference",
+                    "sample": "%d x %d windows x %d events through EvImConverter::%s (normalised u8, libref.so = EventConversion.cc unmodified), "
+                              "thread pool over windows, %.1f s" % (reps, nwin_sample, per, "ev2im_gauss" if mode == 1 else "ev2mci_gg_f", dt)}
+    except Exception:
+        pass
+    import oracle_lib as O
+    k = max(1, min(nwin_sample, 16))
+    t0 = time.perf_counter()
+    for i in range(k):
+        O.ev_accumulate(ev[i * per:(i + 1) * per], w, h, sigma, mode=mode, Tcw=Tcw, depth=depth, K=K, normalize=True)
+    dt = time.perf_counter() - t0
+    return {"value": k * per / dt / 1e6, "unit": "Mev/s", "cores": 1, "kind": "port", "sample": "%d windows x %d events, oracle port, one core" % (k, per)}
+
+
+def bench_events(api, torch, dev, steps, warmup, world=1, rank=0, dist=None, cpu=True):
+    """configs[1]: DAVIS240 stream, fixed 2000-event windows -> Gaussian event frames (+ running normalisation).
+    Windows are partitioned over the ranks (every rank owns 512 windows of its own stream, no collective); the
+    reported value is the aggregate over ranks, timed as the max over ranks."""
     from eorb_slam_b200 import synth
     nwin, per, w, h = 512, 2000, 240, 180
-    ev = synth.make_events(nwin * per, seed=1, w=w, h=h)
+    ev = synth.make_events(nwin * per, seed=1 + 1000 * rank, w=w, h=h)
     cv = api.EvImConverter(dev, nwin, nwin * per, w, h)
     st = torch.cuda.current_stream().cuda_stream
     cv.set_stream(st)
@@ -181,18 +295,25 @@ def bench_events(api, torch, dev, steps, warmup):
         cv.accumulate_batch_device(d_ev.data_ptr(), offs, p, d_img.data_ptr(), d_u8.data_ptr())
     t.stop(st)
     ms = t.elapsed_ms() / steps
+    ms_rank = ms
+    if world > 1:
+        tm = torch.tensor([ms], device="cuda"); dist.all_reduce(tm, op=dist.ReduceOp.MAX); ms = float(tm.item())
     launches = cv.launch_count() - l0
     nev = nwin * per
     algo_bytes = nev * 24 + nwin * (4 * w * h + w * h)
     peak, _ = _peaks()
-    out = {"metric": "event_frames_mev_per_s", "value": nev / ms / 1e3, "unit": "Mev/s", "ms_per_step": ms,
-           "workload": "configs[1]: %d windows x %d events, 240x180, sigma 1 (49 taps/event), normalised to u8" % (nwin, per),
+    out = {"metric": "event_frames_mev_per_s", "value": world * nev / ms / 1e3, "unit": "Mev/s", "ms_per_step": ms, "n_gpus": world,
+           "scaling": "weak", "per_gpu_mev_per_s": nev / ms_rank / 1e3,
+           "workload": "configs[1]: %d windows x %d events per GPU, 240x180, sigma 1 (49 taps/event), normalised to u8; windows partitioned "
+                       "over the ranks, no collective" % (nwin, per),
            "atomic_adds_per_s": nev * 49 / (ms * 1e-3), "gpu_launches": launches,
            "roofline": {"bound": "hbm", "achieved": algo_bytes / (ms * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
                         "frac": algo_bytes / (ms * 1e-3) / 1e9 / peak, "traffic": None,
                         "note": "7x7 splat accumulates in shared memory (int32 fixed point, native ATOMS.ADD), frame written once; "
                                 "bounded by instruction issue + smem atomics, not HBM; see atomic_adds_per_s"}}
     cv.set_stream(None)
+    if cpu and rank == 0 and world == 1:
+        out["cpu_baseline"] = _events_cpu_baseline(ev, per, w, h, 1.0, 1, None, 1.0, None, nwin)
     # configs[1] as ONE device pipeline: the windows above -> u8 event frames -> single-level event extractor (N = 400, FAST 0/0,
     # keypoints only, EvETHZ.yaml:185-199) on the frames where they lie in HBM
     try:
@@ -245,16 +366,27 @@ def bench_events(api, torch, dev, steps, warmup):
             cv2_.accumulate_batch_device(d_ev2.data_ptr(), offs2, p2, d_img2.data_ptr(), d_u82.data_ptr())
         t.stop(st)
         ms2 = t.elapsed_ms() / 10
-        out["mc_346x260"] = {"value": nw2 * per2 / ms2 / 1e3, "unit": "Mev/s", "ms_per_step": ms2,
-                             "workload": "configs[4]: %d windows x %d events, 346x260, SE3 motion compensation, sigma 1, MINMAX u8" % (nw2, per2)}
+        out["mc_346x260"] = {"value": nw2 * per2 / ms2 / 1e3, "unit": "Mev/s", "ms_per_step": ms2, "n_gpus": world,
+                             "workload": "configs[4]: %d windows x %d events per GPU, 346x260, SE3 motion compensation, sigma 1, MINMAX u8" % (nw2, per2)}
+        if cpu and rank == 0 and world == 1:
+            out["mc_346x260"]["cpu_baseline"] = _events_cpu_baseline(ev2, per2, w2, h2, 1.0, 2, T, 1.0, (226.38, 226.15, 173.65, 133.73), nw2)
         cv2_.set_stream(None)
     except Exception as e:   # the second workload never invalidates the first
         out["mc_346x260"] = {"error": repr(e)}
+    if world > 1:   # aggregate over ranks, max-over-ranks time (outside the try: every rank reaches this collective)
+        mine = out["mc_346x260"].get("ms_per_step", 0.0)
+        tm = torch.tensor([mine], device="cuda"); dist.all_reduce(tm, op=dist.ReduceOp.MAX)
+        if "ms_per_step" in out["mc_346x260"]:
+            out["mc_346x260"]["ms_per_step"] = float(tm.item())
+            out["mc_346x260"]["value"] = world * out["mc_346x260"]["value"] * mine / float(tm.item())
     return out
 
 
-def bench_hamming(api, torch, dev, steps, warmup, world, rank, dist):
-    """configs[3]: 2000 queries vs a 16M-row database, row-sharded over the ranks, all-gather of per-shard best-2."""
+def bench_hamming(api, torch, dev, steps, warmup, world, rank, dist, cpu=True):
+    """configs[3]: 2000 queries vs a 16M-row database, row-sharded over the ranks, all-gather of per-shard best-2.
+    Outside the timed region rank 0 rebuilds every shard (same device generator seeds), runs the threaded CPU best-2 over the
+    whole database and compares all 2000 (distance, index, second distance, accepted) records with the merged GPU result:
+    that run is both the parity check of every cross-rank merge and the Hamming leg's cpu_baseline."""
     nq, ndb_total = 2000, 16 * 1024 * 1024
     per = ndb_total // world
     g = torch.Generator(device="cuda"); g.manual_seed(1234 + rank)
@@ -278,7 +410,7 @@ def bench_hamming(api, torch, dev, steps, warmup, world, rank, dist):
 
     def step():
         # shard scan + ncclAllGather (nq x 16 B per rank) + merge, one C-ABI call on the matcher's stream
-        m.search_sharded(d_q.data_ptr(), nq, comm, world, out.data_ptr())
+        m.search_sharded(d_q.data_ptr(), nq, comm, world, out.data_ptr(), th=50)
 
     for _ in range(warmup):
         step()
@@ -300,7 +432,27 @@ def bench_hamming(api, torch, dev, steps, warmup, world, rank, dist):
     popc_peak = api.probe_popc_rate(dev)
     m.set_stream(None)
     api.nccl_comm_destroy(comm)
-    return {"metric": "hamming_gmatch_per_s", "value": pairs / (ms * 1e-3) / 1e9, "unit": "Gmatch/s", "ms_per_step": ms,
+    parity, cpu_line = None, None
+    if cpu and rank == 0:
+        import oracle_lib as O
+        cores = os.cpu_count() or 1
+        db_host = np.empty((ndb_total, 32), np.uint8)
+        for r in range(world):
+            gr = torch.Generator(device="cuda"); gr.manual_seed(1234 + r)
+            shard = d_db if r == rank else torch.randint(0, 256, (per, 32), dtype=torch.uint8, device="cuda", generator=gr)
+            db_host[r * per:(r + 1) * per] = shard.cpu().numpy()
+            del shard
+        q_host = d_q.cpu().numpy()
+        t0 = time.perf_counter()
+        exp = O.hamming_best2(q_host, db_host, 50, 0.7, 0, cores)
+        dt = time.perf_counter() - t0
+        same = {k2: bool(np.array_equal(res[k1], exp[k2])) for k1, k2 in (("d", "best_dist"), ("i", "best_idx"), ("s", "second_dist"), ("a", "accepted"))}
+        parity = {"records": int(nq), "database_rows": int(ndb_total), "shards": world, "fields_equal": same, "all_equal": all(same.values()),
+                  "accepted": int(exp["accepted"].sum()), "checker": "oracle threaded popcount scan (lowest index wins ties), %d threads" % cores}
+        cpu_line = {"value": pairs / dt / 1e9, "unit": "Gmatch/s", "cores": cores, "kind": "port",
+                    "sample": "all %d queries x %d rows, __builtin_popcountll, cache-blocked scan, std::thread pool over query blocks, %.1f s" % (nq, ndb_total, dt)}
+        del db_host
+    return {"parity_checked": parity, "cpu_baseline": cpu_line, "metric": "hamming_gmatch_per_s", "value": pairs / (ms * 1e-3) / 1e9, "unit": "Gmatch/s", "ms_per_step": ms,
             "workload": "configs[3]: 2000 queries x 16Mi rows, %d shard(s), best-2 + ratio 0.7; eorb_matcher_search_sharded (scan + ncclAllGather + merge)" % world,
             "planted_matches_found": ok, "gpu_launches": m.launch_count() - l0,
             "roofline": {"bound": "int-pipe (POPC)", "achieved": 8 * pairs / world / (ms * 1e-3) / 1e12, "peak": popc_peak / 1e12,
@@ -645,7 +797,7 @@ def run_ours(args):
         step_e2e()
     if world > 1:
         dist.barrier()
-    e2e_steps = max(1, min(args.steps, 3))
+    e2e_steps = max(args.steps, 10)
     t0 = time.perf_counter()
     for _ in range(e2e_steps):
         step_e2e()
@@ -702,7 +854,7 @@ def run_ours(args):
     extra = {}
     if not args.no_extras:
         try:
-            extra["events"] = bench_events(api, torch, dev, max(args.steps, 20), max(args.warmup, 3))   # 0.07 ms steps: 20 for a stable mean
+            extra["events"] = bench_events(api, torch, dev, max(args.steps, 20), max(args.warmup, 3), world, rank, dist, not args.no_cpu)   # 0.07 ms steps: 20 for a stable mean
         except Exception as e:   # extras never invalidate the headline line
             extra["events"] = {"error": repr(e)}
         try:
@@ -741,39 +893,129 @@ def run_ours(args):
         except Exception as e:
             extra["bow"] = {"error": repr(e)}
         try:
-            extra["hamming"] = bench_hamming(api, torch, dev, max(min(args.steps, 3), 1), 3, world, rank, dist)
+            extra["hamming"] = bench_hamming(api, torch, dev, max(min(args.steps, 3), 1), 3, world, rank, dist, not args.no_cpu)
         except Exception as e:
             extra["hamming"] = {"error": repr(e)}
 
-    cpu = None
-    if rank == 0 and world == 1 and not args.no_cpu:
+    cpu, cpu_cv2, parity = None, None, None
+    if rank == 0 and not args.no_cpu:
+        # ---- parity of the WHOLE timed batch, outside the timed region: every frame's keypoint count against the oracle (the
+        #      pinned restatement: == the reference's own code, tests/test_ref_pin.py) and the first frames' full keypoint and
+        #      descriptor bytes.  The oracle pass over the batch is CPU work on all host cores.
         import oracle_lib as O
         cores = os.cpu_count() or 1
-        nsamp = min(nfr, max(cores, 256 * cores))   # ~5-10 s of CPU work on the box's cores
-        O.orb_extract_batch_mt(frames[:cores], cores)
         t0 = time.perf_counter()
-        O.orb_extract_batch_mt(frames[:nsamp], cores)
-        dt = time.perf_counter() - t0
-        cpu = {"value": nsamp / dt, "unit": "frames/s", "cores": cores, "kind": "port",
-               "sample": "first %d frames of the same batch, std::thread pool over frames, one extractor per thread, %.1f s" % (nsamp, dt)}
+        _, ocounts = O.orb_extract_batch_mt(frames, cores)
+        dt_orc = time.perf_counter() - t0
+        gcounts = d_n.cpu().numpy()
+        nfull = min(nfr, 64)
+        gk = d_kps[:nfull * cap * 28].cpu().numpy().reshape(nfull, cap * 28)
+        gd = d_desc[:nfull * cap * 32].cpu().numpy().reshape(nfull, cap, 32)
+        orc = O.OrbOracle(ORB_KW["nfeatures"], ORB_KW["scale_factor"], ORB_KW["nlevels"], ORB_KW["ini_th"], ORB_KW["min_th"], ORB_KW["edge_th"], W, H)
+        full_ok = 0
+        for f in range(nfull):
+            _, ok_, od_ = orc.extract(frames[f])
+            n_ = len(ok_)
+            full_ok += int(n_ == int(gcounts[f]) and gk[f][:n_ * 28].tobytes() == ok_.tobytes() and np.array_equal(gd[f][:n_], od_))
+        parity = {"frames_count_checked": int(nfr), "frame_counts_equal": int((gcounts == ocounts).sum()),
+                  "frames_full_checked": int(nfull), "frames_full_equal": int(full_ok),
+                  "all_equal": bool((gcounts == ocounts).all() and full_ok == nfull),
+                  "checker": "oracle (pinned byte for byte to the reference's ORBextractor.cc, tests/golden/ref_*.npz), %d threads, %.1f s" % (cores, dt_orc)}
+        if world == 1:
+            fn, kind, what = _cpu_reference_extractor()
+            fn(frames[:cores], cores)
+            t0 = time.perf_counter()
+            fn(frames, cores)
+            dt = time.perf_counter() - t0
+            cpu = {"value": nfr / dt, "unit": "frames/s", "cores": cores, "kind": kind,
+                   "sample": "all %d frames of the same batch, std::thread pool over frames, one extractor per thread, %.1f s; %s" % (nfr, dt, what),
+                   "oracle_port_frames_per_s": nfr / dt_orc}
+            try:    # BASELINE.md section 3 line 2, in its own process (a fork pool beside an initialised CUDA context is not safe)
+                import subprocess
+                r = subprocess.run([sys.executable, os.path.abspath(__file__), "--cv2-baseline"], capture_output=True, text=True, timeout=600)
+                cpu_cv2 = json.loads(r.stdout.strip().splitlines()[-1])
+            except Exception as e:
+                cpu_cv2 = {"error": repr(e)}
+
+    # ---- strong scaling of configs[2] as written: 4096 frames in total, split by frame over the ranks
+    strong = None
+    if world > 1:
+        share = FRAMES_PER_GPU // world
+
+        def step_share():
+            for f0 in range(0, share, chunk):
+                nb = min(chunk, share - f0)
+                ex.extract_batch_raw(d_frames.data_ptr() + f0 * W * H, nb, W, H, W, W * H, (0, 1000), True,
+                                     d_kps.data_ptr() + f0 * cap * 28, d_desc.data_ptr() + f0 * cap * 32, cap,
+                                     d_n.data_ptr() + f0 * 4, d_mono.data_ptr() + f0 * 4, device=True)
+        ex.set_stream(st)
+        for _ in range(3):
+            step_share()
+        torch.cuda.synchronize(); dist.barrier()
+        t.start(st)
+        for _ in range(args.steps):
+            step_share()
+        t.stop(st)
+        ms_s = t.elapsed_ms() / args.steps
+        tm = torch.tensor([ms_s], device="cuda"); dist.all_reduce(tm, op=dist.ReduceOp.MAX); ms_s = float(tm.item())
+        strong = {"metric": "orb_frames_per_sec", "scaling": "strong", "value": share * world / (ms_s * 1e-3), "unit": "frames/s",
+                  "ms_per_step": ms_s, "frames_total": share * world, "frames_per_gpu": share,
+                  "workload": "configs[2] as written: %d frames in total, partitioned by frame over %d GPUs, no collective" % (share * world, world)}
+        ex.set_stream(None)
+
+    # ---- host link: PCIe generation / width per GPU, and the H2D rate of every GPU alone and with all ranks copying at once
+    link = None
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        hh = pynvml.nvmlDeviceGetHandleByIndex(local)
+        mine = [float(pynvml.nvmlDeviceGetCurrPcieLinkGeneration(hh)), float(pynvml.nvmlDeviceGetCurrPcieLinkWidth(hh))]
+    except Exception:
+        mine = [0.0, 0.0]
+    if world > 1:
+        def h2d_rate():
+            ev0.record()
+            d_frames.copy_(h_frames, non_blocking=True)
+            ev1.record(); torch.cuda.synchronize()
+            return nfr * W * H / (ev0.elapsed_time(ev1) * 1e-3) / 1e9
+        solo = 0.0
+        for r in range(world):
+            dist.barrier()
+            if r == rank:
+                solo = h2d_rate()
+        dist.barrier()
+        conc = h2d_rate()
+        tl = torch.tensor(mine + [solo, conc], device="cuda")
+        allv = [torch.zeros_like(tl) for _ in range(world)]
+        dist.all_gather(allv, tl)
+        link = [{"gpu": i, "pcie_gen": int(v[0].item()), "pcie_width": int(v[1].item()), "h2d_gbs_alone": float(v[2].item()),
+                 "h2d_gbs_all_ranks_at_once": float(v[3].item())} for i, v in enumerate(allv)]
+        h2d_gbs = conc          # the ceiling of the end-to-end number is the CONCURRENT rate
+        tm = torch.tensor([conc], device="cuda"); dist.all_reduce(tm, op=dist.ReduceOp.SUM); h2d_sum = float(tm.item())
+    else:
+        link = [{"gpu": 0, "pcie_gen": int(mine[0]), "pcie_width": int(mine[1]), "h2d_gbs_alone": h2d_gbs}]
+        h2d_sum = h2d_gbs
 
     if rank == 0:
         line = {
             "metric": "orb_frames_per_sec", "value": value, "unit": "frames/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "u8", "data": "synthetic",
-            "config": {"workload": "configs[2]: ORB 752x480 nFeatures=1000 8 levels 1.2 FAST 20/7, %d frames per GPU per step" % nfr,
-                       "frames_per_gpu": nfr, "chunk_frames_per_launch_set": chunk, "ms_per_step_serial_stage_timed": ms_serial,
-                       "l2_policy": "inputs larger than L2 (%.0f MB of frames per step per GPU)" % (nfr * W * H / 1e6),
-                       "partition": "by frame, no collective", "host_cpu_affinity_first4": numa},
+            "config": _config(nfr),
+            "run": {"chunk_frames_per_launch_set": chunk, "ms_per_step_serial_stage_timed": ms_serial, "host_cpu_affinity_first4": numa,
+                    "e2e_steps_timed": e2e_steps},
             "clocks": clk,
             "e2e": {"value": e2e_value, "unit": "frames/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "ms_per_step": e2e_ms, "call": "eorb_orb_extract_batch (pinned host buffers)",
-                    "pcie_h2d_gbs_measured": h2d_gbs, "pcie_bound_frames_per_s": world * h2d_gbs * 1e9 / (W * H)},
+                    "pcie_h2d_gbs_measured": h2d_gbs, "pcie_bound_frames_per_s": h2d_sum * 1e9 / (W * H),
+                    "frac_of_pcie_bound": e2e_value / (h2d_sum * 1e9 / (W * H)), "host_link": link},
             "gpu_launches": int(launches),
             "roofline": roof,
             "stages": per_stage,
             "cpu_baseline": cpu,
+            "cpu_baseline_cv2_assisted": cpu_cv2,
+            "parity_checked": {"orb": parity, "hamming": (extra.get("hamming") or {}).get("parity_checked")},
+            "strong_scaling": strong,
             "extra": extra,
         }
         _emit(line)
@@ -810,7 +1052,12 @@ def main():
     ap.add_argument("--chunk", type=int, default=CHUNK, help="frames per launch set")
     ap.add_argument("--no-extras", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--cv2-baseline", action="store_true", help=argparse.SUPPRESS)
     args = ap.parse_args()
+    if args.cv2_baseline:
+        cores = os.cpu_count() or 1
+        _emit(cv2_assisted_baseline(make_batch(min(16 * cores, 1024), 0), cores))
+        return 0
     if args.impl == "reference":
         return run_reference(args)
     return run_ours(args)

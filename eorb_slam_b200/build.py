@@ -26,16 +26,43 @@ def is_stale() -> bool:
     return any(os.path.getmtime(d) > t for d in deps)
 
 
+def _obj_stale(src: str, obj: str) -> bool:
+    if not os.path.exists(obj):
+        return True
+    t = os.path.getmtime(obj)
+    deps = [src] + [os.path.join(CSRC, f) for f in HEADERS] + [os.path.abspath(__file__)]
+    return any(os.path.getmtime(d) > t for d in deps)
+
+
 def build_lib(force: bool = False, verbose: bool = False) -> str:
+    """one object per translation unit (compiled in parallel, rebuilt only when it or a header changed), then one link"""
     if not force and not is_stale():
         return LIB
+    from concurrent.futures import ThreadPoolExecutor
     nvcc = os.environ.get("NVCC", "nvcc")
-    cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", LIB] + [os.path.join(CSRC, s) for s in SOURCES]
-    r = subprocess.run(cmd, capture_output=True, text=True)
-    if verbose or r.returncode != 0:
-        sys.stderr.write(r.stdout + r.stderr)
-    if r.returncode != 0:
+    objdir = os.path.join(HERE, "build")
+    os.makedirs(objdir, exist_ok=True)
+    cflags = [f for f in NVCC_FLAGS if f not in ("-shared", "-ldl")]
+    cflags = [f for i, f in enumerate(cflags) if not (f == "static" or f == "-cudart")]
+
+    def compile_one(s):
+        src, obj = os.path.join(CSRC, s), os.path.join(objdir, s + ".o")
+        if not force and not _obj_stale(src, obj):
+            return obj, 0, ""
+        r = subprocess.run([nvcc] + cflags + (["-Xptxas", "-v"] if verbose else []) + ["-c", "-o", obj, src], capture_output=True, text=True)
+        return obj, r.returncode, r.stdout + r.stderr
+
+    with ThreadPoolExecutor(max_workers=min(len(SOURCES), os.cpu_count() or 4)) as ex:
+        results = list(ex.map(compile_one, SOURCES))
+    for obj, rc, out in results:
+        if verbose or rc != 0:
+            sys.stderr.write(out)
+    if any(rc != 0 for _, rc, _ in results):
         raise RuntimeError("nvcc failed building libeorb_b200.so")
+    r = subprocess.run([nvcc] + NVCC_FLAGS + ["-o", LIB] + [o for o, _, _ in results], capture_output=True, text=True)
+    if r.returncode != 0:
+        sys.stderr.write(r.stdout + r.stderr)
+        raise RuntimeError("nvcc failed linking libeorb_b200.so")
     return LIB
 
 

@@ -9,6 +9,7 @@
 // Tie rule: lowest database index wins (sequential scan, strict '<'), pinned against cv2.BFMatcher in tests.
 #include "oracle.h"
 
+#include <algorithm>
 #include <atomic>
 #include <cmath>
 #include <thread>
@@ -39,23 +40,40 @@ static inline int hamming256(const uint64_t* a, const uint64_t* b) {
 void orc_hamming_best2(const uint8_t* q, int nq, const uint8_t* db, int64_t ndb, int th, float ratio, int ratio_mode,
                        orc_match* out, int nthreads) {
     if (nthreads < 1) nthreads = 1;
+    // Work item = a block of QB queries; the database is walked in tiles of TILE rows that stay in cache while the block's
+    // queries scan them.  Every query still sees the rows in ascending order, so the result is the sequential scan's.
+    const int QB = 16;
+    const int64_t TILE = 2048;
+    const int nblocks = (nq + QB - 1) / QB;
     std::atomic<int> next(0);
     auto worker = [&]() {
         for (;;) {
-            int i = next.fetch_add(1);
-            if (i >= nq) break;
-            const uint64_t* qa = reinterpret_cast<const uint64_t*>(q + (size_t)i * 32);
-            int best = 256, second = 256, idx = -1;   // 256 == "no candidate" (SearchByBoW :318-320)
-            for (int64_t j = 0; j < ndb; j++) {
-                int d = hamming256(qa, reinterpret_cast<const uint64_t*>(db + (size_t)j * 32));
-                if (d < best) { second = best; best = d; idx = (int)j; }
-                else if (d < second) second = d;
+            const int b = next.fetch_add(1);
+            if (b >= nblocks) break;
+            const int q0 = b * QB, q1 = std::min(nq, q0 + QB);
+            int best[QB], second[QB], idx[QB];
+            for (int k = 0; k < QB; k++) { best[k] = 256; second[k] = 256; idx[k] = -1; }   // 256 == "no candidate" (SearchByBoW :318-320)
+            for (int64_t t0 = 0; t0 < ndb; t0 += TILE) {
+                const int64_t t1 = std::min(ndb, t0 + TILE);
+                for (int i = q0; i < q1; i++) {
+                    const uint64_t* qa = reinterpret_cast<const uint64_t*>(q + (size_t)i * 32);
+                    int bs = best[i - q0], sc = second[i - q0], ix = idx[i - q0];
+                    for (int64_t j = t0; j < t1; j++) {
+                        int d = hamming256(qa, reinterpret_cast<const uint64_t*>(db + (size_t)j * 32));
+                        if (d < bs) { sc = bs; bs = d; ix = (int)j; }
+                        else if (d < sc) sc = d;
+                    }
+                    best[i - q0] = bs; second[i - q0] = sc; idx[i - q0] = ix;
+                }
             }
-            orc_match m;
-            m.best_dist = best; m.best_idx = idx; m.second_dist = second;
-            bool okr = ratio_mode ? ((float)best < (float)second * ratio) : ((float)best < ratio * (float)second);
-            m.accepted = (idx >= 0 && best <= th && okr) ? 1 : 0;
-            out[i] = m;
+            for (int i = q0; i < q1; i++) {
+                orc_match m;
+                const int bs = best[i - q0], sc = second[i - q0], ix = idx[i - q0];
+                m.best_dist = bs; m.best_idx = ix; m.second_dist = sc;
+                bool okr = ratio_mode ? ((float)bs < (float)sc * ratio) : ((float)bs < ratio * (float)sc);
+                m.accepted = (ix >= 0 && bs <= th && okr) ? 1 : 0;
+                out[i] = m;
+            }
         }
     };
     std::vector<std::thread> t;
