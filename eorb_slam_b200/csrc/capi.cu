@@ -216,7 +216,7 @@ struct eorb_orb {
     int planW = 0, planH = 0;
     OrbPlan hp{};
     std::vector<CellPlan> cells;
-    OrbPlan* d_plan = nullptr; CellPlan* d_cells = nullptr; short4* d_xtab = nullptr; int4* d_ytab = nullptr; int2* d_icTab = nullptr;
+    OrbPlan* d_plan = nullptr; CellPlan* d_cells = nullptr; short4* d_xtab = nullptr; int4* d_ytab = nullptr; int4* d_ytabT = nullptr; int2* d_icTab = nullptr;
     float* d_invScale = nullptr;
     // slabs (maxBatch frames): `main` serves the device entry points and single calls; `pipe` holds the extra
     // slots (own stream + slabs + pinned staging) that eorb_orb_extract_batch cycles through so that the H2D copy
@@ -230,6 +230,7 @@ struct eorb_orb {
         uint32_t* d_kpList = nullptr;
         float* d_levelAngle = nullptr;
         CUtensorMap* d_tmaps = nullptr;   // [nlevels] maps of this slab's pyramid levels >= 1
+        CUtensorMap pyrMaps[EORB_MAX_LEVELS];   // host: source map of the TMA-staged resize INTO level l (l >= 2; level 1's source is the caller's frame)
         eorb_keypoint* d_outKps = nullptr; uint8_t* d_outDesc = nullptr; int* d_outN = nullptr; int* d_outMono = nullptr;
         eorb_keypoint* h_kps = nullptr; uint8_t* h_desc = nullptr; int* h_n = nullptr; int* h_mono = nullptr;   // pinned
         cudaStream_t stream = nullptr; cudaEvent_t done = nullptr;   // pipeline slots only
@@ -252,6 +253,8 @@ struct eorb_orb {
     int graphKey[4] = {-1, 0, 0, 0};
     long long graphLaunches = 0;   // kernel launches inside the captured graph
     bool useGraph = true;          // EORB_ORB_GRAPH=0 disables
+    bool usePyrTma = true;         // EORB_PYR_TMA=0: every pyramid level through pyr_resize_kernel (direct global loads), for A/B
+    int pyrTileRows = 64;          // EORB_PYR_TH: destination rows per TMA-staged tile (tuning)
 };
 
 static cudaEvent_t* orbStageEvents(eorb_orb* h) {
@@ -308,6 +311,13 @@ static int orbAllocBufs(eorb_orb* h, eorb_orb::Bufs& b, bool pipeline) {
         }
         CU(devAlloc(&b.d_tmaps, (size_t)nl));
         CU(cudaMemcpy(b.d_tmaps, maps.data(), maps.size() * sizeof(CUtensorMap), cudaMemcpyHostToDevice));
+        memset(b.pyrMaps, 0, sizeof(b.pyrMaps));
+        for (int l = 2; l < nl; l++) {
+            if (P.lv[l].pyrTW <= 0) continue;
+            int rct = tmaEncodeFrames(&b.pyrMaps[l], b.d_pyr + P.lv[l - 1].off, P.lv[l - 1].w, P.lv[l - 1].h, (int)B, (size_t)P.lv[l - 1].pitch,
+                                      (size_t)P.pyrBytesPerFrame, P.lv[l].pyrBW, P.lv[l].pyrBH);
+            if (rct != EORB_OK) return rct;
+        }
     }
     CU(devAlloc(&b.d_outKps, B * (size_t)h->cap));
     CU(devAlloc(&b.d_outDesc, B * (size_t)h->cap * 32));
@@ -331,8 +341,8 @@ static void orbDropGraph(eorb_orb* h) {
 
 static void orbFreePlan(eorb_orb* h) {
     orbDropGraph(h);
-    cudaFree(h->d_plan); cudaFree(h->d_cells); cudaFree(h->d_xtab); cudaFree(h->d_ytab); cudaFree(h->d_invScale); cudaFree(h->d_icTab);
-    h->d_plan = nullptr; h->d_cells = nullptr; h->d_xtab = nullptr; h->d_ytab = nullptr; h->d_invScale = nullptr; h->d_icTab = nullptr;
+    cudaFree(h->d_plan); cudaFree(h->d_cells); cudaFree(h->d_xtab); cudaFree(h->d_ytab); cudaFree(h->d_ytabT); cudaFree(h->d_invScale); cudaFree(h->d_icTab);
+    h->d_plan = nullptr; h->d_cells = nullptr; h->d_xtab = nullptr; h->d_ytab = nullptr; h->d_ytabT = nullptr; h->d_invScale = nullptr; h->d_icTab = nullptr;
     orbFreeBufs(h->main);
     for (auto& b : h->pipe) orbFreeBufs(b);
     h->pipe.clear();
@@ -488,6 +498,27 @@ static int orbBuildPlan(eorb_orb* h, int W, int H) {
                 t.z = (int)satShort((1.f - fy) * 2048.f) << 16; t.w = (int)satShort(fy * 2048.f) << 16;
                 ytab.push_back(t);
             }
+            // TMA-staged resize (orb_tiles.cu): even partition of the level into destination tiles of at most 128 x 64 pixels; the
+            // source box is the largest footprint over the tiles (first tap column rounded down to 16 bytes .. last 8-byte window)
+            lp.pyrTW = lp.pyrTH = lp.pyrBW = lp.pyrBH = 0;
+            if (h->usePyrTma && sw >= 16 && sh >= 2 && lp.w >= 4 && scale_x <= 2.0 && scale_y <= 4.0) {
+                const int ntx = (lp.w + 127) / 128;
+                const int TW = roundUp((lp.w + ntx - 1) / ntx, 4);
+                const int thMax = h->pyrTileRows;
+                int TH = roundUp((lp.h + (lp.h + thMax - 1) / thMax - 1) / ((lp.h + thMax - 1) / thMax), 4);
+                for (;;) {
+                    int BW = 16, BH = 2;
+                    for (int x0 = 0; x0 < lp.w; x0 += TW) {
+                        const int first = xtab[lp.xtabOff + x0].x & ~15, last = xtab[lp.xtabOff + std::min(x0 + TW, lp.w) - 1].x;
+                        BW = std::max(BW, roundUp((last - first) + 8, 16));
+                    }
+                    for (int y0 = 0; y0 < lp.h; y0 += TH)
+                        BH = std::max(BH, ytab[lp.ytabOff + std::min(y0 + TH, lp.h) - 1].y - ytab[lp.ytabOff + y0].x + 1);
+                    if (BW <= 256 && BH <= 256 && BW * BH + 32 <= 40 * 1024) { lp.pyrTW = TW; lp.pyrTH = TH; lp.pyrBW = BW; lp.pyrBH = BH; break; }
+                    if (TH <= 8 || BW > 256) break;       // cannot be tiled within the box limits: direct-load kernel
+                    TH = roundUp(TH / 2, 4);
+                }
+            }
         }
     }
     P.nCells = (int)h->cells.size();
@@ -516,6 +547,7 @@ static int orbBuildPlan(eorb_orb* h, int W, int H) {
     CU(devAlloc(&h->d_cells, h->cells.size()));
     CU(devAlloc(&h->d_xtab, xtab.size()));
     CU(devAlloc(&h->d_ytab, ytab.size()));
+    CU(devAlloc(&h->d_ytabT, ytab.size()));
     CU(devAlloc(&h->d_invScale, (size_t)nl));
     {   // IC_Angle weight table (:77-104): for alignment a = (x-15)&3, row r = v+15, aligned word k the four columns are
         // u = 4k + j - a - 15; weight u (m10) / v (m01) inside the circle |u| <= umax[|v|], 0 outside; row 31 is padding
@@ -543,6 +575,15 @@ static int orbBuildPlan(eorb_orb* h, int W, int H) {
     if (!h->cells.empty()) CU(cudaMemcpy(h->d_cells, h->cells.data(), h->cells.size() * sizeof(CellPlan), cudaMemcpyHostToDevice));
     if (!xtab.empty()) CU(cudaMemcpy(h->d_xtab, xtab.data(), xtab.size() * sizeof(short4), cudaMemcpyHostToDevice));
     if (!ytab.empty()) CU(cudaMemcpy(h->d_ytab, ytab.data(), ytab.size() * sizeof(int4), cudaMemcpyHostToDevice));
+    {   // the TMA path's y taps carry tile-row byte offsets (row index x box width of the level)
+        std::vector<int4> yt2(ytab);
+        for (int l = 1; l < nl; l++)
+            for (int dy = 0; dy < P.lv[l].h && P.lv[l].pyrTW > 0; dy++) {
+                int4& t = yt2[(size_t)P.lv[l].ytabOff + dy];
+                t.x *= P.lv[l].pyrBW; t.y *= P.lv[l].pyrBW;
+            }
+        if (!yt2.empty()) CU(cudaMemcpy(h->d_ytabT, yt2.data(), yt2.size() * sizeof(int4), cudaMemcpyHostToDevice));
+    }
     CU(cudaMemcpy(h->d_invScale, h->invScale.data(), nl * sizeof(float), cudaMemcpyHostToDevice));
     CU(orb_kernels_configure(P));
     h->planW = W; h->planH = H;
@@ -552,7 +593,7 @@ static int orbBuildPlan(eorb_orb* h, int W, int H) {
 static OrbArgs orbArgs(eorb_orb* h, eorb_orb::Bufs& b, const uint8_t* lvl0, long long pitch0, long long frameStride0, int lap0, int lap1,
                        int wantDesc, eorb_keypoint* kps, uint8_t* desc, int cap, int* nOut, int* monoOut) {
     OrbArgs a{};
-    a.plan = h->d_plan; a.cells = h->d_cells; a.xtab = h->d_xtab; a.ytab = h->d_ytab;
+    a.plan = h->d_plan; a.cells = h->d_cells; a.xtab = h->d_xtab; a.ytab = h->d_ytab; a.ytabT = h->d_ytabT;
     a.lvl0 = lvl0; a.lvl0Pitch = pitch0; a.lvl0FrameStride = frameStride0;
     a.tmaps = b.d_tmaps;
     a.pyr = b.d_pyr; a.blur = b.d_blur; a.cellCount = b.d_cellCount; a.cand = b.d_cand; a.okeys = b.d_okeys;
@@ -576,6 +617,8 @@ extern "C" int eorb_orb_create(const eorb_orb_params* params, int device, int ma
     eorb_orb* h = new eorb_orb();
     h->par = *params; h->device = device; h->maxBatch = max_batch;
     if (const char* e = getenv("EORB_ORB_GRAPH")) h->useGraph = atoi(e) != 0;
+    if (const char* e = getenv("EORB_PYR_TMA")) h->usePyrTma = atoi(e) != 0;
+    if (const char* e = getenv("EORB_PYR_TH")) h->pyrTileRows = std::min(std::max(atoi(e), 8), 200);
     h->pipeBatch = std::min(max_batch, 128);   // measured on B200: H2D/compute/D2H overlap is best with 128-frame slots
     cudaDeviceProp prop;
     CU(cudaGetDeviceProperties(&prop, device));
@@ -688,6 +731,14 @@ extern "C" int eorb_orb_max_keypoints(const eorb_orb* h) {
     return eorb_orb_max_keypoints_for_size(h, h->par.imW, h->par.imH);                 // the size announced at construction
 }
 
+// the pyramid's TMA source maps for one launch set: the slab's maps plus level 1's source = the caller's frames
+static int orbPyrMaps(eorb_orb* h, eorb_orb::Bufs& b, const uint8_t* lvl0, int w, int hgt, int nframes, long long p0, long long fs0, CUtensorMap* out) {
+    memcpy(out, b.pyrMaps, sizeof(b.pyrMaps));
+    if (h->nlevels > 1 && h->hp.lv[1].pyrTW > 0)
+        return tmaEncodeFrames(&out[1], lvl0, w, hgt, nframes, (size_t)p0, (size_t)fs0, h->hp.lv[1].pyrBW, h->hp.lv[1].pyrBH);
+    return EORB_OK;
+}
+
 static bool lvl0ZeroCopyOk(const uint8_t* p, int w, size_t rowStride, size_t frameStride) {
     // TMA (FAST cell tiles) needs a 16-byte aligned base and 16-byte strides; the vectorised kernels read whole words
     return ((uintptr_t)p % 16 == 0) && (rowStride % 16 == 0) && (frameStride % 16 == 0) && rowStride >= (size_t)roundUp(w, 4);
@@ -714,7 +765,10 @@ extern "C" int eorb_orb_extract_batch_device(eorb_orb* h, const uint8_t* d_imgs,
     CUtensorMap tm0;
     rc = tmaEncodeFrames(&tm0, lvl0, w, hgt, nframes, (size_t)p0, (size_t)fs0, h->hp.cellTileStride, h->hp.cellTileRows);
     if (rc != EORB_OK) return rc;
-    CU(launch_orb_pipeline(a, h->hp, nframes, tm0, h->stream, &h->launches, orbStageEvents(h)));
+    CUtensorMap pm[EORB_MAX_LEVELS];
+    rc = orbPyrMaps(h, h->main, lvl0, w, hgt, nframes, p0, fs0, pm);
+    if (rc != EORB_OK) return rc;
+    CU(launch_orb_pipeline(a, h->hp, nframes, tm0, h->stream, &h->launches, orbStageEvents(h), pm));
     h->lastLvl0 = lvl0; h->lastPitch0 = p0; h->lastFrameStride0 = fs0; h->lastFrames = nframes;
     return EORB_OK;
 }
@@ -790,7 +844,10 @@ extern "C" int eorb_orb_extract_batch(eorb_orb* h, const uint8_t* imgs, int nfra
             CUtensorMap tm0;
             int rct = tmaEncodeFrames(&tm0, b.d_img0, w, hgt, nb, (size_t)h->pitch0, (size_t)h->pitch0 * hgt, h->hp.cellTileStride, h->hp.cellTileRows);
             if (rct != EORB_OK) return rct;
-            CU(launch_orb_pipeline(a, h->hp, nb, tm0, st, launchCounter, stageEv));
+            CUtensorMap pm[EORB_MAX_LEVELS];
+            rct = orbPyrMaps(h, b, b.d_img0, w, hgt, nb, h->pitch0, (long long)h->pitch0 * hgt, pm);
+            if (rct != EORB_OK) return rct;
+            CU(launch_orb_pipeline(a, h->hp, nb, tm0, st, launchCounter, stageEv, pm));
             CU(cudaMemcpyAsync(b.h_n, b.d_outN, nb * sizeof(int), cudaMemcpyDeviceToHost, st));
             CU(cudaMemcpyAsync(b.h_mono, b.d_outMono, nb * sizeof(int), cudaMemcpyDeviceToHost, st));
             CU(cudaMemcpyAsync(kdst, b.d_outKps, (size_t)nb * icap * sizeof(eorb_keypoint), cudaMemcpyDeviceToHost, st));
@@ -929,7 +986,10 @@ static int orbTracked(eorb_orb* h, const uint8_t* img, int w, int hgt, size_t st
     if (rc != EORB_OK) return rc;
     CU(cudaMemcpy2DAsync(h->main.d_img0, h->pitch0, img, stride, w, hgt, cudaMemcpyHostToDevice, h->stream));
     OrbArgs a = orbArgs(h, h->main, h->main.d_img0, h->pitch0, (long long)h->pitch0 * hgt, 0, 0, 1, h->main.d_outKps, h->main.d_outDesc, h->cap, h->main.d_outN, h->main.d_outMono);
-    CU(launch_pyramid_and_blur(a, h->hp, h->stream, &h->launches));
+    CUtensorMap pm[EORB_MAX_LEVELS];
+    rc = orbPyrMaps(h, h->main, h->main.d_img0, w, hgt, 1, h->pitch0, (long long)h->pitch0 * hgt, pm);
+    if (rc != EORB_OK) return rc;
+    CU(launch_pyramid_and_blur(a, h->hp, h->stream, &h->launches, pm));
     eorb_keypoint* d_k = nullptr; uint8_t* d_ref = nullptr; uint8_t* d_desc = nullptr; int* d_dist = nullptr;
     CU(devAlloc(&d_k, (size_t)n));
     CU(cudaMemcpyAsync(d_k, kps, (size_t)n * sizeof(eorb_keypoint), cudaMemcpyHostToDevice, h->stream));

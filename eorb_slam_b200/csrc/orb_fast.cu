@@ -29,36 +29,9 @@
 #include "eorb_math.cuh"
 #include "fast_score.cuh"
 #include "orb_kernels.h"
+#include "tma_utils.cuh"
 
 namespace eorb {
-
-// ---- mbarrier / TMA ------------------------------------------------------------------------------------------
-__device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
-
-__device__ __forceinline__ void mbar_init(unsigned bar, unsigned count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
-}
-__device__ __forceinline__ void mbar_expect_tx(unsigned bar, unsigned bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(unsigned bar, unsigned parity) {
-    asm volatile(
-        "{\n"
-        ".reg .pred p;\n"
-        "WAIT_%=:\n"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
-        "@p bra DONE_%=;\n"
-        "bra WAIT_%=;\n"
-        "DONE_%=:\n"
-        "}\n" ::"r"(bar), "r"(parity)
-        : "memory");
-}
-__device__ __forceinline__ void tma_load_3d(unsigned dst, const CUtensorMap* tm, int x, int y, int z, unsigned bar) {
-    asm volatile(
-        "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];" ::"r"(dst),
-        "l"(tm), "r"(x), "r"(y), "r"(z), "r"(bar)
-        : "memory");
-}
 
 // ---- phase-1 helper: bit 7 of byte j set  <=>  pixel j may be a corner at the threshold encoded in K ---------------
 __device__ __forceinline__ unsigned fast_compass4(unsigned C, unsigned N, unsigned S, unsigned E, unsigned W, unsigned K) {
@@ -120,8 +93,7 @@ __global__ void __launch_bounds__(EORB_FAST_WARPS * 32) fast_cells_kernel(OrbArg
     // ---- stage: one TMA tile per cell
     if (lane == 0) {
         mbar_init(bar, 1);
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        mbar_fence_init();
         mbar_expect_tx(bar, (unsigned)(TS * K0.tileRows));
         const CUtensorMap* tm = c.level == 0 ? &tm0 : a.tmaps + c.level;
         tma_load_3d(smem_u32(tile), tm, c.x0 & ~15, c.y0, f, bar);

@@ -740,15 +740,22 @@ cudaError_t launch_selftest_math(const int* fastIn, int nFast, int* fastOut, con
 // ------------------------------------------------------------------------------------------------ launches
 static inline unsigned cdiv(unsigned a, unsigned b) { return (a + b - 1) / b; }
 
+static cudaError_t launch_pyramid_level(const OrbArgs& a, const OrbPlan& hp, int l, int nframes, cudaStream_t st, const CUtensorMap* pyrMaps) {
+    if (pyrMaps && hp.lv[l].pyrTW > 0) return launch_pyr_tma(a, hp, l, nframes, pyrMaps[l], st);
+    dim3 blk(32, 4), grd(cdiv(hp.lv[l].w, 128), cdiv(hp.lv[l].h, 4 * EORB_PYR_BAND), nframes);
+    pyr_resize_kernel<<<grd, blk, 0, st>>>(a, l);
+    return cudaGetLastError();
+}
+
 cudaError_t launch_orb_pipeline(const OrbArgs& a, const OrbPlan& hp, int nframes, const CUtensorMap& tm0, cudaStream_t st,
-                                long long* launches, cudaEvent_t* ev) {
+                                long long* launches, cudaEvent_t* ev, const CUtensorMap* pyrMaps) {
     // ev (optional, EORB_ORB_STAGES+1 events): recorded around every stage for the per-kernel timings of bench.py
     if (ev) cudaEventRecord(ev[0], st);
     // K1: pyramid, level by level (each level is resized from the previous one)
     for (int l = 1; l < hp.nlevels; l++) {
         if (hp.lv[l].w <= 0 || hp.lv[l].h <= 0) continue;
-        dim3 blk(32, 4), grd(cdiv(hp.lv[l].w, 128), cdiv(hp.lv[l].h, 4 * EORB_PYR_BAND), nframes);
-        pyr_resize_kernel<<<grd, blk, 0, st>>>(a, l);
+        cudaError_t e = launch_pyramid_level(a, hp, l, nframes, st, pyrMaps);
+        if (e != cudaSuccess) return e;
         (*launches)++;
     }
     if (ev) cudaEventRecord(ev[1], st);
@@ -787,11 +794,11 @@ cudaError_t launch_orb_pipeline(const OrbArgs& a, const OrbPlan& hp, int nframes
     return cudaGetLastError();
 }
 
-cudaError_t launch_pyramid_and_blur(const OrbArgs& a, const OrbPlan& hp, cudaStream_t st, long long* launches) {
+cudaError_t launch_pyramid_and_blur(const OrbArgs& a, const OrbPlan& hp, cudaStream_t st, long long* launches, const CUtensorMap* pyrMaps) {
     for (int l = 1; l < hp.nlevels; l++) {
         if (hp.lv[l].w <= 0 || hp.lv[l].h <= 0) continue;
-        dim3 blk(32, 4), grd(cdiv(hp.lv[l].w, 128), cdiv(hp.lv[l].h, 4 * EORB_PYR_BAND), 1);
-        pyr_resize_kernel<<<grd, blk, 0, st>>>(a, l);
+        cudaError_t e = launch_pyramid_level(a, hp, l, 1, st, pyrMaps);
+        if (e != cudaSuccess) return e;
         (*launches)++;
     }
     if (hp.blurTasksTotal > 0) {

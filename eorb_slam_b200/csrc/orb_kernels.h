@@ -16,6 +16,7 @@ struct OrbArgs {
     const CellPlan* cells;       // device
     const short4* xtab;          // device: resize taps per destination column  {sx, sx+1, a0, a1}
     const int4* ytab;            // device: resize taps per destination row     {sy0, sy1, b0 << 16, b1 << 16}
+    const int4* ytabT;           // device: the same for the TMA-staged resize  {sy0 * BW, sy1 * BW, b0 << 16, b1 << 16} (BW = the level's box width)
     const uint8_t* lvl0;         // level 0 = the input frames (zero-copy when aligned, else staged)
     long long lvl0Pitch, lvl0FrameStride;
     const CUtensorMap* tmaps;    // device: [nlevels] TMA maps {x, y, frame} of the pyramid levels >= 1 (entry 0 unused:
@@ -42,13 +43,24 @@ struct OrbArgs {
     int wantDesc;
 };
 
+// constants of one TMA-staged pyramid launch (orb_tiles.cu), passed by value
+struct PyrTileConst {
+    int TW, TH, BW, BH, barOff;
+    int dw, dh, dpitch;
+    int xtabOff, ytabOff;
+    long long doff, pyrBytes;
+};
+cudaError_t launch_pyr_tma(const OrbArgs& a, const OrbPlan& hp, int level, int nframes, const CUtensorMap& tmSrc, cudaStream_t st);
+
 cudaError_t orb_kernels_configure(const OrbPlan& hp);
 #define EORB_ORB_STAGES 6   // pyramid, fast, octree, index, blur, orient+desc
+// pyrMaps (host array, [nlevels], may be null): TMA map of the SOURCE of level l (= level l-1) with that level's box, for the
+// levels whose plan says pyrTW > 0; null or pyrTW == 0 -> pyr_resize_kernel
 cudaError_t launch_orb_pipeline(const OrbArgs& a, const OrbPlan& hp, int nframes, const CUtensorMap& tm0, cudaStream_t st,
-                                long long* launches, cudaEvent_t* ev);
+                                long long* launches, cudaEvent_t* ev, const CUtensorMap* pyrMaps = nullptr);
 cudaError_t launch_fast_cells(const OrbArgs& a, const OrbPlan& hp, int nframes, const CUtensorMap& tm0, cudaStream_t st);
 cudaError_t fast_cells_configure(const OrbPlan& hp);
-cudaError_t launch_pyramid_and_blur(const OrbArgs& a, const OrbPlan& hp, cudaStream_t st, long long* launches);
+cudaError_t launch_pyramid_and_blur(const OrbArgs& a, const OrbPlan& hp, cudaStream_t st, long long* launches, const CUtensorMap* pyrMaps = nullptr);
 cudaError_t launch_tracked_desc(const OrbArgs& a, const OrbPlan& hp, const eorb_keypoint* d_kps, int n, int mode,
                                 const float* d_invScale, const uint8_t* d_refDesc, uint8_t* d_desc, int* d_dist,
                                 cudaStream_t st, long long* launches);

@@ -33,6 +33,9 @@ struct LevelPlan {
     float sizeF;                   // (float)(int)(31*scale)
     int xtabOff, ytabOff;          // offsets (in entries) into the resize tables (levels >= 1)
     int blurTaskBase;              // first flattened (32-row band, 128-column strip) task of this level (blur grid)
+    // TMA-staged resize of level l-1 into this level (orb_tiles.cu): destination tile TW x TH (TW multiple of 4, <= 128; TH multiple of
+    // 4), source box BW x BH bytes (BW multiple of 16, <= 256); pyrTW == 0: the level uses pyr_resize_kernel (direct global loads)
+    int pyrTW, pyrTH, pyrBW, pyrBH;
 };
 
 struct CellPlan {
