@@ -253,6 +253,7 @@ struct eorb_orb {
     int graphKey[4] = {-1, 0, 0, 0};
     long long graphLaunches = 0;   // kernel launches inside the captured graph
     bool useGraph = true;          // EORB_ORB_GRAPH=0 disables
+    bool fastPadTile = true;       // EORB_FAST_PAD=0: FAST tile pitch left at the next multiple of 16 (for A/B)
     bool usePyrTma = true;         // EORB_PYR_TMA=0: every pyramid level through pyr_resize_kernel (direct global loads), for A/B
     int pyrTileRows = 64;          // EORB_PYR_TH: destination rows per TMA-staged tile (tuning)
 };
@@ -529,6 +530,10 @@ static int orbBuildPlan(eorb_orb* h, int W, int H) {
     P.blurTasksTotal = rowBlocks;
     // FAST smem region of one warp: [TMA tile BW x BH][score map (ch+2) x MS][survivor list u16][flagged groups u32][mbarrier]
     P.cellTileStride = roundUp(maxCW + 15, 16);   // the TMA box starts at x0 & ~15 (16-byte inner-coordinate rule)
+    // A row pitch that is a multiple of 32 words maps rows two apart onto the same banks: the byte gathers of the exact-score phase
+    // (lanes on different rows of one cell) then serialise 2.5-2.7 deep (ncu r01k: 46 % of the kernel's shared-memory wavefronts were
+    // bank conflicts, and the shared-memory pipe was its busiest unit at 82 %).  16 bytes more spread eight rows over all banks.
+    if (h->fastPadTile && P.cellTileStride % 32 == 0 && P.cellTileStride + 16 <= 256) P.cellTileStride += 16;
     P.cellTileRows = maxCH;
     P.cellMapStride = roundUp(maxCW - 6 + 2, 4);
     P.cellMapOff = roundUp(P.cellTileRows * P.cellTileStride, 16);
@@ -618,6 +623,7 @@ extern "C" int eorb_orb_create(const eorb_orb_params* params, int device, int ma
     h->par = *params; h->device = device; h->maxBatch = max_batch;
     if (const char* e = getenv("EORB_ORB_GRAPH")) h->useGraph = atoi(e) != 0;
     if (const char* e = getenv("EORB_PYR_TMA")) h->usePyrTma = atoi(e) != 0;
+    if (const char* e = getenv("EORB_FAST_PAD")) h->fastPadTile = atoi(e) != 0;
     if (const char* e = getenv("EORB_PYR_TH")) h->pyrTileRows = std::min(std::max(atoi(e), 8), 200);
     h->pipeBatch = std::min(max_batch, 128);   // measured on B200: H2D/compute/D2H overlap is best with 128-frame slots
     cudaDeviceProp prop;
