@@ -959,6 +959,96 @@ __global__ void __launch_bounds__(256) guided_resolve_map_kernel(const eorb_trac
     if (tid == 0) *nmatchesOut = sNm;
 }
 
+// Register path of SearchByBoW for one vocabulary node (one warp): the node's frame features sit in registers, S per lane
+// (feature p of the node's list <-> slot p / 32 of lane p % 32: index, descriptor, free flag); the keyframe side is loaded 32
+// features at a time, one per lane, and broadcast by shuffles, so the ordered loop over the keyframe features touches no memory.
+// S = 1 covers the usual ~10 features per node; S = 2 / 4 / 8 cover crowded nodes up to 256 features (a coarse vocabulary level or a
+// repetitive scene), which used to fall to the memory-resident loop below (509 us for 10 nodes x 100 features against 19.5 us).
+// Ties: the key is (distance << 16) | list position, so the smallest position wins like the reference's strict "<" scan
+// (ORBmatcher.cc:318-378).  Returns the number of matches made (the caller adds it to work[32]).
+template <int S>
+__device__ __forceinline__ int bow_node_registers(const GuidedBowSide& kf, const uint8_t* __restrict__ validKF, const GuidedBowSide& f, int w,
+                                                  int fb, int fe, float nnratio, int checkOri, int32_t* matchF, int* work, int lane) {
+    auto rotBin = [&](int ik, int jf) -> int {
+        float rot = __fsub_rn(kf.kps[ik].angle, f.kps[jf].angle);
+        if (rot < 0.0f) rot = __fadd_rn(rot, 360.0f);
+        int bin = (int)roundf(__fmul_rn(rot, 1.0f / 30));
+        if (bin == 30) bin = 0;
+        return (bin >= 0 && bin < 30) ? bin : -1;
+    };
+    int jf[S], mine[S];
+    uint32_t fd[S][8];
+    unsigned freeMask = 0;
+#pragma unroll
+    for (int s = 0; s < S; s++) {
+        const int p = fb + s * 32 + lane;
+        const bool has = p < fe;
+        jf[s] = has ? (int)f.feats[p] : 0;
+        mine[s] = -1;
+#pragma unroll
+        for (int j = 0; j < 8; j++) fd[s][j] = 0;
+        if (has) {
+            const uint4* dp = reinterpret_cast<const uint4*>(f.desc + (size_t)jf[s] * 32);
+            const uint4 x = __ldg(dp), y = __ldg(dp + 1);
+            fd[s][0] = x.x; fd[s][1] = x.y; fd[s][2] = x.z; fd[s][3] = x.w; fd[s][4] = y.x; fd[s][5] = y.y; fd[s][6] = y.z; fd[s][7] = y.w;
+            freeMask |= 1u << s;
+        }
+    }
+    int nm = 0;
+    for (int a0 = kf.start[w], ke = kf.start[w + 1]; a0 < ke; a0 += 32) {
+        const int cnt = min(32, ke - a0);
+        int ikL = -1;
+        uint32_t kd[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+        if (lane < cnt) {
+            const int t = (int)kf.feats[a0 + lane];
+            if (validKF[t]) {
+                ikL = t;
+                const uint4* qp = reinterpret_cast<const uint4*>(kf.desc + (size_t)t * 32);
+                const uint4 x = __ldg(qp), y = __ldg(qp + 1);
+                kd[0] = x.x; kd[1] = x.y; kd[2] = x.z; kd[3] = x.w; kd[4] = y.x; kd[5] = y.y; kd[6] = y.z; kd[7] = y.w;
+            }
+        }
+        unsigned todo = __ballot_sync(FULLMASK, ikL >= 0);
+        while (todo) {
+            const int sl = __ffs(todo) - 1;
+            todo &= todo - 1;
+            uint32_t q[8];
+#pragma unroll
+            for (int j = 0; j < 8; j++) q[j] = __shfl_sync(FULLMASK, kd[j], sl);
+            uint32_t k1 = 0xffffffffu, k2 = 0xffffffffu;     // this lane's best and second-best key over its free slots
+#pragma unroll
+            for (int s = 0; s < S; s++) {
+                int dist = 0;
+#pragma unroll
+                for (int j = 0; j < 8; j++) dist += __popc(q[j] ^ fd[s][j]);
+                const uint32_t key = (freeMask >> s) & 1u ? (((uint32_t)dist << 16) | (uint32_t)(s * 32 + lane)) : 0xffffffffu;
+                if (key < k1) { k2 = k1; k1 = key; } else if (key < k2) k2 = key;
+            }
+            const uint32_t m1 = __reduce_min_sync(FULLMASK, k1);
+            if (m1 == 0xffffffffu) break;                      // every frame feature of the node is matched
+            const uint32_t m2 = __reduce_min_sync(FULLMASK, k1 == m1 ? k2 : k1);
+            const int d1 = (int)(m1 >> 16), d2 = m2 != 0xffffffffu ? (int)(m2 >> 16) : 256;
+            if (d1 <= 50 && (float)d1 < __fmul_rn(nnratio, (float)d2)) {
+                const int ik = __shfl_sync(FULLMASK, ikL, sl);
+                const int pos = (int)(m1 & 0xffffu);
+                if (lane == (pos & 31)) {
+#pragma unroll
+                    for (int s = 0; s < S; s++)
+                        if (s == (pos >> 5)) { freeMask &= ~(1u << s); mine[s] = ik; }
+                }
+                nm++;
+            }
+        }
+    }
+#pragma unroll
+    for (int s = 0; s < S; s++)
+        if (mine[s] >= 0) {
+            matchF[jf[s]] = mine[s];
+            if (checkOri) { const int bin = rotBin(mine[s], jf[s]); if (bin >= 0) atomicAdd(&work[bin], 1); }
+        }
+    return nm;
+}
+
 // ------------------------------------------------------------------------------------------------ SearchByBoW
 // ORBmatcher::SearchByBoW(pKF, F, vpMapPointMatches) (ORBmatcher.cc:276-478), monocular.  A frame feature belongs to exactly one
 // vocabulary node, so the "already matched" state (:330-331) never crosses nodes: the nodes are independent, only the keyframe
@@ -991,59 +1081,12 @@ __global__ void __launch_bounds__(BOW_WARPS * 32) search_by_bow_kernel(GuidedBow
         if (lo < f.nnodes && f.nodes[lo] == node) {
             const int fb = f.start[lo], fe = f.start[lo + 1];
             int nm = 0;
-            if (fe - fb <= 32) {
-                // register path (the usual case: ~10 features per node): lane L keeps frame feature L of the node (index,
-                // descriptor, free flag); the keyframe side is loaded 32 features at a time, one per lane, and broadcast by
-                // shuffles, so the ordered loop touches no memory.  A lane is matched at most once: its rotation bin is added
-                // after the loop.
-                const bool hasF = fb + lane < fe;
-                const int jf = hasF ? (int)f.feats[fb + lane] : 0;
-                uint32_t fd[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-                if (hasF) {
-                    const uint4* dp = reinterpret_cast<const uint4*>(f.desc + (size_t)jf * 32);
-                    const uint4 x = __ldg(dp), y = __ldg(dp + 1);
-                    fd[0] = x.x; fd[1] = x.y; fd[2] = x.z; fd[3] = x.w; fd[4] = y.x; fd[5] = y.y; fd[6] = y.z; fd[7] = y.w;
-                }
-                bool freeF = hasF;
-                int mine = -1;
-                for (int a0 = kf.start[w], ke = kf.start[w + 1]; a0 < ke; a0 += 32) {
-                    const int cnt = min(32, ke - a0);
-                    int ikL = -1;
-                    uint32_t kd[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-                    if (lane < cnt) {
-                        const int t = (int)kf.feats[a0 + lane];
-                        if (validKF[t]) {
-                            ikL = t;
-                            const uint4* qp = reinterpret_cast<const uint4*>(kf.desc + (size_t)t * 32);
-                            const uint4 x = __ldg(qp), y = __ldg(qp + 1);
-                            kd[0] = x.x; kd[1] = x.y; kd[2] = x.z; kd[3] = x.w; kd[4] = y.x; kd[5] = y.y; kd[6] = y.z; kd[7] = y.w;
-                        }
-                    }
-                    unsigned todo = __ballot_sync(FULLMASK, ikL >= 0);
-                    while (todo) {
-                        const int sl = __ffs(todo) - 1;
-                        todo &= todo - 1;
-                        int dist = 0;
-#pragma unroll
-                        for (int j = 0; j < 8; j++) dist += __popc(__shfl_sync(FULLMASK, kd[j], sl) ^ fd[j]);
-                        const uint32_t key = freeF ? (((uint32_t)dist << 16) | (uint32_t)lane) : 0xffffffffu;
-                        const uint32_t m1 = __reduce_min_sync(FULLMASK, key);
-                        if (m1 == 0xffffffffu) break;                      // every frame feature of the node is matched
-                        const uint32_t m2 = __reduce_min_sync(FULLMASK, key == m1 ? 0xffffffffu : key);
-                        const int d1 = (int)(m1 >> 16), d2 = m2 != 0xffffffffu ? (int)(m2 >> 16) : 256;
-                        if (d1 <= 50 && (float)d1 < __fmul_rn(nnratio, (float)d2)) {
-                            const int ik = __shfl_sync(FULLMASK, ikL, sl);
-                            if (lane == (int)(m1 & 0xffffu)) { freeF = false; mine = ik; }
-                            nm++;
-                        }
-                    }
-                }
-                if (mine >= 0) {
-                    matchF[jf] = mine;
-                    if (checkOri) { const int bin = rotBin(mine, jf); if (bin >= 0) atomicAdd(&work[bin], 1); }
-                }
-            } else
-            for (int a = kf.start[w], ke = kf.start[w + 1]; a < ke; a++) {
+            if (fe - fb <= 32) nm = bow_node_registers<1>(kf, validKF, f, w, fb, fe, nnratio, checkOri, matchF, work, lane);
+            else if (fe - fb <= 64) nm = bow_node_registers<2>(kf, validKF, f, w, fb, fe, nnratio, checkOri, matchF, work, lane);
+            else if (fe - fb <= 128) nm = bow_node_registers<4>(kf, validKF, f, w, fb, fe, nnratio, checkOri, matchF, work, lane);
+            else if (fe - fb <= 256) nm = bow_node_registers<8>(kf, validKF, f, w, fb, fe, nnratio, checkOri, matchF, work, lane);
+            else
+            for (int a = kf.start[w], ke = kf.start[w + 1]; a < ke; a++) {   // nodes above 256 frame features: descriptors stay in memory
                 const int ik = (int)kf.feats[a];
                 if (!validKF[ik]) continue;
                 uint32_t qd[8];

@@ -237,7 +237,10 @@ def _bow_case(api, n1, n2, seed, k, L, levelsup, valid_frac=0.8, max_flips=24):
 @pytest.mark.parametrize("n1,n2,seed,k,L,levelsup,ratio,ori", [
     (500, 520, 41, 6, 3, 2, 0.7, True), (500, 520, 42, 6, 3, 1, 0.9, True), (500, 520, 43, 6, 3, 0, 0.7, False),
     (1009, 1009, 44, 10, 4, 2, 0.7, True),       # Tracking::TrackReferenceKeyFrame shape: ORBmatcher(0.7, true), ~100 nodes
-    (5000, 5000, 45, 10, 3, 2, 0.75, True),      # 10 nodes of ~500 features: long per-node lists
+    (5000, 5000, 45, 10, 3, 2, 0.75, True),      # 10 nodes of ~500 features: long per-node lists (memory-resident loop)
+    (600, 600, 61, 10, 2, 1, 0.7, True),         # 10 nodes of ~60 frame features: two register slots per lane
+    (1009, 1009, 62, 10, 3, 2, 0.7, True),       # 10 nodes of ~100: four slots (the shape of smoke())
+    (2000, 2000, 63, 10, 2, 1, 0.8, True),       # 10 nodes of ~200: eight slots
     (800, 800, 46, 5, 2, 4, 0.8, True),          # levelsup >= L: everything under the root, one ordered list
     (0, 10, 47, 6, 3, 2, 0.7, True), (300, 1, 48, 6, 3, 2, 0.7, True), (1, 300, 49, 6, 3, 2, 0.7, True)])
 def test_search_by_bow(n1, n2, seed, k, L, levelsup, ratio, ori):
