@@ -253,6 +253,7 @@ struct eorb_orb {
     int graphKey[4] = {-1, 0, 0, 0};
     long long graphLaunches = 0;   // kernel launches inside the captured graph
     bool useGraph = true;          // EORB_ORB_GRAPH=0 disables
+    OrbFork graphFork;             // side stream + events of the captured single-call graph (blur beside FAST / octree)
     bool fastPadTile = true;       // EORB_FAST_PAD=0: FAST tile pitch left at the next multiple of 16 (for A/B)
     bool usePyrTma = true;         // EORB_PYR_TMA=0: every pyramid level through pyr_resize_kernel (direct global loads), for A/B
     int pyrTileRows = 64;          // EORB_PYR_TH: destination rows per TMA-staged tile (tuning)
@@ -636,6 +637,13 @@ extern "C" int eorb_orb_create(const eorb_orb_params* params, int device, int ma
     return EORB_OK;
 }
 
+static void orbFreeFork(OrbFork& f) {
+    if (f.forked) cudaEventDestroy(f.forked);
+    if (f.joined) cudaEventDestroy(f.joined);
+    if (f.side) cudaStreamDestroy(f.side);
+    f = OrbFork();
+}
+
 extern "C" int eorb_orb_destroy(eorb_orb* h) {
     if (!h) return EORB_OK;
     cudaSetDevice(h->device);
@@ -643,6 +651,7 @@ extern "C" int eorb_orb_destroy(eorb_orb* h) {
     orbFreePlan(h);
     for (cudaEvent_t e : h->evPool) cudaEventDestroy(e);
     orbDropGraph(h);
+    orbFreeFork(h->graphFork);
     cudaStreamDestroy(h->ownStream);
     delete h;
     return EORB_OK;
@@ -846,6 +855,7 @@ extern "C" int eorb_orb_extract_batch(eorb_orb* h, const uint8_t* imgs, int nfra
         eorb_keypoint* kdst = direct ? kps + (size_t)f0 * cap : b.h_kps;
         uint8_t* ddst = direct ? desc + (size_t)f0 * cap * 32 : b.h_desc;
         // the launch set and its result copies; with `capturing` they are recorded into a graph instead of being executed
+        bool capturing = false;
         auto issue = [&](long long* launchCounter, cudaEvent_t* stageEv) -> int {
             CUtensorMap tm0;
             int rct = tmaEncodeFrames(&tm0, b.d_img0, w, hgt, nb, (size_t)h->pitch0, (size_t)h->pitch0 * hgt, h->hp.cellTileStride, h->hp.cellTileRows);
@@ -853,7 +863,7 @@ extern "C" int eorb_orb_extract_batch(eorb_orb* h, const uint8_t* imgs, int nfra
             CUtensorMap pm[EORB_MAX_LEVELS];
             rct = orbPyrMaps(h, b, b.d_img0, w, hgt, nb, h->pitch0, (long long)h->pitch0 * hgt, pm);
             if (rct != EORB_OK) return rct;
-            CU(launch_orb_pipeline(a, h->hp, nb, tm0, st, launchCounter, stageEv, pm));
+            CU(launch_orb_pipeline(a, h->hp, nb, tm0, st, launchCounter, stageEv, pm, capturing ? &h->graphFork : nullptr));
             CU(cudaMemcpyAsync(b.h_n, b.d_outN, nb * sizeof(int), cudaMemcpyDeviceToHost, st));
             CU(cudaMemcpyAsync(b.h_mono, b.d_outMono, nb * sizeof(int), cudaMemcpyDeviceToHost, st));
             CU(cudaMemcpyAsync(kdst, b.d_outKps, (size_t)nb * icap * sizeof(eorb_keypoint), cudaMemcpyDeviceToHost, st));
@@ -862,6 +872,11 @@ extern "C" int eorb_orb_extract_batch(eorb_orb* h, const uint8_t* imgs, int nfra
         };
         // single launch set on the handle's own stream, small batch: replay a CUDA graph (the call is launch bound)
         const bool graphable = h->useGraph && nslots == 0 && !h->stageTiming && st == h->ownStream && nb <= 8;
+        if (graphable && !h->graphFork.side) {
+            CU(cudaStreamCreateWithFlags(&h->graphFork.side, cudaStreamNonBlocking));
+            CU(cudaEventCreateWithFlags(&h->graphFork.forked, cudaEventDisableTiming));
+            CU(cudaEventCreateWithFlags(&h->graphFork.joined, cudaEventDisableTiming));
+        }
         if (graphable) {
             const int key[4] = {nb, lap0, lap1, want_desc};
             if (!h->graphExec || memcmp(key, h->graphKey, sizeof(key)) != 0) {
@@ -869,7 +884,9 @@ extern "C" int eorb_orb_extract_batch(eorb_orb* h, const uint8_t* imgs, int nfra
                 cudaGraph_t g = nullptr;
                 long long cnt = 0;
                 CU(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
+                capturing = true;
                 const int rci = issue(&cnt, nullptr);
+                capturing = false;
                 const cudaError_t ce = cudaStreamEndCapture(st, &g);
                 if (rci != EORB_OK) { if (g) cudaGraphDestroy(g); return rci; }
                 if (ce != cudaSuccess) return fail(EORB_ERR_CUDA, "cudaStreamEndCapture failed: %s", cudaGetErrorString(ce));

@@ -748,7 +748,8 @@ static cudaError_t launch_pyramid_level(const OrbArgs& a, const OrbPlan& hp, int
 }
 
 cudaError_t launch_orb_pipeline(const OrbArgs& a, const OrbPlan& hp, int nframes, const CUtensorMap& tm0, cudaStream_t st,
-                                long long* launches, cudaEvent_t* ev, const CUtensorMap* pyrMaps) {
+                                long long* launches, cudaEvent_t* ev, const CUtensorMap* pyrMaps, const OrbFork* fork) {
+    const bool forkBlur = fork && fork->side && !ev && a.wantDesc && hp.blurTasksTotal > 0;
     // ev (optional, EORB_ORB_STAGES+1 events): recorded around every stage for the per-kernel timings of bench.py
     if (ev) cudaEventRecord(ev[0], st);
     // K1: pyramid, level by level (each level is resized from the previous one)
@@ -759,6 +760,14 @@ cudaError_t launch_orb_pipeline(const OrbArgs& a, const OrbPlan& hp, int nframes
         (*launches)++;
     }
     if (ev) cudaEventRecord(ev[1], st);
+    if (forkBlur) {   // K5 beside K2 / K3 / K7
+        cudaEventRecord(fork->forked, st);
+        cudaStreamWaitEvent(fork->side, fork->forked, 0);
+        dim3 blk(32, 4), grd(cdiv(hp.blurTasksTotal, 4), nframes);
+        blur_kernel<<<grd, blk, 0, fork->side>>>(a);
+        (*launches)++;
+        cudaEventRecord(fork->joined, fork->side);
+    }
     // K2: FAST over every cell of every level
     if (hp.nCells > 0) {
         cudaError_t e = launch_fast_cells(a, hp, nframes, tm0, st);
@@ -778,7 +787,9 @@ cudaError_t launch_orb_pipeline(const OrbArgs& a, const OrbPlan& hp, int nframes
     (*launches)++;
     if (ev) cudaEventRecord(ev[4], st);
     // K5: blur (only needed for descriptors)
-    if (a.wantDesc && hp.blurTasksTotal > 0) {
+    if (forkBlur) {
+        cudaStreamWaitEvent(st, fork->joined, 0);
+    } else if (a.wantDesc && hp.blurTasksTotal > 0) {
         dim3 blk(32, 4), grd(cdiv(hp.blurTasksTotal, 4), nframes);
         blur_kernel<<<grd, blk, 0, st>>>(a);
         (*launches)++;

@@ -54,10 +54,14 @@ cudaError_t launch_pyr_tma(const OrbArgs& a, const OrbPlan& hp, int level, int n
 
 cudaError_t orb_kernels_configure(const OrbPlan& hp);
 #define EORB_ORB_STAGES 6   // pyramid, fast, octree, index, blur, orient+desc
+// side-stream fork of one launch set (small batches inside the captured graph only: a single frame leaves the GPU mostly idle, so the
+// blur, which only depends on the pyramid, runs beside FAST / octree / index and joins before orientation + BRIEF; at 1024-frame
+// launch sets the same fork was measured neutral, 17.69 vs 17.73 ms per 4096 frames: every kernel fills the machine on its own)
+struct OrbFork { cudaStream_t side = nullptr; cudaEvent_t forked = nullptr, joined = nullptr; };
 // pyrMaps (host array, [nlevels], may be null): TMA map of the SOURCE of level l (= level l-1) with that level's box, for the
 // levels whose plan says pyrTW > 0; null or pyrTW == 0 -> pyr_resize_kernel
 cudaError_t launch_orb_pipeline(const OrbArgs& a, const OrbPlan& hp, int nframes, const CUtensorMap& tm0, cudaStream_t st,
-                                long long* launches, cudaEvent_t* ev, const CUtensorMap* pyrMaps = nullptr);
+                                long long* launches, cudaEvent_t* ev, const CUtensorMap* pyrMaps = nullptr, const OrbFork* fork = nullptr);
 cudaError_t launch_fast_cells(const OrbArgs& a, const OrbPlan& hp, int nframes, const CUtensorMap& tm0, cudaStream_t st);
 cudaError_t fast_cells_configure(const OrbPlan& hp);
 cudaError_t launch_pyramid_and_blur(const OrbArgs& a, const OrbPlan& hp, cudaStream_t st, long long* launches, const CUtensorMap* pyrMaps = nullptr);
