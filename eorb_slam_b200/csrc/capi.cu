@@ -12,6 +12,7 @@
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
+#include <memory>
 #include <mutex>
 #include <string>
 #include <vector>
@@ -53,6 +54,19 @@ static cudaError_t devAlloc(T** p, size_t count) {
 }
 
 static inline int roundUp(int v, int a) { return (v + a - 1) / a * a; }
+
+// grow-only device buffer: the capacity is zeroed before the old block is freed and set only after the new one exists, so a
+// failed allocation never leaves a stale capacity beside a null pointer
+template <typename T>
+static int growBuf(T** p, size_t* cap, size_t need) {
+    if (need <= *cap) return EORB_OK;
+    *cap = 0;
+    cudaFree(*p); *p = nullptr;
+    CU(devAlloc(p, need));
+    *cap = need;
+    return EORB_OK;
+}
+
 
 // ---- TMA tensor maps (driver entry point resolved through the runtime: no link-time dependency on libcuda)
 static PFN_cuTensorMapEncodeTiled_v12000 g_tmaEncode = nullptr;
@@ -98,10 +112,10 @@ extern "C" int eorb_device_count(void) {
 struct EorbTimer { cudaEvent_t a, b; };
 extern "C" int eorb_timer_create(void** t) {
     if (!t) return fail(EORB_ERR_ARG, "null timer");
-    EorbTimer* x = new EorbTimer();
+    std::unique_ptr<EorbTimer> x(new EorbTimer());
     CU(cudaEventCreate(&x->a));
-    CU(cudaEventCreate(&x->b));
-    *t = x;
+    if (cudaEventCreate(&x->b) != cudaSuccess) { cudaEventDestroy(x->a); return fail(EORB_ERR_CUDA, "cudaEventCreate failed"); }
+    *t = x.release();
     return EORB_OK;
 }
 extern "C" int eorb_timer_destroy(void* t) {
@@ -620,7 +634,8 @@ extern "C" int eorb_orb_create(const eorb_orb_params* params, int device, int ma
     if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) { cudaGetLastError(); return fail(EORB_ERR_CUDA, "no CUDA device: eorb_b200 has no CPU fallback"); }
     if (device < 0 || device >= ndev) return fail(EORB_ERR_ARG, "device %d out of range", device);
     CU(cudaSetDevice(device));
-    eorb_orb* h = new eorb_orb();
+    std::unique_ptr<eorb_orb> guard(new eorb_orb());      // released to *out only when every CUDA call below succeeded
+    eorb_orb* h = guard.get();
     h->par = *params; h->device = device; h->maxBatch = max_batch;
     if (const char* e = getenv("EORB_ORB_GRAPH")) h->useGraph = atoi(e) != 0;
     if (const char* e = getenv("EORB_PYR_TMA")) h->usePyrTma = atoi(e) != 0;
@@ -633,7 +648,7 @@ extern "C" int eorb_orb_create(const eorb_orb_params* params, int device, int ma
     CU(cudaStreamCreateWithFlags(&h->ownStream, cudaStreamNonBlocking));
     h->stream = h->ownStream;
     orbTables(h);
-    *out = h;
+    *out = guard.release();
     return EORB_OK;
 }
 
@@ -659,6 +674,7 @@ extern "C" int eorb_orb_destroy(eorb_orb* h) {
 
 extern "C" int eorb_orb_set_stream(eorb_orb* h, void* s) {
     if (!h) return fail(EORB_ERR_ARG, "null handle");
+    CU(cudaSetDevice(h->device));
     CU(cudaStreamSynchronize(h->stream));
     orbDropGraph(h);
     h->stream = (cudaStream_t)s;   // NULL is the CUDA legacy default stream, a legitimate choice
@@ -666,7 +682,9 @@ extern "C" int eorb_orb_set_stream(eorb_orb* h, void* s) {
 }
 extern "C" int eorb_orb_reset_stream(eorb_orb* h) {
     if (!h) return fail(EORB_ERR_ARG, "null handle");
+    CU(cudaSetDevice(h->device));
     CU(cudaStreamSynchronize(h->stream));
+    orbDropGraph(h);               // as set_stream: a graph captured for another stream configuration is not reused
     h->stream = h->ownStream;
     return EORB_OK;
 }
@@ -833,6 +851,19 @@ extern "C" int eorb_orb_extract_batch(eorb_orb* h, const uint8_t* imgs, int nfra
         int rcb = orbAllocBufs(h, h->pipe.back(), true);
         if (rcb != EORB_OK) { orbFreeBufs(h->pipe.back()); h->pipe.pop_back(); return rcb; }
     }
+    // A slot marked pending belongs to THIS call only: flags left over from a call that failed half-way are dropped here, and the
+    // guard below drains every slot on any early return, so no D2H copy into the caller's (possibly pinned) arrays is still in
+    // flight and no later call collects a stale (f0, nb) range.
+    h->main.pending = false;
+    for (auto& pb : h->pipe) pb.pending = false;
+    struct PendingGuard {
+        eorb_orb* h; bool armed = true;
+        ~PendingGuard() {
+            if (!armed) return;
+            for (auto& pb : h->pipe) { if (pb.stream) cudaStreamSynchronize(pb.stream); pb.pending = false; }
+            cudaStreamSynchronize(h->stream); h->main.pending = false;
+        }
+    } pendingGuard{h};
     // when the caller's arrays are pinned and laid out like ours, D2H goes straight into them (no staging copy)
     const bool direct = nslots > 0 && cap == icap && isPinnedHost(kps) && (!want_desc || isPinnedHost(desc));
     if (nslots > 0) CU(cudaStreamSynchronize(h->stream));   // order after earlier work on the handle's stream
@@ -915,6 +946,7 @@ extern "C" int eorb_orb_extract_batch(eorb_orb* h, const uint8_t* imgs, int nfra
         int rcc = orbCollect(h, h->main, want_desc, kps, desc, cap, n_out, mono_out, false);
         if (rcc != EORB_OK) status = rcc;
     }
+    pendingGuard.armed = false;     // every slot was collected above
     return status;
 }
 
@@ -1061,7 +1093,8 @@ struct eorb_matcher {
     eorb_best2* d_partial = nullptr; size_t partialCap = 0;
     uint8_t* d_q = nullptr; size_t qCap = 0;
     eorb_match* d_out = nullptr; size_t outCap = 0;
-    eorb_best2* d_mine = nullptr; eorb_best2* d_gathered = nullptr; size_t gatherCap = 0;   // sharded search: own + all shards' partials
+    eorb_best2* d_mine = nullptr; size_t mineCap = 0;           // sharded search: this shard's best-2 per query (nq entries)
+    eorb_best2* d_gathered = nullptr; size_t gatherCap = 0;     //                 every shard's best-2 (nshards * nq entries)
     long long launches = 0;
 };
 
@@ -1144,9 +1177,7 @@ extern "C" int eorb_matcher_set_db_host(eorb_matcher* m, const uint8_t* db, int6
 }
 
 static int matcherReserve(eorb_matcher* m, int nq) {
-    const size_t needP = (size_t)std::max(m->nchunks, 1) * nq;
-    if (needP > m->partialCap) { cudaFree(m->d_partial); CU(devAlloc(&m->d_partial, needP)); m->partialCap = needP; }
-    return EORB_OK;
+    return growBuf(&m->d_partial, &m->partialCap, (size_t)std::max(m->nchunks, 1) * nq);
 }
 
 extern "C" int eorb_matcher_search_device(eorb_matcher* m, const uint8_t* d_q, int nq, eorb_best2* d_partial) {
@@ -1250,12 +1281,12 @@ extern "C" int eorb_matcher_search_sharded(eorb_matcher* m, const uint8_t* d_q, 
     int rc = ncclApi();
     if (rc != EORB_OK) return rc;
     CU(cudaSetDevice(m->device));
-    const size_t need = (size_t)nshards * nq;
-    if (need > m->gatherCap) {
-        cudaFree(m->d_gathered); cudaFree(m->d_mine);
-        CU(devAlloc(&m->d_gathered, need)); CU(devAlloc(&m->d_mine, (size_t)nq));
-        m->gatherCap = need;
-    }
+    // the two buffers grow independently: 8 shards x 100 queries followed by 2 shards x 400 needs a larger d_mine, not a larger gather
+    if (((size_t)nq > m->mineCap) || ((size_t)nshards * nq > m->gatherCap)) CU(cudaStreamSynchronize(m->stream));
+    rc = growBuf(&m->d_mine, &m->mineCap, (size_t)nq);
+    if (rc != EORB_OK) return rc;
+    rc = growBuf(&m->d_gathered, &m->gatherCap, (size_t)nshards * nq);
+    if (rc != EORB_OK) return rc;
     rc = eorb_matcher_search_device(m, d_q, nq, m->d_mine);
     if (rc != EORB_OK) return rc;
     NCCL_CALL(g_nccl.allGather(m->d_mine, m->d_gathered, (size_t)nq * sizeof(eorb_best2), /*ncclChar*/ 0, nccl_comm, m->stream));
@@ -1266,8 +1297,10 @@ extern "C" int eorb_matcher_search(eorb_matcher* m, const uint8_t* q, int nq, in
     if (!m || !out || (!q && nq > 0)) return fail(EORB_ERR_ARG, "null argument");
     if (nq <= 0) return EORB_OK;
     CU(cudaSetDevice(m->device));
-    if ((size_t)nq * 32 > m->qCap) { cudaFree(m->d_q); CU(devAlloc(&m->d_q, (size_t)nq * 32)); m->qCap = (size_t)nq * 32; }
-    if ((size_t)nq > m->outCap) { cudaFree(m->d_out); CU(devAlloc(&m->d_out, (size_t)nq)); m->outCap = nq; }
+    int rcg = growBuf(&m->d_q, &m->qCap, (size_t)nq * 32);
+    if (rcg != EORB_OK) return rcg;
+    rcg = growBuf(&m->d_out, &m->outCap, (size_t)nq);
+    if (rcg != EORB_OK) return rcg;
     int rc = matcherReserve(m, nq);
     if (rc != EORB_OK) return rc;
     CU(cudaMemcpyAsync(m->d_q, q, (size_t)nq * 32, cudaMemcpyHostToDevice, m->stream));
@@ -1460,7 +1493,8 @@ extern "C" int eorb_ev_accumulate_batch_device(eorb_evconv* c, const eorb_event*
     }
     CU(cudaMemcpyAsync(c->d_wins, c->h_wins.data(), (size_t)nwin * sizeof(EvWindow), cudaMemcpyHostToDevice, c->stream));
     float2* xy = nullptr;
-    if ((p->mode == EORB_EV_SE3 || p->mode == EORB_EV_SE2) && (size_t)k.width * k.height * 4 > 200 * 1024) {
+    const bool ordered = p->pol && p->normalize == EORB_NORM_RUNNING;   // order-dependent extremes: ev_ordered_kernel reads warped positions
+    if ((p->mode == EORB_EV_SE3 || p->mode == EORB_EV_SE2) && ((size_t)k.width * k.height * 4 > 200 * 1024 || ordered)) {
         const long long need = win_offsets[nwin];
         if (need > c->xyCap) {
             CU(cudaStreamSynchronize(c->stream));

@@ -518,13 +518,113 @@ cudaError_t launch_ev_jac(const eorb_event* d_evs, const EvWindow* d_win, long l
 
 // whole path: zero + splat + min/max + normalise.  7x7 Gaussian windows take the shared-memory kernel (which also
 // zeroes and, for single-band frames, normalises); everything else the L2-reduction kernels.
+// ---- ordered frames: polarity-signed sums WITH the reference's running normalisation ------------------------------------------------
+// With pol = true the reference's resolveMinMaxVals (EventConversion.cc:30-38, called after every tap :201, :257, :341, :432) sees every
+// INTERMEDIATE pixel value: a pixel that climbs to +3 and is pulled back to 0 by negative events still raised maxVal to 3, so the
+// extremes used by normalizeImage are a function of the event ORDER, not of the final frame (with pol = false every tap is positive and
+// the two coincide).  This kernel replays the window in order: one block per window, one thread per tap, one event per step, a block
+// barrier between events.  Every pixel therefore receives its contributions in the reference's order (the float frame equals the
+// serial sum up to expf rounding) and every thread tracks the extremes of the values it writes.  It is a latency-bound replay
+// (about 0.05 us per event with the frame in shared memory, about 1 us in global memory); only pol && NORM_RUNNING takes it.
+__global__ void __launch_bounds__(256) ev_ordered_kernel(const eorb_event* __restrict__ evs, const EvWindow* __restrict__ wins, EvConst c,
+                                                         int frameInSmem, float* __restrict__ img, float* __restrict__ minmax,
+                                                         const float2* __restrict__ xy) {
+    extern __shared__ __align__(16) float s_frame[];
+    __shared__ float s_mn[8], s_mx[8];
+    const EvWindow w = wins[blockIdx.x];
+    const int W = c.width, H = c.height, npix = W * H, tid = threadIdx.x;
+    float* gim = img + (size_t)blockIdx.x * (size_t)npix;
+    float* im = frameInSmem ? s_frame : gim;
+    for (int i = tid; i < npix; i += blockDim.x) im[i] = 0.0f;
+    __syncthreads();
+    const bool nearest = c.mode == EORB_EV_NEAREST;
+    const int side = nearest ? 1 : 2 * c.half + 1, ntaps = side * side;
+    const float den = __fmul_rn(2.0f, c.sig2);
+    float mn = 0.0f, mx = -1000000.0f;            // EventConversion.cc:177-178, 219-220
+    const long long nev = w.end - w.begin;
+    for (long long e = 0; e < nev; e++) {
+        const eorb_event* evp = evs + w.begin + e;
+        const float polSign = (c.pol && evp->p == 0) ? -1.0f : 1.0f;
+        for (int t = tid; t < ntaps; t += blockDim.x) {
+            if (nearest) {
+                const int px = (int)roundf(evp->x), py = (int)roundf(evp->y);
+                if (px >= 0 && px < W && py >= 0 && py < H) {
+                    const float nv = __fadd_rn(im[(size_t)py * W + px], __fmul_rn(polSign, 0.001f));
+                    im[(size_t)py * W + px] = nv;
+                    mx = fmaxf(mx, nv); mn = fminf(mn, nv);
+                }
+            } else {
+                float X, Y;
+                if (xy) { const float2 v = __ldg(xy + w.begin + e); X = v.x; Y = v.y; }
+                else { X = evp->x; Y = evp->y; }
+                const float fxi = floorf(X), fyi = floorf(Y);
+                if (fxi >= (float)(-c.half - 1) && fxi <= (float)(W + c.half) && fyi >= (float)(-c.half - 1) && fyi <= (float)(H + c.half)) {
+                    const int xi = (int)fxi, yi = (int)fyi;
+                    const int i = t / side - c.half, j = t % side - c.half;      // the reference's loops: i over x outside, j over y inside
+                    const int xn = xi + i, yn = yi + j;
+                    if (xn >= 0 && xn < W && yn >= 0 && yn < H) {
+                        const float dx = __fsub_rn((float)i, __fsub_rn(X, (float)xi)), dy = __fsub_rn((float)j, __fsub_rn(Y, (float)yi));
+                        const float dd = __fdiv_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), den);
+                        const float val = __fdiv_rn(expf(-dd), c.norm);
+                        const float nv = __fadd_rn(im[(size_t)yn * W + xn], __fmul_rn(polSign, val));
+                        im[(size_t)yn * W + xn] = nv;
+                        mx = fmaxf(mx, nv); mn = fminf(mn, nv);
+                    }
+                }
+            }
+        }
+        __syncthreads();                          // the next event may touch the same pixels
+    }
+    if (frameInSmem)
+        for (int i = tid; i < npix; i += blockDim.x) gim[i] = s_frame[i];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        mn = fminf(mn, __shfl_xor_sync(0xffffffffu, mn, o));
+        mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    }
+    if ((tid & 31) == 0) { s_mn[tid >> 5] = mn; s_mx[tid >> 5] = mx; }
+    __syncthreads();
+    if (tid == 0) {
+        for (int k = 1; k < (int)(blockDim.x >> 5); k++) { mn = fminf(mn, s_mn[k]); mx = fmaxf(mx, s_mx[k]); }
+        minmax[2 * blockIdx.x] = mn; minmax[2 * blockIdx.x + 1] = mx;
+    }
+}
+
 cudaError_t launch_ev_frames(const eorb_event* d_evs, const EvWindow* d_wins, int nwin, long long maxEventsPerWindow, const EvConst& c,
                              int normMode, float* d_img, float* d_minmax, uint8_t* d_u8, cudaStream_t st, long long* launches,
                              float2* d_xyScratch) {
     if (nwin <= 0) return cudaSuccess;
     const int npix = c.width * c.height;
     const size_t smemBudget = 200 * 1024;
-    if (c.mode != EORB_EV_NEAREST && c.half == EV_SMEM_HALF && maxEventsPerWindow > 0 && (size_t)c.width * 4 * 8 <= smemBudget) {
+    if (c.pol && normMode == EORB_NORM_RUNNING && maxEventsPerWindow > 0) {
+        // order-dependent extremes: replay the window in order (see ev_ordered_kernel)
+        const float2* xy = nullptr;
+        if (c.mode == EORB_EV_SE3 || c.mode == EORB_EV_SE2) {
+            if (!d_xyScratch) return cudaErrorInvalidValue;
+            dim3 gw((unsigned)((maxEventsPerWindow + 255) / 256), nwin);
+            ev_warp_kernel<<<gw, 256, 0, st>>>(d_evs, d_wins, c, d_xyScratch);
+            (*launches)++;
+            xy = d_xyScratch;
+        }
+        const size_t fb = (size_t)npix * sizeof(float);
+        const int inSmem = fb <= smemBudget ? 1 : 0;
+        cudaError_t ea = cudaFuncSetAttribute(ev_ordered_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemBudget + 4096);
+        if (ea != cudaSuccess) return ea;
+        ev_ordered_kernel<<<nwin, 256, inSmem ? fb : 0, st>>>(d_evs, d_wins, c, inSmem, d_img, d_minmax, xy);
+        (*launches)++;
+        cudaError_t e = cudaGetLastError();
+        if (e != cudaSuccess) return e;
+        if (d_u8) {
+            dim3 grd((npix / 4 + 255) / 256 + 1, nwin);
+            ev_normalize_kernel<<<grd, 256, 0, st>>>(d_img, npix, normMode, d_minmax, d_u8);
+            (*launches)++;
+        }
+        return cudaGetLastError();
+    }
+    // fixed-point guard of the shared-memory path: its scale 2^k shrinks with the window (k = floor(log2(2^31 / (events * peakTap)))),
+    // and below k = 13 (more than 1.6 M events per window at sigma = 1) the accumulated rounding approaches the 1e-4 * peak bar
+    const bool fixedOk = (double)maxEventsPerWindow * (1.0 / (double)c.norm) + 1.0 <= 2147483648.0 / 8192.0;
+    if (fixedOk && c.mode != EORB_EV_NEAREST && c.half == EV_SMEM_HALF && maxEventsPerWindow > 0 && (size_t)c.width * 4 * 8 <= smemBudget) {
         const int bands = (int)(((size_t)npix * 4 + smemBudget - 1) / smemBudget);
         const int bandRows = (c.height + bands - 1) / bands;
         const size_t smem = ((((size_t)bandRows * c.width + 2 * EV_SMEM_PAD) * 4) + 15) & ~(size_t)15;

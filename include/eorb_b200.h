@@ -131,7 +131,9 @@ int eorb_orb_extract(eorb_orb* h, const uint8_t* img, int w, int hgt, size_t str
 
 /* Config-3 shape: nframes images (host), frame f at imgs + f*frame_stride.  Outputs are [nframes][cap]
  * (kps), [nframes][cap][32] (desc), [nframes] (n_out, mono_out).  Frames are processed max_batch at a time
- * with H2D / compute / D2H overlapped on internal streams. */
+ * with H2D / compute / D2H overlapped on internal streams.  Entries of kps / desc past n_out[f] are unspecified (when the
+ * caller's arrays are pinned the device writes whole slabs straight into them).  On an error return every internal copy
+ * has been drained: no write into the caller's arrays is still in flight. */
 int eorb_orb_extract_batch(eorb_orb* h, const uint8_t* imgs, int nframes, int w, int hgt, size_t row_stride,
                            size_t frame_stride, int lap0, int lap1, int want_desc,
                            eorb_keypoint* kps, uint8_t* desc, int cap, int* n_out, int* mono_out);
@@ -219,7 +221,10 @@ int eorb_rotation_filter(const float* angle1, const float* angle2, int32_t* matc
 #define EORB_EV_SE2     3   /* ev2mci_gg_f(params2D)       :362-448 */
 
 #define EORB_NORM_NONE    0
-#define EORB_NORM_RUNNING 1 /* normalizeImage(max,min) as inside ev2im* when normalized=true */
+#define EORB_NORM_RUNNING 1 /* normalizeImage(max,min) as inside ev2im* when normalized=true.  The reference's extremes are RUNNING
+                             * extremes of every intermediate pixel value (resolveMinMaxVals after each tap, EventConversion.cc:30-38,
+                             * 201, 257): with pol == 0 they equal the final frame's; with pol != 0 they depend on the event order,
+                             * and the window is then replayed in order on the device (ev_ordered_kernel) to reproduce them */
 #define EORB_NORM_MINMAX  2 /* cv::normalize(img,img,255,0,NORM_MINMAX,CV_8UC1) as in EvImBuilder */
 
 typedef struct eorb_ev_params {

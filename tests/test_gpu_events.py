@@ -257,3 +257,42 @@ def test_random_parameter_fuzz_of_the_other_rows():
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     r = subprocess.run([sys.executable, os.path.join(root, "tools", "gpu_fuzz_rest.py"), "40", "11"], capture_output=True, text=True, timeout=900)
     assert r.returncode == 0 and "0 mismatches" in r.stdout, r.stdout[-3000:] + r.stderr[-2000:]
+
+
+@pytest.mark.parametrize("mode", ["nearest", "gauss", "se3", "se2"])
+def test_polarity_frames_with_running_normalisation_follow_the_event_order(mode):
+    """pol = true + normalized = true: the reference normalises with the RUNNING extremes of every intermediate pixel value
+    (EventConversion.cc:30-38), which depend on the event order; the device replays the window in order (ev_ordered_kernel)"""
+    api = _api()
+    ev = synth.make_events(6000, seed=77, w=240, h=180)
+    cv = api.EvImConverter(0, 1, 100000, 346, 260)
+    T = synth.rotation_tcw(np.array([0.5, -0.7, 1.5]) * float(ev["ts"][-1] - ev["ts"][0]))
+    if mode == "nearest":
+        u8 = cv.ev2im(ev, 240, 180, True, True); f = cv.ev2im(ev, 240, 180, True, False)
+        rf, _, ru = O.ev_accumulate(ev, 240, 180, 1.0, mode=0, pol=True, normalize=True)
+    elif mode == "gauss":
+        f, u8 = cv.ev2im_gauss(ev, 240, 180, 1.0, True, True, both=True)
+        rf, _, ru = O.ev_accumulate(ev, 240, 180, 1.0, mode=1, pol=True, normalize=True)
+    elif mode == "se3":
+        f, u8 = cv.ev2mci_gg_f(ev, K_ETHZ, T, 1.0, 240, 180, 1.0, True, True, both=True)
+        rf, _, ru = O.ev_accumulate(ev, 240, 180, 1.0, mode=2, Tcw=T, depth=1.0, K=K_ETHZ, pol=True, normalize=True)
+    else:
+        f, u8 = cv.ev2mci_gg_f_2d(ev, K_ETHZ, [0.02, 1.0, -0.5], 240, 180, 1.0, True, True, both=True)
+        rf, _, ru = O.ev_accumulate(ev, 240, 180, 1.0, mode=3, K=K_ETHZ, se2=[0.02, 1.0, -0.5], pol=True, normalize=True)
+    if mode != "nearest":
+        _close(f, rf)
+    else:
+        _close(f, rf)
+    assert ru is not None and int(np.abs(u8.astype(int) - ru.astype(int)).max()) <= 1, "u8 frame with the reference's running extremes"
+    # the final-frame extremes would NOT give this image: the running maximum is larger than the final one on this stream
+    assert float(rf.max()) > 0 and float(rf.min()) < 0
+
+
+def test_gauss_frame_of_a_very_large_window_stays_inside_the_tolerance():
+    """one million events in one 240x180 window: the fixed-point scale of the shared-memory path is down to 2^13 here"""
+    api = _api()
+    ev = synth.make_events(1000000, seed=5, w=240, h=180)
+    cv = api.EvImConverter(0, 1, 1 << 20, 240, 180)
+    img = cv.ev2im_gauss(ev, 240, 180, 1.0, False, False)
+    ref, _, _ = O.ev_accumulate(ev, 240, 180, 1.0, mode=1)
+    _close(img, ref)
