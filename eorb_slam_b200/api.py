@@ -58,7 +58,7 @@ def _load():
         "eorb_probe_popc_rate": ([i, C.POINTER(C.c_double)], i), "eorb_selftest_math": ([i, C.POINTER(i)], i),
         "eorb_orb_create": ([C.POINTER(_OrbParams), i, i, C.POINTER(vp)], i), "eorb_orb_destroy": ([vp], i),
         "eorb_orb_set_stream": ([vp, vp], i), "eorb_orb_reset_stream": ([vp], i), "eorb_orb_get_stream": ([vp], vp), "eorb_orb_synchronize": ([vp], i),
-        "eorb_orb_tables": ([vp, vp, vp, vp, vp, vp, vp, vp], i), "eorb_orb_max_keypoints": ([vp], i), "eorb_orb_max_keypoints_for_size": ([vp, i, i], i),
+        "eorb_orb_tables": ([vp, vp, vp, vp, vp, vp, vp, vp], i), "eorb_orb_params_tables": ([vp, vp, vp, vp, vp, vp, vp, vp], i), "eorb_orb_max_keypoints": ([vp], i), "eorb_orb_max_keypoints_for_size": ([vp, i, i], i),
         "eorb_orb_extract": ([vp, vp, i, i, sz, i, i, i, vp, vp, i, vp], i),
         "eorb_orb_extract_batch": ([vp, vp, i, i, i, sz, sz, i, i, i, vp, vp, i, vp, vp], i),
         "eorb_orb_extract_batch_device": ([vp, vp, i, i, i, sz, sz, i, i, i, vp, vp, i, vp, vp], i),

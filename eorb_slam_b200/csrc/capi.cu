@@ -740,6 +740,17 @@ extern "C" int eorb_orb_tables(const eorb_orb* h, int* nlevels, int* edge, float
     return EORB_OK;
 }
 
+extern "C" int eorb_orb_params_tables(const eorb_orb_params* params, int* nlevels, int* edge, float* scale, float* inv_scale, float* sigma2,
+                                      float* inv_sigma2, int* fpl) {
+    if (!params) return fail(EORB_ERR_ARG, "null argument");
+    if (params->nlevels < 1 || params->nlevels > EORB_MAX_LEVELS) return fail(EORB_ERR_ARG, "nlevels must be 1..%d", EORB_MAX_LEVELS);
+    if (params->nfeatures < 0 || !(params->scaleFactor >= 1.0f)) return fail(EORB_ERR_ARG, "bad nfeatures/scaleFactor");
+    eorb_orb tmp;                      // host fields only; no CUDA call is made
+    tmp.par = *params;
+    orbTables(&tmp);
+    return eorb_orb_tables(&tmp, nlevels, edge, scale, inv_scale, sigma2, inv_sigma2, fpl);
+}
+
 // Upper bound of the keypoints one frame of size w x hgt can produce: per level the octree ends with at most quota + 2 nodes
 // (its last splits add up to 3 to a list below the quota) or, when the quota is tiny, with the 4 * nIni children of its first
 // pass (:562-563, 620-683; nIni = round(width / height) of the level's FAST region, so elongated images have many roots).

@@ -130,6 +130,10 @@ float EvImConverter::measureImageFocus(const cv::Mat& image) { return focus(imag
 float EvImConverter::measureImageFocusLocal(const cv::Mat& image, const bool avg) { return focus(image, EORB_FOCUS_LOCAL_STD, avg); }
 float EvImConverter::measureImageFocusGlobal(const cv::Mat& image) { return focus(image, EORB_FOCUS_GLOBAL_STD, true); }
 float EvImConverter::imageMeanLocal(const cv::Mat& image, const bool avg) { return focus(image, EORB_FOCUS_LOCAL_MEAN, avg); }
+float EvImConverter::imageMean(const cv::Mat& image, const bool global, const bool avg)   // EventConversion.cc:152-161: cv::mean or the local form
+{
+    return global ? focus(image, 3 /* global mean */, true) : focus(image, EORB_FOCUS_LOCAL_MEAN, avg);
+}
 
 
 bool EvImConverter::ev2mci_gg_f_jac(const std::vector<EventData> &vEvData, ORB_SLAM3::GeometricCamera* pCamera, const double Rt12[12],

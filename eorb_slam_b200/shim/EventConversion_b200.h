@@ -38,6 +38,7 @@ namespace EORB_SLAM
         static float measureImageFocusLocal(const cv::Mat& image, bool avg = true);
         static float measureImageFocusGlobal(const cv::Mat& image);
         static float imageMeanLocal(const cv::Mat& image, bool avg = true);
+        static float imageMean(const cv::Mat& image, bool global = false, bool avg = true);
 
         // Jacobian of the contrast objective (EventConversion.h:65-68, EventConversion.cc:533-662).  The reference takes the
         // g2o vertex; here its estimate is passed as plain doubles so that the shim needs neither g2o nor Eigen:

@@ -3,6 +3,7 @@
 
 #include <cassert>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 
 #include "eorb_b200.h"
@@ -20,32 +21,56 @@ ORBxParams::ORBxParams(int _nfeatures, float _scaleFactor, int _nlevels, int _in
         nfeatures(_nfeatures), scaleFactor(_scaleFactor), nlevels(_nlevels), iniThFAST(_iniThFAST),
         minThFAST(_minThFAST), edgeTh(_edgeTh), patchSize(31), imSize(imSz) {}
 
+static int& defaultDevice()
+{
+    static int dev = [] { const char* e = std::getenv("EORB_DEVICE"); return e ? std::atoi(e) : 0; }();
+    return dev;
+}
+void ORBextractor::SetDevice(int device) { defaultDevice() = device; }
+int ORBextractor::GetDevice() { return defaultDevice(); }
+
 ORBextractor::ORBextractor(const ORBxParams& p) :
         nfeatures(p.nfeatures), scaleFactor(p.scaleFactor), nlevels(p.nlevels), iniThFAST(p.iniThFAST),
-        minThFAST(p.minThFAST), mpHandle(nullptr)
+        minThFAST(p.minThFAST), mpParams(new eorb_orb_params())
 {
-    eorb_orb_params cp;
+    eorb_orb_params& cp = *mpParams;
     cp.nfeatures = p.nfeatures; cp.scaleFactor = p.scaleFactor; cp.nlevels = p.nlevels;
     cp.iniThFAST = p.iniThFAST; cp.minThFAST = p.minThFAST; cp.edgeTh = p.edgeTh;
     cp.imW = p.imSize.width; cp.imH = p.imSize.height;
-    if (eorb_orb_create(&cp, 0, 1, &mpHandle) != EORB_OK) {
-        // the reference has no error channel in the constructor either; log like its LOG(ERROR) sites
-        std::fprintf(stderr, "ORBextractor(b200): %s\n", eorb_last_error());
-        mpHandle = nullptr;
-    }
     mvScaleFactor.resize(nlevels); mvInvScaleFactor.resize(nlevels);
     mvLevelSigma2.resize(nlevels); mvInvLevelSigma2.resize(nlevels);
     mnFeaturesPerLevel.resize(nlevels);
     mvImagePyramid.resize(nlevels);
-    if (mpHandle)
-        eorb_orb_tables(mpHandle, nullptr, nullptr, mvScaleFactor.data(), mvInvScaleFactor.data(), mvLevelSigma2.data(),
-                        mvInvLevelSigma2.data(), mnFeaturesPerLevel.data());
+    // the constructor's tables are host arithmetic (ORBextractor.cc:420-489): no device is touched here
+    if (eorb_orb_params_tables(&cp, nullptr, nullptr, mvScaleFactor.data(), mvInvScaleFactor.data(), mvLevelSigma2.data(),
+                               mvInvLevelSigma2.data(), mnFeaturesPerLevel.data()) != EORB_OK)
+        std::fprintf(stderr, "ORBextractor(b200): %s\n", eorb_last_error());   // the reference has no error channel here either
 }
 
-ORBextractor::~ORBextractor() { eorb_orb_destroy(mpHandle); }
+ORBextractor::~ORBextractor()
+{
+    for (auto& kv : mHandles) eorb_orb_destroy(kv.second);
+    delete mpParams;
+}
+
+eorb_orb* ORBextractor::handle()
+{
+    std::lock_guard<std::mutex> lk(mHandleMutex);
+    auto it = mHandles.find(std::this_thread::get_id());
+    if (it != mHandles.end()) return it->second;
+    eorb_orb* h = nullptr;
+    if (eorb_orb_create(mpParams, defaultDevice(), 1, &h) != EORB_OK) {
+        std::fprintf(stderr, "ORBextractor(b200): %s\n", eorb_last_error());
+        h = nullptr;                                           // no CPU fallback: the call returns -1 like an empty image
+    }
+    mHandles[std::this_thread::get_id()] = h;
+    return h;
+}
 
 void ORBextractor::downloadPyramid()
 {
+    eorb_orb* mpHandle = handle();
+    if (!mpHandle) return;
     for (int l = 0; l < nlevels; l++) {
         int w = 0, h = 0;
         if (eorb_orb_level_size(mpHandle, l, &w, &h) != EORB_OK) return;
@@ -54,21 +79,22 @@ void ORBextractor::downloadPyramid()
     }
 }
 
-int ORBextractor::extract(cv::InputArray _image, std::vector<cv::KeyPoint>& _keypoints, cv::Mat* desc, std::vector<int>& lap)
+int ORBextractor::extract(cv::InputArray _image, std::vector<cv::KeyPoint>& _keypoints, std::vector<unsigned char>* desc, std::vector<int>& lap)
 {
     if (_image.empty())
         return -1;                                             // ORBextractor.cc:1096
+    eorb_orb* mpHandle = handle();
     if (!mpHandle)
         return -1;
     cv::Mat image = _image.getMat();
     assert(image.type() == CV_8UC1);                           // ORBextractor.cc:1100
     const int cap = eorb_orb_max_keypoints_for_size(mpHandle, image.cols, image.rows);
     _keypoints = std::vector<cv::KeyPoint>(cap);
-    if (desc) mScratchDesc.resize((size_t)cap * DEF_DESC_LEN);
+    if (desc) desc->resize((size_t)cap * DEF_DESC_LEN);
     int n = 0;
     const int lap0 = lap.size() > 0 ? lap[0] : 0, lap1 = lap.size() > 1 ? lap[1] : 0;
     int ret = eorb_orb_extract(mpHandle, image.data, image.cols, image.rows, image.step, lap0, lap1, desc ? 1 : 0,
-                               reinterpret_cast<eorb_keypoint*>(_keypoints.data()), desc ? mScratchDesc.data() : nullptr,
+                               reinterpret_cast<eorb_keypoint*>(_keypoints.data()), desc ? desc->data() : nullptr,
                                cap, &n);
     if (ret < -1) {
         std::fprintf(stderr, "ORBextractor(b200)::operator(): %s\n", eorb_last_error());
@@ -83,16 +109,16 @@ int ORBextractor::extract(cv::InputArray _image, std::vector<cv::KeyPoint>& _key
 int ORBextractor::operator()( cv::InputArray _image, cv::InputArray /*_mask*/, std::vector<cv::KeyPoint>& _keypoints,
                               cv::OutputArray _descriptors, std::vector<int> &vLappingArea)
 {
-    cv::Mat dummy;
-    int ret = extract(_image, _keypoints, &dummy, vLappingArea);
-    if (_image.empty() || !mpHandle) return ret;
+    std::vector<unsigned char> scratch;                        // per call: two threads may drive one extractor
+    int ret = extract(_image, _keypoints, &scratch, vLappingArea);
+    if (_image.empty() || ret < 0) return ret;
     const int n = (int)_keypoints.size();
     if (n == 0) {
         _descriptors.release();                                // ORBextractor.cc:1114-1115
     } else {
         _descriptors.create(n, DEF_DESC_LEN, CV_8U);
         cv::Mat d = _descriptors.getMat();
-        for (int i = 0; i < n; i++) std::memcpy(d.ptr<unsigned char>(i), &mScratchDesc[(size_t)i * DEF_DESC_LEN], DEF_DESC_LEN);
+        for (int i = 0; i < n; i++) std::memcpy(d.ptr<unsigned char>(i), &scratch[(size_t)i * DEF_DESC_LEN], DEF_DESC_LEN);
     }
     return ret;
 }
@@ -105,6 +131,7 @@ int ORBextractor::operator()( cv::InputArray _image, cv::InputArray /*_mask*/, s
 
 void ORBextractor::AssignKPtLevelByBestDesc(const cv::Mat &refDescs, const cv::Mat &trackedImage, std::vector<cv::KeyPoint> &trackedKPts)
 {
+    eorb_orb* mpHandle = trackedImage.empty() ? nullptr : handle();
     if (trackedImage.empty() || !mpHandle)
         return;
     const int n = (int)trackedKPts.size();
@@ -117,6 +144,7 @@ void ORBextractor::AssignKPtLevelByBestDesc(const cv::Mat &refDescs, const cv::M
 
 void ORBextractor::ComputeTrackedKPtsDesc(const cv::Mat &trackedImage, const std::vector<cv::KeyPoint> &trackedKPts, cv::Mat &refDescs)
 {
+    eorb_orb* mpHandle = trackedImage.empty() ? nullptr : handle();
     if (trackedImage.empty() || !mpHandle)
         return;
     const int n = (int)trackedKPts.size();

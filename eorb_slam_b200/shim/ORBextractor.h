@@ -6,9 +6,13 @@
 
 #include <vector>
 #include <list>
+#include <map>
+#include <mutex>
+#include <thread>
 #include <opencv2/core/core.hpp>
 
 struct eorb_orb;
+struct eorb_orb_params;
 
 namespace ORB_SLAM3
 {
@@ -55,7 +59,8 @@ public:
     std::vector<float> inline GetScaleSigmaSquares() { return mvLevelSigma2; }
     std::vector<float> inline GetInverseScaleSigmaSquares() { return mvInvLevelSigma2; }
 
-    // Filled lazily (device -> host) after every call; Frame::ComputeStereoMatches reads it (Frame.cc:876,966-985).
+    // Device -> host copy of the pyramid after a call, only when mbDownloadPyramid is set: the one reader is
+    // Frame::ComputeStereoMatches (Frame.cc:876,966-985), i.e. rectified-stereo frames.
     std::vector<cv::Mat> mvImagePyramid;
 
     int GetNumFeatures() const { return nfeatures; }
@@ -63,11 +68,19 @@ public:
     void AssignKPtLevelByBestDesc(const cv::Mat& refDescs, const cv::Mat& trackedImage, std::vector<cv::KeyPoint>& trackedKPts);
     void ComputeTrackedKPtsDesc(const cv::Mat& trackedImage, const std::vector<cv::KeyPoint>& trackedKPts, cv::Mat& refDescs);
 
-    // When false, mvImagePyramid is not downloaded after operator() (monocular callers never read it).
-    bool mbDownloadPyramid = true;
+    // ---- additions of this implementation (not in the reference header) ----------------------------------------------
+    // mvImagePyramid is downloaded after operator() only when set.  Off by default: monocular, RGB-D and event frames never read
+    // it (Frame.cc:327), and the copy is 1.1 MB per 752x480 call; the rectified-stereo Frame constructor sets it on its two
+    // extractors.
+    bool mbDownloadPyramid = false;
+    // CUDA device of the handles created after the call (default: $EORB_DEVICE, else 0).  Handles are created lazily, one per
+    // calling thread and extractor, on first use: constructing an extractor touches no device, and two threads may drive the same
+    // extractor object at once (the reference's left / right extractors run in two threads, Frame.cc:146-149).
+    static void SetDevice(int device);
+    static int GetDevice();
 
 protected:
-    int extract(cv::InputArray image, std::vector<cv::KeyPoint>& kps, cv::Mat* desc, std::vector<int>& lap);
+    int extract(cv::InputArray image, std::vector<cv::KeyPoint>& kps, std::vector<unsigned char>* desc, std::vector<int>& lap);
     void downloadPyramid();
 
     int nfeatures;
@@ -82,8 +95,10 @@ protected:
     std::vector<float> mvLevelSigma2;
     std::vector<float> mvInvLevelSigma2;
 
-    eorb_orb* mpHandle;
-    std::vector<unsigned char> mScratchDesc;
+    eorb_orb* handle();                                   // the calling thread's device handle (created on first use)
+    eorb_orb_params* mpParams;                            // the constructor's parameters, kept for lazy handle creation
+    std::mutex mHandleMutex;
+    std::map<std::thread::id, eorb_orb*> mHandles;
 };
 
 } //namespace ORB_SLAM3

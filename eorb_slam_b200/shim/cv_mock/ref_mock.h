@@ -69,10 +69,10 @@ public:
 class ORBmatcher {   // the members this path touches (ORBmatcher.h:39-42, 67-68, 96-113)
 public:
     int SearchForInitialization(Frame& F1, Frame& F2, std::vector<cv::Point2f>& vbPrevMatched, std::vector<int>& vnMatches12, int windowSize = 10);
-    int SearchByProjection(Frame& CurrentFrame, const Frame& LastFrame, const float th, const bool bMono);
+    int SearchByProjection(Frame &CurrentFrame, const Frame &LastFrame, float th, bool bMono);
     int SearchByBoW(KeyFrame* pKF, Frame& F, std::vector<MapPoint*>& vpMapPointMatches);
-    int SearchByProjection(Frame& F, const std::vector<MapPoint*>& vpMapPoints, const float th = 3, const bool bFarPoints = false,
-                           const float thFarPoints = 50.0f);
+    int SearchByProjection(Frame &F, const std::vector<MapPoint*> &vpMapPoints, float th=3,
+            bool bFarPoints = false, float thFarPoints = 50.0f);
     explicit ORBmatcher(float nnratio = 0.6, bool checkOri = true) : mfNNratio(nnratio), mbCheckOrientation(checkOri) {}
     static int DescriptorDistance(const cv::Mat& a, const cv::Mat& b);
     static const int TH_LOW;

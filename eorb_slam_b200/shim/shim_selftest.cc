@@ -4,6 +4,8 @@
 #include <cstdio>
 #include <cmath>
 #include <cstdlib>
+#include <cstring>
+#include <thread>
 #include <vector>
 
 #include "ORBextractor.h"
@@ -21,6 +23,7 @@ int main(int argc, char** argv)
     for (int y = 0; y < H; y++) for (int x = 0; x < W; x++) { s = s * 1664525u + 1013904223u; im.at<unsigned char>(y, x) = (unsigned char)(((x / 24 + y / 24) & 1) * 90 + 60 + (s >> 28)); }
     ORB_SLAM3::ORBxParams par(1000, 1.2f, 8, 20, 7, 19, cv::Size(W, H));
     ORB_SLAM3::ORBextractor ex(par);
+    ex.mbDownloadPyramid = true;      // as the rectified-stereo Frame constructor does (ComputeStereoMatches reads mvImagePyramid)
     std::vector<cv::KeyPoint> kps, kps2;
     cv::Mat desc, mask;
     std::vector<int> lap = {0, 1000};
@@ -30,6 +33,20 @@ int main(int argc, char** argv)
                 ret2, kps2.size(), ex.GetLevels(), ex.mvImagePyramid[0].cols, ex.mvImagePyramid[0].rows);
     cv::Mat empty;
     std::printf("empty_ret=%d\n", ex(empty, mask, kps2, lap));
+    {   // two threads drive ONE extractor object at once: each gets its own device handle, results are those of the serial call
+        std::vector<cv::KeyPoint> ka, kb;
+        cv::Mat da, db;
+        int ra = -2, rb = -2;
+        std::thread ta([&] { std::vector<int> l = {0, 1000}; cv::Mat m; for (int i = 0; i < 3; i++) ra = ex(im, m, ka, da, l); });
+        std::thread tb([&] { std::vector<int> l = {0, 1000}; cv::Mat m; for (int i = 0; i < 3; i++) rb = ex(im, m, kb, db, l); });
+        ta.join(); tb.join();
+        bool same = ra == ret && rb == ret && ka.size() == kps.size() && kb.size() == kps.size() && da.rows == desc.rows && db.rows == desc.rows;
+        for (size_t i = 0; same && i < kps.size(); i++)
+            same = ka[i].pt.x == kps[i].pt.x && ka[i].pt.y == kps[i].pt.y && kb[i].pt.x == kps[i].pt.x && kb[i].angle == kps[i].angle &&
+                   std::memcmp(da.ptr<unsigned char>((int)i), desc.ptr<unsigned char>((int)i), 32) == 0 &&
+                   std::memcmp(db.ptr<unsigned char>((int)i), desc.ptr<unsigned char>((int)i), 32) == 0;
+        std::printf("threads_equal=%d\n", same ? 1 : 0);
+    }
     if (desc.rows >= 2) {
         std::printf("dist01=%d\n", ORB_SLAM3::ORBmatcher::DescriptorDistance(desc.row(0), desc.row(1)));
         ORB_SLAM3::BruteForceBest2 bf(0.9f, true);

@@ -115,6 +115,10 @@ int eorb_orb_synchronize(eorb_orb* h);
  * (ORBextractor.h:83-101), mnFeaturesPerLevel and the per-instance EDGE_THRESHOLD.  Any pointer may be NULL. */
 int eorb_orb_tables(const eorb_orb* h, int* nlevels, int* edge_threshold, float* scale, float* inv_scale,
                     float* sigma2, float* inv_sigma2, int* features_per_level);
+/* the same tables straight from the parameters: host arithmetic only (the constructor's, ORBextractor.cc:420-489), no device and no
+ * handle needed -- lets ORBextractor::ORBextractor fill its tables on any thread and create device handles lazily per calling thread */
+int eorb_orb_params_tables(const eorb_orb_params* params, int* nlevels, int* edge_threshold, float* scale, float* inv_scale,
+                           float* sigma2, float* inv_sigma2, int* features_per_level);
 /* capacity a caller must provide per frame of w x hgt pixels: per level max(quota + 3, 4 * nIni) keypoints, nIni = round of the
  * level's aspect ratio (the octree's first pass yields up to 4 children per root, ORBextractor.cc:562-563, 620-683).
  * eorb_orb_max_keypoints: the same for the size of the last extracted frames, before the first call for the (imW, imH) of the

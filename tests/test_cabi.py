@@ -68,3 +68,21 @@ def test_no_cpu_fallback_without_device():
         api.ORBmatcher(0.7)
     with pytest.raises(api.EorbError):
         api.EvImConverter()
+
+
+def test_constructor_tables_need_no_gpu():
+    """eorb_orb_params_tables = ORBextractor::ORBextractor's host arithmetic (ORBextractor.cc:420-489) without a device or a handle;
+    equals the oracle's (= the reference's, tests/test_ref_pin.py) tables"""
+    import oracle_lib as O
+    from eorb_slam_b200 import api
+    for (nf, sf, nl, edge, w, h) in [(1000, 1.2, 8, 19, 752, 480), (400, 1.0, 1, 9, 240, 180), (2500, 1.26, 6, -1, 863, 517), (1, 1.5, 2, 25, 300, 200)]:
+        p = api._OrbParams(nf, sf, nl, 20, 7, edge, w, h)
+        n = C.c_int(0); e = C.c_int(0)
+        arrs = [np.zeros(nl, np.float32) for _ in range(4)]; fpl = np.zeros(nl, np.int32)
+        rc = api.lib.eorb_orb_params_tables(C.byref(p), C.byref(n), C.byref(e), *[a.ctypes.data_as(C.c_void_p) for a in arrs],
+                                            fpl.ctypes.data_as(C.c_void_p))
+        assert rc == 0 and n.value == nl
+        orc = O.OrbOracle(nf, sf, nl, 20, 7, edge, w, h)
+        assert e.value == orc.edge and list(fpl) == list(orc.features_per_level())
+        for a, b in zip(arrs, orc.scale_factors()):
+            assert a.tobytes() == b.tobytes()

@@ -16,7 +16,7 @@ EXE = os.path.join(SHIM, "_shim_selftest")
 def _build():
     srcs = [os.path.join(SHIM, f) for f in ("shim_selftest.cc", "ORBextractor.cc", "ORBmatcher_b200.cc", "EventConversion_b200.cc", "KLT_b200.cc", "ORBmatcher_guided_b200.cc", "ORBVocabulary_b200.cc")]
     cmd = ["g++", "-std=c++17", "-O1", "-DEORB_SHIM_MOCK", "-I" + os.path.join(SHIM, "cv_mock"), "-I" + SHIM,
-           "-I" + os.path.join(ROOT, "include"), "-o", EXE] + srcs + ["-L" + os.path.join(ROOT, "eorb_slam_b200"), "-leorb_b200",
+           "-I" + os.path.join(ROOT, "include"), "-pthread", "-o", EXE] + srcs + ["-L" + os.path.join(ROOT, "eorb_slam_b200"), "-leorb_b200",
                                                                       "-Wl,-rpath," + os.path.join(ROOT, "eorb_slam_b200")]
     subprocess.check_call(cmd)
 
@@ -63,6 +63,7 @@ def test_shims_match_oracle_on_gpu():
     oret, okps, odesc = O.OrbOracle().extract(_lcg_image())
     assert (ret, n, drows, ret2, n2, levels, pw, ph) == (oret, len(okps), len(okps), oret, len(okps), 8, 752, 480)
     assert "empty_ret=-1" in out
+    assert "threads_equal=1" in out, "two threads on one extractor object (a device handle per calling thread)"
     d01 = int(re.search(r"dist01=(\d+)", out).group(1))
     assert d01 == O.descriptor_distance(odesc[0], odesc[1])
     sm = re.search(r"selfmatch=(\d+) of (\d+)", out)
