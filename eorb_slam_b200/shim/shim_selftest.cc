@@ -37,6 +37,7 @@ int main(int argc, char** argv)
         std::vector<cv::KeyPoint> ka, kb;
         cv::Mat da, db;
         int ra = -2, rb = -2;
+        ex.mbDownloadPyramid = false;   // mvImagePyramid is ONE public member per extractor: concurrent callers must not ask for it
         std::thread ta([&] { std::vector<int> l = {0, 1000}; cv::Mat m; for (int i = 0; i < 3; i++) ra = ex(im, m, ka, da, l); });
         std::thread tb([&] { std::vector<int> l = {0, 1000}; cv::Mat m; for (int i = 0; i < 3; i++) rb = ex(im, m, kb, db, l); });
         ta.join(); tb.join();
