@@ -172,6 +172,18 @@ int orc_search_for_initialization(const orc_keypoint* kps1, const uint8_t* desc1
 int orc_search_by_projection(const float* x3Dc, const uint8_t* valid1, const int32_t* obs1, const orc_keypoint* kps1,
                              const uint8_t* descMP, int n1, const orc_keypoint* kps2, const uint8_t* desc2, int n2, const float* bounds4,
                              const float* K4, const float* scale_factors, int nlevels, float th, int check_ori, int32_t* match_cur) {
+    return orc_search_by_projection_ex(x3Dc, valid1, obs1, kps1, descMP, n1, kps2, desc2, n2, bounds4, K4, scale_factors, nlevels, th, check_ori,
+                                       0, 0.f, nullptr, match_cur);
+}
+
+// The same with the rectified-stereo branches (Nleft == -1, mvuRight set): level_mode = 1 when bForward, 2 when bBackward
+// (tlc.z against the baseline mb, :1989-1990; only for !bMono), which turn the level window [oct-1, oct+1] into [oct, inf) /
+// [0, oct] (:2024-2029); u_right2 = CurrentFrame.mvuRight (n2 floats, null for a monocular frame) and mbf = CurrentFrame.mbf: a
+// candidate with a right coordinate is dropped when |(u - mbf * invzc) - uRight| > radius (:2049-2055).
+int orc_search_by_projection_ex(const float* x3Dc, const uint8_t* valid1, const int32_t* obs1, const orc_keypoint* kps1,
+                                const uint8_t* descMP, int n1, const orc_keypoint* kps2, const uint8_t* desc2, int n2, const float* bounds4,
+                                const float* K4, const float* scale_factors, int nlevels, float th, int check_ori, int level_mode, float mbf,
+                                const float* u_right2, int32_t* match_cur) {
     const int TH_HIGH = 100, HISTO_LENGTH = 30;
     const GridGeom g(bounds4);
     std::vector<int> cellStart(GC * GR + 1), cellIdx(std::max(n2, 1));
@@ -192,12 +204,19 @@ int orc_search_by_projection(const float* x3Dc, const uint8_t* valid1, const int
         const int oct = kps1[i].octave;
         const int lv = oct < 0 ? 0 : (oct >= nlevels ? nlevels - 1 : oct);
         const float radius = th * scale_factors[lv];
-        featuresInArea(kps2, g, cellStart.data(), cellIdx.data(), u, v, radius, oct - 1, oct + 1, vIndices2);
+        if (level_mode == 1) featuresInArea(kps2, g, cellStart.data(), cellIdx.data(), u, v, radius, oct, -1, vIndices2);
+        else if (level_mode == 2) featuresInArea(kps2, g, cellStart.data(), cellIdx.data(), u, v, radius, 0, oct, vIndices2);
+        else featuresInArea(kps2, g, cellStart.data(), cellIdx.data(), u, v, radius, oct - 1, oct + 1, vIndices2);
         if (vIndices2.empty()) continue;
         const uint8_t* dMP = descMP + (size_t)i * 32;
         int bestDist = 256, bestIdx2 = -1;
         for (int i2 : vIndices2) {
             if (match_cur[i2] >= 0 && obs1[match_cur[i2]] > 0) continue;
+            if (u_right2 && u_right2[i2] > 0) {
+                const float ur = u - mbf * invzc;
+                const float er = std::fabs(ur - u_right2[i2]);
+                if (er > radius) continue;
+            }
             const int dist = orc_descriptor_distance(dMP, desc2 + (size_t)i2 * 32);
             if (dist < bestDist) { bestDist = dist; bestIdx2 = i2; }
         }
@@ -244,6 +263,16 @@ int orc_search_by_projection_map_points(const orc_track_point* pts, const uint8_
                                         const uint8_t* desc2, const uint8_t* held2, int n2, const float* bounds4,
                                         const float* scale_factors, int nlevels, float th, int far_points, float th_far, float nnratio,
                                         int32_t* match_cur) {
+    return orc_search_by_projection_map_points_ex(pts, nullptr, descMP, n1, kps2, desc2, held2, nullptr, n2, bounds4, scale_factors, nlevels, th,
+                                                  far_points, th_far, nnratio, match_cur);
+}
+
+// The same with the rectified-stereo test (:91-96): proj_xr[i] = mTrackProjXR of map point i, u_right2 = F.mvuRight; a candidate
+// with a right coordinate is dropped when |mTrackProjXR - uRight| > r * mvScaleFactors[level].
+int orc_search_by_projection_map_points_ex(const orc_track_point* pts, const float* proj_xr, const uint8_t* descMP, int n1,
+                                           const orc_keypoint* kps2, const uint8_t* desc2, const uint8_t* held2, const float* u_right2, int n2,
+                                           const float* bounds4, const float* scale_factors, int nlevels, float th, int far_points,
+                                           float th_far, float nnratio, int32_t* match_cur) {
     const int TH_HIGH = 100;
     const GridGeom g(bounds4);
     std::vector<int> cellStart(GC * GR + 1), cellIdx(std::max(n2, 1));
@@ -268,6 +297,10 @@ int orc_search_by_projection_map_points(const orc_track_point* pts, const uint8_
         int bestDist = 256, bestLevel = -1, bestDist2 = 256, bestLevel2 = -1, bestIdx = -1;
         for (int idx : vIndices) {
             if (match_cur[idx] >= 0 ? pts[match_cur[idx]].observations > 0 : (held2 && held2[idx])) continue;
+            if (u_right2 && proj_xr && u_right2[idx] > 0) {
+                const float er = std::fabs(proj_xr[iMP] - u_right2[idx]);
+                if (er > r * scale_factors[lv]) continue;
+            }
             const int dist = orc_descriptor_distance(dMP, desc2 + (size_t)idx * 32);
             if (dist < bestDist) {
                 bestDist2 = bestDist; bestDist = dist; bestLevel2 = bestLevel; bestLevel = kps2[idx].octave; bestIdx = idx;
@@ -279,6 +312,75 @@ int orc_search_by_projection_map_points(const orc_track_point* pts, const uint8_
             if (bestLevel == bestLevel2 && bestDist > nnratio * bestDist2) continue;
             match_cur[bestIdx] = iMP;
             nmatches++;
+        }
+    }
+    return nmatches;
+}
+
+// ORBmatcher::SearchByProjection(Frame& CurrentFrame, KeyFrame* pKF, const set<MapPoint*>& sAlreadyFound, float th, int ORBdist)
+// (src/ORBmatcher.cc:2189-2312; Tracking::Relocalization, src/Tracking-1.cc:2700-2730 after the PnP refinement).  Per keyframe map point
+// in index order: present, not bad, not already found (valid1, formed by the caller); projection WITHOUT a depth-sign test (:2218,
+// unlike the frame-to-frame search) and the image-bounds test (:2220-2223); the distance-invariance gate and PredictScale (:2226-2237)
+// are host arithmetic on the map point and arrive as level1[i] (valid1[i] = 0 when the gate fails); window th * scale[level],
+// levels [level-1, level+1] (:2240-2242); best distance over the candidates whose slot holds NO map point at all (:2253-2254: held on
+// entry or set earlier in this call); accepted when <= ORBdist (:2266); rotation histogram of the keyframe keypoint's angle against the
+// frame keypoint's (:2273-2281) and the three-maxima filter (:2287-2308).
+int orc_search_by_projection_reloc(const float* x3Dc, const uint8_t* valid1, const int32_t* level1, const orc_keypoint* kps1,
+                                   const uint8_t* descMP, int n1, const orc_keypoint* kps2, const uint8_t* desc2, const uint8_t* held2, int n2,
+                                   const float* bounds4, const float* K4, const float* scale_factors, int nlevels, float th, int orb_dist,
+                                   int check_ori, int32_t* match_cur) {
+    const int HISTO_LENGTH = 30;
+    const GridGeom g(bounds4);
+    std::vector<int> cellStart(GC * GR + 1), cellIdx(std::max(n2, 1));
+    orc_frame_grid(kps2, n2, bounds4, cellStart.data(), cellIdx.data());
+    for (int i = 0; i < n2; i++) match_cur[i] = -1;
+    int nmatches = 0;
+    std::vector<int> rotHist[HISTO_LENGTH];
+    const float factor = 1.0f / HISTO_LENGTH;
+    std::vector<int> vIndices2;
+    for (int i = 0; i < n1; i++) {
+        if (!valid1[i]) continue;
+        const float xc = x3Dc[3 * i], yc = x3Dc[3 * i + 1], zc = x3Dc[3 * i + 2];
+        const float u = K4[0] * xc / zc + K4[2], v = K4[1] * yc / zc + K4[3];
+        if (u < bounds4[0] || u > bounds4[2]) continue;
+        if (v < bounds4[1] || v > bounds4[3]) continue;
+        const int lvl = level1[i];
+        const int lv = lvl < 0 ? 0 : (lvl >= nlevels ? nlevels - 1 : lvl);
+        const float radius = th * scale_factors[lv];
+        featuresInArea(kps2, g, cellStart.data(), cellIdx.data(), u, v, radius, lvl - 1, lvl + 1, vIndices2);
+        if (vIndices2.empty()) continue;
+        const uint8_t* dMP = descMP + (size_t)i * 32;
+        int bestDist = 256, bestIdx2 = -1;
+        for (int i2 : vIndices2) {
+            if (match_cur[i2] >= 0 || (held2 && held2[i2])) continue;
+            const int dist = orc_descriptor_distance(dMP, desc2 + (size_t)i2 * 32);
+            if (dist < bestDist) { bestDist = dist; bestIdx2 = i2; }
+        }
+        if (bestDist <= orb_dist) {
+            match_cur[bestIdx2] = i;
+            nmatches++;
+            if (check_ori) {
+                float rot = kps1[i].angle - kps2[bestIdx2].angle;
+                if (rot < 0.0) rot += 360.0f;
+                int bin = (int)std::round(rot * factor);
+                if (bin == HISTO_LENGTH) bin = 0;
+                rotHist[bin].push_back(bestIdx2);
+            }
+        }
+    }
+    if (check_ori) {
+        int max1 = 0, max2 = 0, max3 = 0, ind1 = -1, ind2 = -1, ind3 = -1;
+        for (int i = 0; i < HISTO_LENGTH; i++) {
+            const int s = (int)rotHist[i].size();
+            if (s > max1) { max3 = max2; max2 = max1; max1 = s; ind3 = ind2; ind2 = ind1; ind1 = i; }
+            else if (s > max2) { max3 = max2; max2 = s; ind3 = ind2; ind2 = i; }
+            else if (s > max3) { max3 = s; ind3 = i; }
+        }
+        if (max2 < 0.1f * (float)max1) { ind2 = -1; ind3 = -1; }
+        else if (max3 < 0.1f * (float)max1) { ind3 = -1; }
+        for (int i = 0; i < HISTO_LENGTH; i++) {
+            if (i != ind1 && i != ind2 && i != ind3)
+                for (int idx : rotHist[i]) { match_cur[idx] = -1; nmatches--; }
         }
     }
     return nmatches;

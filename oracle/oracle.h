@@ -132,6 +132,20 @@ int   orc_search_by_projection(const float* x3Dc, const uint8_t* valid1, const i
                                const float* bounds4, const float* K4, const float* scale_factors, int nlevels, float th, int check_ori,
                                int32_t* match_cur);
 
+/* the same with the rectified-stereo branches (:1989-1990, 2024-2029, 2049-2055): level_mode 0 = [oct-1, oct+1], 1 = bForward [oct, inf),
+   2 = bBackward [0, oct]; u_right2 = CurrentFrame.mvuRight (n2 floats or NULL), mbf = CurrentFrame.mbf */
+int   orc_search_by_projection_ex(const float* x3Dc, const uint8_t* valid1, const int32_t* obs1, const orc_keypoint* kps1,
+                                  const uint8_t* descMP, int n1, const orc_keypoint* kps2, const uint8_t* desc2, int n2,
+                                  const float* bounds4, const float* K4, const float* scale_factors, int nlevels, float th, int check_ori,
+                                  int level_mode, float mbf, const float* u_right2, int32_t* match_cur);
+/* ORBmatcher::SearchByProjection(CurrentFrame, pKF, sAlreadyFound, th, ORBdist) (ORBmatcher.cc:2189-2312; Tracking::Relocalization):
+   valid1 = keyframe map point present, not bad, not already found, inside its distance invariance; level1 = its predicted scale level;
+   held2 (may be null) = slots of the frame that hold any map point on entry */
+int   orc_search_by_projection_reloc(const float* x3Dc, const uint8_t* valid1, const int32_t* level1, const orc_keypoint* kps1,
+                                     const uint8_t* descMP, int n1, const orc_keypoint* kps2, const uint8_t* desc2, const uint8_t* held2, int n2,
+                                     const float* bounds4, const float* K4, const float* scale_factors, int nlevels, float th, int orb_dist,
+                                     int check_ori, int32_t* match_cur);
+
 /* ORBmatcher::SearchByProjection(F, vpMapPoints, th, bFarPoints, thFarPoints) (ORBmatcher.cc:44-218), monocular frame.
    orc_track_point = the MapPoint fields Frame::isInFrustum fills (mTrackProjX/Y, mTrackViewCos, mTrackDepth, mnTrackScaleLevel,
    mbTrackInView) + Observations() + isBad(); held2 (may be null) = slots of F that hold a point with observations on entry;
@@ -145,6 +159,12 @@ int   orc_search_by_projection_map_points(const orc_track_point* pts, const uint
                                           const uint8_t* desc2, const uint8_t* held2, int n2, const float* bounds4,
                                           const float* scale_factors, int nlevels, float th, int far_points, float th_far,
                                           float nnratio, int32_t* match_cur);
+
+/* the same with the rectified-stereo test (:91-96): proj_xr = mTrackProjXR per map point, u_right2 = F.mvuRight (either may be NULL) */
+int   orc_search_by_projection_map_points_ex(const orc_track_point* pts, const float* proj_xr, const uint8_t* descMP, int n1,
+                                             const orc_keypoint* kps2, const uint8_t* desc2, const uint8_t* held2, const float* u_right2, int n2,
+                                             const float* bounds4, const float* scale_factors, int nlevels, float th, int far_points,
+                                             float th_far, float nnratio, int32_t* match_cur);
 
 /* ORBmatcher::SearchByBoW(pKF, F, vpMapPointMatches) (ORBmatcher.cc:276-478), monocular; FeatureVectors in the CSR form of
    orc_vocab_transform; valid_kf = keyframe map point present and not bad; match_f[n2] = keyframe feature index or -1 */

@@ -13,6 +13,7 @@ public:
     explicit GeometricCamera(std::vector<float> p) : mvParameters(std::move(p)) {}
     virtual ~GeometricCamera() = default;
     virtual cv::Point2f project(const cv::Point3f& p3D) = 0;
+    virtual cv::Point2f project(const cv::Mat& m3D) = 0;
     virtual Eigen::Vector2d project(const Eigen::Vector3d& v3D) = 0;
     virtual cv::Point3f unproject(const cv::Point2f& p2D) = 0;
     virtual Eigen::Matrix<double, 2, 3> projectJac(const Eigen::Vector3d& v3D) = 0;

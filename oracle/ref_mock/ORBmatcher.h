@@ -1,15 +1,33 @@
 // oracle/ref_mock/ORBmatcher.h — TEST INFRASTRUCTURE ONLY.
-// Stand-in for the reference's include/ORBmatcher.h, found first on the include path when src/ORBextractor.cc (compiled
-// unmodified into oracle/_ref) says #include "ORBmatcher.h".  The real header drags in Frame/KeyFrame/MapPoint/g2o/DBoW2;
-// ORBextractor.cc uses one static member of it (ORBextractor.cc:1305), declared here with the reference's signature
-// (include/ORBmatcher.h:42).  Its BODY is the reference's own text: oracle/Makefile cuts ORBmatcher.cc:2360-2378 out of
-// the reference source at build time into oracle/_ref/gen_descriptor_distance.inc.
+// Stand-in for the reference's include/ORBmatcher.h, found first on the include path when src/ORBextractor.cc (compiled unmodified
+// into oracle/_ref) says #include "ORBmatcher.h".  The real header drags in g2o / DBoW2 / the whole map; this one declares, with the
+// reference's signatures (include/ORBmatcher.h:35-114), the members whose BODIES the Makefile cuts out of src/ORBmatcher.cc at build
+// time: DescriptorDistance :2360-2378 (_ref/gen_descriptor_distance.inc) and the tracking-thread searches, RadiusByViewingCos and
+// ComputeThreeMaxima (_ref/gen_matcher.inc: :44-227, :276-478, :714-831, :1969-2187, :2189-2312, :2314-2355).
 #pragma once
+#include <set>
+#include <vector>
 #include <opencv2/core/core.hpp>
+#include "Frame.h"
 
 namespace ORB_SLAM3 {
 class ORBmatcher {
 public:
+    ORBmatcher(float nnratio = 0.6, bool checkOri = true) : mfNNratio(nnratio), mbCheckOrientation(checkOri) {}
     static int DescriptorDistance(const cv::Mat& a, const cv::Mat& b);
+    int SearchByProjection(Frame& F, const std::vector<MapPoint*>& vpMapPoints, const float th = 3, const bool bFarPoints = false,
+                           const float thFarPoints = 50.0f);
+    int SearchByProjection(Frame& CurrentFrame, const Frame& LastFrame, const float th, const bool bMono);
+    int SearchByProjection(Frame& CurrentFrame, KeyFrame* pKF, const std::set<MapPoint*>& sAlreadyFound, const float th, const int ORBdist);
+    int SearchByBoW(KeyFrame* pKF, Frame& F, std::vector<MapPoint*>& vpMapPointMatches);
+    int SearchForInitialization(Frame& F1, Frame& F2, std::vector<cv::Point2f>& vbPrevMatched, std::vector<int>& vnMatches12, int windowSize = 10);
+    static const int TH_LOW;
+    static const int TH_HIGH;
+    static const int HISTO_LENGTH;
+protected:
+    float RadiusByViewingCos(const float& viewCos);
+    void ComputeThreeMaxima(std::vector<int>* histo, const int L, int& ind1, int& ind2, int& ind3);
+    float mfNNratio;
+    bool mbCheckOrientation;
 };
 }  // namespace ORB_SLAM3

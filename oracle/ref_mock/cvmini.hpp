@@ -191,6 +191,12 @@ public:
     }
     inline void copyTo(OutputArray dst) const;
     inline void convertTo(OutputArray dst, int rtype, double alpha = 1, double beta = 0) const;
+    Mat t() const {
+        if (flags != CV_32F) CVMINI_FAIL("Mat::t");
+        Mat r(cols, rows, CV_32F);
+        for (int y = 0; y < rows; y++) for (int x = 0; x < cols; x++) r.at<float>(x, y) = at<float>(y, x);
+        return r;
+    }
     Mat mul(const Mat& o) const {
         if (flags != CV_32F || o.flags != CV_32F || rows != o.rows || cols != o.cols) CVMINI_FAIL("Mat::mul");
         Mat r(rows, cols, CV_32F);
@@ -223,6 +229,40 @@ private:
     std::shared_ptr<uchar> buf_;
     int bufRows_ = 0;
 };
+// ---- the little matrix algebra the matcher functions use on 3x3 / 3x1 / 4x4 CV_32F matrices (Rcw * x3Dw + tcw, -Rcw.t() * tcw,
+// cv::norm): cv::gemm accumulates 32-bit products in double and rounds once (GEMMSingleMul<float, double>)
+static inline Mat operator*(const Mat& a, const Mat& b) {
+    if (a.type() != CV_32F || b.type() != CV_32F || a.cols != b.rows) CVMINI_FAIL("Mat * Mat");
+    Mat r(a.rows, b.cols, CV_32F);
+    for (int i = 0; i < a.rows; i++)
+        for (int j = 0; j < b.cols; j++) {
+            double acc = 0;
+            for (int k = 0; k < a.cols; k++) acc += (double)a.at<float>(i, k) * (double)b.at<float>(k, j);
+            r.at<float>(i, j) = (float)acc;
+        }
+    return r;
+}
+static inline Mat matAddSub(const Mat& a, const Mat& b, float sb) {
+    if (a.type() != CV_32F || b.type() != CV_32F || a.rows != b.rows || a.cols != b.cols) CVMINI_FAIL("Mat +/- Mat");
+    Mat r(a.rows, a.cols, CV_32F);
+    for (int i = 0; i < a.rows; i++) for (int j = 0; j < a.cols; j++) r.at<float>(i, j) = a.at<float>(i, j) + sb * b.at<float>(i, j);
+    return r;
+}
+static inline Mat operator+(const Mat& a, const Mat& b) { return matAddSub(a, b, 1.f); }
+static inline Mat operator-(const Mat& a, const Mat& b) { return matAddSub(a, b, -1.f); }
+static inline Mat operator-(const Mat& a) {
+    if (a.type() != CV_32F) CVMINI_FAIL("-Mat");
+    Mat r(a.rows, a.cols, CV_32F);
+    for (int i = 0; i < a.rows; i++) for (int j = 0; j < a.cols; j++) r.at<float>(i, j) = -a.at<float>(i, j);
+    return r;
+}
+static inline double norm(const Mat& a) {
+    if (a.type() != CV_32F) CVMINI_FAIL("norm");
+    double s = 0;
+    for (int i = 0; i < a.rows; i++) for (int j = 0; j < a.cols; j++) s += (double)a.at<float>(i, j) * (double)a.at<float>(i, j);
+    return std::sqrt(s);
+}
+
 static inline std::ostream& operator<<(std::ostream& os, const Mat& m) { return os << "Mat(" << m.rows << "x" << m.cols << ")"; }
 
 class _InputArray {

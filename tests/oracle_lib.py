@@ -403,6 +403,61 @@ def search_by_projection(x3Dc, valid1, obs1, kps1, descMP, kps2, desc2, bounds, 
     return n, mc[:len(k2)].copy()
 
 
+def _guided_args(kps1, kps2, descMP, desc2, bounds, scale_factors):
+    k1 = np.ascontiguousarray(kps1, KEYPOINT_DTYPE); k2 = np.ascontiguousarray(kps2, KEYPOINT_DTYPE)
+    dm = np.ascontiguousarray(descMP, np.uint8); d2 = np.ascontiguousarray(desc2, np.uint8)
+    b = np.ascontiguousarray(bounds, np.float32); sf = np.ascontiguousarray(scale_factors, np.float32)
+    return k1, k2, dm, d2, b, sf
+
+
+def search_by_projection_ex(x3Dc, valid1, obs1, kps1, descMP, kps2, desc2, bounds, K4, scale_factors, th=15.0, check_ori=True, level_mode=0,
+                            mbf=0.0, u_right2=None, L=None, fn="orc_search_by_projection_ex"):
+    """SearchByProjection(CurrentFrame, LastFrame, th, bMono) with the rectified-stereo branches -> (nmatches, match_cur[n2]).
+    L / fn select the library (the oracle by default; tests/ref_lib.py passes libref and the ref_ name)"""
+    L = L or lib()
+    x = np.ascontiguousarray(x3Dc, np.float32).reshape(-1, 3); v = np.ascontiguousarray(valid1, np.uint8); o = np.ascontiguousarray(obs1, np.int32)
+    k1, k2, dm, d2, b, sf = _guided_args(kps1, kps2, descMP, desc2, bounds, scale_factors)
+    K = np.ascontiguousarray(K4, np.float32)
+    ur = None if u_right2 is None else np.ascontiguousarray(u_right2, np.float32)
+    mc = np.full(max(len(k2), 1), -1, np.int32)
+    f = getattr(L, fn); f.restype = C.c_int
+    n = f(_p(x), _p(v), _p(o), _p(k1), _p(dm), C.c_int(len(k1)), _p(k2), _p(d2), C.c_int(len(k2)), _p(b), _p(K), _p(sf), C.c_int(len(sf)),
+          C.c_float(th), C.c_int(int(check_ori)), C.c_int(level_mode), C.c_float(mbf), _p(ur), _p(mc))
+    return n, mc[:len(k2)].copy()
+
+
+def search_by_projection_reloc(x3Dc, valid1, level1, kps1, descMP, kps2, desc2, held2, bounds, K4, scale_factors, th=10.0, orb_dist=100,
+                               check_ori=True, L=None, fn="orc_search_by_projection_reloc"):
+    """SearchByProjection(CurrentFrame, pKF, sAlreadyFound, th, ORBdist) (Tracking::Relocalization) -> (nmatches, match_cur[n2])"""
+    L = L or lib()
+    x = np.ascontiguousarray(x3Dc, np.float32).reshape(-1, 3); v = np.ascontiguousarray(valid1, np.uint8); lv = np.ascontiguousarray(level1, np.int32)
+    k1, k2, dm, d2, b, sf = _guided_args(kps1, kps2, descMP, desc2, bounds, scale_factors)
+    K = np.ascontiguousarray(K4, np.float32)
+    hd = None if held2 is None else np.ascontiguousarray(held2, np.uint8)
+    mc = np.full(max(len(k2), 1), -1, np.int32)
+    f = getattr(L, fn); f.restype = C.c_int
+    n = f(_p(x), _p(v), _p(lv), _p(k1), _p(dm), C.c_int(len(k1)), _p(k2), _p(d2), _p(hd), C.c_int(len(k2)), _p(b), _p(K), _p(sf), C.c_int(len(sf)),
+          C.c_float(th), C.c_int(int(orb_dist)), C.c_int(int(check_ori)), _p(mc))
+    return n, mc[:len(k2)].copy()
+
+
+def search_by_projection_map_points_ex(pts, proj_xr, descMP, kps2, desc2, held2, u_right2, bounds, scale_factors, th=1.0, far_points=False,
+                                       th_far=0.0, nnratio=0.8, L=None, fn="orc_search_by_projection_map_points_ex"):
+    """SearchByProjection(F, vpMapPoints, ...) with the rectified-stereo test -> (nmatches, match_cur[n2])"""
+    from eorb_slam_b200.synth import TRACK_POINT_DTYPE
+    L = L or lib()
+    p = np.ascontiguousarray(pts, TRACK_POINT_DTYPE)
+    _, k2, dm, d2, b, sf = _guided_args(np.zeros(0, KEYPOINT_DTYPE), kps2, descMP, desc2, bounds, scale_factors)
+    hd = None if held2 is None else np.ascontiguousarray(held2, np.uint8)
+    xr = None if proj_xr is None else np.ascontiguousarray(proj_xr, np.float32)
+    ur = None if u_right2 is None else np.ascontiguousarray(u_right2, np.float32)
+    mc = np.full(max(len(k2), 1), -1, np.int32)
+    f = getattr(L, fn); f.restype = C.c_int
+    n = f(_p(p), _p(xr), _p(dm), C.c_int(len(p)), _p(k2), _p(d2), _p(hd), _p(ur), C.c_int(len(k2)), _p(b), _p(sf), C.c_int(len(sf)),
+          C.c_float(th), C.c_int(int(far_points)), C.c_float(th_far), C.c_float(nnratio), _p(mc))
+    return n, mc[:len(k2)].copy()
+
+
 def search_by_projection_map_points(pts, descMP, kps2, desc2, held2, bounds, scale_factors, th=1.0, far_points=False, th_far=0.0,
                                     nnratio=0.8):
     """ORBmatcher::SearchByProjection(F, vpMapPoints, th, bFarPoints, thFarPoints), monocular -> (nmatches, match_cur[n2])"""

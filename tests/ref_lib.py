@@ -199,3 +199,47 @@ def ev_accumulate(evs, w, h, sigma=1.0, mode=1, Tcw=None, depth=1.0, K=None, se2
                                 int(normalize), _p(img), _p(u8))
     assert r >= 0
     return img, (u8 if r == 1 else None)
+
+
+# ----------------------------------------------------------------------------- tracking-thread matchers (ORBmatcher.cc, cut out verbatim)
+def search_by_projection(*a, **kw):
+    return O.search_by_projection_ex(*a, L=lib(), fn="ref_search_by_projection", **kw)
+
+
+def search_by_projection_reloc(*a, **kw):
+    return O.search_by_projection_reloc(*a, L=lib(), fn="ref_search_by_projection_reloc", **kw)
+
+
+def search_by_projection_map_points(*a, **kw):
+    return O.search_by_projection_map_points_ex(*a, L=lib(), fn="ref_search_by_projection_map_points", **kw)
+
+
+def search_for_initialization(kps1, desc1, kps2, desc2, bounds, prev_xy, window_size=100, nnratio=0.9, check_ori=True):
+    k1 = np.ascontiguousarray(kps1, O.KEYPOINT_DTYPE); k2 = np.ascontiguousarray(kps2, O.KEYPOINT_DTYPE)
+    d1 = np.ascontiguousarray(desc1, np.uint8); d2 = np.ascontiguousarray(desc2, np.uint8)
+    b = np.ascontiguousarray(bounds, np.float32); pv = np.ascontiguousarray(prev_xy, np.float32).copy()
+    m12 = np.full(max(len(k1), 1), -1, np.int32)
+    f = lib().ref_search_for_initialization; f.restype = C.c_int
+    n = f(_p(k1), _p(d1), C.c_int(len(k1)), _p(k2), _p(d2), C.c_int(len(k2)), _p(b), _p(pv), C.c_int(window_size), C.c_float(nnratio),
+          C.c_int(int(check_ori)), _p(m12))
+    return n, m12[:len(k1)].copy(), pv
+
+
+def search_by_bow(kps_kf, desc_kf, valid_kf, fv_kf, kps_f, desc_f, fv_f, nnratio=0.7, check_ori=True):
+    k1 = np.ascontiguousarray(kps_kf, O.KEYPOINT_DTYPE); k2 = np.ascontiguousarray(kps_f, O.KEYPOINT_DTYPE)
+    d1 = np.ascontiguousarray(desc_kf, np.uint8); d2 = np.ascontiguousarray(desc_f, np.uint8); v = np.ascontiguousarray(valid_kf, np.uint8)
+    a = [np.ascontiguousarray(fv_kf[0], np.uint32), np.ascontiguousarray(fv_kf[1], np.int32), np.ascontiguousarray(fv_kf[2], np.uint32)]
+    b = [np.ascontiguousarray(fv_f[0], np.uint32), np.ascontiguousarray(fv_f[1], np.int32), np.ascontiguousarray(fv_f[2], np.uint32)]
+    mf = np.full(max(len(k2), 1), -1, np.int32)
+    f = lib().ref_search_by_bow; f.restype = C.c_int
+    n = f(_p(k1), _p(d1), _p(v), _p(a[0]), _p(a[1]), _p(a[2]), C.c_int(len(a[0])), C.c_int(len(k1)), _p(k2), _p(d2), C.c_int(len(k2)), _p(b[0]),
+          _p(b[1]), _p(b[2]), C.c_int(len(b[0])), C.c_float(nnratio), C.c_int(int(check_ori)), _p(mf))
+    return n, mf[:len(k2)].copy()
+
+
+def features_in_area(kps, bounds, x, y, r, min_level=-1, max_level=-1):
+    k = np.ascontiguousarray(kps, O.KEYPOINT_DTYPE); b = np.ascontiguousarray(bounds, np.float32)
+    out = np.zeros(max(len(k), 1), np.int32)
+    f = lib().ref_features_in_area; f.restype = C.c_int
+    n = f(_p(k), C.c_int(len(k)), _p(b), C.c_float(x), C.c_float(y), C.c_float(r), C.c_int(min_level), C.c_int(max_level), _p(out), C.c_int(len(out)))
+    return out[:n].copy()

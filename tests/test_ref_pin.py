@@ -144,3 +144,40 @@ def test_libref_events_vs_oracle_fresh_cases():
             rf, ru = R.ev_accumulate(ev, 346, 260, 1.0, normalize=True, **kw)
             of, _, ou = O.ev_accumulate(ev, 346, 260, 1.0, normalize=True, **kw)
             assert rf.tobytes() == of.tobytes() and np.array_equal(ru, ou), kw
+
+
+# ------------------------------------------------------------------------------------------------ tracking-thread matchers
+def test_oracle_matchers_equal_reference_golden():
+    """SearchByProjection (last frame: mono, forward / backward level windows, rectified-stereo column test; local map: mono and stereo;
+    relocalisation), SearchForInitialization and SearchByBoW: the oracle reproduces every match array the reference's own function
+    bodies produced (tests/golden/ref_guided.npz, 96 cases)"""
+    g = RC.guided_golden()
+    ncase = 0
+    for key, kind, a, kw in RC.guided_cases():
+        r = RC.guided_run(O, kind, a, kw)
+        assert r[0] == int(g[key + "_n"][0]) and np.array_equal(r[1], g[key]), key
+        if kind == "init":
+            assert r[2].tobytes() == g[key + "_prev"].tobytes(), key
+        ncase += 1
+    assert ncase == sum(k.endswith("_n") for k in g.files)
+
+
+def test_libref_matchers_vs_oracle_fresh_cases():
+    R = _ref()
+    g = RC.guided_golden()
+    for j, (key, kind, a, kw) in enumerate(RC.guided_cases()):
+        if j % 5 == 0:                                   # the fixtures are not stale
+            r = RC.guided_run(R, kind, a, kw)
+            assert r[0] == int(g[key + "_n"][0]) and np.array_equal(r[1], g[key]), key
+    rng = np.random.default_rng(77)
+    for seed in (901, 902, 903):                         # cases that are not in the fixtures
+        c = synth.make_projection_case(700, 650, seed, zero_obs_frac=0.2)
+        ur = RC._stereo_u_right(rng, c["kps2"])
+        a = (c["x3Dc"], c["valid1"], c["obs1"], c["kps1"], c["descMP"], c["kps2"], c["desc2"], c["bounds"], c["K"], c["scale_factors"])
+        for mode in (0, 1, 2):
+            kw = dict(th=15.0, check_ori=True, level_mode=mode, mbf=40.0, u_right2=ur)
+            o = O.search_by_projection_ex(*a, **kw); r = R.search_by_projection(*a, **kw)
+            assert o[0] == r[0] and np.array_equal(o[1], r[1]), (seed, mode)
+        cb = RC.bow_case(700, 650, seed, levelsup=2)
+        o = O.search_by_bow(*cb, 0.7, True); r = R.search_by_bow(*cb, 0.7, True)
+        assert o[0] == r[0] and np.array_equal(o[1], r[1]), seed
