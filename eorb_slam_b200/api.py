@@ -97,6 +97,12 @@ def _load():
         "eorb_guided_search_for_initialization_device": ([vp, vp, vp, i, vp, vp, i, vp, vp, i, f, i, vp, vp], i),
         "eorb_guided_search_by_projection": ([vp, vp, vp, vp, vp, vp, i, vp, vp, i, vp, vp, vp, i, f, i, vp, vp], i),
         "eorb_guided_search_by_projection_device": ([vp, vp, vp, vp, vp, vp, i, vp, vp, i, vp, vp, vp, i, f, i, vp, vp], i),
+        "eorb_guided_search_by_projection_stereo": ([vp, vp, vp, vp, vp, vp, i, vp, vp, vp, i, vp, vp, vp, i, f, i, i, f, vp, vp], i),
+        "eorb_guided_search_by_projection_stereo_device": ([vp, vp, vp, vp, vp, vp, i, vp, vp, vp, i, vp, vp, vp, i, f, i, i, f, vp, vp], i),
+        "eorb_guided_search_by_projection_reloc": ([vp, vp, vp, vp, vp, vp, i, vp, vp, vp, i, vp, vp, vp, i, f, i, i, vp, vp], i),
+        "eorb_guided_search_by_projection_reloc_device": ([vp, vp, vp, vp, vp, vp, i, vp, vp, vp, i, vp, vp, vp, i, f, i, i, vp, vp], i),
+        "eorb_guided_search_by_projection_map_points_stereo": ([vp, vp, vp, vp, i, vp, vp, vp, vp, i, vp, vp, i, f, i, f, f, vp, vp], i),
+        "eorb_guided_search_by_projection_map_points_stereo_device": ([vp, vp, vp, vp, i, vp, vp, vp, vp, i, vp, vp, i, f, i, f, f, vp, vp], i),
         "eorb_guided_search_by_bow": ([vp, vp, vp, vp, i, vp, vp, vp, i, vp, vp, i, vp, vp, vp, i, f, i, vp, vp], i),
         "eorb_guided_search_by_bow_device": ([vp, vp, vp, vp, i, vp, vp, vp, i, vp, vp, i, vp, vp, vp, i, f, i, vp, vp], i),
         "eorb_guided_search_by_projection_map_points": ([vp, vp, vp, i, vp, vp, vp, i, vp, vp, i, f, i, f, f, vp, vp], i),
@@ -691,6 +697,57 @@ class GuidedMatcher:
         _check(lib.eorb_guided_search_by_projection(self.h, _p(x), _p(v), _p(o), _p(k1), _p(dm), len(k1), _p(k2), _p(d2), len(k2), _p(b), _p(K),
                                                     _p(sf), len(sf), float(th), int(self.mbCheckOrientation), _p(mc), C.byref(nm)),
                "SearchByProjection")
+        return nm.value, mc[:len(k2)].copy()
+
+    def SearchByProjectionStereo(self, x3Dc, valid1, obs1, kps1, descMP, kps2, desc2, bounds, K4, scale_factors, th=15.0, level_mode=0,
+                                 mbf=0.0, u_right2=None):
+        """SearchByProjection(CurrentFrame, LastFrame, th, bMono=false) for a rectified-stereo / RGB-D frame (:1989-1990 forward /
+        backward level windows, :2049-2055 right-column test) -> (nmatches, match_cur[n2])"""
+        x = np.ascontiguousarray(x3Dc, np.float32).reshape(-1, 3); v = np.ascontiguousarray(valid1, np.uint8); o = np.ascontiguousarray(obs1, np.int32)
+        k1 = np.ascontiguousarray(kps1, KEYPOINT_DTYPE); k2 = np.ascontiguousarray(kps2, KEYPOINT_DTYPE)
+        dm = np.ascontiguousarray(descMP, np.uint8); d2 = np.ascontiguousarray(desc2, np.uint8)
+        b = np.ascontiguousarray(bounds, np.float32); K = np.ascontiguousarray(K4, np.float32); sf = np.ascontiguousarray(scale_factors, np.float32)
+        ur = None if u_right2 is None else np.ascontiguousarray(u_right2, np.float32)
+        mc = np.full(max(len(k2), 1), -1, np.int32)
+        nm = C.c_int(0)
+        _check(lib.eorb_guided_search_by_projection_stereo(self.h, _p(x), _p(v), _p(o), _p(k1), _p(dm), len(k1), _p(k2), _p(d2),
+                                                           _p(ur) if ur is not None else None, len(k2), _p(b), _p(K), _p(sf), len(sf), float(th),
+                                                           int(self.mbCheckOrientation), int(level_mode), float(mbf), _p(mc), C.byref(nm)),
+               "SearchByProjection(stereo)")
+        return nm.value, mc[:len(k2)].copy()
+
+    def SearchByProjectionReloc(self, x3Dc, valid1, level1, kps1, descMP, kps2, desc2, held2, bounds, K4, scale_factors, th=10.0, ORBdist=100):
+        """ORBmatcher::SearchByProjection(CurrentFrame, pKF, sAlreadyFound, th, ORBdist) (:2189-2312; Tracking::Relocalization)
+        -> (nmatches, match_cur[n2])"""
+        x = np.ascontiguousarray(x3Dc, np.float32).reshape(-1, 3); v = np.ascontiguousarray(valid1, np.uint8); lv = np.ascontiguousarray(level1, np.int32)
+        k1 = np.ascontiguousarray(kps1, KEYPOINT_DTYPE); k2 = np.ascontiguousarray(kps2, KEYPOINT_DTYPE)
+        dm = np.ascontiguousarray(descMP, np.uint8); d2 = np.ascontiguousarray(desc2, np.uint8)
+        b = np.ascontiguousarray(bounds, np.float32); K = np.ascontiguousarray(K4, np.float32); sf = np.ascontiguousarray(scale_factors, np.float32)
+        hd = None if held2 is None else np.ascontiguousarray(held2, np.uint8)
+        mc = np.full(max(len(k2), 1), -1, np.int32)
+        nm = C.c_int(0)
+        _check(lib.eorb_guided_search_by_projection_reloc(self.h, _p(x), _p(v), _p(lv), _p(k1), _p(dm), len(k1), _p(k2), _p(d2),
+                                                          _p(hd) if hd is not None else None, len(k2), _p(b), _p(K), _p(sf), len(sf), float(th),
+                                                          int(ORBdist), int(self.mbCheckOrientation), _p(mc), C.byref(nm)),
+               "SearchByProjection(relocalisation)")
+        return nm.value, mc[:len(k2)].copy()
+
+    def SearchByProjectionMapPointsStereo(self, pts, proj_xr, descMP, kps2, desc2, held2, u_right2, bounds, scale_factors, th=1.0, bFarPoints=False,
+                                          thFarPoints=0.0):
+        """SearchByProjection(F, vpMapPoints, ...) for a rectified-stereo / RGB-D frame (:91-96) -> (nmatches, match_cur[n2])"""
+        p = np.ascontiguousarray(pts, TRACK_POINT_DTYPE); k2 = np.ascontiguousarray(kps2, KEYPOINT_DTYPE)
+        dm = np.ascontiguousarray(descMP, np.uint8); d2 = np.ascontiguousarray(desc2, np.uint8)
+        hd = None if held2 is None else np.ascontiguousarray(held2, np.uint8)
+        xr = None if proj_xr is None else np.ascontiguousarray(proj_xr, np.float32)
+        ur = None if u_right2 is None else np.ascontiguousarray(u_right2, np.float32)
+        b = np.ascontiguousarray(bounds, np.float32); sf = np.ascontiguousarray(scale_factors, np.float32)
+        mc = np.full(max(len(k2), 1), -1, np.int32)
+        nm = C.c_int(0)
+        _check(lib.eorb_guided_search_by_projection_map_points_stereo(self.h, _p(p), _p(xr) if xr is not None else None, _p(dm), len(p), _p(k2), _p(d2),
+                                                                      _p(hd) if hd is not None else None, _p(ur) if ur is not None else None,
+                                                                      len(k2), _p(b), _p(sf), len(sf), C.c_float(th), int(bool(bFarPoints)),
+                                                                      C.c_float(thFarPoints), C.c_float(self.mfNNratio), _p(mc), C.byref(nm)),
+               "SearchByProjection(map points, stereo)")
         return nm.value, mc[:len(k2)].copy()
 
     def SearchByProjectionMapPoints(self, pts, descMP, kps2, desc2, held2, bounds, scale_factors, th=1.0, bFarPoints=False, thFarPoints=0.0):

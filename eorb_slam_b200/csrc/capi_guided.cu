@@ -36,6 +36,9 @@ struct eorb_guided {
     float* d_x3 = nullptr; uint8_t* d_valid = nullptr; int32_t* d_obs = nullptr; int pCap1 = 0;
     int32_t* d_mc = nullptr; int pCap2 = 0;
     uint8_t* d_held = nullptr; int heldCap = 0;
+    // rectified-stereo / relocalisation extras: per query (n1) the predicted right column and the predicted level, per slot (n2) mvuRight
+    float* d_qUr = nullptr; float* d_xr = nullptr; int32_t* d_lvl = nullptr; int exCap1 = 0;
+    float* d_ur2 = nullptr; int exCap2 = 0;
     // SearchByBoW host call: every input packed into ONE pinned blob -> one H2D copy; [nmatches | match table] -> one D2H copy
     unsigned char* d_blob = nullptr; unsigned char* h_blob = nullptr; size_t blobCap = 0;
     unsigned char* d_outb = nullptr; unsigned char* h_outb = nullptr; size_t outbCap = 0;
@@ -92,7 +95,7 @@ extern "C" int eorb_guided_destroy(eorb_guided* g) {
     cudaSetDevice(g->device);
     cudaStreamSynchronize(g->stream);
     for (int k = 0; k < 2; k++) { cudaFree(g->d_kps[k]); cudaFree(g->d_desc[k]); }
-    cudaFree(g->d_prev); cudaFree(g->d_m12); cudaFree(g->d_x3); cudaFree(g->d_valid); cudaFree(g->d_obs); cudaFree(g->d_mc); cudaFree(g->d_held); cudaFree(g->d_blob); cudaFreeHost(g->h_blob); cudaFree(g->d_outb); cudaFreeHost(g->h_outb); cudaFree(g->d_bowWork); cudaFree(g->w.q);
+    cudaFree(g->d_prev); cudaFree(g->d_m12); cudaFree(g->d_x3); cudaFree(g->d_valid); cudaFree(g->d_obs); cudaFree(g->d_mc); cudaFree(g->d_held); cudaFree(g->d_qUr); cudaFree(g->d_xr); cudaFree(g->d_lvl); cudaFree(g->d_ur2); cudaFree(g->d_blob); cudaFreeHost(g->h_blob); cudaFree(g->d_outb); cudaFreeHost(g->h_outb); cudaFree(g->d_bowWork); cudaFree(g->w.q);
     cudaFree(g->w.cellStart); cudaFree(g->w.cellIdx); cudaFree(g->w.assigned); cudaFree(g->w.candOff); cudaFree(g->w.candCnt);
     cudaFree(g->w.top); cudaFree(g->w.bin); cudaFree(g->w.cand);
     cudaFree(g->d_nm); cudaFreeHost(g->h_nm); cudaFree(g->d_q); cudaFree(g->d_cnt); cudaFree(g->d_out);
@@ -291,11 +294,52 @@ static int projConst(const float* bounds4, const float* K4, const float* scale_f
     return EORB_OK;
 }
 
+// per-query / per-slot scratch of the stereo and relocalisation variants
+static int reserveExtras(eorb_guided* g, int n1, int n2) {
+    if (n1 > g->exCap1) {
+        CU(cudaStreamSynchronize(g->stream));
+        cudaFree(g->d_qUr); cudaFree(g->d_xr); cudaFree(g->d_lvl);
+        g->d_qUr = nullptr; g->d_xr = nullptr; g->d_lvl = nullptr; g->exCap1 = 0;
+        const int cap = std::max(1024, n1);
+        CU(cudaMalloc((void**)&g->d_qUr, (size_t)cap * sizeof(float)));
+        CU(cudaMalloc((void**)&g->d_xr, (size_t)cap * sizeof(float)));
+        CU(cudaMalloc((void**)&g->d_lvl, (size_t)cap * sizeof(int32_t)));
+        g->exCap1 = cap;
+    }
+    if (n2 > g->exCap2) {
+        CU(cudaStreamSynchronize(g->stream));
+        cudaFree(g->d_ur2); g->d_ur2 = nullptr; g->exCap2 = 0;
+        const int cap = std::max(1024, n2);
+        CU(cudaMalloc((void**)&g->d_ur2, (size_t)cap * sizeof(float)));
+        g->exCap2 = cap;
+    }
+    return EORB_OK;
+}
+static int reserveHeld(eorb_guided* g, int n2) {
+    if (n2 > g->heldCap) {
+        CU(cudaStreamSynchronize(g->stream));
+        cudaFree(g->d_held); g->d_held = nullptr; g->heldCap = 0;
+        const int cap = std::max(1024, n2);
+        CU(cudaMalloc((void**)&g->d_held, (size_t)cap));
+        g->heldCap = cap;
+    }
+    return EORB_OK;
+}
+
+// what the variants add to the monocular frame-to-frame search (all pointers are device pointers, any may be null)
+struct ProjExtras { int levelMode = 0; int reloc = 0; float mbf = 0.f; const int32_t* d_level1 = nullptr; const float* d_uRight2 = nullptr;
+                    const uint8_t* d_held2 = nullptr; int thHigh = 100; };
+
 static int searchProjRun(eorb_guided* g, const float* d_x3, const uint8_t* d_valid, const int32_t* d_obs, const eorb_keypoint* d_k1,
                          const uint8_t* d_dmp, int n1, const eorb_keypoint* d_k2, const uint8_t* d_d2, int n2, const float* bounds4,
-                         const GuidedProj& pr, int checkOri, int32_t* d_mc, int* nmatches) {
+                         const GuidedProj& pr, int checkOri, int32_t* d_mc, int* nmatches, const ProjExtras& ex = ProjExtras()) {
     int rc = reserveWork(g, n1, n2);
     if (rc != EORB_OK) return rc;
+    GuidedProjMode md{ex.levelMode, ex.reloc, ex.mbf, ex.d_level1, nullptr};
+    if (ex.d_uRight2) {
+        if ((rc = reserveExtras(g, n1, 0)) != EORB_OK) return rc;
+        md.qUr = g->d_qUr;
+    }
     if (n1 > g->q1Cap) {   // claim[n1] lives in the matches12 staging buffer
         CU(cudaStreamSynchronize(g->stream));
         cudaFree(g->d_prev); cudaFree(g->d_m12);
@@ -308,7 +352,8 @@ static int searchProjRun(eorb_guided* g, const float* d_x3, const uint8_t* d_val
     GuidedFrame f2{d_k2, d_d2, n2};
     const GuidedGrid gg = gridGeom(bounds4);
     for (int attempt = 0; attempt < 2; attempt++) {
-        CU(launch_search_proj(d_x3, d_valid, d_obs, d_k1, d_dmp, n1, f2, gg, pr, checkOri, g->w, g->d_m12, d_mc, g->d_nm, g->stream, &g->launches));
+        CU(launch_search_proj(d_x3, d_valid, d_obs, d_k1, d_dmp, n1, f2, gg, pr, checkOri, g->w, g->d_m12, d_mc, g->d_nm, g->stream, &g->launches, md,
+                              ex.d_uRight2, ex.d_held2, ex.thHigh));
         CU(cudaMemcpyAsync(g->h_nm, g->d_nm, 2 * sizeof(int), cudaMemcpyDeviceToHost, g->stream));
         CU(cudaStreamSynchronize(g->stream));
         if (g->h_nm[1] <= g->w.candCap) { if (nmatches) *nmatches = g->h_nm[0]; return EORB_OK; }
@@ -338,16 +383,19 @@ extern "C" int eorb_guided_search_by_projection_device(eorb_guided* g, const flo
     return searchProjRun(g, d_x3Dc, d_valid1, d_obs1, d_kps1, d_descMP, n1, d_kps2, d_desc2, n2, bounds4, pr, check_ori, d_match_cur, nmatches);
 }
 
-extern "C" int eorb_guided_search_by_projection(eorb_guided* g, const float* x3Dc, const uint8_t* valid1, const int32_t* obs1,
-                                                const eorb_keypoint* kps1, const uint8_t* descMP, int n1, const eorb_keypoint* kps2,
-                                                const uint8_t* desc2, int n2, const float* bounds4, const float* K4, const float* scale_factors,
-                                                int nlevels, float th, int check_ori, int32_t* match_cur, int* nmatches) {
-    if (!g) return gFail(EORB_ERR_ARG, "eorb_guided_search_by_projection", "null handle");
+// host-pointer runner shared by the three frame-to-frame entry points: obs1 == null and level1 != null for the relocalisation search
+static int searchProjHost(eorb_guided* g, const char* what, const float* x3Dc, const uint8_t* valid1, const int32_t* obs1, const int32_t* level1,
+                          const eorb_keypoint* kps1, const uint8_t* descMP, int n1, const eorb_keypoint* kps2, const uint8_t* desc2,
+                          const uint8_t* held2, const float* u_right2, int n2, const float* bounds4, const float* K4, const float* scale_factors,
+                          int nlevels, float th, int check_ori, int level_mode, float mbf, int reloc, int th_high, int32_t* match_cur,
+                          int* nmatches) {
+    if (!g) return gFail(EORB_ERR_ARG, what, "null handle");
     int rc = checkFrames(kps1, n1, kps2, n2, bounds4);
     if (rc != EORB_OK) return rc;
     if (nmatches) *nmatches = 0;
     if (n2 == 0) return EORB_OK;
-    if (!match_cur || !desc2 || (n1 > 0 && (!x3Dc || !valid1 || !obs1 || !descMP))) return gFail(EORB_ERR_ARG, "eorb_guided_search_by_projection", "null argument");
+    if (!match_cur || !desc2 || (n1 > 0 && (!x3Dc || !valid1 || (!obs1 && !reloc) || (reloc && !level1) || !descMP))) return gFail(EORB_ERR_ARG, what, "null argument");
+    if (level_mode < 0 || level_mode > 2) return gFail(EORB_ERR_ARG, what, "level_mode must be 0, 1 (forward) or 2 (backward)");
     GuidedProj pr;
     if ((rc = projConst(bounds4, K4, scale_factors, nlevels, th, pr)) != EORB_OK) return rc;
     CU(cudaSetDevice(g->device));
@@ -370,17 +418,94 @@ extern "C" int eorb_guided_search_by_projection(eorb_guided* g, const float* x3D
         CU(cudaMalloc((void**)&g->d_mc, (size_t)cap * sizeof(int32_t)));
         g->pCap2 = cap;
     }
+    ProjExtras ex;
+    ex.levelMode = level_mode; ex.reloc = reloc; ex.mbf = mbf; ex.thHigh = th_high;
+    if (level1 || u_right2) {
+        if ((rc = reserveExtras(g, n1, n2)) != EORB_OK) return rc;
+    }
+    if (held2 && (rc = reserveHeld(g, n2)) != EORB_OK) return rc;
     if (n1 > 0) {
         CU(cudaMemcpyAsync(g->d_x3, x3Dc, (size_t)n1 * 3 * sizeof(float), cudaMemcpyHostToDevice, g->stream));
         CU(cudaMemcpyAsync(g->d_valid, valid1, (size_t)n1, cudaMemcpyHostToDevice, g->stream));
-        CU(cudaMemcpyAsync(g->d_obs, obs1, (size_t)n1 * sizeof(int32_t), cudaMemcpyHostToDevice, g->stream));
+        if (obs1) CU(cudaMemcpyAsync(g->d_obs, obs1, (size_t)n1 * sizeof(int32_t), cudaMemcpyHostToDevice, g->stream));
+        if (level1) { CU(cudaMemcpyAsync(g->d_lvl, level1, (size_t)n1 * sizeof(int32_t), cudaMemcpyHostToDevice, g->stream)); ex.d_level1 = g->d_lvl; }
     }
-    rc = searchProjRun(g, g->d_x3, g->d_valid, g->d_obs, g->d_kps[0], g->d_desc[0], n1, g->d_kps[1], g->d_desc[1], n2, bounds4, pr, check_ori,
-                       g->d_mc, nmatches);
+    if (u_right2) { CU(cudaMemcpyAsync(g->d_ur2, u_right2, (size_t)n2 * sizeof(float), cudaMemcpyHostToDevice, g->stream)); ex.d_uRight2 = g->d_ur2; }
+    if (held2) { CU(cudaMemcpyAsync(g->d_held, held2, (size_t)n2, cudaMemcpyHostToDevice, g->stream)); ex.d_held2 = g->d_held; }
+    rc = searchProjRun(g, g->d_x3, g->d_valid, obs1 ? g->d_obs : nullptr, g->d_kps[0], g->d_desc[0], n1, g->d_kps[1], g->d_desc[1], n2, bounds4, pr,
+                       check_ori, g->d_mc, nmatches, ex);
     if (rc != EORB_OK) return rc;
     CU(cudaMemcpyAsync(match_cur, g->d_mc, (size_t)n2 * sizeof(int32_t), cudaMemcpyDeviceToHost, g->stream));
     CU(cudaStreamSynchronize(g->stream));
     return EORB_OK;
+}
+
+extern "C" int eorb_guided_search_by_projection(eorb_guided* g, const float* x3Dc, const uint8_t* valid1, const int32_t* obs1,
+                                                const eorb_keypoint* kps1, const uint8_t* descMP, int n1, const eorb_keypoint* kps2,
+                                                const uint8_t* desc2, int n2, const float* bounds4, const float* K4, const float* scale_factors,
+                                                int nlevels, float th, int check_ori, int32_t* match_cur, int* nmatches) {
+    return searchProjHost(g, "eorb_guided_search_by_projection", x3Dc, valid1, obs1, nullptr, kps1, descMP, n1, kps2, desc2, nullptr, nullptr, n2,
+                          bounds4, K4, scale_factors, nlevels, th, check_ori, 0, 0.f, 0, 100, match_cur, nmatches);
+}
+
+extern "C" int eorb_guided_search_by_projection_stereo(eorb_guided* g, const float* x3Dc, const uint8_t* valid1, const int32_t* obs1,
+                                                       const eorb_keypoint* kps1, const uint8_t* descMP, int n1, const eorb_keypoint* kps2,
+                                                       const uint8_t* desc2, const float* u_right2, int n2, const float* bounds4, const float* K4,
+                                                       const float* scale_factors, int nlevels, float th, int check_ori, int level_mode, float mbf,
+                                                       int32_t* match_cur, int* nmatches) {
+    return searchProjHost(g, "eorb_guided_search_by_projection_stereo", x3Dc, valid1, obs1, nullptr, kps1, descMP, n1, kps2, desc2, nullptr, u_right2,
+                          n2, bounds4, K4, scale_factors, nlevels, th, check_ori, level_mode, mbf, 0, 100, match_cur, nmatches);
+}
+
+extern "C" int eorb_guided_search_by_projection_reloc(eorb_guided* g, const float* x3Dc, const uint8_t* valid1, const int32_t* level1,
+                                                      const eorb_keypoint* kps1, const uint8_t* descMP, int n1, const eorb_keypoint* kps2,
+                                                      const uint8_t* desc2, const uint8_t* held2, int n2, const float* bounds4, const float* K4,
+                                                      const float* scale_factors, int nlevels, float th, int orb_dist, int check_ori,
+                                                      int32_t* match_cur, int* nmatches) {
+    return searchProjHost(g, "eorb_guided_search_by_projection_reloc", x3Dc, valid1, nullptr, level1, kps1, descMP, n1, kps2, desc2, held2, nullptr,
+                          n2, bounds4, K4, scale_factors, nlevels, th, check_ori, 0, 0.f, 1, orb_dist, match_cur, nmatches);
+}
+
+static int searchProjDeviceCommon(eorb_guided* g, const char* what, const float* d_x3Dc, const uint8_t* d_valid1, const int32_t* d_obs1,
+                                  const eorb_keypoint* d_kps1, const uint8_t* d_descMP, int n1, const eorb_keypoint* d_kps2, const uint8_t* d_desc2,
+                                  int n2, const float* bounds4, const float* K4, const float* scale_factors, int nlevels, float th, int check_ori,
+                                  const ProjExtras& ex, int32_t* d_match_cur, int* nmatches) {
+    if (!g) return gFail(EORB_ERR_ARG, what, "null handle");
+    int rc = checkFrames(d_kps1, n1, d_kps2, n2, bounds4);
+    if (rc != EORB_OK) return rc;
+    if (nmatches) *nmatches = 0;
+    if (n2 == 0) return EORB_OK;
+    if (!d_match_cur || !d_desc2 || (n1 > 0 && (!d_x3Dc || !d_valid1 || (!d_obs1 && !ex.reloc) || (ex.reloc && !ex.d_level1) || !d_descMP)))
+        return gFail(EORB_ERR_ARG, what, "null argument");
+    if (ex.levelMode < 0 || ex.levelMode > 2) return gFail(EORB_ERR_ARG, what, "level_mode must be 0, 1 (forward) or 2 (backward)");
+    if (((uintptr_t)d_descMP | (uintptr_t)d_desc2) & 15) return gFail(EORB_ERR_ARG, what, "descriptors must be 16-byte aligned");
+    GuidedProj pr;
+    if ((rc = projConst(bounds4, K4, scale_factors, nlevels, th, pr)) != EORB_OK) return rc;
+    CU(cudaSetDevice(g->device));
+    return searchProjRun(g, d_x3Dc, d_valid1, d_obs1, d_kps1, d_descMP, n1, d_kps2, d_desc2, n2, bounds4, pr, check_ori, d_match_cur, nmatches, ex);
+}
+
+extern "C" int eorb_guided_search_by_projection_stereo_device(eorb_guided* g, const float* d_x3Dc, const uint8_t* d_valid1, const int32_t* d_obs1,
+                                                              const eorb_keypoint* d_kps1, const uint8_t* d_descMP, int n1,
+                                                              const eorb_keypoint* d_kps2, const uint8_t* d_desc2, const float* d_u_right2, int n2,
+                                                              const float* bounds4, const float* K4, const float* scale_factors, int nlevels,
+                                                              float th, int check_ori, int level_mode, float mbf, int32_t* d_match_cur,
+                                                              int* nmatches) {
+    ProjExtras ex;
+    ex.levelMode = level_mode; ex.mbf = mbf; ex.d_uRight2 = d_u_right2;
+    return searchProjDeviceCommon(g, "eorb_guided_search_by_projection_stereo_device", d_x3Dc, d_valid1, d_obs1, d_kps1, d_descMP, n1, d_kps2, d_desc2,
+                                  n2, bounds4, K4, scale_factors, nlevels, th, check_ori, ex, d_match_cur, nmatches);
+}
+
+extern "C" int eorb_guided_search_by_projection_reloc_device(eorb_guided* g, const float* d_x3Dc, const uint8_t* d_valid1, const int32_t* d_level1,
+                                                             const eorb_keypoint* d_kps1, const uint8_t* d_descMP, int n1,
+                                                             const eorb_keypoint* d_kps2, const uint8_t* d_desc2, const uint8_t* d_held2, int n2,
+                                                             const float* bounds4, const float* K4, const float* scale_factors, int nlevels,
+                                                             float th, int orb_dist, int check_ori, int32_t* d_match_cur, int* nmatches) {
+    ProjExtras ex;
+    ex.reloc = 1; ex.d_level1 = d_level1; ex.d_held2 = d_held2; ex.thHigh = orb_dist;
+    return searchProjDeviceCommon(g, "eorb_guided_search_by_projection_reloc_device", d_x3Dc, d_valid1, nullptr, d_kps1, d_descMP, n1, d_kps2, d_desc2,
+                                  n2, bounds4, K4, scale_factors, nlevels, th, check_ori, ex, d_match_cur, nmatches);
 }
 
 // ------------------------------------------------------------------------------------------------ SearchByProjection (map points)
@@ -388,13 +513,14 @@ static_assert(sizeof(eorb_track_point) == sizeof(eorb_keypoint), "the host entry
 
 static int searchMapRun(eorb_guided* g, const eorb_track_point* d_pts, const uint8_t* d_dmp, int n1, const eorb_keypoint* d_k2, const uint8_t* d_d2,
                         const uint8_t* d_held, int n2, const float* bounds4, const GuidedProj& pr, int farPoints, float thFar, float nnratio,
-                        int32_t* d_mc, int* nmatches) {
+                        int32_t* d_mc, int* nmatches, const float* d_projXR = nullptr, const float* d_uRight2 = nullptr) {
     int rc = reserveWork(g, n1, n2);
     if (rc != EORB_OK) return rc;
     GuidedFrame f2{d_k2, d_d2, n2};
     const GuidedGrid gg = gridGeom(bounds4);
     for (int attempt = 0; attempt < 2; attempt++) {
-        CU(launch_search_map_points(d_pts, d_dmp, n1, f2, d_held, gg, pr, farPoints, thFar, nnratio, g->w, d_mc, g->d_nm, g->stream, &g->launches));
+        CU(launch_search_map_points(d_pts, d_dmp, n1, f2, d_held, gg, pr, farPoints, thFar, nnratio, g->w, d_mc, g->d_nm, g->stream, &g->launches,
+                                    d_projXR, d_uRight2));
         CU(cudaMemcpyAsync(g->h_nm, g->d_nm, 2 * sizeof(int), cudaMemcpyDeviceToHost, g->stream));
         CU(cudaStreamSynchronize(g->stream));
         if (g->h_nm[1] <= g->w.candCap) { if (nmatches) *nmatches = g->h_nm[0]; return EORB_OK; }
@@ -414,35 +540,54 @@ static int mapConst(const float* scale_factors, int nlevels, float th, GuidedPro
     return EORB_OK;
 }
 
+static int searchMapDeviceCommon(eorb_guided* g, const char* what, const eorb_track_point* d_pts, const float* d_proj_xr, const uint8_t* d_descMP,
+                                 int n1, const eorb_keypoint* d_kps2, const uint8_t* d_desc2, const uint8_t* d_held2, const float* d_u_right2, int n2,
+                                 const float* bounds4, const float* scale_factors, int nlevels, float th, int far_points, float th_far,
+                                 float nnratio, int32_t* d_match_cur, int* nmatches) {
+    if (!g) return gFail(EORB_ERR_ARG, what, "null handle");
+    int rc = checkFrames(d_pts, n1, d_kps2, n2, bounds4);
+    if (rc != EORB_OK) return rc;
+    if (nmatches) *nmatches = 0;
+    if (n2 == 0) return EORB_OK;
+    if (!d_match_cur || !d_desc2 || (n1 > 0 && !d_descMP)) return gFail(EORB_ERR_ARG, what, "null argument");
+    if (((uintptr_t)d_descMP | (uintptr_t)d_desc2) & 15) return gFail(EORB_ERR_ARG, what, "descriptors must be 16-byte aligned");
+    GuidedProj pr;
+    if ((rc = mapConst(scale_factors, nlevels, th, pr)) != EORB_OK) return rc;
+    CU(cudaSetDevice(g->device));
+    const bool stereo = d_proj_xr && d_u_right2;
+    return searchMapRun(g, d_pts, d_descMP, n1, d_kps2, d_desc2, d_held2, n2, bounds4, pr, far_points, th_far, nnratio, d_match_cur, nmatches,
+                        stereo ? d_proj_xr : nullptr, stereo ? d_u_right2 : nullptr);
+}
+
 extern "C" int eorb_guided_search_by_projection_map_points_device(eorb_guided* g, const eorb_track_point* d_pts, const uint8_t* d_descMP, int n1,
                                                                   const eorb_keypoint* d_kps2, const uint8_t* d_desc2, const uint8_t* d_held2,
                                                                   int n2, const float* bounds4, const float* scale_factors, int nlevels, float th,
                                                                   int far_points, float th_far, float nnratio, int32_t* d_match_cur,
                                                                   int* nmatches) {
-    if (!g) return gFail(EORB_ERR_ARG, "eorb_guided_search_by_projection_map_points_device", "null handle");
-    int rc = checkFrames(d_pts, n1, d_kps2, n2, bounds4);
-    if (rc != EORB_OK) return rc;
-    if (nmatches) *nmatches = 0;
-    if (n2 == 0) return EORB_OK;
-    if (!d_match_cur || !d_desc2 || (n1 > 0 && !d_descMP)) return gFail(EORB_ERR_ARG, "eorb_guided_search_by_projection_map_points_device", "null argument");
-    if (((uintptr_t)d_descMP | (uintptr_t)d_desc2) & 15)
-        return gFail(EORB_ERR_ARG, "eorb_guided_search_by_projection_map_points_device", "descriptors must be 16-byte aligned");
-    GuidedProj pr;
-    if ((rc = mapConst(scale_factors, nlevels, th, pr)) != EORB_OK) return rc;
-    CU(cudaSetDevice(g->device));
-    return searchMapRun(g, d_pts, d_descMP, n1, d_kps2, d_desc2, d_held2, n2, bounds4, pr, far_points, th_far, nnratio, d_match_cur, nmatches);
+    return searchMapDeviceCommon(g, "eorb_guided_search_by_projection_map_points_device", d_pts, nullptr, d_descMP, n1, d_kps2, d_desc2, d_held2, nullptr,
+                                 n2, bounds4, scale_factors, nlevels, th, far_points, th_far, nnratio, d_match_cur, nmatches);
 }
 
-extern "C" int eorb_guided_search_by_projection_map_points(eorb_guided* g, const eorb_track_point* pts, const uint8_t* descMP, int n1,
-                                                           const eorb_keypoint* kps2, const uint8_t* desc2, const uint8_t* held2, int n2,
-                                                           const float* bounds4, const float* scale_factors, int nlevels, float th, int far_points,
-                                                           float th_far, float nnratio, int32_t* match_cur, int* nmatches) {
-    if (!g) return gFail(EORB_ERR_ARG, "eorb_guided_search_by_projection_map_points", "null handle");
+extern "C" int eorb_guided_search_by_projection_map_points_stereo_device(eorb_guided* g, const eorb_track_point* d_pts, const float* d_proj_xr,
+                                                                         const uint8_t* d_descMP, int n1, const eorb_keypoint* d_kps2,
+                                                                         const uint8_t* d_desc2, const uint8_t* d_held2, const float* d_u_right2,
+                                                                         int n2, const float* bounds4, const float* scale_factors, int nlevels,
+                                                                         float th, int far_points, float th_far, float nnratio,
+                                                                         int32_t* d_match_cur, int* nmatches) {
+    return searchMapDeviceCommon(g, "eorb_guided_search_by_projection_map_points_stereo_device", d_pts, d_proj_xr, d_descMP, n1, d_kps2, d_desc2, d_held2,
+                                 d_u_right2, n2, bounds4, scale_factors, nlevels, th, far_points, th_far, nnratio, d_match_cur, nmatches);
+}
+
+static int searchMapHost(eorb_guided* g, const char* what, const eorb_track_point* pts, const float* proj_xr, const uint8_t* descMP, int n1,
+                         const eorb_keypoint* kps2, const uint8_t* desc2, const uint8_t* held2, const float* u_right2, int n2, const float* bounds4,
+                         const float* scale_factors, int nlevels, float th, int far_points, float th_far, float nnratio, int32_t* match_cur,
+                         int* nmatches) {
+    if (!g) return gFail(EORB_ERR_ARG, what, "null handle");
     int rc = checkFrames(pts, n1, kps2, n2, bounds4);
     if (rc != EORB_OK) return rc;
     if (nmatches) *nmatches = 0;
     if (n2 == 0) return EORB_OK;
-    if (!match_cur || !desc2 || (n1 > 0 && !descMP)) return gFail(EORB_ERR_ARG, "eorb_guided_search_by_projection_map_points", "null argument");
+    if (!match_cur || !desc2 || (n1 > 0 && !descMP)) return gFail(EORB_ERR_ARG, what, "null argument");
     GuidedProj pr;
     if ((rc = mapConst(scale_factors, nlevels, th, pr)) != EORB_OK) return rc;
     CU(cudaSetDevice(g->device));
@@ -455,20 +600,38 @@ extern "C" int eorb_guided_search_by_projection_map_points(eorb_guided* g, const
         CU(cudaMalloc((void**)&g->d_mc, (size_t)cap * sizeof(int32_t)));
         g->pCap2 = cap;
     }
-    if (held2 && n2 > g->heldCap) {
-        CU(cudaStreamSynchronize(g->stream));
-        cudaFree(g->d_held); g->d_held = nullptr; g->heldCap = 0;
-        const int cap = std::max(1024, n2);
-        CU(cudaMalloc((void**)&g->d_held, (size_t)cap));
-        g->heldCap = cap;
-    }
+    if (held2 && (rc = reserveHeld(g, n2)) != EORB_OK) return rc;
     if (held2) CU(cudaMemcpyAsync(g->d_held, held2, (size_t)n2, cudaMemcpyHostToDevice, g->stream));
+    const bool stereo = proj_xr && u_right2 && n1 > 0;     // the rectified-stereo column test needs both sides (ORBmatcher.cc:91-96)
+    if (stereo) {
+        if ((rc = reserveExtras(g, n1, n2)) != EORB_OK) return rc;
+        CU(cudaMemcpyAsync(g->d_xr, proj_xr, (size_t)n1 * sizeof(float), cudaMemcpyHostToDevice, g->stream));
+        CU(cudaMemcpyAsync(g->d_ur2, u_right2, (size_t)n2 * sizeof(float), cudaMemcpyHostToDevice, g->stream));
+    }
     rc = searchMapRun(g, reinterpret_cast<const eorb_track_point*>(g->d_kps[0]), g->d_desc[0], n1, g->d_kps[1], g->d_desc[1],
-                      held2 ? g->d_held : nullptr, n2, bounds4, pr, far_points, th_far, nnratio, g->d_mc, nmatches);
+                      held2 ? g->d_held : nullptr, n2, bounds4, pr, far_points, th_far, nnratio, g->d_mc, nmatches, stereo ? g->d_xr : nullptr,
+                      stereo ? g->d_ur2 : nullptr);
     if (rc != EORB_OK) return rc;
     CU(cudaMemcpyAsync(match_cur, g->d_mc, (size_t)n2 * sizeof(int32_t), cudaMemcpyDeviceToHost, g->stream));
     CU(cudaStreamSynchronize(g->stream));
     return EORB_OK;
+}
+
+extern "C" int eorb_guided_search_by_projection_map_points(eorb_guided* g, const eorb_track_point* pts, const uint8_t* descMP, int n1,
+                                                           const eorb_keypoint* kps2, const uint8_t* desc2, const uint8_t* held2, int n2,
+                                                           const float* bounds4, const float* scale_factors, int nlevels, float th, int far_points,
+                                                           float th_far, float nnratio, int32_t* match_cur, int* nmatches) {
+    return searchMapHost(g, "eorb_guided_search_by_projection_map_points", pts, nullptr, descMP, n1, kps2, desc2, held2, nullptr, n2, bounds4,
+                         scale_factors, nlevels, th, far_points, th_far, nnratio, match_cur, nmatches);
+}
+
+extern "C" int eorb_guided_search_by_projection_map_points_stereo(eorb_guided* g, const eorb_track_point* pts, const float* proj_xr,
+                                                                  const uint8_t* descMP, int n1, const eorb_keypoint* kps2, const uint8_t* desc2,
+                                                                  const uint8_t* held2, const float* u_right2, int n2, const float* bounds4,
+                                                                  const float* scale_factors, int nlevels, float th, int far_points, float th_far,
+                                                                  float nnratio, int32_t* match_cur, int* nmatches) {
+    return searchMapHost(g, "eorb_guided_search_by_projection_map_points_stereo", pts, proj_xr, descMP, n1, kps2, desc2, held2, u_right2, n2, bounds4,
+                         scale_factors, nlevels, th, far_points, th_far, nnratio, match_cur, nmatches);
 }
 
 // ------------------------------------------------------------------------------------------------ SearchByBoW

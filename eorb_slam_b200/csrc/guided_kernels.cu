@@ -218,8 +218,12 @@ __device__ __forceinline__ u64 warp_sort32(u64 v, int lane) {
 // Queries: SearchForInitialization (qs == nullptr): frame-1 keypoint i1 at level 0, window `r0win` around prevXY[i1], levels
 // [0, 0] (ORBmatcher.cc:732-736).  SearchByProjection (qs != nullptr): the window and level range guided_project_kernel
 // prepared for last-frame keypoint i1 (r <= 0: no query); f1.desc then holds the map points' descriptors.
+// Rectified stereo (uRight2 != nullptr; Nleft == -1 with mvuRight set): a candidate with a right-image column is dropped when it lies
+// further than the window radius from the query's predicted right column qUr[i1] (ORBmatcher.cc:91-96, :2049-2055).  The test does
+// not depend on the order of the queries, so it is part of the candidate filter.
 __global__ void __launch_bounds__(256) guided_candidates_kernel(GuidedFrame f1, GuidedFrame f2, GuidedGrid g, const float* __restrict__ prevXY,
-                                                                float r0win, const eorb_area_query* __restrict__ qs, GuidedWork w) {
+                                                                float r0win, const eorb_area_query* __restrict__ qs, GuidedWork w,
+                                                                const float* __restrict__ uRight2, const float* __restrict__ qUr) {
     const int i1 = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
     if (i1 >= f1.n) return;
     const unsigned lt = (1u << lane) - 1u;
@@ -237,6 +241,13 @@ __global__ void __launch_bounds__(256) guided_candidates_kernel(GuidedFrame f1, 
         live = level1 <= 0;
     }
     const bool check = minL > 0 || maxL >= 0;              // bCheckLevels (Frame.cc:746)
+    const bool stereo = uRight2 != nullptr && qUr != nullptr;
+    const float ur = stereo ? qUr[i1] : 0.0f;
+    auto stereoOk = [&](int i2) {
+        if (!stereo) return true;
+        const float u2 = uRight2[i2];
+        return !(u2 > 0.0f && fabsf(__fsub_rn(ur, u2)) > r);
+    };
     int c0 = 0, c1 = -1, r0 = 0, r1 = 0;
     live = live && area_cells(g, x, y, r, c0, c1, r0, r1);
     // pass 1: count
@@ -246,7 +257,8 @@ __global__ void __launch_bounds__(256) guided_candidates_kernel(GuidedFrame f1, 
             const int b = w.cellStart[ix * EORB_GRID_ROWS + r0], e = w.cellStart[ix * EORB_GRID_ROWS + r1 + 1];
             for (int base = b; base < e; base += 32) {
                 const int j = base + lane;
-                const bool ok = j < e && area_accept(f2.kps, w.cellIdx[j], x, y, r, check, minL, maxL);
+                bool ok = false;
+                if (j < e) { const int i2 = w.cellIdx[j]; ok = area_accept(f2.kps, i2, x, y, r, check, minL, maxL) && stereoOk(i2); }
                 cnt += __popc(__ballot_sync(FULLMASK, ok));
             }
         }
@@ -271,7 +283,7 @@ __global__ void __launch_bounds__(256) guided_candidates_kernel(GuidedFrame f1, 
             const int j = base + lane;
             int i2 = 0;
             bool ok = false;
-            if (j < e) { i2 = w.cellIdx[j]; ok = area_accept(f2.kps, i2, x, y, r, check, minL, maxL); }
+            if (j < e) { i2 = w.cellIdx[j]; ok = area_accept(f2.kps, i2, x, y, r, check, minL, maxL) && stereoOk(i2); }
             const unsigned m = __ballot_sync(FULLMASK, ok);
             if (m == 0) continue;
             u64 key = ~0ull;
@@ -514,23 +526,32 @@ __global__ void __launch_bounds__(256) guided_resolve_kernel(GuidedFrame f1, Gui
 // float (Pinhole.cpp:30-33), image-bounds test, radius = th * mvScaleFactors[clamp(octave)], levels [octave-1, octave+1].
 __global__ void __launch_bounds__(256) guided_project_kernel(const float* __restrict__ x3Dc, const uint8_t* __restrict__ valid1,
                                                              const eorb_keypoint* __restrict__ kps1, int n1, GuidedProj pr,
-                                                             eorb_area_query* __restrict__ qs) {
+                                                             eorb_area_query* __restrict__ qs, GuidedProjMode md) {
     const int i = blockIdx.x * 256 + threadIdx.x;
     if (i >= n1) return;
     eorb_area_query q;
     q.x = 0.f; q.y = 0.f; q.r = -1.f; q.min_level = 0; q.max_level = -1;
+    float ur = 0.0f;
     if (valid1[i]) {
         const float xc = x3Dc[3 * i], yc = x3Dc[3 * i + 1], zc = x3Dc[3 * i + 2];
-        if (zc > 0.0f || zc != zc) {   // invzc = 1.0 / zc < 0 (and the undefined z == 0) are skipped; NaN passes like in the reference
+        // frame-to-frame: invzc = 1.0 / zc < 0 (and the undefined z == 0) are skipped, NaN passes like in the reference (:2002-2006);
+        // the relocalisation search has no depth-sign test (:2218)
+        if (md.reloc || zc > 0.0f || zc != zc) {
             const float u = __fadd_rn(__fdiv_rn(__fmul_rn(pr.fx, xc), zc), pr.cx), v = __fadd_rn(__fdiv_rn(__fmul_rn(pr.fy, yc), zc), pr.cy);
             if (!(u < pr.minX || u > pr.maxX) && !(v < pr.minY || v > pr.maxY)) {
-                const int oct = kps1[i].octave;
+                const int oct = md.level1 ? md.level1[i] : kps1[i].octave;      // nPredictedLevel (:2237) / nLastOctave (:2016)
                 const int lv = oct < 0 ? 0 : (oct >= pr.nlevels ? pr.nlevels - 1 : oct);
-                q.x = u; q.y = v; q.r = __fmul_rn(pr.th, pr.scale[lv]); q.min_level = oct - 1; q.max_level = oct + 1;
+                q.x = u; q.y = v; q.r = __fmul_rn(pr.th, pr.scale[lv]);
+                if (md.levelMode == 1) { q.min_level = oct; q.max_level = -1; }          // bForward: [oct, inf) (:2024-2025)
+                else if (md.levelMode == 2) { q.min_level = 0; q.max_level = oct; }      // bBackward: [0, oct] (:2026-2027)
+                else { q.min_level = oct - 1; q.max_level = oct + 1; }
+                // ur = uv.x - mbf * invzc, invzc = (float)(1.0 / zc): the double quotient rounds to the same float as the float division
+                ur = __fsub_rn(u, __fmul_rn(md.mbf, __fdiv_rn(1.0f, zc)));
             }
         }
     }
     qs[i] = q;
+    if (md.qUr) md.qUr[i] = ur;
 }
 
 // P3 guided_resolve_proj_kernel: the order-dependent part (:2042-2070): a current-frame keypoint whose slot holds a map point
@@ -538,9 +559,12 @@ __global__ void __launch_bounds__(256) guided_project_kernel(const float* __rest
 // sorted head.  Same structure as guided_resolve_kernel (one ordered warp, seven staging warps, full-list slow path); a
 // query's claim is recorded in claim[i]; the owner of a slot is its LAST claimer; every claim enters the rotation histogram
 // (:2073-2089) and a claim in a non-maximal bin un-sets its slot whoever owns it by then (:2141-2150).
+// Relocalisation variant (ORBmatcher.cc:2189-2312): obs1 == nullptr (every set slot blocks, :2253), held2 = slots holding a point on
+// entry, thHigh = ORBdist (:2266).
 __global__ void __launch_bounds__(256) guided_resolve_proj_kernel(const eorb_keypoint* __restrict__ kps1, const int32_t* __restrict__ obs1, int n1,
                                                                   GuidedFrame f2, int checkOri, GuidedWork w, int32_t* __restrict__ claim,
-                                                                  int32_t* __restrict__ matchCur, int* __restrict__ nmatchesOut) {
+                                                                  int32_t* __restrict__ matchCur, int* __restrict__ nmatchesOut,
+                                                                  const uint8_t* __restrict__ held2, int thHigh) {
     extern __shared__ __align__(16) unsigned char sm[];
     const int n2 = f2.n, n2r = (n2 + 3) & ~3;
     u64* stop = reinterpret_cast<u64*>(sm);                               // [2][GUIDED_STAGE][32]
@@ -559,7 +583,7 @@ __global__ void __launch_bounds__(256) guided_resolve_proj_kernel(const eorb_key
         if (tid == 0) *nmatchesOut = -1;
         return;
     }
-    for (int i = tid; i < n2; i += 256) { owner[i] = GUIDED_NONE; blk[i] = 0; ctab[i] = 0xffffffffu; }
+    for (int i = tid; i < n2; i += 256) { owner[i] = GUIDED_NONE; blk[i] = (held2 && held2[i]) ? 1 : 0; ctab[i] = 0xffffffffu; }
     for (int i = tid; i < n1; i += 256) claim[i] = -1;
     if (tid < 32) hist[tid] = 0;
     if (tid == 0) sNm = 0;
@@ -572,7 +596,7 @@ __global__ void __launch_bounds__(256) guided_resolve_proj_kernel(const eorb_key
             const int q = r * GUIDED_STAGE + k, o = (r & 1) * GUIDED_STAGE + k;
             scnt[o] = q < nact ? w.candCnt[qlist[q]] : 0;
             soff[o] = q < nact ? w.candOff[qlist[q]] : 0;
-            sobs[o] = q < nact ? obs1[qlist[q]] : 0;
+            sobs[o] = q < nact ? (obs1 ? obs1[qlist[q]] : 1) : 0;
         }
     };
     if (nrounds > 0) loadStage(0, 0, 256);
@@ -604,7 +628,7 @@ __global__ void __launch_bounds__(256) guided_resolve_proj_kernel(const eorb_key
                     k1 = __reduce_min_sync(FULLMASK, k1);
                     if (k1 != 0xffffffffu) { bestDist = (int)(k1 >> 16); bestIdx = (int)(w.cand[off + (k1 & 0xffffu)] & 0xffffu); }
                 }
-                if (bestDist <= 100) {                                    // TH_HIGH (:2068)
+                if (bestDist <= thHigh) {                                 // TH_HIGH (:2068) / ORBdist (:2266)
                     if (lane == 0) {
                         const int i1 = qlist[r * GUIDED_STAGE + k];
                         owner[bestIdx] = (unsigned short)i1;
@@ -638,7 +662,7 @@ __global__ void __launch_bounds__(256) guided_resolve_proj_kernel(const eorb_key
                     }
                     slow = b1 == 0xffffffffu && scnt[so + q] > EORB_GUIDED_TOP;
                 }
-                const bool acc = have && !slow && b1 != 0xffffffffu && (b1 >> 16) <= 100u;
+                const bool acc = have && !slow && b1 != 0xffffffffu && (int)(b1 >> 16) <= thHigh;
                 if (acc) atomicMin(&ctab[b1 & 0xffffu], (unsigned)lane);
                 __syncwarp();
                 const bool dirty = have && b1 != 0xffffffffu && ctab[b1 & 0xffffu] < (unsigned)lane;
@@ -1209,7 +1233,7 @@ cudaError_t launch_search_init(const GuidedFrame& f1, const GuidedFrame& f2, Gui
     if (e != cudaSuccess) return e;
     (*launches)++;
     if (f1.n > 0) {
-        guided_candidates_kernel<<<(f1.n + 7) / 8, 256, 0, st>>>(f1, f2, g, d_prevXY, (float)window, nullptr, w);
+        guided_candidates_kernel<<<(f1.n + 7) / 8, 256, 0, st>>>(f1, f2, g, d_prevXY, (float)window, nullptr, w, nullptr, nullptr);
         (*launches)++;
     }
     guided_resolve_kernel<<<1, 256, resolveSmem(f1.n, f2.n), st>>>(f1, f2, d_prevXY, nnratio, checkOri, w, d_matches12, d_nmatches);
@@ -1219,26 +1243,29 @@ cudaError_t launch_search_init(const GuidedFrame& f1, const GuidedFrame& f2, Gui
 
 cudaError_t launch_search_proj(const float* d_x3Dc, const uint8_t* d_valid1, const int32_t* d_obs1, const eorb_keypoint* d_kps1,
                                const uint8_t* d_descMP, int n1, const GuidedFrame& f2, GuidedGrid g, const GuidedProj& pr, int checkOri,
-                               const GuidedWork& w, int32_t* d_claim, int32_t* d_matchCur, int* d_nmatches, cudaStream_t st, long long* launches) {
+                               const GuidedWork& w, int32_t* d_claim, int32_t* d_matchCur, int* d_nmatches, cudaStream_t st, long long* launches,
+                               const GuidedProjMode& md, const float* d_uRight2, const uint8_t* d_held2, int thHigh) {
     cudaError_t e = cudaMemsetAsync(w.total, 0, sizeof(int), st);
     if (e != cudaSuccess) return e;
     e = launch_frame_grid(f2.kps, f2.n, g, w.cellStart, w.cellIdx, w.assigned, st);
     if (e != cudaSuccess) return e;
     (*launches)++;
     if (n1 > 0) {
-        guided_project_kernel<<<(n1 + 255) / 256, 256, 0, st>>>(d_x3Dc, d_valid1, d_kps1, n1, pr, w.q);
+        guided_project_kernel<<<(n1 + 255) / 256, 256, 0, st>>>(d_x3Dc, d_valid1, d_kps1, n1, pr, w.q, md);
         GuidedFrame f1{d_kps1, d_descMP, n1};
-        guided_candidates_kernel<<<(n1 + 7) / 8, 256, 0, st>>>(f1, f2, g, nullptr, 0.f, w.q, w);
+        guided_candidates_kernel<<<(n1 + 7) / 8, 256, 0, st>>>(f1, f2, g, nullptr, 0.f, w.q, w, d_uRight2, d_uRight2 ? md.qUr : nullptr);
         (*launches) += 2;
     }
-    guided_resolve_proj_kernel<<<1, 256, resolveProjSmem(n1, f2.n), st>>>(d_kps1, d_obs1, n1, f2, checkOri, w, d_claim, d_matchCur, d_nmatches);
+    guided_resolve_proj_kernel<<<1, 256, resolveProjSmem(n1, f2.n), st>>>(d_kps1, d_obs1, n1, f2, checkOri, w, d_claim, d_matchCur, d_nmatches, d_held2,
+                                                                          thHigh);
     (*launches)++;
     return cudaGetLastError();
 }
 
 cudaError_t launch_search_map_points(const eorb_track_point* d_pts, const uint8_t* d_descMP, int n1, const GuidedFrame& f2,
                                      const uint8_t* d_held2, GuidedGrid g, const GuidedProj& pr, int farPoints, float thFar, float nnratio,
-                                     const GuidedWork& w, int32_t* d_matchCur, int* d_nmatches, cudaStream_t st, long long* launches) {
+                                     const GuidedWork& w, int32_t* d_matchCur, int* d_nmatches, cudaStream_t st, long long* launches,
+                                     const float* d_projXR, const float* d_uRight2) {
     cudaError_t e = cudaMemsetAsync(w.total, 0, sizeof(int), st);
     if (e != cudaSuccess) return e;
     e = launch_frame_grid(f2.kps, f2.n, g, w.cellStart, w.cellIdx, w.assigned, st);
@@ -1247,7 +1274,7 @@ cudaError_t launch_search_map_points(const eorb_track_point* d_pts, const uint8_
     if (n1 > 0) {
         guided_mappoint_query_kernel<<<(n1 + 255) / 256, 256, 0, st>>>(d_pts, n1, pr, farPoints, thFar, w.q);
         GuidedFrame f1{nullptr, d_descMP, n1};
-        guided_candidates_kernel<<<(n1 + 7) / 8, 256, 0, st>>>(f1, f2, g, nullptr, 0.f, w.q, w);
+        guided_candidates_kernel<<<(n1 + 7) / 8, 256, 0, st>>>(f1, f2, g, nullptr, 0.f, w.q, w, d_uRight2, d_projXR);
         (*launches) += 2;
     }
     guided_resolve_map_kernel<<<1, 256, resolveMapSmem(n1, f2.n), st>>>(d_pts, n1, f2, d_held2, nnratio, w, d_matchCur, d_nmatches);

@@ -42,14 +42,21 @@ cudaError_t launch_search_init(const GuidedFrame& f1, const GuidedFrame& f2, Gui
                                long long* launches);
 // SearchByProjection(CurrentFrame, LastFrame, th, bMono = true): projection constants (Pinhole intrinsics, image bounds, scale table)
 struct GuidedProj { float fx, fy, cx, cy, minX, minY, maxX, maxY, th; int nlevels; float scale[32]; };
+// variants of the projection window (guided_project_kernel): levelMode 0 = [oct-1, oct+1], 1 = bForward [oct, inf), 2 = bBackward
+// [0, oct] (ORBmatcher.cc:2024-2029); level1 != nullptr: the predicted level per map point instead of the keypoint octave and
+// reloc = 1: no depth-sign test (SearchByProjection(CurrentFrame, pKF, sAlreadyFound, ...), :2189-2312); qUr != nullptr receives
+// ur = u - mbf / zc per query for the rectified-stereo column test (:2049-2055)
+struct GuidedProjMode { int levelMode; int reloc; float mbf; const int32_t* level1; float* qUr; };
+// d_obs1 == nullptr: every set slot blocks; d_held2 (may be null): slots taken on entry; thHigh: acceptance threshold
 cudaError_t launch_search_proj(const float* d_x3Dc, const uint8_t* d_valid1, const int32_t* d_obs1, const eorb_keypoint* d_kps1,
                                const uint8_t* d_descMP, int n1, const GuidedFrame& f2, GuidedGrid g, const GuidedProj& pr, int checkOri,
                                const GuidedWork& w, int32_t* d_claim, int32_t* d_matchCur, int* d_nmatches, cudaStream_t st,
-                               long long* launches);
+                               long long* launches, const GuidedProjMode& md, const float* d_uRight2, const uint8_t* d_held2, int thHigh);
 // SearchByProjection(F, vpMapPoints, th, bFarPoints, thFarPoints), monocular (ORBmatcher.cc:44-148); pr carries th, nlevels, scale
 cudaError_t launch_search_map_points(const eorb_track_point* d_pts, const uint8_t* d_descMP, int n1, const GuidedFrame& f2,
                                      const uint8_t* d_held2, GuidedGrid g, const GuidedProj& pr, int farPoints, float thFar, float nnratio,
-                                     const GuidedWork& w, int32_t* d_matchCur, int* d_nmatches, cudaStream_t st, long long* launches);
+                                     const GuidedWork& w, int32_t* d_matchCur, int* d_nmatches, cudaStream_t st, long long* launches,
+                                     const float* d_projXR /* mTrackProjXR per point or null */, const float* d_uRight2 /* F.mvuRight or null */);
 // SearchByBoW(pKF, F, vpMapPointMatches), monocular (ORBmatcher.cc:276-478): one side = keypoints, descriptors and the
 // FeatureVector in CSR form (nodes ascending, features of node q = feats[start[q] .. start[q+1]))
 struct GuidedBowSide { const eorb_keypoint* kps; const uint8_t* desc; const uint32_t* nodes; const int32_t* start; const uint32_t* feats; int nnodes, n; };

@@ -4,6 +4,7 @@
 // matcher.SearchForInitialization(mInitialFrame, mCurrentFrame, mvbPrevMatched, mvIniMatches, 100) unchanged).
 // The Frame grid (AssignFeaturesToGrid / GetFeaturesInArea, src/Frame.cc:431-460, 709-793) is rebuilt on the device from
 // F2's undistorted keypoints and the static image bounds, so Frame::mGrid is not read.
+#include <cmath>
 #include <cstdio>
 #include <cstring>
 #include <mutex>
@@ -76,10 +77,22 @@ int ORBmatcher::SearchForInitialization(Frame &F1, Frame &F2, std::vector<cv::Po
 }
 int ORBmatcher::SearchByProjection(Frame &CurrentFrame, const Frame &LastFrame, const float th, const bool bMono)
 {
-    // stereo / fisheye frames use the forward / backward level ranges and the right-image test (:1990-1991, 2050-2056): keep the
-    // reference's implementation for those (rename it and call it here); the monocular path below is the tracking-rate case
-    (void)bMono;
+    // Monocular, rectified-stereo and RGB-D frames (Nleft == -1) run on the device, including the forward / backward level windows and
+    // the right-column test (:1989-1990, :2024-2029, :2049-2055).  A fisheye rig (Nleft != -1) has a second pass over the right
+    // camera's own grid (:2093-2160): rename the reference body and call it for those frames.
     const int n1 = LastFrame.numAllKPts(), n2 = CurrentFrame.numAllKPts();
+    int levelMode = 0;
+    if (!bMono && !CurrentFrame.mTcw.empty() && !LastFrame.mTcw.empty()) {
+        // tlc = Rlw * twc + tlw with twc = -Rcw^T * tcw (:1980-1987); only its z component is read
+        const cv::Mat& Tc = CurrentFrame.mTcw; const cv::Mat& Tl = LastFrame.mTcw;
+        float twc[3];
+        for (int r = 0; r < 3; r++)
+            twc[r] = -(Tc.at<float>(0, r) * Tc.at<float>(0, 3) + Tc.at<float>(1, r) * Tc.at<float>(1, 3) + Tc.at<float>(2, r) * Tc.at<float>(2, 3));
+        const float tlcz = Tl.at<float>(2, 0) * twc[0] + Tl.at<float>(2, 1) * twc[1] + Tl.at<float>(2, 2) * twc[2] + Tl.at<float>(2, 3);
+        if (tlcz > CurrentFrame.mb) levelMode = 1;            // bForward
+        else if (-tlcz > CurrentFrame.mb) levelMode = 2;      // bBackward
+    }
+    const bool haveRight = CurrentFrame.numKPtsLeft() == -1 && (int)CurrentFrame.mvuRight.size() == n2;
     eorb_guided* g = threadHandle();
     if (!g || n1 == 0 || n2 == 0) return 0;
     std::vector<eorb_keypoint> k1(n1), k2;
@@ -113,8 +126,10 @@ int ORBmatcher::SearchByProjection(Frame &CurrentFrame, const Frame &LastFrame, 
     const std::vector<float> sf = CurrentFrame.getAllORBScaleFactors();
     std::vector<int> mc(n2, -1);
     int nmatches = 0;
-    const int rc = eorb_guided_search_by_projection(g, x3.data(), valid.data(), obs.data(), k1.data(), dmp.data(), n1, k2.data(), d2.data(), n2, bounds,
-                                                    K4, sf.data(), (int)sf.size(), th, mbCheckOrientation ? 1 : 0, mc.data(), &nmatches);
+    const int rc = eorb_guided_search_by_projection_stereo(g, x3.data(), valid.data(), obs.data(), k1.data(), dmp.data(), n1, k2.data(), d2.data(),
+                                                           haveRight ? CurrentFrame.mvuRight.data() : nullptr, n2, bounds, K4, sf.data(),
+                                                           (int)sf.size(), th, mbCheckOrientation ? 1 : 0, levelMode, CurrentFrame.mbf, mc.data(),
+                                                           &nmatches);
     if (rc != EORB_OK) {
         std::fprintf(stderr, "ORBmatcher(b200)::SearchByProjection: %s\n", eorb_last_error());
         return 0;
@@ -124,8 +139,9 @@ int ORBmatcher::SearchByProjection(Frame &CurrentFrame, const Frame &LastFrame, 
     return nmatches;
 }
 
-// ORBmatcher::SearchByProjection(F, vpMapPoints, th, bFarPoints, thFarPoints) (:44-218; Tracking::SearchLocalPoints), monocular frame.
-// Stereo / fisheye frames (Nleft != -1 or mvuRight > 0) keep the reference's implementation.
+// ORBmatcher::SearchByProjection(F, vpMapPoints, th, bFarPoints, thFarPoints) (:44-218; Tracking::SearchLocalPoints): monocular,
+// rectified-stereo and RGB-D frames (Nleft == -1; the right-column test :91-96 runs on the device).  A fisheye rig (Nleft != -1) keeps
+// the reference's implementation for its right-camera block (:149-216).
 int ORBmatcher::SearchByProjection(Frame &F, const std::vector<MapPoint*> &vpMapPoints, const float th, const bool bFarPoints, const float thFarPoints)
 {
     const int n1 = (int)vpMapPoints.size(), n2 = F.numAllKPts();
@@ -134,11 +150,14 @@ int ORBmatcher::SearchByProjection(Frame &F, const std::vector<MapPoint*> &vpMap
     std::vector<eorb_track_point> pts(n1);
     std::vector<unsigned char> dmp((size_t)n1 * 32, 0), d2, held(n2, 0);
     std::vector<eorb_keypoint> k2;
+    std::vector<float> projXR(n1, 0.f);
+    const bool haveRight = F.numKPtsLeft() == -1 && (int)F.mvuRight.size() == n2;
     for (int i = 0; i < n1; i++) {
         MapPoint* pMP = vpMapPoints[i];
         eorb_track_point& p = pts[i];
         std::memset(&p, 0, sizeof(p));
         if (!pMP || !pMP->mbTrackInView) continue;
+        projXR[i] = pMP->mTrackProjXR;
         p.proj_x = pMP->mTrackProjX; p.proj_y = pMP->mTrackProjY; p.view_cos = pMP->mTrackViewCos; p.depth = pMP->mTrackDepth;
         p.scale_level = pMP->mnTrackScaleLevel; p.observations = pMP->Observations();
         p.in_view = 1; p.bad = pMP->isBad() ? 1 : 0;
@@ -154,14 +173,72 @@ int ORBmatcher::SearchByProjection(Frame &F, const std::vector<MapPoint*> &vpMap
     const std::vector<float> sf = F.getAllORBScaleFactors();
     std::vector<int> mc(n2, -1);
     int nmatches = 0;
-    const int rc = eorb_guided_search_by_projection_map_points(g, pts.data(), dmp.data(), n1, k2.data(), d2.data(), held.data(), n2, bounds, sf.data(),
-                                                               (int)sf.size(), th, bFarPoints ? 1 : 0, thFarPoints, mfNNratio, mc.data(), &nmatches);
+    const int rc = eorb_guided_search_by_projection_map_points_stereo(g, pts.data(), haveRight ? projXR.data() : nullptr, dmp.data(), n1, k2.data(),
+                                                                      d2.data(), held.data(), haveRight ? F.mvuRight.data() : nullptr, n2, bounds,
+                                                                      sf.data(), (int)sf.size(), th, bFarPoints ? 1 : 0, thFarPoints, mfNNratio,
+                                                                      mc.data(), &nmatches);
     if (rc != EORB_OK) {
         std::fprintf(stderr, "ORBmatcher(b200)::SearchByProjection(map points): %s\n", eorb_last_error());
         return 0;
     }
     for (int i2 = 0; i2 < n2; i2++)
         if (mc[i2] >= 0) F.setMapPoint(i2, vpMapPoints[mc[i2]]);
+    return nmatches;
+}
+
+// ORBmatcher::SearchByProjection(CurrentFrame, pKF, sAlreadyFound, th, ORBdist) (:2189-2312; Tracking::Relocalization after the PnP
+// refinement).  The per-point host arithmetic of the reference stays here with its own expressions: camera centre Ow = -Rcw^T tcw,
+// dist3D = norm(x3Dw - Ow), the distance-invariance gate and MapPoint::PredictScale (:2196, :2226-2237).
+int ORBmatcher::SearchByProjection(Frame &CurrentFrame, KeyFrame *pKF, const std::set<MapPoint*> &sAlreadyFound, const float th, const int ORBdist)
+{
+    const std::vector<MapPoint*> vpMPs = pKF->GetMapPointMatches();
+    const int n1 = (int)vpMPs.size(), n2 = CurrentFrame.numAllKPts();
+    eorb_guided* g = threadHandle();
+    if (!g || n1 == 0 || n2 == 0) return 0;
+    const cv::Mat& T = CurrentFrame.mTcw;
+    float Ow[3];
+    for (int r = 0; r < 3; r++)
+        Ow[r] = -(T.at<float>(0, r) * T.at<float>(0, 3) + T.at<float>(1, r) * T.at<float>(1, 3) + T.at<float>(2, r) * T.at<float>(2, 3));
+    std::vector<eorb_keypoint> k1(n1), k2;
+    std::vector<unsigned char> dmp((size_t)n1 * 32, 0), d2, valid(n1, 0), held(n2, 0);
+    std::vector<float> x3(3 * (size_t)n1, 0.f);
+    std::vector<int> level(n1, 0);
+    for (int i = 0; i < n1; i++) {
+        const cv::KeyPoint kp = pKF->getUndistKPtMono(i);
+        k1[i].x = kp.pt.x; k1[i].y = kp.pt.y; k1[i].size = kp.size; k1[i].angle = kp.angle; k1[i].response = kp.response;
+        k1[i].octave = kp.octave; k1[i].class_id = kp.class_id;
+        MapPoint* pMP = vpMPs[i];
+        if (!pMP || pMP->isBad() || sAlreadyFound.count(pMP)) continue;
+        const cv::Mat x3Dw = pMP->GetWorldPos();
+        float po[3];
+        for (int r = 0; r < 3; r++) {
+            x3[3 * i + r] = T.at<float>(r, 0) * x3Dw.at<float>(0, 0) + T.at<float>(r, 1) * x3Dw.at<float>(1, 0) + T.at<float>(r, 2) * x3Dw.at<float>(2, 0) + T.at<float>(r, 3);
+            po[r] = x3Dw.at<float>(r, 0) - Ow[r];
+        }
+        const float dist3D = (float)std::sqrt((double)po[0] * po[0] + (double)po[1] * po[1] + (double)po[2] * po[2]);   // cv::norm accumulates in double
+        if (dist3D < pMP->GetMinDistanceInvariance() || dist3D > pMP->GetMaxDistanceInvariance()) continue;
+        level[i] = pMP->PredictScale(dist3D, &CurrentFrame);
+        valid[i] = 1;
+        const cv::Mat dMP = pMP->GetDescriptor();
+        std::memcpy(&dmp[(size_t)i * 32], dMP.ptr<unsigned char>(), 32);
+    }
+    packFrame(CurrentFrame, k2, d2);
+    for (int i2 = 0; i2 < n2; i2++) held[i2] = CurrentFrame.getMapPoint(i2) ? 1 : 0;
+    const float bounds[4] = {Frame::mnMinX, Frame::mnMinY, Frame::mnMaxX, Frame::mnMaxY};
+    const float K4[4] = {CurrentFrame.mpCamera->getParameter(0), CurrentFrame.mpCamera->getParameter(1), CurrentFrame.mpCamera->getParameter(2),
+                         CurrentFrame.mpCamera->getParameter(3)};
+    const std::vector<float> sf = CurrentFrame.getAllORBScaleFactors();
+    std::vector<int> mc(n2, -1);
+    int nmatches = 0;
+    const int rc = eorb_guided_search_by_projection_reloc(g, x3.data(), valid.data(), level.data(), k1.data(), dmp.data(), n1, k2.data(), d2.data(),
+                                                          held.data(), n2, bounds, K4, sf.data(), (int)sf.size(), th, ORBdist,
+                                                          mbCheckOrientation ? 1 : 0, mc.data(), &nmatches);
+    if (rc != EORB_OK) {
+        std::fprintf(stderr, "ORBmatcher(b200)::SearchByProjection(relocalisation): %s\n", eorb_last_error());
+        return 0;
+    }
+    for (int i2 = 0; i2 < n2; i2++)
+        if (mc[i2] >= 0) CurrentFrame.setMapPoint(i2, vpMPs[mc[i2]]);
     return nmatches;
 }
 

@@ -2,6 +2,7 @@
 // reference tree (which does not travel with this repository).  A real build includes the reference headers:
 //   include/ORBmatcher.h:35-114, include/Event/EventData.h:36-58, include/CameraModels/GeometricCamera.h:41-134
 #pragma once
+#include <set>
 #include <vector>
 #include <opencv2/core/core.hpp>
 #include "../ORBVocabulary_b200.h"   // the DBoW2::FeatureVector stand-in (a real build has Thirdparty/DBoW2)
@@ -23,8 +24,14 @@ public:
     int Observations() { return mnObs; }
     bool isBad() { return mbBad; }
     // tracking fields Frame::isInFrustum fills (include/MapPoint.h:133-144)
-    float mTrackProjX = 0.f, mTrackProjY = 0.f, mTrackDepth = 0.f, mTrackViewCos = 1.f;
+    float mTrackProjX = 0.f, mTrackProjY = 0.f, mTrackDepth = 0.f, mTrackViewCos = 1.f, mTrackProjXR = 0.f;
     int mnTrackScaleLevel = 0;
+    // what the relocalisation search reads (include/MapPoint.h:104-106)
+    float GetMinDistanceInvariance() { return mfMinDistance; }
+    float GetMaxDistanceInvariance() { return mfMaxDistance; }
+    int PredictScale(const float& currentDist, class Frame* pF);
+    float mfMinDistance = 0.f, mfMaxDistance = 1e30f;
+    int mnPredictedLevel = 0;
     bool mbTrackInView = false, mbTrackInViewR = false;
     bool mbBad = false;
 protected:
@@ -39,6 +46,10 @@ public:
     bool getMPOutlier(int idx) const { return mvbOutlier[idx]; }
     std::vector<float> getAllORBScaleFactors() const { return mvScaleFactors; }
     cv::Mat mTcw;                                // 4x4 CV_32F
+    int numKPtsLeft() const { return Nleft; }     // -1: monocular / rectified stereo / RGB-D; >= 0: fisheye rig (include/Frame.h)
+    int Nleft = -1;
+    std::vector<float> mvuRight;                 // right-image column per keypoint, negative = none (include/Frame.h:296)
+    float mbf = 0.f, mb = 0.f;                   // baseline * fx, baseline in metres (include/Frame.h:268-271)
     GeometricCamera* mpCamera = nullptr;
     std::vector<MapPoint*> mvpMapPoints;
     std::vector<bool> mvbOutlier;
@@ -53,6 +64,8 @@ public:
     cv::Mat mDescriptors;
     DBoW2::FeatureVector mFeatVec;                // include/Frame.h:332
 };
+
+inline int MapPoint::PredictScale(const float&, Frame*) { return mnPredictedLevel; }
 
 class KeyFrame {   // what SearchByBoW reads (include/KeyFrame.h:343, 395, 400, 407, 523)
 public:
@@ -71,6 +84,7 @@ public:
     int SearchForInitialization(Frame& F1, Frame& F2, std::vector<cv::Point2f>& vbPrevMatched, std::vector<int>& vnMatches12, int windowSize = 10);
     int SearchByProjection(Frame &CurrentFrame, const Frame &LastFrame, float th, bool bMono);
     int SearchByBoW(KeyFrame* pKF, Frame& F, std::vector<MapPoint*>& vpMapPointMatches);
+    int SearchByProjection(Frame &CurrentFrame, KeyFrame* pKF, const std::set<MapPoint*> &sAlreadyFound, float th, int ORBdist);
     int SearchByProjection(Frame &F, const std::vector<MapPoint*> &vpMapPoints, float th=3,
             bool bFarPoints = false, float thFarPoints = 50.0f);
     explicit ORBmatcher(float nnratio = 0.6, bool checkOri = true) : mfNNratio(nnratio), mbCheckOrientation(checkOri) {}

@@ -146,6 +146,30 @@ int main(int argc, char** argv)
         int lset = 0, lsame = 0;
         for (size_t i = 0; i < kps.size(); i++) { lset += (F2.mvpMapPoints[i] != nullptr); lsame += (F2.mvpMapPoints[i] == mps[i]); }
         std::printf("slp_nm=%d slp_set=%d slp_same=%d\n", nl, lset, lsame);
+        // rectified stereo: every keypoint has a right column consistent with its depth (ur = u - mbf / z), so the right-column test
+        // passes everywhere and the result equals the monocular one; level window = forward (the last frame sits 1 m behind)
+        F2.mvpMapPoints.assign(kps.size(), nullptr);
+        F2.mbf = 40.f; F2.mb = 0.1f;
+        F2.mvuRight.assign(kps.size(), -1.f);
+        for (size_t i = 0; i < kps.size(); i++) F2.mvuRight[i] = F2.mvKeysUn[i].pt.x - 40.f / 4.f;
+        F1.mTcw = F2.mTcw.clone();
+        const int ns = matcher.SearchByProjection(F2, F1, 15.f, false);
+        int sset = 0;
+        for (size_t i = 0; i < kps.size(); i++) sset += (F2.mvpMapPoints[i] != nullptr);
+        std::printf("sbs_nm=%d sbs_set=%d\n", ns, sset);
+        // ORBmatcher::SearchByProjection(CurrentFrame, pKF, sAlreadyFound, th, ORBdist): the same points seen from a keyframe
+        {
+            ORB_SLAM3::KeyFrame KF;
+            KF.mvKeysUn = kps; KF.mDescriptors = desc; KF.mvpMapPoints = mps;
+            for (size_t i = 0; i < kps.size(); i++) mps[i]->mnPredictedLevel = F2.mvKeysUn[i].octave;
+            F2.mvpMapPoints.assign(kps.size(), nullptr);
+            std::set<ORB_SLAM3::MapPoint*> found;
+            if (!mps.empty()) found.insert(mps[0]);
+            const int nr = matcher.SearchByProjection(F2, &KF, found, 10.f, 100);
+            int rset = 0, rsame = 0;
+            for (size_t i = 0; i < kps.size(); i++) { rset += (F2.mvpMapPoints[i] != nullptr); rsame += (F2.mvpMapPoints[i] == mps[i]); }
+            std::printf("sbr_nm=%d sbr_set=%d sbr_same=%d sbr_skipped_found=%d\n", nr, rset, rsame, (int)(mps.empty() || F2.mvpMapPoints[0] != mps[0]));
+        }
         for (auto* p : mps) delete p;
     }
     // ORBVocabulary::transform through a text file in ORB-SLAM's vocabulary format (k = 3, L = 2: 3 inner nodes, 9 words whose

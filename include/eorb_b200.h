@@ -363,6 +363,40 @@ int eorb_guided_search_by_projection_device(eorb_guided* g, const float* d_x3Dc,
                                             const uint8_t* d_desc2, int n2, const float* bounds4, const float* K4,
                                             const float* scale_factors, int nlevels, float th, int check_ori, int32_t* d_match_cur,
                                             int* nmatches);
+/* The same for a RECTIFIED-STEREO / RGB-D frame (Nleft == -1, mvuRight set; Tracking::TrackWithMotionModel with bMono = false):
+ * level_mode = 1 when bForward, 2 when bBackward, 0 otherwise (tlc.z against CurrentFrame.mb, src/ORBmatcher.cc:1989-1990; the
+ * level window becomes [octave, inf) / [0, octave], :2024-2029); u_right2 = CurrentFrame.mvuRight (n2 floats, may be NULL) and
+ * mbf = CurrentFrame.mbf: a candidate with a right-image column is skipped when |(u - mbf / zc) - uRight| > radius (:2049-2055).
+ * (The second pass over a fisheye rig's right camera, Nleft != -1, :2093-2160, stays with the reference body.) */
+int eorb_guided_search_by_projection_stereo(eorb_guided* g, const float* x3Dc, const uint8_t* valid1, const int32_t* obs1,
+                                            const eorb_keypoint* kps1, const uint8_t* descMP, int n1, const eorb_keypoint* kps2,
+                                            const uint8_t* desc2, const float* u_right2, int n2, const float* bounds4, const float* K4,
+                                            const float* scale_factors, int nlevels, float th, int check_ori, int level_mode, float mbf,
+                                            int32_t* match_cur, int* nmatches);
+int eorb_guided_search_by_projection_stereo_device(eorb_guided* g, const float* d_x3Dc, const uint8_t* d_valid1, const int32_t* d_obs1,
+                                                   const eorb_keypoint* d_kps1, const uint8_t* d_descMP, int n1, const eorb_keypoint* d_kps2,
+                                                   const uint8_t* d_desc2, const float* d_u_right2, int n2, const float* bounds4,
+                                                   const float* K4, const float* scale_factors, int nlevels, float th, int check_ori,
+                                                   int level_mode, float mbf, int32_t* d_match_cur, int* nmatches);
+
+/* eorb_guided_search_by_projection_reloc replaces ORBmatcher::SearchByProjection(Frame& CurrentFrame, KeyFrame* pKF,
+ * const set<MapPoint*>& sAlreadyFound, const float th, const int ORBdist) (src/ORBmatcher.cc:2189-2312; Tracking::Relocalization
+ * after the PnP refinement).  Per keyframe map point i: x3Dc = Rcw * x3Dw + tcw, valid1[i] != 0 = the point exists, is not bad, is
+ * not in sAlreadyFound and dist3D lies inside its distance invariance (:2205-2232); level1[i] = PredictScale(dist3D, &CurrentFrame)
+ * (:2234; host arithmetic on the map point); kps1[i].angle = the keyframe's undistorted keypoint; descMP = GetDescriptor().
+ * held2[i2] != 0 (may be NULL) = CurrentFrame.getMapPoint(i2) is set on entry.  No depth-sign test (:2218); window th *
+ * scale[level], levels [level-1, level+1]; a slot that holds ANY point is skipped (:2253); accepted when the best distance is
+ * <= orb_dist (:2266); rotation filter as in the other searches.  match_cur[i2] = keyframe index set into the frame, or -1. */
+int eorb_guided_search_by_projection_reloc(eorb_guided* g, const float* x3Dc, const uint8_t* valid1, const int32_t* level1,
+                                           const eorb_keypoint* kps1, const uint8_t* descMP, int n1, const eorb_keypoint* kps2,
+                                           const uint8_t* desc2, const uint8_t* held2, int n2, const float* bounds4, const float* K4,
+                                           const float* scale_factors, int nlevels, float th, int orb_dist, int check_ori,
+                                           int32_t* match_cur, int* nmatches);
+int eorb_guided_search_by_projection_reloc_device(eorb_guided* g, const float* d_x3Dc, const uint8_t* d_valid1, const int32_t* d_level1,
+                                                  const eorb_keypoint* d_kps1, const uint8_t* d_descMP, int n1, const eorb_keypoint* d_kps2,
+                                                  const uint8_t* d_desc2, const uint8_t* d_held2, int n2, const float* bounds4,
+                                                  const float* K4, const float* scale_factors, int nlevels, float th, int orb_dist,
+                                                  int check_ori, int32_t* d_match_cur, int* nmatches);
 
 /* eorb_guided_search_by_projection_map_points replaces ORBmatcher::SearchByProjection(Frame& F, const vector<MapPoint*>&
  * vpMapPoints, const float th, const bool bFarPoints, const float thFarPoints) (src/ORBmatcher.cc:44-218) as called by
@@ -386,6 +420,20 @@ int eorb_guided_search_by_projection_map_points_device(eorb_guided* g, const eor
                                                        int n2, const float* bounds4, const float* scale_factors, int nlevels, float th,
                                                        int far_points, float th_far, float nnratio, int32_t* d_match_cur,
                                                        int* nmatches);
+/* The same for a RECTIFIED-STEREO / RGB-D frame (Nleft == -1, mvuRight set): proj_xr[i] = mTrackProjXR of map point i, u_right2 =
+ * F.mvuRight; a candidate with a right-image column is skipped when |mTrackProjXR - uRight| > r * mvScaleFactors[level]
+ * (src/ORBmatcher.cc:91-96).  (The right-camera block of a fisheye rig, Nleft != -1, :149-216, stays with the reference body.) */
+int eorb_guided_search_by_projection_map_points_stereo(eorb_guided* g, const eorb_track_point* pts, const float* proj_xr,
+                                                       const uint8_t* descMP, int n1, const eorb_keypoint* kps2, const uint8_t* desc2,
+                                                       const uint8_t* held2, const float* u_right2, int n2, const float* bounds4,
+                                                       const float* scale_factors, int nlevels, float th, int far_points, float th_far,
+                                                       float nnratio, int32_t* match_cur, int* nmatches);
+int eorb_guided_search_by_projection_map_points_stereo_device(eorb_guided* g, const eorb_track_point* d_pts, const float* d_proj_xr,
+                                                              const uint8_t* d_descMP, int n1, const eorb_keypoint* d_kps2,
+                                                              const uint8_t* d_desc2, const uint8_t* d_held2, const float* d_u_right2,
+                                                              int n2, const float* bounds4, const float* scale_factors, int nlevels,
+                                                              float th, int far_points, float th_far, float nnratio,
+                                                              int32_t* d_match_cur, int* nmatches);
 
 /* eorb_guided_search_by_bow replaces ORBmatcher::SearchByBoW(KeyFrame* pKF, Frame& F, vector<MapPoint*>& vpMapPointMatches)
  * (src/ORBmatcher.cc:276-478) as called by Tracking::TrackReferenceKeyFrame and Relocalization (src/Tracking-1.cc:1680, 2625)

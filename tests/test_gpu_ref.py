@@ -132,3 +132,47 @@ def test_cuda_event_frames_equal_reference():
             assert int(np.abs(u8.astype(int) - g["u%d" % i].astype(int)).max()) <= 1, (i, s)
         checked += 1
     assert checked >= 4
+
+
+def _guided_cuda(api, gm, kind, a, kw):
+    """one case of tests/ref_cases.py::guided_cases through the C ABI (host-pointer entry points)"""
+    if kind == "proj":
+        gm.mbCheckOrientation = kw["check_ori"]
+        if kw["level_mode"] == 0 and kw["u_right2"] is None:
+            return gm.SearchByProjection(*a, th=kw["th"])
+        return gm.SearchByProjectionStereo(*a, th=kw["th"], level_mode=kw["level_mode"], mbf=kw["mbf"], u_right2=kw["u_right2"])
+    if kind == "reloc":
+        gm.mbCheckOrientation = kw["check_ori"]
+        return gm.SearchByProjectionReloc(*a, th=kw["th"], ORBdist=kw["orb_dist"])
+    if kind == "map":
+        gm.mfNNratio = kw["nnratio"]
+        pts, xr, dmp, k2, d2, held, ur, b, sf = a
+        if xr is None:
+            return gm.SearchByProjectionMapPoints(pts, dmp, k2, d2, held, b, sf, th=kw["th"], bFarPoints=kw["far_points"], thFarPoints=kw["th_far"])
+        return gm.SearchByProjectionMapPointsStereo(pts, xr, dmp, k2, d2, held, ur, b, sf, th=kw["th"], bFarPoints=kw["far_points"],
+                                                    thFarPoints=kw["th_far"])
+    if kind == "init":
+        gm.mfNNratio = kw["nnratio"]; gm.mbCheckOrientation = kw["check_ori"]
+        return gm.SearchForInitialization(*a, windowSize=kw["window_size"])
+    if kind == "bow":
+        gm.mfNNratio = kw["nnratio"]; gm.mbCheckOrientation = kw["check_ori"]
+        return gm.SearchByBoW(*a)
+    raise KeyError(kind)
+
+
+def test_cuda_matchers_equal_reference_golden():
+    """every tracking-thread matcher on the device against the match arrays the REFERENCE'S OWN function bodies produced
+    (tests/golden/ref_guided.npz: last-frame search mono / forward / backward / rectified stereo, relocalisation search, local-map
+    search mono / stereo, SearchForInitialization, SearchByBoW; 96 cases), bit for bit"""
+    api = _api()
+    g = RC.guided_golden()
+    gm = api.GuidedMatcher()
+    bad = []
+    for key, kind, a, kw in RC.guided_cases():
+        r = _guided_cuda(api, gm, kind, a, kw)
+        ok = r[0] == int(g[key + "_n"][0]) and np.array_equal(r[1], g[key])
+        if ok and kind == "init":
+            ok = np.asarray(r[2], np.float32).tobytes() == g[key + "_prev"].tobytes()
+        if not ok:
+            bad.append((key, r[0], int(g[key + "_n"][0]), int((r[1] != g[key]).sum())))
+    assert not bad, bad[:5]

@@ -50,6 +50,7 @@ def test_shims_compile_and_fail_loudly_without_device():
     assert "no CUDA device" in err
     assert "lk_ok=0 lk_n=0" in out
     assert "sfi_nm=0 sfi_self=0" in out and "sbp_nm=0 sbp_set=0" in out and "slp_nm=0 slp_set=0" in out and "sbb_nm=0 sbb_set=0" in out
+    assert "sbs_nm=0 sbs_set=0" in out and "sbr_nm=0 sbr_set=0" in out
     assert "voc_ok=0" in out and "undist_ok=0" in out
 
 
@@ -98,6 +99,13 @@ def test_shims_match_oracle_on_gpu():
     nlp, lset, lsame = map(int, sl.groups())
     # SearchByProjection(F, vpMapPoints, ...): all points have observations, so nmatches = slots set; most at their own keypoint
     assert nlp == lset and nlp > 0.8 * len(okps) and lsame > 0.9 * lset
+    ss = re.search(r"sbs_nm=(\d+) sbs_set=(\d+)", out)
+    # rectified stereo with consistent right columns, forward level window [octave, inf): nearly the monocular result
+    assert int(ss.group(1)) == int(ss.group(2)) and int(ss.group(1)) > 0.9 * len(okps)
+    sr = re.search(r"sbr_nm=(\d+) sbr_set=(\d+) sbr_same=(\d+) sbr_skipped_found=(\d)", out)
+    nr, rset, rsame, skipped = map(int, sr.groups())
+    # relocalisation search from a keyframe holding the same points: one point is in sAlreadyFound and must not come back
+    assert nr == rset and nr > 0.9 * len(okps) and rsame > 0.95 * rset and skipped == 1
     bb = re.search(r"sbb_nm=(\d+) sbb_set=(\d+) sbb_self=(\d+)", out)
     nbb, bset, bself = map(int, bb.groups())
     # SearchByBoW of a frame against a keyframe with the same features: distance 0 to itself, so every match is the feature itself
