@@ -699,6 +699,113 @@ def bench_bow(api, torch, dev, steps, warmup):
             "undistort_keypoints": {"ms_per_call": ms_un, "n": len(k1), "note": "Frame::UndistortKeyPoints, host call (malloc + H2D + kernel + D2H)"}}
 
 
+def bench_chain(api, torch, dev, steps, warmup):
+    """The tracking thread's per-frame chain with the frame data resident in HBM (Tracking::TrackReferenceKeyFrame + SearchLocalPoints,
+    src/Tracking-1.cc:1690, 1818, 2436): frame (host) -> ORB extraction -> Frame::UndistortKeyPoints -> Frame::ComputeBoW ->
+    ORBmatcher(0.7).SearchByBoW(pKF, F) -> ORBmatcher(0.8).SearchByProjection(F, local map points, th = 3).  Only the frame, three counts
+    and the two match tables cross PCIe; keypoints, descriptors and the FeatureVector never leave the device.  Next to it: the same
+    five steps through the CPU oracle ports, one core, and the result check."""
+    import oracle_lib as O
+    from eorb_slam_b200 import synth
+    Wc, Hc = 752, 480
+    img1 = synth.make_frame(31)
+    img2 = np.roll(img1, (2, -3), axis=(0, 1))
+    K, D = (458.654, 457.296, 367.215, 248.375), (0.0, 0.0, 0.0, 0.0, 0.0)   # rectified input: UndistortKeyPoints copies (Frame.cc:807-811)
+    voc = synth.make_vocabulary(10, 4, 7)
+    p = api.ORBxParams(1000, 1.2, 8, 20, 7, 19, (Wc, Hc))
+    ex = api.ORBextractor(p, dev, 1)
+    cap = ex.cap
+    s = torch.cuda.Stream()
+    st = s.cuda_stream
+    ex.set_stream(st)
+    v = api.ORBVocabulary(voc, dev); v.set_stream(st)
+    gm = api.GuidedMatcher(dev, 0.7, True); gm.set_stream(st)
+    gl = api.GuidedMatcher(dev, 0.8, True); gl.set_stream(st)
+    sf = np.ones(8, np.float32)
+    for i in range(1, 8):
+        sf[i] = np.float32(np.float64(sf[i - 1]) * np.float64(np.float32(1.2)))
+    bnd = np.array([0, 0, Wc, Hc], np.float32)
+    with torch.cuda.stream(s):
+        h_img = torch.from_numpy(np.stack([img1, img2])).pin_memory()
+        d_img = torch.empty((Hc, Wc), dtype=torch.uint8, device="cuda")
+        d_kps = [torch.zeros(cap * 28, dtype=torch.uint8, device="cuda") for _ in range(2)]
+        d_un = torch.zeros(cap * 28, dtype=torch.uint8, device="cuda")
+        d_desc = [torch.zeros(cap * 32, dtype=torch.uint8, device="cuda") for _ in range(2)]
+        d_n = torch.zeros(1, dtype=torch.int32, device="cuda"); d_mono = torch.zeros(1, dtype=torch.int32, device="cuda")
+        h_n = torch.zeros(1, dtype=torch.int32).pin_memory()
+        fv = [[torch.zeros(cap + 1, dtype=torch.int32, device="cuda") for _ in range(3)] for _ in range(2)]
+        d_mf = torch.zeros(cap, dtype=torch.int32, device="cuda"); d_mc = torch.zeros(cap, dtype=torch.int32, device="cuda")
+        h_mf = torch.zeros(cap, dtype=torch.int32).pin_memory(); h_mc = torch.zeros(cap, dtype=torch.int32).pin_memory()
+
+        def extract(k):
+            d_img.copy_(h_img[k], non_blocking=True)
+            ex.extract_batch_raw(d_img.data_ptr(), 1, Wc, Hc, Wc, Wc * Hc, (0, 0), True, d_kps[k].data_ptr(), d_desc[k].data_ptr(), cap,
+                                 d_n.data_ptr(), d_mono.data_ptr(), device=True)
+            h_n.copy_(d_n, non_blocking=True)
+            s.synchronize()
+            return int(h_n[0])
+
+        # the keyframe: extracted once, FeatureVector kept on the device, 85 % of its features carry a map point
+        n1 = extract(0)
+        _, nf1 = v.transform_resident(d_desc[0].data_ptr(), n1, 2, fv[0][0].data_ptr(), fv[0][1].data_ptr(), fv[0][2].data_ptr())
+        rng = np.random.default_rng(5)
+        valid = (rng.random(n1) < 0.85).astype(np.uint8)
+        d_valid = torch.from_numpy(valid).cuda()
+        s.synchronize()
+        k1 = np.frombuffer(d_kps[0].cpu().numpy().tobytes(), api.KEYPOINT_DTYPE)[:n1]
+        pts = np.zeros(n1, synth.TRACK_POINT_DTYPE)
+        pts["proj_x"] = k1["x"] - 3.0 + rng.normal(0, 0.7, n1).astype(np.float32); pts["proj_y"] = k1["y"] + 2.0 + rng.normal(0, 0.7, n1).astype(np.float32)
+        pts["view_cos"] = rng.uniform(0.99, 1.0, n1).astype(np.float32); pts["depth"] = 5.0
+        pts["scale_level"] = k1["octave"]; pts["observations"] = rng.integers(1, 4, n1); pts["in_view"] = 1
+        d_pts = torch.from_numpy(pts.view(np.uint8).copy()).cuda()
+        d_held = torch.zeros(cap, dtype=torch.uint8, device="cuda")
+
+        def frame_step():
+            n2 = extract(1)
+            api.UndistortKeyPoints_device(d_kps[1].data_ptr(), d_un.data_ptr(), n2, K, D, st)
+            _, nf2 = v.transform_resident(d_desc[1].data_ptr(), n2, 2, fv[1][0].data_ptr(), fv[1][1].data_ptr(), fv[1][2].data_ptr())
+            nb = gm.SearchByBoW_device(d_kps[0].data_ptr(), d_desc[0].data_ptr(), d_valid.data_ptr(), n1, tuple(t.data_ptr() for t in fv[0]), nf1,
+                                       d_un.data_ptr(), d_desc[1].data_ptr(), n2, tuple(t.data_ptr() for t in fv[1]), nf2, d_mf.data_ptr())
+            torch.ge(d_mf[:n2], 0, out=d_held[:n2].view(torch.bool))          # slots TrackReferenceKeyFrame filled are held in the local-map search
+            nl = gl.SearchByProjectionMapPoints_device(d_pts.data_ptr(), d_desc[0].data_ptr(), n1, d_un.data_ptr(), d_desc[1].data_ptr(),
+                                                       d_held.data_ptr(), n2, bnd, sf, d_mc.data_ptr(), 3.0)
+            h_mf[:n2].copy_(d_mf[:n2], non_blocking=True); h_mc[:n2].copy_(d_mc[:n2], non_blocking=True)
+            s.synchronize()
+            return n2, nb, nl
+
+        for _ in range(max(warmup, 5)):
+            n2, nb, nl = frame_step()
+        reps = max(steps, 3) * 20
+        ts = []
+        for _ in range(reps):
+            t0 = time.perf_counter(); frame_step(); ts.append(time.perf_counter() - t0)
+        ms = float(np.median(ts)) * 1e3
+        mf = h_mf[:n2].numpy().copy(); mc = h_mc[:n2].numpy().copy()
+    for hdl in (ex, v, gm, gl):
+        hdl.set_stream(None)
+    # the same chain through the CPU ports (one core) + the result check
+    orc = O.OrbOracle(1000, 1.2, 8, 20, 7, 19, Wc, Hc)
+    vo = O.VocabOracle(voc)
+    _, ok1, od1 = orc.extract(img1, (0, 0), True)
+    e1 = vo.transform(od1, 2)
+    cpu = {}
+    t0 = time.perf_counter(); _, ok2, od2 = orc.extract(img2, (0, 0), True); cpu["extract"] = (time.perf_counter() - t0) * 1e3
+    t0 = time.perf_counter(); e2 = vo.transform(od2, 2); cpu["transform"] = (time.perf_counter() - t0) * 1e3
+    f1 = (e1["fv_nodes"], e1["fv_start"], e1["fv_feats"]); f2 = (e2["fv_nodes"], e2["fv_start"], e2["fv_feats"])
+    t0 = time.perf_counter(); en, emf = O.search_by_bow(ok1, od1, valid, f1, ok2, od2, f2, 0.7, True); cpu["search_by_bow"] = (time.perf_counter() - t0) * 1e3
+    held = (emf >= 0).astype(np.uint8)
+    t0 = time.perf_counter()
+    eln, elmc = O.search_by_projection_map_points(pts, od1, ok2, od2, held, bnd, sf, 3.0, False, 0.0, 0.8)
+    cpu["search_local_points"] = (time.perf_counter() - t0) * 1e3
+    ok = bool(n2 == len(ok2) and nb == en and np.array_equal(mf, emf) and nl == eln and np.array_equal(mc, elmc))
+    return {"metric": "tracking_chain_latency_ms", "value": ms, "unit": "ms", "p90": float(np.percentile(ts, 90)) * 1e3,
+            "workload": "one 752x480 frame (pinned host) -> extract -> undistort -> ComputeBoW (k=10 L=4 vocabulary, levelsup 2) -> SearchByBoW against a "
+                        "%d-feature keyframe -> SearchByProjection(F, %d local map points, th 3); %d + %d matches; data resident in HBM, "
+                        "3 counts + 2 match tables come back" % (n1, n1, nb, nl),
+            "bit_exact_vs_oracle": ok,
+            "cpu_baseline": {"kind": "port", "cores": 1, "ms_per_frame": float(sum(cpu.values())), "stages_ms": cpu}}
+
+
 # ------------------------------------------------------------------------------------------------ main arm
 def run_ours(args):
     import torch
@@ -892,6 +999,11 @@ def run_ours(args):
                 extra["bow"] = bench_bow(api, torch, dev, args.steps, args.warmup)
         except Exception as e:
             extra["bow"] = {"error": repr(e)}
+        try:
+            if rank == 0:
+                extra["tracking_chain"] = bench_chain(api, torch, dev, args.steps, args.warmup)
+        except Exception as e:
+            extra["tracking_chain"] = {"error": repr(e)}
         try:
             extra["hamming"] = bench_hamming(api, torch, dev, max(min(args.steps, 3), 1), 3, world, rank, dist, not args.no_cpu)
         except Exception as e:

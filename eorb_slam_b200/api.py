@@ -111,6 +111,7 @@ def _load():
         "eorb_vocab_set_stream": ([vp, vp], i), "eorb_vocab_reset_stream": ([vp], i), "eorb_vocab_launch_count": ([vp], C.c_longlong),
         "eorb_vocab_transform": ([vp, vp, i, i, vp, vp, vp, vp, vp, vp, vp, vp, vp], i),
         "eorb_vocab_transform_device": ([vp, vp, i, i, vp, vp, vp, vp, vp, vp, vp, vp, vp], i),
+        "eorb_vocab_transform_resident": ([vp, vp, i, i, vp, vp, vp, vp, vp, vp, vp], i),
         "eorb_undistort_keypoints": ([vp, i, vp, vp, vp], i), "eorb_undistort_keypoints_device": ([vp, vp, i, vp, vp, vp], i),
     }
     for name, (args, res) in sig.items():
@@ -855,8 +856,23 @@ class ORBVocabulary:
         f = np.ascontiguousarray(features, np.uint8).reshape(-1, 32)
         return self._run(lib.eorb_vocab_transform, _p(f), len(f), levelsup)
 
+    def transform_resident(self, d_feats_ptr, n, levelsup, d_fv_nodes, d_fv_start, d_fv_feats, d_bow_ids=0, d_bow_vals=0):
+        """descriptors AND results in HBM (device addresses as ints) -> (nbow, nfv)"""
+        nb, nf = C.c_int(0), C.c_int(0)
+        _check(lib.eorb_vocab_transform_resident(self.h, C.c_void_p(d_feats_ptr), int(n), int(levelsup), C.c_void_p(d_bow_ids) if d_bow_ids else None,
+                                                 C.c_void_p(d_bow_vals) if d_bow_vals else None, C.byref(nb), C.c_void_p(d_fv_nodes),
+                                                 C.c_void_p(d_fv_start), C.c_void_p(d_fv_feats), C.byref(nf)), "transform_resident")
+        return nb.value, nf.value
+
     def transform_device(self, d_feats_ptr, n, levelsup=4):
         return self._run(lib.eorb_vocab_transform_device, C.c_void_p(d_feats_ptr), n, levelsup)
+
+
+def UndistortKeyPoints_device(d_in, d_out, n, K4, distCoef5, stream=None):
+    """Frame::UndistortKeyPoints on device arrays (ints = device addresses; d_out may equal d_in)"""
+    K = np.ascontiguousarray(K4, np.float32); D = np.ascontiguousarray(distCoef5, np.float32)
+    _check(lib.eorb_undistort_keypoints_device(C.c_void_p(d_in), C.c_void_p(d_out), int(n), _p(K), _p(D), C.c_void_p(stream) if stream else None),
+           "UndistortKeyPoints_device")
 
 
 def UndistortKeyPoints(keypoints, K4, distCoef5):

@@ -186,6 +186,35 @@ extern "C" int eorb_vocab_transform_device(eorb_vocab* v, const uint8_t* d_feats
     return transformRun(v, d_feats, n, levelsup, bow_ids, bow_vals, nbow, fv_nodes, fv_start, fv_feats, nfv, word_id, node_id);
 }
 
+// The same with the RESULTS left in HBM as well (the tracking chain: extract -> transform -> SearchByBoW without a host round trip of
+// the vectors): the BowVector and the CSR FeatureVector are copied device-to-device into the caller's arrays (n entries each,
+// d_fv_start n + 1), only the two counts cross PCIe.
+extern "C" int eorb_vocab_transform_resident(eorb_vocab* v, const uint8_t* d_feats, int n, int levelsup, uint32_t* d_bow_ids, double* d_bow_vals,
+                                             int* nbow, uint32_t* d_fv_nodes, int32_t* d_fv_start, uint32_t* d_fv_feats, int* nfv) {
+    if (!v) return bFail(EORB_ERR_ARG, "eorb_vocab_transform_resident", "null handle");
+    if (n < 0 || (n > 0 && !d_feats) || !nbow || !nfv || !d_fv_nodes || !d_fv_start || !d_fv_feats)
+        return bFail(EORB_ERR_ARG, "eorb_vocab_transform_resident", "null argument");
+    if (n > EORB_BOW_MAX_FEATS) return bFail(EORB_ERR_CAPACITY, "eorb_vocab_transform_resident", "more than EORB_BOW_MAX_FEATURES features");
+    *nbow = 0; *nfv = 0;
+    CU(cudaSetDevice(v->device));
+    if (n == 0 || v->nnodes <= 1) { CU(cudaMemsetAsync(d_fv_start, 0, sizeof(int32_t), v->stream)); CU(cudaStreamSynchronize(v->stream)); return EORB_OK; }
+    if ((uintptr_t)d_feats & 15) return bFail(EORB_ERR_ARG, "eorb_vocab_transform_resident", "descriptors must be 16-byte aligned");
+    const int norm = v->scoring == 1 ? 2 : (v->scoring == 5 ? 0 : 1);
+    const int accumulate = v->weighting == 0 || v->weighting == 1;
+    VocabDev vd{v->d_childStart, v->d_children, v->d_desc, v->d_weight, v->d_wordId, v->nnodes, v->L};
+    CU(launch_bow_transform(vd, d_feats, n, levelsup, accumulate, norm, v->o, v->stream, &v->launches));
+    int* hc = reinterpret_cast<int*>(v->h_pin);
+    CU(cudaMemcpyAsync(hc, v->o.counts, 2 * sizeof(int), cudaMemcpyDeviceToHost, v->stream));
+    CU(cudaMemcpyAsync(d_fv_nodes, v->o.fvNodes, (size_t)n * 4, cudaMemcpyDeviceToDevice, v->stream));
+    CU(cudaMemcpyAsync(d_fv_start, v->o.fvStart, (size_t)(n + 1) * 4, cudaMemcpyDeviceToDevice, v->stream));
+    CU(cudaMemcpyAsync(d_fv_feats, v->o.fvFeats, (size_t)n * 4, cudaMemcpyDeviceToDevice, v->stream));
+    if (d_bow_ids) CU(cudaMemcpyAsync(d_bow_ids, v->o.bowIds, (size_t)n * 4, cudaMemcpyDeviceToDevice, v->stream));
+    if (d_bow_vals) CU(cudaMemcpyAsync(d_bow_vals, v->o.bowVals, (size_t)n * 8, cudaMemcpyDeviceToDevice, v->stream));
+    CU(cudaStreamSynchronize(v->stream));
+    *nbow = hc[0]; *nfv = hc[1];
+    return EORB_OK;
+}
+
 // ------------------------------------------------------------------------------------------------ undistortion
 extern "C" int eorb_undistort_keypoints_device(const eorb_keypoint* d_in, eorb_keypoint* d_out, int n, const float* K4, const float* dist5,
                                                void* cuda_stream) {

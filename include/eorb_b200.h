@@ -479,6 +479,11 @@ int eorb_vocab_transform(eorb_vocab* v, const uint8_t* feats, int n, int levelsu
 /* the same with the descriptors resident in HBM (16-byte aligned), e.g. straight from eorb_orb_extract_batch_device */
 int eorb_vocab_transform_device(eorb_vocab* v, const uint8_t* d_feats, int n, int levelsup, uint32_t* bow_ids, double* bow_vals, int* nbow,
                                 uint32_t* fv_nodes, int32_t* fv_start, uint32_t* fv_feats, int* nfv, uint32_t* word_id, uint32_t* node_id);
+/* the same with the results left in HBM too: BowVector and CSR FeatureVector are written to the caller's DEVICE arrays (n entries each,
+ * d_fv_start n + 1; d_bow_ids / d_bow_vals may be NULL), only the counts *nbow / *nfv come back to the host.  For chaining
+ * eorb_orb_extract_batch_device -> here -> eorb_guided_search_by_bow_device without a host round trip of the vectors. */
+int eorb_vocab_transform_resident(eorb_vocab* v, const uint8_t* d_feats, int n, int levelsup, uint32_t* d_bow_ids, double* d_bow_vals,
+                                  int* nbow, uint32_t* d_fv_nodes, int32_t* d_fv_start, uint32_t* d_fv_feats, int* nfv);
 /* K4 = fx, fy, cx, cy; dist5 = k1, k2, p1, p2, k3 (mDistCoef).  Positions are replaced, the other fields copied
  * (Frame.cc:833-838); k1 == 0 copies the keypoints unchanged (:807-811).  out may alias kps. */
 int eorb_undistort_keypoints(const eorb_keypoint* kps, int n, const float* K4, const float* dist5, eorb_keypoint* out);
