@@ -101,10 +101,12 @@ class ClockSampler:
 
 
 def _traffic():
-    """DRAM bytes per frame of each stage from the committed `ncu --set full` capture (profiles/r01_traffic.json)"""
-    p = os.path.join(ROOT, "profiles", "r01_traffic.json")
+    """DRAM bytes per frame of each stage from the committed `ncu --set full` capture at the TIMED launch-set size (profiles/r02_traffic.json:
+    1024 frames per launch, tools/ncu_traffic.py on gpurun_out/prof_r02c.ncu-rep)"""
+    p = os.path.join(ROOT, "profiles", "r02_traffic.json")
     if os.path.exists(p):
         d = json.load(open(p))
+        _traffic.frames_per_launch = d.get("frames_per_launch")
         _traffic.inst = {k: v.get("warp_inst_per_frame") for k, v in d["stages"].items()}
         return {k: v["dram_bytes_per_frame"] for k, v in d["stages"].items()}, d.get("source")
     _traffic.inst = {}
@@ -932,7 +934,7 @@ def run_ours(args):
             e["ncu_dram_bytes_per_frame"] = traffic[k]
         wi = getattr(_traffic, "inst", {}).get(k)
         if wi and v > 0:
-            # instruction-issue roofline: executed warp instructions per frame (ncu, profiles/r01_traffic.json) over the live
+            # instruction-issue roofline: executed warp instructions per frame (ncu, profiles/r02_traffic.json) over the live
             # CUDA-event time, against SMs x 4 schedulers x 1 warp instruction per clock at the sampled SM clock
             e["warp_inst_per_frame"] = wi
             e["issue_slots_frac"] = (wi * frames_timed / (v * 1e-3)) / (148 * 4 * (clk.get("sm_mhz") or 1965.0) * 1e6)
@@ -943,7 +945,7 @@ def run_ours(args):
         achieved = dom_bytes_launch / (dom_ms_launch * 1e-3) / 1e9
         roof = {"kernel": dom, "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                 "traffic": (traffic[dom] * chunk / (stage_launches[dom] / (frames_timed / chunk))) if dom in traffic else None,
-                "traffic_source": ("profiles/r01_traffic.json (%s), bytes per frame x frames per launch" % traffic_src) if dom in traffic else None,
+                "traffic_source": ("profiles/r02_traffic.json (%s: ncu --set full of this command at %s frames per launch set), bytes per frame x frames per launch" % (traffic_src, getattr(_traffic, "frames_per_launch", None))) if dom in traffic else None,
                 "peak_source": peak_src, "avg_launch_ms": dom_ms_launch, "algo_bytes_per_launch": dom_bytes_launch,
                 "note": "byte-granular integer kernel: issue-bound on the ALU pipe, not on HBM (see profiles/ and DESIGN.md)",
                 "issue_roofline": {"bound": "instruction issue (integer pipes)", "frac": per_stage[dom].get("issue_slots_frac"),

@@ -244,6 +244,7 @@ struct eorb_orb {
         uint32_t* d_kpList = nullptr;
         float* d_levelAngle = nullptr;
         CUtensorMap* d_tmaps = nullptr;   // [nlevels] maps of this slab's pyramid levels >= 1
+        CUtensorMap* d_blurMaps = nullptr;   // [nlevels] the same levels with blur_tma_kernel's box (EORB_BLUR_TMA=1)
         CUtensorMap pyrMaps[EORB_MAX_LEVELS];   // host: source map of the TMA-staged resize INTO level l (l >= 2; level 1's source is the caller's frame)
         eorb_keypoint* d_outKps = nullptr; uint8_t* d_outDesc = nullptr; int* d_outN = nullptr; int* d_outMono = nullptr;
         eorb_keypoint* h_kps = nullptr; uint8_t* h_desc = nullptr; int* h_n = nullptr; int* h_mono = nullptr;   // pinned
@@ -269,6 +270,7 @@ struct eorb_orb {
     bool useGraph = true;          // EORB_ORB_GRAPH=0 disables
     OrbFork graphFork;             // side stream + events of the captured single-call graph (blur beside FAST / octree)
     bool fastPadTile = true;       // EORB_FAST_PAD=0: FAST tile pitch left at the next multiple of 16 (for A/B)
+    int useBlurTma = 3;           // blur_tma_kernel variant (TMA-staged strips; 3 = 64-row bands, neighbour words read from the tile: 0.705 -> 0.609 us/frame); EORB_BLUR_TMA=0: blur_kernel (direct global loads), for A/B
     bool usePyrTma = true;         // EORB_PYR_TMA=0: every pyramid level through pyr_resize_kernel (direct global loads), for A/B
     int pyrTileRows = 64;          // EORB_PYR_TH: destination rows per TMA-staged tile (tuning)
 };
@@ -292,7 +294,7 @@ static cudaEvent_t* orbStageEvents(eorb_orb* h) {
 static void orbFreeBufs(eorb_orb::Bufs& b) {
     cudaFree(b.d_img0); cudaFree(b.d_pyr); cudaFree(b.d_blur); cudaFree(b.d_cellCount); cudaFree(b.d_cand);
     cudaFree(b.d_okeys); cudaFree(b.d_knode); cudaFree(b.d_sel); cudaFree(b.d_selCount); cudaFree(b.d_candCount);
-    cudaFree(b.d_dstIdx); cudaFree(b.d_kpList); cudaFree(b.d_levelAngle); cudaFree(b.d_tmaps); cudaFree(b.d_outKps); cudaFree(b.d_outDesc);
+    cudaFree(b.d_dstIdx); cudaFree(b.d_kpList); cudaFree(b.d_levelAngle); cudaFree(b.d_tmaps); cudaFree(b.d_blurMaps); cudaFree(b.d_outKps); cudaFree(b.d_outDesc);
     cudaFree(b.d_outN); cudaFree(b.d_outMono);
     cudaFreeHost(b.h_kps); cudaFreeHost(b.h_desc); cudaFreeHost(b.h_n); cudaFreeHost(b.h_mono);
     if (b.done) cudaEventDestroy(b.done);
@@ -327,6 +329,18 @@ static int orbAllocBufs(eorb_orb* h, eorb_orb::Bufs& b, bool pipeline) {
         }
         CU(devAlloc(&b.d_tmaps, (size_t)nl));
         CU(cudaMemcpy(b.d_tmaps, maps.data(), maps.size() * sizeof(CUtensorMap), cudaMemcpyHostToDevice));
+        bool blurTmaOk = h->useBlurTma != 0;
+        for (int l = 0; l < nl; l++)   // degenerate levels (rows bounce more than once) stay with blur_kernel's per-pixel path
+            if (P.lv[l].w > 0 && P.lv[l].h > 0 && (P.lv[l].h < 3 || P.lv[l].w < 8)) blurTmaOk = false;
+        if (blurTmaOk) {
+            for (int l = 1; l < nl; l++) {
+                int rct = tmaEncodeFrames(&maps[l], b.d_pyr + P.lv[l].off, P.lv[l].w, P.lv[l].h, (int)B, (size_t)P.lv[l].pitch,
+                                          (size_t)P.pyrBytesPerFrame, blur_tma_box_w(), blur_tma_box_h(h->useBlurTma));
+                if (rct != EORB_OK) return rct;
+            }
+            CU(devAlloc(&b.d_blurMaps, (size_t)nl));
+            CU(cudaMemcpy(b.d_blurMaps, maps.data(), maps.size() * sizeof(CUtensorMap), cudaMemcpyHostToDevice));
+        }
         memset(b.pyrMaps, 0, sizeof(b.pyrMaps));
         for (int l = 2; l < nl; l++) {
             if (P.lv[l].pyrTW <= 0) continue;
@@ -616,6 +630,8 @@ static OrbArgs orbArgs(eorb_orb* h, eorb_orb::Bufs& b, const uint8_t* lvl0, long
     a.plan = h->d_plan; a.cells = h->d_cells; a.xtab = h->d_xtab; a.ytab = h->d_ytab; a.ytabT = h->d_ytabT;
     a.lvl0 = lvl0; a.lvl0Pitch = pitch0; a.lvl0FrameStride = frameStride0;
     a.tmaps = b.d_tmaps;
+    a.blurMaps = b.d_blurMaps;
+    a.blurVariant = h->useBlurTma;
     a.pyr = b.d_pyr; a.blur = b.d_blur; a.cellCount = b.d_cellCount; a.cand = b.d_cand; a.okeys = b.d_okeys;
     a.knode = b.d_knode; a.sel = b.d_sel; a.selCount = b.d_selCount; a.candCount = b.d_candCount;
     a.dstIdx = b.d_dstIdx; a.kpList = b.d_kpList; a.icTab = h->d_icTab; a.levelAngle = b.d_levelAngle;
@@ -639,6 +655,7 @@ extern "C" int eorb_orb_create(const eorb_orb_params* params, int device, int ma
     h->par = *params; h->device = device; h->maxBatch = max_batch;
     if (const char* e = getenv("EORB_ORB_GRAPH")) h->useGraph = atoi(e) != 0;
     if (const char* e = getenv("EORB_PYR_TMA")) h->usePyrTma = atoi(e) != 0;
+    if (const char* e = getenv("EORB_BLUR_TMA")) h->useBlurTma = atoi(e);
     if (const char* e = getenv("EORB_FAST_PAD")) h->fastPadTile = atoi(e) != 0;
     if (const char* e = getenv("EORB_PYR_TH")) h->pyrTileRows = std::min(std::max(atoi(e), 8), 200);
     h->pipeBatch = std::min(max_batch, 128);   // measured on B200: H2D/compute/D2H overlap is best with 128-frame slots
@@ -778,6 +795,10 @@ extern "C" int eorb_orb_max_keypoints(const eorb_orb* h) {
 // the pyramid's TMA source maps for one launch set: the slab's maps plus level 1's source = the caller's frames
 static int orbPyrMaps(eorb_orb* h, eorb_orb::Bufs& b, const uint8_t* lvl0, int w, int hgt, int nframes, long long p0, long long fs0, CUtensorMap* out) {
     memcpy(out, b.pyrMaps, sizeof(b.pyrMaps));
+    if (b.d_blurMaps) {   // slot 0 is free (level 0 has no source): the blur's map of level 0 = the caller's frames
+        int rcb = tmaEncodeFrames(&out[0], lvl0, w, hgt, nframes, (size_t)p0, (size_t)fs0, blur_tma_box_w(), blur_tma_box_h(h->useBlurTma));
+        if (rcb != EORB_OK) return rcb;
+    }
     if (h->nlevels > 1 && h->hp.lv[1].pyrTW > 0)
         return tmaEncodeFrames(&out[1], lvl0, w, hgt, nframes, (size_t)p0, (size_t)fs0, h->hp.lv[1].pyrBW, h->hp.lv[1].pyrBH);
     return EORB_OK;

@@ -16,6 +16,7 @@
 #include "fast_score.cuh"
 #include "octree_core.cuh"
 #include "orb_kernels.h"
+#include "tma_utils.cuh"
 
 namespace eorb {
 
@@ -484,6 +485,129 @@ __global__ void __launch_bounds__(128, EORB_BLUR_MINB) blur_kernel(OrbArgs a) {
 #undef PACK
 }
 
+// ------------------------------------------------------------------------------------------------ K5t
+// The same blur with the strip's source rows staged by TMA (A/B of the design north_star names; EORB_BLUR_TMA=1 selects it, see
+// DESIGN.md for the measurement).  One warp = one block owns 128 columns x EORB_BLUR_TBAND rows: ONE cp.async.bulk.tensor tile of
+// 160 columns (the strip, 16 bytes either side: TMA's inner coordinate must be a multiple of 16 bytes) x (band + 4) rows of the
+// level's {x, y, frame} map, zero fill outside the level.  REFLECT_101 needs no extra data: mirrored rows lie inside the tile (they
+// are rows 1, 2 / h-2, h-3 of the level) and are reached by index; mirrored columns are handled by the per-lane selectors exactly
+// as in blur_kernel, which never read a byte outside the level.  The arithmetic (blur_hrow, row-pair ring) is blur_kernel's.
+#define EORB_BLUR_TBOXW 160
+// W = own word, L / R = the neighbour words read from the tile (instead of two shuffles and the edge lanes' conditional loads)
+__device__ __forceinline__ void blur_hrow_lds(unsigned L, unsigned W, unsigned R, const BlurLane& bl, unsigned* h) {
+    const unsigned WT = 0x39403927u;
+    const unsigned q0 = __byte_perm(L, W, bl.selQ0);
+    const unsigned q1 = __byte_perm(L, W, bl.selQ1);
+    const unsigned Wc = __byte_perm(L, W, bl.selW);
+    const unsigned q3 = __byte_perm(W, R, bl.selQ3);
+    const unsigned Rc = __byte_perm(W, R, bl.selR);
+    h[0] = __dp4a(Wc, 0x00270000u, __dp4a(q0, WT, 0u));
+    h[1] = __dp4a(Wc, 0x27000000u, __dp4a(q1, WT, 0u));
+    h[2] = __dp4a(Rc, 0x00000027u, __dp4a(Wc, WT, 0u));
+    h[3] = __dp4a(Rc, 0x00002700u, __dp4a(q3, WT, 0u));
+}
+template <int EORB_BLUR_TBAND, bool LDSNB>
+__global__ void __launch_bounds__(32) blur_tma_kernel(OrbArgs a, const __grid_constant__ CUtensorMap tmL0, int tasksTotal) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    const OrbPlan& P = *a.plan;
+    const int f = blockIdx.y, lane = threadIdx.x;
+    int task = blockIdx.x;
+    if (task >= tasksTotal) return;
+    int level = 0, strips = 0;
+    for (;; level++) {          // tasks of a level: ceil(h / TBAND) bands x ceil(w / 128) strips, levels in order
+        strips = (P.lv[level].w + 127) >> 7;
+        const int nt = ((P.lv[level].h + EORB_BLUR_TBAND - 1) / EORB_BLUR_TBAND) * strips;
+        if (task < nt || level + 1 >= P.nlevels) break;
+        task -= nt;
+    }
+    const LevelPlan& lp = P.lv[level];
+    const int w = lp.w, hgt = lp.h, bp = lp.bpitch;
+    const int band = task / strips, strip = task - band * strips;
+    const int x0t = strip * 128, x0 = x0t + lane * 4;
+    const int y0 = band * EORB_BLUR_TBAND;
+    const int y1 = min(y0 + EORB_BLUR_TBAND, hgt);
+    const unsigned bar = smem_u32(smem_raw + (EORB_BLUR_TBAND + 4) * EORB_BLUR_TBOXW);
+    if (lane == 0) {
+        mbar_init(bar, 1);
+        mbar_fence_init();
+        mbar_expect_tx(bar, (unsigned)((EORB_BLUR_TBAND + 4) * EORB_BLUR_TBOXW));
+        const CUtensorMap* tm = level == 0 ? &tmL0 : a.blurMaps + level;
+        tma_load_3d(smem_u32(smem_raw), tm, x0t - 16, y0 - 2, f, bar);
+    }
+    uint8_t* __restrict__ dst = a.blur + (size_t)f * (size_t)P.blurBytesPerFrame + (size_t)lp.blurOff;
+    const int lastWord = ((w + 3) & ~3) - 4;
+    const int off = min(x0, lastWord);
+    const bool store = x0 < w;
+    BlurLane bl;
+    bl.loadL = (lane == 0) && off >= 4;
+    bl.loadR = (lane == 31) && off + 4 <= lastWord;
+    if (w < 8) blur_selectors<true>(bl, x0, w);
+    else blur_selectors<false>(bl, x0, w);
+    // tile row of level row r = r - (y0 - 2); tile byte of level column c = c - (x0t - 16)
+    const unsigned char* tcol = smem_raw + (off - x0t + 16) - (y0 - 2) * EORB_BLUR_TBOXW;
+    const bool edgeLane = bl.loadL || bl.loadR;
+    const int eoff = bl.loadL ? -4 : 4;
+    uint8_t* dp = dst + (size_t)y0 * bp + off;
+    int yy = y0 - 2;
+    __syncwarp();
+    mbar_wait(bar, 0);
+#define TLOADROW(Wv, Xv) do { const unsigned char* rp_ = tcol + reflect101_near(yy, hgt) * EORB_BLUR_TBOXW; \
+        Wv = *reinterpret_cast<const unsigned*>(rp_); Xv = edgeLane ? *reinterpret_cast<const unsigned*>(rp_ + eoff) : 0u; yy++; } while (0)
+#define THROW(dstv) do { if (LDSNB) { const unsigned char* rp_ = tcol + reflect101_near(yy, hgt) * EORB_BLUR_TBOXW; yy++;              \
+            blur_hrow_lds(*reinterpret_cast<const unsigned*>(rp_ - 4), *reinterpret_cast<const unsigned*>(rp_),                      \
+                          *reinterpret_cast<const unsigned*>(rp_ + 4), bl, dstv); }                                                   \
+        else { unsigned w_, x_; TLOADROW(w_, x_); blur_hrow(w_, x_, bl, dstv); } } while (0)
+#define PACK(P, E, L)                                                                               \
+    do {                                                                                            \
+        _Pragma("unroll") for (int j_ = 0; j_ < 4; j_++) P[j_] = __byte_perm(E[j_], L[j_], 0x5410);   \
+    } while (0)
+#define OUT(P1, P2, HN)                                                                             \
+    do {                                                                                            \
+        unsigned acc_[4];                                                                           \
+        _Pragma("unroll") for (int j_ = 0; j_ < 4; j_++)                                              \
+            acc_[j_] = 39u * HN[j_] + __dp2a_lo(P2[j_], 0x00003940u, __dp2a_lo(P1[j_], 0x00003927u, 32768u)); \
+        const unsigned lo_ = __byte_perm(acc_[0], acc_[1], 0x0062);                                 \
+        const unsigned hi_ = __byte_perm(acc_[2], acc_[3], 0x0062);                                 \
+        const unsigned o_ = __byte_perm(lo_, hi_, 0x5410);                                          \
+        if (store) *reinterpret_cast<unsigned*>(dp) = o_;                                           \
+        dp += bp;                                                                                   \
+    } while (0)
+    unsigned pa[4], pb[4], pc[4], pd[4], hx[4], hy[4];
+    {
+        unsigned h0[4], h1[4];
+        THROW(h0); THROW(h1); PACK(pa, h0, h1);
+        THROW(h0); PACK(pb, h1, h0);
+        THROW(hy); PACK(pc, h0, hy);
+    }
+    int y = y0;
+    for (; y + 4 <= y1; y += 4) {
+        THROW(hx); PACK(pd, hy, hx); OUT(pa, pc, hx);
+        THROW(hy); PACK(pa, hx, hy); OUT(pb, pd, hy);
+        THROW(hx); PACK(pb, hy, hx); OUT(pc, pa, hx);
+        THROW(hy); PACK(pc, hx, hy); OUT(pd, pb, hy);
+    }
+    if (y < y1) {
+        THROW(hx); PACK(pd, hy, hx); OUT(pa, pc, hx);
+        if (y + 1 < y1) {
+            THROW(hy); PACK(pa, hx, hy); OUT(pb, pd, hy);
+            if (y + 2 < y1) { THROW(hx); OUT(pc, pa, hx); }
+        }
+    }
+#undef TLOADROW
+#undef THROW
+#undef OUT
+#undef PACK
+}
+
+static int blur_tma_band(int variant) { return (variant == 2 || variant == 3) ? 64 : 32; }
+static int blur_tma_tasks(const OrbPlan& hp, int band) {
+    int t = 0;
+    for (int l = 0; l < hp.nlevels; l++) t += ((hp.lv[l].h + band - 1) / band) * ((hp.lv[l].w + 127) >> 7);
+    return t;
+}
+int blur_tma_box_w() { return EORB_BLUR_TBOXW; }
+int blur_tma_box_h(int variant) { return blur_tma_band(variant) + 4; }
+
 // ------------------------------------------------------------------------------------------------ K4 + K6
 // One warp per selected keypoint (taken from the compact list K7 writes), EORB_KP_GROUP keypoints per block.
 // Orientation (IC_Angle): the 31x31 patch is read as aligned 32-bit words, 9 words per row; lane <-> (row, word)
@@ -760,11 +884,27 @@ cudaError_t launch_orb_pipeline(const OrbArgs& a, const OrbPlan& hp, int nframes
         (*launches)++;
     }
     if (ev) cudaEventRecord(ev[1], st);
+    const bool blurTma = a.blurMaps != nullptr && pyrMaps != nullptr;
+    auto launchBlur = [&](cudaStream_t s) {
+        if (blurTma) {
+            const int band = blur_tma_band(a.blurVariant), nt = blur_tma_tasks(hp, band);
+            const size_t sm = (size_t)(band + 4) * EORB_BLUR_TBOXW + 16;
+            const dim3 g(nt, nframes);
+            switch (a.blurVariant) {
+                case 2: blur_tma_kernel<64, false><<<g, 32, sm, s>>>(a, pyrMaps[0], nt); break;
+                case 3: blur_tma_kernel<64, true><<<g, 32, sm, s>>>(a, pyrMaps[0], nt); break;
+                case 4: blur_tma_kernel<32, true><<<g, 32, sm, s>>>(a, pyrMaps[0], nt); break;
+                default: blur_tma_kernel<32, false><<<g, 32, sm, s>>>(a, pyrMaps[0], nt); break;
+            }
+        } else {
+            dim3 blk(32, 4), grd(cdiv(hp.blurTasksTotal, 4), nframes);
+            blur_kernel<<<grd, blk, 0, s>>>(a);
+        }
+    };
     if (forkBlur) {   // K5 beside K2 / K3 / K7
         cudaEventRecord(fork->forked, st);
         cudaStreamWaitEvent(fork->side, fork->forked, 0);
-        dim3 blk(32, 4), grd(cdiv(hp.blurTasksTotal, 4), nframes);
-        blur_kernel<<<grd, blk, 0, fork->side>>>(a);
+        launchBlur(fork->side);
         (*launches)++;
         cudaEventRecord(fork->joined, fork->side);
     }
@@ -790,8 +930,7 @@ cudaError_t launch_orb_pipeline(const OrbArgs& a, const OrbPlan& hp, int nframes
     if (forkBlur) {
         cudaStreamWaitEvent(st, fork->joined, 0);
     } else if (a.wantDesc && hp.blurTasksTotal > 0) {
-        dim3 blk(32, 4), grd(cdiv(hp.blurTasksTotal, 4), nframes);
-        blur_kernel<<<grd, blk, 0, st>>>(a);
+        launchBlur(st);
         (*launches)++;
     }
     if (ev) cudaEventRecord(ev[5], st);

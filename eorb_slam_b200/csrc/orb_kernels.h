@@ -21,6 +21,9 @@ struct OrbArgs {
     long long lvl0Pitch, lvl0FrameStride;
     const CUtensorMap* tmaps;    // device: [nlevels] TMA maps {x, y, frame} of the pyramid levels >= 1 (entry 0 unused:
                                  //         level 0 is the caller's buffer, its map travels as a kernel parameter)
+    const CUtensorMap* blurMaps; // device: [nlevels] maps of the levels >= 1 with the box of blur_tma_kernel, or nullptr (blur_kernel is used);
+                                 //         level 0's travels as pyrMaps[0] of launch_orb_pipeline
+    int blurVariant;             // EORB_BLUR_TMA value (1..4: band rows 32 / 64, neighbour words by shuffle / from the tile)
     uint8_t* pyr;                // [B][pyrBytesPerFrame]   levels >= 1
     uint8_t* blur;               // [B][blurBytesPerFrame]  all levels
     uint16_t* cellCount;         // [B][nCells]
@@ -53,6 +56,8 @@ struct PyrTileConst {
 cudaError_t launch_pyr_tma(const OrbArgs& a, const OrbPlan& hp, int level, int nframes, const CUtensorMap& tmSrc, cudaStream_t st);
 
 cudaError_t orb_kernels_configure(const OrbPlan& hp);
+int blur_tma_box_w();
+int blur_tma_box_h(int variant);
 #define EORB_ORB_STAGES 6   // pyramid, fast, octree, index, blur, orient+desc
 // side-stream fork of one launch set (small batches inside the captured graph only: a single frame leaves the GPU mostly idle, so the
 // blur, which only depends on the pyramid, runs beside FAST / octree / index and joins before orientation + BRIEF; at 1024-frame
