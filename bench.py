@@ -35,7 +35,7 @@ sys.path.insert(0, os.path.join(ROOT, "tests"))
 W, H = 752, 480
 ORB_KW = dict(nfeatures=1000, scale_factor=1.2, nlevels=8, ini_th=20, min_th=7, edge_th=19)
 FRAMES_PER_GPU = 4096
-CHUNK = 1024                     # frames per launch set of the device-resident path (the host path pipelines 128-frame slots)
+CHUNK = 4096                     # frames per launch set of the device-resident path (the host path pipelines 128-frame slots)
 UNIQUE_FRAMES = 256              # generated frames; the rest are circular shifts of these (all distinct)
 # algorithmic bytes per frame (SURVEY.md §8d / BASELINE.md §2 / DESIGN.md)
 LEVELS = [(752, 480), (627, 400), (522, 333), (435, 278), (363, 231), (302, 193), (252, 161), (210, 134)]
