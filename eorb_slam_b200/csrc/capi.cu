@@ -230,9 +230,6 @@ struct eorb_orb {
     int planW = 0, planH = 0;
     OrbPlan hp{};
     std::vector<CellPlan> cells;
-    std::vector<SegPlan> segs;     // FAST band kernel work units (empty: per-cell kernel)
-    SegPlan* d_segs = nullptr;
-    int useFastBand = 1;           // EORB_FAST_BAND=0: fast_cells_kernel (one warp per cell), for A/B
     OrbPlan* d_plan = nullptr; CellPlan* d_cells = nullptr; short4* d_xtab = nullptr; int4* d_ytab = nullptr; int4* d_ytabT = nullptr; int2* d_icTab = nullptr;
     float* d_invScale = nullptr;
     // slabs (maxBatch frames): `main` serves the device entry points and single calls; `pipe` holds the extra
@@ -247,7 +244,6 @@ struct eorb_orb {
         uint32_t* d_kpList = nullptr;
         float* d_levelAngle = nullptr;
         CUtensorMap* d_tmaps = nullptr;   // [nlevels] maps of this slab's pyramid levels >= 1
-        CUtensorMap* d_bandMaps = nullptr;   // [nlevels] the same levels with fast_band_kernel's box
         CUtensorMap* d_blurMaps = nullptr;   // [nlevels] the same levels with blur_tma_kernel's box (EORB_BLUR_TMA=1)
         CUtensorMap pyrMaps[EORB_MAX_LEVELS];   // host: source map of the TMA-staged resize INTO level l (l >= 2; level 1's source is the caller's frame)
         eorb_keypoint* d_outKps = nullptr; uint8_t* d_outDesc = nullptr; int* d_outN = nullptr; int* d_outMono = nullptr;
@@ -298,7 +294,7 @@ static cudaEvent_t* orbStageEvents(eorb_orb* h) {
 static void orbFreeBufs(eorb_orb::Bufs& b) {
     cudaFree(b.d_img0); cudaFree(b.d_pyr); cudaFree(b.d_blur); cudaFree(b.d_cellCount); cudaFree(b.d_cand);
     cudaFree(b.d_okeys); cudaFree(b.d_knode); cudaFree(b.d_sel); cudaFree(b.d_selCount); cudaFree(b.d_candCount);
-    cudaFree(b.d_dstIdx); cudaFree(b.d_kpList); cudaFree(b.d_levelAngle); cudaFree(b.d_tmaps); cudaFree(b.d_bandMaps); cudaFree(b.d_blurMaps); cudaFree(b.d_outKps); cudaFree(b.d_outDesc);
+    cudaFree(b.d_dstIdx); cudaFree(b.d_kpList); cudaFree(b.d_levelAngle); cudaFree(b.d_tmaps); cudaFree(b.d_blurMaps); cudaFree(b.d_outKps); cudaFree(b.d_outDesc);
     cudaFree(b.d_outN); cudaFree(b.d_outMono);
     cudaFreeHost(b.h_kps); cudaFreeHost(b.h_desc); cudaFreeHost(b.h_n); cudaFreeHost(b.h_mono);
     if (b.done) cudaEventDestroy(b.done);
@@ -333,15 +329,6 @@ static int orbAllocBufs(eorb_orb* h, eorb_orb::Bufs& b, bool pipeline) {
         }
         CU(devAlloc(&b.d_tmaps, (size_t)nl));
         CU(cudaMemcpy(b.d_tmaps, maps.data(), maps.size() * sizeof(CUtensorMap), cudaMemcpyHostToDevice));
-        if (P.nSegs > 0) {
-            for (int l = 1; l < nl; l++) {
-                int rct = tmaEncodeFrames(&maps[l], b.d_pyr + P.lv[l].off, P.lv[l].w, P.lv[l].h, (int)B, (size_t)P.lv[l].pitch,
-                                          (size_t)P.pyrBytesPerFrame, P.bandTS, P.bandRows);
-                if (rct != EORB_OK) return rct;
-            }
-            CU(devAlloc(&b.d_bandMaps, (size_t)nl));
-            CU(cudaMemcpy(b.d_bandMaps, maps.data(), maps.size() * sizeof(CUtensorMap), cudaMemcpyHostToDevice));
-        }
         bool blurTmaOk = h->useBlurTma != 0;
         for (int l = 0; l < nl; l++)   // degenerate levels (rows bounce more than once) stay with blur_kernel's per-pixel path
             if (P.lv[l].w > 0 && P.lv[l].h > 0 && (P.lv[l].h < 3 || P.lv[l].w < 8)) blurTmaOk = false;
@@ -384,7 +371,7 @@ static void orbDropGraph(eorb_orb* h) {
 
 static void orbFreePlan(eorb_orb* h) {
     orbDropGraph(h);
-    cudaFree(h->d_plan); cudaFree(h->d_cells); cudaFree(h->d_segs); h->d_segs = nullptr; cudaFree(h->d_xtab); cudaFree(h->d_ytab); cudaFree(h->d_ytabT); cudaFree(h->d_invScale); cudaFree(h->d_icTab);
+    cudaFree(h->d_plan); cudaFree(h->d_cells); cudaFree(h->d_xtab); cudaFree(h->d_ytab); cudaFree(h->d_ytabT); cudaFree(h->d_invScale); cudaFree(h->d_icTab);
     h->d_plan = nullptr; h->d_cells = nullptr; h->d_xtab = nullptr; h->d_ytab = nullptr; h->d_ytabT = nullptr; h->d_invScale = nullptr; h->d_icTab = nullptr;
     orbFreeBufs(h->main);
     for (auto& b : h->pipe) orbFreeBufs(b);
@@ -446,8 +433,7 @@ static int orbBuildPlan(eorb_orb* h, int W, int H) {
     if (E < 3) return fail(EORB_ERR_ARG, "edge threshold %d < 3 is unsupported (the FAST region would start outside the image)", E);
     P.nlevels = nl; P.edge = E; P.iniTh = h->par.iniThFAST; P.minTh = h->par.minThFAST; P.W = W; P.H = H;
     for (int i = 0; i < 16; i++) P.umax[i] = h->umax[i];
-    h->cells.clear(); h->segs.clear();
-    int bandMaxW = 0, bandMaxH = 0, bandMaxNp = 1, bandMaxInterior = 1;
+    h->cells.clear();
     std::vector<short4> xtab;
     std::vector<int4> ytab;   // {sy0, sy1, b0 << 16, b1 << 16}
     long long pyrOff = 0, blurOff = 0;
@@ -506,36 +492,6 @@ static int orbBuildPlan(eorb_orb* h, int W, int H) {
         }
         lp.nCells = (int)h->cells.size() - lp.cellBase;
         lp.slotCount = slot - lp.slotBase;
-        // segments of the band kernel: the cells of one cell row (consecutive in cells[]) in runs of <= EORB_FAST_SEG_CELLS, evenly
-        // sized; the run must fit the 256-byte TMA box (union ROI + 15 alignment bytes)
-        for (int c0 = lp.cellBase; c0 < lp.cellBase + lp.nCells;) {
-            int c1 = c0;
-            while (c1 < lp.cellBase + lp.nCells && h->cells[c1].y0 == h->cells[c0].y0) c1++;
-            const int nrow = c1 - c0;
-            int kmax = EORB_FAST_SEG_CELLS;
-            while (kmax > 1 && kmax * lp.wCell + 6 + 15 > 240) kmax--;
-            const int nseg = (nrow + kmax - 1) / kmax;
-            for (int sgi = 0, cs = c0; sgi < nseg; sgi++) {
-                const int n = nrow / nseg + (sgi < nrow % nseg ? 1 : 0);
-                const CellPlan& first = h->cells[cs];
-                const CellPlan& last = h->cells[cs + n - 1];
-                SegPlan sg{};
-                sg.x0 = first.x0; sg.y0 = first.y0; sg.w = (short)(last.x0 + last.w - first.x0); sg.h = first.h;
-                sg.level = (short)l; sg.ncell = (short)n; sg.firstCell = cs; sg.ox = first.ox; sg.oy = first.oy; sg.wCell = (short)lp.wCell;
-                const int aoff = sg.x0 & 15, p0 = (aoff + 3) >> 3;
-                const int np = std::max(((aoff + sg.w - 4) >> 3) - p0 + 1, 1);
-                const int lastBits = aoff + sg.w - 3 - 8 * (p0 + np - 1);
-                sg.aoff = (unsigned char)aoff; sg.p0 = (unsigned char)p0; sg.np = (unsigned char)np;
-                sg.firstMask = (unsigned char)((0xffu << ((aoff + 3) & 7)) & 0xffu);
-                sg.lastMask = (unsigned char)(lastBits >= 8 ? 0xffu : (lastBits <= 0 ? 0u : ((1u << lastBits) - 1u)));
-                sg.rcpNp = (unsigned short)((65536 + np - 1) / np);
-                bandMaxW = std::max(bandMaxW, (int)sg.w); bandMaxH = std::max(bandMaxH, (int)sg.h); bandMaxNp = std::max(bandMaxNp, np);
-                bandMaxInterior = std::max(bandMaxInterior, (int)sg.w - 6);
-                h->segs.push_back(sg);
-                cs += n;
-            }
-            c0 = c1;
-        }
         if (lp.slotCount > (1 << 20)) return fail(EORB_ERR_ARG, "level %d too large for the 20-bit candidate index", l);
         // octree roots (:562-563)
         lp.nIni = 0; lp.hX = 1.f;
@@ -615,25 +571,6 @@ static int orbBuildPlan(eorb_orb* h, int W, int H) {
     P.cellBarOff = roundUp(P.cellTaskOff + maxTasks * 4, 16);
     P.cellSmemPerWarp = roundUp(P.cellBarOff + 16, 128);
     if (P.cellTileStride > 256 || P.cellTileRows > 256) return fail(EORB_ERR_ARG, "FAST cell %dx%d exceeds the TMA box limit", maxCW, maxCH);
-    // band kernel: [TMA tile TS x rows][score map (ch+2) x MS][column lut TS][cell table][4 x survivor list u16][4 x group list u32][mbarrier]
-    P.nSegs = 0;
-    if (h->useFastBand && !h->segs.empty() && bandMaxW + 15 <= 256 && bandMaxH <= 256 && bandMaxH - 6 <= 252) {
-        const int chMax = std::max(bandMaxH - 6, 1), rowsW = (chMax + 3) / 4;
-        P.bandTS = roundUp(bandMaxW + 15, 16);
-        if (P.bandTS % 128 == 0 && P.bandTS + 16 <= 256) P.bandTS += 16;
-        P.bandRows = bandMaxH;
-        P.bandMS = roundUp(bandMaxInterior + 2, 4);
-        P.bandMapOff = roundUp(P.bandRows * P.bandTS, 16);
-        P.bandLutOff = P.bandMapOff + roundUp((chMax + 2) * P.bandMS, 16);
-        P.bandCellOff = P.bandLutOff + roundUp(P.bandTS, 16);
-        P.bandListPerWarp = roundUp(rowsW * bandMaxInterior + 32, 8);
-        P.bandListOff = P.bandCellOff + EORB_FAST_BAND_CELL_BYTES;
-        P.bandTaskPerWarp = roundUp(rowsW * bandMaxNp + 32, 4);
-        P.bandTaskOff = roundUp(P.bandListOff + 4 * P.bandListPerWarp * 2, 16);
-        P.bandBarOff = roundUp(P.bandTaskOff + 4 * P.bandTaskPerWarp * 4, 16);
-        P.bandSmem = roundUp(P.bandBarOff + 16, 128);
-        if (P.bandSmem <= 100 * 1024) P.nSegs = (int)h->segs.size();
-    }
     P.octSmemBytes = octSmem;
     if (P.cellSmemPerWarp * EORB_FAST_WARPS > 200 * 1024 || octSmem > 200 * 1024)
         return fail(EORB_ERR_ARG, "shared-memory budget exceeded (fast %d B, octree %d B)", P.cellSmemPerWarp * EORB_FAST_WARPS, octSmem);
@@ -642,7 +579,6 @@ static int orbBuildPlan(eorb_orb* h, int W, int H) {
     h->cap = eorb_orb_max_keypoints_for_size(h, W, H);
     CU(devAlloc(&h->d_plan, 1));
     CU(devAlloc(&h->d_cells, h->cells.size()));
-    CU(devAlloc(&h->d_segs, h->segs.size()));
     CU(devAlloc(&h->d_xtab, xtab.size()));
     CU(devAlloc(&h->d_ytab, ytab.size()));
     CU(devAlloc(&h->d_ytabT, ytab.size()));
@@ -671,7 +607,6 @@ static int orbBuildPlan(eorb_orb* h, int W, int H) {
     }
     CU(cudaMemcpy(h->d_plan, &P, sizeof(P), cudaMemcpyHostToDevice));
     if (!h->cells.empty()) CU(cudaMemcpy(h->d_cells, h->cells.data(), h->cells.size() * sizeof(CellPlan), cudaMemcpyHostToDevice));
-    if (!h->segs.empty()) CU(cudaMemcpy(h->d_segs, h->segs.data(), h->segs.size() * sizeof(SegPlan), cudaMemcpyHostToDevice));
     if (!xtab.empty()) CU(cudaMemcpy(h->d_xtab, xtab.data(), xtab.size() * sizeof(short4), cudaMemcpyHostToDevice));
     if (!ytab.empty()) CU(cudaMemcpy(h->d_ytab, ytab.data(), ytab.size() * sizeof(int4), cudaMemcpyHostToDevice));
     {   // the TMA path's y taps carry tile-row byte offsets (row index x box width of the level)
@@ -696,8 +631,6 @@ static OrbArgs orbArgs(eorb_orb* h, eorb_orb::Bufs& b, const uint8_t* lvl0, long
     a.lvl0 = lvl0; a.lvl0Pitch = pitch0; a.lvl0FrameStride = frameStride0;
     a.tmaps = b.d_tmaps;
     a.blurMaps = b.d_blurMaps;
-    a.segs = h->hp.nSegs > 0 ? h->d_segs : nullptr;
-    a.bandMaps = b.d_bandMaps;
     a.blurVariant = h->useBlurTma;
     a.pyr = b.d_pyr; a.blur = b.d_blur; a.cellCount = b.d_cellCount; a.cand = b.d_cand; a.okeys = b.d_okeys;
     a.knode = b.d_knode; a.sel = b.d_sel; a.selCount = b.d_selCount; a.candCount = b.d_candCount;
@@ -723,7 +656,6 @@ extern "C" int eorb_orb_create(const eorb_orb_params* params, int device, int ma
     if (const char* e = getenv("EORB_ORB_GRAPH")) h->useGraph = atoi(e) != 0;
     if (const char* e = getenv("EORB_PYR_TMA")) h->usePyrTma = atoi(e) != 0;
     if (const char* e = getenv("EORB_BLUR_TMA")) h->useBlurTma = atoi(e);
-    if (const char* e = getenv("EORB_FAST_BAND")) h->useFastBand = atoi(e);
     if (const char* e = getenv("EORB_FAST_PAD")) h->fastPadTile = atoi(e) != 0;
     if (const char* e = getenv("EORB_PYR_TH")) h->pyrTileRows = std::min(std::max(atoi(e), 8), 200);
     h->pipeBatch = std::min(max_batch, 128);   // measured on B200: H2D/compute/D2H overlap is best with 128-frame slots
@@ -901,13 +833,7 @@ extern "C" int eorb_orb_extract_batch_device(eorb_orb* h, const uint8_t* d_imgs,
     CUtensorMap pm[EORB_MAX_LEVELS];
     rc = orbPyrMaps(h, h->main, lvl0, w, hgt, nframes, p0, fs0, pm);
     if (rc != EORB_OK) return rc;
-    CUtensorMap tmBand0;
-    const bool band = h->hp.nSegs > 0 && h->main.d_bandMaps;
-    if (band) {
-        rc = tmaEncodeFrames(&tmBand0, lvl0, w, hgt, nframes, (size_t)p0, (size_t)fs0, h->hp.bandTS, h->hp.bandRows);
-        if (rc != EORB_OK) return rc;
-    }
-    CU(launch_orb_pipeline(a, h->hp, nframes, tm0, h->stream, &h->launches, orbStageEvents(h), pm, nullptr, band ? &tmBand0 : nullptr));
+    CU(launch_orb_pipeline(a, h->hp, nframes, tm0, h->stream, &h->launches, orbStageEvents(h), pm));
     h->lastLvl0 = lvl0; h->lastPitch0 = p0; h->lastFrameStride0 = fs0; h->lastFrames = nframes;
     return EORB_OK;
 }
@@ -1000,13 +926,7 @@ extern "C" int eorb_orb_extract_batch(eorb_orb* h, const uint8_t* imgs, int nfra
             CUtensorMap pm[EORB_MAX_LEVELS];
             rct = orbPyrMaps(h, b, b.d_img0, w, hgt, nb, h->pitch0, (long long)h->pitch0 * hgt, pm);
             if (rct != EORB_OK) return rct;
-            CUtensorMap tmBand0;
-            const bool band = h->hp.nSegs > 0 && b.d_bandMaps;
-            if (band) {
-                rct = tmaEncodeFrames(&tmBand0, b.d_img0, w, hgt, nb, (size_t)h->pitch0, (size_t)h->pitch0 * hgt, h->hp.bandTS, h->hp.bandRows);
-                if (rct != EORB_OK) return rct;
-            }
-            CU(launch_orb_pipeline(a, h->hp, nb, tm0, st, launchCounter, stageEv, pm, capturing ? &h->graphFork : nullptr, band ? &tmBand0 : nullptr));
+            CU(launch_orb_pipeline(a, h->hp, nb, tm0, st, launchCounter, stageEv, pm, capturing ? &h->graphFork : nullptr));
             CU(cudaMemcpyAsync(b.h_n, b.d_outN, nb * sizeof(int), cudaMemcpyDeviceToHost, st));
             CU(cudaMemcpyAsync(b.h_mono, b.d_outMono, nb * sizeof(int), cudaMemcpyDeviceToHost, st));
             CU(cudaMemcpyAsync(kdst, b.d_outKps, (size_t)nb * icap * sizeof(eorb_keypoint), cudaMemcpyDeviceToHost, st));

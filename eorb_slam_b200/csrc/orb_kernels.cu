@@ -872,8 +872,7 @@ static cudaError_t launch_pyramid_level(const OrbArgs& a, const OrbPlan& hp, int
 }
 
 cudaError_t launch_orb_pipeline(const OrbArgs& a, const OrbPlan& hp, int nframes, const CUtensorMap& tm0, cudaStream_t st,
-                                long long* launches, cudaEvent_t* ev, const CUtensorMap* pyrMaps, const OrbFork* fork,
-                                const CUtensorMap* tmBand0) {
+                                long long* launches, cudaEvent_t* ev, const CUtensorMap* pyrMaps, const OrbFork* fork) {
     const bool forkBlur = fork && fork->side && !ev && a.wantDesc && hp.blurTasksTotal > 0;
     // ev (optional, EORB_ORB_STAGES+1 events): recorded around every stage for the per-kernel timings of bench.py
     if (ev) cudaEventRecord(ev[0], st);
@@ -911,8 +910,7 @@ cudaError_t launch_orb_pipeline(const OrbArgs& a, const OrbPlan& hp, int nframes
     }
     // K2: FAST over every cell of every level
     if (hp.nCells > 0) {
-        const bool band = hp.nSegs > 0 && a.segs && a.bandMaps && tmBand0;
-        cudaError_t e = band ? launch_fast_band(a, hp, nframes, *tmBand0, st) : launch_fast_cells(a, hp, nframes, tm0, st);
+        cudaError_t e = launch_fast_cells(a, hp, nframes, tm0, st);
         if (e != cudaSuccess) return e;
         (*launches)++;
     }
@@ -973,8 +971,6 @@ cudaError_t launch_tracked_desc(const OrbArgs& a, const OrbPlan& hp, const eorb_
 
 cudaError_t orb_kernels_configure(const OrbPlan& hp) {
     cudaError_t e = fast_cells_configure(hp);
-    if (e != cudaSuccess) return e;
-    e = fast_band_configure();
     if (e != cudaSuccess) return e;
     // per-kernel attribute shared by every extractor of the process: set once to the plan limit (see fast_cells_configure)
     static std::mutex mu;

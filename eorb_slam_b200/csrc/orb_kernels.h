@@ -23,8 +23,6 @@ struct OrbArgs {
                                  //         level 0 is the caller's buffer, its map travels as a kernel parameter)
     const CUtensorMap* blurMaps; // device: [nlevels] maps of the levels >= 1 with the box of blur_tma_kernel, or nullptr (blur_kernel is used);
                                  //         level 0's travels as pyrMaps[0] of launch_orb_pipeline
-    const SegPlan* segs;         // device: FAST band kernel segments (plan.nSegs entries) or nullptr
-    const CUtensorMap* bandMaps; // device: [nlevels] maps of the levels >= 1 with the band kernel's box, or nullptr (fast_cells_kernel is used)
     int blurVariant;             // EORB_BLUR_TMA value (1..4: band rows 32 / 64, neighbour words by shuffle / from the tile)
     uint8_t* pyr;                // [B][pyrBytesPerFrame]   levels >= 1
     uint8_t* blur;               // [B][blurBytesPerFrame]  all levels
@@ -67,12 +65,8 @@ int blur_tma_box_h(int variant);
 struct OrbFork { cudaStream_t side = nullptr; cudaEvent_t forked = nullptr, joined = nullptr; };
 // pyrMaps (host array, [nlevels], may be null): TMA map of the SOURCE of level l (= level l-1) with that level's box, for the
 // levels whose plan says pyrTW > 0; null or pyrTW == 0 -> pyr_resize_kernel
-// tmBand0 (may be null): level 0's map with the FAST band kernel's box; with a.bandMaps / a.segs set it selects fast_band_kernel
 cudaError_t launch_orb_pipeline(const OrbArgs& a, const OrbPlan& hp, int nframes, const CUtensorMap& tm0, cudaStream_t st,
-                                long long* launches, cudaEvent_t* ev, const CUtensorMap* pyrMaps = nullptr, const OrbFork* fork = nullptr,
-                                const CUtensorMap* tmBand0 = nullptr);
-cudaError_t launch_fast_band(const OrbArgs& a, const OrbPlan& hp, int nframes, const CUtensorMap& tmBand0, cudaStream_t st);
-cudaError_t fast_band_configure();
+                                long long* launches, cudaEvent_t* ev, const CUtensorMap* pyrMaps = nullptr, const OrbFork* fork = nullptr);
 cudaError_t launch_fast_cells(const OrbArgs& a, const OrbPlan& hp, int nframes, const CUtensorMap& tm0, cudaStream_t st);
 cudaError_t fast_cells_configure(const OrbPlan& hp);
 cudaError_t launch_pyramid_and_blur(const OrbArgs& a, const OrbPlan& hp, cudaStream_t st, long long* launches, const CUtensorMap* pyrMaps = nullptr);

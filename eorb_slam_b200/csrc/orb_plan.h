@@ -52,23 +52,6 @@ struct CellPlan {
     unsigned short rcpNpM1;        // ceil(65536 / np) - 1: lane / np == (lane * (rcpNpM1 + 1)) >> 16 for lane < 32
 };
 
-// FAST band kernel (orb_fast_band.cu): a SEGMENT = up to EORB_FAST_SEG_CELLS consecutive cells of one cell row, processed by one
-// 4-warp block on ONE TMA tile (the union of the cells' ROIs).  Cell ci of the segment owns tile columns
-// [aoff + 3 + ci*wCell, + its interior width); the phase-1 walk covers the union interior in np aligned groups of 8 columns.
-#define EORB_FAST_SEG_CELLS 5
-#define EORB_FAST_BAND_CELL_BYTES 640   // the block's cell table (BandCells in orb_fast_band.cu)
-struct SegPlan {
-    short x0, y0;                  // union ROI origin in level coordinates (the first cell's iniX, iniY)
-    short w, h;                    // union ROI size (last cell's maxX - x0, maxY - iniY), includes the 3-px FAST apron
-    short level, ncell;
-    int firstCell;                 // index of the first cell in cells[] (the segment's cells are consecutive)
-    short ox, oy;                  // the first cell's j*wCell, i*hCell
-    short wCell, _pad0;
-    unsigned char aoff, p0, np, _pad1;
-    unsigned char firstMask, lastMask;
-    unsigned short rcpNp;          // ceil(65536 / np): id / np == (id * rcpNp) >> 16 for the ids of one warp's walk
-};
-
 struct OrbPlan {
     int nlevels, edge, iniTh, minTh;
     int W, H;
@@ -85,10 +68,6 @@ struct OrbPlan {
     int cellTaskOff;               // FAST: byte offset of the flagged-group list of phase 1
     int cellBarOff;                // FAST: byte offset of the warp's mbarrier
     int cellSmemPerWarp;           // bytes (multiple of 128: TMA destinations are 128-byte aligned)
-    // FAST band kernel: segments and the shared-memory layout of one block (0 segments: the per-cell kernel is used)
-    int nSegs;
-    int bandTS, bandRows, bandMS;  // TMA box width / height, score-map stride
-    int bandMapOff, bandLutOff, bandCellOff, bandListOff, bandListPerWarp, bandTaskOff, bandTaskPerWarp, bandBarOff, bandSmem;
     int octSmemBytes;              // max over levels
     int blurTasksTotal;            // blur grid: total (band, strip) tasks over all levels
     int umax[16];
