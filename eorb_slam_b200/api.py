@@ -42,7 +42,7 @@ class _OrbParams(C.Structure):
 class _EvParams(C.Structure):
     _fields_ = [("mode", C.c_int), ("width", C.c_int), ("height", C.c_int), ("sigma", C.c_float), ("pol", C.c_int),
                 ("normalize", C.c_int), ("Tcw", C.c_float * 16), ("med_depth", C.c_float), ("K", C.c_float * 4),
-                ("se2", C.c_float * 4), ("se2_n", C.c_int)]
+                ("se2", C.c_float * 4), ("se2_n", C.c_int), ("cam_model", C.c_int), ("kb", C.c_float * 4)]
 
 
 def _load():
@@ -481,6 +481,11 @@ class EvImConverter:
         cam = (1.0, 1.0, 0.0, 0.0) if camera is None else camera
         for k in range(4):
             p.K[k] = float(cam[k])
+        p.cam_model = 0
+        if len(cam) >= 8:                      # a KannalaBrandt8 camera carries fx, fy, cx, cy, k1..k4 (KannalaBrandt8.h mvParameters)
+            p.cam_model = 1
+            for k in range(4):
+                p.kb[k] = float(cam[4 + k])
         p.se2_n = 0
         if params2D is not None:
             s = np.asarray(params2D, np.float32).reshape(-1)

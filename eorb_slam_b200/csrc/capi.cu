@@ -1500,6 +1500,9 @@ static int evConst(const eorb_ev_params* p, EvConst& c) {
     c.fx = p->K[0]; c.fy = p->K[1]; c.cx = p->K[2]; c.cy = p->K[3];
     for (int i = 0; i < 4; i++) c.se2[i] = p->se2[i];
     c.se2_n = p->se2_n;
+    if (p->cam_model < 0 || p->cam_model > 1) return fail(EORB_ERR_ARG, "bad camera model %d (0 Pinhole, 1 KannalaBrandt8)", p->cam_model);
+    c.cam = p->cam_model;
+    for (int i = 0; i < 4; i++) c.kb[i] = p->kb[i];
     return EORB_OK;
 }
 

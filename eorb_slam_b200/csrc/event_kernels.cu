@@ -46,13 +46,62 @@ __device__ __forceinline__ void splat_taps(float* __restrict__ im, int W, int H,
     }
 }
 
+// ---- KannalaBrandt8 (src/CameraModels/KannalaBrandt8.cpp): unproject :163-190 (ten Newton steps on theta in float, precision 1e-6), project
+// (cv::Point3f) :86-103, project (Eigen::Vector3d) :111-129.  Float operation order as in the reference, no contraction; atan2f / tanf / cos
+// / sin are CUDA's (within 2 ulp of glibc's), which moves a warped position by < 1e-5 px -- inside the 1e-4 * peak parity bar of the frames.
+__device__ __forceinline__ void kb8_unproject(const EvConst& c, float x, float y, float& X, float& Y) {
+    const float pwx = __fdiv_rn(__fsub_rn(x, c.cx), c.fx), pwy = __fdiv_rn(__fsub_rn(y, c.cy), c.fy);
+    float scale = 1.f;
+    float theta_d = sqrtf(__fadd_rn(__fmul_rn(pwx, pwx), __fmul_rn(pwy, pwy)));
+    theta_d = fminf(fmaxf(-1.57079637f, theta_d), 1.57079637f);
+    if ((double)theta_d > 1e-8) {
+        float theta = theta_d;
+        for (int j = 0; j < 10; j++) {
+            const float theta2 = __fmul_rn(theta, theta), theta4 = __fmul_rn(theta2, theta2), theta6 = __fmul_rn(theta4, theta2),
+                        theta8 = __fmul_rn(theta4, theta4);
+            const float k0 = __fmul_rn(c.kb[0], theta2), k1 = __fmul_rn(c.kb[1], theta4), k2 = __fmul_rn(c.kb[2], theta6), k3 = __fmul_rn(c.kb[3], theta8);
+            const float num = __fsub_rn(__fmul_rn(theta, __fadd_rn(__fadd_rn(__fadd_rn(__fadd_rn(1.f, k0), k1), k2), k3)), theta_d);
+            const float den = __fadd_rn(__fadd_rn(__fadd_rn(__fadd_rn(1.f, __fmul_rn(3.f, k0)), __fmul_rn(5.f, k1)), __fmul_rn(7.f, k2)), __fmul_rn(9.f, k3));
+            const float fix = __fdiv_rn(num, den);
+            theta = __fsub_rn(theta, fix);
+            if (fabsf(fix) < 1e-6f) break;
+        }
+        scale = __fdiv_rn(tanf(theta), theta_d);
+    }
+    X = __fmul_rn(pwx, scale); Y = __fmul_rn(pwy, scale);
+}
+__device__ __forceinline__ void kb8_project_d(const EvConst& c, double x, double y, double z, float& U, float& V) {
+    const double x2y2 = x * x + y * y;
+    const double theta = (double)atan2f(sqrtf((float)x2y2), (float)z);
+    const double psi = (double)atan2f((float)y, (float)x);
+    const double t2 = theta * theta, t3 = theta * t2, t5 = t3 * t2, t7 = t5 * t2, t9 = t7 * t2;
+    const double r = theta + (double)c.kb[0] * t3 + (double)c.kb[1] * t5 + (double)c.kb[2] * t7 + (double)c.kb[3] * t9;
+    double sp, cp;
+    sincos(psi, &sp, &cp);
+    U = (float)((double)c.fx * r * cp + (double)c.cx);
+    V = (float)((double)c.fy * r * sp + (double)c.cy);
+}
+__device__ __forceinline__ void kb8_project_f(const EvConst& c, float x, float y, float z, float& U, float& V) {
+    const float x2y2 = __fadd_rn(__fmul_rn(x, x), __fmul_rn(y, y));
+    const float theta = atan2f(sqrtf(x2y2), z);
+    const float psi = atan2f(y, x);
+    const float t2 = __fmul_rn(theta, theta), t3 = __fmul_rn(theta, t2), t5 = __fmul_rn(t3, t2), t7 = __fmul_rn(t5, t2), t9 = __fmul_rn(t7, t2);
+    const float r = __fadd_rn(__fadd_rn(__fadd_rn(__fadd_rn(theta, __fmul_rn(c.kb[0], t3)), __fmul_rn(c.kb[1], t5)), __fmul_rn(c.kb[2], t7)), __fmul_rn(c.kb[3], t9));
+    double sp, cp;
+    sincos((double)psi, &sp, &cp);                       // the reference's cos(psi) / sin(psi) are the double functions on the float angle
+    U = (float)((double)__fmul_rn(c.fx, r) * cp + (double)c.cx);
+    V = (float)((double)__fmul_rn(c.fy, r) * sp + (double)c.cy);
+}
+
 // per-event warp of the SE3 (:279-360) and SE2 (:362-448) overloads; X, Y come in as the event position
 __device__ __forceinline__ void ev_warp_point(const eorb_event* __restrict__ evs, const EvWindow& w, const EvConst& c, double ts, float ex,
                                               float ey, float& X, float& Y) {
     if (c.mode == EORB_EV_SE3) {
         const double t1 = evs[w.end - 1].ts, DT = t1 - evs[w.begin].ts;
         const double rate = DT > 0 ? (t1 - ts) * (1.0 / DT) : 0.0;
-        const float Xs = __fdiv_rn(__fsub_rn(ex, c.cx), c.fx), Ys = __fdiv_rn(__fsub_rn(ey, c.cy), c.fy);
+        float Xs, Ys;
+        if (c.cam == 1) kb8_unproject(c, ex, ey, Xs, Ys);
+        else { Xs = __fdiv_rn(__fsub_rn(ex, c.cx), c.fx); Ys = __fdiv_rn(__fsub_rn(ey, c.cy), c.fy); }
         const double P0 = (double)Xs, P1 = (double)Ys, P2 = 1.0;
         // Eigen::AngleAxisd(angle*rate, axis).toRotationMatrix()
         const double ang = w.angle * rate;
@@ -71,8 +120,11 @@ __device__ __forceinline__ void ev_warp_point(const eorb_event* __restrict__ evs
         const double n0 = (dep * R00) * P0 + (dep * R01) * P1 + (dep * R02) * P2 + w.t[0] * rate;
         const double n1 = (dep * R10) * P0 + (dep * R11) * P1 + (dep * R12) * P2 + w.t[1] * rate;
         const double n2 = (dep * R20) * P0 + (dep * R21) * P1 + (dep * R22) * P2 + w.t[2] * rate;
-        X = (float)((double)c.fx * n0 / n2 + (double)c.cx);
-        Y = (float)((double)c.fy * n1 / n2 + (double)c.cy);
+        if (c.cam == 1) kb8_project_d(c, n0, n1, n2, X, Y);
+        else {
+            X = (float)((double)c.fx * n0 / n2 + (double)c.cx);
+            Y = (float)((double)c.fy * n1 / n2 + (double)c.cy);
+        }
     } else if (c.mode == EORB_EV_SE2) {
         const double t1 = evs[w.end - 1].ts;
         const float DT = (float)(t1 - evs[w.begin].ts);
@@ -81,14 +133,19 @@ __device__ __forceinline__ void ev_warp_point(const eorb_event* __restrict__ evs
         const float sc = c.se2_n > 3 ? c.se2[3] : 1.f;
         const float scDiff = __fsub_rn(1.f, sc);
         const float tk = (float)(t1 - ts);
-        const float Xs = __fdiv_rn(__fsub_rn(ex, c.cx), c.fx), Ys = __fdiv_rn(__fsub_rn(ey, c.cy), c.fy);
+        float Xs, Ys;
+        if (c.cam == 1) kb8_unproject(c, ex, ey, Xs, Ys);
+        else { Xs = __fdiv_rn(__fsub_rn(ex, c.cx), c.fx); Ys = __fdiv_rn(__fsub_rn(ey, c.cy), c.fy); }
         const float th = __fmul_rn(tk, omega0);
         const float cs = __fadd_rn(__fmul_rn(scDiff, __fsub_rn(1.f, __fmul_rn(tk, invDT))), sc);
         const float ct = cosf(th), st = sinf(th);
         const float xp = __fadd_rn(__fmul_rn(cs, __fsub_rn(__fmul_rn(Xs, ct), __fmul_rn(Ys, st))), __fmul_rn(vx0, tk));
         const float yp = __fadd_rn(__fmul_rn(cs, __fadd_rn(__fmul_rn(Xs, st), __fmul_rn(Ys, ct))), __fmul_rn(vy0, tk));
-        X = __fadd_rn(__fdiv_rn(__fmul_rn(c.fx, xp), 1.f), c.cx);
-        Y = __fadd_rn(__fdiv_rn(__fmul_rn(c.fy, yp), 1.f), c.cy);
+        if (c.cam == 1) kb8_project_f(c, xp, yp, 1.f, X, Y);
+        else {
+            X = __fadd_rn(__fdiv_rn(__fmul_rn(c.fx, xp), 1.f), c.cx);
+            Y = __fadd_rn(__fdiv_rn(__fmul_rn(c.fy, yp), 1.f), c.cy);
+        }
     }
 }
 

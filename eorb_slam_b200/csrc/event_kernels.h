@@ -23,6 +23,8 @@ struct EvConst {
     float fx, fy, cx, cy;
     float se2[4];
     int se2_n;
+    int cam;                   // 0 Pinhole, 1 KannalaBrandt8
+    float kb[4];               // k1..k4
 };
 
 cudaError_t launch_ev_splat(const eorb_event* d_evs, const EvWindow* d_wins, int nwin, long long maxEventsPerWindow,

@@ -59,6 +59,10 @@ void baseParams(eorb_ev_params& p, int mode, unsigned w, unsigned h, float sigma
 void camParams(eorb_ev_params& p, ORB_SLAM3::GeometricCamera* cam)
 {
     for (int i = 0; i < 4; i++) p.K[i] = cam->getParameter(i);   // fx, fy, cx, cy (Pinhole.cpp:30-62)
+    if (cam->GetType() == cam->CAM_FISHEYE) {                    // KannalaBrandt8: k1..k4 follow (KannalaBrandt8.cpp:86-103)
+        p.cam_model = 1;
+        for (int i = 0; i < 4; i++) p.kb[i] = cam->getParameter(4 + i);
+    }
 }
 }  // namespace
 

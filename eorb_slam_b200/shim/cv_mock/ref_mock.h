@@ -10,10 +10,14 @@
 namespace ORB_SLAM3 {
 class GeometricCamera {
 public:
-    explicit GeometricCamera(std::vector<float> p) : mvParameters(std::move(p)) {}
+    explicit GeometricCamera(std::vector<float> p) : mvParameters(std::move(p)), mnType(mvParameters.size() >= 8 ? 1u : 0u) {}
     float getParameter(const int i) { return mvParameters[i]; }   // GeometricCamera.h:133
+    unsigned int GetType() { return mnType; }                     // GeometricCamera.h:144-147
+    const unsigned int CAM_PINHOLE = 0;
+    const unsigned int CAM_FISHEYE = 1;
 protected:
-    std::vector<float> mvParameters;   // fx, fy, cx, cy (Pinhole)
+    std::vector<float> mvParameters;   // fx, fy, cx, cy (Pinhole) [+ k1..k4 (KannalaBrandt8)]
+    unsigned int mnType;
 };
 
 class MapPoint {   // what SearchByProjection reads (include/MapPoint.h: GetWorldPos, GetDescriptor, Observations)

@@ -242,6 +242,9 @@ typedef struct eorb_ev_params {
     float K[4];            /* Pinhole fx, fy, cx, cy (Pinhole.cpp:30-62) for SE3/SE2 */
     float se2[4];          /* SE2: omega, vx, vy, [scale] */
     int   se2_n;           /* 3 or 4 */
+    int   cam_model;       /* 0: Pinhole; 1: KannalaBrandt8 (the camera of Examples/Event/EvMVSEC.yaml:50): K = fx, fy, cx, cy and kb = k1..k4,
+                            * unproject / project as src/CameraModels/KannalaBrandt8.cpp:86-129, 163-190 */
+    float kb[4];
 } eorb_ev_params;
 
 int eorb_ev_create(int device, int max_windows, int64_t max_events, int max_width, int max_height, eorb_evconv** out);

@@ -101,6 +101,57 @@ void rotFromAngleAxis(double angle, const double a[3], double R[3][3]) {
     R[0][0] = ca[0] * a[0] + c; R[1][1] = ca[1] * a[1] + c; R[2][2] = ca[2] * a[2] + c;
 }
 
+// ---- camera models of the motion-compensation warp.  Pinhole: src/CameraModels/Pinhole.cpp:30-62.  KannalaBrandt8 (the camera of
+// Examples/Event/EvMVSEC.yaml:50): src/CameraModels/KannalaBrandt8.cpp:86-103 (project, cv::Point3f), :111-129 (project, Eigen), :163-190
+// (unproject: ten Newton steps on theta in float, precision = KB8_DEF_PRECISION = 1e-6, include/CameraModels/KannalaBrandt8.h:35).
+// cam[0..3] = fx, fy, cx, cy; cam[4..7] = k1..k4 (KannalaBrandt8 only).
+struct CamModel {
+    int model; const float* p;
+    void unproject(float x, float y, float& X, float& Y, float& Z) const {
+        if (model == 0) { X = (x - p[2]) / p[0]; Y = (y - p[3]) / p[1]; Z = 1.f; return; }
+        const float pwx = (x - p[2]) / p[0], pwy = (y - p[3]) / p[1];
+        float scale = 1.f;
+        float theta_d = sqrtf(pwx * pwx + pwy * pwy);
+        theta_d = fminf(fmaxf(-3.1415926535897932384626433832795 / 2.f, theta_d), 3.1415926535897932384626433832795 / 2.f);
+        if (theta_d > 1e-8) {
+            float theta = theta_d;
+            for (int j = 0; j < 10; j++) {
+                float theta2 = theta * theta, theta4 = theta2 * theta2, theta6 = theta4 * theta2, theta8 = theta4 * theta4;
+                float k0_theta2 = p[4] * theta2, k1_theta4 = p[5] * theta4;
+                float k2_theta6 = p[6] * theta6, k3_theta8 = p[7] * theta8;
+                float theta_fix = (theta * (1 + k0_theta2 + k1_theta4 + k2_theta6 + k3_theta8) - theta_d) /
+                                  (1 + 3 * k0_theta2 + 5 * k1_theta4 + 7 * k2_theta6 + 9 * k3_theta8);
+                theta = theta - theta_fix;
+                if (fabsf(theta_fix) < 1e-6f) break;
+            }
+            scale = std::tan(theta) / theta_d;
+        }
+        X = pwx * scale; Y = pwy * scale; Z = 1.f;
+    }
+    // Eigen::Vector2d project(const Eigen::Vector3d&)
+    void projectD(const double v[3], double& u, double& w) const {
+        if (model == 0) { u = p[0] * v[0] / v[2] + p[2]; w = p[1] * v[1] / v[2] + p[3]; return; }
+        const double x2_plus_y2 = v[0] * v[0] + v[1] * v[1];
+        const double theta = atan2f(sqrtf(x2_plus_y2), v[2]);
+        const double psi = atan2f(v[1], v[0]);
+        const double theta2 = theta * theta, theta3 = theta * theta2, theta5 = theta3 * theta2, theta7 = theta5 * theta2, theta9 = theta7 * theta2;
+        const double r = theta + p[4] * theta3 + p[5] * theta5 + p[6] * theta7 + p[7] * theta9;
+        u = p[0] * r * cos(psi) + p[2];
+        w = p[1] * r * sin(psi) + p[3];
+    }
+    // cv::Point2f project(const cv::Point3f&)
+    void projectF(float x, float y, float z, float& u, float& w) const {
+        if (model == 0) { u = p[0] * x / z + p[2]; w = p[1] * y / z + p[3]; return; }
+        const float x2_plus_y2 = x * x + y * y;
+        const float theta = atan2f(sqrtf(x2_plus_y2), z);
+        const float psi = atan2f(y, x);
+        const float theta2 = theta * theta, theta3 = theta * theta2, theta5 = theta3 * theta2, theta7 = theta5 * theta2, theta9 = theta7 * theta2;
+        const float r = theta + p[4] * theta3 + p[5] * theta5 + p[6] * theta7 + p[7] * theta9;
+        u = (float)(p[0] * r * cos(psi) + p[2]);
+        w = (float)(p[1] * r * sin(psi) + p[3]);
+    }
+};
+
 }  // namespace
 
 extern "C" {
@@ -110,6 +161,13 @@ float orc_image_focus(const float* img, int w, int h, int patch, int what, int a
 int orc_ev_accumulate(const orc_event* evs, int64_t n, int w, int h, float sigma, int mode, const float* Tcw16,
                       float depth, const float* K4, const float* se2, int se2_n, int pol, int normalize,
                       float* img, float* minmax2) {
+    return orc_ev_accumulate_cam(evs, n, w, h, sigma, mode, Tcw16, depth, K4, 0, se2, se2_n, pol, normalize, img, minmax2);
+}
+
+int orc_ev_accumulate_cam(const orc_event* evs, int64_t n, int w, int h, float sigma, int mode, const float* Tcw16,
+                          float depth, const float* cam8, int cam_model, const float* se2, int se2_n, int pol, int normalize,
+                          float* img, float* minmax2) {
+    const CamModel cam{cam_model, cam8};
     std::memset(img, 0, sizeof(float) * (size_t)w * h);
     float mn = 0.0f, mx = -1000000.0f;
     if (mode == 0) {
@@ -135,11 +193,11 @@ int orc_ev_accumulate(const orc_event* evs, int64_t n, int w, int h, float sigma
         for (int r = 0; r < 3; r++) { for (int c = 0; c < 3; c++) R[r][c] = (double)Tcw16[r * 4 + c]; tt[r] = (double)Tcw16[r * 4 + 3]; }
         double ang, ax[3];
         angleAxisFromR(R, ang, ax);
-        const float fx = K4[0], fy = K4[1], cx = K4[2], cy = K4[3];
         double t1 = evs[n - 1].ts, DT = t1 - evs[0].ts, invDT = 1.0 / DT;
         for (int64_t k = 0; k < n; k++) {
             double rate = DT > 0 ? (t1 - evs[k].ts) * invDT : 0.0;
-            float X = (evs[k].x - cx) / fx, Y = (evs[k].y - cy) / fy, Z = 1.f;
+            float X, Y, Z;
+            cam.unproject(evs[k].x, evs[k].y, X, Y, Z);
             double P[3] = {(double)X, (double)Y, (double)Z};
             double nR[3][3];
             rotFromAngleAxis(ang * rate, ax, nR);
@@ -148,12 +206,12 @@ int orc_ev_accumulate(const orc_event* evs, int64_t n, int w, int h, float sigma
                 double md[3] = {(double)depth * nR[r][0], (double)depth * nR[r][1], (double)depth * nR[r][2]};
                 np[r] = (md[0] * P[0] + md[1] * P[1] + md[2] * P[2]) + tt[r] * rate;
             }
-            double u = fx * np[0] / np[2] + cx, v = fy * np[1] / np[2] + cy;
+            double u, v;
+            cam.projectD(np, u, v);
             sp.add((float)u, (float)v, evs[k].p != 0);
         }
     } else if (mode == 3) {
         if (n <= 0) { if (minmax2) { minmax2[0] = mn; minmax2[1] = mx; } return 0; }
-        const float fx = K4[0], fy = K4[1], cx = K4[2], cy = K4[3];
         double t1 = evs[n - 1].ts;
         float DT = static_cast<float>(t1 - evs[0].ts);
         float invDT = 1.f / DT;
@@ -163,12 +221,14 @@ int orc_ev_accumulate(const orc_event* evs, int64_t n, int w, int h, float sigma
         float scDiff = 1.f - sc;
         for (int64_t k = 0; k < n; k++) {
             float tk = static_cast<float>(t1 - evs[k].ts);
-            float X = (evs[k].x - cx) / fx, Y = (evs[k].y - cy) / fy, Z = 1.f;
+            float X, Y, Z;
+            cam.unproject(evs[k].x, evs[k].y, X, Y, Z);
             float th = tk * omega0;
             float cs = scDiff * (1 - tk * invDT) + sc;
             float xp = cs * (X * cosf(th) - Y * sinf(th)) + vx0 * tk;
             float yp = cs * (X * sinf(th) + Y * cosf(th)) + vy0 * tk;
-            float u = fx * xp / Z + cx, v = fy * yp / Z + cy;
+            float u, v;
+            cam.projectF(xp, yp, Z, u, v);
             sp.add(u, v, evs[k].p != 0);
         }
     } else {

@@ -193,6 +193,11 @@ void  orc_undistort_points(const float* xy, int n, const float* K4, const float*
 int   orc_ev_accumulate(const orc_event* evs, int64_t n, int w, int h, float sigma, int mode,
                         const float* Tcw16, float depth, const float* K4, const float* se2, int se2_n,
                         int pol, int normalize, float* img_f32, float* minmax2);
+/* the same with a camera model: cam_model 0 = Pinhole (cam8[0..3] = fx, fy, cx, cy), 1 = KannalaBrandt8 (cam8[4..7] = k1..k4;
+   src/CameraModels/KannalaBrandt8.cpp:86-129, 163-190) */
+int   orc_ev_accumulate_cam(const orc_event* evs, int64_t n, int w, int h, float sigma, int mode,
+                            const float* Tcw16, float depth, const float* cam8, int cam_model, const float* se2, int se2_n,
+                            int pol, int normalize, float* img_f32, float* minmax2);
 /* normalizeImage(convertTo) : u8 = sat(rint(v*alpha+beta)), alpha=255/(max-min), beta=-min*alpha */
 void  orc_normalize_convert_u8(const float* img, int n, float maxVal, float minVal, uint8_t* out);
 /* cv::normalize(img,out,255,0,NORM_MINMAX,CV_8UC1) */

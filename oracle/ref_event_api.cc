@@ -13,6 +13,7 @@
 
 #include "EventConversion.h"   // the reference's include/Event/EventConversion.h
 #include "Pinhole.h"
+#include "KannalaBrandt8.h"
 #include "oracle.h"
 
 #include "gen_event_deps.inc"
@@ -29,10 +30,12 @@ std::vector<EventData> toEvents(const orc_event* evs, int64_t n) {
     return v;
 }
 cv::Mat run(const std::vector<EventData>& v, int w, int h, float sigma, int mode, const float* Tcw16, float depth, const float* K4,
-            const float* se2, int se2_n, bool pol, bool normalized) {
+            const float* se2, int se2_n, bool pol, bool normalized, int camModel = 0) {
     if (mode == 0) return EvImConverter::ev2im(v, w, h, pol, normalized);
     if (mode == 1) return EvImConverter::ev2im_gauss(v, w, h, sigma, pol, normalized);
-    ORB_SLAM3::Pinhole cam(std::vector<float>(K4, K4 + 4));
+    ORB_SLAM3::Pinhole pin(std::vector<float>(K4, K4 + 4));
+    ORB_SLAM3::KannalaBrandt8 kb(camModel == 1 ? std::vector<float>(K4, K4 + 8) : std::vector<float>(8, 0.f));
+    ORB_SLAM3::GeometricCamera& cam = camModel == 1 ? static_cast<ORB_SLAM3::GeometricCamera&>(kb) : static_cast<ORB_SLAM3::GeometricCamera&>(pin);
     if (mode == 2) {
         cv::Mat Tcw(4, 4, CV_32FC1);
         for (int r = 0; r < 4; r++) for (int c = 0; c < 4; c++) Tcw.at<float>(r, c) = Tcw16[r * 4 + c];
@@ -58,6 +61,21 @@ int ref_ev_accumulate(const orc_event* evs, int64_t n, int w, int h, float sigma
     for (int y = 0; y < h; y++) std::memcpy(img_f32 + (size_t)y * w, f.ptr<float>(y), sizeof(float) * (size_t)w);
     if (!normalize) return 0;
     cv::Mat g = run(v, w, h, sigma, mode, Tcw16, depth, K4, se2, se2_n, pol != 0, true);
+    if (g.type() != CV_8UC1) return 0;
+    for (int y = 0; y < h; y++) std::memcpy(u8 + (size_t)y * w, g.ptr(y), (size_t)w);
+    return 1;
+}
+
+/* the same with a camera model: cam_model 0 = Pinhole (cam8[0..3]), 1 = KannalaBrandt8 (cam8[0..7]; src/CameraModels/KannalaBrandt8.cpp) */
+int ref_ev_accumulate_cam(const orc_event* evs, int64_t n, int w, int h, float sigma, int mode, const float* Tcw16, float depth,
+                          const float* cam8, int cam_model, const float* se2, int se2_n, int pol, int normalize, float* img_f32, uint8_t* u8) {
+    if (mode < 0 || mode > 3 || cam_model < 0 || cam_model > 1) return -3;
+    std::vector<EventData> v = toEvents(evs, n);
+    cv::Mat f = run(v, w, h, sigma, mode, Tcw16, depth, cam8, se2, se2_n, pol != 0, false, cam_model);
+    if (f.type() != CV_32FC1 || f.rows != h || f.cols != w) return -4;
+    for (int y = 0; y < h; y++) std::memcpy(img_f32 + (size_t)y * w, f.ptr<float>(y), sizeof(float) * (size_t)w);
+    if (!normalize) return 0;
+    cv::Mat g = run(v, w, h, sigma, mode, Tcw16, depth, cam8, se2, se2_n, pol != 0, true, cam_model);
     if (g.type() != CV_8UC1) return 0;
     for (int y = 0; y < h; y++) std::memcpy(u8 + (size_t)y * w, g.ptr(y), (size_t)w);
     return 1;

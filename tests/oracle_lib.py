@@ -272,17 +272,20 @@ def rotation_filter(angle1, angle2, match12):
 
 
 # ----------------------------------------------------------------------------- events
-def ev_accumulate(evs, w, h, sigma=1.0, mode=1, Tcw=None, depth=1.0, K=None, se2=None, pol=False, normalize=False):
-    """-> (img_f32 (h,w), (min,max), u8 or None)"""
+def ev_accumulate(evs, w, h, sigma=1.0, mode=1, Tcw=None, depth=1.0, K=None, se2=None, pol=False, normalize=False, kb8=None):
+    """-> (img_f32 (h,w), (min,max), u8 or None).  kb8 = (k1, k2, k3, k4): the camera is a KannalaBrandt8 with K = fx, fy, cx, cy"""
     evs = np.ascontiguousarray(evs)
     assert evs.dtype.itemsize == 24
     img = np.zeros((h, w), np.float32)
     mm = np.zeros(2, np.float32)
     T = np.ascontiguousarray(Tcw, np.float32).reshape(16) if Tcw is not None else None
     Kc = np.ascontiguousarray(K, np.float32) if K is not None else None
+    if kb8 is not None:
+        Kc = np.ascontiguousarray(list(K) + list(kb8), np.float32)
     s2 = np.ascontiguousarray(se2, np.float32) if se2 is not None else None
-    r = lib().orc_ev_accumulate(_p(evs), len(evs), w, h, sigma, mode, _p(T), depth, _p(Kc), _p(s2),
-                                0 if s2 is None else len(s2), int(pol), int(normalize), _p(img), _p(mm))
+    f = lib().orc_ev_accumulate_cam; f.restype = C.c_int
+    r = f(_p(evs), C.c_int64(len(evs)), w, h, C.c_float(sigma), mode, _p(T), C.c_float(depth), _p(Kc), 0 if kb8 is None else 1, _p(s2),
+          0 if s2 is None else len(s2), int(pol), int(normalize), _p(img), _p(mm))
     assert r >= 0
     u8 = None
     if r == 1:

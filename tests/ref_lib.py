@@ -186,7 +186,7 @@ def orb_extract_batch_mt(frames, nthreads, want_desc=True, **kw):
 
 
 # ----------------------------------------------------------------------------- events (EventConversion.cc, unmodified)
-def ev_accumulate(evs, w, h, sigma=1.0, mode=1, Tcw=None, depth=1.0, K=None, se2=None, pol=False, normalize=False):
+def ev_accumulate(evs, w, h, sigma=1.0, mode=1, Tcw=None, depth=1.0, K=None, se2=None, pol=False, normalize=False, kb8=None):
     """same contract as oracle_lib.ev_accumulate: -> (img_f32, (min, max) as the reference tracked them, u8 or None)"""
     evs = np.ascontiguousarray(evs)
     assert evs.dtype.itemsize == 24
@@ -194,9 +194,12 @@ def ev_accumulate(evs, w, h, sigma=1.0, mode=1, Tcw=None, depth=1.0, K=None, se2
     u8 = np.zeros((h, w), np.uint8)
     T = np.ascontiguousarray(Tcw, np.float32).reshape(16) if Tcw is not None else None
     Kc = np.ascontiguousarray(K, np.float32) if K is not None else None
+    if kb8 is not None:
+        Kc = np.ascontiguousarray(list(K) + list(kb8), np.float32)
     s2 = np.ascontiguousarray(se2, np.float32) if se2 is not None else None
-    r = lib().ref_ev_accumulate(_p(evs), len(evs), w, h, sigma, mode, _p(T), depth, _p(Kc), _p(s2), 0 if s2 is None else len(s2), int(pol),
-                                int(normalize), _p(img), _p(u8))
+    f = lib().ref_ev_accumulate_cam; f.restype = C.c_int
+    r = f(_p(evs), C.c_int64(len(evs)), w, h, C.c_float(sigma), mode, _p(T), C.c_float(depth), _p(Kc), 0 if kb8 is None else 1, _p(s2),
+          0 if s2 is None else len(s2), int(pol), int(normalize), _p(img), _p(u8))
     assert r >= 0
     return img, (u8 if r == 1 else None)
 

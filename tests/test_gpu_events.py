@@ -81,6 +81,27 @@ def test_motion_compensation_mvsec_shape():
         _close(img, ref)
 
 
+def test_motion_compensation_kannala_brandt8_camera():
+    """the camera MVSEC actually uses (Examples/Event/EvMVSEC.yaml:50-63): KannalaBrandt8 unproject / project inside the SE3 and SE2
+    warps, against the oracle (which equals the reference's own KannalaBrandt8.cpp bit for bit, tests/test_ref_pin.py)"""
+    api = _api()
+    K8 = (226.38018519795807, 226.15002947047415, 173.6470807871759, 133.73271487507847,
+          -0.048031442223833355, 0.011330957517194437, -0.055378166304281135, 0.021500973881459395)
+    ev = synth.make_events(50000, seed=78, w=346, h=260, mean_dt=2e-7)
+    cv = api.EvImConverter(0, 1, 100000, 346, 260)
+    for omega, t in (([0.01, -0.02, 0.03], (0, 0, 0)), ([0.02, 0.01, -0.015], (0.01, -0.02, 0.005))):
+        T = synth.rotation_tcw(omega, t)
+        img = cv.ev2mci_gg_f(ev, K8, T, 1.2, 346, 260, 1.0, False, False)
+        ref, _, _ = O.ev_accumulate(ev, 346, 260, 1.0, mode=2, Tcw=T, depth=1.2, K=K8[:4], kb8=K8[4:])
+        _close(img, ref)
+        pin, _, _ = O.ev_accumulate(ev, 346, 260, 1.0, mode=2, Tcw=T, depth=1.2, K=K8[:4])
+        assert np.abs(ref - pin).max() > 0.5
+    for se2 in ([0.03, 0.01, -0.02], [0.02, -0.01, 0.015, 0.97]):
+        img = cv.ev2mci_gg_f_2d(ev, K8, se2, 346, 260, 1.0, False, False)
+        ref, _, _ = O.ev_accumulate(ev, 346, 260, 1.0, mode=3, K=K8[:4], kb8=K8[4:], se2=np.array(se2, np.float32))
+        _close(img, ref)
+
+
 def test_empty_and_out_of_image():
     api = _api()
     cv = api.EvImConverter(0, 1, 1000, 240, 180)

@@ -181,3 +181,41 @@ def test_libref_matchers_vs_oracle_fresh_cases():
         cb = RC.bow_case(700, 650, seed, levelsup=2)
         o = O.search_by_bow(*cb, 0.7, True); r = R.search_by_bow(*cb, 0.7, True)
         assert o[0] == r[0] and np.array_equal(o[1], r[1]), seed
+
+
+# ------------------------------------------------------------------------------------------------ KannalaBrandt8 motion compensation
+KB8_K = (226.38018519795807, 226.15002947047415, 173.6470807871759, 133.73271487507847)          # Examples/Event/EvMVSEC.yaml:53-63
+KB8_D = (-0.048031442223833355, 0.011330957517194437, -0.055378166304281135, 0.021500973881459395)
+
+
+def kb8_cases():
+    T = np.eye(4, dtype=np.float32)
+    c, s = np.cos(0.07), np.sin(0.07)
+    T[:3, :3] = np.array([[c, -s, 0], [s, c, 0], [0, 0, 1]], np.float32); T[:3, 3] = [0.01, 0.0, -0.01]
+    for seed in (201, 202):
+        ev = synth.make_events(20000, seed, 346, 260)
+        yield "se3_%d" % seed, ev, dict(mode=2, Tcw=T, depth=1.2, K=KB8_K, kb8=KB8_D)
+        yield "se2_%d" % seed, ev, dict(mode=3, se2=[0.02, -1.0, 0.5], K=KB8_K, kb8=KB8_D)
+        yield "se2s_%d" % seed, ev, dict(mode=3, se2=[0.02, -1.0, 0.5, 0.9], K=KB8_K, kb8=KB8_D)
+
+
+def test_oracle_kb8_motion_compensation_equals_reference(golden_dir):
+    """ev2mci_gg_f through the reference's own KannalaBrandt8::unproject / project (src/CameraModels/KannalaBrandt8.cpp:86-129, 163-190, cut
+    into libref): float frames bit for bit (tests/golden/ref_events_kb8.npz, written by this test's generator below when libref exists)"""
+    path = os.path.join(golden_dir, "ref_events_kb8.npz")
+    import ref_lib as R
+    if R.available() and os.environ.get("EORB_WRITE_GOLDEN") == "1":
+        out = {}
+        for key, ev, kw in kb8_cases():
+            f, u8 = R.ev_accumulate(ev, 346, 260, 1.0, normalize=True, **kw)
+            out[key + "_sha"] = np.array(RC.sha(f)); out[key + "_u8sha"] = np.array(RC.sha(u8)); out[key + "_max"] = np.array([f.max()], np.float32)
+        np.savez_compressed(path, **out)
+    g = np.load(path)
+    for key, ev, kw in kb8_cases():
+        f, _, u8 = O.ev_accumulate(ev, 346, 260, 1.0, normalize=True, **kw)
+        assert RC.sha(f) == str(g[key + "_sha"]) and RC.sha(u8) == str(g[key + "_u8sha"]), key
+        pin, _, _ = O.ev_accumulate(ev, 346, 260, 1.0, **{k: v for k, v in kw.items() if k != "kb8"})
+        assert np.abs(f - pin).max() > 0.5, "the fisheye model must differ from the pinhole one on this camera"
+        if R.available():
+            rf, ru = R.ev_accumulate(ev, 346, 260, 1.0, normalize=True, **kw)
+            assert rf.tobytes() == f.tobytes() and np.array_equal(ru, u8), key
