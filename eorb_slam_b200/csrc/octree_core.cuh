@@ -43,7 +43,7 @@ __device__ __forceinline__ int oct_atomic_min(int* p, int v) { return atomicMin(
 namespace eorb {
 
 #ifndef OCT_MAX_THREADS
-#define OCT_MAX_THREADS 128
+#define OCT_MAX_THREADS 512   // largest block the kernels are launched with (scratch sizing); launch sets use 128 threads
 #endif
 
 #ifndef OCT_KU

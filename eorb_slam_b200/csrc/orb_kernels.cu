@@ -95,25 +95,30 @@ __device__ __forceinline__ unsigned pyr_vrow(const unsigned* __restrict__ h0, co
 #ifndef EORB_PYR_MINB
 #define EORB_PYR_MINB 8
 #endif
-__global__ void __launch_bounds__(128, EORB_PYR_MINB) pyr_resize_kernel(OrbArgs a, int level) {
+// one block = 128 destination columns x 4 warps x BAND rows of `level`, at tile (bx, by) of frame f
+// `ready()` is called by every warp after its per-lane tap constants are formed and before the first source row is read (the chained
+// single-launch pyramid waits for the source level there, so the table loads overlap the wait)
+struct PyrNoWait { __device__ __forceinline__ void operator()() const {} };
+template <int BAND, class Ready>
+__device__ __forceinline__ void pyr_resize_block(const OrbArgs& a, int level, int bx, int by, int f, Ready ready) {
     const OrbPlan& P = *a.plan;
     const int dw = P.lv[level].w, dh = P.lv[level].h, dpitch = P.lv[level].pitch;
     const int sw = P.lv[level - 1].w;
     const int xtabOff = P.lv[level].xtabOff, ytabOff = P.lv[level].ytabOff;
     const long long doff = P.lv[level].off;
     const long long pyrBytes = P.pyrBytesPerFrame;
-    const int f = blockIdx.z;
     const int lane = threadIdx.x;
-    const int dx0 = blockIdx.x * 128 + lane * 4;
-    const int y0 = (blockIdx.y * blockDim.y + threadIdx.y) * EORB_PYR_BAND;
-    if (y0 >= dh || blockIdx.x * 128 >= dw) return;     // warp-uniform
-    const int y1 = min(y0 + EORB_PYR_BAND, dh);
+    const int dx0 = bx * 128 + lane * 4;
+    const int y0 = (by * (int)blockDim.y + (int)threadIdx.y) * BAND;
+    if (y0 >= dh || bx * 128 >= dw) return;     // warp-uniform
+    const int y1 = min(y0 + BAND, dh);
     int sp;
     const uint8_t* __restrict__ src = level_ptr(a, P.lv[level - 1], level - 1, f, sp);
     uint8_t* __restrict__ dst = a.pyr + (size_t)f * (size_t)pyrBytes + (size_t)doff + dx0;
     const int4* __restrict__ ytab = a.ytab + ytabOff;
     const bool active = dx0 < dw;
     if (sw < 8) {   // degenerate source width: plain per-pixel evaluation (the windows below need two whole words)
+        ready();
         if (active)
             for (int dy = y0; dy < y1; dy++) {
                 const int4 yt = __ldg(&ytab[dy]);
@@ -152,6 +157,7 @@ __global__ void __launch_bounds__(128, EORB_PYR_MINB) pyr_resize_kernel(OrbArgs 
     const uint8_t* __restrict__ laneA = src + baseA;
     const uint8_t* __restrict__ laneB = src + baseB;
     uint8_t* dp = dst + (size_t)y0 * dpitch;
+    ready();
 #if EORB_PYR_HOIST
     // two destination rows per step, all sixteen source words requested before the first interpolation
     for (int dy = y0; dy < y1; dy += 2) {
@@ -189,13 +195,67 @@ __global__ void __launch_bounds__(128, EORB_PYR_MINB) pyr_resize_kernel(OrbArgs 
 #endif
 }
 
+__global__ void __launch_bounds__(128, EORB_PYR_MINB) pyr_resize_kernel(OrbArgs a, int level) {
+    pyr_resize_block<EORB_PYR_BAND>(a, level, blockIdx.x, blockIdx.y, blockIdx.z, PyrNoWait());
+}
+
+// K1c: EVERY level in one launch, for small batches (the single-frame call is launch bound: seven dependent launches cost 47 us for
+// 8 us of work).  Blocks are laid out level by level (blockIdx.x) per frame (blockIdx.y); a block of level l waits until all tiles of
+// level l-1 of its frame have been published (done[f][l-1], release / acquire through __threadfence + a volatile poll), computes its
+// tile with pyr_resize_block and publishes itself.  A block only ever waits for blocks of LOWER linear index, which the hardware has
+// dispatched before it, so the wait cannot deadlock however many blocks are resident.  done[] is zeroed by the host before the launch.
+#ifndef EORB_PYR_CHAIN_BAND
+#define EORB_PYR_CHAIN_BAND 4   // destination rows per warp in the single-launch pyramid: short bands = many blocks = short critical path per level
+#endif
+__global__ void __launch_bounds__(128, EORB_PYR_MINB) pyr_chain_kernel(OrbArgs a, int* __restrict__ done) {
+    const OrbPlan& P = *a.plan;
+    const int f = blockIdx.y;
+    int t = blockIdx.x, level = 1, gx = 1, tiles = 0;
+    for (;; level++) {
+        gx = (P.lv[level].w + 127) >> 7;
+        tiles = gx * ((P.lv[level].h + 4 * EORB_PYR_CHAIN_BAND - 1) / (4 * EORB_PYR_CHAIN_BAND));
+        if (t < tiles || level + 1 >= P.nlevels) break;
+        t -= tiles;
+    }
+    if (t >= tiles) return;
+    int* flags = done + (size_t)f * EORB_MAX_LEVELS;
+    int need = 0;
+    if (level > 1) {
+        const int gxp = (P.lv[level - 1].w + 127) >> 7;
+        need = gxp * ((P.lv[level - 1].h + 4 * EORB_PYR_CHAIN_BAND - 1) / (4 * EORB_PYR_CHAIN_BAND));
+    }
+    const volatile int* fl = flags + (level - 1);
+    auto ready = [&]() {   // per warp: lane 0 polls the source level's counter (acquire), the warp follows
+        if (need > 0) {
+            if (threadIdx.x == 0) { while (*fl < need) __nanosleep(20); }
+            __syncwarp();
+            __threadfence();
+        }
+    };
+    pyr_resize_block<EORB_PYR_CHAIN_BAND>(a, level, t % gx, t / gx, f, ready);
+    __syncthreads();
+    if (threadIdx.x == 0 && threadIdx.y == 0) {
+        __threadfence();
+        atomicAdd(flags + level, 1);
+    }
+}
+
+static int pyr_chain_tiles(const OrbPlan& hp) {
+    int t = 0;
+    for (int l = 1; l < hp.nlevels; l++) t += ((hp.lv[l].w + 127) / 128) * ((hp.lv[l].h + 4 * EORB_PYR_CHAIN_BAND - 1) / (4 * EORB_PYR_CHAIN_BAND));
+    return t;
+}
+
 // ------------------------------------------------------------------------------------------------ K3
 // One block per (level, frame).  Gathers the level's per-cell candidate lists into the reference's order
 // (cell-row-major, pixel-row-major inside a cell), then runs the shared level-synchronous distribution.
-__global__ void __launch_bounds__(OCT_MAX_THREADS) octree_kernel(OrbArgs a) {
+// NT threads per block: 128 for launch sets (many blocks hide each other's barriers), NT for small batches, where the
+// level-0 block of a single frame is the critical path and its passes over ~2000 keys are NT-wide.
+template <int NT>
+__global__ void __launch_bounds__(NT) octree_kernel(OrbArgs a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    __shared__ int s_arr[OCT_MAX_THREADS];
-    __shared__ int s_scr[OCT_MAX_THREADS];
+    __shared__ int s_arr[NT];
+    __shared__ int s_scr[NT];
     const OrbPlan& P = *a.plan;
     const int level = blockIdx.x, f = blockIdx.y;
     const LevelPlan& lp = P.lv[level];
@@ -205,12 +265,12 @@ __global__ void __launch_bounds__(OCT_MAX_THREADS) octree_kernel(OrbArgs a) {
     const uint16_t* counts = a.cellCount + (size_t)f * P.nCells + lp.cellBase;
     const uint32_t* cand = a.cand + (size_t)f * P.slotsPerFrame;
     int n = 0;
-    for (int c0 = 0; c0 < lp.nCells; c0 += OCT_MAX_THREADS) {
+    for (int c0 = 0; c0 < lp.nCells; c0 += NT) {
         const int ci = c0 + tid;
         const int cnt = (ci < lp.nCells) ? (int)counts[ci] : 0;
         s_arr[tid] = cnt;
         __syncthreads();
-        const int tot = oct_exclusive_scan(s_arr, OCT_MAX_THREADS, s_scr);
+        const int tot = oct_exclusive_scan(s_arr, NT, s_scr);
         if (cnt > 0) {
             const uint32_t* src = cand + a.cells[lp.cellBase + ci].slotOff;
             uint32_t* dst = okeys + n + s_arr[tid];
@@ -241,9 +301,10 @@ __global__ void __launch_bounds__(OCT_MAX_THREADS) octree_kernel(OrbArgs a) {
 // One block per frame: final position of every selected keypoint.  The reference walks levels in order and
 // keypoints in octree-list order, writing keypoints inside the lapping area from the END of the output and
 // the others from the front (:1152-1172); positions are prefix counts of the "inside" flag.
-__global__ void __launch_bounds__(OCT_MAX_THREADS) orb_index_kernel(OrbArgs a) {
-    __shared__ int s_arr[OCT_MAX_THREADS];
-    __shared__ int s_scr[OCT_MAX_THREADS];
+template <int NT>
+__global__ void __launch_bounds__(NT) orb_index_kernel(OrbArgs a) {
+    __shared__ int s_arr[NT];
+    __shared__ int s_scr[NT];
     __shared__ int s_start[EORB_MAX_LEVELS + 1];
     const OrbPlan& P = *a.plan;
     const int f = blockIdx.x, tid = threadIdx.x;
@@ -258,7 +319,7 @@ __global__ void __launch_bounds__(OCT_MAX_THREADS) orb_index_kernel(OrbArgs a) {
     int* dstIdx = a.dstIdx + (size_t)f * P.selPerFrame;
     const float lap0 = (float)a.lap0, lap1 = (float)a.lap1;
     int stereoRun = 0;
-    for (int g0 = 0; g0 < nk; g0 += OCT_MAX_THREADS) {
+    for (int g0 = 0; g0 < nk; g0 += NT) {
         const int g = g0 + tid;
         int flag = 0, slot = 0;
         if (g < nk) {
@@ -273,7 +334,7 @@ __global__ void __launch_bounds__(OCT_MAX_THREADS) orb_index_kernel(OrbArgs a) {
         }
         s_arr[tid] = flag;
         __syncthreads();
-        const int tot = oct_exclusive_scan(s_arr, OCT_MAX_THREADS, s_scr);
+        const int tot = oct_exclusive_scan(s_arr, NT, s_scr);
         if (g < nk) {
             const int stereoBefore = stereoRun + s_arr[tid];
             dstIdx[slot] = flag ? (nk - 1 - stereoBefore) : (g - stereoBefore);
@@ -877,6 +938,12 @@ cudaError_t launch_orb_pipeline(const OrbArgs& a, const OrbPlan& hp, int nframes
     // ev (optional, EORB_ORB_STAGES+1 events): recorded around every stage for the per-kernel timings of bench.py
     if (ev) cudaEventRecord(ev[0], st);
     // K1: pyramid, level by level (each level is resized from the previous one)
+    if (a.pyrDone && nframes <= 8 && hp.nlevels > 1) {   // one launch for all levels (pyr_chain_kernel)
+        cudaError_t e = cudaMemsetAsync(a.pyrDone, 0, (size_t)nframes * EORB_MAX_LEVELS * sizeof(int), st);
+        if (e != cudaSuccess) return e;
+        pyr_chain_kernel<<<dim3(pyr_chain_tiles(hp), nframes), dim3(32, 4), 0, st>>>(a, a.pyrDone);
+        (*launches)++;
+    } else
     for (int l = 1; l < hp.nlevels; l++) {
         if (hp.lv[l].w <= 0 || hp.lv[l].h <= 0) continue;
         cudaError_t e = launch_pyramid_level(a, hp, l, nframes, st, pyrMaps);
@@ -918,12 +985,14 @@ cudaError_t launch_orb_pipeline(const OrbArgs& a, const OrbPlan& hp, int nframes
     // K3: octree distribution per (level, frame)
     {
         dim3 grd(hp.nlevels, nframes);
-        octree_kernel<<<grd, OCT_MAX_THREADS, hp.octSmemBytes, st>>>(a);
+        if (nframes <= 8) octree_kernel<OCT_MAX_THREADS><<<grd, OCT_MAX_THREADS, hp.octSmemBytes, st>>>(a);
+        else octree_kernel<128><<<grd, 128, hp.octSmemBytes, st>>>(a);
         (*launches)++;
     }
     if (ev) cudaEventRecord(ev[3], st);
     // K7: output order
-    orb_index_kernel<<<nframes, OCT_MAX_THREADS, 0, st>>>(a);
+    if (nframes <= 8) orb_index_kernel<OCT_MAX_THREADS><<<nframes, OCT_MAX_THREADS, 0, st>>>(a);
+    else orb_index_kernel<128><<<nframes, 128, 0, st>>>(a);
     (*launches)++;
     if (ev) cudaEventRecord(ev[4], st);
     // K5: blur (only needed for descriptors)
@@ -980,7 +1049,8 @@ cudaError_t orb_kernels_configure(const OrbPlan& hp) {
     if (e != cudaSuccess) return e;
     std::lock_guard<std::mutex> lk(mu);
     if (dev >= 0 && dev < 64 && done[dev]) return cudaSuccess;
-    e = cudaFuncSetAttribute(octree_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    e = cudaFuncSetAttribute(octree_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(octree_kernel<OCT_MAX_THREADS>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
     if (e == cudaSuccess && dev >= 0 && dev < 64) done[dev] = true;
     return e;
 }

@@ -23,6 +23,7 @@ struct OrbArgs {
                                  //         level 0 is the caller's buffer, its map travels as a kernel parameter)
     const CUtensorMap* blurMaps; // device: [nlevels] maps of the levels >= 1 with the box of blur_tma_kernel, or nullptr (blur_kernel is used);
                                  //         level 0's travels as pyrMaps[0] of launch_orb_pipeline
+    int* pyrDone;                // device: [8][EORB_MAX_LEVELS] tile counters of pyr_chain_kernel (small batches), or nullptr
     int blurVariant;             // EORB_BLUR_TMA value (1..4: band rows 32 / 64, neighbour words by shuffle / from the tile)
     uint8_t* pyr;                // [B][pyrBytesPerFrame]   levels >= 1
     uint8_t* blur;               // [B][blurBytesPerFrame]  all levels
