@@ -89,6 +89,10 @@ def _load():
         "eorb_lk_set_ref": ([vp, vp, i, i, sz, vp, i, i, i], i), "eorb_lk_set_ref_device": ([vp, vp, i, i, sz, vp, i, i, i], i),
         "eorb_lk_track": ([vp, vp, sz, vp, i, C.c_double, f, vp, vp, vp], i),
         "eorb_lk_track_device": ([vp, vp, sz, vp, i, C.c_double, f, vp, vp, vp], i),
+        "eorb_lk_set_ref_keypoints": ([vp, vp, i, i, sz, i, vp, i, i, i], i), "eorb_lk_set_last_tracked": ([vp, vp, i], i),
+        "eorb_lk_get_last_tracked": ([vp, vp], i),
+        "eorb_lk_track_and_match": ([vp, vp, sz, i, i, C.c_double, f, i, vp, vp, vp, vp], i),
+        "eorb_lk_track_and_match_device": ([vp, vp, sz, i, C.c_double, f, i, vp, vp, vp, vp], i),
         "eorb_guided_create": ([i, C.POINTER(vp)], i), "eorb_guided_destroy": ([vp], i),
         "eorb_guided_set_stream": ([vp, vp], i), "eorb_guided_reset_stream": ([vp], i), "eorb_guided_launch_count": ([vp], C.c_longlong),
         "eorb_guided_frame_grid": ([vp, vp, i, vp, vp, vp, vp], i),
@@ -619,6 +623,53 @@ class ELK_Tracker:
         self.levels_used = _check(lib.eorb_lk_track(self.h, _p(currImage), currImage.strides[0], _p(init), self.maxItr, float(self.eps), 1e-4,
                                                     _p(out), _p(status), _p(err)), "lk_track")
         return out, status, err
+
+    # ---- the tracker with its state on the device (KLT_Tracker.cpp:22-46, 99-262)
+    def setRefImageKPts(self, image, refKPts):
+        """setRefImage(image, vector<KeyPoint>) :22-46: reference keypoints, reference points and last tracked points (= the points)
+        go to the device and stay there"""
+        image = np.ascontiguousarray(image, np.uint8)
+        kps = np.ascontiguousarray(refKPts, KEYPOINT_DTYPE)
+        rc = _check(lib.eorb_lk_set_ref_keypoints(self.h, _p(image), image.shape[1], image.shape[0], image.strides[0], 0, _p(kps), len(kps),
+                                                  self.mPatchSz, self.mMaxLevel), "lk_set_ref_keypoints")
+        self.n = len(kps) if rc == 0 else 0
+        self.shape = image.shape
+        return rc
+
+    def setLastTrackedPts(self, currTrackedPts):
+        kps = np.ascontiguousarray(currTrackedPts, KEYPOINT_DTYPE)
+        return _check(lib.eorb_lk_set_last_tracked(self.h, _p(kps), len(kps)), "lk_set_last_tracked")
+
+    def getLastTrackedPts(self):
+        out = np.zeros((self.n, 2), np.float32)
+        _check(lib.eorb_lk_get_last_tracked(self.h, _p(out)), "lk_get_last_tracked")
+        return out
+
+    def trackAndMatchCurrImage(self, image, vMatches12=None, vCntMatches=None, init=False):
+        """trackAndMatchCurrImage :215-234 (init=True: trackAndMatchCurrImageInit :236-242)
+        -> (nMatches, trackedKPts, vMatches12, vCntMatches, vPxDisp).  vMatches12 / vCntMatches: the caller's vectors, updated the way
+        the reference updates them in place (None = empty vectors, which the reference resizes to -1 / 1)."""
+        image = np.ascontiguousarray(image, np.uint8)
+        assert image.shape == self.shape
+        n = self.n
+        tr = np.zeros(n, KEYPOINT_DTYPE); matched = np.zeros(n, np.uint8); disp = np.zeros(n, np.float32); c2 = np.zeros(2, np.int32)
+        rc = _check(lib.eorb_lk_track_and_match(self.h, _p(image), image.strides[0], 0, self.maxItr, float(self.eps), 1e-4, 1 if init else 0,
+                                                _p(tr), _p(matched), _p(disp), _p(c2)), "lk_track_and_match")
+        m12 = np.full(n, -1, np.int32) if vMatches12 is None else np.array(vMatches12, np.int32)
+        cnt = np.ones(n, np.int32) if vCntMatches is None else np.array(vCntMatches, np.int32)
+        if rc == EORB_EMPTY:
+            return 0, tr[:0], m12, cnt, disp[:0]
+        self.levels_used = rc
+        passed = (matched & 1).astype(bool)
+        idx = np.arange(n, dtype=np.int32)
+        # refineTrackedPts :140-145 on the caller's vectors
+        m12 = np.where(passed, idx, m12).astype(np.int32); cnt = (cnt + passed).astype(np.int32); nm = int(passed.sum())
+        if init:   # refineFirstOctaveLevel :166-176: every entry 0 <= vMatches12[i] < n on an upper reference octave, stale ones included
+            hit = (m12 >= 0) & (m12 < n) & (tr["octave"] > 0)
+            m12[hit] = -1; cnt[hit] -= 1; nm = (nm - int(hit.sum())) & 0xffffffff   # nMatches is unsigned in the reference
+        if vMatches12 is None:
+            assert nm == int(c2[0])
+        return nm, tr, m12, cnt, disp[:c2[1]].copy()
 
 
 # ================================================================================================ guided matching

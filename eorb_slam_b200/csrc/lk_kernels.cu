@@ -248,6 +248,62 @@ __global__ void __launch_bounds__(LK_THREADS) lk_track_kernel(LkLevels LV, LkPar
     }
 }
 
+// ------------------------------------------------------------------------------------------------ post-LK bookkeeping
+// ELK_Tracker::refineTrackedPts (src/Event/KLT_Tracker.cpp:105-155) and refineFirstOctaveLevel (:157-183) for one LK result, ONE block:
+//   tracked[i] = KeyPoint(curr[i], ref[i].size, ref[i].angle, ref[i].response, ref[i].octave, ref[i].class_id)        (:138)
+//   matched[i] bit 0 = status[i] == 1 && 0 <= x < W && 0 <= y < H (isInImage :99-102, the test of :140); bit 1 = bit 0 and not un-matched
+//                by the first-octave filter
+//   pxDisp     = the matched points' sqrtf(dx*dx + dy*dy) in index order (push_back :147) -- an ordered compaction
+//   counts[0]  = nMatches after the optional first-octave filter (ref octave > 0 un-matches, :171-175), counts[1] = pxDisp entries
+// (the filter runs after refineTrackedPts in trackAndMatchCurrImageInit :236-242, so pxDisp keeps the filtered matches' entries).
+#define LK_REFINE_THREADS 256
+__global__ void __launch_bounds__(LK_REFINE_THREADS) lk_refine_kernel(const float2* __restrict__ curr, const uint8_t* __restrict__ status,
+                                                                      const eorb_keypoint* __restrict__ ref, int n, int W, int H,
+                                                                      int firstOctaveOnly, eorb_keypoint* __restrict__ tracked,
+                                                                      uint8_t* __restrict__ matched, float* __restrict__ pxDisp,
+                                                                      int* __restrict__ counts) {
+    __shared__ int s_warp[LK_REFINE_THREADS / 32];
+    __shared__ int s_base, s_kept;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (tid == 0) { s_base = 0; s_kept = 0; }
+    __syncthreads();
+    const float fw = (float)W, fh = (float)H;
+    for (int i0 = 0; i0 < n; i0 += LK_REFINE_THREADS) {
+        const int i = i0 + tid;
+        bool m = false, keep = false;
+        float disp = 0.f;
+        if (i < n) {
+            const float2 c = curr[i];
+            eorb_keypoint k = ref[i];
+            const float dx = fsub(c.x, k.x), dy = fsub(c.y, k.y);
+            m = status[i] == 1 && c.x >= 0.f && c.x < fw && c.y >= 0.f && c.y < fh;
+            keep = m && !(firstOctaveOnly && k.octave > 0);
+            disp = __fsqrt_rn(fadd(fmul(dx, dx), fmul(dy, dy)));
+            k.x = c.x; k.y = c.y;
+            tracked[i] = k;
+            matched[i] = (uint8_t)((m ? 1 : 0) | (keep ? 2 : 0));
+        }
+        const unsigned bal = __ballot_sync(0xffffffffu, m);
+        const unsigned kbal = __ballot_sync(0xffffffffu, keep);
+        if (lane == 0) s_warp[warp] = __popc(bal);
+        __syncthreads();
+        int before = s_base;
+        for (int w = 0; w < warp; w++) before += s_warp[w];
+        if (m) pxDisp[before + __popc(bal & ((1u << lane) - 1u))] = disp;
+        if (lane == 0 && kbal) atomicAdd(&s_kept, __popc(kbal));
+        __syncthreads();
+        if (tid == 0) { int t = 0; for (int w = 0; w < LK_REFINE_THREADS / 32; w++) t += s_warp[w]; s_base += t; }
+        __syncthreads();
+    }
+    if (tid == 0) { counts[0] = s_kept; counts[1] = s_base; }
+}
+
+cudaError_t launch_lk_refine(const float2* curr, const uint8_t* status, const eorb_keypoint* ref, int n, int W, int H, int firstOctaveOnly,
+                             eorb_keypoint* tracked, uint8_t* matched, float* pxDisp, int* counts, cudaStream_t st) {
+    lk_refine_kernel<<<1, LK_REFINE_THREADS, 0, st>>>(curr, status, ref, n, W, H, firstOctaveOnly, tracked, matched, pxDisp, counts);
+    return cudaGetLastError();
+}
+
 cudaError_t launch_lk_pyrdown(const uint8_t* src, int w, int h, int pitch, uint8_t* dst, int dw, int dh, int dpitch, cudaStream_t st) {
     dim3 blk(32, 8), grd((dw + 31) / 32, (dh + 7) / 8);
     lk_pyrdown_kernel<<<grd, blk, 0, st>>>(src, w, h, pitch, dst, dw, dh, dpitch);

@@ -3,6 +3,8 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include "../../include/eorb_b200.h"
+
 namespace eorb {
 
 #define EORB_LK_MAX_LEVELS 8
@@ -30,5 +32,8 @@ cudaError_t launch_lk_pyrdown(const uint8_t* src, int w, int h, int pitch, uint8
 cudaError_t launch_lk_scharr(const uint8_t* src, int w, int h, int pitch, short2* dst, cudaStream_t st);
 cudaError_t launch_lk_track(const LkLevels& L, const LkParams& p, const float2* prevPts, float2* nextPts, int n, uint8_t* status, float* err,
                             cudaStream_t st);
+// ELK_Tracker::refineTrackedPts / refineFirstOctaveLevel on one LK result (one block; see lk_kernels.cu)
+cudaError_t launch_lk_refine(const float2* curr, const uint8_t* status, const eorb_keypoint* ref, int n, int W, int H, int firstOctaveOnly,
+                             eorb_keypoint* tracked, uint8_t* matched, float* pxDisp, int* counts, cudaStream_t st);
 
 }  // namespace eorb

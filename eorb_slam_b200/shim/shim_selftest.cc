@@ -91,6 +91,18 @@ int main(int argc, char** argv)
         int good = 0, tracked = 0;
         for (size_t i = 0; i < st.size(); i++) if (st[i]) { tracked++; const float dx = p1[i].x - p0[i].x - 2.f, dy = p1[i].y - p0[i].y - 1.f; good += (dx * dx + dy * dy < 0.25f); }
         std::printf("lk_ok=%d lk_n=%zu lk_tracked=%d lk_good=%d\n", (int)okk, p1.size(), tracked, good);
+        // the tracker object with its state on the device: two frames, the second from the first one's tracked points
+        EORB_SLAM::b200::ELK_Tracker trk(23, 1, 10, 0.03);
+        trk.setRefImage(im, kps);
+        std::vector<cv::KeyPoint> tk; std::vector<int> m12, cntm; std::vector<float> disp;
+        const unsigned nm1 = trk.trackAndMatchCurrImage(im2, tk, m12, cntm, disp);
+        int good1 = 0;
+        for (size_t i = 0; i < tk.size(); i++) if (m12[i] == (int)i) { const float dx = tk[i].pt.x - kps[i].pt.x - 2.f, dy = tk[i].pt.y - kps[i].pt.y - 1.f; good1 += (dx * dx + dy * dy < 0.25f); }
+        const unsigned nm2 = trk.trackAndMatchCurrImageInit(im2, tk, m12, cntm, disp);
+        int lvl0 = 0, cnt3 = 0;
+        for (size_t i = 0; i < tk.size(); i++) { lvl0 += (m12[i] == (int)i && kps[i].octave == 0); cnt3 += (cntm[i] == 3); }
+        std::printf("elk_n=%zu elk_nm1=%u elk_good1=%d elk_disp=%zu elk_nm2=%u elk_lvl0=%d elk_cnt3=%d elk_last=%zu\n", tk.size(), nm1, good1, disp.size(),
+                    nm2, lvl0, cnt3, trk.getLastTrackedPts().size());
     }
     // ORBmatcher::SearchForInitialization, the reference signature: a frame against a copy whose keypoints moved by (3, -2)
     {

@@ -307,6 +307,33 @@ int eorb_lk_track(eorb_lk* h, const uint8_t* img, size_t stride, const float* in
 int eorb_lk_track_device(eorb_lk* h, const uint8_t* d_img, size_t stride, const float* init_xy, int max_iter, double eps, float min_eig,
                          float* out_xy, uint8_t* status, float* err);
 
+/* ELK_Tracker with its state in HBM: what follows every LK call in the reference (src/Event/KLT_Tracker.cpp)
+ *   eorb_lk_set_ref_keypoints   replaces setRefImage(image, vector<KeyPoint>) :22-46 (mRefKPoints, mRefPoints, mLastTrackedPts = the points)
+ *   eorb_lk_set_last_tracked    replaces setLastTrackedPts :252-262 (a list of another size switches the next call to "no initial flow", :63-70)
+ *   eorb_lk_get_last_tracked    reads mLastTrackedPts back (n x 2 floats); returns n
+ *   eorb_lk_track_and_match     replaces trackAndMatchCurrImage :215-234 (first_octave_only = 0) and trackAndMatchCurrImageInit :236-242
+ *                               (= 1): LK from the resident last tracked points with OPTFLOW_USE_INITIAL_FLOW, then refineTrackedPts
+ *                               :105-155 and refineFirstOctaveLevel :157-183 on the device.  The tracked points stay on the device as the
+ *                               next call's initial flow; ONE device-to-host copy returns
+ *        tracked[n]   KeyPoint(currPt, size / angle / response / octave / class_id of the reference keypoint)  (p1 / trackedKPts)
+ *        matched[n]   bit 0: the point passed refineTrackedPts' test (status == 1 and inside the image, :140), i.e. the reference does
+ *                     vMatches12[i] = i, vCntMatches[i]++, nMatches++ and pushes its displacement; bit 1: bit 0 and the match survives
+ *                     refineFirstOctaveLevel (reference keypoint on octave 0, :171-175; equal to bit 0 without first_octave_only)
+ *        px_disp[]    sqrtf(dx^2 + dy^2) of the points with bit 0, in index order (vPxDisp)
+ *        counts2      {points with bit 1 = the reference's return value when the caller's vMatches12 came in empty, px_disp entries}
+ *     The caller owns the vectors the reference updates in place; with vectors carried over from earlier calls the shim replays the two
+ *     loops on them from bit 0 and the reference keypoints' octaves (stale entries on upper octaves are un-matched and counted, :166-176).
+ *     Returns the last pyramid level used, EORB_EMPTY without reference keypoints (the reference logs and returns 0, :218-221).
+ *   _device: image and outputs are device pointers, asynchronous on the tracker's stream. */
+int eorb_lk_set_ref_keypoints(eorb_lk* h, const uint8_t* img, int w, int hgt, size_t stride, int img_on_device,
+                              const eorb_keypoint* ref_kps, int n, int win, int max_level);
+int eorb_lk_set_last_tracked(eorb_lk* h, const eorb_keypoint* kps, int n);
+int eorb_lk_get_last_tracked(eorb_lk* h, float* pts_xy);
+int eorb_lk_track_and_match(eorb_lk* h, const uint8_t* img, size_t stride, int img_on_device, int max_iter, double eps, float min_eig,
+                            int first_octave_only, eorb_keypoint* tracked, uint8_t* matched, float* px_disp, int* counts2);
+int eorb_lk_track_and_match_device(eorb_lk* h, const uint8_t* d_img, size_t stride, int max_iter, double eps, float min_eig,
+                                   int first_octave_only, eorb_keypoint* d_tracked, uint8_t* d_matched, float* d_px_disp, int* d_counts2);
+
 /* ---------------------------------------------------------------- guided matching (third "next" row)
  * The per-frame callers of DescriptorDistance in tracking:
  *   eorb_guided_frame_grid            replaces Frame::AssignFeaturesToGrid + Frame::PosInGrid (src/Frame.cc:431-460, 783-793)

@@ -30,6 +30,8 @@
 #include <algorithm>
 #include <vector>
 
+#include "oracle.h"
+
 extern "C" {
 
 static inline int lk_reflect101(int p, int len) {
@@ -233,6 +235,38 @@ int orc_lk_track(const uint8_t* prevImg, const uint8_t* nextImg, int w, int h, s
         }
     }
     return maxLevel;
+}
+
+/* ELK_Tracker::refineTrackedPts (src/Event/KLT_Tracker.cpp:105-155) followed, when first_octave_only is set, by
+ * refineFirstOctaveLevel (:157-183) as trackAndMatchCurrImageInit chains them (:236-242).  The reference's vectors are passed flat:
+ * matches12 / cnt_matches are in-out (resize(n, -1) / resize(n, 1) keep what the caller left in them, :113-133), px_disp receives the
+ * push_back sequence (:147), counts2 = {nMatches returned, px_disp entries}. */
+void orc_lk_refine(const float* curr_xy, const uint8_t* status, const orc_keypoint* ref_kps, int n, int img_w, int img_h, int first_octave_only,
+                   orc_keypoint* tracked, int32_t* matches12, int32_t* cnt_matches, float* px_disp, int32_t* counts2) {
+    unsigned nMatches = 0;
+    int nd = 0;
+    for (int i = 0; i < n; i++) {
+        const float cx = curr_xy[2 * i], cy = curr_xy[2 * i + 1];
+        const orc_keypoint pre = ref_kps[i];
+        orc_keypoint k = pre;                       /* KeyPoint(currPt, prePt.size, prePt.angle, prePt.response, prePt.octave, prePt.class_id) :138 */
+        k.x = cx; k.y = cy;
+        tracked[i] = k;
+        const bool inImage = cx >= 0 && cx < (float)img_w && cy >= 0 && cy < (float)img_h;   /* isInImage :99-102 */
+        if (status[i] == 1 && inImage) {            /* :140 */
+            cnt_matches[i]++;
+            matches12[i] = i;
+            nMatches++;
+            const float dx = cx - pre.x, dy = cy - pre.y;
+            px_disp[nd++] = sqrtf(dx * dx + dy * dy);   /* sqrtf(powf(dx, 2) + powf(dy, 2)) :147; powf(x, 2) is x * x (exact square, one rounding) */
+        }
+    }
+    if (first_octave_only) {                        /* :157-183, nTrackedPts == n */
+        for (int i = 0; i < n; i++) {
+            const int cur = matches12[i];
+            if (cur >= 0 && cur < n && ref_kps[i].octave > 0) { matches12[i] = -1; cnt_matches[i]--; nMatches--; }
+        }
+    }
+    counts2[0] = (int32_t)nMatches; counts2[1] = nd;
 }
 
 }  // extern "C"

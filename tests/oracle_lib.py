@@ -334,6 +334,21 @@ def lk_track(prev_img, next_img, prev_pts, next_pts=None, win=23, max_level=1, m
     return npts, status, err, lv
 
 
+def lk_refine(curr_xy, status, ref_kps, w, h, first_octave_only=False, matches12=None, cnt_matches=None):
+    """ELK_Tracker::refineTrackedPts (+ refineFirstOctaveLevel) restatement (KLT_Tracker.cpp:105-183)
+    -> (nMatches, tracked, matches12, cnt_matches, px_disp).  Without matches12 / cnt_matches the caller's vectors are empty, i.e.
+    they start as -1 / 1 (resize(n, -1) / resize(n, 1), :113-133)."""
+    f = lib().orc_lk_refine; f.restype = None
+    f.argtypes = [C.c_void_p] * 3 + [C.c_int] * 4 + [C.c_void_p] * 5
+    cur = np.ascontiguousarray(curr_xy, np.float32).reshape(-1, 2); st = np.ascontiguousarray(status, np.uint8)
+    rk = np.ascontiguousarray(ref_kps, KEYPOINT_DTYPE); n = len(rk)
+    m12 = np.ascontiguousarray(matches12, np.int32).copy() if matches12 is not None else np.full(n, -1, np.int32)
+    cnt = np.ascontiguousarray(cnt_matches, np.int32).copy() if cnt_matches is not None else np.ones(n, np.int32)
+    tr = np.zeros(n, KEYPOINT_DTYPE); disp = np.zeros(n, np.float32); c2 = np.zeros(2, np.int32)
+    f(_p(cur), _p(st), _p(rk), n, w, h, 1 if first_octave_only else 0, _p(tr), _p(m12), _p(cnt), _p(disp), _p(c2))
+    return int(c2[0]), tr, m12, cnt, disp[:c2[1]].copy()
+
+
 # ----------------------------------------------------------------------------- contrast metric (SURVEY §8f rank 2)
 FOCUS_LOCAL_STD, FOCUS_GLOBAL_STD, FOCUS_LOCAL_MEAN = 0, 1, 2
 

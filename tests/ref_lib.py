@@ -246,3 +246,20 @@ def features_in_area(kps, bounds, x, y, r, min_level=-1, max_level=-1):
     f = lib().ref_features_in_area; f.restype = C.c_int
     n = f(_p(k), C.c_int(len(k)), _p(b), C.c_float(x), C.c_float(y), C.c_float(r), C.c_int(min_level), C.c_int(max_level), _p(out), C.c_int(len(out)))
     return out[:n].copy()
+
+
+def lk_refine(curr_xy, status, ref_kps, w, h, first_octave_only=False, matches12=None, cnt_matches=None):
+    """the reference's own ELK_Tracker::refineTrackedPts (+ refineFirstOctaveLevel) (KLT_Tracker.cpp:105-183, cut into libref)
+    -> (nMatches, tracked, matches12, cnt_matches, px_disp); matches12 / cnt_matches given = the caller's non-empty vectors"""
+    f = lib().ref_lk_refine; f.restype = C.c_int
+    f.argtypes = [C.c_void_p] * 3 + [C.c_int] * 5 + [C.c_void_p] * 5
+    cur = np.ascontiguousarray(curr_xy, np.float32).reshape(-1, 2); st = np.ascontiguousarray(status, np.uint8)
+    rk = np.ascontiguousarray(ref_kps, O.KEYPOINT_DTYPE); n = len(rk)
+    have = matches12 is not None
+    m12 = np.ascontiguousarray(matches12, np.int32).copy() if have else np.zeros(n, np.int32)
+    cnt = np.ascontiguousarray(cnt_matches, np.int32).copy() if have else np.zeros(n, np.int32)
+    tr = np.zeros(n, O.KEYPOINT_DTYPE); disp = np.zeros(n, np.float32); c2 = np.zeros(2, np.int32)
+    p = lambda a: a.ctypes.data_as(C.c_void_p)
+    rc = f(p(cur), p(st), p(rk), n, w, h, 1 if first_octave_only else 0, 1 if have else 0, p(tr), p(m12), p(cnt), p(disp), p(c2))
+    assert rc == 0
+    return int(c2[0]), tr, m12, cnt, disp[:c2[1]].copy()

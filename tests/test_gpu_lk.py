@@ -96,3 +96,52 @@ def test_lk_on_event_frames_and_edge_cases():
     with pytest.raises(api.EorbError):
         tr2.n = 1; tr2.shape = i0.shape
         tr2.trackCurrImage(i0)
+
+
+@pytest.mark.parametrize("init", [False, True])
+def test_track_and_match_state_stays_on_device(init):
+    """trackAndMatchCurrImage / trackAndMatchCurrImageInit (KLT_Tracker.cpp:215-242) over three event-sized frames: the tracked points
+    stay in HBM as the next call's initial flow, refineTrackedPts (+ refineFirstOctaveLevel) runs on the device; every output of every
+    frame equals the oracle chain (LK oracle -> refine oracle) bit for bit, with the caller's vectors carried from frame to frame."""
+    api = _api()
+    w, h = 240, 180
+    img, _ = _pair(5, w, h)
+    frames = [_pair(5, w, h, shift=(0.8 * k, -0.5 * k), angle=0.2 * k)[1] for k in (1, 2, 3)]
+    pts = _points(img, 60, 77)
+    rng = np.random.default_rng(3)
+    ref = np.zeros(len(pts), api.KEYPOINT_DTYPE)
+    ref["x"] = pts[:, 0]; ref["y"] = pts[:, 1]; ref["size"] = 31; ref["angle"] = rng.uniform(0, 360, len(pts))
+    ref["response"] = rng.integers(1, 100, len(pts)); ref["octave"] = rng.integers(0, 3, len(pts)); ref["class_id"] = -1
+    tr = api.ELK_Tracker(23, 1, 10, 0.03, max_size=(w, h), max_points=len(pts) + 5)
+    assert tr.setRefImageKPts(img, ref) == 0
+    last = pts.copy()
+    m12 = cnt = em12 = ecnt = None
+    for k, f in enumerate(frames):
+        nm, tk, m12, cnt, disp = tr.trackAndMatchCurrImage(f, m12, cnt, init=init)
+        ep, es, _, _ = O.lk_track(img, f, pts, last, 23, 1, 10, 0.03)
+        enm, etk, em12, ecnt, edisp = O.lk_refine(ep, es, ref, w, h, init, em12, ecnt)
+        assert nm == enm and tk.tobytes() == etk.tobytes(), k
+        assert np.array_equal(m12, em12) and np.array_equal(cnt, ecnt) and disp.tobytes() == edisp.tobytes(), k
+        assert tr.getLastTrackedPts().tobytes() == ep.tobytes()
+        last = ep
+    assert 0 < nm < len(pts)
+    # setLastTrackedPts with a list of another size: the next call starts from the reference points without initial flow (:63-70)
+    tr.setLastTrackedPts(ref[:10])
+    nm, tk, _, _, _ = tr.trackAndMatchCurrImage(frames[0], init=init)
+    ep, es, _, _ = O.lk_track(img, frames[0], pts, None, 23, 1, 10, 0.03)
+    enm, etk, _, _, _ = O.lk_refine(ep, es, ref, w, h, init)
+    assert nm == enm and tk.tobytes() == etk.tobytes()
+    # ... and with a full list it is the initial flow
+    moved = ref.copy(); moved["x"] += 1.0
+    tr.setLastTrackedPts(moved)
+    nm, tk, _, _, _ = tr.trackAndMatchCurrImage(frames[1], init=init)
+    ep, es, _, _ = O.lk_track(img, frames[1], pts, np.stack([moved["x"], moved["y"]], 1), 23, 1, 10, 0.03)
+    enm, etk, _, _, _ = O.lk_refine(ep, es, ref, w, h, init)
+    assert nm == enm and tk.tobytes() == etk.tobytes()
+
+
+def test_track_and_match_without_reference_is_empty():
+    api = _api()
+    tr = api.ELK_Tracker(max_size=(64, 64), max_points=8)
+    tr.n = 0; tr.shape = (64, 64)
+    assert tr.trackAndMatchCurrImage(np.zeros((64, 64), np.uint8))[0] == 0

@@ -219,3 +219,36 @@ def test_oracle_kb8_motion_compensation_equals_reference(golden_dir):
         if R.available():
             rf, ru = R.ev_accumulate(ev, 346, 260, 1.0, normalize=True, **kw)
             assert rf.tobytes() == f.tobytes() and np.array_equal(ru, u8), key
+
+
+# ------------------------------------------------------------------------------------------------ ELK_Tracker post-LK bookkeeping
+def _lk_refine_case(seed, n=700, w=240, h=180):
+    rng = np.random.default_rng(seed)
+    ref = np.zeros(n, O.KEYPOINT_DTYPE)
+    ref["x"] = rng.uniform(0, w, n).astype(np.float32); ref["y"] = rng.uniform(0, h, n).astype(np.float32)
+    ref["size"] = 31; ref["angle"] = rng.uniform(0, 360, n).astype(np.float32); ref["response"] = rng.integers(1, 200, n)
+    ref["octave"] = rng.integers(0, 3, n); ref["class_id"] = rng.integers(-1, 50, n)
+    cur = np.stack([ref["x"], ref["y"]], 1) + rng.normal(0, 6, (n, 2)).astype(np.float32)
+    edge = rng.integers(0, n, 40)   # points exactly on and just past the image edges (isInImage :99-102: 0 <= x < W)
+    cur[edge[:10], 0] = 0.0; cur[edge[10:20], 0] = np.float32(w); cur[edge[20:30], 1] = np.nextafter(np.float32(h), np.float32(0)); cur[edge[30:], 1] = -0.0
+    status = (rng.uniform(0, 1, n) < 0.8).astype(np.uint8)
+    status[rng.integers(0, n, 5)] = 2   # the test is status == 1, not != 0
+    return cur.astype(np.float32), status, ref
+
+
+def test_oracle_lk_refine_equals_reference():
+    """oracle == the reference's own refineTrackedPts / refineFirstOctaveLevel bodies, byte for byte, fresh and carried-over vectors"""
+    R = _ref()
+    for seed in range(6):
+        cur, st, ref = _lk_refine_case(seed)
+        for init in (False, True):
+            a = R.lk_refine(cur, st, ref, 240, 180, init)
+            b = O.lk_refine(cur, st, ref, 240, 180, init)
+            assert a[0] == b[0] and a[1].tobytes() == b[1].tobytes() and np.array_equal(a[2], b[2]) and np.array_equal(a[3], b[3])
+            assert a[4].tobytes() == b[4].tobytes()
+            # second frame with the vectors of the first (the event trackers keep them across frames)
+            cur2, st2, _ = _lk_refine_case(100 + seed)
+            a2 = R.lk_refine(cur2, st2, ref, 240, 180, init, a[2], a[3])
+            b2 = O.lk_refine(cur2, st2, ref, 240, 180, init, b[2], b[3])
+            assert a2[0] == b2[0] and a2[1].tobytes() == b2[1].tobytes() and np.array_equal(a2[2], b2[2]) and np.array_equal(a2[3], b2[3])
+            assert a2[4].tobytes() == b2[4].tobytes()

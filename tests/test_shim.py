@@ -48,7 +48,7 @@ def test_shims_compile_and_fail_loudly_without_device():
         pytest.skip("a CUDA device is present")
     assert "ret=-1 n=0" in out and "empty_ret=-1" in out
     assert "no CUDA device" in err
-    assert "lk_ok=0 lk_n=0" in out
+    assert "lk_ok=0 lk_n=0" in out and "elk_n=0 elk_nm1=0" in out
     assert "sfi_nm=0 sfi_self=0" in out and "sbp_nm=0 sbp_set=0" in out and "slp_nm=0 slp_set=0" in out and "sbb_nm=0 sbb_set=0" in out
     assert "sbs_nm=0 sbs_set=0" in out and "sbr_nm=0 sbr_set=0" in out
     assert "voc_ok=0" in out and "undist_ok=0" in out
@@ -75,6 +75,10 @@ def test_shims_match_oracle_on_gpu():
     lk = re.search(r"lk_ok=(\d+) lk_n=(\d+) lk_tracked=(\d+) lk_good=(\d+)", out)
     assert lk and int(lk.group(1)) == 1 and int(lk.group(2)) == len(okps)
     assert int(lk.group(3)) > 0.8 * len(okps) and int(lk.group(4)) > 0.9 * int(lk.group(3))      # the (2, 1) shift is recovered
+    ek = re.search(r"elk_n=(\d+) elk_nm1=(\d+) elk_good1=(\d+) elk_disp=(\d+) elk_nm2=(\d+) elk_lvl0=(\d+) elk_cnt3=(\d+) elk_last=(\d+)", out)
+    en, nm1, good1, ndisp, nm2, lvl0, cnt3, nlast = map(int, ek.groups())
+    assert en == len(okps) == nlast and 0 <= int(lk.group(3)) - nm1 <= 5 and 0 <= int(lk.group(4)) - good1 <= 5   # first frame == the plain LK call (minus points outside the image)
+    assert 0 < nm2 <= lvl0 < nm1 and ndisp >= lvl0 and 0.9 * lvl0 < cnt3 <= lvl0                    # Init: only octave-0 references stay matched
     fo = re.search(r"focus=([\d.]+) focus_med=([\d.]+) focus_glob=([\d.]+) mean_loc=([\d.]+)", out)
     fv = [float(fo.group(k)) for k in range(1, 5)]
     assert fv[0] > 0 and fv[1] > 0 and fv[2] > fv[0] * 0.5 and abs(fv[3] * 240 * 180 - float(ev.group(1))) < 0.02 * float(ev.group(1))   # mean x pixels = sum
