@@ -522,6 +522,24 @@ def bench_lk(api, torch, dev, steps, warmup):
            "workload": "ELK_Tracker: %d keypoints of a 240x180 event frame tracked into the next one, win 23, maxLevel 1, 10 it, eps 0.03" % len(pts),
            "gpu_launches_per_call": int(launches), "bit_exact_vs_oracle": bool(p.tobytes() == ep.tobytes() and np.array_equal(s, es)),
            "cpu_baseline": {"kind": "port", "cores": 1, "ms_per_call": ms_port, "value": len(pts) / (ms_port * 1e-3), "unit": "points/s"}}
+    # the tracker with its state on the device: trackAndMatchCurrImage (LK from the resident last tracked points + refineTrackedPts on the
+    # device, one D2H), against the plain call followed by the host bookkeeping it replaces
+    tr2 = api.ELK_Tracker(23, 1, 10, 0.03, dev, (w, h), len(pts))
+    tr2.setRefImageKPts(i0, kps)
+    for _ in range(max(warmup, 3)):
+        tr2.trackAndMatchCurrImage(i1)
+    tr2.setRefImageKPts(i0, kps)
+    t0 = time.perf_counter()
+    for _ in range(n):
+        nm, tk, m12, cnt, disp = tr2.trackAndMatchCurrImage(i1)
+    ms_tm = (time.perf_counter() - t0) * 1e3 / n
+    tr2.setRefImageKPts(i0, kps)
+    nm, tk, m12, cnt, disp = tr2.trackAndMatchCurrImage(i1)
+    enm, etk, em12, ecnt, edisp = O.lk_refine(ep, es, kps, w, h)
+    out["track_and_match"] = {"ms_per_call": ms_tm, "matches": int(nm),
+                              "bit_exact_vs_oracle": bool(nm == enm and tk.tobytes() == etk.tobytes() and np.array_equal(m12, em12)
+                                                          and disp.tobytes() == edisp.tobytes()),
+                              "note": "trackAndMatchCurrImage: tracked points stay in HBM as the next initial flow, refineTrackedPts on the device"}
     try:
         import cv2
         crit = (cv2.TERM_CRITERIA_COUNT + cv2.TERM_CRITERIA_EPS, 10, 0.03)

@@ -245,6 +245,7 @@ struct eorb_orb {
         float* d_levelAngle = nullptr;
         CUtensorMap* d_tmaps = nullptr;   // [nlevels] maps of this slab's pyramid levels >= 1
         int* d_pyrDone = nullptr;            // [8][EORB_MAX_LEVELS] (pyr_chain_kernel)
+        CUtensorMap* d_briefMaps = nullptr;  // [nlevels] maps of the blurred levels, box = one keypoint's BRIEF patch (orient_desc_kernel)
         CUtensorMap* d_blurMaps = nullptr;   // [nlevels] the same levels with blur_tma_kernel's box (EORB_BLUR_TMA=1)
         CUtensorMap pyrMaps[EORB_MAX_LEVELS];   // host: source map of the TMA-staged resize INTO level l (l >= 2; level 1's source is the caller's frame)
         eorb_keypoint* d_outKps = nullptr; uint8_t* d_outDesc = nullptr; int* d_outN = nullptr; int* d_outMono = nullptr;
@@ -272,6 +273,7 @@ struct eorb_orb {
     OrbFork graphFork;             // side stream + events of the captured single-call graph (blur beside FAST / octree)
     bool fastPadTile = true;       // EORB_FAST_PAD=0: FAST tile pitch left at the next multiple of 16 (for A/B)
     int useBlurTma = 3;           // blur_tma_kernel variant (TMA-staged strips; 3 = 64-row bands, neighbour words read from the tile: 0.705 -> 0.609 us/frame); EORB_BLUR_TMA=0: blur_kernel (direct global loads), for A/B
+    bool useBriefTma = true;       // EORB_BRIEF_TMA=0: orient_desc_kernel gathers the BRIEF samples from global memory (for A/B)
     bool usePyrChain = true;       // EORB_PYR_CHAIN=0: small batches launch the pyramid level by level like launch sets do
     bool usePyrTma = true;         // EORB_PYR_TMA=0: every pyramid level through pyr_resize_kernel (direct global loads), for A/B
     int pyrTileRows = 64;          // EORB_PYR_TH: destination rows per TMA-staged tile (tuning)
@@ -296,7 +298,7 @@ static cudaEvent_t* orbStageEvents(eorb_orb* h) {
 static void orbFreeBufs(eorb_orb::Bufs& b) {
     cudaFree(b.d_img0); cudaFree(b.d_pyr); cudaFree(b.d_blur); cudaFree(b.d_cellCount); cudaFree(b.d_cand);
     cudaFree(b.d_okeys); cudaFree(b.d_knode); cudaFree(b.d_sel); cudaFree(b.d_selCount); cudaFree(b.d_candCount);
-    cudaFree(b.d_dstIdx); cudaFree(b.d_kpList); cudaFree(b.d_levelAngle); cudaFree(b.d_tmaps); cudaFree(b.d_pyrDone); cudaFree(b.d_blurMaps); cudaFree(b.d_outKps); cudaFree(b.d_outDesc);
+    cudaFree(b.d_dstIdx); cudaFree(b.d_kpList); cudaFree(b.d_levelAngle); cudaFree(b.d_tmaps); cudaFree(b.d_pyrDone); cudaFree(b.d_blurMaps); cudaFree(b.d_briefMaps); cudaFree(b.d_outKps); cudaFree(b.d_outDesc);
     cudaFree(b.d_outN); cudaFree(b.d_outMono);
     cudaFreeHost(b.h_kps); cudaFreeHost(b.h_desc); cudaFreeHost(b.h_n); cudaFreeHost(b.h_mono);
     if (b.done) cudaEventDestroy(b.done);
@@ -343,6 +345,18 @@ static int orbAllocBufs(eorb_orb* h, eorb_orb::Bufs& b, bool pipeline) {
             }
             CU(devAlloc(&b.d_blurMaps, (size_t)nl));
             CU(cudaMemcpy(b.d_blurMaps, maps.data(), maps.size() * sizeof(CUtensorMap), cudaMemcpyHostToDevice));
+        }
+        if (h->useBriefTma) {   // the blurred levels with the box of one keypoint's BRIEF patch
+            bool ok = true;
+            for (int l = 0; l < nl && ok; l++) {
+                if (P.lv[l].w <= 0 || P.lv[l].h <= 0) { memset(&maps[l], 0, sizeof(CUtensorMap)); continue; }
+                ok = tmaEncodeFrames(&maps[l], b.d_blur + P.lv[l].blurOff, P.lv[l].w, P.lv[l].h, (int)B, (size_t)P.lv[l].bpitch,
+                                     (size_t)P.blurBytesPerFrame, brief_tma_box_w(), brief_tma_box_h()) == EORB_OK;
+            }
+            if (ok) {
+                CU(devAlloc(&b.d_briefMaps, (size_t)nl));
+                CU(cudaMemcpy(b.d_briefMaps, maps.data(), maps.size() * sizeof(CUtensorMap), cudaMemcpyHostToDevice));
+            }
         }
         memset(b.pyrMaps, 0, sizeof(b.pyrMaps));
         for (int l = 2; l < nl; l++) {
@@ -634,6 +648,7 @@ static OrbArgs orbArgs(eorb_orb* h, eorb_orb::Bufs& b, const uint8_t* lvl0, long
     a.lvl0 = lvl0; a.lvl0Pitch = pitch0; a.lvl0FrameStride = frameStride0;
     a.tmaps = b.d_tmaps;
     a.blurMaps = b.d_blurMaps;
+    a.briefMaps = b.d_briefMaps;
     a.pyrDone = h->usePyrChain ? b.d_pyrDone : nullptr;
     a.blurVariant = h->useBlurTma;
     a.pyr = b.d_pyr; a.blur = b.d_blur; a.cellCount = b.d_cellCount; a.cand = b.d_cand; a.okeys = b.d_okeys;
@@ -661,6 +676,7 @@ extern "C" int eorb_orb_create(const eorb_orb_params* params, int device, int ma
     if (const char* e = getenv("EORB_PYR_TMA")) h->usePyrTma = atoi(e) != 0;
     if (const char* e = getenv("EORB_BLUR_TMA")) h->useBlurTma = atoi(e);
     if (const char* e = getenv("EORB_PYR_CHAIN")) h->usePyrChain = atoi(e) != 0;
+    if (const char* e = getenv("EORB_BRIEF_TMA")) h->useBriefTma = atoi(e) != 0;
     if (const char* e = getenv("EORB_FAST_PAD")) h->fastPadTile = atoi(e) != 0;
     if (const char* e = getenv("EORB_PYR_TH")) h->pyrTileRows = std::min(std::max(atoi(e), 8), 200);
     h->pipeBatch = std::min(max_batch, 128);   // measured on B200: H2D/compute/D2H overlap is best with 128-frame slots

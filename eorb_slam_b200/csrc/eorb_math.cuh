@@ -123,6 +123,13 @@ __device__ __forceinline__ int round_rne_small(float v) { return __float_as_int(
 #else
 inline int round_rne_small(float v) { return round_rne(v); }
 #endif
+#ifdef __CUDACC__
+// the same two roundings left as raw bits: value = 0x4B400000 + round(v); the caller removes the bias where it is cheapest
+__device__ __forceinline__ void brief_offset_biased(float fx, float fy, float a, float b, unsigned& row, unsigned& col) {
+    row = (unsigned)__float_as_int(__fadd_rn(fadd(fmul(fx, b), fmul(fy, a)), 12582912.0f));
+    col = (unsigned)__float_as_int(__fadd_rn(fsub(fmul(fx, a), fmul(fy, b)), 12582912.0f));
+}
+#endif
 EORB_HD void brief_offset_f(float fx, float fy, float a, float b, int& row, int& col) {
     row = round_rne_small(fadd(fmul(fx, b), fmul(fy, a)));
     col = round_rne_small(fsub(fmul(fx, a), fmul(fy, b)));

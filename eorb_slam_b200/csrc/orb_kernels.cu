@@ -695,7 +695,17 @@ __device__ __forceinline__ int dp4a_u8_s8(unsigned data, int weights, int acc) {
 #define EORB_OD_BATCH 4
 #endif
 
+// BRIEF patch staged by TMA: the rotated pattern reaches 19 pixels from the keypoint (safe path), the box starts at the 16-byte
+// aligned column at or before x - 19 (TMA's inner coordinate must be a multiple of 16 bytes), so 64 columns x 39 rows always cover it.
+#define EORB_BRIEF_BOXW 64
+#define EORB_BRIEF_BOXH 39
+#define EORB_BRIEF_TILE 2560               // 64 * 39 = 2496, padded to a multiple of 128 (TMA destination alignment)
+int brief_tma_box_w() { return EORB_BRIEF_BOXW; }
+int brief_tma_box_h() { return EORB_BRIEF_BOXH; }
+
 __global__ void __launch_bounds__(32 * EORB_KP_GROUP, EORB_OD_MINB) orient_desc_kernel(OrbArgs a) {
+    __shared__ __align__(128) uint8_t s_tile[EORB_KP_GROUP][EORB_BRIEF_TILE];
+    __shared__ __align__(8) unsigned long long s_bar[EORB_KP_GROUP];
     __shared__ float s_angle[EORB_KP_GROUP], s_cos[EORB_KP_GROUP], s_sin[EORB_KP_GROUP];
     const OrbPlan& P = *a.plan;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -716,6 +726,26 @@ __global__ void __launch_bounds__(32 * EORB_KP_GROUP, EORB_OD_MINB) orient_desc_
     }
     const LevelPlan& lp = P.lv[level];
 
+    // ---- the keypoint's patch of the BLURRED level starts its way into shared memory now (one TMA tile, L2 -> shared memory without
+    //      passing the L1 / LSU path: the 512 byte gathers of the descriptor were what bound this kernel, 87 % L1/TEX throughput)
+    int dst = -1;
+    bool staged = false;
+    if (valid) {
+        dst = a.dstIdx[(size_t)f * P.selPerFrame + slot];
+        const bool safe = (x >= 19) && (y >= 19) && (x + 19 < lp.w) && (y + 19 < lp.h);
+        staged = a.briefMaps != nullptr && a.wantDesc && safe && dst >= 0 && dst < a.cap;
+        if (staged) {
+            if (lane == 0) {
+                const unsigned bar = smem_u32(&s_bar[warp]);
+                mbar_init(bar, 1);
+                mbar_fence_init();
+                mbar_expect_tx(bar, EORB_BRIEF_BOXW * EORB_BRIEF_BOXH);
+                tma_load_3d(smem_u32(s_tile[warp]), a.briefMaps + level, (x - 19) & ~15, y - 19, f, bar);
+            }
+            __syncwarp();
+        }
+    }
+
     // ---- orientation (one warp per keypoint)
     if (valid) {
         int sp;
@@ -727,19 +757,23 @@ __global__ void __launch_bounds__(32 * EORB_KP_GROUP, EORB_OD_MINB) orient_desc_
             const int wAligned = (lp.w + 3) & ~3;
             const int2* __restrict__ tab = a.icTab + (xs & 3) * EORB_IC_TASKS + lane;
             const uint8_t* base = img + (size_t)(y - 15) * sp + xa;
-            // task i = it*32 + lane <-> (row r = i / 9, word k = i % 9); stepping i by 32 moves (r, k) by (3, 5) with a
-            // carry.  Words past the row's last aligned word and the padding row 31 only meet zero weights, so their
-            // addresses are clamped instead of predicated.
-            int r = (lane * 57) >> 9, k = lane - r * EORB_IC_WORDS;
-            const int kMax = (wAligned - 4 - xa) >> 2;
+            // task i = it*32 + lane <-> (row r = i / 9, word k = i % 9).  r and the word's byte offset are formed arithmetically from
+            // the lane (three integer instructions, independent of every load: taking them from the table entry was measured SLOWER,
+            // 1.00 -> 1.13 us/frame, because the pixel load then waits for the table load) and the address is one multiply-add plus an
+            // unsigned 32-bit offset.  Words past the row's last aligned word and the padding row 31 only meet zero weights, so
+            // their addresses are clamped instead of predicated.
+            const int k4Max = wAligned - 4 - xa;
+            const int lane4 = 4 * lane;
 #pragma unroll
             for (int it = 0; it < EORB_IC_TASKS / 32; it++) {
-                const int2 wgt = __ldg(tab + it * 32);
-                const unsigned data = __ldg(reinterpret_cast<const unsigned*>(base + min(r, 30) * sp + 4 * min(k, kMax)));
-                m10 = dp4a_u8_s8(data, wgt.x, m10);
-                m01 = dp4a_u8_s8(data, wgt.y, m01);
-                r += 3; k += 5;
-                if (k >= EORB_IC_WORDS) { k -= EORB_IC_WORDS; r++; }
+                const int2 t = __ldg(tab + it * 32);
+                int r = ((lane + 32 * it) * 57) >> 9;                  // i / 9 for i < 512
+                const int k4 = lane4 + 128 * it - 36 * r;              // 4 * (i % 9)
+                if (it == EORB_IC_TASKS / 32 - 1) r = min(r, 30);
+                const unsigned off = (unsigned)(r * sp + min(k4, k4Max));
+                const unsigned data = __ldg(reinterpret_cast<const unsigned*>(base + off));
+                m10 = dp4a_u8_s8(data, t.x, m10);
+                m01 = dp4a_u8_s8(data, t.y, m01);
             }
         } else if (lane < 31) {   // patch crosses the level border (margin < 15): REFLECT_101, byte by byte
             const int u = lane - 15;
@@ -779,7 +813,6 @@ __global__ void __launch_bounds__(32 * EORB_KP_GROUP, EORB_OD_MINB) orient_desc_
 
     // ---- keypoint record + steered BRIEF on the blurred level
     const float angle = s_angle[warp], ca = s_cos[warp], sa = s_sin[warp];
-    const int dst = a.dstIdx[(size_t)f * P.selPerFrame + slot];
     if (a.levelAngle && lane == 0) a.levelAngle[(size_t)f * P.selPerFrame + slot] = angle;
     if (dst < 0 || dst >= a.cap) return;
     if (lane == 0) {
@@ -800,24 +833,45 @@ __global__ void __launch_bounds__(32 * EORB_KP_GROUP, EORB_OD_MINB) orient_desc_
     const bool safe = (x >= 19) && (y >= 19) && (x + 19 < lp.w) && (y + 19 < lp.h);
     const uint8_t* Bc = B + (size_t)y * bp + x;
     uint32_t myword = 0;
-    if (safe) {
+    if (staged) {
+        // sample address in the tile: row / column leave the 1.5 * 2^23 rounding trick as integers biased by 0x4B400000; the bias times
+        // (tile pitch + 1), the patch origin (-19, -19) and the tile's alignment offset are ONE per-warp constant folded into the base
+        const unsigned base = smem_u32(s_tile[warp]) + (unsigned)((x - 19) & 15) - (0x4B400000u - 19u) * (unsigned)(EORB_BRIEF_BOXW + 1);
+        mbar_wait(smem_u32(&s_bar[warp]), 0);
+#pragma unroll
+        for (int j = 0; j < 8; j++) {
+            const float4 pt = __ldg(reinterpret_cast<const float4*>(d_brief_pattern_f) + 32 * j + lane);
+            unsigned r0, c0, r1, c1;
+            brief_offset_biased(pt.x, pt.y, ca, sa, r0, c0);
+            brief_offset_biased(pt.z, pt.w, ca, sa, r1, c1);
+            const unsigned t0 = lds_u8(r0 * EORB_BRIEF_BOXW + c0 + base), t1 = lds_u8(r1 * EORB_BRIEF_BOXW + c1 + base);
+            const uint32_t word = __ballot_sync(FULL, t0 < t1);
+            if (lane == j) myword = word;
+        }
+    } else if (safe) {
         // the warp's gathers are requested EORB_OD_BATCH rounds at a time before the first comparison.  (Staging the 39 x 39
         // window in shared memory with coalesced word loads and gathering from there was measured SLOWER, 1.01 -> 1.10
         // us/frame: the kernel is bound by instruction issue (74 % of the slots), not by the sectors its gathers touch.)
+        // A sample's address: row / column leave the 1.5 * 2^23 rounding trick as integers biased by 0x4B400000; the bias, times
+        // (pitch + 1), and the patch origin (-19, -19) are folded into ONE per-warp constant, so that a sample costs a multiply-add, a
+        // subtract and an unsigned 32-bit offset from the patch's top-left corner (it was nine integer instructions with signed 64-bit
+        // row and column terms).
+        const uint8_t* Bo = Bc - 19 * bp - 19;
+        const unsigned kBias = (0x4B400000u - 19u) * (unsigned)(bp + 1);
 #pragma unroll
         for (int j0 = 0; j0 < 8; j0 += EORB_OD_BATCH) {
-            int o0[EORB_OD_BATCH], o1[EORB_OD_BATCH];
+            unsigned o0[EORB_OD_BATCH], o1[EORB_OD_BATCH];
 #pragma unroll
             for (int u = 0; u < EORB_OD_BATCH; u++) {
                 const float4 pt = __ldg(reinterpret_cast<const float4*>(d_brief_pattern_f) + 32 * (j0 + u) + lane);
-                int r0, c0, r1, c1;
-                brief_offset_f(pt.x, pt.y, ca, sa, r0, c0);
-                brief_offset_f(pt.z, pt.w, ca, sa, r1, c1);
-                o0[u] = r0 * bp + c0; o1[u] = r1 * bp + c1;
+                unsigned r0, c0, r1, c1;
+                brief_offset_biased(pt.x, pt.y, ca, sa, r0, c0);
+                brief_offset_biased(pt.z, pt.w, ca, sa, r1, c1);
+                o0[u] = r0 * (unsigned)bp + c0 - kBias; o1[u] = r1 * (unsigned)bp + c1 - kBias;
             }
             int t0[EORB_OD_BATCH], t1[EORB_OD_BATCH];
 #pragma unroll
-            for (int u = 0; u < EORB_OD_BATCH; u++) { t0[u] = __ldg(Bc + o0[u]); t1[u] = __ldg(Bc + o1[u]); }
+            for (int u = 0; u < EORB_OD_BATCH; u++) { t0[u] = __ldg(Bo + o0[u]); t1[u] = __ldg(Bo + o1[u]); }
 #pragma unroll
             for (int u = 0; u < EORB_OD_BATCH; u++) {
                 const uint32_t word = __ballot_sync(FULL, t0[u] < t1[u]);

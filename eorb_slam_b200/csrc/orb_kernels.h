@@ -23,6 +23,7 @@ struct OrbArgs {
                                  //         level 0 is the caller's buffer, its map travels as a kernel parameter)
     const CUtensorMap* blurMaps; // device: [nlevels] maps of the levels >= 1 with the box of blur_tma_kernel, or nullptr (blur_kernel is used);
                                  //         level 0's travels as pyrMaps[0] of launch_orb_pipeline
+    const CUtensorMap* briefMaps;// device: [nlevels] maps of the BLURRED levels with the 64 x 39 box orient_desc_kernel stages a keypoint's patch with, or nullptr
     int* pyrDone;                // device: [8][EORB_MAX_LEVELS] tile counters of pyr_chain_kernel (small batches), or nullptr
     int blurVariant;             // EORB_BLUR_TMA value (1..4: band rows 32 / 64, neighbour words by shuffle / from the tile)
     uint8_t* pyr;                // [B][pyrBytesPerFrame]   levels >= 1
@@ -58,6 +59,8 @@ cudaError_t launch_pyr_tma(const OrbArgs& a, const OrbPlan& hp, int level, int n
 
 cudaError_t orb_kernels_configure(const OrbPlan& hp);
 int blur_tma_box_w();
+int brief_tma_box_w();   // box of one keypoint's BRIEF patch on the blurred level (orient_desc_kernel)
+int brief_tma_box_h();
 int blur_tma_box_h(int variant);
 #define EORB_ORB_STAGES 6   // pyramid, fast, octree, index, blur, orient+desc
 // side-stream fork of one launch set (small batches inside the captured graph only: a single frame leaves the GPU mostly idle, so the

@@ -39,4 +39,11 @@ __device__ __forceinline__ void tma_load_3d(unsigned dst, const CUtensorMap* tm,
         : "memory");
 }
 
+// one byte from a 32-bit shared-memory address
+__device__ __forceinline__ unsigned lds_u8(unsigned addr) {
+    unsigned v;
+    asm volatile("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(addr));
+    return v;
+}
+
 }  // namespace eorb
