@@ -245,6 +245,7 @@ struct eorb_orb {
         float* d_levelAngle = nullptr;
         CUtensorMap* d_tmaps = nullptr;   // [nlevels] maps of this slab's pyramid levels >= 1
         int* d_pyrDone = nullptr;            // [8][EORB_MAX_LEVELS] (pyr_chain_kernel)
+        CUtensorMap* d_icMaps = nullptr;     // [nlevels] maps of the levels >= 1, box = one keypoint's orientation patch (orient_desc_kernel)
         CUtensorMap* d_briefMaps = nullptr;  // [nlevels] maps of the blurred levels, box = one keypoint's BRIEF patch (orient_desc_kernel)
         CUtensorMap* d_blurMaps = nullptr;   // [nlevels] the same levels with blur_tma_kernel's box (EORB_BLUR_TMA=1)
         CUtensorMap pyrMaps[EORB_MAX_LEVELS];   // host: source map of the TMA-staged resize INTO level l (l >= 2; level 1's source is the caller's frame)
@@ -298,7 +299,7 @@ static cudaEvent_t* orbStageEvents(eorb_orb* h) {
 static void orbFreeBufs(eorb_orb::Bufs& b) {
     cudaFree(b.d_img0); cudaFree(b.d_pyr); cudaFree(b.d_blur); cudaFree(b.d_cellCount); cudaFree(b.d_cand);
     cudaFree(b.d_okeys); cudaFree(b.d_knode); cudaFree(b.d_sel); cudaFree(b.d_selCount); cudaFree(b.d_candCount);
-    cudaFree(b.d_dstIdx); cudaFree(b.d_kpList); cudaFree(b.d_levelAngle); cudaFree(b.d_tmaps); cudaFree(b.d_pyrDone); cudaFree(b.d_blurMaps); cudaFree(b.d_briefMaps); cudaFree(b.d_outKps); cudaFree(b.d_outDesc);
+    cudaFree(b.d_dstIdx); cudaFree(b.d_kpList); cudaFree(b.d_levelAngle); cudaFree(b.d_tmaps); cudaFree(b.d_pyrDone); cudaFree(b.d_blurMaps); cudaFree(b.d_briefMaps); cudaFree(b.d_icMaps); cudaFree(b.d_outKps); cudaFree(b.d_outDesc);
     cudaFree(b.d_outN); cudaFree(b.d_outMono);
     cudaFreeHost(b.h_kps); cudaFreeHost(b.h_desc); cudaFreeHost(b.h_n); cudaFreeHost(b.h_mono);
     if (b.done) cudaEventDestroy(b.done);
@@ -356,6 +357,16 @@ static int orbAllocBufs(eorb_orb* h, eorb_orb::Bufs& b, bool pipeline) {
             if (ok) {
                 CU(devAlloc(&b.d_briefMaps, (size_t)nl));
                 CU(cudaMemcpy(b.d_briefMaps, maps.data(), maps.size() * sizeof(CUtensorMap), cudaMemcpyHostToDevice));
+            }
+            memset(&maps[0], 0, sizeof(CUtensorMap));   // level 0 = the caller's frames: its map is made per call (orbIcMap0)
+            for (int l = 1; l < nl && ok; l++) {
+                if (P.lv[l].w <= 0 || P.lv[l].h <= 0) { memset(&maps[l], 0, sizeof(CUtensorMap)); continue; }
+                ok = tmaEncodeFrames(&maps[l], b.d_pyr + P.lv[l].off, P.lv[l].w, P.lv[l].h, (int)B, (size_t)P.lv[l].pitch,
+                                     (size_t)P.pyrBytesPerFrame, ic_tma_box_w(), ic_tma_box_h()) == EORB_OK;
+            }
+            if (ok) {
+                CU(devAlloc(&b.d_icMaps, (size_t)nl));
+                CU(cudaMemcpy(b.d_icMaps, maps.data(), maps.size() * sizeof(CUtensorMap), cudaMemcpyHostToDevice));
             }
         }
         memset(b.pyrMaps, 0, sizeof(b.pyrMaps));
@@ -649,6 +660,7 @@ static OrbArgs orbArgs(eorb_orb* h, eorb_orb::Bufs& b, const uint8_t* lvl0, long
     a.tmaps = b.d_tmaps;
     a.blurMaps = b.d_blurMaps;
     a.briefMaps = b.d_briefMaps;
+    a.icMaps = b.d_icMaps;
     a.pyrDone = h->usePyrChain ? b.d_pyrDone : nullptr;
     a.blurVariant = h->useBlurTma;
     a.pyr = b.d_pyr; a.blur = b.d_blur; a.cellCount = b.d_cellCount; a.cand = b.d_cand; a.okeys = b.d_okeys;
@@ -825,6 +837,16 @@ static int orbPyrMaps(eorb_orb* h, eorb_orb::Bufs& b, const uint8_t* lvl0, int w
     return EORB_OK;
 }
 
+// orient_desc_kernel's map of level 0 (the caller's frames) with the orientation patch's box; *use = false when there is none
+static int orbIcMap0(eorb_orb::Bufs& b, const uint8_t* lvl0, int w, int hgt, int nframes, long long p0, long long fs0, CUtensorMap* out, bool* use) {
+    *use = false;
+    if (!b.d_icMaps) return EORB_OK;
+    int rc = tmaEncodeFrames(out, lvl0, w, hgt, nframes, (size_t)p0, (size_t)fs0, ic_tma_box_w(), ic_tma_box_h());
+    if (rc != EORB_OK) return rc;
+    *use = true;
+    return EORB_OK;
+}
+
 static bool lvl0ZeroCopyOk(const uint8_t* p, int w, size_t rowStride, size_t frameStride) {
     // TMA (FAST cell tiles) needs a 16-byte aligned base and 16-byte strides; the vectorised kernels read whole words
     return ((uintptr_t)p % 16 == 0) && (rowStride % 16 == 0) && (frameStride % 16 == 0) && rowStride >= (size_t)roundUp(w, 4);
@@ -854,7 +876,11 @@ extern "C" int eorb_orb_extract_batch_device(eorb_orb* h, const uint8_t* d_imgs,
     CUtensorMap pm[EORB_MAX_LEVELS];
     rc = orbPyrMaps(h, h->main, lvl0, w, hgt, nframes, p0, fs0, pm);
     if (rc != EORB_OK) return rc;
-    CU(launch_orb_pipeline(a, h->hp, nframes, tm0, h->stream, &h->launches, orbStageEvents(h), pm));
+    CUtensorMap ic0; bool useIc0 = false;
+    rc = orbIcMap0(h->main, lvl0, w, hgt, nframes, p0, fs0, &ic0, &useIc0);
+    if (rc != EORB_OK) return rc;
+    if (!useIc0) a.icMaps = nullptr;
+    CU(launch_orb_pipeline(a, h->hp, nframes, tm0, h->stream, &h->launches, orbStageEvents(h), pm, nullptr, useIc0 ? &ic0 : nullptr));
     h->lastLvl0 = lvl0; h->lastPitch0 = p0; h->lastFrameStride0 = fs0; h->lastFrames = nframes;
     return EORB_OK;
 }
@@ -947,7 +973,12 @@ extern "C" int eorb_orb_extract_batch(eorb_orb* h, const uint8_t* imgs, int nfra
             CUtensorMap pm[EORB_MAX_LEVELS];
             rct = orbPyrMaps(h, b, b.d_img0, w, hgt, nb, h->pitch0, (long long)h->pitch0 * hgt, pm);
             if (rct != EORB_OK) return rct;
-            CU(launch_orb_pipeline(a, h->hp, nb, tm0, st, launchCounter, stageEv, pm, capturing ? &h->graphFork : nullptr));
+            CUtensorMap ic0; bool useIc0 = false;
+            rct = orbIcMap0(b, b.d_img0, w, hgt, nb, h->pitch0, (long long)h->pitch0 * hgt, &ic0, &useIc0);
+            if (rct != EORB_OK) return rct;
+            OrbArgs aa = a;
+            if (!useIc0) aa.icMaps = nullptr;
+            CU(launch_orb_pipeline(aa, h->hp, nb, tm0, st, launchCounter, stageEv, pm, capturing ? &h->graphFork : nullptr, useIc0 ? &ic0 : nullptr));
             CU(cudaMemcpyAsync(b.h_n, b.d_outN, nb * sizeof(int), cudaMemcpyDeviceToHost, st));
             CU(cudaMemcpyAsync(b.h_mono, b.d_outMono, nb * sizeof(int), cudaMemcpyDeviceToHost, st));
             CU(cudaMemcpyAsync(kdst, b.d_outKps, (size_t)nb * icap * sizeof(eorb_keypoint), cudaMemcpyDeviceToHost, st));

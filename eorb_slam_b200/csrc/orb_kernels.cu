@@ -689,79 +689,117 @@ __device__ __forceinline__ int dp4a_u8_s8(unsigned data, int weights, int acc) {
 }
 
 #ifndef EORB_OD_MINB
-#define EORB_OD_MINB 16
+#define EORB_OD_MINB 11
 #endif
 #ifndef EORB_OD_BATCH
 #define EORB_OD_BATCH 4
 #endif
 
-// BRIEF patch staged by TMA: the rotated pattern reaches 19 pixels from the keypoint (safe path), the box starts at the 16-byte
-// aligned column at or before x - 19 (TMA's inner coordinate must be a multiple of 16 bytes), so 64 columns x 39 rows always cover it.
-#define EORB_BRIEF_BOXW 64
+// Both patches of a keypoint are staged by TMA (L2 -> shared memory past the L1 / LSU path; ncu: the kernel was bound by L1/TEX data-pipe
+// wavefronts, 87 %, not by issue):
+//   BRIEF  the rotated pattern reaches 19 pixels from the keypoint (safe path); the box starts at the 16-byte aligned column at or
+//          before x - 19 (TMA's inner coordinate must be a multiple of 16 bytes), so 39 rows x (39 + 15 <= 64) columns cover it.  The
+//          box is 80 bytes wide: a row pitch of 20 words spreads the 32 scattered byte gathers of one instruction over the banks
+//          (with 64 bytes only (row & 1) and the column select the bank).
+//   IC     31 rows x 48 columns of the level itself from the 16-byte aligned column at or before x - 15: the nine aligned words of
+//          every row lie inside (offset <= 12, 12 + 36 = 48); the padding task row 31 reads the tile's own 48 bytes of slack.
+#ifndef EORB_BRIEF_BOXW
+#define EORB_BRIEF_BOXW 80
+#endif
 #define EORB_BRIEF_BOXH 39
-#define EORB_BRIEF_TILE 2560               // 64 * 39 = 2496, padded to a multiple of 128 (TMA destination alignment)
+#define EORB_BRIEF_TILE ((EORB_BRIEF_BOXW * EORB_BRIEF_BOXH + 127) / 128 * 128)   // TMA destination alignment
+#define EORB_IC_BOXW 48
+#define EORB_IC_BOXH 31
+#define EORB_IC_TILE 1536                  // 48 * 31 = 1488 + one more row for the padding tasks
 int brief_tma_box_w() { return EORB_BRIEF_BOXW; }
 int brief_tma_box_h() { return EORB_BRIEF_BOXH; }
+int ic_tma_box_w() { return EORB_IC_BOXW; }
+int ic_tma_box_h() { return EORB_IC_BOXH; }
 
-__global__ void __launch_bounds__(32 * EORB_KP_GROUP, EORB_OD_MINB) orient_desc_kernel(OrbArgs a) {
+__global__ void __launch_bounds__(32 * EORB_KP_GROUP, EORB_OD_MINB) orient_desc_kernel(OrbArgs a, const __grid_constant__ CUtensorMap icMap0,
+                                                                                      const __grid_constant__ OdLevels L) {
     __shared__ __align__(128) uint8_t s_tile[EORB_KP_GROUP][EORB_BRIEF_TILE];
-    __shared__ __align__(8) unsigned long long s_bar[EORB_KP_GROUP];
+    __shared__ __align__(128) uint8_t s_ic[EORB_KP_GROUP][EORB_IC_TILE];
+    __shared__ __align__(8) unsigned long long s_bar[EORB_KP_GROUP][2];
     __shared__ float s_angle[EORB_KP_GROUP], s_cos[EORB_KP_GROUP], s_sin[EORB_KP_GROUP];
     const OrbPlan& P = *a.plan;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int f = blockIdx.y;
-    const int nk = min(a.outN[f], P.selPerFrame);
+    const int nk = min(a.outN[f], L.selPerFrame);
     const int kidx = blockIdx.x * EORB_KP_GROUP + warp;
     if (blockIdx.x * EORB_KP_GROUP >= nk) return;      // block-uniform
     const bool valid = kidx < nk;
     const unsigned FULL = 0xffffffffu;
 
-    int slot = 0, level = 0, x = 0, y = 0;
+    // per-level constants come with the kernel parameters (constant bank), not from the plan in global memory
+    int slot = 0, level = 0, x = 0, y = 0, lw = 0, lh = 0;
     uint32_t key = 0;
     if (valid) {
-        const uint32_t e = a.kpList[(size_t)f * P.selPerFrame + kidx];
+        const uint32_t e = a.kpList[(size_t)f * L.selPerFrame + kidx];
         slot = e & 0xffffff; level = e >> 24;
-        key = a.sel[(size_t)f * P.selPerFrame + slot];
-        x = oct_key_x(key) + P.lv[level].minBX; y = oct_key_y(key) + P.lv[level].minBY;
+        key = a.sel[(size_t)f * L.selPerFrame + slot];
+        const int4 g = L.geo[level];
+        x = oct_key_x(key) + g.x; y = oct_key_y(key) + g.y; lw = g.z; lh = g.w;
     }
-    const LevelPlan& lp = P.lv[level];
 
-    // ---- the keypoint's patch of the BLURRED level starts its way into shared memory now (one TMA tile, L2 -> shared memory without
-    //      passing the L1 / LSU path: the 512 byte gathers of the descriptor were what bound this kernel, 87 % L1/TEX throughput)
+    // ---- the keypoint's two patches start their way into shared memory now
     int dst = -1;
-    bool staged = false;
+    bool staged = false, stagedIc = false;
+    const bool inside = (x >= 15) && (y >= 15) && (x + 15 < lw) && (y + 15 < lh);
+    const bool safe = (x >= 19) && (y >= 19) && (x + 19 < lw) && (y + 19 < lh);
     if (valid) {
-        dst = a.dstIdx[(size_t)f * P.selPerFrame + slot];
-        const bool safe = (x >= 19) && (y >= 19) && (x + 19 < lp.w) && (y + 19 < lp.h);
+        dst = a.dstIdx[(size_t)f * L.selPerFrame + slot];
         staged = a.briefMaps != nullptr && a.wantDesc && safe && dst >= 0 && dst < a.cap;
-        if (staged) {
-            if (lane == 0) {
-                const unsigned bar = smem_u32(&s_bar[warp]);
-                mbar_init(bar, 1);
-                mbar_fence_init();
-                mbar_expect_tx(bar, EORB_BRIEF_BOXW * EORB_BRIEF_BOXH);
-                tma_load_3d(smem_u32(s_tile[warp]), a.briefMaps + level, (x - 19) & ~15, y - 19, f, bar);
+        stagedIc = a.icMaps != nullptr && inside;
+        if (lane == 0 && (staged || stagedIc)) {
+            const unsigned bar0 = smem_u32(&s_bar[warp][0]), bar1 = smem_u32(&s_bar[warp][1]);
+            mbar_init(bar0, 1);
+            mbar_init(bar1, 1);
+            mbar_fence_init();
+            if (stagedIc) {
+                mbar_expect_tx(bar0, EORB_IC_BOXW * EORB_IC_BOXH);
+                tma_load_3d(smem_u32(s_ic[warp]), level == 0 ? &icMap0 : a.icMaps + level, (x - 15) & ~15, y - 15, f, bar0);
             }
-            __syncwarp();
+            if (staged) {
+                mbar_expect_tx(bar1, EORB_BRIEF_BOXW * EORB_BRIEF_BOXH);
+                tma_load_3d(smem_u32(s_tile[warp]), a.briefMaps + level, (x - 19) & ~15, y - 19, f, bar1);
+            }
         }
+        __syncwarp();
     }
+    const LevelPlan& lp = P.lv[level];   // only the paths that are not staged read it
 
     // ---- orientation (one warp per keypoint)
     if (valid) {
-        int sp;
-        const uint8_t* img = level_ptr(a, lp, level, f, sp);
         int m10 = 0, m01 = 0;
-        const bool inside = (x >= 15) && (y >= 15) && (x + 15 < lp.w) && (y + 15 < lp.h);
-        if (inside) {
+        if (stagedIc) {
+            // task i = it*32 + lane <-> (row r = i / 9, word k = i % 9) of the 31 x 9 aligned words covering the patch; the circular
+            // mask and the u / v weights of every (alignment, task) come from the table
+            const int xs = x - 15;
+            const int2* __restrict__ tab = a.icTab + (xs & 3) * EORB_IC_TASKS + lane;
+            const unsigned tbase = smem_u32(s_ic[warp]) + (unsigned)((xs & ~3) - (xs & ~15)) + 4u * (unsigned)lane;
+            int2 t[EORB_IC_TASKS / 32];
+#pragma unroll
+            for (int it = 0; it < EORB_IC_TASKS / 32; it++) t[it] = __ldg(tab + it * 32);
+            mbar_wait(smem_u32(&s_bar[warp][0]), 0);
+#pragma unroll
+            for (int it = 0; it < EORB_IC_TASKS / 32; it++) {
+                const int r = ((lane + 32 * it) * 57) >> 9;                       // i / 9 for i < 512
+                const unsigned data = lds_u32(tbase + 128 * it + (unsigned)(r * (EORB_IC_BOXW - 36)));   // r * 48 + 4 * (i - 9 r)
+                m10 = dp4a_u8_s8(data, t[it].x, m10);
+                m01 = dp4a_u8_s8(data, t[it].y, m01);
+            }
+        } else if (inside) {
+            int sp;
+            const uint8_t* img = level_ptr(a, lp, level, f, sp);
             const int xs = x - 15, xa = xs & ~3;
             const int wAligned = (lp.w + 3) & ~3;
             const int2* __restrict__ tab = a.icTab + (xs & 3) * EORB_IC_TASKS + lane;
             const uint8_t* base = img + (size_t)(y - 15) * sp + xa;
-            // task i = it*32 + lane <-> (row r = i / 9, word k = i % 9).  r and the word's byte offset are formed arithmetically from
-            // the lane (three integer instructions, independent of every load: taking them from the table entry was measured SLOWER,
-            // 1.00 -> 1.13 us/frame, because the pixel load then waits for the table load) and the address is one multiply-add plus an
-            // unsigned 32-bit offset.  Words past the row's last aligned word and the padding row 31 only meet zero weights, so
-            // their addresses are clamped instead of predicated.
+            // r and the word's byte offset are formed arithmetically from the lane (three integer instructions, independent of every
+            // load: taking them from the table entry was measured SLOWER, 1.00 -> 1.13 us/frame, because the pixel load then waits for
+            // the table load).  Words past the row's last aligned word and the padding row 31 only meet zero weights, so their
+            // addresses are clamped instead of predicated.
             const int k4Max = wAligned - 4 - xa;
             const int lane4 = 4 * lane;
 #pragma unroll
@@ -776,6 +814,8 @@ __global__ void __launch_bounds__(32 * EORB_KP_GROUP, EORB_OD_MINB) orient_desc_
                 m01 = dp4a_u8_s8(data, t.y, m01);
             }
         } else if (lane < 31) {   // patch crosses the level border (margin < 15): REFLECT_101, byte by byte
+            int sp;
+            const uint8_t* img = level_ptr(a, lp, level, f, sp);
             const int u = lane - 15;
             const int au = u < 0 ? -u : u;
             const int xx = reflect101(x + u, lp.w);
@@ -813,14 +853,15 @@ __global__ void __launch_bounds__(32 * EORB_KP_GROUP, EORB_OD_MINB) orient_desc_
 
     // ---- keypoint record + steered BRIEF on the blurred level
     const float angle = s_angle[warp], ca = s_cos[warp], sa = s_sin[warp];
-    if (a.levelAngle && lane == 0) a.levelAngle[(size_t)f * P.selPerFrame + slot] = angle;
+    if (a.levelAngle && lane == 0) a.levelAngle[(size_t)f * L.selPerFrame + slot] = angle;
     if (dst < 0 || dst >= a.cap) return;
     if (lane == 0) {
+        const float2 sc = L.sc[level];
         eorb_keypoint kp;
         const float xf = (float)x, yf = (float)y;
-        kp.x = level ? fmul(xf, lp.scale) : xf;
-        kp.y = level ? fmul(yf, lp.scale) : yf;
-        kp.size = lp.sizeF;
+        kp.x = level ? fmul(xf, sc.x) : xf;
+        kp.y = level ? fmul(yf, sc.x) : yf;
+        kp.size = sc.y;
         kp.angle = angle;
         kp.response = (float)oct_key_score(key);
         kp.octave = level;
@@ -828,16 +869,12 @@ __global__ void __launch_bounds__(32 * EORB_KP_GROUP, EORB_OD_MINB) orient_desc_
         a.outKps[(size_t)f * a.cap + dst] = kp;
     }
     if (!a.wantDesc) return;
-    const uint8_t* B = a.blur + (size_t)f * (size_t)P.blurBytesPerFrame + (size_t)lp.blurOff;
-    const int bp = lp.bpitch;
-    const bool safe = (x >= 19) && (y >= 19) && (x + 19 < lp.w) && (y + 19 < lp.h);
-    const uint8_t* Bc = B + (size_t)y * bp + x;
     uint32_t myword = 0;
     if (staged) {
         // sample address in the tile: row / column leave the 1.5 * 2^23 rounding trick as integers biased by 0x4B400000; the bias times
         // (tile pitch + 1), the patch origin (-19, -19) and the tile's alignment offset are ONE per-warp constant folded into the base
         const unsigned base = smem_u32(s_tile[warp]) + (unsigned)((x - 19) & 15) - (0x4B400000u - 19u) * (unsigned)(EORB_BRIEF_BOXW + 1);
-        mbar_wait(smem_u32(&s_bar[warp]), 0);
+        mbar_wait(smem_u32(&s_bar[warp][1]), 0);
 #pragma unroll
         for (int j = 0; j < 8; j++) {
             const float4 pt = __ldg(reinterpret_cast<const float4*>(d_brief_pattern_f) + 32 * j + lane);
@@ -849,13 +886,10 @@ __global__ void __launch_bounds__(32 * EORB_KP_GROUP, EORB_OD_MINB) orient_desc_
             if (lane == j) myword = word;
         }
     } else if (safe) {
-        // the warp's gathers are requested EORB_OD_BATCH rounds at a time before the first comparison.  (Staging the 39 x 39
-        // window in shared memory with coalesced word loads and gathering from there was measured SLOWER, 1.01 -> 1.10
-        // us/frame: the kernel is bound by instruction issue (74 % of the slots), not by the sectors its gathers touch.)
-        // A sample's address: row / column leave the 1.5 * 2^23 rounding trick as integers biased by 0x4B400000; the bias, times
-        // (pitch + 1), and the patch origin (-19, -19) are folded into ONE per-warp constant, so that a sample costs a multiply-add, a
-        // subtract and an unsigned 32-bit offset from the patch's top-left corner (it was nine integer instructions with signed 64-bit
-        // row and column terms).
+        // not staged (EORB_BRIEF_TMA=0 or no tensor map): the samples are gathered from global memory, EORB_OD_BATCH rounds requested
+        // before the first comparison; same biased 32-bit offsets, from the patch's top-left corner
+        const int bp = lp.bpitch;
+        const uint8_t* Bc = a.blur + (size_t)f * (size_t)P.blurBytesPerFrame + (size_t)lp.blurOff + (size_t)y * bp + x;
         const uint8_t* Bo = Bc - 19 * bp - 19;
         const unsigned kBias = (0x4B400000u - 19u) * (unsigned)(bp + 1);
 #pragma unroll
@@ -879,6 +913,8 @@ __global__ void __launch_bounds__(32 * EORB_KP_GROUP, EORB_OD_MINB) orient_desc_
             }
         }
     } else {   // margin < 19: the reference reads out of bounds; pinned to REFLECT_101 (see oracle)
+        const int bp = lp.bpitch;
+        const uint8_t* B = a.blur + (size_t)f * (size_t)P.blurBytesPerFrame + (size_t)lp.blurOff;
 #pragma unroll 1
         for (int j = 0; j < 8; j++) {
             const float4 pt = __ldg(reinterpret_cast<const float4*>(d_brief_pattern_f) + 32 * j + lane);
@@ -987,7 +1023,7 @@ static cudaError_t launch_pyramid_level(const OrbArgs& a, const OrbPlan& hp, int
 }
 
 cudaError_t launch_orb_pipeline(const OrbArgs& a, const OrbPlan& hp, int nframes, const CUtensorMap& tm0, cudaStream_t st,
-                                long long* launches, cudaEvent_t* ev, const CUtensorMap* pyrMaps, const OrbFork* fork) {
+                                long long* launches, cudaEvent_t* ev, const CUtensorMap* pyrMaps, const OrbFork* fork, const CUtensorMap* icMap0) {
     const bool forkBlur = fork && fork->side && !ev && a.wantDesc && hp.blurTasksTotal > 0;
     // ev (optional, EORB_ORB_STAGES+1 events): recorded around every stage for the per-kernel timings of bench.py
     if (ev) cudaEventRecord(ev[0], st);
@@ -1060,7 +1096,16 @@ cudaError_t launch_orb_pipeline(const OrbArgs& a, const OrbPlan& hp, int nframes
     // K4 + K6
     {
         dim3 grd(cdiv(hp.selPerFrame, EORB_KP_GROUP), nframes);
-        orient_desc_kernel<<<grd, 32 * EORB_KP_GROUP, 0, st>>>(a);
+        OdLevels L;
+        memset(&L, 0, sizeof(L));
+        L.selPerFrame = hp.selPerFrame;
+        for (int l = 0; l < hp.nlevels && l < EORB_MAX_LEVELS; l++) {
+            L.geo[l] = make_int4(hp.lv[l].minBX, hp.lv[l].minBY, hp.lv[l].w, hp.lv[l].h);
+            L.sc[l] = make_float2(hp.lv[l].scale, hp.lv[l].sizeF);
+        }
+        CUtensorMap ic0;
+        if (icMap0) ic0 = *icMap0; else memset(&ic0, 0, sizeof(ic0));
+        orient_desc_kernel<<<grd, 32 * EORB_KP_GROUP, 0, st>>>(a, ic0, L);
         (*launches)++;
     }
     if (ev) cudaEventRecord(ev[6], st);

@@ -23,7 +23,9 @@ struct OrbArgs {
                                  //         level 0 is the caller's buffer, its map travels as a kernel parameter)
     const CUtensorMap* blurMaps; // device: [nlevels] maps of the levels >= 1 with the box of blur_tma_kernel, or nullptr (blur_kernel is used);
                                  //         level 0's travels as pyrMaps[0] of launch_orb_pipeline
-    const CUtensorMap* briefMaps;// device: [nlevels] maps of the BLURRED levels with the 64 x 39 box orient_desc_kernel stages a keypoint's patch with, or nullptr
+    const CUtensorMap* briefMaps;// device: [nlevels] maps of the BLURRED levels with the box orient_desc_kernel stages a keypoint's BRIEF patch with, or nullptr
+    const CUtensorMap* icMaps;   // device: [nlevels] maps of the levels >= 1 with the box of the orientation patch (level 0's travels as a kernel
+                                 //         parameter: icMap0 of launch_orb_pipeline), or nullptr
     int* pyrDone;                // device: [8][EORB_MAX_LEVELS] tile counters of pyr_chain_kernel (small batches), or nullptr
     int blurVariant;             // EORB_BLUR_TMA value (1..4: band rows 32 / 64, neighbour words by shuffle / from the tile)
     uint8_t* pyr;                // [B][pyrBytesPerFrame]   levels >= 1
@@ -48,6 +50,14 @@ struct OrbArgs {
     int wantDesc;
 };
 
+// per-level constants of orient_desc_kernel, passed with the kernel parameters (constant bank)
+struct OdLevels {
+    int4 geo[EORB_MAX_LEVELS];     // minBX, minBY, w, h
+    float2 sc[EORB_MAX_LEVELS];    // mvScaleFactor[level], (float)(int)(31 * scale)
+    int selPerFrame;
+};
+
+
 // constants of one TMA-staged pyramid launch (orb_tiles.cu), passed by value
 struct PyrTileConst {
     int TW, TH, BW, BH, barOff;
@@ -61,6 +71,8 @@ cudaError_t orb_kernels_configure(const OrbPlan& hp);
 int blur_tma_box_w();
 int brief_tma_box_w();   // box of one keypoint's BRIEF patch on the blurred level (orient_desc_kernel)
 int brief_tma_box_h();
+int ic_tma_box_w();      // box of one keypoint's orientation patch on the level (orient_desc_kernel)
+int ic_tma_box_h();
 int blur_tma_box_h(int variant);
 #define EORB_ORB_STAGES 6   // pyramid, fast, octree, index, blur, orient+desc
 // side-stream fork of one launch set (small batches inside the captured graph only: a single frame leaves the GPU mostly idle, so the
@@ -70,7 +82,8 @@ struct OrbFork { cudaStream_t side = nullptr; cudaEvent_t forked = nullptr, join
 // pyrMaps (host array, [nlevels], may be null): TMA map of the SOURCE of level l (= level l-1) with that level's box, for the
 // levels whose plan says pyrTW > 0; null or pyrTW == 0 -> pyr_resize_kernel
 cudaError_t launch_orb_pipeline(const OrbArgs& a, const OrbPlan& hp, int nframes, const CUtensorMap& tm0, cudaStream_t st,
-                                long long* launches, cudaEvent_t* ev, const CUtensorMap* pyrMaps = nullptr, const OrbFork* fork = nullptr);
+                                long long* launches, cudaEvent_t* ev, const CUtensorMap* pyrMaps = nullptr, const OrbFork* fork = nullptr,
+                                const CUtensorMap* icMap0 = nullptr);
 cudaError_t launch_fast_cells(const OrbArgs& a, const OrbPlan& hp, int nframes, const CUtensorMap& tm0, cudaStream_t st);
 cudaError_t fast_cells_configure(const OrbPlan& hp);
 cudaError_t launch_pyramid_and_blur(const OrbArgs& a, const OrbPlan& hp, cudaStream_t st, long long* launches, const CUtensorMap* pyrMaps = nullptr);

@@ -46,4 +46,10 @@ __device__ __forceinline__ unsigned lds_u8(unsigned addr) {
     return v;
 }
 
+__device__ __forceinline__ unsigned lds_u32(unsigned addr) {
+    unsigned v;
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr));
+    return v;
+}
+
 }  // namespace eorb
