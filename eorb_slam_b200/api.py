@@ -73,6 +73,7 @@ def _load():
         "eorb_matcher_set_stream": ([vp, vp], i), "eorb_matcher_reset_stream": ([vp], i), "eorb_matcher_synchronize": ([vp], i),
         "eorb_matcher_launch_count": ([vp], C.c_longlong),
         "eorb_matcher_set_db_host": ([vp, vp, i64, i64], i), "eorb_matcher_set_db_device": ([vp, vp, i64, i64], i),
+        "eorb_matcher_set_engine": ([vp, i], i), "eorb_matcher_last_engine": ([vp], i),
         "eorb_matcher_search": ([vp, vp, i, i, f, vp], i), "eorb_matcher_search_device": ([vp, vp, i, vp], i),
         "eorb_matcher_merge_device": ([vp, vp, i, i, i, f, vp], i),
         "eorb_matcher_search_sharded": ([vp, vp, i, i, f, vp, i, vp], i),
@@ -391,6 +392,14 @@ class ORBmatcher:
             _check(lib.eorb_matcher_set_stream(self.h, C.c_void_p(int(stream))), "set_stream")
     def synchronize(self): _check(lib.eorb_matcher_synchronize(self.h), "synchronize")
     def launch_count(self): return lib.eorb_matcher_launch_count(self.h)
+
+    HAMMING_POPC, HAMMING_TENSOR, HAMMING_AUTO = 0, 1, 2
+
+    def set_engine(self, engine):
+        """scan engine: POPC (integer pipe), TENSOR (tcgen05 int8 contraction, bit-identical results) or AUTO"""
+        _check(lib.eorb_matcher_set_engine(self.h, int(engine)), "set_engine")
+
+    def last_engine(self): return lib.eorb_matcher_last_engine(self.h)
 
     def set_db(self, db, index_offset=0):
         db = np.ascontiguousarray(db, np.uint8)

@@ -11,7 +11,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libeorb_b200.so")
-SOURCES = ["capi.cu", "capi_lk.cu", "orb_kernels.cu", "orb_fast.cu", "orb_tiles.cu", "match_kernels.cu", "event_kernels.cu", "lk_kernels.cu", "guided_kernels.cu", "capi_guided.cu", "bow_kernels.cu", "capi_bow.cu"]
+SOURCES = ["capi.cu", "capi_lk.cu", "orb_kernels.cu", "orb_fast.cu", "orb_tiles.cu", "match_kernels.cu", "hamming_tc.cu", "event_kernels.cu", "lk_kernels.cu", "guided_kernels.cu", "capi_guided.cu", "bow_kernels.cu", "capi_bow.cu"]
 HEADERS = ["eorb_math.cuh", "tma_utils.cuh", "fast_score.cuh", "octree_core.cuh", "orb_plan.h", "orb_kernels.h", "match_kernels.h", "event_kernels.h", "lk_kernels.h", "guided_kernels.h", "bow_kernels.h",
            "brief_pattern_31.inc", os.path.join("..", "..", "include", "eorb_b200.h")]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "--fmad=true",

@@ -1179,6 +1179,9 @@ struct eorb_matcher {
     eorb_match* d_out = nullptr; size_t outCap = 0;
     eorb_best2* d_mine = nullptr; size_t mineCap = 0;           // sharded search: this shard's best-2 per query (nq entries)
     eorb_best2* d_gathered = nullptr; size_t gatherCap = 0;     //                 every shard's best-2 (nshards * nq entries)
+    int engine = EORB_HAMMING_AUTO;                               // eorb_matcher_set_engine
+    int lastEngine = EORB_HAMMING_POPC;                           // what the last search ran on
+    bool tensorOk = false;                                        // compute capability 10.x (tcgen05)
     long long launches = 0;
 };
 
@@ -1202,11 +1205,20 @@ extern "C" int eorb_matcher_create(int device, eorb_matcher** out) {
     cudaDeviceProp prop;
     CU(cudaGetDeviceProperties(&prop, device));
     m->sms = prop.multiProcessorCount;
+    m->tensorOk = prop.major == 10;
+    if (const char* e = getenv("EORB_HAMMING_ENGINE")) m->engine = std::min(std::max(atoi(e), 0), 2);
     CU(cudaStreamCreateWithFlags(&m->ownStream, cudaStreamNonBlocking));
     m->stream = m->ownStream;
     *out = m;
     return EORB_OK;
 }
+extern "C" int eorb_matcher_set_engine(eorb_matcher* m, int engine) {
+    if (!m || engine < EORB_HAMMING_POPC || engine > EORB_HAMMING_AUTO) return fail(EORB_ERR_ARG, "engine must be 0 (POPC), 1 (tensor) or 2 (auto)");
+    if (engine == EORB_HAMMING_TENSOR && !m->tensorOk) return fail(EORB_ERR_CUDA, "the tensor engine needs tcgen05 (compute capability 10.x)");
+    m->engine = engine;
+    return EORB_OK;
+}
+extern "C" int eorb_matcher_last_engine(const eorb_matcher* m) { return m ? m->lastEngine : -1; }
 extern "C" int eorb_matcher_destroy(eorb_matcher* m) {
     if (!m) return EORB_OK;
     cudaSetDevice(m->device);
@@ -1260,8 +1272,32 @@ extern "C" int eorb_matcher_set_db_host(eorb_matcher* m, const uint8_t* db, int6
     return matcherAdopt(m, m->ownedDb, ndb, index_offset);
 }
 
-static int matcherReserve(eorb_matcher* m, int nq) {
-    return growBuf(&m->d_partial, &m->partialCap, (size_t)std::max(m->nchunks, 1) * nq);
+// scan of the whole database for nq queries: per-chunk partial best-2 arrays in m->d_partial, *nparts of them.
+// Engine: the tensor cores (hamming_tc.cu) pay off when the accumulator's 128 query rows are mostly real queries and the database is
+// large enough to amortise the per-CTA setup; small searches stay on the POPC kernel.
+static int matcherScan(eorb_matcher* m, const uint8_t* d_q, int nq, int* nparts) {
+    *nparts = 0;
+    if (m->ndb <= 0) return growBuf(&m->d_partial, &m->partialCap, (size_t)nq);
+    const bool tensor = m->tensorOk && (m->engine == EORB_HAMMING_TENSOR || (m->engine == EORB_HAMMING_AUTO && nq >= 96 && m->ndb >= 65536));
+    if (tensor) {
+        long long rows = 0;
+        const int nch = hamming_tc_chunks(m->ndb, nq, m->sms, &rows);
+        const int parts = nch * hamming_tc_parts_per_chunk();
+        int rc = growBuf(&m->d_partial, &m->partialCap, (size_t)parts * nq);
+        if (rc != EORB_OK) return rc;
+        CU(launch_hamming_best2_tc(d_q, nq, m->d_db, m->ndb, m->indexOffset, rows, nch, m->d_partial, m->stream));
+        m->launches++;
+        m->lastEngine = EORB_HAMMING_TENSOR;
+        *nparts = parts;
+        return EORB_OK;
+    }
+    int rc = growBuf(&m->d_partial, &m->partialCap, (size_t)std::max(m->nchunks, 1) * nq);
+    if (rc != EORB_OK) return rc;
+    CU(launch_hamming_best2(d_q, nq, m->d_db, m->ndb, m->indexOffset, m->chunkRows, m->nchunks, m->d_partial, m->stream));
+    m->launches++;
+    m->lastEngine = EORB_HAMMING_POPC;
+    *nparts = m->nchunks;
+    return EORB_OK;
 }
 
 extern "C" int eorb_matcher_search_device(eorb_matcher* m, const uint8_t* d_q, int nq, eorb_best2* d_partial) {
@@ -1269,13 +1305,10 @@ extern "C" int eorb_matcher_search_device(eorb_matcher* m, const uint8_t* d_q, i
     if (nq <= 0) return EORB_OK;
     if ((uintptr_t)d_q % 16 != 0) return fail(EORB_ERR_ARG, "query pointer must be 16-byte aligned");
     CU(cudaSetDevice(m->device));
-    int rc = matcherReserve(m, nq);
+    int nparts = 0;
+    int rc = matcherScan(m, d_q, nq, &nparts);
     if (rc != EORB_OK) return rc;
-    if (m->nchunks > 0) {
-        CU(launch_hamming_best2(d_q, nq, m->d_db, m->ndb, m->indexOffset, m->chunkRows, m->nchunks, m->d_partial, m->stream));
-        m->launches++;
-    }
-    CU(launch_merge_best2(m->d_partial, m->nchunks, nq, d_partial, nullptr, 0, 0.f, m->stream));
+    CU(launch_merge_best2(m->d_partial, nparts, nq, d_partial, nullptr, 0, 0.f, m->stream));
     m->launches++;
     return EORB_OK;
 }
@@ -1385,14 +1418,11 @@ extern "C" int eorb_matcher_search(eorb_matcher* m, const uint8_t* q, int nq, in
     if (rcg != EORB_OK) return rcg;
     rcg = growBuf(&m->d_out, &m->outCap, (size_t)nq);
     if (rcg != EORB_OK) return rcg;
-    int rc = matcherReserve(m, nq);
-    if (rc != EORB_OK) return rc;
     CU(cudaMemcpyAsync(m->d_q, q, (size_t)nq * 32, cudaMemcpyHostToDevice, m->stream));
-    if (m->nchunks > 0) {
-        CU(launch_hamming_best2(m->d_q, nq, m->d_db, m->ndb, m->indexOffset, m->chunkRows, m->nchunks, m->d_partial, m->stream));
-        m->launches++;
-    }
-    CU(launch_merge_best2(m->d_partial, m->nchunks, nq, nullptr, m->d_out, th, ratio, m->stream));
+    int nparts = 0;
+    int rc = matcherScan(m, m->d_q, nq, &nparts);
+    if (rc != EORB_OK) return rc;
+    CU(launch_merge_best2(m->d_partial, nparts, nq, nullptr, m->d_out, th, ratio, m->stream));
     m->launches++;
     CU(cudaMemcpyAsync(out, m->d_out, (size_t)nq * sizeof(eorb_match), cudaMemcpyDeviceToHost, m->stream));
     CU(cudaStreamSynchronize(m->stream));

@@ -1,0 +1,315 @@
+// hamming_tc.cu — 256-bit Hamming best-2 search on the 5th-generation tensor cores (tcgen05.mma kind::i8, accumulators in TMEM).
+//
+// Reference: ORBmatcher::DescriptorDistance src/ORBmatcher.cc:2360-2378 and the best / second-best scan with strict '<'
+// (:741-770, :318-378); brute-force shape of src/Frame.cc:1228-1235.  Same contract as hamming_best2_kernel (match_kernels.cu):
+// per (database chunk, query) the two smallest keys (dist << 32 | global row) in scan order, merged by merge_best2_kernel.
+//
+// A 256-bit Hamming distance is an exact +-1 contraction: with a_i = 1 - 2 q_i and b_i = 1 - 2 r_i (int8),
+//     sum_i a_i b_i = 256 - 2 popcount(q xor r)      =>      dist = (256 - dot) / 2      (int32 accumulation, no rounding anywhere).
+// One CTA (one per SM) owns 128 queries (the M = 128 rows of the accumulator = the 128 TMEM lanes) and walks a chunk of the database in
+// tiles of 256 rows (N = 256 accumulator columns); K = 256 bits = 8 instructions of K = 32.
+//   warp 0          allocates TMEM (512 columns = two accumulators) and issues the MMAs (one elected thread)
+//   warps 1-4       producers: packed database rows (32 B) -> int8 +-1 rows (256 B) in the no-swizzle K-major core-matrix layout the
+//                   shared-memory descriptors describe (8 rows x 16 bytes per core matrix), through a 256-entry byte -> 8-byte table;
+//                   two 64 KB stages
+//   warps 5-12      epilogue: thread = one query (TMEM lane), tcgen05.ld 32 accumulator columns at a time.  The scan order makes
+//                   "this row enters the best two" equivalent to dot > 256 - 2 * (second-best distance), so the fast path is a max
+//                   over the 32 dots and one compare; the rare slow path replays the 32 columns in order with the packed-key
+//                   min / max network of the POPC kernel (lowest index wins ties, as the reference's sequential scan).
+// Pipelines: full / empty mbarriers per shared-memory stage (producers <-> MMA, the "empty" side arrives through tcgen05.commit) and
+// per accumulator (MMA <-> epilogue).  Every wait is bounded: a broken pipeline traps instead of hanging the GPU.
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <mutex>
+
+#include "../../include/eorb_b200.h"
+#include "match_kernels.h"
+#include "tma_utils.cuh"
+
+namespace eorb {
+
+#define HT_THREADS 416
+#define HT_M 128
+#define HT_N 256
+#define HT_A_BYTES (HT_M * 256)
+#define HT_B_BYTES (HT_N * 256)
+#define HT_LUT_OFF (HT_A_BYTES + 2 * HT_B_BYTES)
+#define HT_BAR_OFF (HT_LUT_OFF + 2048)
+#define HT_SMEM (HT_BAR_OFF + 128)
+#define HT_TMEM_COLS 512
+
+__device__ __forceinline__ void ht_wait(unsigned bar, unsigned parity) {
+    unsigned done = 0;
+    for (unsigned spin = 0; !done; spin++) {
+        asm volatile(
+            "{\n"
+            ".reg .pred p;\n"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+            "selp.u32 %0, 1, 0, p;\n"
+            "}\n"
+            : "=r"(done)
+            : "r"(bar), "r"(parity)
+            : "memory");
+        if (!done && spin > (1u << 24)) __trap();   // a broken pipeline must not hang the device
+    }
+}
+__device__ __forceinline__ void ht_arrive(unsigned bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void ht_commit(unsigned bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void ht_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void ht_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+// shared-memory matrix descriptor, K-major, no swizzle: core matrix = 8 rows x 16 bytes (128 contiguous bytes);
+// LBO = distance between the two core matrices of one K = 32 step, SBO = distance between 8-row groups (both in bytes)
+__device__ __forceinline__ unsigned long long ht_desc(unsigned smemAddr, unsigned lbo, unsigned sbo) {
+    return (unsigned long long)((smemAddr >> 4) & 0x3FFFu) | ((unsigned long long)((lbo >> 4) & 0x3FFFu) << 16) |
+           ((unsigned long long)((sbo >> 4) & 0x3FFFu) << 32) | (1ull << 46);
+}
+__device__ __forceinline__ void ht_mma_i8(unsigned tmemD, unsigned long long descA, unsigned long long descB, unsigned idesc, unsigned accumulate) {
+    const unsigned z = 0;
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "setp.ne.b32 p, %4, 0;\n"
+        "tcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, {%5, %6, %7, %8}, p;\n"
+        "}\n" ::"r"(tmemD),
+        "l"(descA), "l"(descB), "r"(idesc), "r"(accumulate), "r"(z), "r"(z), "r"(z), "r"(z)
+        : "memory");
+}
+__device__ __forceinline__ void ht_tmem_ld32(unsigned addr, int* v) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, %17, %18, %19, %20, "
+        "%21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];\n"
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]), "=r"(v[9]), "=r"(v[10]),
+          "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]),
+          "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]),
+          "=r"(v[31])
+        : "r"(addr)
+        : "memory");
+}
+__device__ __forceinline__ void ht_tmem_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// 16 descriptor bits (two bytes) -> 16 int8 values (+1 for a 0 bit, -1 for a 1 bit), bit i of byte b <-> K index 8 b + i
+__device__ __forceinline__ uint4 ht_expand16(const uint2* lut, unsigned twoBytes) {
+    const uint2 lo = lut[twoBytes & 0xffu], hi = lut[(twoBytes >> 8) & 0xffu];
+    return make_uint4(lo.x, lo.y, hi.x, hi.y);
+}
+// one packed row (8 words) -> 16 core-matrix rows of 16 bytes; dst = address of (k chunk 0, this row), chunkStride = bytes between k chunks
+__device__ __forceinline__ void ht_expand_row(const uint2* lut, const uint4& a, const uint4& b, unsigned char* dst, unsigned chunkStride) {
+    const unsigned w[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+#pragma unroll
+    for (int kc = 0; kc < 16; kc++) {
+        const unsigned two = (w[kc >> 1] >> ((kc & 1) * 16)) & 0xffffu;
+        *reinterpret_cast<uint4*>(dst + (size_t)kc * chunkStride) = ht_expand16(lut, two);
+    }
+}
+
+__global__ void __launch_bounds__(HT_THREADS, 1) hamming_tc_kernel(const uint4* __restrict__ q, int nq, const uint4* __restrict__ db, long long ndb,
+                                                                   long long chunkRows, long long indexOffset, eorb_best2* __restrict__ partial) {
+    extern __shared__ __align__(1024) unsigned char smem[];
+    __shared__ unsigned s_tmemBase;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    unsigned char* sA = smem;
+    unsigned char* sB = smem + HT_A_BYTES;
+    uint2* lut = reinterpret_cast<uint2*>(smem + HT_LUT_OFF);
+    const unsigned barBase = smem_u32(smem + HT_BAR_OFF);
+    // barriers (8 bytes each): fullB[0..1] @0,8  emptyB[0..1] @16,24  tmemFull[0..1] @32,40  tmemEmpty[0..1] @48,56
+    const unsigned fullB = barBase, emptyB = barBase + 16, tmemFull = barBase + 32, tmemEmpty = barBase + 48;
+
+    const long long j0 = (long long)blockIdx.x * chunkRows;
+    const long long j1 = (j0 + chunkRows < ndb) ? j0 + chunkRows : ndb;
+    const long long rows = j1 > j0 ? j1 - j0 : 0;
+    const int ntiles = (int)((rows + HT_N - 1) / HT_N);
+    const int q0 = blockIdx.y * HT_M;
+
+    // ---- setup: table, barriers, TMEM, the CTA's 128 queries as int8
+    for (int v = tid; v < 256; v += HT_THREADS) {
+        unsigned lo = 0, hi = 0;
+#pragma unroll
+        for (int i = 0; i < 4; i++) {
+            lo |= (((v >> i) & 1) ? 0xFFu : 0x01u) << (8 * i);
+            hi |= (((v >> (4 + i)) & 1) ? 0xFFu : 0x01u) << (8 * i);
+        }
+        lut[v] = make_uint2(lo, hi);
+    }
+    if (tid == 0) {
+        mbar_init(fullB, 128); mbar_init(fullB + 8, 128);
+        mbar_init(emptyB, 1); mbar_init(emptyB + 8, 1);
+        mbar_init(tmemFull, 1); mbar_init(tmemFull + 8, 1);
+        mbar_init(tmemEmpty, 8); mbar_init(tmemEmpty + 8, 8);
+        mbar_fence_init();
+    }
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&s_tmemBase)), "r"(HT_TMEM_COLS) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    __syncthreads();   // the table is complete
+    if (warp >= 1 && warp <= 4) {
+        const int m = tid - 32;   // query row of the tile
+        const int qi = q0 + m;
+        uint4 a = make_uint4(0, 0, 0, 0), b = a;
+        if (qi < nq) { a = __ldg(&q[2 * qi]); b = __ldg(&q[2 * qi + 1]); }
+        ht_expand_row(lut, a, b, sA + (m >> 3) * 128 + (m & 7) * 16, (HT_M / 8) * 128);
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> visible to the tensor core's reads
+    }
+    ht_fence_before();
+    __syncthreads();
+    ht_fence_after();
+    const unsigned tmemBase = s_tmemBase;
+
+    if (warp == 0) {
+        // ================================================================= MMA issuer (the warp waits together, one lane issues)
+        // instruction descriptor (kind::i8): D = S32 (bits 4-5 = 2), A = B = signed 8 bit (bits 7-9, 10-12 = 1), both K-major,
+        // N >> 3 at bit 17, M >> 4 at bit 24
+        const unsigned idesc = (2u << 4) | (1u << 7) | (1u << 10) | ((unsigned)(HT_N >> 3) << 17) | ((unsigned)(HT_M >> 4) << 24);
+        const unsigned aAddr = smem_u32(sA), bAddr = smem_u32(sB);
+        for (int t = 0; t < ntiles; t++) {
+            const int s = t & 1;
+            const unsigned ph = (unsigned)(t >> 1) & 1u;
+            ht_wait(fullB + 8 * s, ph);
+            ht_wait(tmemEmpty + 8 * s, ph ^ 1u);
+            ht_fence_after();
+            if (lane == 0) {
+#pragma unroll
+                for (int j = 0; j < 8; j++) {
+                    const unsigned long long da = ht_desc(aAddr + (unsigned)j * 2u * (HT_M / 8) * 128u, (HT_M / 8) * 128u, 128u);
+                    const unsigned long long dbd = ht_desc(bAddr + (unsigned)s * HT_B_BYTES + (unsigned)j * 2u * (HT_N / 8) * 128u, (HT_N / 8) * 128u, 128u);
+                    ht_mma_i8(tmemBase + (unsigned)s * HT_N, da, dbd, idesc, j > 0 ? 1u : 0u);
+                }
+                ht_commit(emptyB + 8 * s);     // the stage may be refilled once these MMAs have read it
+                ht_commit(tmemFull + 8 * s);   // ... and the accumulator is complete
+            }
+            __syncwarp();
+        }
+    } else if (warp <= 4) {
+        // ================================================================= producers
+        const int p = tid - 32;   // rows p and p + 128 of every tile
+        uint4 r[4];
+        auto load = [&](int t) {
+            const long long base = j0 + (long long)t * HT_N;
+#pragma unroll
+            for (int h = 0; h < 2; h++) {
+                const long long row = base + p + 128 * h;
+                if (row < j1) { r[2 * h] = __ldg(&db[2 * row]); r[2 * h + 1] = __ldg(&db[2 * row + 1]); }
+                else { r[2 * h] = make_uint4(0, 0, 0, 0); r[2 * h + 1] = r[2 * h]; }
+            }
+        };
+        if (ntiles > 0) load(0);
+        for (int t = 0; t < ntiles; t++) {
+            const int s = t & 1;
+            const unsigned ph = (unsigned)(t >> 1) & 1u;
+            const uint4 c0 = r[0], c1 = r[1], c2 = r[2], c3 = r[3];
+            if (t + 1 < ntiles) load(t + 1);   // next tile's rows are in flight while this one is expanded
+            ht_wait(emptyB + 8 * s, ph ^ 1u);
+            unsigned char* stage = sB + (size_t)s * HT_B_BYTES;
+            ht_expand_row(lut, c0, c1, stage + (p >> 3) * 128 + (p & 7) * 16, (HT_N / 8) * 128);
+            ht_expand_row(lut, c2, c3, stage + ((p + 128) >> 3) * 128 + (p & 7) * 16, (HT_N / 8) * 128);
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            ht_arrive(fullB + 8 * s);
+        }
+    } else {
+        // ================================================================= epilogue: thread <-> query 32 * (warp & 3) + lane
+        const int quarter = warp & 3;                 // the TMEM lanes this warp may read
+        const int half = (warp - 5) >> 2;             // columns [128 * half, 128 * half + 128) of every tile
+        const unsigned laneAddr = tmemBase + ((unsigned)(quarter * 32) << 16);
+        uint32_t k1 = 0xFFFFFFFFu, k2 = 0xFFFFFFFFu;
+        int thrDot = -100000;                         // dot > thrDot  <=>  the row enters the best two
+        for (int t = 0; t < ntiles; t++) {
+            const int s = t & 1;
+            const unsigned ph = (unsigned)(t >> 1) & 1u;
+            const long long left = rows - (long long)t * HT_N;
+            const int cnt = left < HT_N ? (int)left : HT_N;
+            ht_wait(tmemFull + 8 * s, ph);
+            ht_fence_after();
+#pragma unroll 1
+            for (int c = 0; c < 4; c++) {
+                const int col0 = half * 128 + c * 32;
+                int v[32];
+                __syncwarp();
+                ht_tmem_ld32(laneAddr + (unsigned)(s * HT_N + col0), v);
+                ht_tmem_wait_ld();
+                if (col0 >= cnt) continue;            // warp-uniform
+                bool slow = col0 + 32 > cnt;          // the chunk's last tile may be partial: columns >= cnt are not rows
+                if (!slow) {
+                    int m = v[0];
+#pragma unroll
+                    for (int i = 1; i < 32; i++) m = max(m, v[i]);
+                    slow = m > thrDot;
+                }
+                if (slow) {
+                    const uint32_t local0 = (uint32_t)(t * HT_N + col0);
+#pragma unroll
+                    for (int i = 0; i < 32; i++) {
+                        if (col0 + i < cnt) {
+                            const uint32_t dist = (uint32_t)(256 - v[i]) >> 1;
+                            const uint32_t key = (dist << 22) | (local0 + (uint32_t)i);
+                            const uint32_t hi = max(k1, key);
+                            k1 = min(k1, key);
+                            k2 = min(k2, hi);
+                        }
+                    }
+                    thrDot = (k2 == 0xFFFFFFFFu) ? -100000 : 256 - 2 * (int)(k2 >> 22);
+                }
+            }
+            ht_fence_before();
+            __syncwarp();
+            if (lane == 0) ht_arrive(tmemEmpty + 8 * s);
+        }
+        const int qi = q0 + quarter * 32 + lane;
+        if (qi < nq) {
+            eorb_best2 o;
+            const unsigned long long base = (unsigned long long)(indexOffset + j0);
+            o.key1 = (k1 == 0xFFFFFFFFu) ? ~0ull : (((unsigned long long)(k1 >> 22)) << 32) | (base + (k1 & 0x3FFFFFu));
+            o.key2 = (k2 == 0xFFFFFFFFu) ? ~0ull : (((unsigned long long)(k2 >> 22)) << 32) | (base + (k2 & 0x3FFFFFu));
+            partial[((size_t)blockIdx.x * 2 + half) * nq + qi] = o;
+        }
+    }
+    ht_fence_before();
+    __syncthreads();
+    if (warp == 0) {
+        ht_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmemBase), "r"(HT_TMEM_COLS) : "memory");
+    }
+}
+
+// chunks of the tensor-core search: multiples of 256 rows, <= 2^22 rows (22-bit local index), about two waves of CTAs
+int hamming_tc_chunks(long long ndb, int nq, int sms, long long* chunkRows) {
+    const int qtiles = (nq + HT_M - 1) / HT_M;
+    long long want = ((long long)sms * 2 + qtiles - 1) / qtiles;
+    if (want < 1) want = 1;
+    long long rows = (ndb + want - 1) / want;
+    if (rows < HT_N) rows = HT_N;
+    rows = (rows + HT_N - 1) / HT_N * HT_N;
+    if (rows > (1ll << 22)) rows = 1ll << 22;
+    *chunkRows = rows;
+    return (int)((ndb + rows - 1) / rows);
+}
+int hamming_tc_parts_per_chunk() { return 2; }
+
+cudaError_t launch_hamming_best2_tc(const uint8_t* d_q, int nq, const uint8_t* d_db, long long ndb, long long indexOffset, long long chunkRows,
+                                    int nchunks, eorb_best2* d_partial, cudaStream_t st) {
+    if (nq <= 0 || nchunks <= 0) return cudaSuccess;
+    static std::mutex mu;
+    static bool done[64] = {false};
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return e;
+    {
+        std::lock_guard<std::mutex> lk(mu);
+        if (!(dev >= 0 && dev < 64 && done[dev])) {
+            e = cudaFuncSetAttribute(hamming_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, HT_SMEM);
+            if (e != cudaSuccess) return e;
+            if (dev >= 0 && dev < 64) done[dev] = true;
+        }
+    }
+    dim3 grd(nchunks, (nq + HT_M - 1) / HT_M);
+    hamming_tc_kernel<<<grd, HT_THREADS, HT_SMEM, st>>>(reinterpret_cast<const uint4*>(d_q), nq, reinterpret_cast<const uint4*>(d_db), ndb, chunkRows,
+                                                        indexOffset, d_partial);
+    return cudaGetLastError();
+}
+
+}  // namespace eorb

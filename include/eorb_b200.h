@@ -190,6 +190,15 @@ long long eorb_matcher_launch_count(const eorb_matcher* m);
 int eorb_matcher_set_db_host(eorb_matcher* m, const uint8_t* db, int64_t ndb, int64_t index_offset);
 int eorb_matcher_set_db_device(eorb_matcher* m, const uint8_t* d_db, int64_t ndb, int64_t index_offset);
 /* one-call brute force, host buffers: best-2 + threshold + ratio -> out[nq] */
+/* Scan engine.  POPC: 8 x popcount(xor) per pair on the integer pipe (the reference's DescriptorDistance, ORBmatcher.cc:2360-2378, as is).
+ * TENSOR: the same distance as an exact +-1 int8 contraction, dist = (256 - dot) / 2, on the 5th-generation tensor cores (tcgen05.mma
+ * kind::i8, accumulators in TMEM; compute capability 10.x only).  AUTO (default; environment EORB_HAMMING_ENGINE=0/1/2 overrides at
+ * creation): TENSOR for at least 96 queries against at least 65536 rows, POPC otherwise.  Results are identical bit for bit. */
+#define EORB_HAMMING_POPC   0
+#define EORB_HAMMING_TENSOR 1
+#define EORB_HAMMING_AUTO   2
+int eorb_matcher_set_engine(eorb_matcher* m, int engine);
+int eorb_matcher_last_engine(const eorb_matcher* m);   /* the engine the last search ran on */
 int eorb_matcher_search(eorb_matcher* m, const uint8_t* q, int nq, int th, float ratio, eorb_match* out);
 /* per-shard partials, device buffers, asynchronous: d_partial[nq] */
 int eorb_matcher_search_device(eorb_matcher* m, const uint8_t* d_q, int nq, eorb_best2* d_partial);
