@@ -4,20 +4,25 @@
 // (:741-770, :318-378); brute-force shape of src/Frame.cc:1228-1235.  Same contract as hamming_best2_kernel (match_kernels.cu):
 // per (database chunk, query) the two smallest keys (dist << 32 | global row) in scan order, merged by merge_best2_kernel.
 //
-// A 256-bit Hamming distance is an exact +-1 contraction: with a_i = 1 - 2 q_i and b_i = 1 - 2 r_i (int8),
-//     sum_i a_i b_i = 256 - 2 popcount(q xor r)      =>      dist = (256 - dot) / 2      (int32 accumulation, no rounding anywhere).
+// A 256-bit Hamming distance is an exact int8 contraction.  With a_i = 1 - 2 q_i (+-1, the queries) and b_i = -r_i (0 / -1, the database),
+//     sum_i a_i b_i = -popc(r) + 2 popc(q & r)      =>      dist = popc(q) + popc(r) - 2 popc(q & r) = popc(q) - dot
+// (int32 accumulation, no rounding anywhere; popc(q) is one constant per query).  The asymmetric encoding makes the database side one
+// PRMT per four elements: `prmt` with the sign-replicate bit turns the top bit of each byte of (word << k) into 0x00 / 0xFF.  Element
+// order along K is therefore not bit order but (word w, shift k, byte b) <-> bit 8 b + 7 - k of word w, the same for both operands.
 // One CTA (one per SM) owns 128 queries (the M = 128 rows of the accumulator = the 128 TMEM lanes) and walks a chunk of the database in
 // tiles of 256 rows (N = 256 accumulator columns); K = 256 bits = 8 instructions of K = 32.
 //   warp 0          allocates TMEM (512 columns = two accumulators) and issues the MMAs (one elected thread)
-//   warps 1-4       producers: packed database rows (32 B) -> int8 +-1 rows (256 B) in the no-swizzle K-major core-matrix layout the
-//                   shared-memory descriptors describe (8 rows x 16 bytes per core matrix), through a 256-entry byte -> 8-byte table;
-//                   two 64 KB stages
-//   warps 5-12      epilogue: thread = one query (TMEM lane), tcgen05.ld 32 accumulator columns at a time.  The scan order makes
-//                   "this row enters the best two" equivalent to dot > 256 - 2 * (second-best distance), so the fast path is a max
-//                   over the 32 dots and one compare; the rare slow path replays the 32 columns in order with the packed-key
-//                   min / max network of the POPC kernel (lowest index wins ties, as the reference's sequential scan).
+//   warps 1-8       producers: thread = one database row of the tile, packed 32 B -> 256 int8 in the no-swizzle K-major core-matrix
+//                   layout the shared-memory descriptors describe (8 rows x 16 bytes per core matrix); two 64 KB stages
+//   warps 9-16      epilogue: thread = one query (TMEM lane), tcgen05.ld 32 accumulator columns at a time, the next load in flight while
+//                   the current columns are examined.  The scan order makes "this row enters the best two" equivalent to
+//                   dot > popc(q) - (second-best distance), so the fast path is a max over the 32 dots and one compare; the rare slow
+//                   path replays the 32 columns in order with the packed-key min / max network of the POPC kernel (lowest index wins
+//                   ties, as the reference's sequential scan).
 // Pipelines: full / empty mbarriers per shared-memory stage (producers <-> MMA, the "empty" side arrives through tcgen05.commit) and
 // per accumulator (MMA <-> epilogue).  Every wait is bounded: a broken pipeline traps instead of hanging the GPU.
+// Per tile the shared memory moves 96 KB into the tensor core and 64 KB from the producers (1280 cycles at 128 B/clk) against 1085
+// cycles of int8 math at the B200's dense rate: the kernel is bound by shared-memory bandwidth, then by the tensor pipe.
 #include <cuda_runtime.h>
 #include <stdint.h>
 
@@ -29,13 +34,12 @@
 
 namespace eorb {
 
-#define HT_THREADS 416
+#define HT_THREADS 544
 #define HT_M 128
 #define HT_N 256
 #define HT_A_BYTES (HT_M * 256)
 #define HT_B_BYTES (HT_N * 256)
-#define HT_LUT_OFF (HT_A_BYTES + 2 * HT_B_BYTES)
-#define HT_BAR_OFF (HT_LUT_OFF + 2048)
+#define HT_BAR_OFF (HT_A_BYTES + 2 * HT_B_BYTES)
 #define HT_SMEM (HT_BAR_OFF + 128)
 #define HT_TMEM_COLS 512
 
@@ -93,18 +97,25 @@ __device__ __forceinline__ void ht_tmem_ld32(unsigned addr, int* v) {
 }
 __device__ __forceinline__ void ht_tmem_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
-// 16 descriptor bits (two bytes) -> 16 int8 values (+1 for a 0 bit, -1 for a 1 bit), bit i of byte b <-> K index 8 b + i
-__device__ __forceinline__ uint4 ht_expand16(const uint2* lut, unsigned twoBytes) {
-    const uint2 lo = lut[twoBytes & 0xffu], hi = lut[(twoBytes >> 8) & 0xffu];
-    return make_uint4(lo.x, lo.y, hi.x, hi.y);
+// every byte -> 0xFF when its top bit is set, else 0x00: prmt with the sign-replicate bit (8) in every selector nibble
+// (the __byte_perm intrinsic masks the selector to three bits per nibble, hence the PTX)
+__device__ __forceinline__ unsigned ht_sign_bytes(unsigned x) {
+    unsigned d;
+    asm("prmt.b32 %0, %1, %1, 0xBA98;" : "=r"(d) : "r"(x));
+    return d;
 }
-// one packed row (8 words) -> 16 core-matrix rows of 16 bytes; dst = address of (k chunk 0, this row), chunkStride = bytes between k chunks
-__device__ __forceinline__ void ht_expand_row(const uint2* lut, const uint4& a, const uint4& b, unsigned char* dst, unsigned chunkStride) {
+// one packed row (8 words) -> 256 int8: element (w, k, b) = -(bit 8 b + 7 - k of word w) for the database (orMask = 0), or
+// +1 / -1 for the queries (orMask = 0x01010101 turns the 0x00 of a clear bit into +1).  K chunk 2 w + (k >> 2) holds shifts k of
+// word w as its four 32-bit words; dst = address of (k chunk 0, this row), chunkStride = bytes between k chunks.
+__device__ __forceinline__ void ht_expand_row(const uint4& a, const uint4& b, unsigned char* dst, unsigned chunkStride, unsigned orMask) {
     const unsigned w[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
 #pragma unroll
     for (int kc = 0; kc < 16; kc++) {
-        const unsigned two = (w[kc >> 1] >> ((kc & 1) * 16)) & 0xffffu;
-        *reinterpret_cast<uint4*>(dst + (size_t)kc * chunkStride) = ht_expand16(lut, two);
+        const unsigned x = w[kc >> 1];
+        unsigned o[4];
+#pragma unroll
+        for (int j = 0; j < 4; j++) o[j] = ht_sign_bytes(x << ((kc & 1) * 4 + j)) | orMask;
+        *reinterpret_cast<uint4*>(dst + (size_t)kc * chunkStride) = make_uint4(o[0], o[1], o[2], o[3]);
     }
 }
 
@@ -115,7 +126,6 @@ __global__ void __launch_bounds__(HT_THREADS, 1) hamming_tc_kernel(const uint4* 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     unsigned char* sA = smem;
     unsigned char* sB = smem + HT_A_BYTES;
-    uint2* lut = reinterpret_cast<uint2*>(smem + HT_LUT_OFF);
     const unsigned barBase = smem_u32(smem + HT_BAR_OFF);
     // barriers (8 bytes each): fullB[0..1] @0,8  emptyB[0..1] @16,24  tmemFull[0..1] @32,40  tmemEmpty[0..1] @48,56
     const unsigned fullB = barBase, emptyB = barBase + 16, tmemFull = barBase + 32, tmemEmpty = barBase + 48;
@@ -126,18 +136,9 @@ __global__ void __launch_bounds__(HT_THREADS, 1) hamming_tc_kernel(const uint4* 
     const int ntiles = (int)((rows + HT_N - 1) / HT_N);
     const int q0 = blockIdx.y * HT_M;
 
-    // ---- setup: table, barriers, TMEM, the CTA's 128 queries as int8
-    for (int v = tid; v < 256; v += HT_THREADS) {
-        unsigned lo = 0, hi = 0;
-#pragma unroll
-        for (int i = 0; i < 4; i++) {
-            lo |= (((v >> i) & 1) ? 0xFFu : 0x01u) << (8 * i);
-            hi |= (((v >> (4 + i)) & 1) ? 0xFFu : 0x01u) << (8 * i);
-        }
-        lut[v] = make_uint2(lo, hi);
-    }
+    // ---- setup: barriers, TMEM, the CTA's 128 queries as int8
     if (tid == 0) {
-        mbar_init(fullB, 128); mbar_init(fullB + 8, 128);
+        mbar_init(fullB, 256); mbar_init(fullB + 8, 256);
         mbar_init(emptyB, 1); mbar_init(emptyB + 8, 1);
         mbar_init(tmemFull, 1); mbar_init(tmemFull + 8, 1);
         mbar_init(tmemEmpty, 8); mbar_init(tmemEmpty + 8, 8);
@@ -147,13 +148,12 @@ __global__ void __launch_bounds__(HT_THREADS, 1) hamming_tc_kernel(const uint4* 
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&s_tmemBase)), "r"(HT_TMEM_COLS) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
-    __syncthreads();   // the table is complete
     if (warp >= 1 && warp <= 4) {
         const int m = tid - 32;   // query row of the tile
         const int qi = q0 + m;
         uint4 a = make_uint4(0, 0, 0, 0), b = a;
         if (qi < nq) { a = __ldg(&q[2 * qi]); b = __ldg(&q[2 * qi + 1]); }
-        ht_expand_row(lut, a, b, sA + (m >> 3) * 128 + (m & 7) * 16, (HT_M / 8) * 128);
+        ht_expand_row(a, b, sA + (m >> 3) * 128 + (m & 7) * 16, (HT_M / 8) * 128, 0x01010101u);
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> visible to the tensor core's reads
     }
     ht_fence_before();
@@ -185,79 +185,91 @@ __global__ void __launch_bounds__(HT_THREADS, 1) hamming_tc_kernel(const uint4* 
             }
             __syncwarp();
         }
-    } else if (warp <= 4) {
-        // ================================================================= producers
-        const int p = tid - 32;   // rows p and p + 128 of every tile
-        uint4 r[4];
+    } else if (warp <= 8) {
+        // ================================================================= producers: thread <-> row p of every tile
+        const int p = tid - 32;
+        uint4 r0, r1;
         auto load = [&](int t) {
-            const long long base = j0 + (long long)t * HT_N;
-#pragma unroll
-            for (int h = 0; h < 2; h++) {
-                const long long row = base + p + 128 * h;
-                if (row < j1) { r[2 * h] = __ldg(&db[2 * row]); r[2 * h + 1] = __ldg(&db[2 * row + 1]); }
-                else { r[2 * h] = make_uint4(0, 0, 0, 0); r[2 * h + 1] = r[2 * h]; }
-            }
+            const long long row = j0 + (long long)t * HT_N + p;
+            if (row < j1) { r0 = __ldg(&db[2 * row]); r1 = __ldg(&db[2 * row + 1]); }
+            else { r0 = make_uint4(0, 0, 0, 0); r1 = r0; }
         };
         if (ntiles > 0) load(0);
         for (int t = 0; t < ntiles; t++) {
             const int s = t & 1;
             const unsigned ph = (unsigned)(t >> 1) & 1u;
-            const uint4 c0 = r[0], c1 = r[1], c2 = r[2], c3 = r[3];
-            if (t + 1 < ntiles) load(t + 1);   // next tile's rows are in flight while this one is expanded
+            const uint4 c0 = r0, c1 = r1;
+            if (t + 1 < ntiles) load(t + 1);   // the next tile's row is in flight while this one is expanded
             ht_wait(emptyB + 8 * s, ph ^ 1u);
-            unsigned char* stage = sB + (size_t)s * HT_B_BYTES;
-            ht_expand_row(lut, c0, c1, stage + (p >> 3) * 128 + (p & 7) * 16, (HT_N / 8) * 128);
-            ht_expand_row(lut, c2, c3, stage + ((p + 128) >> 3) * 128 + (p & 7) * 16, (HT_N / 8) * 128);
+            ht_expand_row(c0, c1, sB + (size_t)s * HT_B_BYTES + (p >> 3) * 128 + (p & 7) * 16, (HT_N / 8) * 128, 0u);
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
             ht_arrive(fullB + 8 * s);
         }
     } else {
         // ================================================================= epilogue: thread <-> query 32 * (warp & 3) + lane
         const int quarter = warp & 3;                 // the TMEM lanes this warp may read
-        const int half = (warp - 5) >> 2;             // columns [128 * half, 128 * half + 128) of every tile
+        const int half = (warp - 9) >> 2;             // columns [128 * half, 128 * half + 128) of every tile
         const unsigned laneAddr = tmemBase + ((unsigned)(quarter * 32) << 16);
+        const int qmine = q0 + quarter * 32 + lane;
+        int pq = 0;                                   // popc of this thread's query
+        if (qmine < nq) {
+            const uint4 a = __ldg(&q[2 * qmine]), b = __ldg(&q[2 * qmine + 1]);
+            pq = __popc(a.x) + __popc(a.y) + __popc(a.z) + __popc(a.w) + __popc(b.x) + __popc(b.y) + __popc(b.z) + __popc(b.w);
+        }
         uint32_t k1 = 0xFFFFFFFFu, k2 = 0xFFFFFFFFu;
-        int thrDot = -100000;                         // dot > thrDot  <=>  the row enters the best two
+        int thrDot = -100000;                         // dot > thrDot  <=>  dist < second-best distance  <=>  the row enters the best two
+        auto examine = [&](const int* v, int t, int col0, int cnt) {
+            if (col0 >= cnt) return;                  // warp-uniform
+            bool slow = col0 + 32 > cnt;              // the chunk's last tile may be partial: columns >= cnt are not rows
+            if (!slow) {
+                int m = v[0];
+#pragma unroll
+                for (int i = 1; i < 32; i++) m = max(m, v[i]);
+                slow = m > thrDot;
+            }
+            if (slow) {
+                const uint32_t local0 = (uint32_t)(t * HT_N + col0);
+#pragma unroll
+                for (int i = 0; i < 32; i++) {
+                    if (col0 + i < cnt) {
+                        const uint32_t dist = (uint32_t)(pq - v[i]);
+                        const uint32_t key = (dist << 22) | (local0 + (uint32_t)i);
+                        const uint32_t hi = max(k1, key);
+                        k1 = min(k1, key);
+                        k2 = min(k2, hi);
+                    }
+                }
+                thrDot = (k2 == 0xFFFFFFFFu) ? -100000 : pq - (int)(k2 >> 22);
+            }
+        };
         for (int t = 0; t < ntiles; t++) {
             const int s = t & 1;
             const unsigned ph = (unsigned)(t >> 1) & 1u;
             const long long left = rows - (long long)t * HT_N;
             const int cnt = left < HT_N ? (int)left : HT_N;
+            const unsigned colAddr = laneAddr + (unsigned)(s * HT_N + half * 128);
+            const int col0 = half * 128;
+            int va[32], vb[32];
             ht_wait(tmemFull + 8 * s, ph);
             ht_fence_after();
-#pragma unroll 1
-            for (int c = 0; c < 4; c++) {
-                const int col0 = half * 128 + c * 32;
-                int v[32];
-                __syncwarp();
-                ht_tmem_ld32(laneAddr + (unsigned)(s * HT_N + col0), v);
-                ht_tmem_wait_ld();
-                if (col0 >= cnt) continue;            // warp-uniform
-                bool slow = col0 + 32 > cnt;          // the chunk's last tile may be partial: columns >= cnt are not rows
-                if (!slow) {
-                    int m = v[0];
-#pragma unroll
-                    for (int i = 1; i < 32; i++) m = max(m, v[i]);
-                    slow = m > thrDot;
-                }
-                if (slow) {
-                    const uint32_t local0 = (uint32_t)(t * HT_N + col0);
-#pragma unroll
-                    for (int i = 0; i < 32; i++) {
-                        if (col0 + i < cnt) {
-                            const uint32_t dist = (uint32_t)(256 - v[i]) >> 1;
-                            const uint32_t key = (dist << 22) | (local0 + (uint32_t)i);
-                            const uint32_t hi = max(k1, key);
-                            k1 = min(k1, key);
-                            k2 = min(k2, hi);
-                        }
-                    }
-                    thrDot = (k2 == 0xFFFFFFFFu) ? -100000 : 256 - 2 * (int)(k2 >> 22);
-                }
-            }
-            ht_fence_before();
             __syncwarp();
-            if (lane == 0) ht_arrive(tmemEmpty + 8 * s);
+            ht_tmem_ld32(colAddr, va);
+            ht_tmem_wait_ld();
+            ht_tmem_ld32(colAddr + 32, vb);
+            examine(va, t, col0, cnt);
+            __syncwarp();
+            ht_tmem_wait_ld();
+            ht_tmem_ld32(colAddr + 64, va);
+            examine(vb, t, col0 + 32, cnt);
+            __syncwarp();
+            ht_tmem_wait_ld();
+            ht_tmem_ld32(colAddr + 96, vb);
+            examine(va, t, col0 + 64, cnt);
+            __syncwarp();
+            ht_tmem_wait_ld();
+            ht_fence_before();
+            if (lane == 0) ht_arrive(tmemEmpty + 8 * s);   // every column of this warp's half is in registers: the accumulator may be overwritten
+            examine(vb, t, col0 + 96, cnt);
         }
         const int qi = q0 + quarter * 32 + lane;
         if (qi < nq) {
