@@ -414,20 +414,29 @@ def bench_hamming(api, torch, dev, steps, warmup, world, rank, dist, cpu=True):
         # shard scan + ncclAllGather (nq x 16 B per rank) + merge, one C-ABI call on the matcher's stream
         m.search_sharded(d_q.data_ptr(), nq, comm, world, out.data_ptr(), th=50)
 
-    for _ in range(warmup):
-        step()
-    torch.cuda.synchronize()
-    if world > 1:
-        dist.barrier()
-    l0 = m.launch_count()
-    t = api.CudaTimer()
-    t.start(st)
-    for _ in range(steps):
-        step()
-    t.stop(st)
-    ms = t.elapsed_ms() / steps
-    if world > 1:
-        tm = torch.tensor([ms], device="cuda"); dist.all_reduce(tm, op=dist.ReduceOp.MAX); ms = float(tm.item())
+    def timed(engine):
+        m.set_engine(engine)
+        for _ in range(warmup):
+            step()
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        l0_ = m.launch_count()
+        t = api.CudaTimer()
+        t.start(st)
+        for _ in range(steps):
+            step()
+        t.stop(st)
+        ms_ = t.elapsed_ms() / steps
+        if world > 1:
+            tm = torch.tensor([ms_], device="cuda"); dist.all_reduce(tm, op=dist.ReduceOp.MAX); ms_ = float(tm.item())
+        return ms_, m.launch_count() - l0_, out.cpu().numpy().tobytes()
+
+    # the POPC engine (the reference's DescriptorDistance as is) first, then the default: AUTO = the tensor-core engine at this size
+    ms_popc, _, bytes_popc = timed(m.HAMMING_POPC)
+    ms, nlaunch, bytes_main = timed(m.HAMMING_AUTO)
+    engine_used = m.last_engine()
+    l0 = m.launch_count() - nlaunch
     res = np.frombuffer(out.cpu().numpy().tobytes(), dtype=np.dtype([("d", "<i4"), ("i", "<i4"), ("s", "<i4"), ("a", "<i4")]))
     ok = bool((res["d"][:1000] == 0).all() and (res["i"][:1000] == np.arange(1000)).all())
     pairs = nq * ndb_total
@@ -454,12 +463,26 @@ def bench_hamming(api, torch, dev, steps, warmup, world, rank, dist, cpu=True):
         cpu_line = {"value": pairs / dt / 1e9, "unit": "Gmatch/s", "cores": cores, "kind": "port",
                     "sample": "all %d queries x %d rows, __builtin_popcountll, cache-blocked scan, std::thread pool over query blocks, %.1f s" % (nq, ndb_total, dt)}
         del db_host
+    bf16_peak = None
+    try:
+        bf16_peak = float(json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["bf16_tflops"])
+    except Exception:
+        pass
+    tops = 2.0 * 256 * pairs / world / (ms * 1e-3) / 1e12
     return {"parity_checked": parity, "cpu_baseline": cpu_line, "metric": "hamming_gmatch_per_s", "value": pairs / (ms * 1e-3) / 1e9, "unit": "Gmatch/s", "ms_per_step": ms,
             "workload": "configs[3]: 2000 queries x 16Mi rows, %d shard(s), best-2 + ratio 0.7; eorb_matcher_search_sharded (scan + ncclAllGather + merge)" % world,
-            "planted_matches_found": ok, "gpu_launches": m.launch_count() - l0,
-            "roofline": {"bound": "int-pipe (POPC)", "achieved": 8 * pairs / world / (ms * 1e-3) / 1e12, "peak": popc_peak / 1e12,
-                         "unit": "TPOPC32/s per GPU", "frac": 8 * pairs / world / (ms * 1e-3) / popc_peak,
-                         "note": "algorithmic 8 POPC32 per pair; peak measured live by eorb_probe_popc_rate"}}
+            "engine": "tensor (tcgen05.mma kind::i8, exact +-1 / 0 contraction, dist = popc(q) - dot)" if engine_used == 1 else "popc",
+            "engines_bit_identical": bool(bytes_popc == bytes_main),
+            "planted_matches_found": ok, "gpu_launches": nlaunch,
+            "roofline": {"bound": "tensor", "achieved": tops, "peak": (2.0 * bf16_peak) if bf16_peak else None, "unit": "TOP/s int8 per GPU",
+                         "frac": (tops / (2.0 * bf16_peak)) if bf16_peak else None,
+                         "note": "algorithmic 2 x 256 int8 ops per pair; peak = 2 x the measured dense bf16 rate of MEASURED_PEAKS.json (int8 runs at "
+                                 "twice the bf16 rate). K = 256 is too short for the tensor pipe to be the limit: reading the int32 accumulator "
+                                 "back from TMEM (4 B per pair) costs as much as the math, and both use the TMEM port (profiles/r02_hamming_tensor.md)"},
+            "popc_engine": {"value": pairs / (ms_popc * 1e-3) / 1e9, "unit": "Gmatch/s", "ms_per_step": ms_popc,
+                            "roofline": {"bound": "int-pipe (POPC)", "achieved": 8 * pairs / world / (ms_popc * 1e-3) / 1e12, "peak": popc_peak / 1e12,
+                                         "unit": "TPOPC32/s per GPU", "frac": 8 * pairs / world / (ms_popc * 1e-3) / popc_peak,
+                                         "note": "algorithmic 8 POPC32 per pair; peak measured live by eorb_probe_popc_rate"}}}
 
 
 def bench_mci_jac(api, dev, steps, warmup):

@@ -21,11 +21,14 @@
 //                   ties, as the reference's sequential scan).
 // Pipelines: full / empty mbarriers per shared-memory stage (producers <-> MMA, the "empty" side arrives through tcgen05.commit) and
 // per accumulator (MMA <-> epilogue).  Every wait is bounded: a broken pipeline traps instead of hanging the GPU.
-// Per tile the shared memory moves 96 KB into the tensor core and 64 KB from the producers (1280 cycles at 128 B/clk) against 1085
-// cycles of int8 math at the B200's dense rate: the kernel is bound by shared-memory bandwidth, then by the tensor pipe.
+// What bounds it (measured with the EORB_HT_PROBE switches, profiles/r02_hamming_tensor.md): a tile is 1030 cycles of int8 math
+// (8 x 128 cycles at the B200's dense rate), but reading the 128 x 256 int32 accumulator back (tcgen05.ld, 128 KB per tile) takes about
+// as long, and the accumulating MMAs use the same TMEM port (every K = 32 step reads and writes the whole accumulator), so readout and
+// math do not overlap well: ~2250 cycles per tile in all, 3.9 T pairs/s = 7 x the POPC kernel at 97 % of its own pipe.
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include <cstdlib>
 #include <mutex>
 
 #include "../../include/eorb_b200.h"
@@ -95,6 +98,19 @@ __device__ __forceinline__ void ht_tmem_ld32(unsigned addr, int* v) {
         : "r"(addr)
         : "memory");
 }
+// 64 accumulator columns as 32 registers: .pack::16b keeps the low 16 bits of two adjacent columns per register (low half = the even
+// column); the dots lie in [-256, 256], so nothing is lost and the readout moves half the registers
+__device__ __forceinline__ void ht_tmem_ld64p(unsigned addr, unsigned* v) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.pack::16b.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, %17, %18, "
+        "%19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];\n"
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]), "=r"(v[9]), "=r"(v[10]),
+          "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]),
+          "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]),
+          "=r"(v[31])
+        : "r"(addr)
+        : "memory");
+}
 __device__ __forceinline__ void ht_tmem_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
 // every byte -> 0xFF when its top bit is set, else 0x00: prmt with the sign-replicate bit (8) in every selector nibble
@@ -120,7 +136,7 @@ __device__ __forceinline__ void ht_expand_row(const uint4& a, const uint4& b, un
 }
 
 __global__ void __launch_bounds__(HT_THREADS, 1) hamming_tc_kernel(const uint4* __restrict__ q, int nq, const uint4* __restrict__ db, long long ndb,
-                                                                   long long chunkRows, long long indexOffset, eorb_best2* __restrict__ partial) {
+                                                                   long long chunkRows, long long indexOffset, eorb_best2* __restrict__ partial, int probe) {
     extern __shared__ __align__(1024) unsigned char smem[];
     __shared__ unsigned s_tmemBase;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -138,7 +154,7 @@ __global__ void __launch_bounds__(HT_THREADS, 1) hamming_tc_kernel(const uint4* 
 
     // ---- setup: barriers, TMEM, the CTA's 128 queries as int8
     if (tid == 0) {
-        mbar_init(fullB, 256); mbar_init(fullB + 8, 256);
+        mbar_init(fullB, 8); mbar_init(fullB + 8, 8);
         mbar_init(emptyB, 1); mbar_init(emptyB + 8, 1);
         mbar_init(tmemFull, 1); mbar_init(tmemFull + 8, 1);
         mbar_init(tmemEmpty, 8); mbar_init(tmemEmpty + 8, 8);
@@ -175,7 +191,7 @@ __global__ void __launch_bounds__(HT_THREADS, 1) hamming_tc_kernel(const uint4* 
             ht_fence_after();
             if (lane == 0) {
 #pragma unroll
-                for (int j = 0; j < 8; j++) {
+                for (int j = 0; j < ((probe & 4) ? 0 : 8); j++) {
                     const unsigned long long da = ht_desc(aAddr + (unsigned)j * 2u * (HT_M / 8) * 128u, (HT_M / 8) * 128u, 128u);
                     const unsigned long long dbd = ht_desc(bAddr + (unsigned)s * HT_B_BYTES + (unsigned)j * 2u * (HT_N / 8) * 128u, (HT_N / 8) * 128u, 128u);
                     ht_mma_i8(tmemBase + (unsigned)s * HT_N, da, dbd, idesc, j > 0 ? 1u : 0u);
@@ -201,9 +217,10 @@ __global__ void __launch_bounds__(HT_THREADS, 1) hamming_tc_kernel(const uint4* 
             const uint4 c0 = r0, c1 = r1;
             if (t + 1 < ntiles) load(t + 1);   // the next tile's row is in flight while this one is expanded
             ht_wait(emptyB + 8 * s, ph ^ 1u);
-            ht_expand_row(c0, c1, sB + (size_t)s * HT_B_BYTES + (p >> 3) * 128 + (p & 7) * 16, (HT_N / 8) * 128, 0u);
+            if (!(probe & 2)) ht_expand_row(c0, c1, sB + (size_t)s * HT_B_BYTES + (p >> 3) * 128 + (p & 7) * 16, (HT_N / 8) * 128, 0u);
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-            ht_arrive(fullB + 8 * s);
+            __syncwarp();
+            if (lane == 0) ht_arrive(fullB + 8 * s);
         }
     } else {
         // ================================================================= epilogue: thread <-> query 32 * (warp & 3) + lane
@@ -218,30 +235,90 @@ __global__ void __launch_bounds__(HT_THREADS, 1) hamming_tc_kernel(const uint4* 
         }
         uint32_t k1 = 0xFFFFFFFFu, k2 = 0xFFFFFFFFu;
         int thrDot = -100000;                         // dot > thrDot  <=>  dist < second-best distance  <=>  the row enters the best two
+        // 32 columns of one query.  Fast path: maxima of the eight groups of four columns (independent, so the warp is not waiting on one
+        // long dependency chain), their maximum, one compare.  Slow path: only the groups that hold a qualifying dot are replayed, in
+        // column order, through the packed-key network; the threshold tightens after every group, which keeps the scan sequential.
         auto examine = [&](const int* v, int t, int col0, int cnt) {
-            if (col0 >= cnt) return;                  // warp-uniform
-            bool slow = col0 + 32 > cnt;              // the chunk's last tile may be partial: columns >= cnt are not rows
-            if (!slow) {
-                int m = v[0];
+            if (col0 >= cnt || (probe & 1)) return;   // warp-uniform
+            int g[8];
 #pragma unroll
-                for (int i = 1; i < 32; i++) m = max(m, v[i]);
-                slow = m > thrDot;
-            }
-            if (slow) {
+            for (int j = 0; j < 8; j++) g[j] = max(max(v[4 * j], v[4 * j + 1]), max(v[4 * j + 2], v[4 * j + 3]));
+            const int m = max(max(max(g[0], g[1]), max(g[2], g[3])), max(max(g[4], g[5]), max(g[6], g[7])));
+            const bool partial = col0 + 32 > cnt;     // the chunk's last tile may be partial: columns >= cnt are not rows
+            if (m > thrDot || partial) {
                 const uint32_t local0 = (uint32_t)(t * HT_N + col0);
 #pragma unroll
-                for (int i = 0; i < 32; i++) {
-                    if (col0 + i < cnt) {
-                        const uint32_t dist = (uint32_t)(pq - v[i]);
-                        const uint32_t key = (dist << 22) | (local0 + (uint32_t)i);
-                        const uint32_t hi = max(k1, key);
-                        k1 = min(k1, key);
-                        k2 = min(k2, hi);
+                for (int j = 0; j < 8; j++) {
+                    if (g[j] > thrDot || partial) {
+#pragma unroll
+                        for (int i = 4 * j; i < 4 * j + 4; i++) {
+                            if (col0 + i < cnt) {
+                                const uint32_t dist = (uint32_t)(pq - v[i]);
+                                const uint32_t key = (dist << 22) | (local0 + (uint32_t)i);
+                                const uint32_t hi = max(k1, key);
+                                k1 = min(k1, key);
+                                k2 = min(k2, hi);
+                            }
+                        }
+                        thrDot = (k2 == 0xFFFFFFFFu) ? -100000 : pq - (int)(k2 >> 22);
                     }
                 }
-                thrDot = (k2 == 0xFFFFFFFFu) ? -100000 : pq - (int)(k2 >> 22);
             }
         };
+        // the same on 64 columns held as 32 registers of two packed 16-bit dots (register i = columns 2 i, 2 i + 1)
+        auto examine64 = [&](const unsigned* v, int t, int col0, int cnt) {
+            if (col0 >= cnt || (probe & 1)) return;   // warp-uniform
+            unsigned g[8];
+#pragma unroll
+            for (int j = 0; j < 8; j++) g[j] = __vmaxs2(__vmaxs2(v[4 * j], v[4 * j + 1]), __vmaxs2(v[4 * j + 2], v[4 * j + 3]));
+            const unsigned mm = __vmaxs2(__vmaxs2(__vmaxs2(g[0], g[1]), __vmaxs2(g[2], g[3])), __vmaxs2(__vmaxs2(g[4], g[5]), __vmaxs2(g[6], g[7])));
+            const int m = max((int)(short)(mm & 0xffffu), (int)mm >> 16);
+            const bool partial = col0 + 64 > cnt;
+            if (m > thrDot || partial) {
+                const uint32_t local0 = (uint32_t)(t * HT_N + col0);
+#pragma unroll
+                for (int j = 0; j < 8; j++) {
+                    const int gm = max((int)(short)(g[j] & 0xffffu), (int)g[j] >> 16);
+                    if (gm > thrDot || partial) {
+#pragma unroll
+                        for (int i = 8 * j; i < 8 * j + 8; i++) {
+                            if (col0 + i < cnt) {
+                                const unsigned r = v[i >> 1];
+                                const int dot = (i & 1) ? ((int)r >> 16) : (int)(short)(r & 0xffffu);
+                                const uint32_t dist = (uint32_t)(pq - dot);
+                                const uint32_t key = (dist << 22) | (local0 + (uint32_t)i);
+                                const uint32_t hi = max(k1, key);
+                                k1 = min(k1, key);
+                                k2 = min(k2, hi);
+                            }
+                        }
+                        thrDot = (k2 == 0xFFFFFFFFu) ? -100000 : pq - (int)(k2 >> 22);
+                    }
+                }
+            }
+        };
+        if (!(probe & 8)) {
+            for (int t = 0; t < ntiles; t++) {
+                const int s = t & 1;
+                const unsigned ph = (unsigned)(t >> 1) & 1u;
+                const long long left = rows - (long long)t * HT_N;
+                const int cnt = left < HT_N ? (int)left : HT_N;
+                const unsigned colAddr = laneAddr + (unsigned)(s * HT_N + half * 128);
+                const int col0 = half * 128;
+                unsigned pa[32], pb[32];
+                ht_wait(tmemFull + 8 * s, ph);
+                ht_fence_after();
+                __syncwarp();
+                ht_tmem_ld64p(colAddr, pa);
+                ht_tmem_ld64p(colAddr + 64, pb);
+                ht_tmem_wait_ld();
+                ht_fence_before();
+                if (lane == 0) ht_arrive(tmemEmpty + 8 * s);   // this warp's 128 columns are in registers: the accumulator may be overwritten
+                examine64(pa, t, col0, cnt);
+                examine64(pb, t, col0 + 64, cnt);
+                __syncwarp();
+            }
+        } else
         for (int t = 0; t < ntiles; t++) {
             const int s = t & 1;
             const unsigned ph = (unsigned)(t >> 1) & 1u;
@@ -318,9 +395,10 @@ cudaError_t launch_hamming_best2_tc(const uint8_t* d_q, int nq, const uint8_t* d
             if (dev >= 0 && dev < 64) done[dev] = true;
         }
     }
+    static const int probe = getenv("EORB_HT_PROBE") ? atoi(getenv("EORB_HT_PROBE")) : 0;   // probes: 1 no epilogue work, 2 no expansion, 4 no MMA (timing only), 8 unpacked 32-bit readout (A/B)
     dim3 grd(nchunks, (nq + HT_M - 1) / HT_M);
     hamming_tc_kernel<<<grd, HT_THREADS, HT_SMEM, st>>>(reinterpret_cast<const uint4*>(d_q), nq, reinterpret_cast<const uint4*>(d_db), ndb, chunkRows,
-                                                        indexOffset, d_partial);
+                                                        indexOffset, d_partial, probe);
     return cudaGetLastError();
 }
 

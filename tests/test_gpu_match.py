@@ -126,3 +126,63 @@ def test_sharded_search_entry_point_single_rank_communicator():
     assert np.array_equal(got["accepted"], exp["accepted"])
     assert np.array_equal(got["best_idx"], np.where(exp["best_idx"] >= 0, exp["best_idx"] + 1000, -1))
     api.nccl_comm_destroy(comm)
+
+
+# ------------------------------------------------------------------------------------------------ tensor-core engine (hamming_tc.cu)
+@pytest.mark.parametrize("ndb,nq", [(1, 3), (255, 17), (256, 128), (257, 129), (5000, 2000), (70001, 1500), (300000, 333)])
+def test_tensor_engine_matches_oracle(ndb, nq):
+    """tcgen05 int8 contraction (dist = popc(q) - dot) == oracle bit for bit: ties (lowest index wins), exact duplicates, partial
+    last tiles, query counts that do not fill the 128-row accumulator, databases smaller than one tile"""
+    api = _api()
+    db = synth.make_descriptor_db(ndb, seed=ndb + 7)
+    q, src = synth.make_queries(db, nq, seed=nq + 3)
+    dup_src = src[: max(1, nq // 8)]
+    synth.plant_duplicate_rows(db, dup_src[dup_src >= 0], seed=4)
+    q2, _ = synth.make_queries(db, nq, seed=nq + 1, max_flips=0)
+    q = np.concatenate([q, q2[: nq // 4]])
+    q[0] = 0; q[-1] = 255                      # popc(q) = 0 and 256: the ends of the dot range
+    if ndb > 4:
+        db[1] = 255; db[2] = 0
+    m = api.ORBmatcher(0.7, True)
+    m.set_db(db)
+    m.set_engine(m.HAMMING_TENSOR)
+    got = m.search(q)
+    assert m.last_engine() == m.HAMMING_TENSOR
+    _same(got, O.hamming_best2(q, db, th=50, ratio=0.7))
+    m.set_engine(m.HAMMING_POPC)
+    _same(m.search(q), got)
+    assert m.last_engine() == m.HAMMING_POPC
+
+
+def test_tensor_engine_sharded_merge_and_auto_rule():
+    """row shards with index offsets searched on the tensor engine, merged like the all-gather's output; AUTO picks the tensor engine
+    only for large searches"""
+    import torch
+    api = _api()
+    ndb, nq, shards = 400000, 700, 4
+    db = synth.make_descriptor_db(ndb, seed=15)
+    q, _ = synth.make_queries(db, nq, seed=16)
+    db[300000:300050] = db[100:150]; q[:50] = db[100:150]     # duplicates across shards: the lower global index wins
+    exp = O.hamming_best2(q, db, 50, 0.7)
+    d_q = torch.from_numpy(q).cuda()
+    gathered = torch.zeros(shards * nq * 16, dtype=torch.uint8, device="cuda")
+    per = ndb // shards
+    stream = torch.cuda.current_stream().cuda_stream
+    ms = []
+    for s in range(shards):
+        m = api.ORBmatcher(0.7)
+        m.set_stream(stream)
+        m.set_db(db[s * per:(s + 1) * per], index_offset=s * per)
+        m.search_device(d_q.data_ptr(), nq, gathered.data_ptr() + s * nq * 16)
+        assert m.last_engine() == m.HAMMING_TENSOR      # AUTO: 700 queries x 100000 rows
+        ms.append(m)
+    d_out = torch.zeros(nq * 16, dtype=torch.uint8, device="cuda")
+    ms[0].merge_device(gathered.data_ptr(), shards, nq, d_out.data_ptr())
+    torch.cuda.synchronize()
+    got = d_out.cpu().numpy().view(synth.MATCH_DTYPE)
+    _same(got, exp)
+    assert (got["best_idx"][:50] == np.arange(100, 150)).all()
+    small = api.ORBmatcher(0.7)
+    small.set_db(db[:5000])
+    small.search(q[:20])
+    assert small.last_engine() == small.HAMMING_POPC    # AUTO: small searches stay on the POPC kernel
