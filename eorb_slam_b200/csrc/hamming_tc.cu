@@ -365,15 +365,21 @@ __global__ void __launch_bounds__(HT_THREADS, 1) hamming_tc_kernel(const uint4* 
     }
 }
 
-// chunks of the tensor-core search: multiples of 256 rows, <= 2^22 rows (22-bit local index), about two waves of CTAs
+// chunks of the tensor-core search: multiples of 256 rows, <= 2^22 rows (22-bit local index), and a CTA count (query tiles x chunks) that
+// fills whole waves of one CTA per SM: with 16 query tiles, 19 chunks are 304 CTAs on 148 SMs, i.e. a third wave of 8 CTAs that costs as
+// much as a full one (measured: 2.09 ms against 1.45 ms with 9 chunks = 144 CTAs in one wave)
 int hamming_tc_chunks(long long ndb, int nq, int sms, long long* chunkRows) {
     const int qtiles = (nq + HT_M - 1) / HT_M;
-    long long want = ((long long)sms * 2 + qtiles - 1) / qtiles;
-    if (want < 1) want = 1;
-    long long rows = (ndb + want - 1) / want;
-    if (rows < HT_N) rows = HT_N;
-    rows = (rows + HT_N - 1) / HT_N * HT_N;
-    if (rows > (1ll << 22)) rows = 1ll << 22;
+    long long rows = HT_N;
+    for (int waves = 1; waves <= 4096; waves++) {
+        long long want = (long long)sms * waves / qtiles;
+        if (want < 1) want = 1;
+        rows = (ndb + want - 1) / want;
+        if (rows < HT_N) rows = HT_N;
+        rows = (rows + HT_N - 1) / HT_N * HT_N;
+        if (rows <= (1ll << 22)) break;
+        rows = 1ll << 22;
+    }
     *chunkRows = rows;
     return (int)((ndb + rows - 1) / rows);
 }
