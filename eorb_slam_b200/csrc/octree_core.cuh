@@ -114,21 +114,41 @@ OCT_DEV int oct_exclusive_scan(int* a, int n, int* scratch) {
     const int b = tid * per, e = (b + per < n) ? b + per : n;
     int sum = 0;
     for (int i = b; i < e; i++) sum += a[i];
-    scratch[tid] = sum;
-    OCT_SYNC();
 #ifdef EORB_HOST_MODEL
-    int total = scratch[0];
+    int total = sum;
     int off = 0;
 #else
-    // Hillis-Steele over nt partials
-    for (int d = 1; d < nt; d <<= 1) {
-        int v = (tid >= d) ? scratch[tid - d] : 0;
+    int total, off;
+    if (nt > 128) {
+        // big blocks (the single-frame call: one 512-thread block per level, where the barriers ARE the latency): warp-shuffle scan of
+        // the per-thread sums and a serial pass over the <= 16 warp totals, two barriers instead of 2 * log2(nt).  (With the 128-thread
+        // blocks of a launch set the same change was measured slower, 0.48 -> 0.53 us/frame, so those keep the Hillis-Steele form.)
+        const int lane = tid & 31, wp = tid >> 5, nw = nt >> 5;
+        int incl = sum;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const int v = __shfl_up_sync(0xffffffffu, incl, d);
+            if (lane >= d) incl += v;
+        }
+        if (lane == 31) scratch[wp] = incl;
         OCT_SYNC();
-        scratch[tid] += v;
+        int before = 0;
+        total = 0;
+        for (int j = 0; j < nw; j++) { const int t = scratch[j]; total += t; if (j < wp) before += t; }
+        off = before + incl - sum;
+    } else {
+        // Hillis-Steele over nt partials
+        scratch[tid] = sum;
         OCT_SYNC();
+        for (int d = 1; d < nt; d <<= 1) {
+            int v = (tid >= d) ? scratch[tid - d] : 0;
+            OCT_SYNC();
+            scratch[tid] += v;
+            OCT_SYNC();
+        }
+        total = scratch[nt - 1];
+        off = scratch[tid] - sum;
     }
-    int total = scratch[nt - 1];
-    int off = scratch[tid] - sum;
 #endif
     for (int i = b; i < e; i++) { int v = a[i]; a[i] = off; off += v; }
     OCT_SYNC();
