@@ -58,7 +58,7 @@ __device__ __forceinline__ void ht_wait(unsigned bar, unsigned parity) {
             : "=r"(done)
             : "r"(bar), "r"(parity)
             : "memory");
-        if (!done && spin > (1u << 24)) __trap();   // a broken pipeline must not hang the device
+        if (!done && spin > (1u << 28)) __trap();   // a broken pipeline must not hang the device (seconds; legitimate waits are microseconds)
     }
 }
 __device__ __forceinline__ void ht_arrive(unsigned bar) {
@@ -365,238 +365,12 @@ __global__ void __launch_bounds__(HT_THREADS, 1) hamming_tc_kernel(const uint4* 
     }
 }
 
-// =====================================================================================================================================
-// Variant 2 (the default): the queries live in TENSOR MEMORY (A operand of tcgen05.mma from TMEM: 128 lanes x 64 columns, four int8 per
-// column in K order), tiles of 192 database rows (two accumulators of 192 columns + 64 columns of A = 448 of the 512 TMEM columns).
-// Variant 1 above is bound by shared-memory bandwidth: per 256-row tile the tensor core reads 32 KB of A and 64 KB of B and the
-// producers write 64 KB, 1280 cycles at 128 B/clk against 1030 cycles of math.  Without the A reads a 192-row tile moves 96 KB
-// (768 cycles) for 768 cycles of math and 750 cycles of accumulator readout.
-#define HT2_N 192
-#define HT2_THREADS 480                    // warp 0: MMA; warps 1-6: producers (one row each); warps 7-14: epilogue
-#define HT2_B_BYTES (HT2_N * 256)
-#define HT2_BAR_OFF (2 * HT2_B_BYTES)
-#define HT2_SMEM (HT2_BAR_OFF + 128)
-#define HT2_A_COL 384
-
-__device__ __forceinline__ void ht_mma_i8_ts(unsigned tmemD, unsigned tmemA, unsigned long long descB, unsigned idesc, unsigned accumulate) {
-    const unsigned z = 0;
-    asm volatile(
-        "{\n"
-        ".reg .pred p;\n"
-        "setp.ne.b32 p, %4, 0;\n"
-        "tcgen05.mma.cta_group::1.kind::i8 [%0], [%1], %2, %3, {%5, %6, %7, %8}, p;\n"
-        "}\n" ::"r"(tmemD),
-        "r"(tmemA), "l"(descB), "r"(idesc), "r"(accumulate), "r"(z), "r"(z), "r"(z), "r"(z)
-        : "memory");
-}
-// 32 accumulator columns as 16 registers of two packed 16-bit dots
-__device__ __forceinline__ void ht_tmem_ld32p(unsigned addr, unsigned* v) {
-    asm volatile(
-        "tcgen05.ld.sync.aligned.32x32b.x16.pack::16b.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];\n"
-        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]), "=r"(v[9]), "=r"(v[10]),
-          "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
-        : "r"(addr)
-        : "memory");
-}
-// 64 TMEM columns of this thread's lane from 64 registers
-__device__ __forceinline__ void ht_tmem_st64(unsigned addr, const unsigned* v) {
-    asm volatile(
-        "tcgen05.st.sync.aligned.32x32b.x64.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, %17, %18, %19, %20, "
-        "%21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32, %33, %34, %35, %36, %37, %38, %39, %40, %41, %42, %43, %44, %45, %46, %47, "
-        "%48, %49, %50, %51, %52, %53, %54, %55, %56, %57, %58, %59, %60, %61, %62, %63, %64};\n" ::"r"(addr),
-        "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]), "r"(v[8]), "r"(v[9]), "r"(v[10]), "r"(v[11]),
-        "r"(v[12]), "r"(v[13]), "r"(v[14]), "r"(v[15]), "r"(v[16]), "r"(v[17]), "r"(v[18]), "r"(v[19]), "r"(v[20]), "r"(v[21]), "r"(v[22]),
-        "r"(v[23]), "r"(v[24]), "r"(v[25]), "r"(v[26]), "r"(v[27]), "r"(v[28]), "r"(v[29]), "r"(v[30]), "r"(v[31]), "r"(v[32]), "r"(v[33]),
-        "r"(v[34]), "r"(v[35]), "r"(v[36]), "r"(v[37]), "r"(v[38]), "r"(v[39]), "r"(v[40]), "r"(v[41]), "r"(v[42]), "r"(v[43]), "r"(v[44]),
-        "r"(v[45]), "r"(v[46]), "r"(v[47]), "r"(v[48]), "r"(v[49]), "r"(v[50]), "r"(v[51]), "r"(v[52]), "r"(v[53]), "r"(v[54]), "r"(v[55]),
-        "r"(v[56]), "r"(v[57]), "r"(v[58]), "r"(v[59]), "r"(v[60]), "r"(v[61]), "r"(v[62]), "r"(v[63])
-        : "memory");
-}
-
-__global__ void __launch_bounds__(HT2_THREADS, 1) hamming_tc2_kernel(const uint4* __restrict__ q, int nq, const uint4* __restrict__ db, long long ndb,
-                                                                     long long chunkRows, long long indexOffset, eorb_best2* __restrict__ partial, int probe) {
-    extern __shared__ __align__(1024) unsigned char smem[];
-    __shared__ unsigned s_tmemBase;
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    unsigned char* sB = smem;
-    const unsigned barBase = smem_u32(smem + HT2_BAR_OFF);
-    const unsigned fullB = barBase, emptyB = barBase + 16, tmemFull = barBase + 32, tmemEmpty = barBase + 48;
-
-    const long long j0 = (long long)blockIdx.x * chunkRows;
-    const long long j1 = (j0 + chunkRows < ndb) ? j0 + chunkRows : ndb;
-    const long long rows = j1 > j0 ? j1 - j0 : 0;
-    const int ntiles = (int)((rows + HT2_N - 1) / HT2_N);
-    const int q0 = blockIdx.y * HT_M;
-
-    if (tid == 0) {
-        mbar_init(fullB, 6); mbar_init(fullB + 8, 6);
-        mbar_init(emptyB, 1); mbar_init(emptyB + 8, 1);
-        mbar_init(tmemFull, 1); mbar_init(tmemFull + 8, 1);
-        mbar_init(tmemEmpty, 8); mbar_init(tmemEmpty + 8, 8);
-        mbar_fence_init();
-    }
-    if (warp == 0) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&s_tmemBase)), "r"(HT_TMEM_COLS) : "memory");
-        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
-    }
-    ht_fence_before();
-    __syncthreads();
-    ht_fence_after();
-    const unsigned tmemBase = s_tmemBase;
-    const int quarter = warp & 3;
-    const int qmine = q0 + quarter * 32 + lane;
-    if (warp >= 7 && warp <= 10) {
-        // ---- the CTA's 128 queries into tensor memory: lane = query, column c = K elements 4c .. 4c+3 (the order ht_expand_row writes)
-        uint4 a = make_uint4(0, 0, 0, 0), b = a;
-        if (qmine < nq) { a = __ldg(&q[2 * qmine]); b = __ldg(&q[2 * qmine + 1]); }
-        const unsigned w[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
-        unsigned o[64];
-#pragma unroll
-        for (int c = 0; c < 64; c++) o[c] = ht_sign_bytes(w[c >> 3] << (c & 7)) | 0x01010101u;   // c = 4 kc + j, kc = 2 w + (k >> 2), k = 4 (kc & 1) + j
-        ht_tmem_st64(tmemBase + ((unsigned)(quarter * 32) << 16) + HT2_A_COL, o);
-        asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
-    }
-    ht_fence_before();
-    __syncthreads();
-    ht_fence_after();
-
-    if (warp == 0) {
-        const unsigned idesc = (2u << 4) | (1u << 7) | (1u << 10) | ((unsigned)(HT2_N >> 3) << 17) | ((unsigned)(HT_M >> 4) << 24);
-        const unsigned bAddr = smem_u32(sB);
-        for (int t = 0; t < ntiles; t++) {
-            const int s = t & 1;
-            const unsigned ph = (unsigned)(t >> 1) & 1u;
-            ht_wait(fullB + 8 * s, ph);
-            ht_wait(tmemEmpty + 8 * s, ph ^ 1u);
-            ht_fence_after();
-            if (lane == 0) {
-#pragma unroll
-                for (int j = 0; j < ((probe & 4) ? 0 : 8); j++) {
-                    const unsigned long long dbd = ht_desc(bAddr + (unsigned)s * HT2_B_BYTES + (unsigned)j * 2u * (HT2_N / 8) * 128u, (HT2_N / 8) * 128u, 128u);
-                    ht_mma_i8_ts(tmemBase + (unsigned)s * HT2_N, tmemBase + HT2_A_COL + 8u * (unsigned)j, dbd, idesc, j > 0 ? 1u : 0u);
-                }
-                ht_commit(emptyB + 8 * s);
-                ht_commit(tmemFull + 8 * s);
-            }
-            __syncwarp();
-        }
-    } else if (warp <= 6) {
-        const int p = tid - 32;
-        uint4 r0, r1;
-        auto load = [&](int t) {
-            const long long row = j0 + (long long)t * HT2_N + p;
-            if (row < j1) { r0 = __ldg(&db[2 * row]); r1 = __ldg(&db[2 * row + 1]); }
-            else { r0 = make_uint4(0, 0, 0, 0); r1 = r0; }
-        };
-        if (ntiles > 0) load(0);
-        for (int t = 0; t < ntiles; t++) {
-            const int s = t & 1;
-            const unsigned ph = (unsigned)(t >> 1) & 1u;
-            const uint4 c0 = r0, c1 = r1;
-            if (t + 1 < ntiles) load(t + 1);
-            ht_wait(emptyB + 8 * s, ph ^ 1u);
-            if (!(probe & 2)) ht_expand_row(c0, c1, sB + (size_t)s * HT2_B_BYTES + (p >> 3) * 128 + (p & 7) * 16, (HT2_N / 8) * 128, 0u);
-            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-            __syncwarp();
-            if (lane == 0) ht_arrive(fullB + 8 * s);
-        }
-    } else {
-        const int half = (warp - 7) >> 2;             // columns [96 * half, 96 * half + 96) of every tile
-        const unsigned laneAddr = tmemBase + ((unsigned)(quarter * 32) << 16);
-        int pq = 0;
-        if (qmine < nq) {
-            const uint4 a = __ldg(&q[2 * qmine]), b = __ldg(&q[2 * qmine + 1]);
-            pq = __popc(a.x) + __popc(a.y) + __popc(a.z) + __popc(a.w) + __popc(b.x) + __popc(b.y) + __popc(b.z) + __popc(b.w);
-        }
-        uint32_t k1 = 0xFFFFFFFFu, k2 = 0xFFFFFFFFu;
-        int thrDot = -100000;
-        // NR registers of two packed 16-bit dots = 2 NR columns (register i = columns 2 i, 2 i + 1); groups of four registers
-        auto examine = [&](const unsigned* v, const int NR, int t, int col0, int cnt) {
-            if (col0 >= cnt || (probe & 1)) return;   // warp-uniform
-            unsigned g[8];
-            unsigned mm = 0x80008000u;
-#pragma unroll
-            for (int j = 0; j < 8; j++) {
-                if (4 * j < NR) {
-                    g[j] = __vmaxs2(__vmaxs2(v[4 * j], v[4 * j + 1]), __vmaxs2(v[4 * j + 2], v[4 * j + 3]));
-                    mm = __vmaxs2(mm, g[j]);
-                }
-            }
-            const int m = max((int)(short)(mm & 0xffffu), (int)mm >> 16);
-            const bool partial = col0 + 2 * NR > cnt;
-            if (m > thrDot || partial) {
-                const uint32_t local0 = (uint32_t)(t * HT2_N + col0);
-#pragma unroll
-                for (int j = 0; j < 8; j++) {
-                    if (4 * j < NR) {
-                        const int gm = max((int)(short)(g[j] & 0xffffu), (int)g[j] >> 16);
-                        if (gm > thrDot || partial) {
-#pragma unroll
-                            for (int i = 8 * j; i < 8 * j + 8; i++) {
-                                if (col0 + i < cnt) {
-                                    const unsigned r = v[i >> 1];
-                                    const int dot = (i & 1) ? ((int)r >> 16) : (int)(short)(r & 0xffffu);
-                                    const uint32_t dist = (uint32_t)(pq - dot);
-                                    const uint32_t key = (dist << 22) | (local0 + (uint32_t)i);
-                                    const uint32_t hi = max(k1, key);
-                                    k1 = min(k1, key);
-                                    k2 = min(k2, hi);
-                                }
-                            }
-                            thrDot = (k2 == 0xFFFFFFFFu) ? -100000 : pq - (int)(k2 >> 22);
-                        }
-                    }
-                }
-            }
-        };
-        for (int t = 0; t < ntiles; t++) {
-            const int s = t & 1;
-            const unsigned ph = (unsigned)(t >> 1) & 1u;
-            const long long left = rows - (long long)t * HT2_N;
-            const int cnt = left < HT2_N ? (int)left : HT2_N;
-            const unsigned colAddr = laneAddr + (unsigned)(s * HT2_N + half * 96);
-            const int col0 = half * 96;
-            unsigned pa[32], pb[16];
-            ht_wait(tmemFull + 8 * s, ph);
-            ht_fence_after();
-            __syncwarp();
-            ht_tmem_ld64p(colAddr, pa);
-            ht_tmem_ld32p(colAddr + 64, pb);
-            ht_tmem_wait_ld();
-            ht_fence_before();
-            if (lane == 0) ht_arrive(tmemEmpty + 8 * s);
-            examine(pa, 32, t, col0, cnt);
-            examine(pb, 16, t, col0 + 64, cnt);
-            __syncwarp();
-        }
-        if (qmine < nq) {
-            eorb_best2 o;
-            const unsigned long long base = (unsigned long long)(indexOffset + j0);
-            o.key1 = (k1 == 0xFFFFFFFFu) ? ~0ull : (((unsigned long long)(k1 >> 22)) << 32) | (base + (k1 & 0x3FFFFFu));
-            o.key2 = (k2 == 0xFFFFFFFFu) ? ~0ull : (((unsigned long long)(k2 >> 22)) << 32) | (base + (k2 & 0x3FFFFFu));
-            partial[((size_t)blockIdx.x * 2 + half) * nq + qmine] = o;
-        }
-    }
-    ht_fence_before();
-    __syncthreads();
-    if (warp == 0) {
-        ht_fence_after();
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmemBase), "r"(HT_TMEM_COLS) : "memory");
-    }
-}
-
-static int ht_variant() {
-    static const int v = getenv("EORB_HT_VARIANT") ? atoi(getenv("EORB_HT_VARIANT")) : 2;   // 1: A in shared memory, 256-row tiles (for A/B)
-    return v == 1 ? 1 : 2;
-}
-static int ht_tile_rows() { return ht_variant() == 1 ? HT_N : HT2_N; }
-
 // chunks of the tensor-core search: multiples of 256 rows, <= 2^22 rows (22-bit local index), and a CTA count (query tiles x chunks) that
 // fills whole waves of one CTA per SM: with 16 query tiles, 19 chunks are 304 CTAs on 148 SMs, i.e. a third wave of 8 CTAs that costs as
 // much as a full one (measured: 2.09 ms against 1.45 ms with 9 chunks = 144 CTAs in one wave)
 int hamming_tc_chunks(long long ndb, int nq, int sms, long long* chunkRows) {
     const int qtiles = (nq + HT_M - 1) / HT_M;
-    const long long TN = ht_tile_rows();
+    const long long TN = HT_N;
     const long long maxRows = (1ll << 22) / TN * TN;
     long long rows = TN;
     for (int waves = 1; waves <= 4096; waves++) {
@@ -625,19 +399,14 @@ cudaError_t launch_hamming_best2_tc(const uint8_t* d_q, int nq, const uint8_t* d
         std::lock_guard<std::mutex> lk(mu);
         if (!(dev >= 0 && dev < 64 && done[dev])) {
             e = cudaFuncSetAttribute(hamming_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, HT_SMEM);
-            if (e == cudaSuccess) e = cudaFuncSetAttribute(hamming_tc2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, HT2_SMEM);
             if (e != cudaSuccess) return e;
             if (dev >= 0 && dev < 64) done[dev] = true;
         }
     }
-    static const int probe = getenv("EORB_HT_PROBE") ? atoi(getenv("EORB_HT_PROBE")) : 0;   // probes: 1 no epilogue work, 2 no expansion, 4 no MMA (timing only), 8 unpacked 32-bit readout (variant 1, A/B)
+    static const int probe = getenv("EORB_HT_PROBE") ? atoi(getenv("EORB_HT_PROBE")) : 0;   // probes: 1 no epilogue work, 2 no expansion, 4 no MMA (timing only), 8 unpacked 32-bit readout (A/B)
     dim3 grd(nchunks, (nq + HT_M - 1) / HT_M);
-    if (ht_variant() == 1)
-        hamming_tc_kernel<<<grd, HT_THREADS, HT_SMEM, st>>>(reinterpret_cast<const uint4*>(d_q), nq, reinterpret_cast<const uint4*>(d_db), ndb, chunkRows,
-                                                            indexOffset, d_partial, probe);
-    else
-        hamming_tc2_kernel<<<grd, HT2_THREADS, HT2_SMEM, st>>>(reinterpret_cast<const uint4*>(d_q), nq, reinterpret_cast<const uint4*>(d_db), ndb,
-                                                               chunkRows, indexOffset, d_partial, probe);
+    hamming_tc_kernel<<<grd, HT_THREADS, HT_SMEM, st>>>(reinterpret_cast<const uint4*>(d_q), nq, reinterpret_cast<const uint4*>(d_db), ndb, chunkRows,
+                                                        indexOffset, d_partial, probe);
     return cudaGetLastError();
 }
 
