@@ -841,9 +841,8 @@ static int orbPyrMaps(eorb_orb* h, eorb_orb::Bufs& b, const uint8_t* lvl0, int w
 static int orbIcMap0(eorb_orb::Bufs& b, const uint8_t* lvl0, int w, int hgt, int nframes, long long p0, long long fs0, CUtensorMap* out, bool* use) {
     *use = false;
     if (!b.d_icMaps) return EORB_OK;
-    int rc = tmaEncodeFrames(out, lvl0, w, hgt, nframes, (size_t)p0, (size_t)fs0, ic_tma_box_w(), ic_tma_box_h());
-    if (rc != EORB_OK) return rc;
-    *use = true;
+    // a frame the box cannot be encoded for is not an error: the kernel then reads the orientation patches from global memory
+    *use = tmaEncodeFrames(out, lvl0, w, hgt, nframes, (size_t)p0, (size_t)fs0, ic_tma_box_w(), ic_tma_box_h()) == EORB_OK;
     return EORB_OK;
 }
 
