@@ -108,6 +108,8 @@ OCT_DEV void oct_carve(OctSmem& s, unsigned char* base, int nc) {
 }
 
 // in-place exclusive scan of a[0..n) by the whole block; returns the total (same value in every thread)
+// NTC: the block size when it is a compile-time constant above 128 (selects the shuffle form), 0 otherwise
+template <int NTC = 0>
 OCT_DEV int oct_exclusive_scan(int* a, int n, int* scratch) {
     const int tid = OCT_TID, nt = OCT_NT;
     const int per = (n + nt - 1) / nt;
@@ -119,7 +121,7 @@ OCT_DEV int oct_exclusive_scan(int* a, int n, int* scratch) {
     int off = 0;
 #else
     int total, off;
-    if (nt > 128) {
+    if (NTC > 128) {
         // big blocks (the single-frame call: one 512-thread block per level, where the barriers ARE the latency): warp-shuffle scan of
         // the per-thread sums and a serial pass over the <= 16 warp totals, two barriers instead of 2 * log2(nt).  (With the 128-thread
         // blocks of a launch set the same change was measured slower, 0.48 -> 0.53 us/frame, so those keep the Hillis-Steele form.)
@@ -198,6 +200,7 @@ OCT_DEV OctBox oct_child_box(const OctBox& b, int c) {
 // Runs the distribution.  keys[n]: packed candidates in the reference's order (cell-row-major, then pixel
 // row-major).  knode[n]: scratch.  out[<= nodeCap]: selected keys in final list order.  Returns the count.
 // All threads of the block must call; smem must hold oct_smem_bytes(nodeCap).
+template <int NTC = 0>
 OCT_DEV int oct_distribute(const uint32_t* keys, uint16_t* knode, int n, int width, int height, int nIni, float hX,
                            int N, int nodeCap, unsigned char* smem, uint32_t* out) {
     OctSmem s;
@@ -233,7 +236,7 @@ OCT_DEV int oct_distribute(const uint32_t* keys, uint16_t* knode, int n, int wid
     // drop empty roots (:590-603)
     for (int i = tid; i < nIni; i += nt) s.scanA[i] = s.cnt[cur][i] > 0 ? 1 : 0;
     OCT_SYNC();
-    int L = oct_exclusive_scan(s.scanA, nIni, s.scratch);
+    int L = oct_exclusive_scan<NTC>(s.scanA, nIni, s.scratch);
     for (int i = tid; i < nIni; i += nt) {
         if (s.cnt[cur][i] > 0) {
             int np = s.scanA[i];
@@ -278,7 +281,7 @@ OCT_DEV int oct_distribute(const uint32_t* keys, uint16_t* knode, int n, int wid
             // every candidate is split, processing order = list order (:620-683)
             for (int p = tid; p < L; p += nt) { s.scanA[p] = s.nch[p]; s.split[p] = cand[p]; }
             OCT_SYNC();
-            T = oct_exclusive_scan(s.scanA, L, s.scratch);
+            T = oct_exclusive_scan<NTC>(s.scanA, L, s.scratch);
             for (int p = tid; p < L; p += nt) s.gfirst[p] = s.scanA[p];
             OCT_SYNC();
         } else {
@@ -296,7 +299,7 @@ OCT_DEV int oct_distribute(const uint32_t* keys, uint16_t* knode, int n, int wid
             // m = number of candidates = first zero key
             for (int q = tid; q < L; q += nt) s.scanA[q] = s.skey[q] ? s.nch[(int)(s.skey[q] & 0xFFFFu)] : 0;
             OCT_SYNC();
-            int total = oct_exclusive_scan(s.scanA, L, s.scratch);
+            int total = oct_exclusive_scan<NTC>(s.scanA, L, s.scratch);
             (void)total;
             for (int q = tid; q < L; q += nt) {
                 if (s.skey[q]) {
@@ -319,12 +322,12 @@ OCT_DEV int oct_distribute(const uint32_t* keys, uint16_t* knode, int n, int wid
             // T = children of the split prefix
             for (int p = tid; p < L; p += nt) s.scanA[p] = s.split[p] ? s.nch[p] : 0;
             OCT_SYNC();
-            T = oct_exclusive_scan(s.scanA, L, s.scratch);
+            T = oct_exclusive_scan<NTC>(s.scanA, L, s.scratch);
         }
         // ---- untouched nodes keep their order behind the new children
         for (int p = tid; p < L; p += nt) s.newpos[p] = s.split[p] ? 0 : 1;
         OCT_SYNC();
-        const int U = oct_exclusive_scan(s.newpos, L, s.scratch);
+        const int U = oct_exclusive_scan<NTC>(s.newpos, L, s.scratch);
         const int Lnew = T + U;
         if (Lnew > nodeCap) return -1;   // cannot happen (bounded by max(N+2, 4*nIni)); guards smem
         OctBox* nbox = s.box[cur ^ 1]; int* ncnt = s.cnt[cur ^ 1]; int* nseq = s.seq[cur ^ 1]; int* ncand = s.cand[cur ^ 1];
@@ -365,7 +368,7 @@ OCT_DEV int oct_distribute(const uint32_t* keys, uint16_t* knode, int n, int wid
         L = Lnew;
         for (int p = tid; p < L; p += nt) s.scanA[p] = s.cand[cur][p];
         OCT_SYNC();
-        const int nToExpand = oct_exclusive_scan(s.scanA, L, s.scratch);
+        const int nToExpand = oct_exclusive_scan<NTC>(s.scanA, L, s.scratch);
         if (L >= N || L == prevL) break;
         if (!finalPhase && L + 3 * nToExpand > N) finalPhase = true;
     }

@@ -270,7 +270,7 @@ __global__ void __launch_bounds__(NT) octree_kernel(OrbArgs a) {
         const int cnt = (ci < lp.nCells) ? (int)counts[ci] : 0;
         s_arr[tid] = cnt;
         __syncthreads();
-        const int tot = oct_exclusive_scan(s_arr, NT, s_scr);
+        const int tot = oct_exclusive_scan<NT>(s_arr, NT, s_scr);
         if (cnt > 0) {
             const uint32_t* src = cand + a.cells[lp.cellBase + ci].slotOff;
             uint32_t* dst = okeys + n + s_arr[tid];
@@ -289,7 +289,7 @@ __global__ void __launch_bounds__(NT) octree_kernel(OrbArgs a) {
     uint32_t* out = a.sel + (size_t)f * P.selPerFrame + lp.selBase;
     int L = 0;
     if (lp.maxBX > lp.minBX && lp.maxBY > lp.minBY)
-        L = oct_distribute(okeys, knode, n, lp.maxBX - lp.minBX, lp.maxBY - lp.minBY, lp.nIni, lp.hX, lp.quota,
+        L = oct_distribute<NT>(okeys, knode, n, lp.maxBX - lp.minBX, lp.maxBY - lp.minBY, lp.nIni, lp.hX, lp.quota,
                            lp.nodeCap, smem_raw, out);
     if (tid == 0) {
         a.selCount[(size_t)f * P.nlevels + level] = L < 0 ? 0 : L;
@@ -334,7 +334,7 @@ __global__ void __launch_bounds__(NT) orb_index_kernel(OrbArgs a) {
         }
         s_arr[tid] = flag;
         __syncthreads();
-        const int tot = oct_exclusive_scan(s_arr, NT, s_scr);
+        const int tot = oct_exclusive_scan<NT>(s_arr, NT, s_scr);
         if (g < nk) {
             const int stereoBefore = stereoRun + s_arr[tid];
             dstIdx[slot] = flag ? (nk - 1 - stereoBefore) : (g - stereoBefore);
