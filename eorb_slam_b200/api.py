@@ -654,6 +654,19 @@ class ELK_Tracker:
         _check(lib.eorb_lk_get_last_tracked(self.h, _p(out)), "lk_get_last_tracked")
         return out
 
+    def trackAndMatchCurrImage_device(self, d_image, stride, d_tracked, d_matched, d_px_disp, d_counts2, init=False):
+        """the same with the frame and every output resident on the device (raw pointers); asynchronous on the tracker's stream.
+        Outputs: tracked KEYPOINT_DTYPE[n], matched uint8[n] (bit 0 passed, bit 1 kept), px_disp float32[n], counts int32[2]."""
+        return _check(lib.eorb_lk_track_and_match_device(self.h, C.c_void_p(int(d_image)), stride, self.maxItr, float(self.eps), 1e-4,
+                                                         1 if init else 0, C.c_void_p(int(d_tracked)), C.c_void_p(int(d_matched)),
+                                                         C.c_void_p(int(d_px_disp)), C.c_void_p(int(d_counts2))), "lk_track_and_match_device")
+
+    def set_stream(self, stream):
+        if stream is None:
+            _check(lib.eorb_lk_reset_stream(self.h), "lk_reset_stream")
+        else:
+            _check(lib.eorb_lk_set_stream(self.h, C.c_void_p(int(stream))), "lk_set_stream")
+
     def trackAndMatchCurrImage(self, image, vMatches12=None, vCntMatches=None, init=False):
         """trackAndMatchCurrImage :215-234 (init=True: trackAndMatchCurrImageInit :236-242)
         -> (nMatches, trackedKPts, vMatches12, vCntMatches, vPxDisp).  vMatches12 / vCntMatches: the caller's vectors, updated the way

@@ -145,3 +145,38 @@ def test_track_and_match_without_reference_is_empty():
     tr = api.ELK_Tracker(max_size=(64, 64), max_points=8)
     tr.n = 0; tr.shape = (64, 64)
     assert tr.trackAndMatchCurrImage(np.zeros((64, 64), np.uint8))[0] == 0
+
+
+def test_track_and_match_device_variant_equals_host_variant():
+    """eorb_lk_track_and_match_device: frame and outputs resident on the device (the event front end's frames are produced there) ==
+    the host-buffer call, byte for byte, over two frames"""
+    import torch
+    api = _api()
+    w, h = 240, 180
+    img, _ = _pair(9, w, h)
+    frames = [_pair(9, w, h, shift=(0.7 * k, 0.4 * k), angle=0.15 * k)[1] for k in (1, 2)]
+    pts = _points(img, 40, 5)
+    ref = np.zeros(len(pts), api.KEYPOINT_DTYPE)
+    ref["x"] = pts[:, 0]; ref["y"] = pts[:, 1]; ref["size"] = 31; ref["angle"] = 10.0; ref["response"] = 50; ref["octave"] = np.arange(len(pts)) % 2
+    ref["class_id"] = -1
+    n = len(pts)
+    a = api.ELK_Tracker(23, 1, 10, 0.03, max_size=(w, h), max_points=n)
+    b = api.ELK_Tracker(23, 1, 10, 0.03, max_size=(w, h), max_points=n)
+    assert a.setRefImageKPts(img, ref) == 0 and b.setRefImageKPts(img, ref) == 0
+    st = torch.cuda.Stream()
+    b.set_stream(st.cuda_stream)
+    d_tr = torch.zeros(n * 28, dtype=torch.uint8, device="cuda"); d_m = torch.zeros(n, dtype=torch.uint8, device="cuda")
+    d_disp = torch.zeros(n, dtype=torch.float32, device="cuda"); d_c = torch.zeros(2, dtype=torch.int32, device="cuda")
+    for f in frames:
+        nm, tk, m12, cnt, disp = a.trackAndMatchCurrImage(f, init=True)
+        d_f = torch.from_numpy(f).cuda()
+        torch.cuda.synchronize()
+        b.trackAndMatchCurrImage_device(d_f.data_ptr(), w, d_tr.data_ptr(), d_m.data_ptr(), d_disp.data_ptr(), d_c.data_ptr(), init=True)
+        st.synchronize()
+        c = d_c.cpu().numpy()
+        assert int(c[0]) == nm and int(c[1]) == len(disp)
+        assert d_tr.cpu().numpy().tobytes() == tk.tobytes()
+        assert d_disp.cpu().numpy()[:c[1]].tobytes() == disp.tobytes()
+        kept = (d_m.cpu().numpy() & 2) != 0
+        assert np.array_equal(kept, m12 == np.arange(n))
+    b.set_stream(None)
