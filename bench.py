@@ -563,6 +563,44 @@ def bench_lk(api, torch, dev, steps, warmup):
                               "bit_exact_vs_oracle": bool(nm == enm and tk.tobytes() == etk.tobytes() and np.array_equal(m12, em12)
                                                           and disp.tobytes() == edisp.tobytes()),
                               "note": "trackAndMatchCurrImage: tracked points stay in HBM as the next initial flow, refineTrackedPts on the device"}
+    # the event front end of the L1 tracker with nothing but two counts leaving the device per window: events (HBM) -> event frame
+    # (ev2im_gauss, normalised u8) -> trackAndMatchCurrImage against the reference frame's keypoints (EvAsynchTracker.cpp:588-594)
+    try:
+        nw = 16
+        evs = synth.make_events(per * (nw + 1), seed=11, w=w, h=h)
+        cvd = api.EvImConverter(dev, nw + 1, per, w, h)
+        s2 = torch.cuda.Stream(); st2 = s2.cuda_stream
+        cvd.set_stream(st2)
+        tr3 = api.ELK_Tracker(23, 1, 10, 0.03, dev, (w, h), len(pts)); tr3.set_stream(st2)
+        with torch.cuda.stream(s2):
+            d_ev = torch.from_numpy(evs.view(np.uint8).reshape(-1)).cuda()
+            d_f32 = torch.empty(h * w, dtype=torch.float32, device="cuda"); d_u8 = torch.empty(h * w, dtype=torch.uint8, device="cuda")
+            d_tr = torch.zeros(len(pts) * 28, dtype=torch.uint8, device="cuda"); d_m = torch.zeros(len(pts), dtype=torch.uint8, device="cuda")
+            d_dp = torch.zeros(len(pts), dtype=torch.float32, device="cuda"); d_c = torch.zeros(2, dtype=torch.int32, device="cuda")
+            h_c = torch.zeros(2, dtype=torch.int32).pin_memory()
+        pp = cvd.make_params(api.EV_GAUSS, w, h, 1.0, False, api.NORM_RUNNING)
+        tr3.setRefImageKPts(i0, kps)
+
+        def window(k):
+            offs = np.array([k * per, (k + 1) * per], np.int64)
+            cvd.accumulate_batch_device(d_ev.data_ptr(), offs, pp, d_f32.data_ptr(), d_u8.data_ptr())
+            tr3.trackAndMatchCurrImage_device(d_u8.data_ptr(), w, d_tr.data_ptr(), d_m.data_ptr(), d_dp.data_ptr(), d_c.data_ptr())
+            with torch.cuda.stream(s2):
+                h_c.copy_(d_c, non_blocking=True)
+            s2.synchronize()
+            return int(h_c[0])
+        for k in range(3):
+            window(k)
+        tr3.setRefImageKPts(i0, kps)
+        t0 = time.perf_counter()
+        nms = [window(k) for k in range(1, nw + 1)]
+        ms_w = (time.perf_counter() - t0) * 1e3 / nw
+        out["event_front_end"] = {"ms_per_window": ms_w, "matches_first_last": [nms[0], nms[-1]],
+                                  "workload": "%d consecutive windows of %d events: events in HBM -> 240x180 event frame (u8) -> LK from the resident last "
+                                              "tracked points + refineTrackedPts on the device; two counts come back per window" % (nw, per)}
+        cvd.set_stream(None); tr3.set_stream(None)
+    except Exception as ex:
+        out["event_front_end"] = {"error": repr(ex)}
     try:
         import cv2
         crit = (cv2.TERM_CRITERIA_COUNT + cv2.TERM_CRITERIA_EPS, 10, 0.03)
