@@ -277,7 +277,7 @@ struct eorb_orb {
     bool useBriefTma = true;       // EORB_BRIEF_TMA=0: orient_desc_kernel gathers the BRIEF samples from global memory (for A/B)
     bool usePyrChain = true;       // EORB_PYR_CHAIN=0: small batches launch the pyramid level by level like launch sets do
     bool usePyrTma = true;         // EORB_PYR_TMA=0: every pyramid level through pyr_resize_kernel (direct global loads), for A/B
-    int pyrTileRows = 64;          // EORB_PYR_TH: destination rows per TMA-staged tile (tuning)
+    int pyrTileRows = 112;         // EORB_PYR_TH: destination rows per TMA-staged tile (sweep on B200, us/frame of the pyramid: 32 -> 0.657, 48 -> 0.609, 64 -> 0.591, 80 -> 0.575, 96 -> 0.570, 112 -> 0.568, 128 -> 0.570, 144 -> 0.590, 192 -> 0.606)
 };
 
 static cudaEvent_t* orbStageEvents(eorb_orb* h) {
