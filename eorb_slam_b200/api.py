@@ -110,6 +110,8 @@ def _load():
         "eorb_guided_search_by_projection_map_points_stereo_device": ([vp, vp, vp, vp, i, vp, vp, vp, vp, i, vp, vp, i, f, i, f, f, vp, vp], i),
         "eorb_guided_search_by_bow": ([vp, vp, vp, vp, i, vp, vp, vp, i, vp, vp, i, vp, vp, vp, i, f, i, vp, vp], i),
         "eorb_guided_search_by_bow_device": ([vp, vp, vp, vp, i, vp, vp, vp, i, vp, vp, i, vp, vp, vp, i, f, i, vp, vp], i),
+        "eorb_guided_search_by_bow_kf": ([vp, vp, vp, vp, i, vp, vp, vp, i, vp, vp, vp, i, vp, vp, vp, i, f, i, vp, vp], i),
+        "eorb_guided_search_by_bow_kf_device": ([vp, vp, vp, vp, i, vp, vp, vp, i, vp, vp, vp, i, vp, vp, vp, i, f, i, vp, vp, vp], i),
         "eorb_guided_search_by_projection_map_points": ([vp, vp, vp, i, vp, vp, vp, i, vp, vp, i, f, i, f, f, vp, vp], i),
         "eorb_guided_search_by_projection_map_points_device": ([vp, vp, vp, i, vp, vp, vp, i, vp, vp, i, f, i, f, f, vp, vp], i),
         "eorb_vocab_create": ([i, i, i, i, i, i, vp, vp, vp, vp, C.POINTER(vp)], i), "eorb_vocab_destroy": ([vp], i),
@@ -857,6 +859,21 @@ class GuidedMatcher:
                                              _p(b[0]), _p(b[1]), _p(b[2]), len(b[0]), C.c_float(self.mfNNratio), int(self.mbCheckOrientation), _p(mf),
                                              C.byref(nm)), "SearchByBoW")
         return nm.value, mf[:len(k2)].copy()
+
+    def SearchByBoW_KF(self, kps1, desc1, valid1, fv1, kps2, desc2, valid2, fv2):
+        """ORBmatcher::SearchByBoW(pKF1, pKF2, vpMatches12) (:833-990, monocular keyframes) -> (nmatches, match12[n1]): match12[i1] = feature
+        index of keyframe 2 whose map point the reference stores in vpMatches12[i1], or -1; valid* = a map point that is not bad"""
+        k1 = np.ascontiguousarray(kps1, KEYPOINT_DTYPE); k2 = np.ascontiguousarray(kps2, KEYPOINT_DTYPE)
+        d1 = np.ascontiguousarray(desc1, np.uint8); d2 = np.ascontiguousarray(desc2, np.uint8)
+        v1 = np.ascontiguousarray(valid1, np.uint8); v2 = np.ascontiguousarray(valid2, np.uint8)
+        a = [np.ascontiguousarray(fv1[0], np.uint32), np.ascontiguousarray(fv1[1], np.int32), np.ascontiguousarray(fv1[2], np.uint32)]
+        b = [np.ascontiguousarray(fv2[0], np.uint32), np.ascontiguousarray(fv2[1], np.int32), np.ascontiguousarray(fv2[2], np.uint32)]
+        m12 = np.full(max(len(k1), 1), -1, np.int32)
+        nm = C.c_int(0)
+        _check(lib.eorb_guided_search_by_bow_kf(self.h, _p(k1), _p(d1), _p(v1), len(k1), _p(a[0]), _p(a[1]), _p(a[2]), len(a[0]), _p(k2), _p(d2), _p(v2),
+                                                len(k2), _p(b[0]), _p(b[1]), _p(b[2]), len(b[0]), C.c_float(self.mfNNratio),
+                                                int(self.mbCheckOrientation), _p(m12), C.byref(nm)), "SearchByBoW_KF")
+        return nm.value, m12[:len(k1)].copy()
 
     def SearchByBoW_device(self, d_kpsKF, d_descKF, d_validKF, n1, d_fvKF, nkf, d_kpsF, d_descF, n2, d_fvF, nf, d_match_f):
         """device pointers (ints); d_fv* = (nodes, start, feats) device pointers; returns nmatches"""

@@ -648,55 +648,79 @@ static int checkFeatureVector(const char* who, const uint32_t* nodes, const int3
     return EORB_OK;
 }
 
-extern "C" int eorb_guided_search_by_bow_device(eorb_guided* g, const eorb_keypoint* d_kps_kf, const uint8_t* d_desc_kf, const uint8_t* d_valid_kf,
-                                                int n1, const uint32_t* d_kf_nodes, const int32_t* d_kf_start, const uint32_t* d_kf_feats, int nkf,
-                                                const eorb_keypoint* d_kps_f, const uint8_t* d_desc_f, int n2, const uint32_t* d_f_nodes,
-                                                const int32_t* d_f_start, const uint32_t* d_f_feats, int nf, float nnratio, int check_ori,
-                                                int32_t* d_match_f, int* nmatches) {
-    const char* who = "eorb_guided_search_by_bow_device";
+// device-resident SearchByBoW, both forms: d_valid_f / d_match12 given = ORBmatcher::SearchByBoW(pKF1, pKF2, vpMatches12) (ORBmatcher.cc:833-990)
+static int guidedBowDevice(eorb_guided* g, const char* who, const eorb_keypoint* d_kps_kf, const uint8_t* d_desc_kf, const uint8_t* d_valid_kf, int n1,
+                           const uint32_t* d_kf_nodes, const int32_t* d_kf_start, const uint32_t* d_kf_feats, int nkf, const eorb_keypoint* d_kps_f,
+                           const uint8_t* d_desc_f, const uint8_t* d_valid_f, int n2, const uint32_t* d_f_nodes, const int32_t* d_f_start,
+                           const uint32_t* d_f_feats, int nf, float nnratio, int check_ori, int32_t* d_match_f, int32_t* d_match12, int* nmatches) {
     if (!g) return gFail(EORB_ERR_ARG, who, "null handle");
     if (n1 < 0 || n2 < 0 || nkf < 0 || nf < 0) return gFail(EORB_ERR_ARG, who, "negative size");
     if (n1 > EORB_GUIDED_MAX_KEYPOINTS || n2 > EORB_GUIDED_MAX_KEYPOINTS) return gFail(EORB_ERR_CAPACITY, who, "more than EORB_GUIDED_MAX_KEYPOINTS keypoints");
     if (nmatches) *nmatches = 0;
+    CU(cudaSetDevice(g->device));
+    if (d_match12 && n1 > 0) CU(cudaMemsetAsync(d_match12, 0xff, (size_t)n1 * sizeof(int32_t), g->stream));
     if (n2 == 0) return EORB_OK;
     if (!d_match_f || !d_kps_f || !d_desc_f || (n1 > 0 && (!d_kps_kf || !d_desc_kf || !d_valid_kf)) ||
         (nkf > 0 && (!d_kf_nodes || !d_kf_start || !d_kf_feats)) || (nf > 0 && (!d_f_nodes || !d_f_start || !d_f_feats)))
         return gFail(EORB_ERR_ARG, who, "null argument");
     if (((uintptr_t)d_desc_kf | (uintptr_t)d_desc_f) & 15) return gFail(EORB_ERR_ARG, who, "descriptors must be 16-byte aligned");
-    CU(cudaSetDevice(g->device));
     GuidedBowSide a{d_kps_kf, d_desc_kf, d_kf_nodes, d_kf_start, d_kf_feats, nkf, n1}, b{d_kps_f, d_desc_f, d_f_nodes, d_f_start, d_f_feats, nf, n2};
     if (!g->d_bowWork) CU(cudaMalloc((void**)&g->d_bowWork, 64 * sizeof(int)));
-    CU(launch_search_by_bow(a, d_valid_kf, b, nnratio, check_ori, d_match_f, g->d_bowWork, g->d_nm, g->stream, &g->launches));
+    CU(launch_search_by_bow(a, d_valid_kf, b, nnratio, check_ori, d_match_f, g->d_bowWork, g->d_nm, g->stream, &g->launches, d_valid_f, d_match12));
     CU(cudaMemcpyAsync(g->h_nm, g->d_nm, sizeof(int), cudaMemcpyDeviceToHost, g->stream));
     CU(cudaStreamSynchronize(g->stream));
     if (nmatches) *nmatches = g->h_nm[0];
     return EORB_OK;
 }
 
-extern "C" int eorb_guided_search_by_bow(eorb_guided* g, const eorb_keypoint* kps_kf, const uint8_t* desc_kf, const uint8_t* valid_kf, int n1,
-                                         const uint32_t* kf_nodes, const int32_t* kf_start, const uint32_t* kf_feats, int nkf,
-                                         const eorb_keypoint* kps_f, const uint8_t* desc_f, int n2, const uint32_t* f_nodes, const int32_t* f_start,
-                                         const uint32_t* f_feats, int nf, float nnratio, int check_ori, int32_t* match_f, int* nmatches) {
-    const char* who = "eorb_guided_search_by_bow";
+extern "C" int eorb_guided_search_by_bow_device(eorb_guided* g, const eorb_keypoint* d_kps_kf, const uint8_t* d_desc_kf, const uint8_t* d_valid_kf,
+                                                int n1, const uint32_t* d_kf_nodes, const int32_t* d_kf_start, const uint32_t* d_kf_feats, int nkf,
+                                                const eorb_keypoint* d_kps_f, const uint8_t* d_desc_f, int n2, const uint32_t* d_f_nodes,
+                                                const int32_t* d_f_start, const uint32_t* d_f_feats, int nf, float nnratio, int check_ori,
+                                                int32_t* d_match_f, int* nmatches) {
+    return guidedBowDevice(g, "eorb_guided_search_by_bow_device", d_kps_kf, d_desc_kf, d_valid_kf, n1, d_kf_nodes, d_kf_start, d_kf_feats, nkf, d_kps_f,
+                           d_desc_f, nullptr, n2, d_f_nodes, d_f_start, d_f_feats, nf, nnratio, check_ori, d_match_f, nullptr, nmatches);
+}
+
+extern "C" int eorb_guided_search_by_bow_kf_device(eorb_guided* g, const eorb_keypoint* d_kps1, const uint8_t* d_desc1, const uint8_t* d_valid1, int n1,
+                                                   const uint32_t* d_nodes1, const int32_t* d_start1, const uint32_t* d_feats1, int nn1,
+                                                   const eorb_keypoint* d_kps2, const uint8_t* d_desc2, const uint8_t* d_valid2, int n2,
+                                                   const uint32_t* d_nodes2, const int32_t* d_start2, const uint32_t* d_feats2, int nn2, float nnratio,
+                                                   int check_ori, int32_t* d_match12, int32_t* d_scratch_n2, int* nmatches) {
+    const char* who = "eorb_guided_search_by_bow_kf_device";
+    if (!d_match12 || (n2 > 0 && (!d_scratch_n2 || !d_valid2))) return gFail(EORB_ERR_ARG, who, "null argument");
+    return guidedBowDevice(g, who, d_kps1, d_desc1, d_valid1, n1, d_nodes1, d_start1, d_feats1, nn1, d_kps2, d_desc2, d_valid2, n2, d_nodes2, d_start2,
+                           d_feats2, nn2, nnratio, check_ori, d_scratch_n2, d_match12, nmatches);
+}
+
+// host-buffer SearchByBoW, both forms (valid_f / match12 given = the keyframe-keyframe form): one H2D blob, one launch, one D2H blob
+static int guidedBowHost(eorb_guided* g, const char* who, const eorb_keypoint* kps_kf, const uint8_t* desc_kf, const uint8_t* valid_kf, int n1,
+                         const uint32_t* kf_nodes, const int32_t* kf_start, const uint32_t* kf_feats, int nkf, const eorb_keypoint* kps_f,
+                         const uint8_t* desc_f, const uint8_t* valid_f, int n2, const uint32_t* f_nodes, const int32_t* f_start, const uint32_t* f_feats,
+                         int nf, float nnratio, int check_ori, int32_t* match_f, int32_t* match12, int* nmatches) {
+    const bool kfForm = match12 != nullptr;
     if (!g) return gFail(EORB_ERR_ARG, who, "null handle");
     if (n1 < 0 || n2 < 0) return gFail(EORB_ERR_ARG, who, "negative size");
     if (n1 > EORB_GUIDED_MAX_KEYPOINTS || n2 > EORB_GUIDED_MAX_KEYPOINTS) return gFail(EORB_ERR_CAPACITY, who, "more than EORB_GUIDED_MAX_KEYPOINTS keypoints");
     if (nmatches) *nmatches = 0;
+    if (kfForm) for (int i = 0; i < n1; i++) match12[i] = -1;
     if (n2 == 0) return EORB_OK;
-    if (!match_f || !kps_f || !desc_f || (n1 > 0 && (!kps_kf || !desc_kf || !valid_kf))) return gFail(EORB_ERR_ARG, who, "null argument");
+    if ((!kfForm && !match_f) || !kps_f || !desc_f || (n1 > 0 && (!kps_kf || !desc_kf || !valid_kf)) || (kfForm && !valid_f))
+        return gFail(EORB_ERR_ARG, who, "null argument");
     int rc;
     if ((rc = checkFeatureVector(who, kf_nodes, kf_start, kf_feats, nkf, n1)) != EORB_OK) return rc;
     if ((rc = checkFeatureVector(who, f_nodes, f_start, f_feats, nf, n2)) != EORB_OK) return rc;
     CU(cudaSetDevice(g->device));
-    // one blob, every part 16-byte aligned: [kf kps | kf desc | f kps | f desc | kf nodes | kf start | kf feats | f nodes | f start | f feats | valid]
+    // one blob, every part 16-byte aligned: [kf kps | kf desc | f kps | f desc | kf nodes | kf start | kf feats | f nodes | f start | f feats | valid kf | valid f]
     const int nfk = nkf > 0 ? kf_start[nkf] : 0, nff = nf > 0 ? f_start[nf] : 0;
     auto al = [](size_t v) { return (v + 15) & ~(size_t)15; };
-    const int NP = 11;
+    const int NP = 12;
     const int32_t zero2[2] = {0, 0};
     const size_t sz[NP] = {(size_t)n1 * sizeof(eorb_keypoint), (size_t)n1 * 32, (size_t)n2 * sizeof(eorb_keypoint), (size_t)n2 * 32, (size_t)nkf * 4,
-                           (size_t)(nkf + 1) * 4, (size_t)nfk * 4, (size_t)nf * 4, (size_t)(nf + 1) * 4, (size_t)nff * 4, (size_t)n1};
+                           (size_t)(nkf + 1) * 4, (size_t)nfk * 4, (size_t)nf * 4, (size_t)(nf + 1) * 4, (size_t)nff * 4, (size_t)n1,
+                           kfForm ? (size_t)n2 : 0};
     const void* src[NP] = {kps_kf, desc_kf, kps_f, desc_f, kf_nodes, nkf > 0 ? (const void*)kf_start : (const void*)zero2, kf_feats,
-                           f_nodes, nf > 0 ? (const void*)f_start : (const void*)zero2, f_feats, valid_kf};
+                           f_nodes, nf > 0 ? (const void*)f_start : (const void*)zero2, f_feats, valid_kf, valid_f};
     size_t off[NP + 1]; off[0] = 0;
     for (int i = 0; i < NP; i++) off[i + 1] = off[i] + al(sz[i]);
     if (off[NP] > g->blobCap) {
@@ -707,7 +731,9 @@ extern "C" int eorb_guided_search_by_bow(eorb_guided* g, const eorb_keypoint* kp
         CU(cudaMallocHost((void**)&g->h_blob, cap));
         g->blobCap = cap;
     }
-    const size_t outBytes = 16 + (size_t)n2 * sizeof(int32_t);
+    // output blob: [nmatches (16 bytes) | match_f[n2] | match12[n1] (keyframe-keyframe form)]
+    const size_t o12 = 16 + al((size_t)n2 * sizeof(int32_t));
+    const size_t outBytes = o12 + (kfForm ? (size_t)n1 * sizeof(int32_t) : 0);
     if (outBytes > g->outbCap) {
         CU(cudaStreamSynchronize(g->stream));
         cudaFree(g->d_outb); cudaFreeHost(g->h_outb); g->d_outb = nullptr; g->h_outb = nullptr; g->outbCap = 0;
@@ -723,10 +749,29 @@ extern "C" int eorb_guided_search_by_bow(eorb_guided* g, const eorb_keypoint* kp
     GuidedBowSide a{(const eorb_keypoint*)(B + off[0]), B + off[1], (const uint32_t*)(B + off[4]), (const int32_t*)(B + off[5]), (const uint32_t*)(B + off[6]), nkf, n1};
     GuidedBowSide b{(const eorb_keypoint*)(B + off[2]), B + off[3], (const uint32_t*)(B + off[7]), (const int32_t*)(B + off[8]), (const uint32_t*)(B + off[9]), nf, n2};
     if (!g->d_bowWork) CU(cudaMalloc((void**)&g->d_bowWork, 64 * sizeof(int)));
-    CU(launch_search_by_bow(a, B + off[10], b, nnratio, check_ori, (int32_t*)(g->d_outb + 16), g->d_bowWork, (int*)g->d_outb, g->stream, &g->launches));
+    CU(launch_search_by_bow(a, B + off[10], b, nnratio, check_ori, (int32_t*)(g->d_outb + 16), g->d_bowWork, (int*)g->d_outb, g->stream, &g->launches,
+                            kfForm ? B + off[11] : nullptr, kfForm && n1 > 0 ? (int32_t*)(g->d_outb + o12) : nullptr));
     CU(cudaMemcpyAsync(g->h_outb, g->d_outb, outBytes, cudaMemcpyDeviceToHost, g->stream));
     CU(cudaStreamSynchronize(g->stream));
-    std::memcpy(match_f, g->h_outb + 16, (size_t)n2 * sizeof(int32_t));
+    if (match_f) std::memcpy(match_f, g->h_outb + 16, (size_t)n2 * sizeof(int32_t));
+    if (kfForm && n1 > 0) std::memcpy(match12, g->h_outb + o12, (size_t)n1 * sizeof(int32_t));
     if (nmatches) *nmatches = *(const int*)g->h_outb;
     return EORB_OK;
+}
+
+extern "C" int eorb_guided_search_by_bow(eorb_guided* g, const eorb_keypoint* kps_kf, const uint8_t* desc_kf, const uint8_t* valid_kf, int n1,
+                                         const uint32_t* kf_nodes, const int32_t* kf_start, const uint32_t* kf_feats, int nkf,
+                                         const eorb_keypoint* kps_f, const uint8_t* desc_f, int n2, const uint32_t* f_nodes, const int32_t* f_start,
+                                         const uint32_t* f_feats, int nf, float nnratio, int check_ori, int32_t* match_f, int* nmatches) {
+    return guidedBowHost(g, "eorb_guided_search_by_bow", kps_kf, desc_kf, valid_kf, n1, kf_nodes, kf_start, kf_feats, nkf, kps_f, desc_f, nullptr, n2,
+                         f_nodes, f_start, f_feats, nf, nnratio, check_ori, match_f, nullptr, nmatches);
+}
+
+extern "C" int eorb_guided_search_by_bow_kf(eorb_guided* g, const eorb_keypoint* kps1, const uint8_t* desc1, const uint8_t* valid1, int n1,
+                                            const uint32_t* nodes1, const int32_t* start1, const uint32_t* feats1, int nn1, const eorb_keypoint* kps2,
+                                            const uint8_t* desc2, const uint8_t* valid2, int n2, const uint32_t* nodes2, const int32_t* start2,
+                                            const uint32_t* feats2, int nn2, float nnratio, int check_ori, int32_t* match12, int* nmatches) {
+    if (!match12 && n1 > 0) return gFail(EORB_ERR_ARG, "eorb_guided_search_by_bow_kf", "null output");
+    return guidedBowHost(g, "eorb_guided_search_by_bow_kf", kps1, desc1, valid1, n1, nodes1, start1, feats1, nn1, kps2, desc2, valid2, n2, nodes2, start2,
+                         feats2, nn2, nnratio, check_ori, nullptr, match12, nmatches);
 }

@@ -992,7 +992,8 @@ __global__ void __launch_bounds__(256) guided_resolve_map_kernel(const eorb_trac
 // (ORBmatcher.cc:318-378).  Returns the number of matches made (the caller adds it to work[32]).
 template <int S>
 __device__ __forceinline__ int bow_node_registers(const GuidedBowSide& kf, const uint8_t* __restrict__ validKF, const GuidedBowSide& f, int w,
-                                                  int fb, int fe, float nnratio, int checkOri, int32_t* matchF, int* work, int lane) {
+                                                  int fb, int fe, float nnratio, int checkOri, int32_t* matchF, int* work, int lane,
+                                                  const uint8_t* __restrict__ validF, int thLow) {
     auto rotBin = [&](int ik, int jf) -> int {
         float rot = __fsub_rn(kf.kps[ik].angle, f.kps[jf].angle);
         if (rot < 0.0f) rot = __fadd_rn(rot, 360.0f);
@@ -1015,7 +1016,7 @@ __device__ __forceinline__ int bow_node_registers(const GuidedBowSide& kf, const
             const uint4* dp = reinterpret_cast<const uint4*>(f.desc + (size_t)jf[s] * 32);
             const uint4 x = __ldg(dp), y = __ldg(dp + 1);
             fd[s][0] = x.x; fd[s][1] = x.y; fd[s][2] = x.z; fd[s][3] = x.w; fd[s][4] = y.x; fd[s][5] = y.y; fd[s][6] = y.z; fd[s][7] = y.w;
-            freeMask |= 1u << s;
+            if (!validF || validF[jf[s]]) freeMask |= 1u << s;   // keyframe-keyframe form: a candidate needs a good map point too
         }
     }
     int nm = 0;
@@ -1052,7 +1053,7 @@ __device__ __forceinline__ int bow_node_registers(const GuidedBowSide& kf, const
             if (m1 == 0xffffffffu) break;                      // every frame feature of the node is matched
             const uint32_t m2 = __reduce_min_sync(FULLMASK, k1 == m1 ? k2 : k1);
             const int d1 = (int)(m1 >> 16), d2 = m2 != 0xffffffffu ? (int)(m2 >> 16) : 256;
-            if (d1 <= 50 && (float)d1 < __fmul_rn(nnratio, (float)d2)) {
+            if (d1 <= thLow && (float)d1 < __fmul_rn(nnratio, (float)d2)) {
                 const int ik = __shfl_sync(FULLMASK, ikL, sl);
                 const int pos = (int)(m1 & 0xffffu);
                 if (lane == (pos & 31)) {
@@ -1086,7 +1087,8 @@ __device__ __forceinline__ int bow_node_registers(const GuidedBowSide& kf, const
 // work[0..29] rotation histogram, work[32] nmatches, work[33] blocks finished (zeroed before the launch); matchF preset to -1
 __global__ void __launch_bounds__(BOW_WARPS * 32) search_by_bow_kernel(GuidedBowSide kf, const uint8_t* __restrict__ validKF, GuidedBowSide f,
                                                                         float nnratio, int checkOri, int32_t* matchF, int* work,
-                                                                        int* __restrict__ nmatchesOut) {
+                                                                        int* __restrict__ nmatchesOut, const uint8_t* __restrict__ validF,
+                                                                        int thLow, int32_t* __restrict__ match12) {
     __shared__ int sInd[3], sLast;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     volatile int32_t* taken = matchF;
@@ -1105,10 +1107,10 @@ __global__ void __launch_bounds__(BOW_WARPS * 32) search_by_bow_kernel(GuidedBow
         if (lo < f.nnodes && f.nodes[lo] == node) {
             const int fb = f.start[lo], fe = f.start[lo + 1];
             int nm = 0;
-            if (fe - fb <= 32) nm = bow_node_registers<1>(kf, validKF, f, w, fb, fe, nnratio, checkOri, matchF, work, lane);
-            else if (fe - fb <= 64) nm = bow_node_registers<2>(kf, validKF, f, w, fb, fe, nnratio, checkOri, matchF, work, lane);
-            else if (fe - fb <= 128) nm = bow_node_registers<4>(kf, validKF, f, w, fb, fe, nnratio, checkOri, matchF, work, lane);
-            else if (fe - fb <= 256) nm = bow_node_registers<8>(kf, validKF, f, w, fb, fe, nnratio, checkOri, matchF, work, lane);
+            if (fe - fb <= 32) nm = bow_node_registers<1>(kf, validKF, f, w, fb, fe, nnratio, checkOri, matchF, work, lane, validF, thLow);
+            else if (fe - fb <= 64) nm = bow_node_registers<2>(kf, validKF, f, w, fb, fe, nnratio, checkOri, matchF, work, lane, validF, thLow);
+            else if (fe - fb <= 128) nm = bow_node_registers<4>(kf, validKF, f, w, fb, fe, nnratio, checkOri, matchF, work, lane, validF, thLow);
+            else if (fe - fb <= 256) nm = bow_node_registers<8>(kf, validKF, f, w, fb, fe, nnratio, checkOri, matchF, work, lane, validF, thLow);
             else
             for (int a = kf.start[w], ke = kf.start[w + 1]; a < ke; a++) {   // nodes above 256 frame features: descriptors stay in memory
                 const int ik = (int)kf.feats[a];
@@ -1122,7 +1124,7 @@ __global__ void __launch_bounds__(BOW_WARPS * 32) search_by_bow_kernel(GuidedBow
                 uint32_t k1 = 0xffffffffu, k2 = 0xffffffffu;
                 for (int p = fb + lane; p < fe; p += 32) {
                     const int jf = (int)f.feats[p];
-                    if (taken[jf] >= 0) continue;
+                    if (taken[jf] >= 0 || (validF && !validF[jf])) continue;
                     const uint4* dp = reinterpret_cast<const uint4*>(f.desc + (size_t)jf * 32);
                     const uint4 x = __ldg(dp), y = __ldg(dp + 1);
                     const int dist = __popc(x.x ^ qd[0]) + __popc(x.y ^ qd[1]) + __popc(x.z ^ qd[2]) + __popc(x.w ^ qd[3]) + __popc(y.x ^ qd[4]) +
@@ -1134,7 +1136,7 @@ __global__ void __launch_bounds__(BOW_WARPS * 32) search_by_bow_kernel(GuidedBow
                 const uint32_t m2 = __reduce_min_sync(FULLMASK, k1 == m1 ? k2 : k1);
                 if (m1 == 0xffffffffu) continue;
                 const int d1 = (int)(m1 >> 16), d2 = m2 != 0xffffffffu ? (int)(m2 >> 16) : 256;
-                if (d1 <= 50 && (float)d1 < __fmul_rn(nnratio, (float)d2)) {       // TH_LOW, mfNNratio
+                if (d1 <= thLow && (float)d1 < __fmul_rn(nnratio, (float)d2)) {    // TH_LOW (<= 50, or < 50 = <= 49 in the keyframe-keyframe form), mfNNratio
                     if (lane == 0) {
                         const int jf = (int)f.feats[fb + (int)(m1 & 0xffffu)];
                         taken[jf] = ik;
@@ -1178,6 +1180,11 @@ __global__ void __launch_bounds__(BOW_WARPS * 32) search_by_bow_kernel(GuidedBow
             if (b >= 0 && b != sInd[0] && b != sInd[1] && b != sInd[2]) { matchF[i] = -1; atomicSub(&work[32], 1); }
         }
     __syncthreads();
+    if (match12)   // keyframe-keyframe form: the result is indexed by the first keyframe's feature (vpMatches12[idx1], ORBmatcher.cc:916)
+        for (int i = tid; i < f.n; i += BOW_WARPS * 32) {
+            const int ik = __ldcg(&matchF[i]);
+            if (ik >= 0) match12[ik] = i;
+        }
     if (tid == 0) *nmatchesOut = atomicAdd(&work[32], 0);
 }
 
@@ -1283,13 +1290,20 @@ cudaError_t launch_search_map_points(const eorb_track_point* d_pts, const uint8_
 }
 
 cudaError_t launch_search_by_bow(const GuidedBowSide& kf, const uint8_t* d_validKF, const GuidedBowSide& f, float nnratio, int checkOri,
-                                 int32_t* d_matchF, int* d_work, int* d_nmatches, cudaStream_t st, long long* launches) {
+                                 int32_t* d_matchF, int* d_work, int* d_nmatches, cudaStream_t st, long long* launches,
+                                 const uint8_t* d_validF, int32_t* d_match12) {
     cudaError_t e = cudaMemsetAsync(d_matchF, 0xff, (size_t)f.n * sizeof(int32_t), st);
     if (e != cudaSuccess) return e;
     e = cudaMemsetAsync(d_work, 0, 64 * sizeof(int), st);
     if (e != cudaSuccess) return e;
+    if (d_match12) {
+        e = cudaMemsetAsync(d_match12, 0xff, (size_t)kf.n * sizeof(int32_t), st);
+        if (e != cudaSuccess) return e;
+    }
     const int blocks = kf.nnodes > 0 ? (kf.nnodes + BOW_WARPS - 1) / BOW_WARPS : 1;
-    search_by_bow_kernel<<<blocks, BOW_WARPS * 32, 0, st>>>(kf, d_validKF, f, nnratio, checkOri, d_matchF, d_work, d_nmatches);
+    // the keyframe-keyframe form (d_match12 given) accepts bestDist1 < TH_LOW, the keyframe-frame form bestDist1 <= TH_LOW
+    search_by_bow_kernel<<<blocks, BOW_WARPS * 32, 0, st>>>(kf, d_validKF, f, nnratio, checkOri, d_matchF, d_work, d_nmatches, d_validF,
+                                                           d_match12 ? 49 : 50, d_match12);
     (*launches)++;
     return cudaGetLastError();
 }

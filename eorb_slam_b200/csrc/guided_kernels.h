@@ -61,7 +61,9 @@ cudaError_t launch_search_map_points(const eorb_track_point* d_pts, const uint8_
 // FeatureVector in CSR form (nodes ascending, features of node q = feats[start[q] .. start[q+1]))
 struct GuidedBowSide { const eorb_keypoint* kps; const uint8_t* desc; const uint32_t* nodes; const int32_t* start; const uint32_t* feats; int nnodes, n; };
 cudaError_t launch_search_by_bow(const GuidedBowSide& kf, const uint8_t* d_validKF, const GuidedBowSide& f, float nnratio, int checkOri,
-                                 int32_t* d_matchF, int* d_work /* 64 ints */, int* d_nmatches, cudaStream_t st, long long* launches);
+                                 int32_t* d_matchF, int* d_work /* 64 ints */, int* d_nmatches, cudaStream_t st, long long* launches,
+                                 const uint8_t* d_validF = nullptr /* keyframe-keyframe form: good map points of side 2 */,
+                                 int32_t* d_match12 = nullptr /* keyframe-keyframe form: result indexed by side 1 (kf.n entries) */);
 cudaError_t guided_configure();
 
 }  // namespace eorb

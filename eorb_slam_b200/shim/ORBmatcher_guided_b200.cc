@@ -291,4 +291,46 @@ int ORBmatcher::SearchByBoW(KeyFrame* pKF, Frame &F, std::vector<MapPoint*> &vpM
         if (mf[i2] >= 0) vpMapPointMatches[i2] = vpMapPointsKF[mf[i2]];
     return nmatches;
 }
+
+// ORBmatcher::SearchByBoW(pKF1, pKF2, vpMatches12) (:833-990; loop closing / place recognition), monocular keyframes
+int ORBmatcher::SearchByBoW(KeyFrame* pKF1, KeyFrame* pKF2, std::vector<MapPoint*> &vpMatches12)
+{
+    const std::vector<MapPoint*> vpMapPoints1 = pKF1->GetMapPointMatches();
+    const std::vector<MapPoint*> vpMapPoints2 = pKF2->GetMapPointMatches();
+    const int n1 = pKF1->numAllKPts(), n2 = pKF2->numAllKPts();
+    vpMatches12 = std::vector<MapPoint*>(vpMapPoints1.size(), static_cast<MapPoint*>(NULL));
+    eorb_guided* g = threadHandle();
+    if (!g || n1 == 0 || n2 == 0) return 0;
+    struct Side { std::vector<eorb_keypoint> k; std::vector<unsigned char> d, valid; std::vector<unsigned> nodes, feats; std::vector<int> start; };
+    Side s[2];
+    KeyFrame* kf[2] = {pKF1, pKF2};
+    const std::vector<MapPoint*>* mps[2] = {&vpMapPoints1, &vpMapPoints2};
+    for (int side = 0; side < 2; side++) {
+        const int n = side ? n2 : n1;
+        s[side].k.resize(n); s[side].d.resize((size_t)n * 32); s[side].valid.assign(n, 0);
+        for (int i = 0; i < n; i++) {
+            const cv::KeyPoint kp = kf[side]->getUndistKPtMono(i);
+            eorb_keypoint& o = s[side].k[i];
+            o.x = kp.pt.x; o.y = kp.pt.y; o.size = kp.size; o.angle = kp.angle; o.response = kp.response; o.octave = kp.octave; o.class_id = kp.class_id;
+            const cv::Mat d = kf[side]->getORBDescriptor(i);
+            std::memcpy(&s[side].d[(size_t)i * 32], d.ptr<unsigned char>(), 32);
+            MapPoint* pMP = i < (int)mps[side]->size() ? (*mps[side])[i] : NULL;
+            s[side].valid[i] = (pMP && !pMP->isBad()) ? 1 : 0;
+        }
+        flattenFeatureVector(kf[side]->mFeatVec, s[side].nodes, s[side].start, s[side].feats);
+    }
+    std::vector<int> m12(n1, -1);
+    int nmatches = 0;
+    const int rc = eorb_guided_search_by_bow_kf(g, s[0].k.data(), s[0].d.data(), s[0].valid.data(), n1, s[0].nodes.data(), s[0].start.data(),
+                                                s[0].feats.data(), (int)s[0].nodes.size(), s[1].k.data(), s[1].d.data(), s[1].valid.data(), n2,
+                                                s[1].nodes.data(), s[1].start.data(), s[1].feats.data(), (int)s[1].nodes.size(), mfNNratio,
+                                                mbCheckOrientation ? 1 : 0, m12.data(), &nmatches);
+    if (rc != EORB_OK) {
+        std::fprintf(stderr, "ORBmatcher(b200)::SearchByBoW(KF, KF): %s\n", eorb_last_error());
+        return 0;
+    }
+    for (int i1 = 0; i1 < n1 && i1 < (int)vpMatches12.size(); i1++)
+        if (m12[i1] >= 0) vpMatches12[i1] = vpMapPoints2[m12[i1]];
+    return nmatches;
+}
 } // namespace ORB_SLAM3

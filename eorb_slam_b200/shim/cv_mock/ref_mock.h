@@ -88,6 +88,7 @@ public:
     int SearchForInitialization(Frame& F1, Frame& F2, std::vector<cv::Point2f>& vbPrevMatched, std::vector<int>& vnMatches12, int windowSize = 10);
     int SearchByProjection(Frame &CurrentFrame, const Frame &LastFrame, float th, bool bMono);
     int SearchByBoW(KeyFrame* pKF, Frame& F, std::vector<MapPoint*>& vpMapPointMatches);
+    int SearchByBoW(KeyFrame* pKF1, KeyFrame* pKF2, std::vector<MapPoint*>& vpMatches12);
     int SearchByProjection(Frame &CurrentFrame, KeyFrame* pKF, const std::set<MapPoint*> &sAlreadyFound, float th, int ORBdist);
     int SearchByProjection(Frame &F, const std::vector<MapPoint*> &vpMapPoints, float th=3,
             bool bFarPoints = false, float thFarPoints = 50.0f);

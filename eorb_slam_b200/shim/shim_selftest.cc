@@ -226,6 +226,13 @@ int main(int argc, char** argv)
             int bset = 0, bself = 0;
             for (size_t i = 0; i < mm.size(); i++) { bset += (mm[i] != nullptr); bself += (mm[i] != nullptr && mm[i] == own[i]); }
             std::printf("sbb_nm=%d sbb_set=%d sbb_self=%d\n", nb, bset, bself);
+            // the keyframe-keyframe form on the same data: every feature matches itself, the result is indexed by the first keyframe
+            ORB_SLAM3::KeyFrame KF2; KF2.mvKeysUn = kps; KF2.mDescriptors = desc; KF2.mFeatVec = fv; KF2.mvpMapPoints = own;
+            std::vector<ORB_SLAM3::MapPoint*> m12;
+            const int nk = okv ? m07.SearchByBoW(&KF, &KF2, m12) : 0;
+            int kset = 0, kself = 0;
+            for (size_t i = 0; i < m12.size(); i++) { kset += (m12[i] != nullptr); kself += (m12[i] != nullptr && m12[i] == own[i]); }
+            std::printf("sbk_nm=%d sbk_set=%d sbk_self=%d\n", nk, kset, kself);
             for (auto* p : own) delete p;
         }
         cv::Mat Kc = cv::Mat::zeros(3, 3, CV_32F), Dc = cv::Mat::zeros(4, 1, CV_32F);

@@ -490,6 +490,20 @@ int eorb_guided_search_by_bow_device(eorb_guided* g, const eorb_keypoint* d_kps_
                                      const eorb_keypoint* d_kps_f, const uint8_t* d_desc_f, int n2, const uint32_t* d_f_nodes,
                                      const int32_t* d_f_start, const uint32_t* d_f_feats, int nf, float nnratio, int check_ori,
                                      int32_t* d_match_f, int* nmatches);
+/* eorb_guided_search_by_bow_kf replaces ORBmatcher::SearchByBoW(KeyFrame* pKF1, KeyFrame* pKF2, vector<MapPoint*>& vpMatches12)
+ * (src/ORBmatcher.cc:833-990; loop closing / place recognition), monocular keyframes.  Same node walk as the keyframe-frame form; the
+ * candidates of the second keyframe need a good map point too (valid2, :889-893), the acceptance is bestDist1 < TH_LOW (strict, :912)
+ * and the result is indexed by the FIRST keyframe's feature: match12[i1] = feature index of keyframe 2 whose map point goes to
+ * vpMatches12[i1], or -1.  _device: every array resident, d_scratch_n2 = n2 ints of scratch. */
+int eorb_guided_search_by_bow_kf(eorb_guided* g, const eorb_keypoint* kps1, const uint8_t* desc1, const uint8_t* valid1, int n1,
+                                 const uint32_t* nodes1, const int32_t* start1, const uint32_t* feats1, int nn1, const eorb_keypoint* kps2,
+                                 const uint8_t* desc2, const uint8_t* valid2, int n2, const uint32_t* nodes2, const int32_t* start2,
+                                 const uint32_t* feats2, int nn2, float nnratio, int check_ori, int32_t* match12, int* nmatches);
+int eorb_guided_search_by_bow_kf_device(eorb_guided* g, const eorb_keypoint* d_kps1, const uint8_t* d_desc1, const uint8_t* d_valid1, int n1,
+                                        const uint32_t* d_nodes1, const int32_t* d_start1, const uint32_t* d_feats1, int nn1,
+                                        const eorb_keypoint* d_kps2, const uint8_t* d_desc2, const uint8_t* d_valid2, int n2,
+                                        const uint32_t* d_nodes2, const int32_t* d_start2, const uint32_t* d_feats2, int nn2, float nnratio,
+                                        int check_ori, int32_t* d_match12, int32_t* d_scratch_n2, int* nmatches);
 
 /* ---------------------------------------------------------------- bag of words + undistortion (fourth "next" row)
  * The two steps that follow extraction in the reference's Frame:

@@ -452,4 +452,68 @@ int orc_search_by_bow(const orc_keypoint* kps_kf, const uint8_t* desc_kf, const 
     return nmatches;
 }
 
+// ORBmatcher::SearchByBoW(KeyFrame* pKF1, KeyFrame* pKF2, vector<MapPoint*>& vpMatches12) (src/ORBmatcher.cc:833-990; loop closing /
+// place recognition), monocular keyframes.  Same walk of the common nodes as the keyframe-frame form, with three differences: the
+// candidates of the second keyframe need a good map point too (:889-893), the acceptance is `bestDist1 < TH_LOW` (strict, :912), and the
+// result is indexed by the FIRST keyframe's feature (vpMatches12[idx1] = map point of idx2, :916; the histogram holds idx1, :929).
+// valid1 / valid2 = a map point that is not bad; match12[i1] = feature index of keyframe 2 or -1; returns nmatches.
+int orc_search_by_bow_kf(const orc_keypoint* kps1, const uint8_t* desc1, const uint8_t* valid1, const uint32_t* nodes1, const int32_t* start1,
+                         const uint32_t* feats1, int nn1, int n1, const orc_keypoint* kps2, const uint8_t* desc2, const uint8_t* valid2,
+                         const uint32_t* nodes2, const int32_t* start2, const uint32_t* feats2, int nn2, int n2, float nnratio, int check_ori,
+                         int32_t* match12) {
+    const int TH_LOW = 50, HISTO_LENGTH = 30;
+    for (int i = 0; i < n1; i++) match12[i] = -1;
+    std::vector<bool> vbMatched2((size_t)n2, false);
+    int nmatches = 0;
+    std::vector<int> rotHist[HISTO_LENGTH];
+    const float factor = 1.0f / HISTO_LENGTH;
+    int a = 0, b = 0;
+    while (a < nn1 && b < nn2) {
+        if (nodes1[a] == nodes2[b]) {
+            for (int i1 = start1[a]; i1 < start1[a + 1]; i1++) {
+                const unsigned idx1 = feats1[i1];
+                if (!valid1[idx1]) continue;
+                const uint8_t* d1 = desc1 + (size_t)idx1 * 32;
+                int bestDist1 = 256, bestIdx2 = -1, bestDist2 = 256;
+                for (int i2 = start2[b]; i2 < start2[b + 1]; i2++) {
+                    const unsigned idx2 = feats2[i2];
+                    if (vbMatched2[idx2] || !valid2[idx2]) continue;
+                    const int dist = orc_descriptor_distance(d1, desc2 + (size_t)idx2 * 32);
+                    if (dist < bestDist1) { bestDist2 = bestDist1; bestDist1 = dist; bestIdx2 = (int)idx2; }
+                    else if (dist < bestDist2) bestDist2 = dist;
+                }
+                if (bestDist1 < TH_LOW && (float)bestDist1 < nnratio * (float)bestDist2) {
+                    match12[idx1] = bestIdx2;
+                    vbMatched2[(size_t)bestIdx2] = true;
+                    if (check_ori) {
+                        float rot = kps1[idx1].angle - kps2[bestIdx2].angle;
+                        if (rot < 0.0) rot += 360.0f;
+                        int bin = (int)std::round(rot * factor);
+                        if (bin == HISTO_LENGTH) bin = 0;
+                        if (bin >= 0 && bin < HISTO_LENGTH) rotHist[bin].push_back((int)idx1);
+                    }
+                    nmatches++;
+                }
+            }
+            a++; b++;
+        } else if (nodes1[a] < nodes2[b]) a++;
+        else b++;
+    }
+    if (check_ori) {
+        int max1 = 0, max2 = 0, max3 = 0, ind1 = -1, ind2 = -1, ind3 = -1;
+        for (int i = 0; i < HISTO_LENGTH; i++) {
+            const int s = (int)rotHist[i].size();
+            if (s > max1) { max3 = max2; max2 = max1; max1 = s; ind3 = ind2; ind2 = ind1; ind1 = i; }
+            else if (s > max2) { max3 = max2; max2 = s; ind3 = ind2; ind2 = i; }
+            else if (s > max3) { max3 = s; ind3 = i; }
+        }
+        if (max2 < 0.1f * (float)max1) { ind2 = -1; ind3 = -1; }
+        else if (max3 < 0.1f * (float)max1) { ind3 = -1; }
+        for (int i = 0; i < HISTO_LENGTH; i++)
+            if (i != ind1 && i != ind2 && i != ind3)
+                for (int idx : rotHist[i]) { match12[idx] = -1; nmatches--; }
+    }
+    return nmatches;
+}
+
 }  // extern "C"

@@ -173,6 +173,12 @@ int   orc_search_by_bow(const orc_keypoint* kps_kf, const uint8_t* desc_kf, cons
                         int n2, const uint32_t* f_nodes, const int32_t* f_start, const uint32_t* f_feats, int nf, float nnratio,
                         int check_ori, int32_t* match_f);
 
+/* ORBmatcher::SearchByBoW(pKF1, pKF2, vpMatches12) (ORBmatcher.cc:833-990), monocular keyframes; match12[n1] = feature index of keyframe 2 or -1 */
+int   orc_search_by_bow_kf(const orc_keypoint* kps1, const uint8_t* desc1, const uint8_t* valid1, const uint32_t* nodes1, const int32_t* start1,
+                           const uint32_t* feats1, int nn1, int n1, const orc_keypoint* kps2, const uint8_t* desc2, const uint8_t* valid2,
+                           const uint32_t* nodes2, const int32_t* start2, const uint32_t* feats2, int nn2, int n2, float nnratio, int check_ori,
+                           int32_t* match12);
+
 /* ---- bag of words + undistortion (bow_oracle.cc) ---- */
 typedef struct orc_vocab orc_vocab;
 /* flat form of what TemplatedVocabulary::loadFromTextFile builds: node 0 = root, parent[nid] < nid, children in id order,

@@ -213,4 +213,23 @@ int ref_search_by_bow(const orc_keypoint* kps_kf, const uint8_t* desc_kf, const 
     return nm;
 }
 
+/* ORBmatcher::SearchByBoW(pKF1, pKF2, vpMatches12) (ORBmatcher.cc:833-990); same contract as orc_search_by_bow_kf */
+int ref_search_by_bow_kf(const orc_keypoint* kps1, const uint8_t* desc1, const uint8_t* valid1, const uint32_t* nodes1, const int32_t* start1,
+                         const uint32_t* feats1, int nn1, int n1, const orc_keypoint* kps2, const uint8_t* desc2, const uint8_t* valid2,
+                         const uint32_t* nodes2, const int32_t* start2, const uint32_t* feats2, int nn2, int n2, float nnratio, int check_ori,
+                         int32_t* match12) {
+    KeyFrame k1, k2;
+    k1.mvKeysUn = toKps(kps1, n1); k1.mDescriptors = descMat(desc1, n1); fillFeatVec(k1.mFeatVec, nodes1, start1, feats1, nn1);
+    k2.mvKeysUn = toKps(kps2, n2); k2.mDescriptors = descMat(desc2, n2); fillFeatVec(k2.mFeatVec, nodes2, start2, feats2, nn2);
+    std::vector<MapPoint> m1((size_t)n1), m2((size_t)n2);
+    k1.mvpMapPoints.assign((size_t)n1, nullptr); k2.mvpMapPoints.assign((size_t)n2, nullptr);
+    for (int i = 0; i < n1; i++) { m1[i].id = i; if (valid1[i]) k1.mvpMapPoints[i] = &m1[i]; }
+    for (int i = 0; i < n2; i++) { m2[i].id = i; if (valid2[i]) k2.mvpMapPoints[i] = &m2[i]; }
+    std::vector<MapPoint*> out;
+    ORBmatcher matcher(nnratio, check_ori != 0);
+    const int nm = matcher.SearchByBoW(&k1, &k2, out);
+    for (int i = 0; i < n1; i++) match12[i] = out[i] ? out[i]->id : -1;
+    return nm;
+}
+
 }  // extern "C"

@@ -95,5 +95,9 @@ public:
     cv::KeyPoint getUndistKPtMono(const int idx) const { return mvKeysUn[idx]; }
     cv::KeyPoint getKPtRight(const int idx) const { return mvKeysRight[idx]; }
     cv::Mat getORBDescriptor(const int idx) const { return mDescriptors.row(idx); }
+    // SearchByBoW(KeyFrame*, KeyFrame*, ...) (ORBmatcher.cc:833-846)
+    const std::vector<cv::KeyPoint>& getAllUndistKPtsMono() const { return mvKeysUn; }
+    const cv::Mat& getAllORBDescriptors() const { return mDescriptors; }
+    int numAllKPts() const { return (int)mvKeysUn.size(); }
 };
 }  // namespace ORB_SLAM3

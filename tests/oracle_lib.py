@@ -507,6 +507,21 @@ def search_by_bow(kps_kf, desc_kf, valid_kf, fv_kf, kps_f, desc_f, fv_f, nnratio
     return n, mf[:len(k2)].copy()
 
 
+def search_by_bow_kf(kps1, desc1, valid1, fv1, kps2, desc2, valid2, fv2, nnratio=0.7, check_ori=True, _fn=None):
+    """ORBmatcher::SearchByBoW(pKF1, pKF2, vpMatches12) (ORBmatcher.cc:833-990), monocular keyframes -> (nmatches, match12[n1])"""
+    k1 = np.ascontiguousarray(kps1, KEYPOINT_DTYPE); k2 = np.ascontiguousarray(kps2, KEYPOINT_DTYPE)
+    d1 = np.ascontiguousarray(desc1, np.uint8); d2 = np.ascontiguousarray(desc2, np.uint8)
+    v1 = np.ascontiguousarray(valid1, np.uint8); v2 = np.ascontiguousarray(valid2, np.uint8)
+    a = [np.ascontiguousarray(fv1[0], np.uint32), np.ascontiguousarray(fv1[1], np.int32), np.ascontiguousarray(fv1[2], np.uint32)]
+    b = [np.ascontiguousarray(fv2[0], np.uint32), np.ascontiguousarray(fv2[1], np.int32), np.ascontiguousarray(fv2[2], np.uint32)]
+    m12 = np.full(max(len(k1), 1), -1, np.int32)
+    f = _fn or lib().orc_search_by_bow_kf
+    f.restype = C.c_int
+    n = f(_p(k1), _p(d1), _p(v1), _p(a[0]), _p(a[1]), _p(a[2]), C.c_int(len(a[0])), C.c_int(len(k1)), _p(k2), _p(d2), _p(v2), _p(b[0]), _p(b[1]),
+          _p(b[2]), C.c_int(len(b[0])), C.c_int(len(k2)), C.c_float(nnratio), C.c_int(int(check_ori)), _p(m12))
+    return n, m12[:len(k1)].copy()
+
+
 # ---- bag of words + undistortion (SURVEY 8f rank 4)
 class VocabOracle:
     def __init__(self, voc):

@@ -240,6 +240,11 @@ def search_by_bow(kps_kf, desc_kf, valid_kf, fv_kf, kps_f, desc_f, fv_f, nnratio
     return n, mf[:len(k2)].copy()
 
 
+def search_by_bow_kf(*a, **kw):
+    """the reference's own SearchByBoW(KeyFrame*, KeyFrame*, ...) body (cut into libref)"""
+    return O.search_by_bow_kf(*a, _fn=lib().ref_search_by_bow_kf, **kw)
+
+
 def features_in_area(kps, bounds, x, y, r, min_level=-1, max_level=-1):
     k = np.ascontiguousarray(kps, O.KEYPOINT_DTYPE); b = np.ascontiguousarray(bounds, np.float32)
     out = np.zeros(max(len(k), 1), np.int32)

@@ -256,6 +256,34 @@ def test_search_by_bow(n1, n2, seed, k, L, levelsup, ratio, ori):
         assert en > 50
 
 
+@pytest.mark.parametrize("n1,n2,seed,k,L,levelsup,ratio,ori", [
+    (1009, 1009, 71, 10, 4, 2, 0.7, True), (1009, 1009, 72, 10, 4, 2, 0.9, False), (5000, 5000, 73, 10, 3, 2, 0.75, True),
+    (2000, 2000, 74, 10, 2, 1, 0.8, True), (800, 800, 75, 5, 2, 4, 0.8, True), (0, 10, 76, 6, 3, 2, 0.7, True), (300, 1, 77, 6, 3, 2, 0.7, True)])
+def test_search_by_bow_keyframe_keyframe(n1, n2, seed, k, L, levelsup, ratio, ori):
+    """ORBmatcher::SearchByBoW(pKF1, pKF2, vpMatches12) (ORBmatcher.cc:833-990): second-side validity, strict TH_LOW, result indexed by the
+    first keyframe; bit-exact against the oracle (which equals the reference's own body, tests/test_ref_pin.py)"""
+    api = _api()
+    k1, d1, v1, fv1, k2, d2, fv2 = _bow_case(api, n1, n2, seed, k, L, levelsup)
+    v2 = (np.random.default_rng(seed).random(len(k2)) < 0.7).astype(np.uint8)
+    gm = api.GuidedMatcher(0, ratio, ori)
+    for rep in range(2):
+        n, m12 = gm.SearchByBoW_KF(k1, d1, v1, fv1, k2, d2, v2, fv2)
+        en, em12 = O.search_by_bow_kf(k1, d1, v1, fv1, k2, d2, v2, fv2, ratio, ori)
+        assert n == en and np.array_equal(m12, em12)
+    if n1 >= 500 and levelsup >= 2:
+        assert en > 30
+    # a distance of exactly TH_LOW = 50 is accepted by the keyframe-frame form (<=) and rejected here (<)
+    if n1 >= 1009 and ori:
+        q = d2[:1].copy()
+        bits = np.unpackbits(q[0]); bits[:50] ^= 1
+        kk1 = k1[:1]; dd1 = np.packbits(bits)[None, :]
+        one = (np.array([0], np.uint32), np.array([0, 1], np.int32), np.array([0], np.uint32))
+        gm2 = api.GuidedMatcher(0, 0.99, False)
+        assert gm2.SearchByBoW(kk1, dd1, np.ones(1, np.uint8), one, k2[:1], q, one)[0] == 1
+        assert gm2.SearchByBoW_KF(kk1, dd1, np.ones(1, np.uint8), one, k2[:1], q, np.ones(1, np.uint8), one)[0] == 0
+        assert O.search_by_bow_kf(kk1, dd1, np.ones(1, np.uint8), one, k2[:1], q, np.ones(1, np.uint8), one, 0.99, False)[0] == 0
+
+
 def test_search_by_bow_rejects_malformed_feature_vectors():
     api = _api()
     c = list(_bow_case(api, 200, 200, 51, 6, 3, 2))

@@ -181,6 +181,12 @@ def test_libref_matchers_vs_oracle_fresh_cases():
         cb = RC.bow_case(700, 650, seed, levelsup=2)
         o = O.search_by_bow(*cb, 0.7, True); r = R.search_by_bow(*cb, 0.7, True)
         assert o[0] == r[0] and np.array_equal(o[1], r[1]), seed
+        # keyframe-keyframe form (ORBmatcher.cc:833-990): the second side needs good map points too, strict TH_LOW, result indexed by side 1
+        k1, d1, v1, fv1, k2, d2, fv2 = cb
+        v2 = (np.random.default_rng(seed).random(len(k2)) < 0.75).astype(np.uint8)
+        for ratio, ori in ((0.7, True), (0.9, False)):
+            o = O.search_by_bow_kf(k1, d1, v1, fv1, k2, d2, v2, fv2, ratio, ori); r = R.search_by_bow_kf(k1, d1, v1, fv1, k2, d2, v2, fv2, ratio, ori)
+            assert o[0] == r[0] and np.array_equal(o[1], r[1]) and o[0] > 0, (seed, ratio, ori)
 
 
 # ------------------------------------------------------------------------------------------------ KannalaBrandt8 motion compensation

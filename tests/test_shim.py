@@ -49,7 +49,7 @@ def test_shims_compile_and_fail_loudly_without_device():
     assert "ret=-1 n=0" in out and "empty_ret=-1" in out
     assert "no CUDA device" in err
     assert "lk_ok=0 lk_n=0" in out and "elk_n=0 elk_nm1=0" in out
-    assert "sfi_nm=0 sfi_self=0" in out and "sbp_nm=0 sbp_set=0" in out and "slp_nm=0 slp_set=0" in out and "sbb_nm=0 sbb_set=0" in out
+    assert "sfi_nm=0 sfi_self=0" in out and "sbp_nm=0 sbp_set=0" in out and "slp_nm=0 slp_set=0" in out and "sbb_nm=0 sbb_set=0" in out and "sbk_nm=0 sbk_set=0" in out
     assert "sbs_nm=0 sbs_set=0" in out and "sbr_nm=0 sbr_set=0" in out
     assert "voc_ok=0" in out and "undist_ok=0" in out
 
@@ -114,3 +114,6 @@ def test_shims_match_oracle_on_gpu():
     nbb, bset, bself = map(int, bb.groups())
     # SearchByBoW of a frame against a keyframe with the same features: distance 0 to itself, so every match is the feature itself
     assert nbb == bset == bself and nbb > 0.5 * len(okps)
+    kk = re.search(r"sbk_nm=(\d+) sbk_set=(\d+) sbk_self=(\d+)", out)
+    nkk, kset, kself = map(int, kk.groups())
+    assert nkk == kset == kself == nbb         # keyframe-keyframe form on the same data: the same self matches, indexed by the first keyframe
