@@ -110,6 +110,8 @@ def _load():
         "eorb_guided_search_by_projection_map_points_stereo_device": ([vp, vp, vp, vp, i, vp, vp, vp, vp, i, vp, vp, i, f, i, f, f, vp, vp], i),
         "eorb_guided_search_by_bow": ([vp, vp, vp, vp, i, vp, vp, vp, i, vp, vp, i, vp, vp, vp, i, f, i, vp, vp], i),
         "eorb_guided_search_by_bow_device": ([vp, vp, vp, vp, i, vp, vp, vp, i, vp, vp, i, vp, vp, vp, i, f, i, vp, vp], i),
+        "eorb_guided_search_windows": ([vp, vp, vp, vp, i, vp, vp, vp, vp, i, vp, vp, vp, i, i, i, vp, vp, vp, vp], i),
+        "eorb_guided_search_windows_device": ([vp, vp, vp, vp, i, vp, vp, vp, vp, i, vp, vp, vp, i, i, i, vp, vp, vp, vp], i),
         "eorb_guided_search_by_bow_kf": ([vp, vp, vp, vp, i, vp, vp, vp, i, vp, vp, vp, i, vp, vp, vp, i, f, i, vp, vp], i),
         "eorb_guided_search_by_bow_kf_device": ([vp, vp, vp, vp, i, vp, vp, vp, i, vp, vp, vp, i, vp, vp, vp, i, f, i, vp, vp, vp], i),
         "eorb_guided_search_by_projection_map_points": ([vp, vp, vp, i, vp, vp, vp, i, vp, vp, i, f, i, f, f, vp, vp], i),
@@ -845,6 +847,38 @@ class GuidedMatcher:
                                                                C.c_float(thFarPoints), C.c_float(self.mfNNratio), _p(mc), C.byref(nm)),
                "SearchByProjection(map points)")
         return nm.value, mc[:len(k2)].copy()
+
+    def SearchWindows(self, queries, ur, descMP, kps2, desc2, held2, u_right2, bounds, query_min_xy=None, inv_level_sigma2=None, blocking=False,
+                      th_high=50):
+        """eorb_guided_search_windows: the matching core of the keyframe-side searches -- ORBmatcher::SearchByProjection(KeyFrame*, Scw, ...)
+        (:480, :595), Fuse (:1407, :1619), SearchBySim3 (:1743) -> (nmatches, best_idx[n1], best_dist[n1], match2[n2])"""
+        q = np.ascontiguousarray(queries, AREA_QUERY_DTYPE)
+        k2 = np.ascontiguousarray(kps2, KEYPOINT_DTYPE); dm = np.ascontiguousarray(descMP, np.uint8); d2 = np.ascontiguousarray(desc2, np.uint8)
+        b = np.ascontiguousarray(bounds, np.float32)
+        opt = lambda a, t: None if a is None else np.ascontiguousarray(a, t)
+        urq, hd, ur2, qm, inv = opt(ur, np.float32), opt(held2, np.uint8), opt(u_right2, np.float32), opt(query_min_xy, np.float32), opt(inv_level_sigma2, np.float32)
+        pp = lambda a: _p(a) if a is not None else None
+        bi = np.full(max(len(q), 1), -1, np.int32); bd = np.full(max(len(q), 1), 256, np.int32); m2 = np.full(max(len(k2), 1), -1, np.int32)
+        nm = C.c_int(0)
+        _check(lib.eorb_guided_search_windows(self.h, _p(q), pp(urq), _p(dm), len(q), _p(k2), _p(d2), pp(hd), pp(ur2), len(k2), _p(b), pp(qm), pp(inv),
+                                              0 if inv is None else len(inv), int(blocking), int(th_high), _p(bi), _p(bd), _p(m2), C.byref(nm)),
+               "SearchWindows")
+        return nm.value, bi[:len(q)].copy(), bd[:len(q)].copy(), m2[:len(k2)].copy()
+
+    def SearchWindows_device(self, d_queries, d_ur, d_descMP, n1, d_kps2, d_desc2, d_held2, d_u_right2, n2, bounds, d_best_idx, d_best_dist,
+                             d_match2, query_min_xy=None, inv_level_sigma2=None, blocking=False, th_high=50):
+        """device pointers (ints; optional ones may be 0); returns nmatches"""
+        b = np.ascontiguousarray(bounds, np.float32)
+        qm = None if query_min_xy is None else np.ascontiguousarray(query_min_xy, np.float32)
+        inv = None if inv_level_sigma2 is None else np.ascontiguousarray(inv_level_sigma2, np.float32)
+        nm = C.c_int(0)
+        vp = lambda a: C.c_void_p(a) if a else None
+        _check(lib.eorb_guided_search_windows_device(self.h, vp(d_queries), vp(d_ur), vp(d_descMP), n1, vp(d_kps2), vp(d_desc2), vp(d_held2),
+                                                     vp(d_u_right2), n2, _p(b), _p(qm) if qm is not None else None,
+                                                     _p(inv) if inv is not None else None, 0 if inv is None else len(inv), int(blocking),
+                                                     int(th_high), vp(d_best_idx), vp(d_best_dist), vp(d_match2), C.byref(nm)),
+               "SearchWindows_device")
+        return nm.value
 
     def SearchByBoW(self, kpsKF, descKF, validKF, fvKF, kpsF, descF, fvF):
         """ORBmatcher::SearchByBoW(pKF, F, vpMapPointMatches) (:276-478, monocular) -> (nmatches, match_f[n2]); fv* = (nodes, start,

@@ -5,6 +5,7 @@
 #include <cuda_runtime.h>
 
 #include <algorithm>
+#include <vector>
 #include <cstdio>
 #include <cstring>
 #include <mutex>
@@ -506,6 +507,143 @@ extern "C" int eorb_guided_search_by_projection_reloc_device(eorb_guided* g, con
     ex.reloc = 1; ex.d_level1 = d_level1; ex.d_held2 = d_held2; ex.thHigh = orb_dist;
     return searchProjDeviceCommon(g, "eorb_guided_search_by_projection_reloc_device", d_x3Dc, d_valid1, nullptr, d_kps1, d_descMP, n1, d_kps2, d_desc2,
                                   n2, bounds4, K4, scale_factors, nlevels, th, check_ori, ex, d_match_cur, nmatches);
+}
+
+// ------------------------------------------------------------------------------------------------ keyframe-side window searches
+static int searchWindowsRun(eorb_guided* g, const char* what, const eorb_area_query* d_q, const float* d_ur, const uint8_t* d_dmp, int n1,
+                            const eorb_keypoint* d_k2, const uint8_t* d_d2, const uint8_t* d_held, const float* d_ur2, int n2, const float* bounds4,
+                            const float* query_min_xy, const GuidedCandExtra& cx, int blocking, int thHigh, int32_t* d_bestIdx, int32_t* d_bestDist, int32_t* d_match2,
+                            int* nmatches) {
+    int rc = reserveWork(g, n1, n2);
+    if (rc != EORB_OK) return rc;
+    if (n1 > g->q1Cap) {   // claim[n1] of the blocking form lives in the matches12 staging buffer
+        CU(cudaStreamSynchronize(g->stream));
+        cudaFree(g->d_prev); cudaFree(g->d_m12);
+        g->d_prev = nullptr; g->d_m12 = nullptr; g->q1Cap = 0;
+        const int cap = std::max(1024, n1);
+        CU(cudaMalloc((void**)&g->d_prev, (size_t)cap * 2 * sizeof(float)));
+        CU(cudaMalloc((void**)&g->d_m12, (size_t)cap * sizeof(int32_t)));
+        g->q1Cap = cap;
+    }
+    if (blocking && !d_match2) {      // the ordered resolve always writes its slot table
+        if (n2 > g->pCap2) {
+            CU(cudaStreamSynchronize(g->stream));
+            cudaFree(g->d_mc); g->d_mc = nullptr; g->pCap2 = 0;
+            const int cap = std::max(1024, n2);
+            CU(cudaMalloc((void**)&g->d_mc, (size_t)cap * sizeof(int32_t)));
+            g->pCap2 = cap;
+        }
+        d_match2 = g->d_mc;
+    }
+    GuidedFrame f2{d_k2, d_d2, n2};
+    const GuidedGrid gg = gridGeom(bounds4);
+    GuidedGrid gq = gg;                       // KeyFrame::GetFeaturesInArea subtracts the keyframe's INT bounds (include/KeyFrame.h:529)
+    if (query_min_xy) { gq.minX = query_min_xy[0]; gq.minY = query_min_xy[1]; }
+    for (int attempt = 0; attempt < 2; attempt++) {
+        CU(launch_search_windows(d_q, d_ur, d_dmp, n1, f2, d_held, d_ur2, gg, gq, cx, blocking, thHigh, g->w, g->d_m12, d_bestIdx, d_bestDist, d_match2,
+                                 g->d_nm, g->stream, &g->launches));
+        CU(cudaMemcpyAsync(g->h_nm, g->d_nm, 2 * sizeof(int), cudaMemcpyDeviceToHost, g->stream));
+        CU(cudaStreamSynchronize(g->stream));
+        if (g->h_nm[1] <= g->w.candCap) { if (nmatches) *nmatches = g->h_nm[0]; return EORB_OK; }
+        cudaFree(g->w.cand); g->w.cand = nullptr;
+        g->w.candCap = g->h_nm[1] + g->h_nm[1] / 4;
+        CU(cudaMalloc((void**)&g->w.cand, (size_t)g->w.candCap * sizeof(uint32_t)));
+    }
+    return gFail(EORB_ERR_STATE, what, "candidate buffer overflow after growth");
+}
+
+static int windowsArgs(eorb_guided* g, const char* what, const void* queries, const void* descMP, int n1, const void* kps2, const void* desc2, int n2,
+                       const float* bounds4, const float* inv_level_sigma2, int nlevels, int th_high, const void* best_idx, int* nmatches,
+                       GuidedCandExtra& cx) {
+    if (!g) return gFail(EORB_ERR_ARG, what, "null handle");
+    int rc = checkFrames(queries, n1, kps2, n2, bounds4);
+    if (rc != EORB_OK) return rc;
+    if (nmatches) *nmatches = 0;
+    if ((n1 > 0 && (!descMP || !best_idx)) || (n2 > 0 && !desc2)) return gFail(EORB_ERR_ARG, what, "null argument");
+    if (th_high < 0 || th_high > 255) return gFail(EORB_ERR_ARG, what, "th_high must lie in [0, 255]");
+    cx = GuidedCandExtra{};
+    if (inv_level_sigma2) {
+        if (nlevels < 1 || nlevels > 32) return gFail(EORB_ERR_ARG, what, "bad level table (1..32 levels)");
+        cx.chi2 = 1;
+        for (int i = 0; i < 32; i++) cx.invSigma2[i] = inv_level_sigma2[i < nlevels ? i : nlevels - 1];
+    }
+    return EORB_OK;
+}
+
+extern "C" int eorb_guided_search_windows_device(eorb_guided* g, const eorb_area_query* d_queries, const float* d_ur, const uint8_t* d_descMP, int n1,
+                                                 const eorb_keypoint* d_kps2, const uint8_t* d_desc2, const uint8_t* d_held2,
+                                                 const float* d_u_right2, int n2, const float* bounds4, const float* query_min_xy, const float* inv_level_sigma2,
+                                                 int nlevels, int blocking, int th_high, int32_t* d_best_idx, int32_t* d_best_dist, int32_t* d_match2,
+                                                 int* nmatches) {
+    const char* what = "eorb_guided_search_windows_device";
+    GuidedCandExtra cx;
+    int rc = windowsArgs(g, what, d_queries, d_descMP, n1, d_kps2, d_desc2, n2, bounds4, inv_level_sigma2, nlevels, th_high, d_best_idx, nmatches, cx);
+    if (rc != EORB_OK) return rc;
+    if (n1 == 0) return EORB_OK;
+    if (((uintptr_t)d_descMP | (uintptr_t)d_desc2) & 15) return gFail(EORB_ERR_ARG, what, "descriptors must be 16-byte aligned");
+    CU(cudaSetDevice(g->device));
+    if (n2 == 0) {
+        CU(cudaMemsetAsync(d_best_idx, 0xff, (size_t)n1 * sizeof(int32_t), g->stream));
+        if (d_best_dist) {
+            std::vector<int32_t> none((size_t)n1, 256);
+            CU(cudaMemcpyAsync(d_best_dist, none.data(), (size_t)n1 * sizeof(int32_t), cudaMemcpyHostToDevice, g->stream));
+        }
+        CU(cudaStreamSynchronize(g->stream));
+        return EORB_OK;
+    }
+    return searchWindowsRun(g, what, d_queries, d_ur, d_descMP, n1, d_kps2, d_desc2, d_held2, d_u_right2, n2, bounds4, query_min_xy, cx, blocking != 0,
+                            th_high, d_best_idx, d_best_dist, d_match2, nmatches);
+}
+
+extern "C" int eorb_guided_search_windows(eorb_guided* g, const eorb_area_query* queries, const float* ur, const uint8_t* descMP, int n1,
+                                          const eorb_keypoint* kps2, const uint8_t* desc2, const uint8_t* held2, const float* u_right2, int n2,
+                                          const float* bounds4, const float* query_min_xy, const float* inv_level_sigma2, int nlevels, int blocking,
+                                          int th_high, int32_t* best_idx, int32_t* best_dist, int32_t* match2, int* nmatches) {
+    const char* what = "eorb_guided_search_windows";
+    GuidedCandExtra cx;
+    int rc = windowsArgs(g, what, queries, descMP, n1, kps2, desc2, n2, bounds4, inv_level_sigma2, nlevels, th_high, best_idx, nmatches, cx);
+    if (rc != EORB_OK) return rc;
+    for (int i = 0; i < n2 && match2; i++) match2[i] = -1;
+    for (int i = 0; i < n1; i++) { best_idx[i] = -1; if (best_dist) best_dist[i] = 256; }
+    if (n1 == 0 || n2 == 0) return EORB_OK;
+    CU(cudaSetDevice(g->device));
+    // staging: the map points' descriptors in frame slot 0 (its keypoint array receives the per-point results), the windows in w.q
+    if (n1 > g->kpCap[0]) {
+        CU(cudaStreamSynchronize(g->stream));
+        cudaFree(g->d_kps[0]); cudaFree(g->d_desc[0]);
+        g->d_kps[0] = nullptr; g->d_desc[0] = nullptr; g->kpCap[0] = 0;
+        const int cap = std::max(1024, n1);
+        CU(cudaMalloc((void**)&g->d_kps[0], (size_t)cap * sizeof(eorb_keypoint)));
+        CU(cudaMalloc((void**)&g->d_desc[0], (size_t)cap * 32));
+        g->kpCap[0] = cap;
+    }
+    if ((rc = stageFrame(g, 1, kps2, desc2, n2)) != EORB_OK) return rc;
+    if ((rc = reserveWork(g, n1, n2)) != EORB_OK) return rc;
+    if ((rc = reserveExtras(g, n1, n2)) != EORB_OK) return rc;
+    if (held2 && (rc = reserveHeld(g, n2)) != EORB_OK) return rc;
+    if (n2 > g->pCap2) {
+        CU(cudaStreamSynchronize(g->stream));
+        cudaFree(g->d_mc); g->d_mc = nullptr; g->pCap2 = 0;
+        const int cap = std::max(1024, n2);
+        CU(cudaMalloc((void**)&g->d_mc, (size_t)cap * sizeof(int32_t)));
+        g->pCap2 = cap;
+    }
+    static_assert(2 * sizeof(int32_t) <= sizeof(eorb_keypoint), "best_idx | best_dist are staged in the frame-1 keypoint buffer");
+    CU(cudaMemcpyAsync(g->w.q, queries, (size_t)n1 * sizeof(eorb_area_query), cudaMemcpyHostToDevice, g->stream));
+    CU(cudaMemcpyAsync(g->d_desc[0], descMP, (size_t)n1 * 32, cudaMemcpyHostToDevice, g->stream));
+    if (ur) CU(cudaMemcpyAsync(g->d_qUr, ur, (size_t)n1 * sizeof(float), cudaMemcpyHostToDevice, g->stream));
+    if (u_right2) CU(cudaMemcpyAsync(g->d_ur2, u_right2, (size_t)n2 * sizeof(float), cudaMemcpyHostToDevice, g->stream));
+    if (held2) CU(cudaMemcpyAsync(g->d_held, held2, (size_t)n2, cudaMemcpyHostToDevice, g->stream));
+    int32_t* d_bi = reinterpret_cast<int32_t*>(g->d_kps[0]);           // best_idx[n1] | best_dist[n1] in the (unused) frame-1 keypoint buffer
+    int32_t* d_bd = d_bi + n1;
+    rc = searchWindowsRun(g, what, g->w.q, ur ? g->d_qUr : nullptr, g->d_desc[0], n1, g->d_kps[1], g->d_desc[1], held2 ? g->d_held : nullptr,
+                          u_right2 ? g->d_ur2 : nullptr, n2, bounds4, query_min_xy, cx, blocking != 0, th_high, d_bi, d_bd, g->d_mc, nmatches);
+    if (rc != EORB_OK) return rc;
+    CU(cudaMemcpyAsync(best_idx, d_bi, (size_t)n1 * sizeof(int32_t), cudaMemcpyDeviceToHost, g->stream));
+    if (best_dist) CU(cudaMemcpyAsync(best_dist, d_bd, (size_t)n1 * sizeof(int32_t), cudaMemcpyDeviceToHost, g->stream));
+    if (match2 && blocking) CU(cudaMemcpyAsync(match2, g->d_mc, (size_t)n2 * sizeof(int32_t), cudaMemcpyDeviceToHost, g->stream));
+    CU(cudaStreamSynchronize(g->stream));
+    return EORB_OK;
 }
 
 // ------------------------------------------------------------------------------------------------ SearchByProjection (map points)

@@ -221,9 +221,14 @@ __device__ __forceinline__ u64 warp_sort32(u64 v, int lane) {
 // Rectified stereo (uRight2 != nullptr; Nleft == -1 with mvuRight set): a candidate with a right-image column is dropped when it lies
 // further than the window radius from the query's predicted right column qUr[i1] (ORBmatcher.cc:91-96, :2049-2055).  The test does
 // not depend on the order of the queries, so it is part of the candidate filter.
+// Keyframe-side searches (GuidedCandExtra, eorb_guided_search_windows): held2 != nullptr drops keypoints that are taken on entry (a
+// static filter: nothing is claimed during a non-blocking search); chi2 != 0 replaces the right-column test by the reprojection gate
+// of ORBmatcher::Fuse (ORBmatcher.cc:1532-1558): e2 * invLevelSigma2[octave] > 7.8 with a right column (mvuRight >= 0), > 5.99
+// without, float products compared against the double constants.
 __global__ void __launch_bounds__(256) guided_candidates_kernel(GuidedFrame f1, GuidedFrame f2, GuidedGrid g, const float* __restrict__ prevXY,
                                                                 float r0win, const eorb_area_query* __restrict__ qs, GuidedWork w,
-                                                                const float* __restrict__ uRight2, const float* __restrict__ qUr) {
+                                                                const float* __restrict__ uRight2, const float* __restrict__ qUr,
+                                                                GuidedCandExtra cx) {
     const int i1 = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
     if (i1 >= f1.n) return;
     const unsigned lt = (1u << lane) - 1u;
@@ -242,8 +247,22 @@ __global__ void __launch_bounds__(256) guided_candidates_kernel(GuidedFrame f1, 
     }
     const bool check = minL > 0 || maxL >= 0;              // bCheckLevels (Frame.cc:746)
     const bool stereo = uRight2 != nullptr && qUr != nullptr;
-    const float ur = stereo ? qUr[i1] : 0.0f;
+    const float ur = qUr ? qUr[i1] : 0.0f;
     auto stereoOk = [&](int i2) {
+        if (cx.held2 && cx.held2[i2]) return false;
+        if (cx.chi2) {
+            const eorb_keypoint& kp = f2.kps[i2];
+            const int lv = kp.octave < 0 ? 0 : (kp.octave > 31 ? 31 : kp.octave);
+            const float ex = __fsub_rn(x, kp.x), ey = __fsub_rn(y, kp.y);
+            float e2 = __fadd_rn(__fmul_rn(ex, ex), __fmul_rn(ey, ey));
+            const float u2 = uRight2 ? uRight2[i2] : -1.0f;
+            if (u2 >= 0.0f) {
+                const float er = __fsub_rn(ur, u2);
+                e2 = __fadd_rn(e2, __fmul_rn(er, er));
+                return !((double)__fmul_rn(e2, cx.invSigma2[lv]) > 7.8);
+            }
+            return !((double)__fmul_rn(e2, cx.invSigma2[lv]) > 5.99);
+        }
         if (!stereo) return true;
         const float u2 = uRight2[i2];
         return !(u2 > 0.0f && fabsf(__fsub_rn(ur, u2)) > r);
@@ -731,6 +750,49 @@ __global__ void __launch_bounds__(256) guided_resolve_proj_kernel(const eorb_key
     __syncthreads();
     for (int i = tid; i < n2; i += 256) matchCur[i] = (owner[i] != GUIDED_NONE && blk[i] == 0) ? (int)owner[i] : -1;
     if (tid == 0) *nmatchesOut = sNm;
+}
+
+// ------------------------------------------------------------------------------------------------ keyframe-side window searches
+// W1 guided_best_kernel: the non-blocking searches of local mapping / loop closing pick, per map point on its own, the candidate with
+// the smallest distance, the first one visited among equals (strict `dist < bestDist`: ORBmatcher::Fuse :1520-1571 and :1706-1724,
+// SearchBySim3 :1838-1858 and :1918-1938) -- entry 0 of the sorted head.  bestDist[i] = that distance (256: no candidate),
+// bestIdx[i] = its keypoint when bestDist <= thHigh, else -1.
+__global__ void __launch_bounds__(256) guided_best_kernel(int n1, GuidedWork w, int thHigh, int32_t* __restrict__ bestIdx,
+                                                          int32_t* __restrict__ bestDist, int* __restrict__ nmatchesOut) {
+    const int i = blockIdx.x * 256 + threadIdx.x;
+    const bool over = *w.total > w.candCap;
+    int acc = 0;
+    if (i < n1 && !over) {
+        int d = 256, idx = -1;
+        if (w.candCnt[i] > 0) {
+            const u64 e = w.top[(size_t)i * EORB_GUIDED_TOP];
+            d = (int)(e >> 32);
+            if (d <= thHigh) { idx = (int)(e & 0xffffu); acc = 1; }
+        }
+        bestIdx[i] = idx;
+        if (bestDist) bestDist[i] = d;
+    }
+    const int nb = __syncthreads_count(acc);
+    if (threadIdx.x == 0 && nb) atomicAdd(nmatchesOut, nb);     // zeroed by the launcher; the candidate total sits next to it (w.total)
+}
+
+// W2 guided_claim_dist_kernel: distance of every claim of a blocking search (the reference's bestDist of an accepted point)
+__global__ void __launch_bounds__(256) guided_claim_dist_kernel(const uint8_t* __restrict__ descMP, const uint8_t* __restrict__ desc2, int n1,
+                                                                const int32_t* __restrict__ claim, int32_t* __restrict__ bestIdx,
+                                                                int32_t* __restrict__ bestDist) {
+    const int i = blockIdx.x * 256 + threadIdx.x;
+    if (i >= n1) return;
+    const int c = claim[i];
+    int d = 256;
+    if (c >= 0) {
+        const uint4* a = reinterpret_cast<const uint4*>(descMP + (size_t)i * 32);
+        const uint4* b = reinterpret_cast<const uint4*>(desc2 + (size_t)c * 32);
+        const uint4 a0 = __ldg(a), a1 = __ldg(a + 1), b0 = __ldg(b), b1 = __ldg(b + 1);
+        d = __popc(a0.x ^ b0.x) + __popc(a0.y ^ b0.y) + __popc(a0.z ^ b0.z) + __popc(a0.w ^ b0.w) + __popc(a1.x ^ b1.x) + __popc(a1.y ^ b1.y) +
+            __popc(a1.z ^ b1.z) + __popc(a1.w ^ b1.w);
+    }
+    bestIdx[i] = c;
+    if (bestDist) bestDist[i] = d;
 }
 
 // ------------------------------------------------------------------------------------------------ SearchByProjection (map points)
@@ -1240,7 +1302,7 @@ cudaError_t launch_search_init(const GuidedFrame& f1, const GuidedFrame& f2, Gui
     if (e != cudaSuccess) return e;
     (*launches)++;
     if (f1.n > 0) {
-        guided_candidates_kernel<<<(f1.n + 7) / 8, 256, 0, st>>>(f1, f2, g, d_prevXY, (float)window, nullptr, w, nullptr, nullptr);
+        guided_candidates_kernel<<<(f1.n + 7) / 8, 256, 0, st>>>(f1, f2, g, d_prevXY, (float)window, nullptr, w, nullptr, nullptr, GuidedCandExtra{});
         (*launches)++;
     }
     guided_resolve_kernel<<<1, 256, resolveSmem(f1.n, f2.n), st>>>(f1, f2, d_prevXY, nnratio, checkOri, w, d_matches12, d_nmatches);
@@ -1260,7 +1322,7 @@ cudaError_t launch_search_proj(const float* d_x3Dc, const uint8_t* d_valid1, con
     if (n1 > 0) {
         guided_project_kernel<<<(n1 + 255) / 256, 256, 0, st>>>(d_x3Dc, d_valid1, d_kps1, n1, pr, w.q, md);
         GuidedFrame f1{d_kps1, d_descMP, n1};
-        guided_candidates_kernel<<<(n1 + 7) / 8, 256, 0, st>>>(f1, f2, g, nullptr, 0.f, w.q, w, d_uRight2, d_uRight2 ? md.qUr : nullptr);
+        guided_candidates_kernel<<<(n1 + 7) / 8, 256, 0, st>>>(f1, f2, g, nullptr, 0.f, w.q, w, d_uRight2, d_uRight2 ? md.qUr : nullptr, GuidedCandExtra{});
         (*launches) += 2;
     }
     guided_resolve_proj_kernel<<<1, 256, resolveProjSmem(n1, f2.n), st>>>(d_kps1, d_obs1, n1, f2, checkOri, w, d_claim, d_matchCur, d_nmatches, d_held2,
@@ -1281,7 +1343,7 @@ cudaError_t launch_search_map_points(const eorb_track_point* d_pts, const uint8_
     if (n1 > 0) {
         guided_mappoint_query_kernel<<<(n1 + 255) / 256, 256, 0, st>>>(d_pts, n1, pr, farPoints, thFar, w.q);
         GuidedFrame f1{nullptr, d_descMP, n1};
-        guided_candidates_kernel<<<(n1 + 7) / 8, 256, 0, st>>>(f1, f2, g, nullptr, 0.f, w.q, w, d_uRight2, d_projXR);
+        guided_candidates_kernel<<<(n1 + 7) / 8, 256, 0, st>>>(f1, f2, g, nullptr, 0.f, w.q, w, d_uRight2, d_projXR, GuidedCandExtra{});
         (*launches) += 2;
     }
     guided_resolve_map_kernel<<<1, 256, resolveMapSmem(n1, f2.n), st>>>(d_pts, n1, f2, d_held2, nnratio, w, d_matchCur, d_nmatches);
@@ -1305,6 +1367,39 @@ cudaError_t launch_search_by_bow(const GuidedBowSide& kf, const uint8_t* d_valid
     search_by_bow_kernel<<<blocks, BOW_WARPS * 32, 0, st>>>(kf, d_validKF, f, nnratio, checkOri, d_matchF, d_work, d_nmatches, d_validF,
                                                            d_match12 ? 49 : 50, d_match12);
     (*launches)++;
+    return cudaGetLastError();
+}
+
+cudaError_t launch_search_windows(const eorb_area_query* d_q, const float* d_qUr, const uint8_t* d_descMP, int n1, const GuidedFrame& f2,
+                                  const uint8_t* d_held2, const float* d_uRight2, GuidedGrid g, GuidedGrid gq, const GuidedCandExtra& cx, int blocking,
+                                  int thHigh, const GuidedWork& w, int32_t* d_claim, int32_t* d_bestIdx, int32_t* d_bestDist, int32_t* d_match2, int* d_nmatches,
+                                  cudaStream_t st, long long* launches) {
+    cudaError_t e = cudaMemsetAsync(w.total, 0, sizeof(int), st);
+    if (e != cudaSuccess) return e;
+    e = cudaMemsetAsync(d_nmatches, 0, sizeof(int), st);
+    if (e != cudaSuccess) return e;
+    e = launch_frame_grid(f2.kps, f2.n, g, w.cellStart, w.cellIdx, w.assigned, st);
+    if (e != cudaSuccess) return e;
+    (*launches)++;
+    GuidedFrame f1{nullptr, d_descMP, n1};
+    GuidedCandExtra c2 = cx;
+    c2.held2 = blocking ? nullptr : d_held2;      // the blocking resolve keeps its own table of taken slots
+    if (n1 > 0) {
+        guided_candidates_kernel<<<(n1 + 7) / 8, 256, 0, st>>>(f1, f2, gq, nullptr, 0.f, d_q, w, d_uRight2, d_qUr, c2);
+        (*launches)++;
+    }
+    if (blocking) {
+        // vpMatched[idx] != NULL skips the keypoint whatever the point (ORBmatcher.cc:563, :678): the relocalisation form of the ordered resolve
+        guided_resolve_proj_kernel<<<1, 256, resolveProjSmem(n1, f2.n), st>>>(nullptr, nullptr, n1, f2, 0, w, d_claim, d_match2, d_nmatches, d_held2, thHigh);
+        (*launches)++;
+        if (n1 > 0) {
+            guided_claim_dist_kernel<<<(n1 + 255) / 256, 256, 0, st>>>(d_descMP, f2.desc, n1, d_claim, d_bestIdx, d_bestDist);
+            (*launches)++;
+        }
+    } else if (n1 > 0) {
+        guided_best_kernel<<<(n1 + 255) / 256, 256, 0, st>>>(n1, w, thHigh, d_bestIdx, d_bestDist, d_nmatches);
+        (*launches)++;
+    }
     return cudaGetLastError();
 }
 

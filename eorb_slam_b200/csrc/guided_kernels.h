@@ -64,6 +64,14 @@ cudaError_t launch_search_by_bow(const GuidedBowSide& kf, const uint8_t* d_valid
                                  int32_t* d_matchF, int* d_work /* 64 ints */, int* d_nmatches, cudaStream_t st, long long* launches,
                                  const uint8_t* d_validF = nullptr /* keyframe-keyframe form: good map points of side 2 */,
                                  int32_t* d_match12 = nullptr /* keyframe-keyframe form: result indexed by side 1 (kf.n entries) */);
+// Keyframe-side window searches (eorb_guided_search_windows): the caller's windows (x, y, r, level range) per map point; static
+// candidate filters: slots taken on entry (non-blocking searches) and the reprojection gate of Fuse (chi2, invSigma2 = mvInvLevelSigma2).
+// g = geometry the keypoints were binned with (the Frame's float bounds), gq = geometry of the window lookup (the KeyFrame's int bounds)
+struct GuidedCandExtra { const uint8_t* held2 = nullptr; int chi2 = 0; float invSigma2[32] = {0}; };
+cudaError_t launch_search_windows(const eorb_area_query* d_q, const float* d_qUr, const uint8_t* d_descMP, int n1, const GuidedFrame& f2,
+                                  const uint8_t* d_held2, const float* d_uRight2, GuidedGrid g, GuidedGrid gq, const GuidedCandExtra& cx, int blocking,
+                                  int thHigh, const GuidedWork& w, int32_t* d_claim, int32_t* d_bestIdx, int32_t* d_bestDist, int32_t* d_match2, int* d_nmatches,
+                                  cudaStream_t st, long long* launches);
 cudaError_t guided_configure();
 
 }  // namespace eorb

@@ -474,6 +474,41 @@ int eorb_guided_search_by_projection_map_points_stereo_device(eorb_guided* g, co
                                                               float th, int far_points, float th_far, float nnratio,
                                                               int32_t* d_match_cur, int* nmatches);
 
+/* eorb_guided_search_windows: the matching core of the KEYFRAME-side searches of local mapping and loop closing, which all have one
+ * shape -- per map point a window in a keyframe (GetFeaturesInArea(u, v, radius), src/KeyFrame.cc:873-917), keypoints of level
+ * [nPredictedLevel - 1, nPredictedLevel], smallest descriptor distance, first visited among equals:
+ *   ORBmatcher::SearchByProjection(KeyFrame* pKF, cv::Mat Scw, const vector<MapPoint*>& vpPoints, vector<MapPoint*>& vpMatched, int th,
+ *       float ratioHamming) (src/ORBmatcher.cc:480-593) and the overload with vpPointsKFs / vpMatchedKF (:595-712): blocking = 1 (a
+ *       keypoint with vpMatched[idx] set -- on entry = held2, or by an earlier point of this call -- is skipped, :563, :678),
+ *       th_high = (int)floor(TH_LOW * ratioHamming);
+ *   ORBmatcher::Fuse(KeyFrame* pKF, const vector<MapPoint*>& vpMapPoints, float th, bool bRight) (:1407-1617): blocking = 0,
+ *       inv_level_sigma2 = mvInvLevelSigma2 (the reprojection gate :1532-1558: e2 * invSigma2[octave] > 5.99, or > 7.8 with the
+ *       right-image term when u_right2[idx] >= 0, ur[i] = uv.x - bf * invz), th_high = TH_LOW;
+ *   ORBmatcher::Fuse(KeyFrame* pKF, cv::Mat Scw, const vector<MapPoint*>& vpPoints, float th, vector<MapPoint*>& vpReplacePoint)
+ *       (:1619-1741): blocking = 0, no gate, th_high = TH_LOW;
+ *   ORBmatcher::SearchBySim3 (:1743-1967): one call per direction, blocking = 0, th_high = TH_HIGH; the agreement test stays on the host.
+ * queries[i] = the window of map point i as the reference forms it on the host from the MapPoint / KeyFrame accessors (projection
+ * through the keyframe's camera, IsInImage, distance and viewing-angle gates, PredictScale): x, y = uv, r = th * scale[level],
+ * min_level = level - 1, max_level = level; r <= 0 = the point failed a gate (no query).  descMP = GetDescriptor() per point.
+ * kps2 / desc2 = the keyframe's undistorted keypoints and descriptors, held2 (may be NULL) = slots to skip.  bounds4 = the image bounds
+ * the keyframe's grid was built with (the Frame's floats, src/KeyFrame.cc:73-110 copies F.mGrid); query_min_xy (may be NULL = bounds4's)
+ * = (float)mnMinX, (float)mnMinY of the KeyFrame, which are INTS (include/KeyFrame.h:529: the window lookup subtracts the truncated
+ * bounds, the two differ for distorted cameras).
+ * best_idx[i] = the keypoint map point i matched (best candidate with distance <= th_high; blocking: that it claimed), else -1;
+ * best_dist[i] (may be NULL) = non-blocking: distance of the best candidate whether accepted or not (256: no candidate); blocking:
+ * distance of the claimed keypoint (256: no claim); match2[i2] (blocking only, may be NULL) = the point that claimed keypoint i2 or -1;
+ * *nmatches = number of points with best_idx >= 0.  The map updates that follow (Replace / AddObservation / vpMatched) stay with the
+ * caller, in the order of the points, as in the reference. */
+int eorb_guided_search_windows(eorb_guided* g, const eorb_area_query* queries, const float* ur, const uint8_t* descMP, int n1,
+                               const eorb_keypoint* kps2, const uint8_t* desc2, const uint8_t* held2, const float* u_right2, int n2,
+                               const float* bounds4, const float* query_min_xy, const float* inv_level_sigma2, int nlevels, int blocking,
+                               int th_high, int32_t* best_idx, int32_t* best_dist, int32_t* match2, int* nmatches);
+/* the same with every array resident in HBM (results are written on the device, *nmatches after a stream synchronisation) */
+int eorb_guided_search_windows_device(eorb_guided* g, const eorb_area_query* d_queries, const float* d_ur, const uint8_t* d_descMP, int n1,
+                                      const eorb_keypoint* d_kps2, const uint8_t* d_desc2, const uint8_t* d_held2, const float* d_u_right2,
+                                      int n2, const float* bounds4, const float* query_min_xy, const float* inv_level_sigma2, int nlevels,
+                                      int blocking, int th_high, int32_t* d_best_idx, int32_t* d_best_dist, int32_t* d_match2, int* nmatches);
+
 /* eorb_guided_search_by_bow replaces ORBmatcher::SearchByBoW(KeyFrame* pKF, Frame& F, vector<MapPoint*>& vpMapPointMatches)
  * (src/ORBmatcher.cc:276-478) as called by Tracking::TrackReferenceKeyFrame and Relocalization (src/Tracking-1.cc:1680, 2625)
  * for a monocular frame.  kps_kf / desc_kf = the keyframe's undistorted keypoints and descriptors, valid_kf[i] != 0 =

@@ -516,4 +516,65 @@ int orc_search_by_bow_kf(const orc_keypoint* kps1, const uint8_t* desc1, const u
     return nmatches;
 }
 
+// The matching core the keyframe-side searches share -- ORBmatcher::SearchByProjection(KeyFrame*, cv::Mat Scw, ...)
+// (src/ORBmatcher.cc:480-593 and :595-712), ORBmatcher::Fuse (:1407-1617 and :1619-1741), ORBmatcher::SearchBySim3 (:1743-1967):
+// per map point i, in list order, the window the caller formed (x, y, r <= 0: the point failed a gate; KeyFrame::GetFeaturesInArea,
+// src/KeyFrame.cc:873-917, has no level arguments: the level test `kpLevel < nPredictedLevel-1 || kpLevel > nPredictedLevel` sits in
+// the candidate loop, :568-569 / :1526-1527 / :1713-1714 / :1846-1847), the smallest DescriptorDistance with strict `<`, accepted when
+// <= th_high.  blocking: `if(vpMatched[idx]) continue;` (:563, :678) with vpMatched = held2 on entry + this call's own matches.
+// inv_level_sigma2 != NULL: Fuse's reprojection gate (:1532-1558) in float, the product compared with the double constants.
+int orc_search_windows(const orc_area_query* queries, const float* ur, const uint8_t* descMP, int n1, const orc_keypoint* kps2, const uint8_t* desc2,
+                       const uint8_t* held2, const float* u_right2, int n2, const float* bounds4, const float* query_min_xy,
+                       const float* inv_level_sigma2, int nlevels, int blocking, int th_high, int32_t* best_idx, int32_t* best_dist,
+                       int32_t* match2) {
+    GridGeom g(bounds4);      // the keypoints are binned with the Frame's float bounds (orc_frame_grid below) ...
+    if (query_min_xy) { g.minX = query_min_xy[0]; g.minY = query_min_xy[1]; }   // ... the lookup subtracts the KeyFrame's int bounds
+    std::vector<int> cellStart(GC * GR + 1), cellIdx((size_t)std::max(n2, 1));
+    orc_frame_grid(kps2, n2, bounds4, cellStart.data(), cellIdx.data());
+    std::vector<uint8_t> taken((size_t)std::max(n2, 1), 0);
+    for (int i = 0; i < n2; i++) { taken[i] = held2 && held2[i] ? 1 : 0; if (match2) match2[i] = -1; }
+    int nmatches = 0;
+    std::vector<int> vIndices;
+    for (int i = 0; i < n1; i++) {
+        best_idx[i] = -1;
+        if (best_dist) best_dist[i] = 256;
+        const orc_area_query& q = queries[i];
+        if (!(q.r > 0.0f)) continue;
+        featuresInArea(kps2, g, cellStart.data(), cellIdx.data(), q.x, q.y, q.r, -1, -1, vIndices);
+        const uint8_t* dMP = descMP + (size_t)i * 32;
+        int bestDist = 256, bestIdx = -1;
+        for (int idx : vIndices) {
+            if (taken[idx]) continue;
+            const orc_keypoint& kp = kps2[idx];
+            const int kpLevel = kp.octave;
+            if (q.min_level > 0 || q.max_level >= 0) {
+                if (kpLevel < q.min_level) continue;
+                if (q.max_level >= 0 && kpLevel > q.max_level) continue;
+            }
+            if (inv_level_sigma2) {
+                const int lv = kpLevel < 0 ? 0 : (kpLevel >= nlevels ? nlevels - 1 : kpLevel);
+                const float ex = q.x - kp.x, ey = q.y - kp.y;
+                if (u_right2 && u_right2[idx] >= 0) {
+                    const float er = (ur ? ur[i] : 0.0f) - u_right2[idx];
+                    const float e2 = ex * ex + ey * ey + er * er;
+                    if (e2 * inv_level_sigma2[lv] > 7.8) continue;
+                } else {
+                    const float e2 = ex * ex + ey * ey;
+                    if (e2 * inv_level_sigma2[lv] > 5.99) continue;
+                }
+            }
+            const int dist = orc_descriptor_distance(dMP, desc2 + (size_t)idx * 32);
+            if (dist < bestDist) { bestDist = dist; bestIdx = idx; }
+        }
+        // reported distance: the best candidate's (non-blocking searches); the claimed keypoint's, 256 without a claim (blocking searches)
+        if (best_dist) best_dist[i] = (!blocking || (bestIdx >= 0 && bestDist <= th_high)) ? bestDist : 256;
+        if (bestIdx >= 0 && bestDist <= th_high) {
+            best_idx[i] = bestIdx;
+            nmatches++;
+            if (blocking) { taken[bestIdx] = 1; if (match2) match2[bestIdx] = i; }
+        }
+    }
+    return nmatches;
+}
+
 }  // extern "C"

@@ -146,6 +146,15 @@ int   orc_search_by_projection_reloc(const float* x3Dc, const uint8_t* valid1, c
                                      const float* bounds4, const float* K4, const float* scale_factors, int nlevels, float th, int orb_dist,
                                      int check_ori, int32_t* match_cur);
 
+/* matching core of the keyframe-side searches (ORBmatcher.cc:480-712 SearchByProjection(KeyFrame*, Scw, ...), :1407-1741 Fuse,
+   :1743-1967 SearchBySim3): the caller's window per map point, best candidate of level [min_level, max_level], optional blocking
+   (vpMatched) and optional reprojection gate of Fuse; returns the number of accepted points */
+typedef struct orc_area_query { float x, y, r; int32_t min_level, max_level; } orc_area_query;
+int   orc_search_windows(const orc_area_query* queries, const float* ur, const uint8_t* descMP, int n1, const orc_keypoint* kps2,
+                         const uint8_t* desc2, const uint8_t* held2, const float* u_right2, int n2, const float* bounds4,
+                         const float* query_min_xy, const float* inv_level_sigma2, int nlevels, int blocking, int th_high, int32_t* best_idx, int32_t* best_dist,
+                         int32_t* match2);
+
 /* ORBmatcher::SearchByProjection(F, vpMapPoints, th, bFarPoints, thFarPoints) (ORBmatcher.cc:44-218), monocular frame.
    orc_track_point = the MapPoint fields Frame::isInFrustum fills (mTrackProjX/Y, mTrackViewCos, mTrackDepth, mnTrackScaleLevel,
    mbTrackInView) + Observations() + isBad(); held2 (may be null) = slots of F that hold a point with observations on entry;

@@ -8,6 +8,7 @@
 #include <cmath>
 #include <map>
 #include <set>
+#include <tuple>
 #include <vector>
 #include <opencv2/core/core.hpp>
 #include "GeometricCamera.h"
@@ -35,9 +36,22 @@ public:
     int Observations() { return nObs; }
     cv::Mat GetDescriptor() { return desc.clone(); }
     cv::Mat GetWorldPos() { return pos.clone(); }
-    float GetMaxDistanceInvariance() { return 1e30f; }
-    float GetMinDistanceInvariance() { return 0.0f; }
+    float GetMaxDistanceInvariance() { return maxDist; }
+    float GetMinDistanceInvariance() { return minDist; }
     int PredictScale(const float&, Frame*) { return predictedLevel; }
+    // keyframe-side searches (ORBmatcher.cc:480-712, :1407-1967): the map-graph calls are recorded, not performed
+    int PredictScale(const float&, KeyFrame*) { return predictedLevel; }
+    cv::Mat GetNormal() { return normal.clone(); }
+    bool IsInKeyFrame(KeyFrame*) { return inKF; }
+    static std::vector<std::pair<MapPoint*, MapPoint*> >& replaceLog() { static std::vector<std::pair<MapPoint*, MapPoint*> > v; return v; }
+    void Replace(MapPoint* p) { replacedBy = p; replaceLog().push_back(std::make_pair(this, p)); }
+    void AddObservation(KeyFrame*, int idx) { addedObsIdx = idx; }
+    std::tuple<int, int> GetIndexInKeyFrame(KeyFrame*) { return std::tuple<int, int>(idxInOtherKF, -1); }
+    float maxDist = 1e30f, minDist = 0.0f;
+    cv::Mat normal;
+    bool inKF = false;
+    MapPoint* replacedBy = nullptr;
+    int addedObsIdx = -1, idxInOtherKF = -1;
     bool bad = false;
     int nObs = 1, predictedLevel = 0, id = -1;
     cv::Mat desc, pos;
@@ -95,6 +109,31 @@ public:
     cv::KeyPoint getUndistKPtMono(const int idx) const { return mvKeysUn[idx]; }
     cv::KeyPoint getKPtRight(const int idx) const { return mvKeysRight[idx]; }
     cv::Mat getORBDescriptor(const int idx) const { return mDescriptors.row(idx); }
+    // keyframe-side searches: calibration, pose, grid (KeyFrame::GetFeaturesInArea / IsInImage are the reference's own text,
+    // src/KeyFrame.cc:873-922, cut at build time), level tables, map-point slots
+    float fx = 0, fy = 0, cx = 0, cy = 0, mbf = 0;
+    GeometricCamera* mpCamera = nullptr;
+    int N = 0;
+    int mnMinX = 0, mnMinY = 0, mnMaxX = 0, mnMaxY = 0;          // include/KeyFrame.h: const int
+    int mnGridCols = FRAME_GRID_COLS, mnGridRows = FRAME_GRID_ROWS;
+    float mfGridElementWidthInv = 0, mfGridElementHeightInv = 0;
+    std::vector<std::vector<std::vector<std::size_t> > > mGrid, mGridRight;
+    std::vector<float> mvuRight, mvScaleFactors, mvInvLevelSigma2;
+    cv::Mat Rcw, tcw, Ow;
+    cv::Mat GetRotation() { return Rcw.clone(); }
+    cv::Mat GetTranslation() { return tcw.clone(); }
+    cv::Mat GetCameraCenter() { return Ow.clone(); }
+    cv::Mat GetRightRotation() { return Rcw.clone(); }
+    cv::Mat GetRightTranslation() { return tcw.clone(); }
+    cv::Mat GetRightCameraCenter() { return Ow.clone(); }
+    float getORBScaleFactor(const int level) const { return mvScaleFactors[level]; }
+    float getORBInvLevelSigma2(const int level) const { return mvInvLevelSigma2[level]; }
+    int getKPtLevelMono(const int idx) const { return mvKeysUn[idx].octave; }        // KeyFrame.cc:1428-1431
+    MapPoint* GetMapPoint(const std::size_t& idx) { return mvpMapPoints[idx]; }
+    void AddMapPoint(MapPoint* p, const std::size_t& idx) { mvpMapPoints[idx] = p; }
+    std::set<MapPoint*> GetMapPoints() { std::set<MapPoint*> s; for (MapPoint* p : mvpMapPoints) if (p) s.insert(p); return s; }
+    std::vector<std::size_t> GetFeaturesInArea(const float& x, const float& y, const float& r, const bool bRight = false) const;
+    bool IsInImage(const float& x, const float& y) const;
     // SearchByBoW(KeyFrame*, KeyFrame*, ...) (ORBmatcher.cc:833-846)
     const std::vector<cv::KeyPoint>& getAllUndistKPtsMono() const { return mvKeysUn; }
     const cv::Mat& getAllORBDescriptors() const { return mDescriptors; }

@@ -199,6 +199,7 @@ public:
         for (int y = 0; y < rows; y++) for (int x = 0; x < cols; x++) r.at<float>(x, y) = at<float>(y, x);
         return r;
     }
+    inline double dot(const Mat& o) const;
     Mat mul(const Mat& o) const {
         if (flags != CV_32F || o.flags != CV_32F || rows != o.rows || cols != o.cols) CVMINI_FAIL("Mat::mul");
         Mat r(rows, cols, CV_32F);
@@ -258,6 +259,55 @@ static inline Mat operator-(const Mat& a) {
     for (int i = 0; i < a.rows; i++) for (int j = 0; j < a.cols; j++) r.at<float>(i, j) = -a.at<float>(i, j);
     return r;
 }
+// 3 x 3 CV_32F inverse the way cv::invert's small-matrix path forms it: determinant and cofactors in double, one rounding per element
+static inline Mat matInv3(const Mat& m) {
+    if (m.type() != CV_32F || m.rows != 3 || m.cols != 3) CVMINI_FAIL("Mat::inv (3x3 CV_32F only)");
+    auto S = [&](int y, int x) { return (double)m.at<float>(y, x); };
+    double d = S(0, 0) * (S(1, 1) * S(2, 2) - S(1, 2) * S(2, 1)) - S(0, 1) * (S(1, 0) * S(2, 2) - S(1, 2) * S(2, 0)) + S(0, 2) * (S(1, 0) * S(2, 1) - S(1, 1) * S(2, 0));
+    Mat r = Mat::zeros(3, 3, CV_32F);
+    if (d == 0.) return r;
+    d = 1. / d;
+    r.at<float>(0, 0) = (float)((S(1, 1) * S(2, 2) - S(1, 2) * S(2, 1)) * d);
+    r.at<float>(0, 1) = (float)((S(0, 2) * S(2, 1) - S(0, 1) * S(2, 2)) * d);
+    r.at<float>(0, 2) = (float)((S(0, 1) * S(1, 2) - S(0, 2) * S(1, 1)) * d);
+    r.at<float>(1, 0) = (float)((S(1, 2) * S(2, 0) - S(1, 0) * S(2, 2)) * d);
+    r.at<float>(1, 1) = (float)((S(0, 0) * S(2, 2) - S(0, 2) * S(2, 0)) * d);
+    r.at<float>(1, 2) = (float)((S(0, 2) * S(1, 0) - S(0, 0) * S(1, 2)) * d);
+    r.at<float>(2, 0) = (float)((S(1, 0) * S(2, 1) - S(1, 1) * S(2, 0)) * d);
+    r.at<float>(2, 1) = (float)((S(0, 1) * S(2, 0) - S(0, 0) * S(2, 1)) * d);
+    r.at<float>(2, 2) = (float)((S(0, 0) * S(1, 1) - S(0, 1) * S(1, 0)) * d);
+    return r;
+}
+// cv::Mat_<float>(r, c) << a, b, c ... (Pinhole::SkewSymmetricMatrix): row-major fill
+template <class T> struct MatCommaInit_ {
+    Mat m; int idx = 0;
+    explicit MatCommaInit_(const Mat& mm) : m(mm) {}
+    template <class V> MatCommaInit_& operator,(V v) { m.at<T>(idx / m.cols, idx % m.cols) = (T)v; idx++; return *this; }
+    operator Mat() const { return m; }
+};
+template <class T> struct Mat_ : public Mat {
+    Mat_(int r, int c) : Mat(r, c, CV_32F) { static_assert(sizeof(T) == 4, "Mat_<float> only"); }
+    template <class V> MatCommaInit_<T> operator<<(V v) { MatCommaInit_<T> ci(*this); ci, v; return ci; }
+};
+// scalar scaling and the dot product of the keyframe-side searches (sRcw / scw, s12 * R12, (1.0 / s12) * R12.t(), row.dot(row),
+// PO.dot(Pn): ORBmatcher.cc:491-494, :538, :1757-1759): element * double factor rounded once, dot accumulated in double like cv::Mat::dot.
+// The pin only calls these with factor 1 and identity rotations, where every formula OpenCV could use gives the same floats.
+static inline Mat matScale(const Mat& a, double f) {
+    if (a.type() != CV_32F) CVMINI_FAIL("Mat * scalar");
+    Mat r(a.rows, a.cols, CV_32F);
+    for (int i = 0; i < a.rows; i++) for (int j = 0; j < a.cols; j++) r.at<float>(i, j) = (float)((double)a.at<float>(i, j) * f);
+    return r;
+}
+static inline Mat operator*(double f, const Mat& a) { return matScale(a, f); }
+static inline Mat operator*(const Mat& a, double f) { return matScale(a, f); }
+static inline Mat operator/(const Mat& a, double f) { return matScale(a, 1.0 / f); }
+static inline double matDot(const Mat& a, const Mat& b) {
+    if (a.type() != CV_32F || b.type() != CV_32F || a.rows != b.rows || a.cols != b.cols) CVMINI_FAIL("Mat::dot");
+    double s = 0;
+    for (int i = 0; i < a.rows; i++) for (int j = 0; j < a.cols; j++) s += (double)a.at<float>(i, j) * (double)b.at<float>(i, j);
+    return s;
+}
+inline double Mat::dot(const Mat& o) const { return matDot(*this, o); }
 static inline double norm(const Mat& a) {
     if (a.type() != CV_32F) CVMINI_FAIL("norm");
     double s = 0;

@@ -459,6 +459,24 @@ def search_by_projection_reloc(x3Dc, valid1, level1, kps1, descMP, kps2, desc2, 
     return n, mc[:len(k2)].copy()
 
 
+AREA_QUERY_DTYPE = np.dtype([("x", "<f4"), ("y", "<f4"), ("r", "<f4"), ("min_level", "<i4"), ("max_level", "<i4")])
+
+
+def search_windows(queries, ur, descMP, kps2, desc2, held2, u_right2, bounds, query_min_xy=None, inv_level_sigma2=None, blocking=False,
+                   th_high=50):
+    """matching core of the keyframe-side searches (orc_search_windows) -> (nmatches, best_idx[n1], best_dist[n1], match2[n2])"""
+    q = np.ascontiguousarray(queries, AREA_QUERY_DTYPE)
+    k2 = np.ascontiguousarray(kps2, KEYPOINT_DTYPE); dm = np.ascontiguousarray(descMP, np.uint8); d2 = np.ascontiguousarray(desc2, np.uint8)
+    b = np.ascontiguousarray(bounds, np.float32)
+    opt = lambda a, t: None if a is None else np.ascontiguousarray(a, t)
+    urq, hd, ur2, qm, inv = opt(ur, np.float32), opt(held2, np.uint8), opt(u_right2, np.float32), opt(query_min_xy, np.float32), opt(inv_level_sigma2, np.float32)
+    bi = np.full(max(len(q), 1), -1, np.int32); bd = np.full(max(len(q), 1), 256, np.int32); m2 = np.full(max(len(k2), 1), -1, np.int32)
+    f = lib().orc_search_windows; f.restype = C.c_int
+    n = f(_p(q), _p(urq), _p(dm), C.c_int(len(q)), _p(k2), _p(d2), _p(hd), _p(ur2), C.c_int(len(k2)), _p(b), _p(qm), _p(inv),
+          C.c_int(0 if inv is None else len(inv)), C.c_int(int(blocking)), C.c_int(int(th_high)), _p(bi), _p(bd), _p(m2))
+    return n, bi[:len(q)].copy(), bd[:len(q)].copy(), m2[:len(k2)].copy()
+
+
 def search_by_projection_map_points_ex(pts, proj_xr, descMP, kps2, desc2, held2, u_right2, bounds, scale_factors, th=1.0, far_points=False,
                                        th_far=0.0, nnratio=0.8, L=None, fn="orc_search_by_projection_map_points_ex"):
     """SearchByProjection(F, vpMapPoints, ...) with the rectified-stereo test -> (nmatches, match_cur[n2])"""

@@ -268,3 +268,52 @@ def lk_refine(curr_xy, status, ref_kps, w, h, first_octave_only=False, matches12
     rc = f(p(cur), p(st), p(rk), n, w, h, 1 if first_octave_only else 0, 1 if have else 0, p(tr), p(m12), p(cnt), p(disp), p(c2))
     assert rc == 0
     return int(c2[0]), tr, m12, cnt, disp[:c2[1]].copy()
+
+
+# ----------------------------------------------------------------------------- keyframe-side searches (oracle/ref_guided_kf_api.cc)
+def _kf_common(c):
+    k2 = np.ascontiguousarray(c["kps2"], O.KEYPOINT_DTYPE); d2 = np.ascontiguousarray(c["desc2"], np.uint8)
+    b = np.ascontiguousarray(c["bounds"], np.float32); K = np.ascontiguousarray(c["K"], np.float32); sf = np.ascontiguousarray(c["scale_factors"], np.float32)
+    return k2, d2, b, K, sf
+
+
+def search_by_projection_kf(c, overload):
+    """ORBmatcher::SearchByProjection(KeyFrame*, Scw, ...) (:480 / :595) on a case of tests/kf_cases.py -> (nmatches, match2[n2])"""
+    k2, d2, b, K, sf = _kf_common(c)
+    pt = np.ascontiguousarray(c["pt8"], np.float32); lv = np.ascontiguousarray(c["level1"], np.int32); fl = np.ascontiguousarray(c["flags1"], np.uint8)
+    dm = np.ascontiguousarray(c["descMP"], np.uint8); hd = np.ascontiguousarray(c["held_id2"], np.int32)
+    m2 = np.full(max(len(k2), 1), -1, np.int32)
+    f = lib().ref_search_by_projection_kf; f.restype = C.c_int
+    n = f(C.c_int(overload), _p(pt), _p(lv), _p(fl), _p(dm), C.c_int(len(lv)), _p(k2), _p(d2), _p(hd), C.c_int(len(k2)), _p(b), _p(K), _p(sf),
+          C.c_int(len(sf)), C.c_int(int(c["th"])), C.c_float(c["ratio"]), _p(m2))
+    return n, m2[:len(k2)].copy()
+
+
+def fuse(c, overload):
+    """ORBmatcher::Fuse (:1407 / :1619) -> (nFused, events[k, 3])"""
+    k2, d2, b, K, sf = _kf_common(c)
+    pt = np.ascontiguousarray(c["pt8"], np.float32); lv = np.ascontiguousarray(c["level1"], np.int32); fl = np.ascontiguousarray(c["flags1"], np.uint8)
+    ob = np.ascontiguousarray(c["obs1"], np.int32); pr = np.ascontiguousarray(c["present1"], np.uint8); dm = np.ascontiguousarray(c["descMP"], np.uint8)
+    oc = np.ascontiguousarray(c["occupied2"], np.uint8); oo = np.ascontiguousarray(c["occ_obs2"], np.int32)
+    ur = None if c.get("u_right2") is None else np.ascontiguousarray(c["u_right2"], np.float32)
+    inv = np.ascontiguousarray(c["inv_sigma2"], np.float32)
+    cap = len(lv) + 8
+    ev = np.zeros((cap, 3), np.int32); ne = C.c_int(0)
+    f = lib().ref_fuse; f.restype = C.c_int
+    n = f(C.c_int(overload), _p(pt), _p(lv), _p(ob), _p(fl), _p(pr), _p(dm), C.c_int(len(lv)), _p(k2), _p(d2), _p(oc), _p(oo), _p(ur), C.c_int(len(k2)),
+          _p(b), _p(K), C.c_float(c["mbf"]), _p(sf), _p(inv), C.c_int(len(sf)), C.c_float(c["th"]), _p(ev), C.c_int(cap), C.byref(ne))
+    assert ne.value <= cap
+    return n, ev[:ne.value].copy()
+
+
+def search_by_sim3(c):
+    """ORBmatcher::SearchBySim3 (:1743) -> (nFound, match12[n1])"""
+    k2, d2, b, K, sf = _kf_common(c)
+    k1 = np.ascontiguousarray(c["kps1"], O.KEYPOINT_DTYPE); d1 = np.ascontiguousarray(c["desc1"], np.uint8)
+    a = [np.ascontiguousarray(c[k + "_1"], t) for k, t in (("pt8", np.float32), ("level", np.int32), ("flags", np.uint8), ("present", np.uint8))]
+    e = [np.ascontiguousarray(c[k + "_2"], t) for k, t in (("pt8", np.float32), ("level", np.int32), ("flags", np.uint8), ("present", np.uint8))]
+    mi = np.ascontiguousarray(c["matched12_in"], np.int32); m12 = np.full(max(len(k1), 1), -1, np.int32)
+    f = lib().ref_search_by_sim3; f.restype = C.c_int
+    n = f(_p(a[0]), _p(a[1]), _p(a[2]), _p(a[3]), _p(k1), _p(d1), C.c_int(len(k1)), _p(e[0]), _p(e[1]), _p(e[2]), _p(e[3]), _p(k2), _p(d2),
+          C.c_int(len(k2)), _p(mi), _p(b), _p(K), _p(sf), C.c_int(len(sf)), C.c_float(c["th"]), _p(m12))
+    return n, m12[:len(k1)].copy()

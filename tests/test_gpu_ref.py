@@ -176,3 +176,58 @@ def test_cuda_matchers_equal_reference_golden():
         if not ok:
             bad.append((key, r[0], int(g[key + "_n"][0]), int((r[1] != g[key]).sum())))
     assert not bad, bad[:5]
+
+
+def test_cuda_keyframe_searches_equal_reference_golden():
+    """the keyframe-side searches of local mapping / loop closing -- SearchByProjection(KeyFrame*, Scw, ...) (:480, :595), Fuse (:1407,
+    :1619), SearchBySim3 (:1743) -- with their matching core on the device (eorb_guided_search_windows) against what the REFERENCE'S OWN
+    function bodies produced (tests/golden/ref_guided_kf.npz, 30 cases), bit for bit"""
+    import kf_cases as KC
+    api = _api()
+    g = KC.kf_golden()
+    gm = api.GuidedMatcher()
+    bad = []
+    for key, kind, ov, c in KC.kf_cases():
+        r = KC.run_composed(gm.SearchWindows, kind, ov, c)
+        if not (r[0] == int(g[key + "_n"][0]) and r[1].shape == g[key].shape and np.array_equal(r[1], g[key])):
+            bad.append((key, r[0], int(g[key + "_n"][0])))
+    assert not bad, bad[:5]
+
+
+def test_cuda_search_windows_equals_oracle_raw_outputs():
+    """every output array of the matching core (best_idx, best_dist, match2, nmatches) against the oracle: blocking and not, with the
+    reprojection gate and right-image columns, held slots, distorted-camera bounds, whole-image windows (candidate-buffer growth), empty sides"""
+    import kf_cases as KC
+    import oracle_lib as O
+    api = _api()
+    gm = api.GuidedMatcher()
+    rng = np.random.default_rng(5)
+    ncmp = 0
+    for key, kind, ov, c in KC.kf_cases(3):
+        if kind != "fuse" or ov != 0:
+            continue
+        n1 = len(c["level1"])
+        q, ur = KC.host_windows(c["pt8"], c["level1"], np.zeros(n1, bool), c["bounds"], c["K"], c["scale_factors"], 8.0, 0, mbf=40.0)
+        held = (rng.random(len(c["kps2"])) < 0.3).astype(np.uint8)
+        ur2 = np.where(rng.random(len(c["kps2"])) < 0.5, c["kps2"]["x"] - 5, -1).astype(np.float32)
+        qm = KC._qmin(c["bounds"])
+        variants = [dict(blocking=False, th_high=50), dict(blocking=True, th_high=50), dict(blocking=False, th_high=100, inv_level_sigma2=c["inv_sigma2"]),
+                    dict(blocking=True, th_high=255, inv_level_sigma2=c["inv_sigma2"]), dict(blocking=True, th_high=0)]
+        for kw in variants:
+            for hd in (None, held):
+                for u2 in (None, ur2):
+                    a = (q, ur if u2 is not None else None, c["descMP"], c["kps2"], c["desc2"], hd, u2, c["bounds"])
+                    o = O.search_windows(*a, query_min_xy=qm, **kw); r = gm.SearchWindows(*a, query_min_xy=qm, **kw)
+                    assert o[0] == r[0] and all(np.array_equal(x, y) for x, y in zip(o[1:], r[1:])), (key, kw, hd is None, u2 is None)
+                    ncmp += 1
+        big = q.copy(); big["r"] = np.where(big["r"] > 0, 2000.0, -1).astype(np.float32)          # every keypoint of the level range is a candidate
+        for blocking in (False, True):
+            o = O.search_windows(big, None, c["descMP"], c["kps2"], c["desc2"], held, None, c["bounds"], blocking=blocking, th_high=100)
+            r = gm.SearchWindows(big, None, c["descMP"], c["kps2"], c["desc2"], held, None, c["bounds"], blocking=blocking, th_high=100)
+            assert o[0] == r[0] and all(np.array_equal(x, y) for x, y in zip(o[1:], r[1:])), (key, "whole image", blocking)
+        r = gm.SearchWindows(q[:0], None, c["descMP"][:0], c["kps2"], c["desc2"], None, None, c["bounds"])
+        assert r[0] == 0 and len(r[1]) == 0
+        r = gm.SearchWindows(q, None, c["descMP"], c["kps2"][:0], c["desc2"][:0], None, None, c["bounds"])
+        assert r[0] == 0 and (r[1] == -1).all() and (r[2] == 256).all()
+    assert ncmp >= 40
+

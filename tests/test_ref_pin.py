@@ -189,6 +189,52 @@ def test_libref_matchers_vs_oracle_fresh_cases():
             assert o[0] == r[0] and np.array_equal(o[1], r[1]) and o[0] > 0, (seed, ratio, ori)
 
 
+# ------------------------------------------------------------------------------------------------ keyframe-side searches
+def test_oracle_keyframe_searches_equal_reference_golden():
+    """SearchByProjection(KeyFrame*, Scw, ...) (both overloads), Fuse (both overloads) and SearchBySim3: the host part of
+    tests/kf_cases.py + the oracle's matching core reproduce what the reference's own function bodies produced
+    (tests/golden/ref_guided_kf.npz, 30 cases: match tables, the ordered Add / Replace events of Fuse, nmatches)"""
+    import kf_cases as KC
+    g = KC.kf_golden()
+    ncase = 0
+    for key, kind, ov, c in KC.kf_cases():
+        r = KC.run_composed(O.search_windows, kind, ov, c)
+        assert r[0] == int(g[key + "_n"][0]) and r[1].shape == g[key].shape and np.array_equal(r[1], g[key]), key
+        assert r[0] > 50, key                                    # the cases are not vacuous
+        ncase += 1
+    assert ncase == sum(k.endswith("_n") for k in g.files)
+
+
+def test_libref_keyframe_searches_reproduce_golden():
+    import kf_cases as KC
+    R = _ref()
+    g = KC.kf_golden()
+    for key, kind, ov, c in KC.kf_cases():
+        r = KC.run_ref(R, kind, ov, c)
+        assert r[0] == int(g[key + "_n"][0]) and np.array_equal(r[1], g[key]), key
+
+
+def test_oracle_search_windows_edge_cases():
+    """no queries / no keypoints / every point gated out / every slot held"""
+    import kf_cases as KC
+    key, kind, ov, c = next(iter(KC.kf_cases(1)))
+    q, _ = KC.host_windows(c["pt8"], c["level1"], np.zeros(len(c["level1"]), bool), c["bounds"], c["K"], c["scale_factors"], 6, 0)
+    n, bi, bd, m2 = O.search_windows(q[:0], None, c["descMP"][:0], c["kps2"], c["desc2"], None, None, c["bounds"])
+    assert n == 0 and len(bi) == 0 and (m2 == -1).all()
+    n, bi, bd, m2 = O.search_windows(q, None, c["descMP"], c["kps2"][:0], c["desc2"][:0], None, None, c["bounds"])
+    assert n == 0 and (bi == -1).all() and (bd == 256).all()
+    q0 = q.copy(); q0["r"] = -1
+    n, bi, bd, _ = O.search_windows(q0, None, c["descMP"], c["kps2"], c["desc2"], None, None, c["bounds"])
+    assert n == 0 and (bi == -1).all() and (bd == 256).all()
+    held = np.ones(len(c["kps2"]), np.uint8)
+    for blocking in (False, True):
+        n, bi, bd, _ = O.search_windows(q, None, c["descMP"], c["kps2"], c["desc2"], held, None, c["bounds"], blocking=blocking, th_high=100)
+        assert n == 0 and (bi == -1).all() and (bd == 256).all()
+    n_nb, bi_nb, _, _ = O.search_windows(q, None, c["descMP"], c["kps2"], c["desc2"], None, None, c["bounds"], blocking=False, th_high=100)
+    n_b, bi_b, _, m2 = O.search_windows(q, None, c["descMP"], c["kps2"], c["desc2"], None, None, c["bounds"], blocking=True, th_high=100)
+    assert n_b <= n_nb and len(set(bi_b[bi_b >= 0])) == n_b and n_b == int((m2 >= 0).sum())     # blocking: one point per keypoint
+
+
 # ------------------------------------------------------------------------------------------------ KannalaBrandt8 motion compensation
 KB8_K = (226.38018519795807, 226.15002947047415, 173.6470807871759, 133.73271487507847)          # Examples/Event/EvMVSEC.yaml:53-63
 KB8_D = (-0.048031442223833355, 0.011330957517194437, -0.055378166304281135, 0.021500973881459395)
