@@ -1385,7 +1385,9 @@ cudaError_t launch_search_windows(const eorb_area_query* d_q, const float* d_qUr
     GuidedCandExtra c2 = cx;
     c2.held2 = blocking ? nullptr : d_held2;      // the blocking resolve keeps its own table of taken slots
     if (n1 > 0) {
-        guided_candidates_kernel<<<(n1 + 7) / 8, 256, 0, st>>>(f1, f2, gq, nullptr, 0.f, d_q, w, d_uRight2, d_qUr, c2);
+        // the right-image columns only enter through Fuse's reprojection gate; without it they are ignored (no rectified-stereo column test here)
+        guided_candidates_kernel<<<(n1 + 7) / 8, 256, 0, st>>>(f1, f2, gq, nullptr, 0.f, d_q, w, cx.chi2 ? d_uRight2 : nullptr,
+                                                               cx.chi2 ? d_qUr : nullptr, c2);
         (*launches)++;
     }
     if (blocking) {
