@@ -15,6 +15,7 @@ namespace cv {
 typedef unsigned char uchar;
 struct Size { int width = 0, height = 0; Size() {} Size(int w, int h) : width(w), height(h) {} };
 struct Point2f { float x = 0, y = 0; Point2f() {} Point2f(float a, float b) : x(a), y(b) {} };
+struct Point3f { float x = 0, y = 0, z = 0; Point3f() {} Point3f(float a, float b, float c) : x(a), y(b), z(c) {} };
 struct KeyPoint {
     Point2f pt; float size = 0, angle = -1, response = 0; int octave = 0, class_id = -1;
 };

@@ -182,6 +182,51 @@ int main(int argc, char** argv)
             for (size_t i = 0; i < kps.size(); i++) { rset += (F2.mvpMapPoints[i] != nullptr); rsame += (F2.mvpMapPoints[i] == mps[i]); }
             std::printf("sbr_nm=%d sbr_set=%d sbr_same=%d sbr_skipped_found=%d\n", nr, rset, rsame, (int)(mps.empty() || F2.mvpMapPoints[0] != mps[0]));
         }
+        // the keyframe-side searches of local mapping / loop closing (ORBmatcher_kf_b200.cc): the same map points against a keyframe at the
+        // identity pose whose keypoints are F2's; every point projects onto "its" keypoint and carries that keypoint's descriptor
+        {
+            ORB_SLAM3::KeyFrame KA, KB;
+            for (ORB_SLAM3::KeyFrame* K : {&KA, &KB}) {
+                K->mvKeysUn = F2.mvKeysUn; K->mDescriptors = desc; K->mvpMapPoints.assign(kps.size(), nullptr);
+                K->fx = 458.654f; K->fy = 457.296f; K->cx = 367.215f; K->cy = 248.375f; K->mpCamera = &cam2;
+                K->mnMinX = 0; K->mnMinY = 0; K->mnMaxX = W; K->mnMaxY = H;
+                K->mvScaleFactors = F2.mvScaleFactors; K->mvInvLevelSigma2.clear();
+                for (float sf : F2.mvScaleFactors) K->mvInvLevelSigma2.push_back(1.f / (sf * sf));
+                K->mvuRight.assign(kps.size(), -1.f);
+                K->mRcw = cv::Mat::zeros(3, 3, CV_32F); for (int i = 0; i < 3; i++) K->mRcw.at<float>(i, i) = 1.f;
+                K->mtcw = cv::Mat::zeros(3, 1, CV_32F); K->mOw = cv::Mat::zeros(3, 1, CV_32F);
+            }
+            for (size_t i = 0; i < kps.size(); i++) {
+                cv::Mat pos = mps[i]->GetWorldPos(), nrm(3, 1, CV_32F);
+                const float l = std::sqrt(pos.at<float>(0, 0) * pos.at<float>(0, 0) + pos.at<float>(1, 0) * pos.at<float>(1, 0) + pos.at<float>(2, 0) * pos.at<float>(2, 0));
+                for (int r = 0; r < 3; r++) nrm.at<float>(r, 0) = pos.at<float>(r, 0) / l;
+                mps[i]->mNormal = nrm; mps[i]->mnPredictedLevel = F2.mvKeysUn[i].octave;
+            }
+            cv::Mat I4 = cv::Mat::zeros(4, 4, CV_32F); for (int i = 0; i < 4; i++) I4.at<float>(i, i) = 1.f;
+            std::vector<ORB_SLAM3::MapPoint*> vpMatched(kps.size(), nullptr);
+            const int k1n = matcher.SearchByProjection(&KA, I4, mps, vpMatched, 5, 1.0f);
+            int k1same = 0; for (size_t i = 0; i < kps.size(); i++) k1same += (vpMatched[i] != nullptr && vpMatched[i] == mps[i]);
+            std::vector<ORB_SLAM3::MapPoint*> vpMatched2(kps.size(), nullptr);
+            std::vector<ORB_SLAM3::KeyFrame*> vpKFs(kps.size(), &KB), vpMatchedKF(kps.size(), nullptr);
+            const int k2n = matcher.SearchByProjection(&KA, I4, mps, vpKFs, vpMatched2, vpMatchedKF, 5, 1.0f);
+            int k2kf = 0; for (size_t i = 0; i < kps.size(); i++) k2kf += (vpMatched2[i] != nullptr && vpMatchedKF[i] == &KB);
+            std::printf("kfp_nm=%d kfp_same=%d kfq_nm=%d kfq_kf=%d\n", k1n, k1same, k2n, k2kf);
+            const int f1n = matcher.Fuse(&KA, mps, 3.0f, false);               // empty keyframe: every fusion adds an observation
+            int f1add = 0; for (size_t i = 0; i < kps.size(); i++) f1add += (KA.mvpMapPoints[i] != nullptr && mps[i]->mnAddedObs >= 0);
+            ORB_SLAM3::MapPoint other(mps.empty() ? cv::Mat() : mps[0]->GetWorldPos(), mps.empty() ? cv::Mat() : mps[0]->GetDescriptor(), 9);
+            KB.mvpMapPoints.assign(kps.size(), &other);                        // occupied keyframe: every fusion proposes a replacement
+            std::vector<ORB_SLAM3::MapPoint*> vpReplace(kps.size(), nullptr);
+            const int f2n = matcher.Fuse(&KB, I4, mps, 3.0f, vpReplace);
+            int f2rep = 0; for (size_t i = 0; i < kps.size(); i++) f2rep += (vpReplace[i] == &other);
+            std::printf("fuse_n=%d fuse_add=%d fuse2_n=%d fuse2_rep=%d\n", f1n, f1add, f2n, f2rep);
+            KA.mvpMapPoints = mps; KB.mvpMapPoints = mps;                      // two keyframes seeing the same points, identity relative pose
+            cv::Mat R12 = cv::Mat::zeros(3, 3, CV_32F), t12 = cv::Mat::zeros(3, 1, CV_32F); for (int i = 0; i < 3; i++) R12.at<float>(i, i) = 1.f;
+            std::vector<ORB_SLAM3::MapPoint*> vp12(kps.size(), nullptr);
+            const float s12 = 1.f;
+            const int s3n = matcher.SearchBySim3(&KA, &KB, vp12, s12, R12, t12, 7.5f);
+            int s3same = 0; for (size_t i = 0; i < kps.size(); i++) s3same += (vp12[i] != nullptr && vp12[i] == mps[i]);
+            std::printf("sim3_n=%d sim3_same=%d\n", s3n, s3same);
+        }
         for (auto* p : mps) delete p;
     }
     // ORBVocabulary::transform through a text file in ORB-SLAM's vocabulary format (k = 3, L = 2: 3 inner nodes, 9 words whose

@@ -14,7 +14,7 @@ EXE = os.path.join(SHIM, "_shim_selftest")
 
 
 def _build():
-    srcs = [os.path.join(SHIM, f) for f in ("shim_selftest.cc", "ORBextractor.cc", "ORBmatcher_b200.cc", "EventConversion_b200.cc", "KLT_b200.cc", "ORBmatcher_guided_b200.cc", "ORBVocabulary_b200.cc")]
+    srcs = [os.path.join(SHIM, f) for f in ("shim_selftest.cc", "ORBextractor.cc", "ORBmatcher_b200.cc", "EventConversion_b200.cc", "KLT_b200.cc", "ORBmatcher_guided_b200.cc", "ORBmatcher_kf_b200.cc", "ORBVocabulary_b200.cc")]
     cmd = ["g++", "-std=c++17", "-O1", "-DEORB_SHIM_MOCK", "-I" + os.path.join(SHIM, "cv_mock"), "-I" + SHIM,
            "-I" + os.path.join(ROOT, "include"), "-pthread", "-o", EXE] + srcs + ["-L" + os.path.join(ROOT, "eorb_slam_b200"), "-leorb_b200",
                                                                       "-Wl,-rpath," + os.path.join(ROOT, "eorb_slam_b200")]
@@ -51,6 +51,7 @@ def test_shims_compile_and_fail_loudly_without_device():
     assert "lk_ok=0 lk_n=0" in out and "elk_n=0 elk_nm1=0" in out
     assert "sfi_nm=0 sfi_self=0" in out and "sbp_nm=0 sbp_set=0" in out and "slp_nm=0 slp_set=0" in out and "sbb_nm=0 sbb_set=0" in out and "sbk_nm=0 sbk_set=0" in out
     assert "sbs_nm=0 sbs_set=0" in out and "sbr_nm=0 sbr_set=0" in out
+    assert "kfp_nm=0 kfp_same=0 kfq_nm=0" in out and "fuse_n=0 fuse_add=0 fuse2_n=0" in out and "sim3_n=0" in out
     assert "voc_ok=0" in out and "undist_ok=0" in out
 
 
@@ -110,6 +111,17 @@ def test_shims_match_oracle_on_gpu():
     nr, rset, rsame, skipped = map(int, sr.groups())
     # relocalisation search from a keyframe holding the same points: one point is in sAlreadyFound and must not come back
     assert nr == rset and nr > 0.9 * len(okps) and rsame > 0.95 * rset and skipped == 1
+    kf = re.search(r"kfp_nm=(\d+) kfp_same=(\d+) kfq_nm=(\d+) kfq_kf=(\d+)", out)
+    k1n, k1same, k2n, k2kf = map(int, kf.groups())
+    # keyframe-side SearchByProjection (both overloads): every point finds its own keypoint (distance 0), one point per keypoint
+    assert k1n == k2n == k2kf and k1n > 0.9 * len(okps) and k1same > 0.95 * k1n
+    fu = re.search(r"fuse_n=(\d+) fuse_add=(\d+) fuse2_n=(\d+) fuse2_rep=(\d+)", out)
+    f1n, f1add, f2n, f2rep = map(int, fu.groups())
+    # Fuse into an empty keyframe adds, into an occupied one proposes replacements; the non-blocking core gives both the same matches
+    assert f1n > 0.9 * len(okps) and f2n == f2rep == f1n and 0 < f1add <= f1n
+    s3 = re.search(r"sim3_n=(\d+) sim3_same=(\d+)", out)
+    s3n, s3same = map(int, s3.groups())
+    assert s3n == s3same and s3n > 0.9 * len(okps)      # both directions agree on the point itself
     bb = re.search(r"sbb_nm=(\d+) sbb_set=(\d+) sbb_self=(\d+)", out)
     nbb, bset, bself = map(int, bb.groups())
     # SearchByBoW of a frame against a keyframe with the same features: distance 0 to itself, so every match is the feature itself
