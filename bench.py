@@ -700,7 +700,36 @@ def bench_guided(api, torch, dev, steps, warmup):
                "cpu_port_ms_per_call": lms_port}
     except Exception as e:
         loc = {"error": repr(e)}
-    return {"search_by_projection": proj, "search_local_points": loc, "metric": "search_for_initialization_calls_per_s", "value": 1e3 / ms, "unit": "calls/s", "ms_per_call": ms,
+    # LocalMapping::SearchInNeighbors / LoopClosing::SearchAndFuse: ORBmatcher::Fuse's matching core, 3000 map points into a 1009-feature keyframe
+    # (windows formed by the caller as the reference's host code does, reprojection gate on the device, no blocking)
+    fus = {}
+    try:
+        c = synth.make_local_map_case(3000, 1009, 47)
+        q = np.zeros(3000, api.AREA_QUERY_DTYPE)
+        lv = np.clip(c["pts"]["scale_level"], 0, len(c["scale_factors"]) - 1)
+        q["x"] = c["pts"]["proj_x"]; q["y"] = c["pts"]["proj_y"]; q["r"] = np.float32(3.0) * c["scale_factors"][lv]
+        q["min_level"] = lv - 1; q["max_level"] = lv
+        inv = (np.float32(1.0) / (c["scale_factors"] ** 2)).astype(np.float32)
+        gf = api.GuidedMatcher(dev, 0.8, True)
+        a = (q, None, c["descMP"], c["kps2"], c["desc2"], None, None, c["bounds"])
+        kw = dict(inv_level_sigma2=inv, blocking=False, th_high=50)
+        for _ in range(3):
+            fr = gf.SearchWindows(*a, **kw)
+        t0 = time.perf_counter()
+        for _ in range(reps):
+            fr = gf.SearchWindows(*a, **kw)
+        fms = (time.perf_counter() - t0) * 1e3 / reps
+        fo = O.search_windows(*a, **kw)
+        t0 = time.perf_counter()
+        for _ in range(20):
+            O.search_windows(*a, **kw)
+        fms_port = (time.perf_counter() - t0) * 1e3 / 20
+        fus = {"ms_per_call": fms, "workload": "matching core of ORBmatcher::Fuse (eorb_guided_search_windows): 3000 map points x 1009 keypoints, th 3, reprojection "
+               "gate, %d fusions; host call" % fo[0], "bit_exact_vs_oracle": bool(fr[0] == fo[0] and all(np.array_equal(x, y) for x, y in zip(fr[1:], fo[1:]))),
+               "cpu_port_ms_per_call": fms_port}
+    except Exception as e:
+        fus = {"error": repr(e)}
+    return {"search_by_projection": proj, "search_local_points": loc, "fuse_core": fus, "metric": "search_for_initialization_calls_per_s", "value": 1e3 / ms, "unit": "calls/s", "ms_per_call": ms,
             "ms_per_call_device_resident": float(np.median(dev_ms)),
             "workload": "ORBmatcher::SearchForInitialization: 5000 x 5000 keypoints (%d level-0 queries), window 100, ratio 0.9, "
                         "rotation check; %d matches" % (lvl0, en),

@@ -110,6 +110,7 @@ def _load():
         "eorb_guided_search_by_projection_map_points_stereo_device": ([vp, vp, vp, vp, i, vp, vp, vp, vp, i, vp, vp, i, f, i, f, f, vp, vp], i),
         "eorb_guided_search_by_bow": ([vp, vp, vp, vp, i, vp, vp, vp, i, vp, vp, i, vp, vp, vp, i, f, i, vp, vp], i),
         "eorb_guided_search_by_bow_device": ([vp, vp, vp, vp, i, vp, vp, vp, i, vp, vp, i, vp, vp, vp, i, f, i, vp, vp], i),
+        "eorb_guided_search_for_triangulation": ([vp, vp, vp, vp, i, vp, vp, vp, i, vp, vp, vp, i, vp, vp, vp, i, vp, vp, vp, vp, i, i, i, vp, vp], i),
         "eorb_guided_search_windows": ([vp, vp, vp, vp, i, vp, vp, vp, vp, i, vp, vp, vp, i, i, i, vp, vp, vp, vp], i),
         "eorb_guided_search_windows_device": ([vp, vp, vp, vp, i, vp, vp, vp, vp, i, vp, vp, vp, i, i, i, vp, vp, vp, vp], i),
         "eorb_guided_search_by_bow_kf": ([vp, vp, vp, vp, i, vp, vp, vp, i, vp, vp, vp, i, vp, vp, vp, i, f, i, vp, vp], i),
@@ -847,6 +848,23 @@ class GuidedMatcher:
                                                                C.c_float(thFarPoints), C.c_float(self.mfNNratio), _p(mc), C.byref(nm)),
                "SearchByProjection(map points)")
         return nm.value, mc[:len(k2)].copy()
+
+    def SearchForTriangulation(self, kps1, desc1, flags1, fv1, kps2, desc2, flags2, fv2, F12, epipole2, scale_factors2, level_sigma2_2, bCoarse=False):
+        """ORBmatcher::SearchForTriangulation (:975-1214), pinhole keyframes -> (nmatches, match12[n1]); flags: bit 0 = takes part, bit 1 = bStereo"""
+        k1 = np.ascontiguousarray(kps1, KEYPOINT_DTYPE); k2 = np.ascontiguousarray(kps2, KEYPOINT_DTYPE)
+        d1 = np.ascontiguousarray(desc1, np.uint8); d2 = np.ascontiguousarray(desc2, np.uint8)
+        f1 = np.ascontiguousarray(flags1, np.uint8); f2 = np.ascontiguousarray(flags2, np.uint8)
+        a = [np.ascontiguousarray(fv1[0], np.uint32), np.ascontiguousarray(fv1[1], np.int32), np.ascontiguousarray(fv1[2], np.uint32)]
+        b = [np.ascontiguousarray(fv2[0], np.uint32), np.ascontiguousarray(fv2[1], np.int32), np.ascontiguousarray(fv2[2], np.uint32)]
+        F = np.ascontiguousarray(F12, np.float32).reshape(9); e = np.ascontiguousarray(epipole2, np.float32)
+        sc = np.ascontiguousarray(scale_factors2, np.float32); sg = np.ascontiguousarray(level_sigma2_2, np.float32)
+        m12 = np.full(max(len(k1), 1), -1, np.int32)
+        nm = C.c_int(0)
+        _check(lib.eorb_guided_search_for_triangulation(self.h, _p(k1), _p(d1), _p(f1), len(k1), _p(a[0]), _p(a[1]), _p(a[2]), len(a[0]), _p(k2), _p(d2),
+                                                        _p(f2), len(k2), _p(b[0]), _p(b[1]), _p(b[2]), len(b[0]), _p(F), _p(e), _p(sc), _p(sg), len(sc),
+                                                        int(bCoarse), int(self.mbCheckOrientation), _p(m12), C.byref(nm)),
+               "SearchForTriangulation")
+        return nm.value, m12[:len(k1)].copy()
 
     def SearchWindows(self, queries, ur, descMP, kps2, desc2, held2, u_right2, bounds, query_min_xy=None, inv_level_sigma2=None, blocking=False,
                       th_high=50):

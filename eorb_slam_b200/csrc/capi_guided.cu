@@ -913,3 +913,75 @@ extern "C" int eorb_guided_search_by_bow_kf(eorb_guided* g, const eorb_keypoint*
     return guidedBowHost(g, "eorb_guided_search_by_bow_kf", kps1, desc1, valid1, n1, nodes1, start1, feats1, nn1, kps2, desc2, valid2, n2, nodes2, start2,
                          feats2, nn2, nnratio, check_ori, nullptr, match12, nmatches);
 }
+
+// ------------------------------------------------------------------------------------------------ SearchForTriangulation
+extern "C" int eorb_guided_search_for_triangulation(eorb_guided* g, const eorb_keypoint* kps1, const uint8_t* desc1, const uint8_t* flags1, int n1,
+                                                    const uint32_t* nodes1, const int32_t* start1, const uint32_t* feats1, int nn1,
+                                                    const eorb_keypoint* kps2, const uint8_t* desc2, const uint8_t* flags2, int n2,
+                                                    const uint32_t* nodes2, const int32_t* start2, const uint32_t* feats2, int nn2, const float* F12,
+                                                    const float* epipole2, const float* scale_factors2, const float* level_sigma2_2, int nlevels,
+                                                    int coarse, int check_ori, int32_t* match12, int* nmatches) {
+    const char* who = "eorb_guided_search_for_triangulation";
+    if (!g) return gFail(EORB_ERR_ARG, who, "null handle");
+    if (n1 < 0 || n2 < 0) return gFail(EORB_ERR_ARG, who, "negative size");
+    if (n1 > EORB_GUIDED_MAX_KEYPOINTS || n2 > EORB_GUIDED_MAX_KEYPOINTS) return gFail(EORB_ERR_CAPACITY, who, "more than EORB_GUIDED_MAX_KEYPOINTS keypoints");
+    if (nmatches) *nmatches = 0;
+    if (n1 > 0 && !match12) return gFail(EORB_ERR_ARG, who, "null output");
+    for (int i = 0; i < n1; i++) match12[i] = -1;
+    if (n1 == 0 || n2 == 0) return EORB_OK;
+    if (!kps1 || !desc1 || !flags1 || !kps2 || !desc2 || !flags2 || !F12 || !epipole2 || !scale_factors2 || !level_sigma2_2) return gFail(EORB_ERR_ARG, who, "null argument");
+    if (nlevels < 1 || nlevels > 32) return gFail(EORB_ERR_ARG, who, "bad level tables (1..32 levels)");
+    int rc;
+    if ((rc = checkFeatureVector(who, nodes1, start1, feats1, nn1, n1)) != EORB_OK) return rc;
+    if ((rc = checkFeatureVector(who, nodes2, start2, feats2, nn2, n2)) != EORB_OK) return rc;
+    CU(cudaSetDevice(g->device));
+    GuidedTriGeom tg;
+    for (int i = 0; i < 9; i++) tg.F[i] = F12[i];
+    tg.ep[0] = epipole2[0]; tg.ep[1] = epipole2[1]; tg.coarse = coarse ? 1 : 0;
+    for (int i = 0; i < 32; i++) { tg.scale2[i] = scale_factors2[i < nlevels ? i : nlevels - 1]; tg.sigma2[i] = level_sigma2_2[i < nlevels ? i : nlevels - 1]; }
+    // one blob, every part 16-byte aligned: [kps1 | desc1 | kps2 | desc2 | nodes1 | start1 | feats1 | nodes2 | start2 | feats2 | flags1 | flags2]
+    const int nf1 = nn1 > 0 ? start1[nn1] : 0, nf2 = nn2 > 0 ? start2[nn2] : 0;
+    auto al = [](size_t v) { return (v + 15) & ~(size_t)15; };
+    const int NP = 12;
+    const int32_t zero2[2] = {0, 0};
+    const size_t sz[NP] = {(size_t)n1 * sizeof(eorb_keypoint), (size_t)n1 * 32, (size_t)n2 * sizeof(eorb_keypoint), (size_t)n2 * 32, (size_t)nn1 * 4,
+                           (size_t)(nn1 + 1) * 4, (size_t)nf1 * 4, (size_t)nn2 * 4, (size_t)(nn2 + 1) * 4, (size_t)nf2 * 4, (size_t)n1, (size_t)n2};
+    const void* src[NP] = {kps1, desc1, kps2, desc2, nodes1, nn1 > 0 ? (const void*)start1 : (const void*)zero2, feats1,
+                           nodes2, nn2 > 0 ? (const void*)start2 : (const void*)zero2, feats2, flags1, flags2};
+    size_t off[NP + 1]; off[0] = 0;
+    for (int i = 0; i < NP; i++) off[i + 1] = off[i] + al(sz[i]);
+    if (off[NP] > g->blobCap) {
+        CU(cudaStreamSynchronize(g->stream));
+        cudaFree(g->d_blob); cudaFreeHost(g->h_blob); g->d_blob = nullptr; g->h_blob = nullptr; g->blobCap = 0;
+        const size_t cap = std::max<size_t>(off[NP] + off[NP] / 4, 1 << 18);
+        CU(cudaMalloc((void**)&g->d_blob, cap));
+        CU(cudaMallocHost((void**)&g->h_blob, cap));
+        g->blobCap = cap;
+    }
+    // output blob: [nmatches (16 bytes) | match12[n1] | rotation bin per feature of keyframe 1 (device scratch)]
+    const size_t oBin = 16 + al((size_t)n1 * sizeof(int32_t));
+    const size_t outBytes = oBin + al((size_t)n1);
+    if (outBytes > g->outbCap) {
+        CU(cudaStreamSynchronize(g->stream));
+        cudaFree(g->d_outb); cudaFreeHost(g->h_outb); g->d_outb = nullptr; g->h_outb = nullptr; g->outbCap = 0;
+        const size_t cap = std::max<size_t>(outBytes + outBytes / 4, 1 << 14);
+        CU(cudaMalloc((void**)&g->d_outb, cap));
+        CU(cudaMallocHost((void**)&g->h_outb, cap));
+        g->outbCap = cap;
+    }
+    for (int i = 0; i < NP; i++)
+        if (sz[i] > 0) std::memcpy(g->h_blob + off[i], src[i], sz[i]);
+    CU(cudaMemcpyAsync(g->d_blob, g->h_blob, off[NP], cudaMemcpyHostToDevice, g->stream));
+    unsigned char* B = g->d_blob;
+    GuidedBowSide a{(const eorb_keypoint*)(B + off[0]), B + off[1], (const uint32_t*)(B + off[4]), (const int32_t*)(B + off[5]), (const uint32_t*)(B + off[6]), nn1, n1};
+    GuidedBowSide b{(const eorb_keypoint*)(B + off[2]), B + off[3], (const uint32_t*)(B + off[7]), (const int32_t*)(B + off[8]), (const uint32_t*)(B + off[9]), nn2, n2};
+    if (!g->d_bowWork) CU(cudaMalloc((void**)&g->d_bowWork, 64 * sizeof(int)));
+    CU(launch_search_triangulation(a, B + off[10], b, B + off[11], tg, check_ori, (int32_t*)(g->d_outb + 16), (signed char*)(g->d_outb + oBin), g->d_bowWork,
+                                   (int*)g->d_outb, g->stream, &g->launches));
+    CU(cudaMemcpyAsync(g->h_outb, g->d_outb, oBin, cudaMemcpyDeviceToHost, g->stream));
+    CU(cudaStreamSynchronize(g->stream));
+    std::memcpy(match12, g->h_outb + 16, (size_t)n1 * sizeof(int32_t));
+    if (nmatches) *nmatches = *(const int*)g->h_outb;
+    return EORB_OK;
+}
+

@@ -72,6 +72,13 @@ cudaError_t launch_search_windows(const eorb_area_query* d_q, const float* d_qUr
                                   const uint8_t* d_held2, const float* d_uRight2, GuidedGrid g, GuidedGrid gq, const GuidedCandExtra& cx, int blocking,
                                   int thHigh, const GuidedWork& w, int32_t* d_claim, int32_t* d_bestIdx, int32_t* d_bestDist, int32_t* d_match2, int* d_nmatches,
                                   cudaStream_t st, long long* launches);
+// SearchForTriangulation (ORBmatcher.cc:975-1214), pinhole keyframes: F = F12 row-major as Pinhole::epipolarConstrain forms it, ep = the epipole
+// in the second image, scale2 / sigma2 = mvScaleFactors / mvLevelSigma2 of the second keyframe, coarse = bCoarse.  flags bit 0: the feature takes
+// part (no map point; stereo when bOnlyStereo), bit 1: it has a right-image column (bStereo)
+struct GuidedTriGeom { float F[9]; float ep[2]; float scale2[32]; float sigma2[32]; int coarse; };
+cudaError_t launch_search_triangulation(const GuidedBowSide& k1, const uint8_t* d_flags1, const GuidedBowSide& k2, const uint8_t* d_flags2,
+                                        const GuidedTriGeom& tg, int checkOri, int32_t* d_match12, signed char* d_binOf, int* d_work /* 64 ints */,
+                                        int* d_nmatches, cudaStream_t st, long long* launches);
 cudaError_t guided_configure();
 
 }  // namespace eorb

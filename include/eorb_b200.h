@@ -474,6 +474,23 @@ int eorb_guided_search_by_projection_map_points_stereo_device(eorb_guided* g, co
                                                               float th, int far_points, float th_far, float nnratio,
                                                               int32_t* d_match_cur, int* nmatches);
 
+/* eorb_guided_search_for_triangulation replaces ORBmatcher::SearchForTriangulation(KeyFrame* pKF1, KeyFrame* pKF2, cv::Mat F12,
+ * vector<pair<size_t, size_t>>& vMatchedPairs, bool bOnlyStereo, bool bCoarse) (src/ORBmatcher.cc:975-1214; LocalMapping::CreateNewMapPoints,
+ * src/LocalMapping.cc:507, and Tracking's keyframe insertion, src/Tracking.cc:3212) for keyframes with one PINHOLE camera each (mpCamera2 ==
+ * NULL; KannalaBrandt8::epipolarConstrain triangulates every candidate pair and is not taken over).  Keypoints / descriptors / FeatureVectors
+ * of both keyframes as in eorb_guided_search_by_bow_kf.  flags{1,2}[i]: bit 0 = the feature takes part (GetMapPoint(i) == NULL, and
+ * mvuRight[i] >= 0 when bOnlyStereo), bit 1 = mvuRight[i] >= 0 (bStereo).  F12[9] = the fundamental matrix Pinhole::epipolarConstrain forms,
+ * K1.t().inv() * SkewSymmetricMatrix(t12) * R12 * K2.inv() (src/CameraModels/Pinhole.cpp:137-140; the argument F12 of the reference function
+ * is not read by it), row-major, computed by the caller with the camera's own cv::Mat arithmetic; epipole2 = pKF2->mpCamera->project(R2w * Cw
+ * + t2w) (:982-988); scale_factors2 / level_sigma2_2 = mvScaleFactors / mvLevelSigma2 of pKF2 (:1081, :1131).  match12[i1] = the feature
+ * of pKF2 matched to feature i1 of pKF1 or -1 (vMatchedPairs = the pairs (i1, match12[i1]) in ascending i1, :1200-1208). */
+int eorb_guided_search_for_triangulation(eorb_guided* g, const eorb_keypoint* kps1, const uint8_t* desc1, const uint8_t* flags1, int n1,
+                                         const uint32_t* nodes1, const int32_t* start1, const uint32_t* feats1, int nn1,
+                                         const eorb_keypoint* kps2, const uint8_t* desc2, const uint8_t* flags2, int n2,
+                                         const uint32_t* nodes2, const int32_t* start2, const uint32_t* feats2, int nn2, const float* F12,
+                                         const float* epipole2, const float* scale_factors2, const float* level_sigma2_2, int nlevels,
+                                         int coarse, int check_ori, int32_t* match12, int* nmatches);
+
 /* eorb_guided_search_windows: the matching core of the KEYFRAME-side searches of local mapping and loop closing, which all have one
  * shape -- per map point a window in a keyframe (GetFeaturesInArea(u, v, radius), src/KeyFrame.cc:873-917), keypoints of level
  * [nPredictedLevel - 1, nPredictedLevel], smallest descriptor distance, first visited among equals:

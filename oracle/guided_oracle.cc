@@ -577,4 +577,92 @@ int orc_search_windows(const orc_area_query* queries, const float* ur, const uin
     return nmatches;
 }
 
+// ORBmatcher::SearchForTriangulation(pKF1, pKF2, F12, vMatchedPairs, bOnlyStereo, bCoarse) (src/ORBmatcher.cc:975-1214), keyframes with one
+// pinhole camera each (mpCamera2 == NULL).  flags bit 0: the feature takes part (no map point, :1034-1038 / :1057-1059; stereo when
+// bOnlyStereo, :1040-1044 / :1061-1065), bit 1: bStereo.  F = the matrix Pinhole::epipolarConstrain forms (Pinhole.cpp:137-140), row-major;
+// the gate itself is :143-156.  The loops and the running `dist > TH_LOW || dist > bestDist` rule are the reference's (vbMatched2 is never
+// set in this version of the function); match12[i1] = bestIdx2 or -1 after the rotation filter (:1177-1198).
+int orc_search_for_triangulation(const orc_keypoint* kps1, const uint8_t* desc1, const uint8_t* flags1, int n1, const uint32_t* nodes1,
+                                 const int32_t* start1, const uint32_t* feats1, int nn1, const orc_keypoint* kps2, const uint8_t* desc2,
+                                 const uint8_t* flags2, int n2, const uint32_t* nodes2, const int32_t* start2, const uint32_t* feats2, int nn2,
+                                 const float* F, const float* ep, const float* scale2, const float* sigma2, int nlevels, int coarse, int check_ori,
+                                 int32_t* match12) {
+    (void)n2;
+    const int TH_LOW = 50, HISTO_LENGTH = 30;
+    const float factor = 1.0f / HISTO_LENGTH;
+    int nmatches = 0;
+    for (int i = 0; i < n1; i++) match12[i] = -1;
+    std::vector<int> rotHist[30];
+    auto lvl = [&](int o) { return o < 0 ? 0 : (o >= nlevels ? nlevels - 1 : o); };
+    int q1 = 0, q2 = 0;
+    while (q1 < nn1 && q2 < nn2) {
+        if (nodes1[q1] == nodes2[q2]) {
+            for (int a = start1[q1]; a < start1[q1 + 1]; a++) {
+                const int idx1 = (int)feats1[a];
+                if (!(flags1[idx1] & 1)) continue;
+                const bool bStereo1 = (flags1[idx1] & 2) != 0;
+                const orc_keypoint& kp1 = kps1[idx1];
+                int bestDist = TH_LOW, bestIdx2 = -1;
+                for (int b = start2[q2]; b < start2[q2 + 1]; b++) {
+                    const int idx2 = (int)feats2[b];
+                    if (!(flags2[idx2] & 1)) continue;
+                    const bool bStereo2 = (flags2[idx2] & 2) != 0;
+                    const int dist = orc_descriptor_distance(desc1 + (size_t)idx1 * 32, desc2 + (size_t)idx2 * 32);
+                    if (dist > TH_LOW || dist > bestDist) continue;
+                    const orc_keypoint& kp2 = kps2[idx2];
+                    if (!bStereo1 && !bStereo2) {
+                        const float distex = ep[0] - kp2.x, distey = ep[1] - kp2.y;
+                        if (distex * distex + distey * distey < 100 * scale2[lvl(kp2.octave)]) continue;
+                    }
+                    bool ok = coarse != 0;
+                    if (!ok) {   // Pinhole::epipolarConstrain
+                        const float la = kp1.x * F[0] + kp1.y * F[3] + F[6];
+                        const float lb = kp1.x * F[1] + kp1.y * F[4] + F[7];
+                        const float lc = kp1.x * F[2] + kp1.y * F[5] + F[8];
+                        const float num = la * kp2.x + lb * kp2.y + lc;
+                        const float den = la * la + lb * lb;
+                        if (den != 0) {
+                            const float dsqr = num * num / den;
+                            ok = dsqr < 3.84f * sigma2[lvl(kp2.octave)];
+                        }
+                    }
+                    if (ok) { bestIdx2 = idx2; bestDist = dist; }
+                }
+                if (bestIdx2 >= 0) {
+                    match12[idx1] = bestIdx2;
+                    nmatches++;
+                    if (check_ori) {
+                        float rot = kp1.angle - kps2[bestIdx2].angle;
+                        if (rot < 0.0) rot += 360.0f;
+                        int bin = (int)std::round(rot * factor);
+                        if (bin == HISTO_LENGTH) bin = 0;
+                        rotHist[bin].push_back(idx1);
+                    }
+                }
+            }
+            q1++; q2++;
+        } else if (nodes1[q1] < nodes2[q2]) {
+            while (q1 < nn1 && nodes1[q1] < nodes2[q2]) q1++;      // lower_bound
+        } else {
+            while (q2 < nn2 && nodes2[q2] < nodes1[q1]) q2++;
+        }
+    }
+    if (check_ori) {
+        int max1 = 0, max2 = 0, max3 = 0, ind1 = -1, ind2 = -1, ind3 = -1;
+        for (int i = 0; i < HISTO_LENGTH; i++) {
+            const int s = (int)rotHist[i].size();
+            if (s > max1) { max3 = max2; max2 = max1; max1 = s; ind3 = ind2; ind2 = ind1; ind1 = i; }
+            else if (s > max2) { max3 = max2; max2 = s; ind3 = ind2; ind2 = i; }
+            else if (s > max3) { max3 = s; ind3 = i; }
+        }
+        if (max2 < 0.1f * (float)max1) { ind2 = -1; ind3 = -1; }
+        else if (max3 < 0.1f * (float)max1) { ind3 = -1; }
+        for (int i = 0; i < HISTO_LENGTH; i++) {
+            if (i == ind1 || i == ind2 || i == ind3) continue;
+            for (int idx : rotHist[i]) { match12[idx] = -1; nmatches--; }
+        }
+    }
+    return nmatches;
+}
+
 }  // extern "C"

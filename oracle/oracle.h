@@ -149,6 +149,13 @@ int   orc_search_by_projection_reloc(const float* x3Dc, const uint8_t* valid1, c
 /* matching core of the keyframe-side searches (ORBmatcher.cc:480-712 SearchByProjection(KeyFrame*, Scw, ...), :1407-1741 Fuse,
    :1743-1967 SearchBySim3): the caller's window per map point, best candidate of level [min_level, max_level], optional blocking
    (vpMatched) and optional reprojection gate of Fuse; returns the number of accepted points */
+/* ORBmatcher::SearchForTriangulation (ORBmatcher.cc:975-1214), pinhole keyframes; flags bit 0 = takes part, bit 1 = bStereo; F = the
+   fundamental matrix of Pinhole::epipolarConstrain (row-major), ep = epipole in image 2; returns nmatches, match12[n1] */
+int   orc_search_for_triangulation(const orc_keypoint* kps1, const uint8_t* desc1, const uint8_t* flags1, int n1, const uint32_t* nodes1,
+                                   const int32_t* start1, const uint32_t* feats1, int nn1, const orc_keypoint* kps2, const uint8_t* desc2,
+                                   const uint8_t* flags2, int n2, const uint32_t* nodes2, const int32_t* start2, const uint32_t* feats2, int nn2,
+                                   const float* F, const float* ep, const float* scale2, const float* sigma2, int nlevels, int coarse,
+                                   int check_ori, int32_t* match12);
 typedef struct orc_area_query { float x, y, r; int32_t min_level, max_level; } orc_area_query;
 int   orc_search_windows(const orc_area_query* queries, const float* ur, const uint8_t* descMP, int n1, const orc_keypoint* kps2,
                          const uint8_t* desc2, const uint8_t* held2, const float* u_right2, int n2, const float* bounds4,

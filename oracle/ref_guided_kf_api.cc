@@ -183,4 +183,53 @@ int ref_search_by_sim3(const float* pt8_1, const int32_t* level_1, const uint8_t
     return nFound;
 }
 
+/* ORBmatcher::SearchForTriangulation(pKF1, pKF2, F12, vMatchedPairs, bOnlyStereo, bCoarse) (:975-1214) for two keyframes with the same
+   pinhole camera, rotations the identity, translations t1w / t2w.  has_mp{1,2}[i] != 0: the keyframe holds a map point at i;
+   u_right{1,2} (may be NULL) = mvuRight.  Also returns what the function forms inside and the device path receives from its caller:
+   F12_out[9] = K1.t().inv() * SkewSymmetricMatrix(t12) * R12 * K2.inv() (Pinhole.cpp:137-140, the same expression on the same stand-in
+   algebra) and ep_out[2] = the epipole (:982-988).  match12[i1] = second index of the pair (i1, .) in vMatchedPairs or -1. */
+int ref_search_for_triangulation(const orc_keypoint* kps1, const uint8_t* desc1, const uint8_t* has_mp1, const float* u_right1, int n1,
+                                 const uint32_t* nodes1, const int32_t* start1, const uint32_t* feats1, int nn1, const orc_keypoint* kps2,
+                                 const uint8_t* desc2, const uint8_t* has_mp2, const float* u_right2, int n2, const uint32_t* nodes2,
+                                 const int32_t* start2, const uint32_t* feats2, int nn2, const float* K4, const float* t1w, const float* t2w,
+                                 const float* scale_factors, const float* level_sigma2, int nlevels, int only_stereo, int coarse, int check_ori,
+                                 int32_t* match12, float* F12_out, float* ep_out) {
+    Pinhole cam(std::vector<float>(K4, K4 + 4));
+    const float b4[4] = {0.f, 0.f, 1.f, 1.f};
+    KeyFrame k1, k2;
+    fillKeyFrame(k1, &cam, kps1, desc1, n1, b4, K4, scale_factors, nullptr, nlevels, u_right1);
+    fillKeyFrame(k2, &cam, kps2, desc2, n2, b4, K4, scale_factors, nullptr, nlevels, u_right2);
+    k1.mvLevelSigma2.assign(level_sigma2, level_sigma2 + nlevels); k2.mvLevelSigma2 = k1.mvLevelSigma2;
+    k1.tcw = vec3(t1w); k2.tcw = vec3(t2w);
+    k1.Ow = -k1.Rcw.t() * k1.tcw; k2.Ow = -k2.Rcw.t() * k2.tcw;           // KeyFrame::SetPose: Ow = -Rwc * tcw
+    for (int q = 0; q < nn1; q++) k1.mFeatVec[nodes1[q]] = std::vector<unsigned int>(feats1 + start1[q], feats1 + start1[q + 1]);
+    for (int q = 0; q < nn2; q++) k2.mFeatVec[nodes2[q]] = std::vector<unsigned int>(feats2 + start2[q], feats2 + start2[q + 1]);
+    MapPoint held;
+    for (int i = 0; i < n1; i++) if (has_mp1[i]) k1.mvpMapPoints[i] = &held;
+    for (int i = 0; i < n2; i++) if (has_mp2[i]) k2.mvpMapPoints[i] = &held;
+    // what the function computes for itself (:982-1000, Pinhole.cpp:137-140), for the caller of the device path
+    {
+        cv::Mat R1w = k1.GetRotation(), t1 = k1.GetTranslation(), R2w = k2.GetRotation(), t2 = k2.GetTranslation();
+        cv::Mat R12 = R1w * R2w.t();
+        cv::Mat t12 = -R1w * R2w.t() * t2 + t1;
+        cv::Mat F = cam.toK().t().inv() * cam.SkewSymmetricMatrix(t12) * R12 * cam.toK().inv();
+        for (int r = 0; r < 3; r++) for (int c = 0; c < 3; c++) F12_out[3 * r + c] = F.at<float>(r, c);
+        cv::Mat C2 = R2w * k1.GetCameraCenter() + t2;
+        const cv::Point2f ep = cam.project(C2);
+        ep_out[0] = ep.x; ep_out[1] = ep.y;
+    }
+    std::vector<std::pair<size_t, size_t> > pairs;
+    ORBmatcher matcher(0.6f, check_ori != 0);
+    const int nm = matcher.SearchForTriangulation(&k1, &k2, cv::Mat(), pairs, only_stereo != 0, coarse != 0);
+    for (int i = 0; i < n1; i++) match12[i] = -1;
+    size_t prev = 0;
+    for (size_t k = 0; k < pairs.size(); k++) {
+        if (k > 0 && pairs[k].first <= prev) return -1000;               // ascending first index (:1203-1208)
+        prev = pairs[k].first;
+        match12[pairs[k].first] = (int32_t)pairs[k].second;
+    }
+    if ((int)pairs.size() != nm) return -1001;
+    return nm;
+}
+
 }  // extern "C"

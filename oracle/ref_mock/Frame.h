@@ -128,6 +128,8 @@ public:
     cv::Mat GetRightCameraCenter() { return Ow.clone(); }
     float getORBScaleFactor(const int level) const { return mvScaleFactors[level]; }
     float getORBInvLevelSigma2(const int level) const { return mvInvLevelSigma2[level]; }
+    float getORBLevelSigma2(const int level) const { return mvLevelSigma2[level]; }
+    std::vector<float> mvLevelSigma2;
     int getKPtLevelMono(const int idx) const { return mvKeysUn[idx].octave; }        // KeyFrame.cc:1428-1431
     MapPoint* GetMapPoint(const std::size_t& idx) { return mvpMapPoints[idx]; }
     void AddMapPoint(MapPoint* p, const std::size_t& idx) { mvpMapPoints[idx] = p; }

@@ -200,6 +200,7 @@ public:
         return r;
     }
     inline double dot(const Mat& o) const;
+    inline Mat inv() const;
     Mat mul(const Mat& o) const {
         if (flags != CV_32F || o.flags != CV_32F || rows != o.rows || cols != o.cols) CVMINI_FAIL("Mat::mul");
         Mat r(rows, cols, CV_32F);
@@ -308,6 +309,7 @@ static inline double matDot(const Mat& a, const Mat& b) {
     return s;
 }
 inline double Mat::dot(const Mat& o) const { return matDot(*this, o); }
+inline Mat Mat::inv() const { return matInv3(*this); }
 static inline double norm(const Mat& a) {
     if (a.type() != CV_32F) CVMINI_FAIL("norm");
     double s = 0;

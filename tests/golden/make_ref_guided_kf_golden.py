@@ -27,6 +27,16 @@ def main():
         assert r[0] == o[0] and r[1].shape == o[1].shape and np.array_equal(r[1], o[1]), ("host part + oracle core != libref", key)
         out[key + "_n"] = np.array([r[0]], np.int32); out[key] = r[1].astype(np.int32)
         total += int(r[0])
+    # SearchForTriangulation (:975-1214): match table + what the function forms inside and the device path gets from its caller (F12, epipole)
+    tri, ntri = {}, 0
+    for key, a, kw in KC.tri_cases():
+        r = R.search_for_triangulation(*a, **kw)
+        o = KC.tri_compose(O.search_for_triangulation, a, kw, r[2], r[3])
+        assert r[0] == o[0] and np.array_equal(r[1], o[1]), ("oracle != libref", key)
+        tri[key + "_n"] = np.array([r[0]], np.int32); tri[key] = r[1].astype(np.int32); tri[key + "_F"] = r[2]; tri[key + "_ep"] = r[3]
+        ntri += int(r[0])
+    np.savez_compressed(os.path.join(HERE, "ref_triangulation.npz"), **tri)
+    print("ref_triangulation.npz: %d cases, %d matches, oracle == libref on every one" % (sum(k.endswith("_n") for k in tri), ntri))
     np.savez_compressed(os.path.join(HERE, "ref_guided_kf.npz"), **out)
     print("ref_guided_kf.npz: %d cases, %d matches / fusions, host part + oracle core == libref on every one" % (sum(k.endswith("_n") for k in out), total))
 

@@ -223,3 +223,41 @@ def run_composed(search, kind, overload, c):
 
 def kf_golden():
     return np.load(os.path.join(GOLDEN, "ref_guided_kf.npz"))
+
+
+# ----------------------------------------------------------------------------- SearchForTriangulation (ORBmatcher.cc:975-1214)
+def tri_cases(nseeds=4):
+    """(key, args of ref_lib.search_for_triangulation, kwargs).  Geometries: a sideways translation along the image flow (epipole at infinity,
+    true matches lie near their epipolar lines), and a forward motion that puts the epipole inside the image (epipole-distance gate, most
+    matches off their lines).  Variants: right-image columns, bOnlyStereo, bCoarse, rotation check off."""
+    import ref_cases as RC
+    K = np.array([458.654, 457.296, 367.215, 248.375], F32)
+    for seed in range(nseeds):
+        rng = np.random.default_rng(8000 + seed)
+        k1, d1, _, fv1, k2, d2, fv2 = RC.bow_case(600, 640, 700 + seed, levelsup=1 + seed % 3, max_flips=30)
+        nl = 8
+        sc = np.ones(nl, F32)
+        for i in range(1, nl):
+            sc[i] = F32(np.float64(sc[i - 1]) * np.float64(F32(1.2)))
+        sg = (sc * sc).astype(F32)
+        h1 = (rng.random(len(k1)) < 0.3).astype(np.uint8); h2 = (rng.random(len(k2)) < 0.3).astype(np.uint8)
+        u1 = np.where(rng.random(len(k1)) < 0.4, k1["x"] - 5, -1).astype(F32); u2 = np.where(rng.random(len(k2)) < 0.4, k2["x"] - 5, -1).astype(F32)
+        geos = {"side": (np.zeros(3, F32), np.array([-0.07, 0.04, 0.0], F32)), "fwd": (np.array([0.01, 0.0, 0.0], F32), np.array([0.02, -0.03, -1.0], F32))}
+        for gname, (t1, t2) in geos.items():
+            for var, (ur, only, coarse, ori) in {"mono": (False, False, False, True), "st": (True, False, False, True), "only": (True, True, False, bool(seed % 2)),
+                                                 "coarse": (False, False, True, True), "noori": (False, False, False, False)}.items():
+                a = (k1, d1, h1, u1 if ur else None, fv1, k2, d2, h2, u2 if ur else None, fv2, K, t1, t2, sc, sg)
+                yield "tri_%s_%s_s%d" % (gname, var, seed), a, dict(only_stereo=only, coarse=coarse, check_ori=ori)
+
+
+def tri_compose(search, a, kw, F12, ep):
+    """the device-path call for one case: flags from the map-point slots / right columns, F12 and the epipole as the caller forms them"""
+    import oracle_lib as O
+    k1, d1, h1, u1, fv1, k2, d2, h2, u2, fv2, K, t1, t2, sc, sg = a
+    f1 = O.triangulation_flags(h1, u1, kw["only_stereo"]); f2 = O.triangulation_flags(h2, u2, kw["only_stereo"])
+    return search(k1, d1, f1, fv1, k2, d2, f2, fv2, F12, ep, sc, sg, kw["coarse"], kw["check_ori"])
+
+
+def tri_golden():
+    return np.load(os.path.join(GOLDEN, "ref_triangulation.npz"))
+

@@ -459,6 +459,33 @@ def search_by_projection_reloc(x3Dc, valid1, level1, kps1, descMP, kps2, desc2, 
     return n, mc[:len(k2)].copy()
 
 
+def _fv(fv):
+    return [np.ascontiguousarray(fv[0], np.uint32), np.ascontiguousarray(fv[1], np.int32), np.ascontiguousarray(fv[2], np.uint32)]
+
+
+def triangulation_flags(has_mp, u_right, only_stereo):
+    """per-feature flags of SearchForTriangulation: bit 0 = takes part (no map point; stereo when bOnlyStereo), bit 1 = bStereo"""
+    has_mp = np.asarray(has_mp).astype(bool)
+    st = np.zeros(len(has_mp), bool) if u_right is None else (np.asarray(u_right, np.float32) >= 0)
+    part = ~has_mp & (st if only_stereo else True)
+    return (part.astype(np.uint8) | (st.astype(np.uint8) << 1)).astype(np.uint8)
+
+
+def search_for_triangulation(kps1, desc1, flags1, fv1, kps2, desc2, flags2, fv2, F12, ep, scale2, sigma2, coarse=False, check_ori=True):
+    """ORBmatcher::SearchForTriangulation (pinhole keyframes) -> (nmatches, match12[n1])"""
+    k1 = np.ascontiguousarray(kps1, KEYPOINT_DTYPE); k2 = np.ascontiguousarray(kps2, KEYPOINT_DTYPE)
+    d1 = np.ascontiguousarray(desc1, np.uint8); d2 = np.ascontiguousarray(desc2, np.uint8)
+    f1 = np.ascontiguousarray(flags1, np.uint8); f2 = np.ascontiguousarray(flags2, np.uint8)
+    a, b = _fv(fv1), _fv(fv2)
+    F = np.ascontiguousarray(F12, np.float32).reshape(9); e = np.ascontiguousarray(ep, np.float32)
+    sc = np.ascontiguousarray(scale2, np.float32); sg = np.ascontiguousarray(sigma2, np.float32)
+    m12 = np.full(max(len(k1), 1), -1, np.int32)
+    f = lib().orc_search_for_triangulation; f.restype = C.c_int
+    n = f(_p(k1), _p(d1), _p(f1), C.c_int(len(k1)), _p(a[0]), _p(a[1]), _p(a[2]), C.c_int(len(a[0])), _p(k2), _p(d2), _p(f2), C.c_int(len(k2)),
+          _p(b[0]), _p(b[1]), _p(b[2]), C.c_int(len(b[0])), _p(F), _p(e), _p(sc), _p(sg), C.c_int(len(sc)), C.c_int(int(coarse)), C.c_int(int(check_ori)), _p(m12))
+    return n, m12[:len(k1)].copy()
+
+
 AREA_QUERY_DTYPE = np.dtype([("x", "<f4"), ("y", "<f4"), ("r", "<f4"), ("min_level", "<i4"), ("max_level", "<i4")])
 
 

@@ -317,3 +317,22 @@ def search_by_sim3(c):
     n = f(_p(a[0]), _p(a[1]), _p(a[2]), _p(a[3]), _p(k1), _p(d1), C.c_int(len(k1)), _p(e[0]), _p(e[1]), _p(e[2]), _p(e[3]), _p(k2), _p(d2),
           C.c_int(len(k2)), _p(mi), _p(b), _p(K), _p(sf), C.c_int(len(sf)), C.c_float(c["th"]), _p(m12))
     return n, m12[:len(k1)].copy()
+
+
+def search_for_triangulation(kps1, desc1, has_mp1, u_right1, fv1, kps2, desc2, has_mp2, u_right2, fv2, K4, t1w, t2w, scale_factors, level_sigma2,
+                             only_stereo=False, coarse=False, check_ori=True):
+    """ORBmatcher::SearchForTriangulation (:975-1214) -> (nmatches, match12[n1], F12[9], epipole[2])"""
+    k1 = np.ascontiguousarray(kps1, O.KEYPOINT_DTYPE); k2 = np.ascontiguousarray(kps2, O.KEYPOINT_DTYPE)
+    d1 = np.ascontiguousarray(desc1, np.uint8); d2 = np.ascontiguousarray(desc2, np.uint8)
+    h1 = np.ascontiguousarray(has_mp1, np.uint8); h2 = np.ascontiguousarray(has_mp2, np.uint8)
+    u1 = None if u_right1 is None else np.ascontiguousarray(u_right1, np.float32); u2 = None if u_right2 is None else np.ascontiguousarray(u_right2, np.float32)
+    a, b = O._fv(fv1), O._fv(fv2)
+    K = np.ascontiguousarray(K4, np.float32); t1 = np.ascontiguousarray(t1w, np.float32); t2 = np.ascontiguousarray(t2w, np.float32)
+    sc = np.ascontiguousarray(scale_factors, np.float32); sg = np.ascontiguousarray(level_sigma2, np.float32)
+    m12 = np.full(max(len(k1), 1), -1, np.int32); F = np.zeros(9, np.float32); ep = np.zeros(2, np.float32)
+    f = lib().ref_search_for_triangulation; f.restype = C.c_int
+    n = f(_p(k1), _p(d1), _p(h1), _p(u1), C.c_int(len(k1)), _p(a[0]), _p(a[1]), _p(a[2]), C.c_int(len(a[0])), _p(k2), _p(d2), _p(h2), _p(u2), C.c_int(len(k2)),
+          _p(b[0]), _p(b[1]), _p(b[2]), C.c_int(len(b[0])), _p(K), _p(t1), _p(t2), _p(sc), _p(sg), C.c_int(len(sc)), C.c_int(int(only_stereo)),
+          C.c_int(int(coarse)), C.c_int(int(check_ori)), _p(m12), _p(F), _p(ep))
+    return n, m12[:len(k1)].copy(), F, ep
+

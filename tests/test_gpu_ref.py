@@ -231,3 +231,31 @@ def test_cuda_search_windows_equals_oracle_raw_outputs():
         assert r[0] == 0 and (r[1] == -1).all() and (r[2] == 256).all()
     assert ncmp >= 40
 
+
+def test_cuda_search_for_triangulation_equals_reference_golden():
+    """ORBmatcher::SearchForTriangulation (:975-1214) on the device against the pairs the REFERENCE'S OWN function body + Pinhole::epipolarConstrain
+    produced (tests/golden/ref_triangulation.npz, 40 cases), bit for bit; plus the empty / disjoint inputs"""
+    import kf_cases as KC
+    import oracle_lib as O
+    api = _api()
+    g = KC.tri_golden()
+    bad = []
+    for key, a, kw in KC.tri_cases():
+        gm = api.GuidedMatcher(0, 0.6, kw["check_ori"])
+        r = KC.tri_compose(lambda *x: gm.SearchForTriangulation(*x[:-2], bCoarse=x[-2]), a, kw, g[key + "_F"], g[key + "_ep"])
+        if not (r[0] == int(g[key + "_n"][0]) and np.array_equal(r[1], g[key])):
+            bad.append((key, r[0], int(g[key + "_n"][0]), int((r[1] != g[key]).sum())))
+    assert not bad, bad[:5]
+    key, a, kw = next(iter(KC.tri_cases(1)))
+    k1, d1, h1, u1, fv1, k2, d2, h2, u2, fv2, K, t1, t2, sc, sg = a
+    F, ep = g[key + "_F"], g[key + "_ep"]
+    f1 = O.triangulation_flags(h1, None, False); f2 = O.triangulation_flags(h2, None, False)
+    gm = api.GuidedMatcher()
+    n, m = gm.SearchForTriangulation(k1, d1, np.zeros_like(f1), fv1, k2, d2, f2, fv2, F, ep, sc, sg)
+    assert n == 0 and (m == -1).all()
+    far = (fv2[0] + np.uint32(1 << 20), fv2[1], fv2[2])
+    n, m = gm.SearchForTriangulation(k1, d1, f1, fv1, k2, d2, f2, far, F, ep, sc, sg)
+    assert n == 0 and (m == -1).all()
+    n, m = gm.SearchForTriangulation(k1[:0], d1[:0], f1[:0], (fv1[0][:0], np.zeros(1, np.int32), fv1[2][:0]), k2, d2, f2, fv2, F, ep, sc, sg)
+    assert n == 0 and len(m) == 0
+

@@ -214,6 +214,35 @@ def test_libref_keyframe_searches_reproduce_golden():
         assert r[0] == int(g[key + "_n"][0]) and np.array_equal(r[1], g[key]), key
 
 
+def test_oracle_search_for_triangulation_equals_reference_golden():
+    """ORBmatcher::SearchForTriangulation (:975-1214, pinhole keyframes): the oracle reproduces the pairs the reference's own function body and
+    Pinhole::epipolarConstrain produced (tests/golden/ref_triangulation.npz, 40 cases: epipole at infinity / inside the image, right-image
+    columns, bOnlyStereo, bCoarse, rotation check off); libref, where it exists, still reproduces the file, F12 and epipole included"""
+    import kf_cases as KC
+    g = KC.tri_golden()
+    ncase = 0
+    import ref_lib
+    R = ref_lib if ref_lib.available() else None
+    for key, a, kw in KC.tri_cases():
+        o = KC.tri_compose(O.search_for_triangulation, a, kw, g[key + "_F"], g[key + "_ep"])
+        assert o[0] == int(g[key + "_n"][0]) and np.array_equal(o[1], g[key]), key
+        if R is not None and ncase % 4 == 0:
+            r = R.search_for_triangulation(*a, **kw)
+            assert r[0] == o[0] and np.array_equal(r[1], g[key]) and r[2].tobytes() == g[key + "_F"].tobytes() and r[3].tobytes() == g[key + "_ep"].tobytes(), key
+        ncase += 1
+    assert ncase == sum(k.endswith("_n") for k in g.files) == 40
+    # nothing to match: empty sides, no common node, every feature holding a map point
+    key, a, kw = next(iter(KC.tri_cases(1)))
+    k1, d1, h1, u1, fv1, k2, d2, h2, u2, fv2, K, t1, t2, sc, sg = a
+    F, ep = g[key + "_F"], g[key + "_ep"]
+    f1 = O.triangulation_flags(h1, None, False); f2 = O.triangulation_flags(h2, None, False)
+    n, m = O.search_for_triangulation(k1, d1, np.zeros_like(f1), fv1, k2, d2, f2, fv2, F, ep, sc, sg)
+    assert n == 0 and (m == -1).all()
+    far = (fv2[0] + np.uint32(1 << 20), fv2[1], fv2[2])
+    n, m = O.search_for_triangulation(k1, d1, f1, fv1, k2, d2, f2, far, F, ep, sc, sg)
+    assert n == 0 and (m == -1).all()
+
+
 def test_oracle_search_windows_edge_cases():
     """no queries / no keypoints / every point gated out / every slot held"""
     import kf_cases as KC
