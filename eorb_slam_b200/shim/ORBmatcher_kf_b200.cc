@@ -18,6 +18,7 @@
 #include <cstring>
 #include <set>
 #include <tuple>
+#include <utility>
 #include <vector>
 
 #include "eorb_b200.h"
@@ -334,5 +335,99 @@ int ORBmatcher::SearchBySim3(KeyFrame *pKF1, KeyFrame *pKF2, std::vector<MapPoin
         if (idx2 >= 0 && idx2 < N2 && vnMatch2[idx2] == i1) { vpMatches12[i1] = vpMapPoints2[idx2]; nFound++; }
     }
     return nFound;
+}
+// ORBmatcher::SearchForTriangulation(pKF1, pKF2, F12, vMatchedPairs, bOnlyStereo, bCoarse) (:975-1214; LocalMapping::CreateNewMapPoints,
+// src/LocalMapping.cc:507; Tracking.cc:3212) for keyframes with one pinhole camera each.  The host forms what the reference forms once per
+// call -- the epipole (:982-988), R12 / t12 (:998-999) and the fundamental matrix Pinhole::epipolarConstrain rebuilds for every candidate pair
+// (src/CameraModels/Pinhole.cpp:137-140; the argument F12 is not read by the reference function either) -- the node walk, descriptor search,
+// both gates and the rotation filter run on the device.
+namespace {
+void flattenFV(const DBoW2::FeatureVector& fv, std::vector<unsigned>& nodes, std::vector<int>& start, std::vector<unsigned>& feats)
+{
+    nodes.clear(); feats.clear(); start.assign(1, 0);
+    for (DBoW2::FeatureVector::const_iterator it = fv.begin(); it != fv.end(); ++it) {
+        nodes.push_back(it->first);
+        feats.insert(feats.end(), it->second.begin(), it->second.end());
+        start.push_back((int)feats.size());
+    }
+}
+} // namespace
+
+int ORBmatcher::SearchForTriangulation(KeyFrame *pKF1, KeyFrame* pKF2, cv::Mat F12, std::vector<pair<size_t, size_t> > &vMatchedPairs, bool bOnlyStereo, bool bCoarse)
+{
+    (void)F12;
+    vMatchedPairs.clear();
+    GeometricCamera* pCamera1 = pKF1->mpCamera; GeometricCamera* pCamera2 = pKF2->mpCamera;
+    if (pKF1->mpCamera2 || pKF2->mpCamera2 || pCamera1->GetType() != pCamera1->CAM_PINHOLE || pCamera2->GetType() != pCamera2->CAM_PINHOLE) {
+        std::fprintf(stderr, "ORBmatcher(b200)::SearchForTriangulation: only pinhole keyframes with one camera are taken over\n");
+        return 0;
+    }
+    eorb_guided* g = kfHandle();
+    KfView v1, v2;
+    if (!g || !packKeyFrame(pKF1, v1, true) || !packKeyFrame(pKF2, v2, true) || v1.n == 0 || v2.n == 0) return 0;
+    float Cw[3], R1w[9], t1w[3], R2w[9], t2w[3], C2[3];
+    vecTo(pKF1->GetCameraCenter(), Cw);
+    matTo(pKF1->GetRotation(), R1w); vecTo(pKF1->GetTranslation(), t1w);
+    matTo(pKF2->GetRotation(), R2w); vecTo(pKF2->GetTranslation(), t2w);
+    rigid(R2w, t2w, Cw, C2);                                                   // C2 = R2w * Cw + t2w
+    const cv::Point2f ep = pCamera2->project(cv::Point3f(C2[0], C2[1], C2[2]));
+    float Fm[9];
+#ifndef EORB_SHIM_MOCK
+    {   // the reference's own expressions on cv::Mat (ORBmatcher.cc:998-999, Pinhole.cpp:137-140, :175-180)
+        const cv::Mat R1 = pKF1->GetRotation(), R2 = pKF2->GetRotation();
+        const cv::Mat R12 = R1 * R2.t();
+        const cv::Mat t12 = -R1 * R2.t() * pKF2->GetTranslation() + pKF1->GetTranslation();
+        const cv::Mat t12x = (cv::Mat_<float>(3, 3) << 0, -t12.at<float>(2), t12.at<float>(1), t12.at<float>(2), 0, -t12.at<float>(0), -t12.at<float>(1), t12.at<float>(0), 0);
+        const cv::Mat K1 = pCamera1->toK(), K2 = pCamera2->toK();
+        const cv::Mat F = K1.t().inv() * t12x * R12 * K2.inv();
+        for (int r = 0; r < 3; r++) for (int c = 0; c < 3; c++) Fm[3 * r + c] = F.at<float>(r, c);
+    }
+#else
+    {   // the same with the stand-in cv::Mat (no matrix algebra): written out on floats, products accumulated in double
+        float R12[9], t12[3], tmp[3];
+        for (int r = 0; r < 3; r++) for (int c = 0; c < 3; c++)
+            R12[3 * r + c] = (float)((double)R1w[3 * r] * R2w[3 * c] + (double)R1w[3 * r + 1] * R2w[3 * c + 1] + (double)R1w[3 * r + 2] * R2w[3 * c + 2]);
+        rigid(R12, nullptr, t2w, tmp);
+        for (int r = 0; r < 3; r++) t12[r] = -tmp[r] + t1w[r];
+        const float tx[9] = {0.f, -t12[2], t12[1], t12[2], 0.f, -t12[0], -t12[1], t12[0], 0.f};
+        const double fx1 = pCamera1->getParameter(0), fy1 = pCamera1->getParameter(1), cx1 = pCamera1->getParameter(2), cy1 = pCamera1->getParameter(3);
+        const double fx2 = pCamera2->getParameter(0), fy2 = pCamera2->getParameter(1), cx2 = pCamera2->getParameter(2), cy2 = pCamera2->getParameter(3);
+        const float K1tInv[9] = {(float)(1.0 / fx1), 0.f, 0.f, 0.f, (float)(1.0 / fy1), 0.f, (float)(-cx1 / fx1), (float)(-cy1 / fy1), 1.f};
+        const float K2Inv[9] = {(float)(1.0 / fx2), 0.f, (float)(-cx2 / fx2), 0.f, (float)(1.0 / fy2), (float)(-cy2 / fy2), 0.f, 0.f, 1.f};
+        auto mul = [](const float* A, const float* B, float* Cm) {
+            for (int r = 0; r < 3; r++) for (int c = 0; c < 3; c++)
+                Cm[3 * r + c] = (float)((double)A[3 * r] * B[c] + (double)A[3 * r + 1] * B[3 + c] + (double)A[3 * r + 2] * B[6 + c]);
+        };
+        float A[9], B[9];
+        mul(K1tInv, tx, A); mul(A, R12, B); mul(B, K2Inv, Fm);
+    }
+#endif
+    std::vector<unsigned char> f1(v1.n, 0), f2(v2.n, 0);
+    for (int i = 0; i < v1.n; i++) {
+        const bool st = v1.uRight[i] >= 0;
+        f1[i] = (unsigned char)(((!pKF1->GetMapPoint(i) && (!bOnlyStereo || st)) ? 1 : 0) | (st ? 2 : 0));
+    }
+    for (int i = 0; i < v2.n; i++) {
+        const bool st = v2.uRight[i] >= 0;
+        f2[i] = (unsigned char)(((!pKF2->GetMapPoint(i) && (!bOnlyStereo || st)) ? 1 : 0) | (st ? 2 : 0));
+    }
+    std::vector<unsigned> nodes1, feats1, nodes2, feats2;
+    std::vector<int> start1, start2;
+    flattenFV(pKF1->mFeatVec, nodes1, start1, feats1); flattenFV(pKF2->mFeatVec, nodes2, start2, feats2);
+    const int nl = pKF2->getORBNLevels();
+    std::vector<float> sc(nl), sg(nl);
+    for (int l = 0; l < nl; l++) { sc[l] = pKF2->getORBScaleFactor(l); sg[l] = pKF2->getORBLevelSigma2(l); }
+    const float epf[2] = {ep.x, ep.y};
+    std::vector<int> m12(v1.n, -1);
+    int nmatches = 0;
+    const int rc = eorb_guided_search_for_triangulation(g, v1.kps.data(), v1.desc.data(), f1.data(), v1.n, nodes1.data(), start1.data(), feats1.data(),
+                                                        (int)nodes1.size(), v2.kps.data(), v2.desc.data(), f2.data(), v2.n, nodes2.data(), start2.data(),
+                                                        feats2.data(), (int)nodes2.size(), Fm, epf, sc.data(), sg.data(), nl, bCoarse ? 1 : 0,
+                                                        mbCheckOrientation ? 1 : 0, m12.data(), &nmatches);
+    if (rc != EORB_OK) { std::fprintf(stderr, "ORBmatcher(b200)::SearchForTriangulation: %s\n", eorb_last_error()); return 0; }
+    vMatchedPairs.reserve(nmatches);
+    for (int i = 0; i < v1.n; i++)
+        if (m12[i] >= 0) vMatchedPairs.push_back(std::make_pair((size_t)i, (size_t)m12[i]));
+    return nmatches;
 }
 } // namespace ORB_SLAM3

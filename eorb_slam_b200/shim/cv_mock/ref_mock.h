@@ -113,13 +113,14 @@ public:
     int getORBNLevels() const { return (int)mvScaleFactors.size(); }
     float getORBScaleFactor(const int level) const { return mvScaleFactors[level]; }
     float getORBInvLevelSigma2(const int level) const { return mvInvLevelSigma2[level]; }
+    float getORBLevelSigma2(const int level) const { return 1.0f / mvInvLevelSigma2[level]; }
     bool IsInImage(const float& x, const float& y) const { return (x >= mnMinX && x < mnMaxX && y >= mnMinY && y < mnMaxY); }
     MapPoint* GetMapPoint(const size_t& idx) { return mvpMapPoints[idx]; }
     void AddMapPoint(MapPoint* p, const size_t& idx) { mvpMapPoints[idx] = p; }
     std::set<MapPoint*> GetMapPoints() { std::set<MapPoint*> s; for (MapPoint* p : mvpMapPoints) if (p) s.insert(p); return s; }
 };
 
-using std::vector;   // include/ORBmatcher.h declares Fuse with the bare name
+using std::vector; using std::pair;   // include/ORBmatcher.h declares Fuse / SearchForTriangulation with the bare names
 class ORBmatcher {   // the members this path touches (ORBmatcher.h:39-42, 67-68, 96-113)
 public:
     int SearchForInitialization(Frame& F1, Frame& F2, std::vector<cv::Point2f>& vbPrevMatched, std::vector<int>& vnMatches12, int windowSize = 10);
@@ -133,6 +134,7 @@ public:
     int SearchByProjection(KeyFrame* pKF, cv::Mat Scw, const std::vector<MapPoint*> &vpPoints, std::vector<MapPoint*> &vpMatched, int th, float ratioHamming=1.0);
     int SearchByProjection(KeyFrame* pKF, cv::Mat Scw, const std::vector<MapPoint*> &vpPoints, const std::vector<KeyFrame*> &vpPointsKFs,
             std::vector<MapPoint*> &vpMatched, std::vector<KeyFrame*> &vpMatchedKF, int th, float ratioHamming=1.0);
+    int SearchForTriangulation(KeyFrame *pKF1, KeyFrame* pKF2, cv::Mat F12, std::vector<pair<size_t, size_t> > &vMatchedPairs, bool bOnlyStereo, bool bCoarse = false);
     int SearchBySim3(KeyFrame* pKF1, KeyFrame* pKF2, std::vector<MapPoint *> &vpMatches12, const float &s12, const cv::Mat &R12, const cv::Mat &t12, float th);
     int Fuse(KeyFrame* pKF, const vector<MapPoint *> &vpMapPoints, float th=3.0, bool bRight = false);       // bare `vector`: as the reference writes it
     int Fuse(KeyFrame* pKF, cv::Mat Scw, const std::vector<MapPoint*> &vpPoints, float th, vector<MapPoint *> &vpReplacePoint);

@@ -226,6 +226,20 @@ int main(int argc, char** argv)
             const int s3n = matcher.SearchBySim3(&KA, &KB, vp12, s12, R12, t12, 7.5f);
             int s3same = 0; for (size_t i = 0; i < kps.size(); i++) s3same += (vp12[i] != nullptr && vp12[i] == mps[i]);
             std::printf("sim3_n=%d sim3_same=%d\n", s3n, s3same);
+            // SearchForTriangulation: the first keyframe sees the unshifted keypoints, the second one is moved sideways along the (3, -2) image
+            // flow, so every feature lies on its epipolar line; all features under one vocabulary node, no map points yet
+            KA.mvKeysUn = kps;
+            KA.mvpMapPoints.assign(kps.size(), nullptr); KB.mvpMapPoints.assign(kps.size(), nullptr);
+            KB.mtcw.at<float>(0, 0) = -0.03f; KB.mtcw.at<float>(1, 0) = 0.02f;
+            KB.mOw.at<float>(0, 0) = 0.03f; KB.mOw.at<float>(1, 0) = -0.02f;
+            std::vector<unsigned int> all;
+            for (size_t i = 0; i < kps.size(); i++) all.push_back((unsigned int)i);
+            KA.mFeatVec.clear(); KB.mFeatVec.clear();
+            if (!all.empty()) { KA.mFeatVec[7] = all; KB.mFeatVec[7] = all; }
+            std::vector<std::pair<size_t, size_t> > pairs;
+            const int tn = matcher.SearchForTriangulation(&KA, &KB, cv::Mat(), pairs, false, false);
+            int tsame = 0; for (auto& pr : pairs) tsame += (pr.first == pr.second);
+            std::printf("tri_nm=%d tri_pairs=%zu tri_same=%d\n", tn, pairs.size(), tsame);
         }
         for (auto* p : mps) delete p;
     }

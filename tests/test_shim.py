@@ -51,7 +51,7 @@ def test_shims_compile_and_fail_loudly_without_device():
     assert "lk_ok=0 lk_n=0" in out and "elk_n=0 elk_nm1=0" in out
     assert "sfi_nm=0 sfi_self=0" in out and "sbp_nm=0 sbp_set=0" in out and "slp_nm=0 slp_set=0" in out and "sbb_nm=0 sbb_set=0" in out and "sbk_nm=0 sbk_set=0" in out
     assert "sbs_nm=0 sbs_set=0" in out and "sbr_nm=0 sbr_set=0" in out
-    assert "kfp_nm=0 kfp_same=0 kfq_nm=0" in out and "fuse_n=0 fuse_add=0 fuse2_n=0" in out and "sim3_n=0" in out
+    assert "kfp_nm=0 kfp_same=0 kfq_nm=0" in out and "fuse_n=0 fuse_add=0 fuse2_n=0" in out and "sim3_n=0" in out and "tri_nm=0 tri_pairs=0" in out
     assert "voc_ok=0" in out and "undist_ok=0" in out
 
 
@@ -122,6 +122,9 @@ def test_shims_match_oracle_on_gpu():
     s3 = re.search(r"sim3_n=(\d+) sim3_same=(\d+)", out)
     s3n, s3same = map(int, s3.groups())
     assert s3n == s3same and s3n > 0.9 * len(okps)      # both directions agree on the point itself
+    tr = re.search(r"tri_nm=(\d+) tri_pairs=(\d+) tri_same=(\d+)", out)
+    tn, tp, tsame = map(int, tr.groups())
+    assert tn == tp and tn > 0.8 * len(okps) and tsame > 0.95 * tn   # SearchForTriangulation: features on their epipolar lines match themselves
     bb = re.search(r"sbb_nm=(\d+) sbb_set=(\d+) sbb_self=(\d+)", out)
     nbb, bset, bself = map(int, bb.groups())
     # SearchByBoW of a frame against a keyframe with the same features: distance 0 to itself, so every match is the feature itself
