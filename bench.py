@@ -801,7 +801,34 @@ def bench_bow(api, torch, dev, steps, warmup):
                (len(fv1[0]), len(fv2[0]), ben), "bit_exact_vs_oracle": bool(bn == ben and np.array_equal(bmf, bemf)), "cpu_port_ms_per_call": bms_port}
     except Exception as e:
         sbb = {"error": repr(e)}
-    return {"search_by_bow": sbb, "metric": "bow_transform_features_per_s", "value": len(feats) / (ms * 1e-3), "unit": "features/s", "ms_per_call": ms,
+    # LocalMapping::CreateNewMapPoints: SearchForTriangulation between the same two feature sets (coarse = the descriptor search + epipole gate)
+    tri = {}
+    try:
+        nl = 8
+        sc = (np.float32(1.2) ** np.arange(nl)).astype(np.float32); sg = (sc * sc).astype(np.float32)
+        F12 = np.array([0, 0, 0, 0, 0, -1e-4, 0, 1e-4, 0], np.float32); ep = np.array([-np.inf, 248.0], np.float32)   # sideways motion: horizontal epipolar lines
+        f1 = O.triangulation_flags(np.zeros(len(kk1)), None, False); f2 = O.triangulation_flags(np.zeros(len(kk2)), None, False)
+        a = (kk1, dkf, f1, fv1, kk2, df, f2, fv2, F12, ep, sc, sg)
+        gt = api.GuidedMatcher(dev, 0.6, True)
+        for _ in range(3):
+            tn, tm = gt.SearchForTriangulation(*a, bCoarse=True)
+        t0 = time.perf_counter()
+        for _ in range(reps):
+            tn, tm = gt.SearchForTriangulation(*a, bCoarse=True)
+        tms = (time.perf_counter() - t0) * 1e3 / reps
+        ten, tem = O.search_for_triangulation(*a, coarse=True, check_ori=True)
+        t0 = time.perf_counter()
+        for _ in range(20):
+            O.search_for_triangulation(*a, coarse=True, check_ori=True)
+        tms_port = (time.perf_counter() - t0) * 1e3 / 20
+        tn2, tm2 = gt.SearchForTriangulation(*a, bCoarse=False)
+        ten2, tem2 = O.search_for_triangulation(*a, coarse=False, check_ori=True)
+        tri = {"ms_per_call": tms, "workload": "ORBmatcher::SearchForTriangulation(pKF1, pKF2, bCoarse): 1009 x 1009 features over %d / %d vocabulary nodes, %d pairs; "
+               "host call" % (len(fv1[0]), len(fv2[0]), ten),
+               "bit_exact_vs_oracle": bool(tn == ten and np.array_equal(tm, tem) and tn2 == ten2 and np.array_equal(tm2, tem2)), "cpu_port_ms_per_call": tms_port}
+    except Exception as e:
+        tri = {"error": repr(e)}
+    return {"search_by_bow": sbb, "search_for_triangulation": tri, "metric": "bow_transform_features_per_s", "value": len(feats) / (ms * 1e-3), "unit": "features/s", "ms_per_call": ms,
             "workload": "ORBVocabulary::transform: %d descriptors, vocabulary k=10 L=6 (%d nodes, %d words), levelsup 4, host call" %
                         (len(feats), len(voc["parent"]), len(leaves)),
             "gpu_launches_per_call": int(launches), "bit_exact_vs_oracle": bool(same), "bow_words": int(len(exp["bow_ids"])),
