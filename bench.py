@@ -1245,6 +1245,35 @@ def run_ours(args):
         link = [{"gpu": 0, "pcie_gen": int(mine[0]), "pcie_width": int(mine[1]), "h2d_gbs_alone": h2d_gbs}]
         h2d_sum = h2d_gbs
 
+    # ---- the same link with BOTH directions busy, as in the end-to-end step: the frames going in while the previous results come out
+    # (all ranks at once at N > 1).  PCIe is full duplex, the host's memory system is not: when the two directions share it, this is the ceiling.
+    bidir_sum = None
+    try:
+        s_in, s_out = torch.cuda.Stream(), torch.cuda.Stream()
+        cur = torch.cuda.current_stream()
+
+        def bidir_once():
+            torch.cuda.synchronize()
+            if world > 1:
+                dist.barrier()
+            ev0.record()
+            s_in.wait_event(ev0); s_out.wait_event(ev0)
+            with torch.cuda.stream(s_in):
+                d_frames.copy_(h_frames, non_blocking=True)
+            with torch.cuda.stream(s_out):
+                h_kps.copy_(d_kps, non_blocking=True); h_desc.copy_(d_desc, non_blocking=True)
+            cur.wait_stream(s_in); cur.wait_stream(s_out)
+            ev1.record(); torch.cuda.synchronize()
+            return ev0.elapsed_time(ev1)
+        bidir_once()
+        t_b = bidir_once()
+        tm = torch.tensor([nfr / (t_b * 1e-3)], device="cuda")
+        if world > 1:
+            dist.all_reduce(tm, op=dist.ReduceOp.SUM)
+        bidir_sum = float(tm.item())
+    except Exception:
+        bidir_sum = None
+
     if rank == 0:
         line = {
             "metric": "orb_frames_per_sec", "value": value, "unit": "frames/s", "n_gpus": world, "steps": args.steps,
@@ -1257,7 +1286,9 @@ def run_ours(args):
             "e2e": {"value": e2e_value, "unit": "frames/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "ms_per_step": e2e_ms, "call": "eorb_orb_extract_batch (pinned host buffers)",
                     "pcie_h2d_gbs_measured": h2d_gbs, "pcie_bound_frames_per_s": h2d_sum * 1e9 / (W * H),
-                    "frac_of_pcie_bound": e2e_value / (h2d_sum * 1e9 / (W * H)), "host_link": link},
+                    "frac_of_pcie_bound": e2e_value / (h2d_sum * 1e9 / (W * H)),
+                    "pcie_bidir_bound_frames_per_s": bidir_sum, "frac_of_pcie_bidir_bound": (e2e_value / bidir_sum) if bidir_sum else None,
+                    "host_link": link},
             "gpu_launches": int(launches),
             "roofline": roof,
             "stages": per_stage,
