@@ -314,6 +314,27 @@ def bench_events(api, torch, dev, steps, warmup, world=1, rank=0, dist=None, cpu
                         "note": "7x7 splat accumulates in shared memory (int32 fixed point, native ATOMS.ADD), frame written once; "
                                 "bounded by instruction issue + smem atomics, not HBM; see atomic_adds_per_s"}}
     cv.set_stream(None)
+    # end to end through the host entry point: pinned host events in (24 B each), u8 event frames back in pinned host memory, copies inside
+    # the timed region (eorb_ev_accumulate_batch: one H2D, the batch kernels, one D2H)
+    try:
+        h_ev = torch.from_numpy(ev.view(np.uint8).reshape(-1).copy()).pin_memory()
+        h_u8 = torch.empty(nwin * h * w, dtype=torch.uint8).pin_memory()
+        for _ in range(3):
+            cv.accumulate_batch(h_ev.data_ptr(), offs, p, None, h_u8.data_ptr())
+        if world > 1:
+            dist.barrier()
+        nrep = max(steps, 10)
+        t0 = time.perf_counter()
+        for _ in range(nrep):
+            cv.accumulate_batch(h_ev.data_ptr(), offs, p, None, h_u8.data_ptr())
+        ems = (time.perf_counter() - t0) * 1e3 / nrep
+        if world > 1:
+            tm = torch.tensor([ems], device="cuda"); dist.all_reduce(tm, op=dist.ReduceOp.MAX); ems = float(tm.item())
+        same = bool(torch.equal(h_u8, d_u8.cpu()))
+        out["e2e"] = {"value": world * nev / ems / 1e3, "unit": "Mev/s", "ms_per_step": ems, "h2d_bytes_per_step": nev * 24, "d2h_bytes_per_step": nwin * h * w,
+                      "call": "eorb_ev_accumulate_batch (pinned host events in, u8 frames out)", "frames_equal_resident_path": same}
+    except Exception as e:
+        out["e2e"] = {"error": repr(e)}
     if cpu and rank == 0 and world == 1:
         out["cpu_baseline"] = _events_cpu_baseline(ev, per, w, h, 1.0, 1, None, 1.0, None, nwin)
     # configs[1] as ONE device pipeline: the windows above -> u8 event frames -> single-level event extractor (N = 400, FAST 0/0,

@@ -83,6 +83,7 @@ def _load():
         "eorb_ev_set_stream": ([vp, vp], i), "eorb_ev_reset_stream": ([vp], i), "eorb_ev_synchronize": ([vp], i), "eorb_ev_launch_count": ([vp], C.c_longlong),
         "eorb_ev_accumulate": ([vp, vp, i64, C.POINTER(_EvParams), vp, vp, vp], i),
         "eorb_ev_accumulate_batch_device": ([vp, vp, vp, i, C.POINTER(_EvParams), vp, vp, vp], i),
+        "eorb_ev_accumulate_batch": ([vp, vp, vp, i, C.POINTER(_EvParams), vp, vp, vp], i),
         "eorb_ev_mci_jac": ([vp, vp, i64, i, i, f, vp, f, vp, i, i, vp], i),
         "eorb_ev_image_focus_device": ([vp, vp, i, i, i, i, i, vp], i), "eorb_ev_image_focus": ([vp, vp, i, i, sz, i, i, vp], i),
         "eorb_lk_create": ([i, i, i, i, C.POINTER(vp)], i), "eorb_lk_destroy": ([vp], i),
@@ -587,6 +588,14 @@ class EvImConverter:
         ps = np.ascontiguousarray(poses, np.float32) if poses is not None else None
         _check(lib.eorb_ev_accumulate_batch_device(self.h, _p(d_evs), _p(offs), len(offs) - 1, C.byref(p), _p(ps), _p(d_img_f32),
                                                    _p(d_img_u8)), "ev_accumulate_batch_device")
+
+
+    def accumulate_batch(self, evs, win_offsets, p, img_f32=None, img_u8=None, poses=None):
+        """host buffers: evs = EVENT_DTYPE array (or an int address of pinned memory), outputs = numpy arrays / int addresses [nwin][h][w]"""
+        offs = np.ascontiguousarray(win_offsets, np.int64)
+        ps = np.ascontiguousarray(poses, np.float32) if poses is not None else None
+        _check(lib.eorb_ev_accumulate_batch(self.h, _p(evs), _p(offs), len(offs) - 1, C.byref(p), _p(ps), _p(img_f32), _p(img_u8)),
+               "ev_accumulate_batch")
 
 
 class ELK_Tracker:

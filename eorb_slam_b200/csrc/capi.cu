@@ -1482,6 +1482,7 @@ struct eorb_evconv {
     eorb_event* d_evs = nullptr; float* d_img = nullptr; uint8_t* d_u8 = nullptr; float* d_minmax = nullptr;
     float2* d_xy = nullptr; long long xyCap = 0;   // warped event positions (multi-band motion-compensated frames), grown on demand
     float* d_jac = nullptr;   // 7 frames (I, dI/d[wx wy wz vx vy vz]) of ev2mci_gg_f_jac, allocated on first use
+    float* d_bimg = nullptr; uint8_t* d_bu8 = nullptr; size_t bCap = 0;   // [nwin][h][w] frames of the host batch call, allocated on first use
     EvWindow* d_wins = nullptr;
     std::vector<EvWindow> h_wins;
     long long launches = 0;
@@ -1509,7 +1510,7 @@ extern "C" int eorb_ev_destroy(eorb_evconv* c) {
     if (!c) return EORB_OK;
     cudaSetDevice(c->device);
     cudaStreamSynchronize(c->stream);
-    cudaFree(c->d_evs); cudaFree(c->d_img); cudaFree(c->d_u8); cudaFree(c->d_minmax); cudaFree(c->d_jac); cudaFree(c->d_wins); cudaFree(c->d_xy);
+    cudaFree(c->d_evs); cudaFree(c->d_img); cudaFree(c->d_u8); cudaFree(c->d_minmax); cudaFree(c->d_bimg); cudaFree(c->d_bu8); cudaFree(c->d_jac); cudaFree(c->d_wins); cudaFree(c->d_xy);
     cudaStreamDestroy(c->ownStream);
     delete c;
     return EORB_OK;
@@ -1621,6 +1622,37 @@ extern "C" int eorb_ev_accumulate_batch_device(eorb_evconv* c, const eorb_event*
         xy = c->d_xy;
     }
     CU(launch_ev_frames(d_evs, c->d_wins, nwin, maxEv, k, p->normalize, d_img_f32, c->d_minmax, d_img_u8, c->stream, &c->launches, xy));
+    return EORB_OK;
+}
+
+// nwin windows, HOST buffers: one H2D copy of the events, the batch kernels, one D2H copy per requested output
+extern "C" int eorb_ev_accumulate_batch(eorb_evconv* c, const eorb_event* evs, const int64_t* win_offsets, int nwin, const eorb_ev_params* p,
+                                        const float* poses, float* img_f32, uint8_t* img_u8) {
+    if (!c || !win_offsets || !p || (!img_f32 && !img_u8)) return fail(EORB_ERR_ARG, "null argument");
+    if (nwin < 1) return EORB_OK;
+    if (nwin > c->maxWindows) return fail(EORB_ERR_CAPACITY, "nwin %d > max_windows %d", nwin, c->maxWindows);
+    const long long nev = win_offsets[nwin];
+    if (win_offsets[0] != 0 || nev < 0) return fail(EORB_ERR_ARG, "window offsets must start at 0");
+    if (nev > c->maxEvents) return fail(EORB_ERR_CAPACITY, "%lld events > max_events %lld", nev, c->maxEvents);
+    if (nev > 0 && !evs) return fail(EORB_ERR_ARG, "null events");
+    if (p->width < 1 || p->height < 1 || (long long)p->width * p->height > (long long)c->maxW * c->maxH)
+        return fail(EORB_ERR_CAPACITY, "image %dx%d exceeds the converter's %dx%d", p->width, p->height, c->maxW, c->maxH);
+    if (img_u8 && p->normalize == EORB_NORM_NONE) return fail(EORB_ERR_ARG, "a u8 output needs a normalisation mode");
+    CU(cudaSetDevice(c->device));
+    const size_t npix = (size_t)p->width * p->height, need = npix * (size_t)nwin;
+    if (need > c->bCap) {
+        CU(cudaStreamSynchronize(c->stream));
+        cudaFree(c->d_bimg); cudaFree(c->d_bu8); c->d_bimg = nullptr; c->d_bu8 = nullptr; c->bCap = 0;
+        CU(devAlloc(&c->d_bimg, need));
+        CU(devAlloc(&c->d_bu8, need));
+        c->bCap = need;
+    }
+    if (nev > 0) CU(cudaMemcpyAsync(c->d_evs, evs, (size_t)nev * sizeof(eorb_event), cudaMemcpyHostToDevice, c->stream));
+    const int rc = eorb_ev_accumulate_batch_device(c, c->d_evs, win_offsets, nwin, p, poses, c->d_bimg, p->normalize != EORB_NORM_NONE ? c->d_bu8 : nullptr);
+    if (rc != EORB_OK) return rc;
+    if (img_f32) CU(cudaMemcpyAsync(img_f32, c->d_bimg, need * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
+    if (img_u8) CU(cudaMemcpyAsync(img_u8, c->d_bu8, need, cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
     return EORB_OK;
 }
 

@@ -275,6 +275,12 @@ int eorb_ev_accumulate_batch_device(eorb_evconv* c, const eorb_event* d_evs, con
                                     const eorb_ev_params* p, const float* poses,
                                     float* d_img_f32, uint8_t* d_img_u8);
 
+/* the same with HOST buffers (the fixed-count windows of one event packet, EvTrackManager.cpp:272-286, in one call): events and offsets on
+ * the host, frames [nwin][h][w] back on the host; img_f32 / img_u8 may each be NULL (not both; img_u8 needs a normalisation mode).  One H2D
+ * copy, the batch kernels, one D2H copy per output; synchronous. */
+int eorb_ev_accumulate_batch(eorb_evconv* c, const eorb_event* evs, const int64_t* win_offsets, int nwin, const eorb_ev_params* p,
+                             const float* poses, float* img_f32, uint8_t* img_u8);
+
 /* contrast metric of event frames (second "next" row): EvImConverter::measureImageFocusLocal (what = 0),
  * measureImageFocusGlobal (1), imageMeanLocal (2) — src/Event/EventConversion.cc:79-162, 30x30 cells, cv::meanStdDev
  * per cell; avg != 0: average of the cell values (measureImageFocus), avg == 0: their median.  The reference picks the

@@ -147,6 +147,49 @@ def test_windows_batch_device_then_orb_on_event_frames():
     cv.set_stream(None)
 
 
+def test_windows_batch_host_entry_matches_oracle_and_device_entry():
+    """eorb_ev_accumulate_batch (host events + offsets in, frames back on the host): ragged windows incl. an empty one, float and u8 outputs,
+    per-window SE3 poses; == the oracle per window (tolerance of the file) and == the device entry point bit for bit"""
+    import torch
+    api = _api()
+    sizes = [2000, 0, 1500, 3100, 1, 2400]
+    offs = np.concatenate([[0], np.cumsum(sizes)]).astype(np.int64)
+    ev = synth.make_events(int(offs[-1]), seed=15, w=240, h=180)
+    nwin = len(sizes)
+    cv = api.EvImConverter(0, nwin, int(offs[-1]), 240, 180)
+    p = cv.make_params(api.EV_GAUSS, 240, 180, 1.0, False, api.NORM_RUNNING)
+    f32 = np.zeros((nwin, 180, 240), np.float32); u8 = np.zeros((nwin, 180, 240), np.uint8)
+    cv.accumulate_batch(ev, offs, p, f32, u8)
+    d_ev = torch.from_numpy(ev.view(np.uint8).reshape(-1)).cuda()
+    d_img = torch.zeros(nwin * 180 * 240, dtype=torch.float32, device="cuda"); d_u8 = torch.zeros(nwin * 180 * 240, dtype=torch.uint8, device="cuda")
+    cv.accumulate_batch_device(d_ev.data_ptr(), offs, p, d_img.data_ptr(), d_u8.data_ptr())
+    cv.synchronize()
+    assert f32.tobytes() == d_img.cpu().numpy().tobytes() and u8.tobytes() == d_u8.cpu().numpy().tobytes()
+    for i, n in enumerate(sizes):
+        if n == 0:
+            assert not f32[i].any() and not u8[i].any()
+            continue
+        ref, _, ref8 = O.ev_accumulate(ev[offs[i]:offs[i + 1]], 240, 180, 1.0, mode=1, normalize=True)
+        _close(f32[i], ref)
+        assert np.abs(u8[i].astype(int) - ref8.astype(int)).max() <= 1
+    # float frames only, motion-compensated with one pose per window
+    K = (199.09, 198.83, 132.19, 110.71)
+    poses = np.tile(np.eye(4, dtype=np.float32), (nwin, 1, 1))
+    for i in range(nwin):
+        a = 0.01 * (i + 1)
+        poses[i, :3, :3] = np.array([[np.cos(a), -np.sin(a), 0], [np.sin(a), np.cos(a), 0], [0, 0, 1]], np.float32)
+    pm = cv.make_params(api.EV_SE3, 240, 180, 1.0, False, api.NORM_NONE, Tcw=poses[0], medDepth=1.0, camera=K)
+    g32 = np.zeros((nwin, 180, 240), np.float32)
+    cv.accumulate_batch(ev, offs, pm, g32, None, poses=poses.reshape(nwin, 16))
+    for i, n in enumerate(sizes):
+        if n < 2:
+            continue
+        ref, _, _ = O.ev_accumulate(ev[offs[i]:offs[i + 1]], 240, 180, 1.0, mode=2, Tcw=poses[i], depth=1.0, K=np.array(K, np.float32))
+        _close(g32[i], ref)
+    with pytest.raises(Exception):
+        cv.accumulate_batch(ev, offs, pm, None, u8)          # a u8 output needs a normalisation mode
+
+
 def test_config5_mvsec_mc_frames_orb_and_frame_to_frame_matching():
     """configs[4]: MVSEC-shaped 346x260, 50k events/window, motion-compensated frames from a synthetic rotation
     (t = 0, medDepth = 1) -> cv::normalize(MINMAX) -> ORB (EvMVSEC_ETHZ.yaml values, margin raised to 19 for the
