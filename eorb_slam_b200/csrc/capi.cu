@@ -1483,6 +1483,7 @@ struct eorb_evconv {
     float2* d_xy = nullptr; long long xyCap = 0;   // warped event positions (multi-band motion-compensated frames), grown on demand
     float* d_jac = nullptr;   // 7 frames (I, dI/d[wx wy wz vx vy vz]) of ev2mci_gg_f_jac, allocated on first use
     float* d_bimg = nullptr; uint8_t* d_bu8 = nullptr; size_t bCap = 0;   // [nwin][h][w] frames of the host batch call, allocated on first use
+    cudaStream_t pipeS[2] = {nullptr, nullptr};                            // the host batch call's two pipeline streams
     EvWindow* d_wins = nullptr;
     std::vector<EvWindow> h_wins;
     long long launches = 0;
@@ -1511,6 +1512,7 @@ extern "C" int eorb_ev_destroy(eorb_evconv* c) {
     cudaSetDevice(c->device);
     cudaStreamSynchronize(c->stream);
     cudaFree(c->d_evs); cudaFree(c->d_img); cudaFree(c->d_u8); cudaFree(c->d_minmax); cudaFree(c->d_bimg); cudaFree(c->d_bu8); cudaFree(c->d_jac); cudaFree(c->d_wins); cudaFree(c->d_xy);
+    for (int i = 0; i < 2; i++) if (c->pipeS[i]) cudaStreamDestroy(c->pipeS[i]);
     cudaStreamDestroy(c->ownStream);
     delete c;
     return EORB_OK;
@@ -1588,6 +1590,35 @@ static int evConst(const eorb_ev_params* p, EvConst& c) {
     return EORB_OK;
 }
 
+// windows [i0, i0 + n) of win_offsets on stream `st`; their EvWindow records and extremes live in slots [i0, i0 + n) of d_wins / d_minmax,
+// so that disjoint window ranges can be in flight on different streams (the pipelined host call below)
+static int evBatchRun(eorb_evconv* c, const eorb_event* d_evs, const int64_t* win_offsets, int i0, int n, long long totalEvents, const eorb_ev_params* p,
+                      const EvConst& k, const float* poses, float* d_img_f32, uint8_t* d_img_u8, cudaStream_t st) {
+    long long maxEv = 0;
+    for (int i = i0; i < i0 + n; i++) {
+        EvWindow& w = c->h_wins[i];
+        w.begin = win_offsets[i]; w.end = win_offsets[i + 1];
+        if (w.end < w.begin) return fail(EORB_ERR_ARG, "window offsets must be non-decreasing");
+        maxEv = std::max(maxEv, w.end - w.begin);
+        w.angle = 0; w.axis[0] = 1; w.axis[1] = w.axis[2] = 0; w.t[0] = w.t[1] = w.t[2] = 0;
+        if (p->mode == EORB_EV_SE3) angleAxisFromPose(poses ? poses + 16 * (size_t)i : p->Tcw, w);
+    }
+    CU(cudaMemcpyAsync(c->d_wins + i0, c->h_wins.data() + i0, (size_t)n * sizeof(EvWindow), cudaMemcpyHostToDevice, st));
+    float2* xy = nullptr;
+    const bool ordered = p->pol && p->normalize == EORB_NORM_RUNNING;   // order-dependent extremes: ev_ordered_kernel reads warped positions
+    if ((p->mode == EORB_EV_SE3 || p->mode == EORB_EV_SE2) && ((size_t)k.width * k.height * 4 > 200 * 1024 || ordered)) {
+        if (totalEvents > c->xyCap) {
+            CU(cudaDeviceSynchronize());
+            cudaFree(c->d_xy); c->d_xy = nullptr; c->xyCap = 0;
+            CU(devAlloc(&c->d_xy, (size_t)totalEvents));
+            c->xyCap = totalEvents;
+        }
+        xy = c->d_xy;
+    }
+    CU(launch_ev_frames(d_evs, c->d_wins + i0, n, maxEv, k, p->normalize, d_img_f32, c->d_minmax + 2 * (size_t)i0, d_img_u8, st, &c->launches, xy));
+    return EORB_OK;
+}
+
 extern "C" int eorb_ev_accumulate_batch_device(eorb_evconv* c, const eorb_event* d_evs, const int64_t* win_offsets, int nwin,
                                                const eorb_ev_params* p, const float* poses, float* d_img_f32, uint8_t* d_img_u8) {
     if (!c || !d_evs || !win_offsets || !d_img_f32) return fail(EORB_ERR_ARG, "null argument");
@@ -1599,33 +1630,16 @@ extern "C" int eorb_ev_accumulate_batch_device(eorb_evconv* c, const eorb_event*
     if (p->normalize != EORB_NORM_NONE && !d_img_u8) return fail(EORB_ERR_ARG, "normalize requested without a u8 output");
     CU(cudaSetDevice(c->device));
     c->h_wins.resize(nwin);
-    long long maxEv = 0;
-    for (int i = 0; i < nwin; i++) {
-        EvWindow& w = c->h_wins[i];
-        w.begin = win_offsets[i]; w.end = win_offsets[i + 1];
-        if (w.end < w.begin) return fail(EORB_ERR_ARG, "window offsets must be non-decreasing");
-        maxEv = std::max(maxEv, w.end - w.begin);
-        w.angle = 0; w.axis[0] = 1; w.axis[1] = w.axis[2] = 0; w.t[0] = w.t[1] = w.t[2] = 0;
-        if (p->mode == EORB_EV_SE3) angleAxisFromPose(poses ? poses + 16 * (size_t)i : p->Tcw, w);
-    }
-    CU(cudaMemcpyAsync(c->d_wins, c->h_wins.data(), (size_t)nwin * sizeof(EvWindow), cudaMemcpyHostToDevice, c->stream));
-    float2* xy = nullptr;
-    const bool ordered = p->pol && p->normalize == EORB_NORM_RUNNING;   // order-dependent extremes: ev_ordered_kernel reads warped positions
-    if ((p->mode == EORB_EV_SE3 || p->mode == EORB_EV_SE2) && ((size_t)k.width * k.height * 4 > 200 * 1024 || ordered)) {
-        const long long need = win_offsets[nwin];
-        if (need > c->xyCap) {
-            CU(cudaStreamSynchronize(c->stream));
-            cudaFree(c->d_xy); c->d_xy = nullptr; c->xyCap = 0;
-            CU(devAlloc(&c->d_xy, (size_t)need));
-            c->xyCap = need;
-        }
-        xy = c->d_xy;
-    }
-    CU(launch_ev_frames(d_evs, c->d_wins, nwin, maxEv, k, p->normalize, d_img_f32, c->d_minmax, d_img_u8, c->stream, &c->launches, xy));
-    return EORB_OK;
+    return evBatchRun(c, d_evs, win_offsets, 0, nwin, win_offsets[nwin], p, k, poses, d_img_f32, d_img_u8, c->stream);
 }
 
-// nwin windows, HOST buffers: one H2D copy of the events, the batch kernels, one D2H copy per requested output
+// like CU(), but records the failure in `status` instead of returning: the caller drains its streams first
+#define CUS(call)                                                                                        \
+    do {                                                                                                 \
+        cudaError_t e__ = (call);                                                                        \
+        if (e__ != cudaSuccess) status = fail(EORB_ERR_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e__), __FILE__, __LINE__); \
+    } while (0)
+// nwin windows, HOST buffers: the events go in, the batch kernels run, the requested outputs come back -- pipelined over window ranges
 extern "C" int eorb_ev_accumulate_batch(eorb_evconv* c, const eorb_event* evs, const int64_t* win_offsets, int nwin, const eorb_ev_params* p,
                                         const float* poses, float* img_f32, uint8_t* img_u8) {
     if (!c || !win_offsets || !p || (!img_f32 && !img_u8)) return fail(EORB_ERR_ARG, "null argument");
@@ -1647,12 +1661,39 @@ extern "C" int eorb_ev_accumulate_batch(eorb_evconv* c, const eorb_event* evs, c
         CU(devAlloc(&c->d_bu8, need));
         c->bCap = need;
     }
-    if (nev > 0) CU(cudaMemcpyAsync(c->d_evs, evs, (size_t)nev * sizeof(eorb_event), cudaMemcpyHostToDevice, c->stream));
-    const int rc = eorb_ev_accumulate_batch_device(c, c->d_evs, win_offsets, nwin, p, poses, c->d_bimg, p->normalize != EORB_NORM_NONE ? c->d_bu8 : nullptr);
+    EvConst k;
+    int rc = evConst(p, k);
     if (rc != EORB_OK) return rc;
-    if (img_f32) CU(cudaMemcpyAsync(img_f32, c->d_bimg, need * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
-    if (img_u8) CU(cudaMemcpyAsync(img_u8, c->d_bu8, need, cudaMemcpyDeviceToHost, c->stream));
-    CU(cudaStreamSynchronize(c->stream));
+    c->h_wins.resize(nwin);
+    uint8_t* d_u8 = p->normalize != EORB_NORM_NONE ? c->d_bu8 : nullptr;
+    // Large packets run as up to four ranges of windows on two streams, so that the events of one range go in while the frames of the
+    // range before come out (PCIe is full duplex); the windows' records and extremes sit in disjoint slots.  (The per-event scratch of the
+    // multi-band / ordered paths is indexed by event position, so disjoint ranges do not collide there either.)
+    const int nparts = (nwin >= 16 && nev >= 65536) ? 4 : 1;
+    if (nparts > 1 && !c->pipeS[0]) {
+        for (int i = 0; i < 2; i++) CU(cudaStreamCreateWithFlags(&c->pipeS[i], cudaStreamNonBlocking));
+    }
+    if (nparts > 1) CU(cudaStreamSynchronize(c->stream));      // order after earlier work on the converter's stream
+    int status = EORB_OK;
+    for (int part = 0; part < nparts && status == EORB_OK; part++) {
+        const int i0 = (int)((long long)nwin * part / nparts), i1 = (int)((long long)nwin * (part + 1) / nparts);
+        if (i1 <= i0) continue;
+        cudaStream_t st = nparts > 1 ? c->pipeS[part & 1] : c->stream;
+        const long long e0 = win_offsets[i0], e1 = win_offsets[i1];
+        if (e1 < e0) { status = fail(EORB_ERR_ARG, "window offsets must be non-decreasing"); break; }
+        if (e1 > e0) CUS(cudaMemcpyAsync(c->d_evs + e0, evs + e0, (size_t)(e1 - e0) * sizeof(eorb_event), cudaMemcpyHostToDevice, st));
+        if (status != EORB_OK) break;
+        status = evBatchRun(c, c->d_evs, win_offsets, i0, i1 - i0, nev, p, k, poses, c->d_bimg + npix * (size_t)i0, d_u8 ? d_u8 + npix * (size_t)i0 : nullptr, st);
+        if (status != EORB_OK) break;
+        const size_t cnt = npix * (size_t)(i1 - i0);
+        if (img_f32) CUS(cudaMemcpyAsync(img_f32 + npix * (size_t)i0, c->d_bimg + npix * (size_t)i0, cnt * sizeof(float), cudaMemcpyDeviceToHost, st));
+        if (img_u8 && status == EORB_OK) CUS(cudaMemcpyAsync(img_u8 + npix * (size_t)i0, c->d_bu8 + npix * (size_t)i0, cnt, cudaMemcpyDeviceToHost, st));
+    }
+    // every stream is drained before returning, also on an error path: no copy into the caller's arrays stays in flight
+    cudaError_t es = cudaStreamSynchronize(c->stream);
+    if (nparts > 1) for (int i = 0; i < 2; i++) { const cudaError_t e2 = cudaStreamSynchronize(c->pipeS[i]); if (es == cudaSuccess) es = e2; }
+    if (status != EORB_OK) return status;
+    CU(es);
     return EORB_OK;
 }
 

@@ -188,6 +188,38 @@ def test_windows_batch_host_entry_matches_oracle_and_device_entry():
         _close(g32[i], ref)
     with pytest.raises(Exception):
         cv.accumulate_batch(ev, offs, pm, None, u8)          # a u8 output needs a normalisation mode
+    # a large packet takes the pipelined path (four window ranges on two streams): == the device entry point bit for bit, oracle on samples;
+    # plain, motion-compensated (per-window poses) and the order-dependent pol = true normalisation
+    rng = np.random.default_rng(3)
+    sizes = [int(v) for v in rng.integers(2500, 4500, 26)]
+    sizes[5] = 0; sizes[17] = 1
+    offs = np.concatenate([[0], np.cumsum(sizes)]).astype(np.int64)
+    nwin = len(sizes)
+    assert offs[-1] >= 65536
+    ev = synth.make_events(int(offs[-1]), seed=16, w=240, h=180)
+    cv2_ = api.EvImConverter(0, nwin, int(offs[-1]), 240, 180)
+    d_ev = torch.from_numpy(ev.view(np.uint8).reshape(-1)).cuda()
+    poses = np.tile(np.eye(4, dtype=np.float32), (nwin, 1, 1))
+    for i in range(nwin):
+        a = 0.002 * (i + 1)
+        poses[i, :3, :3] = np.array([[np.cos(a), -np.sin(a), 0], [np.sin(a), np.cos(a), 0], [0, 0, 1]], np.float32)
+    variants = [cv2_.make_params(api.EV_GAUSS, 240, 180, 1.0, False, api.NORM_RUNNING),
+                cv2_.make_params(api.EV_SE3, 240, 180, 1.0, False, api.NORM_MINMAX, Tcw=poses[0], medDepth=1.0, camera=K),
+                cv2_.make_params(api.EV_GAUSS, 240, 180, 1.0, True, api.NORM_RUNNING)]
+    for vi, pv in enumerate(variants):
+        f32 = np.zeros((nwin, 180, 240), np.float32); u8 = np.zeros((nwin, 180, 240), np.uint8)
+        ps = poses.reshape(nwin, 16) if vi == 1 else None
+        cv2_.accumulate_batch(ev, offs, pv, f32, u8, poses=ps)
+        d_img = torch.zeros(nwin * 180 * 240, dtype=torch.float32, device="cuda"); d_u8 = torch.zeros(nwin * 180 * 240, dtype=torch.uint8, device="cuda")
+        cv2_.accumulate_batch_device(d_ev.data_ptr(), offs, pv, d_img.data_ptr(), d_u8.data_ptr(), poses=ps)
+        cv2_.synchronize()
+        assert f32.tobytes() == d_img.cpu().numpy().tobytes() and u8.tobytes() == d_u8.cpu().numpy().tobytes(), vi
+        if vi == 0:
+            for i in (0, 6, 13, 25):
+                ref, _, ref8 = O.ev_accumulate(ev[offs[i]:offs[i + 1]], 240, 180, 1.0, mode=1, normalize=True)
+                _close(f32[i], ref)
+                assert np.abs(u8[i].astype(int) - ref8.astype(int)).max() <= 1
+            assert not f32[5].any()
 
 
 def test_config5_mvsec_mc_frames_orb_and_frame_to_frame_matching():
