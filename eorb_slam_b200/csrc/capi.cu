@@ -244,7 +244,7 @@ struct eorb_orb {
         uint32_t* d_kpList = nullptr;
         float* d_levelAngle = nullptr;
         CUtensorMap* d_tmaps = nullptr;   // [nlevels] maps of this slab's pyramid levels >= 1
-        int* d_pyrDone = nullptr;            // [8][EORB_MAX_LEVELS] (pyr_chain_kernel)
+        int* d_pyrDone = nullptr;            // [8][EORB_MAX_LEVELS][64 block rows] (pyr_chain_kernel)
         CUtensorMap* d_icMaps = nullptr;     // [nlevels] maps of the levels >= 1, box = one keypoint's orientation patch (orient_desc_kernel)
         CUtensorMap* d_briefMaps = nullptr;  // [nlevels] maps of the blurred levels, box = one keypoint's BRIEF patch (orient_desc_kernel)
         CUtensorMap* d_blurMaps = nullptr;   // [nlevels] the same levels with blur_tma_kernel's box (EORB_BLUR_TMA=1)
@@ -334,7 +334,7 @@ static int orbAllocBufs(eorb_orb* h, eorb_orb::Bufs& b, bool pipeline) {
         }
         CU(devAlloc(&b.d_tmaps, (size_t)nl));
         CU(cudaMemcpy(b.d_tmaps, maps.data(), maps.size() * sizeof(CUtensorMap), cudaMemcpyHostToDevice));
-        CU(devAlloc(&b.d_pyrDone, (size_t)8 * EORB_MAX_LEVELS));
+        CU(devAlloc(&b.d_pyrDone, (size_t)8 * EORB_MAX_LEVELS * 64));   // [8][EORB_MAX_LEVELS][EORB_PYR_CHAIN_ROWS]
         bool blurTmaOk = h->useBlurTma != 0;
         for (int l = 0; l < nl; l++)   // degenerate levels (rows bounce more than once) stay with blur_kernel's per-pixel path
             if (P.lv[l].w > 0 && P.lv[l].h > 0 && (P.lv[l].h < 3 || P.lv[l].w < 8)) blurTmaOk = false;

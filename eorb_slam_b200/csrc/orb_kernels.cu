@@ -207,6 +207,7 @@ __global__ void __launch_bounds__(128, EORB_PYR_MINB) pyr_resize_kernel(OrbArgs 
 #ifndef EORB_PYR_CHAIN_BAND
 #define EORB_PYR_CHAIN_BAND 4   // destination rows per warp in the single-launch pyramid: short bands = many blocks = short critical path per level
 #endif
+#define EORB_PYR_CHAIN_ROWS 64   // block rows (16 destination rows each) a level can have in the chain kernel: levels up to 1024 rows
 __global__ void __launch_bounds__(128, EORB_PYR_MINB) pyr_chain_kernel(OrbArgs a, int* __restrict__ done) {
     const OrbPlan& P = *a.plan;
     const int f = blockIdx.y;
@@ -218,25 +219,42 @@ __global__ void __launch_bounds__(128, EORB_PYR_MINB) pyr_chain_kernel(OrbArgs a
         t -= tiles;
     }
     if (t >= tiles) return;
-    int* flags = done + (size_t)f * EORB_MAX_LEVELS;
-    int need = 0;
+    // One counter per (level, block row): a warp of level L waits only for the block rows of level L - 1 that hold its source rows
+    // (two or three of them), so the levels pipeline instead of running one after the other.  Source blocks always have lower block
+    // indices than their readers, so a waiting block never waits for one that cannot have been scheduled.
+    int* flags = done + (size_t)f * EORB_MAX_LEVELS * EORB_PYR_CHAIN_ROWS;
+    const int by = t / gx;
+    int need = 0, br0 = 0, br1 = -1;
     if (level > 1) {
-        const int gxp = (P.lv[level - 1].w + 127) >> 7;
-        need = gxp * ((P.lv[level - 1].h + 4 * EORB_PYR_CHAIN_BAND - 1) / (4 * EORB_PYR_CHAIN_BAND));
+        need = (P.lv[level - 1].w + 127) >> 7;
+        const int dh = P.lv[level].h;
+        const int y0 = (by * 4 + (int)threadIdx.y) * EORB_PYR_CHAIN_BAND;
+        if (y0 < dh) {
+            const int y1 = min(y0 + EORB_PYR_CHAIN_BAND, dh);
+            const int4* __restrict__ ytab = a.ytab + P.lv[level].ytabOff;
+            const int syA = __ldg(&ytab[y0]).x, syB = __ldg(&ytab[y1 - 1]).y;      // first / last source row (clamped into the level)
+            const int lastRow = (P.lv[level - 1].h + 4 * EORB_PYR_CHAIN_BAND - 1) / (4 * EORB_PYR_CHAIN_BAND) - 1;
+            br0 = min(max(syA / (4 * EORB_PYR_CHAIN_BAND), 0), lastRow);
+            br1 = min(max(syB / (4 * EORB_PYR_CHAIN_BAND), 0), lastRow);
+        }
     }
-    const volatile int* fl = flags + (level - 1);
-    auto ready = [&]() {   // per warp: lane 0 polls the source level's counter (acquire), the warp follows
+    const volatile int* fl = flags + (size_t)(level - 1) * EORB_PYR_CHAIN_ROWS;
+    auto ready = [&]() {   // per warp: lane 0 polls the counters of its source block rows (acquire), the warp follows
         if (need > 0) {
-            if (threadIdx.x == 0) { while (*fl < need) __nanosleep(20); }
+            if (threadIdx.x == 0)
+                for (int b = br0; b <= br1; b++) {
+                    unsigned spins = 0;
+                    while (fl[b] < need && ++spins < (1u << 24)) __nanosleep(20);   // bounded: a wrong result fails a test, a hang costs the box
+                }
             __syncwarp();
             __threadfence();
         }
     };
-    pyr_resize_block<EORB_PYR_CHAIN_BAND>(a, level, t % gx, t / gx, f, ready);
+    pyr_resize_block<EORB_PYR_CHAIN_BAND>(a, level, t % gx, by, f, ready);
     __syncthreads();
     if (threadIdx.x == 0 && threadIdx.y == 0) {
         __threadfence();
-        atomicAdd(flags + level, 1);
+        atomicAdd(flags + (size_t)level * EORB_PYR_CHAIN_ROWS + by, 1);
     }
 }
 
@@ -1028,8 +1046,10 @@ cudaError_t launch_orb_pipeline(const OrbArgs& a, const OrbPlan& hp, int nframes
     // ev (optional, EORB_ORB_STAGES+1 events): recorded around every stage for the per-kernel timings of bench.py
     if (ev) cudaEventRecord(ev[0], st);
     // K1: pyramid, level by level (each level is resized from the previous one)
-    if (a.pyrDone && nframes <= 8 && hp.nlevels > 1) {   // one launch for all levels (pyr_chain_kernel)
-        cudaError_t e = cudaMemsetAsync(a.pyrDone, 0, (size_t)nframes * EORB_MAX_LEVELS * sizeof(int), st);
+    bool chainFits = true;                                // a counter per block row: levels of at most 16 * EORB_PYR_CHAIN_ROWS rows
+    for (int l = 1; l < hp.nlevels; l++) chainFits = chainFits && (hp.lv[l].h + 4 * EORB_PYR_CHAIN_BAND - 1) / (4 * EORB_PYR_CHAIN_BAND) <= EORB_PYR_CHAIN_ROWS;
+    if (a.pyrDone && nframes <= 8 && hp.nlevels > 1 && chainFits) {   // one launch for all levels (pyr_chain_kernel)
+        cudaError_t e = cudaMemsetAsync(a.pyrDone, 0, (size_t)nframes * EORB_MAX_LEVELS * EORB_PYR_CHAIN_ROWS * sizeof(int), st);
         if (e != cudaSuccess) return e;
         pyr_chain_kernel<<<dim3(pyr_chain_tiles(hp), nframes), dim3(32, 4), 0, st>>>(a, a.pyrDone);
         (*launches)++;
