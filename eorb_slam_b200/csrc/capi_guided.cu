@@ -976,7 +976,7 @@ extern "C" int eorb_guided_search_for_triangulation(eorb_guided* g, const eorb_k
     GuidedBowSide a{(const eorb_keypoint*)(B + off[0]), B + off[1], (const uint32_t*)(B + off[4]), (const int32_t*)(B + off[5]), (const uint32_t*)(B + off[6]), nn1, n1};
     GuidedBowSide b{(const eorb_keypoint*)(B + off[2]), B + off[3], (const uint32_t*)(B + off[7]), (const int32_t*)(B + off[8]), (const uint32_t*)(B + off[9]), nn2, n2};
     if (!g->d_bowWork) CU(cudaMalloc((void**)&g->d_bowWork, 64 * sizeof(int)));
-    CU(launch_search_triangulation(a, B + off[10], b, B + off[11], tg, check_ori, (int32_t*)(g->d_outb + 16), (signed char*)(g->d_outb + oBin), g->d_bowWork,
+    CU(launch_search_triangulation(a, B + off[10], b, B + off[11], tg, check_ori, nf1, (int32_t*)(g->d_outb + 16), (signed char*)(g->d_outb + oBin), g->d_bowWork,
                                    (int*)g->d_outb, g->stream, &g->launches));
     CU(cudaMemcpyAsync(g->h_outb, g->d_outb, oBin, cudaMemcpyDeviceToHost, g->stream));
     CU(cudaStreamSynchronize(g->stream));

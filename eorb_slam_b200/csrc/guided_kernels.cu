@@ -1271,82 +1271,81 @@ static size_t resolveMapSmem(int n1, int n2) {
 // ------------------------------------------------------------------------------------------------ SearchForTriangulation
 // ORBmatcher::SearchForTriangulation(pKF1, pKF2, F12, vMatchedPairs, bOnlyStereo, bCoarse) (src/ORBmatcher.cc:975-1214; LocalMapping::
 // CreateNewMapPoints, Tracking's keyframe insertion), keyframes with ONE pinhole camera each (mpCamera2 == NULL).  In this version of the
-// function vbMatched2 is never set (:1008 declares it, nothing writes it), so the features of KF1 do not interact: one warp per common
-// vocabulary node, one lane per KF1 feature of the node, every lane walks the node's KF2 features.  The running rule `dist > TH_LOW ||
+// function vbMatched2 is never set (:1008 declares it, nothing writes it), so the features of KF1 do not interact: one warp per KF1 feature,
+// the lanes stride over the KF2 features of the same vocabulary node.  The running rule `dist > TH_LOW ||
 // dist > bestDist -> skip, ... -> bestIdx2 = idx2, bestDist = dist` (:1066-1140) keeps the LAST feature among those with the smallest
 // distance that pass the static gates, i.e. the minimum of (dist << 16 | 0xffff - position).  Gates: flag bit 0 (no map point, and stereo
 // when bOnlyStereo), the epipole distance for monocular pairs (:1077-1085), Pinhole::epipolarConstrain (src/CameraModels/Pinhole.cpp:
 // 134-157) with the fundamental matrix the camera forms from R12 / t12 passed in by the caller -- float arithmetic in the reference's order.
 __global__ void __launch_bounds__(BOW_WARPS * 32) search_triangulation_kernel(GuidedBowSide k1, const uint8_t* __restrict__ flags1, GuidedBowSide k2,
                                                                                const uint8_t* __restrict__ flags2, GuidedTriGeom tg, int checkOri,
-                                                                               int32_t* __restrict__ match12, signed char* __restrict__ binOf,
-                                                                               int* __restrict__ work) {
-    const int lane = threadIdx.x & 31, w = blockIdx.x * BOW_WARPS + (threadIdx.x >> 5);
-    if (w >= k1.nnodes) return;
-    const uint32_t node = k1.nodes[w];
-    int lo = 0, hi = k2.nnodes;
+                                                                               int nEntries1, int32_t* __restrict__ match12,
+                                                                               signed char* __restrict__ binOf, int* __restrict__ work) {
+    // one warp per FeatureVector entry of the first keyframe (= one feature; a feature lies under exactly one node), the lanes stride over the
+    // second keyframe's features of the same node: the work is a few hundred 8-POPC distances, so the critical path is what matters
+    const int lane = threadIdx.x & 31, a = blockIdx.x * BOW_WARPS + (threadIdx.x >> 5);
+    if (a >= nEntries1) return;
+    const int i1 = (int)k1.feats[a];
+    const unsigned f1 = flags1[i1];
+    if (!(f1 & 1u)) return;
+    int lo = 0, hi = k1.nnodes;                        // node of entry a: the last q with start[q] <= a
+    while (hi - lo > 1) { const int mid = (lo + hi) >> 1; if (k1.start[mid] <= a) lo = mid; else hi = mid; }
+    const uint32_t node = k1.nodes[lo];
+    lo = 0; hi = k2.nnodes;
     while (lo < hi) { const int mid = (lo + hi) >> 1; if (k2.nodes[mid] < node) lo = mid + 1; else hi = mid; }
     if (lo >= k2.nnodes || k2.nodes[lo] != node) return;
     const int fb = k2.start[lo], fe = k2.start[lo + 1];
-    int nm = 0;
-    for (int a = k1.start[w] + lane, ae = k1.start[w + 1]; a < ae; a += 32) {
-        const int i1 = (int)k1.feats[a];
-        const unsigned f1 = flags1[i1];
-        if (!(f1 & 1u)) continue;
-        const eorb_keypoint kp1 = k1.kps[i1];
-        uint32_t q[8];
-        {
-            const uint4* qp = reinterpret_cast<const uint4*>(k1.desc + (size_t)i1 * 32);
-            const uint4 u = __ldg(qp), v = __ldg(qp + 1);
-            q[0] = u.x; q[1] = u.y; q[2] = u.z; q[3] = u.w; q[4] = v.x; q[5] = v.y; q[6] = v.z; q[7] = v.w;
-        }
-        // epipolar line in the second image l = x1' F12 = [a b c] (Pinhole.cpp:143-145)
-        const float la = __fadd_rn(__fadd_rn(__fmul_rn(kp1.x, tg.F[0]), __fmul_rn(kp1.y, tg.F[3])), tg.F[6]);
-        const float lb = __fadd_rn(__fadd_rn(__fmul_rn(kp1.x, tg.F[1]), __fmul_rn(kp1.y, tg.F[4])), tg.F[7]);
-        const float lc = __fadd_rn(__fadd_rn(__fmul_rn(kp1.x, tg.F[2]), __fmul_rn(kp1.y, tg.F[5])), tg.F[8]);
-        const float den = __fadd_rn(__fmul_rn(la, la), __fmul_rn(lb, lb));
-        uint32_t best = 0xffffffffu;
-        for (int j = fb; j < fe; j++) {
-            const int i2 = (int)k2.feats[j];
-            const unsigned f2 = flags2[i2];
-            if (!(f2 & 1u)) continue;
-            const uint4* dp = reinterpret_cast<const uint4*>(k2.desc + (size_t)i2 * 32);
-            const uint4 u = __ldg(dp), v = __ldg(dp + 1);
-            const int dist = __popc(u.x ^ q[0]) + __popc(u.y ^ q[1]) + __popc(u.z ^ q[2]) + __popc(u.w ^ q[3]) + __popc(v.x ^ q[4]) + __popc(v.y ^ q[5]) +
-                             __popc(v.z ^ q[6]) + __popc(v.w ^ q[7]);
-            if (dist > 50) continue;                                       // TH_LOW
-            const eorb_keypoint kp2 = k2.kps[i2];
-            if (!((f1 | f2) & 2u)) {                                       // neither side stereo: not too close to the epipole (:1077-1085)
-                const float dx = __fsub_rn(tg.ep[0], kp2.x), dy = __fsub_rn(tg.ep[1], kp2.y);
-                const int lv = kp2.octave < 0 ? 0 : (kp2.octave > 31 ? 31 : kp2.octave);
-                if (__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)) < __fmul_rn(100.0f, tg.scale2[lv])) continue;
-            }
-            if (!tg.coarse) {
-                if (den == 0.0f) continue;
-                const float num = __fadd_rn(__fadd_rn(__fmul_rn(la, kp2.x), __fmul_rn(lb, kp2.y)), lc);
-                const float dsqr = __fdiv_rn(__fmul_rn(num, num), den);
-                const int lv = kp2.octave < 0 ? 0 : (kp2.octave > 31 ? 31 : kp2.octave);
-                if (!(dsqr < __fmul_rn(3.84f, tg.sigma2[lv]))) continue;   // DEF_EC_DIST_COEF * unc (include/CameraModels/Pinhole.h:36)
-            }
-            const uint32_t key = ((uint32_t)dist << 16) | (uint32_t)(0xffff - (j - fb));
-            best = min(best, key);
-        }
-        if (best == 0xffffffffu) continue;
-        const int i2 = (int)k2.feats[fb + (0xffff - (int)(best & 0xffffu))];
-        match12[i1] = i2;
-        nm++;
-        int bin = -1;
-        if (checkOri) {
-            float rot = __fsub_rn(kp1.angle, k2.kps[i2].angle);
-            if (rot < 0.0f) rot = __fadd_rn(rot, 360.0f);
-            bin = (int)roundf(__fmul_rn(rot, 1.0f / 30));
-            if (bin == 30) bin = 0;
-            if (bin >= 0 && bin < 30) atomicAdd(&work[bin], 1); else bin = -1;
-        }
-        binOf[i1] = (signed char)bin;
+    const eorb_keypoint kp1 = k1.kps[i1];
+    uint32_t q[8];
+    {
+        const uint4* qp = reinterpret_cast<const uint4*>(k1.desc + (size_t)i1 * 32);
+        const uint4 u = __ldg(qp), v = __ldg(qp + 1);
+        q[0] = u.x; q[1] = u.y; q[2] = u.z; q[3] = u.w; q[4] = v.x; q[5] = v.y; q[6] = v.z; q[7] = v.w;
     }
-    nm = __reduce_add_sync(FULLMASK, nm);
-    if (lane == 0 && nm) atomicAdd(&work[32], nm);
+    // epipolar line in the second image l = x1' F12 = [a b c] (Pinhole.cpp:143-145)
+    const float la = __fadd_rn(__fadd_rn(__fmul_rn(kp1.x, tg.F[0]), __fmul_rn(kp1.y, tg.F[3])), tg.F[6]);
+    const float lb = __fadd_rn(__fadd_rn(__fmul_rn(kp1.x, tg.F[1]), __fmul_rn(kp1.y, tg.F[4])), tg.F[7]);
+    const float lc = __fadd_rn(__fadd_rn(__fmul_rn(kp1.x, tg.F[2]), __fmul_rn(kp1.y, tg.F[5])), tg.F[8]);
+    const float den = __fadd_rn(__fmul_rn(la, la), __fmul_rn(lb, lb));
+    uint32_t best = 0xffffffffu;
+    for (int j = fb + lane; j < fe; j += 32) {
+        const int i2 = (int)k2.feats[j];
+        const unsigned f2 = flags2[i2];
+        if (!(f2 & 1u)) continue;
+        const uint4* dp = reinterpret_cast<const uint4*>(k2.desc + (size_t)i2 * 32);
+        const uint4 u = __ldg(dp), v = __ldg(dp + 1);
+        const int dist = __popc(u.x ^ q[0]) + __popc(u.y ^ q[1]) + __popc(u.z ^ q[2]) + __popc(u.w ^ q[3]) + __popc(v.x ^ q[4]) + __popc(v.y ^ q[5]) +
+                         __popc(v.z ^ q[6]) + __popc(v.w ^ q[7]);
+        if (dist > 50) continue;                                       // TH_LOW
+        const eorb_keypoint kp2 = k2.kps[i2];
+        if (!((f1 | f2) & 2u)) {                                       // neither side stereo: not too close to the epipole (:1077-1085)
+            const float dx = __fsub_rn(tg.ep[0], kp2.x), dy = __fsub_rn(tg.ep[1], kp2.y);
+            const int lv = kp2.octave < 0 ? 0 : (kp2.octave > 31 ? 31 : kp2.octave);
+            if (__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)) < __fmul_rn(100.0f, tg.scale2[lv])) continue;
+        }
+        if (!tg.coarse) {
+            if (den == 0.0f) continue;
+            const float num = __fadd_rn(__fadd_rn(__fmul_rn(la, kp2.x), __fmul_rn(lb, kp2.y)), lc);
+            const float dsqr = __fdiv_rn(__fmul_rn(num, num), den);
+            const int lv = kp2.octave < 0 ? 0 : (kp2.octave > 31 ? 31 : kp2.octave);
+            if (!(dsqr < __fmul_rn(3.84f, tg.sigma2[lv]))) continue;   // DEF_EC_DIST_COEF * unc (include/CameraModels/Pinhole.h:36)
+        }
+        best = min(best, ((uint32_t)dist << 16) | (uint32_t)(0xffff - (j - fb)));
+    }
+    best = __reduce_min_sync(FULLMASK, best);
+    if (best == 0xffffffffu || lane != 0) return;
+    const int i2 = (int)k2.feats[fb + (0xffff - (int)(best & 0xffffu))];
+    match12[i1] = i2;
+    int bin = -1;
+    if (checkOri) {
+        float rot = __fsub_rn(kp1.angle, k2.kps[i2].angle);
+        if (rot < 0.0f) rot = __fadd_rn(rot, 360.0f);
+        bin = (int)roundf(__fmul_rn(rot, 1.0f / 30));
+        if (bin == 30) bin = 0;
+        if (bin >= 0 && bin < 30) atomicAdd(&work[bin], 1); else bin = -1;
+    }
+    binOf[i1] = (signed char)bin;
+    atomicAdd(&work[32], 1);
 }
 
 // rotation consistency (:1177-1198): matches in the bins that are not among the three maxima are taken back
@@ -1378,15 +1377,15 @@ __global__ void __launch_bounds__(256) triangulation_rot_kernel(int n1, int chec
 }
 
 cudaError_t launch_search_triangulation(const GuidedBowSide& k1, const uint8_t* d_flags1, const GuidedBowSide& k2, const uint8_t* d_flags2,
-                                        const GuidedTriGeom& tg, int checkOri, int32_t* d_match12, signed char* d_binOf, int* d_work /* 64 ints */,
-                                        int* d_nmatches, cudaStream_t st, long long* launches) {
+                                        const GuidedTriGeom& tg, int checkOri, int nEntries1, int32_t* d_match12, signed char* d_binOf,
+                                        int* d_work /* 64 ints */, int* d_nmatches, cudaStream_t st, long long* launches) {
     cudaError_t e = cudaMemsetAsync(d_match12, 0xff, (size_t)(k1.n > 0 ? k1.n : 1) * sizeof(int32_t), st);
     if (e != cudaSuccess) return e;
     e = cudaMemsetAsync(d_work, 0, 64 * sizeof(int), st);
     if (e != cudaSuccess) return e;
-    if (k1.nnodes > 0 && k2.nnodes > 0) {
-        search_triangulation_kernel<<<(k1.nnodes + BOW_WARPS - 1) / BOW_WARPS, BOW_WARPS * 32, 0, st>>>(k1, d_flags1, k2, d_flags2, tg, checkOri, d_match12,
-                                                                                                       d_binOf, d_work);
+    if (k1.nnodes > 0 && k2.nnodes > 0 && nEntries1 > 0) {
+        search_triangulation_kernel<<<(nEntries1 + BOW_WARPS - 1) / BOW_WARPS, BOW_WARPS * 32, 0, st>>>(k1, d_flags1, k2, d_flags2, tg, checkOri, nEntries1,
+                                                                                                       d_match12, d_binOf, d_work);
         (*launches)++;
     }
     triangulation_rot_kernel<<<1, 256, 0, st>>>(k1.n, checkOri, d_match12, d_binOf, d_work, d_nmatches);

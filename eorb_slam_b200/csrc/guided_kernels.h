@@ -77,8 +77,8 @@ cudaError_t launch_search_windows(const eorb_area_query* d_q, const float* d_qUr
 // part (no map point; stereo when bOnlyStereo), bit 1: it has a right-image column (bStereo)
 struct GuidedTriGeom { float F[9]; float ep[2]; float scale2[32]; float sigma2[32]; int coarse; };
 cudaError_t launch_search_triangulation(const GuidedBowSide& k1, const uint8_t* d_flags1, const GuidedBowSide& k2, const uint8_t* d_flags2,
-                                        const GuidedTriGeom& tg, int checkOri, int32_t* d_match12, signed char* d_binOf, int* d_work /* 64 ints */,
-                                        int* d_nmatches, cudaStream_t st, long long* launches);
+                                        const GuidedTriGeom& tg, int checkOri, int nEntries1 /* start1[nnodes1] */, int32_t* d_match12, signed char* d_binOf,
+                                        int* d_work /* 64 ints */, int* d_nmatches, cudaStream_t st, long long* launches);
 cudaError_t guided_configure();
 
 }  // namespace eorb
