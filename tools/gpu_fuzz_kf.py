@@ -13,6 +13,7 @@ ncases = int(sys.argv[1]) if len(sys.argv) > 1 else 200
 rng = np.random.default_rng(int(sys.argv[2]) if len(sys.argv) > 2 else 1)
 gm = api.GuidedMatcher()
 bad = 0
+tot = [0, 0]
 for it in range(ncases):
     n1 = int(rng.choice([0, 1, 7, 50, 400, 1500, 3000])); n2 = int(rng.choice([0, 1, 9, 64, 500, 1200, 4000]))
     nl = int(rng.integers(1, 9))
@@ -46,10 +47,11 @@ for it in range(ncases):
         kw = dict(query_min_xy=qm, inv_level_sigma2=inv, blocking=blocking, th_high=int(rng.choice([0, 30, 50, 100, 255])))
         a = (q, ur, dm, k2, d2, held, ur2, b)
         o = O.search_windows(*a, **kw); r = gm.SearchWindows(*a, **kw)
+        tot[int(blocking)] += int(o[0])
         ok = o[0] == r[0] and all(np.array_equal(x, y) for x, y in zip(o[1:], r[1:]))
         if not ok:
             bad += 1
             print("MISMATCH case", it, "n1", n1, "n2", n2, "blocking", blocking, kw["th_high"], "crowd", crowd, "nm", o[0], r[0],
                   [int((x != y).sum()) for x, y in zip(o[1:], r[1:])])
-print("search_windows fuzz: %d cases x 2, %d mismatches" % (ncases, bad))
+print("search_windows fuzz: %d cases x 2, %d mismatches; %d non-blocking and %d blocking matches compared" % (ncases, bad, tot[0], tot[1]))
 sys.exit(1 if bad else 0)
