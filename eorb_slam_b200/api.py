@@ -112,6 +112,7 @@ def _load():
         "eorb_guided_search_by_bow": ([vp, vp, vp, vp, i, vp, vp, vp, i, vp, vp, i, vp, vp, vp, i, f, i, vp, vp], i),
         "eorb_guided_search_by_bow_device": ([vp, vp, vp, vp, i, vp, vp, vp, i, vp, vp, i, vp, vp, vp, i, f, i, vp, vp], i),
         "eorb_guided_search_for_triangulation": ([vp, vp, vp, vp, i, vp, vp, vp, i, vp, vp, vp, i, vp, vp, vp, i, vp, vp, vp, vp, i, i, i, vp, vp], i),
+        "eorb_guided_search_for_triangulation_device": ([vp, vp, vp, vp, i, vp, vp, vp, i, i, vp, vp, vp, i, vp, vp, vp, i, vp, vp, vp, vp, i, i, i, vp, vp], i),
         "eorb_guided_search_windows": ([vp, vp, vp, vp, i, vp, vp, vp, vp, i, vp, vp, vp, i, i, i, vp, vp, vp, vp], i),
         "eorb_guided_search_windows_device": ([vp, vp, vp, vp, i, vp, vp, vp, vp, i, vp, vp, vp, i, i, i, vp, vp, vp, vp], i),
         "eorb_guided_search_by_bow_kf": ([vp, vp, vp, vp, i, vp, vp, vp, i, vp, vp, vp, i, vp, vp, vp, i, f, i, vp, vp], i),
@@ -874,6 +875,19 @@ class GuidedMatcher:
                                                         int(bCoarse), int(self.mbCheckOrientation), _p(m12), C.byref(nm)),
                "SearchForTriangulation")
         return nm.value, m12[:len(k1)].copy()
+
+    def SearchForTriangulation_device(self, d_kps1, d_desc1, d_flags1, n1, d_fv1, nn1, nentries1, d_kps2, d_desc2, d_flags2, n2, d_fv2, nn2, F12, epipole2,
+                                      scale_factors2, level_sigma2_2, d_match12, bCoarse=False):
+        """device pointers (ints); d_fv = (nodes, start, feats) pointers; returns nmatches"""
+        F = np.ascontiguousarray(F12, np.float32).reshape(9); e = np.ascontiguousarray(epipole2, np.float32)
+        sc = np.ascontiguousarray(scale_factors2, np.float32); sg = np.ascontiguousarray(level_sigma2_2, np.float32)
+        nm = C.c_int(0)
+        vp = C.c_void_p
+        _check(lib.eorb_guided_search_for_triangulation_device(self.h, vp(d_kps1), vp(d_desc1), vp(d_flags1), n1, vp(d_fv1[0]), vp(d_fv1[1]), vp(d_fv1[2]), nn1,
+                                                               nentries1, vp(d_kps2), vp(d_desc2), vp(d_flags2), n2, vp(d_fv2[0]), vp(d_fv2[1]), vp(d_fv2[2]),
+                                                               nn2, _p(F), _p(e), _p(sc), _p(sg), len(sc), int(bCoarse), int(self.mbCheckOrientation),
+                                                               vp(d_match12), C.byref(nm)), "SearchForTriangulation_device")
+        return nm.value
 
     def SearchWindows(self, queries, ur, descMP, kps2, desc2, held2, u_right2, bounds, query_min_xy=None, inv_level_sigma2=None, blocking=False,
                       th_high=50):

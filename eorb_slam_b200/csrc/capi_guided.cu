@@ -985,3 +985,49 @@ extern "C" int eorb_guided_search_for_triangulation(eorb_guided* g, const eorb_k
     return EORB_OK;
 }
 
+/* the same with every array resident in HBM (FeatureVectors in the CSR form eorb_vocab_transform_resident leaves there); nentries1 = start1[nn1],
+   d_match12 (n1 entries) is written on the device, *nmatches after a stream synchronisation */
+extern "C" int eorb_guided_search_for_triangulation_device(eorb_guided* g, const eorb_keypoint* d_kps1, const uint8_t* d_desc1, const uint8_t* d_flags1,
+                                                           int n1, const uint32_t* d_nodes1, const int32_t* d_start1, const uint32_t* d_feats1, int nn1,
+                                                           int nentries1, const eorb_keypoint* d_kps2, const uint8_t* d_desc2, const uint8_t* d_flags2,
+                                                           int n2, const uint32_t* d_nodes2, const int32_t* d_start2, const uint32_t* d_feats2, int nn2,
+                                                           const float* F12, const float* epipole2, const float* scale_factors2,
+                                                           const float* level_sigma2_2, int nlevels, int coarse, int check_ori, int32_t* d_match12,
+                                                           int* nmatches) {
+    const char* who = "eorb_guided_search_for_triangulation_device";
+    if (!g) return gFail(EORB_ERR_ARG, who, "null handle");
+    if (n1 < 0 || n2 < 0 || nn1 < 0 || nn2 < 0 || nentries1 < 0 || nentries1 > n1) return gFail(EORB_ERR_ARG, who, "bad size");
+    if (n1 > EORB_GUIDED_MAX_KEYPOINTS || n2 > EORB_GUIDED_MAX_KEYPOINTS) return gFail(EORB_ERR_CAPACITY, who, "more than EORB_GUIDED_MAX_KEYPOINTS keypoints");
+    if (nmatches) *nmatches = 0;
+    if (n1 == 0) return EORB_OK;
+    if (!d_match12 || !F12 || !epipole2 || !scale_factors2 || !level_sigma2_2) return gFail(EORB_ERR_ARG, who, "null argument");
+    if (n2 > 0 && nn1 > 0 && nn2 > 0 && (!d_kps1 || !d_desc1 || !d_flags1 || !d_nodes1 || !d_start1 || !d_feats1 || !d_kps2 || !d_desc2 || !d_flags2 || !d_nodes2 ||
+                                        !d_start2 || !d_feats2))
+        return gFail(EORB_ERR_ARG, who, "null argument");
+    if (nlevels < 1 || nlevels > 32) return gFail(EORB_ERR_ARG, who, "bad level tables (1..32 levels)");
+    if (((uintptr_t)d_desc1 | (uintptr_t)d_desc2) & 15) return gFail(EORB_ERR_ARG, who, "descriptors must be 16-byte aligned");
+    CU(cudaSetDevice(g->device));
+    GuidedTriGeom tg;
+    for (int i = 0; i < 9; i++) tg.F[i] = F12[i];
+    tg.ep[0] = epipole2[0]; tg.ep[1] = epipole2[1]; tg.coarse = coarse ? 1 : 0;
+    for (int i = 0; i < 32; i++) { tg.scale2[i] = scale_factors2[i < nlevels ? i : nlevels - 1]; tg.sigma2[i] = level_sigma2_2[i < nlevels ? i : nlevels - 1]; }
+    const size_t outBytes = 16 + (((size_t)n1 + 15) & ~(size_t)15);            // [nmatches | rotation bin per feature]
+    if (outBytes > g->outbCap) {
+        CU(cudaStreamSynchronize(g->stream));
+        cudaFree(g->d_outb); cudaFreeHost(g->h_outb); g->d_outb = nullptr; g->h_outb = nullptr; g->outbCap = 0;
+        const size_t cap = std::max<size_t>(outBytes + outBytes / 4, 1 << 14);
+        CU(cudaMalloc((void**)&g->d_outb, cap));
+        CU(cudaMallocHost((void**)&g->h_outb, cap));
+        g->outbCap = cap;
+    }
+    if (!g->d_bowWork) CU(cudaMalloc((void**)&g->d_bowWork, 64 * sizeof(int)));
+    GuidedBowSide a{d_kps1, d_desc1, d_nodes1, d_start1, d_feats1, (n2 > 0 ? nn1 : 0), n1};
+    GuidedBowSide b{d_kps2, d_desc2, d_nodes2, d_start2, d_feats2, nn2, n2};
+    CU(launch_search_triangulation(a, d_flags1, b, d_flags2, tg, check_ori, nentries1, d_match12, (signed char*)(g->d_outb + 16), g->d_bowWork,
+                                   (int*)g->d_outb, g->stream, &g->launches));
+    CU(cudaMemcpyAsync(g->h_outb, g->d_outb, sizeof(int), cudaMemcpyDeviceToHost, g->stream));
+    CU(cudaStreamSynchronize(g->stream));
+    if (nmatches) *nmatches = *(const int*)g->h_outb;
+    return EORB_OK;
+}
+

@@ -497,6 +497,16 @@ int eorb_guided_search_for_triangulation(eorb_guided* g, const eorb_keypoint* kp
                                          const float* epipole2, const float* scale_factors2, const float* level_sigma2_2, int nlevels,
                                          int coarse, int check_ori, int32_t* match12, int* nmatches);
 
+/* the same with every array resident in HBM (the FeatureVectors in the CSR form eorb_vocab_transform_resident leaves there); nentries1 =
+ * start1[nn1] (the number of feature entries of the first FeatureVector); d_match12 is written on the device, *nmatches after a stream
+ * synchronisation.  F12 / epipole2 / the level tables stay host arrays (they are per-call constants). */
+int eorb_guided_search_for_triangulation_device(eorb_guided* g, const eorb_keypoint* d_kps1, const uint8_t* d_desc1, const uint8_t* d_flags1, int n1,
+                                                const uint32_t* d_nodes1, const int32_t* d_start1, const uint32_t* d_feats1, int nn1, int nentries1,
+                                                const eorb_keypoint* d_kps2, const uint8_t* d_desc2, const uint8_t* d_flags2, int n2,
+                                                const uint32_t* d_nodes2, const int32_t* d_start2, const uint32_t* d_feats2, int nn2,
+                                                const float* F12, const float* epipole2, const float* scale_factors2, const float* level_sigma2_2,
+                                                int nlevels, int coarse, int check_ori, int32_t* d_match12, int* nmatches);
+
 /* eorb_guided_search_windows: the matching core of the KEYFRAME-side searches of local mapping and loop closing, which all have one
  * shape -- per map point a window in a keyframe (GetFeaturesInArea(u, v, radius), src/KeyFrame.cc:873-917), keypoints of level
  * [nPredictedLevel - 1, nPredictedLevel], smallest descriptor distance, first visited among equals:

@@ -258,4 +258,17 @@ def test_cuda_search_for_triangulation_equals_reference_golden():
     assert n == 0 and (m == -1).all()
     n, m = gm.SearchForTriangulation(k1[:0], d1[:0], f1[:0], (fv1[0][:0], np.zeros(1, np.int32), fv1[2][:0]), k2, d2, f2, fv2, F, ep, sc, sg)
     assert n == 0 and len(m) == 0
+    # the device-resident entry point on the same case == the host entry point
+    import torch
+    from eorb_slam_b200.synth import KEYPOINT_DTYPE
+    dev = lambda a_: torch.from_numpy(np.ascontiguousarray(a_).view(np.uint8).reshape(-1).copy()).cuda()
+    tk1, td1, tf1, tk2, td2, tf2 = dev(np.ascontiguousarray(k1, KEYPOINT_DTYPE)), dev(d1), dev(f1), dev(np.ascontiguousarray(k2, KEYPOINT_DTYPE)), dev(d2), dev(f2)
+    t1 = [dev(np.ascontiguousarray(fv1[0], np.uint32)), dev(np.ascontiguousarray(fv1[1], np.int32)), dev(np.ascontiguousarray(fv1[2], np.uint32))]
+    t2 = [dev(np.ascontiguousarray(fv2[0], np.uint32)), dev(np.ascontiguousarray(fv2[1], np.int32)), dev(np.ascontiguousarray(fv2[2], np.uint32))]
+    d_m = torch.zeros(len(k1), dtype=torch.int32, device="cuda")
+    nh, mh = gm.SearchForTriangulation(k1, d1, f1, fv1, k2, d2, f2, fv2, F, ep, sc, sg)
+    nd = gm.SearchForTriangulation_device(tk1.data_ptr(), td1.data_ptr(), tf1.data_ptr(), len(k1), [t.data_ptr() for t in t1], len(fv1[0]), int(fv1[1][-1]),
+                                          tk2.data_ptr(), td2.data_ptr(), tf2.data_ptr(), len(k2), [t.data_ptr() for t in t2], len(fv2[0]), F, ep, sc, sg,
+                                          d_m.data_ptr())
+    assert nd == nh and nh > 0 and np.array_equal(d_m.cpu().numpy(), mh)
 
